@@ -1,0 +1,196 @@
+"""Synthetic dense conic instances for the parity tests and bench.py.
+
+All data float64 from numpy.random.Generator(PCG64(seed)).  Recipe: a
+strictly feasible primal-dual pair is planted so that the first iterate is interior:
+G ~ N(0,1)^{q x n} (rows of matrix-cone blocks svec-scaled: off-diagonals * sqrt 2, like
+scale_svec!, reference src/Cones/arrayutilities.jl:136-156), x0 ~ N(0,1)^n, s0 / z0 = the
+cone's central point perturbed like the reference's cone tests (test/cone.jl:236-248),
+h = G x0 + s0, c = -G'z0 - A'y0, b = A x0.  Instances are stated post-preprocessing, i.e. as
+the (n, p, q, G, A, cones) that load(syssolver, solver) sees (reference
+src/Solvers/Solvers.jl:334).
+
+`linearopt` restates examples/linearopt/native.jl:15-30 (BASELINE config 1).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import models as M
+from .point import Point
+
+RT2 = np.sqrt(2.0)
+
+_RAYS = np.array([
+    [-0.827838387, 0.805102007, 1.290927686], [-0.689607388, 0.724605082, 1.224617936],
+    [-0.584372665, 0.68128058, 1.182421942], [-0.503499342, 0.65448622, 1.153053152],
+    [-0.440285893, 0.636444224, 1.131466926], [-0.389979809, 0.623569352, 1.114979519],
+    [-0.349255921, 0.613978276, 1.102013921], [-0.315769104, 0.606589839, 1.091577908],
+    [-0.287837744, 0.600745284, 1.083013], [-0.264242734, 0.596019009, 1.075868782]])
+
+
+def _central_ray_hypoperlog(d):
+    # numerical data of the reference (src/Cones/hypoperlog.jl:289-319)
+    if d <= 10:
+        return _RAYS[d - 1]
+    x = 1.0 / d
+    if d <= 70:
+        return np.array([4.657876 * x * x - 3.116192 * x + 0.000647, 0.424682 * x + 0.553392,
+                         0.760412 * x + 1.001795])
+    return np.array([-3.011166 * x - 0.000122, 0.395308 * x + 0.553955, 0.837545 * x + 1.000024])
+
+
+def _svec_diag_idx(side):
+    j = np.arange(side)
+    return j * (j + 1) // 2 + j
+
+
+def _svec_offdiag_mask(side):
+    mask = np.ones(side * (side + 1) // 2, dtype=bool)
+    mask[_svec_diag_idx(side)] = False
+    return mask
+
+
+def cone_initial_point(spec):
+    """Central primal point of one cone (set_initial_point!; nonnegative.jl:42,
+    epinormeucl.jl:44-52, possemideftri.jl:69-78, hypoperlogdettri.jl:82-94,
+    hyporootdettri.jl:82-98)."""
+    arr = np.zeros(spec.dim)
+    if spec.ctype == M.CONE_NONNEGATIVE:
+        arr[:] = 1.0
+    elif spec.ctype == M.CONE_EPINORMEUCL:
+        arr[0] = RT2
+    elif spec.ctype == M.CONE_POSSEMIDEFTRI:
+        arr[_svec_diag_idx(spec.side)] = 1.0
+    elif spec.ctype == M.CONE_HYPOPERLOGDETTRI:
+        u, v, w = _central_ray_hypoperlog(spec.side)
+        arr[0], arr[1] = u, v
+        arr[2 + _svec_diag_idx(spec.side)] = w
+    elif spec.ctype == M.CONE_HYPOROOTDETTRI:
+        d = spec.side
+        c1 = np.sqrt(5.0 * d * d + 2 * d + 1)
+        c2 = arr[0] = -np.sqrt((3 * d + 1 - c1) / (2.0 * d + 2))
+        arr[1 + _svec_diag_idx(d)] = -c2 * (d + 1 + c1) / (2.0 * d)
+    return arr
+
+
+def _cone_dual_initial(spec, prim):
+    """-grad at the central point, closed form per cone (dual of the central point)."""
+    if spec.ctype == M.CONE_NONNEGATIVE:
+        return 1.0 / prim
+    if spec.ctype == M.CONE_EPINORMEUCL:
+        return prim.copy()      # central point is self-dual: -g = (u, -w)/dist with dist = 1
+    if spec.ctype == M.CONE_POSSEMIDEFTRI:
+        return prim.copy()
+    d = spec.side
+    out = np.zeros_like(prim)
+    if spec.ctype == M.CONE_HYPOPERLOGDETTRI:
+        u, v, w = prim[0], prim[1], prim[2]
+        phi = d * np.log(w) - d * np.log(v)
+        zeta = v * phi - u
+        out[0] = -1.0 / zeta
+        out[1] = 1.0 / v + (phi - d) / zeta
+        out[2 + _svec_diag_idx(d)] = (1 + v / zeta) / w
+    else:
+        u, w = prim[0], prim[1]
+        phi = w
+        zeta = phi - u
+        out[0] = -1.0 / zeta
+        out[1 + _svec_diag_idx(d)] = (phi / zeta / d + 1) / w
+    return out
+
+
+def _perturb(rng, spec, vec, noise):
+    """vec += U(-noise, noise), with the noise on matrix blocks shrunk by 1/sqrt(side) so the
+    perturbed matrix stays safely positive definite at any side."""
+    if spec.ctype in (M.CONE_NONNEGATIVE, M.CONE_EPINORMEUCL):
+        vec += noise * (2 * rng.random(vec.size) - 1)
+        return vec
+    off = {M.CONE_POSSEMIDEFTRI: 0, M.CONE_HYPOPERLOGDETTRI: 2, M.CONE_HYPOROOTDETTRI: 1}[spec.ctype]
+    vec[:off] += 0.5 * noise * (2 * rng.random(off) - 1)
+    vec[off:] += noise / np.sqrt(spec.side) * (2 * rng.random(vec.size - off) - 1)
+    return vec
+
+
+class Instance:
+    """A model plus an interior starting iterate (x0, y0, z0, tau=1, s0, kap=1)."""
+
+    def __init__(self, name, model, point, mu):
+        self.name, self.model, self.point, self.mu = name, model, point, mu
+
+
+def synthetic(name, n, p, cones, seed, noise=0.1, dtype_rows_chunk=4096):
+    """Planted-feasible dense instance with the given cone list (post-preprocessing)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    q = int(sum(ck.dim for ck in cones))
+    G = np.empty((q, n), order="F")
+    for r0 in range(0, q, dtype_rows_chunk):        # chunked so the transient stays small
+        r1 = min(q, r0 + dtype_rows_chunk)
+        G[r0:r1] = rng.standard_normal((r1 - r0, n))
+    s0 = np.empty(q)
+    z0 = np.empty(q)
+    off = 0
+    for ck in cones:
+        sl = slice(off, off + ck.dim)
+        prim = cone_initial_point(ck)
+        dual = _cone_dual_initial(ck, prim)
+        prim = _perturb(rng, ck, prim, noise)
+        dual = _perturb(rng, ck, dual, noise)
+        if ck.use_dual:
+            s0[sl], z0[sl] = dual, prim
+        else:
+            s0[sl], z0[sl] = prim, dual
+        if ck.side:
+            mo = off + {M.CONE_POSSEMIDEFTRI: 0, M.CONE_HYPOPERLOGDETTRI: 2,
+                        M.CONE_HYPOROOTDETTRI: 1}[ck.ctype]
+            rows = mo + np.nonzero(_svec_offdiag_mask(ck.side))[0]
+            G[rows] *= RT2
+        off += ck.dim
+    A = rng.standard_normal((p, n)) if p else np.zeros((0, n))
+    x0 = rng.standard_normal(n)
+    y0 = rng.standard_normal(p)
+    h = G @ x0 + s0
+    c = -(G.T @ z0)
+    if p:
+        c -= A.T @ y0
+    b = A @ x0
+    model = M.Model(c, A, b, G, h, cones)
+    pt = Point(model)
+    pt.x[:] = x0
+    pt.y[:] = y0
+    pt.z[:] = z0
+    pt.s[:] = s0
+    pt.tau = 1.0
+    pt.kap = 1.0
+    mu = (float(z0 @ s0) + 1.0) / (model.nu + 1)
+    return Instance(name, model, pt, mu)
+
+
+def linearopt(m=200, n=400, seed=1001):
+    """LinearOptNative(m, n, 1.0): A = 10 U(0,1)^{m x n}, b = A 1, c ~ U(0,1)^n, G = -I, h = 0,
+    one Nonnegative(n) (reference: examples/linearopt/native.jl:15-30).  BASELINE config 1."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    A = 10.0 * rng.random((m, n))
+    b = A.sum(axis=1)
+    c = rng.random(n)
+    return M.Model(c, A, b, -np.eye(n), np.zeros(n), [M.Nonnegative(n)])
+
+
+# ---- BASELINE.json configs; `scale` < 1 shrinks every dimension for tests ----
+def config(name, scale=1.0):
+    def sc(v, lo=1):
+        return max(lo, int(round(v * scale)))
+    if name == "C2":     # dense LP after reduction: m = 4000, one Nonnegative(5000)
+        return synthetic("C2", sc(4000), 0, [M.Nonnegative(sc(5000))], 1002)
+    if name == "C3":     # n = 10000, 2000 x EpiNormEucl(25), q = 50000
+        return synthetic("C3", sc(10000), 0, [M.EpiNormEucl(25) for _ in range(sc(2000))], 1003)
+    if name == "C4":     # n = 20000, 50 x PosSemidefTri(side 100), q = 252500
+        side = 100 if scale >= 1 else max(3, int(round(100 * np.sqrt(scale))))
+        return synthetic("C4", sc(20000), 0,
+                         [M.PosSemidefTri(M.svec_length(side)) for _ in range(sc(50, 2))], 1004)
+    if name == "C5b":    # n = 20000: 40 LogDet(side 100) + 10000 SOC(25) + Nonneg(47920)
+        side = 100 if scale >= 1 else max(3, int(round(100 * np.sqrt(scale))))
+        cones = [M.HypoPerLogdetTri(2 + M.svec_length(side)) for _ in range(sc(40, 2))]
+        cones += [M.EpiNormEucl(25) for _ in range(sc(10000))]
+        cones += [M.Nonnegative(sc(47920))]
+        return synthetic("C5b", sc(20000), 0, cones, 1005)
+    raise ValueError(name)

@@ -1,0 +1,151 @@
+"""Conic model container: min c'x : b - Ax = 0, h - Gx in K.
+
+Host-side mirror of the reference's data container (reference:
+src/Models/Models.jl:14-66).  Its field layout (n, p, q, c, A, b, G, h, cones,
+cone_idxs, nu) is the input contract of the system-solver boundary
+(SURVEY.md section 8b).  Arrays are float64; A and G are dense, Fortran
+(column-major) ordered exactly like Julia matrices so that the raw pointers
+can be handed to the C ABI without a transpose.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# cone type codes shared with include/hypatia_b200.h (HYP_CONE_*)
+CONE_NONNEGATIVE = 0
+CONE_EPINORMEUCL = 1
+CONE_POSSEMIDEFTRI = 2
+CONE_HYPOPERLOGDETTRI = 3
+CONE_HYPOROOTDETTRI = 4
+
+CONE_NAMES = {
+    CONE_NONNEGATIVE: "Nonnegative",
+    CONE_EPINORMEUCL: "EpiNormEucl",
+    CONE_POSSEMIDEFTRI: "PosSemidefTri",
+    CONE_HYPOPERLOGDETTRI: "HypoPerLogdetTri",
+    CONE_HYPOROOTDETTRI: "HypoRootdetTri",
+}
+
+
+def svec_length(side: int) -> int:
+    """reference: src/Cones/arrayutilities.jl:71"""
+    return side * (side + 1) // 2
+
+
+def svec_side(length: int) -> int:
+    """reference: src/Cones/arrayutilities.jl:87-91"""
+    side = int((np.sqrt(1 + 8 * length)) // 2)
+    while side * (side + 1) < 2 * length:
+        side += 1
+    while side * (side + 1) > 2 * length:
+        side -= 1
+    if side * (side + 1) != 2 * length:
+        raise ValueError(f"{length} is not a triangular number")
+    return side
+
+
+class ConeSpec:
+    """(type, dim) descriptor of one cone block; nu follows the reference's get_nu."""
+
+    __slots__ = ("ctype", "dim", "use_dual")
+
+    def __init__(self, ctype: int, dim: int, use_dual: bool = False):
+        self.ctype = int(ctype)
+        self.dim = int(dim)
+        self.use_dual = bool(use_dual)
+        if ctype == CONE_NONNEGATIVE:
+            assert dim >= 1
+        elif ctype == CONE_EPINORMEUCL:
+            assert dim >= 2
+        elif ctype == CONE_POSSEMIDEFTRI:
+            svec_side(dim)
+        elif ctype == CONE_HYPOPERLOGDETTRI:
+            assert dim >= 3
+            svec_side(dim - 2)
+        elif ctype == CONE_HYPOROOTDETTRI:
+            assert dim >= 2
+            svec_side(dim - 1)
+        else:
+            raise ValueError(f"unknown cone type {ctype}")
+
+    @property
+    def side(self) -> int:
+        if self.ctype == CONE_POSSEMIDEFTRI:
+            return svec_side(self.dim)
+        if self.ctype == CONE_HYPOPERLOGDETTRI:
+            return svec_side(self.dim - 2)
+        if self.ctype == CONE_HYPOROOTDETTRI:
+            return svec_side(self.dim - 1)
+        return 0
+
+    @property
+    def nu(self) -> float:
+        # nonnegative.jl:40, epinormeucl.jl:42, possemideftri.jl:67,
+        # hypoperlogdettri.jl:80, hyporootdettri.jl:80
+        if self.ctype == CONE_NONNEGATIVE:
+            return float(self.dim)
+        if self.ctype == CONE_EPINORMEUCL:
+            return 2.0
+        if self.ctype == CONE_POSSEMIDEFTRI:
+            return float(self.side)
+        if self.ctype == CONE_HYPOPERLOGDETTRI:
+            return 2.0 + self.side
+        return 1.0 + self.side
+
+    def __repr__(self):
+        return f"{CONE_NAMES[self.ctype]}({self.dim})"
+
+
+def Nonnegative(dim):
+    return ConeSpec(CONE_NONNEGATIVE, dim)
+
+
+def EpiNormEucl(dim):
+    return ConeSpec(CONE_EPINORMEUCL, dim)
+
+
+def PosSemidefTri(dim):
+    return ConeSpec(CONE_POSSEMIDEFTRI, dim)
+
+
+def HypoPerLogdetTri(dim, use_dual=False):
+    return ConeSpec(CONE_HYPOPERLOGDETTRI, dim, use_dual)
+
+
+def HypoRootdetTri(dim, use_dual=False):
+    return ConeSpec(CONE_HYPOROOTDETTRI, dim, use_dual)
+
+
+class Model:
+    """reference: src/Models/Models.jl:14-54 (fields and derived cone_idxs / nu)."""
+
+    def __init__(self, c, A, b, G, h, cones, obj_offset: float = 0.0):
+        self.c = np.ascontiguousarray(c, dtype=np.float64).reshape(-1)
+        self.b = np.ascontiguousarray(b, dtype=np.float64).reshape(-1)
+        self.h = np.ascontiguousarray(h, dtype=np.float64).reshape(-1)
+        self.n = self.c.size
+        self.p = self.b.size
+        self.q = self.h.size
+        A = np.zeros((self.p, self.n)) if A is None else np.asarray(A, dtype=np.float64)
+        self.A = np.asfortranarray(A.reshape(self.p, self.n))
+        self.G = np.asfortranarray(np.asarray(G, dtype=np.float64).reshape(self.q, self.n))
+        self.cones = list(cones)
+        self.obj_offset = float(obj_offset)
+        self._index_cones()
+
+    def _index_cones(self):
+        # reference: build_cone_idxs, Models.jl:56-66 (0-based half-open here)
+        dims = np.array([ck.dim for ck in self.cones], dtype=np.int64)
+        self.cone_dims = dims
+        self.cone_offsets = np.concatenate(([0], np.cumsum(dims)))[:-1].astype(np.int64) \
+            if dims.size else np.zeros(0, dtype=np.int64)
+        if int(dims.sum()) != self.q:
+            raise ValueError("cone dimensions do not sum to q")
+        self.cone_idxs = [slice(int(o), int(o + d)) for o, d in zip(self.cone_offsets, dims)]
+        self.cone_nus = np.array([ck.nu for ck in self.cones], dtype=np.float64)
+        self.nu = float(self.cone_nus.sum()) if dims.size else 0.0
+
+    def copy(self):
+        return Model(self.c.copy(), self.A.copy(), self.b.copy(), self.G.copy(), self.h.copy(),
+                     [ConeSpec(ck.ctype, ck.dim, ck.use_dual) for ck in self.cones],
+                     self.obj_offset)

@@ -1,0 +1,148 @@
+"""Pins the CPU oracle's cone restatements with the reference's own implementation-independent
+oracle identities (reference: test/cone.jl:23-114, sizes from :321-325, :336-340, :463-467,
+:648-655 and the HypoRootdetTri block), at the reference tolerance tol = 1e3*eps."""
+import numpy as np
+import pytest
+
+from oracle import cones as oc
+
+EPS = np.finfo(np.float64).eps
+TOL = 1e3 * EPS
+
+
+def perturb_scale(rng, point, noise, scale):
+    # reference: test/cone.jl:236-248
+    if noise:
+        point += 2 * noise * rng.random(point.size) - noise
+    if scale != 1:
+        point *= scale
+    return point
+
+
+def close(a, b, tol=TOL):
+    # Julia's isapprox(a, b, atol, rtol): norm(a-b) <= max(atol, rtol*max(norm a, norm b))
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return np.linalg.norm(a - b) <= max(tol, tol * max(np.linalg.norm(a), np.linalg.norm(b)))
+
+
+def run_oracles(cone, init_tol=TOL, init_only=False, noise=0.1, scale=0.1, tol=TOL):
+    rng = np.random.default_rng(1)
+    dim = cone.dim
+    cone.setup_data()
+    point = np.zeros(dim)
+    cone.set_initial_point(point)
+    cone.load_point(point)
+    assert cone.is_feas()
+    dual_point = -cone.grad().copy()
+    cone.load_dual_point(dual_point)
+    assert cone.is_dual_feas()
+    assert cone.get_proxsqr(1.0, True) <= 1
+    assert cone.get_proxsqr(1.0, False) <= dim
+    assert close(cone.hess_prod(point), dual_point, tol)
+    if np.isfinite(init_tol):
+        assert close(point, dual_point, init_tol)
+    if init_only:
+        return
+
+    perturb_scale(rng, point, noise, scale)
+    perturb_scale(rng, dual_point, noise, 1 / scale)
+    cone.reset_data()
+    cone.load_point(point)
+    assert cone.is_feas()
+    cone.load_dual_point(dual_point)
+    assert cone.is_dual_feas()
+
+    nu = cone.nu
+    grad = cone.grad().copy()
+    assert abs(point @ grad + nu) <= tol * max(1, nu)
+    hess = np.array(cone.hess())
+    inv_hess = np.array(cone.inv_hess())
+    I = np.eye(dim)
+    assert close(hess @ inv_hess, I, tol)
+    assert close(hess @ point, -grad, tol)
+    assert close(cone.hess_prod(point), -grad, tol)
+    assert close(cone.inv_hess_prod(grad), -point, tol)
+    assert close(cone.hess_prod(inv_hess), I, tol)
+    assert close(cone.inv_hess_prod(hess), I, tol)
+    psi = dual_point + grad
+    proxsqr = psi @ cone.inv_hess_prod(psi)
+    assert abs(cone.get_proxsqr(1.0, False) - proxsqr) <= tol * max(1, abs(proxsqr))
+
+    if cone.use_sqrt_hess_oracles(dim + 1):
+        prod_mat2 = cone.sqrt_hess_prod(inv_hess).T.copy()
+        assert close(cone.sqrt_hess_prod(prod_mat2), I, tol)
+        pm = cone.inv_sqrt_hess_prod(I)
+        assert close(pm.T @ pm, inv_hess, tol)
+
+    if cone.use_dder3():
+        assert close(-cone.dder3(point), grad, tol)
+        direction = perturb_scale(rng, np.zeros(dim), noise, 1.0)
+        d3 = cone.dder3(direction)
+        ref = direction @ hess @ direction
+        assert abs(d3 @ point - ref) <= tol * max(1, abs(ref))
+
+
+@pytest.mark.parametrize("dim", [1, 2, 6])
+def test_nonnegative(dim):
+    run_oracles(oc.Nonnegative(dim))
+
+
+@pytest.mark.parametrize("side", [1, 2, 3, 5])
+def test_possemideftri(side):
+    run_oracles(oc.PosSemidefTri(side * (side + 1) // 2))
+
+
+@pytest.mark.parametrize("dim", [2, 3, 4, 6, 25])
+def test_epinormeucl(dim):
+    run_oracles(oc.EpiNormEucl(dim))
+
+
+@pytest.mark.parametrize("side", [1, 2, 4])
+def test_hypoperlogdettri(side):
+    # reference: test/cone.jl:648-655 (init_tol = 1e-4 for this cone)
+    run_oracles(oc.HypoPerLogdetTri(2 + side * (side + 1) // 2), init_tol=1e-4)
+
+
+@pytest.mark.parametrize("side", [8, 12])
+def test_hypoperlogdettri_init_only(side):
+    run_oracles(oc.HypoPerLogdetTri(2 + side * (side + 1) // 2), init_tol=1e-1, init_only=True)
+
+
+@pytest.mark.parametrize("side", [1, 2, 4, 5])
+def test_hyporootdettri(side):
+    run_oracles(oc.HypoRootdetTri(1 + side * (side + 1) // 2))
+
+
+@pytest.mark.parametrize("side", [3, 6])
+def test_generic_sqrt_oracles_logdet(side):
+    """Cones without closed-form sqrt oracles use the Cholesky of the explicit Hessian
+    (reference: Cones.jl:189-218)."""
+    cone = oc.HypoPerLogdetTri(2 + side * (side + 1) // 2)
+    rng = np.random.default_rng(3)
+    point = np.zeros(cone.dim)
+    cone.set_initial_point(point)
+    perturb_scale(rng, point, 0.05, 0.5)
+    cone.load_point(point)
+    assert cone.is_feas()
+    assert not cone.use_sqrt_hess_oracles(cone.dim - 1)   # array too small
+    assert cone.use_sqrt_hess_oracles(cone.dim)
+    A = rng.standard_normal((cone.dim, 4))
+    RA = cone.sqrt_hess_prod(A)
+    assert close(RA.T @ RA, A.T @ cone.hess_prod(A), 1e-12)
+
+
+def test_svec_roundtrip():
+    from oracle import arrayutil as au
+    rng = np.random.default_rng(0)
+    for side in (1, 2, 5, 9):
+        Mx = rng.standard_normal((side, side))
+        Mx = Mx + Mx.T
+        v = au.smat_to_svec(Mx)
+        assert v.size == au.svec_length(side)
+        assert np.allclose(au.svec_to_smat(v), Mx)
+        # svec is an isometry: <A,B>_F = svec(A)'svec(B)
+        N = rng.standard_normal((side, side))
+        N = N + N.T
+        assert np.isclose(v @ au.smat_to_svec(N), np.sum(Mx * N))
+        K = au.symm_kron(N)
+        assert np.allclose(K @ v, au.smat_to_svec(N @ Mx @ N.T))
