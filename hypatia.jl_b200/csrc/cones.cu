@@ -1,0 +1,507 @@
+// Batched cone barrier oracles (K7-K9 of SURVEY.md section 2.3): cone table, vector cones
+// (Nonnegative, EpiNormEucl) and the type dispatch.  Matrix cones live in cones_mat.cu.
+//
+// reference: src/Cones/Cones.jl:27-310 (generic API, check_numerics, get_proxsqr),
+// nonnegative.jl:42-145, epinormeucl.jl:44-228.  The reference loops `for k in eachindex(cones)`
+// on the host (e.g. qrchol.jl:214-246, search.jl:112-135); here one launch per cone TYPE covers
+// every cone of that type, driven by a device cone table (offset, dim) - "warp per
+// (cone, column)" for second-order cones, "thread per element" for the nonnegative orthant.
+// All kernels are HBM-bound streaming kernels: algorithmic bytes = 16 * rows * ncols per product.
+#include "common.cuh"
+#include "cones_mat.cuh"
+
+namespace {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------ Nonnegative
+// nonnegative.jl:44-60: is_feas = all(point > eps), is_dual_feas likewise, grad = -1 / point
+__global__ void nn_state_kernel(int64_t nrows, const int* __restrict__ rows,
+                                const int* __restrict__ rowcone, const double* __restrict__ point,
+                                const double* __restrict__ dual, double* __restrict__ grad,
+                                uint8_t* feas, uint8_t* dual_feas) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nrows;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int r = rows[i];
+        double s = point[r], z = dual[r];
+        grad[r] = -1.0 / s;
+        if (!(s > HYP_EPS)) feas[rowcone[i]] = 0;
+        if (!(z > HYP_EPS)) dual_feas[rowcone[i]] = 0;
+    }
+}
+
+// nonnegative.jl:82-120: hess arr/s/s, inv_hess arr*s*s, sqrt arr/s, inv_sqrt arr*s
+template <int MODE>
+__global__ void nn_prod_kernel(int64_t nrows, const int* __restrict__ rows,
+                               const double* __restrict__ point, const double* arr, int64_t ld_arr,
+                               double* prod, int64_t ld_prod, int64_t ncols, int64_t row_shift) {
+    for (int64_t j = blockIdx.y; j < ncols; j += gridDim.y) {
+        const double* a = arr + j * ld_arr - row_shift;
+        double* pr = prod + j * ld_prod - row_shift;
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nrows;
+             i += (int64_t)gridDim.x * blockDim.x) {
+            int r = rows[i];
+            double s = point[r], v = a[r];
+            double out;
+            if (MODE == HYP_PROD_HESS) out = v / s / s;
+            else if (MODE == HYP_PROD_INV_HESS) out = v * s * s;
+            else if (MODE == HYP_PROD_SQRT_HESS) out = v / s;
+            else out = v * s;
+            pr[r] = out;
+        }
+    }
+}
+
+// nonnegative.jl:122-125
+__global__ void nn_dder3_kernel(int64_t nrows, const int* __restrict__ rows,
+                                const double* __restrict__ point, const double* __restrict__ dir,
+                                double* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nrows;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int r = rows[i];
+        double s = point[r], t = dir[r] / s;
+        out[r] = t * t / s;
+    }
+}
+
+// ------------------------------------------------------------------ EpiNormEucl
+// one warp per cone.  scal[8*c+0] = dist.  epinormeucl.jl:54-90
+__global__ void soc_state_kernel(int ncones, const int64_t* __restrict__ off,
+                                 const int* __restrict__ dim, const int* __restrict__ kidx,
+                                 const double* __restrict__ point, const double* __restrict__ dual,
+                                 double* __restrict__ grad, double* __restrict__ scal, uint8_t* feas,
+                                 uint8_t* dual_feas) {
+    const int lane = threadIdx.x & 31;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= ncones) return;
+    const int64_t o = off[c];
+    const int d = dim[c];
+    double sw = 0.0, sdw = 0.0;
+    for (int i = 1 + lane; i < d; i += 32) {
+        double w = point[o + i], dw = dual[o + i];
+        sw += w * w;
+        sdw += dw * dw;
+    }
+    sw = warp_sum(sw);
+    sdw = warp_sum(sdw);
+    const double u = point[o], du = dual[o];
+    double dist = 0.0;
+    bool ok = false;
+    if (u > HYP_EPS) {
+        dist = (u * u - sw) / 2;
+        ok = dist > HYP_EPS;
+    }
+    bool dok = (du > HYP_EPS) && ((du * du - sdw) > 2 * HYP_EPS);
+    for (int i = lane; i < d; i += 32) {
+        double v = point[o + i] / dist;
+        grad[o + i] = (i == 0) ? -v : v;
+    }
+    if (lane == 0) {
+        scal[8 * c] = dist;
+        feas[kidx[c]] = ok ? 1 : 0;
+        dual_feas[kidx[c]] = dok ? 1 : 0;
+    }
+}
+
+// one warp per (cone, column).  epinormeucl.jl:121-206
+template <int MODE>
+__global__ void __launch_bounds__(256)
+soc_prod_kernel(int ncones, const int64_t* __restrict__ off, const int* __restrict__ dim,
+                const double* __restrict__ scal, const double* __restrict__ point, const double* arr,
+                int64_t ld_arr, double* prod, int64_t ld_prod, int64_t ncols, int64_t row_shift) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= ncones) return;
+    const int64_t o = off[c];
+    const int d = dim[c];
+    const double dist = scal[8 * c];
+    const double u = point[o];
+    const double rt2 = 1.4142135623730951;
+    for (int64_t j = blockIdx.y; j < ncols; j += gridDim.y) {
+        const double* a = arr + j * ld_arr + (o - row_shift);
+        double* pr = prod + j * ld_prod + (o - row_shift);
+        // pass 1: dot(w, wj); the first chunk of the column stays in a register
+        double dotw = 0.0;
+        const double a_first = (lane < d) ? a[lane] : 0.0;
+        if (lane >= 1 && lane < d) dotw = point[o + lane] * a_first;
+        for (int i = lane + 32; i < d; i += 32) dotw += point[o + i] * a[i];
+        dotw = warp_sum(dotw);
+        const double uj = __shfl_sync(0xffffffffu, a_first, 0);
+        double c0, cw, cj;   // prod[0] = c0 ; prod[i] = cw * w[i] + cj * arr[i]
+        if (MODE == HYP_PROD_HESS) {
+            double ga = (dotw - u * uj) / dist;
+            c0 = (-ga * u - uj) / dist;
+            cw = ga / dist;
+            cj = 1.0 / dist;
+        } else if (MODE == HYP_PROD_INV_HESS) {
+            double pa = u * uj + dotw;
+            c0 = pa * u - dist * uj;
+            cw = pa;
+            cj = dist;
+        } else if (MODE == HYP_PROD_SQRT_HESS) {
+            double distrt2 = dist * rt2, rtdist = sqrt(dist), urtdist = u + rtdist * rt2;
+            c0 = (u * uj - dotw) / distrt2;
+            cw = (dotw / urtdist - uj) / distrt2;
+            cj = 1.0 / rtdist;
+        } else {
+            double rtdist = sqrt(dist), urtdist = u + rtdist * rt2;
+            c0 = (u * uj + dotw) / rt2;
+            cw = (dotw / urtdist + uj) / rt2;
+            cj = rtdist;
+        }
+        if (lane < d) pr[lane] = (lane == 0) ? c0 : (cw * point[o + lane] + cj * a_first);
+        for (int i = lane + 32; i < d; i += 32) pr[i] = cw * point[o + i] + cj * a[i];
+    }
+}
+
+// epinormeucl.jl:208-228
+__global__ void soc_dder3_kernel(int ncones, const int64_t* __restrict__ off,
+                                 const int* __restrict__ dim, const double* __restrict__ scal,
+                                 const double* __restrict__ point, const double* __restrict__ dir,
+                                 double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= ncones) return;
+    const int64_t o = off[c];
+    const int d = dim[c];
+    const double dist = scal[8 * c];
+    const double u = point[o], ud = dir[o];
+    double sww = 0.0, swd = 0.0, sdd = 0.0;
+    for (int i = 1 + lane; i < d; i += 32) {
+        double w = point[o + i], wd = dir[o + i];
+        sww += w * w;
+        swd += w * wd;
+        sdd += wd * wd;
+    }
+    sww = warp_sum(sww);
+    swd = warp_sum(swd);
+    sdd = warp_sum(sdd);
+    const double jdotpd = u * ud - swd;
+    const double ga = (swd - u * ud) / dist;
+    const double h0 = (-ga * u - ud) / dist;                 // (H dir)[0]
+    // (H dir)[i] = (ga * w_i + wd_i) / dist
+    const double dHd = ud * h0 + (ga * swd + sdd) / dist;    // dir' H dir
+    const double pHd = u * h0 + (ga * sww + swd) / dist;     // point' H dir
+    const double dotdHd = -dHd, dotpHd = pHd;
+    const double inv2d = 1.0 / (2 * dist);
+    for (int i = lane; i < d; i += 32) {
+        double r;
+        if (i == 0) {
+            r = h0 * jdotpd - dotdHd * u - dotpHd * ud;
+        } else {
+            double w = point[o + i], wd = dir[o + i];
+            r = (ga * w + wd) / dist * jdotpd + dotdHd * w + dotpHd * wd;
+        }
+        out[o + i] = r * inv2d;
+    }
+}
+
+// ------------------------------------------------------------------ per-cone reductions
+// One CTA per local cone.  check_numerics (Cones.jl:273-290) + get_proxsqr (Cones.jl:294-310;
+// nonnegative.jl:137-145 for the orthant).  v1 = irtmu*dual + grad, v2 = Hinv v1, v3 = Hinv grad.
+__global__ void __launch_bounds__(128)
+cone_prox_kernel(int cone_lo, const int* __restrict__ ctype, const int64_t* __restrict__ coff,
+                 const int64_t* __restrict__ cdim, const double* __restrict__ cnu,
+                 const double* __restrict__ point, const double* __restrict__ dual,
+                 const double* __restrict__ grad, const double* __restrict__ v1,
+                 const double* __restrict__ v2, const double* __restrict__ v3, double irtmu,
+                 int use_max, double* __restrict__ proxsqr, uint8_t* __restrict__ num_ok) {
+    __shared__ double sm[4][4];
+    const int k = cone_lo + blockIdx.x;
+    const int64_t o = coff[k], d = cdim[k];
+    const int type = ctype[k];
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;   // v2.v1, grad.point, v3.grad, nonneg aggregate
+    for (int64_t i = threadIdx.x; i < d; i += blockDim.x) {
+        double g = grad[o + i];
+        a0 += v2[o + i] * v1[o + i];
+        a1 += g * point[o + i];
+        a2 += v3[o + i] * g;
+        if (type == HYP_CONE_NONNEGATIVE) {
+            double t = point[o + i] * dual[o + i] * irtmu - 1.0;
+            t = t * t;
+            a3 = use_max ? fmax(a3, t) : a3 + t;
+        }
+    }
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
+    a2 = warp_sum(a2);
+    if (use_max) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) a3 = fmax(a3, __shfl_xor_sync(0xffffffffu, a3, s));
+    } else {
+        a3 = warp_sum(a3);
+    }
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        sm[w][0] = a0;
+        sm[w][1] = a1;
+        sm[w][2] = a2;
+        sm[w][3] = a3;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double d0 = 0, d1 = 0, d2 = 0, d3 = 0;
+        for (int i = 0; i < 4; i++) {
+            d0 += sm[i][0];
+            d1 += sm[i][1];
+            d2 += sm[i][2];
+            d3 = use_max ? fmax(d3, sm[i][3]) : d3 + sm[i][3];
+        }
+        const double nu = cnu[k];
+        const double gtol = 1.220703125e-4;              // eps^(1/4)
+        const double Htol = 10 * 0.011048543456039806;   // 10 * sqrt(gtol)
+        bool ok = true;
+        if (fabs(1 + d1 / nu) > gtol * (double)d) ok = false;
+        if (ok && fabs(1 - d2 / nu) > Htol * (double)d) ok = false;
+        if (!(d1 == d1) || !(d2 == d2)) ok = false;
+        num_ok[k] = ok ? 1 : 0;
+        double prox;
+        if (type == HYP_CONE_NONNEGATIVE) {
+            prox = d3;
+        } else {
+            const double negtol = 1.4901161193847656e-08;   // sqrt(eps)
+            prox = (d0 < -negtol * (double)d) ? INFINITY : fabs(d0);
+        }
+        proxsqr[k] = prox;
+    }
+}
+
+inline int grid_for(hyp_ctx* ctx, int64_t len, int threads, int mult = 8) {
+    int64_t blocks = (len + threads - 1) / threads;
+    int64_t cap = (int64_t)ctx->sm_count * mult;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+template <typename T>
+T* upload(const std::vector<T>& v) {
+    T* d = nullptr;
+    if (v.empty()) return d;
+    CUDA_TRY(cudaMalloc(&d, v.size() * sizeof(T)));
+    CUDA_TRY(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return d;
+}
+
+template <int MODE>
+void launch_vec_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr, int64_t ncols,
+                     int64_t ld_prod, int64_t ld_arr, int64_t row_shift) {
+    int gy = (int)std::min<int64_t>(ncols, 65535);
+    if (g.type == HYP_CONE_NONNEGATIVE) {
+        int gx = grid_for(ctx, g.rows, 256, ncols > 1 ? 1 : 8);
+        nn_prod_kernel<MODE><<<dim3(gx, gy), 256, 0, ctx->stream>>>(
+            g.rows, g.d_rows, ctx->d_point, arr, ld_arr, prod, ld_prod, ncols, row_shift);
+    } else {
+        int gx = ceil_div(g.count, 8);
+        soc_prod_kernel<MODE><<<dim3(gx, gy), 256, 0, ctx->stream>>>(
+            g.count, g.d_off, g.d_dim, g.d_scal, ctx->d_point, arr, ld_arr, prod, ld_prod, ncols,
+            row_shift);
+    }
+    ctx->launches++;
+}
+
+}  // namespace
+
+void hyp_cones_build_groups(hyp_ctx* ctx) {
+    hyp_cones_free_groups(ctx);
+    for (int type = 0; type < HYP_NUM_CONE_TYPES; type++) {
+        ConeGroup g;
+        g.type = type;
+        std::vector<int> rows, rowcone;
+        for (int k = ctx->cone_lo; k < ctx->cone_hi; k++) {
+            if (ctx->h_cone_type[k] != type) continue;
+            int dim = (int)ctx->h_cone_dim[k];
+            g.h_off.push_back(ctx->h_cone_off[k]);
+            g.h_dim.push_back(dim);
+            g.h_kidx.push_back(k);
+            g.h_dual.push_back(ctx->h_cone_dual[k]);
+            int side = 0;
+            if (type >= HYP_CONE_POSSEMIDEFTRI) {
+                int64_t len = dim - (type == HYP_CONE_HYPOPERLOGDETTRI ? 2 : type == HYP_CONE_HYPOROOTDETTRI ? 1 : 0);
+                side = (int)((std::sqrt(1.0 + 8.0 * (double)len) - 1.0) / 2.0 + 0.5);
+                while ((int64_t)side * (side + 1) / 2 < len) side++;
+                while ((int64_t)side * (side + 1) / 2 > len) side--;
+                if ((int64_t)side * (side + 1) / 2 != len) throw HypError{"matrix cone dimension is not triangular"};
+            }
+            g.h_side.push_back(side);
+            g.h_moff.push_back(g.mat_total);
+            g.mat_total += round_up((int64_t)side * side, 2);
+            g.max_dim = std::max(g.max_dim, dim);
+            g.max_side = std::max(g.max_side, side);
+            g.rows += dim;
+            if (type == HYP_CONE_NONNEGATIVE)
+                for (int i = 0; i < dim; i++) {
+                    rows.push_back((int)(ctx->h_cone_off[k] + i));
+                    rowcone.push_back(k);
+                }
+        }
+        g.count = (int)g.h_off.size();
+        if (g.count == 0) continue;
+        g.d_off = upload(g.h_off);
+        g.d_dim = upload(g.h_dim);
+        g.d_kidx = upload(g.h_kidx);
+        g.d_dual = upload(g.h_dual);
+        g.d_side = upload(g.h_side);
+        g.d_moff = upload(g.h_moff);
+        CUDA_TRY(cudaMalloc(&g.d_scal, (size_t)g.count * 8 * sizeof(double)));
+        CUDA_TRY(cudaMemset(g.d_scal, 0, (size_t)g.count * 8 * sizeof(double)));
+        if (type == HYP_CONE_NONNEGATIVE) {
+            g.d_rows = upload(rows);
+            g.d_rowcone = upload(rowcone);
+        }
+        if (type >= HYP_CONE_POSSEMIDEFTRI) hyp_mat_alloc_group(ctx, g);
+        ctx->groups.push_back(g);
+    }
+}
+
+void hyp_cones_free_groups(hyp_ctx* ctx) {
+    for (auto& g : ctx->groups) {
+        cudaFree(g.d_off);
+        cudaFree(g.d_dim);
+        cudaFree(g.d_kidx);
+        cudaFree(g.d_dual);
+        cudaFree(g.d_side);
+        cudaFree(g.d_moff);
+        cudaFree(g.d_scal);
+        cudaFree(g.d_rows);
+        cudaFree(g.d_rowcone);
+        cudaFree(g.d_W);
+        cudaFree(g.d_U);
+        cudaFree(g.d_Ut);
+        cudaFree(g.d_Ui);
+        cudaFree(g.d_Uit);
+        cudaFree(g.d_Wi);
+    }
+    ctx->groups.clear();
+}
+
+// feas / grad / per-cone factorisations for the points in ctx->d_point / d_dual
+void hyp_cones_update_state(hyp_ctx* ctx) {
+    TimeScope ts(ctx, T_CONE_STATE);
+    if (ctx->K == 0) return;
+    CUDA_TRY(cudaMemsetAsync(ctx->d_feas, 1, ctx->K, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_dual_feas, 1, ctx->K, ctx->stream));
+    for (auto& g : ctx->groups) {
+        if (g.type == HYP_CONE_NONNEGATIVE) {
+            nn_state_kernel<<<grid_for(ctx, g.rows, 256), 256, 0, ctx->stream>>>(
+                g.rows, g.d_rows, g.d_rowcone, ctx->d_point, ctx->d_dual, ctx->d_grad, ctx->d_feas,
+                ctx->d_dual_feas);
+            ctx->launches++;
+        } else if (g.type == HYP_CONE_EPINORMEUCL) {
+            soc_state_kernel<<<ceil_div(g.count, 8), 256, 0, ctx->stream>>>(
+                g.count, g.d_off, g.d_dim, g.d_kidx, ctx->d_point, ctx->d_dual, ctx->d_grad, g.d_scal,
+                ctx->d_feas, ctx->d_dual_feas);
+            ctx->launches++;
+        } else {
+            hyp_mat_update_state(ctx, g);
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    if (ctx->nranks > 1) {
+        hyp_allreduce_min_u8(ctx, ctx->d_feas, ctx->K);
+        hyp_allreduce_min_u8(ctx, ctx->d_dual_feas, ctx->K);
+        hyp_replicate_q(ctx, ctx->d_grad);
+    }
+}
+
+static int resolve_mode(const ConeGroup& g, int k_in_group, int mode) {
+    (void)k_in_group;
+    return mode;
+}
+
+void hyp_cones_prod(hyp_ctx* ctx, double* prod, const double* arr, int64_t ncols, int64_t ld_prod,
+                    int64_t ld_arr, int mode, int64_t row_shift) {
+    if (ncols <= 0) return;
+    for (auto& g : ctx->groups) {
+        int m = resolve_mode(g, 0, mode);
+        if (g.type <= HYP_CONE_EPINORMEUCL) {
+            if (m == HYP_PROD_BLOCK) m = HYP_PROD_HESS;   // no dual-barrier variants of these cones
+            switch (m) {
+                case HYP_PROD_HESS:
+                    launch_vec_prod<HYP_PROD_HESS>(ctx, g, prod, arr, ncols, ld_prod, ld_arr, row_shift);
+                    break;
+                case HYP_PROD_INV_HESS:
+                    launch_vec_prod<HYP_PROD_INV_HESS>(ctx, g, prod, arr, ncols, ld_prod, ld_arr, row_shift);
+                    break;
+                case HYP_PROD_SQRT_HESS:
+                    launch_vec_prod<HYP_PROD_SQRT_HESS>(ctx, g, prod, arr, ncols, ld_prod, ld_arr, row_shift);
+                    break;
+                case HYP_PROD_INV_SQRT_HESS:
+                    launch_vec_prod<HYP_PROD_INV_SQRT_HESS>(ctx, g, prod, arr, ncols, ld_prod, ld_arr, row_shift);
+                    break;
+                default:
+                    throw HypError{"hyp_cones_prod: bad mode"};
+            }
+        } else {
+            hyp_mat_prod(ctx, g, prod, arr, ncols, ld_prod, ld_arr, m, row_shift);
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+}
+
+// Schur pre-pass (qrchol.jl:219-246): HG_k = H_k^{1/2} GQ2_k for cones with closed-form square
+// roots, HG_k = H_k GQ2_k (block_hess_prod!) for the log-det family.
+void hyp_cones_schur_prepass(hyp_ctx* ctx) {
+    TimeScope ts(ctx, T_SQRT_PREPASS);
+    const double* GQ2 = ctx->d_GQ + ctx->p * ctx->ldg;
+    for (auto& g : ctx->groups) {
+        if (g.type <= HYP_CONE_EPINORMEUCL) {
+            launch_vec_prod<HYP_PROD_SQRT_HESS>(ctx, g, ctx->d_HG, GQ2, ctx->nmp, ctx->ldg, ctx->ldg,
+                                                ctx->row_lo);
+        } else if (g.type == HYP_CONE_POSSEMIDEFTRI) {
+            hyp_mat_prod(ctx, g, ctx->d_HG, GQ2, ctx->nmp, ctx->ldg, ctx->ldg, HYP_PROD_SQRT_HESS,
+                         ctx->row_lo);
+        } else {
+            hyp_mat_prod(ctx, g, ctx->d_HG, GQ2, ctx->nmp, ctx->ldg, ctx->ldg, HYP_PROD_BLOCK,
+                         ctx->row_lo);
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+}
+
+void hyp_cones_dder3_dev(hyp_ctx* ctx, double* out, const double* dir) {
+    TimeScope ts(ctx, T_CONE_PROD);
+    for (auto& g : ctx->groups) {
+        if (g.type == HYP_CONE_NONNEGATIVE) {
+            nn_dder3_kernel<<<grid_for(ctx, g.rows, 256), 256, 0, ctx->stream>>>(
+                g.rows, g.d_rows, ctx->d_point, dir, out);
+            ctx->launches++;
+        } else if (g.type == HYP_CONE_EPINORMEUCL) {
+            soc_dder3_kernel<<<ceil_div(g.count, 8), 256, 0, ctx->stream>>>(
+                g.count, g.d_off, g.d_dim, g.d_scal, ctx->d_point, dir, out);
+            ctx->launches++;
+        } else {
+            hyp_mat_dder3(ctx, g, out, dir);
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+}
+
+// check_numerics + get_proxsqr for all local cones -> ctx->d_proxsqr / d_num_ok (global K)
+void hyp_cones_prox_dev(hyp_ctx* ctx, double irtmu, int use_max) {
+    TimeScope ts(ctx, T_CONE_PROD);
+    if (ctx->K == 0) return;
+    int nloc = ctx->cone_hi - ctx->cone_lo;
+    CUDA_TRY(cudaMemsetAsync(ctx->d_proxsqr, 0, ctx->K * sizeof(double), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_num_ok, 1, ctx->K, ctx->stream));
+    if (nloc > 0) {
+        // v1 = irtmu * dual + grad ; v2 = Hinv v1 ; v3 = Hinv grad
+        hyp_lincomb3(ctx, ctx->q, ctx->d_vq1, irtmu, ctx->d_dual, 1.0, ctx->d_grad, 0.0, nullptr);
+        hyp_cones_prod(ctx, ctx->d_vq2, ctx->d_vq1, 1, ctx->q, ctx->q, HYP_PROD_INV_HESS, 0);
+        hyp_cones_prod(ctx, ctx->d_vq3, ctx->d_grad, 1, ctx->q, ctx->q, HYP_PROD_INV_HESS, 0);
+        cone_prox_kernel<<<nloc, 128, 0, ctx->stream>>>(
+            ctx->cone_lo, ctx->d_cone_type, ctx->d_cone_off, ctx->d_cone_dim, ctx->d_cone_nu,
+            ctx->d_point, ctx->d_dual, ctx->d_grad, ctx->d_vq1, ctx->d_vq2, ctx->d_vq3, irtmu, use_max,
+            ctx->d_proxsqr, ctx->d_num_ok);
+        ctx->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    if (ctx->nranks > 1) {
+        hyp_allreduce_sum(ctx, ctx->d_proxsqr, ctx->K);
+        hyp_allreduce_min_u8(ctx, ctx->d_num_ok, ctx->K);
+    }
+}

@@ -1,0 +1,1111 @@
+// C ABI of libhypatia_b200 (include/hypatia_b200.h): context, model load, and the
+// SystemSolver entry points - device restatement of the reference's QRCholDenseSystemSolver.
+//
+// reference: src/Solvers/systemsolvers/qrchol.jl:16-37 (setup_rhs3), :39-85 (solve_subsystem3),
+// :138-179 (load), :181-257 (update_lhs, update_lhs_fact); common.jl:79-121 (apply_lhs),
+// :129-151 (solve_system), :154-182 (solve_subsystem4), :184-211 (setup_point_sub, dot_obj);
+// src/linearalgebra/dense.jl:194-215 (posdef_fact_copy! fallback chain).
+#include "common.cuh"
+
+#include <cmath>
+#include <cstring>
+
+namespace {
+
+const char* kTimingNames[T_NUM] = {"cone_state", "schur_prepass", "schur_syrk", "allreduce", "potrf",
+                                   "ldlt",       "trsv",          "gemv",       "cone_prod", "vec"};
+
+bool is_device_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+template <typename T>
+void dalloc(T** p, int64_t count) {
+    *p = nullptr;
+    if (count <= 0) count = 1;
+    CUDA_TRY(cudaMalloc((void**)p, (size_t)count * sizeof(T)));
+    CUDA_TRY(cudaMemset(*p, 0, (size_t)count * sizeof(T)));
+}
+
+template <typename T>
+void dfree(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+// device view of an input array: the pointer itself when it already lives on the device, else a
+// copy in `buf` (which must hold `len` doubles)
+const double* stage_in(hyp_ctx* ctx, const double* p, int64_t len, double* buf) {
+    if (len <= 0) return buf;
+    if (!p) throw HypError{"null input pointer"};
+    if (is_device_ptr(p)) return p;
+    CUDA_TRY(cudaMemcpyAsync(buf, p, (size_t)len * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    return buf;
+}
+
+void stage_out(hyp_ctx* ctx, double* p, int64_t len, const double* dev) {
+    if (len <= 0) return;
+    if (!p) throw HypError{"null output pointer"};
+    if (is_device_ptr(p)) {
+        if (p != dev)
+            CUDA_TRY(cudaMemcpyAsync(p, dev, (size_t)len * sizeof(double), cudaMemcpyDeviceToDevice,
+                                     ctx->stream));
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(p, dev, (size_t)len * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+}
+
+void stage_out_u8(hyp_ctx* ctx, uint8_t* p, int64_t len, const uint8_t* dev) {
+    if (len <= 0 || !p) return;
+    if (is_device_ptr(p)) {
+        CUDA_TRY(cudaMemcpyAsync(p, dev, (size_t)len, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(p, dev, (size_t)len, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+}
+
+void ensure_stage(hyp_ctx* ctx, int64_t doubles) {
+    if (doubles <= ctx->stage_doubles) return;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    dfree(ctx->d_stage);
+    dalloc(&ctx->d_stage, doubles);
+    ctx->stage_doubles = doubles;
+}
+
+// copy a (rows x cols, ld) host-or-device matrix into a device matrix with leading dim dld
+void upload_matrix(hyp_ctx* ctx, double* dst, int64_t dld, const double* src, int64_t sld,
+                   int64_t rows, int64_t cols) {
+    if (rows <= 0 || cols <= 0) return;
+    if (!src) throw HypError{"null matrix pointer"};
+    cudaMemcpyKind kind = is_device_ptr(src) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)dld * 8, src, (size_t)sld * 8, (size_t)rows * 8, (size_t)cols,
+                               kind, ctx->stream));
+}
+
+void free_model(hyp_ctx* ctx) {
+    hyp_cones_free_groups(ctx);
+    if (ctx->d_GQ != ctx->d_Graw) dfree(ctx->d_GQ);
+    ctx->d_GQ = nullptr;
+    dfree(ctx->d_Graw);
+    dfree(ctx->d_HG);
+    dfree(ctx->d_PG);
+    dfree(ctx->d_A);
+    dfree(ctx->d_Q);
+    dfree(ctx->d_R);
+    dfree(ctx->d_Rdinv);
+    dfree(ctx->d_cbh);
+    dfree(ctx->d_cone_nu);
+    dfree(ctx->d_cone_off);
+    dfree(ctx->d_cone_dim);
+    dfree(ctx->d_cone_type);
+    dfree(ctx->d_row_dual);
+    dfree(ctx->d_point);
+    dfree(ctx->d_dual);
+    dfree(ctx->d_grad);
+    dfree(ctx->d_feas);
+    dfree(ctx->d_dual_feas);
+    dfree(ctx->d_num_ok);
+    dfree(ctx->d_proxsqr);
+    dfree(ctx->d_matwork);
+    ctx->matwork_doubles = 0;
+    dfree(ctx->d_S);
+    dfree(ctx->d_F);
+    dfree(ctx->d_Dinv);
+    dfree(ctx->d_info);
+    dfree(ctx->d_ipiv);
+    dfree(ctx->d_ldl_work);
+    dfree(ctx->d_flags);
+    dfree(ctx->d_rhs);
+    dfree(ctx->d_sol);
+    dfree(ctx->d_sub_sol);
+    dfree(ctx->d_sub_rhs);
+    dfree(ctx->d_const_sol);
+    dfree(ctx->d_const_rhs);
+    dfree(ctx->d_Gx_const);
+    dfree(ctx->d_t);
+    dfree(ctx->d_t2);
+    dfree(ctx->d_Gx);
+    dfree(ctx->d_HGx);
+    dfree(ctx->d_vq1);
+    dfree(ctx->d_vq2);
+    dfree(ctx->d_vq3);
+    dfree(ctx->d_vq4);
+    dfree(ctx->d_vp1);
+    dfree(ctx->d_vp2);
+    dfree(ctx->d_partial);
+    dfree(ctx->d_scalars);
+    dfree(ctx->d_stage);
+    ctx->stage_doubles = 0;
+    ctx->model_loaded = ctx->lhs_ready = ctx->cones_loaded = false;
+}
+
+// ---- small device kernels of the Point-level glue ------------------------------------------
+__global__ void negate_kernel(int64_t len, double* __restrict__ out, const double* __restrict__ in) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < len;
+         i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = -in[i];
+}
+
+// setup_rhs3 pre-step: v = rhs.z on primal-barrier rows, -rhs.z - rhs.s on dual-barrier rows
+__global__ void rhs3_pre_kernel(int64_t q, const uint8_t* __restrict__ row_dual,
+                                const double* __restrict__ rz, const double* __restrict__ rs,
+                                double* __restrict__ v) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < q;
+         i += (int64_t)gridDim.x * blockDim.x)
+        v[i] = (row_dual && row_dual[i]) ? (-rz[i] - rs[i]) : rz[i];
+}
+
+// setup_rhs3 post-step: out = -Hv - rhs.s (primal rows) or Hinv v (dual rows)
+__global__ void rhs3_post_kernel(int64_t q, const uint8_t* __restrict__ row_dual,
+                                 const double* __restrict__ hv, const double* __restrict__ rs,
+                                 double* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < q;
+         i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (row_dual && row_dual[i]) ? hv[i] : (-hv[i] - rs[i]);
+}
+
+// primal / dual views of a direction (point.jl:46-51): primal = s (z on dual-barrier rows)
+__global__ void primal_dual_kernel(int64_t q, const uint8_t* __restrict__ row_dual,
+                                   const double* __restrict__ z, const double* __restrict__ s,
+                                   double* __restrict__ prim, double* __restrict__ dual) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < q;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        bool d = row_dual && row_dual[i];
+        prim[i] = d ? z[i] : s[i];
+        dual[i] = d ? s[i] : z[i];
+    }
+}
+
+// tau lift of solve_subsystem4 / solve_system (common.jl:171-175,147-148); scal[0] = dot_obj(sol_sub),
+// scal[1] = dot_obj(sol_const); writes scal[2] = tau, sol[tau_idx] = tau, sol[kap_idx] = kap
+__global__ void tau_kernel(double* __restrict__ scal, const double* __restrict__ rhs,
+                           double* __restrict__ sol, int64_t tau_idx, int64_t kap_idx, double mu_tt) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double num = rhs[tau_idx] + rhs[kap_idx] + scal[0];
+        double den = mu_tt - scal[1];
+        double tau = num / den;
+        scal[2] = tau;
+        sol[tau_idx] = tau;
+        sol[kap_idx] = -mu_tt * tau + rhs[kap_idx];
+    }
+}
+
+// s = -(Gx_sub + tau * Gx_const) + h * tau - rhs.z   (common.jl:143-144 with G*x split)
+__global__ void s_lift_kernel(int64_t q, const double* __restrict__ scal,
+                              const double* __restrict__ gx, const double* __restrict__ gxc,
+                              const double* __restrict__ h, const double* __restrict__ rz,
+                              double* __restrict__ s) {
+    const double tau = scal[2];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < q;
+         i += (int64_t)gridDim.x * blockDim.x)
+        s[i] = -(gx[i] + tau * gxc[i]) + h[i] * tau - rz[i];
+}
+
+// apply_lhs tail (common.jl:97-120): res.tau and res.kap from the device dot products
+__global__ void lhs_tail_kernel(const double* __restrict__ scal, const double* __restrict__ dir,
+                                double* __restrict__ res, int64_t tau_idx, int64_t kap_idx,
+                                double mu_tt) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double tau_dir = dir[tau_idx], kap_dir = dir[kap_idx];
+        res[tau_idx] = -scal[3] - kap_dir;
+        res[kap_idx] = mu_tt * tau_dir + kap_dir;
+    }
+}
+
+// out = a * x + b * y + cs * dir[idx] * z   (scalar taken from a Point entry on the device)
+__global__ void axpbypcz_dev_kernel(int64_t len, double* __restrict__ out, double a,
+                                    const double* __restrict__ x, double b, const double* __restrict__ y,
+                                    double cs, const double* __restrict__ sptr,
+                                    const double* __restrict__ z) {
+    const double c = cs * sptr[0];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < len;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        double v = c * z[i];
+        if (x) v += a * x[i];
+        if (y) v += b * y[i];
+        out[i] = v;
+    }
+}
+
+inline int vgrid(hyp_ctx* ctx, int64_t len) {
+    int64_t blocks = (len + 255) / 256;
+    int64_t cap = (int64_t)ctx->sm_count * 8;
+    return (int)std::max<int64_t>(1, std::min(blocks, cap));
+}
+
+// ---- G passes (local row panel; results re-replicated across ranks) ------------------------
+// y(n) = alpha * G' v(q) + beta * y       (qrchol.jl:52, common.jl:91)
+void G_t(hyp_ctx* ctx, const double* Gp, const double* vq, double alpha, double beta, double* yn,
+         int64_t ncols = -1) {
+    if (ncols < 0) ncols = ctx->n;
+    if (ctx->nranks == 1) {
+        hyp_gemv_t(ctx, ctx->qloc, ncols, Gp, ctx->ldg, vq + ctx->row_lo, alpha, beta, yn);
+    } else {
+        hyp_gemv_t(ctx, ctx->qloc, ncols, Gp, ctx->ldg, vq + ctx->row_lo, alpha, 0.0, ctx->d_t2);
+        hyp_allreduce_sum(ctx, ctx->d_t2, ncols);
+        hyp_axpby(ctx, ncols, 1.0, ctx->d_t2, beta, yn);
+    }
+}
+// out(q)[local rows] = G x   (qrchol.jl:73); other rows untouched
+void G_n(hyp_ctx* ctx, const double* Gp, const double* xn, double* outq, int64_t ncols = -1) {
+    if (ncols < 0) ncols = ctx->n;
+    hyp_gemv_n(ctx, ctx->qloc, ncols, Gp, ctx->ldg, xn, 1.0, 0.0, outq + ctx->row_lo);
+}
+
+void potrs(hyp_ctx* ctx, double* x) {
+    if (ctx->fact_kind == 0) {
+        hyp_trsv_upper(ctx, ctx->d_F, ctx->lds, ctx->nmp, ctx->d_Dinv, x, true);
+        hyp_trsv_upper(ctx, ctx->d_F, ctx->lds, ctx->nmp, ctx->d_Dinv, x, false);
+    } else {
+        hyp_ldlt_solve(ctx, ctx->d_F, ctx->lds, ctx->nmp, ctx->d_ipiv, x);
+    }
+}
+
+// solve_subsystem3 (qrchol.jl:39-85) on device sub Points; leaves G*sol.x in ctx->d_Gx and
+// H*G*sol.x in ctx->d_HGx
+void solve_subsystem3_dev(hyp_ctx* ctx, double* sol, const double* rhs) {
+    const int64_t n = ctx->n, p = ctx->p, q = ctx->q, nmp = ctx->nmp;
+    if (sol != rhs) hyp_copy(ctx, n + p + q, sol, rhs);
+    double* x = sol;
+    double* y = sol + n;
+    double* z = sol + n + p;
+    double* t = ctx->d_t;
+
+    // t = Q'(x + G'z)
+    hyp_copy(ctx, n, t, x);
+    G_t(ctx, ctx->d_Graw, z, 1.0, 1.0, t);
+    if (ctx->d_Q) {
+        hyp_gemv_t(ctx, n, n, ctx->d_Q, ctx->ldqm, t, 1.0, 0.0, ctx->d_vq4 /*n <= ? see alloc*/);
+        hyp_copy(ctx, n, t, ctx->d_vq4);
+    }
+    if (p > 0) {
+        // y = R' \ y ; x_sub1 = y
+        hyp_trsv_upper(ctx, ctx->d_R, ctx->ldr, p, ctx->d_Rdinv, y, true);
+        hyp_copy(ctx, p, x, y);
+        if (nmp > 0) {
+            // Q2div -= GQ2' H GQ1 y
+            G_n(ctx, ctx->d_GQ, y, ctx->d_vq1, p);
+            hyp_cones_prod(ctx, ctx->d_vq2, ctx->d_vq1, 1, q, q, HYP_PROD_BLOCK, 0);
+            G_t(ctx, ctx->d_GQ + p * ctx->ldg, ctx->d_vq2, -1.0, 1.0, t + p, nmp);
+        }
+    }
+    if (nmp > 0) {
+        potrs(ctx, t + p);
+        hyp_copy(ctx, nmp, x + p, t + p);
+    }
+    if (ctx->d_Q) {
+        // x = Q x
+        hyp_gemv_n(ctx, n, n, ctx->d_Q, ctx->ldqm, x, 1.0, 0.0, ctx->d_vq4);
+        hyp_copy(ctx, n, x, ctx->d_vq4);
+    }
+    // z = H G x - z
+    G_n(ctx, ctx->d_Graw, x, ctx->d_Gx);
+    {
+        TimeScope ts(ctx, T_CONE_PROD);
+        hyp_cones_prod(ctx, ctx->d_HGx, ctx->d_Gx, 1, q, q, HYP_PROD_BLOCK, 0);
+    }
+    if (ctx->nranks > 1) {
+        hyp_replicate_q(ctx, ctx->d_Gx);
+        hyp_replicate_q(ctx, ctx->d_HGx);
+    }
+    hyp_axpby(ctx, q, 1.0, ctx->d_HGx, -1.0, z);
+    if (p > 0) {
+        // y = R \ (Q1'(x + G'z) - GQ1' H G x)
+        hyp_copy(ctx, p, y, t);
+        G_t(ctx, ctx->d_GQ, ctx->d_HGx, -1.0, 1.0, y, p);
+        hyp_trsv_upper(ctx, ctx->d_R, ctx->ldr, p, ctx->d_Rdinv, y, false);
+    }
+}
+
+// solve_system (common.jl:129-151) on device full Points
+void solve_system_dev(hyp_ctx* ctx, double* sol, const double* rhs) {
+    const int64_t n = ctx->n, p = ctx->p, q = ctx->q;
+    const int64_t dim3 = n + p + q, tau_idx = dim3, kap_idx = dim3 + q + 1;
+    const double* rz = rhs + n + p;
+    const double* rs = rhs + tau_idx + 1;
+    double* sub_rhs = ctx->d_sub_rhs;
+    double* sub_sol = ctx->d_sub_sol;
+    // rhs_sub.x = rhs.x ; rhs_sub.y = -rhs.y
+    hyp_copy(ctx, n, sub_rhs, rhs);
+    if (p > 0) {
+        negate_kernel<<<vgrid(ctx, p), 256, 0, ctx->stream>>>(p, sub_rhs + n, rhs + n);
+        ctx->launches++;
+    }
+    // setup_rhs3 (qrchol.jl:16-37)
+    if (q > 0) {
+        TimeScope ts(ctx, T_CONE_PROD);
+        const double* v = rz;
+        if (ctx->any_dual) {
+            rhs3_pre_kernel<<<vgrid(ctx, q), 256, 0, ctx->stream>>>(q, ctx->d_row_dual, rz, rs, ctx->d_vq1);
+            ctx->launches++;
+            v = ctx->d_vq1;
+        }
+        hyp_cones_prod(ctx, ctx->d_vq2, v, 1, q, q, HYP_PROD_BLOCK, 0);
+        if (ctx->nranks > 1) hyp_replicate_q(ctx, ctx->d_vq2);
+        rhs3_post_kernel<<<vgrid(ctx, q), 256, 0, ctx->stream>>>(q, ctx->d_row_dual, ctx->d_vq2, rs,
+                                                              sub_rhs + n + p);
+        ctx->launches++;
+    }
+    solve_subsystem3_dev(ctx, sub_sol, sub_rhs);
+    // tau lift (common.jl:171-179)
+    hyp_dot(ctx, dim3, ctx->d_cbh, sub_sol, ctx->d_scalars + 0, false);
+    const double mu_tt = ctx->mu / ctx->tau_bar / ctx->tau_bar;
+    tau_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_scalars, rhs, sol, tau_idx, kap_idx, mu_tt);
+    ctx->launches++;
+    hyp_axpy_dev(ctx, dim3, sol, 1.0, sub_sol, ctx->d_scalars + 2, 1.0, ctx->d_const_sol);
+    // s = -G x + h tau - rhs.z  with  G x = G x_sub + tau G x_const
+    if (q > 0) {
+        s_lift_kernel<<<vgrid(ctx, q), 256, 0, ctx->stream>>>(q, ctx->d_scalars, ctx->d_Gx, ctx->d_Gx_const,
+                                                           ctx->d_cbh + n + p, rz, sol + tau_idx + 1);
+        ctx->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+}
+
+// apply_lhs (common.jl:79-121) on device full Points
+void apply_lhs_dev(hyp_ctx* ctx, double* res, const double* dir) {
+    const int64_t n = ctx->n, p = ctx->p, q = ctx->q;
+    const int64_t dim3 = n + p + q, tau_idx = dim3, kap_idx = dim3 + q + 1;
+    const double* dx = dir;
+    const double* dy = dir + n;
+    const double* dz = dir + n + p;
+    const double* ds = dir + tau_idx + 1;
+    const double* c = ctx->d_cbh;
+    const double* b = ctx->d_cbh + n;
+    const double* h = ctx->d_cbh + n + p;
+    // res.x = G'z + A'y + c tau
+    axpbypcz_dev_kernel<<<vgrid(ctx, n), 256, 0, ctx->stream>>>(n, res, 0.0, nullptr, 0.0, nullptr, 1.0,
+                                                             dir + tau_idx, c);
+    ctx->launches++;
+    G_t(ctx, ctx->d_Graw, dz, 1.0, 1.0, res);
+    if (p > 0) {
+        hyp_gemv_t(ctx, p, n, ctx->d_A, ctx->lda, dy, 1.0, 1.0, res);
+        // res.y = b tau - A x
+        axpbypcz_dev_kernel<<<vgrid(ctx, p), 256, 0, ctx->stream>>>(p, res + n, 0.0, nullptr, 0.0, nullptr,
+                                                                 1.0, dir + tau_idx, b);
+        ctx->launches++;
+        hyp_gemv_n(ctx, p, n, ctx->d_A, ctx->lda, dx, -1.0, 1.0, res + n);
+    }
+    if (q > 0) {
+        // res.z = h tau - s - G x
+        G_n(ctx, ctx->d_Graw, dx, ctx->d_vq1);
+        if (ctx->nranks > 1) hyp_replicate_q(ctx, ctx->d_vq1);
+        axpbypcz_dev_kernel<<<vgrid(ctx, q), 256, 0, ctx->stream>>>(q, res + n + p, -1.0, ds, -1.0, ctx->d_vq1,
+                                                                 1.0, dir + tau_idx, h);
+        ctx->launches++;
+        // res.s = H prim + dual   (hess_prod_slow! = hess_prod! for these cones)
+        TimeScope ts(ctx, T_CONE_PROD);
+        const double* prim = ds;
+        const double* dual = dz;
+        if (ctx->any_dual) {
+            primal_dual_kernel<<<vgrid(ctx, q), 256, 0, ctx->stream>>>(q, ctx->d_row_dual, dz, ds, ctx->d_vq2,
+                                                                    ctx->d_vq3);
+            ctx->launches++;
+            prim = ctx->d_vq2;
+            dual = ctx->d_vq3;
+        }
+        hyp_cones_prod(ctx, ctx->d_vq4, prim, 1, q, q, HYP_PROD_HESS, 0);
+        if (ctx->nranks > 1) hyp_replicate_q(ctx, ctx->d_vq4);
+        hyp_lincomb3(ctx, q, res + tau_idx + 1, 1.0, ctx->d_vq4, 1.0, dual, 0.0, nullptr);
+    }
+    // res.tau = -c'x - b'y - h'z - kap ; res.kap = mu/tau^2 * tau_dir + kap_dir
+    hyp_dot(ctx, dim3, ctx->d_cbh, dir, ctx->d_scalars + 3, false);
+    const double mu_tt = ctx->mu / ctx->tau_bar / ctx->tau_bar;
+    lhs_tail_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_scalars, dir, res, tau_idx, kap_idx, mu_tt);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+}
+
+// Schur assembly + factorisation (update_lhs_fact, qrchol.jl:201-257)
+int update_lhs_fact(hyp_ctx* ctx) {
+    const int64_t nmp = ctx->nmp, p = ctx->p;
+    hyp_cones_schur_prepass(ctx);
+    {
+        TimeScope ts(ctx, T_SYRK);
+        const double* P = ctx->d_HG;
+        if (ctx->d_PG) {
+            // mixed model: P rows = H^{1/2} G (sqrt cones) / G (log-det family), R rows = HG
+            hyp_build_pg(ctx);
+            P = ctx->d_PG;
+        }
+        if (ctx->qloc > 0)
+            hyp_atb_upper(ctx, P, ctx->ldg, ctx->d_HG, ctx->ldg, ctx->qloc, nmp, ctx->d_S, ctx->lds, 1.0, 0.0);
+        else
+            CUDA_TRY(cudaMemsetAsync(ctx->d_S, 0, (size_t)ctx->lds * nmp * 8, ctx->stream));
+    }
+    if (ctx->nranks > 1) hyp_allreduce_sum(ctx, ctx->d_S, ctx->lds * nmp);
+    (void)p;
+    // posdef_fact_copy! (dense.jl:194-215): Cholesky -> Bunch-Kaufman -> shifted Bunch-Kaufman
+    int info = 0;
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_F, ctx->d_S, (size_t)ctx->lds * nmp * 8, cudaMemcpyDeviceToDevice,
+                             ctx->stream));
+    hyp_potrf_upper(ctx, ctx->d_F, ctx->lds, nmp, ctx->d_Dinv, ctx->d_info);
+    CUDA_TRY(cudaMemcpyAsync(&info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->fact_kind = 0;
+    if (info == 0) return 0;
+    for (int attempt = 1; attempt <= 2; attempt++) {
+        TimeScope ts(ctx, T_LDLT);
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_F, ctx->d_S, (size_t)ctx->lds * nmp * 8, cudaMemcpyDeviceToDevice,
+                                 ctx->stream));
+        if (attempt == 2) hyp_increase_diag(ctx, ctx->d_F, ctx->lds, nmp);
+        if (!ctx->d_ipiv) {
+            dalloc(&ctx->d_ipiv, nmp + 8);
+            dalloc(&ctx->d_ldl_work, 4 * nmp + 64);
+        }
+        hyp_ldlt_factor(ctx, ctx->d_F, ctx->lds, nmp, ctx->d_ipiv, ctx->d_info);
+        CUDA_TRY(cudaMemcpyAsync(&info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        ctx->fact_kind = attempt;
+        if (info == 0) return 1;
+    }
+    return 2;
+}
+
+template <typename F>
+int guarded(hyp_ctx* ctx, F&& f) {
+    if (!ctx) return -1;
+    try {
+        cudaError_t e = cudaSetDevice(ctx->device);
+        if (e != cudaSuccess) throw HypError{std::string("cudaSetDevice: ") + cudaGetErrorString(e)};
+        return f();
+    } catch (HypError& e) {
+        ctx->last_error = e.msg;
+        cudaGetLastError();
+        return -1;
+    } catch (std::exception& e) {
+        ctx->last_error = e.what();
+        return -1;
+    } catch (...) {
+        ctx->last_error = "unknown exception";
+        return -1;
+    }
+}
+
+void need_model(hyp_ctx* ctx) {
+    if (!ctx->model_loaded) throw HypError{"no model loaded (call hyp_load_model first)"};
+}
+
+}  // namespace
+
+// P operand of the mixed Schur product: copy of HG on sqrt-cone rows, GQ2 on the other rows
+__global__ void build_pg_kernel(int64_t qloc, int64_t nmp, int64_t ldg, const uint8_t* __restrict__ row_ns,
+                                const double* __restrict__ GQ2, const double* __restrict__ HG,
+                                double* __restrict__ PG) {
+    for (int64_t j = blockIdx.y; j < nmp; j += gridDim.y)
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < qloc;
+             i += (int64_t)gridDim.x * blockDim.x)
+            PG[i + j * ldg] = row_ns[i] ? GQ2[i + j * ldg] : HG[i + j * ldg];
+}
+
+void hyp_build_pg(hyp_ctx* ctx) {
+    dim3 grid(std::max(1, std::min(ceil_div(ctx->qloc, 256), ctx->sm_count * 4)),
+              (unsigned)std::min<int64_t>(ctx->nmp, 65535));
+    build_pg_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->qloc, ctx->nmp, ctx->ldg, ctx->d_row_ns,
+                                                   ctx->d_GQ + ctx->p * ctx->ldg, ctx->d_HG, ctx->d_PG);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+}
+
+extern "C" {
+
+int hyp_version(void) { return 100; }
+
+hyp_ctx* hyp_create(int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return nullptr;
+    if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return nullptr;
+    if (prop.major != 10) {
+        fprintf(stderr, "libhypatia_b200: device %d is sm_%d%d; this library is built for sm_100a only\n",
+                device, prop.major, prop.minor);
+        return nullptr;
+    }
+    hyp_ctx* ctx = new hyp_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return nullptr;
+    }
+    return ctx;
+}
+
+void hyp_destroy(hyp_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_model(ctx);
+    hyp_comm_destroy(ctx);
+    for (int i = 0; i < T_NUM; i++) {
+        if (ctx->timing[i].e0) cudaEventDestroy(ctx->timing[i].e0);
+        if (ctx->timing[i].e1) cudaEventDestroy(ctx->timing[i].e1);
+    }
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* hyp_last_error(hyp_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+void* hyp_stream(hyp_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int hyp_sync(hyp_ctx* ctx) {
+    return guarded(ctx, [&] {
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    });
+}
+
+int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* G_local, int64_t ldG,
+                   const double* A, int64_t ldA, const double* c, const double* b, const double* h, int K,
+                   const int* cone_type, const int64_t* cone_dim, const int* cone_dual, int cone_lo,
+                   int cone_hi, const double* Ap_Q, const double* Ap_R) {
+    return guarded(ctx, [&] {
+        if (n < 0 || p < 0 || q < 0 || K < 0 || p > n) throw HypError{"hyp_load_model: bad dimensions"};
+        if (cone_lo < 0 || cone_hi > K || cone_lo > cone_hi) throw HypError{"hyp_load_model: bad cone range"};
+        if (p > 0 && (!Ap_Q || !Ap_R || !A))
+            throw HypError{"hyp_load_model: p > 0 needs A and the QR factors Ap_Q, Ap_R of A'"};
+        free_model(ctx);
+        ctx->n = n;
+        ctx->p = p;
+        ctx->q = q;
+        ctx->nmp = n - p;
+        ctx->K = K;
+        ctx->cone_lo = cone_lo;
+        ctx->cone_hi = cone_hi;
+        ctx->h_cone_type.assign(cone_type, cone_type + K);
+        ctx->h_cone_dim.assign(cone_dim, cone_dim + K);
+        ctx->h_cone_dual.assign(K, 0);
+        if (cone_dual) ctx->h_cone_dual.assign(cone_dual, cone_dual + K);
+        ctx->h_cone_off.assign(K + 1, 0);
+        ctx->h_cone_nu.assign(K, 0.0);
+        ctx->any_dual = false;
+        bool any_ns = false, any_sqrt = false;
+        for (int k = 0; k < K; k++) {
+            int t = cone_type[k];
+            int64_t d = cone_dim[k];
+            if (t < 0 || t >= HYP_NUM_CONE_TYPES || d < 1) throw HypError{"hyp_load_model: bad cone entry"};
+            ctx->h_cone_off[k + 1] = ctx->h_cone_off[k] + d;
+            if (ctx->h_cone_dual[k]) {
+                if (t < HYP_CONE_HYPOPERLOGDETTRI)
+                    throw HypError{"hyp_load_model: use_dual_barrier is only defined for the log-det family"};
+                ctx->any_dual = true;
+            }
+            double side = 0;
+            if (t == HYP_CONE_POSSEMIDEFTRI) side = (std::sqrt(1.0 + 8.0 * d) - 1) / 2;
+            if (t == HYP_CONE_HYPOPERLOGDETTRI) side = (std::sqrt(1.0 + 8.0 * (d - 2)) - 1) / 2;
+            if (t == HYP_CONE_HYPOROOTDETTRI) side = (std::sqrt(1.0 + 8.0 * (d - 1)) - 1) / 2;
+            side = std::floor(side + 0.5);
+            // get_nu: nonnegative.jl:40, epinormeucl.jl:42, possemideftri.jl:67,
+            // hypoperlogdettri.jl:80, hyporootdettri.jl:80
+            ctx->h_cone_nu[k] = t == HYP_CONE_NONNEGATIVE ? (double)d
+                                : t == HYP_CONE_EPINORMEUCL ? 2.0
+                                : t == HYP_CONE_POSSEMIDEFTRI ? side
+                                : t == HYP_CONE_HYPOPERLOGDETTRI ? 2.0 + side
+                                                                 : 1.0 + side;
+            if (k >= cone_lo && k < cone_hi) {
+                if (t >= HYP_CONE_HYPOPERLOGDETTRI) any_ns = true; else any_sqrt = true;
+            }
+        }
+        if (ctx->h_cone_off[K] != q) throw HypError{"hyp_load_model: cone dimensions do not sum to q"};
+        ctx->row_lo = ctx->h_cone_off[cone_lo];
+        ctx->row_hi = ctx->h_cone_off[cone_hi];
+        ctx->qloc = ctx->row_hi - ctx->row_lo;
+        ctx->ldg = round_up(std::max<int64_t>(ctx->qloc, 2), 2);
+        const int64_t nmp = ctx->nmp;
+
+        // G panel (+ GQ = G * Ap_Q when p > 0, qrchol.jl:154)
+        dalloc(&ctx->d_Graw, ctx->ldg * std::max<int64_t>(n, 1));
+        upload_matrix(ctx, ctx->d_Graw, ctx->ldg, G_local, ldG, ctx->qloc, n);
+        ctx->d_GQ = ctx->d_Graw;
+        if (p > 0) {
+            ctx->lda = round_up(p, 2);
+            ctx->ldqm = round_up(n, 2);
+            ctx->ldr = round_up(p, 2);
+            dalloc(&ctx->d_A, ctx->lda * n);
+            dalloc(&ctx->d_Q, ctx->ldqm * n);
+            dalloc(&ctx->d_R, ctx->ldr * p);
+            upload_matrix(ctx, ctx->d_A, ctx->lda, A, ldA, p, n);
+            upload_matrix(ctx, ctx->d_Q, ctx->ldqm, Ap_Q, n, n, n);
+            upload_matrix(ctx, ctx->d_R, ctx->ldr, Ap_R, p, p, p);
+            dalloc(&ctx->d_Rdinv, (int64_t)ceil_div(p, 128) * 128 * 128);
+            hyp_trtri_diag(ctx, ctx->d_R, ctx->ldr, p, ctx->d_Rdinv);
+            dalloc(&ctx->d_GQ, ctx->ldg * n);
+            hyp_gemm_simple(ctx, false, false, ctx->qloc, n, n, ctx->d_Graw, ctx->ldg, ctx->d_Q, ctx->ldqm,
+                            ctx->d_GQ, ctx->ldg);
+        }
+        dalloc(&ctx->d_HG, ctx->ldg * std::max<int64_t>(nmp, 1));
+        if (any_ns && nmp > 0) {
+            dalloc(&ctx->d_PG, ctx->ldg * nmp);
+            std::vector<uint8_t> row_ns((size_t)std::max<int64_t>(ctx->qloc, 1), 0);
+            for (int k = cone_lo; k < cone_hi; k++)
+                if (cone_type[k] >= HYP_CONE_HYPOPERLOGDETTRI)
+                    for (int64_t r = ctx->h_cone_off[k]; r < ctx->h_cone_off[k + 1]; r++) row_ns[r - ctx->row_lo] = 1;
+            dalloc(&ctx->d_row_ns, (int64_t)row_ns.size());
+            CUDA_TRY(cudaMemcpy(ctx->d_row_ns, row_ns.data(), row_ns.size(), cudaMemcpyHostToDevice));
+        }
+        (void)any_sqrt;
+
+        // (c, b, h) and the constant right-hand side (-c, b, h)  (common.jl:203-205)
+        const int64_t dim3 = n + p + q, dim6 = n + p + 2 * q + 2;
+        dalloc(&ctx->d_cbh, dim3);
+        dalloc(&ctx->d_const_rhs, dim3);
+        dalloc(&ctx->d_const_sol, dim3);
+        dalloc(&ctx->d_sub_rhs, dim3);
+        dalloc(&ctx->d_sub_sol, dim3);
+        dalloc(&ctx->d_rhs, dim6);
+        dalloc(&ctx->d_sol, dim6);
+        if (n) CUDA_TRY(cudaMemcpy(ctx->d_cbh, c, n * 8, cudaMemcpyDefault));
+        if (p) CUDA_TRY(cudaMemcpy(ctx->d_cbh + n, b, p * 8, cudaMemcpyDefault));
+        if (q) CUDA_TRY(cudaMemcpy(ctx->d_cbh + n + p, h, q * 8, cudaMemcpyDefault));
+        CUDA_TRY(cudaMemcpy(ctx->d_const_rhs, ctx->d_cbh, dim3 * 8, cudaMemcpyDeviceToDevice));
+        if (n) {
+            negate_kernel<<<vgrid(ctx, n), 256, 0, ctx->stream>>>(n, ctx->d_const_rhs, ctx->d_cbh);
+            ctx->launches++;
+        }
+
+        // cone table
+        dalloc(&ctx->d_cone_nu, K);
+        dalloc(&ctx->d_cone_off, K + 1);
+        dalloc(&ctx->d_cone_dim, K);
+        dalloc(&ctx->d_cone_type, K);
+        if (K) {
+            CUDA_TRY(cudaMemcpy(ctx->d_cone_nu, ctx->h_cone_nu.data(), K * 8, cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(ctx->d_cone_off, ctx->h_cone_off.data(), (K + 1) * 8, cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(ctx->d_cone_dim, ctx->h_cone_dim.data(), K * 8, cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(ctx->d_cone_type, ctx->h_cone_type.data(), K * 4, cudaMemcpyHostToDevice));
+        }
+        if (ctx->any_dual) {
+            std::vector<uint8_t> rd((size_t)q, 0);
+            for (int k = 0; k < K; k++)
+                if (ctx->h_cone_dual[k])
+                    for (int64_t r = ctx->h_cone_off[k]; r < ctx->h_cone_off[k + 1]; r++) rd[r] = 1;
+            dalloc(&ctx->d_row_dual, q);
+            CUDA_TRY(cudaMemcpy(ctx->d_row_dual, rd.data(), q, cudaMemcpyHostToDevice));
+        }
+        hyp_cones_build_groups(ctx);
+
+        // state / work vectors
+        const int64_t qn = std::max<int64_t>(std::max(q, n), 1);
+        dalloc(&ctx->d_point, q);
+        dalloc(&ctx->d_dual, q);
+        dalloc(&ctx->d_grad, q);
+        dalloc(&ctx->d_feas, K);
+        dalloc(&ctx->d_dual_feas, K);
+        dalloc(&ctx->d_num_ok, K);
+        dalloc(&ctx->d_proxsqr, K);
+        dalloc(&ctx->d_Gx, q);
+        dalloc(&ctx->d_HGx, q);
+        dalloc(&ctx->d_Gx_const, q);
+        dalloc(&ctx->d_vq1, qn);
+        dalloc(&ctx->d_vq2, qn);
+        dalloc(&ctx->d_vq3, qn);
+        dalloc(&ctx->d_vq4, qn);
+        dalloc(&ctx->d_t, n);
+        dalloc(&ctx->d_t2, n);
+        dalloc(&ctx->d_vp1, p);
+        dalloc(&ctx->d_vp2, p);
+        dalloc(&ctx->d_scalars, 64);
+        ctx->partial_doubles = std::max<int64_t>(4096, 32 * std::max<int64_t>(std::max(ctx->qloc, n), p));
+        dalloc(&ctx->d_partial, ctx->partial_doubles);
+        dalloc(&ctx->d_info, 8);
+        dalloc(&ctx->d_flags, ceil_div(std::max<int64_t>(std::max(nmp, p), 1), 128) + 8);
+        ctx->trsv_epoch = 0;
+
+        // Schur matrix, factor, inverted diagonal blocks
+        ctx->lds = round_up(std::max<int64_t>(nmp, 2), 2);
+        dalloc(&ctx->d_S, ctx->lds * std::max<int64_t>(nmp, 1));
+        dalloc(&ctx->d_F, ctx->lds * std::max<int64_t>(nmp, 1));
+        dalloc(&ctx->d_Dinv, (int64_t)ceil_div(std::max<int64_t>(nmp, 1), 128) * 128 * 128);
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        ctx->model_loaded = true;
+        return 0;
+    });
+}
+
+int hyp_set_mu_tau(hyp_ctx* ctx, double mu, double tau_bar) {
+    return guarded(ctx, [&] {
+        ctx->mu = mu;
+        ctx->tau_bar = tau_bar;
+        return 0;
+    });
+}
+
+int hyp_cones_load_point(hyp_ctx* ctx, const double* primal, const double* dual, double scal) {
+    return guarded(ctx, [&] {
+        need_model(ctx);
+        const int64_t q = ctx->q;
+        ensure_stage(ctx, 2 * q + 2);
+        const double* dp = stage_in(ctx, primal, q, ctx->d_stage);
+        const double* dd = stage_in(ctx, dual, q, ctx->d_stage + q);
+        // load_point(cone, point, scal): cone.point = scal * point (Cones.jl:157-161)
+        hyp_lincomb3(ctx, q, ctx->d_point, scal, dp, 0.0, nullptr, 0.0, nullptr);
+        hyp_copy(ctx, q, ctx->d_dual, dd);
+        hyp_cones_update_state(ctx);
+        ctx->cones_loaded = true;
+        ctx->lhs_ready = false;
+        return 0;
+    });
+}
+
+int hyp_cones_feas(hyp_ctx* ctx, uint8_t* is_feas, uint8_t* is_dual_feas) {
+    return guarded(ctx, [&] {
+        need_model(ctx);
+        if (!ctx->cones_loaded) throw HypError{"hyp_cones_feas: no point loaded"};
+        stage_out_u8(ctx, is_feas, ctx->K, ctx->d_feas);
+        stage_out_u8(ctx, is_dual_feas, ctx->K, ctx->d_dual_feas);
+        return 0;
+    });
+}
+
+int hyp_cones_grad(hyp_ctx* ctx, double* grad) {
+    return guarded(ctx, [&] {
+        need_model(ctx);
+        if (!ctx->cones_loaded) throw HypError{"hyp_cones_grad: no point loaded"};
+        stage_out(ctx, grad, ctx->q, ctx->d_grad);
+        return 0;
+    });
+}
+
+int hyp_cones_hess_prod(hyp_ctx* ctx, double* prod, const double* arr, int64_t ncols, int64_t ld_prod,
+                        int64_t ld_arr, int mode) {
+    return guarded(ctx, [&] {
+        need_model(ctx);
+        if (!ctx->cones_loaded) throw HypError{"hyp_cones_hess_prod: no point loaded"};
+        if (mode < 0 || mode > HYP_PROD_BLOCK) throw HypError{"hyp_cones_hess_prod: bad mode"};
+        const int64_t q = ctx->q;
+        if (ncols <= 0 || q == 0) return 0;
+        if (ld_arr < q || ld_prod < q) throw HypError{"hyp_cones_hess_prod: leading dimension < q"};
+        bool dev_in = is_device_ptr(arr), dev_out = is_device_ptr(prod);
+        const double* darr = arr;
+        double* dprod = prod;
+        int64_t lda_d = ld_arr, ldp_d = ld_prod;
+        int64_t need = (dev_in ? 0 : q * ncols) + (dev_out ? 0 : q * ncols);
+        ensure_stage(ctx, need + 2);
+        double* buf = ctx->d_stage;
+        if (!dev_in) {
+            CUDA_TRY(cudaMemcpy2DAsync(buf, q * 8, arr, ld_arr * 8, q * 8, ncols, cudaMemcpyHostToDevice,
+                                       ctx->stream));
+            darr = buf;
+            lda_d = q;
+            buf += q * ncols;
+        }
+        if (!dev_out) {
+            dprod = buf;
+            ldp_d = q;
+        }
+        {
+            TimeScope ts(ctx, T_CONE_PROD);
+            hyp_cones_prod(ctx, dprod, darr, ncols, ldp_d, lda_d, mode, 0);
+        }
+        if (ctx->nranks > 1)
+            for (int64_t j = 0; j < ncols; j++) hyp_replicate_q(ctx, dprod + j * ldp_d);
+        if (!dev_out) {
+            CUDA_TRY(cudaMemcpy2DAsync(prod, ld_prod * 8, dprod, q * 8, q * 8, ncols, cudaMemcpyDeviceToHost,
+                                       ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        }
+        return 0;
+    });
+}
+
+int hyp_cones_dder3(hyp_ctx* ctx, double* out, const double* dir) {
+    return guarded(ctx, [&] {
+        need_model(ctx);
+        if (!ctx->cones_loaded) throw HypError{"hyp_cones_dder3: no point loaded"};
+        const int64_t q = ctx->q;
+        ensure_stage(ctx, q + 2);
+        const double* dd = stage_in(ctx, dir, q, ctx->d_stage);
+        hyp_cones_dder3_dev(ctx, ctx->d_vq4, dd);
+        if (ctx->nranks > 1) hyp_replicate_q(ctx, ctx->d_vq4);
+        stage_out(ctx, out, q, ctx->d_vq4);
+        return 0;
+    });
+}
+
+int hyp_cones_proxsqr(hyp_ctx* ctx, double irtmu, int use_max, double* proxsqr, uint8_t* numerics_ok) {
+    return guarded(ctx, [&] {
+        need_model(ctx);
+        if (!ctx->cones_loaded) throw HypError{"hyp_cones_proxsqr: no point loaded"};
+        hyp_cones_prox_dev(ctx, irtmu, use_max);
+        stage_out(ctx, proxsqr, ctx->K, ctx->d_proxsqr);
+        stage_out_u8(ctx, numerics_ok, ctx->K, ctx->d_num_ok);
+        return 0;
+    });
+}
+
+int hyp_update_lhs(hyp_ctx* ctx, int* fact_kind) {
+    return guarded(ctx, [&] {
+        need_model(ctx);
+        if (!ctx->cones_loaded) throw HypError{"hyp_update_lhs: no cone point loaded"};
+        int rc = 0;
+        ctx->fact_kind = 0;
+        if (ctx->nmp > 0) rc = update_lhs_fact(ctx);
+        if (fact_kind) *fact_kind = ctx->fact_kind;
+        // rhs_const.z = H h (block_hess_prod!, qrchol.jl:191-195), then the constant column
+        const int64_t n = ctx->n, p = ctx->p, q = ctx->q;
+        if (q > 0) {
+            TimeScope ts(ctx, T_CONE_PROD);
+            hyp_cones_prod(ctx, ctx->d_const_rhs + n + p, ctx->d_cbh + n + p, 1, q, q, HYP_PROD_BLOCK, 0);
+            if (ctx->nranks > 1) hyp_replicate_q(ctx, ctx->d_const_rhs + n + p);
+        }
+        solve_subsystem3_dev(ctx, ctx->d_const_sol, ctx->d_const_rhs);
+        hyp_copy(ctx, q, ctx->d_Gx_const, ctx->d_Gx);
+        hyp_dot(ctx, n + p + q, ctx->d_cbh, ctx->d_const_sol, ctx->d_scalars + 1, false);
+        ctx->lhs_ready = true;
+        return rc;
+    });
+}
+
+int hyp_solve_subsystem3(hyp_ctx* ctx, double* sol, const double* rhs) {
+    return guarded(ctx, [&] {
+        need_model(ctx);
+        if (!ctx->lhs_ready && ctx->nmp > 0) throw HypError{"hyp_solve_subsystem3: call hyp_update_lhs first"};
+        const int64_t dim3 = ctx->n + ctx->p + ctx->q;
+        const double* drhs = stage_in(ctx, rhs, dim3, ctx->d_sub_rhs);
+        solve_subsystem3_dev(ctx, ctx->d_sub_sol, drhs);
+        stage_out(ctx, sol, dim3, ctx->d_sub_sol);
+        return 0;
+    });
+}
+
+int hyp_solve_system(hyp_ctx* ctx, double* sol, const double* rhs) {
+    return guarded(ctx, [&] {
+        need_model(ctx);
+        if (!ctx->lhs_ready) throw HypError{"hyp_solve_system: call hyp_update_lhs first"};
+        const int64_t dim6 = ctx->n + ctx->p + 2 * ctx->q + 2;
+        const double* drhs = stage_in(ctx, rhs, dim6, ctx->d_rhs);
+        double* dsol = is_device_ptr(sol) ? sol : ctx->d_sol;
+        if (dsol == drhs) dsol = ctx->d_sol;
+        solve_system_dev(ctx, dsol, drhs);
+        stage_out(ctx, sol, dim6, dsol);
+        return 0;
+    });
+}
+
+int hyp_apply_lhs(hyp_ctx* ctx, double* res, const double* dir) {
+    return guarded(ctx, [&] {
+        need_model(ctx);
+        if (!ctx->cones_loaded) throw HypError{"hyp_apply_lhs: no cone point loaded"};
+        const int64_t dim6 = ctx->n + ctx->p + 2 * ctx->q + 2;
+        const double* ddir = stage_in(ctx, dir, dim6, ctx->d_rhs);
+        double* dres = is_device_ptr(res) ? res : ctx->d_sol;
+        if (dres == ddir) dres = ctx->d_sol;
+        apply_lhs_dev(ctx, dres, ddir);
+        stage_out(ctx, res, dim6, dres);
+        return 0;
+    });
+}
+
+int hyp_get_schur(hyp_ctx* ctx, double* S, int64_t ld) {
+    return guarded(ctx, [&] {
+        need_model(ctx);
+        const int64_t nmp = ctx->nmp;
+        if (nmp == 0) return 0;
+        cudaMemcpyKind kind = is_device_ptr(S) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+        CUDA_TRY(cudaMemcpy2DAsync(S, ld * 8, ctx->d_S, ctx->lds * 8, nmp * 8, nmp, kind, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    });
+}
+
+int64_t hyp_launch_count(hyp_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+int hyp_timing_enable(hyp_ctx* ctx, int on) {
+    if (!ctx) return -1;
+    ctx->timing_enabled = on != 0;
+    return 0;
+}
+int hyp_timing_get(hyp_ctx* ctx, int slot, double* total_ms, int64_t* calls) {
+    if (!ctx || slot < 0 || slot >= T_NUM) return -1;
+    if (total_ms) *total_ms = ctx->timing[slot].total_ms;
+    if (calls) *calls = ctx->timing[slot].count;
+    return 0;
+}
+int hyp_timing_reset(hyp_ctx* ctx) {
+    if (!ctx) return -1;
+    for (int i = 0; i < T_NUM; i++) {
+        ctx->timing[i].total_ms = 0;
+        ctx->timing[i].count = 0;
+    }
+    return 0;
+}
+int hyp_timing_slots(void) { return T_NUM; }
+const char* hyp_timing_name(int slot) { return (slot >= 0 && slot < T_NUM) ? kTimingNames[slot] : ""; }
+
+// ---- unit-test entry points --------------------------------------------------------------
+namespace {
+struct TmpDev {
+    hyp_ctx* ctx;
+    std::vector<void*> ptrs;
+    ~TmpDev() {
+        cudaStreamSynchronize(ctx->stream);
+        for (void* p : ptrs) cudaFree(p);
+    }
+    // device copy (or the pointer itself) of a rows x cols matrix; returns new leading dim
+    double* in(const double* src, int64_t ld, int64_t rows, int64_t cols, int64_t* ld_out) {
+        if (is_device_ptr(src)) {
+            *ld_out = ld;
+            return const_cast<double*>(src);
+        }
+        int64_t dld = round_up(std::max<int64_t>(rows, 2), 2);
+        double* d = nullptr;
+        dalloc(&d, dld * std::max<int64_t>(cols, 1));
+        ptrs.push_back(d);
+        upload_matrix(ctx, d, dld, src, ld, rows, cols);
+        *ld_out = dld;
+        return d;
+    }
+    void out(double* dst, int64_t ld, const double* d, int64_t dld, int64_t rows, int64_t cols) {
+        if (dst == d) return;
+        CUDA_TRY(cudaMemcpy2DAsync(dst, ld * 8, d, dld * 8, rows * 8, cols, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+};
+}  // namespace
+
+int hyp_test_atb_upper(hyp_ctx* ctx, const double* P, int64_t ldp, const double* R, int64_t ldr, int64_t klen,
+                       int64_t ncols, double* C, int64_t ldc, double alpha, double beta) {
+    return guarded(ctx, [&] {
+        TmpDev tmp{ctx};
+        int64_t lp, lr, lc;
+        double* dP = tmp.in(P, ldp, klen, ncols, &lp);
+        double* dR = (R == P) ? dP : tmp.in(R, ldr, klen, ncols, &lr);
+        if (R == P) lr = lp;
+        double* dC = tmp.in(C, ldc, ncols, ncols, &lc);
+        hyp_atb_upper(ctx, dP, lp, dR, lr, klen, ncols, dC, lc, alpha, beta);
+        tmp.out(C, ldc, dC, lc, ncols, ncols);
+        return 0;
+    });
+}
+
+int hyp_test_gemm_tn(hyp_ctx* ctx, const double* P, int64_t ldp, const double* R, int64_t ldr, int64_t klen,
+                     int64_t mrows, int64_t ncols, double* C, int64_t ldc, double alpha, double beta) {
+    return guarded(ctx, [&] {
+        TmpDev tmp{ctx};
+        int64_t lp, lr, lc;
+        double* dP = tmp.in(P, ldp, klen, mrows, &lp);
+        double* dR = tmp.in(R, ldr, klen, ncols, &lr);
+        double* dC = tmp.in(C, ldc, mrows, ncols, &lc);
+        hyp_gemm_tn(ctx, dP, lp, dR, lr, klen, mrows, ncols, dC, lc, alpha, beta);
+        tmp.out(C, ldc, dC, lc, mrows, ncols);
+        return 0;
+    });
+}
+
+namespace {
+struct TestFactor {
+    double* dinv = nullptr;
+    int* info = nullptr;
+    int* flags = nullptr;
+    int64_t m = 0;
+} g_tf;
+}  // namespace
+
+int hyp_test_potrf(hyp_ctx* ctx, double* A, int64_t lda, int64_t m, int* info) {
+    return guarded(ctx, [&] {
+        TmpDev tmp{ctx};
+        int64_t la;
+        double* dA = tmp.in(A, lda, m, m, &la);
+        if (g_tf.dinv) cudaFree(g_tf.dinv);
+        if (g_tf.info) cudaFree(g_tf.info);
+        dalloc(&g_tf.dinv, (int64_t)ceil_div(std::max<int64_t>(m, 1), 128) * 128 * 128);
+        dalloc(&g_tf.info, 8);
+        g_tf.m = m;
+        hyp_potrf_upper(ctx, dA, la, m, g_tf.dinv, g_tf.info);
+        int hinfo = 0;
+        CUDA_TRY(cudaMemcpyAsync(&hinfo, g_tf.info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (info) *info = hinfo;
+        tmp.out(A, lda, dA, la, m, m);
+        return 0;
+    });
+}
+
+int hyp_test_potrs(hyp_ctx* ctx, const double* F, int64_t ldf, int64_t m, double* x) {
+    return guarded(ctx, [&] {
+        if (!g_tf.dinv || g_tf.m != m) throw HypError{"hyp_test_potrs: call hyp_test_potrf with the same m first"};
+        TmpDev tmp{ctx};
+        int64_t lf, lx;
+        double* dF = tmp.in(F, ldf, m, m, &lf);
+        double* dx = tmp.in(x, m, m, 1, &lx);
+        int* saved = ctx->d_flags;
+        int* flags = nullptr;
+        dalloc(&flags, ceil_div(m, 128) + 8);
+        tmp.ptrs.push_back(flags);
+        ctx->d_flags = flags;
+        hyp_trsv_upper(ctx, dF, lf, m, g_tf.dinv, dx, true);
+        hyp_trsv_upper(ctx, dF, lf, m, g_tf.dinv, dx, false);
+        ctx->d_flags = saved;
+        tmp.out(x, m, dx, lx, m, 1);
+        return 0;
+    });
+}
+
+int hyp_test_gemv(hyp_ctx* ctx, int trans, int64_t rows, int64_t cols, const double* M, int64_t ld,
+                  const double* x, double alpha, double beta, double* y) {
+    return guarded(ctx, [&] {
+        TmpDev tmp{ctx};
+        int64_t lm, l1, l2;
+        double* dM = tmp.in(M, ld, rows, cols, &lm);
+        int64_t xl = trans ? rows : cols, yl = trans ? cols : rows;
+        double* dx = tmp.in(x, xl, xl, 1, &l1);
+        double* dy = tmp.in(y, yl, yl, 1, &l2);
+        double* saved = ctx->d_partial;
+        int64_t saved_n = ctx->partial_doubles;
+        double* part = nullptr;
+        int64_t pn = std::max<int64_t>(4096, 32 * std::max(rows, cols));
+        dalloc(&part, pn);
+        tmp.ptrs.push_back(part);
+        ctx->d_partial = part;
+        ctx->partial_doubles = pn;
+        if (trans) hyp_gemv_t(ctx, rows, cols, dM, lm, dx, alpha, beta, dy);
+        else hyp_gemv_n(ctx, rows, cols, dM, lm, dx, alpha, beta, dy);
+        ctx->d_partial = saved;
+        ctx->partial_doubles = saved_n;
+        tmp.out(y, yl, dy, l2, yl, 1);
+        return 0;
+    });
+}
+
+int hyp_test_ldlt_solve(hyp_ctx* ctx, const double* A, int64_t lda, int64_t m, double* x, int* info) {
+    return guarded(ctx, [&] {
+        TmpDev tmp{ctx};
+        int64_t la, lx;
+        double* dA0 = tmp.in(A, lda, m, m, &la);
+        double* dA = nullptr;
+        dalloc(&dA, la * m);
+        tmp.ptrs.push_back(dA);
+        CUDA_TRY(cudaMemcpyAsync(dA, dA0, (size_t)la * m * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        double* dx = tmp.in(x, m, m, 1, &lx);
+        int *ipiv = nullptr, *dinfo = nullptr;
+        dalloc(&ipiv, m + 8);
+        dalloc(&dinfo, 8);
+        tmp.ptrs.push_back(ipiv);
+        tmp.ptrs.push_back(dinfo);
+        double* saved_w = ctx->d_ldl_work;
+        double* work = nullptr;
+        dalloc(&work, 4 * m + 64);
+        tmp.ptrs.push_back(work);
+        ctx->d_ldl_work = work;
+        hyp_ldlt_factor(ctx, dA, la, m, ipiv, dinfo);
+        int hinfo = 0;
+        CUDA_TRY(cudaMemcpyAsync(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (info) *info = hinfo;
+        hyp_ldlt_solve(ctx, dA, la, m, ipiv, dx);
+        ctx->d_ldl_work = saved_w;
+        tmp.out(x, m, dx, lx, m, 1);
+        return 0;
+    });
+}
+
+}  // extern "C"

@@ -74,7 +74,9 @@ class ConeBlock:
     def dder3(self, direction):
         raise NotImplementedError
 
-    def check_numerics(self):
+    def check_numerics(self, irtmu=None, use_max_prox=None):
+        """irtmu / use_max_prox let a batched backend answer check_numerics and get_proxsqr
+        (always called back to back, search.jl:126-128) from one device sweep."""
         raise NotImplementedError
 
     def get_proxsqr(self, irtmu, use_max_prox):

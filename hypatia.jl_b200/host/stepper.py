@@ -203,7 +203,7 @@ def check_cone_points(solver, stepper) -> bool:
         return False
     if not cones.is_dual_feas().all():
         return False
-    if not cones.check_numerics().all():
+    if not cones.check_numerics(irtmu, searcher.use_max_prox).all():
         return False
     proxsqr = cones.get_proxsqr(irtmu, searcher.use_max_prox)
     if searcher.use_max_prox:

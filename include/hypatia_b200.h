@@ -1,0 +1,153 @@
+/*
+ * libhypatia_b200 - C ABI of the B200-native (sm_100a) Hypatia KKT / cone-oracle hot path.
+ *
+ * This is the drop-in boundary of SURVEY.md section 8(b): the entry points a Julia
+ * `Solvers.SystemSolver{Float64}` subtype and a batched `Cones.Cone{Float64}` container bind
+ * with `ccall` (julia/HypatiaB200.jl), and that the Python test driver binds with ctypes
+ * (hypatia.jl_b200/capi.py).  Plain pointers and sizes only; every array is Float64, Julia
+ * (column-major) layout.  All file:line citations are relative to the reference tree
+ * (chriscoey/Hypatia.jl v0.5.1).
+ *
+ * Conventions
+ *   - every function returns int: 0 ok; > 0 numerical condition (documented per call);
+ *     < 0 CUDA / NCCL / argument error, message in hyp_last_error(ctx).  Nothing throws or
+ *     aborts across the ABI (the reference never throws on numerical failure either:
+ *     qrchol.jl:252-254, dense.jl:194-215).
+ *   - every data pointer may be a HOST pointer (pageable or pinned) or a DEVICE pointer of
+ *     the context's GPU; the library detects which (cudaPointerGetAttributes) and stages host
+ *     buffers through its own pinned buffer.  Calls are synchronous on return for host
+ *     pointers and stream-ordered on hyp_stream(ctx) for device pointers.
+ *   - one host thread per context; a context owns one GPU (one process per GPU; multi-GPU
+ *     runs create one context per rank and join them with hyp_comm_init).
+ *   - vectors crossing the ABI use the reference's Point layout (point.jl:24-54):
+ *     full Point  = [x(n); y(p); z(q); tau; s(q); kap]   length n+p+2q+2
+ *     sub Point   = [x(n); y(p); z(q)]                   length n+p+q
+ *     q-vectors are cone after cone in model order (Models.jl:56-66), GLOBAL length q on
+ *     every rank.
+ */
+#ifndef HYPATIA_B200_H
+#define HYPATIA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hyp_ctx hyp_ctx;
+
+/* cone type codes (reference types in src/Cones/) */
+#define HYP_CONE_NONNEGATIVE 0      /* nonnegative.jl      */
+#define HYP_CONE_EPINORMEUCL 1      /* epinormeucl.jl      */
+#define HYP_CONE_POSSEMIDEFTRI 2    /* possemideftri.jl (real) */
+#define HYP_CONE_HYPOPERLOGDETTRI 3 /* hypoperlogdettri.jl */
+#define HYP_CONE_HYPOROOTDETTRI 4   /* hyporootdettri.jl   */
+
+/* modes of hyp_cones_hess_prod (Cones.jl oracle names) */
+#define HYP_PROD_HESS 0          /* hess_prod!          */
+#define HYP_PROD_INV_HESS 1      /* inv_hess_prod!      */
+#define HYP_PROD_SQRT_HESS 2     /* sqrt_hess_prod!     (Nonnegative/EpiNormEucl/PosSemidefTri) */
+#define HYP_PROD_INV_SQRT_HESS 3 /* inv_sqrt_hess_prod! (same cones) */
+#define HYP_PROD_BLOCK 4         /* block_hess_prod!, qrchol.jl:87-98 */
+
+/* ---- life cycle -------------------------------------------------------------------- */
+int hyp_version(void);
+/* one context on CUDA device `device`; NULL on failure (no CUDA device => no library) */
+hyp_ctx* hyp_create(int device);
+/* replaces free_memory(syssolver), Solvers.jl:407,582-584 */
+void hyp_destroy(hyp_ctx* ctx);
+const char* hyp_last_error(hyp_ctx* ctx);
+/* cudaStream_t the context launches on (as void*) */
+void* hyp_stream(hyp_ctx* ctx);
+int hyp_sync(hyp_ctx* ctx);
+
+/* ---- multi-GPU: cones / row panels of G sharded over ranks ----------- */
+/* rank 0 creates a 128-byte NCCL unique id, the host broadcasts it, every rank joins. */
+int hyp_comm_unique_id(char* id128);
+int hyp_comm_init(hyp_ctx* ctx, int rank, int nranks, const char* id128);
+
+/* ---- load: replaces load(syssolver::QRCholDenseSystemSolver, solver), qrchol.jl:138-179,
+ *      setup_point_sub common.jl:184-208, and setup_data!(cone) for every cone.
+ * G_local: the rows of model.G owned by this rank, i.e. rows of cones [cone_lo, cone_hi)
+ *          (all q rows when the context is not sharded), q_local x n, leading dim ldG.
+ * A: p x n (NULL when p == 0); c (n), b (p), h (q, GLOBAL).
+ * cone_type/cone_dim/cone_dual: K entries (GLOBAL cone list; offsets are the running sum).
+ * Ap_Q (n x n) / Ap_R (p x p upper): solver.Ap_Q / solver.Ap_R when p > 0 (QR of A'), else NULL.
+ */
+int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* G_local,
+                   int64_t ldG, const double* A, int64_t ldA, const double* c, const double* b,
+                   const double* h, int K, const int* cone_type, const int64_t* cone_dim,
+                   const int* cone_dual, int cone_lo, int cone_hi, const double* Ap_Q,
+                   const double* Ap_R);
+
+/* ---- cone oracles (plugin slot 2; batched over all K cones) ---------------------------- */
+/* load_point(cone, primal_k, scal) + load_dual_point + reset_data for every cone
+ * (Cones.jl:157-161,185-186; caller search.jl:121-123), then update_feas / update_grad and the
+ * per-cone factorisations (K9).  primal/dual: GLOBAL q-vectors. */
+int hyp_cones_load_point(hyp_ctx* ctx, const double* primal, const double* dual, double scal);
+/* is_feas / is_dual_feas for every cone (K bytes each, 1 = feasible) */
+int hyp_cones_feas(hyp_ctx* ctx, uint8_t* is_feas, uint8_t* is_dual_feas);
+/* grad(cone) for every cone (q) */
+int hyp_cones_grad(hyp_ctx* ctx, double* grad);
+/* prod[:, 0:ncols] = oracle(arr[:, 0:ncols]) for every cone block; arr/prod are q x ncols */
+int hyp_cones_hess_prod(hyp_ctx* ctx, double* prod, const double* arr, int64_t ncols,
+                        int64_t ld_prod, int64_t ld_arr, int mode);
+/* dder3(cone, dir_k) for every cone (q) */
+int hyp_cones_dder3(hyp_ctx* ctx, double* out, const double* dir);
+/* check_numerics (Cones.jl:273-290) and get_proxsqr (Cones.jl:294-310, nonnegative.jl:137-145) */
+int hyp_cones_proxsqr(hyp_ctx* ctx, double irtmu, int use_max, double* proxsqr,
+                      uint8_t* numerics_ok);
+
+/* ---- system solver (plugin slot 1) ------------------------------------------------------ */
+/* mu and tau of the current iterate (solver.mu, solver.point.tau[]) used by
+ * solve_subsystem4 / solve_system / apply_lhs (common.jl:117,171-175,147) */
+int hyp_set_mu_tau(hyp_ctx* ctx, double mu, double tau_bar);
+/* update_lhs(syssolver, solver), qrchol.jl:181-257: Schur assembly (K8+K1+K2), factorisation
+ * with the posdef_fact_copy! chain (dense.jl:194-215), constant column solve.
+ * fact_kind: 0 Cholesky, 1 Bunch-Kaufman, 2 shifted Bunch-Kaufman.
+ * returns 0 ok, 1 Cholesky failed but a fallback succeeded, 2 every factorisation failed. */
+int hyp_update_lhs(hyp_ctx* ctx, int* fact_kind);
+/* solve_subsystem3(syssolver, solver, sol, rhs), qrchol.jl:39-85 (sub Points) */
+int hyp_solve_subsystem3(hyp_ctx* ctx, double* sol, const double* rhs);
+/* solve_system(syssolver, solver, sol, rhs), common.jl:129-151 (full Points) */
+int hyp_solve_system(hyp_ctx* ctx, double* sol, const double* rhs);
+/* apply_lhs(stepper, solver) restricted to its data flow: res = LHS6x6 * dir, common.jl:79-121 */
+int hyp_apply_lhs(hyp_ctx* ctx, double* res, const double* dir);
+
+/* ---- introspection used by tests / bench ----------------------------------------------- */
+/* upper triangle of the assembled Schur matrix (n-p x n-p, leading dim ld) */
+int hyp_get_schur(hyp_ctx* ctx, double* S, int64_t ld);
+/* kernels launched by this context so far */
+int64_t hyp_launch_count(hyp_ctx* ctx);
+/* per-phase device timers: enable, then read accumulated ms / calls per slot and reset */
+int hyp_timing_enable(hyp_ctx* ctx, int on);
+int hyp_timing_get(hyp_ctx* ctx, int slot, double* total_ms, int64_t* calls);
+int hyp_timing_reset(hyp_ctx* ctx);
+int hyp_timing_slots(void);
+const char* hyp_timing_name(int slot);
+
+/* ---- building blocks exported for unit tests (tests/test_gpu_kernels.py) ---------------- */
+/* C(upper 128-tiles) = alpha * P' R + beta * C; P, R: klen x ncols col-major (device or host) */
+int hyp_test_atb_upper(hyp_ctx* ctx, const double* P, int64_t ldp, const double* R, int64_t ldr,
+                       int64_t klen, int64_t ncols, double* C, int64_t ldc, double alpha,
+                       double beta);
+/* C = alpha * P' R + beta * C, full mrows x ncols */
+int hyp_test_gemm_tn(hyp_ctx* ctx, const double* P, int64_t ldp, const double* R, int64_t ldr,
+                     int64_t klen, int64_t mrows, int64_t ncols, double* C, int64_t ldc,
+                     double alpha, double beta);
+/* in-place upper Cholesky A = U'U; *info = 0 or index (1-based) of the failing pivot block */
+int hyp_test_potrf(hyp_ctx* ctx, double* A, int64_t lda, int64_t m, int* info);
+/* x = (U'U)^-1 x with the factor of the last hyp_test_potrf */
+int hyp_test_potrs(hyp_ctx* ctx, const double* F, int64_t ldf, int64_t m, double* x);
+/* y = alpha * op(M) x + beta * y */
+int hyp_test_gemv(hyp_ctx* ctx, int trans, int64_t rows, int64_t cols, const double* M,
+                  int64_t ld, const double* x, double alpha, double beta, double* y);
+/* rook-pivoted LDL' factor + solve of a symmetric matrix given by its upper triangle
+ * (device restatement of symm_fact!, dense.jl:164-165); returns info */
+int hyp_test_ldlt_solve(hyp_ctx* ctx, const double* A, int64_t lda, int64_t m, double* x,
+                        int* info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYPATIA_B200_H */

@@ -819,7 +819,7 @@ class OracleConeBlock(ConeBlock):
     def dder3(self, direction):
         return self._map(lambda ck, a: ck.dder3(a), direction)
 
-    def check_numerics(self):
+    def check_numerics(self, irtmu=None, use_max_prox=None):
         return np.array([ck.check_numerics() for ck in self.cones], dtype=bool)
 
     def get_proxsqr(self, irtmu, use_max_prox):

@@ -99,6 +99,7 @@ class QRCholDenseSystemSolver(_ElimSolver):
         self.HGQ2 = np.zeros((q, self.nmp), order="F")
         self.setup_point_sub(model)
         self.fact = None
+        self.fact_kind = 0
         self.lhs = None
         return self
 

@@ -1,0 +1,105 @@
+"""-m gpu parity of the batched device cone oracles against the CPU oracle (oracle/cones.py) on the
+same seeded points, plus the reference's own oracle identities (test/cone.jl:23-114) evaluated
+on the device results.  FP64 tolerance: 1e-11 relative per q-vector unless noted (the oracle
+identities themselves hold to 1e3*eps on well-scaled points)."""
+import numpy as np
+import pytest
+
+from gpu_util import rel
+from hypatia_b200.host import instances as inst
+from hypatia_b200.host import models as M
+
+pytestmark = pytest.mark.gpu
+
+
+def _blocks(model):
+    from hypatia_b200.cones import DeviceConeBlock
+    from oracle.cones import OracleConeBlock
+    return DeviceConeBlock(model), OracleConeBlock(model)
+
+
+CONE_SETS = {
+    "nonneg": [M.Nonnegative(1), M.Nonnegative(6), M.Nonnegative(700)],
+    "soc": [M.EpiNormEucl(2), M.EpiNormEucl(3), M.EpiNormEucl(25), M.EpiNormEucl(33), M.EpiNormEucl(70)],
+    "vecmix": [M.EpiNormEucl(25), M.Nonnegative(9), M.EpiNormEucl(5), M.Nonnegative(1)],
+    "psd": [M.PosSemidefTri(1), M.PosSemidefTri(3), M.PosSemidefTri(6), M.PosSemidefTri(15),
+            M.PosSemidefTri(M.svec_length(40)), M.PosSemidefTri(M.svec_length(129))],
+    "logdet": [M.HypoPerLogdetTri(3), M.HypoPerLogdetTri(5), M.HypoPerLogdetTri(12),
+               M.HypoPerLogdetTri(2 + M.svec_length(33)), M.HypoPerLogdetTri(8, use_dual=True)],
+    "rootdet": [M.HypoRootdetTri(2), M.HypoRootdetTri(4), M.HypoRootdetTri(11),
+                M.HypoRootdetTri(1 + M.svec_length(33)), M.HypoRootdetTri(7, use_dual=True)],
+    "allmix": [M.Nonnegative(5), M.EpiNormEucl(4), M.PosSemidefTri(6), M.HypoPerLogdetTri(8),
+               M.HypoRootdetTri(7), M.EpiNormEucl(3), M.HypoPerLogdetTri(5, use_dual=True)],
+}
+
+
+def _instance(name):
+    return inst.synthetic(name, 4, 0, CONE_SETS[name], seed=100 + sorted(CONE_SETS).index(name))
+
+
+@pytest.mark.parametrize("name", list(CONE_SETS))
+def test_cone_oracles_match_cpu_oracle(name):
+    I = _instance(name)
+    dev, ora = _blocks(I.model)
+    prim, dual = I.point.primal_dual(ora.dual_mask)
+    scal = 1 / np.sqrt(I.mu)
+    dev.load_point(prim, dual, scal)
+    ora.load_point(prim, dual, scal)
+    assert dev.is_feas().all() and ora.is_feas().all()
+    assert (dev.is_dual_feas() == ora.is_dual_feas()).all()
+    g = dev.grad()
+    assert rel(g, ora.grad()) <= 1e-11
+    rng = np.random.default_rng(1)
+    arr = rng.standard_normal((I.model.q, 3))
+    tol = 1e-10
+    assert rel(dev.hess_prod(arr), ora.hess_prod(arr)) <= tol
+    assert rel(dev.inv_hess_prod(arr), ora.inv_hess_prod(arr)) <= tol
+    assert rel(dev.block_hess_prod(arr[:, 0]), ora.block_hess_prod(arr[:, 0])) <= tol
+    assert rel(dev.dder3(arr[:, 1]), ora.dder3(arr[:, 1])) <= tol
+    irtmu = 0.9
+    assert np.allclose(dev.get_proxsqr(irtmu, True), ora.get_proxsqr(irtmu, True), rtol=1e-8, atol=1e-12)
+    assert np.allclose(dev.get_proxsqr(irtmu, False), ora.get_proxsqr(irtmu, False), rtol=1e-8, atol=1e-12)
+    assert (dev.check_numerics(irtmu, True) == ora.check_numerics()).all()
+    # identities of test/cone.jl on the device results
+    pt = scal * prim
+    assert rel(dev.hess_prod(pt), -g) <= 1e-10                      # cone.jl:50,78
+    assert abs(float(pt @ g) + I.model.nu) <= 1e-9 * I.model.nu     # cone.jl:71
+    assert rel(dev.inv_hess_prod(g), -pt) <= 1e-9                   # cone.jl:79
+    assert rel(dev.inv_hess_prod(dev.hess_prod(arr)), arr) <= 1e-8  # cone.jl:81-83
+    dev.free()
+
+
+@pytest.mark.parametrize("name", ["nonneg", "soc", "vecmix", "psd"])
+def test_sqrt_oracles(name):
+    I = _instance(name)
+    dev, ora = _blocks(I.model)
+    prim, dual = I.point.primal_dual(None)
+    dev.load_point(prim, dual, 1.0)
+    ora.load_point(prim, dual, 1.0)
+    rng = np.random.default_rng(2)
+    arr = rng.standard_normal((I.model.q, 4))
+    assert rel(dev.sqrt_hess_prod(arr), ora.sqrt_hess_prod(arr)) <= 1e-10
+    assert rel(dev.inv_sqrt_hess_prod(arr), ora.inv_sqrt_hess_prod(arr)) <= 1e-10
+    # cone.jl:97-102: H^{1/2}' H^{1/2} = H ; inv_sqrt(sqrt(x)) = x
+    s = dev.sqrt_hess_prod(arr)
+    assert rel(dev.inv_sqrt_hess_prod(s), arr) <= 1e-9
+    assert rel(s.T @ s, arr.T @ dev.hess_prod(arr)) <= 1e-9
+    dev.free()
+
+
+def test_infeasible_points_are_flagged():
+    cones = [M.Nonnegative(4), M.EpiNormEucl(5), M.PosSemidefTri(6), M.EpiNormEucl(3)]
+    I = inst.synthetic("infeas", 3, 0, cones, seed=5)
+    dev, ora = _blocks(I.model)
+    prim = I.point.s.copy()
+    dual = I.point.z.copy()
+    prim[1] = -1.0                      # nonnegative block leaves the cone
+    prim[4] = -5.0                      # SOC: u < 0
+    prim[9:15] = [1, 3 * np.sqrt(2), 1, 0, 0, 1]   # PSD: indefinite leading 2x2
+    dual[15] = 0.0                      # last SOC dual: u = 0
+    dev.load_point(prim, dual, 1.0)
+    ora.load_point(prim, dual, 1.0)
+    assert (dev.is_feas() == ora.is_feas()).all()
+    assert (dev.is_feas() == np.array([False, False, False, True])).all()
+    assert (dev.is_dual_feas() == ora.is_dual_feas()).all()
+    dev.free()

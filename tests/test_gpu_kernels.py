@@ -1,0 +1,96 @@
+"""-m gpu unit tests of the building-block kernels, called through the C ABI test entry points
+(hyp_test_*) and checked against NumPy / LAPACK on the same seeded inputs.
+Tolerances: FP64 contractions of length k are compared at 50*k*eps relative (Frobenius)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from gpu_util import ctx, rel
+
+pytestmark = pytest.mark.gpu
+EPS = np.finfo(np.float64).eps
+
+
+@pytest.fixture(scope="module")
+def cx():
+    c = ctx()
+    yield c
+    c.close()
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+@pytest.mark.parametrize("klen,ncols", [(1, 1), (7, 5), (16, 128), (100, 130), (333, 257), (2050, 400)])
+@pytest.mark.parametrize("same", [True, False])
+def test_atb_upper(cx, klen, ncols, same):
+    rng = np.random.default_rng(klen * 1000 + ncols)
+    P = np.asfortranarray(rng.standard_normal((klen, ncols)))
+    R = P if same else np.asfortranarray(rng.standard_normal((klen, ncols)))
+    C0 = np.asfortranarray(rng.standard_normal((ncols, ncols)))
+    for alpha, beta in ((1.0, 0.0), (-1.0, 1.0)):
+        Cm = C0.copy(order="F")
+        rc = cx.lib.hyp_test_atb_upper(cx.h, _p(P), klen, _p(R), klen, klen, ncols, _p(Cm), ncols,
+                                       alpha, beta)
+        cx.check(rc, "atb_upper")
+        ref = alpha * (P.T @ R) + beta * C0
+        iu = np.triu_indices(ncols)
+        assert rel(Cm[iu], ref[iu]) <= 50 * klen * EPS
+
+
+@pytest.mark.parametrize("klen,mrows,ncols", [(3, 2, 9), (100, 100, 700), (128, 128, 1000), (50, 260, 129)])
+def test_gemm_tn(cx, klen, mrows, ncols):
+    rng = np.random.default_rng(klen + mrows + ncols)
+    P = np.asfortranarray(rng.standard_normal((klen, mrows)))
+    R = np.asfortranarray(rng.standard_normal((klen, ncols)))
+    Cm = np.asfortranarray(rng.standard_normal((mrows, ncols)))
+    C0 = Cm.copy()
+    rc = cx.lib.hyp_test_gemm_tn(cx.h, _p(P), klen, _p(R), klen, klen, mrows, ncols, _p(Cm), mrows, 2.0, -1.0)
+    cx.check(rc, "gemm_tn")
+    assert rel(Cm, 2.0 * (P.T @ R) - C0) <= 50 * klen * EPS
+
+
+@pytest.mark.parametrize("m", [1, 5, 128, 129, 300, 1000, 2500])
+def test_potrf_potrs(cx, m):
+    rng = np.random.default_rng(m)
+    B = rng.standard_normal((m + 20, m))
+    A = np.asfortranarray(B.T @ B + 0.5 * np.eye(m))
+    F = A.copy(order="F")
+    info = C.c_int(-1)
+    cx.check(cx.lib.hyp_test_potrf(cx.h, _p(F), m, m, C.byref(info)), "potrf")
+    assert info.value == 0
+    U = np.triu(F)
+    assert rel(U.T @ U, A) <= 100 * m * EPS
+    Uref = np.linalg.cholesky(A).T
+    assert rel(U, Uref) <= 1e-9
+    b = rng.standard_normal(m)
+    x = b.copy()
+    cx.check(cx.lib.hyp_test_potrs(cx.h, _p(F), m, m, _p(x)), "potrs")
+    xref = np.linalg.solve(A, b)
+    assert rel(x, xref) <= 1e-9
+    assert rel(A @ x, b) <= 1e-10 * np.linalg.cond(A)
+
+
+def test_potrf_not_posdef(cx):
+    m = 300
+    rng = np.random.default_rng(3)
+    B = rng.standard_normal((m, m))
+    A = np.asfortranarray(B + B.T)       # indefinite
+    info = C.c_int(0)
+    cx.check(cx.lib.hyp_test_potrf(cx.h, _p(A), m, m, C.byref(info)), "potrf")
+    assert info.value > 0
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 1), (25, 7), (5000, 33), (4097, 300), (300, 4097), (20000, 64)])
+@pytest.mark.parametrize("trans", [0, 1])
+def test_gemv(cx, rows, cols, trans):
+    rng = np.random.default_rng(rows + cols)
+    M = np.asfortranarray(rng.standard_normal((rows, cols)))
+    x = rng.standard_normal(rows if trans else cols)
+    y = rng.standard_normal(cols if trans else rows)
+    y0 = y.copy()
+    cx.check(cx.lib.hyp_test_gemv(cx.h, trans, rows, cols, _p(M), rows, _p(x), 1.5, -0.5, _p(y)), "gemv")
+    ref = 1.5 * (M.T @ x if trans else M @ x) - 0.5 * y0
+    assert rel(y, ref) <= 50 * max(rows, cols) * EPS
