@@ -32,24 +32,18 @@ __device__ __forceinline__ void st_release(int* p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Factor (FACTOR) and invert the 128 x 128 upper-triangular diagonal block(s).
-//   FACTOR:  grid = 1; block at A (already offset to the diagonal), nb valid rows/cols; writes U
-//            back into A (upper part) and U^-1 into dinv; a non-positive pivot sets *info.
-//   !FACTOR: grid = number of diagonal blocks of the m x m triangular matrix A; inverts only.
+// Factor (FACTOR) and invert one upper-triangular diagonal block of at most 128 x 128, by one CTA
+// of 1024 threads.  Ab: the block (upper part is read; U is written back, optionally with zeros
+// below the diagonal); Db receives U^-1 (dn x dn entries, leading dim ldd; rows / columns past nb
+// are identity padding).  Returns the 1-based index of the first non-positive pivot or 0.
 template <bool FACTOR>
-__global__ void __launch_bounds__(1024, 1)
-panel_kernel(double* __restrict__ A, int64_t lda, int64_t m, int64_t blk0, double* __restrict__ dinv,
-             int* __restrict__ info) {
-    extern __shared__ double sU[];            // NB x NB col-major, ld = LDU
-    __shared__ double rowbuf[2][NB];
+__device__ __forceinline__ int panel_body(double* __restrict__ Ab, int64_t lda, int nb,
+                                          double* __restrict__ Db, int ldd, int dn, bool zero_lower,
+                                          double* sU, double (*rowbuf)[NB]) {
     const int tid = threadIdx.x;
     const int tj = tid & 31;                  // row residue
     const int ti = tid >> 5;                  // col residue
-    const int64_t blk = FACTOR ? blk0 : (int64_t)blockIdx.x;
-    const int64_t k0 = blk * NB;
-    const int nb = (int)min((int64_t)NB, m - k0);
-    double* Ab = A + k0 + k0 * lda;
-    double* Db = dinv + blk * (int64_t)NB * NB;
+    int bad = 0;
 
     double v[4][4];   // v[a][b] = element (row tj + 32 a, col ti + 32 b)
 #pragma unroll
@@ -61,13 +55,12 @@ panel_kernel(double* __restrict__ A, int64_t lda, int64_t m, int64_t blk0, doubl
             if (r < nb && c < nb) {
                 if (r <= c) x = Ab[r + (int64_t)c * lda];
             } else if (r == c) {
-                x = 1.0;   // identity padding of a ragged last block
+                x = 1.0;   // identity padding of a ragged block
             }
             v[a][b] = x;
         }
 
     if (FACTOR) {
-        int bad = 0;
         for (int j = 0; j < NB; j++) {
             const int aj = j >> 5, rj = j & 31;
             if (tj == rj) {
@@ -109,19 +102,16 @@ panel_kernel(double* __restrict__ A, int64_t lda, int64_t m, int64_t blk0, doubl
                 }
             }
         }
-        if (bad && tid == 0) {
-            // report the global 1-based index of the first non-positive pivot
-            int val = (int)(k0 + bad);
-            int old = atomicCAS(info, 0, val);
-            (void)old;
-        }
         // write U back (upper part of the valid block); coalesced along rows
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
             for (int b = 0; b < 4; b++) {
                 int r = tj + 32 * a, c = ti + 32 * b;
-                if (r < nb && c < nb && r <= c) Ab[r + (int64_t)c * lda] = v[a][b];
+                if (r < nb && c < nb) {
+                    if (r <= c) Ab[r + (int64_t)c * lda] = v[a][b];
+                    else if (zero_lower) Ab[r + (int64_t)c * lda] = 0.0;
+                }
             }
     }
 
@@ -155,7 +145,45 @@ panel_kernel(double* __restrict__ A, int64_t lda, int64_t m, int64_t blk0, doubl
         }
         __syncthreads();
     }
-    for (int idx = tid; idx < NB * NB; idx += 1024) Db[idx] = sU[(idx & (NB - 1)) + (idx >> 7) * LDU];
+    for (int idx = tid; idx < dn * dn; idx += 1024) {
+        int r = idx % dn, c = idx / dn;
+        Db[r + (int64_t)c * ldd] = sU[r + c * LDU];
+    }
+    return bad;
+}
+
+//   FACTOR:  grid = 1; diagonal block blk0 of the m x m matrix A; a bad pivot sets *info.
+//   !FACTOR: grid = number of diagonal blocks of the m x m triangular matrix A; inverts only.
+template <bool FACTOR>
+__global__ void __launch_bounds__(1024, 1)
+panel_kernel(double* __restrict__ A, int64_t lda, int64_t m, int64_t blk0, double* __restrict__ dinv,
+             int* __restrict__ info) {
+    extern __shared__ double sU[];            // NB x NB col-major, ld = LDU
+    __shared__ double rowbuf[2][NB];
+    const int64_t blk = FACTOR ? blk0 : (int64_t)blockIdx.x;
+    const int64_t k0 = blk * NB;
+    const int nb = (int)min((int64_t)NB, m - k0);
+    int bad = panel_body<FACTOR>(A + k0 + k0 * lda, lda, nb, dinv + blk * (int64_t)NB * NB, NB, NB, false,
+                                 sU, rowbuf);
+    if (FACTOR && bad && threadIdx.x == 0) atomicCAS(info, 0, (int)(k0 + bad));
+}
+
+// Batched variant for the matrix cones: CTA c factors the side x side matrix at U + moff[c]
+// (leading dim = side rounded up to even) in place and writes its inverse to Ui + moff[c].
+// A failed factorisation clears flag[kidx[c]].  Cones with side > 128 are skipped (blocked path).
+__global__ void __launch_bounds__(1024, 1)
+chol_batched_kernel(int ncones, const int* __restrict__ sides, const int64_t* __restrict__ moff,
+                    const int* __restrict__ kidx, double* __restrict__ U, double* __restrict__ Ui,
+                    uint8_t* __restrict__ flag) {
+    extern __shared__ double sU[];
+    __shared__ double rowbuf[2][NB];
+    const int c = blockIdx.x;
+    if (c >= ncones) return;
+    const int side = sides[c];
+    if (side > NB) return;
+    const int lde = (side + 1) & ~1;
+    int bad = panel_body<true>(U + moff[c], lde, side, Ui + moff[c], lde, side, true, sU, rowbuf);
+    if (bad && threadIdx.x == 0) flag[kidx[c]] = 0;
 }
 
 // ---- triangular solve with the blocked factor -------------------------------------------
@@ -296,6 +324,8 @@ void set_panel_attr() {
                                   NB * LDU * 8));
     CUDA_TRY(cudaFuncSetAttribute(panel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   NB * LDU * 8));
+    CUDA_TRY(cudaFuncSetAttribute(chol_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  NB * LDU * 8));
     g_panel_attr_set = true;
 }
 
@@ -348,6 +378,16 @@ void hyp_trsv_upper(hyp_ctx* ctx, const double* F, int64_t ldf, int64_t m, const
         trsv_kernel<true><<<grid, 256, 0, ctx->stream>>>(F, ldf, m, d_dinv, x, ctx->d_flags, nblk, epoch);
     else
         trsv_kernel<false><<<grid, 256, 0, ctx->stream>>>(F, ldf, m, d_dinv, x, ctx->d_flags, nblk, epoch);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+}
+
+void hyp_chol_batched(hyp_ctx* ctx, int ncones, const int* d_sides, const int64_t* d_moff,
+                      const int* d_kidx, double* U, double* Ui, uint8_t* d_flag) {
+    if (ncones <= 0) return;
+    set_panel_attr();
+    chol_batched_kernel<<<ncones, 1024, NB * LDU * 8, ctx->stream>>>(ncones, d_sides, d_moff, d_kidx, U, Ui,
+                                                                    d_flag);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
 }

@@ -133,6 +133,7 @@ struct hyp_ctx {
 
     // ---- cone state (global-length q-vectors) ----
     double *d_point = nullptr, *d_dual = nullptr, *d_grad = nullptr;
+    double* d_wivec = nullptr;         // svec(W^-1) on the rows of matrix cones (q)
     uint8_t *d_feas = nullptr, *d_dual_feas = nullptr, *d_num_ok = nullptr;  // K
     double* d_proxsqr = nullptr;       // K
     double* d_matwork = nullptr;       // scratch for matrix-cone products
@@ -247,6 +248,11 @@ void hyp_atb_upper(hyp_ctx* ctx, const double* P, int64_t ldp, const double* R, 
 void hyp_gemm_tn(hyp_ctx* ctx, const double* P, int64_t ldp, const double* R, int64_t ldr,
                  int64_t klen, int64_t mrows, int64_t ncols, double* C, int64_t ldc, double alpha,
                  double beta);
+// `ngroups` independent products C_g = alpha * P' R_g + beta * C_g, where R_g is the row block
+// [g * r_kstride, g * r_kstride + klen) of R and C_g = C + g * c_group_stride
+void hyp_gemm_tn_grouped(hyp_ctx* ctx, const double* P, int64_t ldp, const double* R, int64_t ldr,
+                         int64_t klen, int64_t mrows, int64_t ncols, int ngroups, int64_t r_kstride,
+                         double* C, int64_t ldc, int64_t c_group_stride, double alpha, double beta);
 // simple CUDA-core GEMM for one-off products at load time: C = op(A) op(B)
 void hyp_gemm_simple(hyp_ctx* ctx, bool transA, bool transB, int64_t M, int64_t N, int64_t Kd,
                      const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
@@ -256,6 +262,9 @@ void hyp_gemm_simple(hyp_ctx* ctx, bool transA, bool transB, int64_t M, int64_t 
 // in-place blocked upper Cholesky; d_dinv receives the inverted 128 x 128 diagonal blocks
 // (ceil(m/128) blocks of 128*128 doubles); d_info[0] = 0 or 1-based index of the first bad pivot
 void hyp_potrf_upper(hyp_ctx* ctx, double* A, int64_t lda, int64_t m, double* d_dinv, int* d_info);
+// batched Cholesky + triangular inverse of the (side <= 128) matrices of a cone group
+void hyp_chol_batched(hyp_ctx* ctx, int ncones, const int* d_sides, const int64_t* d_moff,
+                      const int* d_kidx, double* U, double* Ui, uint8_t* d_flag);
 // inverted diagonal blocks of an already-triangular upper matrix (Ap_R)
 void hyp_trtri_diag(hyp_ctx* ctx, const double* U, int64_t ldu, int64_t m, double* d_dinv);
 // x <- U^-1 x (trans = false) or U^-T x (trans = true)

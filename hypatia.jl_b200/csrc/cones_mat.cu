@@ -1,7 +1,602 @@
+// Matrix-domain cone oracles: PosSemidefTri, HypoPerLogdetTri, HypoRootdetTri (K7-K10 of
+// SURVEY.md section 2.3).
+//
+// reference: src/Cones/possemideftri.jl:80-207, hypoperlogdettri.jl:96-368,
+// hyporootdettri.jl:100-324, arrayutilities.jl:163-236 (svec <-> smat).
+//
+// State per cone (side d, point matrix W = smat(w)): the Cholesky factor W = U'U, U^-1, U', U^-T
+// and W^-1, all d x d column-major, produced by one batched Cholesky + triangular-inverse launch
+// (chol.cu) and one batched post kernel.  Every Hessian-type product of these cones is a congruence
+//     svec(M) -> svec(X' M X),   X = W^-1 (hess), W (inv_hess), U^-1 (sqrt_hess), U' (inv_sqrt_hess)
+// plus, for the log-det / root-det cones, a rank-one correction in the scalars (u, v) and the
+// vectors svec(W^-1) / svec(W).  The reference applies X column by column with triangular solves
+// (possemideftri.jl:126-195); here the columns of a cone block are unpacked side by side and the
+// congruence is two TMA + DMMA GEMMs over the whole column chunk:
+//     T  = [M_1 ... M_c]' X          (one (d c) x d product, row block j = M_j X)
+//     Y_j = X' T_j                   (c grouped d x d products in one launch)
+// Bound: tensor (FP64 DMMA), 4 d^3 flops per column; the unpack / pack passes are HBM-bound.
 #include "cones_mat.cuh"
-void hyp_mat_alloc_group(hyp_ctx*, ConeGroup&) { throw HypError{"matrix cones: not built yet"}; }
-void hyp_mat_update_state(hyp_ctx*, ConeGroup&) { throw HypError{"matrix cones: not built yet"}; }
-void hyp_mat_prod(hyp_ctx*, ConeGroup&, double*, const double*, int64_t, int64_t, int64_t, int, int64_t) {
-    throw HypError{"matrix cones: not built yet"};
+
+namespace {
+
+constexpr double RT2 = 1.4142135623730951;
+constexpr double IRT2 = 0.7071067811865476;
+
+__device__ __forceinline__ void svec_rc(int64_t idx, int& a, int& b) {
+    int bb = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
+    while ((int64_t)(bb + 1) * (bb + 2) / 2 <= idx) bb++;
+    while ((int64_t)bb * (bb + 1) / 2 > idx) bb--;
+    b = bb;
+    a = (int)(idx - (int64_t)bb * (bb + 1) / 2);
 }
-void hyp_mat_dder3(hyp_ctx*, ConeGroup&, double*, const double*) { throw HypError{"matrix cones: not built yet"}; }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ double block_sum(double v, double* sm) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += sm[i];
+    return t;
+}
+
+// smat of the matrix part of `vec` for every cone of the group -> A (and B if given), full symmetric
+__global__ void __launch_bounds__(256)
+unpack_state_kernel(int ncones, const int64_t* __restrict__ off, const int* __restrict__ sides,
+                    const int64_t* __restrict__ moff, int lead, const double* __restrict__ vec,
+                    double* __restrict__ A, double* __restrict__ B) {
+    const int c = blockIdx.x;
+    if (c >= ncones) return;
+    const int d = sides[c], lde = (d + 1) & ~1;
+    const int64_t len = (int64_t)d * (d + 1) / 2;
+    const double* v = vec + off[c] + lead;
+    double* Ac = A + moff[c];
+    double* Bc = B ? B + moff[c] : nullptr;
+    for (int64_t idx = blockIdx.y * (int64_t)blockDim.x + threadIdx.x; idx < len;
+         idx += (int64_t)gridDim.y * blockDim.x) {
+        int a, b;
+        svec_rc(idx, a, b);
+        double x = v[idx];
+        if (a != b) x *= IRT2;
+        Ac[a + (int64_t)b * lde] = x;
+        Ac[b + (int64_t)a * lde] = x;
+        if (Bc) {
+            Bc[a + (int64_t)b * lde] = x;
+            Bc[b + (int64_t)a * lde] = x;
+        }
+    }
+}
+
+// scal layout (8 doubles per cone): 0 logdet W, 1 phi, 2 zeta, 3 u, 4 v, 5 pzd (rootdet) / sigma (logdet)
+// One CTA per cone: U', U^-T, W^-1 (side <= 128; larger cones get W^-1 from a GEMM beforehand),
+// log det, the cone's scalars, feasibility, gradient and svec(W^-1).
+__global__ void __launch_bounds__(256)
+mat_post_kernel(int type, int ncones, const int64_t* __restrict__ off, const int* __restrict__ sides,
+                const int64_t* __restrict__ moff, const int* __restrict__ kidx,
+                const double* __restrict__ point, const double* __restrict__ U,
+                const double* __restrict__ Ui, double* __restrict__ Ut, double* __restrict__ Uit,
+                double* __restrict__ Wi, double* __restrict__ scal, double* __restrict__ grad,
+                double* __restrict__ wivec, uint8_t* __restrict__ feas) {
+    __shared__ double sm[8];
+    const int c = blockIdx.x;
+    if (c >= ncones) return;
+    const int d = sides[c], lde = (d + 1) & ~1;
+    const int64_t mo = moff[c], o = off[c];
+    const double* Uc = U + mo;
+    const double* Uic = Ui + mo;
+    double* Wic = Wi + mo;
+    const int lead = type == HYP_CONE_POSSEMIDEFTRI ? 0 : type == HYP_CONE_HYPOPERLOGDETTRI ? 2 : 1;
+    for (int idx = threadIdx.x; idx < d * d; idx += blockDim.x) {
+        int a = idx % d, b = idx / d;
+        Ut[mo + a + (int64_t)b * lde] = Uc[b + (int64_t)a * lde];
+        Uit[mo + a + (int64_t)b * lde] = Uic[b + (int64_t)a * lde];
+        if (d <= 128 && a <= b) {
+            // W^-1 = U^-1 U^-T : entry (a, b) = sum_{k >= b} Ui[a, k] Ui[b, k]
+            double s = 0.0;
+            for (int k = b; k < d; k++) s += Uic[a + (int64_t)k * lde] * Uic[b + (int64_t)k * lde];
+            Wic[a + (int64_t)b * lde] = s;
+            Wic[b + (int64_t)a * lde] = s;
+        }
+    }
+    double ld = 0.0;
+    for (int k = threadIdx.x; k < d; k += blockDim.x) ld += log(Uc[k + (int64_t)k * lde]);
+    ld = 2.0 * block_sum(ld, sm);
+    __syncthreads();
+    double gscale = -1.0;   // grad matrix part = gscale * svec(W^-1)
+    bool ok = true;
+    double* sc = scal + 8 * c;
+    if (type == HYP_CONE_HYPOPERLOGDETTRI) {
+        // hypoperlogdettri.jl:96-151
+        const double u = point[o], v = point[o + 1];
+        double phi = 0, zeta = 0;
+        if (v > HYP_EPS) {
+            phi = ld - d * log(v);
+            zeta = v * phi - u;
+            ok = zeta > HYP_EPS;
+        } else {
+            ok = false;
+        }
+        gscale = -1.0 - v / zeta;
+        if (threadIdx.x == 0) {
+            sc[0] = ld; sc[1] = phi; sc[2] = zeta; sc[3] = u; sc[4] = v; sc[5] = phi - d;
+            grad[o] = 1.0 / zeta;
+            grad[o + 1] = -1.0 / v - (phi - d) / zeta;
+            wivec[o] = 0.0;
+            wivec[o + 1] = 0.0;
+        }
+    } else if (type == HYP_CONE_HYPOROOTDETTRI) {
+        // hyporootdettri.jl:100-145
+        const double u = point[o];
+        const double phi = exp(ld / d), zeta = phi - u;
+        ok = zeta > HYP_EPS;
+        const double pzd = phi / zeta / d;
+        gscale = -pzd - 1.0;
+        if (threadIdx.x == 0) {
+            sc[0] = ld; sc[1] = phi; sc[2] = zeta; sc[3] = u; sc[4] = 0.0; sc[5] = pzd;
+            grad[o] = 1.0 / zeta;
+            wivec[o] = 0.0;
+        }
+    } else if (threadIdx.x == 0) {
+        sc[0] = ld;
+    }
+    if (!ok && threadIdx.x == 0) feas[kidx[c]] = 0;
+    const int64_t len = (int64_t)d * (d + 1) / 2;
+    for (int64_t idx = threadIdx.x; idx < len; idx += blockDim.x) {
+        int a, b;
+        svec_rc(idx, a, b);
+        double x = Wic[a + (int64_t)b * lde];
+        if (a != b) x *= RT2;
+        wivec[o + lead + idx] = x;
+        grad[o + lead + idx] = gscale * x;
+    }
+}
+
+// dual feasibility beyond "Cholesky of smat(dual) succeeded" (hypoperlogdettri.jl:119-132,
+// hyporootdettri.jl:117-129); U2 holds the factor of the dual matrix
+__global__ void __launch_bounds__(128)
+mat_dualfeas_kernel(int type, int ncones, const int64_t* __restrict__ off, const int* __restrict__ sides,
+                    const int64_t* __restrict__ moff, const int* __restrict__ kidx,
+                    const double* __restrict__ dual, const double* __restrict__ U2,
+                    uint8_t* __restrict__ dual_feas) {
+    __shared__ double sm[4];
+    const int c = blockIdx.x;
+    if (c >= ncones) return;
+    const int d = sides[c], lde = (d + 1) & ~1;
+    const double* Uc = U2 + moff[c];
+    double ld = 0.0;
+    for (int k = threadIdx.x; k < d; k += blockDim.x) ld += log(Uc[k + (int64_t)k * lde]);
+    ld = 2.0 * block_sum(ld, sm);
+    if (threadIdx.x == 0) {
+        const int64_t o = off[c];
+        const double u = dual[o];
+        bool ok = false;
+        if (u < -HYP_EPS) {
+            if (type == HYP_CONE_HYPOPERLOGDETTRI) {
+                const double v = dual[o + 1];
+                ok = (v - u * (ld + d * (1.0 - log(-u)))) > HYP_EPS;
+            } else {
+                ok = (ld - d * log(-u / d)) > HYP_EPS;
+            }
+        }
+        if (!ok) dual_feas[kidx[c]] = 0;
+    }
+}
+
+__global__ void info_to_flag_kernel(const int* __restrict__ info, uint8_t* __restrict__ flag, int k) {
+    if (threadIdx.x == 0 && blockIdx.x == 0 && info[0] != 0) flag[k] = 0;
+}
+
+__global__ void zero_lower_kernel(double* __restrict__ A, int d, int lde) {
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < d * d; idx += gridDim.x * blockDim.x) {
+        int a = idx % d, b = idx / d;
+        if (a > b) A[a + (int64_t)b * lde] = 0.0;
+    }
+}
+
+__global__ void copy_block_kernel(double* __restrict__ dst, int64_t ldd, const double* __restrict__ src,
+                                  int64_t lds, int rows, int cols, double scale) {
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < rows * cols; idx += gridDim.x * blockDim.x) {
+        int a = idx % rows, b = idx / rows;
+        dst[a + (int64_t)b * ldd] = scale * src[a + (int64_t)b * lds];
+    }
+}
+
+// columns [j0, j0 + cc) of one cone block of `arr` -> Mall = [M_0 ... M_{cc-1}], each d x lde (ld lde)
+__global__ void __launch_bounds__(256)
+unpack_cols_kernel(int d, int lde, int64_t len, const double* arr, int64_t ld_arr, int64_t cc,
+                   double* __restrict__ Mall) {
+    for (int64_t j = blockIdx.y; j < cc; j += gridDim.y) {
+        const double* v = arr + j * ld_arr;
+        double* Mj = Mall + j * (int64_t)lde * lde;
+        for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < len;
+             idx += (int64_t)gridDim.x * blockDim.x) {
+            int a, b;
+            svec_rc(idx, a, b);
+            double x = v[idx];
+            if (a != b) x *= IRT2;
+            Mj[a + (int64_t)b * lde] = x;
+            Mj[b + (int64_t)a * lde] = x;
+        }
+        // blocks are lde columns wide (TMA coordinates must be even): keep the pad column finite
+        if (lde > d && blockIdx.x == 0)
+            for (int a = threadIdx.x; a < lde; a += blockDim.x) Mj[a + (int64_t)d * lde] = 0.0;
+    }
+}
+
+// prod[idx, j] = alpha_j * svec(Y_j)[idx] + beta_j * vecB[idx]
+__global__ void __launch_bounds__(256)
+pack_cols_kernel(int d, int lde, int64_t len, const double* __restrict__ Yall, int64_t cc,
+                 const double* __restrict__ alpha, const double* __restrict__ beta,
+                 const double* __restrict__ vecB, double* prod, int64_t ld_prod) {
+    for (int64_t j = blockIdx.y; j < cc; j += gridDim.y) {
+        const double* Yj = Yall + j * (int64_t)lde * lde;
+        double* pr = prod + j * ld_prod;
+        const double al = alpha ? alpha[j] : 1.0;
+        const double be = beta ? beta[j] : 0.0;
+        for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < len;
+             idx += (int64_t)gridDim.x * blockDim.x) {
+            int a, b;
+            svec_rc(idx, a, b);
+            double x = Yj[a + (int64_t)b * lde];
+            if (a != b) x *= RT2;
+            x *= al;
+            if (vecB) x += be * vecB[idx];
+            pr[idx] = x;
+        }
+    }
+}
+
+// Per column of a log-det / root-det cone block: the scalar parts of hess_prod! / inv_hess_prod!
+// (hypoperlogdettri.jl:196-237, :274-319; hyporootdettri.jl:176-212, :246-283) and the coefficients
+// (alpha_j, beta_j) of the matrix part  alpha_j * svec(X' R_j X) + beta_j * vecB.
+// One warp per column.  `a` / `pr` point at the first row of the cone block.
+__global__ void __launch_bounds__(256)
+colscal_kernel(int type, int inverse, int d, int64_t len, const double* __restrict__ sc,
+               const double* __restrict__ vecB, const double* a, int64_t ld_arr, double* pr,
+               int64_t ld_prod, int64_t cc, double* __restrict__ alpha, double* __restrict__ beta) {
+    const int lane = threadIdx.x & 31;
+    const int64_t j = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= cc) return;
+    const int lead = type == HYP_CONE_HYPOPERLOGDETTRI ? 2 : 1;
+    const double* col = a + j * ld_arr;
+    double dot = 0.0;
+    for (int64_t i = lane; i < len; i += 32) dot += col[lead + i] * vecB[i];
+    dot = warp_sum(dot);
+    if (lane != 0) return;
+    double* out = pr + j * ld_prod;
+    const double phi = sc[1], zeta = sc[2], dd = (double)d;
+    if (type == HYP_CONE_HYPOPERLOGDETTRI) {
+        const double v = sc[4], p = col[0], q = col[1];
+        if (!inverse) {
+            const double sigma = phi - dd, qzi = q / zeta;
+            const double c0 = dot / zeta;
+            const double c1 = (v * c0 - p / zeta + sigma * qzi) / zeta;
+            const double c3 = c1 * v - qzi;
+            out[0] = -c1;
+            out[1] = c1 * sigma - c0 + (qzi * dd + q / v) / v;
+            alpha[j] = v / zeta + 1.0;
+            beta[j] = c3;
+        } else {
+            const double zv = zeta + v, zzvi = zeta / zv;
+            const double c3 = v / (zv + dd * v);
+            const double c0 = phi - dd * zzvi;
+            const double c4 = v * c3 * zv;
+            const double t = zeta + v * phi;
+            const double c6 = (v * phi) * (v * phi) + zeta * (zeta + dd * v) - dd * t * t * c3;
+            const double c7 = c4 * c0, c8 = c7 + v * zeta;
+            const double c1 = dot / zv;
+            const double c5 = c0 * p + q + c1;
+            const double c2 = v * (zzvi * p + c3 * c5);
+            out[0] = c6 * p + c7 * q + c8 * c1;
+            out[1] = c4 * c5;
+            alpha[j] = zzvi;
+            beta[j] = c2;
+        }
+    } else {
+        const double pzd = sc[5], di = 1.0 / dd, p = col[0];
+        if (!inverse) {
+            const double c0 = pzd * dot;
+            const double c1 = c0 - p / zeta;
+            const double c2 = pzd * c1 - di * c0;
+            out[0] = -c1 / zeta;
+            alpha[j] = pzd + 1.0;
+            beta[j] = c2;
+        } else {
+            const double phidi = phi * di;
+            const double c2 = 1.0 / (pzd + 1.0);
+            const double c3 = c2 / zeta * di;
+            const double c4 = zeta * zeta + phidi * phi;
+            const double c5 = dot;
+            const double c6 = phidi * (c3 * c5 + p);
+            out[0] = phidi * c5 + c4 * p;
+            alpha[j] = c2;
+            beta[j] = c6;
+        }
+    }
+}
+
+// dder3 combination step (hypoperlogdettri.jl:321-368, hyporootdettri.jl:285-324,
+// possemideftri.jl:197-207): given E = U^-T R U^-1 and E2 = E E, with tr E = <r, svec W^-1> and
+// tr E2, form the matrix  k6 E + k1 E2 + k8 I  (in E2's storage) and the leading entries of dder3.
+__global__ void __launch_bounds__(256)
+dder3_combine_kernel(int type, int d, int lde, const double* __restrict__ sc, const double* __restrict__ E,
+                     double* __restrict__ E2, const double* __restrict__ dir, double* __restrict__ out,
+                     const double* __restrict__ wivec) {
+    __shared__ double sm[8];
+    __shared__ double coef[3];
+    const int64_t len = (int64_t)d * (d + 1) / 2;
+    const int lead = type == HYP_CONE_POSSEMIDEFTRI ? 0 : type == HYP_CONE_HYPOPERLOGDETTRI ? 2 : 1;
+    double t0 = 0.0, t7 = 0.0;
+    for (int k = threadIdx.x; k < d; k += blockDim.x) {
+        t0 += E[k + (int64_t)k * lde];
+        t7 += E2[k + (int64_t)k * lde];
+    }
+    const double trE = block_sum(t0, sm);
+    const double trE2 = block_sum(t7, sm);
+    (void)wivec;
+    (void)len;
+    if (threadIdx.x == 0) {
+        const double dd = (double)d;
+        double k6 = 0.0, k1 = 1.0, k8 = 0.0;
+        if (type == HYP_CONE_HYPOPERLOGDETTRI) {
+            const double phi = sc[1], zeta = sc[2], v = sc[4];
+            const double p = dir[0], q = dir[1];
+            const double sigma = phi - dd, viq = q / v, viq2 = viq * viq, vzi = v / zeta, vzi1 = vzi + 1.0;
+            const double c0 = trE, c7 = trE2;
+            const double zichi = (-p + sigma * q + c0 * v) / zeta;
+            const double c4 = (viq * (-viq * dd + 2 * c0) - c7) / zeta / 2;
+            const double c1 = (zichi * zichi - v * c4) / zeta;
+            const double c3 = -(zichi + viq) / zeta;
+            const double c5 = c3 * q + vzi * viq2;
+            const double c6 = -2 * vzi * viq - c3 * v;
+            const double c8 = c5 + c1 * v;
+            out[0] = -c1;
+            out[1] = c1 * sigma + (viq2 - (dd * c5 + c6 * c0 + vzi * c7)) / v - c4;
+            k6 = c6; k1 = vzi1; k8 = c8;
+        } else if (type == HYP_CONE_HYPOROOTDETTRI) {
+            const double phi = sc[1], zeta = sc[2], pzd = sc[5], di = 1.0 / dd;
+            const double p = dir[0];
+            const double c0 = trE * di, c6 = trE2 * di;
+            const double zichi = (p - phi * c0) / zeta;
+            const double c1 = zichi * zichi + phi / zeta * (c6 - c0 * c0) / 2;
+            const double c7 = pzd * (c1 - c6 / 2 + c0 * (zichi + c0 / 2));
+            const double c8 = -pzd * (zichi + c0);
+            const double c9 = pzd + 1.0;
+            out[0] = -c1 / zeta;
+            k6 = c8; k1 = c9; k8 = c7;
+        }
+        coef[0] = k6; coef[1] = k1; coef[2] = k8;
+    }
+    __syncthreads();
+    const double k6 = coef[0], k1 = coef[1], k8 = coef[2];
+    (void)lead;
+    for (int idx = threadIdx.x; idx < d * d; idx += blockDim.x) {
+        int a = idx % d, b = idx / d;
+        double x = k6 * E[a + (int64_t)b * lde] + k1 * E2[a + (int64_t)b * lde];
+        if (a == b) x += k8;
+        E2[a + (int64_t)b * lde] = x;
+    }
+}
+
+void ensure_matwork(hyp_ctx* ctx, int64_t doubles) {
+    if (doubles <= ctx->matwork_doubles) return;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_matwork) cudaFree(ctx->d_matwork);
+    ctx->d_matwork = nullptr;
+    CUDA_TRY(cudaMalloc(&ctx->d_matwork, (size_t)doubles * sizeof(double)));
+    ctx->matwork_doubles = doubles;
+}
+
+inline int lead_of(int type) {
+    return type == HYP_CONE_POSSEMIDEFTRI ? 0 : type == HYP_CONE_HYPOPERLOGDETTRI ? 2 : 1;
+}
+
+// Cholesky + triangular inverse of one large (side > 128) matrix with the blocked kernels
+void big_chol_inverse(hyp_ctx* ctx, double* U, double* Ui, int d, int lde, uint8_t* d_flag, int kidx) {
+    int nblk = ceil_div(d, 128);
+    int64_t need = (int64_t)nblk * 128 * 128 + (int64_t)lde * 128 + 16;
+    ensure_matwork(ctx, need);
+    double* dinv = ctx->d_matwork;
+    double* T = dinv + (int64_t)nblk * 128 * 128;
+    hyp_potrf_upper(ctx, U, lde, d, dinv, ctx->d_info + 12);
+    info_to_flag_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_info + 12, d_flag, kidx);
+    zero_lower_kernel<<<ceil_div((int64_t)d * d, 256), 256, 0, ctx->stream>>>(U, d, lde);
+    CUDA_TRY(cudaMemsetAsync(Ui, 0, (size_t)lde * d * 8, ctx->stream));
+    ctx->launches += 2;
+    // blocked upper-triangular inverse: Ui[jj] = Dinv_j ; Ui[0:j0, jj] = -Ui[0:j0, 0:j0] U[0:j0, jj] Dinv_j
+    for (int jb = 0; jb < nblk; jb++) {
+        int j0 = jb * 128, nbj = std::min(128, d - j0);
+        const double* Dj = dinv + (int64_t)jb * 128 * 128;
+        copy_block_kernel<<<ceil_div(nbj * nbj, 256), 256, 0, ctx->stream>>>(Ui + j0 + (int64_t)j0 * lde, lde, Dj,
+                                                                            128, nbj, nbj, 1.0);
+        ctx->launches++;
+        if (j0 > 0) {
+            hyp_gemm_simple(ctx, false, false, j0, nbj, nbj, U + (int64_t)j0 * lde, lde, Dj, 128, T, lde);
+            hyp_gemm_simple(ctx, false, false, j0, nbj, j0, Ui, lde, T, lde, Ui + (int64_t)j0 * lde, lde);
+            copy_block_kernel<<<ceil_div(j0 * nbj, 256), 256, 0, ctx->stream>>>(
+                Ui + (int64_t)j0 * lde, lde, Ui + (int64_t)j0 * lde, lde, j0, nbj, -1.0);
+            ctx->launches++;
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+}
+
+// Y_j = X' M_j X for cc matrices stored side by side in Mall (in place); C1 is (d*cc) x d scratch
+void congruence(hyp_ctx* ctx, const double* X, int d, int lde, double* Mall, int64_t cc, double* C1,
+                int64_t ldc1) {
+    // T = [M_1 ... M_cc]' X : row block j (lde rows, the last one padding when d is odd) = M_j X
+    hyp_gemm_tn(ctx, Mall, lde, X, lde, d, (int64_t)lde * cc, d, C1, ldc1, 1.0, 0.0);
+    // Y_j = X' T_j
+    hyp_gemm_tn_grouped(ctx, X, lde, C1, ldc1, d, d, d, (int)cc, lde, Mall, lde, (int64_t)lde * lde, 1.0,
+                        0.0);
+}
+
+}  // namespace
+
+void hyp_mat_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
+    (void)ctx;
+    // per-cone matrices use an even leading dimension (TMA strides are multiples of 16 bytes)
+    g.mat_total = 0;
+    for (int i = 0; i < g.count; i++) {
+        int d = g.h_side[i], lde = (d + 1) & ~1;
+        g.h_moff[i] = g.mat_total;
+        g.mat_total += (int64_t)lde * d;
+    }
+    cudaFree(g.d_moff);
+    g.d_moff = nullptr;
+    CUDA_TRY(cudaMalloc(&g.d_moff, g.count * sizeof(int64_t)));
+    CUDA_TRY(cudaMemcpy(g.d_moff, g.h_moff.data(), g.count * sizeof(int64_t), cudaMemcpyHostToDevice));
+    double** mats[] = {&g.d_W, &g.d_U, &g.d_Ut, &g.d_Ui, &g.d_Uit, &g.d_Wi};
+    for (double** m : mats) {
+        CUDA_TRY(cudaMalloc(m, (size_t)std::max<int64_t>(g.mat_total, 1) * sizeof(double)));
+        CUDA_TRY(cudaMemset(*m, 0, (size_t)std::max<int64_t>(g.mat_total, 1) * sizeof(double)));
+    }
+}
+
+void hyp_mat_update_state(hyp_ctx* ctx, ConeGroup& g) {
+    const int lead = lead_of(g.type);
+    int64_t maxlen = (int64_t)g.max_side * (g.max_side + 1) / 2;
+    dim3 ugrid(g.count, (unsigned)std::max<int64_t>(1, std::min<int64_t>((maxlen + 255) / 256, 64)));
+    // ---- primal: W, Cholesky, inverse (possemideftri.jl:80-107) ----
+    unpack_state_kernel<<<ugrid, 256, 0, ctx->stream>>>(g.count, g.d_off, g.d_side, g.d_moff, lead,
+                                                        ctx->d_point, g.d_W, g.d_U);
+    ctx->launches++;
+    hyp_chol_batched(ctx, g.count, g.d_side, g.d_moff, g.d_kidx, g.d_U, g.d_Ui, ctx->d_feas);
+    for (int i = 0; i < g.count; i++) {
+        int d = g.h_side[i];
+        if (d <= 128) continue;
+        int lde = (d + 1) & ~1;
+        big_chol_inverse(ctx, g.d_U + g.h_moff[i], g.d_Ui + g.h_moff[i], d, lde, ctx->d_feas, g.h_kidx[i]);
+        // W^-1 = U^-1 U^-T
+        hyp_gemm_simple(ctx, false, true, d, d, d, g.d_Ui + g.h_moff[i], lde, g.d_Ui + g.h_moff[i], lde,
+                        g.d_Wi + g.h_moff[i], lde);
+    }
+    mat_post_kernel<<<g.count, 256, 0, ctx->stream>>>(g.type, g.count, g.d_off, g.d_side, g.d_moff, g.d_kidx,
+                                                     ctx->d_point, g.d_U, g.d_Ui, g.d_Ut, g.d_Uit, g.d_Wi,
+                                                     g.d_scal, ctx->d_grad, ctx->d_wivec, ctx->d_feas);
+    ctx->launches++;
+    // ---- dual feasibility (possemideftri.jl:92-95): Cholesky of smat(dual) on scratch ----
+    ensure_matwork(ctx, 2 * g.mat_total + 16);
+    double* U2 = ctx->d_matwork;
+    double* Ui2 = ctx->d_matwork + g.mat_total;
+    bool any_big = g.max_side > 128;
+    if (!any_big) {
+        unpack_state_kernel<<<ugrid, 256, 0, ctx->stream>>>(g.count, g.d_off, g.d_side, g.d_moff, lead,
+                                                            ctx->d_dual, U2, nullptr);
+        ctx->launches++;
+        hyp_chol_batched(ctx, g.count, g.d_side, g.d_moff, g.d_kidx, U2, Ui2, ctx->d_dual_feas);
+        if (g.type != HYP_CONE_POSSEMIDEFTRI) {
+            mat_dualfeas_kernel<<<g.count, 128, 0, ctx->stream>>>(g.type, g.count, g.d_off, g.d_side, g.d_moff,
+                                                                 g.d_kidx, ctx->d_dual, U2, ctx->d_dual_feas);
+            ctx->launches++;
+        }
+    } else {
+        // large cones: factor the dual matrices one by one in a private scratch copy
+        double* scratch = nullptr;
+        CUDA_TRY(cudaMalloc(&scratch, (size_t)(g.mat_total + 16) * sizeof(double)));
+        unpack_state_kernel<<<ugrid, 256, 0, ctx->stream>>>(g.count, g.d_off, g.d_side, g.d_moff, lead,
+                                                            ctx->d_dual, scratch, nullptr);
+        ctx->launches++;
+        for (int i = 0; i < g.count; i++) {
+            int d = g.h_side[i], lde = (d + 1) & ~1;
+            int nblk = ceil_div(d, 128);
+            ensure_matwork(ctx, (int64_t)nblk * 128 * 128 + 16);
+            hyp_potrf_upper(ctx, scratch + g.h_moff[i], lde, d, ctx->d_matwork, ctx->d_info + 12);
+            info_to_flag_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_info + 12, ctx->d_dual_feas, g.h_kidx[i]);
+            ctx->launches++;
+        }
+        if (g.type != HYP_CONE_POSSEMIDEFTRI) {
+            mat_dualfeas_kernel<<<g.count, 128, 0, ctx->stream>>>(g.type, g.count, g.d_off, g.d_side, g.d_moff,
+                                                                 g.d_kidx, ctx->d_dual, scratch, ctx->d_dual_feas);
+            ctx->launches++;
+        }
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        cudaFree(scratch);
+    }
+    CUDA_TRY(cudaGetLastError());
+}
+
+void hyp_mat_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr, int64_t ncols,
+                  int64_t ld_prod, int64_t ld_arr, int mode, int64_t row_shift) {
+    const int lead = lead_of(g.type);
+    if ((mode == HYP_PROD_SQRT_HESS || mode == HYP_PROD_INV_SQRT_HESS) && g.type != HYP_CONE_POSSEMIDEFTRI)
+        throw HypError{"sqrt_hess_prod is not defined for the log-det / root-det cones"};
+    const int64_t budget = (int64_t)48 << 20;   // doubles per workspace matrix (384 MB)
+    for (int i = 0; i < g.count; i++) {
+        const int d = g.h_side[i], lde = (d + 1) & ~1;
+        const int64_t len = (int64_t)d * (d + 1) / 2;
+        int m = mode;
+        if (m == HYP_PROD_BLOCK) m = g.h_dual[i] ? HYP_PROD_INV_HESS : HYP_PROD_HESS;
+        const double* X = (m == HYP_PROD_HESS ? g.d_Wi : m == HYP_PROD_INV_HESS ? g.d_W
+                           : m == HYP_PROD_SQRT_HESS ? g.d_Ui : g.d_Ut) + g.h_moff[i];
+        const int inverse = (m == HYP_PROD_INV_HESS) ? 1 : 0;
+        const int64_t per_col = (int64_t)lde * lde;
+        int64_t cmax = std::max<int64_t>(1, std::min<int64_t>(ncols, budget / per_col));
+        const int64_t ldc1 = (int64_t)lde * cmax;
+        ensure_matwork(ctx, per_col * cmax + ldc1 * d + 2 * cmax + 16);
+        double* Mall = ctx->d_matwork;
+        double* C1 = Mall + per_col * cmax;
+        double* alpha = C1 + ldc1 * d;
+        double* beta = alpha + cmax;
+        const int64_t row0 = g.h_off[i] - row_shift;
+        const double* vecB = nullptr;
+        if (g.type != HYP_CONE_POSSEMIDEFTRI)
+            vecB = (inverse ? ctx->d_point : ctx->d_wivec) + g.h_off[i] + lead;
+        for (int64_t j0 = 0; j0 < ncols; j0 += cmax) {
+            const int64_t cc = std::min(cmax, ncols - j0);
+            const double* a0 = arr + row0 + j0 * ld_arr;
+            double* p0 = prod + row0 + j0 * ld_prod;
+            dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>((len + 255) / 256, cc > 64 ? 8 : 64)),
+                      (unsigned)std::min<int64_t>(cc, 65535));
+            unpack_cols_kernel<<<grid, 256, 0, ctx->stream>>>(d, lde, len, a0 + lead, ld_arr, cc, Mall);
+            ctx->launches++;
+            if (g.type != HYP_CONE_POSSEMIDEFTRI) {
+                colscal_kernel<<<ceil_div(cc, 8), 256, 0, ctx->stream>>>(g.type, inverse, d, len, g.d_scal + 8 * i,
+                                                                       vecB, a0, ld_arr, p0, ld_prod, cc, alpha,
+                                                                       beta);
+                ctx->launches++;
+            }
+            congruence(ctx, X, d, lde, Mall, cc, C1, ldc1);
+            pack_cols_kernel<<<grid, 256, 0, ctx->stream>>>(d, lde, len, Mall, cc,
+                                                            vecB ? alpha : nullptr, vecB ? beta : nullptr, vecB,
+                                                            p0 + lead, ld_prod);
+            ctx->launches++;
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+}
+
+// dder3 for the matrix cones: E = U^-T R U^-1, E2 = E E, M = k6 E + k1 E2 + k8 I, result U^-1 M U^-T
+void hyp_mat_dder3(hyp_ctx* ctx, ConeGroup& g, double* out, const double* dir) {
+    const int lead = lead_of(g.type);
+    for (int i = 0; i < g.count; i++) {
+        const int d = g.h_side[i], lde = (d + 1) & ~1;
+        const int64_t len = (int64_t)d * (d + 1) / 2;
+        const int64_t per = (int64_t)lde * lde;
+        const int64_t ldc1 = lde;
+        ensure_matwork(ctx, 2 * per + ldc1 * d + 16);
+        double* E = ctx->d_matwork;
+        double* E2 = E + per;
+        double* C1 = E2 + per;
+        const int64_t o = g.h_off[i];
+        dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>((len + 255) / 256, 64)), 1);
+        unpack_cols_kernel<<<grid, 256, 0, ctx->stream>>>(d, lde, len, dir + o + lead, ctx->q, 1, E);
+        ctx->launches++;
+        congruence(ctx, g.d_Ui + g.h_moff[i], d, lde, E, 1, C1, ldc1);           // E = U^-T R U^-1
+        hyp_gemm_tn(ctx, E, lde, E, lde, d, d, d, E2, lde, 1.0, 0.0);            // E2 = E' E = E E
+        dder3_combine_kernel<<<1, 256, 0, ctx->stream>>>(g.type, d, lde, g.d_scal + 8 * i, E, E2, dir + o,
+                                                        out + o, ctx->d_wivec + o + lead);
+        ctx->launches++;
+        congruence(ctx, g.d_Uit + g.h_moff[i], d, lde, E2, 1, C1, ldc1);         // U^-1 M U^-T
+        pack_cols_kernel<<<grid, 256, 0, ctx->stream>>>(d, lde, len, E2, 1, nullptr, nullptr, nullptr,
+                                                        out + o + lead, ctx->q);
+        ctx->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+}

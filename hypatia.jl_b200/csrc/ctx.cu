@@ -111,6 +111,8 @@ void free_model(hyp_ctx* ctx) {
     dfree(ctx->d_point);
     dfree(ctx->d_dual);
     dfree(ctx->d_grad);
+    dfree(ctx->d_wivec);
+    dfree(ctx->d_row_ns);
     dfree(ctx->d_feas);
     dfree(ctx->d_dual_feas);
     dfree(ctx->d_num_ok);
@@ -459,7 +461,7 @@ int update_lhs_fact(hyp_ctx* ctx) {
                                  ctx->stream));
         if (attempt == 2) hyp_increase_diag(ctx, ctx->d_F, ctx->lds, nmp);
         if (!ctx->d_ipiv) {
-            dalloc(&ctx->d_ipiv, nmp + 8);
+            dalloc(&ctx->d_ipiv, 3 * nmp + 8);
             dalloc(&ctx->d_ldl_work, 4 * nmp + 64);
         }
         hyp_ldlt_factor(ctx, ctx->d_F, ctx->lds, nmp, ctx->d_ipiv, ctx->d_info);
@@ -698,6 +700,7 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
         dalloc(&ctx->d_point, q);
         dalloc(&ctx->d_dual, q);
         dalloc(&ctx->d_grad, q);
+        dalloc(&ctx->d_wivec, q);
         dalloc(&ctx->d_feas, K);
         dalloc(&ctx->d_dual_feas, K);
         dalloc(&ctx->d_num_ok, K);
@@ -716,7 +719,7 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
         dalloc(&ctx->d_scalars, 64);
         ctx->partial_doubles = std::max<int64_t>(4096, 32 * std::max<int64_t>(std::max(ctx->qloc, n), p));
         dalloc(&ctx->d_partial, ctx->partial_doubles);
-        dalloc(&ctx->d_info, 8);
+        dalloc(&ctx->d_info, 16);
         dalloc(&ctx->d_flags, ceil_div(std::max<int64_t>(std::max(nmp, p), 1), 128) + 8);
         ctx->trsv_epoch = 0;
 
@@ -1087,8 +1090,8 @@ int hyp_test_ldlt_solve(hyp_ctx* ctx, const double* A, int64_t lda, int64_t m, d
         CUDA_TRY(cudaMemcpyAsync(dA, dA0, (size_t)la * m * 8, cudaMemcpyDeviceToDevice, ctx->stream));
         double* dx = tmp.in(x, m, m, 1, &lx);
         int *ipiv = nullptr, *dinfo = nullptr;
-        dalloc(&ipiv, m + 8);
-        dalloc(&dinfo, 8);
+        dalloc(&ipiv, 3 * m + 8);
+        dalloc(&dinfo, 16);
         tmp.ptrs.push_back(ipiv);
         tmp.ptrs.push_back(dinfo);
         double* saved_w = ctx->d_ldl_work;

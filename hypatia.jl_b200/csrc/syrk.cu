@@ -79,9 +79,9 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 atb_upper_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapR,
-                 const int2* __restrict__ tiles, int n_tiles, int nkb, int same_operand,
-                 int64_t mrows, int64_t ncols, double* __restrict__ C, int64_t ldc, double alpha,
-                 double beta) {
+                 const int4* __restrict__ tiles, int n_tiles, int nkb, int same_operand,
+                 int64_t mrows, int64_t ncols, double* __restrict__ Cbase, int64_t ldc,
+                 int64_t c_group_stride, double alpha, double beta) {
     extern __shared__ uint8_t smem_raw[];
     uint32_t base = smem_u32(smem_raw);
     uint32_t tiles_smem = (base + 1023u) & ~1023u;
@@ -106,7 +106,7 @@ atb_upper_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant
             int stage = 0;
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                int2 tile = tiles[t];
+                int4 tile = tiles[t];
                 bool single = same_operand && (tile.x == tile.y);
                 for (int kb = 0; kb < nkb; kb++) {
                     mbar_wait(bar_empty + stage * 8, phase ^ 1u);
@@ -114,7 +114,7 @@ atb_upper_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant
                     mbar_expect_tx(full, single ? TILE_BYTES : STAGE_BYTES);
                     uint32_t dst = tiles_smem + stage * STAGE_BYTES;
                     tma_load_2d(dst, &mapP, kb * BK, tile.x * BM, full);
-                    if (!single) tma_load_2d(dst + TILE_BYTES, &mapR, kb * BK, tile.y * BN, full);
+                    if (!single) tma_load_2d(dst + TILE_BYTES, &mapR, tile.z + kb * BK, tile.y * BN, full);
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1u;
@@ -139,8 +139,9 @@ atb_upper_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant
     int stage = 0;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        int2 tile = tiles[t];
+        int4 tile = tiles[t];
         bool single = same_operand && (tile.x == tile.y);
+        double* __restrict__ C = Cbase + (int64_t)tile.w * c_group_stride;
         double acc[8][4][2];
 #pragma unroll
         for (int i = 0; i < 8; i++)
@@ -232,47 +233,53 @@ void make_map(CUtensorMap* map, const double* base, int64_t klen, int64_t ncols,
     }
 }
 
+// Tile = {row tile, col tile, k offset of the R operand, output group}.
 // Upper-triangular tile list for an nt x nt tile grid, in 8-tile row groups so that the CTAs
 // of one wave share row / column panels in L2.
-std::vector<int2> build_upper_tiles(int nt) {
-    std::vector<int2> tiles;
+std::vector<int4> build_upper_tiles(int nt) {
+    std::vector<int4> tiles;
     tiles.reserve((size_t)nt * (nt + 1) / 2);
     const int GROUP = 8;
     for (int gi = 0; gi < nt; gi += GROUP)
         for (int tj = gi; tj < nt; tj++)
-            for (int ti = gi; ti < std::min(gi + GROUP, tj + 1); ti++) tiles.push_back(make_int2(ti, tj));
+            for (int ti = gi; ti < std::min(gi + GROUP, tj + 1); ti++) tiles.push_back(make_int4(ti, tj, 0, 0));
     return tiles;
 }
 
-std::vector<int2> build_full_tiles(int mt, int nt) {
-    std::vector<int2> tiles;
-    tiles.reserve((size_t)mt * nt);
+// full mt x nt grids for `ngroups` independent products; group g reads R at k offset g * kstride
+std::vector<int4> build_full_tiles(int mt, int nt, int ngroups, int kstride) {
+    std::vector<int4> tiles;
+    tiles.reserve((size_t)mt * nt * ngroups);
     const int GROUP = 8;
-    for (int gi = 0; gi < mt; gi += GROUP)
-        for (int tj = 0; tj < nt; tj++)
-            for (int ti = gi; ti < std::min(gi + GROUP, mt); ti++) tiles.push_back(make_int2(ti, tj));
+    for (int g = 0; g < ngroups; g++)
+        for (int gi = 0; gi < mt; gi += GROUP)
+            for (int tj = 0; tj < nt; tj++)
+                for (int ti = gi; ti < std::min(gi + GROUP, mt); ti++)
+                    tiles.push_back(make_int4(ti, tj, g * kstride, g));
     return tiles;
 }
 
 struct TileCacheEntry {
-    int device, kind, mt, nt;
-    int2* d_tiles;
+    int device, kind, mt, nt, ngroups, kstride;
+    int4* d_tiles;
     int n_tiles;
 };
 std::vector<TileCacheEntry> g_tile_cache;
 
-// device tile lists are cached per (device, shape); they are tiny (8 B per tile)
-void get_tiles(hyp_ctx* ctx, int kind, int mt, int nt, int2** d_tiles, int* n_tiles) {
+// device tile lists are cached per (device, shape); they are tiny (16 B per tile)
+void get_tiles(hyp_ctx* ctx, int kind, int mt, int nt, int ngroups, int kstride, int4** d_tiles,
+               int* n_tiles) {
     for (auto& e : g_tile_cache)
-        if (e.device == ctx->device && e.kind == kind && e.mt == mt && e.nt == nt) {
+        if (e.device == ctx->device && e.kind == kind && e.mt == mt && e.nt == nt &&
+            e.ngroups == ngroups && e.kstride == kstride) {
             *d_tiles = e.d_tiles;
             *n_tiles = e.n_tiles;
             return;
         }
-    std::vector<int2> tiles = kind == 0 ? build_upper_tiles(nt) : build_full_tiles(mt, nt);
-    TileCacheEntry e{ctx->device, kind, mt, nt, nullptr, (int)tiles.size()};
-    CUDA_TRY(cudaMalloc(&e.d_tiles, tiles.size() * sizeof(int2)));
-    CUDA_TRY(cudaMemcpyAsync(e.d_tiles, tiles.data(), tiles.size() * sizeof(int2),
+    std::vector<int4> tiles = kind == 0 ? build_upper_tiles(nt) : build_full_tiles(mt, nt, ngroups, kstride);
+    TileCacheEntry e{ctx->device, kind, mt, nt, ngroups, kstride, nullptr, (int)tiles.size()};
+    CUDA_TRY(cudaMalloc(&e.d_tiles, tiles.size() * sizeof(int4)));
+    CUDA_TRY(cudaMemcpyAsync(e.d_tiles, tiles.data(), tiles.size() * sizeof(int4),
                              cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     g_tile_cache.push_back(e);
@@ -282,25 +289,29 @@ void get_tiles(hyp_ctx* ctx, int kind, int mt, int nt, int2** d_tiles, int* n_ti
 
 void launch_atb(hyp_ctx* ctx, int kind, const double* P, int64_t ldp, const double* R, int64_t ldr,
                 int64_t klen, int64_t mrows, int64_t ncols, double* C, int64_t ldc, double alpha,
-                double beta) {
-    if (ncols <= 0 || mrows <= 0 || klen <= 0) return;
+                double beta, int ngroups = 1, int64_t r_kstride = 0, int64_t c_group_stride = 0) {
+    if (ncols <= 0 || mrows <= 0 || klen <= 0 || ngroups <= 0) return;
+    if (ngroups > 1 && (r_kstride & 1)) throw HypError{"grouped GEMM: the k stride must be even (TMA coordinates are 16-byte aligned)"};
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(atb_upper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       SMEM_BYTES));
         attr_set = true;
     }
-    int2* d_tiles = nullptr;
+    int4* d_tiles = nullptr;
     int n_tiles = 0;
-    get_tiles(ctx, kind, ceil_div(mrows, BM), ceil_div(ncols, BN), &d_tiles, &n_tiles);
+    get_tiles(ctx, kind, ceil_div(mrows, BM), ceil_div(ncols, BN), ngroups, (int)r_kstride, &d_tiles,
+              &n_tiles);
     CUtensorMap mapP, mapR;
     make_map(&mapP, P, klen, mrows, ldp);
-    make_map(&mapR, R, klen, ncols, ldr);
+    // grouped products read R at k offsets g * r_kstride; rows past a group's klen meet the
+    // zero-filled out-of-range rows of P, so they contribute nothing
+    make_map(&mapR, R, ngroups > 1 ? r_kstride * (ngroups - 1) + klen : klen, ncols, ldr);
     int nkb = ceil_div(klen, BK);
     int grid = std::min(n_tiles, ctx->sm_count);
     int same = (kind == 0 && P == R && ldp == ldr) ? 1 : 0;
     atb_upper_kernel<<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(
-        mapP, mapR, d_tiles, n_tiles, nkb, same, mrows, ncols, C, ldc, alpha, beta);
+        mapP, mapR, d_tiles, n_tiles, nkb, same, mrows, ncols, C, ldc, c_group_stride, alpha, beta);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
 }
@@ -354,6 +365,13 @@ void hyp_gemm_tn(hyp_ctx* ctx, const double* P, int64_t ldp, const double* R, in
                  int64_t klen, int64_t mrows, int64_t ncols, double* C, int64_t ldc, double alpha,
                  double beta) {
     launch_atb(ctx, 1, P, ldp, R, ldr, klen, mrows, ncols, C, ldc, alpha, beta);
+}
+
+void hyp_gemm_tn_grouped(hyp_ctx* ctx, const double* P, int64_t ldp, const double* R, int64_t ldr,
+                         int64_t klen, int64_t mrows, int64_t ncols, int ngroups, int64_t r_kstride,
+                         double* C, int64_t ldc, int64_t c_group_stride, double alpha, double beta) {
+    launch_atb(ctx, 1, P, ldp, R, ldr, klen, mrows, ncols, C, ldc, alpha, beta, ngroups, r_kstride,
+               c_group_stride);
 }
 
 void hyp_gemm_simple(hyp_ctx* ctx, bool transA, bool transB, int64_t M, int64_t N, int64_t Kd,

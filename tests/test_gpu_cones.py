@@ -80,10 +80,11 @@ def test_sqrt_oracles(name):
     arr = rng.standard_normal((I.model.q, 4))
     assert rel(dev.sqrt_hess_prod(arr), ora.sqrt_hess_prod(arr)) <= 1e-10
     assert rel(dev.inv_sqrt_hess_prod(arr), ora.inv_sqrt_hess_prod(arr)) <= 1e-10
-    # cone.jl:97-102: H^{1/2}' H^{1/2} = H ; inv_sqrt(sqrt(x)) = x
+    # cone.jl:97-102: (H^{1/2})' H^{1/2} = H and (H^{-1/2})' H^{-1/2} = H^{-1}
     s = dev.sqrt_hess_prod(arr)
-    assert rel(dev.inv_sqrt_hess_prod(s), arr) <= 1e-9
     assert rel(s.T @ s, arr.T @ dev.hess_prod(arr)) <= 1e-9
+    t = dev.inv_sqrt_hess_prod(arr)
+    assert rel(t.T @ t, arr.T @ dev.inv_hess_prod(arr)) <= 1e-9
     dev.free()
 
 

@@ -94,3 +94,29 @@ def test_gemv(cx, rows, cols, trans):
     cx.check(cx.lib.hyp_test_gemv(cx.h, trans, rows, cols, _p(M), rows, _p(x), 1.5, -0.5, _p(y)), "gemv")
     ref = 1.5 * (M.T @ x if trans else M @ x) - 0.5 * y0
     assert rel(y, ref) <= 50 * max(rows, cols) * EPS
+
+
+@pytest.mark.parametrize("m", [1, 2, 7, 60, 300])
+@pytest.mark.parametrize("kind", ["indefinite", "posdef", "saddle"])
+def test_ldlt_rook_solve(cx, m, kind):
+    """Device Bunch-Kaufman (rook) factor + solve against numpy.linalg.solve."""
+    rng = np.random.default_rng(m * 7 + len(kind))
+    B = rng.standard_normal((m, m))
+    if kind == "indefinite":
+        A = B + B.T
+    elif kind == "posdef":
+        A = B @ B.T + np.eye(m)
+    else:   # zero diagonal block forces 2x2 pivots
+        A = B + B.T
+        h = m // 2
+        A[:h, :h] = 0.0
+    A = np.asfortranarray(A)
+    Au = np.asfortranarray(np.triu(A))          # only the upper triangle is read
+    b = rng.standard_normal(m)
+    x = b.copy()
+    info = C.c_int(-1)
+    cx.check(cx.lib.hyp_test_ldlt_solve(cx.h, _p(Au), m, m, _p(x), C.byref(info)), "ldlt")
+    assert info.value == 0
+    xref = np.linalg.solve(A, b)
+    assert rel(x, xref) <= 1e-8 * max(1.0, np.linalg.cond(A) * 1e-6)
+    assert rel(A @ x, b) <= 1e-9 * np.linalg.cond(A)

