@@ -349,6 +349,7 @@ void hyp_cones_build_groups(hyp_ctx* ctx) {
         g.d_moff = upload(g.h_moff);
         CUDA_TRY(cudaMalloc(&g.d_scal, (size_t)g.count * 8 * sizeof(double)));
         CUDA_TRY(cudaMemset(g.d_scal, 0, (size_t)g.count * 8 * sizeof(double)));
+        CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));
         if (type == HYP_CONE_NONNEGATIVE) {
             g.d_rows = upload(rows);
             g.d_rowcone = upload(rowcone);
@@ -356,6 +357,7 @@ void hyp_cones_build_groups(hyp_ctx* ctx) {
         if (type >= HYP_CONE_POSSEMIDEFTRI) hyp_mat_alloc_group(ctx, g);
         ctx->groups.push_back(g);
     }
+    CUDA_TRY(cudaDeviceSynchronize());   // uploads above ran on the legacy stream
 }
 
 void hyp_cones_free_groups(hyp_ctx* ctx) {

@@ -457,6 +457,7 @@ void hyp_mat_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
         CUDA_TRY(cudaMalloc(m, (size_t)std::max<int64_t>(g.mat_total, 1) * sizeof(double)));
         CUDA_TRY(cudaMemset(*m, 0, (size_t)std::max<int64_t>(g.mat_total, 1) * sizeof(double)));
     }
+    CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));
 }
 
 void hyp_mat_update_state(hyp_ctx* ctx, ConeGroup& g) {

@@ -32,6 +32,9 @@ void dalloc(T** p, int64_t count) {
     if (count <= 0) count = 1;
     CUDA_TRY(cudaMalloc((void**)p, (size_t)count * sizeof(T)));
     CUDA_TRY(cudaMemset(*p, 0, (size_t)count * sizeof(T)));
+    // the memset runs on the legacy stream, which does not order with the context's non-blocking
+    // stream: finish it before anything is enqueued on the new buffer
+    CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));
 }
 
 template <typename T>
@@ -652,7 +655,7 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
                 if (cone_type[k] >= HYP_CONE_HYPOPERLOGDETTRI)
                     for (int64_t r = ctx->h_cone_off[k]; r < ctx->h_cone_off[k + 1]; r++) row_ns[r - ctx->row_lo] = 1;
             dalloc(&ctx->d_row_ns, (int64_t)row_ns.size());
-            CUDA_TRY(cudaMemcpy(ctx->d_row_ns, row_ns.data(), row_ns.size(), cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpyAsync(ctx->d_row_ns, row_ns.data(), row_ns.size(), cudaMemcpyHostToDevice, ctx->stream));
         }
         (void)any_sqrt;
 
@@ -665,10 +668,10 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
         dalloc(&ctx->d_sub_sol, dim3);
         dalloc(&ctx->d_rhs, dim6);
         dalloc(&ctx->d_sol, dim6);
-        if (n) CUDA_TRY(cudaMemcpy(ctx->d_cbh, c, n * 8, cudaMemcpyDefault));
-        if (p) CUDA_TRY(cudaMemcpy(ctx->d_cbh + n, b, p * 8, cudaMemcpyDefault));
-        if (q) CUDA_TRY(cudaMemcpy(ctx->d_cbh + n + p, h, q * 8, cudaMemcpyDefault));
-        CUDA_TRY(cudaMemcpy(ctx->d_const_rhs, ctx->d_cbh, dim3 * 8, cudaMemcpyDeviceToDevice));
+        if (n) CUDA_TRY(cudaMemcpyAsync(ctx->d_cbh, c, n * 8, cudaMemcpyDefault, ctx->stream));
+        if (p) CUDA_TRY(cudaMemcpyAsync(ctx->d_cbh + n, b, p * 8, cudaMemcpyDefault, ctx->stream));
+        if (q) CUDA_TRY(cudaMemcpyAsync(ctx->d_cbh + n + p, h, q * 8, cudaMemcpyDefault, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_const_rhs, ctx->d_cbh, dim3 * 8, cudaMemcpyDeviceToDevice, ctx->stream));
         if (n) {
             negate_kernel<<<vgrid(ctx, n), 256, 0, ctx->stream>>>(n, ctx->d_const_rhs, ctx->d_cbh);
             ctx->launches++;
@@ -680,10 +683,10 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
         dalloc(&ctx->d_cone_dim, K);
         dalloc(&ctx->d_cone_type, K);
         if (K) {
-            CUDA_TRY(cudaMemcpy(ctx->d_cone_nu, ctx->h_cone_nu.data(), K * 8, cudaMemcpyHostToDevice));
-            CUDA_TRY(cudaMemcpy(ctx->d_cone_off, ctx->h_cone_off.data(), (K + 1) * 8, cudaMemcpyHostToDevice));
-            CUDA_TRY(cudaMemcpy(ctx->d_cone_dim, ctx->h_cone_dim.data(), K * 8, cudaMemcpyHostToDevice));
-            CUDA_TRY(cudaMemcpy(ctx->d_cone_type, ctx->h_cone_type.data(), K * 4, cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpyAsync(ctx->d_cone_nu, ctx->h_cone_nu.data(), K * 8, cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(ctx->d_cone_off, ctx->h_cone_off.data(), (K + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(ctx->d_cone_dim, ctx->h_cone_dim.data(), K * 8, cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(ctx->d_cone_type, ctx->h_cone_type.data(), K * 4, cudaMemcpyHostToDevice, ctx->stream));
         }
         if (ctx->any_dual) {
             std::vector<uint8_t> rd((size_t)q, 0);
@@ -691,7 +694,7 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
                 if (ctx->h_cone_dual[k])
                     for (int64_t r = ctx->h_cone_off[k]; r < ctx->h_cone_off[k + 1]; r++) rd[r] = 1;
             dalloc(&ctx->d_row_dual, q);
-            CUDA_TRY(cudaMemcpy(ctx->d_row_dual, rd.data(), q, cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpyAsync(ctx->d_row_dual, rd.data(), q, cudaMemcpyHostToDevice, ctx->stream));
         }
         hyp_cones_build_groups(ctx);
 
@@ -729,6 +732,7 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
         dalloc(&ctx->d_F, ctx->lds * std::max<int64_t>(nmp, 1));
         dalloc(&ctx->d_Dinv, (int64_t)ceil_div(std::max<int64_t>(nmp, 1), 128) * 128 * 128);
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(cudaDeviceSynchronize());
         ctx->model_loaded = true;
         return 0;
     });

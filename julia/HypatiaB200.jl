@@ -1,0 +1,196 @@
+#=
+HypatiaB200.jl - the ccall shim that plugs libhypatia_b200.so (include/hypatia_b200.h) into
+Hypatia.jl's two plug-in slots for the per-iteration hot path:
+
+  * Solvers.SystemSolver{Float64}   ->  B200QRCholSystemSolver      (load / update_lhs / solve_system /
+                                                                      solve_subsystem3 / free_memory)
+  * the per-cone oracle loops of the stepper and the line search  ->  batched hyp_cones_* calls
+
+Everything else (Solver, steppers, preprocessing, MOI) stays stock Hypatia.jl; usage:
+
+    using Hypatia, HypatiaB200
+    solver = Solvers.Solver{Float64}(syssolver = HypatiaB200.B200QRCholSystemSolver())
+    Solvers.load(solver, model); Solvers.solve(solver)
+
+NOTE: Julia is not available in the build image, so this file has not been executed there; it is the
+binding a maintainer would add, and the same C entry points are exercised call-for-call by the Python
+host mirror (hypatia.jl_b200/syssolver.py, cones.py) in the GPU test-suite.  Reference line numbers
+refer to Hypatia.jl v0.5.1.
+=#
+module HypatiaB200
+
+using LinearAlgebra
+import Hypatia
+import Hypatia.Cones
+import Hypatia.Models
+import Hypatia.Solvers
+import Hypatia.Solvers: Solver, Point, SystemSolver, QRCholSystemSolver
+
+const LIB = get(ENV, "HYPATIA_B200_LIB", "libhypatia_b200")
+const Ctx = Ptr{Cvoid}
+
+# cone type codes of include/hypatia_b200.h
+cone_code(::Cones.Nonnegative) = Cint(0)
+cone_code(::Cones.EpiNormEucl) = Cint(1)
+cone_code(::Cones.PosSemidefTri{Float64, Float64}) = Cint(2)
+cone_code(::Cones.HypoPerLogdetTri{Float64, Float64}) = Cint(3)
+cone_code(::Cones.HypoRootdetTri{Float64, Float64}) = Cint(4)
+cone_code(c::Cones.Cone) = error("cone $(typeof(c)) is not on the B200 hot path")
+
+function check(ctx::Ctx, rc::Cint, what::String)
+    rc < 0 && error("$what: " * unsafe_string(ccall((:hyp_last_error, LIB), Cstring, (Ctx,), ctx)))
+    return rc
+end
+
+# ---------------------------------------------------------------------------------------------
+# plug-in slot 1: the system solver (replaces QRCholDenseSystemSolver, qrchol.jl:104-257)
+# ---------------------------------------------------------------------------------------------
+mutable struct B200QRCholSystemSolver <: QRCholSystemSolver{Float64}
+    ctx::Ctx
+    device::Int
+    fact_kind::Cint
+    # fields the generic elimination code expects (common.jl:184-208)
+    rhs_sub::Point{Float64}
+    sol_sub::Point{Float64}
+    rhs_const::Point{Float64}
+    sol_const::Point{Float64}
+    B200QRCholSystemSolver(; device::Int = 0) = (s = new(); s.ctx = C_NULL; s.device = device; s)
+end
+
+# load(syssolver, solver): qrchol.jl:138-179.  G is uploaded once; Ap_Q / Ap_R only when p > 0.
+function Solvers.load(syssolver::B200QRCholSystemSolver, solver::Solver{Float64})
+    model = solver.model
+    (n, p, q) = (model.n, model.p, model.q)
+    syssolver.ctx = ccall((:hyp_create, LIB), Ctx, (Cint,), syssolver.device)
+    syssolver.ctx == C_NULL && error("hyp_create failed: no sm_100 CUDA device (no CPU fallback)")
+    G = Matrix{Float64}(model.G)                       # dense column-major, as load() densifies GQ
+    A = Matrix{Float64}(model.A)
+    K = length(model.cones)
+    ctype = Cint[cone_code(c) for c in model.cones]
+    cdim = Int64[Cones.dimension(c) for c in model.cones]
+    cdual = Cint[Cones.use_dual_barrier(c) for c in model.cones]
+    ApQ = iszero(p) ? C_NULL : pointer(Matrix{Float64}(solver.Ap_Q * I(n)))
+    ApR = iszero(p) ? C_NULL : pointer(Matrix{Float64}(solver.Ap_R))
+    GC.@preserve G A ctype cdim cdual begin
+        rc = ccall((:hyp_load_model, LIB), Cint,
+            (Ctx, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Float64},
+             Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Cint}, Ptr{Int64}, Ptr{Cint}, Cint, Cint,
+             Ptr{Float64}, Ptr{Float64}),
+            syssolver.ctx, n, p, q, G, max(q, 1), A, max(p, 1), model.c, model.b, model.h, K,
+            ctype, cdim, cdual, 0, K, ApQ, ApR)
+        check(syssolver.ctx, rc, "hyp_load_model")
+    end
+    Solvers.setup_point_sub(syssolver, model)
+    return syssolver
+end
+
+# update_lhs(syssolver, solver): qrchol.jl:181-257.  The cone state the reference reuses lazily
+# (Cones.jl:56-93) is (re)loaded on the device from the current iterate scaled by 1/sqrt(mu).
+function Solvers.update_lhs(syssolver::B200QRCholSystemSolver, solver::Solver{Float64})
+    ctx = syssolver.ctx
+    point = solver.point
+    irtmu = inv(sqrt(solver.mu))
+    (primal, dual) = primal_dual_vectors(solver.model, point)
+    check(ctx, ccall((:hyp_cones_load_point, LIB), Cint, (Ctx, Ptr{Float64}, Ptr{Float64}, Float64),
+        ctx, primal, dual, irtmu), "hyp_cones_load_point")
+    check(ctx, ccall((:hyp_set_mu_tau, LIB), Cint, (Ctx, Float64, Float64), ctx, solver.mu,
+        point.tau[]), "hyp_set_mu_tau")
+    kind = Ref{Cint}(0)
+    solver.time_upfact += @elapsed rc = check(ctx, ccall((:hyp_update_lhs, LIB), Cint,
+        (Ctx, Ptr{Cint}), ctx, kind), "hyp_update_lhs")
+    syssolver.fact_kind = kind[]
+    # same message, same non-throwing behaviour as qrchol.jl:252-254
+    rc == 2 && println("positive definite linear system factorization failed")
+    return syssolver
+end
+
+# solve_system(syssolver, solver, sol, rhs): common.jl:129-151 (4x4 -> 3x3 reductions included)
+function Solvers.solve_system(syssolver::B200QRCholSystemSolver, solver::Solver{Float64},
+    sol::Point{Float64}, rhs::Point{Float64})
+    check(syssolver.ctx, ccall((:hyp_solve_system, LIB), Cint, (Ctx, Ptr{Float64}, Ptr{Float64}),
+        syssolver.ctx, sol.vec, rhs.vec), "hyp_solve_system")
+    return sol
+end
+
+# solve_subsystem3(syssolver, solver, sol, rhs): qrchol.jl:39-85
+function Solvers.solve_subsystem3(syssolver::B200QRCholSystemSolver, solver::Solver{Float64},
+    sol::Point{Float64}, rhs::Point{Float64})
+    dim3 = solver.model.n + solver.model.p + solver.model.q
+    GC.@preserve sol rhs check(syssolver.ctx, ccall((:hyp_solve_subsystem3, LIB), Cint,
+        (Ctx, Ptr{Float64}, Ptr{Float64}), syssolver.ctx, pointer(sol.vec), pointer(rhs.vec)),
+        "hyp_solve_subsystem3")
+    return sol
+end
+
+# apply_lhs(stepper, solver): common.jl:79-121.  The reference's function is not dispatched on the
+# system solver, so the shim adds a method for solvers that carry the B200 system solver.
+function Solvers.apply_lhs(stepper::Solvers.Stepper{Float64},
+    solver::Solver{Float64, <:Any, B200QRCholSystemSolver})
+    ctx = solver.syssolver.ctx
+    check(ctx, ccall((:hyp_set_mu_tau, LIB), Cint, (Ctx, Float64, Float64), ctx, solver.mu,
+        solver.point.tau[]), "hyp_set_mu_tau")
+    check(ctx, ccall((:hyp_apply_lhs, LIB), Cint, (Ctx, Ptr{Float64}, Ptr{Float64}),
+        ctx, stepper.res.vec, stepper.dir.vec), "hyp_apply_lhs")
+    return stepper.res
+end
+
+# free_memory(syssolver): Solvers.jl:582-584
+function Solvers.free_memory(syssolver::B200QRCholSystemSolver)
+    syssolver.ctx == C_NULL || ccall((:hyp_destroy, LIB), Cvoid, (Ctx,), syssolver.ctx)
+    syssolver.ctx = C_NULL
+    return
+end
+
+# ---------------------------------------------------------------------------------------------
+# plug-in slot 2: batched cone oracles.  The reference loops `for k in eachindex(cones)` over
+# per-cone objects (steppers/common.jl:26-118, search.jl:112-135); on the device one call covers
+# all K cones, so the shim exposes q-vector versions of the oracles and the three callers use them.
+# ---------------------------------------------------------------------------------------------
+function primal_dual_vectors(model::Models.Model{Float64}, point::Point{Float64})
+    primal = copy(point.s)
+    dual = copy(point.z)
+    for (k, cone) in enumerate(model.cones)
+        if Cones.use_dual_barrier(cone)
+            idxs = model.cone_idxs[k]
+            primal[idxs] .= point.z[idxs]
+            dual[idxs] .= point.s[idxs]
+        end
+    end
+    return (primal, dual)
+end
+
+cones_load_point(ctx::Ctx, primal::Vector{Float64}, dual::Vector{Float64}, scal::Float64) =
+    check(ctx, ccall((:hyp_cones_load_point, LIB), Cint, (Ctx, Ptr{Float64}, Ptr{Float64}, Float64),
+        ctx, primal, dual, scal), "hyp_cones_load_point")
+
+function cones_feas(ctx::Ctx, K::Int)
+    (f, d) = (zeros(UInt8, K), zeros(UInt8, K))
+    check(ctx, ccall((:hyp_cones_feas, LIB), Cint, (Ctx, Ptr{UInt8}, Ptr{UInt8}), ctx, f, d),
+        "hyp_cones_feas")
+    return (all(!iszero, f), all(!iszero, d))
+end
+
+cones_grad!(grad::Vector{Float64}, ctx::Ctx) = (check(ctx, ccall((:hyp_cones_grad, LIB), Cint,
+    (Ctx, Ptr{Float64}), ctx, grad), "hyp_cones_grad"); grad)
+
+# mode: 0 hess_prod!, 1 inv_hess_prod!, 2 sqrt_hess_prod!, 3 inv_sqrt_hess_prod!, 4 block_hess_prod!
+function cones_hess_prod!(prod::VecOrMat{Float64}, arr::VecOrMat{Float64}, ctx::Ctx, mode::Int)
+    q = size(arr, 1)
+    check(ctx, ccall((:hyp_cones_hess_prod, LIB), Cint,
+        (Ctx, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Int64, Cint),
+        ctx, prod, arr, size(arr, 2), max(q, 1), max(q, 1), mode), "hyp_cones_hess_prod")
+    return prod
+end
+
+cones_dder3!(out::Vector{Float64}, dir::Vector{Float64}, ctx::Ctx) = (check(ctx,
+    ccall((:hyp_cones_dder3, LIB), Cint, (Ctx, Ptr{Float64}, Ptr{Float64}), ctx, out, dir),
+    "hyp_cones_dder3"); out)
+
+function cones_proxsqr(ctx::Ctx, K::Int, irtmu::Float64, use_max_prox::Bool)
+    (prox, ok) = (zeros(K), zeros(UInt8, K))
+    check(ctx, ccall((:hyp_cones_proxsqr, LIB), Cint, (Ctx, Float64, Cint, Ptr{Float64}, Ptr{UInt8}),
+        ctx, irtmu, use_max_prox, prox, ok), "hyp_cones_proxsqr")
+    return (prox, all(!iszero, ok))
+end
+
+end # module

@@ -1,0 +1,59 @@
+"""-m gpu end-to-end solves with the device system solver AND the device cone oracles plugged into
+the host driver (the stand-in for the reference's Julia stepper): the reference's deterministic
+known-answer instances (test/nativeinstances.jl, tol eps^(1/4)) must come out exactly as they do
+with the CPU oracle plug-ins - same status, same closed-form optimum."""
+import numpy as np
+import pytest
+
+import kat_instances as kat
+from hypatia_b200.host import instances as inst
+from hypatia_b200.host import models as M
+from hypatia_b200.host.solver import Solver
+
+pytestmark = pytest.mark.gpu
+
+
+def _solve_dev(model, **kw):
+    from hypatia_b200.cones import DeviceConeBlock
+    from hypatia_b200.syssolver import QRCholDenseSystemSolver as DevQRChol
+    s = Solver(model, DevQRChol(), DeviceConeBlock, **kw)
+    s.solve()
+    return s
+
+
+def _solve_ora(model, **kw):
+    from oracle.cones import OracleConeBlock
+    from oracle.syssolvers import QRCholDenseSystemSolver as OraQRChol
+    s = Solver(model, OraQRChol(), OracleConeBlock, **kw)
+    s.solve()
+    return s
+
+
+@pytest.mark.parametrize("build", kat.ALL, ids=lambda f: f.__name__)
+def test_kat_device_default(build):
+    model, expected = build()
+    kat.check_solution(_solve_dev(model), model, expected)
+
+
+@pytest.mark.parametrize("build", [kat.nonnegative4, kat.epinormeucl1, kat.possemideftri8,
+                                   kat.hyporootdettri4, kat.hypoperlogdettri4],
+                         ids=lambda f: f.__name__)
+def test_kat_device_no_reduce(build):
+    # reduce=false keeps p > 0: exercises the Ap_Q / Ap_R branch of solve_subsystem3
+    model, expected = build()
+    kat.check_solution(_solve_dev(model, reduce=False), model, expected)
+
+
+def test_linearopt_and_soc_solves_match_oracle_iterates():
+    """Same iteration count and objective as the oracle-driven solve (the two plug-in pairs see
+    the same host driver, so any difference comes from the device arithmetic)."""
+    cases = [inst.linearopt(40, 80, seed=7),
+             inst.synthetic("soc", 60, 0, [M.EpiNormEucl(25) for _ in range(8)], seed=21).model,
+             inst.synthetic("mix", 30, 4, [M.Nonnegative(10), M.PosSemidefTri(15), M.EpiNormEucl(6),
+                                           M.HypoPerLogdetTri(8)], seed=22).model]
+    for model in cases:
+        sd, so = _solve_dev(model), _solve_ora(model)
+        assert sd.status == so.status
+        assert abs(sd.num_iters - so.num_iters) <= 1
+        if so.status == "Optimal":
+            assert abs(sd.primal_obj - so.primal_obj) <= 1e-6 * (1 + abs(so.primal_obj))
