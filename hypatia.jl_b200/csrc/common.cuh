@@ -69,6 +69,11 @@ struct ConeGroup {
     // row list for elementwise cones (Nonnegative): global row of every element
     int* d_rows = nullptr;
     int* d_rowcone = nullptr;     // GLOBAL cone index of every element of d_rows
+    // chunk table of the many-column EpiNormEucl kernel (cones.cu)
+    int n_chunks = 0, chunk_smem = 0;
+    bool chunks_cover_all = false;
+    int64_t* d_crow0 = nullptr;
+    int *d_crows = nullptr, *d_ccone0 = nullptr, *d_ccount = nullptr;
 };
 
 struct TimingSlot {

@@ -158,6 +158,61 @@ soc_prod_kernel(int ncones, const int64_t* __restrict__ off, const int* __restri
     }
 }
 
+// Many-column variant used by the Schur pre-pass (K8): a CTA stages the rows of a chunk of
+// consecutive cones of ONE column in shared memory with fully coalesced loads (a column of the
+// panel is contiguous over all cones), one thread per cone then applies the rank-one update
+// from shared memory (cone dims are mostly odd, e.g. 25: conflict-free strides), and the result
+// goes back with coalesced stores.  chunk table: crow0[b], crows[b] = first row / number of rows
+// of chunk b, ccone0[b], ccount[b] = first cone (index in the group) / number of cones.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+soc_prod_chunk_kernel(const int64_t* __restrict__ crow0, const int* __restrict__ crows,
+                      const int* __restrict__ ccone0, const int* __restrict__ ccount,
+                      const int64_t* __restrict__ off, const int* __restrict__ dim,
+                      const double* __restrict__ scal, const double* __restrict__ point, const double* arr,
+                      int64_t ld_arr, double* prod, int64_t ld_prod, int64_t ncols, int64_t row_shift) {
+    extern __shared__ double srow[];
+    const int b = blockIdx.x;
+    const int64_t r0 = crow0[b];
+    const int nr = crows[b], c0 = ccone0[b], nc = ccount[b];
+    const double rt2 = 1.4142135623730951;
+    for (int64_t j = blockIdx.y; j < ncols; j += gridDim.y) {
+        const double* a = arr + j * ld_arr + (r0 - row_shift);
+        double* pr = prod + j * ld_prod + (r0 - row_shift);
+        for (int i = threadIdx.x; i < nr; i += blockDim.x) srow[i] = a[i];
+        __syncthreads();
+        for (int t = threadIdx.x; t < nc; t += blockDim.x) {
+            const int c = c0 + t;
+            const int64_t o = off[c];
+            const int d = dim[c];
+            double* v = srow + (o - r0);
+            const double* w = point + o;
+            const double dist = scal[8 * c], u = w[0], uj = v[0];
+            double dotw = 0.0;
+            for (int i = 1; i < d; i++) dotw += w[i] * v[i];
+            double k0, kw, kj;
+            if (MODE == HYP_PROD_HESS) {
+                double ga = (dotw - u * uj) / dist;
+                k0 = (-ga * u - uj) / dist; kw = ga / dist; kj = 1.0 / dist;
+            } else if (MODE == HYP_PROD_INV_HESS) {
+                double pa = u * uj + dotw;
+                k0 = pa * u - dist * uj; kw = pa; kj = dist;
+            } else if (MODE == HYP_PROD_SQRT_HESS) {
+                double distrt2 = dist * rt2, rtdist = sqrt(dist), urtdist = u + rtdist * rt2;
+                k0 = (u * uj - dotw) / distrt2; kw = (dotw / urtdist - uj) / distrt2; kj = 1.0 / rtdist;
+            } else {
+                double rtdist = sqrt(dist), urtdist = u + rtdist * rt2;
+                k0 = (u * uj + dotw) / rt2; kw = (dotw / urtdist + uj) / rt2; kj = rtdist;
+            }
+            v[0] = k0;
+            for (int i = 1; i < d; i++) v[i] = kw * w[i] + kj * v[i];
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < nr; i += blockDim.x) pr[i] = srow[i];
+        __syncthreads();
+    }
+}
+
 // epinormeucl.jl:208-228
 __global__ void soc_dder3_kernel(int ncones, const int64_t* __restrict__ off,
                                  const int* __restrict__ dim, const double* __restrict__ scal,
@@ -295,6 +350,10 @@ void launch_vec_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr
         int gx = grid_for(ctx, g.rows, 256, ncols > 1 ? 1 : 8);
         nn_prod_kernel<MODE><<<dim3(gx, gy), 256, 0, ctx->stream>>>(
             g.rows, g.d_rows, ctx->d_point, arr, ld_arr, prod, ld_prod, ncols, row_shift);
+    } else if (ncols >= 16 && g.n_chunks > 0 && g.chunks_cover_all) {
+        soc_prod_chunk_kernel<MODE><<<dim3(g.n_chunks, gy), 256, g.chunk_smem, ctx->stream>>>(
+            g.d_crow0, g.d_crows, g.d_ccone0, g.d_ccount, g.d_off, g.d_dim, g.d_scal, ctx->d_point, arr,
+            ld_arr, prod, ld_prod, ncols, row_shift);
     } else {
         int gx = ceil_div(g.count, 8);
         soc_prod_kernel<MODE><<<dim3(gx, gy), 256, 0, ctx->stream>>>(
@@ -354,6 +413,37 @@ void hyp_cones_build_groups(hyp_ctx* ctx) {
             g.d_rows = upload(rows);
             g.d_rowcone = upload(rowcone);
         }
+        if (type == HYP_CONE_EPINORMEUCL) {
+            // chunks of consecutive cones with at most CHUNK_ROWS rows (shared-memory staging)
+            const int CHUNK_ROWS = 3200, CHUNK_CONES = 256;
+            std::vector<int64_t> crow0;
+            std::vector<int> crows, ccone0, ccount;
+            g.chunks_cover_all = true;
+            int i = 0;
+            while (i < g.count) {
+                if (g.h_dim[i] > CHUNK_ROWS) { g.chunks_cover_all = false; break; }
+                int64_t r0 = g.h_off[i];
+                int rows_c = 0, n_c = 0;
+                while (i < g.count && n_c < CHUNK_CONES && rows_c + g.h_dim[i] <= CHUNK_ROWS &&
+                       g.h_off[i] == r0 + rows_c) {
+                    rows_c += g.h_dim[i];
+                    n_c++;
+                    i++;
+                }
+                crow0.push_back(r0);
+                crows.push_back(rows_c);
+                ccone0.push_back(i - n_c);
+                ccount.push_back(n_c);
+            }
+            if (g.chunks_cover_all) {
+                g.n_chunks = (int)crow0.size();
+                g.chunk_smem = CHUNK_ROWS * (int)sizeof(double);
+                g.d_crow0 = upload(crow0);
+                g.d_crows = upload(crows);
+                g.d_ccone0 = upload(ccone0);
+                g.d_ccount = upload(ccount);
+            }
+        }
         if (type >= HYP_CONE_POSSEMIDEFTRI) hyp_mat_alloc_group(ctx, g);
         ctx->groups.push_back(g);
     }
@@ -371,6 +461,10 @@ void hyp_cones_free_groups(hyp_ctx* ctx) {
         cudaFree(g.d_scal);
         cudaFree(g.d_rows);
         cudaFree(g.d_rowcone);
+        cudaFree(g.d_crow0);
+        cudaFree(g.d_crows);
+        cudaFree(g.d_ccone0);
+        cudaFree(g.d_ccount);
         cudaFree(g.d_W);
         cudaFree(g.d_U);
         cudaFree(g.d_Ut);
