@@ -55,6 +55,10 @@ WORKLOADS = {
 }
 
 
+# DRAM traffic of the Schur SYRK launch from the committed `ncu --set full` capture (per launch)
+NCU_TRAFFIC = {"C3": 31.497622e9 + 0.411380e9}
+
+
 class PanelModel:
     """Model fields the C ABI needs, holding only this rank's row panel of G."""
 
@@ -427,7 +431,9 @@ def run_ours(args):
                                "MEASURED_PEAKS.json has no FP64 entry)",
                 "peak_bf16_measured": peaks.get("bf16_tflops"),
                 "frac_of_bf16_peak": (achieved / peaks["bf16_tflops"]) if achieved and peaks.get("bf16_tflops") else None,
-                "traffic": None,
+                "traffic": NCU_TRAFFIC.get(args.workload) if world == 1 else None,
+                "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, "
+                                "profiles/r01_syrk_schur_ncu_full.txt)",
                 "algorithmic_flops_per_launch": syrk_flops, "avg_launch_ms": syrk_ms,
                 "step_share": syrk_ms / (ms / args.steps) if syrk_ms == syrk_ms else None,
                 "phase_ms": phases}

@@ -40,6 +40,8 @@ _SIGS = {
                                       C.c_int64, C.c_int]),
     "hyp_cones_dder3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "hyp_cones_proxsqr": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]),
+    "hyp_cones_hess_blocks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "hyp_set_syssolver": (C.c_int, [C.c_void_p, C.c_int]),
     "hyp_set_mu_tau": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "hyp_update_lhs": (C.c_int, [C.c_void_p, c_ip]),
     "hyp_solve_subsystem3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -215,7 +217,21 @@ class Context:
                                               ptr(ok)), "hyp_cones_proxsqr")
         return prox, ok.astype(bool)
 
+    def cones_hess_blocks(self, inverse: bool, dims):
+        """Explicit hess / inv_hess of every cone: list of (dim_k, dim_k) arrays."""
+        dims = [int(d) for d in dims]
+        buf = np.zeros(sum(d * d for d in dims))
+        self.check(self.lib.hyp_cones_hess_blocks(self.h, ptr(buf), int(bool(inverse))), "hyp_cones_hess_blocks")
+        out, o = [], 0
+        for d in dims:
+            out.append(buf[o:o + d * d].reshape(d, d, order="F"))
+            o += d * d
+        return out
+
     # ---- system solver ----
+    def set_syssolver(self, kind: int):
+        self.check(self.lib.hyp_set_syssolver(self.h, int(kind)), "hyp_set_syssolver")
+
     def set_mu_tau(self, mu, tau):
         self.check(self.lib.hyp_set_mu_tau(self.h, float(mu), float(tau)), "hyp_set_mu_tau")
 

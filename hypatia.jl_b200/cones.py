@@ -59,6 +59,14 @@ class DeviceConeBlock(ConeBlock):
     def grad(self):
         return self.ctx.cones_grad()
 
+    def hess(self):
+        """hess(cone_k) for every cone (list of dense blocks; Cones.jl:79-84)."""
+        return self.ctx.cones_hess_blocks(False, self.dims)
+
+    def inv_hess(self):
+        """inv_hess(cone_k) for every cone (Cones.jl:86-93)."""
+        return self.ctx.cones_hess_blocks(True, self.dims)
+
     # ---- products ----
     def hess_prod(self, arr):
         return self.ctx.cones_hess_prod(arr, PROD_HESS)

@@ -540,21 +540,34 @@ void hyp_potrf_upper(hyp_ctx* ctx, double* A, int64_t lda, int64_t m, double* d_
     TimeScope ts(ctx, T_POTRF);
     set_panel_attr();
     CUDA_TRY(cudaMemsetAsync(d_info, 0, sizeof(int), ctx->stream));
-    int nblk = ceil_div(m, NB);
-    for (int k = 0; k < nblk; k++) {
-        int64_t k0 = (int64_t)k * NB;
-        int64_t nb = std::min<int64_t>(NB, m - k0);
-        panel_kernel<true><<<1, PT, NB * LDU * 8, ctx->stream>>>(A, lda, m, k, d_dinv, d_info);
-        ctx->launches++;
-        int64_t rest = m - k0 - nb;
-        if (rest > 0) {
+    // Two-level blocking: 128-wide panels inside OB-wide outer blocks.  Inside an outer block a panel
+    // only updates the rows of that outer block (a few tile rows); the rest of the matrix is updated
+    // once per outer block with contraction depth OB, which quarters the read-modify-write traffic on
+    // the trailing matrix and keeps the DMMA main loop long between epilogues.
+    const int64_t OB = 512;
+    for (int64_t K0 = 0; K0 < m; K0 += OB) {
+        const int64_t Kend = std::min(K0 + OB, m);
+        for (int64_t k0 = K0; k0 < Kend; k0 += NB) {
+            const int64_t nb = std::min<int64_t>(NB, m - k0);
+            const int64_t k = k0 / NB;
+            panel_kernel<true><<<1, PT, NB * LDU * 8, ctx->stream>>>(A, lda, m, k, d_dinv, d_info);
+            ctx->launches++;
+            const int64_t rest = m - k0 - nb;
+            if (rest <= 0) continue;
             double* A12 = A + k0 + (k0 + nb) * lda;
             double* A22 = A + (k0 + nb) + (k0 + nb) * lda;
-            const double* Dk = d_dinv + (int64_t)k * NB * NB;
+            const double* Dk = d_dinv + k * NB * NB;
             // U12 = U11^-T A12  (in place: every output tile depends on its own columns only)
             hyp_gemm_tn(ctx, Dk, NB, A12, lda, nb, nb, rest, A12, lda, 1.0, 0.0);
-            // A22 -= U12' U12 (upper tiles)
-            hyp_atb_upper(ctx, A12, lda, A12, lda, nb, rest, A22, lda, -1.0, 1.0);
+            // rows of this outer block below the panel: A22[0:rin, :] -= U12[:, 0:rin]' U12
+            const int64_t rin = Kend - (k0 + nb);
+            if (rin > 0) hyp_gemm_tn(ctx, A12, lda, A12, lda, nb, rin, rest, A22, lda, -1.0, 1.0);
+        }
+        const int64_t rest2 = m - Kend;
+        if (rest2 > 0) {
+            // everything right of / below the outer block: depth-OB update on the upper tiles
+            double* P = A + K0 + Kend * lda;
+            hyp_atb_upper(ctx, P, lda, P, lda, Kend - K0, rest2, A + Kend + Kend * lda, lda, -1.0, 1.0);
         }
     }
     CUDA_TRY(cudaGetLastError());

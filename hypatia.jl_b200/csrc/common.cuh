@@ -20,6 +20,8 @@
 #include "../../include/hypatia_b200.h"
 
 #define HYP_NUM_CONE_TYPES 5
+// internal product mode: inv_hess for primal-barrier cones, hess for dual-barrier cones
+#define HYP_PROD_BLOCK_INV 5
 #define HYP_EPS 2.220446049250313e-16
 
 struct HypError {
@@ -155,6 +157,14 @@ struct hyp_ctx {
     double* d_ldl_work = nullptr;      // LDL' workspace
     int fact_kind = 0;
     double mu = 1.0, tau_bar = 1.0;
+    // ---- SymIndefDense variant (symindef.jl:203-271) ----
+    int solver_kind = 0;               // 0 QRCholDense, 1 SymIndefDense
+    int64_t ld3 = 0;                   // leading dim of the (n+p+q)^2 matrices
+    double* d_L3 = nullptr;            // static part [0 A' G'; . 0 0; . . 0] (upper triangle)
+    double* d_F3 = nullptr;            // factored copy
+    int* d_row_cone = nullptr;         // q: global cone index of every row
+    double* d_blk_arr = nullptr;       // q x maxdim identity pattern / products (2 buffers)
+    int64_t blk_maxdim = 0;
     int* d_flags = nullptr;            // TRSV ticket + block-ready flags
     int trsv_epoch = 0;
 

@@ -516,6 +516,7 @@ void hyp_cones_prod(hyp_ctx* ctx, double* prod, const double* arr, int64_t ncols
         int m = resolve_mode(g, 0, mode);
         if (g.type <= HYP_CONE_EPINORMEUCL) {
             if (m == HYP_PROD_BLOCK) m = HYP_PROD_HESS;   // no dual-barrier variants of these cones
+            if (m == HYP_PROD_BLOCK_INV) m = HYP_PROD_INV_HESS;
             switch (m) {
                 case HYP_PROD_HESS:
                     launch_vec_prod<HYP_PROD_HESS>(ctx, g, prod, arr, ncols, ld_prod, ld_arr, row_shift);

@@ -534,6 +534,7 @@ void hyp_mat_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr, i
         const int64_t len = (int64_t)d * (d + 1) / 2;
         int m = mode;
         if (m == HYP_PROD_BLOCK) m = g.h_dual[i] ? HYP_PROD_INV_HESS : HYP_PROD_HESS;
+        if (m == HYP_PROD_BLOCK_INV) m = g.h_dual[i] ? HYP_PROD_HESS : HYP_PROD_INV_HESS;
         const double* X = (m == HYP_PROD_HESS ? g.d_Wi : m == HYP_PROD_INV_HESS ? g.d_W
                            : m == HYP_PROD_SQRT_HESS ? g.d_Ui : g.d_Ut) + g.h_moff[i];
         const int inverse = (m == HYP_PROD_INV_HESS) ? 1 : 0;

@@ -129,6 +129,11 @@ void free_model(hyp_ctx* ctx) {
     dfree(ctx->d_ipiv);
     dfree(ctx->d_ldl_work);
     dfree(ctx->d_flags);
+    dfree(ctx->d_L3);
+    dfree(ctx->d_F3);
+    dfree(ctx->d_row_cone);
+    dfree(ctx->d_blk_arr);
+    ctx->solver_kind = 0;
     dfree(ctx->d_rhs);
     dfree(ctx->d_sol);
     dfree(ctx->d_sub_sol);
@@ -176,6 +181,14 @@ __global__ void rhs3_post_kernel(int64_t q, const uint8_t* __restrict__ row_dual
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < q;
          i += (int64_t)gridDim.x * blockDim.x)
         out[i] = (row_dual && row_dual[i]) ? hv[i] : (-hv[i] - rs[i]);
+}
+
+__global__ void symindef_rhs3_kernel(int64_t q, const uint8_t* __restrict__ row_dual,
+                                     const double* __restrict__ hinv_rs, const double* __restrict__ rz,
+                                     const double* __restrict__ rs, double* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < q;
+         i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (row_dual && row_dual[i]) ? (-rz[i] - rs[i]) : (-hinv_rs[i] - rz[i]);
 }
 
 // primal / dual views of a direction (point.jl:46-51): primal = s (z on dual-barrier rows)
@@ -280,6 +293,12 @@ void potrs(hyp_ctx* ctx, double* x) {
 void solve_subsystem3_dev(hyp_ctx* ctx, double* sol, const double* rhs) {
     const int64_t n = ctx->n, p = ctx->p, q = ctx->q, nmp = ctx->nmp;
     if (sol != rhs) hyp_copy(ctx, n + p + q, sol, rhs);
+    if (ctx->solver_kind == 1) {
+        // SymIndefDense: ldiv!(sol.vec, fact, rhs.vec) (symindef.jl:263-271); G x kept for the s lift
+        hyp_ldlt_solve(ctx, ctx->d_F3, ctx->ld3, n + p + q, ctx->d_ipiv, sol);
+        if (q > 0) G_n(ctx, ctx->d_Graw, sol, ctx->d_Gx);
+        return;
+    }
     double* x = sol;
     double* y = sol + n;
     double* z = sol + n + p;
@@ -345,6 +364,14 @@ void solve_system_dev(hyp_ctx* ctx, double* sol, const double* rhs) {
         negate_kernel<<<vgrid(ctx, p), 256, 0, ctx->stream>>>(p, sub_rhs + n, rhs + n);
         ctx->launches++;
     }
+    if (q > 0 && ctx->solver_kind == 1) {
+        // setup_rhs3 (symindef.jl:31-52): -Hinv rs - rz on primal-barrier rows, -rz - rs on dual rows
+        TimeScope ts(ctx, T_CONE_PROD);
+        hyp_cones_prod(ctx, ctx->d_vq2, rs, 1, q, q, HYP_PROD_BLOCK_INV, 0);
+        symindef_rhs3_kernel<<<vgrid(ctx, q), 256, 0, ctx->stream>>>(q, ctx->d_row_dual, ctx->d_vq2, rz, rs,
+                                                                   sub_rhs + n + p);
+        ctx->launches++;
+    } else
     // setup_rhs3 (qrchol.jl:16-37)
     if (q > 0) {
         TimeScope ts(ctx, T_CONE_PROD);
@@ -476,6 +503,147 @@ int update_lhs_fact(hyp_ctx* ctx) {
     return 2;
 }
 
+
+// ---- SymIndefDense (symindef.jl:203-271) ---------------------------------------------------
+// out[i + (col0 + r) * ldo] = M[r + i * ldm] : M' into the columns col0.. of the big matrix
+__global__ void transpose_into_kernel(double* __restrict__ out, int64_t ldo, int64_t col0,
+                                      const double* __restrict__ M, int64_t ldm, int64_t rows, int64_t n) {
+    __shared__ double tile[32][33];
+    const int64_t r0 = (int64_t)blockIdx.x * 32, i0 = (int64_t)blockIdx.y * 32;
+    for (int dy = threadIdx.y; dy < 32; dy += 8) {
+        int64_t r = r0 + threadIdx.x, i = i0 + dy;
+        tile[dy][threadIdx.x] = (r < rows && i < n) ? M[r + i * ldm] : 0.0;
+    }
+    __syncthreads();
+    for (int dy = threadIdx.y; dy < 32; dy += 8) {
+        int64_t i = i0 + threadIdx.x, r = r0 + dy;
+        if (r < rows && i < n) out[i + (col0 + r) * ldo] = tile[threadIdx.x][dy];
+    }
+}
+
+// arr[r + j * q] = 1 where j is the index of row r inside its cone
+__global__ void block_identity_kernel(int64_t q, int64_t maxdim, const int* __restrict__ row_cone,
+                                      const int64_t* __restrict__ coff, double* __restrict__ arr) {
+    for (int64_t j = blockIdx.y; j < maxdim; j += gridDim.y)
+        for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < q;
+             r += (int64_t)gridDim.x * blockDim.x)
+            arr[r + j * q] = (r - coff[row_cone[r]] == j) ? 1.0 : 0.0;
+}
+
+// dst[(z0 + r) + (z0 + off_k + j) * ld] = sign * prod[r + j * q] for j < dim_k (k = cone of row r)
+__global__ void scatter_blocks_kernel(int64_t q, int64_t maxdim, const int* __restrict__ row_cone,
+                                      const int64_t* __restrict__ coff, const int64_t* __restrict__ cdim,
+                                      const double* __restrict__ prod, double sign, double* __restrict__ dst,
+                                      int64_t ld, int64_t z0) {
+    for (int64_t j = blockIdx.y; j < maxdim; j += gridDim.y)
+        for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < q;
+             r += (int64_t)gridDim.x * blockDim.x) {
+            const int k = row_cone[r];
+            if (j < cdim[k]) dst[(z0 + r) + (z0 + coff[k] + j) * ld] = sign * prod[r + j * q];
+        }
+}
+
+// packed explicit blocks: out[boff_k + i + j * dim_k] = prod[off_k + i + j * q]
+__global__ void gather_blocks_kernel(int64_t q, int64_t maxdim, const int* __restrict__ row_cone,
+                                     const int64_t* __restrict__ coff, const int64_t* __restrict__ cdim,
+                                     const int64_t* __restrict__ boff, const double* __restrict__ prod,
+                                     double* __restrict__ out) {
+    for (int64_t j = blockIdx.y; j < maxdim; j += gridDim.y)
+        for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < q;
+             r += (int64_t)gridDim.x * blockDim.x) {
+            const int k = row_cone[r];
+            if (j < cdim[k]) out[boff[k] + (r - coff[k]) + j * cdim[k]] = prod[r + j * q];
+        }
+}
+
+void ensure_block_buffers(hyp_ctx* ctx) {
+    if (ctx->d_blk_arr) return;
+    const int64_t q = ctx->q;
+    int64_t maxdim = 1;
+    std::vector<int> rc((size_t)std::max<int64_t>(q, 1), 0);
+    for (int k = 0; k < ctx->K; k++) {
+        maxdim = std::max(maxdim, ctx->h_cone_dim[k]);
+        for (int64_t r = ctx->h_cone_off[k]; r < ctx->h_cone_off[k + 1]; r++) rc[r] = k;
+    }
+    ctx->blk_maxdim = maxdim;
+    dalloc(&ctx->d_row_cone, q);
+    if (q) CUDA_TRY(cudaMemcpyAsync(ctx->d_row_cone, rc.data(), q * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    dalloc(&ctx->d_blk_arr, 2 * q * maxdim);
+}
+
+// explicit Hessian-type blocks of every cone (update_hess / update_inv_hess, K10): the oracle
+// applied to the identity pattern; result (q x maxdim, ld q) in d_blk_arr + q * maxdim
+double* cone_blocks_dev(hyp_ctx* ctx, int mode) {
+    ensure_block_buffers(ctx);
+    const int64_t q = ctx->q, md = ctx->blk_maxdim;
+    if (ctx->nranks > 1) throw HypError{"explicit cone Hessian blocks are single-rank only"};
+    dim3 grid(std::max(1, std::min(ceil_div(q, 256), ctx->sm_count * 2)), (unsigned)std::min<int64_t>(md, 65535));
+    block_identity_kernel<<<grid, 256, 0, ctx->stream>>>(q, md, ctx->d_row_cone, ctx->d_cone_off, ctx->d_blk_arr);
+    ctx->launches++;
+    double* prod = ctx->d_blk_arr + q * md;
+    hyp_cones_prod(ctx, prod, ctx->d_blk_arr, md, q, q, mode, 0);
+    return prod;
+}
+
+void symindef_setup(hyp_ctx* ctx) {
+    if (ctx->nranks > 1) throw HypError{"SymIndefDense is single-rank only"};
+    const int64_t n = ctx->n, p = ctx->p, q = ctx->q, N3 = n + p + q;
+    ctx->ld3 = round_up(std::max<int64_t>(N3, 2), 2);
+    dfree(ctx->d_L3);
+    dfree(ctx->d_F3);
+    dalloc(&ctx->d_L3, ctx->ld3 * std::max<int64_t>(N3, 1));
+    dalloc(&ctx->d_F3, ctx->ld3 * std::max<int64_t>(N3, 1));
+    dim3 blk(32, 8);
+    if (p > 0 && n > 0) {
+        dim3 grid(ceil_div(p, 32), ceil_div(n, 32));
+        transpose_into_kernel<<<grid, blk, 0, ctx->stream>>>(ctx->d_L3, ctx->ld3, n, ctx->d_A, ctx->lda, p, n);
+        ctx->launches++;
+    }
+    if (q > 0 && n > 0) {
+        dim3 grid(ceil_div(q, 32), ceil_div(n, 32));
+        transpose_into_kernel<<<grid, blk, 0, ctx->stream>>>(ctx->d_L3, ctx->ld3, n + p, ctx->d_Graw, ctx->ldg, q, n);
+        ctx->launches++;
+    }
+    dfree(ctx->d_ipiv);
+    dfree(ctx->d_ldl_work);
+    dalloc(&ctx->d_ipiv, 3 * N3 + 8);
+    dalloc(&ctx->d_ldl_work, 4 * N3 + 64);
+    ensure_block_buffers(ctx);
+    // rhs_const.z = h for this solver (common.jl:203-205; no H h product)
+    if (q) hyp_copy(ctx, q, ctx->d_const_rhs + n + p, ctx->d_cbh + n + p);
+    CUDA_TRY(cudaGetLastError());
+}
+
+// update_lhs of SymIndefDense: z/z block = -inv_hess (primal) / -hess (dual), symm_fact_copy! chain
+int symindef_update(hyp_ctx* ctx) {
+    const int64_t n = ctx->n, p = ctx->p, q = ctx->q, N3 = n + p + q;
+    const size_t bytes = (size_t)ctx->ld3 * N3 * 8;
+    int info = 0, rc = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_F3, ctx->d_L3, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (q > 0) {
+            double* prod = cone_blocks_dev(ctx, HYP_PROD_BLOCK_INV);
+            dim3 grid(std::max(1, std::min(ceil_div(q, 256), ctx->sm_count * 2)),
+                      (unsigned)std::min<int64_t>(ctx->blk_maxdim, 65535));
+            scatter_blocks_kernel<<<grid, 256, 0, ctx->stream>>>(q, ctx->blk_maxdim, ctx->d_row_cone, ctx->d_cone_off,
+                                                               ctx->d_cone_dim, prod, -1.0, ctx->d_F3, ctx->ld3, n + p);
+            ctx->launches++;
+        }
+        if (attempt == 1) hyp_increase_diag(ctx, ctx->d_F3, ctx->ld3, N3);   // dense.jl:170-184
+        {
+            TimeScope ts(ctx, T_LDLT);
+            hyp_ldlt_factor(ctx, ctx->d_F3, ctx->ld3, N3, ctx->d_ipiv, ctx->d_info);
+        }
+        CUDA_TRY(cudaMemcpyAsync(&info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        ctx->fact_kind = 1 + attempt;
+        if (info == 0) return rc;
+        rc = (attempt == 0) ? 1 : 2;
+    }
+    return rc;
+}
+
 template <typename F>
 int guarded(hyp_ctx* ctx, F&& f) {
     if (!ctx) return -1;
@@ -576,8 +744,8 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
     return guarded(ctx, [&] {
         if (n < 0 || p < 0 || q < 0 || K < 0 || p > n) throw HypError{"hyp_load_model: bad dimensions"};
         if (cone_lo < 0 || cone_hi > K || cone_lo > cone_hi) throw HypError{"hyp_load_model: bad cone range"};
-        if (p > 0 && (!Ap_Q || !Ap_R || !A))
-            throw HypError{"hyp_load_model: p > 0 needs A and the QR factors Ap_Q, Ap_R of A'"};
+        if (p > 0 && !A) throw HypError{"hyp_load_model: p > 0 needs A"};
+        if ((Ap_Q == nullptr) != (Ap_R == nullptr)) throw HypError{"hyp_load_model: pass both Ap_Q and Ap_R or neither"};
         free_model(ctx);
         ctx->n = n;
         ctx->p = p;
@@ -636,9 +804,11 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
             ctx->ldqm = round_up(n, 2);
             ctx->ldr = round_up(p, 2);
             dalloc(&ctx->d_A, ctx->lda * n);
+            upload_matrix(ctx, ctx->d_A, ctx->lda, A, ldA, p, n);
+        }
+        if (p > 0 && Ap_Q) {
             dalloc(&ctx->d_Q, ctx->ldqm * n);
             dalloc(&ctx->d_R, ctx->ldr * p);
-            upload_matrix(ctx, ctx->d_A, ctx->lda, A, ldA, p, n);
             upload_matrix(ctx, ctx->d_Q, ctx->ldqm, Ap_Q, n, n, n);
             upload_matrix(ctx, ctx->d_R, ctx->ldr, Ap_R, p, p, p);
             dalloc(&ctx->d_Rdinv, (int64_t)ceil_div(p, 128) * 128 * 128);
@@ -734,6 +904,47 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         CUDA_TRY(cudaDeviceSynchronize());
         ctx->model_loaded = true;
+        return 0;
+    });
+}
+
+int hyp_set_syssolver(hyp_ctx* ctx, int kind) {
+    return guarded(ctx, [&] {
+        need_model(ctx);
+        if (kind != 0 && kind != 1) throw HypError{"hyp_set_syssolver: kind must be 0 (QRCholDense) or 1 (SymIndefDense)"};
+        ctx->solver_kind = kind;
+        ctx->lhs_ready = false;
+        if (kind == 1) symindef_setup(ctx);
+        else if (ctx->q) hyp_copy(ctx, ctx->q, ctx->d_const_rhs + ctx->n + ctx->p, ctx->d_cbh + ctx->n + ctx->p);
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    });
+}
+
+int hyp_cones_hess_blocks(hyp_ctx* ctx, double* blocks, int inverse) {
+    return guarded(ctx, [&] {
+        need_model(ctx);
+        if (!ctx->cones_loaded) throw HypError{"hyp_cones_hess_blocks: no point loaded"};
+        const int64_t q = ctx->q;
+        if (q == 0) return 0;
+        double* prod = cone_blocks_dev(ctx, inverse ? HYP_PROD_INV_HESS : HYP_PROD_HESS);
+        std::vector<int64_t> boff(ctx->K + 1, 0);
+        for (int k = 0; k < ctx->K; k++) boff[k + 1] = boff[k] + ctx->h_cone_dim[k] * ctx->h_cone_dim[k];
+        int64_t* d_boff = nullptr;
+        double* d_out = nullptr;
+        dalloc(&d_boff, ctx->K + 1);
+        CUDA_TRY(cudaMemcpyAsync(d_boff, boff.data(), (ctx->K + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        bool dev_out = is_device_ptr(blocks);
+        if (dev_out) d_out = blocks; else dalloc(&d_out, boff[ctx->K]);
+        dim3 grid(std::max(1, std::min(ceil_div(q, 256), ctx->sm_count * 2)),
+                  (unsigned)std::min<int64_t>(ctx->blk_maxdim, 65535));
+        gather_blocks_kernel<<<grid, 256, 0, ctx->stream>>>(q, ctx->blk_maxdim, ctx->d_row_cone, ctx->d_cone_off,
+                                                          ctx->d_cone_dim, d_boff, prod, d_out);
+        ctx->launches++;
+        if (!dev_out) stage_out(ctx, blocks, boff[ctx->K], d_out);
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        cudaFree(d_boff);
+        if (!dev_out) cudaFree(d_out);
         return 0;
     });
 }
@@ -855,11 +1066,17 @@ int hyp_update_lhs(hyp_ctx* ctx, int* fact_kind) {
         if (!ctx->cones_loaded) throw HypError{"hyp_update_lhs: no cone point loaded"};
         int rc = 0;
         ctx->fact_kind = 0;
-        if (ctx->nmp > 0) rc = update_lhs_fact(ctx);
+        const int64_t n = ctx->n, p = ctx->p, q = ctx->q;
+        if (ctx->solver_kind == 1) {
+            rc = symindef_update(ctx);
+        } else if (ctx->p > 0 && !ctx->d_R) {
+            throw HypError{"QRCholDense with p > 0 needs the QR factors Ap_Q, Ap_R (pass them to hyp_load_model)"};
+        } else if (ctx->nmp > 0) {
+            rc = update_lhs_fact(ctx);
+        }
         if (fact_kind) *fact_kind = ctx->fact_kind;
         // rhs_const.z = H h (block_hess_prod!, qrchol.jl:191-195), then the constant column
-        const int64_t n = ctx->n, p = ctx->p, q = ctx->q;
-        if (q > 0) {
+        if (q > 0 && ctx->solver_kind == 0) {
             TimeScope ts(ctx, T_CONE_PROD);
             hyp_cones_prod(ctx, ctx->d_const_rhs + n + p, ctx->d_cbh + n + p, 1, q, q, HYP_PROD_BLOCK, 0);
             if (ctx->nranks > 1) hyp_replicate_q(ctx, ctx->d_const_rhs + n + p);

@@ -48,6 +48,12 @@ def partition_cones(model, nranks):
 
 
 class QRCholDenseSystemSolver:
+    NEEDS_QR = True
+    FAIL_MESSAGE = "positive definite linear system factorization failed"    # qrchol.jl:252-254
+
+    def _after_load(self):
+        pass
+
     def __init__(self, device: int | None = None, dist_group=None):
         self.device = device
         self.dist_group = dist_group
@@ -69,11 +75,12 @@ class QRCholDenseSystemSolver:
         self.cone_range = (lo, hi)
         Q = getattr(solver, "Ap_Q", None)
         R = getattr(solver, "Ap_R", None)
-        if model.p == 0:
+        if model.p == 0 or not self.NEEDS_QR:
             Q = R = None
         elif Q is None:
             raise ValueError("QRCholDenseSystemSolver needs solver.Ap_Q / Ap_R when p > 0")
         self.ctx.load_model(model, cone_lo=lo, cone_hi=hi, Ap_Q=Q, Ap_R=R)
+        self._after_load()
         self.cones = DeviceConeBlock(model, ctx=self.ctx)
         self.nmp = model.n - model.p
         return self
@@ -103,7 +110,7 @@ class QRCholDenseSystemSolver:
         rc, kind = self.ctx.update_lhs()
         self.fact_kind = kind
         if rc == 2:
-            print("positive definite linear system factorization failed")   # qrchol.jl:252-254
+            print(self.FAIL_MESSAGE)
         return self
 
     # ---- solve_system / solve_subsystem3 / apply_lhs: common.jl:129-151, qrchol.jl:39-85,
@@ -132,3 +139,15 @@ class QRCholDenseSystemSolver:
         if self.ctx is not None:
             self.ctx.close()
             self.ctx = None
+
+
+class SymIndefDenseSystemSolver(QRCholDenseSystemSolver):
+    """Device drop-in for the reference's SymIndefDenseSystemSolver (symindef.jl:203-271): dense
+    (n+p+q)^2 symmetric-indefinite LHS [0 A' G'; A 0 0; G 0 -Hinv], rook Bunch-Kaufman with the
+    symm_fact_copy! diagonal-shift retry (dense.jl:170-184).  Same C entry points; the context is
+    switched with hyp_set_syssolver(ctx, 1).  Single GPU."""
+    NEEDS_QR = False
+    FAIL_MESSAGE = "symmetric linear system factorization failed"             # symindef.jl:254-256
+
+    def _after_load(self):
+        self.ctx.set_syssolver(1)

@@ -98,7 +98,16 @@ int hyp_cones_dder3(hyp_ctx* ctx, double* out, const double* dir);
 int hyp_cones_proxsqr(hyp_ctx* ctx, double irtmu, int use_max, double* proxsqr,
                       uint8_t* numerics_ok);
 
+/* explicit hess(cone) (inverse = 0) / inv_hess(cone) (inverse = 1) of every cone, Cones.jl:79-93 and
+ * the per-cone update_hess / update_inv_hess: K column-major dim_k x dim_k blocks packed one after
+ * the other (block k starts at sum_{j<k} dim_j^2). */
+int hyp_cones_hess_blocks(hyp_ctx* ctx, double* blocks, int inverse);
+
 /* ---- system solver (plugin slot 1) ------------------------------------------------------ */
+/* which reference system solver the context restates: 0 = QRCholDenseSystemSolver (default,
+ * qrchol.jl:104-257), 1 = SymIndefDenseSystemSolver (symindef.jl:203-271: dense (n+p+q)^2
+ * symmetric-indefinite LHS, rook Bunch-Kaufman).  Call after hyp_load_model. */
+int hyp_set_syssolver(hyp_ctx* ctx, int kind);
 /* mu and tau of the current iterate (solver.mu, solver.point.tau[]) used by
  * solve_subsystem4 / solve_system / apply_lhs (common.jl:117,171-175,147) */
 int hyp_set_mu_tau(hyp_ctx* ctx, double mu, double tau_bar);

@@ -59,3 +59,20 @@ def test_linearopt_and_soc_solves_match_oracle_iterates():
         assert abs(sd.num_iters - so.num_iters) <= 3
         if so.status == "Optimal":
             assert abs(sd.primal_obj - so.primal_obj) <= 1e-6 * (1 + abs(so.primal_obj))
+
+
+def test_c1_linearopt_symindef_device():
+    """BASELINE config 1 (examples/linearopt native, dense A 200 x 400, Nonnegative, SymIndefDense,
+    no reduction) solved with the device SymIndefDense plug-in; same optimum as the oracle's."""
+    from hypatia_b200.cones import DeviceConeBlock
+    from hypatia_b200.syssolver import SymIndefDenseSystemSolver as DevSym
+    from oracle.cones import OracleConeBlock
+    from oracle.syssolvers import SymIndefDenseSystemSolver as OraSym
+    model = inst.linearopt(60, 120, seed=3)
+    sd = Solver(model, DevSym(), DeviceConeBlock, reduce=False)
+    sd.solve()
+    so = Solver(model, OraSym(), OracleConeBlock, reduce=False)
+    so.solve()
+    assert sd.status == so.status == "Optimal"
+    assert abs(sd.primal_obj - so.primal_obj) <= 1e-6 * (1 + abs(so.primal_obj))
+    kat.check_solution(sd, model, dict(status="Optimal"))

@@ -114,3 +114,50 @@ def test_empty_and_tiny_models():
     I = inst.synthetic("np", 3, 3, [M.Nonnegative(4), M.EpiNormEucl(3)], seed=4)
     Qf, Rf = sla.qr(I.model.A.T, mode="full")
     _check_system(I, (Qf, np.triu(Rf[:3, :3])))
+
+
+@pytest.mark.parametrize("p", [0, 3])
+def test_symindef_dense_device_vs_oracle(p):
+    """SymIndefDenseSystemSolver on the device (hyp_set_syssolver(ctx, 1): explicit inv_hess blocks +
+    rook Bunch-Kaufman) against the oracle's SymIndefDense and QRCholDense."""
+    from hypatia_b200.syssolver import SymIndefDenseSystemSolver as DevSym
+    from oracle.syssolvers import SymIndefDenseSystemSolver as OraSym
+    cones = [M.Nonnegative(5), M.EpiNormEucl(4), M.PosSemidefTri(6), M.HypoPerLogdetTri(8),
+             M.HypoRootdetTri(7), M.EpiNormEucl(3), M.HypoPerLogdetTri(5, use_dual=True)]
+    I = inst.synthetic("mixsym", 12 + p, p, cones, seed=13)
+    dev = iterate_solver(I, DevSym())
+    ora = iterate_solver(I, OraSym())
+    try:
+        assert dev.syssolver.fact_kind == 1
+        rng = np.random.default_rng(9)
+        for _ in range(3):
+            rhs = Point(I.model)
+            rhs.vec[:] = rng.standard_normal(rhs.vec.size)
+            sd, so = Point(I.model), Point(I.model)
+            dev.syssolver.solve_system(dev, sd, rhs)
+            ora.syssolver.solve_system(ora, so, rhs)
+            assert rel(sd.vec, so.vec) <= DIR_TOL
+            ro = Point(I.model)
+            ora.syssolver.apply_lhs(ora, sd, ro)
+            assert rel(ro.vec, rhs.vec) <= 1e-8
+    finally:
+        dev.syssolver.free_memory()
+
+
+def test_explicit_hess_blocks_match_oracle():
+    cones = [M.Nonnegative(3), M.EpiNormEucl(5), M.PosSemidefTri(6), M.HypoPerLogdetTri(8),
+             M.HypoRootdetTri(7)]
+    I = inst.synthetic("blocks", 4, 0, cones, seed=14)
+    from hypatia_b200.cones import DeviceConeBlock
+    from oracle.cones import OracleConeBlock
+    dev, ora = DeviceConeBlock(I.model), OracleConeBlock(I.model)
+    prim, dual = I.point.primal_dual(None)
+    dev.load_point(prim, dual, 0.7)
+    ora.load_point(prim, dual, 0.7)
+    for Hd, Hid, ck in zip(dev.hess(), dev.inv_hess(), ora.cones):
+        Ho, Hio = np.asarray(ck.hess()), np.asarray(ck.inv_hess())
+        if Ho.ndim == 1:                       # the oracle keeps the orthant's Hessian as a diagonal
+            Ho, Hio = np.diag(Ho), np.diag(Hio)
+        assert rel(Hd, Ho) <= 1e-10 and rel(Hid, Hio) <= 1e-10
+        assert rel(Hd @ Hid, np.eye(Hd.shape[0])) <= 1e-8        # cone.jl:73-75
+    dev.free()
