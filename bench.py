@@ -293,6 +293,9 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # keep stdout to the single JSON line: NCCL prints its version banner there at VERSION/INFO
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=device)
     from hypatia_b200 import capi
     from hypatia_b200.cones import DeviceConeBlock
