@@ -312,6 +312,7 @@ def run_ours(args):
         ctx.comm_init(rank, world, uid[0])
     lo, hi = I["cone_range"]
     ctx.load_model(model, G_local=I["G_local"], cone_lo=lo, cone_hi=hi)
+    ctx.set_syrk_mode(1 if args.syrk == "i8" else 0)
     I["G_local"] = None
     cones = DeviceConeBlock(model, ctx=ctx)
 
@@ -480,6 +481,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--syrk", default=os.environ.get("HYP_SCHUR_SYRK", "dmma"), choices=["dmma", "i8"],
+                    help="Schur SYRK kernel: FP64 DMMA or FP64-accurate digit slicing on the int8 tcgen05 pipe")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -42,6 +42,7 @@ _SIGS = {
     "hyp_cones_proxsqr": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]),
     "hyp_cones_hess_blocks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "hyp_set_syssolver": (C.c_int, [C.c_void_p, C.c_int]),
+    "hyp_set_syrk_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "hyp_set_mu_tau": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "hyp_update_lhs": (C.c_int, [C.c_void_p, c_ip]),
     "hyp_solve_subsystem3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -62,6 +63,12 @@ _SIGS = {
     "hyp_test_potrs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "hyp_test_gemv": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
                                 C.c_void_p, C.c_double, C.c_double, C.c_void_p]),
+    "hyp_test_i8_gemm_tn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
+                                      C.c_int64, C.c_int64, C.c_void_p, C.c_int64]),
+    "hyp_test_ozaki_slices": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int,
+                                        C.c_void_p, C.c_void_p]),
+    "hyp_test_ozaki_syrk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
+                                      C.c_int64]),
     "hyp_test_ldlt_solve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, c_ip]),
 }
 
@@ -231,6 +238,9 @@ class Context:
     # ---- system solver ----
     def set_syssolver(self, kind: int):
         self.check(self.lib.hyp_set_syssolver(self.h, int(kind)), "hyp_set_syssolver")
+
+    def set_syrk_mode(self, mode: int):
+        self.check(self.lib.hyp_set_syrk_mode(self.h, int(mode)), "hyp_set_syrk_mode")
 
     def set_mu_tau(self, mu, tau):
         self.check(self.lib.hyp_set_mu_tau(self.h, float(mu), float(tau)), "hyp_set_mu_tau")

@@ -157,6 +157,11 @@ struct hyp_ctx {
     double* d_ldl_work = nullptr;      // LDL' workspace
     int fact_kind = 0;
     double mu = 1.0, tau_bar = 1.0;
+    // ---- Schur SYRK on tcgen05 (ozaki.cu) ----
+    int syrk_mode = 0;                 // 0: FP64 DMMA (syrk.cu), 1: sliced int8 on tcgen05 (ozaki.cu)
+    int8_t* d_digits = nullptr;        // 8 x ldd x nmp digit slices of HG
+    int* d_expo = nullptr;             // nmp column exponents
+    int64_t ldd = 0;
     // ---- SymIndefDense variant (symindef.jl:203-271) ----
     int solver_kind = 0;               // 0 QRCholDense, 1 SymIndefDense
     int64_t ld3 = 0;                   // leading dim of the (n+p+q)^2 matrices
@@ -272,6 +277,12 @@ void hyp_gemm_tn_grouped(hyp_ctx* ctx, const double* P, int64_t ldp, const doubl
 void hyp_gemm_simple(hyp_ctx* ctx, bool transA, bool transB, int64_t M, int64_t N, int64_t Kd,
                      const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                      int64_t ldc);
+
+// ---- ozaki.cu ----
+void hyp_ozaki_slice(hyp_ctx* ctx, const double* A, int64_t lda, int64_t K, int64_t ncols, int8_t* digits,
+                     int64_t ldd, int64_t slice_stride, int* expo);
+void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t slice_stride, const int* expo,
+                    int64_t K, int64_t ncols, double* C, int64_t ldc, double alpha, double beta);
 
 // ---- chol.cu ----
 // in-place blocked upper Cholesky; d_dinv receives the inverted 128 x 128 diagonal blocks

@@ -129,6 +129,8 @@ void free_model(hyp_ctx* ctx) {
     dfree(ctx->d_ipiv);
     dfree(ctx->d_ldl_work);
     dfree(ctx->d_flags);
+    dfree(ctx->d_digits);
+    dfree(ctx->d_expo);
     dfree(ctx->d_L3);
     dfree(ctx->d_F3);
     dfree(ctx->d_row_cone);
@@ -469,7 +471,18 @@ int update_lhs_fact(hyp_ctx* ctx) {
             hyp_build_pg(ctx);
             P = ctx->d_PG;
         }
-        if (ctx->qloc > 0)
+        if (ctx->qloc > 0 && ctx->syrk_mode == 1 && !ctx->d_PG) {
+            // FP64-accurate SYRK on the int8 tensor pipe (tcgen05): slice HG, multiply digit pairs
+            if (!ctx->d_digits) {
+                ctx->ldd = round_up(std::max<int64_t>(ctx->qloc, 16), 16);
+                dalloc(&ctx->d_digits, 8 * ctx->ldd * nmp);
+                dalloc(&ctx->d_expo, nmp);
+            }
+            hyp_ozaki_slice(ctx, ctx->d_HG, ctx->ldg, ctx->qloc, nmp, ctx->d_digits, ctx->ldd, ctx->ldd * nmp,
+                            ctx->d_expo);
+            hyp_ozaki_syrk(ctx, ctx->d_digits, ctx->ldd, ctx->ldd * nmp, ctx->d_expo, ctx->qloc, nmp, ctx->d_S,
+                           ctx->lds, 1.0, 0.0);
+        } else if (ctx->qloc > 0)
             hyp_atb_upper(ctx, P, ctx->ldg, ctx->d_HG, ctx->ldg, ctx->qloc, nmp, ctx->d_S, ctx->lds, 1.0, 0.0);
         else
             CUDA_TRY(cudaMemsetAsync(ctx->d_S, 0, (size_t)ctx->lds * nmp * 8, ctx->stream));
@@ -590,6 +603,8 @@ void symindef_setup(hyp_ctx* ctx) {
     if (ctx->nranks > 1) throw HypError{"SymIndefDense is single-rank only"};
     const int64_t n = ctx->n, p = ctx->p, q = ctx->q, N3 = n + p + q;
     ctx->ld3 = round_up(std::max<int64_t>(N3, 2), 2);
+    dfree(ctx->d_digits);
+    dfree(ctx->d_expo);
     dfree(ctx->d_L3);
     dfree(ctx->d_F3);
     dalloc(&ctx->d_L3, ctx->ld3 * std::max<int64_t>(N3, 1));
@@ -706,6 +721,7 @@ hyp_ctx* hyp_create(int device) {
     }
     hyp_ctx* ctx = new hyp_ctx();
     ctx->device = device;
+    if (const char* e = getenv("HYP_SCHUR_SYRK")) ctx->syrk_mode = (strcmp(e, "i8") == 0) ? 1 : 0;
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx;
@@ -904,6 +920,15 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         CUDA_TRY(cudaDeviceSynchronize());
         ctx->model_loaded = true;
+        return 0;
+    });
+}
+
+int hyp_set_syrk_mode(hyp_ctx* ctx, int mode) {
+    return guarded(ctx, [&] {
+        if (mode != 0 && mode != 1) throw HypError{"hyp_set_syrk_mode: 0 = FP64 DMMA, 1 = sliced int8 tcgen05"};
+        ctx->syrk_mode = mode;
+        ctx->lhs_ready = false;
         return 0;
     });
 }

@@ -1,0 +1,671 @@
+// FP64-accurate Schur SYRK on the 5th-generation tensor cores (tcgen05, kind::i8) by error-free
+// slicing ("Ozaki scheme").  EXPERIMENTAL in round 1: building blocks + unit-test entry points;
+// the product path (syrk.cu, FP64 DMMA) does not depend on this file.
+//
+// Why: tcgen05.mma has no f64 kind, and the FP64 DMMA pipe is saturated by syrk.cu (96 % active,
+// 34 TFLOP/s).  The only way past that roofline is to run the contraction on the int8 pipe
+// (4.5 POP/s dense): every column of the K-major operand is scaled by a power of two and cut into
+// S = 8 signed 7-bit digits  a = 2^e * sum_s 2^-(6 + 7 s) d_s,  d_s in [-64, 64]  (int8 matrices);
+// the 36 digit-pair products with s + t <= 7 are exact in int32 (|sum| <= K * 2^12, K <= 2^15 per
+// launch) and are recombined in FP64:  C_ij = 2^(e_i + e_j) * sum_d 2^-(12 + 7 d) * sum_{s+t=d} (D_s' D_t)_ij.
+//
+// This file: (1) column scaling + slicing kernels, (2) a TMA + tcgen05 int8 TN GEMM
+// (C_int32 = A' B, both operands K-major, SWIZZLE_128B, accumulator in TMEM), (3) a reference
+// recombination used by the tests.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TM = 128, TN = 128;          // output tile
+constexpr int TKB = 128;                   // k bytes per stage (one 128-byte swizzle row)
+constexpr int I8_STAGES = 4;
+constexpr int I8_TILE_BYTES = TM * TKB;    // 16 KB
+constexpr int I8_STAGE_BYTES = 2 * I8_TILE_BYTES;
+constexpr int I8_THREADS = 6 * 32;         // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int I8_SMEM = I8_STAGES * I8_STAGE_BYTES + 1024 + 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address
+// >> 4 in bits [0,14), leading byte offset (unused for swizzled K-major: 1) in [16,30), stride byte
+// offset (8-row group pitch = 1024 B) >> 4 in [32,46), version 1 in [46,48), layout type
+// SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// instruction descriptor, kind::i8: D = S32, A = B = signed int8, both K-major, M = 128, N = 128
+__host__ __device__ constexpr uint32_t make_idesc_i8(int M, int N) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+
+// C (int32, ldc) [tile] = A' B over k in [0, K): A: K x M, B: K x N int8, K-major.
+// One CTA per 128 x 128 output tile.
+__global__ void __launch_bounds__(I8_THREADS, 1)
+i8_gemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int nkb,
+                  int64_t M, int64_t N, int32_t* __restrict__ C, int64_t ldc) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint32_t s_tmem;
+    const uint32_t base = smem_u32(smem_raw);
+    const uint32_t tiles = (base + 1023u) & ~1023u;
+    const uint32_t bar_full = tiles + I8_STAGES * I8_STAGE_BYTES;
+    const uint32_t bar_empty = bar_full + I8_STAGES * 8;
+    const uint32_t bar_done = bar_empty + I8_STAGES * 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tm = blockIdx.x, tn = blockIdx.y;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < I8_STAGES; s++) {
+            mbar_init(bar_full + s * 8, 1);
+            mbar_init(bar_empty + s * 8, 1);
+        }
+        mbar_init(bar_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        // 128 TMEM columns for the 128 x 128 int32 accumulator
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                     "r"(128));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem_acc = s_tmem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < nkb; kb++) {
+                mbar_wait(bar_empty + stage * 8, phase ^ 1u);
+                const uint32_t full = bar_full + stage * 8;
+                mbar_expect_tx(full, I8_STAGE_BYTES);
+                const uint32_t dst = tiles + stage * I8_STAGE_BYTES;
+                tma_load_2d(dst, &mapA, kb * TKB, tm * TM, full);
+                tma_load_2d(dst + I8_TILE_BYTES, &mapB, kb * TKB, tn * TN, full);
+                if (++stage == I8_STAGES) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_i8(TM, TN);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < nkb; kb++) {
+                mbar_wait(bar_full + stage * 8, phase);
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                const uint32_t sa = tiles + stage * I8_STAGE_BYTES;
+                const uint32_t sb = sa + I8_TILE_BYTES;
+#pragma unroll
+                for (int k = 0; k < TKB / 32; k++) {
+                    // advance 32 bytes along K inside the 128-byte swizzle row
+                    const uint64_t ad = make_desc_sw128(sa + k * 32);
+                    const uint64_t bd = make_desc_sw128(sb + k * 32);
+                    umma_i8(tmem_acc, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(bar_empty + stage * 8);     // frees the stage when the MMAs retire
+                if (++stage == I8_STAGES) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+            umma_commit(bar_done);
+        }
+    } else {
+        // epilogue: warp w may touch TMEM lanes 32 * (w % 4) .. + 31
+        mbar_wait(bar_done, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        const int lg = warp & 3;
+        const int64_t row = (int64_t)tm * TM + lg * 32 + lane;
+#pragma unroll 1
+        for (int c0 = 0; c0 < TN; c0 += 32) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_acc + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+                  "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+                  "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+                  "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < M) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const int64_t col = (int64_t)tn * TN + c0 + j;
+                    if (col < N) C[row + col * ldc] = (int32_t)v[j];
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;");
+    }
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(128));
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+        if (!p || qres != cudaDriverEntryPointSuccess) throw HypError{"cuTensorMapEncodeTiled not available"};
+        fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+void make_map_i8(CUtensorMap* map, const int8_t* base, int64_t K, int64_t cols, int64_t ld) {
+    if (((uintptr_t)base & 15) || (ld & 15)) throw HypError{"int8 operand must be 16-byte aligned with ld % 16 == 0"};
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)cols};
+    cuuint64_t strides[1] = {(cuuint64_t)ld};
+    cuuint32_t box[2] = {TKB, TM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)base, dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw HypError{"cuTensorMapEncodeTiled (int8) failed"};
+}
+
+// ---- slicing: column exponents and the S signed 7-bit digit matrices ----------------------------
+__global__ void colmax_kernel(int64_t K, int64_t ncols, const double* __restrict__ A, int64_t lda,
+                              int* __restrict__ expo) {
+    // expo[j] = smallest e with max_k |A[k, j]| < 2^e  (0 for an all-zero column)
+    __shared__ double sm[8];
+    const int64_t j = blockIdx.x;
+    if (j >= ncols) return;
+    const double* col = A + j * lda;
+    double mx = 0.0;
+    for (int64_t k = threadIdx.x; k < K; k += blockDim.x) mx = fmax(mx, fabs(col[k]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) mx = fmax(mx, sm[w]);
+        int e = 0;
+        if (mx > 0.0) {
+            frexp(mx, &e);          // mx = f * 2^e, f in [0.5, 1)  =>  mx < 2^e
+        }
+        expo[j] = e;
+    }
+}
+
+// D[s][k + j * ldd] = s-th signed digit of A[k, j] * 2^-expo[j].  A thread cuts 8 consecutive rows
+// and stores one packed 8-byte word per slice (ldd is a multiple of 16, so the words are aligned).
+__global__ void slice_kernel(int64_t K, int64_t ncols, const double* __restrict__ A, int64_t lda,
+                             const int* __restrict__ expo, int nslices, int8_t* __restrict__ D, int64_t ldd,
+                             int64_t slice_stride) {
+    const int64_t K8 = (K + 7) / 8;
+    for (int64_t j = blockIdx.y; j < ncols; j += gridDim.y) {
+        const double sc = ldexp(1.0, 6 - expo[j]);
+        const double* col = A + j * lda;
+        for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < K8;
+             g += (int64_t)gridDim.x * blockDim.x) {
+            double r[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int64_t k = g * 8 + u;
+                r[u] = (k < K) ? col[k] * sc : 0.0;          // |r| < 64
+            }
+            for (int s = 0; s < nslices; s++) {
+                uint64_t w = 0;
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const double d = rint(r[u]);
+                    w |= (uint64_t)(uint8_t)(int8_t)(int)d << (8 * u);
+                    r[u] = (r[u] - d) * 128.0;               // exact: |r - d| <= 0.5
+                }
+                *reinterpret_cast<uint64_t*>(D + s * slice_stride + g * 8 + j * ldd) = w;
+            }
+        }
+    }
+}
+
+}  // namespace
+namespace {
+// =====================================================================================================
+// Fused FP64-by-slicing SYRK:  C(upper 128-tiles) = alpha * A' A + beta * C,  A given by its digit slices.
+// Per output tile two passes over K, each with four int32 accumulators (128 x 128 each) filling the
+// 512 TMEM columns: pass 0 collects the digit pairs with s + t = 0..3, pass 1 those with s + t = 4..7.
+// Stage = one MMA K step (32 bytes of k): up to 16 SWIZZLE_32B tiles of 128 rows x 32 B.
+// =====================================================================================================
+constexpr int OZ_S = 8;                       // digit slices
+constexpr int OZ_KB = 32;                     // k bytes per stage = MMA K
+constexpr int OZ_TILE = TM * OZ_KB;           // 4 KB
+constexpr int OZ_STAGE = 2 * OZ_S * OZ_TILE;  // 64 KB: A-side slices then B-side slices
+constexpr int OZ_STAGES = 3;
+constexpr int OZ_SMEM = OZ_STAGES * OZ_STAGE + 1024 + 256;
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                            uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// K-major SWIZZLE_32B descriptor: rows of 32 B, 8-row groups 256 B apart
+__device__ __forceinline__ uint64_t make_desc_sw32(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(256 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(I8_THREADS, 1)
+ozaki_syrk_kernel(const __grid_constant__ CUtensorMap mapD, const int4* __restrict__ tiles, int n_tiles,
+                  int k0, int nkb, const int* __restrict__ expo, int64_t ncols, double* __restrict__ C, int64_t ldc,
+                  double alpha, double beta) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint32_t s_tmem;
+    const uint32_t base = smem_u32(smem_raw);
+    const uint32_t stg = (base + 1023u) & ~1023u;
+    const uint32_t bar_full = stg + OZ_STAGES * OZ_STAGE;
+    const uint32_t bar_empty = bar_full + OZ_STAGES * 8;
+    const uint32_t bar_tfull = bar_empty + OZ_STAGES * 8;
+    const uint32_t bar_tempty = bar_tfull + 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < OZ_STAGES; s++) {
+            mbar_init(bar_full + s * 8, 1);
+            mbar_init(bar_empty + s * 8, 1);
+        }
+        mbar_init(bar_tfull, 1);
+        mbar_init(bar_tempty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                     "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem0 = s_tmem;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int4 tile = tiles[t];
+                const bool single = tile.x == tile.y;
+                for (int pass = 0; pass < 2; pass++) {
+                    const int ns = pass == 0 ? 4 : OZ_S;          // slices needed on each side
+                    const uint32_t bytes = (single ? ns : 2 * ns) * OZ_TILE;
+                    for (int kb = 0; kb < nkb; kb++) {
+                        mbar_wait(bar_empty + stage * 8, phase ^ 1u);
+                        const uint32_t full = bar_full + stage * 8;
+                        mbar_expect_tx(full, bytes);
+                        const uint32_t dst = stg + stage * OZ_STAGE;
+                        const int kc = k0 + kb * OZ_KB;
+                        for (int s = 0; s < ns; s++) {
+                            tma_load_3d(dst + s * OZ_TILE, &mapD, kc, tile.x * TM, s, full);
+                            if (!single) tma_load_3d(dst + (OZ_S + s) * OZ_TILE, &mapD, kc, tile.y * TN, s, full);
+                        }
+                        if (++stage == OZ_STAGES) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_i8(TM, TN);
+            int stage = 0;
+            uint32_t phase = 0, item = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int4 tile = tiles[t];
+                const bool single = tile.x == tile.y;
+                for (int pass = 0; pass < 2; pass++, item++) {
+                    // the epilogue must have drained the accumulators of the previous item
+                    if (item > 0) mbar_wait(bar_tempty, (item - 1) & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    const int d0 = pass * 4;
+                    for (int kb = 0; kb < nkb; kb++) {
+                        mbar_wait(bar_full + stage * 8, phase);
+                        asm volatile("tcgen05.fence::after_thread_sync;");
+                        const uint32_t sa = stg + stage * OZ_STAGE;
+                        const uint32_t sb = single ? sa : sa + OZ_S * OZ_TILE;
+                        const int smax = pass == 0 ? 3 : OZ_S - 1;
+                        for (int s = 0; s <= smax; s++) {
+                            const uint64_t ad = make_desc_sw32(sa + s * OZ_TILE);
+                            // t ranges over d0 - s .. d0 + 3 - s, clipped to [0, 7]
+                            int tlo = d0 - s, thi = d0 + 3 - s;
+                            if (tlo < 0) tlo = 0;
+                            if (thi > OZ_S - 1) thi = OZ_S - 1;
+                            for (int tt = tlo; tt <= thi; tt++) {
+                                const uint64_t bd = make_desc_sw32(sb + tt * OZ_TILE);
+                                const int g = s + tt - d0;
+                                // group g is first touched by the pair with the smallest s: s = max(0, d0 + g - 7)
+                                const int sfirst = (d0 + g - (OZ_S - 1)) > 0 ? (d0 + g - (OZ_S - 1)) : 0;
+                                const uint32_t accum = (kb > 0 || s > sfirst) ? 1u : 0u;
+                                umma_i8(tmem0 + (uint32_t)(g * TN), ad, bd, idesc, accum);
+                            }
+                        }
+                        umma_commit(bar_empty + stage * 8);
+                        if (++stage == OZ_STAGES) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                    umma_commit(bar_tfull);
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: int32 groups -> FP64, scaled, into C =====
+        const int lg = warp & 3;
+        uint32_t item = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int4 tile = tiles[t];
+            const int64_t row = (int64_t)tile.x * TM + lg * 32 + lane;
+            const double rs = (row < ncols) ? alpha * ldexp(1.0, expo[row]) : 0.0;
+            for (int pass = 0; pass < 2; pass++, item++) {
+                mbar_wait(bar_tfull, item & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                const int d0 = pass * 4;
+                const double g0 = ldexp(1.0, -(12 + 7 * d0)), g1 = ldexp(1.0, -(12 + 7 * (d0 + 1))),
+                             g2 = ldexp(1.0, -(12 + 7 * (d0 + 2))), g3 = ldexp(1.0, -(12 + 7 * (d0 + 3)));
+#pragma unroll 1
+                for (int c0 = 0; c0 < TN; c0 += 16) {
+                    uint32_t v[4][16];
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        const uint32_t taddr = tmem0 + ((uint32_t)(lg * 32) << 16) + (uint32_t)(g * TN + c0);
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                            : "=r"(v[g][0]), "=r"(v[g][1]), "=r"(v[g][2]), "=r"(v[g][3]), "=r"(v[g][4]),
+                              "=r"(v[g][5]), "=r"(v[g][6]), "=r"(v[g][7]), "=r"(v[g][8]), "=r"(v[g][9]),
+                              "=r"(v[g][10]), "=r"(v[g][11]), "=r"(v[g][12]), "=r"(v[g][13]), "=r"(v[g][14]),
+                              "=r"(v[g][15])
+                            : "r"(taddr));
+                    }
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (row < ncols) {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            const int64_t col = (int64_t)tile.y * TN + c0 + j;
+                            if (col < ncols) {
+                                // smallest terms first
+                                double x = (double)(int32_t)v[3][j] * g3;
+                                x += (double)(int32_t)v[2][j] * g2;
+                                x += (double)(int32_t)v[1][j] * g1;
+                                x += (double)(int32_t)v[0][j] * g0;
+                                x *= rs * ldexp(1.0, expo[col]);
+                                double* cp = C + row + col * ldc;
+                                if (pass == 0) *cp = (beta == 0.0) ? x : (x + beta * *cp);
+                                else *cp += x;
+                            }
+                        }
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty);
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem0), "r"(512));
+    }
+}
+
+void make_map_digits(CUtensorMap* map, const int8_t* base, int64_t K, int64_t cols, int64_t ldd,
+                     int64_t slice_stride, int nslices) {
+    if (((uintptr_t)base & 15) || (ldd & 15) || (slice_stride & 15))
+        throw HypError{"digit slices must be 16-byte aligned with ld % 16 == 0"};
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)cols, (cuuint64_t)nslices};
+    cuuint64_t strides[2] = {(cuuint64_t)ldd, (cuuint64_t)slice_stride};
+    cuuint32_t box[3] = {OZ_KB, TM, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw HypError{"cuTensorMapEncodeTiled (digit slices) failed"};
+}
+
+}  // namespace
+
+// ---- unit-test entry points ----------------------------------------------------------------------
+extern "C" int hyp_test_i8_gemm_tn(hyp_ctx* ctx, const int8_t* A, int64_t lda, const int8_t* B, int64_t ldb,
+                                   int64_t K, int64_t M, int64_t N, int32_t* C, int64_t ldc) {
+    if (!ctx) return -1;
+    try {
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        // device copies with 16-byte aligned leading dimensions
+        const int64_t la = round_up(std::max<int64_t>(K, 16), 16), lb = la;
+        int8_t *dA = nullptr, *dB = nullptr;
+        int32_t* dC = nullptr;
+        CUDA_TRY(cudaMalloc(&dA, (size_t)la * M));
+        CUDA_TRY(cudaMalloc(&dB, (size_t)lb * N));
+        CUDA_TRY(cudaMalloc(&dC, (size_t)M * N * 4));
+        CUDA_TRY(cudaMemsetAsync(dA, 0, (size_t)la * M, ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(dB, 0, (size_t)lb * N, ctx->stream));
+        CUDA_TRY(cudaMemcpy2DAsync(dA, la, A, lda, K, M, cudaMemcpyDefault, ctx->stream));
+        CUDA_TRY(cudaMemcpy2DAsync(dB, lb, B, ldb, K, N, cudaMemcpyDefault, ctx->stream));
+        CUtensorMap mapA, mapB;
+        make_map_i8(&mapA, dA, K, M, la);
+        make_map_i8(&mapB, dB, K, N, lb);
+        static bool attr = false;
+        if (!attr) {
+            CUDA_TRY(cudaFuncSetAttribute(i8_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
+            attr = true;
+        }
+        dim3 grid(ceil_div(M, TM), ceil_div(N, TN));
+        i8_gemm_tn_kernel<<<grid, I8_THREADS, I8_SMEM, ctx->stream>>>(mapA, mapB, ceil_div(K, TKB), M, N, dC, M);
+        ctx->launches++;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpy2DAsync(C, ldc * 4, dC, M * 4, M * 4, N, cudaMemcpyDefault, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        cudaFree(dA);
+        cudaFree(dB);
+        cudaFree(dC);
+        return 0;
+    } catch (HypError& e) {
+        ctx->last_error = e.msg;
+        cudaGetLastError();
+        return -1;
+    }
+}
+
+// digits (nslices x K x ncols int8, host or device) and exponents of a K x ncols FP64 matrix
+extern "C" int hyp_test_ozaki_slices(hyp_ctx* ctx, const double* A, int64_t lda, int64_t K, int64_t ncols,
+                                     int nslices, int8_t* digits, int* expo) {
+    if (!ctx) return -1;
+    try {
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        double* dA = nullptr;
+        int8_t* dD = nullptr;
+        int* dE = nullptr;
+        CUDA_TRY(cudaMalloc(&dA, (size_t)K * ncols * 8));
+        const int64_t ldd = round_up(std::max<int64_t>(K, 16), 16);
+        CUDA_TRY(cudaMalloc(&dD, (size_t)nslices * ldd * ncols));
+        CUDA_TRY(cudaMalloc(&dE, (size_t)ncols * 4));
+        CUDA_TRY(cudaMemcpy2DAsync(dA, K * 8, A, lda * 8, K * 8, ncols, cudaMemcpyDefault, ctx->stream));
+        colmax_kernel<<<(unsigned)ncols, 256, 0, ctx->stream>>>(K, ncols, dA, K, dE);
+        dim3 grid(std::max(1, std::min(ceil_div(K, 2048), 64)), (unsigned)std::min<int64_t>(ncols, 65535));
+        slice_kernel<<<grid, 256, 0, ctx->stream>>>(K, ncols, dA, K, dE, nslices, dD, ldd, ldd * ncols);
+        ctx->launches += 2;
+        CUDA_TRY(cudaGetLastError());
+        for (int s = 0; s < nslices; s++)
+            CUDA_TRY(cudaMemcpy2DAsync(digits + (size_t)s * K * ncols, K, dD + (size_t)s * ldd * ncols, ldd, K, ncols,
+                                       cudaMemcpyDefault, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(expo, dE, (size_t)ncols * 4, cudaMemcpyDefault, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        cudaFree(dA);
+        cudaFree(dD);
+        cudaFree(dE);
+        return 0;
+    } catch (HypError& e) {
+        ctx->last_error = e.msg;
+        cudaGetLastError();
+        return -1;
+    }
+}
+
+// ---- product entry points -------------------------------------------------------------------------
+// digits / exponents of the K x ncols FP64 matrix A (device) into caller-provided device buffers
+void hyp_ozaki_slice(hyp_ctx* ctx, const double* A, int64_t lda, int64_t K, int64_t ncols, int8_t* digits,
+                     int64_t ldd, int64_t slice_stride, int* expo) {
+    if (K <= 0 || ncols <= 0) return;
+    colmax_kernel<<<(unsigned)ncols, 256, 0, ctx->stream>>>(K, ncols, A, lda, expo);
+    dim3 grid(std::max(1, std::min(ceil_div(K, 2048), 32)), (unsigned)std::min<int64_t>(ncols, 65535));
+    slice_kernel<<<grid, 256, 0, ctx->stream>>>(K, ncols, A, lda, expo, OZ_S, digits, ldd, slice_stride);
+    ctx->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+}
+
+// C(upper 128-tiles) = alpha * A' A + beta * C from the digit slices of A
+void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t slice_stride, const int* expo,
+                    int64_t K, int64_t ncols, double* C, int64_t ldc, double alpha, double beta) {
+    if (K <= 0 || ncols <= 0) return;
+    static bool attr = false;
+    if (!attr) {
+        CUDA_TRY(cudaFuncSetAttribute(ozaki_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
+        attr = true;
+    }
+    // upper-triangular tile list (8-tile row groups), cached per size
+    static std::vector<std::pair<int, std::pair<int4*, int>>> cache;
+    const int nt = ceil_div(ncols, TM);
+    int4* d_tiles = nullptr;
+    int n_tiles = 0;
+    for (auto& e : cache)
+        if (e.first == nt) {
+            d_tiles = e.second.first;
+            n_tiles = e.second.second;
+        }
+    if (!d_tiles) {
+        std::vector<int4> tl;
+        const int GROUP = 8;
+        for (int gi = 0; gi < nt; gi += GROUP)
+            for (int tj = gi; tj < nt; tj++)
+                for (int ti = gi; ti < std::min(gi + GROUP, tj + 1); ti++) tl.push_back(make_int4(ti, tj, 0, 0));
+        n_tiles = (int)tl.size();
+        CUDA_TRY(cudaMalloc(&d_tiles, tl.size() * sizeof(int4)));
+        CUDA_TRY(cudaMemcpyAsync(d_tiles, tl.data(), tl.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        cache.push_back({nt, {d_tiles, n_tiles}});
+    }
+    CUtensorMap mapD;
+    make_map_digits(&mapD, digits, K, ncols, ldd, slice_stride, OZ_S);
+    // int32 accumulators hold sums of <= 8 pair products of <= 2^12 each over the chunk: chunk <= 2^15 rows
+    const int64_t CHUNK = 32768;
+    const int grid = std::min(n_tiles, ctx->sm_count);
+    for (int64_t k0 = 0; k0 < K; k0 += CHUNK) {
+        const int64_t klen = std::min(CHUNK, K - k0);
+        ozaki_syrk_kernel<<<grid, I8_THREADS, OZ_SMEM, ctx->stream>>>(mapD, d_tiles, n_tiles, (int)k0,
+                                                                     ceil_div(klen, OZ_KB), expo, ncols, C, ldc, alpha,
+                                                                     k0 == 0 ? beta : 1.0);
+        ctx->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+}
+
+// C = A' A (upper 128-tiles) for a host/device FP64 matrix A, through slicing + tcgen05 (unit test)
+extern "C" int hyp_test_ozaki_syrk(hyp_ctx* ctx, const double* A, int64_t lda, int64_t K, int64_t ncols, double* C,
+                                   int64_t ldc) {
+    if (!ctx) return -1;
+    try {
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        const int64_t ldd = round_up(std::max<int64_t>(K, 16), 16);
+        double *dA = nullptr, *dC = nullptr;
+        int8_t* dD = nullptr;
+        int* dE = nullptr;
+        CUDA_TRY(cudaMalloc(&dA, (size_t)K * ncols * 8));
+        CUDA_TRY(cudaMalloc(&dC, (size_t)ncols * ncols * 8));
+        CUDA_TRY(cudaMalloc(&dD, (size_t)OZ_S * ldd * ncols));
+        CUDA_TRY(cudaMalloc(&dE, (size_t)ncols * 4));
+        CUDA_TRY(cudaMemsetAsync(dD, 0, (size_t)OZ_S * ldd * ncols, ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(dC, 0, (size_t)ncols * ncols * 8, ctx->stream));
+        CUDA_TRY(cudaMemcpy2DAsync(dA, K * 8, A, lda * 8, K * 8, ncols, cudaMemcpyDefault, ctx->stream));
+        hyp_ozaki_slice(ctx, dA, K, K, ncols, dD, ldd, ldd * ncols, dE);
+        hyp_ozaki_syrk(ctx, dD, ldd, ldd * ncols, dE, K, ncols, dC, ncols, 1.0, 0.0);
+        CUDA_TRY(cudaMemcpy2DAsync(C, ldc * 8, dC, ncols * 8, ncols * 8, ncols, cudaMemcpyDefault, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        cudaFree(dA);
+        cudaFree(dC);
+        cudaFree(dD);
+        cudaFree(dE);
+        return 0;
+    } catch (HypError& e) {
+        ctx->last_error = e.msg;
+        cudaGetLastError();
+        return -1;
+    }
+}

@@ -108,6 +108,9 @@ int hyp_cones_hess_blocks(hyp_ctx* ctx, double* blocks, int inverse);
  * qrchol.jl:104-257), 1 = SymIndefDenseSystemSolver (symindef.jl:203-271: dense (n+p+q)^2
  * symmetric-indefinite LHS, rook Bunch-Kaufman).  Call after hyp_load_model. */
 int hyp_set_syssolver(hyp_ctx* ctx, int kind);
+/* how the Schur SYRK runs: 0 = FP64 DMMA (mma.sync), 1 = FP64-accurate digit slicing on the int8
+ * tcgen05 pipe (csrc/ozaki.cu).  Default 0, or 1 when the environment has HYP_SCHUR_SYRK=i8. */
+int hyp_set_syrk_mode(hyp_ctx* ctx, int mode);
 /* mu and tau of the current iterate (solver.mu, solver.point.tau[]) used by
  * solve_subsystem4 / solve_system / apply_lhs (common.jl:117,171-175,147) */
 int hyp_set_mu_tau(hyp_ctx* ctx, double mu, double tau_bar);
@@ -155,6 +158,17 @@ int hyp_test_gemv(hyp_ctx* ctx, int trans, int64_t rows, int64_t cols, const dou
  * (device restatement of symm_fact!, dense.jl:164-165); returns info */
 int hyp_test_ldlt_solve(hyp_ctx* ctx, const double* A, int64_t lda, int64_t m, double* x,
                         int* info);
+
+/* experimental tcgen05 (kind::i8) building blocks of the FP64-by-slicing Schur SYRK (csrc/ozaki.cu):
+ * C (int32) = A' B with int8 K-major operands (A: K x M, B: K x N);  signed 7-bit digit slices and
+ * per-column exponents of a K x ncols FP64 matrix */
+int hyp_test_i8_gemm_tn(hyp_ctx* ctx, const int8_t* A, int64_t lda, const int8_t* B, int64_t ldb,
+                        int64_t K, int64_t M, int64_t N, int32_t* C, int64_t ldc);
+int hyp_test_ozaki_slices(hyp_ctx* ctx, const double* A, int64_t lda, int64_t K, int64_t ncols,
+                          int nslices, int8_t* digits, int* expo);
+/* C(upper 128-tiles) = A' A through slicing + tcgen05 (FP64-accurate) */
+int hyp_test_ozaki_syrk(hyp_ctx* ctx, const double* A, int64_t lda, int64_t K, int64_t ncols, double* C,
+                        int64_t ldc);
 
 #ifdef __cplusplus
 }
