@@ -56,7 +56,8 @@ WORKLOADS = {
 
 
 # DRAM traffic of the Schur SYRK launch from the committed `ncu --set full` capture (per launch)
-NCU_TRAFFIC = {"C3": 31.497622e9 + 0.411380e9}
+NCU_TRAFFIC = {"C3": 31.497622e9 + 0.411380e9,                       # FP64 DMMA kernel, one launch
+               "C3:i8": 124.648986e9 + 0.817550e9 + 57.589292e9 + 0.816429e9}   # tcgen05 kernel, both K chunks
 
 
 class PanelModel:
@@ -428,19 +429,43 @@ def run_ours(args):
         return
     peaks = measured_peaks()
     fp64_peak = dgemm_peak_tflops(torch, device)
-    roofline = {"bound": "tensor", "kernel": "atb_upper_kernel (Schur SYRK, TMA + FP64 DMMA)",
-                "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": (achieved / fp64_peak) if achieved else None,
-                "peak_source": "cuBLAS DGEMM 8192^3 measured live in this run (FP64 tensor pipe; "
-                               "MEASURED_PEAKS.json has no FP64 entry)",
-                "peak_bf16_measured": peaks.get("bf16_tflops"),
-                "frac_of_bf16_peak": (achieved / peaks["bf16_tflops"]) if achieved and peaks.get("bf16_tflops") else None,
-                "traffic": NCU_TRAFFIC.get(args.workload) if world == 1 else None,
-                "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, "
-                                "profiles/r01_syrk_schur_ncu_full.txt)",
-                "algorithmic_flops_per_launch": syrk_flops, "avg_launch_ms": syrk_ms,
-                "step_share": syrk_ms / (ms / args.steps) if syrk_ms == syrk_ms else None,
-                "phase_ms": phases}
+    if args.syrk == "i8":
+        # 36 exact int8 digit-pair products per FP64 product (8 slices, s + t <= 7), upper 128-tiles
+        nt = (m + 127) // 128
+        int8_ops = 2.0 * 36 * float(qloc) * 128 * 128 * (nt * (nt + 1) // 2)
+        int8_tops = int8_ops / (syrk_ms * 1e-3) / 1e12 if achieved else None
+        int8_peak = 2.0 * peaks["bf16_tflops"] if peaks.get("bf16_tflops") else None
+        roofline = {"bound": "tensor",
+                    "kernel": "ozaki_syrk_cluster_kernel (Schur SYRK: FP64-accurate digit slicing, tcgen05 kind::i8, "
+                              "TMEM accumulators, 2x2-cluster TMA multicast) + slice_kernel",
+                    "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s (algorithmic FP64)",
+                    "frac": (achieved / fp64_peak) if achieved else None,
+                    "peak_source": "cuBLAS DGEMM 8192^3 measured live in this run = the FP64 tensor (DMMA) roofline; "
+                                   "frac > 1 because the contraction runs as exact int8 products on tcgen05",
+                    "int8_top_s_executed": int8_tops,
+                    "int8_peak_top_s": int8_peak,
+                    "int8_peak_source": "2 x bf16_tflops of MEASURED_PEAKS.json (int8 dense = 2 x bf16 on B200)",
+                    "int8_frac": (int8_tops / int8_peak) if int8_tops and int8_peak else None,
+                    "traffic": NCU_TRAFFIC.get(args.workload + ":i8") if world == 1 else None,
+                    "traffic_unit": "bytes per SYRK (dram__bytes_read.sum + dram__bytes_write.sum over its launches, "
+                                    "profiles/r01_ozaki_cluster_ncu_full.txt)",
+                    "algorithmic_flops_per_launch": syrk_flops, "avg_launch_ms": syrk_ms,
+                    "step_share": syrk_ms / (ms / args.steps) if syrk_ms == syrk_ms else None,
+                    "phase_ms": phases}
+    else:
+        roofline = {"bound": "tensor", "kernel": "atb_upper_kernel (Schur SYRK, TMA + FP64 DMMA)",
+                    "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                    "frac": (achieved / fp64_peak) if achieved else None,
+                    "peak_source": "cuBLAS DGEMM 8192^3 measured live in this run (FP64 tensor pipe; "
+                                   "MEASURED_PEAKS.json has no FP64 entry)",
+                    "peak_bf16_measured": peaks.get("bf16_tflops"),
+                    "frac_of_bf16_peak": (achieved / peaks["bf16_tflops"]) if achieved and peaks.get("bf16_tflops") else None,
+                    "traffic": NCU_TRAFFIC.get(args.workload) if world == 1 else None,
+                    "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, "
+                                    "profiles/r01_syrk_schur_ncu_full.txt)",
+                    "algorithmic_flops_per_launch": syrk_flops, "avg_launch_ms": syrk_ms,
+                    "step_share": syrk_ms / (ms / args.steps) if syrk_ms == syrk_ms else None,
+                    "phase_ms": phases}
     g_bytes = 8.0 * qloc * n
     gemv_ms = phases.get("gemv")
     if gemv_ms:
@@ -463,6 +488,7 @@ def run_ours(args):
             "config": {"workload": f"{args.workload}: {I['desc']}",
                        "unit_of_work": "load_point + update_lhs + 4 x (solve_system + apply_lhs)",
                        "parallelism": f"cone/row-panel sharding over {world} rank(s)",
+                       "schur_syrk": "tcgen05 int8 digit slicing (FP64-accurate)" if args.syrk == "i8" else "FP64 DMMA",
                        "l2": "inputs larger than L2 (G panel %.1f GB, Schur %.2f GB)" % (g_bytes / 1e9, 8e-9 * m * m)},
             "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                                       "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -481,7 +507,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--syrk", default=os.environ.get("HYP_SCHUR_SYRK", "dmma"), choices=["dmma", "i8"],
+    ap.add_argument("--syrk", default=os.environ.get("HYP_SCHUR_SYRK", "i8"), choices=["dmma", "i8"],
                     help="Schur SYRK kernel: FP64 DMMA or FP64-accurate digit slicing on the int8 tcgen05 pipe")
     args = ap.parse_args()
     if args.impl == "reference":

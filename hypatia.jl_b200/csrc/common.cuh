@@ -158,7 +158,7 @@ struct hyp_ctx {
     int fact_kind = 0;
     double mu = 1.0, tau_bar = 1.0;
     // ---- Schur SYRK on tcgen05 (ozaki.cu) ----
-    int syrk_mode = 0;                 // 0: FP64 DMMA (syrk.cu), 1: sliced int8 on tcgen05 (ozaki.cu)
+    int syrk_mode = 1;                 // 0: FP64 DMMA (syrk.cu), 1: sliced int8 on tcgen05 (ozaki.cu)
     int8_t* d_digits = nullptr;        // 8 x ldd x nmp digit slices of HG
     int* d_expo = nullptr;             // nmp column exponents
     int64_t ldd = 0;

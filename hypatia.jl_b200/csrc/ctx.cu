@@ -721,7 +721,8 @@ hyp_ctx* hyp_create(int device) {
     }
     hyp_ctx* ctx = new hyp_ctx();
     ctx->device = device;
-    if (const char* e = getenv("HYP_SCHUR_SYRK")) ctx->syrk_mode = (strcmp(e, "i8") == 0) ? 1 : 0;
+    ctx->syrk_mode = 1;   // default: FP64-accurate digit slicing on tcgen05 (ozaki.cu)
+    if (const char* e = getenv("HYP_SCHUR_SYRK")) ctx->syrk_mode = (strcmp(e, "dmma") == 0) ? 0 : 1;
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx;

@@ -320,9 +320,10 @@ __device__ __forceinline__ uint64_t make_desc_sw32(uint32_t smem_addr) {
 }
 
 __global__ void __launch_bounds__(I8_THREADS, 1)
-ozaki_syrk_kernel(const __grid_constant__ CUtensorMap mapD, const int4* __restrict__ tiles, int n_tiles,
+ozaki_syrk_kernel(const __grid_constant__ CUtensorMap mapD4, const __grid_constant__ CUtensorMap mapD8,
+                  const int4* __restrict__ tiles, int n_tiles,
                   int k0, int nkb, const int* __restrict__ expo, int64_t ncols, double* __restrict__ C, int64_t ldc,
-                  double alpha, double beta) {
+                  double alpha, double beta, int dbg_no_tma) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint32_t s_tmem;
     const uint32_t base = smem_u32(smem_raw);
@@ -361,17 +362,34 @@ ozaki_syrk_kernel(const __grid_constant__ CUtensorMap mapD, const int4* __restri
                 const int4 tile = tiles[t];
                 const bool single = tile.x == tile.y;
                 for (int pass = 0; pass < 2; pass++) {
-                    const int ns = pass == 0 ? 4 : OZ_S;          // slices needed on each side
-                    const uint32_t bytes = (single ? ns : 2 * ns) * OZ_TILE;
-                    for (int kb = 0; kb < nkb; kb++) {
+                    // pass 0: a stage carries TWO k steps of the 4 leading slices (2 x 32 KB);
+                    // pass 1: one k step of all 8 slices (64 KB).  One TMA box per side and k step.
+                    const int nst = pass == 0 ? (nkb + 1) / 2 : nkb;
+                    const uint32_t bytes = pass == 0 ? (single ? 2u : 4u) * 4 * OZ_TILE : (single ? 1u : 2u) * OZ_S * OZ_TILE;
+                    for (int st = 0; st < nst; st++) {
                         mbar_wait(bar_empty + stage * 8, phase ^ 1u);
                         const uint32_t full = bar_full + stage * 8;
+                        if (dbg_no_tma) {   // micro-benchmark of the MMA rate: no loads, stale operands
+                            mbar_arrive(full);
+                            if (++stage == OZ_STAGES) {
+                                stage = 0;
+                                phase ^= 1u;
+                            }
+                            continue;
+                        }
                         mbar_expect_tx(full, bytes);
                         const uint32_t dst = stg + stage * OZ_STAGE;
-                        const int kc = k0 + kb * OZ_KB;
-                        for (int s = 0; s < ns; s++) {
-                            tma_load_3d(dst + s * OZ_TILE, &mapD, kc, tile.x * TM, s, full);
-                            if (!single) tma_load_3d(dst + (OZ_S + s) * OZ_TILE, &mapD, kc, tile.y * TN, s, full);
+                        if (pass == 0) {
+                            for (int h = 0; h < 2; h++) {
+                                const int kc = k0 + (2 * st + h) * OZ_KB;
+                                tma_load_3d(dst + h * (OZ_STAGE / 2), &mapD4, kc, tile.x * TM, 0, full);
+                                if (!single)
+                                    tma_load_3d(dst + h * (OZ_STAGE / 2) + 4 * OZ_TILE, &mapD4, kc, tile.y * TN, 0, full);
+                            }
+                        } else {
+                            const int kc = k0 + st * OZ_KB;
+                            tma_load_3d(dst, &mapD8, kc, tile.x * TM, 0, full);
+                            if (!single) tma_load_3d(dst + OZ_S * OZ_TILE, &mapD8, kc, tile.y * TN, 0, full);
                         }
                         if (++stage == OZ_STAGES) {
                             stage = 0;
@@ -395,25 +413,29 @@ ozaki_syrk_kernel(const __grid_constant__ CUtensorMap mapD, const int4* __restri
                     if (item > 0) mbar_wait(bar_tempty, (item - 1) & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     const int d0 = pass * 4;
-                    for (int kb = 0; kb < nkb; kb++) {
+                    const int nst = pass == 0 ? (nkb + 1) / 2 : nkb;
+                    const int nhalf = pass == 0 ? 2 : 1;
+                    const int smax = pass == 0 ? 3 : OZ_S - 1;
+                    const uint32_t b_off = pass == 0 ? 4 * OZ_TILE : OZ_S * OZ_TILE;
+                    for (int st = 0; st < nst; st++) {
                         mbar_wait(bar_full + stage * 8, phase);
                         asm volatile("tcgen05.fence::after_thread_sync;");
-                        const uint32_t sa = stg + stage * OZ_STAGE;
-                        const uint32_t sb = single ? sa : sa + OZ_S * OZ_TILE;
-                        const int smax = pass == 0 ? 3 : OZ_S - 1;
-                        for (int s = 0; s <= smax; s++) {
-                            const uint64_t ad = make_desc_sw32(sa + s * OZ_TILE);
-                            // t ranges over d0 - s .. d0 + 3 - s, clipped to [0, 7]
-                            int tlo = d0 - s, thi = d0 + 3 - s;
-                            if (tlo < 0) tlo = 0;
-                            if (thi > OZ_S - 1) thi = OZ_S - 1;
-                            for (int tt = tlo; tt <= thi; tt++) {
-                                const uint64_t bd = make_desc_sw32(sb + tt * OZ_TILE);
-                                const int g = s + tt - d0;
-                                // group g is first touched by the pair with the smallest s: s = max(0, d0 + g - 7)
-                                const int sfirst = (d0 + g - (OZ_S - 1)) > 0 ? (d0 + g - (OZ_S - 1)) : 0;
-                                const uint32_t accum = (kb > 0 || s > sfirst) ? 1u : 0u;
-                                umma_i8(tmem0 + (uint32_t)(g * TN), ad, bd, idesc, accum);
+                        for (int h = 0; h < nhalf; h++) {
+                            const uint32_t sa = stg + stage * OZ_STAGE + h * (OZ_STAGE / 2);
+                            const uint32_t sb = single ? sa : sa + b_off;
+                            for (int s = 0; s <= smax; s++) {
+                                const uint64_t ad = make_desc_sw32(sa + s * OZ_TILE);
+                                // t ranges over d0 - s .. d0 + 3 - s, clipped to [0, 7]
+                                int tlo = d0 - s, thi = d0 + 3 - s;
+                                if (tlo < 0) tlo = 0;
+                                if (thi > OZ_S - 1) thi = OZ_S - 1;
+                                for (int tt = tlo; tt <= thi; tt++) {
+                                    const uint64_t bd = make_desc_sw32(sb + tt * OZ_TILE);
+                                    const int g = s + tt - d0;
+                                    // every group of a pass is first touched by the pairs with s = 0
+                                    const uint32_t accum = (st > 0 || h > 0 || s > 0) ? 1u : 0u;
+                                    umma_i8(tmem0 + (uint32_t)(g * TN), ad, bd, idesc, accum);
+                                }
                             }
                         }
                         umma_commit(bar_empty + stage * 8);
@@ -486,13 +508,233 @@ ozaki_syrk_kernel(const __grid_constant__ CUtensorMap mapD, const int4* __restri
     }
 }
 
+// ---- 2 x 2 cluster variant: TMA multicast halves the L2 -> shared-memory traffic ------------------
+// The single-CTA kernel is bound by L2 bandwidth (every CTA streams all digit slices of its row and
+// column panels: ~7.5 TB/s measured).  Here a cluster of 4 CTAs computes the 2 x 2 block of output
+// tiles (2 SI + ri, 2 SJ + rj): the A-side slices of tile row I are needed by both CTAs of that row,
+// the B-side slices of tile column J by both CTAs of that column, so every CTA loads HALF of the
+// slices of each side and multicasts them to its row / column peer.  Stage release is cluster-wide:
+// a CTA refills a stage only after itself, its row peer and its column peer have retired the MMAs
+// that read it (tcgen05.commit multicast onto the three empty barriers).
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                               uint32_t bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(bar), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(I8_THREADS, 1)
+ozaki_syrk_cluster_kernel(const __grid_constant__ CUtensorMap mapD2, const __grid_constant__ CUtensorMap mapD4,
+                          int n_super_rows, int k0, int nkb, const int* __restrict__ expo, int64_t ncols,
+                          double* __restrict__ C, int64_t ldc, double alpha, double beta) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint32_t s_tmem;
+    const uint32_t base = smem_u32(smem_raw);
+    const uint32_t stg = (base + 1023u) & ~1023u;
+    const uint32_t bar_full = stg + OZ_STAGES * OZ_STAGE;
+    const uint32_t bar_empty = bar_full + OZ_STAGES * 8;
+    const uint32_t bar_tfull = bar_empty + OZ_STAGES * 8;
+    const uint32_t bar_tempty = bar_tfull + 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t crank, cid, ncl;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(cid));
+    asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(ncl));
+    const int ri = (int)(crank >> 1), rj = (int)(crank & 1);
+    const uint16_t mask_row = (uint16_t)((1u << (ri * 2)) | (1u << (ri * 2 + 1)));        // same tile row
+    const uint16_t mask_col = (uint16_t)((1u << rj) | (1u << (2 + rj)));                  // same tile column
+    const uint16_t mask_rel = (uint16_t)(mask_row | mask_col);                            // me + both peers
+    const int n_super = n_super_rows * (n_super_rows + 1) / 2;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < OZ_STAGES; s++) {
+            mbar_init(bar_full + s * 8, 1);
+            mbar_init(bar_empty + s * 8, 3);
+        }
+        mbar_init(bar_tfull, 1);
+        mbar_init(bar_tempty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                     "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    cluster_sync_all();                       // every peer's barriers exist before any remote arrival
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem0 = s_tmem;
+
+    // super tile st -> (SI, SJ), SI <= SJ, column-major over the upper triangle
+    auto super_coords = [&](int st, int& SI, int& SJ) {
+        int sj = (int)((sqrtf(8.0f * (float)st + 1.0f) - 1.0f) * 0.5f);
+        while ((sj + 1) * (sj + 2) / 2 <= st) sj++;
+        while (sj * (sj + 1) / 2 > st) sj--;
+        SJ = sj;
+        SI = st - sj * (sj + 1) / 2;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int st = (int)cid; st < n_super; st += (int)ncl) {
+                int SI, SJ;
+                super_coords(st, SI, SJ);
+                const int tI = 2 * SI + ri, tJ = 2 * SJ + rj;
+                for (int pass = 0; pass < 2; pass++) {
+                    const int ns = pass == 0 ? 4 : OZ_S;
+                    const int hs = ns / 2;                                 // slices this CTA loads per side
+                    const int nst = pass == 0 ? (nkb + 1) / 2 : nkb;
+                    const uint32_t bytes = (pass == 0 ? 2u : 1u) * 2u * ns * OZ_TILE;
+                    const CUtensorMap* mp = pass == 0 ? &mapD2 : &mapD4;
+                    for (int it = 0; it < nst; it++) {
+                        mbar_wait(bar_empty + stage * 8, phase ^ 1u);
+                        const uint32_t full = bar_full + stage * 8;
+                        mbar_expect_tx(full, bytes);
+                        const uint32_t dst = stg + stage * OZ_STAGE;
+                        const int nh = pass == 0 ? 2 : 1;
+                        for (int h = 0; h < nh; h++) {
+                            const int kc = k0 + (pass == 0 ? (2 * it + h) : it) * OZ_KB;
+                            const uint32_t d0s = dst + h * (OZ_STAGE / 2);
+                            // A side: my half of the slices of tile row tI -> me and my row peer
+                            tma_load_3d_mc(d0s + (rj * hs) * OZ_TILE, mp, kc, tI * TM, rj * hs, full, mask_row);
+                            // B side: my half of the slices of tile column tJ -> me and my column peer
+                            tma_load_3d_mc(d0s + (ns + ri * hs) * OZ_TILE, mp, kc, tJ * TN, ri * hs, full, mask_col);
+                        }
+                        if (++stage == OZ_STAGES) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_i8(TM, TN);
+            int stage = 0;
+            uint32_t phase = 0, item = 0;
+            for (int st = (int)cid; st < n_super; st += (int)ncl) {
+                for (int pass = 0; pass < 2; pass++, item++) {
+                    if (item > 0) mbar_wait(bar_tempty, (item - 1) & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    const int d0 = pass * 4;
+                    const int nst = pass == 0 ? (nkb + 1) / 2 : nkb;
+                    const int nhalf = pass == 0 ? 2 : 1;
+                    const int smax = pass == 0 ? 3 : OZ_S - 1;
+                    const uint32_t b_off = pass == 0 ? 4 * OZ_TILE : OZ_S * OZ_TILE;
+                    for (int it = 0; it < nst; it++) {
+                        mbar_wait(bar_full + stage * 8, phase);
+                        asm volatile("tcgen05.fence::after_thread_sync;");
+                        for (int h = 0; h < nhalf; h++) {
+                            const uint32_t sa = stg + stage * OZ_STAGE + h * (OZ_STAGE / 2);
+                            const uint32_t sb = sa + b_off;
+                            for (int s = 0; s <= smax; s++) {
+                                const uint64_t ad = make_desc_sw32(sa + s * OZ_TILE);
+                                int tlo = d0 - s, thi = d0 + 3 - s;
+                                if (tlo < 0) tlo = 0;
+                                if (thi > OZ_S - 1) thi = OZ_S - 1;
+                                for (int tt = tlo; tt <= thi; tt++) {
+                                    const uint64_t bd = make_desc_sw32(sb + tt * OZ_TILE);
+                                    const int g = s + tt - d0;
+                                    const uint32_t accum = (it > 0 || h > 0 || s > 0) ? 1u : 0u;
+                                    umma_i8(tmem0 + (uint32_t)(g * TN), ad, bd, idesc, accum);
+                                }
+                            }
+                        }
+                        umma_commit_mc(bar_empty + stage * 8, mask_rel);     // release in all three CTAs
+                        if (++stage == OZ_STAGES) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                    umma_commit(bar_tfull);
+                }
+            }
+        }
+    } else {
+        const int lg = warp & 3;
+        uint32_t item = 0;
+        for (int st = (int)cid; st < n_super; st += (int)ncl) {
+            int SI, SJ;
+            super_coords(st, SI, SJ);
+            const int tI = 2 * SI + ri, tJ = 2 * SJ + rj;
+            const int64_t row = (int64_t)tI * TM + lg * 32 + lane;
+            const bool store = tI <= tJ;                 // the lower tile of a diagonal super tile is not needed
+            const double rs = (row < ncols) ? alpha * ldexp(1.0, expo[row]) : 0.0;
+            for (int pass = 0; pass < 2; pass++, item++) {
+                mbar_wait(bar_tfull, item & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                const int d0 = pass * 4;
+                const double g0 = ldexp(1.0, -(12 + 7 * d0)), g1 = ldexp(1.0, -(12 + 7 * (d0 + 1))),
+                             g2 = ldexp(1.0, -(12 + 7 * (d0 + 2))), g3 = ldexp(1.0, -(12 + 7 * (d0 + 3)));
+#pragma unroll 1
+                for (int c0 = 0; c0 < TN; c0 += 16) {
+                    uint32_t v[4][16];
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        const uint32_t taddr = tmem0 + ((uint32_t)(lg * 32) << 16) + (uint32_t)(g * TN + c0);
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                            : "=r"(v[g][0]), "=r"(v[g][1]), "=r"(v[g][2]), "=r"(v[g][3]), "=r"(v[g][4]),
+                              "=r"(v[g][5]), "=r"(v[g][6]), "=r"(v[g][7]), "=r"(v[g][8]), "=r"(v[g][9]),
+                              "=r"(v[g][10]), "=r"(v[g][11]), "=r"(v[g][12]), "=r"(v[g][13]), "=r"(v[g][14]),
+                              "=r"(v[g][15])
+                            : "r"(taddr));
+                    }
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (store && row < ncols) {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            const int64_t col = (int64_t)tJ * TN + c0 + j;
+                            if (col < ncols) {
+                                double x = (double)(int32_t)v[3][j] * g3;
+                                x += (double)(int32_t)v[2][j] * g2;
+                                x += (double)(int32_t)v[1][j] * g1;
+                                x += (double)(int32_t)v[0][j] * g0;
+                                x *= rs * ldexp(1.0, expo[col]);
+                                double* cp = C + row + col * ldc;
+                                if (pass == 0) *cp = (beta == 0.0) ? x : (x + beta * *cp);
+                                else *cp += x;
+                            }
+                        }
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty);
+            }
+        }
+    }
+    __syncthreads();
+    cluster_sync_all();                       // no CTA leaves while a peer may still signal its barriers
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem0), "r"(512));
+    }
+}
+
 void make_map_digits(CUtensorMap* map, const int8_t* base, int64_t K, int64_t cols, int64_t ldd,
-                     int64_t slice_stride, int nslices) {
+                     int64_t slice_stride, int nslices, int box_slices) {
     if (((uintptr_t)base & 15) || (ldd & 15) || (slice_stride & 15))
         throw HypError{"digit slices must be 16-byte aligned with ld % 16 == 0"};
     cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)cols, (cuuint64_t)nslices};
     cuuint64_t strides[2] = {(cuuint64_t)ldd, (cuuint64_t)slice_stride};
-    cuuint32_t box[3] = {OZ_KB, TM, 1};
+    cuuint32_t box[3] = {OZ_KB, TM, (cuuint32_t)box_slices};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
@@ -622,16 +864,63 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         cache.push_back({nt, {d_tiles, n_tiles}});
     }
-    CUtensorMap mapD;
-    make_map_digits(&mapD, digits, K, ncols, ldd, slice_stride, OZ_S);
+    CUtensorMap mapD2, mapD4, mapD8;
+    make_map_digits(&mapD2, digits, K, ncols, ldd, slice_stride, OZ_S, 2);
+    make_map_digits(&mapD4, digits, K, ncols, ldd, slice_stride, OZ_S, 4);
+    make_map_digits(&mapD8, digits, K, ncols, ldd, slice_stride, OZ_S, 8);
+    static int use_cluster = -1;
+    static int max_clusters = 0;
+    if (use_cluster < 0) {
+        const char* e = getenv("HYP_OZAKI_CLUSTER");
+        use_cluster = (e && e[0] == '0') ? 0 : 1;
+        if (use_cluster) {
+            CUDA_TRY(cudaFuncSetAttribute(ozaki_syrk_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
+            cudaLaunchConfig_t q = {};
+            q.gridDim = dim3(4 * 64);
+            q.blockDim = dim3(I8_THREADS);
+            q.dynamicSmemBytes = OZ_SMEM;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 4;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            q.attrs = at;
+            q.numAttrs = 1;
+            if (cudaOccupancyMaxActiveClusters(&max_clusters, ozaki_syrk_cluster_kernel, &q) != cudaSuccess ||
+                max_clusters < 1) {
+                cudaGetLastError();
+                use_cluster = 0;
+            }
+        }
+    }
     // int32 accumulators hold sums of <= 8 pair products of <= 2^12 each over the chunk: chunk <= 2^15 rows
     const int64_t CHUNK = 32768;
     const int grid = std::min(n_tiles, ctx->sm_count);
     for (int64_t k0 = 0; k0 < K; k0 += CHUNK) {
         const int64_t klen = std::min(CHUNK, K - k0);
-        ozaki_syrk_kernel<<<grid, I8_THREADS, OZ_SMEM, ctx->stream>>>(mapD, d_tiles, n_tiles, (int)k0,
+        if (use_cluster) {
+            const int nsr = (nt + 1) / 2;
+            const int n_super = nsr * (nsr + 1) / 2;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(4 * std::min(n_super, max_clusters));
+            cfg.blockDim = dim3(I8_THREADS);
+            cfg.dynamicSmemBytes = OZ_SMEM;
+            cfg.stream = ctx->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 4;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            CUDA_TRY(cudaLaunchKernelEx(&cfg, ozaki_syrk_cluster_kernel, mapD2, mapD4, nsr, (int)k0,
+                                        (int)ceil_div(klen, OZ_KB), expo, ncols, C, ldc, alpha, k0 == 0 ? beta : 1.0));
+            ctx->launches++;
+            continue;
+        }
+        ozaki_syrk_kernel<<<grid, I8_THREADS, OZ_SMEM, ctx->stream>>>(mapD4, mapD8, d_tiles, n_tiles, (int)k0,
                                                                      ceil_div(klen, OZ_KB), expo, ncols, C, ldc, alpha,
-                                                                     k0 == 0 ? beta : 1.0);
+                                                                     k0 == 0 ? beta : 1.0, getenv("HYP_OZAKI_NO_TMA") ? 1 : 0);
         ctx->launches++;
     }
     CUDA_TRY(cudaGetLastError());

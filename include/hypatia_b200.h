@@ -109,7 +109,8 @@ int hyp_cones_hess_blocks(hyp_ctx* ctx, double* blocks, int inverse);
  * symmetric-indefinite LHS, rook Bunch-Kaufman).  Call after hyp_load_model. */
 int hyp_set_syssolver(hyp_ctx* ctx, int kind);
 /* how the Schur SYRK runs: 0 = FP64 DMMA (mma.sync), 1 = FP64-accurate digit slicing on the int8
- * tcgen05 pipe (csrc/ozaki.cu).  Default 0, or 1 when the environment has HYP_SCHUR_SYRK=i8. */
+ * tcgen05 pipe (csrc/ozaki.cu).  Default 1 (0 when the environment has HYP_SCHUR_SYRK=dmma).  Models
+ * that mix square-root and non-square-root cones (two-operand product) always use mode 0. */
 int hyp_set_syrk_mode(hyp_ctx* ctx, int mode);
 /* mu and tau of the current iterate (solver.mu, solver.point.tau[]) used by
  * solve_subsystem4 / solve_system / apply_lhs (common.jl:117,171-175,147) */

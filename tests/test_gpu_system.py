@@ -58,8 +58,34 @@ def _check_system(I, Ap=None, schur_tol=1e-12):
 
 
 @pytest.mark.parametrize("name,scale", [("C2", 0.05), ("C3", 0.02), ("C3", 0.1)])
-def test_vector_cone_configs(name, scale):
+@pytest.mark.parametrize("syrk", ["i8", "dmma"])
+def test_vector_cone_configs(name, scale, syrk, monkeypatch):
+    # both Schur SYRK kernels: FP64-accurate digit slicing on tcgen05 (default) and FP64 DMMA
+    monkeypatch.setenv("HYP_SCHUR_SYRK", syrk)
     _check_system(inst.config(name, scale))
+
+
+@pytest.mark.parametrize("syrk", ["i8", "dmma"])
+def test_schur_matrix_accuracy_vs_extended_precision(syrk, monkeypatch):
+    """The assembled Schur matrix against a long-double reference of G'HG: both kernels must be at
+    FP64 level (the sliced tcgen05 product is exact up to the final FP64 rounding of each entry)."""
+    from hypatia_b200.syssolver import QRCholDenseSystemSolver as DevQRChol
+    from oracle.cones import OracleConeBlock
+    monkeypatch.setenv("HYP_SCHUR_SYRK", syrk)
+    I = inst.config("C3", 0.05)
+    dev = iterate_solver(I, DevQRChol())
+    try:
+        ora = OracleConeBlock(I.model)
+        ora.load_point(I.point.s, I.point.z, 1 / np.sqrt(I.mu))
+        HG = ora.sqrt_hess_prod(I.model.G).astype(np.longdouble)
+        ref = (HG.T @ HG)
+        bound = (np.abs(HG).T @ np.abs(HG)).astype(np.float64)
+        S = dev.syssolver.ctx.get_schur()
+        iu = np.triu_indices(I.model.n)
+        err = np.abs(S[iu] - ref[iu].astype(np.float64)) / bound[iu]
+        assert err.max() <= (16 if syrk == "i8" else 4 * np.sqrt(I.model.q)) * np.finfo(np.float64).eps
+    finally:
+        dev.syssolver.free_memory()
 
 
 def test_matrix_cone_configs():
