@@ -161,6 +161,7 @@ struct hyp_ctx {
     int syrk_mode = 1;                 // 0: FP64 DMMA (syrk.cu), 1: sliced int8 on tcgen05 (ozaki.cu)
     int8_t* d_digits = nullptr;        // 8 x ldd x nmp digit slices of HG
     int* d_expo = nullptr;             // nmp column exponents
+    double* d_dscale = nullptr;        // 2^expo
     int64_t ldd = 0;
     // ---- SymIndefDense variant (symindef.jl:203-271) ----
     int solver_kind = 0;               // 0 QRCholDense, 1 SymIndefDense
@@ -280,9 +281,9 @@ void hyp_gemm_simple(hyp_ctx* ctx, bool transA, bool transB, int64_t M, int64_t 
 
 // ---- ozaki.cu ----
 void hyp_ozaki_slice(hyp_ctx* ctx, const double* A, int64_t lda, int64_t K, int64_t ncols, int8_t* digits,
-                     int64_t ldd, int64_t slice_stride, int* expo);
+                     int64_t ldd, int64_t slice_stride, int* expo, double* dscale);
 void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t slice_stride, const int* expo,
-                    int64_t K, int64_t ncols, double* C, int64_t ldc, double alpha, double beta);
+                    const double* dscale, int64_t K, int64_t ncols, double* C, int64_t ldc, double alpha, double beta);
 
 // ---- chol.cu ----
 // in-place blocked upper Cholesky; d_dinv receives the inverted 128 x 128 diagonal blocks

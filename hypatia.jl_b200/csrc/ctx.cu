@@ -131,6 +131,7 @@ void free_model(hyp_ctx* ctx) {
     dfree(ctx->d_flags);
     dfree(ctx->d_digits);
     dfree(ctx->d_expo);
+    dfree(ctx->d_dscale);
     dfree(ctx->d_L3);
     dfree(ctx->d_F3);
     dfree(ctx->d_row_cone);
@@ -477,10 +478,11 @@ int update_lhs_fact(hyp_ctx* ctx) {
                 ctx->ldd = round_up(std::max<int64_t>(ctx->qloc, 16), 16);
                 dalloc(&ctx->d_digits, 8 * ctx->ldd * nmp);
                 dalloc(&ctx->d_expo, nmp);
+                dalloc(&ctx->d_dscale, nmp);
             }
             hyp_ozaki_slice(ctx, ctx->d_HG, ctx->ldg, ctx->qloc, nmp, ctx->d_digits, ctx->ldd, ctx->ldd * nmp,
-                            ctx->d_expo);
-            hyp_ozaki_syrk(ctx, ctx->d_digits, ctx->ldd, ctx->ldd * nmp, ctx->d_expo, ctx->qloc, nmp, ctx->d_S,
+                            ctx->d_expo, ctx->d_dscale);
+            hyp_ozaki_syrk(ctx, ctx->d_digits, ctx->ldd, ctx->ldd * nmp, ctx->d_expo, ctx->d_dscale, ctx->qloc, nmp, ctx->d_S,
                            ctx->lds, 1.0, 0.0);
         } else if (ctx->qloc > 0)
             hyp_atb_upper(ctx, P, ctx->ldg, ctx->d_HG, ctx->ldg, ctx->qloc, nmp, ctx->d_S, ctx->lds, 1.0, 0.0);
@@ -605,6 +607,7 @@ void symindef_setup(hyp_ctx* ctx) {
     ctx->ld3 = round_up(std::max<int64_t>(N3, 2), 2);
     dfree(ctx->d_digits);
     dfree(ctx->d_expo);
+    dfree(ctx->d_dscale);
     dfree(ctx->d_L3);
     dfree(ctx->d_F3);
     dalloc(&ctx->d_L3, ctx->ld3 * std::max<int64_t>(N3, 1));

@@ -229,7 +229,7 @@ void make_map_i8(CUtensorMap* map, const int8_t* base, int64_t K, int64_t cols, 
 
 // ---- slicing: column exponents and the S signed 7-bit digit matrices ----------------------------
 __global__ void colmax_kernel(int64_t K, int64_t ncols, const double* __restrict__ A, int64_t lda,
-                              int* __restrict__ expo) {
+                              int* __restrict__ expo, double* __restrict__ dscale) {
     // expo[j] = smallest e with max_k |A[k, j]| < 2^e  (0 for an all-zero column)
     __shared__ double sm[8];
     const int64_t j = blockIdx.x;
@@ -248,6 +248,7 @@ __global__ void colmax_kernel(int64_t K, int64_t ncols, const double* __restrict
             frexp(mx, &e);          // mx = f * 2^e, f in [0.5, 1)  =>  mx < 2^e
         }
         expo[j] = e;
+        if (dscale) dscale[j] = ldexp(1.0, e);
     }
 }
 
@@ -537,7 +538,7 @@ __device__ __forceinline__ void cluster_sync_all() {
 
 __global__ void __launch_bounds__(I8_THREADS, 1)
 ozaki_syrk_cluster_kernel(const __grid_constant__ CUtensorMap mapD2, const __grid_constant__ CUtensorMap mapD4,
-                          int n_super_rows, int k0, int nkb, const int* __restrict__ expo, int64_t ncols,
+                          int n_super_rows, int k0, int nkb, const double* __restrict__ dscale, int64_t ncols,
                           double* __restrict__ C, int64_t ldc, double alpha, double beta) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint32_t s_tmem;
@@ -675,7 +676,7 @@ ozaki_syrk_cluster_kernel(const __grid_constant__ CUtensorMap mapD2, const __gri
             const int tI = 2 * SI + ri, tJ = 2 * SJ + rj;
             const int64_t row = (int64_t)tI * TM + lg * 32 + lane;
             const bool store = tI <= tJ;                 // the lower tile of a diagonal super tile is not needed
-            const double rs = (row < ncols) ? alpha * ldexp(1.0, expo[row]) : 0.0;
+            const double rs = (row < ncols) ? alpha * dscale[row] : 0.0;
             for (int pass = 0; pass < 2; pass++, item++) {
                 mbar_wait(bar_tfull, item & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;");
@@ -707,7 +708,7 @@ ozaki_syrk_cluster_kernel(const __grid_constant__ CUtensorMap mapD2, const __gri
                                 x += (double)(int32_t)v[2][j] * g2;
                                 x += (double)(int32_t)v[1][j] * g1;
                                 x += (double)(int32_t)v[0][j] * g0;
-                                x *= rs * ldexp(1.0, expo[col]);
+                                x *= rs * dscale[col];
                                 double* cp = C + row + col * ldc;
                                 if (pass == 0) *cp = (beta == 0.0) ? x : (x + beta * *cp);
                                 else *cp += x;
@@ -800,7 +801,7 @@ extern "C" int hyp_test_ozaki_slices(hyp_ctx* ctx, const double* A, int64_t lda,
         CUDA_TRY(cudaMalloc(&dD, (size_t)nslices * ldd * ncols));
         CUDA_TRY(cudaMalloc(&dE, (size_t)ncols * 4));
         CUDA_TRY(cudaMemcpy2DAsync(dA, K * 8, A, lda * 8, K * 8, ncols, cudaMemcpyDefault, ctx->stream));
-        colmax_kernel<<<(unsigned)ncols, 256, 0, ctx->stream>>>(K, ncols, dA, K, dE);
+        colmax_kernel<<<(unsigned)ncols, 256, 0, ctx->stream>>>(K, ncols, dA, K, dE, nullptr);
         dim3 grid(std::max(1, std::min(ceil_div(K, 2048), 64)), (unsigned)std::min<int64_t>(ncols, 65535));
         slice_kernel<<<grid, 256, 0, ctx->stream>>>(K, ncols, dA, K, dE, nslices, dD, ldd, ldd * ncols);
         ctx->launches += 2;
@@ -824,9 +825,9 @@ extern "C" int hyp_test_ozaki_slices(hyp_ctx* ctx, const double* A, int64_t lda,
 // ---- product entry points -------------------------------------------------------------------------
 // digits / exponents of the K x ncols FP64 matrix A (device) into caller-provided device buffers
 void hyp_ozaki_slice(hyp_ctx* ctx, const double* A, int64_t lda, int64_t K, int64_t ncols, int8_t* digits,
-                     int64_t ldd, int64_t slice_stride, int* expo) {
+                     int64_t ldd, int64_t slice_stride, int* expo, double* dscale) {
     if (K <= 0 || ncols <= 0) return;
-    colmax_kernel<<<(unsigned)ncols, 256, 0, ctx->stream>>>(K, ncols, A, lda, expo);
+    colmax_kernel<<<(unsigned)ncols, 256, 0, ctx->stream>>>(K, ncols, A, lda, expo, dscale);
     dim3 grid(std::max(1, std::min(ceil_div(K, 2048), 32)), (unsigned)std::min<int64_t>(ncols, 65535));
     slice_kernel<<<grid, 256, 0, ctx->stream>>>(K, ncols, A, lda, expo, OZ_S, digits, ldd, slice_stride);
     ctx->launches += 2;
@@ -835,7 +836,8 @@ void hyp_ozaki_slice(hyp_ctx* ctx, const double* A, int64_t lda, int64_t K, int6
 
 // C(upper 128-tiles) = alpha * A' A + beta * C from the digit slices of A
 void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t slice_stride, const int* expo,
-                    int64_t K, int64_t ncols, double* C, int64_t ldc, double alpha, double beta) {
+                    const double* dscale, int64_t K, int64_t ncols, double* C, int64_t ldc, double alpha,
+                    double beta) {
     if (K <= 0 || ncols <= 0) return;
     static bool attr = false;
     if (!attr) {
@@ -914,7 +916,7 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
             cfg.attrs = at;
             cfg.numAttrs = 1;
             CUDA_TRY(cudaLaunchKernelEx(&cfg, ozaki_syrk_cluster_kernel, mapD2, mapD4, nsr, (int)k0,
-                                        (int)ceil_div(klen, OZ_KB), expo, ncols, C, ldc, alpha, k0 == 0 ? beta : 1.0));
+                                        (int)ceil_div(klen, OZ_KB), dscale, ncols, C, ldc, alpha, k0 == 0 ? beta : 1.0));
             ctx->launches++;
             continue;
         }
@@ -940,16 +942,19 @@ extern "C" int hyp_test_ozaki_syrk(hyp_ctx* ctx, const double* A, int64_t lda, i
         CUDA_TRY(cudaMalloc(&dC, (size_t)ncols * ncols * 8));
         CUDA_TRY(cudaMalloc(&dD, (size_t)OZ_S * ldd * ncols));
         CUDA_TRY(cudaMalloc(&dE, (size_t)ncols * 4));
+        double* dSc = nullptr;
+        CUDA_TRY(cudaMalloc(&dSc, (size_t)ncols * 8));
         CUDA_TRY(cudaMemsetAsync(dD, 0, (size_t)OZ_S * ldd * ncols, ctx->stream));
         CUDA_TRY(cudaMemsetAsync(dC, 0, (size_t)ncols * ncols * 8, ctx->stream));
         CUDA_TRY(cudaMemcpy2DAsync(dA, K * 8, A, lda * 8, K * 8, ncols, cudaMemcpyDefault, ctx->stream));
-        hyp_ozaki_slice(ctx, dA, K, K, ncols, dD, ldd, ldd * ncols, dE);
-        hyp_ozaki_syrk(ctx, dD, ldd, ldd * ncols, dE, K, ncols, dC, ncols, 1.0, 0.0);
+        hyp_ozaki_slice(ctx, dA, K, K, ncols, dD, ldd, ldd * ncols, dE, dSc);
+        hyp_ozaki_syrk(ctx, dD, ldd, ldd * ncols, dE, dSc, K, ncols, dC, ncols, 1.0, 0.0);
         CUDA_TRY(cudaMemcpy2DAsync(C, ldc * 8, dC, ncols * 8, ncols * 8, ncols, cudaMemcpyDefault, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         cudaFree(dA);
         cudaFree(dC);
         cudaFree(dD);
+        cudaFree(dSc);
         cudaFree(dE);
         return 0;
     } catch (HypError& e) {
