@@ -57,7 +57,7 @@ WORKLOADS = {
 
 # DRAM traffic of the Schur SYRK launch from the committed `ncu --set full` capture (per launch)
 NCU_TRAFFIC = {"C3": 31.497622e9 + 0.411380e9,                       # FP64 DMMA kernel, one launch
-               "C3:i8": 124.648986e9 + 0.817550e9 + 57.589292e9 + 0.816429e9}   # tcgen05 kernel, both K chunks
+               "C3:i8": 119.23e9 + 0.81553e9 + 65.82e9 + 0.81341e9}   # tcgen05 pair kernel, both K chunks
 
 
 class PanelModel:
@@ -436,8 +436,8 @@ def run_ours(args):
         int8_tops = int8_ops / (syrk_ms * 1e-3) / 1e12 if achieved else None
         int8_peak = 2.0 * peaks["bf16_tflops"] if peaks.get("bf16_tflops") else None
         roofline = {"bound": "tensor",
-                    "kernel": "ozaki_syrk_cluster_kernel (Schur SYRK: FP64-accurate digit slicing, tcgen05 kind::i8, "
-                              "TMEM accumulators, 2x2-cluster TMA multicast) + slice_kernel",
+                    "kernel": "ozaki_syrk_pair_kernel (Schur SYRK: FP64-accurate digit slicing, tcgen05 kind::i8 "
+                              "cta_group::2 M=256, TMEM accumulators, 3-D TMA) + slice_kernel",
                     "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s (algorithmic FP64)",
                     "frac": (achieved / fp64_peak) if achieved else None,
                     "peak_source": "cuBLAS DGEMM 8192^3 measured live in this run = the FP64 tensor (DMMA) roofline; "
@@ -448,7 +448,7 @@ def run_ours(args):
                     "int8_frac": (int8_tops / int8_peak) if int8_tops and int8_peak else None,
                     "traffic": NCU_TRAFFIC.get(args.workload + ":i8") if world == 1 else None,
                     "traffic_unit": "bytes per SYRK (dram__bytes_read.sum + dram__bytes_write.sum over its launches, "
-                                    "profiles/r01_ozaki_cluster_ncu_full.txt)",
+                                    "profiles/r01_ozaki_pair_ncu.txt)",
                     "algorithmic_flops_per_launch": syrk_flops, "avg_launch_ms": syrk_ms,
                     "step_share": syrk_ms / (ms / args.steps) if syrk_ms == syrk_ms else None,
                     "phase_ms": phases}

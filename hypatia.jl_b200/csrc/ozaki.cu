@@ -727,13 +727,242 @@ ozaki_syrk_cluster_kernel(const __grid_constant__ CUtensorMap mapD2, const __gri
     }
 }
 
+// ---- CTA-pair variant (cta_group::2, M = 256): the production kernel --------------------------------
+// The 128 x 128 x 32 int8 MMA with both operands in shared memory reads 8 KB per 64 cycles - exactly
+// the 128 B/cycle shared-memory port, which (together with the TMA writes) bounds the kernels above.
+// A CTA pair sharing one tile column J issues M = 256 MMAs instead: each SM reads its own 128-row A
+// tile but only HALF (64 rows) of the B tile, and each CTA loads only that half: 25 % fewer operand
+// reads and TMA writes per MAC, and a 48 KB stage (4 stages instead of 3).
+// CTA r of the pair owns output tile (2 P + r, J).  Both CTAs run a TMA producer whose loads signal
+// the LEADER's full barrier; the leader's MMA thread issues tcgen05.mma.cta_group::2 and commits
+// (multicast) to both CTAs' empty / accumulator-full barriers; both CTAs run the epilogue on their own
+// TMEM half and report back to the leader's accumulator-empty barrier.
+constexpr int OZP_STAGE = OZ_S * OZ_TILE + OZ_S * (OZ_TILE / 2);   // 48 KB: A slices, then B half slices
+constexpr int OZP_STAGES = 4;
+constexpr int OZP_SMEM = OZP_STAGES * OZP_STAGE + 1024 + 256;
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                                uint32_t leader_bar_cluster_addr) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(leader_bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void umma_i8_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(bar), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+__global__ void __launch_bounds__(I8_THREADS, 1)
+ozaki_syrk_pair_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid_constant__ CUtensorMap mapA8,
+                       const __grid_constant__ CUtensorMap mapB4, const __grid_constant__ CUtensorMap mapB8,
+                       const int2* __restrict__ pairs, int n_pairs, int k0, int nkb,
+                       const double* __restrict__ dscale, int64_t ncols, double* __restrict__ C, int64_t ldc,
+                       double alpha, double beta) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint32_t s_tmem;
+    const uint32_t base = smem_u32(smem_raw);
+    const uint32_t stg = (base + 1023u) & ~1023u;
+    const uint32_t bar_full = stg + OZP_STAGES * OZP_STAGE;
+    const uint32_t bar_empty = bar_full + OZP_STAGES * 8;
+    const uint32_t bar_tfull = bar_empty + OZP_STAGES * 8;
+    const uint32_t bar_tempty = bar_tfull + 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t crank, cid, ncl;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(cid));
+    asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(ncl));
+    const bool leader = crank == 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < OZP_STAGES; s++) {
+            mbar_init(bar_full + s * 8, 1);      // leader: its own expect_tx arrival (+ the bytes of both CTAs)
+            mbar_init(bar_empty + s * 8, 1);     // one multicast commit from the leader
+        }
+        mbar_init(bar_tfull, 1);
+        mbar_init(bar_tempty, 8);                // 4 epilogue warps of each CTA (used in the leader only)
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                     "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem0 = s_tmem;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): my A tile and my half of the B tile =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int pi = (int)cid; pi < n_pairs; pi += (int)ncl) {
+                const int2 pr = pairs[pi];
+                const int tI = 2 * pr.x + (int)crank, tJ = pr.y;
+                for (int pass = 0; pass < 2; pass++) {
+                    const int ns = pass == 0 ? 4 : OZ_S;
+                    const int nst = pass == 0 ? (nkb + 1) / 2 : nkb;
+                    const int nh = pass == 0 ? 2 : 1;
+                    const CUtensorMap* ma = pass == 0 ? &mapA4 : &mapA8;
+                    const CUtensorMap* mb = pass == 0 ? &mapB4 : &mapB8;
+                    for (int it = 0; it < nst; it++) {
+                        mbar_wait(bar_empty + stage * 8, phase ^ 1u);
+                        const uint32_t full_leader = mapa_u32(bar_full + stage * 8, 0);
+                        if (leader) mbar_expect_tx(bar_full + stage * 8, 2u * OZP_STAGE);
+                        const uint32_t dst = stg + stage * OZP_STAGE;
+                        for (int h = 0; h < nh; h++) {
+                            const int kc = k0 + (pass == 0 ? (2 * it + h) : it) * OZ_KB;
+                            const uint32_t d0s = dst + h * (OZP_STAGE / 2);
+                            tma_load_3d_2sm(d0s, ma, kc, tI * TM, 0, full_leader);
+                            tma_load_3d_2sm(d0s + ns * OZ_TILE, mb, kc, tJ * TN + (int)crank * (TN / 2), 0, full_leader);
+                        }
+                        if (++stage == OZP_STAGES) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA only) =====
+        if (leader && lane == 0) {
+            const uint32_t idesc = make_idesc_i8(2 * TM, TN);
+            int stage = 0;
+            uint32_t phase = 0, item = 0;
+            for (int pi = (int)cid; pi < n_pairs; pi += (int)ncl) {
+                for (int pass = 0; pass < 2; pass++, item++) {
+                    if (item > 0) mbar_wait(bar_tempty, (item - 1) & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    const int d0 = pass * 4;
+                    const int ns = pass == 0 ? 4 : OZ_S;
+                    const int nst = pass == 0 ? (nkb + 1) / 2 : nkb;
+                    const int nhalf = pass == 0 ? 2 : 1;
+                    const int smax = pass == 0 ? 3 : OZ_S - 1;
+                    for (int it = 0; it < nst; it++) {
+                        mbar_wait(bar_full + stage * 8, phase);
+                        asm volatile("tcgen05.fence::after_thread_sync;");
+                        for (int h = 0; h < nhalf; h++) {
+                            const uint32_t sa = stg + stage * OZP_STAGE + h * (OZP_STAGE / 2);
+                            const uint32_t sb = sa + ns * OZ_TILE;
+                            for (int s = 0; s <= smax; s++) {
+                                const uint64_t ad = make_desc_sw32(sa + s * OZ_TILE);
+                                int tlo = d0 - s, thi = d0 + 3 - s;
+                                if (tlo < 0) tlo = 0;
+                                if (thi > OZ_S - 1) thi = OZ_S - 1;
+                                for (int tt = tlo; tt <= thi; tt++) {
+                                    const uint64_t bd = make_desc_sw32(sb + tt * (OZ_TILE / 2));
+                                    const int g = s + tt - d0;
+                                    const uint32_t accum = (it > 0 || h > 0 || s > 0) ? 1u : 0u;
+                                    umma_i8_2sm(tmem0 + (uint32_t)(g * TN), ad, bd, idesc, accum);
+                                }
+                            }
+                        }
+                        umma_commit_2sm(bar_empty + stage * 8, 3);       // frees the stage in both CTAs
+                        if (++stage == OZP_STAGES) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                    umma_commit_2sm(bar_tfull, 3);                        // accumulators ready in both CTAs
+                }
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs, own TMEM half) =====
+        const int lg = warp & 3;
+        const uint32_t tempty_leader = mapa_u32(bar_tempty, 0);
+        uint32_t item = 0;
+        for (int pi = (int)cid; pi < n_pairs; pi += (int)ncl) {
+            const int2 pr = pairs[pi];
+            const int tI = 2 * pr.x + (int)crank, tJ = pr.y;
+            const int64_t row = (int64_t)tI * TM + lg * 32 + lane;
+            const bool store = tI <= tJ;
+            const double rs = (row < ncols) ? alpha * dscale[row] : 0.0;
+            for (int pass = 0; pass < 2; pass++, item++) {
+                mbar_wait(bar_tfull, item & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                const int d0 = pass * 4;
+                const double g0 = ldexp(1.0, -(12 + 7 * d0)), g1 = ldexp(1.0, -(12 + 7 * (d0 + 1))),
+                             g2 = ldexp(1.0, -(12 + 7 * (d0 + 2))), g3 = ldexp(1.0, -(12 + 7 * (d0 + 3)));
+#pragma unroll 1
+                for (int c0 = 0; c0 < TN; c0 += 16) {
+                    uint32_t v[4][16];
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        const uint32_t taddr = tmem0 + ((uint32_t)(lg * 32) << 16) + (uint32_t)(g * TN + c0);
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                            : "=r"(v[g][0]), "=r"(v[g][1]), "=r"(v[g][2]), "=r"(v[g][3]), "=r"(v[g][4]),
+                              "=r"(v[g][5]), "=r"(v[g][6]), "=r"(v[g][7]), "=r"(v[g][8]), "=r"(v[g][9]),
+                              "=r"(v[g][10]), "=r"(v[g][11]), "=r"(v[g][12]), "=r"(v[g][13]), "=r"(v[g][14]),
+                              "=r"(v[g][15])
+                            : "r"(taddr));
+                    }
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (store && row < ncols) {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            const int64_t col = (int64_t)tJ * TN + c0 + j;
+                            if (col < ncols) {
+                                double x = (double)(int32_t)v[3][j] * g3;
+                                x += (double)(int32_t)v[2][j] * g2;
+                                x += (double)(int32_t)v[1][j] * g1;
+                                x += (double)(int32_t)v[0][j] * g0;
+                                x *= rs * dscale[col];
+                                double* cp = C + row + col * ldc;
+                                if (pass == 0) *cp = (beta == 0.0) ? x : (x + beta * *cp);
+                                else *cp += x;
+                            }
+                        }
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(tempty_leader);
+            }
+        }
+    }
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem0), "r"(512));
+    }
+}
+
 void make_map_digits(CUtensorMap* map, const int8_t* base, int64_t K, int64_t cols, int64_t ldd,
-                     int64_t slice_stride, int nslices, int box_slices) {
+                     int64_t slice_stride, int nslices, int box_slices, int box_rows = TM) {
     if (((uintptr_t)base & 15) || (ldd & 15) || (slice_stride & 15))
         throw HypError{"digit slices must be 16-byte aligned with ld % 16 == 0"};
     cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)cols, (cuuint64_t)nslices};
     cuuint64_t strides[2] = {(cuuint64_t)ldd, (cuuint64_t)slice_stride};
-    cuuint32_t box[3] = {OZ_KB, TM, (cuuint32_t)box_slices};
+    cuuint32_t box[3] = {OZ_KB, (cuuint32_t)box_rows, (cuuint32_t)box_slices};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
@@ -872,8 +1101,29 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
     static int max_clusters = 0;
     if (use_cluster < 0) {
         const char* e = getenv("HYP_OZAKI_CLUSTER");
-        use_cluster = (e && e[0] == '0') ? 0 : 1;
-        if (use_cluster) {
+        // 0: one CTA per tile; 1: 2 x 2 clusters with TMA multicast; 2 (default): CTA pairs, cta_group::2
+        use_cluster = e ? (e[0] - '0') : 2;
+        if (use_cluster < 0 || use_cluster > 2) use_cluster = 2;
+        if (use_cluster == 2) {
+            CUDA_TRY(cudaFuncSetAttribute(ozaki_syrk_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZP_SMEM));
+            cudaLaunchConfig_t q = {};
+            q.gridDim = dim3(2 * 128);
+            q.blockDim = dim3(I8_THREADS);
+            q.dynamicSmemBytes = OZP_SMEM;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            q.attrs = at;
+            q.numAttrs = 1;
+            if (cudaOccupancyMaxActiveClusters(&max_clusters, ozaki_syrk_pair_kernel, &q) != cudaSuccess ||
+                max_clusters < 1) {
+                cudaGetLastError();
+                use_cluster = 1;
+            }
+        }
+        if (use_cluster == 1) {
             CUDA_TRY(cudaFuncSetAttribute(ozaki_syrk_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
             cudaLaunchConfig_t q = {};
             q.gridDim = dim3(4 * 64);
@@ -898,7 +1148,48 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
     const int grid = std::min(n_tiles, ctx->sm_count);
     for (int64_t k0 = 0; k0 < K; k0 += CHUNK) {
         const int64_t klen = std::min(CHUNK, K - k0);
-        if (use_cluster) {
+        if (use_cluster == 2) {
+            // (P, J): tile rows 2P, 2P+1 of tile column J, for 2P <= J, column by column
+            static std::vector<std::pair<int, std::pair<int2*, int>>> pcache;
+            int2* d_pairs = nullptr;
+            int n_pairs = 0;
+            for (auto& e : pcache)
+                if (e.first == nt) {
+                    d_pairs = e.second.first;
+                    n_pairs = e.second.second;
+                }
+            if (!d_pairs) {
+                std::vector<int2> pl;
+                for (int tj = 0; tj < nt; tj++)
+                    for (int pp = 0; 2 * pp <= tj; pp++) pl.push_back(make_int2(pp, tj));
+                n_pairs = (int)pl.size();
+                CUDA_TRY(cudaMalloc(&d_pairs, pl.size() * sizeof(int2)));
+                CUDA_TRY(cudaMemcpyAsync(d_pairs, pl.data(), pl.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+                CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+                pcache.push_back({nt, {d_pairs, n_pairs}});
+            }
+            CUtensorMap mapB4, mapB8;
+            make_map_digits(&mapB4, digits, K, ncols, ldd, slice_stride, OZ_S, 4, TN / 2);
+            make_map_digits(&mapB8, digits, K, ncols, ldd, slice_stride, OZ_S, 8, TN / 2);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(2 * std::min(n_pairs, max_clusters));
+            cfg.blockDim = dim3(I8_THREADS);
+            cfg.dynamicSmemBytes = OZP_SMEM;
+            cfg.stream = ctx->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            CUDA_TRY(cudaLaunchKernelEx(&cfg, ozaki_syrk_pair_kernel, mapD4, mapD8, mapB4, mapB8, (const int2*)d_pairs,
+                                        n_pairs, (int)k0, (int)ceil_div(klen, OZ_KB), dscale, ncols, C, ldc, alpha,
+                                        k0 == 0 ? beta : 1.0));
+            ctx->launches++;
+            continue;
+        }
+        if (use_cluster == 1) {
             const int nsr = (nt + 1) / 2;
             const int n_super = nsr * (nsr + 1) / 2;
             // super tiles column by column over the upper triangle (the clusters running at the same time
