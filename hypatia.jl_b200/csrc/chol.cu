@@ -539,37 +539,81 @@ void hyp_potrf_upper(hyp_ctx* ctx, double* A, int64_t lda, int64_t m, double* d_
     if (m <= 0) return;
     TimeScope ts(ctx, T_POTRF);
     set_panel_attr();
-    CUDA_TRY(cudaMemsetAsync(d_info, 0, sizeof(int), ctx->stream));
-    // Two-level blocking: 128-wide panels inside OB-wide outer blocks.  Inside an outer block a panel
-    // only updates the rows of that outer block (a few tile rows); the rest of the matrix is updated
-    // once per outer block with contraction depth OB, which quarters the read-modify-write traffic on
-    // the trailing matrix and keeps the DMMA main loop long between epilogues.
+    cudaStream_t bulk = ctx->stream, chain = ctx->stream2;
+    CUDA_TRY(cudaMemsetAsync(d_info, 0, sizeof(int), bulk));
+    // Two-level blocking with look-ahead.  Outer blocks of OB = 512 columns; inside an outer block four
+    // 128-wide panels.
+    //   chain stream: factors the OB x OB diagonal block (panel kernel + TRSM / update restricted to that
+    //                 block: a handful of tiles) - the latency-bound part;
+    //   bulk stream:  block row U12 = U11^-T A12 for the columns right of the block, then the depth-OB
+    //                 update of the trailing matrix - the throughput-bound part.  The first thing it
+    //                 updates is the NEXT diagonal block, after which the chain stream starts on it while
+    //                 the bulk stream finishes the update (its persistent grids leave 8 SMs free).
     const int64_t OB = 512;
-    for (int64_t K0 = 0; K0 < m; K0 += OB) {
+    const bool lookahead = m > 2 * OB;
+    auto on = [&](cudaStream_t s, int cap) {
+        ctx->launch_stream = s;
+        ctx->grid_cap = cap;
+    };
+    const int cap = lookahead ? std::max(1, ctx->sm_count - 8) : 0;
+    int nblk_outer = 0;
+    // the chain may start once the input matrix is in place (everything before us on the bulk stream)
+    CUDA_TRY(cudaEventRecord(ctx->ev_bulk[0], bulk));
+    CUDA_TRY(cudaStreamWaitEvent(chain, ctx->ev_bulk[0], 0));
+    for (int64_t K0 = 0; K0 < m; K0 += OB, nblk_outer++) {
         const int64_t Kend = std::min(K0 + OB, m);
+        const int64_t rest2 = m - Kend;
+        // ---- chain: diagonal block ----
+        on(chain, 0);
         for (int64_t k0 = K0; k0 < Kend; k0 += NB) {
             const int64_t nb = std::min<int64_t>(NB, m - k0);
             const int64_t k = k0 / NB;
-            panel_kernel<true><<<1, PT, NB * LDU * 8, ctx->stream>>>(A, lda, m, k, d_dinv, d_info);
+            panel_kernel<true><<<1, PT, NB * LDU * 8, chain>>>(A, lda, m, k, d_dinv, d_info);
             ctx->launches++;
-            const int64_t rest = m - k0 - nb;
-            if (rest <= 0) continue;
-            double* A12 = A + k0 + (k0 + nb) * lda;
-            double* A22 = A + (k0 + nb) + (k0 + nb) * lda;
-            const double* Dk = d_dinv + k * NB * NB;
-            // U12 = U11^-T A12  (in place: every output tile depends on its own columns only)
-            hyp_gemm_tn(ctx, Dk, NB, A12, lda, nb, nb, rest, A12, lda, 1.0, 0.0);
-            // rows of this outer block below the panel: A22[0:rin, :] -= U12[:, 0:rin]' U12
-            const int64_t rin = Kend - (k0 + nb);
-            if (rin > 0) hyp_gemm_tn(ctx, A12, lda, A12, lda, nb, rin, rest, A22, lda, -1.0, 1.0);
+            const int64_t rin = Kend - (k0 + nb);       // columns / rows of this outer block right of / below the panel
+            if (rin > 0) {
+                double* A12 = A + k0 + (k0 + nb) * lda;
+                double* A22 = A + (k0 + nb) + (k0 + nb) * lda;
+                const double* Dk = d_dinv + k * NB * NB;
+                hyp_gemm_tn(ctx, Dk, NB, A12, lda, nb, nb, rin, A12, lda, 1.0, 0.0);
+                hyp_atb_upper(ctx, A12, lda, A12, lda, nb, rin, A22, lda, -1.0, 1.0);
+            }
         }
-        const int64_t rest2 = m - Kend;
-        if (rest2 > 0) {
-            // everything right of / below the outer block: depth-OB update on the upper tiles
-            double* P = A + K0 + Kend * lda;
-            hyp_atb_upper(ctx, P, lda, P, lda, Kend - K0, rest2, A + Kend + Kend * lda, lda, -1.0, 1.0);
+        CUDA_TRY(cudaEventRecord(ctx->ev_chain[nblk_outer & 1], chain));
+        if (rest2 <= 0) break;
+        // ---- bulk: block row right of the outer block, panel by panel ----
+        CUDA_TRY(cudaStreamWaitEvent(bulk, ctx->ev_chain[nblk_outer & 1], 0));
+        on(bulk, cap);
+        for (int64_t k0 = K0; k0 < Kend; k0 += NB) {
+            const int64_t nb = std::min<int64_t>(NB, m - k0);
+            const int64_t k = k0 / NB;
+            double* A12r = A + k0 + Kend * lda;                 // rows of the panel, columns >= Kend
+            const double* Dk = d_dinv + k * NB * NB;
+            hyp_gemm_tn(ctx, Dk, NB, A12r, lda, nb, nb, rest2, A12r, lda, 1.0, 0.0);
+            const int64_t rin = Kend - (k0 + nb);
+            if (rin > 0) {
+                // rows below the panel inside the outer block: A[k0+nb:Kend, Kend:] -= U[panel, k0+nb:Kend]' U12r
+                const double* Pu = A + k0 + (k0 + nb) * lda;
+                hyp_gemm_tn(ctx, Pu, lda, A12r, lda, nb, rin, rest2, A + (k0 + nb) + Kend * lda, lda, -1.0, 1.0);
+            }
+        }
+        // ---- bulk: depth-OB trailing update; the next diagonal block first ----
+        double* P = A + K0 + Kend * lda;
+        double* T = A + Kend + Kend * lda;
+        const int64_t kd = Kend - K0;
+        const int64_t dn = std::min<int64_t>(OB, rest2);
+        hyp_atb_upper(ctx, P, lda, P, lda, kd, dn, T, lda, -1.0, 1.0);
+        CUDA_TRY(cudaEventRecord(ctx->ev_bulk[nblk_outer & 1], bulk));
+        CUDA_TRY(cudaStreamWaitEvent(chain, ctx->ev_bulk[nblk_outer & 1], 0));
+        if (rest2 > dn) {
+            // rows of the next diagonal block x the columns right of it, then everything below
+            hyp_gemm_tn(ctx, P, lda, P + dn * lda, lda, kd, dn, rest2 - dn, T + dn * lda, lda, -1.0, 1.0);
+            hyp_atb_upper(ctx, P + dn * lda, lda, P + dn * lda, lda, kd, rest2 - dn, T + dn + dn * lda, lda, -1.0, 1.0);
         }
     }
+    // the caller's stream continues after the last diagonal block
+    CUDA_TRY(cudaStreamWaitEvent(bulk, ctx->ev_chain[nblk_outer & 1], 0));
+    on(nullptr, 0);
     CUDA_TRY(cudaGetLastError());
 }
 

@@ -103,6 +103,10 @@ struct hyp_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;    // side stream of the Cholesky look-ahead chain
+    cudaStream_t launch_stream = nullptr;   // stream the GEMM / panel launch helpers use (stream or stream2)
+    int grid_cap = 0;                  // > 0: persistent GEMM grids leave SMs free for the side stream
+    cudaEvent_t ev_chain[2] = {nullptr, nullptr}, ev_bulk[2] = {nullptr, nullptr};
     std::string last_error;
 
     // ---- model ----

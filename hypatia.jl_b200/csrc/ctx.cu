@@ -727,9 +727,14 @@ hyp_ctx* hyp_create(int device) {
     ctx->syrk_mode = 1;   // default: FP64-accurate digit slicing on tcgen05 (ozaki.cu)
     if (const char* e = getenv("HYP_SCHUR_SYRK")) ctx->syrk_mode = (strcmp(e, "dmma") == 0) ? 0 : 1;
     ctx->sm_count = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx;
         return nullptr;
+    }
+    for (int i = 0; i < 2; i++) {
+        cudaEventCreateWithFlags(&ctx->ev_chain[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_bulk[i], cudaEventDisableTiming);
     }
     return ctx;
 }
@@ -744,6 +749,11 @@ void hyp_destroy(hyp_ctx* ctx) {
         if (ctx->timing[i].e0) cudaEventDestroy(ctx->timing[i].e0);
         if (ctx->timing[i].e1) cudaEventDestroy(ctx->timing[i].e1);
     }
+    for (int i = 0; i < 2; i++) {
+        if (ctx->ev_chain[i]) cudaEventDestroy(ctx->ev_chain[i]);
+        if (ctx->ev_bulk[i]) cudaEventDestroy(ctx->ev_bulk[i]);
+    }
+    cudaStreamDestroy(ctx->stream2);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -309,8 +309,9 @@ void launch_atb(hyp_ctx* ctx, int kind, const double* P, int64_t ldp, const doub
     make_map(&mapR, R, ngroups > 1 ? r_kstride * (ngroups - 1) + klen : klen, ncols, ldr);
     int nkb = ceil_div(klen, BK);
     int grid = std::min(n_tiles, ctx->sm_count);
+    if (ctx->grid_cap > 0) grid = std::min(grid, ctx->grid_cap);
     int same = (kind == 0 && P == R && ldp == ldr) ? 1 : 0;
-    atb_upper_kernel<<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(
+    atb_upper_kernel<<<grid, NUM_THREADS, SMEM_BYTES, ctx->launch_stream ? ctx->launch_stream : ctx->stream>>>(
         mapP, mapR, d_tiles, n_tiles, nkb, same, mrows, ncols, C, ldc, c_group_stride, alpha, beta);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
