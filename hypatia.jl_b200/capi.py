@@ -33,6 +33,7 @@ _SIGS = {
     "hyp_load_model": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
                                  C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                  c_ip, c_i64p, c_ip, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "hyp_set_cone_params": (C.c_int, [C.c_void_p, C.c_int, c_ip, c_dp]),
     "hyp_cones_load_point": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]),
     "hyp_cones_feas": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "hyp_cones_grad": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -173,6 +174,10 @@ class Context:
         A = np.asfortranarray(model.A, dtype=np.float64)
         Q = None if Ap_Q is None else np.asfortranarray(Ap_Q, dtype=np.float64)
         R = None if Ap_R is None else np.asfortranarray(Ap_R, dtype=np.float64)
+        hkind = np.array([getattr(ck, "hkind", 0) for ck in model.cones], dtype=np.int32)
+        hparam = np.array([getattr(ck, "hparam", 0.0) for ck in model.cones], dtype=np.float64)
+        self.check(self.lib.hyp_set_cone_params(self.h, K, hkind.ctypes.data_as(c_ip),
+                                                hparam.ctypes.data_as(c_dp)), "hyp_set_cone_params")
         self._keep = (G_local, A, Q, R, ctype, cdim, cdual)
         c, b, h = _f64(model.c), _f64(model.b), _f64(model.h)
         rc = self.lib.hyp_load_model(

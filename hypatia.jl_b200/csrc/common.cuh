@@ -19,7 +19,7 @@
 
 #include "../../include/hypatia_b200.h"
 
-#define HYP_NUM_CONE_TYPES 5
+#define HYP_NUM_CONE_TYPES 8
 // internal product mode: inv_hess for primal-barrier cones, hess for dual-barrier cones
 #define HYP_PROD_BLOCK_INV 5
 #define HYP_EPS 2.220446049250313e-16
@@ -38,6 +38,27 @@ struct HypError {
             throw HypError{buf__};                                                         \
         }                                                                                  \
     } while (0)
+
+// ---- cone type classes ----
+// matrix-domain cones keep `lead` scalars in front of an svec block
+static inline bool cone_is_matrix(int t) {
+    return t == HYP_CONE_POSSEMIDEFTRI || t == HYP_CONE_HYPOPERLOGDETTRI || t == HYP_CONE_HYPOROOTDETTRI ||
+           t == HYP_CONE_EPIPERSEPSPECTRAL_MAT;
+}
+static inline int cone_mat_lead(int t) {
+    return t == HYP_CONE_POSSEMIDEFTRI ? 0 : t == HYP_CONE_HYPOROOTDETTRI ? 1 : 2;
+}
+// cones whose Schur contribution uses the closed-form sqrt_hess_prod! (use_sqrt_hess_oracles = true:
+// nonnegative.jl:38, epinormeucl.jl:40, possemideftri.jl:54, epipersquare.jl:48)
+static inline bool cone_has_sqrt(int t) {
+    return t == HYP_CONE_NONNEGATIVE || t == HYP_CONE_EPINORMEUCL || t == HYP_CONE_POSSEMIDEFTRI ||
+           t == HYP_CONE_EPIPERSQUARE;
+}
+// cones that accept use_dual_barrier = true
+static inline bool cone_allows_dual(int t) {
+    return t == HYP_CONE_HYPOPERLOGDETTRI || t == HYP_CONE_HYPOROOTDETTRI ||
+           t == HYP_CONE_EPIPERSEPSPECTRAL_MAT || t == HYP_CONE_HYPOPERLOG;
+}
 
 static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
@@ -68,6 +89,15 @@ struct ConeGroup {
     double* d_Uit = nullptr;      // U^-T (lower)
     double* d_Wi = nullptr;       // W^-1 (full symmetric)
     double* d_scal = nullptr;     // per-cone scalars (8 per cone)
+    // EpiPerSepSpectral (cones_spec.cu): spectral function of each cone, per-cone vectors
+    // (8 arrays of side doubles at d_voff; d_voff7 = offset of the 8th array)
+    std::vector<int> h_hkind;
+    std::vector<double> h_hparam;
+    std::vector<int64_t> h_voff;
+    int* d_hkind = nullptr;
+    double* d_hparam = nullptr;
+    int64_t *d_voff = nullptr, *d_voff7 = nullptr;
+    double* d_vecs = nullptr;
     // row list for elementwise cones (Nonnegative): global row of every element
     int* d_rows = nullptr;
     int* d_rowcone = nullptr;     // GLOBAL cone index of every element of d_rows
@@ -120,6 +150,8 @@ struct hyp_ctx {
     std::vector<int> h_cone_type, h_cone_dual;
     std::vector<int64_t> h_cone_dim, h_cone_off;
     std::vector<double> h_cone_nu;
+    std::vector<int> h_cone_hkind;     // per global cone: HYP_SSF_* (EpiPerSepSpectral), set by hyp_set_cone_params
+    std::vector<double> h_cone_hparam;
     std::vector<int> h_cone_sqrt;      // per global cone: 1 = sqrt-form in the Schur assembly
     double* d_Graw = nullptr;          // qloc x n (model.G panel)
     double* d_GQ = nullptr;            // qloc x n, G*Ap_Q when p > 0 (else alias of d_Graw)
@@ -146,6 +178,7 @@ struct hyp_ctx {
     double *d_point = nullptr, *d_dual = nullptr, *d_grad = nullptr;
     double* d_wivec = nullptr;         // svec(W^-1) on the rows of matrix cones (q)
     uint8_t *d_feas = nullptr, *d_dual_feas = nullptr, *d_num_ok = nullptr;  // K
+    uint8_t* d_tmpflag = nullptr;      // K scratch flags (Cholesky gate of the spectral cones' dual check)
     double* d_proxsqr = nullptr;       // K
     double* d_matwork = nullptr;       // scratch for matrix-cone products
     int64_t matwork_doubles = 0;

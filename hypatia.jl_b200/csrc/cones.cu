@@ -379,8 +379,8 @@ void hyp_cones_build_groups(hyp_ctx* ctx) {
             g.h_kidx.push_back(k);
             g.h_dual.push_back(ctx->h_cone_dual[k]);
             int side = 0;
-            if (type >= HYP_CONE_POSSEMIDEFTRI) {
-                int64_t len = dim - (type == HYP_CONE_HYPOPERLOGDETTRI ? 2 : type == HYP_CONE_HYPOROOTDETTRI ? 1 : 0);
+            if (cone_is_matrix(type)) {
+                int64_t len = dim - cone_mat_lead(type);
                 side = (int)((std::sqrt(1.0 + 8.0 * (double)len) - 1.0) / 2.0 + 0.5);
                 while ((int64_t)side * (side + 1) / 2 < len) side++;
                 while ((int64_t)side * (side + 1) / 2 > len) side--;
@@ -444,7 +444,8 @@ void hyp_cones_build_groups(hyp_ctx* ctx) {
                 g.d_ccount = upload(ccount);
             }
         }
-        if (type >= HYP_CONE_POSSEMIDEFTRI) hyp_mat_alloc_group(ctx, g);
+        if (type == HYP_CONE_EPIPERSEPSPECTRAL_MAT) hyp_spec_alloc_group(ctx, g);
+        else if (cone_is_matrix(type)) hyp_mat_alloc_group(ctx, g);
         ctx->groups.push_back(g);
     }
     CUDA_TRY(cudaDeviceSynchronize());   // uploads above ran on the legacy stream
@@ -471,6 +472,11 @@ void hyp_cones_free_groups(hyp_ctx* ctx) {
         cudaFree(g.d_Ui);
         cudaFree(g.d_Uit);
         cudaFree(g.d_Wi);
+        cudaFree(g.d_hkind);
+        cudaFree(g.d_hparam);
+        cudaFree(g.d_voff);
+        cudaFree(g.d_voff7);
+        cudaFree(g.d_vecs);
     }
     ctx->groups.clear();
 }
@@ -492,6 +498,8 @@ void hyp_cones_update_state(hyp_ctx* ctx) {
                 g.count, g.d_off, g.d_dim, g.d_kidx, ctx->d_point, ctx->d_dual, ctx->d_grad, g.d_scal,
                 ctx->d_feas, ctx->d_dual_feas);
             ctx->launches++;
+        } else if (g.type == HYP_CONE_EPIPERSEPSPECTRAL_MAT) {
+            hyp_spec_update_state(ctx, g);
         } else {
             hyp_mat_update_state(ctx, g);
         }
@@ -533,6 +541,8 @@ void hyp_cones_prod(hyp_ctx* ctx, double* prod, const double* arr, int64_t ncols
                 default:
                     throw HypError{"hyp_cones_prod: bad mode"};
             }
+        } else if (g.type == HYP_CONE_EPIPERSEPSPECTRAL_MAT) {
+            hyp_spec_prod(ctx, g, prod, arr, ncols, ld_prod, ld_arr, m, row_shift);
         } else {
             hyp_mat_prod(ctx, g, prod, arr, ncols, ld_prod, ld_arr, m, row_shift);
         }
@@ -552,6 +562,8 @@ void hyp_cones_schur_prepass(hyp_ctx* ctx) {
         } else if (g.type == HYP_CONE_POSSEMIDEFTRI) {
             hyp_mat_prod(ctx, g, ctx->d_HG, GQ2, ctx->nmp, ctx->ldg, ctx->ldg, HYP_PROD_SQRT_HESS,
                          ctx->row_lo);
+        } else if (g.type == HYP_CONE_EPIPERSEPSPECTRAL_MAT) {
+            hyp_spec_prod(ctx, g, ctx->d_HG, GQ2, ctx->nmp, ctx->ldg, ctx->ldg, HYP_PROD_BLOCK, ctx->row_lo);
         } else {
             hyp_mat_prod(ctx, g, ctx->d_HG, GQ2, ctx->nmp, ctx->ldg, ctx->ldg, HYP_PROD_BLOCK,
                          ctx->row_lo);
@@ -571,6 +583,8 @@ void hyp_cones_dder3_dev(hyp_ctx* ctx, double* out, const double* dir) {
             soc_dder3_kernel<<<ceil_div(g.count, 8), 256, 0, ctx->stream>>>(
                 g.count, g.d_off, g.d_dim, g.d_scal, ctx->d_point, dir, out);
             ctx->launches++;
+        } else if (g.type == HYP_CONE_EPIPERSEPSPECTRAL_MAT) {
+            hyp_spec_dder3(ctx, g, out, dir);
         } else {
             hyp_mat_dder3(ctx, g, out, dir);
         }

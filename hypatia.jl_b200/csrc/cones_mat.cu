@@ -16,62 +16,18 @@
 //     Y_j = X' T_j                   (c grouped d x d products in one launch)
 // Bound: tensor (FP64 DMMA), 4 d^3 flops per column; the unpack / pack passes are HBM-bound.
 #include "cones_mat.cuh"
+#include "cones_mat_kernels.cuh"
+
+using hypdev::block_sum;
+using hypdev::pack_cols_kernel;
+using hypdev::svec_rc;
+using hypdev::unpack_cols_kernel;
+using hypdev::unpack_state_kernel;
+using hypdev::warp_sum;
 
 namespace {
 
 constexpr double RT2 = 1.4142135623730951;
-constexpr double IRT2 = 0.7071067811865476;
-
-__device__ __forceinline__ void svec_rc(int64_t idx, int& a, int& b) {
-    int bb = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
-    while ((int64_t)(bb + 1) * (bb + 2) / 2 <= idx) bb++;
-    while ((int64_t)bb * (bb + 1) / 2 > idx) bb--;
-    b = bb;
-    a = (int)(idx - (int64_t)bb * (bb + 1) / 2);
-}
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-__device__ double block_sum(double v, double* sm) {
-    v = warp_sum(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double t = 0.0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += sm[i];
-    return t;
-}
-
-// smat of the matrix part of `vec` for every cone of the group -> A (and B if given), full symmetric
-__global__ void __launch_bounds__(256)
-unpack_state_kernel(int ncones, const int64_t* __restrict__ off, const int* __restrict__ sides,
-                    const int64_t* __restrict__ moff, int lead, const double* __restrict__ vec,
-                    double* __restrict__ A, double* __restrict__ B) {
-    const int c = blockIdx.x;
-    if (c >= ncones) return;
-    const int d = sides[c], lde = (d + 1) & ~1;
-    const int64_t len = (int64_t)d * (d + 1) / 2;
-    const double* v = vec + off[c] + lead;
-    double* Ac = A + moff[c];
-    double* Bc = B ? B + moff[c] : nullptr;
-    for (int64_t idx = blockIdx.y * (int64_t)blockDim.x + threadIdx.x; idx < len;
-         idx += (int64_t)gridDim.y * blockDim.x) {
-        int a, b;
-        svec_rc(idx, a, b);
-        double x = v[idx];
-        if (a != b) x *= IRT2;
-        Ac[a + (int64_t)b * lde] = x;
-        Ac[b + (int64_t)a * lde] = x;
-        if (Bc) {
-            Bc[a + (int64_t)b * lde] = x;
-            Bc[b + (int64_t)a * lde] = x;
-        }
-    }
-}
 
 // scal layout (8 doubles per cone): 0 logdet W, 1 phi, 2 zeta, 3 u, 4 v, 5 pzd (rootdet) / sigma (logdet)
 // One CTA per cone: U', U^-T, W^-1 (side <= 128; larger cones get W^-1 from a GEMM beforehand),
@@ -204,51 +160,6 @@ __global__ void copy_block_kernel(double* __restrict__ dst, int64_t ldd, const d
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < rows * cols; idx += gridDim.x * blockDim.x) {
         int a = idx % rows, b = idx / rows;
         dst[a + (int64_t)b * ldd] = scale * src[a + (int64_t)b * lds];
-    }
-}
-
-// columns [j0, j0 + cc) of one cone block of `arr` -> Mall = [M_0 ... M_{cc-1}], each d x lde (ld lde)
-__global__ void __launch_bounds__(256)
-unpack_cols_kernel(int d, int lde, int64_t len, const double* arr, int64_t ld_arr, int64_t cc,
-                   double* __restrict__ Mall) {
-    for (int64_t j = blockIdx.y; j < cc; j += gridDim.y) {
-        const double* v = arr + j * ld_arr;
-        double* Mj = Mall + j * (int64_t)lde * lde;
-        for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < len;
-             idx += (int64_t)gridDim.x * blockDim.x) {
-            int a, b;
-            svec_rc(idx, a, b);
-            double x = v[idx];
-            if (a != b) x *= IRT2;
-            Mj[a + (int64_t)b * lde] = x;
-            Mj[b + (int64_t)a * lde] = x;
-        }
-        // blocks are lde columns wide (TMA coordinates must be even): keep the pad column finite
-        if (lde > d && blockIdx.x == 0)
-            for (int a = threadIdx.x; a < lde; a += blockDim.x) Mj[a + (int64_t)d * lde] = 0.0;
-    }
-}
-
-// prod[idx, j] = alpha_j * svec(Y_j)[idx] + beta_j * vecB[idx]
-__global__ void __launch_bounds__(256)
-pack_cols_kernel(int d, int lde, int64_t len, const double* __restrict__ Yall, int64_t cc,
-                 const double* __restrict__ alpha, const double* __restrict__ beta,
-                 const double* __restrict__ vecB, double* prod, int64_t ld_prod) {
-    for (int64_t j = blockIdx.y; j < cc; j += gridDim.y) {
-        const double* Yj = Yall + j * (int64_t)lde * lde;
-        double* pr = prod + j * ld_prod;
-        const double al = alpha ? alpha[j] : 1.0;
-        const double be = beta ? beta[j] : 0.0;
-        for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < len;
-             idx += (int64_t)gridDim.x * blockDim.x) {
-            int a, b;
-            svec_rc(idx, a, b);
-            double x = Yj[a + (int64_t)b * lde];
-            if (a != b) x *= RT2;
-            x *= al;
-            if (vecB) x += be * vecB[idx];
-            pr[idx] = x;
-        }
     }
 }
 
@@ -438,6 +349,13 @@ void congruence(hyp_ctx* ctx, const double* X, int d, int lde, double* Mall, int
 }
 
 }  // namespace
+
+void hyp_mat_ensure_work(hyp_ctx* ctx, int64_t doubles) { ensure_matwork(ctx, doubles); }
+
+void hyp_mat_congruence(hyp_ctx* ctx, const double* X, int d, int lde, double* Mall, int64_t cc, double* C1,
+                        int64_t ldc1) {
+    congruence(ctx, X, d, lde, Mall, cc, C1, ldc1);
+}
 
 void hyp_mat_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
     (void)ctx;

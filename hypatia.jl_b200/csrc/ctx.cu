@@ -119,6 +119,7 @@ void free_model(hyp_ctx* ctx) {
     dfree(ctx->d_feas);
     dfree(ctx->d_dual_feas);
     dfree(ctx->d_num_ok);
+    dfree(ctx->d_tmpflag);
     dfree(ctx->d_proxsqr);
     dfree(ctx->d_matwork);
     ctx->matwork_doubles = 0;
@@ -776,7 +777,13 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
         if (cone_lo < 0 || cone_hi > K || cone_lo > cone_hi) throw HypError{"hyp_load_model: bad cone range"};
         if (p > 0 && !A) throw HypError{"hyp_load_model: p > 0 needs A"};
         if ((Ap_Q == nullptr) != (Ap_R == nullptr)) throw HypError{"hyp_load_model: pass both Ap_Q and Ap_R or neither"};
+        // per-cone parameters staged by hyp_set_cone_params survive the free below
+        std::vector<int> hkind_in = ctx->h_cone_hkind;
+        std::vector<double> hparam_in = ctx->h_cone_hparam;
+        const bool have_params = (int)hkind_in.size() == K && K > 0;
         free_model(ctx);
+        ctx->h_cone_hkind = have_params ? hkind_in : std::vector<int>((size_t)K, 0);
+        ctx->h_cone_hparam = have_params ? hparam_in : std::vector<double>((size_t)K, 0.0);
         ctx->n = n;
         ctx->p = p;
         ctx->q = q;
@@ -798,24 +805,33 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
             if (t < 0 || t >= HYP_NUM_CONE_TYPES || d < 1) throw HypError{"hyp_load_model: bad cone entry"};
             ctx->h_cone_off[k + 1] = ctx->h_cone_off[k] + d;
             if (ctx->h_cone_dual[k]) {
-                if (t < HYP_CONE_HYPOPERLOGDETTRI)
-                    throw HypError{"hyp_load_model: use_dual_barrier is only defined for the log-det family"};
+                if (!cone_allows_dual(t))
+                    throw HypError{"hyp_load_model: use_dual_barrier is not defined for this cone type"};
                 ctx->any_dual = true;
             }
             double side = 0;
-            if (t == HYP_CONE_POSSEMIDEFTRI) side = (std::sqrt(1.0 + 8.0 * d) - 1) / 2;
-            if (t == HYP_CONE_HYPOPERLOGDETTRI) side = (std::sqrt(1.0 + 8.0 * (d - 2)) - 1) / 2;
-            if (t == HYP_CONE_HYPOROOTDETTRI) side = (std::sqrt(1.0 + 8.0 * (d - 1)) - 1) / 2;
-            side = std::floor(side + 0.5);
-            // get_nu: nonnegative.jl:40, epinormeucl.jl:42, possemideftri.jl:67,
-            // hypoperlogdettri.jl:80, hyporootdettri.jl:80
+            if (cone_is_matrix(t)) side = std::floor((std::sqrt(1.0 + 8.0 * (d - cone_mat_lead(t))) - 1) / 2 + 0.5);
+            // get_nu: nonnegative.jl:40, epinormeucl.jl:42, possemideftri.jl:67, hypoperlogdettri.jl:80,
+            // hyporootdettri.jl:80, epipersepspectral.jl:79, epipersquare.jl:50, hypoperlog.jl:54
             ctx->h_cone_nu[k] = t == HYP_CONE_NONNEGATIVE ? (double)d
                                 : t == HYP_CONE_EPINORMEUCL ? 2.0
                                 : t == HYP_CONE_POSSEMIDEFTRI ? side
                                 : t == HYP_CONE_HYPOPERLOGDETTRI ? 2.0 + side
-                                                                 : 1.0 + side;
+                                : t == HYP_CONE_HYPOROOTDETTRI ? 1.0 + side
+                                : t == HYP_CONE_EPIPERSEPSPECTRAL_MAT ? 2.0 + side
+                                : t == HYP_CONE_EPIPERSQUARE ? 2.0
+                                                             : (double)d;
+            if ((t == HYP_CONE_EPIPERSQUARE || t == HYP_CONE_HYPOPERLOG || t == HYP_CONE_EPIPERSEPSPECTRAL_MAT) && d < 3)
+                throw HypError{"hyp_load_model: this cone type needs dimension >= 3"};
+            if (t == HYP_CONE_EPIPERSEPSPECTRAL_MAT) {
+                if (!have_params) throw HypError{"hyp_load_model: EpiPerSepSpectral cones need hyp_set_cone_params first"};
+                const int hk = ctx->h_cone_hkind[k];
+                const double hp = ctx->h_cone_hparam[k];
+                if (hk < HYP_SSF_INV || hk > HYP_SSF_POWER12 || (hk == HYP_SSF_POWER12 && !(hp > 1.0 && hp <= 2.0)))
+                    throw HypError{"hyp_load_model: bad separable spectral function"};
+            }
             if (k >= cone_lo && k < cone_hi) {
-                if (t >= HYP_CONE_HYPOPERLOGDETTRI) any_ns = true; else any_sqrt = true;
+                if (!cone_has_sqrt(t)) any_ns = true; else any_sqrt = true;
             }
         }
         if (ctx->h_cone_off[K] != q) throw HypError{"hyp_load_model: cone dimensions do not sum to q"};
@@ -852,7 +868,7 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
             dalloc(&ctx->d_PG, ctx->ldg * nmp);
             std::vector<uint8_t> row_ns((size_t)std::max<int64_t>(ctx->qloc, 1), 0);
             for (int k = cone_lo; k < cone_hi; k++)
-                if (cone_type[k] >= HYP_CONE_HYPOPERLOGDETTRI)
+                if (!cone_has_sqrt(cone_type[k]))
                     for (int64_t r = ctx->h_cone_off[k]; r < ctx->h_cone_off[k + 1]; r++) row_ns[r - ctx->row_lo] = 1;
             dalloc(&ctx->d_row_ns, (int64_t)row_ns.size());
             CUDA_TRY(cudaMemcpyAsync(ctx->d_row_ns, row_ns.data(), row_ns.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -907,6 +923,7 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
         dalloc(&ctx->d_feas, K);
         dalloc(&ctx->d_dual_feas, K);
         dalloc(&ctx->d_num_ok, K);
+        dalloc(&ctx->d_tmpflag, K);
         dalloc(&ctx->d_proxsqr, K);
         dalloc(&ctx->d_Gx, q);
         dalloc(&ctx->d_HGx, q);
@@ -934,6 +951,15 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         CUDA_TRY(cudaDeviceSynchronize());
         ctx->model_loaded = true;
+        return 0;
+    });
+}
+
+int hyp_set_cone_params(hyp_ctx* ctx, int K, const int* ssf_kind, const double* ssf_param) {
+    return guarded(ctx, [&] {
+        if (K < 0 || (K > 0 && (!ssf_kind || !ssf_param))) throw HypError{"hyp_set_cone_params: bad arguments"};
+        ctx->h_cone_hkind.assign(ssf_kind, ssf_kind + K);
+        ctx->h_cone_hparam.assign(ssf_param, ssf_param + K);
         return 0;
     });
 }

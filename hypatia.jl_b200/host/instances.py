@@ -50,10 +50,34 @@ def _svec_offdiag_mask(side):
     return mask
 
 
+def ssf_initial_point(hkind, d):
+    """get_initial_point of the separable spectral functions (sepspectralfun.jl:29-32, :49-52,
+    :69-72, :112-115): (u, v, w_ii)."""
+    return (2.0 * d, 1.0, 1.0) if hkind in (M.SSF_INV, M.SSF_POWER12) else (1.0, 1.0, 1.0)
+
+
+def ssf_eval(hkind, hparam, x):
+    """(h, h', h'') of a separable spectral function at the scalar x (sepspectralfun.jl:17-110)."""
+    if hkind == M.SSF_INV:
+        return 1 / x, -x ** -2.0, 2 * x ** -3.0
+    if hkind == M.SSF_NEGLOG:
+        return -np.log(x), -1 / x, x ** -2.0
+    if hkind == M.SSF_NEGENTROPY:
+        return x * np.log(x), 1 + np.log(x), 1 / x
+    return x ** hparam, hparam * x ** (hparam - 1), hparam * (hparam - 1) * x ** (hparam - 2)
+
+
+def mat_offset(spec):
+    """Number of scalar entries in front of the svec block of a matrix cone."""
+    return {M.CONE_POSSEMIDEFTRI: 0, M.CONE_HYPOPERLOGDETTRI: 2, M.CONE_HYPOROOTDETTRI: 1,
+            M.CONE_EPIPERSEPSPECTRAL_MAT: 2}[spec.ctype]
+
+
 def cone_initial_point(spec):
     """Central primal point of one cone (set_initial_point!; nonnegative.jl:42,
     epinormeucl.jl:44-52, possemideftri.jl:69-78, hypoperlogdettri.jl:82-94,
-    hyporootdettri.jl:82-98)."""
+    hyporootdettri.jl:82-98, matrixcsqr.jl:75-88 (not central), epipersquare.jl:59-64,
+    hypoperlog.jl:62-69)."""
     arr = np.zeros(spec.dim)
     if spec.ctype == M.CONE_NONNEGATIVE:
         arr[:] = 1.0
@@ -70,6 +94,16 @@ def cone_initial_point(spec):
         c1 = np.sqrt(5.0 * d * d + 2 * d + 1)
         c2 = arr[0] = -np.sqrt((3 * d + 1 - c1) / (2.0 * d + 2))
         arr[1 + _svec_diag_idx(d)] = -c2 * (d + 1 + c1) / (2.0 * d)
+    elif spec.ctype == M.CONE_EPIPERSEPSPECTRAL_MAT:
+        u, v, w = ssf_initial_point(spec.hkind, spec.side)
+        arr[0], arr[1] = u, v
+        arr[2 + _svec_diag_idx(spec.side)] = w
+    elif spec.ctype == M.CONE_EPIPERSQUARE:
+        arr[0] = arr[1] = 1.0
+    elif spec.ctype == M.CONE_HYPOPERLOG:
+        u, v, w = _central_ray_hypoperlog(spec.dim - 2)
+        arr[0], arr[1] = u, v
+        arr[2:] = w
     return arr
 
 
@@ -81,8 +115,32 @@ def _cone_dual_initial(spec, prim):
         return prim.copy()      # central point is self-dual: -g = (u, -w)/dist with dist = 1
     if spec.ctype == M.CONE_POSSEMIDEFTRI:
         return prim.copy()
-    d = spec.side
+    if spec.ctype == M.CONE_EPIPERSQUARE:
+        return prim.copy()      # (1, 1, 0...): -g = (v, u, -w) / dist with dist = u v - |w|^2 / 2 = 1
     out = np.zeros_like(prim)
+    if spec.ctype == M.CONE_HYPOPERLOG:
+        # hypoperlog.jl:99-113 at w = w0 * 1
+        d = spec.dim - 2
+        u, v, w = prim[0], prim[1], prim[2]
+        phi = d * np.log(w / v)
+        zeta = v * phi - u
+        out[0] = -1.0 / zeta
+        out[1] = 1.0 / v + (phi - d) / zeta
+        out[2:] = (1 + v / zeta) / w
+        return out
+    d = spec.side
+    if spec.ctype == M.CONE_EPIPERSEPSPECTRAL_MAT:
+        # matrixcsqr.jl:140-165 at W = w0 * I
+        u, v, w = prim[0], prim[1], prim[2]
+        lam = w / v
+        hv, h1, _ = ssf_eval(spec.hkind, spec.hparam, lam)
+        phi = d * hv
+        zeta = u - v * phi
+        sigma = phi - d * lam * h1
+        out[0] = 1.0 / zeta
+        out[1] = 1.0 / v - sigma / zeta
+        out[2 + _svec_diag_idx(d)] = -(h1 / zeta - 1.0 / w)
+        return out
     if spec.ctype == M.CONE_HYPOPERLOGDETTRI:
         u, v, w = prim[0], prim[1], prim[2]
         phi = d * np.log(w) - d * np.log(v)
@@ -105,7 +163,13 @@ def _perturb(rng, spec, vec, noise):
     if spec.ctype in (M.CONE_NONNEGATIVE, M.CONE_EPINORMEUCL):
         vec += noise * (2 * rng.random(vec.size) - 1)
         return vec
-    off = {M.CONE_POSSEMIDEFTRI: 0, M.CONE_HYPOPERLOGDETTRI: 2, M.CONE_HYPOROOTDETTRI: 1}[spec.ctype]
+    if spec.ctype in (M.CONE_EPIPERSQUARE, M.CONE_HYPOPERLOG):
+        vec[:2] += 0.5 * noise * (2 * rng.random(2) - 1)
+        vec[2:] += noise / np.sqrt(vec.size - 2) * (2 * rng.random(vec.size - 2) - 1)
+        return vec
+    if spec.ctype == M.CONE_EPIPERSEPSPECTRAL_MAT:
+        noise = noise / (2.0 * spec.side)   # the initial point is not central: stay close to it
+    off = mat_offset(spec)
     vec[:off] += 0.5 * noise * (2 * rng.random(off) - 1)
     vec[off:] += noise / np.sqrt(spec.side) * (2 * rng.random(vec.size - off) - 1)
     return vec
@@ -140,8 +204,7 @@ def synthetic(name, n, p, cones, seed, noise=0.1, dtype_rows_chunk=4096):
         else:
             s0[sl], z0[sl] = prim, dual
         if ck.side:
-            mo = off + {M.CONE_POSSEMIDEFTRI: 0, M.CONE_HYPOPERLOGDETTRI: 2,
-                        M.CONE_HYPOROOTDETTRI: 1}[ck.ctype]
+            mo = off + mat_offset(ck)
             rows = mo + np.nonzero(_svec_offdiag_mask(ck.side))[0]
             G[rows] *= RT2
         off += ck.dim

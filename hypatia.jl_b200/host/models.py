@@ -17,6 +17,12 @@ CONE_EPINORMEUCL = 1
 CONE_POSSEMIDEFTRI = 2
 CONE_HYPOPERLOGDETTRI = 3
 CONE_HYPOROOTDETTRI = 4
+CONE_EPIPERSEPSPECTRAL_MAT = 5
+CONE_EPIPERSQUARE = 6
+CONE_HYPOPERLOG = 7
+
+# separable spectral functions of EpiPerSepSpectral (sepspectralfun.jl:17-116), HYP_SSF_*
+SSF_INV, SSF_NEGLOG, SSF_NEGENTROPY, SSF_POWER12 = 0, 1, 2, 3
 
 CONE_NAMES = {
     CONE_NONNEGATIVE: "Nonnegative",
@@ -24,6 +30,9 @@ CONE_NAMES = {
     CONE_POSSEMIDEFTRI: "PosSemidefTri",
     CONE_HYPOPERLOGDETTRI: "HypoPerLogdetTri",
     CONE_HYPOROOTDETTRI: "HypoRootdetTri",
+    CONE_EPIPERSEPSPECTRAL_MAT: "EpiPerSepSpectral{MatrixCSqr}",
+    CONE_EPIPERSQUARE: "EpiPerSquare",
+    CONE_HYPOPERLOG: "HypoPerLog",
 }
 
 
@@ -47,12 +56,15 @@ def svec_side(length: int) -> int:
 class ConeSpec:
     """(type, dim) descriptor of one cone block; nu follows the reference's get_nu."""
 
-    __slots__ = ("ctype", "dim", "use_dual")
+    __slots__ = ("ctype", "dim", "use_dual", "hkind", "hparam")
 
-    def __init__(self, ctype: int, dim: int, use_dual: bool = False):
+    def __init__(self, ctype: int, dim: int, use_dual: bool = False, hkind: int = 0,
+                 hparam: float = 0.0):
         self.ctype = int(ctype)
         self.dim = int(dim)
         self.use_dual = bool(use_dual)
+        self.hkind = int(hkind)        # EpiPerSepSpectral: which separable spectral function
+        self.hparam = float(hparam)    # ... and its parameter (the power of Power12SSF)
         if ctype == CONE_NONNEGATIVE:
             assert dim >= 1
         elif ctype == CONE_EPINORMEUCL:
@@ -65,6 +77,14 @@ class ConeSpec:
         elif ctype == CONE_HYPOROOTDETTRI:
             assert dim >= 2
             svec_side(dim - 1)
+        elif ctype == CONE_EPIPERSEPSPECTRAL_MAT:
+            assert dim >= 3 and hkind in (SSF_INV, SSF_NEGLOG, SSF_NEGENTROPY, SSF_POWER12)
+            assert hkind != SSF_POWER12 or 1 < hparam <= 2
+            svec_side(dim - 2)
+        elif ctype == CONE_EPIPERSQUARE:
+            assert dim >= 3
+        elif ctype == CONE_HYPOPERLOG:
+            assert dim >= 3
         else:
             raise ValueError(f"unknown cone type {ctype}")
 
@@ -72,7 +92,7 @@ class ConeSpec:
     def side(self) -> int:
         if self.ctype == CONE_POSSEMIDEFTRI:
             return svec_side(self.dim)
-        if self.ctype == CONE_HYPOPERLOGDETTRI:
+        if self.ctype in (CONE_HYPOPERLOGDETTRI, CONE_EPIPERSEPSPECTRAL_MAT):
             return svec_side(self.dim - 2)
         if self.ctype == CONE_HYPOROOTDETTRI:
             return svec_side(self.dim - 1)
@@ -81,16 +101,24 @@ class ConeSpec:
     @property
     def nu(self) -> float:
         # nonnegative.jl:40, epinormeucl.jl:42, possemideftri.jl:67,
-        # hypoperlogdettri.jl:80, hyporootdettri.jl:80
+        # hypoperlogdettri.jl:80, hyporootdettri.jl:80, epipersepspectral.jl:79,
+        # epipersquare.jl:57, hypoperlog.jl:60
         if self.ctype == CONE_NONNEGATIVE:
             return float(self.dim)
         if self.ctype == CONE_EPINORMEUCL:
             return 2.0
         if self.ctype == CONE_POSSEMIDEFTRI:
             return float(self.side)
-        if self.ctype == CONE_HYPOPERLOGDETTRI:
+        if self.ctype in (CONE_HYPOPERLOGDETTRI, CONE_EPIPERSEPSPECTRAL_MAT):
             return 2.0 + self.side
+        if self.ctype == CONE_EPIPERSQUARE:
+            return 2.0
+        if self.ctype == CONE_HYPOPERLOG:
+            return float(self.dim)
         return 1.0 + self.side
+
+    def clone(self):
+        return ConeSpec(self.ctype, self.dim, self.use_dual, self.hkind, self.hparam)
 
     def __repr__(self):
         return f"{CONE_NAMES[self.ctype]}({self.dim})"
@@ -114,6 +142,20 @@ def HypoPerLogdetTri(dim, use_dual=False):
 
 def HypoRootdetTri(dim, use_dual=False):
     return ConeSpec(CONE_HYPOROOTDETTRI, dim, use_dual)
+
+
+def EpiPerSepSpectralMat(dim, hkind=SSF_NEGLOG, hparam=1.5, use_dual=False):
+    """EpiPerSepSpectral{MatrixCSqr{Float64, Float64}}(h, side), dim = 2 + svec_length(side)."""
+    return ConeSpec(CONE_EPIPERSEPSPECTRAL_MAT, dim, use_dual, hkind,
+                    hparam if hkind == SSF_POWER12 else 0.0)
+
+
+def EpiPerSquare(dim, use_dual=False):
+    return ConeSpec(CONE_EPIPERSQUARE, dim, use_dual)
+
+
+def HypoPerLog(dim, use_dual=False):
+    return ConeSpec(CONE_HYPOPERLOG, dim, use_dual)
 
 
 class Model:
@@ -147,5 +189,5 @@ class Model:
 
     def copy(self):
         return Model(self.c.copy(), self.A.copy(), self.b.copy(), self.G.copy(), self.h.copy(),
-                     [ConeSpec(ck.ctype, ck.dim, ck.use_dual) for ck in self.cones],
+                     [ck.clone() for ck in self.cones],
                      self.obj_offset)

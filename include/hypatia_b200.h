@@ -42,6 +42,15 @@ typedef struct hyp_ctx hyp_ctx;
 #define HYP_CONE_POSSEMIDEFTRI 2    /* possemideftri.jl (real) */
 #define HYP_CONE_HYPOPERLOGDETTRI 3 /* hypoperlogdettri.jl */
 #define HYP_CONE_HYPOROOTDETTRI 4   /* hyporootdettri.jl   */
+#define HYP_CONE_EPIPERSEPSPECTRAL_MAT 5 /* epipersepspectral/{epipersepspectral,matrixcsqr}.jl (real) */
+#define HYP_CONE_EPIPERSQUARE 6     /* epipersquare.jl     */
+#define HYP_CONE_HYPOPERLOG 7       /* hypoperlog.jl       */
+
+/* separable spectral functions of EpiPerSepSpectral (epipersepspectral/sepspectralfun.jl:17-116) */
+#define HYP_SSF_INV 0        /* InvSSF        x -> 1/x      */
+#define HYP_SSF_NEGLOG 1     /* NegLogSSF     x -> -log x   */
+#define HYP_SSF_NEGENTROPY 2 /* NegEntropySSF x -> x log x  */
+#define HYP_SSF_POWER12 3    /* Power12SSF(p) x -> x^p, 1 < p <= 2 */
 
 /* modes of hyp_cones_hess_prod (Cones.jl oracle names) */
 #define HYP_PROD_HESS 0          /* hess_prod!          */
@@ -65,6 +74,12 @@ int hyp_sync(hyp_ctx* ctx);
 /* rank 0 creates a 128-byte NCCL unique id, the host broadcasts it, every rank joins. */
 int hyp_comm_unique_id(char* id128);
 int hyp_comm_init(hyp_ctx* ctx, int rank, int nranks, const char* id128);
+
+/* ---- per-cone parameters beyond (type, dim, use_dual): the `h::SepSpectralFun` field of
+ *      EpiPerSepSpectral (epipersepspectral.jl:28-32).  ssf_kind[k] = HYP_SSF_*, ssf_param[k] = the power
+ *      of Power12SSF; entries of other cone types are ignored.  Call BEFORE hyp_load_model (the
+ *      values are consumed by the next load); models without such cones need not call it. */
+int hyp_set_cone_params(hyp_ctx* ctx, int K, const int* ssf_kind, const double* ssf_param);
 
 /* ---- load: replaces load(syssolver::QRCholDenseSystemSolver, solver), qrchol.jl:138-179,
  *      setup_point_sub common.jl:184-208, and setup_data!(cone) for every cone.

@@ -1,0 +1,42 @@
+#include "cuda_emu.h"
+
+thread_local dim3 threadIdx;
+thread_local dim3 blockIdx;
+dim3 blockDim;
+dim3 gridDim;
+namespace emu {
+BlockState* g_block = nullptr;
+void* g_dyn_smem = nullptr;
+
+void launch(dim3 grid, dim3 block, size_t dyn_smem, const std::function<void()>& body) {
+    gridDim = grid;
+    blockDim = block;
+    const int nt = (int)block.x;
+    std::vector<char> smem(dyn_smem + 64);
+    g_dyn_smem = (void*)(((uintptr_t)smem.data() + 63) & ~(uintptr_t)63);
+    for (unsigned by = 0; by < grid.y; by++)
+        for (unsigned bx = 0; bx < grid.x; bx++) {
+            BlockState st;
+            st.nthreads = nt;
+            pthread_barrier_init(&st.bar, nullptr, nt);
+            const int nw = (nt + 31) / 32;
+            st.warp_bar.resize(nw);
+            for (int w = 0; w < nw; w++) pthread_barrier_init(&st.warp_bar[w], nullptr, std::min(32, nt - 32 * w));
+            st.shf.assign(nt, 0.0);
+            g_block = &st;
+            std::vector<std::thread> th;
+            th.reserve(nt);
+            for (int t = 0; t < nt; t++)
+                th.emplace_back([&, t] {
+                    threadIdx = dim3(t, 0, 0);
+                    blockIdx = dim3(bx, by, 0);
+                    body();
+                });
+            for (auto& x : th) x.join();
+            pthread_barrier_destroy(&st.bar);
+            for (auto& wb : st.warp_bar) pthread_barrier_destroy(&wb);
+        }
+    g_block = nullptr;
+    g_dyn_smem = nullptr;
+}
+}  // namespace emu

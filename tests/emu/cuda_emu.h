@@ -1,0 +1,71 @@
+// Minimal host emulation of the CUDA execution model for the kernel headers under
+// hypatia.jl_b200/csrc/*_kernels.cuh (test infrastructure; CPU-only test tier).
+//
+// One pthread per CUDA thread of a block, blocks run one after the other; __syncthreads is a
+// pthread barrier over the block, warp shuffles exchange through a per-block buffer guarded by
+// per-warp barriers; __shared__ variables become function-level statics (blocks are sequential, so
+// a static is "per block").  Only what the kernel headers use is provided.
+#pragma once
+#include <pthread.h>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <thread>
+#include <vector>
+
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+
+namespace emu {
+struct BlockState {
+    pthread_barrier_t bar;
+    std::vector<pthread_barrier_t> warp_bar;
+    std::vector<double> shf;
+    int nthreads = 0;
+};
+extern BlockState* g_block;
+extern void* g_dyn_smem;
+}  // namespace emu
+
+extern thread_local dim3 threadIdx;
+extern thread_local dim3 blockIdx;
+extern dim3 blockDim;
+extern dim3 gridDim;
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __shared__ static
+#define HYP_DYN_SMEM(type, name) type* name = (type*)emu::g_dyn_smem
+#define INFINITY_EMU INFINITY
+
+static inline void __syncthreads() { pthread_barrier_wait(&emu::g_block->bar); }
+
+static inline double emu_shfl(double v, int src_lane_abs) {
+    emu::BlockState* b = emu::g_block;
+    const int tid = (int)threadIdx.x;
+    const int w = tid >> 5;
+    b->shf[tid] = v;
+    pthread_barrier_wait(&b->warp_bar[w]);
+    double out = (src_lane_abs >= 0 && src_lane_abs < b->nthreads) ? b->shf[src_lane_abs] : v;
+    pthread_barrier_wait(&b->warp_bar[w]);
+    return out;
+}
+static inline double __shfl_xor_sync(unsigned, double v, int o) {
+    return emu_shfl(v, (int)(threadIdx.x ^ (unsigned)o));
+}
+static inline double __shfl_sync(unsigned, double v, int lane) {
+    return emu_shfl(v, (int)((threadIdx.x & ~31u) + (unsigned)lane));
+}
+
+namespace emu {
+// run `body` for every thread of every block of the grid (1-D blocks, up to 2-D grids)
+void launch(dim3 grid, dim3 block, size_t dyn_smem, const std::function<void()>& body);
+}

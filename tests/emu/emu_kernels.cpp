@@ -1,0 +1,97 @@
+// Host-emulated launches of the kernel headers (test infrastructure, CPU-only test tier): the very
+// same __global__ functions nvcc compiles for sm_100a, run with one pthread per CUDA thread.
+#define HYP_EMU 1
+#include "cuda_emu.h"
+#include "../../hypatia.jl_b200/csrc/eig_kernels.cuh"
+
+extern "C" {
+
+// eigen-decomposition of nmat matrices through syevj_batched_kernel; smem = 1: shared-memory
+// variant (emulated dynamic smem), 0: global-scratch variant
+int emu_syevj(int nmat, int max_side, const int* sides, const int64_t* in_off, const double* Ain, double* Vout,
+              const int64_t* lam_off, double* lam, const double* divv, const int64_t* div_off, int div_idx,
+              int smem, int threads) {
+    const bool wantv = Vout != nullptr;
+    const int64_t wd = hypdev::syevj_work_doubles(max_side, true);
+    std::vector<double> gwork((size_t)wd * nmat + 8);
+    auto run = [&](auto kern, size_t dyn) {
+        emu::launch(dim3(nmat), dim3(threads), dyn, [&] {
+            kern(nmat, sides, in_off, Ain, Vout, lam_off, lam, divv, div_off, div_idx, gwork.data(), wd);
+        });
+    };
+    if (smem) {
+        if (wantv) run(hypdev::syevj_batched_kernel<true, true>, wd * 8);
+        else run(hypdev::syevj_batched_kernel<true, false>, wd * 8);
+    } else {
+        if (wantv) run(hypdev::syevj_batched_kernel<false, true>, 0);
+        else run(hypdev::syevj_batched_kernel<false, false>, 0);
+    }
+    return 0;
+}
+
+}  // extern "C"
+
+#include "../../hypatia.jl_b200/csrc/cones_mat_kernels.cuh"
+#include "../../hypatia.jl_b200/csrc/cones_spec_kernels.cuh"
+
+extern "C" {
+
+int emu_unpack_state(int ncones, const int64_t* off, const int* sides, const int64_t* moff, int lead,
+                     const double* vec, double* A, double* B, int gy) {
+    emu::launch(dim3(ncones, gy), dim3(64), 0,
+                [&] { hypdev::unpack_state_kernel(ncones, off, sides, moff, lead, vec, A, B); });
+    return 0;
+}
+
+int emu_unpack_cols(int d, int lde, int64_t len, const double* arr, int64_t ld_arr, int64_t cc, double* Mall,
+                    int gx) {
+    emu::launch(dim3(gx, (unsigned)cc), dim3(64), 0,
+                [&] { hypdev::unpack_cols_kernel(d, lde, len, arr, ld_arr, cc, Mall); });
+    return 0;
+}
+
+int emu_pack_cols(int d, int lde, int64_t len, const double* Yall, int64_t cc, const double* alpha,
+                  const double* beta, const double* vecB, double* prod, int64_t ld_prod, int gx) {
+    emu::launch(dim3(gx, (unsigned)cc), dim3(64), 0,
+                [&] { hypdev::pack_cols_kernel(d, lde, len, Yall, cc, alpha, beta, vecB, prod, ld_prod); });
+    return 0;
+}
+
+int emu_spec_post(int ncones, const int64_t* off, const int* sides, const int64_t* moff, const int64_t* voff,
+                  const int* kidx, const int* hkind, const double* hparam, const double* point, const double* V,
+                  double* Vt, double* theta, double* Dh, double* vecs, double* scal, double* grad, uint8_t* feas,
+                  int threads) {
+    emu::launch(dim3(ncones), dim3(threads), 0, [&] {
+        hypdev::spec_post_kernel(ncones, off, sides, moff, voff, kidx, hkind, hparam, point, V, Vt, theta, Dh, vecs,
+                                 scal, grad, feas);
+    });
+    return 0;
+}
+
+int emu_spec_dualfeas(int ncones, const int64_t* off, const int* sides, const int64_t* lam_off, const int* kidx,
+                      const int* hkind, const double* hparam, const double* dual, const double* lamd,
+                      const uint8_t* chol_ok, uint8_t* dual_feas) {
+    emu::launch(dim3(ncones), dim3(64), 0, [&] {
+        hypdev::spec_dualfeas_kernel(ncones, off, sides, lam_off, kidx, hkind, hparam, dual, lamd, chol_ok,
+                                     dual_feas);
+    });
+    return 0;
+}
+
+int emu_spec_mid(int inverse, int d, int lde, const double* sc, const double* vecs, const double* theta,
+                 const double* Dh, double* Mall, const double* arr, int64_t ld_arr, double* pr, int64_t ld_prod,
+                 int64_t cc, int grid, int threads) {
+    emu::launch(dim3(grid), dim3(threads), 0, [&] {
+        hypdev::spec_mid_kernel(inverse, d, lde, sc, vecs, theta, Dh, Mall, arr, ld_arr, pr, ld_prod, cc);
+    });
+    return 0;
+}
+
+int emu_spec_dder3(int d, int lde, const double* sc, const double* vecs, const double* Dh, const double* R,
+                   double* X, double* OUT, const double* dir, double* out, int threads) {
+    emu::launch(dim3(1), dim3(threads), 0,
+                [&] { hypdev::spec_dder3_kernel(d, lde, sc, vecs, Dh, R, X, OUT, dir, out); });
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,181 @@
+"""Host emulation of the CUDA kernel headers (hypatia.jl_b200/csrc/*_kernels.cuh) for the CPU-only
+test tier: tests/emu/ compiles the very same __global__ functions with g++ (one pthread per CUDA
+thread) into tests/emu/_build/libemu.so; the wrappers below mirror the launch sequences of the
+host code in csrc/ so that the device arithmetic is checked against the oracle without a GPU.
+Test infrastructure only - the product library has no CPU path."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU = os.path.join(HERE, "emu")
+BUILD = os.path.join(EMU, "_build")
+LIB = os.path.join(BUILD, "libemu.so")
+CSRC = os.path.join(os.path.dirname(HERE), "hypatia.jl_b200", "csrc")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    os.makedirs(BUILD, exist_ok=True)
+    srcs = [os.path.join(EMU, f) for f in ("emu_kernels.cpp", "cuda_emu.cpp")]
+    deps = srcs + [os.path.join(EMU, "cuda_emu.h")] + \
+        [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith("_kernels.cuh") or f == "devdefs.cuh"]
+    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", LIB] + srcs
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("emulation build failed:\n" + r.stderr)
+    _lib = C.CDLL(LIB)
+    return _lib
+
+
+def p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def i64(x):
+    return C.c_int64(int(x))
+
+
+class MatLayout:
+    """Per-cone d x d blocks with an even leading dimension, as hyp_mat_alloc_group lays them out."""
+
+    def __init__(self, sides):
+        self.sides = np.asarray(sides, dtype=np.int32)
+        self.lde = (self.sides + 1) & ~1
+        sizes = self.lde.astype(np.int64) * self.sides
+        self.moff = np.concatenate(([0], np.cumsum(sizes)))[:-1].astype(np.int64)
+        self.total = int(sizes.sum())
+
+    def get(self, buf, c):
+        d, lde = int(self.sides[c]), int(self.lde[c])
+        return buf[self.moff[c]:self.moff[c] + lde * d].reshape(lde, d, order="F")[:d]
+
+
+def syevj(layout, Ain, want_vectors=True, divv=None, div_off=None, div_idx=0, smem=True, threads=64):
+    n = len(layout.sides)
+    lam_off = np.concatenate(([0], np.cumsum(layout.sides)))[:-1].astype(np.int64)
+    lam = np.zeros(int(layout.sides.sum()))
+    V = np.zeros(layout.total) if want_vectors else None
+    lib().emu_syevj(n, int(layout.sides.max()), p(layout.sides), p(layout.moff), p(Ain), p(V), p(lam_off), p(lam),
+                    p(divv), p(div_off), div_idx, int(smem), threads)
+    return lam, lam_off, V
+
+
+class EmuSpecGroup:
+    """Mirrors hyp_spec_update_state / hyp_spec_prod / hyp_spec_dder3 (csrc/cones_spec.cu) for a list
+    of EpiPerSepSpectral{MatrixCSqr} cones laid out one after the other in a q-vector; the two
+    congruences around the middle kernel are NumPy products here (TMA + DMMA GEMMs on the device)."""
+
+    def __init__(self, specs, threads=64):
+        self.specs = specs
+        self.K = len(specs)
+        self.threads = threads
+        self.dims = np.array([s.dim for s in specs], dtype=np.int64)
+        self.off = np.concatenate(([0], np.cumsum(self.dims)))[:-1].astype(np.int64)
+        self.q = int(self.dims.sum())
+        self.lay = MatLayout([s.side for s in specs])
+        d = self.lay.sides.astype(np.int64)
+        self.voff = np.concatenate(([0], np.cumsum(8 * d)))[:-1].astype(np.int64)
+        self.voff7 = self.voff + 7 * d
+        self.kidx = np.arange(self.K, dtype=np.int32)
+        self.hkind = np.array([s.hkind for s in specs], dtype=np.int32)
+        self.hparam = np.array([s.hparam for s in specs], dtype=np.float64)
+        self.vecs = np.zeros(int(8 * d.sum()))
+        self.scal = np.zeros(8 * self.K)
+
+    def load_point(self, point, dual):
+        L = lib()
+        lay, K = self.lay, self.K
+        self.point = np.ascontiguousarray(point, dtype=np.float64)
+        self.dual = np.ascontiguousarray(dual, dtype=np.float64)
+        self.feas = np.ones(K, dtype=np.uint8)
+        self.dual_feas = np.ones(K, dtype=np.uint8)
+        self.grad = np.zeros(self.q)
+        W = np.zeros(lay.total)
+        Wc = np.zeros(lay.total)
+        L.emu_unpack_state(K, p(self.off), p(lay.sides), p(lay.moff), 2, p(self.point), p(W), p(Wc), 2)
+        for c in range(K):                          # Cholesky gate (hyp_chol_batched on the device)
+            try:
+                np.linalg.cholesky(lay.get(Wc, c))
+            except np.linalg.LinAlgError:
+                self.feas[c] = 0
+        self.V = np.zeros(lay.total)
+        L.emu_syevj(K, int(lay.sides.max()), p(lay.sides), p(lay.moff), p(W), p(self.V), p(self.voff), p(self.vecs),
+                    p(self.point), p(self.off), 1, 1, self.threads)
+        self.Vt = np.zeros(lay.total)
+        self.theta = np.zeros(lay.total)
+        self.Dh = np.zeros(lay.total)
+        L.emu_spec_post(K, p(self.off), p(lay.sides), p(lay.moff), p(self.voff), p(self.kidx), p(self.hkind),
+                        p(self.hparam), p(self.point), p(self.V), p(self.Vt), p(self.theta), p(self.Dh),
+                        p(self.vecs), p(self.scal), p(self.grad), p(self.feas), self.threads)
+        # dual feasibility
+        Wd = np.zeros(lay.total)
+        L.emu_unpack_state(K, p(self.off), p(lay.sides), p(lay.moff), 2, p(self.dual), p(Wd), None, 1)
+        chol_ok = np.ones(K, dtype=np.uint8)
+        for c in range(K):
+            try:
+                np.linalg.cholesky(lay.get(Wd, c))
+            except np.linalg.LinAlgError:
+                chol_ok[c] = 0
+        L.emu_syevj(K, int(lay.sides.max()), p(lay.sides), p(lay.moff), p(Wd), None, p(self.voff7), p(self.vecs),
+                    p(self.dual), p(self.off), 0, 1, self.threads)
+        L.emu_spec_dualfeas(K, p(self.off), p(lay.sides), p(self.voff7), p(self.kidx), p(self.hkind),
+                            p(self.hparam), p(self.dual), p(self.vecs), p(chol_ok), p(self.dual_feas))
+
+    def _congr(self, Mall, X, d, lde, cc):
+        """Y_j = X' M_j X in place for the cc matrices of Mall (what `congruence` does on the device)."""
+        per = lde * lde
+        for j in range(cc):
+            Mj = Mall[j * per:(j + 1) * per].reshape(lde, lde, order="F")
+            Mj[:d, :d] = X.T @ Mj[:d, :d] @ X
+
+    def prod(self, arr, inverse):
+        L = lib()
+        a = np.asfortranarray(np.asarray(arr, dtype=np.float64).reshape(self.q, -1, order="F"))
+        ncols = a.shape[1]
+        out = np.zeros_like(a, order="F")
+        for c in range(self.K):
+            d, lde = int(self.lay.sides[c]), int(self.lay.lde[c])
+            ln = d * (d + 1) // 2
+            Mall = np.zeros(lde * lde * ncols)
+            a0 = a[self.off[c]:, :]
+            base_a = a.ctypes.data + 8 * int(self.off[c])
+            base_o = out.ctypes.data + 8 * int(self.off[c])
+            L.emu_unpack_cols(d, lde, i64(ln), C.c_void_p(base_a + 16), i64(self.q), i64(ncols), p(Mall), 2)
+            self._congr(Mall, self.lay.get(self.V, c), d, lde, ncols)
+            vec_c = self.vecs[self.voff[c]:]
+            L.emu_spec_mid(int(inverse), d, lde, p(self.scal[8 * c:]), p(vec_c), p(self.theta[self.lay.moff[c]:]),
+                           p(self.Dh[self.lay.moff[c]:]), p(Mall), C.c_void_p(base_a), i64(self.q),
+                           C.c_void_p(base_o), i64(self.q), i64(ncols), min(ncols, 3), self.threads)
+            self._congr(Mall, self.lay.get(self.Vt, c), d, lde, ncols)
+            L.emu_pack_cols(d, lde, i64(ln), p(Mall), i64(ncols), None, None, None, C.c_void_p(base_o + 16),
+                            i64(self.q), 2)
+            del a0
+        return out[:, 0] if np.ndim(arr) == 1 else out
+
+    def dder3(self, direction):
+        L = lib()
+        dirv = np.ascontiguousarray(direction, dtype=np.float64)
+        out = np.zeros(self.q)
+        for c in range(self.K):
+            d, lde = int(self.lay.sides[c]), int(self.lay.lde[c])
+            ln = d * (d + 1) // 2
+            per = lde * lde
+            E = np.zeros(per)
+            X = np.zeros(per)
+            OUT = np.zeros(per)
+            base_d = dirv.ctypes.data + 8 * int(self.off[c])
+            base_o = out.ctypes.data + 8 * int(self.off[c])
+            L.emu_unpack_cols(d, lde, i64(ln), C.c_void_p(base_d + 16), i64(self.q), i64(1), p(E), 2)
+            self._congr(E, self.lay.get(self.V, c), d, lde, 1)
+            L.emu_spec_dder3(d, lde, p(self.scal[8 * c:]), p(self.vecs[self.voff[c]:]), p(self.Dh[self.lay.moff[c]:]),
+                             p(E), p(X), p(OUT), C.c_void_p(base_d), C.c_void_p(base_o), self.threads)
+            self._congr(OUT, self.lay.get(self.Vt, c), d, lde, 1)
+            L.emu_pack_cols(d, lde, i64(ln), p(OUT), i64(1), None, None, None, C.c_void_p(base_o + 16), i64(self.q), 2)
+        return out

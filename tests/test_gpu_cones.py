@@ -28,8 +28,18 @@ CONE_SETS = {
                M.HypoPerLogdetTri(2 + M.svec_length(33)), M.HypoPerLogdetTri(8, use_dual=True)],
     "rootdet": [M.HypoRootdetTri(2), M.HypoRootdetTri(4), M.HypoRootdetTri(11),
                 M.HypoRootdetTri(1 + M.svec_length(33)), M.HypoRootdetTri(7, use_dual=True)],
+    "sepspec": [M.EpiPerSepSpectralMat(2 + M.svec_length(1), M.SSF_NEGLOG),
+                M.EpiPerSepSpectralMat(2 + M.svec_length(3), M.SSF_NEGENTROPY),
+                M.EpiPerSepSpectralMat(2 + M.svec_length(6), M.SSF_INV),
+                M.EpiPerSepSpectralMat(2 + M.svec_length(12), M.SSF_POWER12, 1.5),
+                M.EpiPerSepSpectralMat(2 + M.svec_length(33), M.SSF_NEGLOG),
+                M.EpiPerSepSpectralMat(2 + M.svec_length(5), M.SSF_NEGENTROPY, use_dual=True),
+                M.EpiPerSepSpectralMat(2 + M.svec_length(100), M.SSF_NEGENTROPY)],
+    "sepspec_big": [M.EpiPerSepSpectralMat(2 + M.svec_length(130), M.SSF_NEGLOG),
+                    M.EpiPerSepSpectralMat(2 + M.svec_length(4), M.SSF_POWER12, 2.0)],
     "allmix": [M.Nonnegative(5), M.EpiNormEucl(4), M.PosSemidefTri(6), M.HypoPerLogdetTri(8),
-               M.HypoRootdetTri(7), M.EpiNormEucl(3), M.HypoPerLogdetTri(5, use_dual=True)],
+               M.HypoRootdetTri(7), M.EpiNormEucl(3), M.HypoPerLogdetTri(5, use_dual=True),
+               M.EpiPerSepSpectralMat(2 + M.svec_length(4), M.SSF_NEGENTROPY)],
 }
 
 

@@ -131,6 +131,60 @@ def test_generic_sqrt_oracles_logdet(side):
     assert close(RA.T @ RA, A.T @ cone.hess_prod(A), 1e-12)
 
 
+SSF = [(0, 0.0), (1, 0.0), (2, 0.0), (3, 1.5), (3, 2.0), (3, 1.1)]   # Inv, NegLog, NegEntropy, Power12(p)
+
+
+@pytest.mark.parametrize("side", [1, 2, 3, 6])
+@pytest.mark.parametrize("hkind,hparam", SSF)
+def test_epipersepspectral_matrix(side, hkind, hparam):
+    # reference: test/cone.jl:672-676 (d in [1, 2, 3, 6], every separable spectral function, init_tol = Inf)
+    from oracle.cones_sepspec import EpiPerSepSpectralMat
+    run_oracles(EpiPerSepSpectralMat(2 + side * (side + 1) // 2, hkind, hparam), init_tol=np.inf)
+
+
+@pytest.mark.parametrize("hkind,hparam", SSF)
+def test_epipersepspectral_matrix_barrier(hkind, hparam):
+    """test_barrier of test/cone.jl:117-160, :688-698 with central differences in place of ForwardDiff:
+    grad, hess_prod and dder3 against derivatives of the barrier
+    -log(u - v * sum h(eig(W) / v)) - log(v) - sum log eig(W)."""
+    from oracle import arrayutil as au
+    from oracle.cones_sepspec import EpiPerSepSpectralMat, SepSpectralFun
+    side = 3
+    cone = EpiPerSepSpectralMat(2 + side * (side + 1) // 2, hkind, hparam)
+    h = SepSpectralFun(hkind, hparam)
+
+    def barrier(s):
+        lam = np.linalg.eigvalsh(au.svec_to_smat(s[2:]))
+        return -np.log(s[0] - s[1] * h.val(lam / s[1])) - np.log(s[1]) - np.sum(np.log(lam))
+
+    rng = np.random.default_rng(1)
+    point = np.zeros(cone.dim)
+    cone.set_initial_point(point)
+    perturb_scale(rng, point, 0.1, 1.0)
+
+    def grad_at(s):
+        cone.reset_data()
+        cone.load_point(s)
+        assert cone.is_feas()
+        return cone.grad().copy()
+
+    g = grad_at(point)
+    eps = 1e-6
+    fd_grad = np.array([(barrier(point + eps * e) - barrier(point - eps * e)) / (2 * eps)
+                        for e in np.eye(cone.dim)])
+    assert close(g, fd_grad, 1e-7)
+    direction = rng.standard_normal(cone.dim)
+    fd_hess_dir = (grad_at(point + eps * direction) - grad_at(point - eps * direction)) / (2 * eps)
+    grad_at(point)
+    assert close(cone.hess_prod(direction), fd_hess_dir, 1e-7)
+    assert close(cone.hess() @ direction, fd_hess_dir, 1e-7)
+    # -2 dder3 = third directional derivative (cone.jl:155): second difference of the gradient
+    e2 = 1e-4
+    fd_third = (grad_at(point + e2 * direction) - 2 * g + grad_at(point - e2 * direction)) / e2 ** 2
+    grad_at(point)
+    assert close(-2 * cone.dder3(direction), fd_third, 1e-5)
+
+
 def test_svec_roundtrip():
     from oracle import arrayutil as au
     rng = np.random.default_rng(0)
