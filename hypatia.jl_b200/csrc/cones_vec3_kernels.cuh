@@ -1,0 +1,272 @@
+// Device oracles of EpiPerSquare and HypoPerLog: vector cones with two leading scalars (u, v) and a
+// w block; one warp per cone for the state, one warp per (cone, column) for the products.
+//
+// reference: src/Cones/epipersquare.jl:59-274 (update_feas, is_dual_feas, update_grad, hess_prod!,
+// inv_hess_prod!, sqrt_hess_prod!, inv_sqrt_hess_prod!, dder3), src/Cones/hypoperlog.jl:62-287
+// (update_feas, is_dual_feas, update_grad, hess_prod!, inv_hess_prod!, dder3).
+// scal (8 doubles per cone): EpiPerSquare 0 dist; HypoPerLog 1 phi, 2 zeta.
+// HBM-bound streaming kernels: 16 * rows * ncols algorithmic bytes per product.
+#pragma once
+#include "devdefs.cuh"
+
+#define V3_EPIPERSQUARE 6   // = HYP_CONE_EPIPERSQUARE
+#define V3_HYPOPERLOG 7     // = HYP_CONE_HYPOPERLOG
+// product modes (= HYP_PROD_*)
+#define V3_HESS 0
+#define V3_INV_HESS 1
+#define V3_SQRT_HESS 2
+#define V3_INV_SQRT_HESS 3
+
+namespace hypdev {
+
+static __global__ void __launch_bounds__(256)
+v3_state_kernel(int type, int ncones, const int64_t* __restrict__ off, const int* __restrict__ dim,
+                const int* __restrict__ kidx, const double* __restrict__ point,
+                const double* __restrict__ dual, double* __restrict__ grad, double* __restrict__ scal,
+                uint8_t* feas, uint8_t* dual_feas) {
+    const int lane = threadIdx.x & 31;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= ncones) return;   // whole warps leave together
+    const int64_t o = off[c];
+    const int d = dim[c];
+    const double u = point[o], v = point[o + 1], du = dual[o], dv = dual[o + 1];
+    if (type == V3_EPIPERSQUARE) {
+        // epipersquare.jl:59-100
+        double sw = 0.0, sdw = 0.0;
+        for (int i = 2 + lane; i < d; i += 32) {
+            const double w = point[o + i], dw = dual[o + i];
+            sw += w * w;
+            sdw += dw * dw;
+        }
+        sw = warp_sum(sw);
+        sdw = warp_sum(sdw);
+        double dist = 0.0;
+        bool ok = false;
+        if (u > HYP_EPS && v > HYP_EPS) {
+            dist = u * v - sw / 2;
+            ok = dist > HYP_EPS;
+        }
+        const bool dok = (du > HYP_EPS && dv > HYP_EPS) && ((du * dv - sdw / 2) > HYP_EPS);
+        for (int i = lane; i < d; i += 32) {
+            double g;
+            if (i == 0) g = -v / dist;
+            else if (i == 1) g = -u / dist;
+            else g = point[o + i] / dist;
+            grad[o + i] = g;
+        }
+        if (lane == 0) {
+            scal[8 * c] = dist;
+            if (!ok) feas[kidx[c]] = 0;
+            if (!dok) dual_feas[kidx[c]] = 0;
+        }
+    } else {
+        // hypoperlog.jl:62-113
+        const int dw = d - 2;
+        double nbad = 0.0, dbad = 0.0, phi = 0.0, sumlog = 0.0;
+        for (int i = 2 + lane; i < d; i += 32) {
+            const double w = point[o + i], z = dual[o + i];
+            if (!(w > HYP_EPS)) nbad += 1.0;
+            if (!(z > HYP_EPS)) dbad += 1.0;
+            phi += log(w / v);
+            sumlog += log(z / -du);
+        }
+        nbad = warp_sum(nbad);
+        dbad = warp_sum(dbad);
+        phi = warp_sum(phi);
+        sumlog = warp_sum(sumlog);
+        const double zeta = v * phi - u;
+        const bool ok = v > HYP_EPS && nbad == 0.0 && zeta > HYP_EPS;
+        const bool dok = dbad == 0.0 && du < -HYP_EPS && (dv - du * (sumlog + dw)) > HYP_EPS;
+        const double vzi1 = -1.0 - v / zeta;
+        for (int i = lane; i < d; i += 32) {
+            double g;
+            if (i == 0) g = 1.0 / zeta;
+            else if (i == 1) g = -(phi - dw) / zeta - 1.0 / v;
+            else g = vzi1 / point[o + i];
+            grad[o + i] = g;
+        }
+        if (lane == 0) {
+            scal[8 * c + 1] = phi;
+            scal[8 * c + 2] = zeta;
+            if (!ok) feas[kidx[c]] = 0;
+            if (!dok) dual_feas[kidx[c]] = 0;
+        }
+    }
+}
+
+// prod[:, j] = oracle(arr[:, j]) on the rows of every cone of the group.  `dualf` (may be null):
+// per-cone use_dual_barrier flag, only read when mode is one of the block modes (4: hess for primal
+// / inv_hess for dual-barrier cones, 5: the other way round).
+static __global__ void __launch_bounds__(256)
+v3_prod_kernel(int type, int mode_in, int ncones, const int64_t* __restrict__ off,
+               const int* __restrict__ dim, const int* __restrict__ dualf,
+               const double* __restrict__ scal, const double* __restrict__ point, const double* arr,
+               int64_t ld_arr, double* prod, int64_t ld_prod, int64_t ncols, int64_t row_shift) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= ncones) return;
+    const int64_t o = off[c];
+    const int d = dim[c];
+    int mode = mode_in;
+    if (mode == 4) mode = (dualf && dualf[c]) ? V3_INV_HESS : V3_HESS;
+    if (mode == 5) mode = (dualf && dualf[c]) ? V3_HESS : V3_INV_HESS;
+    const double u = point[o], v = point[o + 1];
+    for (int64_t j = blockIdx.y; j < ncols; j += gridDim.y) {
+        const double* a = arr + j * ld_arr + (o - row_shift);
+        double* pr = prod + j * ld_prod + (o - row_shift);
+        const double p = a[0], q = a[1];
+        if (type == V3_EPIPERSQUARE) {
+            // every oracle is  coef * vec + kap * J a  with J a = (-a_2, -a_1, a_w):
+            //   vec = J point / point / sqrt-vectors of epipersquare.jl:156-191, coef from one dot product
+            const double dist = scal[8 * c];
+            const double rtdist = sqrt(dist), denom = 2 * rtdist + u + v;
+            double v0, v1, sc, kap;   // vec = (v0, v1, sc * w)
+            if (mode == V3_HESS) {
+                v0 = -v; v1 = -u; sc = 1.0; kap = 1.0 / dist;
+            } else if (mode == V3_INV_HESS) {
+                v0 = u; v1 = v; sc = 1.0; kap = dist;
+            } else if (mode == V3_SQRT_HESS) {
+                v0 = -v / rtdist - 1.0; v1 = -u / rtdist - 1.0; sc = 1.0 / rtdist; kap = 1.0 / rtdist;
+            } else {
+                v0 = u + rtdist; v1 = v + rtdist; sc = 1.0; kap = rtdist;
+            }
+            double dot = 0.0;
+            for (int i = 2 + lane; i < d; i += 32) dot += point[o + i] * a[i];
+            dot = sc * warp_sum(dot) + v0 * p + v1 * q;
+            double coef;
+            if (mode == V3_HESS) coef = dot / (dist * dist);
+            else if (mode == V3_INV_HESS) coef = dot;
+            else coef = dot / denom;
+            for (int i = lane; i < d; i += 32) {
+                double x;
+                if (i == 0) x = coef * v0 - kap * q;
+                else if (i == 1) x = coef * v1 - kap * p;
+                else x = coef * sc * point[o + i] + kap * a[i];
+                pr[i] = x;
+            }
+        } else {
+            const double phi = scal[8 * c + 1], zeta = scal[8 * c + 2];
+            const double dd = (double)(d - 2);
+            if (mode == V3_HESS) {
+                // hypoperlog.jl:153-183
+                const double sigma = phi - dd, vzi1 = v / zeta + 1.0;
+                double s = 0.0;
+                for (int i = 2 + lane; i < d; i += 32) s += a[i] / point[o + i];
+                s = warp_sum(s);
+                const double qzi = q / zeta, c0 = s / zeta;
+                const double c1 = (v * c0 - p / zeta + sigma * qzi) / zeta;
+                const double c3 = c1 * v - qzi;
+                for (int i = lane; i < d; i += 32) {
+                    double x;
+                    if (i == 0) x = -c1;
+                    else if (i == 1) x = c1 * sigma - c0 + (qzi * dd + q / v) / v;
+                    else {
+                        const double w = point[o + i];
+                        x = (c3 + vzi1 * (a[i] / w)) / w;
+                    }
+                    pr[i] = x;
+                }
+            } else {
+                // hypoperlog.jl:221-257
+                const double zv = zeta + v, zzvi = zeta / zv;
+                const double c3 = v / (zv + dd * v);
+                const double c0 = phi - dd * zzvi;
+                const double c4 = v * c3 * zv;
+                const double t = zeta + v * phi;
+                const double c6 = (v * phi) * (v * phi) + zeta * (zeta + dd * v) - dd * t * t * c3;
+                const double c7 = c4 * c0, c8 = c7 + v * zeta;
+                double s = 0.0;
+                for (int i = 2 + lane; i < d; i += 32) s += a[i] * point[o + i];
+                s = warp_sum(s);
+                const double c1 = s / zv;
+                const double c5 = c0 * p + q + c1;
+                const double c2 = v * (zzvi * p + c3 * c5);
+                for (int i = lane; i < d; i += 32) {
+                    double x;
+                    if (i == 0) x = c6 * p + c7 * q + c8 * c1;
+                    else if (i == 1) x = c4 * c5;
+                    else {
+                        const double w = point[o + i];
+                        x = (c2 + zzvi * (a[i] * w)) * w;
+                    }
+                    pr[i] = x;
+                }
+            }
+        }
+    }
+}
+
+// epipersquare.jl:246-274, hypoperlog.jl:259-287
+static __global__ void __launch_bounds__(256)
+v3_dder3_kernel(int type, int ncones, const int64_t* __restrict__ off, const int* __restrict__ dim,
+                const double* __restrict__ scal, const double* __restrict__ point,
+                const double* __restrict__ dir, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= ncones) return;
+    const int64_t o = off[c];
+    const int d = dim[c];
+    const double u = point[o], v = point[o + 1], p = dir[o], q = dir[o + 1];
+    if (type == V3_EPIPERSQUARE) {
+        const double dist = scal[8 * c];
+        double sww = 0.0, swd = 0.0, sdd = 0.0;
+        for (int i = 2 + lane; i < d; i += 32) {
+            const double w = point[o + i], wd = dir[o + i];
+            sww += w * w;
+            swd += w * wd;
+            sdd += wd * wd;
+        }
+        sww = warp_sum(sww);
+        swd = warp_sum(swd);
+        sdd = warp_sum(sdd);
+        const double jdotpd = u * q + v * p - swd;
+        const double ga = (swd - v * p - u * q) / dist;
+        const double h0 = (-ga * v - q) / dist, h1 = (-ga * u - p) / dist;   // (H dir)[0], [1]
+        // (H dir)[i] = (ga w_i + wd_i) / dist
+        const double dHd = p * h0 + q * h1 + (ga * swd + sdd) / dist;
+        const double pHd = u * h0 + v * h1 + (ga * sww + swd) / dist;
+        const double dotdHd = -dHd, dotpHd = pHd;
+        const double inv2d = 1.0 / (2 * dist);
+        for (int i = lane; i < d; i += 32) {
+            double r;
+            if (i == 0) r = h0 * jdotpd - dotdHd * v - dotpHd * q;
+            else if (i == 1) r = h1 * jdotpd - dotdHd * u - dotpHd * p;
+            else {
+                const double w = point[o + i], wd = dir[o + i];
+                r = (ga * w + wd) / dist * jdotpd + dotdHd * w + dotpHd * wd;
+            }
+            out[o + i] = r * inv2d;
+        }
+    } else {
+        const double phi = scal[8 * c + 1], zeta = scal[8 * c + 2];
+        const double dd = (double)(d - 2);
+        const double sigma = phi - dd, viq = q / v, viq2 = viq * viq, vzi = v / zeta, vzi1 = vzi + 1.0;
+        double c0 = 0.0, c7 = 0.0;
+        for (int i = 2 + lane; i < d; i += 32) {
+            const double r = dir[o + i] / point[o + i];
+            c0 += r;
+            c7 += r * r;
+        }
+        c0 = warp_sum(c0);
+        c7 = warp_sum(c7);
+        const double zichi = (-p + sigma * q + c0 * v) / zeta;
+        const double c4 = (viq * (-viq * dd + 2 * c0) - c7) / zeta / 2;
+        const double c1 = (zichi * zichi - v * c4) / zeta;
+        const double c3 = -(zichi + viq) / zeta;
+        const double c5 = c3 * q + vzi * viq2;
+        const double c6 = -2 * vzi * viq - c3 * v;
+        const double c8 = c5 + c1 * v;
+        for (int i = lane; i < d; i += 32) {
+            double x;
+            if (i == 0) x = -c1;
+            else if (i == 1) x = c1 * sigma + (viq2 - (dd * c5 + c6 * c0 + vzi * c7)) / v - c4;
+            else {
+                const double w = point[o + i], r = dir[o + i] / w;
+                x = (c8 + r * (c6 + vzi1 * r)) / w;
+            }
+            out[o + i] = x;
+        }
+    }
+}
+
+}  // namespace hypdev

@@ -1,0 +1,288 @@
+"""CPU restatement of EpiPerSquare and HypoPerLog (oracle; test infrastructure).
+
+reference: src/Cones/epipersquare.jl:42-274 (rotated second-order cone (u, v, w): 2uv >= |w|^2,
+barrier -log(2uv - |w|^2), nu = 2, self-dual, closed-form sqrt oracles),
+src/Cones/hypoperlog.jl:54-287 (hypograph of the perspective of sum-log, (u, v, w):
+u <= v sum log(w_i / v), barrier -log(v sum log(w_i/v) - u) - log v - sum log w_i, nu = dim).
+"""
+import numpy as np
+
+from hypatia_b200.host import models as M
+from .cones import Cone, EPS, _as2d, _ret, get_central_ray_hypoperlog
+
+
+class EpiPerSquare(Cone):
+    ctype = M.CONE_EPIPERSQUARE
+    nu = 2.0
+
+    def __init__(self, dim, use_dual=False):
+        assert not use_dual            # epipersquare.jl:42 (self-dual cone)
+        super().__init__(dim)
+
+    def set_initial_point(self, arr):
+        arr[:] = 0.0
+        arr[:2] = 1.0
+        return arr
+
+    def update_feas(self):
+        u, v = self.point[0], self.point[1]
+        if u > EPS and v > EPS:
+            w = self.point[2:]
+            self.dist = u * v - float(w @ w) / 2
+            return self.dist > EPS
+        return False
+
+    def is_dual_feas(self):
+        u, v = self.dual_point[0], self.dual_point[1]
+        if u > EPS and v > EPS:
+            w = self.dual_point[2:]
+            return (u * v - float(w @ w) / 2) > EPS
+        return False
+
+    def update_grad(self):
+        g = self._grad
+        g[:] = self.point / self.dist
+        g2 = g[1]
+        g[1] = -g[0]
+        g[0] = -g2
+
+    def update_hess(self):
+        g = self.grad()
+        H = np.outer(g, g)
+        inv_dist = 1.0 / self.dist
+        idx = np.arange(2, self.dim)
+        H[idx, idx] += inv_dist
+        H[0, 1] -= inv_dist
+        H[1, 0] -= inv_dist
+        return H
+
+    def update_inv_hess(self):
+        Hi = np.outer(self.point, self.point)
+        idx = np.arange(2, self.dim)
+        Hi[idx, idx] += self.dist
+        Hi[0, 1] -= self.dist
+        Hi[1, 0] -= self.dist
+        return Hi
+
+    def use_sqrt_hess_oracles(self, arr_dim):
+        return True
+
+    @staticmethod
+    def _swap(a):
+        """J a = (-a_2, -a_1, a_w)."""
+        out = a.copy()
+        out[0] = -a[1]
+        out[1] = -a[0]
+        return out
+
+    def hess_prod(self, arr):
+        assert self.is_feas()
+        a, vec = _as2d(arr)
+        u, v, w = self.point[0], self.point[1], self.point[2:]
+        uj, vj, wj = a[0], a[1], a[2:]
+        ga = (w @ wj - v * uj - u * vj) / self.dist
+        prod = np.empty_like(a)
+        prod[0] = -ga * v - vj
+        prod[1] = -ga * u - uj
+        prod[2:] = ga[None, :] * w[:, None] + wj
+        prod /= self.dist
+        return _ret(prod, vec)
+
+    def inv_hess_prod(self, arr):
+        assert self.is_feas()
+        a, vec = _as2d(arr)
+        pa = self.point @ a
+        prod = pa[None, :] * self.point[:, None] + self.dist * self._swap(a)
+        return _ret(prod, vec)
+
+    def sqrt_hess_prod(self, arr):
+        assert self.is_feas()
+        a, vec = _as2d(arr)
+        rtdist = np.sqrt(self.dist)
+        denom = 2 * rtdist + self.point[0] + self.point[1]
+        sv = self.point / rtdist
+        sv[0] = -self.point[1] / rtdist - 1
+        sv[1] = -self.point[0] / rtdist - 1
+        dotj = (sv @ a) / denom
+        prod = dotj[None, :] * sv[:, None] + self._swap(a) / rtdist
+        return _ret(prod, vec)
+
+    def inv_sqrt_hess_prod(self, arr):
+        assert self.is_feas()
+        a, vec = _as2d(arr)
+        rtdist = np.sqrt(self.dist)
+        denom = 2 * rtdist + self.point[0] + self.point[1]
+        sv = self.point.copy()
+        sv[:2] += rtdist
+        dotj = (sv @ a) / denom
+        prod = dotj[None, :] * sv[:, None] + self._swap(a) * rtdist
+        return _ret(prod, vec)
+
+    def dder3(self, direction):
+        self.grad()
+        point = self.point
+        u, v, w = point[0], point[1], point[2:]
+        u_dir, v_dir, w_dir = direction[0], direction[1], direction[2:]
+        jdotpd = u * v_dir + v * u_dir - float(w @ w_dir)
+        d3 = self.hess_prod(direction).copy()
+        dotdHd = -float(direction @ d3)
+        dotpHd = float(point @ d3)
+        d3 *= jdotpd
+        d3[2:] += dotdHd * w + dotpHd * w_dir
+        d3[0] += -dotdHd * v - dotpHd * v_dir
+        d3[1] += -dotdHd * u - dotpHd * u_dir
+        d3 /= 2 * self.dist
+        return d3
+
+
+class HypoPerLog(Cone):
+    ctype = M.CONE_HYPOPERLOG
+
+    def __init__(self, dim, use_dual=False):
+        self.use_dual_barrier = use_dual
+        super().__init__(dim)
+
+    @property
+    def nu(self):
+        return float(self.dim)
+
+    def set_initial_point(self, arr):
+        u, v, w = get_central_ray_hypoperlog(self.dim - 2)
+        arr[0], arr[1] = u, v
+        arr[2:] = w
+        return arr
+
+    def update_feas(self):
+        v, w = self.point[1], self.point[2:]
+        if v > EPS and (w > EPS).all():
+            u = self.point[0]
+            self.phi = float(np.sum(np.log(w / v)))
+            self.zeta = v * self.phi - u
+            return self.zeta > EPS
+        return False
+
+    def is_dual_feas(self):
+        u, w = self.dual_point[0], self.dual_point[2:]
+        if (w > EPS).all() and u < -EPS:
+            v = self.dual_point[1]
+            sumlog = float(np.sum(np.log(w / -u)))
+            return (v - u * (sumlog + w.size)) > EPS
+        return False
+
+    def update_grad(self):
+        v, w = self.point[1], self.point[2:]
+        d = w.size
+        zeta = self.zeta
+        g = self._grad
+        g[0] = 1.0 / zeta
+        g[1] = -(self.phi - d) / zeta - 1.0 / v
+        g[2:] = (-1 - v / zeta) / w
+
+    def update_hess(self):
+        g = self.grad()
+        v, w = self.point[1], self.point[2:]
+        d = w.size
+        zeta = self.zeta
+        sigzi = (self.phi - d) / zeta
+        vzi = v / zeta
+        wivzi = vzi / w
+        H = np.zeros((self.dim, self.dim))
+        H[0, 0] = zeta ** -2
+        H[0, 1] = H[1, 0] = -sigzi / zeta
+        H[1, 1] = v ** -2 + sigzi ** 2 + d / zeta / v
+        H[0, 2:] = H[2:, 0] = (-vzi / zeta) / w
+        H[1, 2:] = H[2:, 1] = (((self.phi - d) * vzi - 1) / zeta) / w
+        H[2:, 2:] = np.outer(wivzi, wivzi)
+        idx = np.arange(2, self.dim)
+        H[idx, idx] -= g[2:] / w
+        return H
+
+    def hess_prod(self, arr):
+        self.grad()
+        a, vec = _as2d(arr)
+        v, w = self.point[1], self.point[2:]
+        zeta = self.zeta
+        d = w.size
+        sigma = self.phi - d
+        vzi1 = v / zeta + 1
+        p, q = a[0], a[1]
+        rwi = a[2:] / w[:, None]
+        qzi = q / zeta
+        c0 = rwi.sum(axis=0) / zeta
+        c1 = (v * c0 - p / zeta + sigma * qzi) / zeta
+        c3 = c1 * v - qzi
+        prod = np.empty_like(a)
+        prod[0] = -c1
+        prod[1] = c1 * sigma - c0 + (qzi * d + q / v) / v
+        prod[2:] = (c3[None, :] + vzi1 * rwi) / w[:, None]
+        return _ret(prod, vec)
+
+    def _ih_consts(self):
+        v, w = self.point[1], self.point[2:]
+        d = w.size
+        zeta, phi = self.zeta, self.phi
+        zv = zeta + v
+        zzvi = zeta / zv
+        c3 = v / (zv + d * v)
+        c0 = phi - d * zzvi
+        c4 = v * c3 * zv
+        c6 = (v * phi) ** 2 + zeta * (zeta + d * v) - d * (zeta + v * phi) ** 2 * c3
+        return v, w, d, zeta, phi, zv, zzvi, c3, c0, c4, c6
+
+    def update_inv_hess(self):
+        self.grad()
+        v, w, d, zeta, phi, zv, zzvi, c3, c0, c4, c6 = self._ih_consts()
+        c2 = v * c3
+        c1 = v * zzvi + c0 * c2
+        Hi = np.zeros((self.dim, self.dim))
+        Hi[0, 0] = c6
+        Hi[0, 1] = Hi[1, 0] = c0 * c4
+        Hi[1, 1] = c4
+        Hi[0, 2:] = Hi[2:, 0] = c1 * w
+        Hi[1, 2:] = Hi[2:, 1] = c2 * w
+        Hi[2:, 2:] = zzvi * np.diag(w ** 2) + (c2 / zv) * np.outer(w, w)
+        return Hi
+
+    def inv_hess_prod(self, arr):
+        self.grad()
+        a, vec = _as2d(arr)
+        v, w, d, zeta, phi, zv, zzvi, c3, c0, c4, c6 = self._ih_consts()
+        c7 = c4 * c0
+        c8 = c7 + v * zeta
+        p, q = a[0], a[1]
+        rw = a[2:] * w[:, None]
+        c1 = rw.sum(axis=0) / zv
+        c5 = c0 * p + q + c1
+        c2 = v * (zzvi * p + c3 * c5)
+        prod = np.empty_like(a)
+        prod[0] = c6 * p + c7 * q + c8 * c1
+        prod[1] = c4 * c5
+        prod[2:] = (c2[None, :] + zzvi * rw) * w[:, None]
+        return _ret(prod, vec)
+
+    def dder3(self, direction):
+        self.grad()
+        v, w = self.point[1], self.point[2:]
+        p, q = direction[0], direction[1]
+        zeta = self.zeta
+        d = w.size
+        sigma = self.phi - d
+        viq = q / v
+        viq2 = viq ** 2
+        vzi = v / zeta
+        vzi1 = vzi + 1
+        rwi = direction[2:] / w
+        c0 = float(rwi.sum())
+        c7 = float((rwi ** 2).sum())
+        zichi = (-p + sigma * q + c0 * v) / zeta
+        c4 = (viq * (-viq * d + 2 * c0) - c7) / zeta / 2
+        c1 = (zichi ** 2 - v * c4) / zeta
+        c3 = -(zichi + viq) / zeta
+        c5 = c3 * q + vzi * viq2
+        c6 = -2 * vzi * viq - c3 * v
+        c8 = c5 + c1 * v
+        d3 = np.empty(self.dim)
+        d3[0] = -c1
+        d3[1] = c1 * sigma + (viq2 - (d * c5 + c6 * c0 + vzi * c7)) / v - c4
+        d3[2:] = (c8 + rwi * (c6 + vzi1 * rwi)) / w
+        return d3

@@ -179,3 +179,40 @@ class EmuSpecGroup:
             self._congr(OUT, self.lay.get(self.Vt, c), d, lde, 1)
             L.emu_pack_cols(d, lde, i64(ln), p(OUT), i64(1), None, None, None, C.c_void_p(base_o + 16), i64(self.q), 2)
         return out
+
+
+class EmuVec3Group:
+    """Mirrors the launches of cones.cu for a list of EpiPerSquare or HypoPerLog cones (one type)."""
+
+    def __init__(self, specs):
+        self.type = specs[0].ctype
+        assert all(s.ctype == self.type for s in specs)
+        self.K = len(specs)
+        self.dims = np.array([s.dim for s in specs], dtype=np.int32)
+        self.off = np.concatenate(([0], np.cumsum(self.dims)))[:-1].astype(np.int64)
+        self.q = int(self.dims.sum())
+        self.kidx = np.arange(self.K, dtype=np.int32)
+        self.dualf = np.array([1 if s.use_dual else 0 for s in specs], dtype=np.int32)
+        self.scal = np.zeros(8 * self.K)
+
+    def load_point(self, point, dual):
+        self.point = np.ascontiguousarray(point, dtype=np.float64)
+        self.dual = np.ascontiguousarray(dual, dtype=np.float64)
+        self.feas = np.ones(self.K, dtype=np.uint8)
+        self.dual_feas = np.ones(self.K, dtype=np.uint8)
+        self.grad = np.zeros(self.q)
+        lib().emu_v3_state(self.type, self.K, p(self.off), p(self.dims), p(self.kidx), p(self.point), p(self.dual),
+                           p(self.grad), p(self.scal), p(self.feas), p(self.dual_feas))
+
+    def prod(self, arr, mode, in_place=False):
+        a = np.asfortranarray(np.asarray(arr, dtype=np.float64).reshape(self.q, -1, order="F")).copy(order="F")
+        out = a if in_place else np.zeros_like(a, order="F")
+        lib().emu_v3_prod(self.type, int(mode), self.K, p(self.off), p(self.dims), p(self.dualf), p(self.scal),
+                          p(self.point), p(a), i64(self.q), p(out), i64(self.q), i64(a.shape[1]), i64(0), 2)
+        return out[:, 0] if np.ndim(arr) == 1 else out
+
+    def dder3(self, direction):
+        d = np.ascontiguousarray(direction, dtype=np.float64)
+        out = np.zeros(self.q)
+        lib().emu_v3_dder3(self.type, self.K, p(self.off), p(self.dims), p(self.scal), p(self.point), p(d), p(out))
+        return out

@@ -2,7 +2,8 @@
 (reference: test/nativeinstances.jl; line ranges per instance below).  Each entry returns
 (model, expected) where `expected` holds the closed-form values the reference asserts at
 tol = eps^(1/4) (nativeinstances.jl:29).  Only instances whose cones are on the hot path
-(Nonnegative, EpiNormEucl, PosSemidefTri, HypoPerLogdetTri, HypoRootdetTri) are restated."""
+(Nonnegative, EpiNormEucl, PosSemidefTri, HypoPerLogdetTri, HypoRootdetTri, EpiPerSquare, HypoPerLog,
+EpiPerSepSpectral{MatrixCSqr}) are restated."""
 import numpy as np
 
 from hypatia_b200.host import models as M
@@ -11,11 +12,18 @@ RT2 = np.sqrt(2.0)
 RT3 = np.sqrt(3.0)
 
 
-def _m(c, A, b, G, h, cones):
+def _m(c, A, b, G, h, cones, obj_offset=0.0):
     c = np.asarray(c, float)
     A = np.zeros((0, c.size)) if A is None else np.asarray(A, float)
     return M.Model(c, A, np.asarray(b if b is not None else [], float), np.asarray(G, float),
-                   np.asarray(h, float), cones)
+                   np.asarray(h, float), cones, obj_offset)
+
+
+def _sparse(rows, cols, vals, m, n):
+    G = np.zeros((m, n))
+    for i, j, v in zip(rows, cols, vals):
+        G[i - 1, j - 1] += v      # 1-based like the reference's sparse(...) calls
+    return G
 
 
 def dimension1():  # nativeinstances.jl:88-108
@@ -129,6 +137,176 @@ def dualinfeas_lp():
     return _m([-1, 0], None, None, -np.eye(2), np.zeros(2), [M.Nonnegative(2)]), \
         dict(status="DualInfeasible")
 
+
+def primalinfeas3():  # :196-207
+    return _m(np.zeros(3), -np.eye(3), [1, 1, 3], -np.eye(3), np.zeros(3), [M.HypoPerLog(3)]), \
+        dict(status="PrimalInfeasible")
+
+
+def dualinfeas2():  # :223-234
+    return _m([-1, 0], None, None, [[-1, 0], [0, 0], [0, -1]], [0, 1, 0], [M.EpiPerSquare(3)]), \
+        dict(status="DualInfeasible")
+
+
+def dualinfeas3():  # :236-247
+    return _m([0, 1, 1, 0], None, None, -np.eye(4), np.zeros(4), [M.EpiPerSquare(4)]), \
+        dict(status="DualInfeasible")
+
+
+def epipersquare1():  # :963-977
+    return _m([0, 0, -1, -1], [[1, 0, 0, 0], [0, 1, 0, 0]], [0.5, 1], -np.eye(4), np.zeros(4),
+              [M.EpiPerSquare(4)]), dict(status="Optimal", primal_obj=-RT2,
+                                         x_idx={2: 1 / RT2, 3: 1 / RT2})
+
+
+def epipersquare2():  # :979-994
+    i2 = 1 / RT2
+    return _m([0, 0, -1], [[1, 0, 0], [0, 1, 0]], [i2 / 2, i2], -np.eye(3), np.zeros(3),
+              [M.EpiPerSquare(3)], obj_offset=-1.0), \
+        dict(status="Optimal", primal_obj=-i2 - 1, x_idx={1: i2})
+
+
+def epipersquare3():  # :996-1009
+    return _m([0, 1, -1, -1], [[1, 0, 0, 0]], [0], -np.eye(4), np.zeros(4), [M.EpiPerSquare(4)]), \
+        dict(status="Optimal", primal_obj=0, x=[0, 0, 0, 0])
+
+
+def epipersquare4():  # :1011-1036
+    G = _sparse([1, 1, 2, 2, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11], [1, 7, 2, 3, 4, 2, 3, 5, 4, 7, 6, 5, 6, 7],
+                [1, -0.5, 1, 1, 1, -1, -1, -1, -1, -0.5, -1, -1, -1, -1], 11, 7)
+    h = np.zeros(11)
+    h[1] = 3
+    c = np.zeros(7)
+    c[0] = -1
+    i3 = 1 / 3
+    r3 = i3 * RT2
+    return _m(c, None, None, G, h, [M.Nonnegative(2), M.EpiPerSquare(3), M.EpiPerSquare(3),
+                                    M.EpiPerSquare(3)]), dict(
+        status="Optimal", primal_obj=-1, x=[1, 1, 1, 1, RT2, RT2, 2],
+        s=[0, 0, 1, 1, RT2, 1, 1, RT2, RT2, RT2, 2],
+        z=[1, i3, i3, i3, -r3, i3, i3, -r3, r3, r3, -2 * i3])
+
+
+def hypoperlog1():  # :1677-1693
+    e = np.exp(0.5)
+    return _m([1, 1, 1], [[0, 1, 0], [1, 0, 0]], [2, 1], -np.eye(3), np.zeros(3), [M.HypoPerLog(3)]), \
+        dict(status="Optimal", primal_obj=2 * e + 3, x=[1, 2, 2 * e], y=[-(1 + e / 2), -(1 + e)])
+
+
+def hypoperlog2():  # :1695-1707
+    return _m([-1, 0, 0], [[0, 1, 0]], [0], -np.eye(3), np.zeros(3), [M.HypoPerLog(3)]), \
+        dict(status="Optimal", primal_obj=0)
+
+
+def hypoperlog3():  # :1709-1723
+    G = _sparse([1, 2, 3, 4], [1, 2, 3, 1], [-1, -1, -1, -1], 4, 3)
+    return _m([1, 1, 1], None, None, G, np.zeros(4), [M.HypoPerLog(3), M.Nonnegative(1)]), \
+        dict(status="Optimal", primal_obj=0, x=[0, 0, 0])
+
+
+def hypoperlog4():  # :1725-1739
+    e2 = np.exp(-2.0)
+    return _m([0, 0, 1], [[0, 1, 0], [1, 0, 0]], [1, -1], -np.eye(3), np.zeros(3),
+              [M.HypoPerLog(3, use_dual=True)]), dict(status="Optimal", primal_obj=e2, x=[-1, 1, e2])
+
+
+def hypoperlog5():  # :1741-1756
+    lq = np.log(0.25)
+    G = _sparse([1, 3, 4], [1, 2, 3], [-1, -1, -1], 4, 3)
+    return _m([-1, 0, 0], [[0, 1, 1]], [1], G, [0, 1, 0, 0], [M.HypoPerLog(4)]), \
+        dict(status="Optimal", primal_obj=-lq, x=[lq, 0.5, 0.5], y=[2])
+
+
+def hypoperlog6():  # :1758-1772
+    G = _sparse([1, 3, 4], [1, 2, 3], [-1, -1, -1], 4, 3)
+    return _m([-1, 0, 0], None, None, G, np.zeros(4), [M.HypoPerLog(4)]), \
+        dict(status="Optimal", primal_obj=0, x_idx={0: 0.0})
+
+
+def hypoperlog7():  # :1774-1795
+    G = _sparse([1, 2, 2, 3, 4, 5, 6], [2, 1, 3, 4, 4, 3, 2], [1, 1, -1, -1, -1, -1, -1], 6, 4)
+    h = np.zeros(6)
+    h[0] = 2
+    return _m([-2, 0, 0, 0], None, None, G, h, [M.Nonnegative(3), M.HypoPerLog(3)]), dict(
+        status="Optimal", primal_obj=-4, x=[2, 2, 2, 0], s=[0, 0, 0, 0, 2, 2], z=[2, 2, 2, -2, -2, 2])
+
+
+# the separable spectral functions the reference's tests loop over (sep_spectral_funs, test/cone.jl /
+# nativeinstances.jl): (HYP_SSF kind, parameter)
+SEP_SPECTRAL_FUNS = [(M.SSF_INV, 0.0), (M.SSF_NEGLOG, 0.0), (M.SSF_NEGENTROPY, 0.0), (M.SSF_POWER12, 1.5)]
+
+
+def _ssf(hkind, hparam):
+    from oracle.cones_sepspec import SepSpectralFun
+    return SepSpectralFun(hkind, hparam)
+
+
+def _svec(W):
+    from oracle import arrayutil as au
+    return au.smat_to_svec(W)
+
+
+def _spectral_matrix1(d, hkind, hparam):  # :2009-2037 (real case): min u : (u, 1, W) in K => h(eig W)
+    rng = np.random.default_rng(1)
+    W = rng.random((d, d))
+    W = W @ W.T + np.eye(d)
+    dim = 2 + M.svec_length(d)
+    G = np.zeros((dim, 1))
+    G[0, 0] = -1
+    h = np.zeros(dim)
+    h[1] = 1
+    h[2:] = _svec(W)
+    return _m([1], None, None, G, h, [M.EpiPerSepSpectralMat(dim, hkind, hparam)]), \
+        dict(status="Optimal", primal_obj=_ssf(hkind, hparam).val(np.linalg.eigvalsh(W)))
+
+
+def _spectral_matrix2(d, hkind, hparam):  # :2039-2070: dual barrier => conjugate of h
+    rng = np.random.default_rng(1)
+    W = rng.random((d, d))
+    f = _ssf(hkind, hparam)
+    if f.conj_dom_pos():
+        W = W @ W.T + np.eye(d)
+    else:
+        W = (W + W.T) / 2     # the reference reads the upper triangle of a random square matrix
+    dim = 2 + M.svec_length(d)
+    G = np.zeros((dim, 1))
+    G[1, 0] = -1
+    h = np.zeros(dim)
+    h[0] = 1
+    h[2:] = _svec(W)
+    return _m([1], None, None, G, h, [M.EpiPerSepSpectralMat(dim, hkind, hparam, use_dual=True)]), \
+        dict(status="Optimal", primal_obj=f.conj(np.linalg.eigvalsh(W)))
+
+
+def _spectral_matrix3(d, hkind, hparam):  # :2072-2098
+    dim = 2 + M.svec_length(d)
+    c = np.zeros(dim)
+    c[0] = 1
+    A = np.zeros((1, dim))
+    A[0, 1] = 1
+    return _m(c, A, [0], -np.eye(dim), np.zeros(dim), [M.EpiPerSepSpectralMat(dim, hkind, hparam)]), \
+        dict(status="Optimal", primal_obj=0, x_idx={0: 0.0, 1: 0.0})
+
+
+def _named(fn, name):
+    fn.__name__ = name
+    return fn
+
+
+SPECTRAL = []
+for _k, (_hk, _hp) in enumerate(SEP_SPECTRAL_FUNS):
+    for _d in (1, 3):
+        SPECTRAL.append(_named(lambda d=_d, hk=_hk, hp=_hp: _spectral_matrix1(d, hk, hp),
+                               f"epipersepspectral_matrix1_d{_d}_h{_hk}"))
+        SPECTRAL.append(_named(lambda d=_d, hk=_hk, hp=_hp: _spectral_matrix2(d, hk, hp),
+                               f"epipersepspectral_matrix2_d{_d}_h{_hk}"))
+    for _d in (2, 4):
+        SPECTRAL.append(_named(lambda d=_d, hk=_hk, hp=_hp: _spectral_matrix3(d, hk, hp),
+                               f"epipersepspectral_matrix3_d{_d}_h{_hk}"))
+
+NEW_CONES = [primalinfeas3, dualinfeas2, dualinfeas3, epipersquare1, epipersquare2, epipersquare3,
+             epipersquare4, hypoperlog1, hypoperlog2, hypoperlog3, hypoperlog4, hypoperlog5, hypoperlog6,
+             hypoperlog7]
 
 ALL = [dimension1, nonnegative4, possemideftri1, possemideftri2, possemideftri8, possemideftri9,
        epinormeucl1, epinormeucl2, epinormeucl3, hyporootdettri4, hypoperlogdettri4,

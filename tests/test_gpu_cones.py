@@ -37,9 +37,14 @@ CONE_SETS = {
                 M.EpiPerSepSpectralMat(2 + M.svec_length(100), M.SSF_NEGENTROPY)],
     "sepspec_big": [M.EpiPerSepSpectralMat(2 + M.svec_length(130), M.SSF_NEGLOG),
                     M.EpiPerSepSpectralMat(2 + M.svec_length(4), M.SSF_POWER12, 2.0)],
+    "epipersquare": [M.EpiPerSquare(3), M.EpiPerSquare(4), M.EpiPerSquare(25), M.EpiPerSquare(34),
+                     M.EpiPerSquare(70)],
+    "hypoperlog": [M.HypoPerLog(3), M.HypoPerLog(7), M.HypoPerLog(34), M.HypoPerLog(80),
+                   M.HypoPerLog(6, use_dual=True)],
     "allmix": [M.Nonnegative(5), M.EpiNormEucl(4), M.PosSemidefTri(6), M.HypoPerLogdetTri(8),
                M.HypoRootdetTri(7), M.EpiNormEucl(3), M.HypoPerLogdetTri(5, use_dual=True),
-               M.EpiPerSepSpectralMat(2 + M.svec_length(4), M.SSF_NEGENTROPY)],
+               M.EpiPerSepSpectralMat(2 + M.svec_length(4), M.SSF_NEGENTROPY), M.EpiPerSquare(6),
+               M.HypoPerLog(5), M.HypoPerLog(4, use_dual=True)],
 }
 
 
@@ -79,7 +84,7 @@ def test_cone_oracles_match_cpu_oracle(name):
     dev.free()
 
 
-@pytest.mark.parametrize("name", ["nonneg", "soc", "vecmix", "psd"])
+@pytest.mark.parametrize("name", ["nonneg", "soc", "vecmix", "psd", "epipersquare"])
 def test_sqrt_oracles(name):
     I = _instance(name)
     dev, ora = _blocks(I.model)

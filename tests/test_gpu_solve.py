@@ -35,6 +35,19 @@ def test_kat_device_default(build):
     kat.check_solution(_solve_dev(model), model, expected)
 
 
+# the reference's instances for the cones added in the widening step (EpiPerSquare, HypoPerLog,
+# EpiPerSepSpectral{MatrixCSqr} with every separable spectral function, primal and dual barrier)
+NEW_CONE_KATS = [kat.primalinfeas3, kat.dualinfeas2, kat.epipersquare1, kat.epipersquare2, kat.epipersquare4,
+                 kat.hypoperlog1, kat.hypoperlog4, kat.hypoperlog5, kat.hypoperlog7] + \
+    [f for f in kat.SPECTRAL if "_d3_" in f.__name__ or "_d2_" in f.__name__]
+
+
+@pytest.mark.parametrize("build", NEW_CONE_KATS, ids=lambda f: f.__name__)
+def test_kat_device_new_cones(build):
+    model, expected = build()
+    kat.check_solution(_solve_dev(model), model, expected)
+
+
 @pytest.mark.parametrize("build", [kat.nonnegative4, kat.epinormeucl1, kat.possemideftri8,
                                    kat.hyporootdettri4, kat.hypoperlogdettri4],
                          ids=lambda f: f.__name__)

@@ -122,6 +122,29 @@ def test_mixed_cones_with_equalities(p):
     _check_system(I, Ap)
 
 
+@pytest.mark.parametrize("p", [0, 4])
+def test_spectral_and_perspective_cones(p):
+    """EpiPerSepSpectral{MatrixCSqr} (hess_prod! + GEMM branch of the Schur assembly), EpiPerSquare
+    (sqrt branch) and HypoPerLog (primal and dual barrier) next to the other cone types."""
+    cones = [M.EpiPerSepSpectralMat(2 + M.svec_length(6), M.SSF_NEGENTROPY), M.EpiPerSquare(7),
+             M.HypoPerLog(6), M.Nonnegative(4), M.EpiPerSepSpectralMat(2 + M.svec_length(3), M.SSF_INV),
+             M.EpiPerSepSpectralMat(2 + M.svec_length(4), M.SSF_POWER12, 1.5, use_dual=True),
+             M.HypoPerLog(5, use_dual=True), M.EpiNormEucl(5), M.EpiPerSquare(3),
+             M.EpiPerSepSpectralMat(2 + M.svec_length(5), M.SSF_NEGLOG)]
+    I = inst.synthetic("specmix", 20 + p, p, cones, seed=21)
+    Ap = None
+    if p:
+        Qf, Rf = sla.qr(I.model.A.T, mode="full")
+        Ap = (Qf, np.triu(Rf[:p, :p]))
+    _check_system(I, Ap)
+
+
+def test_sqrt_only_model_with_epipersquare_uses_the_syrk_path():
+    # all cones have closed-form square roots: the one-operand SYRK (tcgen05 digit slicing) assembles S
+    cones = [M.EpiPerSquare(25) for _ in range(40)] + [M.Nonnegative(30), M.EpiNormEucl(12)]
+    _check_system(inst.synthetic("rsoc", 150, 0, cones, seed=22))
+
+
 @pytest.mark.parametrize("p", [0, 5, 150])
 def test_vector_cones_with_equalities(p):
     cones = [M.Nonnegative(50), M.EpiNormEucl(25), M.EpiNormEucl(25), M.Nonnegative(1), M.EpiNormEucl(300)]
@@ -172,7 +195,8 @@ def test_symindef_dense_device_vs_oracle(p):
 
 def test_explicit_hess_blocks_match_oracle():
     cones = [M.Nonnegative(3), M.EpiNormEucl(5), M.PosSemidefTri(6), M.HypoPerLogdetTri(8),
-             M.HypoRootdetTri(7)]
+             M.HypoRootdetTri(7), M.EpiPerSepSpectralMat(2 + M.svec_length(3), M.SSF_NEGENTROPY),
+             M.EpiPerSquare(5), M.HypoPerLog(6)]
     I = inst.synthetic("blocks", 4, 0, cones, seed=14)
     from hypatia_b200.cones import DeviceConeBlock
     from oracle.cones import OracleConeBlock

@@ -131,6 +131,27 @@ def test_generic_sqrt_oracles_logdet(side):
     assert close(RA.T @ RA, A.T @ cone.hess_prod(A), 1e-12)
 
 
+@pytest.mark.parametrize("dim", [3, 4, 6, 25])
+def test_epipersquare(dim):
+    # reference: test/cone.jl EpiPerSquare block (dims 3, 4, 6)
+    from oracle.cones_vec3 import EpiPerSquare
+    run_oracles(EpiPerSquare(dim))
+
+
+@pytest.mark.parametrize("dw", [1, 2, 5])
+def test_hypoperlog(dw):
+    # reference: test/cone.jl:627-630 (init_tol = 1e-5)
+    from oracle.cones_vec3 import HypoPerLog
+    run_oracles(HypoPerLog(2 + dw), init_tol=1e-5)
+
+
+@pytest.mark.parametrize("dw", [15, 40, 100])
+def test_hypoperlog_init_only(dw):
+    # reference: test/cone.jl:631-633
+    from oracle.cones_vec3 import HypoPerLog
+    run_oracles(HypoPerLog(2 + dw), init_tol=1e-1, init_only=True)
+
+
 SSF = [(0, 0.0), (1, 0.0), (2, 0.0), (3, 1.5), (3, 2.0), (3, 1.1)]   # Inv, NegLog, NegEntropy, Power12(p)
 
 

@@ -19,7 +19,7 @@ def solve(model, syssolver, **kw):
     return s
 
 
-@pytest.mark.parametrize("build", kat.ALL, ids=lambda f: f.__name__)
+@pytest.mark.parametrize("build", kat.ALL + kat.NEW_CONES + kat.SPECTRAL, ids=lambda f: f.__name__)
 def test_kat_qrchol_default(build):
     model, expected = build()
     s = solve(model, osys.QRCholDenseSystemSolver())
@@ -30,6 +30,17 @@ def test_kat_qrchol_default(build):
 @pytest.mark.parametrize("sys_cls", [osys.QRCholDenseSystemSolver, osys.SymIndefDenseSystemSolver,
                                      osys.NaiveDenseSystemSolver], ids=lambda c: c.__name__)
 def test_kat_all_syssolvers_no_reduce(build, sys_cls):
+    model, expected = build()
+    s = solve(model, sys_cls(), reduce=False)
+    kat.check_solution(s, model, expected)
+
+
+@pytest.mark.parametrize("build", [kat.epipersquare4, kat.hypoperlog1, kat.hypoperlog4, kat.hypoperlog7,
+                                   kat.SPECTRAL[2], kat.SPECTRAL[9], kat.SPECTRAL[14]],
+                         ids=lambda f: f.__name__)
+@pytest.mark.parametrize("sys_cls", [osys.SymIndefDenseSystemSolver, osys.NaiveDenseSystemSolver],
+                         ids=lambda c: c.__name__)
+def test_kat_new_cones_other_syssolvers(build, sys_cls):
     model, expected = build()
     s = solve(model, sys_cls(), reduce=False)
     kat.check_solution(s, model, expected)
