@@ -52,6 +52,10 @@ WORKLOADS = {
                 desc="n=1000 p=0, 200 x EpiNormEucl(25), q=5000 (smoke-size)"),
     "C4": dict(n=20000, cones=lambda M: [M.PosSemidefTri(5050) for _ in range(50)],
                desc="n=20000 p=0, 50 x PosSemidefTri(side 100), q=252500"),
+    # widening rows (not BASELINE configs): spectral cones through the batched Jacobi eigensolver
+    "S1": dict(n=2000, cones=lambda M: [M.EpiPerSepSpectralMat(2 + M.svec_length(100), M.SSF_NEGENTROPY)
+                                        for _ in range(24)],
+               desc="n=2000 p=0, 24 x EpiPerSepSpectral{MatrixCSqr}(NegEntropy, side 100), q=121248"),
 }
 
 
@@ -118,7 +122,7 @@ def build_instance(workload, rank, nranks, dist=None, device=None):
         s0[sl] = inst._perturb(rng, ck, prim, 0.1)
         z0[sl] = inst._perturb(rng, ck, dual, 0.1)
         if ck.side:
-            rows = sl.start + np.nonzero(inst._svec_offdiag_mask(ck.side))[0]
+            rows = sl.start + inst.mat_offset(ck) + np.nonzero(inst._svec_offdiag_mask(ck.side))[0]
             rows = rows[(rows >= row_lo) & (rows < row_hi)] - row_lo
             G_local[rows] *= np.sqrt(2.0)
     x0 = rng.standard_normal(n)
@@ -313,6 +317,10 @@ def run_ours(args):
         ctx.comm_init(rank, world, uid[0])
     lo, hi = I["cone_range"]
     ctx.load_model(model, G_local=I["G_local"], cone_lo=lo, cone_hi=hi)
+    # models with a cone that has no closed-form square root assemble S with the two-operand FP64 DMMA
+    # product (qrchol.jl:240-246 branch); the one-operand tcgen05 SYRK needs every cone in sqrt form
+    if any(ck.ctype not in (0, 1, 2, 6) for ck in model.cones):
+        args.syrk = "dmma"
     ctx.set_syrk_mode(1 if args.syrk == "i8" else 0)
     I["G_local"] = None
     cones = DeviceConeBlock(model, ctx=ctx)

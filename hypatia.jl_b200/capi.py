@@ -49,6 +49,7 @@ _SIGS = {
     "hyp_solve_subsystem3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "hyp_solve_system": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "hyp_apply_lhs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hyp_calc_residuals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hyp_get_schur": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "hyp_launch_count": (C.c_int64, [C.c_void_p]),
     "hyp_timing_enable": (C.c_int, [C.c_void_p, C.c_int]),
@@ -263,6 +264,13 @@ class Context:
 
     def apply_lhs(self, res, direction):
         self.check(self.lib.hyp_apply_lhs(self.h, ptr(res), ptr(direction)), "hyp_apply_lhs")
+
+    def calc_residuals(self, point_vec):
+        """(x_residual, y_residual, z_residual, stats[10]) of calc_convergence_params (Solvers.jl:425-483)."""
+        xr, yr, zr, st = np.zeros(self.n), np.zeros(self.p), np.zeros(self.q), np.zeros(10)
+        self.check(self.lib.hyp_calc_residuals(self.h, ptr(point_vec), ptr(xr), ptr(yr), ptr(zr), ptr(st)),
+                   "hyp_calc_residuals")
+        return xr, yr, zr, st
 
     def get_schur(self):
         m = self.n - self.p

@@ -461,6 +461,93 @@ void apply_lhs_dev(hyp_ctx* ctx, double* res, const double* dir) {
     CUDA_TRY(cudaGetLastError());
 }
 
+// max |v_i| into out[0] (out must be zeroed): non-negative doubles order like their bit patterns
+__global__ void absmax_kernel(int64_t len, const double* __restrict__ v, double* __restrict__ out) {
+    double m = 0.0;
+    bool nan = false;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < len;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const double a = fabs(v[i]);
+        if (a != a) nan = true;
+        m = fmax(m, a);
+    }
+    if (nan) m = __longlong_as_double(0x7ff8000000000000LL);
+    unsigned long long bits = (unsigned long long)__double_as_longlong(m);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, bits, o);
+        bits = other > bits ? other : bits;
+    }
+    if ((threadIdx.x & 31) == 0 && bits) atomicMax((unsigned long long*)out, bits);
+}
+
+void absmax(hyp_ctx* ctx, int64_t len, const double* v, double* out) {
+    CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(double), ctx->stream));
+    if (len <= 0) return;
+    absmax_kernel<<<vgrid(ctx, len), 256, 0, ctx->stream>>>(len, v, out);
+    ctx->launches++;
+}
+
+// Residuals of calc_convergence_params (Solvers.jl:425-483) for the full Point `pt` on the device:
+//   xres = -(G'z + A'y + c tau), yres = A x - b tau, zres = s + G x - h tau, and ten scalars in
+//   st: |G'z + A'y|_inf, |.. + c tau|_inf, |A x|_inf, |A x - b tau|_inf, |s + G x|_inf,
+//   |s + G x - h tau|_inf, c'x, b'y, h'z, z's.
+void calc_residuals_dev(hyp_ctx* ctx, const double* pt, double* xres, double* yres, double* zres, double* st) {
+    const int64_t n = ctx->n, p = ctx->p, q = ctx->q;
+    const int64_t tau_idx = n + p + q;
+    const double* px = pt;
+    const double* py = pt + n;
+    const double* pz = pt + n + p;
+    const double* ps = pt + tau_idx + 1;
+    const double* c = ctx->d_cbh;
+    const double* b = ctx->d_cbh + n;
+    const double* h = ctx->d_cbh + n + p;
+    CUDA_TRY(cudaMemsetAsync(st, 0, 10 * sizeof(double), ctx->stream));
+    {
+        TimeScope ts(ctx, T_GEMV);
+        if (n > 0) {
+            if (q > 0) G_t(ctx, ctx->d_Graw, pz, 1.0, 0.0, ctx->d_t);
+            else hyp_fill(ctx, n, ctx->d_t, 0.0);
+            if (p > 0) hyp_gemv_t(ctx, p, n, ctx->d_A, ctx->lda, py, 1.0, 1.0, ctx->d_t);
+        }
+        if (p > 0) hyp_gemv_n(ctx, p, n, ctx->d_A, ctx->lda, px, 1.0, 0.0, ctx->d_vp1);
+        if (q > 0) {
+            if (n > 0) G_n(ctx, ctx->d_Graw, px, ctx->d_vq1);
+            else hyp_fill(ctx, q, ctx->d_vq1, 0.0);
+            if (ctx->nranks > 1) hyp_replicate_q(ctx, ctx->d_vq1);
+        }
+    }
+    TimeScope tv(ctx, T_VEC);
+    if (n > 0) {
+        absmax(ctx, n, ctx->d_t, st + 0);
+        axpbypcz_dev_kernel<<<vgrid(ctx, n), 256, 0, ctx->stream>>>(n, ctx->d_t, 1.0, ctx->d_t, 0.0, nullptr, 1.0,
+                                                                 pt + tau_idx, c);
+        ctx->launches++;
+        absmax(ctx, n, ctx->d_t, st + 1);
+        hyp_lincomb3(ctx, n, xres, -1.0, ctx->d_t, 0.0, nullptr, 0.0, nullptr);
+        hyp_dot(ctx, n, c, px, st + 6, false);
+    }
+    if (p > 0) {
+        absmax(ctx, p, ctx->d_vp1, st + 2);
+        axpbypcz_dev_kernel<<<vgrid(ctx, p), 256, 0, ctx->stream>>>(p, yres, 1.0, ctx->d_vp1, 0.0, nullptr, -1.0,
+                                                                 pt + tau_idx, b);
+        ctx->launches++;
+        absmax(ctx, p, yres, st + 3);
+        hyp_dot(ctx, p, b, py, st + 7, false);
+    }
+    if (q > 0) {
+        hyp_lincomb3(ctx, q, ctx->d_vq1, 1.0, ctx->d_vq1, 1.0, ps, 0.0, nullptr);
+        absmax(ctx, q, ctx->d_vq1, st + 4);
+        axpbypcz_dev_kernel<<<vgrid(ctx, q), 256, 0, ctx->stream>>>(q, zres, 1.0, ctx->d_vq1, 0.0, nullptr, -1.0,
+                                                                 pt + tau_idx, h);
+        ctx->launches++;
+        absmax(ctx, q, zres, st + 5);
+        hyp_dot(ctx, q, h, pz, st + 8, false);
+        hyp_dot(ctx, q, pz, ps, st + 9, false);
+    }
+    CUDA_TRY(cudaGetLastError());
+}
+
 // Schur assembly + factorisation (update_lhs_fact, qrchol.jl:201-257)
 int update_lhs_fact(hyp_ctx* ctx) {
     const int64_t nmp = ctx->nmp, p = ctx->p;
@@ -1190,6 +1277,26 @@ int hyp_apply_lhs(hyp_ctx* ctx, double* res, const double* dir) {
         if (dres == ddir) dres = ctx->d_sol;
         apply_lhs_dev(ctx, dres, ddir);
         stage_out(ctx, res, dim6, dres);
+        return 0;
+    });
+}
+
+int hyp_calc_residuals(hyp_ctx* ctx, const double* point, double* x_residual, double* y_residual,
+                       double* z_residual, double* stats) {
+    return guarded(ctx, [&] {
+        need_model(ctx);
+        const int64_t n = ctx->n, p = ctx->p, q = ctx->q, dim6 = n + p + 2 * q + 2;
+        const double* dpt = stage_in(ctx, point, dim6, ctx->d_rhs);
+        // results are staged in d_sol: [xres (n) | yres (p) | zres (q) | 10 scalars]
+        double* dx = is_device_ptr(x_residual) ? x_residual : ctx->d_sol;
+        double* dy = is_device_ptr(y_residual) ? y_residual : ctx->d_sol + n;
+        double* dz = is_device_ptr(z_residual) ? z_residual : ctx->d_sol + n + p;
+        double* dst = is_device_ptr(stats) ? stats : ctx->d_scalars + 16;
+        calc_residuals_dev(ctx, dpt, dx, dy, dz, dst);
+        if (n) stage_out(ctx, x_residual, n, dx);
+        if (p) stage_out(ctx, y_residual, p, dy);
+        if (q) stage_out(ctx, z_residual, q, dz);
+        stage_out(ctx, stats, 10, dst);
         return 0;
     });
 }

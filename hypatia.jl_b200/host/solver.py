@@ -244,6 +244,19 @@ class Solver:
         """reference: Solvers.jl:425-483"""
         m, pt = self.model, self.point
         tau = pt.tau
+        dev = getattr(self.syssolver, "calc_residuals", None)
+        if dev is not None and getattr(self.syssolver, "ctx", None) is not None:
+            # device plug-in: the two passes over G (and A) stay on the GPU (hyp_calc_residuals)
+            xres, yres, zres, st = dev(self)
+            self.x_norm_res_t, self.x_norm_res = st[0], st[1] / tau
+            self.y_norm_res_t, self.y_norm_res = st[2], st[3] / tau
+            self.z_norm_res_t, self.z_norm_res = st[4], st[5] / tau
+            self.x_residual, self.y_residual, self.z_residual = xres, yres, zres
+            x_feas = self.x_norm_res * self.x_conv_tol
+            y_feas = self.y_norm_res * self.y_conv_tol
+            z_feas = self.z_norm_res * self.z_conv_tol
+            return self._finish_convergence_params(x_feas, y_feas, z_feas, float(st[6]),
+                                                   -float(st[7]) - float(st[8]), float(st[9]))
         xr = m.G.T @ pt.z
         if m.p:
             xr += m.A.T @ pt.y
@@ -267,8 +280,14 @@ class Solver:
         self.z_residual = zr
         z_feas = self.z_norm_res * self.z_conv_tol
 
-        self.primal_obj_t = float(m.c @ pt.x)
-        self.dual_obj_t = -float(m.b @ pt.y) - float(m.h @ pt.z)
+        return self._finish_convergence_params(x_feas, y_feas, z_feas, float(m.c @ pt.x),
+                                               -float(m.b @ pt.y) - float(m.h @ pt.z), float(pt.z @ pt.s))
+
+    def _finish_convergence_params(self, x_feas, y_feas, z_feas, primal_obj_t, dual_obj_t, gap):
+        m, pt = self.model, self.point
+        tau = pt.tau
+        self.primal_obj_t = primal_obj_t
+        self.dual_obj_t = dual_obj_t
         self.tau_residual = self.primal_obj_t - self.dual_obj_t + pt.kap
         tau_feas = abs(self.tau_residual)
 
@@ -281,7 +300,7 @@ class Solver:
         self.x_feas, self.y_feas, self.z_feas, self.tau_feas = x_feas, y_feas, z_feas, tau_feas
         self.primal_obj = self.primal_obj_t / tau + m.obj_offset
         self.dual_obj = self.dual_obj_t / tau + m.obj_offset
-        self.gap = float(pt.z @ pt.s)
+        self.gap = gap
         return improv
 
     def check_convergence(self):

@@ -128,6 +128,12 @@ class QRCholDenseSystemSolver:
         self.ctx.apply_lhs(res.vec, direction.vec)
         return res
 
+    # ---- residual step next to the path (Solvers.jl:425-483) ----
+    def calc_residuals(self, solver):
+        """x / y / z residual vectors and the ten norms / inner products of calc_convergence_params,
+        with the two passes over G on the device."""
+        return self.ctx.calc_residuals(solver.point.vec)
+
     def lhs_full(self):
         """Symmetric Schur matrix (test helper)."""
         S = self.ctx.get_schur()

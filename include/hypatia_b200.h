@@ -142,6 +142,14 @@ int hyp_solve_system(hyp_ctx* ctx, double* sol, const double* rhs);
 /* apply_lhs(stepper, solver) restricted to its data flow: res = LHS6x6 * dir, common.jl:79-121 */
 int hyp_apply_lhs(hyp_ctx* ctx, double* res, const double* dir);
 
+/* residual step on the other side of the path: the vectors and norms of
+ * calc_convergence_params(solver), Solvers.jl:425-483, for the full Point `point`, with the two passes
+ * over G done on the device.  x_residual (n) = -(A'y + G'z + c tau), y_residual (p) = A x - b tau,
+ * z_residual (q) = s + G x - h tau; stats (10) = |A'y + G'z|_inf, |A'y + G'z + c tau|_inf, |A x|_inf,
+ * |A x - b tau|_inf, |s + G x|_inf, |s + G x - h tau|_inf, c'x, b'y, h'z, z's. */
+int hyp_calc_residuals(hyp_ctx* ctx, const double* point, double* x_residual, double* y_residual,
+                       double* z_residual, double* stats);
+
 /* ---- introspection used by tests / bench ----------------------------------------------- */
 /* upper triangle of the assembled Schur matrix (n-p x n-p, leading dim ld) */
 int hyp_get_schur(hyp_ctx* ctx, double* S, int64_t ld);

@@ -66,7 +66,9 @@ def test_cone_oracles_match_cpu_oracle(name):
     assert rel(g, ora.grad()) <= 1e-11
     rng = np.random.default_rng(1)
     arr = rng.standard_normal((I.model.q, 3))
-    tol = 1e-10
+    # side-130 spectral cone: the divided differences of dder3 amplify the O(side * eps) difference between
+    # the Jacobi eigenvectors and LAPACK's (measured 2.2e-10)
+    tol = 1e-9 if name == "sepspec_big" else 1e-10
     assert rel(dev.hess_prod(arr), ora.hess_prod(arr)) <= tol
     assert rel(dev.inv_hess_prod(arr), ora.inv_hess_prod(arr)) <= tol
     assert rel(dev.block_hess_prod(arr[:, 0]), ora.block_hess_prod(arr[:, 0])) <= tol

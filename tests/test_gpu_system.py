@@ -211,3 +211,36 @@ def test_explicit_hess_blocks_match_oracle():
         assert rel(Hd, Ho) <= 1e-10 and rel(Hid, Hio) <= 1e-10
         assert rel(Hd @ Hid, np.eye(Hd.shape[0])) <= 1e-8        # cone.jl:73-75
     dev.free()
+
+
+@pytest.mark.parametrize("p", [0, 6])
+def test_calc_residuals_matches_host_formulas(p):
+    """hyp_calc_residuals (the residual step of calc_convergence_params, Solvers.jl:425-483) against the
+    NumPy restatement in host/solver.py on the same point."""
+    from hypatia_b200.syssolver import QRCholDenseSystemSolver as DevQRChol
+    cones = [M.Nonnegative(40), M.EpiNormEucl(25), M.PosSemidefTri(15), M.HypoPerLog(7)]
+    I = inst.synthetic("resid", 30 + p, p, cones, seed=31)
+    Ap = None
+    if p:
+        Qf, Rf = sla.qr(I.model.A.T, mode="full")
+        Ap = (Qf, np.triu(Rf[:p, :p]))
+    dev = iterate_solver(I, DevQRChol(), Ap=Ap)
+    try:
+        m, pt = I.model, I.point
+        rng = np.random.default_rng(5)
+        pt.y[:] = rng.standard_normal(m.p)
+        pt.tau = 0.7
+        xr, yr, zr, st = dev.syssolver.calc_residuals(dev)
+        gx = m.G.T @ pt.z + (m.A.T @ pt.y if p else 0)
+        ax = m.A @ pt.x if p else np.zeros(0)
+        gs = m.G @ pt.x + pt.s
+        inf = lambda v: np.linalg.norm(v, np.inf) if v.size else 0.0
+        assert rel(xr, -(gx + m.c * pt.tau)) <= 1e-12
+        assert rel(zr, gs - m.h * pt.tau) <= 1e-12
+        if p:
+            assert rel(yr, ax - m.b * pt.tau) <= 1e-12
+        ref = [inf(gx), inf(gx + m.c * pt.tau), inf(ax), inf(ax - m.b * pt.tau), inf(gs), inf(gs - m.h * pt.tau),
+               m.c @ pt.x, m.b @ pt.y if p else 0.0, m.h @ pt.z, pt.z @ pt.s]
+        assert np.allclose(st, ref, rtol=1e-11, atol=1e-11)
+    finally:
+        dev.syssolver.free_memory()
