@@ -52,6 +52,13 @@ WORKLOADS = {
                 desc="n=1000 p=0, 200 x EpiNormEucl(25), q=5000 (smoke-size)"),
     "C4": dict(n=20000, cones=lambda M: [M.PosSemidefTri(5050) for _ in range(50)],
                desc="n=20000 p=0, 50 x PosSemidefTri(side 100), q=252500"),
+    # natvsext-faithful shape of BASELINE config 5 (SURVEY.md 8(d) "C5a"): the largest `nat` log-det
+    # D-optimal-design instance (examples/doptimaldesign/JuMP_benchmark.jl:2-5, native.jl:18-86) after
+    # the QR reduction: one HypoPerLogdetTri of side 1000 (dim 500502 > m, so the hess_prod! + GEMM
+    # branch qrchol.jl:240-246) + two Nonnegative(2000); dense Gaussian G like the other configs
+    "C5a": dict(n=2000, cones=lambda M: [M.Nonnegative(2000), M.Nonnegative(2000),
+                                         M.HypoPerLogdetTri(2 + M.svec_length(1000))],
+                desc="n=2000 p=0, Nonnegative(2000) x 2 + HypoPerLogdetTri(side 1000), q=504502"),
     # widening rows (not BASELINE configs): spectral cones through the batched Jacobi eigensolver
     "S1": dict(n=2000, cones=lambda M: [M.EpiPerSepSpectralMat(2 + M.svec_length(100), M.SSF_NEGENTROPY)
                                         for _ in range(24)],

@@ -364,11 +364,11 @@ void launch_vec_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr
     ctx->launches++;
 }
 
-// EpiPerSquare / HypoPerLog: one warp per (cone, column); mode 4 / 5 = the block modes
+// EpiPerSquare / HypoPerLog / EpiNormInf: one warp per (cone, column); mode 4 / 5 = the block modes
 void launch_v3_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr, int64_t ncols, int64_t ld_prod,
                     int64_t ld_arr, int mode, int64_t row_shift) {
-    if (g.type == HYP_CONE_HYPOPERLOG && (mode == HYP_PROD_SQRT_HESS || mode == HYP_PROD_INV_SQRT_HESS))
-        throw HypError{"sqrt_hess_prod is not defined for HypoPerLog"};
+    if (g.type != HYP_CONE_EPIPERSQUARE && (mode == HYP_PROD_SQRT_HESS || mode == HYP_PROD_INV_SQRT_HESS))
+        throw HypError{"sqrt_hess_prod is not defined for HypoPerLog / EpiNormInf"};
     dim3 grid(ceil_div(g.count, 8), (unsigned)std::min<int64_t>(ncols, 65535));
     hypdev::v3_prod_kernel<<<grid, 256, 0, ctx->stream>>>(g.type, mode, g.count, g.d_off, g.d_dim, g.d_dual, g.d_scal,
                                                          ctx->d_point, arr, ld_arr, prod, ld_prod, ncols, row_shift);
@@ -510,7 +510,7 @@ void hyp_cones_update_state(hyp_ctx* ctx) {
                 g.count, g.d_off, g.d_dim, g.d_kidx, ctx->d_point, ctx->d_dual, ctx->d_grad, g.d_scal,
                 ctx->d_feas, ctx->d_dual_feas);
             ctx->launches++;
-        } else if (g.type == HYP_CONE_EPIPERSQUARE || g.type == HYP_CONE_HYPOPERLOG) {
+        } else if (cone_is_vec3(g.type)) {
             hypdev::v3_state_kernel<<<ceil_div(g.count, 8), 256, 0, ctx->stream>>>(
                 g.type, g.count, g.d_off, g.d_dim, g.d_kidx, ctx->d_point, ctx->d_dual, ctx->d_grad, g.d_scal,
                 ctx->d_feas, ctx->d_dual_feas);
@@ -558,7 +558,7 @@ void hyp_cones_prod(hyp_ctx* ctx, double* prod, const double* arr, int64_t ncols
                 default:
                     throw HypError{"hyp_cones_prod: bad mode"};
             }
-        } else if (g.type == HYP_CONE_EPIPERSQUARE || g.type == HYP_CONE_HYPOPERLOG) {
+        } else if (cone_is_vec3(g.type)) {
             launch_v3_prod(ctx, g, prod, arr, ncols, ld_prod, ld_arr, m, row_shift);
         } else if (g.type == HYP_CONE_EPIPERSEPSPECTRAL_MAT) {
             hyp_spec_prod(ctx, g, prod, arr, ncols, ld_prod, ld_arr, m, row_shift);
@@ -578,7 +578,7 @@ void hyp_cones_schur_prepass(hyp_ctx* ctx) {
         if (g.type <= HYP_CONE_EPINORMEUCL) {
             launch_vec_prod<HYP_PROD_SQRT_HESS>(ctx, g, ctx->d_HG, GQ2, ctx->nmp, ctx->ldg, ctx->ldg,
                                                 ctx->row_lo);
-        } else if (g.type == HYP_CONE_EPIPERSQUARE || g.type == HYP_CONE_HYPOPERLOG) {
+        } else if (cone_is_vec3(g.type)) {
             launch_v3_prod(ctx, g, ctx->d_HG, GQ2, ctx->nmp, ctx->ldg, ctx->ldg,
                            g.type == HYP_CONE_EPIPERSQUARE ? HYP_PROD_SQRT_HESS : HYP_PROD_BLOCK, ctx->row_lo);
         } else if (g.type == HYP_CONE_POSSEMIDEFTRI) {
@@ -605,7 +605,7 @@ void hyp_cones_dder3_dev(hyp_ctx* ctx, double* out, const double* dir) {
             soc_dder3_kernel<<<ceil_div(g.count, 8), 256, 0, ctx->stream>>>(
                 g.count, g.d_off, g.d_dim, g.d_scal, ctx->d_point, dir, out);
             ctx->launches++;
-        } else if (g.type == HYP_CONE_EPIPERSQUARE || g.type == HYP_CONE_HYPOPERLOG) {
+        } else if (cone_is_vec3(g.type)) {
             hypdev::v3_dder3_kernel<<<ceil_div(g.count, 8), 256, 0, ctx->stream>>>(
                 g.type, g.count, g.d_off, g.d_dim, g.d_scal, ctx->d_point, dir, out);
             ctx->launches++;

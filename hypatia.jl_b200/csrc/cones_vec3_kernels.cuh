@@ -1,16 +1,20 @@
-// Device oracles of EpiPerSquare and HypoPerLog: vector cones with two leading scalars (u, v) and a
-// w block; one warp per cone for the state, one warp per (cone, column) for the products.
+// Device oracles of EpiPerSquare, HypoPerLog (two leading scalars (u, v) and a w block) and EpiNormInf
+// (one leading scalar u and a w block); one warp per cone for the state, one warp per (cone, column)
+// for the products.
 //
 // reference: src/Cones/epipersquare.jl:59-274 (update_feas, is_dual_feas, update_grad, hess_prod!,
 // inv_hess_prod!, sqrt_hess_prod!, inv_sqrt_hess_prod!, dder3), src/Cones/hypoperlog.jl:62-287
-// (update_feas, is_dual_feas, update_grad, hess_prod!, inv_hess_prod!, dder3).
-// scal (8 doubles per cone): EpiPerSquare 0 dist; HypoPerLog 1 phi, 2 zeta.
+// (update_feas, is_dual_feas, update_grad, hess_prod!, inv_hess_prod!, dder3), src/Cones/epinorminf.jl:97-406
+// (real case: update_feas, is_dual_feas, update_grad, update_hess_aux, hess_prod!, update_inv_hess_aux,
+// inv_hess_prod!, dder3; the arrow-shaped Hessian is applied from u and w, nothing is stored per entry).
+// scal (8 doubles per cone): EpiPerSquare 0 dist; HypoPerLog 1 phi, 2 zeta; EpiNormInf 0 Huu, 1 schur.
 // HBM-bound streaming kernels: 16 * rows * ncols algorithmic bytes per product.
 #pragma once
 #include "devdefs.cuh"
 
 #define V3_EPIPERSQUARE 6   // = HYP_CONE_EPIPERSQUARE
 #define V3_HYPOPERLOG 7     // = HYP_CONE_HYPOPERLOG
+#define V3_EPINORMINF 8     // = HYP_CONE_EPINORMINF
 // product modes (= HYP_PROD_*)
 #define V3_HESS 0
 #define V3_INV_HESS 1
@@ -30,7 +34,36 @@ v3_state_kernel(int type, int ncones, const int64_t* __restrict__ off, const int
     const int64_t o = off[c];
     const int d = dim[c];
     const double u = point[o], v = point[o + 1], du = dual[o], dv = dual[o + 1];
-    if (type == V3_EPIPERSQUARE) {
+    if (type == V3_EPINORMINF) {
+        // epinorminf.jl:97-142, :144-168 (Huu), :275-300 (schur)
+        const int n = d - 1;
+        double wmax = 0.0, dsum = 0.0, sud = 0.0, sud2 = 0.0, sinv = 0.0;
+        const double usqr = u * u;
+        for (int i = 1 + lane; i < d; i += 32) {
+            const double w = point[o + i];
+            wmax = fmax(wmax, fabs(w));
+            dsum += fabs(dual[o + i]);
+            const double den = 0.5 * (usqr - w * w);
+            const double uden = u / den;
+            sud += uden;
+            sud2 += uden * uden;
+            sinv += 1.0 / (0.5 * (usqr + w * w));
+            grad[o + i] = w / den;
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) wmax = fmax(wmax, __shfl_xor_sync(0xffffffffu, wmax, s));
+        dsum = warp_sum(dsum);
+        sud = warp_sum(sud);
+        sud2 = warp_sum(sud2);
+        sinv = warp_sum(sinv);
+        if (lane == 0) {
+            grad[o] = (n - 1) / u - sud;
+            scal[8 * c] = sud2 - ((n - 1) / u + sud) / u;
+            scal[8 * c + 1] = (1 - n) / usqr + sinv;
+            if (!(u > HYP_EPS && u - wmax > HYP_EPS)) feas[kidx[c]] = 0;
+            if (!(du > HYP_EPS && du - dsum > HYP_EPS)) dual_feas[kidx[c]] = 0;
+        }
+    } else if (type == V3_EPIPERSQUARE) {
         // epipersquare.jl:59-100
         double sw = 0.0, sdw = 0.0;
         for (int i = 2 + lane; i < d; i += 32) {
@@ -115,7 +148,36 @@ v3_prod_kernel(int type, int mode_in, int ncones, const int64_t* __restrict__ of
         const double* a = arr + j * ld_arr + (o - row_shift);
         double* pr = prod + j * ld_prod + (o - row_shift);
         const double p = a[0], q = a[1];
-        if (type == V3_EPIPERSQUARE) {
+        if (type == V3_EPINORMINF) {
+            const double usqr = u * u, ua = p;
+            if (mode == V3_HESS) {
+                // epinorminf.jl:226-244: prod_u = Huu ua + Hure . wa; prod_w = Hure ua + Hrere wa
+                double dot = 0.0;
+                for (int i = 1 + lane; i < d; i += 32) {
+                    const double w = point[o + i], den = 0.5 * (usqr - w * w);
+                    const double hure = -(w / den) * (u / den);
+                    const double ai = a[i];
+                    dot += hure * ai;
+                    pr[i] = hure * ua + ((w / den) * (w / den) + 1.0 / den) * ai;
+                }
+                dot = warp_sum(dot);
+                if (lane == 0) pr[0] = scal[8 * c] * ua + dot;
+            } else {
+                // epinorminf.jl:347-364: prod_u = (ua + Hiure . wa) / schur; prod_w = Hiure prod_u + wa / Hrere
+                double dot = 0.0;
+                for (int i = 1 + lane; i < d; i += 32) {
+                    const double w = point[o + i];
+                    dot += u / (0.5 * (usqr + w * w)) * w * a[i];
+                }
+                const double pu = (ua + warp_sum(dot)) / scal[8 * c + 1];
+                for (int i = 1 + lane; i < d; i += 32) {
+                    const double w = point[o + i], den = 0.5 * (usqr - w * w);
+                    const double hrere = (w / den) * (w / den) + 1.0 / den;
+                    pr[i] = u / (0.5 * (usqr + w * w)) * w * pu + a[i] / hrere;
+                }
+                if (lane == 0) pr[0] = pu;
+            }
+        } else if (type == V3_EPIPERSQUARE) {
             // every oracle is  coef * vec + kap * J a  with J a = (-a_2, -a_1, a_w):
             //   vec = J point / point / sqrt-vectors of epipersquare.jl:156-191, coef from one dot product
             const double dist = scal[8 * c];
@@ -207,7 +269,27 @@ v3_dder3_kernel(int type, int ncones, const int64_t* __restrict__ off, const int
     const int64_t o = off[c];
     const int d = dim[c];
     const double u = point[o], v = point[o + 1], p = dir[o], q = dir[o + 1];
-    if (type == V3_EPIPERSQUARE) {
+    if (type == V3_EPINORMINF) {
+        // epinorminf.jl:366-406 (real case)
+        const int n = d - 1;
+        const double usqr = u * u, udir = p, u3 = 1.5 / u, udu = udir / u;
+        double s0 = 0.0, s1 = 0.0;
+        for (int i = 1 + lane; i < d; i += 32) {
+            const double w = point[o + i], di = dir[o + i];
+            const double den = 0.5 * (usqr - w * w), z = u / den;
+            s0 += z * (u3 - z) * z;
+            const double deni = -4.0 * den, udeni = 2.0 * z, wdeni = 2.0 * w / den;
+            const double suuw = udir * (-1.0 + udeni * u);
+            const double uuw = suuw * wdeni;
+            const double uimim = 1.0 + wdeni * w;
+            const double uimim2 = -udeni * uimim * di;
+            s1 += di * (2.0 * uuw + uimim2) / deni;
+            out[o + i] = (udir * (uuw + 2.0 * uimim2) + di * wdeni * (2.0 + uimim) * di) / deni;
+        }
+        s0 = warp_sum(s0);
+        s1 = warp_sum(s1);
+        if (lane == 0) out[o] = -udir * s0 * udir - udu * (n - 1) / u * udu + s1;
+    } else if (type == V3_EPIPERSQUARE) {
         const double dist = scal[8 * c];
         double sww = 0.0, swd = 0.0, sdd = 0.0;
         for (int i = 2 + lane; i < d; i += 32) {

@@ -780,7 +780,8 @@ ozaki_syrk_pair_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid_c
                        const __grid_constant__ CUtensorMap mapB4, const __grid_constant__ CUtensorMap mapB8,
                        const int2* __restrict__ pairs, int n_pairs, int k0, int nkb,
                        const double* __restrict__ dscale, int64_t ncols, double* __restrict__ C, int64_t ldc,
-                       double alpha, double beta) {
+                       double alpha, double beta, int nsl) {
+    // nsl = number of digit slices that enter the product (7 or 8): pairs with s + t <= nsl - 1
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint32_t s_tmem;
     const uint32_t base = smem_u32(smem_raw);
@@ -863,7 +864,7 @@ ozaki_syrk_pair_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid_c
                     const int ns = pass == 0 ? 4 : OZ_S;
                     const int nst = pass == 0 ? (nkb + 1) / 2 : nkb;
                     const int nhalf = pass == 0 ? 2 : 1;
-                    const int smax = pass == 0 ? 3 : OZ_S - 1;
+                    const int smax = pass == 0 ? 3 : nsl - 1;
                     for (int it = 0; it < nst; it++) {
                         mbar_wait(bar_full + stage * 8, phase);
                         asm volatile("tcgen05.fence::after_thread_sync;");
@@ -874,7 +875,7 @@ ozaki_syrk_pair_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid_c
                                 const uint64_t ad = make_desc_sw32(sa + s * OZ_TILE);
                                 int tlo = d0 - s, thi = d0 + 3 - s;
                                 if (tlo < 0) tlo = 0;
-                                if (thi > OZ_S - 1) thi = OZ_S - 1;
+                                if (thi > nsl - 1 - s) thi = nsl - 1 - s;     // s + t <= nsl - 1
                                 for (int tt = tlo; tt <= thi; tt++) {
                                     const uint64_t bd = make_desc_sw32(sb + tt * (OZ_TILE / 2));
                                     const int g = s + tt - d0;
@@ -908,8 +909,10 @@ ozaki_syrk_pair_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid_c
                 mbar_wait(bar_tfull, item & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const int d0 = pass * 4;
+                // a digit-sum group beyond the last slice pair (d0 + 3 > nsl - 1) was never written: weight 0
                 const double g0 = ldexp(1.0, -(12 + 7 * d0)), g1 = ldexp(1.0, -(12 + 7 * (d0 + 1))),
-                             g2 = ldexp(1.0, -(12 + 7 * (d0 + 2))), g3 = ldexp(1.0, -(12 + 7 * (d0 + 3)));
+                             g2 = ldexp(1.0, -(12 + 7 * (d0 + 2))),
+                             g3 = (d0 + 3 <= nsl - 1) ? ldexp(1.0, -(12 + 7 * (d0 + 3))) : 0.0;
 #pragma unroll 1
                 for (int c0 = 0; c0 < TN; c0 += 16) {
                     uint32_t v[4][16];
@@ -1061,6 +1064,17 @@ void hyp_ozaki_slice(hyp_ctx* ctx, const double* A, int64_t lda, int64_t K, int6
     CUDA_TRY(cudaGetLastError());
 }
 
+// digit slices entering the product (CTA-pair kernel): 8 (default) or 7 (HYP_OZAKI_SLICES=7: 28 instead of
+// 36 pair products; truncation error <= 2^-48 |a_i|_max |a_j|_max K instead of 2^-55)
+static int ozaki_slices() {
+    static int n = 0;
+    if (!n) {
+        const char* e = getenv("HYP_OZAKI_SLICES");
+        n = (e && e[0] == '7') ? 7 : 8;
+    }
+    return n;
+}
+
 // C(upper 128-tiles) = alpha * A' A + beta * C from the digit slices of A
 void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t slice_stride, const int* expo,
                     const double* dscale, int64_t K, int64_t ncols, double* C, int64_t ldc, double alpha,
@@ -1185,7 +1199,7 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
             cfg.numAttrs = 1;
             CUDA_TRY(cudaLaunchKernelEx(&cfg, ozaki_syrk_pair_kernel, mapD4, mapD8, mapB4, mapB8, (const int2*)d_pairs,
                                         n_pairs, (int)k0, (int)ceil_div(klen, OZ_KB), dscale, ncols, C, ldc, alpha,
-                                        k0 == 0 ? beta : 1.0));
+                                        k0 == 0 ? beta : 1.0, ozaki_slices()));
             ctx->launches++;
             continue;
         }

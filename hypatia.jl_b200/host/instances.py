@@ -104,6 +104,8 @@ def cone_initial_point(spec):
         u, v, w = _central_ray_hypoperlog(spec.dim - 2)
         arr[0], arr[1] = u, v
         arr[2:] = w
+    elif spec.ctype == M.CONE_EPINORMINF:
+        arr[0] = np.sqrt(spec.dim)      # epinorminf.jl:88-95
     return arr
 
 
@@ -115,6 +117,8 @@ def _cone_dual_initial(spec, prim):
         return prim.copy()      # central point is self-dual: -g = (u, -w)/dist with dist = 1
     if spec.ctype == M.CONE_POSSEMIDEFTRI:
         return prim.copy()
+    if spec.ctype == M.CONE_EPINORMINF:
+        return prim.copy()      # -g = ((n + 1) / u, 0...) = (sqrt(dim), 0...) at the central point
     if spec.ctype == M.CONE_EPIPERSQUARE:
         return prim.copy()      # (1, 1, 0...): -g = (v, u, -w) / dist with dist = u v - |w|^2 / 2 = 1
     out = np.zeros_like(prim)
@@ -162,6 +166,10 @@ def _perturb(rng, spec, vec, noise):
     perturbed matrix stays safely positive definite at any side."""
     if spec.ctype in (M.CONE_NONNEGATIVE, M.CONE_EPINORMEUCL):
         vec += noise * (2 * rng.random(vec.size) - 1)
+        return vec
+    if spec.ctype == M.CONE_EPINORMINF:
+        vec[0] += 0.5 * noise * (2 * rng.random() - 1)
+        vec[1:] += noise / np.sqrt(vec.size) * (2 * rng.random(vec.size - 1) - 1)
         return vec
     if spec.ctype in (M.CONE_EPIPERSQUARE, M.CONE_HYPOPERLOG):
         vec[:2] += 0.5 * noise * (2 * rng.random(2) - 1)

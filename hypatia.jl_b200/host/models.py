@@ -20,6 +20,7 @@ CONE_HYPOROOTDETTRI = 4
 CONE_EPIPERSEPSPECTRAL_MAT = 5
 CONE_EPIPERSQUARE = 6
 CONE_HYPOPERLOG = 7
+CONE_EPINORMINF = 8
 
 # separable spectral functions of EpiPerSepSpectral (sepspectralfun.jl:17-116), HYP_SSF_*
 SSF_INV, SSF_NEGLOG, SSF_NEGENTROPY, SSF_POWER12 = 0, 1, 2, 3
@@ -33,6 +34,7 @@ CONE_NAMES = {
     CONE_EPIPERSEPSPECTRAL_MAT: "EpiPerSepSpectral{MatrixCSqr}",
     CONE_EPIPERSQUARE: "EpiPerSquare",
     CONE_HYPOPERLOG: "HypoPerLog",
+    CONE_EPINORMINF: "EpiNormInf",
 }
 
 
@@ -85,6 +87,8 @@ class ConeSpec:
             assert dim >= 3
         elif ctype == CONE_HYPOPERLOG:
             assert dim >= 3
+        elif ctype == CONE_EPINORMINF:
+            assert dim >= 2
         else:
             raise ValueError(f"unknown cone type {ctype}")
 
@@ -102,7 +106,7 @@ class ConeSpec:
     def nu(self) -> float:
         # nonnegative.jl:40, epinormeucl.jl:42, possemideftri.jl:67,
         # hypoperlogdettri.jl:80, hyporootdettri.jl:80, epipersepspectral.jl:79,
-        # epipersquare.jl:57, hypoperlog.jl:60
+        # epipersquare.jl:50, hypoperlog.jl:54, epinorminf.jl:86
         if self.ctype == CONE_NONNEGATIVE:
             return float(self.dim)
         if self.ctype == CONE_EPINORMEUCL:
@@ -113,7 +117,7 @@ class ConeSpec:
             return 2.0 + self.side
         if self.ctype == CONE_EPIPERSQUARE:
             return 2.0
-        if self.ctype == CONE_HYPOPERLOG:
+        if self.ctype in (CONE_HYPOPERLOG, CONE_EPINORMINF):
             return float(self.dim)
         return 1.0 + self.side
 
@@ -156,6 +160,11 @@ def EpiPerSquare(dim, use_dual=False):
 
 def HypoPerLog(dim, use_dual=False):
     return ConeSpec(CONE_HYPOPERLOG, dim, use_dual)
+
+
+def EpiNormInf(dim, use_dual=False):
+    """EpiNormInf{Float64, Float64}(dim); use_dual = True gives the l1-norm epigraph."""
+    return ConeSpec(CONE_EPINORMINF, dim, use_dual)
 
 
 class Model:

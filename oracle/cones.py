@@ -757,9 +757,10 @@ def make_cone(spec):
     if spec.ctype == M.CONE_EPIPERSEPSPECTRAL_MAT:
         from .cones_sepspec import EpiPerSepSpectralMat
         return EpiPerSepSpectralMat(spec.dim, spec.hkind, spec.hparam, use_dual=spec.use_dual)
-    if spec.ctype in (M.CONE_EPIPERSQUARE, M.CONE_HYPOPERLOG):
+    if spec.ctype in (M.CONE_EPIPERSQUARE, M.CONE_HYPOPERLOG, M.CONE_EPINORMINF):
         from . import cones_vec3
-        cls = cones_vec3.EpiPerSquare if spec.ctype == M.CONE_EPIPERSQUARE else cones_vec3.HypoPerLog
+        cls = {M.CONE_EPIPERSQUARE: cones_vec3.EpiPerSquare, M.CONE_HYPOPERLOG: cones_vec3.HypoPerLog,
+               M.CONE_EPINORMINF: cones_vec3.EpiNormInf}[spec.ctype]
         return cls(spec.dim, use_dual=spec.use_dual)
     cls = _CLASSES[spec.ctype]
     if spec.ctype in (M.CONE_HYPOPERLOGDETTRI, M.CONE_HYPOROOTDETTRI):

@@ -286,3 +286,118 @@ class HypoPerLog(Cone):
         d3[1] = c1 * sigma + (viq2 - (d * c5 + c6 * c0 + vzi * c7)) / v - c4
         d3[2:] = (c8 + rwi * (c6 + vzi1 * rwi)) / w
         return d3
+
+
+class EpiNormInf(Cone):
+    """epinorminf.jl:8-406 (real case): (u, w) with u >= |w|_inf, barrier
+    -sum_j log(u^2 - w_j^2) + (n - 1) log u, nu = n + 1 = dim; the dual barrier variant
+    (use_dual = true) serves the epigraph of the l1 norm."""
+    ctype = M.CONE_EPINORMINF
+
+    def __init__(self, dim, use_dual=False):
+        self.use_dual_barrier = use_dual
+        self.n = dim - 1
+        super().__init__(dim)
+
+    @property
+    def nu(self):
+        return float(self.n + 1)
+
+    def reset_data(self):
+        super().reset_data()
+        self.hess_aux_updated = self.inv_hess_aux_updated = False
+
+    def set_initial_point(self, arr):
+        arr[:] = 0.0
+        arr[0] = np.sqrt(self.nu)
+        return arr
+
+    def update_feas(self):
+        u, w = self.point[0], self.point[1:]
+        return bool(u > EPS and u - np.abs(w).max() > EPS)
+
+    def is_dual_feas(self):
+        u = self.dual_point[0]
+        return bool(u > EPS and u - np.abs(self.dual_point[1:]).sum() > EPS)
+
+    def update_grad(self):
+        u, w = self.point[0], self.point[1:]
+        self.den = 0.5 * (u * u - w * w)
+        self.uden = u / self.den
+        self.wden = w / self.den
+        self._grad[0] = (self.n - 1) / u - self.uden.sum()
+        self._grad[1:] = self.wden
+
+    def update_hess_aux(self):
+        if self.hess_aux_updated:
+            return
+        self.grad()
+        u = self.point[0]
+        self.Hure = -self.wden * self.uden
+        self.Hrere = self.wden ** 2 + 1.0 / self.den
+        self.Huu = float((self.uden ** 2).sum()) - ((self.n - 1) / u + self.uden.sum()) / u
+        self.hess_aux_updated = True
+
+    def update_hess(self):
+        self.update_hess_aux()
+        H = np.zeros((self.dim, self.dim))
+        H[0, 0] = self.Huu
+        H[0, 1:] = H[1:, 0] = self.Hure
+        idx = np.arange(1, self.dim)
+        H[idx, idx] = self.Hrere
+        return H
+
+    def hess_prod(self, arr):
+        self.update_hess_aux()
+        a, vec = _as2d(arr)
+        prod = np.empty_like(a)
+        prod[0] = self.Huu * a[0] + self.Hure @ a[1:]
+        prod[1:] = self.Hure[:, None] * a[0][None, :] + self.Hrere[:, None] * a[1:]
+        return _ret(prod, vec)
+
+    def update_inv_hess_aux(self):
+        if self.inv_hess_aux_updated:
+            return
+        self.update_hess_aux()
+        u, w = self.point[0], self.point[1:]
+        u2pw2 = 0.5 * (u * u + w * w)
+        self.Hiure = u / u2pw2 * w
+        self.schur = (1 - self.n) / (u * u) + float((1.0 / u2pw2).sum())
+        self.inv_hess_aux_updated = True
+
+    def update_inv_hess(self):
+        self.update_inv_hess_aux()
+        Hi = np.zeros((self.dim, self.dim))
+        Hi[0, 0] = 1.0 / self.schur
+        col = self.Hiure
+        Hi[1:, 0] = Hi[0, 1:] = col / self.schur
+        Hi[1:, 1:] = np.outer(col, col) / self.schur + np.diag(1.0 / self.Hrere)
+        return Hi
+
+    def inv_hess_prod(self, arr):
+        self.update_inv_hess_aux()
+        a, vec = _as2d(arr)
+        prod = np.empty_like(a)
+        prod[0] = (a[0] + self.Hiure @ a[1:]) / self.schur
+        prod[1:] = self.Hiure[:, None] * prod[0][None, :] + a[1:] / self.Hrere[:, None]
+        return _ret(prod, vec)
+
+    def dder3(self, direction):
+        self.grad()
+        u, w = self.point[0], self.point[1:]
+        udir, d = direction[0], direction[1:]
+        u3 = 1.5 / u
+        udu = udir / u
+        z = self.uden
+        d3 = np.empty(self.dim)
+        d3[0] = -udir * float((z * (u3 - z) * z).sum()) * udir - udu * (self.n - 1) / u * udu
+        deni = -4 * self.den
+        udeni = 2 * self.uden
+        suuw = udir * (-1 + udeni * u)
+        wdeni = 2 * self.wden
+        uuw = suuw * wdeni
+        uimim = 1 + wdeni * w
+        uimim2 = -udeni * uimim * d
+        d3[0] += float((d * (2 * uuw + uimim2) / deni).sum())
+        d3[1:] = (udir * (uuw + 2 * uimim2) + d * wdeni * (2 + uimim) * d) / deni
+        return d3

@@ -3,7 +3,7 @@
 (model, expected) where `expected` holds the closed-form values the reference asserts at
 tol = eps^(1/4) (nativeinstances.jl:29).  Only instances whose cones are on the hot path
 (Nonnegative, EpiNormEucl, PosSemidefTri, HypoPerLogdetTri, HypoRootdetTri, EpiPerSquare, HypoPerLog,
-EpiPerSepSpectral{MatrixCSqr}) are restated."""
+EpiNormInf (real), EpiPerSepSpectral{MatrixCSqr}) are restated."""
 import numpy as np
 
 from hypatia_b200.host import models as M
@@ -187,6 +187,49 @@ def epipersquare4():  # :1011-1036
         z=[1, i3, i3, i3, -r3, i3, i3, -r3, r3, r3, -2 * i3])
 
 
+def epinorminf1():  # :791-806
+    i2 = 1 / RT2
+    return _m([0, -1, -1], [[1, 0, 0], [0, 1, 0]], [1, i2], -np.eye(3), np.zeros(3), [M.EpiNormInf(3)]), \
+        dict(status="Optimal", primal_obj=-1 - i2, x=[1, i2, 1], y=[1, 1])
+
+
+def epinorminf2():  # :808-829
+    l = 3
+    L = 2 * l + 1
+    A = np.zeros((2, L))
+    A[0, 0] = A[0, L - 1] = A[1, 0] = 1
+    A[1, L - 1] = -1
+    G = np.vstack((np.zeros((1, L)), np.eye(L), np.zeros((1, L)), 2 * np.eye(L)))
+    h = np.zeros(2 * L + 2)
+    h[0] = 1
+    h[L + 1] = 1
+    return _m(np.arange(-l, l + 1, dtype=float), A, [0, 0], G, h,
+              [M.EpiNormInf(L + 1, use_dual=True), M.EpiNormInf(L + 1)], obj_offset=1.0), \
+        dict(status="Optimal", primal_obj=-l + 2, x_idx={1: 0.5, L - 2: -0.5}, tol_scale=10)
+
+
+def epinorminf3():  # :831-847 (primal barrier)
+    return _m([1, 0, 0, 0, 0, 0], None, None, -np.eye(6), np.zeros(6), [M.EpiNormInf(6)]), \
+        dict(status="Optimal", primal_obj=0, x=np.zeros(6))
+
+
+def epinorminf3_dual():  # :831-847 (dual barrier)
+    return _m([1, 0, 0, 0, 0, 0], None, None, -np.eye(6), np.zeros(6), [M.EpiNormInf(6, use_dual=True)]), \
+        dict(status="Optimal", primal_obj=0, x=np.zeros(6))
+
+
+def epinorminf4():  # :849-863
+    return _m([0, 1, -1], [[1, 0, 0], [0, 1, 0]], [1, -0.4], -np.eye(3), np.zeros(3),
+              [M.EpiNormInf(3, use_dual=True)]), \
+        dict(status="Optimal", primal_obj=-1, x=[1, -0.4, 0.6], y=[1, 0])
+
+
+def dualinfeas1():  # :209-221
+    G = np.vstack((-np.eye(3), -np.eye(3)))
+    return _m([-1, -1, 0], None, None, G, np.zeros(6), [M.EpiNormInf(3), M.EpiNormInf(3, use_dual=True)]), \
+        dict(status="DualInfeasible")
+
+
 def hypoperlog1():  # :1677-1693
     e = np.exp(0.5)
     return _m([1, 1, 1], [[0, 1, 0], [1, 0, 0]], [2, 1], -np.eye(3), np.zeros(3), [M.HypoPerLog(3)]), \
@@ -304,7 +347,8 @@ for _k, (_hk, _hp) in enumerate(SEP_SPECTRAL_FUNS):
         SPECTRAL.append(_named(lambda d=_d, hk=_hk, hp=_hp: _spectral_matrix3(d, hk, hp),
                                f"epipersepspectral_matrix3_d{_d}_h{_hk}"))
 
-NEW_CONES = [primalinfeas3, dualinfeas2, dualinfeas3, epipersquare1, epipersquare2, epipersquare3,
+NEW_CONES = [epinorminf1, epinorminf2, epinorminf3, epinorminf3_dual, epinorminf4, dualinfeas1,
+             primalinfeas3, dualinfeas2, dualinfeas3, epipersquare1, epipersquare2, epipersquare3,
              epipersquare4, hypoperlog1, hypoperlog2, hypoperlog3, hypoperlog4, hypoperlog5, hypoperlog6,
              hypoperlog7]
 
@@ -322,6 +366,7 @@ def _approx(a, b, tol):
 
 def check_solution(solver, model, expected, tol=TOL):
     """Certificate checks of build_solve_check (nativeinstances.jl:32-86) + pinned values."""
+    tol = tol * expected.get("tol_scale", 1)
     assert solver.status == expected["status"], (solver.status, expected["status"])
     x, y, z, s = solver.get_x(), solver.get_y(), solver.get_z(), solver.get_s()
     c, A, b, G, h = model.c, model.A, model.b, model.G, model.h

@@ -1,4 +1,4 @@
-"""CPU-tier checks of the device code of EpiPerSquare and HypoPerLog (csrc/cones_vec3_kernels.cuh,
+"""CPU-tier checks of the device code of EpiPerSquare, HypoPerLog and EpiNormInf (csrc/cones_vec3_kernels.cuh,
 compiled for the host by tests/emu/) against the CPU oracle (oracle/cones_vec3.py)."""
 import numpy as np
 import pytest
@@ -17,6 +17,8 @@ def rel(a, b):
 SETS = {
     "epipersquare": [M.EpiPerSquare(d) for d in (3, 4, 6, 25, 33, 34, 70)],
     "hypoperlog": [M.HypoPerLog(d) for d in (3, 4, 7, 12, 34, 35, 80)],
+    "epinorminf": [M.EpiNormInf(d) for d in (2, 3, 6, 33, 34, 70)],
+    "epinorminf_dual": [M.EpiNormInf(4, use_dual=True), M.EpiNormInf(9), M.EpiNormInf(40, use_dual=True)],
     "hypoperlog_dual": [M.HypoPerLog(5, use_dual=True), M.HypoPerLog(9), M.HypoPerLog(40, use_dual=True)],
 }
 
@@ -69,6 +71,21 @@ def test_vec3_kernels_flag_infeasible_points():
     prim[3] = -0.5             # w_2 < 0
     prim[5] = 50.0             # u above the hypograph
     dual[9] = 0.5              # dual u > 0
+    ora = OracleConeBlock(I.model)
+    ora.load_point(prim, dual, 1.0)
+    dev = eu.EmuVec3Group(cones)
+    dev.load_point(prim, dual)
+    assert (dev.feas.astype(bool) == ora.is_feas()).all() and not dev.feas[:2].any() and dev.feas[2]
+    assert (dev.dual_feas.astype(bool) == ora.is_dual_feas()).all() and not dev.dual_feas[2]
+
+
+def test_epinorminf_kernels_flag_infeasible_points():
+    cones = [M.EpiNormInf(5), M.EpiNormInf(4), M.EpiNormInf(3)]
+    I = inst.synthetic("eniinf", 2, 0, cones, seed=13)
+    prim, dual = (x.copy() for x in I.point.primal_dual(None))
+    prim[0] = -1.0             # u < 0
+    prim[5 + 2] = 9.0          # |w|_inf > u
+    dual[9 + 1] = dual[9] + 1  # |dual w|_1 > dual u
     ora = OracleConeBlock(I.model)
     ora.load_point(prim, dual, 1.0)
     dev = eu.EmuVec3Group(cones)

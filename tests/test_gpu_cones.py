@@ -41,10 +41,12 @@ CONE_SETS = {
                      M.EpiPerSquare(70)],
     "hypoperlog": [M.HypoPerLog(3), M.HypoPerLog(7), M.HypoPerLog(34), M.HypoPerLog(80),
                    M.HypoPerLog(6, use_dual=True)],
+    "epinorminf": [M.EpiNormInf(2), M.EpiNormInf(6), M.EpiNormInf(34), M.EpiNormInf(70),
+                   M.EpiNormInf(9, use_dual=True)],
     "allmix": [M.Nonnegative(5), M.EpiNormEucl(4), M.PosSemidefTri(6), M.HypoPerLogdetTri(8),
                M.HypoRootdetTri(7), M.EpiNormEucl(3), M.HypoPerLogdetTri(5, use_dual=True),
                M.EpiPerSepSpectralMat(2 + M.svec_length(4), M.SSF_NEGENTROPY), M.EpiPerSquare(6),
-               M.HypoPerLog(5), M.HypoPerLog(4, use_dual=True)],
+               M.HypoPerLog(5), M.HypoPerLog(4, use_dual=True), M.EpiNormInf(5), M.EpiNormInf(4, use_dual=True)],
 }
 
 

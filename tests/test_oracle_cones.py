@@ -152,6 +152,13 @@ def test_hypoperlog_init_only(dw):
     run_oracles(HypoPerLog(2 + dw), init_tol=1e-1, init_only=True)
 
 
+@pytest.mark.parametrize("dw", [1, 2, 5])
+def test_epinorminf(dw):
+    # reference: test/cone.jl:443-447
+    from oracle.cones_vec3 import EpiNormInf
+    run_oracles(EpiNormInf(1 + dw))
+
+
 SSF = [(0, 0.0), (1, 0.0), (2, 0.0), (3, 1.5), (3, 2.0), (3, 1.1)]   # Inv, NegLog, NegEntropy, Power12(p)
 
 
