@@ -244,7 +244,10 @@ class Solver:
         """reference: Solvers.jl:425-483"""
         m, pt = self.model, self.point
         tau = pt.tau
-        dev = getattr(self.syssolver, "calc_residuals", None)
+        # the reference computes these residuals in the (host) solver; a device system solver can take the
+        # two passes over G instead (hyp_calc_residuals) when asked to: syssolver.device_residuals = True
+        dev = getattr(self.syssolver, "calc_residuals", None) \
+            if getattr(self.syssolver, "device_residuals", False) else None
         if dev is not None and getattr(self.syssolver, "ctx", None) is not None:
             # device plug-in: the two passes over G (and A) stay on the GPU (hyp_calc_residuals)
             xres, yres, zres, st = dev(self)

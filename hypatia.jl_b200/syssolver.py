@@ -54,9 +54,12 @@ class QRCholDenseSystemSolver:
     def _after_load(self):
         pass
 
-    def __init__(self, device: int | None = None, dist_group=None):
+    def __init__(self, device: int | None = None, dist_group=None, device_residuals: bool = False):
         self.device = device
         self.dist_group = dist_group
+        # True: the driver's calc_convergence_params takes its residuals from hyp_calc_residuals (two
+        # passes over G on the device) instead of the host products the reference does (Solvers.jl:425-483)
+        self.device_residuals = device_residuals
         self.ctx = None
         self.cones = None
         self.fact_kind = 0

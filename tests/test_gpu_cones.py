@@ -68,13 +68,15 @@ def test_cone_oracles_match_cpu_oracle(name):
     assert rel(g, ora.grad()) <= 1e-11
     rng = np.random.default_rng(1)
     arr = rng.standard_normal((I.model.q, 3))
-    # side-130 spectral cone: the divided differences of dder3 amplify the O(side * eps) difference between
-    # the Jacobi eigenvectors and LAPACK's (measured 2.2e-10)
-    tol = 1e-9 if name == "sepspec_big" else 1e-10
+    # side-130 spectral cone: its eigenvalues cluster near 1 (spacing ~1e-3), and the second divided
+    # differences of dder3 (matrixcsqr.jl:449-502) divide by those gaps, amplifying the O(side * eps)
+    # difference between the Jacobi and LAPACK eigen-decompositions (measured 2e-10 .. 1.3e-9)
+    tol = 1e-10
+    d3tol = 1e-8 if name == "sepspec_big" else tol
     assert rel(dev.hess_prod(arr), ora.hess_prod(arr)) <= tol
     assert rel(dev.inv_hess_prod(arr), ora.inv_hess_prod(arr)) <= tol
     assert rel(dev.block_hess_prod(arr[:, 0]), ora.block_hess_prod(arr[:, 0])) <= tol
-    assert rel(dev.dder3(arr[:, 1]), ora.dder3(arr[:, 1])) <= tol
+    assert rel(dev.dder3(arr[:, 1]), ora.dder3(arr[:, 1])) <= d3tol
     irtmu = 0.9
     assert np.allclose(dev.get_proxsqr(irtmu, True), ora.get_proxsqr(irtmu, True), rtol=1e-8, atol=1e-12)
     assert np.allclose(dev.get_proxsqr(irtmu, False), ora.get_proxsqr(irtmu, False), rtol=1e-8, atol=1e-12)

@@ -74,6 +74,24 @@ def test_linearopt_and_soc_solves_match_oracle_iterates():
             assert abs(sd.primal_obj - so.primal_obj) <= 1e-6 * (1 + abs(so.primal_obj))
 
 
+def test_solves_with_device_residuals():
+    """Full solves with the residual step of calc_convergence_params on the device (hyp_calc_residuals,
+    SURVEY.md 8(f) rank 3): same status / optimum as with the host residuals."""
+    from hypatia_b200.cones import DeviceConeBlock
+    from hypatia_b200.syssolver import QRCholDenseSystemSolver as DevQRChol
+    cases = [kat.nonnegative4()[0], kat.epinormeucl1()[0], kat.possemideftri8()[0], kat.hypoperlog5()[0],
+             kat.epinorminf2()[0], inst.linearopt(40, 80, seed=7),
+             inst.synthetic("soc", 60, 0, [M.EpiNormEucl(25) for _ in range(8)], seed=21).model]
+    for model in cases:
+        s1 = Solver(model.copy(), DevQRChol(device_residuals=True), DeviceConeBlock)
+        s1.solve()
+        s0 = _solve_dev(model.copy())
+        assert s1.status == s0.status
+        assert abs(s1.num_iters - s0.num_iters) <= 3
+        if s0.status == "Optimal":
+            assert abs(s1.primal_obj - s0.primal_obj) <= 1e-6 * (1 + abs(s0.primal_obj))
+
+
 def test_c1_linearopt_symindef_device():
     """BASELINE config 1 (examples/linearopt native, dense A 200 x 400, Nonnegative, SymIndefDense,
     no reduction) solved with the device SymIndefDense plug-in; same optimum as the oracle's."""
