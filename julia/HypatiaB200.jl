@@ -35,7 +35,19 @@ cone_code(::Cones.EpiNormEucl) = Cint(1)
 cone_code(::Cones.PosSemidefTri{Float64, Float64}) = Cint(2)
 cone_code(::Cones.HypoPerLogdetTri{Float64, Float64}) = Cint(3)
 cone_code(::Cones.HypoRootdetTri{Float64, Float64}) = Cint(4)
+cone_code(::Cones.EpiPerSepSpectral{Cones.MatrixCSqr{Float64, Float64}, Float64}) = Cint(5)
+cone_code(::Cones.EpiPerSquare) = Cint(6)
+cone_code(::Cones.HypoPerLog) = Cint(7)
+cone_code(::Cones.EpiNormInf{Float64, Float64}) = Cint(8)
 cone_code(c::Cones.Cone) = error("cone $(typeof(c)) is not on the B200 hot path")
+
+# HYP_SSF_* code and parameter of the `h` field of EpiPerSepSpectral (sepspectralfun.jl:17-116)
+ssf_code(::Cones.InvSSF) = (Cint(0), 0.0)
+ssf_code(::Cones.NegLogSSF) = (Cint(1), 0.0)
+ssf_code(::Cones.NegEntropySSF) = (Cint(2), 0.0)
+ssf_code(h::Cones.Power12SSF) = (Cint(3), Float64(h.p))
+cone_ssf(c::Cones.EpiPerSepSpectral) = ssf_code(c.h)
+cone_ssf(::Cones.Cone) = (Cint(0), 0.0)
 
 function check(ctx::Ctx, rc::Cint, what::String)
     rc < 0 && error("$what: " * unsafe_string(ccall((:hyp_last_error, LIB), Cstring, (Ctx,), ctx)))
@@ -71,6 +83,10 @@ function Solvers.load(syssolver::B200QRCholSystemSolver, solver::Solver{Float64}
     cdual = Cint[Cones.use_dual_barrier(c) for c in model.cones]
     ApQ = iszero(p) ? C_NULL : pointer(Matrix{Float64}(solver.Ap_Q * I(n)))
     ApR = iszero(p) ? C_NULL : pointer(Matrix{Float64}(solver.Ap_R))
+    ssf = [cone_ssf(c) for c in model.cones]
+    (hkind, hparam) = (Cint[first(t) for t in ssf], Float64[last(t) for t in ssf])
+    check(syssolver.ctx, ccall((:hyp_set_cone_params, LIB), Cint, (Ctx, Cint, Ptr{Cint}, Ptr{Float64}),
+        syssolver.ctx, K, hkind, hparam), "hyp_set_cone_params")
     GC.@preserve G A ctype cdim cdual begin
         rc = ccall((:hyp_load_model, LIB), Cint,
             (Ctx, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Float64},
@@ -132,6 +148,26 @@ function Solvers.apply_lhs(stepper::Solvers.Stepper{Float64},
     check(ctx, ccall((:hyp_apply_lhs, LIB), Cint, (Ctx, Ptr{Float64}, Ptr{Float64}),
         ctx, stepper.res.vec, stepper.dir.vec), "hyp_apply_lhs")
     return stepper.res
+end
+
+# calc_convergence_params(solver): Solvers.jl:425-483.  Optional: the residual vectors and norms with the
+# two passes over G done on the device (hyp_calc_residuals); the remaining scalar bookkeeping of the
+# reference's function (x_feas .. improv, primal_obj, dual_obj, gap) is unchanged host code.
+function device_residuals!(solver::Solver{Float64, <:Any, B200QRCholSystemSolver})
+    ctx = solver.syssolver.ctx
+    stats = zeros(10)
+    check(ctx, ccall((:hyp_calc_residuals, LIB), Cint,
+        (Ctx, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        ctx, solver.point.vec, solver.x_residual, solver.y_residual, solver.z_residual, stats),
+        "hyp_calc_residuals")
+    tau = solver.point.tau[]
+    (solver.x_norm_res_t, solver.x_norm_res) = (stats[1], stats[2] / tau)
+    (solver.y_norm_res_t, solver.y_norm_res) = (stats[3], stats[4] / tau)
+    (solver.z_norm_res_t, solver.z_norm_res) = (stats[5], stats[6] / tau)
+    solver.primal_obj_t = stats[7]
+    solver.dual_obj_t = -stats[8] - stats[9]
+    solver.gap = stats[10]
+    return solver
 end
 
 # free_memory(syssolver): Solvers.jl:582-584
