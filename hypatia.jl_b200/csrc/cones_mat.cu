@@ -16,6 +16,7 @@
 //     Y_j = X' T_j                   (c grouped d x d products in one launch)
 // Bound: tensor (FP64 DMMA), 4 d^3 flops per column; the unpack / pack passes are HBM-bound.
 #include "cones_mat.cuh"
+#include <cstdlib>
 #include "cones_mat_kernels.cuh"
 
 using hypdev::block_sum;
@@ -180,56 +181,13 @@ colscal_kernel(int type, int inverse, int d, int64_t len, const double* __restri
     for (int64_t i = lane; i < len; i += 32) dot += col[lead + i] * vecB[i];
     dot = warp_sum(dot);
     if (lane != 0) return;
+    double o0 = 0.0, o1 = 0.0, al = 1.0, be = 0.0;
+    hypdev::mat_colscal(type, inverse, d, sc, dot, col[0], col[1], o0, o1, al, be);
     double* out = pr + j * ld_prod;
-    const double phi = sc[1], zeta = sc[2], dd = (double)d;
-    if (type == HYP_CONE_HYPOPERLOGDETTRI) {
-        const double v = sc[4], p = col[0], q = col[1];
-        if (!inverse) {
-            const double sigma = phi - dd, qzi = q / zeta;
-            const double c0 = dot / zeta;
-            const double c1 = (v * c0 - p / zeta + sigma * qzi) / zeta;
-            const double c3 = c1 * v - qzi;
-            out[0] = -c1;
-            out[1] = c1 * sigma - c0 + (qzi * dd + q / v) / v;
-            alpha[j] = v / zeta + 1.0;
-            beta[j] = c3;
-        } else {
-            const double zv = zeta + v, zzvi = zeta / zv;
-            const double c3 = v / (zv + dd * v);
-            const double c0 = phi - dd * zzvi;
-            const double c4 = v * c3 * zv;
-            const double t = zeta + v * phi;
-            const double c6 = (v * phi) * (v * phi) + zeta * (zeta + dd * v) - dd * t * t * c3;
-            const double c7 = c4 * c0, c8 = c7 + v * zeta;
-            const double c1 = dot / zv;
-            const double c5 = c0 * p + q + c1;
-            const double c2 = v * (zzvi * p + c3 * c5);
-            out[0] = c6 * p + c7 * q + c8 * c1;
-            out[1] = c4 * c5;
-            alpha[j] = zzvi;
-            beta[j] = c2;
-        }
-    } else {
-        const double pzd = sc[5], di = 1.0 / dd, p = col[0];
-        if (!inverse) {
-            const double c0 = pzd * dot;
-            const double c1 = c0 - p / zeta;
-            const double c2 = pzd * c1 - di * c0;
-            out[0] = -c1 / zeta;
-            alpha[j] = pzd + 1.0;
-            beta[j] = c2;
-        } else {
-            const double phidi = phi * di;
-            const double c2 = 1.0 / (pzd + 1.0);
-            const double c3 = c2 / zeta * di;
-            const double c4 = zeta * zeta + phidi * phi;
-            const double c5 = dot;
-            const double c6 = phidi * (c3 * c5 + p);
-            out[0] = phidi * c5 + c4 * p;
-            alpha[j] = c2;
-            beta[j] = c6;
-        }
-    }
+    out[0] = o0;
+    if (type == HYP_CONE_HYPOPERLOGDETTRI) out[1] = o1;
+    alpha[j] = al;
+    beta[j] = be;
 }
 
 // dder3 combination step (hypoperlogdettri.jl:321-368, hyporootdettri.jl:285-324,
@@ -446,6 +404,31 @@ void hyp_mat_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr, i
     const int lead = lead_of(g.type);
     if ((mode == HYP_PROD_SQRT_HESS || mode == HYP_PROD_INV_SQRT_HESS) && g.type != HYP_CONE_POSSEMIDEFTRI)
         throw HypError{"sqrt_hess_prod is not defined for the log-det / root-det cones"};
+    // few columns, sides that fit in shared memory: one fused launch for the whole group (CUDA-core FP64,
+    // M and T on chip) instead of the per-cone tensor-GEMM sequence below
+    {
+        static int max_small_cols = -1;
+        if (max_small_cols < 0) {
+            const char* e = getenv("HYP_MAT_SMALL_MAXCOLS");
+            max_small_cols = e ? atoi(e) : 8;
+        }
+        const int64_t smem = (int64_t)2 * g.max_side * (g.max_side | 1) * sizeof(double);
+        if (ncols <= max_small_cols && g.count > 0 && smem <= 226 * 1024) {
+            static bool attr = false;
+            if (!attr) {
+                CUDA_TRY(cudaFuncSetAttribute(hypdev::mat_small_prod_kernel,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+                attr = true;
+            }
+            dim3 grid(g.count, (unsigned)ncols);
+            hypdev::mat_small_prod_kernel<<<grid, 256, smem, ctx->stream>>>(
+                g.type, mode, g.count, g.d_off, g.d_side, g.d_moff, g.d_dual, g.d_W, g.d_Wi, g.d_Ui, g.d_Ut, g.d_scal,
+                ctx->d_point, ctx->d_wivec, arr, ld_arr, prod, ld_prod, row_shift);
+            ctx->launches++;
+            CUDA_TRY(cudaGetLastError());
+            return;
+        }
+    }
     const int64_t budget = (int64_t)48 << 20;   // doubles per workspace matrix (384 MB)
     for (int i = 0; i < g.count; i++) {
         const int d = g.h_side[i], lde = (d + 1) & ~1;

@@ -80,4 +80,194 @@ pack_cols_kernel(int d, int lde, int64_t len, const double* __restrict__ Yall, i
     }
 }
 
+
+// ---- on-chip d x d products for the fused small-matrix kernels: 4 x 4 register tiles per thread ----
+// T = M X : M, T in shared memory (leading dimension ldm), X in global memory (leading dimension lde)
+__device__ __forceinline__ void small_gemm_mx(int d, int ldm, const double* sM, const double* X, int lde,
+                                              double* sT) {
+    const int tpd = (d + 3) >> 2;
+    for (int t = threadIdx.x; t < tpd * tpd; t += blockDim.x) {
+        const int i0 = (t % tpd) * 4, j0 = (t / tpd) * 4;
+        double acc[4][4] = {};
+        for (int k = 0; k < d; k++) {
+            double mv[4], xv[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                mv[u] = (i0 + u < d) ? sM[i0 + u + k * ldm] : 0.0;
+                xv[u] = (j0 + u < d) ? X[k + (int64_t)(j0 + u) * lde] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+                for (int w = 0; w < 4; w++) acc[u][w] += mv[u] * xv[w];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int w = 0; w < 4; w++)
+                if (i0 + u < d && j0 + w < d) sT[i0 + u + (j0 + w) * ldm] = acc[u][w];
+    }
+}
+
+// Y = X' T for the upper triangle: epi(r, s, Y[r, s]) is called once for every r <= s
+template <class Epi>
+__device__ __forceinline__ void small_gemm_xtt(int d, int ldm, const double* X, int lde, const double* sT,
+                                               Epi epi) {
+    const int tpd = (d + 3) >> 2;
+    for (int t = threadIdx.x; t < tpd * tpd; t += blockDim.x) {
+        const int i0 = (t % tpd) * 4, j0 = (t / tpd) * 4;
+        if (i0 > j0) continue;
+        double acc[4][4] = {};
+        for (int k = 0; k < d; k++) {
+            double xv[4], tv[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                xv[u] = (i0 + u < d) ? X[k + (int64_t)(i0 + u) * lde] : 0.0;
+                tv[u] = (j0 + u < d) ? sT[k + (j0 + u) * ldm] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+                for (int w = 0; w < 4; w++) acc[u][w] += xv[u] * tv[w];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                const int r = i0 + u, s = j0 + w;
+                if (r <= s && s < d) epi(r, s, acc[u][w]);
+            }
+    }
+}
+
+// Scalar parts of hess_prod! / inv_hess_prod! of the log-det / root-det cones for one column
+// (hypoperlogdettri.jl:196-237, :274-319; hyporootdettri.jl:176-212, :246-283): given dot = <r, vecB> (vecB =
+// svec(W^-1) for hess, svec(W) for inv_hess) and the leading entries (p, q) of the column, the leading entries of
+// the product (out0, out1; out1 only for the log-det cone) and the coefficients of its matrix part
+// alpha * svec(X' R X) + beta * vecB.  type: 3 = HypoPerLogdetTri, 4 = HypoRootdetTri.
+__device__ __forceinline__ void mat_colscal(int type, int inverse, int d, const double* sc, double dot, double p,
+                                            double q, double& out0, double& out1, double& alpha, double& beta) {
+    const double phi = sc[1], zeta = sc[2], dd = (double)d;
+    if (type == 3) {
+        const double v = sc[4];
+        if (!inverse) {
+            const double sigma = phi - dd, qzi = q / zeta;
+            const double c0 = dot / zeta;
+            const double c1 = (v * c0 - p / zeta + sigma * qzi) / zeta;
+            const double c3 = c1 * v - qzi;
+            out0 = -c1;
+            out1 = c1 * sigma - c0 + (qzi * dd + q / v) / v;
+            alpha = v / zeta + 1.0;
+            beta = c3;
+        } else {
+            const double zv = zeta + v, zzvi = zeta / zv;
+            const double c3 = v / (zv + dd * v);
+            const double c0 = phi - dd * zzvi;
+            const double c4 = v * c3 * zv;
+            const double t = zeta + v * phi;
+            const double c6 = (v * phi) * (v * phi) + zeta * (zeta + dd * v) - dd * t * t * c3;
+            const double c7 = c4 * c0, c8 = c7 + v * zeta;
+            const double c1 = dot / zv;
+            const double c5 = c0 * p + q + c1;
+            const double c2 = v * (zzvi * p + c3 * c5);
+            out0 = c6 * p + c7 * q + c8 * c1;
+            out1 = c4 * c5;
+            alpha = zzvi;
+            beta = c2;
+        }
+    } else {
+        const double pzd = sc[5], di = 1.0 / dd;
+        out1 = 0.0;
+        if (!inverse) {
+            const double c0 = pzd * dot;
+            const double c1 = c0 - p / zeta;
+            const double c2 = pzd * c1 - di * c0;
+            out0 = -c1 / zeta;
+            alpha = pzd + 1.0;
+            beta = c2;
+        } else {
+            const double phidi = phi * di;
+            const double c2 = 1.0 / (pzd + 1.0);
+            const double c3 = c2 / zeta * di;
+            const double c4 = zeta * zeta + phidi * phi;
+            const double c6 = phidi * (c3 * dot + p);
+            out0 = phidi * dot + c4 * p;
+            alpha = c2;
+            beta = c6;
+        }
+    }
+}
+
+// Fused small-matrix product for FEW columns and MANY cones: CTA (c, j) computes column j of the product of
+// cone c of a group of PosSemidefTri / HypoPerLogdetTri / HypoRootdetTri cones entirely on chip:
+//     svec -> M (shared memory) -> T = M X (shared memory) -> Y = X' T -> alpha * svec(Y) + beta * vecB,
+// X = W^-1 (hess), W (inv_hess), U^-1 (sqrt_hess), U' (inv_sqrt_hess) read through L1 from the per-cone state.
+// Replaces the per-cone launch sequence unpack / colscal / two TMA GEMMs / pack (5 launches and 6 tensor maps
+// per cone and product) that dominates models with many small matrix cones when ncols is 1..4 (apply_lhs,
+// setup_rhs3, the z update of solve_subsystem3, the proximity oracles of the line search).
+// mode: 0 hess, 1 inv_hess, 2 sqrt, 3 inv_sqrt, 4 block (hess / inv_hess by dualf), 5 block_inv.
+// Each thread owns 4 x 4 register tiles; CUDA-core FP64 (4 d^3 flop per (cone, column)).
+static __global__ void __launch_bounds__(256)
+mat_small_prod_kernel(int type, int mode_in, int ncones, const int64_t* __restrict__ off,
+                      const int* __restrict__ sides, const int64_t* __restrict__ moff,
+                      const int* __restrict__ dualf, const double* __restrict__ W,
+                      const double* __restrict__ Wi, const double* __restrict__ Ui,
+                      const double* __restrict__ Ut, const double* __restrict__ scal,
+                      const double* __restrict__ point, const double* __restrict__ wivec, const double* arr,
+                      int64_t ld_arr, double* prod, int64_t ld_prod, int64_t row_shift) {
+    HYP_DYN_SMEM(double, dyn);
+    __shared__ double red[8];
+    const int c = blockIdx.x;
+    if (c >= ncones) return;
+    const int64_t j = blockIdx.y;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int d = sides[c], lde = (d + 1) & ~1;
+    const int ldm = d | 1;
+    const int64_t len = (int64_t)d * (d + 1) / 2;
+    const int lead = type == 2 ? 0 : type == 3 ? 2 : 1;
+    int mode = mode_in;
+    if (mode == 4) mode = (dualf && dualf[c]) ? 1 : 0;
+    if (mode == 5) mode = (dualf && dualf[c]) ? 0 : 1;
+    const int inverse = mode == 1;
+    const double* X = (mode == 0 ? Wi : mode == 1 ? W : mode == 2 ? Ui : Ut) + moff[c];
+    const int64_t o = off[c];
+    const double* a = arr + j * ld_arr + (o - row_shift);
+    double* pr = prod + j * ld_prod + (o - row_shift);
+    double* sM = dyn;
+    double* sT = dyn + (int64_t)d * ldm;
+    // ---- svec -> M, and the dot product with vecB for the scalar parts ----
+    const double* vecB = type == 2 ? nullptr : (inverse ? point : wivec) + o + lead;
+    double dot = 0.0;
+    for (int64_t idx = tid; idx < len; idx += nt) {
+        int r, s;
+        svec_rc(idx, r, s);
+        double x = a[lead + idx];
+        if (vecB) dot += x * vecB[idx];
+        if (r != s) x *= HYP_IRT2;
+        sM[r + s * ldm] = x;
+        sM[s + r * ldm] = x;
+    }
+    double alpha = 1.0, beta = 0.0, o0 = 0.0, o1 = 0.0;
+    if (vecB) {
+        dot = block_sum(dot, red);
+        mat_colscal(type, inverse, d, scal + 8 * c, dot, a[0], lead == 2 ? a[1] : 0.0, o0, o1, alpha, beta);
+    } else {
+        __syncthreads();
+    }
+    small_gemm_mx(d, ldm, sM, X, lde, sT);
+    __syncthreads();
+    // ---- Y = X' T (upper triangle), packed straight into the product column ----
+    small_gemm_xtt(d, ldm, X, lde, sT, [&](int r, int s2, double x) {
+        const int64_t idx = (int64_t)s2 * (s2 + 1) / 2 + r;
+        if (r != s2) x *= HYP_RT2;
+        x *= alpha;
+        if (vecB) x += beta * vecB[idx];
+        pr[lead + idx] = x;
+    });
+    if (tid == 0 && lead > 0) {
+        pr[0] = o0;
+        if (lead == 2) pr[1] = o1;
+    }
+}
+
 }  // namespace hypdev

@@ -13,6 +13,7 @@
 #include "cones_mat_kernels.cuh"
 #include "cones_spec_kernels.cuh"
 #include "eig.cuh"
+#include <cstdlib>
 
 using hypdev::pack_cols_kernel;
 using hypdev::spec_dder3_kernel;
@@ -95,6 +96,30 @@ void hyp_spec_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr, 
                    int64_t ld_arr, int mode, int64_t row_shift) {
     if (mode == HYP_PROD_SQRT_HESS || mode == HYP_PROD_INV_SQRT_HESS)
         throw HypError{"sqrt_hess_prod is not defined for EpiPerSepSpectral"};
+    // few columns, sides that fit in shared memory: one fused launch for the whole group
+    {
+        static int max_small_cols = -1;
+        if (max_small_cols < 0) {
+            const char* e = getenv("HYP_MAT_SMALL_MAXCOLS");
+            max_small_cols = e ? atoi(e) : 8;
+        }
+        const int64_t smem = (int64_t)2 * g.max_side * (g.max_side | 1) * sizeof(double);
+        if (ncols <= max_small_cols && g.count > 0 && smem <= 226 * 1024) {
+            static bool attr = false;
+            if (!attr) {
+                CUDA_TRY(cudaFuncSetAttribute(hypdev::spec_small_prod_kernel,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+                attr = true;
+            }
+            dim3 grid(g.count, (unsigned)ncols);
+            hypdev::spec_small_prod_kernel<<<grid, 256, smem, ctx->stream>>>(
+                mode, g.count, g.d_off, g.d_side, g.d_moff, g.d_voff, g.d_dual, g.d_U, g.d_Ut, g.d_Wi, g.d_Ui,
+                g.d_vecs, g.d_scal, arr, ld_arr, prod, ld_prod, row_shift);
+            ctx->launches++;
+            CUDA_TRY(cudaGetLastError());
+            return;
+        }
+    }
     const int64_t budget = (int64_t)48 << 20;   // doubles per workspace matrix (384 MB)
     for (int i = 0; i < g.count; i++) {
         const int d = g.h_side[i], lde = (d + 1) & ~1;

@@ -12,6 +12,7 @@
 //   -> V (.) V' (congruence) -> svec.
 #pragma once
 #include "devdefs.cuh"
+#include "cones_mat_kernels.cuh"
 
 namespace hypdev {
 
@@ -204,14 +205,12 @@ spec_dualfeas_kernel(int ncones, const int64_t* __restrict__ off, const int* __r
 }
 
 // Middle step of hess_prod! (inverse = 0, matrixcsqr.jl:273-319) and inv_hess_prod! (inverse = 1,
-// matrixcsqr.jl:402-447) for cc columns of one cone block: R_j = V' M_j V sits in Mall (d x d, ld
-// lde, stride lde*lde), is transformed in place into the matrix that is rotated back, and the
-// two leading entries of the product are written.  One CTA per column.
-static __global__ void __launch_bounds__(256)
-spec_mid_kernel(int inverse, int d, int lde, const double* __restrict__ sc, const double* __restrict__ vecs,
-                const double* __restrict__ theta, const double* __restrict__ Dh, double* __restrict__ Mall,
-                const double* arr, int64_t ld_arr, double* pr, int64_t ld_prod, int64_t cc) {
-    __shared__ double sm[8];
+// matrixcsqr.jl:402-447) for ONE column: R = V' M V (d x d, leading dimension ldr, shared or global memory) is
+// transformed in place into the matrix that is rotated back, and the two leading entries of the product are
+// written to out.  theta / Dh have leading dimension lde.  Called by every thread of the CTA.
+__device__ __forceinline__ void spec_mid_column(int inverse, int d, int lde, int ldr, const double* sc,
+                                                const double* vecs, const double* theta, const double* Dh,
+                                                double* R, double p, double q, double* out, double* sm) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const double* lam = vecs;
     const double* dh = vecs + d;
@@ -220,59 +219,121 @@ spec_mid_kernel(int inverse, int d, int lde, const double* __restrict__ sc, cons
     const double zeta = sc[1], sigma = sc[2], v = sc[4], c0 = sc[5], c4 = sc[6], c5 = sc[7];
     const double zetai = 1.0 / zeta, zetaivi = zetai / v;
     const int64_t len = (int64_t)d * (d + 1) / 2;
-    for (int64_t j = blockIdx.x; j < cc; j += gridDim.x) {
-        double* R = Mall + j * (int64_t)lde * lde;
-        const double p = arr[j * ld_arr], q = arr[j * ld_arr + 1];
-        double* out = pr + j * ld_prod;
-        if (!inverse) {
-            double s1 = 0.0, s2 = 0.0;
-            for (int i = tid; i < d; i += nt) {
-                const double rii = R[i + (int64_t)i * lde];
-                s1 += dh[i] * rii;
-                s2 += lam[i] * zetaivi * Dh[i + (int64_t)i * lde] * (rii - q * lam[i]);
-            }
-            s1 = block_sum(s1, sm);
-            s2 = block_sum(s2, sm);
-            const double c1 = -zetai * (p - sigma * q - s1) * zetai;
-            for (int64_t idx = tid; idx < len; idx += nt) {
-                int a, b;
-                svec_rc(idx, a, b);
-                double x = theta[a + (int64_t)b * lde] * R[a + (int64_t)b * lde];
-                if (a == b) x += c1 * dh[a] - zetaivi * Dh[a + (int64_t)a * lde] * q * lam[a];
-                R[a + (int64_t)b * lde] = x;
-                R[b + (int64_t)a * lde] = x;
-            }
-            if (tid == 0) {
-                out[0] = -c1;
-                out[1] = c1 * sigma - s2 + q / v / v;
-            }
-        } else {
-            double s1 = 0.0, s2 = 0.0;
-            for (int i = tid; i < d; i += nt) {
-                const double rii = R[i + (int64_t)i * lde];
-                s1 += gamma[i] * rii;
-                s2 += alpha[i] * rii;
-            }
-            s1 = block_sum(s1, sm);
-            s2 = block_sum(s2, sm);
-            const double qgr = q + s1;
-            const double cu = c4 * (c5 * p + c0 * qgr);
-            const double cv = c4 * (c0 * p + qgr);
-            for (int64_t idx = tid; idx < len; idx += nt) {
-                int a, b;
-                svec_rc(idx, a, b);
-                double x = R[a + (int64_t)b * lde] / theta[a + (int64_t)b * lde];
-                if (a == b) x += p * alpha[a] + cv * gamma[a];
-                R[a + (int64_t)b * lde] = x;
-                R[b + (int64_t)a * lde] = x;
-            }
-            if (tid == 0) {
-                out[0] = cu + s2;
-                out[1] = cv;
-            }
+    if (!inverse) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int i = tid; i < d; i += nt) {
+            const double rii = R[i + (int64_t)i * ldr];
+            s1 += dh[i] * rii;
+            s2 += lam[i] * zetaivi * Dh[i + (int64_t)i * lde] * (rii - q * lam[i]);
         }
-        __syncthreads();
+        s1 = block_sum(s1, sm);
+        s2 = block_sum(s2, sm);
+        const double c1 = -zetai * (p - sigma * q - s1) * zetai;
+        for (int64_t idx = tid; idx < len; idx += nt) {
+            int a, b;
+            svec_rc(idx, a, b);
+            double x = theta[a + (int64_t)b * lde] * R[a + (int64_t)b * ldr];
+            if (a == b) x += c1 * dh[a] - zetaivi * Dh[a + (int64_t)a * lde] * q * lam[a];
+            R[a + (int64_t)b * ldr] = x;
+            R[b + (int64_t)a * ldr] = x;
+        }
+        if (tid == 0) {
+            out[0] = -c1;
+            out[1] = c1 * sigma - s2 + q / v / v;
+        }
+    } else {
+        double s1 = 0.0, s2 = 0.0;
+        for (int i = tid; i < d; i += nt) {
+            const double rii = R[i + (int64_t)i * ldr];
+            s1 += gamma[i] * rii;
+            s2 += alpha[i] * rii;
+        }
+        s1 = block_sum(s1, sm);
+        s2 = block_sum(s2, sm);
+        const double qgr = q + s1;
+        const double cu = c4 * (c5 * p + c0 * qgr);
+        const double cv = c4 * (c0 * p + qgr);
+        for (int64_t idx = tid; idx < len; idx += nt) {
+            int a, b;
+            svec_rc(idx, a, b);
+            double x = R[a + (int64_t)b * ldr] / theta[a + (int64_t)b * lde];
+            if (a == b) x += p * alpha[a] + cv * gamma[a];
+            R[a + (int64_t)b * ldr] = x;
+            R[b + (int64_t)a * ldr] = x;
+        }
+        if (tid == 0) {
+            out[0] = cu + s2;
+            out[1] = cv;
+        }
     }
+    __syncthreads();
+}
+
+// The middle step for cc columns of one cone block: R_j sits in Mall (d x d, ld lde, stride lde * lde).
+// One CTA per column.
+static __global__ void __launch_bounds__(256)
+spec_mid_kernel(int inverse, int d, int lde, const double* __restrict__ sc, const double* __restrict__ vecs,
+                const double* __restrict__ theta, const double* __restrict__ Dh, double* __restrict__ Mall,
+                const double* arr, int64_t ld_arr, double* pr, int64_t ld_prod, int64_t cc) {
+    __shared__ double sm[8];
+    for (int64_t j = blockIdx.x; j < cc; j += gridDim.x)
+        spec_mid_column(inverse, d, lde, lde, sc, vecs, theta, Dh, Mall + j * (int64_t)lde * lde, arr[j * ld_arr],
+                        arr[j * ld_arr + 1], pr + j * ld_prod, sm);
+}
+
+// Fused product for FEW columns and MANY spectral cones (cf. mat_small_prod_kernel): CTA (c, j) does
+//     svec -> M -> R = V' M V -> middle step -> V R V' -> svec
+// on chip (M / R and the intermediate T in shared memory, V and V' read through L1).
+// mode: 0 hess, 1 inv_hess, 4 block (hess / inv_hess by dualf), 5 block_inv.
+static __global__ void __launch_bounds__(256)
+spec_small_prod_kernel(int mode_in, int ncones, const int64_t* __restrict__ off, const int* __restrict__ sides,
+                       const int64_t* __restrict__ moff, const int64_t* __restrict__ voff,
+                       const int* __restrict__ dualf, const double* __restrict__ V,
+                       const double* __restrict__ Vt, const double* __restrict__ theta,
+                       const double* __restrict__ Dh, const double* __restrict__ vecs,
+                       const double* __restrict__ scal, const double* arr, int64_t ld_arr, double* prod,
+                       int64_t ld_prod, int64_t row_shift) {
+    HYP_DYN_SMEM(double, dyn);
+    __shared__ double red[8];
+    const int c = blockIdx.x;
+    if (c >= ncones) return;
+    const int64_t j = blockIdx.y;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int d = sides[c], lde = (d + 1) & ~1;
+    const int ldm = d | 1;
+    const int64_t len = (int64_t)d * (d + 1) / 2;
+    int mode = mode_in;
+    if (mode == 4) mode = (dualf && dualf[c]) ? 1 : 0;
+    if (mode == 5) mode = (dualf && dualf[c]) ? 0 : 1;
+    const int64_t o = off[c], mo = moff[c];
+    const double* a = arr + j * ld_arr + (o - row_shift);
+    double* pr = prod + j * ld_prod + (o - row_shift);
+    double* sM = dyn;
+    double* sT = dyn + (int64_t)d * ldm;
+    const double p = a[0], q = a[1];
+    for (int64_t idx = tid; idx < len; idx += nt) {
+        int r, s;
+        svec_rc(idx, r, s);
+        double x = a[2 + idx];
+        if (r != s) x *= HYP_IRT2;
+        sM[r + s * ldm] = x;
+        sM[s + r * ldm] = x;
+    }
+    __syncthreads();
+    small_gemm_mx(d, ldm, sM, V + mo, lde, sT);                // T = M V
+    __syncthreads();
+    small_gemm_xtt(d, ldm, V + mo, lde, sT, [&](int r, int s2, double x) {   // R = V' T -> sM (both triangles)
+        sM[r + s2 * ldm] = x;
+        sM[s2 + r * ldm] = x;
+    });
+    __syncthreads();
+    spec_mid_column(mode == 1, d, lde, ldm, scal + 8 * c, vecs + voff[c], theta + mo, Dh + mo, sM, p, q, pr, red);
+    small_gemm_mx(d, ldm, sM, Vt + mo, lde, sT);               // T = R V'
+    __syncthreads();
+    small_gemm_xtt(d, ldm, Vt + mo, lde, sT, [&](int r, int s2, double x) {  // V T = V R V'
+        if (r != s2) x *= HYP_RT2;
+        pr[2 + (int64_t)s2 * (s2 + 1) / 2 + r] = x;
+    });
 }
 
 // second divided difference of h' over the index triple (i, j, k), update_dder3_aux

@@ -126,3 +126,37 @@ int emu_v3_dder3(int type, int ncones, const int64_t* off, const int* dim, const
 }
 
 }  // extern "C"
+
+extern "C" {
+
+int emu_mat_small_prod(int type, int mode, int ncones, int max_side, const int64_t* off, const int* sides,
+                       const int64_t* moff, const int* dualf, const double* W, const double* Wi, const double* Ui,
+                       const double* Ut, const double* scal, const double* point, const double* wivec,
+                       const double* arr, int64_t ld_arr, double* prod, int64_t ld_prod, int64_t row_shift,
+                       int ncols, int threads) {
+    const size_t smem = (size_t)2 * max_side * (max_side | 1) * sizeof(double);
+    emu::launch(dim3(ncones, ncols), dim3(threads), smem, [&] {
+        hypdev::mat_small_prod_kernel(type, mode, ncones, off, sides, moff, dualf, W, Wi, Ui, Ut, scal, point, wivec,
+                                      arr, ld_arr, prod, ld_prod, row_shift);
+    });
+    return 0;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+int emu_spec_small_prod(int mode, int ncones, int max_side, const int64_t* off, const int* sides,
+                        const int64_t* moff, const int64_t* voff, const int* dualf, const double* V, const double* Vt,
+                        const double* theta, const double* Dh, const double* vecs, const double* scal,
+                        const double* arr, int64_t ld_arr, double* prod, int64_t ld_prod, int64_t row_shift, int ncols,
+                        int threads) {
+    const size_t smem = (size_t)2 * max_side * (max_side | 1) * sizeof(double);
+    emu::launch(dim3(ncones, ncols), dim3(threads), smem, [&] {
+        hypdev::spec_small_prod_kernel(mode, ncones, off, sides, moff, voff, dualf, V, Vt, theta, Dh, vecs, scal, arr,
+                                       ld_arr, prod, ld_prod, row_shift);
+    });
+    return 0;
+}
+
+}  // extern "C"

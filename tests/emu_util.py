@@ -159,6 +159,18 @@ class EmuSpecGroup:
             del a0
         return out[:, 0] if np.ndim(arr) == 1 else out
 
+    def small_prod(self, arr, mode, in_place=False):
+        """The fused few-column kernel (spec_small_prod_kernel): one launch for all cones and columns."""
+        a = np.asfortranarray(np.asarray(arr, dtype=np.float64).reshape(self.q, -1, order="F")).copy(order="F")
+        out = a if in_place else np.zeros_like(a, order="F")
+        lay = self.lay
+        dualf = np.array([1 if s.use_dual else 0 for s in self.specs], dtype=np.int32)
+        lib().emu_spec_small_prod(int(mode), self.K, int(lay.sides.max()), p(self.off), p(lay.sides), p(lay.moff),
+                                  p(self.voff), p(dualf), p(self.V), p(self.Vt), p(self.theta), p(self.Dh),
+                                  p(self.vecs), p(self.scal), p(a), i64(self.q), p(out), i64(self.q), i64(0),
+                                  a.shape[1], self.threads)
+        return out[:, 0] if np.ndim(arr) == 1 else out
+
     def dder3(self, direction):
         L = lib()
         dirv = np.ascontiguousarray(direction, dtype=np.float64)
@@ -216,3 +228,49 @@ class EmuVec3Group:
         out = np.zeros(self.q)
         lib().emu_v3_dder3(self.type, self.K, p(self.off), p(self.dims), p(self.scal), p(self.point), p(d), p(out))
         return out
+
+
+class EmuMatGroup:
+    """State of a group of PosSemidefTri / HypoPerLogdetTri / HypoRootdetTri cones laid out like
+    hyp_mat_update_state leaves it (W, W^-1, U^-1, U' per cone, scal, svec(W^-1)), built here with NumPy from
+    the oracle's cone objects, to drive the fused small-matrix product kernel (mat_small_prod_kernel)."""
+
+    def __init__(self, specs, oracle_cones, point):
+        self.type = specs[0].ctype
+        self.K = len(specs)
+        self.dims = np.array([s.dim for s in specs], dtype=np.int64)
+        self.off = np.concatenate(([0], np.cumsum(self.dims)))[:-1].astype(np.int64)
+        self.q = int(self.dims.sum())
+        self.lay = MatLayout([s.side for s in specs])
+        self.dualf = np.array([1 if s.use_dual else 0 for s in specs], dtype=np.int32)
+        lead = {2: 0, 3: 2, 4: 1}[self.type]
+        lay = self.lay
+        self.W, self.Wi, self.Ui, self.Ut = (np.zeros(lay.total) for _ in range(4))
+        self.scal = np.zeros(8 * self.K)
+        self.wivec = np.zeros(self.q)
+        self.point = np.ascontiguousarray(point, dtype=np.float64)
+        from oracle import arrayutil as au
+        for c, ck in enumerate(oracle_cones):
+            ck.grad()
+            Wm = np.array(ck.mat)
+            U = np.linalg.cholesky(Wm).T
+            lay.get(self.W, c)[:] = Wm
+            lay.get(self.Wi, c)[:] = np.linalg.inv(Wm)
+            lay.get(self.Ui, c)[:] = np.linalg.inv(U)
+            lay.get(self.Ut, c)[:] = U.T
+            o = int(self.off[c])
+            self.wivec[o + lead:o + self.dims[c]] = au.smat_to_svec(np.linalg.inv(Wm))
+            if self.type == 3:
+                self.scal[8 * c + 1], self.scal[8 * c + 2], self.scal[8 * c + 4] = ck.phi, ck.zeta, ck.point[1]
+            elif self.type == 4:
+                self.scal[8 * c + 1], self.scal[8 * c + 2], self.scal[8 * c + 5] = ck.phi, ck.zeta, ck.pzd
+
+    def prod(self, arr, mode, threads=64, in_place=False):
+        a = np.asfortranarray(np.asarray(arr, dtype=np.float64).reshape(self.q, -1, order="F")).copy(order="F")
+        out = a if in_place else np.zeros_like(a, order="F")
+        lay = self.lay
+        lib().emu_mat_small_prod(self.type, int(mode), self.K, int(lay.sides.max()), p(self.off), p(lay.sides),
+                                 p(lay.moff), p(self.dualf), p(self.W), p(self.Wi), p(self.Ui), p(self.Ut),
+                                 p(self.scal), p(self.point), p(self.wivec), p(a), i64(self.q), p(out), i64(self.q),
+                                 i64(0), a.shape[1], threads)
+        return out[:, 0] if np.ndim(arr) == 1 else out

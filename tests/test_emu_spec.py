@@ -90,6 +90,11 @@ def test_spec_kernels_match_oracle(name):
     assert rel(dev.prod(arr, False), ora.hess_prod(arr)) <= 1e-11
     assert rel(dev.prod(arr, True), ora.inv_hess_prod(arr)) <= 1e-11
     assert rel(dev.dder3(arr[:, 1]), ora.dder3(arr[:, 1])) <= 1e-11
+    # the fused few-column kernel (one launch for all cones)
+    assert rel(dev.small_prod(arr, 0), ora.hess_prod(arr)) <= 1e-11
+    assert rel(dev.small_prod(arr, 1), ora.inv_hess_prod(arr)) <= 1e-11
+    assert rel(dev.small_prod(arr, 4), ora.block_hess_prod(arr)) <= 1e-11
+    assert rel(dev.small_prod(arr[:, 2], 1, in_place=True), ora.inv_hess_prod(arr[:, 2])) <= 1e-11
     # identities of test/cone.jl:50-83 on the emulated device results
     pt = scal * prim
     assert rel(dev.prod(pt, False), -dev.grad) <= 1e-11
