@@ -445,14 +445,17 @@ def run_ours(args):
     peaks = measured_peaks()
     fp64_peak = dgemm_peak_tflops(torch, device)
     if args.syrk == "i8":
-        # 36 exact int8 digit-pair products per FP64 product (8 slices, s + t <= 7), upper 128-tiles
+        # exact int8 digit-pair products per FP64 product: 28 (seven balanced radix-256 digits, s + t <= 6; default)
+        # or 36 (eight radix-128 digits, s + t <= 7: HYP_OZAKI_RADIX=128 or the single-CTA / cluster kernels)
+        r128 = os.environ.get("HYP_OZAKI_RADIX") == "128" or os.environ.get("HYP_OZAKI_CLUSTER", "2")[:1] in ("0", "1")
+        npairs = 28 if (not r128 or os.environ.get("HYP_OZAKI_SLICES") == "7") else 36
         nt = (m + 127) // 128
-        int8_ops = 2.0 * 36 * float(qloc) * 128 * 128 * (nt * (nt + 1) // 2)
+        int8_ops = 2.0 * npairs * float(qloc) * 128 * 128 * (nt * (nt + 1) // 2)
         int8_tops = int8_ops / (syrk_ms * 1e-3) / 1e12 if achieved else None
         int8_peak = 2.0 * peaks["bf16_tflops"] if peaks.get("bf16_tflops") else None
         roofline = {"bound": "tensor",
-                    "kernel": "ozaki_syrk_pair_kernel (Schur SYRK: FP64-accurate digit slicing, tcgen05 kind::i8 "
-                              "cta_group::2 M=256, TMEM accumulators, 3-D TMA) + slice_kernel",
+                    "kernel": "ozaki_syrk_pair_kernel (Schur SYRK: FP64-accurate digit slicing, %d exact int8 digit-pair "
+                              "products, tcgen05 kind::i8 cta_group::2 M=256, TMEM accumulators, 3-D TMA) + slicing kernels" % npairs,
                     "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s (algorithmic FP64)",
                     "frac": (achieved / fp64_peak) if achieved else None,
                     "peak_source": "cuBLAS DGEMM 8192^3 measured live in this run = the FP64 tensor (DMMA) roofline; "

@@ -1,13 +1,19 @@
 // FP64-accurate Schur SYRK on the 5th-generation tensor cores (tcgen05, kind::i8) by error-free
-// slicing ("Ozaki scheme").  EXPERIMENTAL in round 1: building blocks + unit-test entry points;
-// the product path (syrk.cu, FP64 DMMA) does not depend on this file.
+// slicing ("Ozaki scheme").  The default Schur SYRK of the library; syrk.cu (FP64 DMMA) is the
+// alternative for two-operand products and for HYP_SCHUR_SYRK=dmma.
 //
 // Why: tcgen05.mma has no f64 kind, and the FP64 DMMA pipe is saturated by syrk.cu (96 % active,
 // 34 TFLOP/s).  The only way past that roofline is to run the contraction on the int8 pipe
 // (4.5 POP/s dense): every column of the K-major operand is scaled by a power of two and cut into
-// S = 8 signed 7-bit digits  a = 2^e * sum_s 2^-(6 + 7 s) d_s,  d_s in [-64, 64]  (int8 matrices);
-// the 36 digit-pair products with s + t <= 7 are exact in int32 (|sum| <= K * 2^12, K <= 2^15 per
-// launch) and are recombined in FP64:  C_ij = 2^(e_i + e_j) * sum_d 2^-(12 + 7 d) * sum_{s+t=d} (D_s' D_t)_ij.
+// signed 8-bit digits (int8 matrices).  Default (radix 256): S = 7 balanced digits
+//     a = 2^e * sum_s 2^-(7 + 8 s) d_s,  d_s in [-128, 127]  (a carry pass removes the +128 rint can give),
+// the 28 digit-pair products with s + t <= 6 are exact in int32 (|sum| <= 7 K 2^14, K <= 2^14 rows per launch)
+// and are recombined in FP64:  C_ij = 2^(e_i + e_j) * sum_d 2^-(14 + 8 d) * sum_{s+t=d} (D_s' D_t)_ij.
+// HYP_OZAKI_RADIX=128 keeps the first scheme: S = 8 digits in [-64, 64], a = 2^e sum_s 2^-(6 + 7 s) d_s,
+// 36 pair products with s + t <= 7, K <= 2^15 rows per launch.  Both carry 56 bits below the column
+// maximum; the chip runs this kernel at its power cap, so the 22 % fewer MMAs of radix 256 are what
+// makes it faster (measured 101 -> 91 ms on C3), not memory traffic (the quad kernel below cuts the
+// L2 -> SM bytes by a third and is not faster).
 //
 // This file: (1) column scaling + slicing kernels, (2) a TMA + tcgen05 int8 TN GEMM
 // (C_int32 = A' B, both operands K-major, SWIZZLE_128B, accumulator in TMEM), (3) a reference
@@ -229,8 +235,9 @@ void make_map_i8(CUtensorMap* map, const int8_t* base, int64_t K, int64_t cols, 
 
 // ---- slicing: column exponents and the S signed 7-bit digit matrices ----------------------------
 __global__ void colmax_kernel(int64_t K, int64_t ncols, const double* __restrict__ A, int64_t lda,
-                              int* __restrict__ expo, double* __restrict__ dscale) {
-    // expo[j] = smallest e with max_k |A[k, j]| < 2^e  (0 for an all-zero column)
+                              int* __restrict__ expo, double* __restrict__ dscale, int radix256) {
+    // expo[j] = smallest e with max_k |A[k, j]| < 2^e  (0 for an all-zero column); radix-256 digits need
+    // max |A| <= (127/128) 2^e so that the leading digit stays below 128 after a carry
     __shared__ double sm[8];
     const int64_t j = blockIdx.x;
     if (j >= ncols) return;
@@ -245,7 +252,8 @@ __global__ void colmax_kernel(int64_t K, int64_t ncols, const double* __restrict
         for (int w = 1; w < (int)(blockDim.x >> 5); w++) mx = fmax(mx, sm[w]);
         int e = 0;
         if (mx > 0.0) {
-            frexp(mx, &e);          // mx = f * 2^e, f in [0.5, 1)  =>  mx < 2^e
+            const double f = frexp(mx, &e);          // mx = f * 2^e, f in [0.5, 1)  =>  mx < 2^e
+            if (radix256 && f > 127.0 / 128.0) e++;
         }
         expo[j] = e;
         if (dscale) dscale[j] = ldexp(1.0, e);
@@ -279,6 +287,50 @@ __global__ void slice_kernel(int64_t K, int64_t ncols, const double* __restrict_
                 }
                 *reinterpret_cast<uint64_t*>(D + s * slice_stride + g * 8 + j * ldd) = w;
             }
+        }
+    }
+}
+
+// Radix-256 variant: balanced signed digits d_s in [-128, 127], a = 2^e sum_s 2^-(7 + 8 s) d_s.  rint can produce
+// +128 (remainder >= 0.498): a backward carry pass turns it into -128 and adds one to the next higher digit; the
+// leading digit cannot overflow because |a| 2^(7 - e) <= 127.  Seven such digits carry the same 56 bits as eight
+// radix-128 digits, so the product needs 28 digit pairs (s + t <= 6) instead of 36 at the same truncation error.
+__global__ void slice256_kernel(int64_t K, int64_t ncols, const double* __restrict__ A, int64_t lda,
+                                const int* __restrict__ expo, int nslices, int8_t* __restrict__ D, int64_t ldd,
+                                int64_t slice_stride) {
+    const int64_t K8 = (K + 7) / 8;
+    for (int64_t j = blockIdx.y; j < ncols; j += gridDim.y) {
+        const double sc = ldexp(1.0, 7 - expo[j]);
+        const double* col = A + j * lda;
+        for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < K8;
+             g += (int64_t)gridDim.x * blockDim.x) {
+            uint64_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int64_t k = g * 8 + u;
+                double r = (k < K) ? col[k] * sc : 0.0;          // |r| <= 127
+                int dg[8];
+#pragma unroll
+                for (int s = 0; s < 8; s++) {
+                    if (s < nslices) {
+                        const double d = rint(r);
+                        dg[s] = (int)d;
+                        r = (r - d) * 256.0;                     // exact: |r - d| <= 0.5
+                    } else {
+                        dg[s] = 0;
+                    }
+                }
+#pragma unroll
+                for (int s = 7; s >= 1; s--)
+                    if (dg[s] >= 128) {
+                        dg[s] -= 256;
+                        dg[s - 1] += 1;
+                    }
+#pragma unroll
+                for (int s = 0; s < 8; s++) w[s] |= (uint64_t)(uint8_t)(int8_t)dg[s] << (8 * u);
+            }
+            for (int s = 0; s < nslices; s++)
+                *reinterpret_cast<uint64_t*>(D + s * slice_stride + g * 8 + j * ldd) = w[s];
         }
     }
 }
@@ -780,8 +832,9 @@ ozaki_syrk_pair_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid_c
                        const __grid_constant__ CUtensorMap mapB4, const __grid_constant__ CUtensorMap mapB8,
                        const int2* __restrict__ pairs, int n_pairs, int k0, int nkb,
                        const double* __restrict__ dscale, int64_t ncols, double* __restrict__ C, int64_t ldc,
-                       double alpha, double beta, int nsl) {
-    // nsl = number of digit slices that enter the product (7 or 8): pairs with s + t <= nsl - 1
+                       double alpha, double beta, int nsl, int wbits) {
+    // nsl = number of digit slices that enter the product (7 or 8): pairs with s + t <= nsl - 1;
+    // wbits = bits per digit (7: radix 128, 8: radix 256): digit s has weight 2^-(wbits - 1 + wbits s)
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint32_t s_tmem;
     const uint32_t base = smem_u32(smem_raw);
@@ -910,9 +963,235 @@ ozaki_syrk_pair_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid_c
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const int d0 = pass * 4;
                 // a digit-sum group beyond the last slice pair (d0 + 3 > nsl - 1) was never written: weight 0
-                const double g0 = ldexp(1.0, -(12 + 7 * d0)), g1 = ldexp(1.0, -(12 + 7 * (d0 + 1))),
-                             g2 = ldexp(1.0, -(12 + 7 * (d0 + 2))),
-                             g3 = (d0 + 3 <= nsl - 1) ? ldexp(1.0, -(12 + 7 * (d0 + 3))) : 0.0;
+                const int wb0 = 2 * (wbits - 1);
+                const double g0 = ldexp(1.0, -(wb0 + wbits * d0)), g1 = ldexp(1.0, -(wb0 + wbits * (d0 + 1))),
+                             g2 = ldexp(1.0, -(wb0 + wbits * (d0 + 2))),
+                             g3 = (d0 + 3 <= nsl - 1) ? ldexp(1.0, -(wb0 + wbits * (d0 + 3))) : 0.0;
+#pragma unroll 1
+                for (int c0 = 0; c0 < TN; c0 += 16) {
+                    uint32_t v[4][16];
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        const uint32_t taddr = tmem0 + ((uint32_t)(lg * 32) << 16) + (uint32_t)(g * TN + c0);
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                            : "=r"(v[g][0]), "=r"(v[g][1]), "=r"(v[g][2]), "=r"(v[g][3]), "=r"(v[g][4]),
+                              "=r"(v[g][5]), "=r"(v[g][6]), "=r"(v[g][7]), "=r"(v[g][8]), "=r"(v[g][9]),
+                              "=r"(v[g][10]), "=r"(v[g][11]), "=r"(v[g][12]), "=r"(v[g][13]), "=r"(v[g][14]),
+                              "=r"(v[g][15])
+                            : "r"(taddr));
+                    }
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (store && row < ncols) {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            const int64_t col = (int64_t)tJ * TN + c0 + j;
+                            if (col < ncols) {
+                                double x = (double)(int32_t)v[3][j] * g3;
+                                x += (double)(int32_t)v[2][j] * g2;
+                                x += (double)(int32_t)v[1][j] * g1;
+                                x += (double)(int32_t)v[0][j] * g0;
+                                x *= rs * dscale[col];
+                                double* cp = C + row + col * ldc;
+                                if (pass == 0) *cp = (beta == 0.0) ? x : (x + beta * *cp);
+                                else *cp += x;
+                            }
+                        }
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(tempty_leader);
+            }
+        }
+    }
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem0), "r"(512));
+    }
+}
+
+// ---- quad variant: two CTA pairs of a 4-CTA cluster share their A tiles ---------------------------------------
+// Quad (P, Jq): tile rows 2P, 2P + 1 and tile columns 2Jq, 2Jq + 1.  Pair p of the cluster (ranks 2p, 2p + 1) owns
+// column 2Jq + p and runs exactly the pair kernel above (cta_group::2, M = 256), but the A tile of row 2P + r is
+// needed by CTA r of BOTH pairs: each of the two loads half of its slices and TMA-multicasts them to the other,
+// which cuts the L2 -> SM bytes per MMA by a third (A is two thirds of a stage).  Barriers: the multicast signals
+// the full barrier of each destination CTA itself, so the second CTA of a pair forwards "my A tile has landed"
+// to its leader with a remote arrive; a stage is refilled only after BOTH pair leaders have retired the MMAs
+// that read it (their commits are multicast to all four CTAs).
+__global__ void __launch_bounds__(I8_THREADS, 1)
+ozaki_syrk_quad_kernel(const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA4,
+                       const __grid_constant__ CUtensorMap mapB4, const __grid_constant__ CUtensorMap mapB8,
+                       const int2* __restrict__ quads, int n_quads, int k0, int nkb,
+                       const double* __restrict__ dscale, int64_t ncols, double* __restrict__ C, int64_t ldc,
+                       double alpha, double beta, int nsl, int wbits) {
+    // nsl = number of digit slices that enter the product (7 or 8): pairs with s + t <= nsl - 1;
+    // wbits = bits per digit (7: radix 128, 8: radix 256): digit s has weight 2^-(wbits - 1 + wbits s)
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint32_t s_tmem;
+    const uint32_t base = smem_u32(smem_raw);
+    const uint32_t stg = (base + 1023u) & ~1023u;
+    const uint32_t bar_full = stg + OZP_STAGES * OZP_STAGE;
+    const uint32_t bar_empty = bar_full + OZP_STAGES * 8;
+    const uint32_t bar_tfull = bar_empty + OZP_STAGES * 8;
+    const uint32_t bar_tempty = bar_tfull + 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t crank, cid, ncl;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(cid));
+    asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(ncl));
+    const uint32_t pr = crank >> 1, r = crank & 1u;        // pair inside the quad, CTA inside the pair
+    const bool leader = r == 0;
+    const uint32_t leader_rank = crank & ~1u;
+    const uint16_t mask_a = (uint16_t)((1u << r) | (1u << (2 + r)));      // the CTAs that hold tile row 2P + r
+    const uint16_t mask_pair = (uint16_t)(3u << (2 * pr));                // my CTA pair
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < OZP_STAGES; s++) {
+            // leader: its own expect_tx arrival + the peer's forwarded "my A tile has landed";
+            // peer: its own expect_tx arrival (A bytes only; its B half signals the leader directly)
+            mbar_init(bar_full + s * 8, leader ? 2 : 1);
+            mbar_init(bar_empty + s * 8, 2);     // one multicast commit from each of the two pair leaders
+        }
+        mbar_init(bar_tfull, 1);
+        mbar_init(bar_tempty, 8);                // 4 epilogue warps of each CTA (used in the leader only)
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                     "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem0 = s_tmem;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): my A tile and my half of the B tile =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int qi = (int)cid; qi < n_quads; qi += (int)ncl) {
+                const int2 qd = quads[qi];
+                const int tI = 2 * qd.x + (int)r, tJ = 2 * qd.y + (int)pr;
+                for (int pass = 0; pass < 2; pass++) {
+                    const int ns = pass == 0 ? 4 : OZ_S;
+                    const int hs = ns / 2;                                 // A slices this CTA loads (and multicasts)
+                    const int nst = pass == 0 ? (nkb + 1) / 2 : nkb;
+                    const int nh = pass == 0 ? 2 : 1;
+                    const CUtensorMap* ma = pass == 0 ? &mapA2 : &mapA4;
+                    const CUtensorMap* mb = pass == 0 ? &mapB4 : &mapB8;
+                    const uint32_t bytes_a = (uint32_t)(nh * ns) * OZ_TILE;
+                    const uint32_t bytes_bh = (uint32_t)(nh * ns) * (OZ_TILE / 2);
+                    for (int it = 0; it < nst; it++) {
+                        mbar_wait(bar_empty + stage * 8, phase ^ 1u);
+                        const uint32_t full = bar_full + stage * 8;
+                        const uint32_t full_leader = mapa_u32(full, leader_rank);
+                        mbar_expect_tx(full, leader ? bytes_a + 2u * bytes_bh : bytes_a);
+                        const uint32_t dst = stg + stage * OZP_STAGE;
+                        for (int h = 0; h < nh; h++) {
+                            const int kc = k0 + (pass == 0 ? (2 * it + h) : it) * OZ_KB;
+                            const uint32_t d0s = dst + h * (OZP_STAGE / 2);
+                            // A: my half of the slices of tile row tI -> me and the same-row CTA of the other pair
+                            tma_load_3d_mc(d0s + ((int)pr * hs) * OZ_TILE, ma, kc, tI * TM, (int)pr * hs, full, mask_a);
+                            // B: my 64-row half of tile column tJ (private to my pair), signals the pair leader
+                            tma_load_3d_2sm(d0s + ns * OZ_TILE, mb, kc, tJ * TN + (int)r * (TN / 2), 0, full_leader);
+                        }
+                        if (++stage == OZP_STAGES) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1 && !leader) {
+        // ===== forwarder (second CTA of a pair): tells the pair leader when my A tile of a stage has landed =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int qi = (int)cid; qi < n_quads; qi += (int)ncl) {
+                for (int pass = 0; pass < 2; pass++) {
+                    const int nst = pass == 0 ? (nkb + 1) / 2 : nkb;
+                    for (int it = 0; it < nst; it++) {
+                        mbar_wait(bar_full + stage * 8, phase);
+                        mbar_arrive_cluster(mapa_u32(bar_full + stage * 8, leader_rank));
+                        if (++stage == OZP_STAGES) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA of each pair) =====
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_i8(2 * TM, TN);
+            int stage = 0;
+            uint32_t phase = 0, item = 0;
+            for (int qi = (int)cid; qi < n_quads; qi += (int)ncl) {
+                for (int pass = 0; pass < 2; pass++, item++) {
+                    if (item > 0) mbar_wait(bar_tempty, (item - 1) & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    const int d0 = pass * 4;
+                    const int ns = pass == 0 ? 4 : OZ_S;
+                    const int nst = pass == 0 ? (nkb + 1) / 2 : nkb;
+                    const int nhalf = pass == 0 ? 2 : 1;
+                    const int smax = pass == 0 ? 3 : nsl - 1;
+                    for (int it = 0; it < nst; it++) {
+                        mbar_wait(bar_full + stage * 8, phase);
+                        asm volatile("tcgen05.fence::after_thread_sync;");
+                        for (int h = 0; h < nhalf; h++) {
+                            const uint32_t sa = stg + stage * OZP_STAGE + h * (OZP_STAGE / 2);
+                            const uint32_t sb = sa + ns * OZ_TILE;
+                            for (int s = 0; s <= smax; s++) {
+                                const uint64_t ad = make_desc_sw32(sa + s * OZ_TILE);
+                                int tlo = d0 - s, thi = d0 + 3 - s;
+                                if (tlo < 0) tlo = 0;
+                                if (thi > nsl - 1 - s) thi = nsl - 1 - s;     // s + t <= nsl - 1
+                                for (int tt = tlo; tt <= thi; tt++) {
+                                    const uint64_t bd = make_desc_sw32(sb + tt * (OZ_TILE / 2));
+                                    const int g = s + tt - d0;
+                                    const uint32_t accum = (it > 0 || h > 0 || s > 0) ? 1u : 0u;
+                                    umma_i8_2sm(tmem0 + (uint32_t)(g * TN), ad, bd, idesc, accum);
+                                }
+                            }
+                        }
+                        umma_commit_2sm(bar_empty + stage * 8, 0xF);     // one of the two releases of this stage, in all four CTAs
+                        if (++stage == OZP_STAGES) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                    umma_commit_2sm(bar_tfull, mask_pair);                // accumulators ready in both CTAs of my pair
+                }
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs, own TMEM half) =====
+        const int lg = warp & 3;
+        const uint32_t tempty_leader = mapa_u32(bar_tempty, leader_rank);
+        uint32_t item = 0;
+        for (int qi = (int)cid; qi < n_quads; qi += (int)ncl) {
+            const int2 qd = quads[qi];
+            const int tI = 2 * qd.x + (int)r, tJ = 2 * qd.y + (int)pr;
+            const int64_t row = (int64_t)tI * TM + lg * 32 + lane;
+            const bool store = tI <= tJ;
+            const double rs = (row < ncols) ? alpha * dscale[row] : 0.0;
+            for (int pass = 0; pass < 2; pass++, item++) {
+                mbar_wait(bar_tfull, item & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                const int d0 = pass * 4;
+                // a digit-sum group beyond the last slice pair (d0 + 3 > nsl - 1) was never written: weight 0
+                const int wb0 = 2 * (wbits - 1);
+                const double g0 = ldexp(1.0, -(wb0 + wbits * d0)), g1 = ldexp(1.0, -(wb0 + wbits * (d0 + 1))),
+                             g2 = ldexp(1.0, -(wb0 + wbits * (d0 + 2))),
+                             g3 = (d0 + 3 <= nsl - 1) ? ldexp(1.0, -(wb0 + wbits * (d0 + 3))) : 0.0;
 #pragma unroll 1
                 for (int c0 = 0; c0 < TN; c0 += 16) {
                     uint32_t v[4][16];
@@ -1021,6 +1300,9 @@ extern "C" int hyp_test_i8_gemm_tn(hyp_ctx* ctx, const int8_t* A, int64_t lda, c
 extern "C" int hyp_test_ozaki_slices(hyp_ctx* ctx, const double* A, int64_t lda, int64_t K, int64_t ncols,
                                      int nslices, int8_t* digits, int* expo) {
     if (!ctx) return -1;
+    // nslices < 0: the radix-256 slicer with -nslices digits
+    const bool r256 = nslices < 0;
+    if (r256) nslices = -nslices;
     try {
         CUDA_TRY(cudaSetDevice(ctx->device));
         double* dA = nullptr;
@@ -1031,9 +1313,12 @@ extern "C" int hyp_test_ozaki_slices(hyp_ctx* ctx, const double* A, int64_t lda,
         CUDA_TRY(cudaMalloc(&dD, (size_t)nslices * ldd * ncols));
         CUDA_TRY(cudaMalloc(&dE, (size_t)ncols * 4));
         CUDA_TRY(cudaMemcpy2DAsync(dA, K * 8, A, lda * 8, K * 8, ncols, cudaMemcpyDefault, ctx->stream));
-        colmax_kernel<<<(unsigned)ncols, 256, 0, ctx->stream>>>(K, ncols, dA, K, dE, nullptr);
+        colmax_kernel<<<(unsigned)ncols, 256, 0, ctx->stream>>>(K, ncols, dA, K, dE, nullptr, r256 ? 1 : 0);
         dim3 grid(std::max(1, std::min(ceil_div(K, 2048), 64)), (unsigned)std::min<int64_t>(ncols, 65535));
-        slice_kernel<<<grid, 256, 0, ctx->stream>>>(K, ncols, dA, K, dE, nslices, dD, ldd, ldd * ncols);
+        if (r256)
+            slice256_kernel<<<grid, 256, 0, ctx->stream>>>(K, ncols, dA, K, dE, nslices, dD, ldd, ldd * ncols);
+        else
+            slice_kernel<<<grid, 256, 0, ctx->stream>>>(K, ncols, dA, K, dE, nslices, dD, ldd, ldd * ncols);
         ctx->launches += 2;
         CUDA_TRY(cudaGetLastError());
         for (int s = 0; s < nslices; s++)
@@ -1054,12 +1339,29 @@ extern "C" int hyp_test_ozaki_slices(hyp_ctx* ctx, const double* A, int64_t lda,
 
 // ---- product entry points -------------------------------------------------------------------------
 // digits / exponents of the K x ncols FP64 matrix A (device) into caller-provided device buffers
+// digit radix of the slicing: 256 (default: seven balanced 8-bit digits, 28 pair products, 56 bits; CTA-pair / quad
+// kernels) or 128 (HYP_OZAKI_RADIX=128, and whenever HYP_OZAKI_CLUSTER selects the single-CTA / 2 x 2 cluster
+// kernels, which only know the radix-128 weights: eight 7-bit digits, 36 pair products, the same 56 bits)
+static int ozaki_radix() {
+    static int r = 0;
+    if (!r) {
+        const char* e = getenv("HYP_OZAKI_RADIX");
+        const char* c = getenv("HYP_OZAKI_CLUSTER");
+        r = ((e && atoi(e) == 128) || (c && (c[0] == '0' || c[0] == '1'))) ? 128 : 256;
+    }
+    return r;
+}
+
 void hyp_ozaki_slice(hyp_ctx* ctx, const double* A, int64_t lda, int64_t K, int64_t ncols, int8_t* digits,
                      int64_t ldd, int64_t slice_stride, int* expo, double* dscale) {
     if (K <= 0 || ncols <= 0) return;
-    colmax_kernel<<<(unsigned)ncols, 256, 0, ctx->stream>>>(K, ncols, A, lda, expo, dscale);
+    const bool r256 = ozaki_radix() == 256;
+    colmax_kernel<<<(unsigned)ncols, 256, 0, ctx->stream>>>(K, ncols, A, lda, expo, dscale, r256 ? 1 : 0);
     dim3 grid(std::max(1, std::min(ceil_div(K, 2048), 32)), (unsigned)std::min<int64_t>(ncols, 65535));
-    slice_kernel<<<grid, 256, 0, ctx->stream>>>(K, ncols, A, lda, expo, OZ_S, digits, ldd, slice_stride);
+    if (r256)
+        slice256_kernel<<<grid, 256, 0, ctx->stream>>>(K, ncols, A, lda, expo, 7, digits, ldd, slice_stride);
+    else
+        slice_kernel<<<grid, 256, 0, ctx->stream>>>(K, ncols, A, lda, expo, OZ_S, digits, ldd, slice_stride);
     ctx->launches += 2;
     CUDA_TRY(cudaGetLastError());
 }
@@ -1115,9 +1417,29 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
     static int max_clusters = 0;
     if (use_cluster < 0) {
         const char* e = getenv("HYP_OZAKI_CLUSTER");
-        // 0: one CTA per tile; 1: 2 x 2 clusters with TMA multicast; 2 (default): CTA pairs, cta_group::2
+        // 0: one CTA per tile; 1: 2 x 2 clusters with TMA multicast; 2 (default): CTA pairs, cta_group::2;
+        // 3: quads = two CTA pairs sharing their A tiles by multicast
         use_cluster = e ? (e[0] - '0') : 2;
-        if (use_cluster < 0 || use_cluster > 2) use_cluster = 2;
+        if (use_cluster < 0 || use_cluster > 3) use_cluster = 2;
+        if (use_cluster == 3) {
+            CUDA_TRY(cudaFuncSetAttribute(ozaki_syrk_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZP_SMEM));
+            cudaLaunchConfig_t q = {};
+            q.gridDim = dim3(4 * 64);
+            q.blockDim = dim3(I8_THREADS);
+            q.dynamicSmemBytes = OZP_SMEM;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 4;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            q.attrs = at;
+            q.numAttrs = 1;
+            if (cudaOccupancyMaxActiveClusters(&max_clusters, ozaki_syrk_quad_kernel, &q) != cudaSuccess ||
+                max_clusters < 1) {
+                cudaGetLastError();
+                use_cluster = 2;
+            }
+        }
         if (use_cluster == 2) {
             CUDA_TRY(cudaFuncSetAttribute(ozaki_syrk_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZP_SMEM));
             cudaLaunchConfig_t q = {};
@@ -1158,10 +1480,57 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
         }
     }
     // int32 accumulators hold sums of <= 8 pair products of <= 2^12 each over the chunk: chunk <= 2^15 rows
-    const int64_t CHUNK = 32768;
+    // (radix 256: <= 7 products of <= 2^14: chunk <= 2^14 rows)
+    const bool r256 = ozaki_radix() == 256;
+    if (r256 && use_cluster < 2)
+        throw HypError{"radix-256 digit slices need the CTA-pair or quad SYRK kernel (set HYP_OZAKI_RADIX=128)"};
+    const int nsl_eff = r256 ? 7 : ozaki_slices();
+    const int wbits = r256 ? 8 : 7;
+    const int64_t CHUNK = r256 ? 16384 : 32768;
     const int grid = std::min(n_tiles, ctx->sm_count);
     for (int64_t k0 = 0; k0 < K; k0 += CHUNK) {
         const int64_t klen = std::min(CHUNK, K - k0);
+        if (use_cluster == 3) {
+            // (P, Jq): tile rows 2P, 2P+1 x tile columns 2Jq, 2Jq+1, for 2P <= 2Jq+1, column pair by column pair
+            static std::vector<std::pair<int, std::pair<int2*, int>>> qcache;
+            int2* d_quads = nullptr;
+            int n_quads = 0;
+            for (auto& e : qcache)
+                if (e.first == nt) {
+                    d_quads = e.second.first;
+                    n_quads = e.second.second;
+                }
+            if (!d_quads) {
+                std::vector<int2> ql;
+                for (int jq = 0; 2 * jq < nt; jq++)
+                    for (int pp = 0; 2 * pp <= 2 * jq + 1 && 2 * pp < nt; pp++) ql.push_back(make_int2(pp, jq));
+                n_quads = (int)ql.size();
+                CUDA_TRY(cudaMalloc(&d_quads, ql.size() * sizeof(int2)));
+                CUDA_TRY(cudaMemcpyAsync(d_quads, ql.data(), ql.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+                CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+                qcache.push_back({nt, {d_quads, n_quads}});
+            }
+            CUtensorMap mapB4, mapB8;
+            make_map_digits(&mapB4, digits, K, ncols, ldd, slice_stride, OZ_S, 4, TN / 2);
+            make_map_digits(&mapB8, digits, K, ncols, ldd, slice_stride, OZ_S, 8, TN / 2);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(4 * std::min(n_quads, max_clusters));
+            cfg.blockDim = dim3(I8_THREADS);
+            cfg.dynamicSmemBytes = OZP_SMEM;
+            cfg.stream = ctx->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 4;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            CUDA_TRY(cudaLaunchKernelEx(&cfg, ozaki_syrk_quad_kernel, mapD2, mapD4, mapB4, mapB8, (const int2*)d_quads,
+                                        n_quads, (int)k0, (int)ceil_div(klen, OZ_KB), dscale, ncols, C, ldc, alpha,
+                                        k0 == 0 ? beta : 1.0, nsl_eff, wbits));
+            ctx->launches++;
+            continue;
+        }
         if (use_cluster == 2) {
             // (P, J): tile rows 2P, 2P+1 of tile column J, for 2P <= J, column by column
             static std::vector<std::pair<int, std::pair<int2*, int>>> pcache;
@@ -1199,7 +1568,7 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
             cfg.numAttrs = 1;
             CUDA_TRY(cudaLaunchKernelEx(&cfg, ozaki_syrk_pair_kernel, mapD4, mapD8, mapB4, mapB8, (const int2*)d_pairs,
                                         n_pairs, (int)k0, (int)ceil_div(klen, OZ_KB), dscale, ncols, C, ldc, alpha,
-                                        k0 == 0 ? beta : 1.0, ozaki_slices()));
+                                        k0 == 0 ? beta : 1.0, nsl_eff, wbits));
             ctx->launches++;
             continue;
         }

@@ -54,6 +54,29 @@ def test_ozaki_slices_reconstruct(cx):
     assert (err <= 2.0 ** -55 * np.maximum(colmax, 1e-300) * 4).all()
 
 
+def test_ozaki_radix256_slices_reconstruct(cx):
+    """Seven balanced radix-256 digits (HYP_OZAKI_RADIX=256): every digit in [-128, 127] after the carry pass,
+    a = 2^e sum_s 2^-(7 + 8 s) d_s to 2^-55 of the column maximum, including values that force carries."""
+    rng = np.random.default_rng(1)
+    K, n, S = 600, 29, 7
+    A = np.asfortranarray(rng.standard_normal((K, n)) * np.exp(rng.uniform(-8, 8, size=(1, n))))
+    A[:, 3] = 0.0
+    A[:40, 5] = np.ldexp(1.0, -3) * (126.498046875 + np.arange(40) * 2.0 ** -20)   # remainders just below 1/2: carries
+    A[:, 6] = 1.0 - 2.0 ** -52 * np.arange(K)                                       # mantissas next to 1: exponent bump
+    D = np.zeros((S, n, K), dtype=np.int8)
+    e = np.zeros(n, dtype=np.int32)
+    cx.check(cx.lib.hyp_test_ozaki_slices(cx.h, _p(A), K, K, n, -S, _p(D), _p(e)), "slices256")
+    Dk = D.transpose(0, 2, 1).astype(np.float64)
+    rec = np.zeros((K, n))
+    for s in range(S):
+        rec += Dk[s] * 2.0 ** -(7 + 8 * s)
+    rec *= 2.0 ** e[None, :].astype(np.float64)
+    colmax = np.abs(A).max(axis=0)
+    assert (colmax * 2.0 ** (7 - e.astype(np.float64)) <= 127).all()
+    err = np.abs(rec - A).max(axis=0)
+    assert (err <= 2.0 ** -56 * 2.0 ** e.astype(np.float64)).all()
+
+
 @pytest.mark.parametrize("K,n", [(64, 128), (1000, 130), (5000, 300), (40000, 256), (33000, 7)])
 def test_ozaki_syrk_matches_fp64(cx, K, n):
     """Sliced int8 tcgen05 SYRK vs an extended-precision reference: the error must be at the level of a
