@@ -7,10 +7,10 @@
 // (4.5 POP/s dense): every column of the K-major operand is scaled by a power of two and cut into
 // signed 8-bit digits (int8 matrices).  Default (radix 256): S = 7 balanced digits
 //     a = 2^e * sum_s 2^-(7 + 8 s) d_s,  d_s in [-128, 127]  (a carry pass removes the +128 rint can give),
-// the 28 digit-pair products with s + t <= 6 are exact in int32 (|sum| <= 7 K 2^14, K <= 2^14 rows per launch)
+// the 28 digit-pair products with s + t <= 6 are exact in int32 (|sum| <= 7 K 2^14, K <= 18688 rows per launch)
 // and are recombined in FP64:  C_ij = 2^(e_i + e_j) * sum_d 2^-(14 + 8 d) * sum_{s+t=d} (D_s' D_t)_ij.
 // HYP_OZAKI_RADIX=128 keeps the first scheme: S = 8 digits in [-64, 64], a = 2^e sum_s 2^-(6 + 7 s) d_s,
-// 36 pair products with s + t <= 7, K <= 2^15 rows per launch.  Both carry 56 bits below the column
+// 36 pair products with s + t <= 7, K <= 65472 rows per launch.  Both carry 56 bits below the column
 // maximum; the chip runs this kernel at its power cap, so the 22 % fewer MMAs of radix 256 are what
 // makes it faster (measured 101 -> 91 ms on C3), not memory traffic (the quad kernel below cuts the
 // L2 -> SM bytes by a third and is not faster).
@@ -1479,14 +1479,19 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
             }
         }
     }
-    // int32 accumulators hold sums of <= 8 pair products of <= 2^12 each over the chunk: chunk <= 2^15 rows
-    // (radix 256: <= 7 products of <= 2^14: chunk <= 2^14 rows)
     const bool r256 = ozaki_radix() == 256;
     if (r256 && use_cluster < 2)
         throw HypError{"radix-256 digit slices need the CTA-pair or quad SYRK kernel (set HYP_OZAKI_RADIX=128)"};
     const int nsl_eff = r256 ? 7 : ozaki_slices();
     const int wbits = r256 ? 8 : 7;
-    const int64_t CHUNK = r256 ? 16384 : 32768;
+    // exactness of the int32 accumulators: the largest digit-sum group has 7 pairs of |d| <= 128 (radix 256) or
+    // 8 pairs of |d| <= 64 (radix 128): rows per launch <= (2^31 - 1) / (7 * 2^14) = 18724 or / (8 * 2^12) = 65535.
+    // K is cut into the fewest equal chunks below that bound (every launch pays two epilogue passes over C).
+    // Chunks are multiples of 64 rows: pass 0 packs two 32-row k steps per stage, and the second one of an odd
+    // last stage must fall beyond K (zero-filled by TMA), never into the next chunk.
+    const int64_t CHUNK_MAX = r256 ? 18688 : 65472;
+    const int64_t nchunks = (K + CHUNK_MAX - 1) / CHUNK_MAX;
+    const int64_t CHUNK = round_up((K + nchunks - 1) / nchunks, 64);
     const int grid = std::min(n_tiles, ctx->sm_count);
     for (int64_t k0 = 0; k0 < K; k0 += CHUNK) {
         const int64_t klen = std::min(CHUNK, K - k0);

@@ -77,7 +77,8 @@ def test_ozaki_radix256_slices_reconstruct(cx):
     assert (err <= 2.0 ** -56 * 2.0 ** e.astype(np.float64)).all()
 
 
-@pytest.mark.parametrize("K,n", [(64, 128), (1000, 130), (5000, 300), (40000, 256), (33000, 7)])
+@pytest.mark.parametrize("K,n", [(64, 128), (1000, 130), (5000, 300), (40000, 256), (33000, 7), (18689, 140),
+                                 (50000, 129), (70001, 40)])
 def test_ozaki_syrk_matches_fp64(cx, K, n):
     """Sliced int8 tcgen05 SYRK vs an extended-precision reference: the error must be at the level of a
     correctly-rounded FP64 result (a few ulp of sum |a_ki a_kj|), i.e. at least as accurate as dsyrk."""
