@@ -487,11 +487,15 @@ def run_ours(args):
     g_bytes = 8.0 * qloc * n
     gemv_ms = phases.get("gemv")
     if gemv_ms:
-        roofline["hbm_phase"] = {"kernel": "gemv_t / gemv_n passes over G",
-                                 "algorithmic_bytes_per_step": 18 * g_bytes,
-                                 "achieved_gbs": 18 * g_bytes / (gemv_ms * 1e-3) / 1e9,
+        # passes over G per step: const column 2 + 4 x (solve_subsystem3 2 + apply_lhs 2) = 18; with one rank
+        # apply_lhs reads G once for both of its products (gemv_nt_kernel): 14
+        npass = 14 if (world == 1 and not os.environ.get("HYP_NO_FUSED_GEMV")) else 18
+        roofline["hbm_phase"] = {"kernel": "gemv_t / gemv_n / gemv_nt passes over G",
+                                 "algorithmic_bytes_per_step": npass * g_bytes,
+                                 "achieved_gbs": npass * g_bytes / (gemv_ms * 1e-3) / 1e9,
                                  "peak_gbs": peaks.get("hbm_gbs"),
-                                 "note": "18 passes per step (reference count 22; the s-lift reuses G*x)"}
+                                 "note": "%d passes per step (reference count 22; the s-lift reuses G*x; apply_lhs "
+                                         "reads G once for G'z and G x when the panel is not sharded)" % npass}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:

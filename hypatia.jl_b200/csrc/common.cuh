@@ -229,6 +229,8 @@ struct hyp_ctx {
     double *d_vp1 = nullptr, *d_vp2 = nullptr;         // p-vectors
     double* d_partial = nullptr;       // reduction workspace
     int64_t partial_doubles = 0;
+    double* d_partial2 = nullptr;      // per-warp partials of the fused G x / G' z pass (gemv.cu)
+    int64_t partial2_doubles = 0;
     double* d_scalars = nullptr;       // small device scalar block (64 doubles)
     double* d_stage = nullptr;         // device staging for host-pointer arguments
     int64_t stage_doubles = 0;
@@ -287,6 +289,9 @@ void hyp_gemv_t(hyp_ctx* ctx, int64_t rows, int64_t ncols, const double* M, int6
 // y[0:rows] = alpha * M x + beta * y
 void hyp_gemv_n(hyp_ctx* ctx, int64_t rows, int64_t ncols, const double* M, int64_t ld,
                 const double* x, double alpha, double beta, double* y);
+// both products in one pass over M: w = alphaN * M x + betaN * w, y = alphaT * M' z + betaT * y
+void hyp_gemv_nt(hyp_ctx* ctx, int64_t rows, int64_t ncols, const double* M, int64_t ld, const double* x,
+                 const double* z, double alphaN, double betaN, double* w, double alphaT, double betaT, double* y);
 
 // ---- cones.cu ----
 void hyp_cones_build_groups(hyp_ctx* ctx);

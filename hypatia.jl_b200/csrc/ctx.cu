@@ -157,6 +157,8 @@ void free_model(hyp_ctx* ctx) {
     dfree(ctx->d_vp2);
     dfree(ctx->d_partial);
     dfree(ctx->d_scalars);
+    dfree(ctx->d_partial2);
+    ctx->partial2_doubles = 0;
     dfree(ctx->d_stage);
     ctx->stage_doubles = 0;
     ctx->model_loaded = ctx->lhs_ready = ctx->cones_loaded = false;
@@ -422,7 +424,12 @@ void apply_lhs_dev(hyp_ctx* ctx, double* res, const double* dir) {
     axpbypcz_dev_kernel<<<vgrid(ctx, n), 256, 0, ctx->stream>>>(n, res, 0.0, nullptr, 0.0, nullptr, 1.0,
                                                              dir + tau_idx, c);
     ctx->launches++;
-    G_t(ctx, ctx->d_Graw, dz, 1.0, 1.0, res);
+    // one pass over G for G'z (here) and G x (res.z below) when the panel is not sharded
+    const bool fuse_g = ctx->nranks == 1 && q > 0 && n > 0;
+    if (fuse_g)
+        hyp_gemv_nt(ctx, ctx->qloc, n, ctx->d_Graw, ctx->ldg, dx, dz, 1.0, 0.0, ctx->d_vq1, 1.0, 1.0, res);
+    else
+        G_t(ctx, ctx->d_Graw, dz, 1.0, 1.0, res);
     if (p > 0) {
         hyp_gemv_t(ctx, p, n, ctx->d_A, ctx->lda, dy, 1.0, 1.0, res);
         // res.y = b tau - A x
@@ -433,7 +440,7 @@ void apply_lhs_dev(hyp_ctx* ctx, double* res, const double* dir) {
     }
     if (q > 0) {
         // res.z = h tau - s - G x
-        G_n(ctx, ctx->d_Graw, dx, ctx->d_vq1);
+        if (!fuse_g) G_n(ctx, ctx->d_Graw, dx, ctx->d_vq1);
         if (ctx->nranks > 1) hyp_replicate_q(ctx, ctx->d_vq1);
         axpbypcz_dev_kernel<<<vgrid(ctx, q), 256, 0, ctx->stream>>>(q, res + n + p, -1.0, ds, -1.0, ctx->d_vq1,
                                                                  1.0, dir + tau_idx, h);
@@ -505,14 +512,18 @@ void calc_residuals_dev(hyp_ctx* ctx, const double* pt, double* xres, double* yr
     CUDA_TRY(cudaMemsetAsync(st, 0, 10 * sizeof(double), ctx->stream));
     {
         TimeScope ts(ctx, T_GEMV);
+        const bool fuse_g = ctx->nranks == 1 && q > 0 && n > 0;
+        if (fuse_g) hyp_gemv_nt(ctx, ctx->qloc, n, ctx->d_Graw, ctx->ldg, px, pz, 1.0, 0.0, ctx->d_vq1, 1.0, 0.0, ctx->d_t);
         if (n > 0) {
-            if (q > 0) G_t(ctx, ctx->d_Graw, pz, 1.0, 0.0, ctx->d_t);
+            if (fuse_g) {
+            } else if (q > 0) G_t(ctx, ctx->d_Graw, pz, 1.0, 0.0, ctx->d_t);
             else hyp_fill(ctx, n, ctx->d_t, 0.0);
             if (p > 0) hyp_gemv_t(ctx, p, n, ctx->d_A, ctx->lda, py, 1.0, 1.0, ctx->d_t);
         }
         if (p > 0) hyp_gemv_n(ctx, p, n, ctx->d_A, ctx->lda, px, 1.0, 0.0, ctx->d_vp1);
         if (q > 0) {
-            if (n > 0) G_n(ctx, ctx->d_Graw, px, ctx->d_vq1);
+            if (fuse_g) {
+            } else if (n > 0) G_n(ctx, ctx->d_Graw, px, ctx->d_vq1);
             else hyp_fill(ctx, q, ctx->d_vq1, 0.0);
             if (ctx->nranks > 1) hyp_replicate_q(ctx, ctx->d_vq1);
         }

@@ -6,6 +6,8 @@
 // loads along the contiguous (row) direction of the column-major panel, several independent
 // loads in flight per thread, and deterministic fixed-order reductions (no atomics).
 #include "common.cuh"
+#include <cstdlib>
+#include "gemv_kernels.cuh"
 
 namespace {
 
@@ -186,4 +188,46 @@ void hyp_gemv_n(hyp_ctx* ctx, int64_t rows, int64_t ncols, const double* M, int6
     gemv_n_reduce_kernel<<<rgrid, 256, 0, ctx->stream>>>(rows, nchunks, ctx->d_partial, alpha, beta, y);
     ctx->launches += 2;
     hyp_time_end(ctx, T_GEMV);
+}
+
+// w[0:rows] = alphaN * M x + betaN * w  AND  y[0:ncols] = alphaT * M' z + betaT * y  in ONE pass over M
+// (gemv_kernels.cuh).  Falls back to the two separate passes when M is not 16-byte aligned with an even leading
+// dimension.  The T partials ((rows / 256) * 4 x ncols doubles) live in ctx->d_partial2.
+void hyp_gemv_nt(hyp_ctx* ctx, int64_t rows, int64_t ncols, const double* M, int64_t ld, const double* x,
+                 const double* z, double alphaN, double betaN, double* w, double alphaT, double betaT, double* y) {
+    const bool vec = (ld % 2 == 0) && ((uintptr_t)M % 16 == 0);
+    static int fused = -1;
+    if (fused < 0) fused = getenv("HYP_NO_FUSED_GEMV") ? 0 : 1;
+    if (!vec || !fused || rows < 4096 || ncols < 64) {
+        hyp_gemv_n(ctx, rows, ncols, M, ld, x, alphaN, betaN, w);
+        hyp_gemv_t(ctx, rows, ncols, M, ld, z, alphaT, betaT, y);
+        return;
+    }
+    hyp_time_begin(ctx, T_GEMV);
+    const int row_blocks = ceil_div(rows, 256);
+    const int64_t target = (int64_t)ctx->sm_count * 8;
+    int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(target / row_blocks, 64));
+    nchunks = (int)std::min<int64_t>(nchunks, (ncols + 63) / 64);
+    while ((int64_t)nchunks * rows > ctx->partial_doubles && nchunks > 1) nchunks--;
+    int64_t cpc = round_up((ncols + nchunks - 1) / nchunks, 8);
+    nchunks = ceil_div(ncols, cpc);
+    const int64_t needT = (int64_t)row_blocks * 4 * ncols;
+    if (needT > ctx->partial2_doubles) {
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_partial2) cudaFree(ctx->d_partial2);
+        ctx->d_partial2 = nullptr;
+        CUDA_TRY(cudaMalloc(&ctx->d_partial2, (size_t)needT * sizeof(double)));
+        ctx->partial2_doubles = needT;
+    }
+    dim3 grid(row_blocks, nchunks);
+    hypdev::gemv_nt_kernel<<<grid, 128, 0, ctx->stream>>>(rows, ncols, M, ld, x, z, cpc, ctx->d_partial,
+                                                         ctx->d_partial2);
+    const int rgrid = (int)std::min<int64_t>(ceil_div(rows, 256), (int64_t)ctx->sm_count * 8);
+    hypdev::gemv_n_reduce2_kernel<<<rgrid, 256, 0, ctx->stream>>>(rows, nchunks, ctx->d_partial, alphaN, betaN, w);
+    const int tgrid = (int)std::min<int64_t>(ceil_div(ncols, 256), (int64_t)ctx->sm_count * 8);
+    hypdev::gemv_t_reduce_kernel<<<tgrid, 256, 0, ctx->stream>>>(ncols, row_blocks * 4, ctx->d_partial2, alphaT,
+                                                                betaT, y);
+    ctx->launches += 3;
+    hyp_time_end(ctx, T_GEMV);
+    CUDA_TRY(cudaGetLastError());
 }

@@ -887,7 +887,10 @@ ozaki_syrk_pair_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid_c
                     for (int it = 0; it < nst; it++) {
                         mbar_wait(bar_empty + stage * 8, phase ^ 1u);
                         const uint32_t full_leader = mapa_u32(bar_full + stage * 8, 0);
-                        if (leader) mbar_expect_tx(bar_full + stage * 8, 2u * OZP_STAGE);
+                        // pass 1 loads only the nsl slices that enter the product (host passes nsl-slice boxes)
+                        if (leader)
+                            mbar_expect_tx(bar_full + stage * 8,
+                                           pass == 0 ? 2u * OZP_STAGE : 2u * (uint32_t)nsl * (OZ_TILE + OZ_TILE / 2));
                         const uint32_t dst = stg + stage * OZP_STAGE;
                         for (int h = 0; h < nh; h++) {
                             const int kc = k0 + (pass == 0 ? (2 * it + h) : it) * OZ_KB;
@@ -1556,9 +1559,10 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
                 CUDA_TRY(cudaStreamSynchronize(ctx->stream));
                 pcache.push_back({nt, {d_pairs, n_pairs}});
             }
-            CUtensorMap mapB4, mapB8;
+            CUtensorMap mapB4, mapB8, mapA8;
             make_map_digits(&mapB4, digits, K, ncols, ldd, slice_stride, OZ_S, 4, TN / 2);
-            make_map_digits(&mapB8, digits, K, ncols, ldd, slice_stride, OZ_S, 8, TN / 2);
+            make_map_digits(&mapB8, digits, K, ncols, ldd, slice_stride, OZ_S, nsl_eff, TN / 2);   // pass 1: nsl slices
+            make_map_digits(&mapA8, digits, K, ncols, ldd, slice_stride, OZ_S, nsl_eff);
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(2 * std::min(n_pairs, max_clusters));
             cfg.blockDim = dim3(I8_THREADS);
@@ -1571,7 +1575,7 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
             at[0].val.clusterDim.z = 1;
             cfg.attrs = at;
             cfg.numAttrs = 1;
-            CUDA_TRY(cudaLaunchKernelEx(&cfg, ozaki_syrk_pair_kernel, mapD4, mapD8, mapB4, mapB8, (const int2*)d_pairs,
+            CUDA_TRY(cudaLaunchKernelEx(&cfg, ozaki_syrk_pair_kernel, mapD4, mapA8, mapB4, mapB8, (const int2*)d_pairs,
                                         n_pairs, (int)k0, (int)ceil_div(klen, OZ_KB), dscale, ncols, C, ldc, alpha,
                                         k0 == 0 ? beta : 1.0, nsl_eff, wbits));
             ctx->launches++;

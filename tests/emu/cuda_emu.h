@@ -15,6 +15,10 @@
 #include <thread>
 #include <vector>
 
+struct double2 {
+    double x, y;
+};
+
 struct dim3 {
     unsigned x, y, z;
     dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}

@@ -160,3 +160,25 @@ int emu_spec_small_prod(int mode, int ncones, int max_side, const int64_t* off, 
 }
 
 }  // extern "C"
+
+#include "../../hypatia.jl_b200/csrc/gemv_kernels.cuh"
+
+extern "C" {
+
+// w = alphaN * M x + betaN * w ; y = alphaT * M' z + betaT * y through the fused one-pass kernel
+int emu_gemv_nt(int64_t rows, int64_t ncols, const double* M, int64_t ld, const double* x, const double* z,
+                int nchunks, double alphaN, double betaN, double* w, double alphaT, double betaT, double* y) {
+    const int rb = (int)((rows + 255) / 256);
+    const int64_t cpc = (ncols + nchunks - 1) / nchunks;
+    nchunks = (int)((ncols + cpc - 1) / cpc);
+    std::vector<double> pN((size_t)nchunks * rows + 2), pT((size_t)rb * 4 * ncols + 2);
+    emu::launch(dim3(rb, nchunks), dim3(128), 0,
+                [&] { hypdev::gemv_nt_kernel(rows, ncols, M, ld, x, z, cpc, pN.data(), pT.data()); });
+    emu::launch(dim3(2), dim3(64), 0,
+                [&] { hypdev::gemv_n_reduce2_kernel(rows, nchunks, pN.data(), alphaN, betaN, w); });
+    emu::launch(dim3(2), dim3(64), 0,
+                [&] { hypdev::gemv_t_reduce_kernel(ncols, rb * 4, pT.data(), alphaT, betaT, y); });
+    return 0;
+}
+
+}  // extern "C"
