@@ -370,7 +370,8 @@ void launch_v3_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr,
     if (g.type != HYP_CONE_EPIPERSQUARE && (mode == HYP_PROD_SQRT_HESS || mode == HYP_PROD_INV_SQRT_HESS))
         throw HypError{"sqrt_hess_prod is not defined for HypoPerLog / EpiNormInf"};
     dim3 grid(ceil_div(g.count, 8), (unsigned)std::min<int64_t>(ncols, 65535));
-    hypdev::v3_prod_kernel<<<grid, 256, 0, ctx->stream>>>(g.type, mode, g.count, g.d_off, g.d_dim, g.d_dual, g.d_scal,
+    hypdev::v3_prod_kernel<<<grid, 256, 0, ctx->stream>>>(g.type, mode, g.count, g.d_off, g.d_dim, g.d_dual, g.d_hkind,
+                                                         g.d_hparam, g.d_scal,
                                                          ctx->d_point, arr, ld_arr, prod, ld_prod, ncols, row_shift);
     ctx->launches++;
 }
@@ -458,6 +459,14 @@ void hyp_cones_build_groups(hyp_ctx* ctx) {
         }
         if (type == HYP_CONE_EPIPERSEPSPECTRAL_MAT) hyp_spec_alloc_group(ctx, g);
         else if (cone_is_matrix(type)) hyp_mat_alloc_group(ctx, g);
+        if (type == HYP_CONE_EPIPERSEPSPECTRAL_VEC) {
+            for (int kk : g.h_kidx) {
+                g.h_hkind.push_back(ctx->h_cone_hkind[kk]);
+                g.h_hparam.push_back(ctx->h_cone_hparam[kk]);
+            }
+            g.d_hkind = upload(g.h_hkind);
+            g.d_hparam = upload(g.h_hparam);
+        }
         ctx->groups.push_back(g);
     }
     CUDA_TRY(cudaDeviceSynchronize());   // uploads above ran on the legacy stream
@@ -512,8 +521,8 @@ void hyp_cones_update_state(hyp_ctx* ctx) {
             ctx->launches++;
         } else if (cone_is_vec3(g.type)) {
             hypdev::v3_state_kernel<<<ceil_div(g.count, 8), 256, 0, ctx->stream>>>(
-                g.type, g.count, g.d_off, g.d_dim, g.d_kidx, ctx->d_point, ctx->d_dual, ctx->d_grad, g.d_scal,
-                ctx->d_feas, ctx->d_dual_feas);
+                g.type, g.count, g.d_off, g.d_dim, g.d_kidx, g.d_hkind, g.d_hparam, ctx->d_point, ctx->d_dual, ctx->d_grad,
+                g.d_scal, ctx->d_feas, ctx->d_dual_feas);
             ctx->launches++;
         } else if (g.type == HYP_CONE_EPIPERSEPSPECTRAL_MAT) {
             hyp_spec_update_state(ctx, g);
@@ -607,7 +616,7 @@ void hyp_cones_dder3_dev(hyp_ctx* ctx, double* out, const double* dir) {
             ctx->launches++;
         } else if (cone_is_vec3(g.type)) {
             hypdev::v3_dder3_kernel<<<ceil_div(g.count, 8), 256, 0, ctx->stream>>>(
-                g.type, g.count, g.d_off, g.d_dim, g.d_scal, ctx->d_point, dir, out);
+                g.type, g.count, g.d_off, g.d_dim, g.d_hkind, g.d_hparam, g.d_scal, ctx->d_point, dir, out);
             ctx->launches++;
         } else if (g.type == HYP_CONE_EPIPERSEPSPECTRAL_MAT) {
             hyp_spec_dder3(ctx, g, out, dir);

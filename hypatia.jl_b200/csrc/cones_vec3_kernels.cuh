@@ -11,10 +11,12 @@
 // HBM-bound streaming kernels: 16 * rows * ncols algorithmic bytes per product.
 #pragma once
 #include "devdefs.cuh"
+#include "ssf.cuh"
 
 #define V3_EPIPERSQUARE 6   // = HYP_CONE_EPIPERSQUARE
 #define V3_HYPOPERLOG 7     // = HYP_CONE_HYPOPERLOG
 #define V3_EPINORMINF 8     // = HYP_CONE_EPINORMINF
+#define V3_SEPSPEC_VEC 9    // = HYP_CONE_EPIPERSEPSPECTRAL_VEC (vectorcsqr.jl; scal: 0 phi, 1 zeta, 2 sigma, 3 c0, 4 c4, 5 c5)
 // product modes (= HYP_PROD_*)
 #define V3_HESS 0
 #define V3_INV_HESS 1
@@ -25,7 +27,8 @@ namespace hypdev {
 
 static __global__ void __launch_bounds__(256)
 v3_state_kernel(int type, int ncones, const int64_t* __restrict__ off, const int* __restrict__ dim,
-                const int* __restrict__ kidx, const double* __restrict__ point,
+                const int* __restrict__ kidx, const int* __restrict__ hkind,
+                const double* __restrict__ hparam, const double* __restrict__ point,
                 const double* __restrict__ dual, double* __restrict__ grad, double* __restrict__ scal,
                 uint8_t* feas, uint8_t* dual_feas) {
     const int lane = threadIdx.x & 31;
@@ -34,7 +37,68 @@ v3_state_kernel(int type, int ncones, const int64_t* __restrict__ off, const int
     const int64_t o = off[c];
     const int d = dim[c];
     const double u = point[o], v = point[o + 1], du = dual[o], dv = dual[o + 1];
-    if (type == V3_EPINORMINF) {
+    if (type == V3_SEPSPEC_VEC) {
+        // vectorcsqr.jl:61-114 (feas, dual feas, grad), :216-246 (inverse-Hessian scalars)
+        const int kind = hkind[c];
+        const double hp = hparam[c];
+        double nbad = 0.0, phi = 0.0, s1 = 0.0, dbad = 0.0, conj = 0.0;
+        for (int i = 2 + lane; i < d; i += 32) {
+            const double w = point[o + i], zd = dual[o + i];
+            if (!(w > HYP_EPS)) nbad += 1.0;
+            if (zd < HYP_EPS) dbad += 1.0;
+            double h, a1, a2, a3;
+            ssf_eval(kind, hp, w / v, h, a1, a2, a3);
+            phi += h;
+            s1 += (w / v) * a1;
+            conj += ssf_conj(kind, hp, zd / du);
+        }
+        nbad = warp_sum(nbad);
+        phi = warp_sum(phi);
+        s1 = warp_sum(s1);
+        dbad = warp_sum(dbad);
+        conj = warp_sum(conj);
+        const double zeta = u - v * phi, sigma = phi - s1, zetai = 1.0 / zeta, zetaivi = zetai / v;
+        const bool ok = v > HYP_EPS && nbad == 0.0 && zeta > HYP_EPS;
+        bool dok = !(du < HYP_EPS);
+        if (ssf_conj_dom_pos(kind) && dbad > 0.0) dok = false;
+        if (dok) dok = (dv - du * conj) > HYP_EPS;
+        double r1 = 0.0, r2 = 0.0;
+        for (int i = 2 + lane; i < d; i += 32) {
+            const double w = point[o + i], viw = w / v;
+            double h, a1, a2, a3;
+            ssf_eval(kind, hp, viw, h, a1, a2, a3);
+            grad[o + i] = -1.0 / w + zetai * a1;
+            const double w1 = zetaivi * a2, m = 1.0 / (w1 + 1.0 / (w * w));
+            r1 += a1 * m * a1;               // dot(dh, alpha)
+            r2 += a1 * m * w1 * viw;         // dot(dh, gamma)
+        }
+        r1 = warp_sum(r1);
+        r2 = warp_sum(r2);
+        const double zeta2beta = zeta * zeta + r1, c0 = sigma + r2, c1 = c0 / zeta2beta;
+        double r3 = 0.0;
+        for (int i = 2 + lane; i < d; i += 32) {
+            const double w = point[o + i], viw = w / v;
+            double h, a1, a2, a3;
+            ssf_eval(kind, hp, viw, h, a1, a2, a3);
+            const double w1 = zetaivi * a2, m = 1.0 / (w1 + 1.0 / (w * w)), w1v = w1 * viw;
+            r3 += (viw + c1 * m * a1 - m * w1v) * w1v;
+        }
+        r3 = warp_sum(r3);
+        const double c3 = 1.0 / (v * v) + sigma * c1 + r3;
+        if (lane == 0) {
+            grad[o] = -zetai;
+            grad[o + 1] = -1.0 / v + zetai * sigma;
+            double* sc = scal + 8 * c;
+            sc[0] = phi;
+            sc[1] = zeta;
+            sc[2] = sigma;
+            sc[3] = c0;
+            sc[4] = 1.0 / (c3 - c0 * c1);
+            sc[5] = zeta2beta * c3;
+            if (!ok) feas[kidx[c]] = 0;
+            if (!dok) dual_feas[kidx[c]] = 0;
+        }
+    } else if (type == V3_EPINORMINF) {
         // epinorminf.jl:97-142, :144-168 (Huu), :275-300 (schur)
         const int n = d - 1;
         double wmax = 0.0, dsum = 0.0, sud = 0.0, sud2 = 0.0, sinv = 0.0;
@@ -132,7 +196,8 @@ v3_state_kernel(int type, int ncones, const int64_t* __restrict__ off, const int
 // / inv_hess for dual-barrier cones, 5: the other way round).
 static __global__ void __launch_bounds__(256)
 v3_prod_kernel(int type, int mode_in, int ncones, const int64_t* __restrict__ off,
-               const int* __restrict__ dim, const int* __restrict__ dualf,
+               const int* __restrict__ dim, const int* __restrict__ dualf, const int* __restrict__ hkind,
+               const double* __restrict__ hparam,
                const double* __restrict__ scal, const double* __restrict__ point, const double* arr,
                int64_t ld_arr, double* prod, int64_t ld_prod, int64_t ncols, int64_t row_shift) {
     const int lane = threadIdx.x & 31;
@@ -148,7 +213,64 @@ v3_prod_kernel(int type, int mode_in, int ncones, const int64_t* __restrict__ of
         const double* a = arr + j * ld_arr + (o - row_shift);
         double* pr = prod + j * ld_prod + (o - row_shift);
         const double p = a[0], q = a[1];
-        if (type == V3_EPINORMINF) {
+        if (type == V3_SEPSPEC_VEC) {
+            const int kind = hkind[c];
+            const double hp = hparam[c];
+            const double* sc = scal + 8 * c;
+            const double zeta = sc[1], sigma = sc[2], zetai = 1.0 / zeta, zetaivi = zetai / v;
+            if (mode == V3_HESS) {
+                // vectorcsqr.jl:172-204
+                const double viq = q / v;
+                double s1 = 0.0, s2 = 0.0;
+                for (int i = 2 + lane; i < d; i += 32) {
+                    const double w = point[o + i], ri = a[i];
+                    double h, a1, a2, a3;
+                    ssf_eval(kind, hp, w / v, h, a1, a2, a3);
+                    s1 += a1 * ri;
+                    s2 += (w / v) * zetaivi * a2 * (ri - viq * w);
+                }
+                s1 = warp_sum(s1);
+                s2 = warp_sum(s2);
+                const double c1 = -zetai * (p - sigma * q - s1) * zetai;
+                for (int i = 2 + lane; i < d; i += 32) {
+                    const double w = point[o + i], ri = a[i];
+                    double h, a1, a2, a3;
+                    ssf_eval(kind, hp, w / v, h, a1, a2, a3);
+                    pr[i] = c1 * a1 + zetaivi * a2 * (ri - viq * w) + ri / (w * w);
+                }
+                if (lane == 0) {
+                    pr[0] = -c1;
+                    pr[1] = c1 * sigma - s2 + viq / v;
+                }
+            } else {
+                // vectorcsqr.jl:275-305
+                const double c0 = sc[3], c4 = sc[4], c5 = sc[5];
+                double s1 = 0.0, s2 = 0.0;
+                for (int i = 2 + lane; i < d; i += 32) {
+                    const double w = point[o + i], ri = a[i];
+                    double h, a1, a2, a3;
+                    ssf_eval(kind, hp, w / v, h, a1, a2, a3);
+                    const double w1 = zetaivi * a2, m = 1.0 / (w1 + 1.0 / (w * w));
+                    s1 += m * w1 * (w / v) * ri;     // dot(gamma, r)
+                    s2 += m * a1 * ri;               // dot(alpha, r)
+                }
+                s1 = warp_sum(s1);
+                s2 = warp_sum(s2);
+                const double qgr = q + s1;
+                const double cu = c4 * (c5 * p + c0 * qgr), cv = c4 * (c0 * p + qgr);
+                for (int i = 2 + lane; i < d; i += 32) {
+                    const double w = point[o + i], ri = a[i];
+                    double h, a1, a2, a3;
+                    ssf_eval(kind, hp, w / v, h, a1, a2, a3);
+                    const double w1 = zetaivi * a2, m = 1.0 / (w1 + 1.0 / (w * w));
+                    pr[i] = p * m * a1 + cv * m * w1 * (w / v) + m * ri;
+                }
+                if (lane == 0) {
+                    pr[0] = cu + s2;
+                    pr[1] = cv;
+                }
+            }
+        } else if (type == V3_EPINORMINF) {
             const double usqr = u * u, ua = p;
             if (mode == V3_HESS) {
                 // epinorminf.jl:226-244: prod_u = Huu ua + Hure . wa; prod_w = Hure ua + Hrere wa
@@ -261,6 +383,7 @@ v3_prod_kernel(int type, int mode_in, int ncones, const int64_t* __restrict__ of
 // epipersquare.jl:246-274, hypoperlog.jl:259-287
 static __global__ void __launch_bounds__(256)
 v3_dder3_kernel(int type, int ncones, const int64_t* __restrict__ off, const int* __restrict__ dim,
+                const int* __restrict__ hkind, const double* __restrict__ hparam,
                 const double* __restrict__ scal, const double* __restrict__ point,
                 const double* __restrict__ dir, double* __restrict__ out) {
     const int lane = threadIdx.x & 31;
@@ -269,7 +392,43 @@ v3_dder3_kernel(int type, int ncones, const int64_t* __restrict__ off, const int
     const int64_t o = off[c];
     const int d = dim[c];
     const double u = point[o], v = point[o + 1], p = dir[o], q = dir[o + 1];
-    if (type == V3_EPINORMINF) {
+    if (type == V3_SEPSPEC_VEC) {
+        // vectorcsqr.jl:314-357
+        const int kind = hkind[c];
+        const double hp = hparam[c];
+        const double* sc = scal + 8 * c;
+        const double zeta = sc[1], sigma = sc[2], zetai = 1.0 / zeta, zetaivi = zetai / v;
+        const double viq = q / v;
+        double s1 = 0.0, s2 = 0.0;
+        for (int i = 2 + lane; i < d; i += 32) {
+            const double w = point[o + i], ri = dir[o + i];
+            double h, a1, a2, a3;
+            ssf_eval(kind, hp, w / v, h, a1, a2, a3);
+            const double xi = ri - viq * w;
+            s1 += a1 * ri;
+            s2 += zetaivi * a2 * xi * xi;
+        }
+        s1 = warp_sum(s1);
+        const double xibxi = warp_sum(s2) / 2;
+        const double zetaichi = zetai * (p - sigma * q - s1);
+        const double c1 = -zetai * (zetaichi * zetaichi + xibxi), c2 = -zetai / 2;
+        double s3 = 0.0;
+        for (int i = 2 + lane; i < d; i += 32) {
+            const double w = point[o + i], ri = dir[o + i];
+            double h, a1, a2, a3;
+            ssf_eval(kind, hp, w / v, h, a1, a2, a3);
+            const double xi = ri - viq * w, xiv = xi / v;
+            const double waux = zetaivi * a2 * xi * (zetaichi + viq) + c2 * a3 * xiv * xiv;
+            s3 += (w / v) * waux;
+            const double rw = ri / w;
+            out[o + i] = c1 * a1 + waux + rw * rw / w;
+        }
+        s3 = warp_sum(s3);
+        if (lane == 0) {
+            out[o] = -c1;
+            out[o + 1] = c1 * sigma - s3 + (xibxi + viq * viq) / v;
+        }
+    } else if (type == V3_EPINORMINF) {
         // epinorminf.jl:366-406 (real case)
         const int n = d - 1;
         const double usqr = u * u, udir = p, u3 = 1.5 / u, udu = udir / u;

@@ -920,9 +920,10 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
                                 : t == HYP_CONE_EPIPERSQUARE ? 2.0
                                                              : (double)d;   // HypoPerLog, EpiNormInf: nu = dim
             if (t == HYP_CONE_EPINORMINF && d < 2) throw HypError{"hyp_load_model: EpiNormInf needs dimension >= 2"};
-            if ((t == HYP_CONE_EPIPERSQUARE || t == HYP_CONE_HYPOPERLOG || t == HYP_CONE_EPIPERSEPSPECTRAL_MAT) && d < 3)
+            if ((t == HYP_CONE_EPIPERSQUARE || t == HYP_CONE_HYPOPERLOG || t == HYP_CONE_EPIPERSEPSPECTRAL_MAT ||
+                 t == HYP_CONE_EPIPERSEPSPECTRAL_VEC) && d < 3)
                 throw HypError{"hyp_load_model: this cone type needs dimension >= 3"};
-            if (t == HYP_CONE_EPIPERSEPSPECTRAL_MAT) {
+            if (t == HYP_CONE_EPIPERSEPSPECTRAL_MAT || t == HYP_CONE_EPIPERSEPSPECTRAL_VEC) {
                 if (!have_params) throw HypError{"hyp_load_model: EpiPerSepSpectral cones need hyp_set_cone_params first"};
                 const int hk = ctx->h_cone_hkind[k];
                 const double hp = ctx->h_cone_hparam[k];

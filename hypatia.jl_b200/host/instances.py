@@ -106,6 +106,10 @@ def cone_initial_point(spec):
         arr[2:] = w
     elif spec.ctype == M.CONE_EPINORMINF:
         arr[0] = np.sqrt(spec.dim)      # epinorminf.jl:88-95
+    elif spec.ctype == M.CONE_EPIPERSEPSPECTRAL_VEC:
+        u, v, w = ssf_initial_point(spec.hkind, spec.dim - 2)   # vectorcsqr.jl:52-59
+        arr[0], arr[1] = u, v
+        arr[2:] = w
     return arr
 
 
@@ -117,6 +121,20 @@ def _cone_dual_initial(spec, prim):
         return prim.copy()      # central point is self-dual: -g = (u, -w)/dist with dist = 1
     if spec.ctype == M.CONE_POSSEMIDEFTRI:
         return prim.copy()
+    if spec.ctype == M.CONE_EPIPERSEPSPECTRAL_VEC:
+        # vectorcsqr.jl:97-114 at w = w0 * 1
+        d = spec.dim - 2
+        u, v, w = prim[0], prim[1], prim[2]
+        lam = w / v
+        hv, h1, _ = ssf_eval(spec.hkind, spec.hparam, lam)
+        phi = d * hv
+        zeta = u - v * phi
+        sigma = phi - d * lam * h1
+        out = np.zeros_like(prim)
+        out[0] = 1.0 / zeta
+        out[1] = 1.0 / v - sigma / zeta
+        out[2:] = 1.0 / w - h1 / zeta
+        return out
     if spec.ctype == M.CONE_EPINORMINF:
         return prim.copy()      # -g = ((n + 1) / u, 0...) = (sqrt(dim), 0...) at the central point
     if spec.ctype == M.CONE_EPIPERSQUARE:
@@ -166,6 +184,9 @@ def _perturb(rng, spec, vec, noise):
     perturbed matrix stays safely positive definite at any side."""
     if spec.ctype in (M.CONE_NONNEGATIVE, M.CONE_EPINORMEUCL):
         vec += noise * (2 * rng.random(vec.size) - 1)
+        return vec
+    if spec.ctype == M.CONE_EPIPERSEPSPECTRAL_VEC:
+        vec += noise / (2.0 * (vec.size - 2)) * (2 * rng.random(vec.size) - 1)   # the initial point is not central
         return vec
     if spec.ctype == M.CONE_EPINORMINF:
         vec[0] += 0.5 * noise * (2 * rng.random() - 1)

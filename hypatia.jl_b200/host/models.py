@@ -21,6 +21,7 @@ CONE_EPIPERSEPSPECTRAL_MAT = 5
 CONE_EPIPERSQUARE = 6
 CONE_HYPOPERLOG = 7
 CONE_EPINORMINF = 8
+CONE_EPIPERSEPSPECTRAL_VEC = 9
 
 # separable spectral functions of EpiPerSepSpectral (sepspectralfun.jl:17-116), HYP_SSF_*
 SSF_INV, SSF_NEGLOG, SSF_NEGENTROPY, SSF_POWER12 = 0, 1, 2, 3
@@ -35,6 +36,7 @@ CONE_NAMES = {
     CONE_EPIPERSQUARE: "EpiPerSquare",
     CONE_HYPOPERLOG: "HypoPerLog",
     CONE_EPINORMINF: "EpiNormInf",
+    CONE_EPIPERSEPSPECTRAL_VEC: "EpiPerSepSpectral{VectorCSqr}",
 }
 
 
@@ -89,6 +91,9 @@ class ConeSpec:
             assert dim >= 3
         elif ctype == CONE_EPINORMINF:
             assert dim >= 2
+        elif ctype == CONE_EPIPERSEPSPECTRAL_VEC:
+            assert dim >= 3 and hkind in (SSF_INV, SSF_NEGLOG, SSF_NEGENTROPY, SSF_POWER12)
+            assert hkind != SSF_POWER12 or 1 < hparam <= 2
         else:
             raise ValueError(f"unknown cone type {ctype}")
 
@@ -117,7 +122,7 @@ class ConeSpec:
             return 2.0 + self.side
         if self.ctype == CONE_EPIPERSQUARE:
             return 2.0
-        if self.ctype in (CONE_HYPOPERLOG, CONE_EPINORMINF):
+        if self.ctype in (CONE_HYPOPERLOG, CONE_EPINORMINF, CONE_EPIPERSEPSPECTRAL_VEC):
             return float(self.dim)
         return 1.0 + self.side
 
@@ -152,6 +157,11 @@ def EpiPerSepSpectralMat(dim, hkind=SSF_NEGLOG, hparam=1.5, use_dual=False):
     """EpiPerSepSpectral{MatrixCSqr{Float64, Float64}}(h, side), dim = 2 + svec_length(side)."""
     return ConeSpec(CONE_EPIPERSEPSPECTRAL_MAT, dim, use_dual, hkind,
                     hparam if hkind == SSF_POWER12 else 0.0)
+
+
+def EpiPerSepSpectralVec(dim, hkind=SSF_NEGLOG, hparam=1.5, use_dual=False):
+    """EpiPerSepSpectral{VectorCSqr{Float64}, Float64}(h, d), dim = 2 + d."""
+    return ConeSpec(CONE_EPIPERSEPSPECTRAL_VEC, dim, use_dual, hkind, hparam if hkind == SSF_POWER12 else 0.0)
 
 
 def EpiPerSquare(dim, use_dual=False):

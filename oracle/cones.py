@@ -757,6 +757,9 @@ def make_cone(spec):
     if spec.ctype == M.CONE_EPIPERSEPSPECTRAL_MAT:
         from .cones_sepspec import EpiPerSepSpectralMat
         return EpiPerSepSpectralMat(spec.dim, spec.hkind, spec.hparam, use_dual=spec.use_dual)
+    if spec.ctype == M.CONE_EPIPERSEPSPECTRAL_VEC:
+        from .cones_sepspec import EpiPerSepSpectralVec
+        return EpiPerSepSpectralVec(spec.dim, spec.hkind, spec.hparam, use_dual=spec.use_dual)
     if spec.ctype in (M.CONE_EPIPERSQUARE, M.CONE_HYPOPERLOG, M.CONE_EPINORMINF):
         from . import cones_vec3
         cls = {M.CONE_EPIPERSQUARE: cones_vec3.EpiPerSquare, M.CONE_HYPOPERLOG: cones_vec3.HypoPerLog,

@@ -356,3 +356,163 @@ class EpiPerSepSpectralMat(Cone):
         d3[1] = c1 * sigma - c2 + xibxi + viq ** 2 / v
         d3[2:] = self._unrot(w_aux[None])[:, 0]
         return d3
+
+
+class EpiPerSepSpectralVec(Cone):
+    """EpiPerSepSpectral{VectorCSqr} (vectorcsqr.jl:1-357): (u, v, w), w in R^d_++, barrier
+    -log(u - v sum h(w_i / v)) - log(v) - sum log(w_i), nu = 2 + d."""
+    ctype = M.CONE_EPIPERSEPSPECTRAL_VEC
+
+    def __init__(self, dim, hkind=H_NEGLOG, hparam=1.5, use_dual=False):
+        self.d = dim - 2
+        self.h = SepSpectralFun(hkind, hparam)
+        self.use_dual_barrier = use_dual
+        super().__init__(dim)
+
+    @property
+    def nu(self):
+        return 2.0 + self.d
+
+    def reset_data(self):
+        super().reset_data()
+        self.hess_aux_updated = self.inv_hess_aux_updated = False
+
+    def set_initial_point(self, arr):
+        u, v, w0 = self.h.initial_point(self.d)
+        arr[0], arr[1] = u, v
+        arr[2:] = w0
+        return arr
+
+    def update_feas(self):
+        v, w = self.point[1], self.point[2:]
+        if v > EPS and (w > EPS).all():
+            self.viw = w / v
+            self.phi = self.h.val(self.viw)
+            self.zeta = self.point[0] - v * self.phi
+            return self.zeta > EPS
+        return False
+
+    def is_dual_feas(self):
+        u = self.dual_point[0]
+        if u < EPS:
+            return False
+        w = self.dual_point[2:]
+        if self.h.conj_dom_pos() and (w < EPS).any():
+            return False
+        return bool(self.dual_point[1] - u * self.h.conj(w / u) > EPS)
+
+    def update_grad(self):
+        v, w = self.point[1], self.point[2:]
+        self.zetai = 1.0 / self.zeta
+        self.dh = self.h.der1(self.viw)
+        self.sigma = self.phi - float(self.viw @ self.dh)
+        self.wi = 1.0 / w
+        g = self._grad
+        g[0] = -self.zetai
+        g[1] = -1.0 / v + self.zetai * self.sigma
+        g[2:] = -self.wi + self.zetai * self.dh
+
+    def update_hess_aux(self):
+        if not self.hess_aux_updated:
+            self.grad()
+            self.d2h = self.h.der2(self.viw)
+            self.hess_aux_updated = True
+
+    def update_hess(self):
+        self.update_hess_aux()
+        v, zetai, sigma = self.point[1], self.zetai, self.sigma
+        viw, wi, dh, d2h = self.viw, self.wi, self.dh, self.d2h
+        zetaivi = zetai / v
+        H = np.zeros((self.dim, self.dim))
+        H[0, 0] = zetai ** 2
+        H[0, 1] = H[1, 0] = -zetai ** 2 * sigma
+        term = viw * zetaivi * d2h
+        H[1, 1] = v ** -2 + (zetai * sigma) ** 2 + float(viw @ term)
+        H[0, 2:] = H[2:, 0] = -zetai ** 2 * dh
+        H[1, 2:] = H[2:, 1] = sigma * zetai ** 2 * dh - term
+        H[2:, 2:] = zetai ** 2 * np.outer(dh, dh) + np.diag(zetaivi * d2h + wi ** 2)
+        return H
+
+    def hess_prod(self, arr):
+        self.update_hess_aux()
+        a, vec = _as2d(arr)
+        v, w = self.point[1], self.point[2:]
+        zetai, sigma = self.zetai, self.sigma
+        zetaivi = zetai / v
+        p, q, r = a[0], a[1], a[2:]
+        viq = q / v
+        xib = (zetaivi * self.d2h)[:, None] * (r - viq[None, :] * w[:, None])
+        c1 = -zetai * (p - sigma * q - self.dh @ r) * zetai
+        prod = np.empty_like(a)
+        prod[0] = -c1
+        prod[1] = c1 * sigma - self.viw @ xib + viq / v
+        prod[2:] = c1[None, :] * self.dh[:, None] + xib + (self.wi ** 2)[:, None] * r
+        return _ret(prod, vec)
+
+    def update_inv_hess_aux(self):
+        if self.inv_hess_aux_updated:
+            return
+        self.update_hess_aux()
+        v, sigma = self.point[1], self.sigma
+        zetaivi = self.zetai / v
+        w1 = zetaivi * self.d2h
+        self.m = 1.0 / (w1 + self.wi ** 2)
+        self.alpha = self.m * self.dh
+        w1 = w1 * self.viw
+        self.gamma = self.m * w1
+        zeta2beta = self.zeta ** 2 + float(self.dh @ self.alpha)
+        c0 = sigma + float(self.dh @ self.gamma)
+        c1 = c0 / zeta2beta
+        sum1 = float(((self.viw + c1 * self.alpha - self.gamma) * w1).sum())
+        c3 = v ** -2 + sigma * c1 + sum1
+        self.c0, self.c4, self.c5 = c0, 1.0 / (c3 - c0 * c1), zeta2beta * c3
+        self.inv_hess_aux_updated = True
+
+    def update_inv_hess(self):
+        self.update_inv_hess_aux()
+        c0, c4, c5 = self.c0, self.c4, self.c5
+        Hi = np.zeros((self.dim, self.dim))
+        Hi[0, 0] = c4 * c5
+        Hi[0, 1] = Hi[1, 0] = c4 * c0
+        Hi[1, 1] = c4
+        Hiv = c4 * self.gamma
+        Hi[1, 2:] = Hi[2:, 1] = Hiv
+        Hi[0, 2:] = Hi[2:, 0] = self.alpha + c0 * Hiv
+        Hi[2:, 2:] = np.outer(Hiv, self.gamma) + np.diag(self.m)
+        return Hi
+
+    def inv_hess_prod(self, arr):
+        self.update_inv_hess_aux()
+        a, vec = _as2d(arr)
+        c0, c4, c5 = self.c0, self.c4, self.c5
+        p, q, r = a[0], a[1], a[2:]
+        qgr = q + self.gamma @ r
+        cu = c4 * (c5 * p + c0 * qgr)
+        cv = c4 * (c0 * p + qgr)
+        prod = np.empty_like(a)
+        prod[0] = cu + self.alpha @ r
+        prod[1] = cv
+        prod[2:] = p[None, :] * self.alpha[:, None] + cv[None, :] * self.gamma[:, None] + self.m[:, None] * r
+        return _ret(prod, vec)
+
+    def dder3(self, direction):
+        self.update_hess_aux()
+        d3h = self.h.der3(self.viw)
+        v, w = self.point[1], self.point[2:]
+        zetai, sigma = self.zetai, self.sigma
+        zetaivi = zetai / v
+        p, q, r = direction[0], direction[1], direction[2:]
+        viq = q / v
+        xi = r - viq * w
+        xib = zetaivi * self.d2h * xi
+        zetaichi = zetai * (p - sigma * q - float(self.dh @ r))
+        xibxi = float(xib @ xi) / 2
+        c1 = -zetai * (zetaichi ** 2 + xibxi)
+        c2 = -zetai / 2
+        xi = xi / v
+        w_aux = xib * (zetaichi + viq) + c2 * d3h * xi * xi
+        d3 = np.empty(self.dim)
+        d3[0] = -c1
+        d3[1] = c1 * sigma - float(self.viw @ w_aux) + (xibxi + viq ** 2) / v
+        d3[2:] = c1 * self.dh + w_aux + (r * self.wi) ** 2 * self.wi
+        return d3

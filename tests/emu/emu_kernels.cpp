@@ -100,28 +100,29 @@ int emu_spec_dder3(int d, int lde, const double* sc, const double* vecs, const d
 
 extern "C" {
 
-int emu_v3_state(int type, int ncones, const int64_t* off, const int* dim, const int* kidx, const double* point,
-                 const double* dual, double* grad, double* scal, uint8_t* feas, uint8_t* dual_feas) {
+int emu_v3_state(int type, int ncones, const int64_t* off, const int* dim, const int* kidx, const int* hkind,
+                 const double* hparam, const double* point, const double* dual, double* grad, double* scal,
+                 uint8_t* feas, uint8_t* dual_feas) {
     emu::launch(dim3((ncones + 1) / 2), dim3(64), 0, [&] {
-        hypdev::v3_state_kernel(type, ncones, off, dim, kidx, point, dual, grad, scal, feas, dual_feas);
+        hypdev::v3_state_kernel(type, ncones, off, dim, kidx, hkind, hparam, point, dual, grad, scal, feas, dual_feas);
     });
     return 0;
 }
 
 int emu_v3_prod(int type, int mode, int ncones, const int64_t* off, const int* dim, const int* dualf,
-                const double* scal, const double* point, const double* arr, int64_t ld_arr, double* prod,
+                const int* hkind, const double* hparam, const double* scal, const double* point, const double* arr, int64_t ld_arr, double* prod,
                 int64_t ld_prod, int64_t ncols, int64_t row_shift, int gy) {
     emu::launch(dim3((ncones + 1) / 2, gy), dim3(64), 0, [&] {
-        hypdev::v3_prod_kernel(type, mode, ncones, off, dim, dualf, scal, point, arr, ld_arr, prod, ld_prod, ncols,
-                               row_shift);
+        hypdev::v3_prod_kernel(type, mode, ncones, off, dim, dualf, hkind, hparam, scal, point, arr, ld_arr, prod,
+                               ld_prod, ncols, row_shift);
     });
     return 0;
 }
 
-int emu_v3_dder3(int type, int ncones, const int64_t* off, const int* dim, const double* scal, const double* point,
-                 const double* dir, double* out) {
+int emu_v3_dder3(int type, int ncones, const int64_t* off, const int* dim, const int* hkind, const double* hparam,
+                 const double* scal, const double* point, const double* dir, double* out) {
     emu::launch(dim3((ncones + 1) / 2), dim3(64), 0,
-                [&] { hypdev::v3_dder3_kernel(type, ncones, off, dim, scal, point, dir, out); });
+                [&] { hypdev::v3_dder3_kernel(type, ncones, off, dim, hkind, hparam, scal, point, dir, out); });
     return 0;
 }
 

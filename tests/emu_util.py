@@ -205,6 +205,8 @@ class EmuVec3Group:
         self.q = int(self.dims.sum())
         self.kidx = np.arange(self.K, dtype=np.int32)
         self.dualf = np.array([1 if s.use_dual else 0 for s in specs], dtype=np.int32)
+        self.hkind = np.array([s.hkind for s in specs], dtype=np.int32)
+        self.hparam = np.array([s.hparam for s in specs], dtype=np.float64)
         self.scal = np.zeros(8 * self.K)
 
     def load_point(self, point, dual):
@@ -213,20 +215,23 @@ class EmuVec3Group:
         self.feas = np.ones(self.K, dtype=np.uint8)
         self.dual_feas = np.ones(self.K, dtype=np.uint8)
         self.grad = np.zeros(self.q)
-        lib().emu_v3_state(self.type, self.K, p(self.off), p(self.dims), p(self.kidx), p(self.point), p(self.dual),
+        lib().emu_v3_state(self.type, self.K, p(self.off), p(self.dims), p(self.kidx), p(self.hkind), p(self.hparam),
+                           p(self.point), p(self.dual),
                            p(self.grad), p(self.scal), p(self.feas), p(self.dual_feas))
 
     def prod(self, arr, mode, in_place=False):
         a = np.asfortranarray(np.asarray(arr, dtype=np.float64).reshape(self.q, -1, order="F")).copy(order="F")
         out = a if in_place else np.zeros_like(a, order="F")
-        lib().emu_v3_prod(self.type, int(mode), self.K, p(self.off), p(self.dims), p(self.dualf), p(self.scal),
+        lib().emu_v3_prod(self.type, int(mode), self.K, p(self.off), p(self.dims), p(self.dualf), p(self.hkind),
+                          p(self.hparam), p(self.scal),
                           p(self.point), p(a), i64(self.q), p(out), i64(self.q), i64(a.shape[1]), i64(0), 2)
         return out[:, 0] if np.ndim(arr) == 1 else out
 
     def dder3(self, direction):
         d = np.ascontiguousarray(direction, dtype=np.float64)
         out = np.zeros(self.q)
-        lib().emu_v3_dder3(self.type, self.K, p(self.off), p(self.dims), p(self.scal), p(self.point), p(d), p(out))
+        lib().emu_v3_dder3(self.type, self.K, p(self.off), p(self.dims), p(self.hkind), p(self.hparam), p(self.scal),
+                           p(self.point), p(d), p(out))
         return out
 
 

@@ -331,6 +331,42 @@ def _spectral_matrix3(d, hkind, hparam):  # :2072-2098
         dict(status="Optimal", primal_obj=0, x_idx={0: 0.0, 1: 0.0})
 
 
+def _spectral_vector1(d, hkind, hparam):  # :1908-1932: min u : (u, 1, w) in K => sum h(w_i)
+    w = np.random.default_rng(1).random(d) + 1
+    G = np.zeros((2 + d, 1))
+    G[0, 0] = -1
+    h = np.concatenate(([0.0, 1.0], w))
+    return _m([1], None, None, G, h, [M.EpiPerSepSpectralVec(2 + d, hkind, hparam)]), \
+        dict(status="Optimal", primal_obj=_ssf(hkind, hparam).val(w))
+
+
+def _spectral_vector2(d, hkind, hparam):  # :1934-1956 (dual barrier)
+    dim = 2 + d
+    c = np.zeros(dim)
+    c[0] = 1
+    A = np.zeros((1, dim))
+    A[0, 0] = 1
+    return _m(c, A, [0], -np.eye(dim), np.zeros(dim), [M.EpiPerSepSpectralVec(dim, hkind, hparam, use_dual=True)]), \
+        dict(status="Optimal", primal_obj=0)
+
+
+def _spectral_vector3(hkind, hparam):  # :1958-1979
+    f = _ssf(hkind, hparam)
+    val = 5 * f.val(np.array([2.0, 3.0]) / 5)
+    return _m([1], None, None, -np.eye(4)[:, :1], [0, 5, 2, 3], [M.EpiPerSepSpectralVec(4, hkind, hparam)]), \
+        dict(status="Optimal", primal_obj=val, s=[val, 5, 2, 3], z_idx={0: 1.0})
+
+
+def _spectral_vector4(hkind, hparam):  # :1981-2007 (dual barrier: conjugate)
+    f = _ssf(hkind, hparam)
+    w = np.array([2.0, 3.0]) * (1 if f.conj_dom_pos() else -1)
+    G = np.zeros((4, 1))
+    G[1, 0] = -1
+    val = 5 * f.conj(w / 5)
+    return _m([1], None, None, G, [5, 0, w[0], w[1]], [M.EpiPerSepSpectralVec(4, hkind, hparam, use_dual=True)]), \
+        dict(status="Optimal", primal_obj=val, s=[5, val, w[0], w[1]], z_idx={1: 1.0})
+
+
 def _named(fn, name):
     fn.__name__ = name
     return fn
@@ -346,6 +382,17 @@ for _k, (_hk, _hp) in enumerate(SEP_SPECTRAL_FUNS):
     for _d in (2, 4):
         SPECTRAL.append(_named(lambda d=_d, hk=_hk, hp=_hp: _spectral_matrix3(d, hk, hp),
                                f"epipersepspectral_matrix3_d{_d}_h{_hk}"))
+
+SPECTRAL_VEC = []
+for _k, (_hk, _hp) in enumerate(SEP_SPECTRAL_FUNS):
+    for _d in (1, 3):
+        SPECTRAL_VEC.append(_named(lambda d=_d, hk=_hk, hp=_hp: _spectral_vector1(d, hk, hp),
+                                   f"epipersepspectral_vector1_d{_d}_h{_hk}"))
+    for _d in (2, 4):
+        SPECTRAL_VEC.append(_named(lambda d=_d, hk=_hk, hp=_hp: _spectral_vector2(d, hk, hp),
+                                   f"epipersepspectral_vector2_d{_d}_h{_hk}"))
+    SPECTRAL_VEC.append(_named(lambda hk=_hk, hp=_hp: _spectral_vector3(hk, hp), f"epipersepspectral_vector3_h{_hk}"))
+    SPECTRAL_VEC.append(_named(lambda hk=_hk, hp=_hp: _spectral_vector4(hk, hp), f"epipersepspectral_vector4_h{_hk}"))
 
 NEW_CONES = [epinorminf1, epinorminf2, epinorminf3, epinorminf3_dual, epinorminf4, dualinfeas1,
              primalinfeas3, dualinfeas2, dualinfeas3, epipersquare1, epipersquare2, epipersquare3,
@@ -393,3 +440,5 @@ def check_solution(solver, model, expected, tol=TOL):
             assert _approx(val, expected[key], tol), (key, val, expected[key])
     for i, v in expected.get("x_idx", {}).items():
         assert _approx(x[i], v, tol)
+    for i, v in expected.get("z_idx", {}).items():
+        assert _approx(z[i], v, tol)

@@ -19,6 +19,11 @@ SETS = {
     "hypoperlog": [M.HypoPerLog(d) for d in (3, 4, 7, 12, 34, 35, 80)],
     "epinorminf": [M.EpiNormInf(d) for d in (2, 3, 6, 33, 34, 70)],
     "epinorminf_dual": [M.EpiNormInf(4, use_dual=True), M.EpiNormInf(9), M.EpiNormInf(40, use_dual=True)],
+    "sepspec_vec": [M.EpiPerSepSpectralVec(2 + d, hk, hp) for d, hk, hp in
+                    ((1, M.SSF_NEGLOG, 0), (3, M.SSF_NEGENTROPY, 0), (6, M.SSF_INV, 0), (33, M.SSF_POWER12, 1.5),
+                     (40, M.SSF_NEGLOG, 0), (70, M.SSF_NEGENTROPY, 0))],
+    "sepspec_vec_dual": [M.EpiPerSepSpectralVec(6, M.SSF_NEGENTROPY, use_dual=True),
+                         M.EpiPerSepSpectralVec(9, M.SSF_INV), M.EpiPerSepSpectralVec(40, M.SSF_POWER12, 2.0, use_dual=True)],
     "hypoperlog_dual": [M.HypoPerLog(5, use_dual=True), M.HypoPerLog(9), M.HypoPerLog(40, use_dual=True)],
 }
 

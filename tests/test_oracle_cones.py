@@ -170,6 +170,14 @@ def test_epipersepspectral_matrix(side, hkind, hparam):
     run_oracles(EpiPerSepSpectralMat(2 + side * (side + 1) // 2, hkind, hparam), init_tol=np.inf)
 
 
+@pytest.mark.parametrize("d", [1, 2, 3, 6])
+@pytest.mark.parametrize("hkind,hparam", SSF)
+def test_epipersepspectral_vector(d, hkind, hparam):
+    # reference: test/cone.jl:672-676 with VectorCSqr
+    from oracle.cones_sepspec import EpiPerSepSpectralVec
+    run_oracles(EpiPerSepSpectralVec(2 + d, hkind, hparam), init_tol=np.inf)
+
+
 @pytest.mark.parametrize("hkind,hparam", SSF)
 def test_epipersepspectral_matrix_barrier(hkind, hparam):
     """test_barrier of test/cone.jl:117-160, :688-698 with central differences in place of ForwardDiff:
