@@ -211,35 +211,11 @@ dder3_combine_kernel(int type, int d, int lde, const double* __restrict__ sc, co
     (void)wivec;
     (void)len;
     if (threadIdx.x == 0) {
-        const double dd = (double)d;
-        double k6 = 0.0, k1 = 1.0, k8 = 0.0;
-        if (type == HYP_CONE_HYPOPERLOGDETTRI) {
-            const double phi = sc[1], zeta = sc[2], v = sc[4];
-            const double p = dir[0], q = dir[1];
-            const double sigma = phi - dd, viq = q / v, viq2 = viq * viq, vzi = v / zeta, vzi1 = vzi + 1.0;
-            const double c0 = trE, c7 = trE2;
-            const double zichi = (-p + sigma * q + c0 * v) / zeta;
-            const double c4 = (viq * (-viq * dd + 2 * c0) - c7) / zeta / 2;
-            const double c1 = (zichi * zichi - v * c4) / zeta;
-            const double c3 = -(zichi + viq) / zeta;
-            const double c5 = c3 * q + vzi * viq2;
-            const double c6 = -2 * vzi * viq - c3 * v;
-            const double c8 = c5 + c1 * v;
-            out[0] = -c1;
-            out[1] = c1 * sigma + (viq2 - (dd * c5 + c6 * c0 + vzi * c7)) / v - c4;
-            k6 = c6; k1 = vzi1; k8 = c8;
-        } else if (type == HYP_CONE_HYPOROOTDETTRI) {
-            const double phi = sc[1], zeta = sc[2], pzd = sc[5], di = 1.0 / dd;
-            const double p = dir[0];
-            const double c0 = trE * di, c6 = trE2 * di;
-            const double zichi = (p - phi * c0) / zeta;
-            const double c1 = zichi * zichi + phi / zeta * (c6 - c0 * c0) / 2;
-            const double c7 = pzd * (c1 - c6 / 2 + c0 * (zichi + c0 / 2));
-            const double c8 = -pzd * (zichi + c0);
-            const double c9 = pzd + 1.0;
-            out[0] = -c1 / zeta;
-            k6 = c8; k1 = c9; k8 = c7;
-        }
+        double k6 = 0.0, k1 = 1.0, k8 = 0.0, o0 = 0.0, o1 = 0.0;
+        hypdev::mat_dder3_coefs(type, d, sc, trE, trE2, dir[0], type == HYP_CONE_HYPOPERLOGDETTRI ? dir[1] : 0.0, o0, o1,
+                                k6, k1, k8);
+        if (type != HYP_CONE_POSSEMIDEFTRI) out[0] = o0;
+        if (type == HYP_CONE_HYPOPERLOGDETTRI) out[1] = o1;
         coef[0] = k6; coef[1] = k1; coef[2] = k8;
     }
     __syncthreads();
@@ -478,6 +454,28 @@ void hyp_mat_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr, i
 // dder3 for the matrix cones: E = U^-T R U^-1, E2 = E E, M = k6 E + k1 E2 + k8 I, result U^-1 M U^-T
 void hyp_mat_dder3(hyp_ctx* ctx, ConeGroup& g, double* out, const double* dir) {
     const int lead = lead_of(g.type);
+    {
+        // sides that fit in shared memory: one fused launch for the whole group
+        static int use_small = -1;
+        if (use_small < 0) {
+            const char* e = getenv("HYP_MAT_SMALL_MAXCOLS");
+            use_small = (e && atoi(e) == 0) ? 0 : 1;
+        }
+        const int64_t smem = (int64_t)2 * g.max_side * (g.max_side | 1) * sizeof(double);
+        if (use_small && g.count > 0 && smem <= 226 * 1024) {
+            static bool attr = false;
+            if (!attr) {
+                CUDA_TRY(cudaFuncSetAttribute(hypdev::mat_small_dder3_kernel,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+                attr = true;
+            }
+            hypdev::mat_small_dder3_kernel<<<g.count, 256, smem, ctx->stream>>>(
+                g.type, g.count, g.d_off, g.d_side, g.d_moff, g.d_Ui, g.d_Uit, g.d_scal, dir, out);
+            ctx->launches++;
+            CUDA_TRY(cudaGetLastError());
+            return;
+        }
+    }
     for (int i = 0; i < g.count; i++) {
         const int d = g.h_side[i], lde = (d + 1) & ~1;
         const int64_t len = (int64_t)d * (d + 1) / 2;

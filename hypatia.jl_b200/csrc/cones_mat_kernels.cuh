@@ -270,4 +270,118 @@ mat_small_prod_kernel(int type, int mode_in, int ncones, const int64_t* __restri
     }
 }
 
+// dder3 of the matrix cones (possemideftri.jl:197-207, hypoperlogdettri.jl:321-368, hyporootdettri.jl:285-324): with
+// E = U^-T R U^-1, tr E and tr E^2, the result is U^-1 (k6 E + k1 E^2 + k8 I) U^-T plus the leading entries (out0, out1).
+__device__ __forceinline__ void mat_dder3_coefs(int type, int d, const double* sc, double trE, double trE2, double p,
+                                                double q, double& out0, double& out1, double& k6, double& k1,
+                                                double& k8) {
+    const double dd = (double)d;
+    k6 = 0.0;
+    k1 = 1.0;
+    k8 = 0.0;
+    out0 = out1 = 0.0;
+    if (type == 3) {
+        const double phi = sc[1], zeta = sc[2], v = sc[4];
+        const double sigma = phi - dd, viq = q / v, viq2 = viq * viq, vzi = v / zeta, vzi1 = vzi + 1.0;
+        const double c0 = trE, c7 = trE2;
+        const double zichi = (-p + sigma * q + c0 * v) / zeta;
+        const double c4 = (viq * (-viq * dd + 2 * c0) - c7) / zeta / 2;
+        const double c1 = (zichi * zichi - v * c4) / zeta;
+        const double c3 = -(zichi + viq) / zeta;
+        const double c5 = c3 * q + vzi * viq2;
+        const double c6 = -2 * vzi * viq - c3 * v;
+        const double c8 = c5 + c1 * v;
+        out0 = -c1;
+        out1 = c1 * sigma + (viq2 - (dd * c5 + c6 * c0 + vzi * c7)) / v - c4;
+        k6 = c6;
+        k1 = vzi1;
+        k8 = c8;
+    } else if (type == 4) {
+        const double phi = sc[1], zeta = sc[2], pzd = sc[5], di = 1.0 / dd;
+        const double c0 = trE * di, c6 = trE2 * di;
+        const double zichi = (p - phi * c0) / zeta;
+        const double c1 = zichi * zichi + phi / zeta * (c6 - c0 * c0) / 2;
+        const double c7 = pzd * (c1 - c6 / 2 + c0 * (zichi + c0 / 2));
+        const double c8 = -pzd * (zichi + c0);
+        out0 = -c1 / zeta;
+        k6 = c8;
+        k1 = pzd + 1.0;
+        k8 = c7;
+    }
+}
+
+// Fused dder3 for a group of small matrix cones: CTA c does  R -> E = U^-T R U^-1 -> E^2 -> M = k6 E + k1 E^2 + k8 I
+// -> U^-1 M U^-T -> svec  on chip (two d x (d|1) buffers in shared memory); replaces 8 launches per cone.
+static __global__ void __launch_bounds__(256)
+mat_small_dder3_kernel(int type, int ncones, const int64_t* __restrict__ off, const int* __restrict__ sides,
+                       const int64_t* __restrict__ moff, const double* __restrict__ Ui,
+                       const double* __restrict__ Uit, const double* __restrict__ scal,
+                       const double* __restrict__ dir, double* __restrict__ out) {
+    HYP_DYN_SMEM(double, dyn);
+    __shared__ double red[8];
+    __shared__ double coef[3];
+    const int c = blockIdx.x;
+    if (c >= ncones) return;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int d = sides[c], lde = (d + 1) & ~1;
+    const int ldm = d | 1;
+    const int64_t len = (int64_t)d * (d + 1) / 2;
+    const int lead = type == 2 ? 0 : type == 3 ? 2 : 1;
+    const int64_t o = off[c], mo = moff[c];
+    const double* a = dir + o;
+    double* pr = out + o;
+    double* sA = dyn;
+    double* sB = dyn + (int64_t)d * ldm;
+    const double p = a[0], q = lead == 2 ? a[1] : 0.0;
+    for (int64_t idx = tid; idx < len; idx += nt) {
+        int r, s;
+        svec_rc(idx, r, s);
+        double x = a[lead + idx];
+        if (r != s) x *= HYP_IRT2;
+        sA[r + s * ldm] = x;
+        sA[s + r * ldm] = x;
+    }
+    __syncthreads();
+    small_gemm_mx(d, ldm, sA, Ui + mo, lde, sB);                       // T = R U^-1
+    __syncthreads();
+    small_gemm_xtt(d, ldm, Ui + mo, lde, sB, [&](int r, int s2, double x) {   // E = U^-T T -> sA, both triangles
+        sA[r + s2 * ldm] = x;
+        sA[s2 + r * ldm] = x;
+    });
+    __syncthreads();
+    small_gemm_mx(d, ldm, sA, sA, ldm, sB);                            // E^2 -> sB
+    __syncthreads();
+    double t0 = 0.0, t7 = 0.0;
+    for (int k = tid; k < d; k += nt) {
+        t0 += sA[k + k * ldm];
+        t7 += sB[k + k * ldm];
+    }
+    const double trE = block_sum(t0, red);
+    const double trE2 = block_sum(t7, red);
+    if (tid == 0) {
+        double o0, o1, k6, k1, k8;
+        mat_dder3_coefs(type, d, scal + 8 * c, trE, trE2, p, q, o0, o1, k6, k1, k8);
+        coef[0] = k6;
+        coef[1] = k1;
+        coef[2] = k8;
+        if (lead >= 1) pr[0] = o0;
+        if (lead == 2) pr[1] = o1;
+    }
+    __syncthreads();
+    const double k6 = coef[0], k1 = coef[1], k8 = coef[2];
+    for (int idx = tid; idx < d * d; idx += nt) {
+        const int r = idx % d, s = idx / d;
+        double x = k6 * sA[r + s * ldm] + k1 * sB[r + s * ldm];
+        if (r == s) x += k8;
+        sB[r + s * ldm] = x;                                           // M
+    }
+    __syncthreads();
+    small_gemm_mx(d, ldm, sB, Uit + mo, lde, sA);                      // T = M U^-T
+    __syncthreads();
+    small_gemm_xtt(d, ldm, Uit + mo, lde, sA, [&](int r, int s2, double x) {  // U^-1 T
+        if (r != s2) x *= HYP_RT2;
+        pr[lead + (int64_t)s2 * (s2 + 1) / 2 + r] = x;
+    });
+}
+
 }  // namespace hypdev

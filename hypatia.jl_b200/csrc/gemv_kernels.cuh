@@ -32,20 +32,24 @@ gemv_nt_kernel(int64_t rows, int64_t ncols, const double* __restrict__ M, int64_
     int64_t j = j0;
     for (; j + 7 < j1; j += 8) {
         double t[8];
+        double2 mm[8];
+        if (ok1) {
+            // all eight 16-byte loads are issued before the first use
+#pragma unroll
+            for (int u = 0; u < 8; u++) mm[u] = __ldg(reinterpret_cast<const double2*>(base + (j + u) * ld));
+        } else {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                mm[u].x = ok0 ? base[(j + u) * ld] : 0.0;
+                mm[u].y = 0.0;
+            }
+        }
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-            double m0 = 0.0, m1 = 0.0;
-            if (ok1) {
-                const double2 m = *reinterpret_cast<const double2*>(base + (j + u) * ld);
-                m0 = m.x;
-                m1 = m.y;
-            } else if (ok0) {
-                m0 = base[(j + u) * ld];
-            }
             const double xj = x[j + u];
-            ax += m0 * xj;
-            ay += m1 * xj;
-            t[u] = m0 * z0 + m1 * z1;
+            ax += mm[u].x * xj;
+            ay += mm[u].y * xj;
+            t[u] = mm[u].x * z0 + mm[u].y * z1;
         }
         // halving butterfly: after the three steps lane L holds the partial sum of column
         // c = 4 * bit4(L) + 2 * bit3(L) + bit2(L) over the 8 lanes that share those bits

@@ -50,6 +50,11 @@ extern dim3 gridDim;
 #define HYP_DYN_SMEM(type, name) type* name = (type*)emu::g_dyn_smem
 #define INFINITY_EMU INFINITY
 
+template <class T>
+static inline T __ldg(const T* p) {
+    return *p;
+}
+
 static inline void __syncthreads() { pthread_barrier_wait(&emu::g_block->bar); }
 
 static inline double emu_shfl(double v, int src_lane_abs) {

@@ -183,3 +183,17 @@ int emu_gemv_nt(int64_t rows, int64_t ncols, const double* M, int64_t ld, const 
 }
 
 }  // extern "C"
+
+extern "C" {
+
+int emu_mat_small_dder3(int type, int ncones, int max_side, const int64_t* off, const int* sides, const int64_t* moff,
+                        const double* Ui, const double* Uit, const double* scal, const double* dir, double* out,
+                        int threads) {
+    const size_t smem = (size_t)2 * max_side * (max_side | 1) * sizeof(double);
+    emu::launch(dim3(ncones), dim3(threads), smem, [&] {
+        hypdev::mat_small_dder3_kernel(type, ncones, off, sides, moff, Ui, Uit, scal, dir, out);
+    });
+    return 0;
+}
+
+}  // extern "C"

@@ -250,7 +250,7 @@ class EmuMatGroup:
         self.dualf = np.array([1 if s.use_dual else 0 for s in specs], dtype=np.int32)
         lead = {2: 0, 3: 2, 4: 1}[self.type]
         lay = self.lay
-        self.W, self.Wi, self.Ui, self.Ut = (np.zeros(lay.total) for _ in range(4))
+        self.W, self.Wi, self.Ui, self.Ut, self.Uit = (np.zeros(lay.total) for _ in range(5))
         self.scal = np.zeros(8 * self.K)
         self.wivec = np.zeros(self.q)
         self.point = np.ascontiguousarray(point, dtype=np.float64)
@@ -263,12 +263,21 @@ class EmuMatGroup:
             lay.get(self.Wi, c)[:] = np.linalg.inv(Wm)
             lay.get(self.Ui, c)[:] = np.linalg.inv(U)
             lay.get(self.Ut, c)[:] = U.T
+            lay.get(self.Uit, c)[:] = np.linalg.inv(U).T
             o = int(self.off[c])
             self.wivec[o + lead:o + self.dims[c]] = au.smat_to_svec(np.linalg.inv(Wm))
             if self.type == 3:
                 self.scal[8 * c + 1], self.scal[8 * c + 2], self.scal[8 * c + 4] = ck.phi, ck.zeta, ck.point[1]
             elif self.type == 4:
                 self.scal[8 * c + 1], self.scal[8 * c + 2], self.scal[8 * c + 5] = ck.phi, ck.zeta, ck.pzd
+
+    def dder3(self, direction, threads=64):
+        d = np.ascontiguousarray(direction, dtype=np.float64)
+        out = np.zeros(self.q)
+        lay = self.lay
+        lib().emu_mat_small_dder3(self.type, self.K, int(lay.sides.max()), p(self.off), p(lay.sides), p(lay.moff),
+                                  p(self.Ui), p(self.Uit), p(self.scal), p(d), p(out), threads)
+        return out
 
     def prod(self, arr, mode, threads=64, in_place=False):
         a = np.asfortranarray(np.asarray(arr, dtype=np.float64).reshape(self.q, -1, order="F")).copy(order="F")

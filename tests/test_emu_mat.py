@@ -1,4 +1,4 @@
-"""CPU-tier check of the fused small-matrix product kernel of the matrix cones (mat_small_prod_kernel,
+"""CPU-tier check of the fused small-matrix kernels of the matrix cones (mat_small_prod_kernel, mat_small_dder3_kernel,
 csrc/cones_mat_kernels.cuh, compiled for the host by tests/emu/) against the CPU oracle."""
 import numpy as np
 import pytest
@@ -39,6 +39,7 @@ def test_small_prod_kernel_matches_oracle(name):
     assert rel(dev.prod(arr, 1), ora.inv_hess_prod(arr)) <= 1e-12
     assert rel(dev.prod(arr, 4), ora.block_hess_prod(arr)) <= 1e-12
     assert rel(dev.prod(arr[:, 0], 0, in_place=True), ora.hess_prod(arr[:, 0])) <= 1e-12
+    assert rel(dev.dder3(arr[:, 1]), ora.dder3(arr[:, 1])) <= 1e-12
     if name == "psd":
         assert rel(dev.prod(arr, 2), ora.sqrt_hess_prod(arr)) <= 1e-12
         assert rel(dev.prod(arr, 3), ora.inv_sqrt_hess_prod(arr)) <= 1e-12
