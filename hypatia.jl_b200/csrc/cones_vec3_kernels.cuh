@@ -16,6 +16,7 @@
 #define V3_EPIPERSQUARE 6   // = HYP_CONE_EPIPERSQUARE
 #define V3_HYPOPERLOG 7     // = HYP_CONE_HYPOPERLOG
 #define V3_EPINORMINF 8     // = HYP_CONE_EPINORMINF
+#define V3_HYPOGEOMEAN 10   // = HYP_CONE_HYPOGEOMEAN (hypogeomean.jl; one leading scalar; scal: 1 phi, 2 zeta, 5 phi / zeta / d)
 #define V3_SEPSPEC_VEC 9    // = HYP_CONE_EPIPERSEPSPECTRAL_VEC (vectorcsqr.jl; scal: 0 phi, 1 zeta, 2 sigma, 3 c0, 4 c4, 5 c5)
 // product modes (= HYP_PROD_*)
 #define V3_HESS 0
@@ -37,7 +38,35 @@ v3_state_kernel(int type, int ncones, const int64_t* __restrict__ off, const int
     const int64_t o = off[c];
     const int d = dim[c];
     const double u = point[o], v = point[o + 1], du = dual[o], dv = dual[o + 1];
-    if (type == V3_SEPSPEC_VEC) {
+    if (type == V3_HYPOGEOMEAN) {
+        // hypogeomean.jl:69-110
+        const int dw = d - 1;
+        double nbad = 0.0, dbad = 0.0, sl = 0.0, dsl = 0.0;
+        for (int i = 1 + lane; i < d; i += 32) {
+            const double w = point[o + i], zd = dual[o + i];
+            if (!(w > HYP_EPS)) nbad += 1.0;
+            if (!(zd > HYP_EPS)) dbad += 1.0;
+            sl += log(w);
+            dsl += log(zd);
+        }
+        nbad = warp_sum(nbad);
+        dbad = warp_sum(dbad);
+        sl = warp_sum(sl);
+        dsl = warp_sum(dsl);
+        const double phi = exp(sl / dw), zeta = phi - u;
+        const bool ok = nbad == 0.0 && zeta > HYP_EPS;
+        const bool dok = du < -HYP_EPS && dbad == 0.0 && (dw * exp(dsl / dw) + du) > HYP_EPS;
+        const double pzd = phi / zeta / dw;
+        for (int i = 1 + lane; i < d; i += 32) grad[o + i] = (-pzd - 1.0) / point[o + i];
+        if (lane == 0) {
+            grad[o] = 1.0 / zeta;
+            scal[8 * c + 1] = phi;
+            scal[8 * c + 2] = zeta;
+            scal[8 * c + 5] = pzd;
+            if (!ok) feas[kidx[c]] = 0;
+            if (!dok) dual_feas[kidx[c]] = 0;
+        }
+    } else if (type == V3_SEPSPEC_VEC) {
         // vectorcsqr.jl:61-114 (feas, dual feas, grad), :216-246 (inverse-Hessian scalars)
         const int kind = hkind[c];
         const double hp = hparam[c];
@@ -213,7 +242,36 @@ v3_prod_kernel(int type, int mode_in, int ncones, const int64_t* __restrict__ of
         const double* a = arr + j * ld_arr + (o - row_shift);
         double* pr = prod + j * ld_prod + (o - row_shift);
         const double p = a[0], q = a[1];
-        if (type == V3_SEPSPEC_VEC) {
+        if (type == V3_HYPOGEOMEAN) {
+            const double phi = scal[8 * c + 1], zeta = scal[8 * c + 2], pzd = scal[8 * c + 5];
+            const double di = 1.0 / (double)(d - 1);
+            if (mode == V3_HESS) {
+                // hypogeomean.jl:141-167
+                double sr = 0.0;
+                for (int i = 1 + lane; i < d; i += 32) sr += a[i] / point[o + i];
+                const double c0 = pzd * warp_sum(sr);
+                const double c1 = c0 - p / zeta;
+                const double c2 = pzd * c1 - di * c0;
+                for (int i = 1 + lane; i < d; i += 32) {
+                    const double w = point[o + i];
+                    pr[i] = (c2 + (pzd + 1.0) * (a[i] / w)) / w;
+                }
+                if (lane == 0) pr[0] = c1 / -zeta;
+            } else {
+                // hypogeomean.jl:202-230
+                const double phidi = phi * di, c2 = 1.0 / (pzd + 1.0), c3 = c2 / zeta * di;
+                const double c4 = zeta * zeta + phidi * phi;
+                double sr = 0.0;
+                for (int i = 1 + lane; i < d; i += 32) sr += a[i] * point[o + i];
+                const double c5 = warp_sum(sr);
+                const double c6 = phidi * (c3 * c5 + p);
+                for (int i = 1 + lane; i < d; i += 32) {
+                    const double w = point[o + i];
+                    pr[i] = (c6 + c2 * (a[i] * w)) * w;
+                }
+                if (lane == 0) pr[0] = phidi * c5 + c4 * p;
+            }
+        } else if (type == V3_SEPSPEC_VEC) {
             const int kind = hkind[c];
             const double hp = hparam[c];
             const double* sc = scal + 8 * c;
@@ -392,7 +450,27 @@ v3_dder3_kernel(int type, int ncones, const int64_t* __restrict__ off, const int
     const int64_t o = off[c];
     const int d = dim[c];
     const double u = point[o], v = point[o + 1], p = dir[o], q = dir[o + 1];
-    if (type == V3_SEPSPEC_VEC) {
+    if (type == V3_HYPOGEOMEAN) {
+        // hypogeomean.jl:232-257
+        const double phi = scal[8 * c + 1], zeta = scal[8 * c + 2], pzd = scal[8 * c + 5];
+        const double di = 1.0 / (double)(d - 1);
+        double s0 = 0.0, s6 = 0.0;
+        for (int i = 1 + lane; i < d; i += 32) {
+            const double r = dir[o + i] / point[o + i];
+            s0 += r;
+            s6 += r * r;
+        }
+        const double c0 = warp_sum(s0) * di, c6 = warp_sum(s6) * di;
+        const double zichi = (p - phi * c0) / zeta;
+        const double c1 = zichi * zichi + phi / zeta * (c6 - c0 * c0) / 2;
+        const double c7 = pzd * (c1 - c6 / 2 + c0 * (zichi + c0 / 2));
+        const double c8 = -pzd * (zichi + c0), c9 = pzd + 1.0;
+        for (int i = 1 + lane; i < d; i += 32) {
+            const double w = point[o + i], r = dir[o + i] / w;
+            out[o + i] = (c7 + r * (c8 + c9 * r)) / w;
+        }
+        if (lane == 0) out[o] = c1 / -zeta;
+    } else if (type == V3_SEPSPEC_VEC) {
         // vectorcsqr.jl:314-357
         const int kind = hkind[c];
         const double hp = hparam[c];

@@ -918,8 +918,9 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
                                 : t == HYP_CONE_HYPOROOTDETTRI ? 1.0 + side
                                 : t == HYP_CONE_EPIPERSEPSPECTRAL_MAT ? 2.0 + side
                                 : t == HYP_CONE_EPIPERSQUARE ? 2.0
-                                                             : (double)d;   // HypoPerLog, EpiNormInf: nu = dim
-            if (t == HYP_CONE_EPINORMINF && d < 2) throw HypError{"hyp_load_model: EpiNormInf needs dimension >= 2"};
+                                                             : (double)d;   // HypoPerLog, EpiNormInf, EpiPerSepSpectral{VectorCSqr}, HypoGeoMean: nu = dim
+            if ((t == HYP_CONE_EPINORMINF || t == HYP_CONE_HYPOGEOMEAN) && d < 2)
+                throw HypError{"hyp_load_model: EpiNormInf / HypoGeoMean need dimension >= 2"};
             if ((t == HYP_CONE_EPIPERSQUARE || t == HYP_CONE_HYPOPERLOG || t == HYP_CONE_EPIPERSEPSPECTRAL_MAT ||
                  t == HYP_CONE_EPIPERSEPSPECTRAL_VEC) && d < 3)
                 throw HypError{"hyp_load_model: this cone type needs dimension >= 3"};

@@ -106,6 +106,11 @@ def cone_initial_point(spec):
         arr[2:] = w
     elif spec.ctype == M.CONE_EPINORMINF:
         arr[0] = np.sqrt(spec.dim)      # epinorminf.jl:88-95
+    elif spec.ctype == M.CONE_HYPOGEOMEAN:
+        d = spec.dim - 1                  # hypogeomean.jl:259-264
+        c = np.sqrt(5.0 * d * d + 2 * d + 1)
+        arr[0] = -np.sqrt((-c + 3 * d + 1) / (2.0 + 2 * d))
+        arr[1:] = (c - d + 1) / np.sqrt((1 + d) * (-2 * c + 6 * d + 2))
     elif spec.ctype == M.CONE_EPIPERSEPSPECTRAL_VEC:
         u, v, w = ssf_initial_point(spec.hkind, spec.dim - 2)   # vectorcsqr.jl:52-59
         arr[0], arr[1] = u, v
@@ -121,6 +126,15 @@ def _cone_dual_initial(spec, prim):
         return prim.copy()      # central point is self-dual: -g = (u, -w)/dist with dist = 1
     if spec.ctype == M.CONE_POSSEMIDEFTRI:
         return prim.copy()
+    if spec.ctype == M.CONE_HYPOGEOMEAN:
+        # hypogeomean.jl:97-110 at w = w0 * 1: phi = w0
+        d = spec.dim - 1
+        u, w = prim[0], prim[1]
+        zeta = w - u
+        out = np.zeros_like(prim)
+        out[0] = -1.0 / zeta
+        out[1:] = (w / zeta / d + 1) / w
+        return out
     if spec.ctype == M.CONE_EPIPERSEPSPECTRAL_VEC:
         # vectorcsqr.jl:97-114 at w = w0 * 1
         d = spec.dim - 2
@@ -187,6 +201,10 @@ def _perturb(rng, spec, vec, noise):
         return vec
     if spec.ctype == M.CONE_EPIPERSEPSPECTRAL_VEC:
         vec += noise / (2.0 * (vec.size - 2)) * (2 * rng.random(vec.size) - 1)   # the initial point is not central
+        return vec
+    if spec.ctype == M.CONE_HYPOGEOMEAN:
+        vec[0] += 0.5 * noise * (2 * rng.random() - 1)
+        vec[1:] += noise / np.sqrt(vec.size) * (2 * rng.random(vec.size - 1) - 1)
         return vec
     if spec.ctype == M.CONE_EPINORMINF:
         vec[0] += 0.5 * noise * (2 * rng.random() - 1)

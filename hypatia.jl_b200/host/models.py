@@ -22,6 +22,7 @@ CONE_EPIPERSQUARE = 6
 CONE_HYPOPERLOG = 7
 CONE_EPINORMINF = 8
 CONE_EPIPERSEPSPECTRAL_VEC = 9
+CONE_HYPOGEOMEAN = 10
 
 # separable spectral functions of EpiPerSepSpectral (sepspectralfun.jl:17-116), HYP_SSF_*
 SSF_INV, SSF_NEGLOG, SSF_NEGENTROPY, SSF_POWER12 = 0, 1, 2, 3
@@ -37,6 +38,7 @@ CONE_NAMES = {
     CONE_HYPOPERLOG: "HypoPerLog",
     CONE_EPINORMINF: "EpiNormInf",
     CONE_EPIPERSEPSPECTRAL_VEC: "EpiPerSepSpectral{VectorCSqr}",
+    CONE_HYPOGEOMEAN: "HypoGeoMean",
 }
 
 
@@ -89,7 +91,7 @@ class ConeSpec:
             assert dim >= 3
         elif ctype == CONE_HYPOPERLOG:
             assert dim >= 3
-        elif ctype == CONE_EPINORMINF:
+        elif ctype in (CONE_EPINORMINF, CONE_HYPOGEOMEAN):
             assert dim >= 2
         elif ctype == CONE_EPIPERSEPSPECTRAL_VEC:
             assert dim >= 3 and hkind in (SSF_INV, SSF_NEGLOG, SSF_NEGENTROPY, SSF_POWER12)
@@ -122,7 +124,7 @@ class ConeSpec:
             return 2.0 + self.side
         if self.ctype == CONE_EPIPERSQUARE:
             return 2.0
-        if self.ctype in (CONE_HYPOPERLOG, CONE_EPINORMINF, CONE_EPIPERSEPSPECTRAL_VEC):
+        if self.ctype in (CONE_HYPOPERLOG, CONE_EPINORMINF, CONE_EPIPERSEPSPECTRAL_VEC, CONE_HYPOGEOMEAN):
             return float(self.dim)
         return 1.0 + self.side
 
@@ -170,6 +172,10 @@ def EpiPerSquare(dim, use_dual=False):
 
 def HypoPerLog(dim, use_dual=False):
     return ConeSpec(CONE_HYPOPERLOG, dim, use_dual)
+
+
+def HypoGeoMean(dim, use_dual=False):
+    return ConeSpec(CONE_HYPOGEOMEAN, dim, use_dual)
 
 
 def EpiNormInf(dim, use_dual=False):

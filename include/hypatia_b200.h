@@ -47,6 +47,7 @@ typedef struct hyp_ctx hyp_ctx;
 #define HYP_CONE_HYPOPERLOG 7       /* hypoperlog.jl       */
 #define HYP_CONE_EPINORMINF 8       /* epinorminf.jl (real); use_dual = 1: l1-norm epigraph */
 #define HYP_CONE_EPIPERSEPSPECTRAL_VEC 9 /* epipersepspectral/{epipersepspectral,vectorcsqr}.jl */
+#define HYP_CONE_HYPOGEOMEAN 10     /* hypogeomean.jl      */
 
 /* separable spectral functions of EpiPerSepSpectral (epipersepspectral/sepspectralfun.jl:17-116) */
 #define HYP_SSF_INV 0        /* InvSSF        x -> 1/x      */

@@ -40,6 +40,7 @@ cone_code(::Cones.EpiPerSquare) = Cint(6)
 cone_code(::Cones.HypoPerLog) = Cint(7)
 cone_code(::Cones.EpiNormInf{Float64, Float64}) = Cint(8)
 cone_code(::Cones.EpiPerSepSpectral{Cones.VectorCSqr{Float64}, Float64}) = Cint(9)
+cone_code(::Cones.HypoGeoMean) = Cint(10)
 cone_code(c::Cones.Cone) = error("cone $(typeof(c)) is not on the B200 hot path")
 
 # HYP_SSF_* code and parameter of the `h` field of EpiPerSepSpectral (sepspectralfun.jl:17-116)

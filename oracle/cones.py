@@ -760,10 +760,10 @@ def make_cone(spec):
     if spec.ctype == M.CONE_EPIPERSEPSPECTRAL_VEC:
         from .cones_sepspec import EpiPerSepSpectralVec
         return EpiPerSepSpectralVec(spec.dim, spec.hkind, spec.hparam, use_dual=spec.use_dual)
-    if spec.ctype in (M.CONE_EPIPERSQUARE, M.CONE_HYPOPERLOG, M.CONE_EPINORMINF):
+    if spec.ctype in (M.CONE_EPIPERSQUARE, M.CONE_HYPOPERLOG, M.CONE_EPINORMINF, M.CONE_HYPOGEOMEAN):
         from . import cones_vec3
         cls = {M.CONE_EPIPERSQUARE: cones_vec3.EpiPerSquare, M.CONE_HYPOPERLOG: cones_vec3.HypoPerLog,
-               M.CONE_EPINORMINF: cones_vec3.EpiNormInf}[spec.ctype]
+               M.CONE_EPINORMINF: cones_vec3.EpiNormInf, M.CONE_HYPOGEOMEAN: cones_vec3.HypoGeoMean}[spec.ctype]
         return cls(spec.dim, use_dual=spec.use_dual)
     cls = _CLASSES[spec.ctype]
     if spec.ctype in (M.CONE_HYPOPERLOGDETTRI, M.CONE_HYPOROOTDETTRI):

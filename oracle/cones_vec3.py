@@ -401,3 +401,120 @@ class EpiNormInf(Cone):
         d3[0] += float((d * (2 * uuw + uimim2) / deni).sum())
         d3[1:] = (udir * (uuw + 2 * uimim2) + d * wdeni * (2 + uimim) * d) / deni
         return d3
+
+
+class HypoGeoMean(Cone):
+    """hypogeomean.jl:8-264: (u, w), w in R^d_++, u <= geomean(w); barrier
+    -log(prod(w_i)^(1/d) - u) - sum log w_i, nu = dim."""
+    ctype = M.CONE_HYPOGEOMEAN
+
+    def __init__(self, dim, use_dual=False):
+        self.use_dual_barrier = use_dual
+        self.d = dim - 1
+        self.di = 1.0 / self.d
+        super().__init__(dim)
+
+    @property
+    def nu(self):
+        return float(self.dim)
+
+    def set_initial_point(self, arr):
+        d = self.d
+        c = np.sqrt(5.0 * d * d + 2 * d + 1)
+        arr[0] = -np.sqrt((-c + 3 * d + 1) / (2.0 + 2 * d))
+        arr[1:] = (c - d + 1) / np.sqrt((1 + d) * (-2 * c + 6 * d + 2))
+        return arr
+
+    def update_feas(self):
+        u, w = self.point[0], self.point[1:]
+        if (w > EPS).all():
+            self.phi = float(np.exp(self.di * np.sum(np.log(w))))
+            self.zeta = self.phi - u
+            return self.zeta > EPS
+        return False
+
+    def is_dual_feas(self):
+        u, w = self.dual_point[0], self.dual_point[1:]
+        if u < -EPS and (w > EPS).all():
+            return bool(w.size * np.exp(self.di * np.sum(np.log(w))) + u > EPS)
+        return False
+
+    def update_grad(self):
+        w = self.point[1:]
+        self.pzd = self.phi / self.zeta * self.di
+        self._grad[0] = 1.0 / self.zeta
+        self._grad[1:] = (-self.pzd - 1) / w
+
+    def update_hess(self):
+        self.grad()
+        w, zeta, pzd = self.point[1:], self.zeta, self.pzd
+        c4 = pzd - self.di
+        c1 = pzd * (1 + c4) + 1
+        H = np.zeros((self.dim, self.dim))
+        H[0, 0] = zeta ** -2
+        H[0, 1:] = H[1:, 0] = -(pzd / w) / zeta
+        wi = 1.0 / w
+        H[1:, 1:] = pzd * c4 * np.outer(wi, wi)
+        idx = np.arange(1, self.dim)
+        H[idx, idx] = c1 * wi * wi
+        return H
+
+    def hess_prod(self, arr):
+        self.grad()
+        a, vec = _as2d(arr)
+        w, zeta, pzd, di = self.point[1:], self.zeta, self.pzd, self.di
+        p = a[0]
+        rwi = a[1:] / w[:, None]
+        c0 = pzd * rwi.sum(axis=0)
+        c1 = c0 - p / zeta
+        c2 = pzd * c1 - di * c0
+        prod = np.empty_like(a)
+        prod[0] = c1 / -zeta
+        prod[1:] = (c2[None, :] + (pzd + 1) * rwi) / w[:, None]
+        return _ret(prod, vec)
+
+    def update_inv_hess(self):
+        self.grad()
+        w, zeta, phi, di = self.point[1:], self.zeta, self.phi, self.di
+        phidi = phi * di
+        c2 = 1.0 / (self.pzd + 1)
+        c3 = c2 / zeta * di
+        Hi = np.zeros((self.dim, self.dim))
+        Hi[0, 0] = zeta ** 2 + phidi * phi
+        Hi[0, 1:] = Hi[1:, 0] = phidi * w
+        Hi[1:, 1:] = c3 * phidi * np.outer(w, w) + np.diag(c2 * w * w)
+        return Hi
+
+    def inv_hess_prod(self, arr):
+        self.grad()
+        a, vec = _as2d(arr)
+        w, zeta, phi, di = self.point[1:], self.zeta, self.phi, self.di
+        phidi = phi * di
+        c2 = 1.0 / (self.pzd + 1)
+        c3 = c2 / zeta * di
+        c4 = zeta ** 2 + phidi * phi
+        p = a[0]
+        rw = a[1:] * w[:, None]
+        c5 = rw.sum(axis=0)
+        c6 = phidi * (c3 * c5 + p)
+        prod = np.empty_like(a)
+        prod[0] = phidi * c5 + c4 * p
+        prod[1:] = (c6[None, :] + c2 * rw) * w[:, None]
+        return _ret(prod, vec)
+
+    def dder3(self, direction):
+        self.grad()
+        w, zeta, phi, di, pzd = self.point[1:], self.zeta, self.phi, self.di, self.pzd
+        p, r = direction[0], direction[1:]
+        rwi = r / w
+        c0 = float(rwi.sum()) * di
+        c6 = float((rwi ** 2).sum()) * di
+        zichi = (p - phi * c0) / zeta
+        c1 = zichi ** 2 + phi / zeta * (c6 - c0 ** 2) / 2
+        c7 = pzd * (c1 - c6 / 2 + c0 * (zichi + c0 / 2))
+        c8 = -pzd * (zichi + c0)
+        c9 = pzd + 1
+        d3 = np.empty(self.dim)
+        d3[0] = c1 / -zeta
+        d3[1:] = (c7 + rwi * (c8 + c9 * rwi)) / w
+        return d3

@@ -230,6 +230,54 @@ def dualinfeas1():  # :209-221
         dict(status="DualInfeasible")
 
 
+def hypogeomean1():  # :1460-1476 (primal barrier)
+    return _m([-1, 0, 0], [[0, 0, 1], [0, 1, 0]], [0.5, 1], -np.eye(3), np.zeros(3), [M.HypoGeoMean(3)]), \
+        dict(status="Optimal", primal_obj=-1 / RT2, x_idx={1: 1.0, 2: 0.5})
+
+
+def hypogeomean1_dual():  # :1460-1476 (dual barrier)
+    return _m([-1, 0, 0], [[0, 0, 1], [0, 1, 0]], [0.5, 1], -np.eye(3), np.zeros(3),
+              [M.HypoGeoMean(3, use_dual=True)]), dict(status="Optimal", primal_obj=0, x_idx={1: 1.0, 2: 0.5})
+
+
+def hypogeomean2():  # :1478-1496 (primal barrier)
+    l = 4
+    A = np.zeros((1, l + 1))
+    A[0, 0] = 1
+    return _m(np.concatenate(([0.0], np.ones(l))), A, [1], -np.eye(l + 1), np.zeros(l + 1), [M.HypoGeoMean(l + 1)]), \
+        dict(status="Optimal", primal_obj=l, x_idx={i: 1.0 for i in range(1, l + 1)})
+
+
+def hypogeomean2_dual():  # :1478-1496 (dual barrier)
+    l = 4
+    A = np.zeros((1, l + 1))
+    A[0, 0] = 1
+    return _m(np.concatenate(([0.0], np.ones(l))), A, [-1], -np.eye(l + 1), np.zeros(l + 1),
+              [M.HypoGeoMean(l + 1, use_dual=True)]), \
+        dict(status="Optimal", primal_obj=1, x_idx={i: 1.0 / l for i in range(1, l + 1)})
+
+
+def hypogeomean4():  # :1517-1532
+    G = np.vstack((-np.eye(4), [[0, 1, 1, 1]]))
+    return _m([-1, 0, 0, 0], None, None, G, [0, 0, 0, 0, 3], [M.HypoGeoMean(4), M.Nonnegative(1)]), \
+        dict(status="Optimal", primal_obj=-1, x=[1, 1, 1, 1], s=[1, 1, 1, 1, 0], z=[-1, 1 / 3, 1 / 3, 1 / 3, 1 / 3])
+
+
+def hypogeomean5():  # :1534-1549
+    G = _sparse([1, 2, 3], [1, 2, 2], [-1, -1, 1], 3, 2)
+    return _m([-2, 0], None, None, G, [0, 0, 2], [M.HypoGeoMean(2), M.Nonnegative(1)]), \
+        dict(status="Optimal", primal_obj=-4, x=[2, 2], s=[2, 2, 0], z=[-2, 2, 2])
+
+
+def hypogeomean6():  # :1551-1567
+    c = np.zeros(10)
+    c[0] = -1
+    A = np.hstack((np.zeros((9, 1)), np.eye(9)))
+    return _m(c, A, np.ones(9), -np.eye(10), np.zeros(10), [M.HypoGeoMean(10)]), \
+        dict(status="Optimal", primal_obj=-1, x=np.ones(10), z=np.concatenate(([-1.0], np.full(9, 1 / 9))),
+             y=np.full(9, 1 / 9))
+
+
 def hypoperlog1():  # :1677-1693
     e = np.exp(0.5)
     return _m([1, 1, 1], [[0, 1, 0], [1, 0, 0]], [2, 1], -np.eye(3), np.zeros(3), [M.HypoPerLog(3)]), \
@@ -394,7 +442,8 @@ for _k, (_hk, _hp) in enumerate(SEP_SPECTRAL_FUNS):
     SPECTRAL_VEC.append(_named(lambda hk=_hk, hp=_hp: _spectral_vector3(hk, hp), f"epipersepspectral_vector3_h{_hk}"))
     SPECTRAL_VEC.append(_named(lambda hk=_hk, hp=_hp: _spectral_vector4(hk, hp), f"epipersepspectral_vector4_h{_hk}"))
 
-NEW_CONES = [epinorminf1, epinorminf2, epinorminf3, epinorminf3_dual, epinorminf4, dualinfeas1,
+NEW_CONES = [hypogeomean1, hypogeomean1_dual, hypogeomean2, hypogeomean2_dual, hypogeomean4, hypogeomean5,
+             hypogeomean6, epinorminf1, epinorminf2, epinorminf3, epinorminf3_dual, epinorminf4, dualinfeas1,
              primalinfeas3, dualinfeas2, dualinfeas3, epipersquare1, epipersquare2, epipersquare3,
              epipersquare4, hypoperlog1, hypoperlog2, hypoperlog3, hypoperlog4, hypoperlog5, hypoperlog6,
              hypoperlog7]

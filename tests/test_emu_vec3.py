@@ -24,6 +24,8 @@ SETS = {
                      (40, M.SSF_NEGLOG, 0), (70, M.SSF_NEGENTROPY, 0))],
     "sepspec_vec_dual": [M.EpiPerSepSpectralVec(6, M.SSF_NEGENTROPY, use_dual=True),
                          M.EpiPerSepSpectralVec(9, M.SSF_INV), M.EpiPerSepSpectralVec(40, M.SSF_POWER12, 2.0, use_dual=True)],
+    "hypogeomean": [M.HypoGeoMean(d) for d in (2, 3, 6, 33, 34, 70)],
+    "hypogeomean_dual": [M.HypoGeoMean(4, use_dual=True), M.HypoGeoMean(9), M.HypoGeoMean(40, use_dual=True)],
     "hypoperlog_dual": [M.HypoPerLog(5, use_dual=True), M.HypoPerLog(9), M.HypoPerLog(40, use_dual=True)],
 }
 

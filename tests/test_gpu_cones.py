@@ -46,11 +46,13 @@ CONE_SETS = {
     "sepspec_vec": [M.EpiPerSepSpectralVec(3, M.SSF_NEGLOG), M.EpiPerSepSpectralVec(8, M.SSF_NEGENTROPY),
                     M.EpiPerSepSpectralVec(35, M.SSF_INV), M.EpiPerSepSpectralVec(72, M.SSF_POWER12, 1.5),
                     M.EpiPerSepSpectralVec(7, M.SSF_NEGENTROPY, use_dual=True)],
+    "hypogeomean": [M.HypoGeoMean(2), M.HypoGeoMean(6), M.HypoGeoMean(34), M.HypoGeoMean(70),
+                    M.HypoGeoMean(9, use_dual=True)],
     "allmix": [M.Nonnegative(5), M.EpiNormEucl(4), M.PosSemidefTri(6), M.HypoPerLogdetTri(8),
                M.HypoRootdetTri(7), M.EpiNormEucl(3), M.HypoPerLogdetTri(5, use_dual=True),
                M.EpiPerSepSpectralMat(2 + M.svec_length(4), M.SSF_NEGENTROPY), M.EpiPerSquare(6),
                M.HypoPerLog(5), M.HypoPerLog(4, use_dual=True), M.EpiNormInf(5), M.EpiNormInf(4, use_dual=True),
-               M.EpiPerSepSpectralVec(6, M.SSF_NEGENTROPY)],
+               M.EpiPerSepSpectralVec(6, M.SSF_NEGENTROPY), M.HypoGeoMean(5), M.HypoGeoMean(4, use_dual=True)],
 }
 
 

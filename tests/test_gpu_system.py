@@ -132,7 +132,8 @@ def test_spectral_and_perspective_cones(p):
              M.HypoPerLog(5, use_dual=True), M.EpiNormEucl(5), M.EpiPerSquare(3),
              M.EpiPerSepSpectralMat(2 + M.svec_length(5), M.SSF_NEGLOG), M.EpiNormInf(6),
              M.EpiNormInf(4, use_dual=True), M.EpiPerSepSpectralVec(7, M.SSF_POWER12, 1.5),
-             M.EpiPerSepSpectralVec(5, M.SSF_NEGLOG, use_dual=True)]
+             M.EpiPerSepSpectralVec(5, M.SSF_NEGLOG, use_dual=True), M.HypoGeoMean(6),
+             M.HypoGeoMean(4, use_dual=True)]
     I = inst.synthetic("specmix", 20 + p, p, cones, seed=21)
     Ap = None
     if p:

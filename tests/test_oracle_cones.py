@@ -159,6 +159,13 @@ def test_epinorminf(dw):
     run_oracles(EpiNormInf(1 + dw))
 
 
+@pytest.mark.parametrize("dw", [1, 2, 5])
+def test_hypogeomean(dw):
+    # reference: test/cone.jl:587-591
+    from oracle.cones_vec3 import HypoGeoMean
+    run_oracles(HypoGeoMean(1 + dw))
+
+
 SSF = [(0, 0.0), (1, 0.0), (2, 0.0), (3, 1.5), (3, 2.0), (3, 1.1)]   # Inv, NegLog, NegEntropy, Power12(p)
 
 
