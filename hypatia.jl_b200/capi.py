@@ -34,6 +34,7 @@ _SIGS = {
                                  C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                  c_ip, c_i64p, c_ip, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "hyp_set_cone_params": (C.c_int, [C.c_void_p, C.c_int, c_ip, c_dp]),
+    "hyp_set_cone_alpha": (C.c_int, [C.c_void_p, C.c_int, c_i64p, c_dp]),
     "hyp_cones_load_point": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]),
     "hyp_cones_feas": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "hyp_cones_grad": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -179,6 +180,11 @@ class Context:
         hparam = np.array([getattr(ck, "hparam", 0.0) for ck in model.cones], dtype=np.float64)
         self.check(self.lib.hyp_set_cone_params(self.h, K, hkind.ctypes.data_as(c_ip),
                                                 hparam.ctypes.data_as(c_dp)), "hyp_set_cone_params")
+        alphas = [np.asarray(getattr(ck, "alpha", ()), dtype=np.float64) for ck in model.cones]
+        aoff = np.concatenate(([0], np.cumsum([a.size for a in alphas]))).astype(np.int64)
+        aval = np.concatenate(alphas) if K and aoff[-1] else np.zeros(1)
+        self.check(self.lib.hyp_set_cone_alpha(self.h, K, aoff.ctypes.data_as(c_i64p), aval.ctypes.data_as(c_dp)),
+                   "hyp_set_cone_alpha")
         self._keep = (G_local, A, Q, R, ctype, cdim, cdual)
         c, b, h = _f64(model.c), _f64(model.b), _f64(model.h)
         rc = self.lib.hyp_load_model(

@@ -19,7 +19,7 @@
 
 #include "../../include/hypatia_b200.h"
 
-#define HYP_NUM_CONE_TYPES 11
+#define HYP_NUM_CONE_TYPES 12
 // internal product mode: inv_hess for primal-barrier cones, hess for dual-barrier cones
 #define HYP_PROD_BLOCK_INV 5
 #define HYP_EPS 2.220446049250313e-16
@@ -58,7 +58,7 @@ static inline bool cone_has_sqrt(int t) {
 static inline bool cone_allows_dual(int t) {
     return t == HYP_CONE_HYPOPERLOGDETTRI || t == HYP_CONE_HYPOROOTDETTRI ||
            t == HYP_CONE_EPIPERSEPSPECTRAL_MAT || t == HYP_CONE_HYPOPERLOG || t == HYP_CONE_EPINORMINF ||
-           t == HYP_CONE_EPIPERSEPSPECTRAL_VEC || t == HYP_CONE_HYPOGEOMEAN;
+           t == HYP_CONE_EPIPERSEPSPECTRAL_VEC || t == HYP_CONE_HYPOGEOMEAN || t == HYP_CONE_GENERALIZEDPOWER;
 }
 // vector cones served by cones_vec3_kernels.cuh
 static inline bool cone_is_vec3(int t) {
@@ -156,6 +156,8 @@ struct hyp_ctx {
     std::vector<int> h_cone_type, h_cone_dual;
     std::vector<int64_t> h_cone_dim, h_cone_off;
     std::vector<double> h_cone_nu;
+    std::vector<int64_t> h_cone_aoff;  // per global cone: offsets into h_cone_alpha (hyp_set_cone_alpha), K + 1 entries
+    std::vector<double> h_cone_alpha;  // powers of the GeneralizedPower cones
     std::vector<int> h_cone_hkind;     // per global cone: HYP_SSF_* (EpiPerSepSpectral), set by hyp_set_cone_params
     std::vector<double> h_cone_hparam;
     std::vector<int> h_cone_sqrt;      // per global cone: 1 = sqrt-form in the Schur assembly
@@ -308,6 +310,13 @@ void hyp_cones_prod(hyp_ctx* ctx, double* prod, const double* arr, int64_t ncols
 void hyp_cones_schur_prepass(hyp_ctx* ctx);
 void hyp_cones_dder3_dev(hyp_ctx* ctx, double* out, const double* dir);
 void hyp_cones_prox_dev(hyp_ctx* ctx, double irtmu, int use_max);
+
+// ---- cones_gpow.cu: GeneralizedPower + the generic inverse-Hessian fallback ----
+void hyp_gpow_alloc_group(hyp_ctx* ctx, ConeGroup& g);
+void hyp_gpow_update_state(hyp_ctx* ctx, ConeGroup& g);
+void hyp_gpow_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr, int64_t ncols, int64_t ld_prod,
+                   int64_t ld_arr, int mode, int64_t row_shift);
+void hyp_gpow_dder3(hyp_ctx* ctx, ConeGroup& g, double* out, const double* dir);
 
 // ---- syrk.cu ----
 // C(upper 128-tiles) = alpha * P' R + beta * C over k in [0, klen); P, R: klen x ncols col-major.

@@ -1,0 +1,100 @@
+// GeneralizedPower on the device, and the generic inverse-Hessian fallback of the Cone API (kernels:
+// cones_gpow_kernels.cuh).
+//
+// reference: src/Cones/generalizedpower.jl:77-236; generic oracles src/Cones/Cones.jl:113-118 (inv_hess_prod! =
+// hess_fact \\ arr), :239-259 (update_hess_fact, update_inv_hess).  ConeGroup fields reused: d_side = dim of the cone
+// (side of its explicit Hessian), d_hkind = number of powers m, d_vecs / d_voff = the powers, d_W = explicit
+// Hessian, d_U = its Cholesky factor (scratch), d_Ui = U^-1.  A Hessian whose Cholesky fails marks the cone
+// infeasible (the reference would go on to Bunch-Kaufman, dense.jl:194-215; the line search backtracks instead).
+#include "cones_mat.cuh"
+#include "cones_gpow_kernels.cuh"
+
+namespace {
+
+template <typename T>
+T* upload_vec(const std::vector<T>& v) {
+    T* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(T)));
+    if (!v.empty()) CUDA_TRY(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return d;
+}
+
+}  // namespace
+
+void hyp_gpow_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
+    std::vector<double> alpha;
+    g.h_voff.assign(g.count, 0);
+    for (int i = 0; i < g.count; i++) {
+        const int k = g.h_kidx[i];
+        if ((int)ctx->h_cone_aoff.size() != ctx->K + 1)
+            throw HypError{"GeneralizedPower cones need hyp_set_cone_alpha before hyp_load_model"};
+        const int64_t a0 = ctx->h_cone_aoff[k], a1 = ctx->h_cone_aoff[k + 1];
+        const int m = (int)(a1 - a0);
+        if (m < 1 || m >= g.h_dim[i]) throw HypError{"GeneralizedPower: need 1 <= number of powers < dim"};
+        if (g.h_dim[i] > 128) throw HypError{"GeneralizedPower: dim above 128 is not supported (batched Cholesky limit)"};
+        double sum = 0.0;
+        for (int64_t a = a0; a < a1; a++) {
+            if (!(ctx->h_cone_alpha[a] > 0.0)) throw HypError{"GeneralizedPower: powers must be positive"};
+            sum += ctx->h_cone_alpha[a];
+        }
+        if (std::abs(sum - 1.0) > 1e-10) throw HypError{"GeneralizedPower: powers must sum to one"};
+        g.h_voff[i] = (int64_t)alpha.size();
+        alpha.insert(alpha.end(), ctx->h_cone_alpha.begin() + a0, ctx->h_cone_alpha.begin() + a1);
+        g.h_hkind.push_back(m);
+        g.h_side[i] = g.h_dim[i];
+    }
+    g.max_side = g.max_dim;
+    cudaFree(g.d_side);
+    g.d_side = upload_vec(g.h_side);
+    g.d_hkind = upload_vec(g.h_hkind);
+    g.d_voff = upload_vec(g.h_voff);
+    CUDA_TRY(cudaMalloc(&g.d_vecs, std::max<size_t>(alpha.size(), 1) * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(g.d_vecs, alpha.data(), alpha.size() * sizeof(double), cudaMemcpyHostToDevice));
+    hyp_mat_alloc_group(ctx, g);   // per-cone dim x dim matrices (even leading dimension)
+}
+
+void hyp_gpow_update_state(hyp_ctx* ctx, ConeGroup& g) {
+    hypdev::gpow_state_kernel<<<ceil_div(g.count, 8), 256, 0, ctx->stream>>>(
+        g.count, g.d_off, g.d_dim, g.d_hkind, g.d_voff, g.d_vecs, g.d_kidx, g.d_moff, ctx->d_point, ctx->d_dual,
+        ctx->d_grad, g.d_scal, g.d_W, ctx->d_feas, ctx->d_dual_feas);
+    ctx->launches++;
+    // hess_fact: Cholesky of the explicit Hessian (copy) and its inverse factor
+    CUDA_TRY(cudaMemcpyAsync(g.d_U, g.d_W, (size_t)std::max<int64_t>(g.mat_total, 1) * sizeof(double),
+                             cudaMemcpyDeviceToDevice, ctx->stream));
+    hyp_chol_batched(ctx, g.count, g.d_side, g.d_moff, g.d_kidx, g.d_U, g.d_Ui, ctx->d_feas);
+    CUDA_TRY(cudaGetLastError());
+}
+
+void hyp_gpow_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr, int64_t ncols, int64_t ld_prod,
+                   int64_t ld_arr, int mode, int64_t row_shift) {
+    if (mode == HYP_PROD_SQRT_HESS || mode == HYP_PROD_INV_SQRT_HESS)
+        throw HypError{"sqrt_hess_prod of GeneralizedPower is not exported (the Schur assembly uses hess_prod)"};
+    dim3 grid(ceil_div(g.count, 8), (unsigned)std::min<int64_t>(ncols, 65535));
+    // which cones take hess_prod / inv_hess_prod: everyone, or split by use_dual_barrier for the block modes
+    int hess_dual = -2, inv_dual = -2;      // -2: kernel not launched, -1: every cone, 0 / 1: cones with that flag
+    if (mode == HYP_PROD_HESS) hess_dual = -1;
+    else if (mode == HYP_PROD_INV_HESS) inv_dual = -1;
+    else if (mode == HYP_PROD_BLOCK) { hess_dual = 0; inv_dual = 1; }
+    else if (mode == HYP_PROD_BLOCK_INV) { hess_dual = 1; inv_dual = 0; }
+    else throw HypError{"hyp_gpow_prod: bad mode"};
+    if (hess_dual > -2) {
+        hypdev::gpow_prod_kernel<<<grid, 256, 0, ctx->stream>>>(g.count, hess_dual, g.d_off, g.d_dim, g.d_hkind,
+                                                               g.d_voff, g.d_vecs, g.d_dual, g.d_scal, ctx->d_point,
+                                                               arr, ld_arr, prod, ld_prod, ncols, row_shift);
+        ctx->launches++;
+    }
+    if (inv_dual > -2) {
+        hypdev::gen_invhess_prod_kernel<<<grid, 256, 0, ctx->stream>>>(g.count, inv_dual, g.d_off, g.d_dim, g.d_moff,
+                                                                      g.d_dual, g.d_Ui, arr, ld_arr, prod, ld_prod,
+                                                                      ncols, row_shift);
+        ctx->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+}
+
+void hyp_gpow_dder3(hyp_ctx* ctx, ConeGroup& g, double* out, const double* dir) {
+    hypdev::gpow_dder3_kernel<<<ceil_div(g.count, 8), 256, 0, ctx->stream>>>(
+        g.count, g.d_off, g.d_dim, g.d_hkind, g.d_voff, g.d_vecs, g.d_scal, ctx->d_point, dir, out);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+}

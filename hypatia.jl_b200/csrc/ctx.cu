@@ -875,7 +875,7 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
         if (cone_lo < 0 || cone_hi > K || cone_lo > cone_hi) throw HypError{"hyp_load_model: bad cone range"};
         if (p > 0 && !A) throw HypError{"hyp_load_model: p > 0 needs A"};
         if ((Ap_Q == nullptr) != (Ap_R == nullptr)) throw HypError{"hyp_load_model: pass both Ap_Q and Ap_R or neither"};
-        // per-cone parameters staged by hyp_set_cone_params survive the free below
+        // per-cone parameters staged by hyp_set_cone_params / hyp_set_cone_alpha survive the free below
         std::vector<int> hkind_in = ctx->h_cone_hkind;
         std::vector<double> hparam_in = ctx->h_cone_hparam;
         const bool have_params = (int)hkind_in.size() == K && K > 0;
@@ -918,6 +918,10 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
                                 : t == HYP_CONE_HYPOROOTDETTRI ? 1.0 + side
                                 : t == HYP_CONE_EPIPERSEPSPECTRAL_MAT ? 2.0 + side
                                 : t == HYP_CONE_EPIPERSQUARE ? 2.0
+                                : t == HYP_CONE_GENERALIZEDPOWER
+                                    ? ((int)ctx->h_cone_aoff.size() == K + 1
+                                           ? (double)(ctx->h_cone_aoff[k + 1] - ctx->h_cone_aoff[k]) + 1.0
+                                           : 0.0)
                                                              : (double)d;   // HypoPerLog, EpiNormInf, EpiPerSepSpectral{VectorCSqr}, HypoGeoMean: nu = dim
             if ((t == HYP_CONE_EPINORMINF || t == HYP_CONE_HYPOGEOMEAN) && d < 2)
                 throw HypError{"hyp_load_model: EpiNormInf / HypoGeoMean need dimension >= 2"};
@@ -1061,6 +1065,17 @@ int hyp_set_cone_params(hyp_ctx* ctx, int K, const int* ssf_kind, const double* 
         if (K < 0 || (K > 0 && (!ssf_kind || !ssf_param))) throw HypError{"hyp_set_cone_params: bad arguments"};
         ctx->h_cone_hkind.assign(ssf_kind, ssf_kind + K);
         ctx->h_cone_hparam.assign(ssf_param, ssf_param + K);
+        return 0;
+    });
+}
+
+int hyp_set_cone_alpha(hyp_ctx* ctx, int K, const int64_t* alpha_off, const double* alpha) {
+    return guarded(ctx, [&] {
+        if (K < 0 || (K > 0 && !alpha_off)) throw HypError{"hyp_set_cone_alpha: bad arguments"};
+        ctx->h_cone_aoff.assign(alpha_off, alpha_off + K + 1);
+        const int64_t tot = K > 0 ? alpha_off[K] : 0;
+        if (tot < 0 || (tot > 0 && !alpha)) throw HypError{"hyp_set_cone_alpha: bad offsets"};
+        ctx->h_cone_alpha.assign(alpha, alpha + tot);
         return 0;
     });
 }

@@ -106,6 +106,8 @@ def cone_initial_point(spec):
         arr[2:] = w
     elif spec.ctype == M.CONE_EPINORMINF:
         arr[0] = np.sqrt(spec.dim)      # epinorminf.jl:88-95
+    elif spec.ctype == M.CONE_GENERALIZEDPOWER:
+        arr[:len(spec.alpha)] = np.sqrt(1 + np.array(spec.alpha))      # generalizedpower.jl:71-75
     elif spec.ctype == M.CONE_HYPOGEOMEAN:
         d = spec.dim - 1                  # hypogeomean.jl:259-264
         c = np.sqrt(5.0 * d * d + 2 * d + 1)
@@ -125,6 +127,9 @@ def _cone_dual_initial(spec, prim):
     if spec.ctype == M.CONE_EPINORMEUCL:
         return prim.copy()      # central point is self-dual: -g = (u, -w)/dist with dist = 1
     if spec.ctype == M.CONE_POSSEMIDEFTRI:
+        return prim.copy()
+    if spec.ctype == M.CONE_GENERALIZEDPOWER:
+        # generalizedpower.jl:107-120 at w = 0: zwzwi = 1, -g_u = (alpha + 1) / u = sqrt(1 + alpha) (central point)
         return prim.copy()
     if spec.ctype == M.CONE_HYPOGEOMEAN:
         # hypogeomean.jl:97-110 at w = w0 * 1: phi = w0
@@ -201,6 +206,9 @@ def _perturb(rng, spec, vec, noise):
         return vec
     if spec.ctype == M.CONE_EPIPERSEPSPECTRAL_VEC:
         vec += noise / (2.0 * (vec.size - 2)) * (2 * rng.random(vec.size) - 1)   # the initial point is not central
+        return vec
+    if spec.ctype == M.CONE_GENERALIZEDPOWER:
+        vec += 0.5 * noise / np.sqrt(vec.size) * (2 * rng.random(vec.size) - 1)
         return vec
     if spec.ctype == M.CONE_HYPOGEOMEAN:
         vec[0] += 0.5 * noise * (2 * rng.random() - 1)

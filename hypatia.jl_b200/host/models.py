@@ -23,6 +23,7 @@ CONE_HYPOPERLOG = 7
 CONE_EPINORMINF = 8
 CONE_EPIPERSEPSPECTRAL_VEC = 9
 CONE_HYPOGEOMEAN = 10
+CONE_GENERALIZEDPOWER = 11
 
 # separable spectral functions of EpiPerSepSpectral (sepspectralfun.jl:17-116), HYP_SSF_*
 SSF_INV, SSF_NEGLOG, SSF_NEGENTROPY, SSF_POWER12 = 0, 1, 2, 3
@@ -39,6 +40,7 @@ CONE_NAMES = {
     CONE_EPINORMINF: "EpiNormInf",
     CONE_EPIPERSEPSPECTRAL_VEC: "EpiPerSepSpectral{VectorCSqr}",
     CONE_HYPOGEOMEAN: "HypoGeoMean",
+    CONE_GENERALIZEDPOWER: "GeneralizedPower",
 }
 
 
@@ -62,15 +64,16 @@ def svec_side(length: int) -> int:
 class ConeSpec:
     """(type, dim) descriptor of one cone block; nu follows the reference's get_nu."""
 
-    __slots__ = ("ctype", "dim", "use_dual", "hkind", "hparam")
+    __slots__ = ("ctype", "dim", "use_dual", "hkind", "hparam", "alpha")
 
     def __init__(self, ctype: int, dim: int, use_dual: bool = False, hkind: int = 0,
-                 hparam: float = 0.0):
+                 hparam: float = 0.0, alpha=()):
         self.ctype = int(ctype)
         self.dim = int(dim)
         self.use_dual = bool(use_dual)
         self.hkind = int(hkind)        # EpiPerSepSpectral: which separable spectral function
         self.hparam = float(hparam)    # ... and its parameter (the power of Power12SSF)
+        self.alpha = tuple(float(a) for a in alpha)   # GeneralizedPower: the powers (sum 1); dim = len(alpha) + n
         if ctype == CONE_NONNEGATIVE:
             assert dim >= 1
         elif ctype == CONE_EPINORMEUCL:
@@ -93,6 +96,9 @@ class ConeSpec:
             assert dim >= 3
         elif ctype in (CONE_EPINORMINF, CONE_HYPOGEOMEAN):
             assert dim >= 2
+        elif ctype == CONE_GENERALIZEDPOWER:
+            assert dim >= 3 and 1 <= len(self.alpha) < dim and all(a > 0 for a in self.alpha)
+            assert abs(sum(self.alpha) - 1) <= 1e-12
         elif ctype == CONE_EPIPERSEPSPECTRAL_VEC:
             assert dim >= 3 and hkind in (SSF_INV, SSF_NEGLOG, SSF_NEGENTROPY, SSF_POWER12)
             assert hkind != SSF_POWER12 or 1 < hparam <= 2
@@ -124,12 +130,14 @@ class ConeSpec:
             return 2.0 + self.side
         if self.ctype == CONE_EPIPERSQUARE:
             return 2.0
+        if self.ctype == CONE_GENERALIZEDPOWER:
+            return float(len(self.alpha) + 1)
         if self.ctype in (CONE_HYPOPERLOG, CONE_EPINORMINF, CONE_EPIPERSEPSPECTRAL_VEC, CONE_HYPOGEOMEAN):
             return float(self.dim)
         return 1.0 + self.side
 
     def clone(self):
-        return ConeSpec(self.ctype, self.dim, self.use_dual, self.hkind, self.hparam)
+        return ConeSpec(self.ctype, self.dim, self.use_dual, self.hkind, self.hparam, self.alpha)
 
     def __repr__(self):
         return f"{CONE_NAMES[self.ctype]}({self.dim})"
@@ -172,6 +180,12 @@ def EpiPerSquare(dim, use_dual=False):
 
 def HypoPerLog(dim, use_dual=False):
     return ConeSpec(CONE_HYPOPERLOG, dim, use_dual)
+
+
+def GeneralizedPower(alpha, n, use_dual=False):
+    """GeneralizedPower{Float64}(alpha, n): (u in R^m_+, w in R^n), prod u_i^alpha_i >= |w|; MOI's PowerCone(a) is
+    GeneralizedPower([a, 1 - a], 1) (MathOptInterface/cones.jl:33-37)."""
+    return ConeSpec(CONE_GENERALIZEDPOWER, len(alpha) + n, use_dual, alpha=alpha)
 
 
 def HypoGeoMean(dim, use_dual=False):

@@ -48,6 +48,7 @@ typedef struct hyp_ctx hyp_ctx;
 #define HYP_CONE_EPINORMINF 8       /* epinorminf.jl (real); use_dual = 1: l1-norm epigraph */
 #define HYP_CONE_EPIPERSEPSPECTRAL_VEC 9 /* epipersepspectral/{epipersepspectral,vectorcsqr}.jl */
 #define HYP_CONE_HYPOGEOMEAN 10     /* hypogeomean.jl      */
+#define HYP_CONE_GENERALIZEDPOWER 11 /* generalizedpower.jl (powers via hyp_set_cone_alpha; dim <= 128) */
 
 /* separable spectral functions of EpiPerSepSpectral (epipersepspectral/sepspectralfun.jl:17-116) */
 #define HYP_SSF_INV 0        /* InvSSF        x -> 1/x      */
@@ -83,6 +84,9 @@ int hyp_comm_init(hyp_ctx* ctx, int rank, int nranks, const char* id128);
  *      of Power12SSF; entries of other cone types are ignored.  Call BEFORE hyp_load_model (the
  *      values are consumed by the next load); models without such cones need not call it. */
 int hyp_set_cone_params(hyp_ctx* ctx, int K, const int* ssf_kind, const double* ssf_param);
+/* the `alpha::Vector` field of GeneralizedPower (generalizedpower.jl:11): cone k owns alpha[alpha_off[k] ..
+ * alpha_off[k + 1]) (empty for other cone types; n = dim_k - number of powers).  Call BEFORE hyp_load_model. */
+int hyp_set_cone_alpha(hyp_ctx* ctx, int K, const int64_t* alpha_off, const double* alpha);
 
 /* ---- load: replaces load(syssolver::QRCholDenseSystemSolver, solver), qrchol.jl:138-179,
  *      setup_point_sub common.jl:184-208, and setup_data!(cone) for every cone.

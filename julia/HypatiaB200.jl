@@ -41,6 +41,9 @@ cone_code(::Cones.HypoPerLog) = Cint(7)
 cone_code(::Cones.EpiNormInf{Float64, Float64}) = Cint(8)
 cone_code(::Cones.EpiPerSepSpectral{Cones.VectorCSqr{Float64}, Float64}) = Cint(9)
 cone_code(::Cones.HypoGeoMean) = Cint(10)
+cone_code(::Cones.GeneralizedPower) = Cint(11)
+cone_alpha(c::Cones.GeneralizedPower) = Vector{Float64}(c.α)
+cone_alpha(::Cones.Cone) = Float64[]
 cone_code(c::Cones.Cone) = error("cone $(typeof(c)) is not on the B200 hot path")
 
 # HYP_SSF_* code and parameter of the `h` field of EpiPerSepSpectral (sepspectralfun.jl:17-116)
@@ -89,6 +92,10 @@ function Solvers.load(syssolver::B200QRCholSystemSolver, solver::Solver{Float64}
     (hkind, hparam) = (Cint[first(t) for t in ssf], Float64[last(t) for t in ssf])
     check(syssolver.ctx, ccall((:hyp_set_cone_params, LIB), Cint, (Ctx, Cint, Ptr{Cint}, Ptr{Float64}),
         syssolver.ctx, K, hkind, hparam), "hyp_set_cone_params")
+    alphas = [cone_alpha(c) for c in model.cones]
+    aoff = Int64[0; cumsum(length.(alphas))]
+    check(syssolver.ctx, ccall((:hyp_set_cone_alpha, LIB), Cint, (Ctx, Cint, Ptr{Int64}, Ptr{Float64}),
+        syssolver.ctx, K, aoff, vcat(alphas..., Float64[0])), "hyp_set_cone_alpha")
     GC.@preserve G A ctype cdim cdual begin
         rc = ccall((:hyp_load_model, LIB), Cint,
             (Ctx, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Float64},

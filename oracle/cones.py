@@ -114,6 +114,16 @@ class Cone:
     def hess_prod_slow(self, arr):
         return self.hess_prod(arr)
 
+    # generic inverse-Hessian oracles for cones without closed forms (Cones.jl:113-118, 253-259)
+    def inv_hess_prod(self, arr):
+        self.update_hess_fact()
+        a, vec = _as2d(arr)
+        return _ret(self.hess_fact.solve(np.array(a, dtype=np.float64, order="F")), vec)
+
+    def update_inv_hess(self):
+        self.update_hess_fact()
+        return self.hess_fact.solve(np.eye(self.dim))
+
     def check_numerics(self, gtol=EPS ** 0.25, Htol=None):
         """Cones.jl:273-290"""
         Htol = 10 * np.sqrt(gtol) if Htol is None else Htol
@@ -760,6 +770,9 @@ def make_cone(spec):
     if spec.ctype == M.CONE_EPIPERSEPSPECTRAL_VEC:
         from .cones_sepspec import EpiPerSepSpectralVec
         return EpiPerSepSpectralVec(spec.dim, spec.hkind, spec.hparam, use_dual=spec.use_dual)
+    if spec.ctype == M.CONE_GENERALIZEDPOWER:
+        from .cones_vec3 import GeneralizedPower
+        return GeneralizedPower(spec.alpha, spec.dim - len(spec.alpha), use_dual=spec.use_dual)
     if spec.ctype in (M.CONE_EPIPERSQUARE, M.CONE_HYPOPERLOG, M.CONE_EPINORMINF, M.CONE_HYPOGEOMEAN):
         from . import cones_vec3
         cls = {M.CONE_EPIPERSQUARE: cones_vec3.EpiPerSquare, M.CONE_HYPOPERLOG: cones_vec3.HypoPerLog,

@@ -518,3 +518,103 @@ class HypoGeoMean(Cone):
         d3[0] = c1 / -zeta
         d3[1:] = (c7 + rwi * (c8 + c9 * rwi)) / w
         return d3
+
+
+class GeneralizedPower(Cone):
+    """generalizedpower.jl:8-236: (u in R^m_++, w in R^n), prod u_i^(alpha_i) >= |w|_2; barrier
+    -log(prod u_i^(2 alpha_i) - |w|^2) - sum (1 - alpha_i) log u_i, nu = m + 1.  No closed-form inverse Hessian:
+    inv_hess_prod!, inv_hess and the sqrt oracles are the generic ones of Cones.jl:113-118, 189-259 (explicit
+    Hessian + posdef_fact_copy!)."""
+    ctype = M.CONE_GENERALIZEDPOWER
+
+    def __init__(self, alpha, n, use_dual=False):
+        self.alpha = np.array(alpha, dtype=np.float64)
+        self.m = self.alpha.size
+        self.n = n
+        self.use_dual_barrier = use_dual
+        super().__init__(self.m + n)
+
+    @property
+    def nu(self):
+        return float(self.m + 1)
+
+    def set_initial_point(self, arr):
+        arr[:] = 0.0
+        arr[:self.m] = np.sqrt(1 + self.alpha)
+        return arr
+
+    def update_feas(self):
+        u, w = self.point[:self.m], self.point[self.m:]
+        if (u > EPS).all():
+            self.z = float(np.exp(2 * np.sum(self.alpha * np.log(u))))
+            self.w2 = float(w @ w)
+            self.zw = self.z - self.w2
+            return self.zw > EPS
+        return False
+
+    def is_dual_feas(self):
+        u, w = self.dual_point[:self.m], self.dual_point[self.m:]
+        if (u > EPS).all():
+            p = float(np.exp(2 * np.sum(self.alpha * np.log(u / self.alpha))))
+            return (p - float(w @ w)) > EPS
+        return False
+
+    def update_grad(self):
+        u, w = self.point[:self.m], self.point[self.m:]
+        self.zwzwi = (self.z + self.w2) / self.zw
+        self._grad[:self.m] = -(self.zwzwi * self.alpha + 1) / u
+        self._grad[self.m:] = 2 * w / self.zw
+
+    def update_hess(self):
+        g = self.grad()
+        m = self.m
+        u = self.point[:m]
+        aui = 2 * self.alpha / u
+        auizzwi = -self.z * aui / self.zw
+        zzwim1 = -self.w2 / self.zw
+        H = np.zeros((self.dim, self.dim))
+        H[:m, :m] = np.outer(aui, auizzwi) * zzwim1
+        H[np.arange(m), np.arange(m)] -= g[:m] / u
+        H[:m, m:] = np.outer(auizzwi, g[m:])
+        H[m:, :m] = H[:m, m:].T
+        H[m:, m:] = np.outer(g[m:], g[m:]) + (2 / self.zw) * np.eye(self.n)
+        return H
+
+    def hess_prod(self, arr):
+        self.grad()
+        a, vec = _as2d(arr)
+        m = self.m
+        u, w = self.point[:m], self.point[m:]
+        prod_u = a[:m] / u[:, None]
+        prod_w = 2 * a[m:] / self.zw
+        dot1 = -4 * (self.alpha @ prod_u) * self.z / self.zw
+        dot2 = (dot1 + 2 * (w @ prod_w)) / self.zw
+        dot3 = dot1 - dot2 * self.z
+        prod = np.empty_like(a)
+        prod[:m] = (prod_u * (1 + self.zwzwi * self.alpha)[:, None] + dot3[None, :] * self.alpha[:, None]) / u[:, None]
+        prod[m:] = prod_w + dot2[None, :] * w[:, None]
+        return _ret(prod, vec)
+
+    def dder3(self, direction):
+        self.grad()
+        m = self.m
+        u, w = self.point[:m], self.point[m:]
+        u_dir, w_dir = direction[:m], direction[m:]
+        alpha, z, zw, w2, zwzwi = self.alpha, self.z, self.zw, self.w2, self.zwzwi
+        zzwi = 2 * z / zw
+        zwi = 2 / zw
+        udu = u_dir / u
+        wwd = 2 * float(w @ w_dir)
+        c15 = wwd / zw
+        audu = float(alpha @ udu)
+        sumaudu2 = float(alpha @ (udu ** 2))
+        c1 = 2 * zwzwi * audu ** 2 + sumaudu2
+        c10 = float(w_dir @ w_dir) + wwd * c15
+        c13 = zzwi * (w2 * c1 - 2 * wwd * zwzwi * audu + c10) / zw
+        c14 = zzwi * (2 * audu * w2 - wwd) / zw
+        d3 = np.empty(self.dim)
+        d3[:m] = (c13 * alpha + ((c14 + zwzwi * udu) * alpha + udu) * udu) / u
+        c6 = zwi * (z * (4 * audu * c15 - c1) - c10) / zw
+        c7 = zwi * (2 * z * audu - wwd) / zw
+        d3[m:] = c7 * w_dir + c6 * w
+        return d3

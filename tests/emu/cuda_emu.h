@@ -57,6 +57,8 @@ static inline T __ldg(const T* p) {
 
 static inline void __syncthreads() { pthread_barrier_wait(&emu::g_block->bar); }
 
+static inline void __syncwarp() { pthread_barrier_wait(&emu::g_block->warp_bar[threadIdx.x >> 5]); }
+
 static inline double emu_shfl(double v, int src_lane_abs) {
     emu::BlockState* b = emu::g_block;
     const int tid = (int)threadIdx.x;

@@ -197,3 +197,46 @@ int emu_mat_small_dder3(int type, int ncones, int max_side, const int64_t* off, 
 }
 
 }  // extern "C"
+
+#include "../../hypatia.jl_b200/csrc/cones_gpow_kernels.cuh"
+
+extern "C" {
+
+int emu_gpow_state(int ncones, const int64_t* off, const int* dim, const int* mu, const int64_t* aoff,
+                   const double* alpha, const int* kidx, const int64_t* moff, const double* point, const double* dual,
+                   double* grad, double* scal, double* H, uint8_t* feas, uint8_t* dual_feas) {
+    emu::launch(dim3((ncones + 1) / 2), dim3(64), 0, [&] {
+        hypdev::gpow_state_kernel(ncones, off, dim, mu, aoff, alpha, kidx, moff, point, dual, grad, scal, H, feas,
+                                  dual_feas);
+    });
+    return 0;
+}
+
+int emu_gpow_prod(int ncones, int want_dual, const int64_t* off, const int* dim, const int* mu, const int64_t* aoff,
+                  const double* alpha, const int* dualf, const double* scal, const double* point, const double* arr,
+                  int64_t ld_arr, double* prod, int64_t ld_prod, int64_t ncols, int64_t row_shift) {
+    emu::launch(dim3((ncones + 1) / 2, 2), dim3(64), 0, [&] {
+        hypdev::gpow_prod_kernel(ncones, want_dual, off, dim, mu, aoff, alpha, dualf, scal, point, arr, ld_arr, prod,
+                                 ld_prod, ncols, row_shift);
+    });
+    return 0;
+}
+
+int emu_gen_invhess_prod(int ncones, int want_dual, const int64_t* off, const int* dim, const int64_t* moff,
+                         const int* dualf, const double* Ui, const double* arr, int64_t ld_arr, double* prod,
+                         int64_t ld_prod, int64_t ncols, int64_t row_shift) {
+    emu::launch(dim3((ncones + 1) / 2, 2), dim3(64), 0, [&] {
+        hypdev::gen_invhess_prod_kernel(ncones, want_dual, off, dim, moff, dualf, Ui, arr, ld_arr, prod, ld_prod, ncols,
+                                        row_shift);
+    });
+    return 0;
+}
+
+int emu_gpow_dder3(int ncones, const int64_t* off, const int* dim, const int* mu, const int64_t* aoff,
+                   const double* alpha, const double* scal, const double* point, const double* dir, double* out) {
+    emu::launch(dim3((ncones + 1) / 2), dim3(64), 0,
+                [&] { hypdev::gpow_dder3_kernel(ncones, off, dim, mu, aoff, alpha, scal, point, dir, out); });
+    return 0;
+}
+
+}  // extern "C"

@@ -288,3 +288,61 @@ class EmuMatGroup:
                                  p(self.scal), p(self.point), p(self.wivec), p(a), i64(self.q), p(out), i64(self.q),
                                  i64(0), a.shape[1], threads)
         return out[:, 0] if np.ndim(arr) == 1 else out
+
+
+class EmuGpowGroup:
+    """Mirrors hyp_gpow_update_state / hyp_gpow_prod / hyp_gpow_dder3 (csrc/cones_gpow.cu) for a list of
+    GeneralizedPower cones; the batched Cholesky + inverse of the explicit Hessians (chol.cu) is NumPy here."""
+
+    def __init__(self, specs):
+        self.K = len(specs)
+        self.dims = np.array([s.dim for s in specs], dtype=np.int32)
+        self.off = np.concatenate(([0], np.cumsum(self.dims)))[:-1].astype(np.int64)
+        self.q = int(self.dims.sum())
+        self.mu = np.array([len(s.alpha) for s in specs], dtype=np.int32)
+        self.aoff = np.concatenate(([0], np.cumsum(self.mu)))[:-1].astype(np.int64)
+        self.alpha = np.concatenate([np.asarray(s.alpha, dtype=np.float64) for s in specs])
+        self.kidx = np.arange(self.K, dtype=np.int32)
+        self.dualf = np.array([1 if s.use_dual else 0 for s in specs], dtype=np.int32)
+        self.lay = MatLayout(self.dims)
+        self.scal = np.zeros(8 * self.K)
+
+    def load_point(self, point, dual):
+        self.point = np.ascontiguousarray(point, dtype=np.float64)
+        self.dual = np.ascontiguousarray(dual, dtype=np.float64)
+        self.feas = np.ones(self.K, dtype=np.uint8)
+        self.dual_feas = np.ones(self.K, dtype=np.uint8)
+        self.grad = np.zeros(self.q)
+        self.H = np.zeros(self.lay.total)
+        lib().emu_gpow_state(self.K, p(self.off), p(self.dims), p(self.mu), p(self.aoff), p(self.alpha), p(self.kidx),
+                             p(self.lay.moff), p(self.point), p(self.dual), p(self.grad), p(self.scal), p(self.H),
+                             p(self.feas), p(self.dual_feas))
+        self.Ui = np.zeros(self.lay.total)
+        for c in range(self.K):
+            Hc = self.lay.get(self.H, c)
+            try:
+                U = np.linalg.cholesky(Hc).T
+                self.lay.get(self.Ui, c)[:] = np.linalg.inv(U)
+            except np.linalg.LinAlgError:
+                self.feas[c] = 0
+
+    def prod(self, arr, mode, in_place=False):
+        a = np.asfortranarray(np.asarray(arr, dtype=np.float64).reshape(self.q, -1, order="F")).copy(order="F")
+        out = a if in_place else np.zeros_like(a, order="F")
+        hess_dual, inv_dual = {0: (-1, -2), 1: (-2, -1), 4: (0, 1), 5: (1, 0)}[int(mode)]
+        L = lib()
+        if hess_dual > -2:
+            L.emu_gpow_prod(self.K, hess_dual, p(self.off), p(self.dims), p(self.mu), p(self.aoff), p(self.alpha),
+                            p(self.dualf), p(self.scal), p(self.point), p(a), i64(self.q), p(out), i64(self.q),
+                            i64(a.shape[1]), i64(0))
+        if inv_dual > -2:
+            L.emu_gen_invhess_prod(self.K, inv_dual, p(self.off), p(self.dims), p(self.lay.moff), p(self.dualf),
+                                   p(self.Ui), p(a), i64(self.q), p(out), i64(self.q), i64(a.shape[1]), i64(0))
+        return out[:, 0] if np.ndim(arr) == 1 else out
+
+    def dder3(self, direction):
+        d = np.ascontiguousarray(direction, dtype=np.float64)
+        out = np.zeros(self.q)
+        lib().emu_gpow_dder3(self.K, p(self.off), p(self.dims), p(self.mu), p(self.aoff), p(self.alpha), p(self.scal),
+                             p(self.point), p(d), p(out))
+        return out

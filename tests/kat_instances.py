@@ -230,6 +230,37 @@ def dualinfeas1():  # :209-221
         dict(status="DualInfeasible")
 
 
+def _generalizedpower1(use_dual):  # :1261-1281
+    v = -RT2 if use_dual else -1 / RT2
+    return _m([0, 0, 1], [[1, 0, 0], [0, 1, 0]], [0.5, 1], -np.eye(3), np.zeros(3),
+              [M.GeneralizedPower([0.5, 0.5], 1, use_dual=use_dual)]), \
+        dict(status="Optimal", primal_obj=v, x=[0.5, 1, v])
+
+
+def _generalizedpower2(use_dual):  # :1283-1304
+    w = 1.0 if use_dual else 0.5
+    return _m([0, 0, -1, -1], [[0, 1, 0, 0], [1, 0, 0, 0]], [0.5, 1], -np.eye(4), np.zeros(4),
+              [M.GeneralizedPower([0.5, 0.5], 2, use_dual=use_dual)]), \
+        dict(status="Optimal", primal_obj=-2.0 if use_dual else -1.0, x=[1, 0.5, w, w])
+
+
+def _generalizedpower3(use_dual):  # :1306-1325
+    l = 4
+    A = np.zeros((2, l + 2))
+    A[0, l] = A[1, l + 1] = 1
+    return _m(np.concatenate((np.full(l, 10.0), [0, 0])), A, [1, 0], -10 * np.eye(l + 2), np.zeros(l + 2),
+              [M.GeneralizedPower(np.full(l, 1 / l), 2, use_dual=use_dual)]), \
+        dict(status="Optimal", primal_obj=10.0 if use_dual else 10.0 * l,
+             x_idx={i: (1 / l if use_dual else 1.0) for i in range(l)})
+
+
+def _generalizedpower4(use_dual):  # :1327-1345
+    l = 4
+    G = np.vstack((np.zeros((3, l)), -np.eye(l)))
+    return _m(np.ones(l), None, None, G, np.zeros(l + 3), [M.GeneralizedPower(np.full(l, 1 / l), 3, use_dual=use_dual)]), \
+        dict(status="Optimal", primal_obj=0, x=np.zeros(l))
+
+
 def hypogeomean1():  # :1460-1476 (primal barrier)
     return _m([-1, 0, 0], [[0, 0, 1], [0, 1, 0]], [0.5, 1], -np.eye(3), np.zeros(3), [M.HypoGeoMean(3)]), \
         dict(status="Optimal", primal_obj=-1 / RT2, x_idx={1: 1.0, 2: 0.5})
@@ -442,7 +473,12 @@ for _k, (_hk, _hp) in enumerate(SEP_SPECTRAL_FUNS):
     SPECTRAL_VEC.append(_named(lambda hk=_hk, hp=_hp: _spectral_vector3(hk, hp), f"epipersepspectral_vector3_h{_hk}"))
     SPECTRAL_VEC.append(_named(lambda hk=_hk, hp=_hp: _spectral_vector4(hk, hp), f"epipersepspectral_vector4_h{_hk}"))
 
-NEW_CONES = [hypogeomean1, hypogeomean1_dual, hypogeomean2, hypogeomean2_dual, hypogeomean4, hypogeomean5,
+GPOW = []
+for _f in (_generalizedpower1, _generalizedpower2, _generalizedpower3, _generalizedpower4):
+    for _ud in (False, True):
+        GPOW.append(_named(lambda f=_f, ud=_ud: f(ud), _f.__name__[1:] + ("_dual" if _ud else "")))
+
+NEW_CONES = GPOW + [hypogeomean1, hypogeomean1_dual, hypogeomean2, hypogeomean2_dual, hypogeomean4, hypogeomean5,
              hypogeomean6, epinorminf1, epinorminf2, epinorminf3, epinorminf3_dual, epinorminf4, dualinfeas1,
              primalinfeas3, dualinfeas2, dualinfeas3, epipersquare1, epipersquare2, epipersquare3,
              epipersquare4, hypoperlog1, hypoperlog2, hypoperlog3, hypoperlog4, hypoperlog5, hypoperlog6,

@@ -1,0 +1,73 @@
+"""CPU-tier checks of the device code of GeneralizedPower and of the generic inverse-Hessian product
+(csrc/cones_gpow_kernels.cuh, compiled for the host by tests/emu/) against the CPU oracle."""
+import numpy as np
+import pytest
+
+import emu_util as eu
+from hypatia_b200.host import instances as inst
+from hypatia_b200.host import models as M
+from oracle.cones import OracleConeBlock
+
+
+def rel(a, b):
+    nb = np.linalg.norm(b)
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / (nb if nb > 0 else 1.0)
+
+
+def _alpha(rng, m):
+    a = rng.random(m) + 0.05
+    return a / a.sum()
+
+
+def _sets():
+    rng = np.random.default_rng(7)
+    return {
+        "gpow": [M.GeneralizedPower(_alpha(rng, m), n) for m, n in ((2, 1), (3, 2), (4, 1), (2, 4), (20, 30), (40, 5))],
+        "gpow_dual": [M.GeneralizedPower(_alpha(rng, 2), 1, use_dual=True), M.GeneralizedPower(_alpha(rng, 3), 3),
+                      M.GeneralizedPower(_alpha(rng, 5), 33, use_dual=True)],
+    }
+
+
+@pytest.mark.parametrize("name", ["gpow", "gpow_dual"])
+def test_gpow_kernels_match_oracle(name):
+    cones = _sets()[name]
+    I = inst.synthetic(name, 3, 0, cones, seed=600 + (name == "gpow_dual"))
+    ora = OracleConeBlock(I.model)
+    prim, dual = I.point.primal_dual(ora.dual_mask)
+    scal = 1 / np.sqrt(I.mu)
+    ora.load_point(prim, dual, scal)
+    assert ora.is_feas().all() and ora.is_dual_feas().all()
+    dev = eu.EmuGpowGroup(cones)
+    dev.load_point(scal * prim, dual)
+    assert dev.feas.all() and dev.dual_feas.all()
+    assert rel(dev.grad, ora.grad()) <= 1e-13
+    for c, ck in enumerate(ora.cones):
+        assert rel(dev.lay.get(dev.H, c), np.asarray(ck.hess())) <= 1e-12      # explicit Hessian
+    rng = np.random.default_rng(5)
+    arr = rng.standard_normal((I.model.q, 3))
+    assert rel(dev.prod(arr, 0), ora.hess_prod(arr)) <= 1e-12
+    assert rel(dev.prod(arr, 1), ora.inv_hess_prod(arr)) <= 1e-10
+    assert rel(dev.prod(arr, 1, in_place=True), ora.inv_hess_prod(arr)) <= 1e-10
+    assert rel(dev.prod(arr, 4), ora.block_hess_prod(arr)) <= 1e-10
+    assert rel(dev.dder3(arr[:, 1]), ora.dder3(arr[:, 1])) <= 1e-12
+    pt = scal * prim
+    assert rel(dev.prod(pt, 0), -dev.grad) <= 1e-12
+    assert rel(dev.prod(dev.grad, 1), -pt) <= 1e-10
+    assert rel(-dev.dder3(pt), dev.grad) <= 1e-11
+
+
+def test_gpow_kernels_flag_infeasible_points():
+    rng = np.random.default_rng(8)
+    cones = [M.GeneralizedPower(_alpha(rng, 2), 2), M.GeneralizedPower(_alpha(rng, 3), 1),
+             M.GeneralizedPower(_alpha(rng, 2), 1)]
+    I = inst.synthetic("gpinf", 2, 0, cones, seed=14)
+    prim, dual = (x.copy() for x in I.point.primal_dual(None))
+    prim[0] = -1.0             # u_1 < 0
+    prim[4 + 3] = 50.0         # |w| above prod u^alpha
+    dual[8 + 2] = 30.0         # dual |w| too large
+    ora = OracleConeBlock(I.model)
+    ora.load_point(prim, dual, 1.0)
+    dev = eu.EmuGpowGroup(cones)
+    dev.load_point(prim, dual)
+    assert (dev.feas.astype(bool) == ora.is_feas()).all() and not dev.feas[:2].any() and dev.feas[2]
+    assert (dev.dual_feas.astype(bool) == ora.is_dual_feas()).all() and not dev.dual_feas[2]

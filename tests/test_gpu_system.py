@@ -133,7 +133,8 @@ def test_spectral_and_perspective_cones(p):
              M.EpiPerSepSpectralMat(2 + M.svec_length(5), M.SSF_NEGLOG), M.EpiNormInf(6),
              M.EpiNormInf(4, use_dual=True), M.EpiPerSepSpectralVec(7, M.SSF_POWER12, 1.5),
              M.EpiPerSepSpectralVec(5, M.SSF_NEGLOG, use_dual=True), M.HypoGeoMean(6),
-             M.HypoGeoMean(4, use_dual=True)]
+             M.HypoGeoMean(4, use_dual=True), M.GeneralizedPower([0.25, 0.75], 1),
+             M.GeneralizedPower([0.2, 0.3, 0.5], 3, use_dual=True)]
     I = inst.synthetic("specmix", 20 + p, p, cones, seed=21)
     Ap = None
     if p:
@@ -199,7 +200,7 @@ def test_symindef_dense_device_vs_oracle(p):
 def test_explicit_hess_blocks_match_oracle():
     cones = [M.Nonnegative(3), M.EpiNormEucl(5), M.PosSemidefTri(6), M.HypoPerLogdetTri(8),
              M.HypoRootdetTri(7), M.EpiPerSepSpectralMat(2 + M.svec_length(3), M.SSF_NEGENTROPY),
-             M.EpiPerSquare(5), M.HypoPerLog(6), M.EpiNormInf(5)]
+             M.EpiPerSquare(5), M.HypoPerLog(6), M.EpiNormInf(5), M.GeneralizedPower([0.4, 0.6], 2)]
     I = inst.synthetic("blocks", 4, 0, cones, seed=14)
     from hypatia_b200.cones import DeviceConeBlock
     from oracle.cones import OracleConeBlock

@@ -166,6 +166,15 @@ def test_hypogeomean(dw):
     run_oracles(HypoGeoMean(1 + dw))
 
 
+@pytest.mark.parametrize("du,dw", [(2, 1), (3, 2), (4, 1), (2, 4)])
+def test_generalizedpower(du, dw):
+    # reference: test/cone.jl:541-545 (random powers); inv_hess / inv_hess_prod / sqrt oracles are the generic
+    # Hessian-factorisation fallbacks of Cones.jl:113-118, 189-259
+    from oracle.cones_vec3 import GeneralizedPower
+    a = np.random.default_rng(du * 10 + dw).random(du) + 1e-3
+    run_oracles(GeneralizedPower(a / a.sum(), dw))
+
+
 SSF = [(0, 0.0), (1, 0.0), (2, 0.0), (3, 1.5), (3, 2.0), (3, 1.1)]   # Inv, NegLog, NegEntropy, Power12(p)
 
 
