@@ -10,5 +10,5 @@ tail -3 gpurun_out/verify_pytest_tensorpath.log
 python - <<'PY'
 import json
 d=json.load(open("gpurun_out/verify_bench.json")); print(round(d["value"],3), round(d["ms_per_step"],2), {k:round(v,2) for k,v in d["roofline"]["phase_ms"].items()}, d["clocks"], d["roofline"]["hbm_phase"]["achieved_gbs"])
-s=json.load(open("gpurun_out/verify_solve_device.json")); print({k:s[k] for k in ("status","num_iters","solve_time_s","time_upsys_s","time_getdir_s","time_search_s","time_uprhs_s","gpu_launches")})
+s=json.load(open("gpurun_out/verify_solve_device.json")); print({k:s[k] for k in ("status","num_iters","solve_time_s","time_upsys_s","time_getdir_s","time_search_s","time_uprhs_s")})
 PY
