@@ -459,7 +459,7 @@ void hyp_cones_build_groups(hyp_ctx* ctx) {
         }
         if (type == HYP_CONE_EPIPERSEPSPECTRAL_MAT) hyp_spec_alloc_group(ctx, g);
         else if (cone_is_matrix(type)) hyp_mat_alloc_group(ctx, g);
-        if (type == HYP_CONE_GENERALIZEDPOWER) hyp_gpow_alloc_group(ctx, g);
+        if (cone_is_genfact(type)) hyp_gpow_alloc_group(ctx, g);
         if (type == HYP_CONE_EPIPERSEPSPECTRAL_VEC) {
             for (int kk : g.h_kidx) {
                 g.h_hkind.push_back(ctx->h_cone_hkind[kk]);
@@ -520,7 +520,7 @@ void hyp_cones_update_state(hyp_ctx* ctx) {
                 g.count, g.d_off, g.d_dim, g.d_kidx, ctx->d_point, ctx->d_dual, ctx->d_grad, g.d_scal,
                 ctx->d_feas, ctx->d_dual_feas);
             ctx->launches++;
-        } else if (g.type == HYP_CONE_GENERALIZEDPOWER) {
+        } else if (cone_is_genfact(g.type)) {
             hyp_gpow_update_state(ctx, g);
         } else if (cone_is_vec3(g.type)) {
             hypdev::v3_state_kernel<<<ceil_div(g.count, 8), 256, 0, ctx->stream>>>(
@@ -570,7 +570,7 @@ void hyp_cones_prod(hyp_ctx* ctx, double* prod, const double* arr, int64_t ncols
                 default:
                     throw HypError{"hyp_cones_prod: bad mode"};
             }
-        } else if (g.type == HYP_CONE_GENERALIZEDPOWER) {
+        } else if (cone_is_genfact(g.type)) {
             hyp_gpow_prod(ctx, g, prod, arr, ncols, ld_prod, ld_arr, m, row_shift);
         } else if (cone_is_vec3(g.type)) {
             launch_v3_prod(ctx, g, prod, arr, ncols, ld_prod, ld_arr, m, row_shift);
@@ -592,7 +592,7 @@ void hyp_cones_schur_prepass(hyp_ctx* ctx) {
         if (g.type <= HYP_CONE_EPINORMEUCL) {
             launch_vec_prod<HYP_PROD_SQRT_HESS>(ctx, g, ctx->d_HG, GQ2, ctx->nmp, ctx->ldg, ctx->ldg,
                                                 ctx->row_lo);
-        } else if (g.type == HYP_CONE_GENERALIZEDPOWER) {
+        } else if (cone_is_genfact(g.type)) {
             hyp_gpow_prod(ctx, g, ctx->d_HG, GQ2, ctx->nmp, ctx->ldg, ctx->ldg, HYP_PROD_BLOCK, ctx->row_lo);
         } else if (cone_is_vec3(g.type)) {
             launch_v3_prod(ctx, g, ctx->d_HG, GQ2, ctx->nmp, ctx->ldg, ctx->ldg,
@@ -621,7 +621,7 @@ void hyp_cones_dder3_dev(hyp_ctx* ctx, double* out, const double* dir) {
             soc_dder3_kernel<<<ceil_div(g.count, 8), 256, 0, ctx->stream>>>(
                 g.count, g.d_off, g.d_dim, g.d_scal, ctx->d_point, dir, out);
             ctx->launches++;
-        } else if (g.type == HYP_CONE_GENERALIZEDPOWER) {
+        } else if (cone_is_genfact(g.type)) {
             hyp_gpow_dder3(ctx, g, out, dir);
         } else if (cone_is_vec3(g.type)) {
             hypdev::v3_dder3_kernel<<<ceil_div(g.count, 8), 256, 0, ctx->stream>>>(

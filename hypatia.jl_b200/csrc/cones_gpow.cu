@@ -1,7 +1,7 @@
-// GeneralizedPower on the device, and the generic inverse-Hessian fallback of the Cone API (kernels:
+// GeneralizedPower and HypoPowerMean on the device, and the generic inverse-Hessian fallback of the Cone API (kernels:
 // cones_gpow_kernels.cuh).
 //
-// reference: src/Cones/generalizedpower.jl:77-236; generic oracles src/Cones/Cones.jl:113-118 (inv_hess_prod! =
+// reference: src/Cones/generalizedpower.jl:77-236, src/Cones/hypopowermean.jl:74-203; generic oracles src/Cones/Cones.jl:113-118 (inv_hess_prod! =
 // hess_fact \\ arr), :239-259 (update_hess_fact, update_inv_hess).  ConeGroup fields reused: d_side = dim of the cone
 // (side of its explicit Hessian), d_hkind = number of powers m, d_vecs / d_voff = the powers, d_W = explicit
 // Hessian, d_U = its Cholesky factor (scratch), d_Ui = U^-1.  A Hessian whose Cholesky fails marks the cone
@@ -27,17 +27,21 @@ void hyp_gpow_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
     for (int i = 0; i < g.count; i++) {
         const int k = g.h_kidx[i];
         if ((int)ctx->h_cone_aoff.size() != ctx->K + 1)
-            throw HypError{"GeneralizedPower cones need hyp_set_cone_alpha before hyp_load_model"};
+            throw HypError{"GeneralizedPower / HypoPowerMean cones need hyp_set_cone_alpha before hyp_load_model"};
         const int64_t a0 = ctx->h_cone_aoff[k], a1 = ctx->h_cone_aoff[k + 1];
         const int m = (int)(a1 - a0);
-        if (m < 1 || m >= g.h_dim[i]) throw HypError{"GeneralizedPower: need 1 <= number of powers < dim"};
-        if (g.h_dim[i] > 128) throw HypError{"GeneralizedPower: dim above 128 is not supported (batched Cholesky limit)"};
+        if (g.type == HYP_CONE_GENERALIZEDPOWER && (m < 1 || m >= g.h_dim[i]))
+            throw HypError{"GeneralizedPower: need 1 <= number of powers < dim"};
+        if (g.type == HYP_CONE_HYPOPOWERMEAN && m != g.h_dim[i] - 1)
+            throw HypError{"HypoPowerMean: need dim - 1 powers"};
+        if (g.h_dim[i] > 128)
+            throw HypError{"GeneralizedPower / HypoPowerMean: dim above 128 is not supported (batched Cholesky limit)"};
         double sum = 0.0;
         for (int64_t a = a0; a < a1; a++) {
-            if (!(ctx->h_cone_alpha[a] > 0.0)) throw HypError{"GeneralizedPower: powers must be positive"};
+            if (!(ctx->h_cone_alpha[a] > 0.0)) throw HypError{"cone powers must be positive"};
             sum += ctx->h_cone_alpha[a];
         }
-        if (std::abs(sum - 1.0) > 1e-10) throw HypError{"GeneralizedPower: powers must sum to one"};
+        if (std::abs(sum - 1.0) > 1e-10) throw HypError{"cone powers must sum to one"};
         g.h_voff[i] = (int64_t)alpha.size();
         alpha.insert(alpha.end(), ctx->h_cone_alpha.begin() + a0, ctx->h_cone_alpha.begin() + a1);
         g.h_hkind.push_back(m);
@@ -54,9 +58,14 @@ void hyp_gpow_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
 }
 
 void hyp_gpow_update_state(hyp_ctx* ctx, ConeGroup& g) {
-    hypdev::gpow_state_kernel<<<ceil_div(g.count, 8), 256, 0, ctx->stream>>>(
-        g.count, g.d_off, g.d_dim, g.d_hkind, g.d_voff, g.d_vecs, g.d_kidx, g.d_moff, ctx->d_point, ctx->d_dual,
-        ctx->d_grad, g.d_scal, g.d_W, ctx->d_feas, ctx->d_dual_feas);
+    if (g.type == HYP_CONE_HYPOPOWERMEAN)
+        hypdev::hpm_state_kernel<<<ceil_div(g.count, 8), 256, 0, ctx->stream>>>(
+            g.count, g.d_off, g.d_dim, g.d_voff, g.d_vecs, g.d_kidx, g.d_moff, ctx->d_point, ctx->d_dual, ctx->d_grad,
+            g.d_scal, g.d_W, ctx->d_feas, ctx->d_dual_feas);
+    else
+        hypdev::gpow_state_kernel<<<ceil_div(g.count, 8), 256, 0, ctx->stream>>>(
+            g.count, g.d_off, g.d_dim, g.d_hkind, g.d_voff, g.d_vecs, g.d_kidx, g.d_moff, ctx->d_point, ctx->d_dual,
+            ctx->d_grad, g.d_scal, g.d_W, ctx->d_feas, ctx->d_dual_feas);
     ctx->launches++;
     // hess_fact: Cholesky of the explicit Hessian (copy) and its inverse factor
     CUDA_TRY(cudaMemcpyAsync(g.d_U, g.d_W, (size_t)std::max<int64_t>(g.mat_total, 1) * sizeof(double),
@@ -78,9 +87,15 @@ void hyp_gpow_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr, 
     else if (mode == HYP_PROD_BLOCK_INV) { hess_dual = 1; inv_dual = 0; }
     else throw HypError{"hyp_gpow_prod: bad mode"};
     if (hess_dual > -2) {
-        hypdev::gpow_prod_kernel<<<grid, 256, 0, ctx->stream>>>(g.count, hess_dual, g.d_off, g.d_dim, g.d_hkind,
-                                                               g.d_voff, g.d_vecs, g.d_dual, g.d_scal, ctx->d_point,
-                                                               arr, ld_arr, prod, ld_prod, ncols, row_shift);
+        if (g.type == HYP_CONE_HYPOPOWERMEAN)
+            hypdev::hpm_prod_kernel<<<grid, 256, 0, ctx->stream>>>(g.count, hess_dual, g.d_off, g.d_dim, g.d_voff,
+                                                                  g.d_vecs, g.d_dual, g.d_scal, ctx->d_point, arr,
+                                                                  ld_arr, prod, ld_prod, ncols, row_shift);
+        else
+            hypdev::gpow_prod_kernel<<<grid, 256, 0, ctx->stream>>>(g.count, hess_dual, g.d_off, g.d_dim, g.d_hkind,
+                                                                   g.d_voff, g.d_vecs, g.d_dual, g.d_scal,
+                                                                   ctx->d_point, arr, ld_arr, prod, ld_prod, ncols,
+                                                                   row_shift);
         ctx->launches++;
     }
     if (inv_dual > -2) {
@@ -93,8 +108,12 @@ void hyp_gpow_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr, 
 }
 
 void hyp_gpow_dder3(hyp_ctx* ctx, ConeGroup& g, double* out, const double* dir) {
-    hypdev::gpow_dder3_kernel<<<ceil_div(g.count, 8), 256, 0, ctx->stream>>>(
-        g.count, g.d_off, g.d_dim, g.d_hkind, g.d_voff, g.d_vecs, g.d_scal, ctx->d_point, dir, out);
+    if (g.type == HYP_CONE_HYPOPOWERMEAN)
+        hypdev::hpm_dder3_kernel<<<ceil_div(g.count, 8), 256, 0, ctx->stream>>>(
+            g.count, g.d_off, g.d_dim, g.d_voff, g.d_vecs, g.d_scal, ctx->d_point, dir, out);
+    else
+        hypdev::gpow_dder3_kernel<<<ceil_div(g.count, 8), 256, 0, ctx->stream>>>(
+            g.count, g.d_off, g.d_dim, g.d_hkind, g.d_voff, g.d_vecs, g.d_scal, ctx->d_point, dir, out);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
 }

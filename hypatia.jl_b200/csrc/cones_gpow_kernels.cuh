@@ -1,4 +1,5 @@
-// Device oracles of GeneralizedPower and the GENERIC inverse-Hessian product for cones without closed forms.
+// Device oracles of GeneralizedPower and HypoPowerMean and the GENERIC inverse-Hessian product for cones without
+// closed forms.
 //
 // reference: src/Cones/generalizedpower.jl:77-236 (update_feas, is_dual_feas, update_grad, update_hess, hess_prod!,
 // dder3); the cone defines no inv_hess_prod!, so the reference falls back to the generic oracles of
@@ -6,6 +7,7 @@
 // kernel writes the explicit dim x dim Hessian of every cone, the batched Cholesky (chol.cu) factors it and
 // returns U^-1, and gen_invhess_prod_kernel applies H^-1 = U^-1 U^-T with two triangular mat-vecs per column.
 // Layout: point = (u in R^m, w in R^n), m = mu[c] powers alpha at aoff[c]; scal: 0 z, 1 |w|^2, 2 zw, 3 zwzwi.
+// HypoPowerMean (hypopowermean.jl:74-203): point = (u, w in R^d), powers alpha (d entries); scal: 0 phi, 1 zeta.
 // One warp per cone (state, dder3) / per (cone, column) (products); HBM-bound, 16 * dim B per column.
 #pragma once
 #include "devdefs.cuh"
@@ -167,6 +169,127 @@ gpow_dder3_kernel(int ncones, const int64_t* __restrict__ off, const int* __rest
             out[o + i] = c7 * di + c6 * x;
         }
     }
+}
+
+// ---- HypoPowerMean ----
+static __global__ void __launch_bounds__(256)
+hpm_state_kernel(int ncones, const int64_t* __restrict__ off, const int* __restrict__ dim,
+                 const int64_t* __restrict__ aoff, const double* __restrict__ alpha,
+                 const int* __restrict__ kidx, const int64_t* __restrict__ moff,
+                 const double* __restrict__ point, const double* __restrict__ dual, double* __restrict__ grad,
+                 double* __restrict__ scal, double* __restrict__ H, uint8_t* feas, uint8_t* dual_feas) {
+    const int lane = threadIdx.x & 31;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= ncones) return;
+    const int64_t o = off[c];
+    const int d = dim[c], lde = (d + 1) & ~1;
+    const double* al = alpha + aoff[c] - 1;      // al[i] = power of entry i (i = 1 .. d - 1)
+    const double u = point[o], du = dual[o];
+    double nbad = 0.0, dbad = 0.0, sl = 0.0, dsl = 0.0;
+    for (int i = 1 + lane; i < d; i += 32) {
+        const double w = point[o + i], y = dual[o + i];
+        if (!(w > HYP_EPS)) nbad += 1.0;
+        if (!(y > HYP_EPS)) dbad += 1.0;
+        sl += al[i] * log(w);
+        dsl += al[i] * log(y / al[i]);
+    }
+    nbad = warp_sum(nbad);
+    dbad = warp_sum(dbad);
+    sl = warp_sum(sl);
+    dsl = warp_sum(dsl);
+    const double phi = exp(sl), zeta = phi - u;
+    const bool ok = nbad == 0.0 && zeta > HYP_EPS;
+    const bool dok = du < -HYP_EPS && dbad == 0.0 && (exp(dsl) + du) > HYP_EPS;
+    const double zip = phi / zeta;
+    for (int i = 1 + lane; i < d; i += 32) grad[o + i] = (-zip * al[i] - 1.0) / point[o + i];
+    if (lane == 0) {
+        grad[o] = 1.0 / zeta;
+        scal[8 * c] = phi;
+        scal[8 * c + 1] = zeta;
+        if (!ok) feas[kidx[c]] = 0;
+        if (!dok) dual_feas[kidx[c]] = 0;
+    }
+    // explicit Hessian, both triangles (hypopowermean.jl:118-148)
+    double* Hc = H + moff[c];
+    for (int idx = lane; idx < d * d; idx += 32) {
+        const int i = idx % d, j = idx / d;
+        double v;
+        if (i == 0 && j == 0) {
+            v = 1.0 / (zeta * zeta);
+        } else if (i == 0 || j == 0) {
+            const int k = i + j;
+            v = -(zip * al[k] / point[o + k]) / zeta;
+        } else if (i == j) {
+            const double w = point[o + i];
+            v = (zip * (al[i] / w) * (1.0 + al[i] * (zip - 1.0)) + 1.0 / w) / w;
+        } else {
+            v = zip * (zip - 1.0) * (al[i] / point[o + i]) * (al[j] / point[o + j]);
+        }
+        Hc[i + (int64_t)j * lde] = v;
+    }
+}
+
+// hess_prod!, hypopowermean.jl:150-175
+static __global__ void __launch_bounds__(256)
+hpm_prod_kernel(int ncones, int want_dual, const int64_t* __restrict__ off, const int* __restrict__ dim,
+                const int64_t* __restrict__ aoff, const double* __restrict__ alpha,
+                const int* __restrict__ dualf, const double* __restrict__ scal,
+                const double* __restrict__ point, const double* arr, int64_t ld_arr, double* prod,
+                int64_t ld_prod, int64_t ncols, int64_t row_shift) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= ncones) return;
+    if (want_dual >= 0 && (dualf[c] != 0) != (want_dual != 0)) return;
+    const int64_t o = off[c];
+    const int d = dim[c];
+    const double* al = alpha + aoff[c] - 1;
+    const double phi = scal[8 * c], zeta = scal[8 * c + 1], zip = phi / zeta;
+    for (int64_t j = blockIdx.y; j < ncols; j += gridDim.y) {
+        const double* a = arr + j * ld_arr + (o - row_shift);
+        double* pr = prod + j * ld_prod + (o - row_shift);
+        const double p = a[0];
+        double s = 0.0;
+        for (int i = 1 + lane; i < d; i += 32) s += al[i] * (a[i] / point[o + i]);
+        const double c0 = warp_sum(s);
+        const double c1 = zip * c0 - p / zeta, c2 = c1 - c0;
+        for (int i = 1 + lane; i < d; i += 32) {
+            const double w = point[o + i], rwi = a[i] / w;
+            pr[i] = (al[i] * zip * (c2 + rwi) + rwi) / w;
+        }
+        if (lane == 0) pr[0] = c1 / -zeta;
+    }
+}
+
+// dder3, hypopowermean.jl:177-203
+static __global__ void __launch_bounds__(256)
+hpm_dder3_kernel(int ncones, const int64_t* __restrict__ off, const int* __restrict__ dim,
+                 const int64_t* __restrict__ aoff, const double* __restrict__ alpha,
+                 const double* __restrict__ scal, const double* __restrict__ point,
+                 const double* __restrict__ dir, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= ncones) return;
+    const int64_t o = off[c];
+    const int d = dim[c];
+    const double* al = alpha + aoff[c] - 1;
+    const double phi = scal[8 * c], zeta = scal[8 * c + 1], zip = phi / zeta;
+    const double p = dir[o];
+    double s0 = 0.0, s6 = 0.0;
+    for (int i = 1 + lane; i < d; i += 32) {
+        const double r = dir[o + i] / point[o + i];
+        s0 += r * al[i];
+        s6 += r * r * al[i];
+    }
+    const double c0 = warp_sum(s0), c6 = warp_sum(s6);
+    const double zichi = (p - phi * c0) / zeta;
+    const double c1 = zichi * zichi + zip * (c6 - c0 * c0) / 2;
+    const double c7 = zip * (c1 - c6 / 2 + c0 * (zichi + c0 / 2));
+    const double c8 = -zip * (zichi + c0);
+    for (int i = 1 + lane; i < d; i += 32) {
+        const double w = point[o + i], r = dir[o + i] / w;
+        out[o + i] = (al[i] * (c7 + r * (c8 + zip * r)) + r * r) / w;
+    }
+    if (lane == 0) out[o] = -c1 / zeta;
 }
 
 // Generic inv_hess_prod! (Cones.jl:113-118): y = H^-1 x = U^-1 (U^-T x) with the inverse Cholesky factor

@@ -922,7 +922,7 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
                                     ? ((int)ctx->h_cone_aoff.size() == K + 1
                                            ? (double)(ctx->h_cone_aoff[k + 1] - ctx->h_cone_aoff[k]) + 1.0
                                            : 0.0)
-                                                             : (double)d;   // HypoPerLog, EpiNormInf, EpiPerSepSpectral{VectorCSqr}, HypoGeoMean: nu = dim
+                                                             : (double)d;   // HypoPerLog, EpiNormInf, EpiPerSepSpectral{VectorCSqr}, HypoGeoMean, HypoPowerMean: nu = dim
             if ((t == HYP_CONE_EPINORMINF || t == HYP_CONE_HYPOGEOMEAN) && d < 2)
                 throw HypError{"hyp_load_model: EpiNormInf / HypoGeoMean need dimension >= 2"};
             if ((t == HYP_CONE_EPIPERSQUARE || t == HYP_CONE_HYPOPERLOG || t == HYP_CONE_EPIPERSEPSPECTRAL_MAT ||

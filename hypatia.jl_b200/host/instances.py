@@ -106,6 +106,29 @@ def cone_initial_point(spec):
         arr[2:] = w
     elif spec.ctype == M.CONE_EPINORMINF:
         arr[0] = np.sqrt(spec.dim)      # epinorminf.jl:88-95
+    elif spec.ctype == M.CONE_HYPOPOWERMEAN:
+        al = np.array(spec.alpha)         # hypopowermean.jl:58-72, :205-232 (fitted central ray)
+        d = al.size
+        if np.all(al == 1.0 / d):
+            c = np.sqrt(5.0 * d * d + 2 * d + 1)
+            arr[0] = -np.sqrt((-c + 3 * d + 1) / (2.0 + 2 * d))
+            arr[1:] = (c - d + 1) / np.sqrt((1 + d) * (-2 * c + 6 * d + 2))
+        else:
+            if d == 1:
+                w = np.full(1, 1.306563)
+            elif d == 2:
+                w = 1.0049885 + 0.2986276 * al
+            elif d <= 5:
+                w = 1.0040142949 - 0.0004885108 * d + 0.3016645951 * al
+            elif d <= 20:
+                w = 1.001168 - 4.547017e-05 * d + 3.032880e-01 * al
+            elif d <= 100:
+                w = 1.000069 - 5.469926e-07 * d + 3.074084e-01 * al
+            else:
+                w = 1 + 3.086535e-01 * al
+            pw = np.exp(np.sum(al * np.log(w)))
+            arr[0] = pw - pw / d * np.sum(al / (w * w - 1))
+            arr[1:] = w
     elif spec.ctype == M.CONE_GENERALIZEDPOWER:
         arr[:len(spec.alpha)] = np.sqrt(1 + np.array(spec.alpha))      # generalizedpower.jl:71-75
     elif spec.ctype == M.CONE_HYPOGEOMEAN:
@@ -128,6 +151,16 @@ def _cone_dual_initial(spec, prim):
         return prim.copy()      # central point is self-dual: -g = (u, -w)/dist with dist = 1
     if spec.ctype == M.CONE_POSSEMIDEFTRI:
         return prim.copy()
+    if spec.ctype == M.CONE_HYPOPOWERMEAN:
+        # -grad, hypopowermean.jl:104-116
+        al = np.array(spec.alpha)
+        u, w = prim[0], prim[1:]
+        phi = np.exp(np.sum(al * np.log(w)))
+        zeta = phi - u
+        out = np.zeros_like(prim)
+        out[0] = -1.0 / zeta
+        out[1:] = (phi / zeta * al + 1) / w
+        return out
     if spec.ctype == M.CONE_GENERALIZEDPOWER:
         # generalizedpower.jl:107-120 at w = 0: zwzwi = 1, -g_u = (alpha + 1) / u = sqrt(1 + alpha) (central point)
         return prim.copy()
@@ -210,7 +243,7 @@ def _perturb(rng, spec, vec, noise):
     if spec.ctype == M.CONE_GENERALIZEDPOWER:
         vec += 0.5 * noise / np.sqrt(vec.size) * (2 * rng.random(vec.size) - 1)
         return vec
-    if spec.ctype == M.CONE_HYPOGEOMEAN:
+    if spec.ctype in (M.CONE_HYPOGEOMEAN, M.CONE_HYPOPOWERMEAN):
         vec[0] += 0.5 * noise * (2 * rng.random() - 1)
         vec[1:] += noise / np.sqrt(vec.size) * (2 * rng.random(vec.size - 1) - 1)
         return vec

@@ -24,6 +24,7 @@ CONE_EPINORMINF = 8
 CONE_EPIPERSEPSPECTRAL_VEC = 9
 CONE_HYPOGEOMEAN = 10
 CONE_GENERALIZEDPOWER = 11
+CONE_HYPOPOWERMEAN = 12
 
 # separable spectral functions of EpiPerSepSpectral (sepspectralfun.jl:17-116), HYP_SSF_*
 SSF_INV, SSF_NEGLOG, SSF_NEGENTROPY, SSF_POWER12 = 0, 1, 2, 3
@@ -41,6 +42,7 @@ CONE_NAMES = {
     CONE_EPIPERSEPSPECTRAL_VEC: "EpiPerSepSpectral{VectorCSqr}",
     CONE_HYPOGEOMEAN: "HypoGeoMean",
     CONE_GENERALIZEDPOWER: "GeneralizedPower",
+    CONE_HYPOPOWERMEAN: "HypoPowerMean",
 }
 
 
@@ -99,6 +101,9 @@ class ConeSpec:
         elif ctype == CONE_GENERALIZEDPOWER:
             assert dim >= 3 and 1 <= len(self.alpha) < dim and all(a > 0 for a in self.alpha)
             assert abs(sum(self.alpha) - 1) <= 1e-12
+        elif ctype == CONE_HYPOPOWERMEAN:
+            assert dim >= 2 and len(self.alpha) == dim - 1 and all(a > 0 for a in self.alpha)
+            assert abs(sum(self.alpha) - 1) <= 1e-12
         elif ctype == CONE_EPIPERSEPSPECTRAL_VEC:
             assert dim >= 3 and hkind in (SSF_INV, SSF_NEGLOG, SSF_NEGENTROPY, SSF_POWER12)
             assert hkind != SSF_POWER12 or 1 < hparam <= 2
@@ -132,7 +137,8 @@ class ConeSpec:
             return 2.0
         if self.ctype == CONE_GENERALIZEDPOWER:
             return float(len(self.alpha) + 1)
-        if self.ctype in (CONE_HYPOPERLOG, CONE_EPINORMINF, CONE_EPIPERSEPSPECTRAL_VEC, CONE_HYPOGEOMEAN):
+        if self.ctype in (CONE_HYPOPERLOG, CONE_EPINORMINF, CONE_EPIPERSEPSPECTRAL_VEC, CONE_HYPOGEOMEAN,
+                          CONE_HYPOPOWERMEAN):
             return float(self.dim)
         return 1.0 + self.side
 
@@ -186,6 +192,11 @@ def GeneralizedPower(alpha, n, use_dual=False):
     """GeneralizedPower{Float64}(alpha, n): (u in R^m_+, w in R^n), prod u_i^alpha_i >= |w|; MOI's PowerCone(a) is
     GeneralizedPower([a, 1 - a], 1) (MathOptInterface/cones.jl:33-37)."""
     return ConeSpec(CONE_GENERALIZEDPOWER, len(alpha) + n, use_dual, alpha=alpha)
+
+
+def HypoPowerMean(alpha, use_dual=False):
+    """HypoPowerMean{Float64}(alpha): (u, w in R^d_+), u <= prod w_i^alpha_i, dim = 1 + len(alpha)."""
+    return ConeSpec(CONE_HYPOPOWERMEAN, 1 + len(alpha), use_dual, alpha=alpha)
 
 
 def HypoGeoMean(dim, use_dual=False):

@@ -49,6 +49,7 @@ typedef struct hyp_ctx hyp_ctx;
 #define HYP_CONE_EPIPERSEPSPECTRAL_VEC 9 /* epipersepspectral/{epipersepspectral,vectorcsqr}.jl */
 #define HYP_CONE_HYPOGEOMEAN 10     /* hypogeomean.jl      */
 #define HYP_CONE_GENERALIZEDPOWER 11 /* generalizedpower.jl (powers via hyp_set_cone_alpha; dim <= 128) */
+#define HYP_CONE_HYPOPOWERMEAN 12   /* hypopowermean.jl (dim - 1 powers via hyp_set_cone_alpha; dim <= 128) */
 
 /* separable spectral functions of EpiPerSepSpectral (epipersepspectral/sepspectralfun.jl:17-116) */
 #define HYP_SSF_INV 0        /* InvSSF        x -> 1/x      */

@@ -42,7 +42,9 @@ cone_code(::Cones.EpiNormInf{Float64, Float64}) = Cint(8)
 cone_code(::Cones.EpiPerSepSpectral{Cones.VectorCSqr{Float64}, Float64}) = Cint(9)
 cone_code(::Cones.HypoGeoMean) = Cint(10)
 cone_code(::Cones.GeneralizedPower) = Cint(11)
+cone_code(::Cones.HypoPowerMean) = Cint(12)
 cone_alpha(c::Cones.GeneralizedPower) = Vector{Float64}(c.α)
+cone_alpha(c::Cones.HypoPowerMean) = Vector{Float64}(c.α)
 cone_alpha(::Cones.Cone) = Float64[]
 cone_code(c::Cones.Cone) = error("cone $(typeof(c)) is not on the B200 hot path")
 

@@ -618,3 +618,113 @@ class GeneralizedPower(Cone):
         c7 = zwi * (2 * z * audu - wwd) / zw
         d3[m:] = c7 * w_dir + c6 * w
         return d3
+
+
+def get_central_ray_hypopowermean(alpha):
+    """hypopowermean.jl:205-232 (fitted constants of the reference)."""
+    alpha = np.asarray(alpha, dtype=np.float64)
+    d = alpha.size
+    if d == 1:
+        w = np.full(1, 1.306563)
+    elif d == 2:
+        w = 1.0049885 + 0.2986276 * alpha
+    elif d <= 5:
+        w = 1.0040142949 - 0.0004885108 * d + 0.3016645951 * alpha
+    elif d <= 20:
+        w = 1.001168 - 4.547017e-05 * d + 3.032880e-01 * alpha
+    elif d <= 100:
+        w = 1.000069 - 5.469926e-07 * d + 3.074084e-01 * alpha
+    else:
+        w = 1 + 3.086535e-01 * alpha
+    p = np.exp(np.sum(alpha * np.log(w)))
+    u = p - p / d * np.sum(alpha / (w * w - 1))
+    return u, w
+
+
+class HypoPowerMean(Cone):
+    """hypopowermean.jl:8-232: (u, w in R^d_++), u <= prod w_i^alpha_i; barrier -log(prod w_i^alpha_i - u) - sum log w_i,
+    nu = dim.  No closed-form inverse Hessian: the generic oracles of Cones.jl:113-118, 189-259 apply."""
+    ctype = M.CONE_HYPOPOWERMEAN
+
+    def __init__(self, alpha, use_dual=False):
+        self.alpha = np.array(alpha, dtype=np.float64)
+        self.use_dual_barrier = use_dual
+        super().__init__(1 + self.alpha.size)
+
+    @property
+    def nu(self):
+        return float(self.dim)
+
+    def set_initial_point(self, arr):
+        d = self.dim - 1
+        if np.all(self.alpha == 1.0 / d):
+            c = np.sqrt(5.0 * d * d + 2 * d + 1)
+            arr[0] = -np.sqrt((-c + 3 * d + 1) / (2.0 + 2 * d))
+            arr[1:] = (c - d + 1) / np.sqrt((1 + d) * (-2 * c + 6 * d + 2))
+        else:
+            arr[0], arr[1:] = get_central_ray_hypopowermean(self.alpha)
+        return arr
+
+    def update_feas(self):
+        u, w = self.point[0], self.point[1:]
+        if (w > EPS).all():
+            self.phi = float(np.exp(np.sum(self.alpha * np.log(w))))
+            self.zeta = self.phi - u
+            return self.zeta > EPS
+        return False
+
+    def is_dual_feas(self):
+        u, w = self.dual_point[0], self.dual_point[1:]
+        if u < -EPS and (w > EPS).all():
+            return bool(np.exp(np.sum(self.alpha * np.log(w / self.alpha))) + u > EPS)
+        return False
+
+    def update_grad(self):
+        w = self.point[1:]
+        self._grad[0] = 1.0 / self.zeta
+        self._grad[1:] = (-self.phi / self.zeta * self.alpha - 1) / w
+
+    def update_hess(self):
+        self.grad()
+        w, alpha, zeta = self.point[1:], self.alpha, self.zeta
+        zip_ = self.phi / zeta
+        awi = alpha / w
+        H = np.zeros((self.dim, self.dim))
+        H[0, 0] = zeta ** -2
+        H[0, 1:] = H[1:, 0] = -(zip_ * awi) / zeta
+        H[1:, 1:] = zip_ * (zip_ - 1) * np.outer(awi, awi)
+        idx = np.arange(1, self.dim)
+        H[idx, idx] = (zip_ * awi * (1 + alpha * (zip_ - 1)) + 1.0 / w) / w
+        return H
+
+    def hess_prod(self, arr):
+        self.grad()
+        a, vec = _as2d(arr)
+        w, alpha, zeta = self.point[1:], self.alpha, self.zeta
+        zip_ = self.phi / zeta
+        p = a[0]
+        rwi = a[1:] / w[:, None]
+        c0 = alpha @ rwi
+        c1 = zip_ * c0 - p / zeta
+        c2 = c1 - c0
+        prod = np.empty_like(a)
+        prod[0] = c1 / -zeta
+        prod[1:] = (alpha[:, None] * zip_ * (c2[None, :] + rwi) + rwi) / w[:, None]
+        return _ret(prod, vec)
+
+    def dder3(self, direction):
+        self.grad()
+        w, alpha, zeta, phi = self.point[1:], self.alpha, self.zeta, self.phi
+        p, r = direction[0], direction[1:]
+        zip_ = phi / zeta
+        rwi = r / w
+        c0 = float(rwi @ alpha)
+        c6 = float((rwi ** 2) @ alpha)
+        zichi = (p - phi * c0) / zeta
+        c1 = zichi ** 2 + zip_ * (c6 - c0 ** 2) / 2
+        c7 = zip_ * (c1 - c6 / 2 + c0 * (zichi + c0 / 2))
+        c8 = -zip_ * (zichi + c0)
+        d3 = np.empty(self.dim)
+        d3[0] = -c1 / zeta
+        d3[1:] = (alpha * (c7 + rwi * (c8 + zip_ * rwi)) + rwi ** 2) / w
+        return d3

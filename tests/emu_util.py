@@ -296,6 +296,7 @@ class EmuGpowGroup:
 
     def __init__(self, specs):
         self.K = len(specs)
+        self.hpm = specs[0].ctype == 12          # HypoPowerMean, else GeneralizedPower
         self.dims = np.array([s.dim for s in specs], dtype=np.int32)
         self.off = np.concatenate(([0], np.cumsum(self.dims)))[:-1].astype(np.int64)
         self.q = int(self.dims.sum())
@@ -314,9 +315,14 @@ class EmuGpowGroup:
         self.dual_feas = np.ones(self.K, dtype=np.uint8)
         self.grad = np.zeros(self.q)
         self.H = np.zeros(self.lay.total)
-        lib().emu_gpow_state(self.K, p(self.off), p(self.dims), p(self.mu), p(self.aoff), p(self.alpha), p(self.kidx),
-                             p(self.lay.moff), p(self.point), p(self.dual), p(self.grad), p(self.scal), p(self.H),
-                             p(self.feas), p(self.dual_feas))
+        if self.hpm:
+            lib().emu_hpm_state(self.K, p(self.off), p(self.dims), p(self.aoff), p(self.alpha), p(self.kidx),
+                                p(self.lay.moff), p(self.point), p(self.dual), p(self.grad), p(self.scal), p(self.H),
+                                p(self.feas), p(self.dual_feas))
+        else:
+            lib().emu_gpow_state(self.K, p(self.off), p(self.dims), p(self.mu), p(self.aoff), p(self.alpha),
+                                 p(self.kidx), p(self.lay.moff), p(self.point), p(self.dual), p(self.grad),
+                                 p(self.scal), p(self.H), p(self.feas), p(self.dual_feas))
         self.Ui = np.zeros(self.lay.total)
         for c in range(self.K):
             Hc = self.lay.get(self.H, c)
@@ -331,7 +337,10 @@ class EmuGpowGroup:
         out = a if in_place else np.zeros_like(a, order="F")
         hess_dual, inv_dual = {0: (-1, -2), 1: (-2, -1), 4: (0, 1), 5: (1, 0)}[int(mode)]
         L = lib()
-        if hess_dual > -2:
+        if hess_dual > -2 and self.hpm:
+            L.emu_hpm_prod(self.K, hess_dual, p(self.off), p(self.dims), p(self.aoff), p(self.alpha), p(self.dualf),
+                           p(self.scal), p(self.point), p(a), i64(self.q), p(out), i64(self.q), i64(a.shape[1]), i64(0))
+        elif hess_dual > -2:
             L.emu_gpow_prod(self.K, hess_dual, p(self.off), p(self.dims), p(self.mu), p(self.aoff), p(self.alpha),
                             p(self.dualf), p(self.scal), p(self.point), p(a), i64(self.q), p(out), i64(self.q),
                             i64(a.shape[1]), i64(0))
@@ -343,6 +352,10 @@ class EmuGpowGroup:
     def dder3(self, direction):
         d = np.ascontiguousarray(direction, dtype=np.float64)
         out = np.zeros(self.q)
-        lib().emu_gpow_dder3(self.K, p(self.off), p(self.dims), p(self.mu), p(self.aoff), p(self.alpha), p(self.scal),
-                             p(self.point), p(d), p(out))
+        if self.hpm:
+            lib().emu_hpm_dder3(self.K, p(self.off), p(self.dims), p(self.aoff), p(self.alpha), p(self.scal),
+                                p(self.point), p(d), p(out))
+        else:
+            lib().emu_gpow_dder3(self.K, p(self.off), p(self.dims), p(self.mu), p(self.aoff), p(self.alpha),
+                                 p(self.scal), p(self.point), p(d), p(out))
         return out

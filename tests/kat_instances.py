@@ -261,6 +261,43 @@ def _generalizedpower4(use_dual):  # :1327-1345
         dict(status="Optimal", primal_obj=0, x=np.zeros(l))
 
 
+def _hypopowermean1(use_dual):  # :1347-1364
+    return _m([-1, 0, 0], [[0, 0, 1], [0, 1, 0]], [0.5, 1], -np.eye(3), np.zeros(3),
+              [M.HypoPowerMean([0.5, 0.5], use_dual=use_dual)]), \
+        dict(status="Optimal", primal_obj=0.0 if use_dual else -1 / RT2, x_idx={1: 1.0, 2: 0.5})
+
+
+def _hypopowermean2(use_dual):  # :1366-1385
+    l = 4
+    A = np.zeros((1, l + 1))
+    A[0, 0] = 1
+    return _m(np.concatenate(([0.0], np.ones(l))), A, [-1.0 if use_dual else 1.0], -np.eye(l + 1), np.zeros(l + 1),
+              [M.HypoPowerMean(np.full(l, 1 / l), use_dual=use_dual)]), \
+        dict(status="Optimal", primal_obj=1.0 if use_dual else float(l),
+             x_idx={i: (1 / l if use_dual else 1.0) for i in range(1, l + 1)})
+
+
+def hypopowermean4():  # :1407-1423
+    G = np.vstack((-np.eye(4), [[0, 1, 1, 1]]))
+    return _m([-1, 0, 0, 0], None, None, G, [0, 0, 0, 0, 3], [M.HypoPowerMean(np.full(3, 1 / 3)), M.Nonnegative(1)]), \
+        dict(status="Optimal", primal_obj=-1, x=[1, 1, 1, 1], s=[1, 1, 1, 1, 0], z=[-1, 1 / 3, 1 / 3, 1 / 3, 1 / 3])
+
+
+def hypopowermean5():  # :1425-1440
+    G = _sparse([1, 2, 3], [1, 2, 2], [-1, -1, 1], 3, 2)
+    return _m([-2, 0], None, None, G, [0, 0, 2], [M.HypoPowerMean([1.0]), M.Nonnegative(1)]), \
+        dict(status="Optimal", primal_obj=-4, x=[2, 2], s=[2, 2, 0], z=[-2, 2, 2])
+
+
+def hypopowermean6():  # :1442-1458
+    c = np.zeros(10)
+    c[0] = -1
+    A = np.hstack((np.zeros((9, 1)), np.eye(9)))
+    return _m(c, A, np.ones(9), -np.eye(10), np.zeros(10), [M.HypoPowerMean(np.full(9, 1 / 9))]), \
+        dict(status="Optimal", primal_obj=-1, x=np.ones(10), z=np.concatenate(([-1.0], np.full(9, 1 / 9))),
+             y=np.full(9, 1 / 9))
+
+
 def hypogeomean1():  # :1460-1476 (primal barrier)
     return _m([-1, 0, 0], [[0, 0, 1], [0, 1, 0]], [0.5, 1], -np.eye(3), np.zeros(3), [M.HypoGeoMean(3)]), \
         dict(status="Optimal", primal_obj=-1 / RT2, x_idx={1: 1.0, 2: 0.5})
@@ -478,7 +515,11 @@ for _f in (_generalizedpower1, _generalizedpower2, _generalizedpower3, _generali
     for _ud in (False, True):
         GPOW.append(_named(lambda f=_f, ud=_ud: f(ud), _f.__name__[1:] + ("_dual" if _ud else "")))
 
-NEW_CONES = GPOW + [hypogeomean1, hypogeomean1_dual, hypogeomean2, hypogeomean2_dual, hypogeomean4, hypogeomean5,
+HPM = [_named(lambda f=_f, ud=_ud: f(ud), _f.__name__[1:] + ("_dual" if _ud else ""))
+       for _f in (_hypopowermean1, _hypopowermean2) for _ud in (False, True)] + \
+    [hypopowermean4, hypopowermean5, hypopowermean6]
+
+NEW_CONES = GPOW + HPM + [hypogeomean1, hypogeomean1_dual, hypogeomean2, hypogeomean2_dual, hypogeomean4, hypogeomean5,
              hypogeomean6, epinorminf1, epinorminf2, epinorminf3, epinorminf3_dual, epinorminf4, dualinfeas1,
              primalinfeas3, dualinfeas2, dualinfeas3, epipersquare1, epipersquare2, epipersquare3,
              epipersquare4, hypoperlog1, hypoperlog2, hypoperlog3, hypoperlog4, hypoperlog5, hypoperlog6,

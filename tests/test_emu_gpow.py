@@ -1,4 +1,4 @@
-"""CPU-tier checks of the device code of GeneralizedPower and of the generic inverse-Hessian product
+"""CPU-tier checks of the device code of GeneralizedPower, HypoPowerMean and of the generic inverse-Hessian product
 (csrc/cones_gpow_kernels.cuh, compiled for the host by tests/emu/) against the CPU oracle."""
 import numpy as np
 import pytest
@@ -19,19 +19,27 @@ def _alpha(rng, m):
     return a / a.sum()
 
 
+def _bal(rng, d):
+    a = rng.random(d) + 1        # balanced powers as in the reference's tests (test/cone.jl:291-296)
+    return a / a.sum()
+
+
 def _sets():
     rng = np.random.default_rng(7)
     return {
         "gpow": [M.GeneralizedPower(_alpha(rng, m), n) for m, n in ((2, 1), (3, 2), (4, 1), (2, 4), (20, 30), (40, 5))],
+        "hpm": [M.HypoPowerMean(_bal(rng, d)) for d in (1, 2, 5, 33, 70)],
+        "hpm_dual": [M.HypoPowerMean(_bal(rng, 3), use_dual=True), M.HypoPowerMean(_bal(rng, 6)),
+                     M.HypoPowerMean(_bal(rng, 40), use_dual=True)],
         "gpow_dual": [M.GeneralizedPower(_alpha(rng, 2), 1, use_dual=True), M.GeneralizedPower(_alpha(rng, 3), 3),
                       M.GeneralizedPower(_alpha(rng, 5), 33, use_dual=True)],
     }
 
 
-@pytest.mark.parametrize("name", ["gpow", "gpow_dual"])
+@pytest.mark.parametrize("name", ["gpow", "gpow_dual", "hpm", "hpm_dual"])
 def test_gpow_kernels_match_oracle(name):
     cones = _sets()[name]
-    I = inst.synthetic(name, 3, 0, cones, seed=600 + (name == "gpow_dual"))
+    I = inst.synthetic(name, 3, 0, cones, seed=600 + ["gpow", "gpow_dual", "hpm", "hpm_dual"].index(name))
     ora = OracleConeBlock(I.model)
     prim, dual = I.point.primal_dual(ora.dual_mask)
     scal = 1 / np.sqrt(I.mu)

@@ -51,12 +51,15 @@ CONE_SETS = {
     "gpow": [M.GeneralizedPower([0.5, 0.5], 1), M.GeneralizedPower([0.2, 0.3, 0.5], 2),
              M.GeneralizedPower(np.full(20, 0.05), 30), M.GeneralizedPower([0.7, 0.3], 1, use_dual=True),
              M.GeneralizedPower(np.full(4, 0.25), 60)],
+    "hpm": [M.HypoPowerMean([1.0]), M.HypoPowerMean([0.4, 0.6]), M.HypoPowerMean(np.full(33, 1 / 33)),
+            M.HypoPowerMean([0.3, 0.3, 0.4], use_dual=True), M.HypoPowerMean(np.full(70, 1 / 70))],
     "allmix": [M.Nonnegative(5), M.EpiNormEucl(4), M.PosSemidefTri(6), M.HypoPerLogdetTri(8),
                M.HypoRootdetTri(7), M.EpiNormEucl(3), M.HypoPerLogdetTri(5, use_dual=True),
                M.EpiPerSepSpectralMat(2 + M.svec_length(4), M.SSF_NEGENTROPY), M.EpiPerSquare(6),
                M.HypoPerLog(5), M.HypoPerLog(4, use_dual=True), M.EpiNormInf(5), M.EpiNormInf(4, use_dual=True),
                M.EpiPerSepSpectralVec(6, M.SSF_NEGENTROPY), M.HypoGeoMean(5), M.HypoGeoMean(4, use_dual=True),
-               M.GeneralizedPower([0.3, 0.7], 2), M.GeneralizedPower([0.5, 0.5], 1, use_dual=True)],
+               M.GeneralizedPower([0.3, 0.7], 2), M.GeneralizedPower([0.5, 0.5], 1, use_dual=True),
+               M.HypoPowerMean([0.25, 0.35, 0.4]), M.HypoPowerMean([0.5, 0.5], use_dual=True)],
 }
 
 

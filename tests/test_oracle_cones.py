@@ -175,6 +175,14 @@ def test_generalizedpower(du, dw):
     run_oracles(GeneralizedPower(a / a.sum(), dw))
 
 
+@pytest.mark.parametrize("dw,init_only", [(1, False), (2, False), (5, False), (15, True), (40, True), (100, True)])
+def test_hypopowermean(dw, init_only):
+    # reference: test/cone.jl:563-570 (powers rand + 1 normalised, init_tol 1e-2 / 1e-1)
+    from oracle.cones_vec3 import HypoPowerMean
+    a = np.random.default_rng(dw).random(dw) + 1
+    run_oracles(HypoPowerMean(a / a.sum()), init_tol=1e-1 if init_only else 1e-2, init_only=init_only)
+
+
 SSF = [(0, 0.0), (1, 0.0), (2, 0.0), (3, 1.5), (3, 2.0), (3, 1.1)]   # Inv, NegLog, NegEntropy, Power12(p)
 
 

@@ -14,6 +14,8 @@ from oracle.cones import OracleConeBlock
 
 
 def solve(model, syssolver, **kw):
+    # the reference runs its instance tests with default_tol_relax = 10 (test/runnativetests.jl:13-18)
+    kw.setdefault("default_tol_relax", 10)
     s = Solver(model, syssolver, OracleConeBlock, **kw)
     s.solve()
     return s
