@@ -68,7 +68,10 @@ WORKLOADS = {
 
 # DRAM traffic of the Schur SYRK launch from the committed `ncu --set full` capture (per launch)
 NCU_TRAFFIC = {"C3": 31.497622e9 + 0.411380e9,                       # FP64 DMMA kernel, one launch
-               "C3:i8": 119.23e9 + 0.81553e9 + 65.82e9 + 0.81341e9}   # tcgen05 pair kernel, both K chunks
+               # tcgen05 CTA-pair kernel, radix-256 digits: the four launches of one SYRK in
+               # profiles/r01_ozaki_pair_radix256_ncu.txt (K cut 3 x 16384 + 848 in that capture; the
+               # current build cuts 3 equal chunks - the traffic is proportional to the rows)
+               "C3:i8": (61.103e9 + 0.814e9) + (66.283e9 + 0.814e9) + (65.187e9 + 0.815e9) + (1.370e9 + 0.571e9)}
 
 
 class PanelModel:
@@ -234,10 +237,13 @@ def dgemm_peak_tflops(torch, device):
 
 
 # --------------------------------------------------------------------------------------------
-def cpu_unit(workload, steps, warmup, budget_s=25.0):
+def cpu_unit(workload, steps, warmup, budget_s=25.0, rhs_list=None):
     """CPU oracle restatement of the same unit on the host cores.  Returns (seconds per unit,
-    sample description, cores).  The SYRK is timed on a bounded row sample when a full unit would
-    exceed the budget (its cost is linear in the rows), everything else runs in full."""
+    sample description, cores, threadpool info, directions of the last unit).  The SYRK is timed on a
+    bounded row sample when a full unit would exceed the budget (its cost is linear in the rows; the
+    factorisation then uses the Schur matrix of one full, untimed assembly), everything else runs in
+    full.  `rhs_list` replaces the oracle's own four right-hand sides (bench.py's parity check hands in
+    the ones the device solved)."""
     import threadpoolctl
     from scipy.linalg import blas as _blas
     from hypatia_b200.host import models as M
@@ -261,7 +267,8 @@ def cpu_unit(workload, steps, warmup, budget_s=25.0):
         frac = max(rs / q, min(1.0, budget_s / (est_full * (steps + warmup))))
     shell = iterate_shell(model, I["s0"], I["z0"], I["x0"], I["mu"], OracleConeBlock,
                           syrk_row_fraction=frac)
-    rhs_list = shell.rhs_list
+    if rhs_list is None:
+        rhs_list = shell.rhs_list
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
@@ -272,14 +279,14 @@ def cpu_unit(workload, steps, warmup, budget_s=25.0):
     sample = (f"{steps} full unit(s) of {workload}" if frac >= 1.0 else
               f"{steps} unit(s) of {workload}; dsyrk timed on the first {frac:.3f} of the rows and "
               f"scaled by 1/{frac:.3f}, Cholesky and all solves in full")
-    return float(np.median(times)), sample, cores, threadpoolctl.threadpool_info()
+    return float(np.median(times)), sample, cores, threadpoolctl.threadpool_info(), shell.sols
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    sec, sample, cores, _ = cpu_unit(args.workload, max(1, args.steps), min(args.warmup, 1))
+    sec, sample, cores, _, _ = cpu_unit(args.workload, max(1, args.steps), min(args.warmup, 1))
     v = 1.0 / sec
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
@@ -466,7 +473,7 @@ def run_ours(args):
                     "int8_frac": (int8_tops / int8_peak) if int8_tops and int8_peak else None,
                     "traffic": NCU_TRAFFIC.get(args.workload + ":i8") if world == 1 else None,
                     "traffic_unit": "bytes per SYRK (dram__bytes_read.sum + dram__bytes_write.sum over its launches, "
-                                    "profiles/r01_ozaki_pair_ncu.txt)",
+                                    "profiles/r01_ozaki_pair_radix256_ncu.txt)",
                     "algorithmic_flops_per_launch": syrk_flops, "avg_launch_ms": syrk_ms,
                     "step_share": syrk_ms / (ms / args.steps) if syrk_ms == syrk_ms else None,
                     "phase_ms": phases}
@@ -496,11 +503,21 @@ def run_ours(args):
                                  "peak_gbs": peaks.get("hbm_gbs"),
                                  "note": "%d passes per step (reference count 22; the s-lift reuses G*x; apply_lhs "
                                          "reads G once for G'z and G x when the panel is not sharded)" % npass}
+    # parity at the benchmarked size (SURVEY.md 8(d) "parity reported with every timing"): the directions
+    # and residuals that came back over the C ABI in the end-to-end pass.  kkt_residual is the size-independent
+    # property ||K d - r|| / ||r|| with the device operator; dir_vs_oracle compares each direction with the CPU
+    # oracle's solve of the SAME right-hand side (filled in by the cpu_baseline leg below, N = 1 only).
+    relerr = lambda a, b: float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+    dev_sols = [t.numpy().copy() for t in host_out["sol"]]
+    parity = {"tol": 1e-8,
+              "kkt_residual": [relerr(host_out["res"][i].numpy(), rhs_list[i]) for i in range(4)],
+              "dir_vs_oracle": None}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            sec, sample, cores, _ = cpu_unit(args.workload, 1, 0)
+            sec, sample, cores, _, ora_sols = cpu_unit(args.workload, 1, 0, rhs_list=rhs_list)
             cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+            parity["dir_vs_oracle"] = [relerr(dev_sols[i], ora_sols[i]) for i in range(4)]
         except Exception as e:      # the baseline is reported, never required
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                    "sample": f"failed: {type(e).__name__}: {e}"}
@@ -514,7 +531,7 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (G panel %.1f GB, Schur %.2f GB)" % (g_bytes / 1e9, 8e-9 * m * m)},
             "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                                       "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "parity": parity}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

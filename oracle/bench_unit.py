@@ -92,10 +92,12 @@ def iterate_shell(model, s0, z0, x0, mu, cone_cls, syrk_row_fraction=1.0):
         sys_.extra_time = 0.0
         sh.cones.load_point(pt.s, pt.z, irtmu)
         sys_.update_lhs(sh)
+        sh.sols = []
         for v in rhs_vecs:
             r.vec[:] = v
             sys_.solve_system(sh, sol, r)
             sys_.apply_lhs(sh, sol, res)
+            sh.sols.append(sol.vec.copy())      # bench.py's full-size direction parity
         return sys_.extra_time
 
     sh.unit = unit

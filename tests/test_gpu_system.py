@@ -65,6 +65,15 @@ def test_vector_cone_configs(name, scale, syrk, monkeypatch):
     _check_system(inst.config(name, scale))
 
 
+@pytest.mark.parametrize("name", ["C2", "C3"])
+def test_baseline_configs_at_full_size(name):
+    """BASELINE.json's configs[0..1] at their FULL sizes (C2: m = 4000, q = 5000; C3: n = 10000,
+    q = 50000, 2000 x EpiNormEucl(25) - the benchmarked workload): Schur matrix, directions, the
+    operator and the 3x3 subsystem against the CPU oracle (one dsyrk + dpotrf of the full size, about
+    10 s of host time for C3), and the KKT round trip apply_lhs(solve_system(r)) = r."""
+    _check_system(inst.config(name, 1.0))
+
+
 @pytest.mark.parametrize("syrk", ["i8", "dmma"])
 def test_schur_matrix_accuracy_vs_extended_precision(syrk, monkeypatch):
     """The assembled Schur matrix against a long-double reference of G'HG: both kernels must be at
