@@ -1,5 +1,6 @@
-// Device oracles of EpiPerSquare, HypoPerLog (two leading scalars (u, v) and a w block) and EpiNormInf
-// (one leading scalar u and a w block); one warp per cone for the state, one warp per (cone, column)
+// Device oracles of EpiPerSquare, HypoPerLog (two leading scalars (u, v) and a w block), EpiNormInf,
+// HypoGeoMean (one leading scalar u and a w block), EpiPerSepSpectral{VectorCSqr} and EpiRelEntropy
+// (u, v block, w block; src/Cones/epirelentropy.jl:91-364); one warp per cone for the state, one warp per (cone, column)
 // for the products.
 //
 // reference: src/Cones/epipersquare.jl:59-274 (update_feas, is_dual_feas, update_grad, hess_prod!,
@@ -17,6 +18,7 @@
 #define V3_HYPOPERLOG 7     // = HYP_CONE_HYPOPERLOG
 #define V3_EPINORMINF 8     // = HYP_CONE_EPINORMINF
 #define V3_HYPOGEOMEAN 10   // = HYP_CONE_HYPOGEOMEAN (hypogeomean.jl; one leading scalar; scal: 1 phi, 2 zeta, 5 phi / zeta / d)
+#define V3_EPIRELENTROPY 13 // = HYP_CONE_EPIRELENTROPY (epirelentropy.jl; (u, v[d], w[d]); scal: 0 z, 1 Hiuu)
 #define V3_SEPSPEC_VEC 9    // = HYP_CONE_EPIPERSEPSPECTRAL_VEC (vectorcsqr.jl; scal: 0 phi, 1 zeta, 2 sigma, 3 c0, 4 c4, 5 c5)
 // product modes (= HYP_PROD_*)
 #define V3_HESS 0
@@ -38,7 +40,42 @@ v3_state_kernel(int type, int ncones, const int64_t* __restrict__ off, const int
     const int64_t o = off[c];
     const int d = dim[c];
     const double u = point[o], v = point[o + 1], du = dual[o], dv = dual[o + 1];
-    if (type == V3_HYPOGEOMEAN) {
+    if (type == V3_EPIRELENTROPY) {
+        // epirelentropy.jl:91-140 (feas, dual feas, grad), :188-222 (Hiuu of the inverse Hessian)
+        const int n = (d - 1) / 2;
+        double nbad = 0.0, ent = 0.0, dbad = 0.0;
+        for (int i = lane; i < n; i += 32) {
+            const double vi = point[o + 1 + i], wi = point[o + 1 + n + i];
+            if (!(vi > HYP_EPS) || !(wi > HYP_EPS)) nbad += 1.0;
+            ent += wi * log(wi / vi);
+            const double dvi = dual[o + 1 + i], dwi = dual[o + 1 + n + i];
+            if (!(dvi > HYP_EPS) || !(du * (1.0 + log(dvi / du)) + dwi > HYP_EPS)) dbad += 1.0;
+        }
+        nbad = warp_sum(nbad);
+        ent = warp_sum(ent);
+        dbad = warp_sum(dbad);
+        const double z = u - ent;
+        const bool ok = nbad == 0.0 && z > HYP_EPS;
+        const bool dok = du > HYP_EPS && dbad == 0.0;
+        double hh = 0.0;
+        for (int i = lane; i < n; i += 32) {
+            const double vi = point[o + 1 + i], wi = point[o + 1 + n + i];
+            const double lwv = log(wi / vi);
+            grad[o + 1 + i] = -wi / vi / z - 1.0 / vi;
+            grad[o + 1 + n + i] = (lwv + 1.0) / z - 1.0 / wi;
+            const double zw = z + wi, z2w = zw + wi, wz2w = wi / z2w;
+            const double uvv = wi * (wi * lwv - z), uww = wi * (z + lwv * zw) * wz2w;
+            hh += wz2w * uvv - uww * (lwv + 1.0);
+        }
+        hh = warp_sum(hh);
+        if (lane == 0) {
+            grad[o] = -1.0 / z;
+            scal[8 * c] = z;
+            scal[8 * c + 1] = z * z - hh;
+            if (!ok) feas[kidx[c]] = 0;
+            if (!dok) dual_feas[kidx[c]] = 0;
+        }
+    } else if (type == V3_HYPOGEOMEAN) {
         // hypogeomean.jl:69-110
         const int dw = d - 1;
         double nbad = 0.0, dbad = 0.0, sl = 0.0, dsl = 0.0;
@@ -242,7 +279,47 @@ v3_prod_kernel(int type, int mode_in, int ncones, const int64_t* __restrict__ of
         const double* a = arr + j * ld_arr + (o - row_shift);
         double* pr = prod + j * ld_prod + (o - row_shift);
         const double p = a[0], q = a[1];
-        if (type == V3_HYPOGEOMEAN) {
+        if (type == V3_EPIRELENTROPY) {
+            const int n = (d - 1) / 2;
+            const double z = scal[8 * c];
+            const double* av = a + 1;
+            const double* aw = a + 1 + n;
+            if (mode == V3_HESS) {
+                // epirelentropy.jl:260-293
+                double sr = 0.0;
+                for (int i = lane; i < n; i += 32) {
+                    const double vi = point[o + 1 + i], wi = point[o + 1 + n + i];
+                    sr += av[i] * (wi / vi / z) - aw[i] * ((log(wi / vi) + 1.0) / z);
+                }
+                const double up = warp_sum(sr) + p / z;
+                for (int i = lane; i < n; i += 32) {
+                    const double vi = point[o + 1 + i], wi = point[o + 1 + n + i];
+                    const double sigma = wi / vi / z, tau = -(log(wi / vi) + 1.0) / z;
+                    const double avi = av[i], awi = aw[i];
+                    pr[1 + i] = sigma * up + (sigma * avi + avi / vi - awi / z) / vi;
+                    pr[1 + n + i] = tau * up + (awi / z + awi / wi) / wi - avi / vi / z;
+                }
+                if (lane == 0) pr[0] = up / z;
+            } else {
+                // epirelentropy.jl:295-321 with the coefficients of :188-222 recomputed per entry
+                const double Hiuu = scal[8 * c + 1];
+                double sr = 0.0;
+                for (int i = lane; i < n; i += 32) {
+                    const double vi = point[o + 1 + i], wi = point[o + 1 + n + i];
+                    const double lwv = log(wi / vi);
+                    const double zw = z + wi, z2w = zw + wi, wz2w = wi / z2w, vz2w = vi / z2w;
+                    const double uvv = wi * (wi * lwv - z);
+                    const double Hiuv = vz2w * uvv, Hiuw = wi * (z + lwv * zw) * wz2w;
+                    const double Hivw = wi * vi * wz2w, Hiww = wi * zw * wz2w, Hivv = vi * zw * vz2w;
+                    const double avi = av[i], awi = aw[i];
+                    sr += avi * Hiuv + awi * Hiuw;
+                    pr[1 + i] = Hiuv * p + Hivv * avi + Hivw * awi;
+                    pr[1 + n + i] = Hiuw * p + Hivw * avi + Hiww * awi;
+                }
+                sr = warp_sum(sr);
+                if (lane == 0) pr[0] = Hiuu * p + sr;
+            }
+        } else if (type == V3_HYPOGEOMEAN) {
             const double phi = scal[8 * c + 1], zeta = scal[8 * c + 2], pzd = scal[8 * c + 5];
             const double di = 1.0 / (double)(d - 1);
             if (mode == V3_HESS) {
@@ -450,7 +527,36 @@ v3_dder3_kernel(int type, int ncones, const int64_t* __restrict__ off, const int
     const int64_t o = off[c];
     const int d = dim[c];
     const double u = point[o], v = point[o + 1], p = dir[o], q = dir[o + 1];
-    if (type == V3_HYPOGEOMEAN) {
+    if (type == V3_EPIRELENTROPY) {
+        // epirelentropy.jl:323-364
+        const int n = (d - 1) / 2;
+        const double z = scal[8 * c], i2z = 1.0 / (2.0 * z);
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        for (int i = lane; i < n; i += 32) {
+            const double vi = point[o + 1 + i], wi = point[o + 1 + n + i];
+            const double dvi = dir[o + 1 + i], dwi = dir[o + 1 + n + i];
+            const double vdv = dvi / vi, wdw = dwi / wi, tau = -(log(wi / vi) + 1.0) / z;
+            s0 += wi * vdv;
+            s1 += tau * dwi;
+            s2 += wi * vdv * vdv + dwi * (wdw - 2.0 * vdv);
+        }
+        s0 = warp_sum(s0);
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        const double const0 = (p + s0) / z + s1;
+        const double const1 = const0 * const0 + s2 * i2z;
+        for (int i = lane; i < n; i += 32) {
+            const double vi = point[o + 1 + i], wi = point[o + 1 + n + i];
+            const double dvi = dir[o + 1 + i], dwi = dir[o + 1 + n + i];
+            const double vdv = dvi / vi, wdw = dwi / wi, tau = -(log(wi / vi) + 1.0) / z;
+            double t = const1 + (const0 + vdv) * vdv - i2z * wdw * dwi;
+            t = t * wi + (z * vdv - dwi) * vdv + (-const0 + i2z * dwi) * dwi;
+            out[o + 1 + i] = t / vi / z;
+            out[o + 1 + n + i] = const1 * tau + ((const0 - wi * vdv / z) / z + (1.0 / wi + i2z) * wdw) * wdw +
+                                 (-const0 + dwi / z - vdv / 2.0) / z * vdv;
+        }
+        if (lane == 0) out[o] = const1 / z;
+    } else if (type == V3_HYPOGEOMEAN) {
         // hypogeomean.jl:232-257
         const double phi = scal[8 * c + 1], zeta = scal[8 * c + 2], pzd = scal[8 * c + 5];
         const double di = 1.0 / (double)(d - 1);

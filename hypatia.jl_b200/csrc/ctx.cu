@@ -922,12 +922,14 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
                                     ? ((int)ctx->h_cone_aoff.size() == K + 1
                                            ? (double)(ctx->h_cone_aoff[k + 1] - ctx->h_cone_aoff[k]) + 1.0
                                            : 0.0)
-                                                             : (double)d;   // HypoPerLog, EpiNormInf, EpiPerSepSpectral{VectorCSqr}, HypoGeoMean, HypoPowerMean: nu = dim
+                                                             : (double)d;   // HypoPerLog, EpiNormInf, EpiPerSepSpectral{VectorCSqr}, HypoGeoMean, HypoPowerMean, EpiRelEntropy: nu = dim
             if ((t == HYP_CONE_EPINORMINF || t == HYP_CONE_HYPOGEOMEAN) && d < 2)
                 throw HypError{"hyp_load_model: EpiNormInf / HypoGeoMean need dimension >= 2"};
             if ((t == HYP_CONE_EPIPERSQUARE || t == HYP_CONE_HYPOPERLOG || t == HYP_CONE_EPIPERSEPSPECTRAL_MAT ||
                  t == HYP_CONE_EPIPERSEPSPECTRAL_VEC) && d < 3)
                 throw HypError{"hyp_load_model: this cone type needs dimension >= 3"};
+            if (t == HYP_CONE_EPIRELENTROPY && (d < 3 || d % 2 == 0))
+                throw HypError{"hyp_load_model: EpiRelEntropy needs an odd dimension >= 3"};   // epirelentropy.jl:51-52
             if (t == HYP_CONE_EPIPERSEPSPECTRAL_MAT || t == HYP_CONE_EPIPERSEPSPECTRAL_VEC) {
                 if (!have_params) throw HypError{"hyp_load_model: EpiPerSepSpectral cones need hyp_set_cone_params first"};
                 const int hk = ctx->h_cone_hkind[k];

@@ -106,6 +106,12 @@ def cone_initial_point(spec):
         arr[2:] = w
     elif spec.ctype == M.CONE_EPINORMINF:
         arr[0] = np.sqrt(spec.dim)      # epinorminf.jl:88-95
+    elif spec.ctype == M.CONE_EPIRELENTROPY:
+        d = (spec.dim - 1) // 2           # epirelentropy.jl:84-89, :377-409
+        u, v, w = _central_ray_epirelentropy(d)
+        arr[0] = u
+        arr[1:1 + d] = v
+        arr[1 + d:] = w
     elif spec.ctype == M.CONE_HYPOPOWERMEAN:
         al = np.array(spec.alpha)         # hypopowermean.jl:58-72, :205-232 (fitted central ray)
         d = al.size
@@ -143,8 +149,37 @@ def cone_initial_point(spec):
     return arr
 
 
+_CENTRAL_EPIRELENTROPY = np.array([      # epirelentropy.jl:398-409
+    [0.827838399, 1.290927714, 0.805102005], [0.708612491, 1.256859155, 0.818070438],
+    [0.622618845, 1.231401008, 0.829317079], [0.558111266, 1.211710888, 0.838978357],
+    [0.508038611, 1.196018952, 0.847300431], [0.468039614, 1.183194753, 0.854521307],
+    [0.435316653, 1.172492397, 0.860840992], [0.408009282, 1.163403374, 0.866420017],
+    [0.38483862, 1.155570329, 0.871385499], [0.364899122, 1.148735192, 0.875838068]])
+
+
+def _central_ray_epirelentropy(d):
+    # epirelentropy.jl:377-396
+    if d <= 10:
+        return _CENTRAL_EPIRELENTROPY[d - 1]
+    rt = np.sqrt(d)
+    if d <= 20:
+        return np.array([1.2023 / rt - 0.015, 0.432 / rt + 1.0125, -0.3057 / rt + 0.972])
+    return np.array([1.1513 / rt - 0.0069, 0.4873 / rt + 1.0008, -0.4247 / rt + 0.9961])
+
+
 def _cone_dual_initial(spec, prim):
     """-grad at the central point, closed form per cone (dual of the central point)."""
+    if spec.ctype == M.CONE_EPIRELENTROPY:
+        # -grad, epirelentropy.jl:123-140
+        d = (spec.dim - 1) // 2
+        u, v, w = prim[0], prim[1:1 + d], prim[1 + d:]
+        lwv = np.log(w / v)
+        z = u - w @ lwv
+        out = np.empty_like(prim)
+        out[0] = 1.0 / z
+        out[1:1 + d] = w / v / z + 1.0 / v
+        out[1 + d:] = -(lwv + 1) / z + 1.0 / w
+        return out
     if spec.ctype == M.CONE_NONNEGATIVE:
         return 1.0 / prim
     if spec.ctype == M.CONE_EPINORMEUCL:
@@ -243,7 +278,7 @@ def _perturb(rng, spec, vec, noise):
     if spec.ctype == M.CONE_GENERALIZEDPOWER:
         vec += 0.5 * noise / np.sqrt(vec.size) * (2 * rng.random(vec.size) - 1)
         return vec
-    if spec.ctype in (M.CONE_HYPOGEOMEAN, M.CONE_HYPOPOWERMEAN):
+    if spec.ctype in (M.CONE_HYPOGEOMEAN, M.CONE_HYPOPOWERMEAN, M.CONE_EPIRELENTROPY):
         vec[0] += 0.5 * noise * (2 * rng.random() - 1)
         vec[1:] += noise / np.sqrt(vec.size) * (2 * rng.random(vec.size - 1) - 1)
         return vec

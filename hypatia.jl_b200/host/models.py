@@ -25,6 +25,7 @@ CONE_EPIPERSEPSPECTRAL_VEC = 9
 CONE_HYPOGEOMEAN = 10
 CONE_GENERALIZEDPOWER = 11
 CONE_HYPOPOWERMEAN = 12
+CONE_EPIRELENTROPY = 13
 
 # separable spectral functions of EpiPerSepSpectral (sepspectralfun.jl:17-116), HYP_SSF_*
 SSF_INV, SSF_NEGLOG, SSF_NEGENTROPY, SSF_POWER12 = 0, 1, 2, 3
@@ -43,6 +44,7 @@ CONE_NAMES = {
     CONE_HYPOGEOMEAN: "HypoGeoMean",
     CONE_GENERALIZEDPOWER: "GeneralizedPower",
     CONE_HYPOPOWERMEAN: "HypoPowerMean",
+    CONE_EPIRELENTROPY: "EpiRelEntropy",
 }
 
 
@@ -96,6 +98,8 @@ class ConeSpec:
             assert dim >= 3
         elif ctype == CONE_HYPOPERLOG:
             assert dim >= 3
+        elif ctype == CONE_EPIRELENTROPY:
+            assert dim >= 3 and dim % 2 == 1      # epirelentropy.jl:51-52
         elif ctype in (CONE_EPINORMINF, CONE_HYPOGEOMEAN):
             assert dim >= 2
         elif ctype == CONE_GENERALIZEDPOWER:
@@ -138,7 +142,7 @@ class ConeSpec:
         if self.ctype == CONE_GENERALIZEDPOWER:
             return float(len(self.alpha) + 1)
         if self.ctype in (CONE_HYPOPERLOG, CONE_EPINORMINF, CONE_EPIPERSEPSPECTRAL_VEC, CONE_HYPOGEOMEAN,
-                          CONE_HYPOPOWERMEAN):
+                          CONE_HYPOPOWERMEAN, CONE_EPIRELENTROPY):
             return float(self.dim)
         return 1.0 + self.side
 
@@ -192,6 +196,11 @@ def GeneralizedPower(alpha, n, use_dual=False):
     """GeneralizedPower{Float64}(alpha, n): (u in R^m_+, w in R^n), prod u_i^alpha_i >= |w|; MOI's PowerCone(a) is
     GeneralizedPower([a, 1 - a], 1) (MathOptInterface/cones.jl:33-37)."""
     return ConeSpec(CONE_GENERALIZEDPOWER, len(alpha) + n, use_dual, alpha=alpha)
+
+
+def EpiRelEntropy(dim, use_dual=False):
+    """EpiRelEntropy{Float64}(dim): (u, v, w), u >= sum w_i log(w_i / v_i), dim = 1 + 2 d (MOI RelativeEntropyCone)."""
+    return ConeSpec(CONE_EPIRELENTROPY, dim, use_dual)
 
 
 def HypoPowerMean(alpha, use_dual=False):

@@ -50,6 +50,7 @@ typedef struct hyp_ctx hyp_ctx;
 #define HYP_CONE_HYPOGEOMEAN 10     /* hypogeomean.jl      */
 #define HYP_CONE_GENERALIZEDPOWER 11 /* generalizedpower.jl (powers via hyp_set_cone_alpha; dim <= 128) */
 #define HYP_CONE_HYPOPOWERMEAN 12   /* hypopowermean.jl (dim - 1 powers via hyp_set_cone_alpha; dim <= 128) */
+#define HYP_CONE_EPIRELENTROPY 13   /* epirelentropy.jl (u, v[d], w[d]); dim = 1 + 2 d */
 
 /* separable spectral functions of EpiPerSepSpectral (epipersepspectral/sepspectralfun.jl:17-116) */
 #define HYP_SSF_INV 0        /* InvSSF        x -> 1/x      */

@@ -43,6 +43,7 @@ cone_code(::Cones.EpiPerSepSpectral{Cones.VectorCSqr{Float64}, Float64}) = Cint(
 cone_code(::Cones.HypoGeoMean) = Cint(10)
 cone_code(::Cones.GeneralizedPower) = Cint(11)
 cone_code(::Cones.HypoPowerMean) = Cint(12)
+cone_code(::Cones.EpiRelEntropy) = Cint(13)
 cone_alpha(c::Cones.GeneralizedPower) = Vector{Float64}(c.α)
 cone_alpha(c::Cones.HypoPowerMean) = Vector{Float64}(c.α)
 cone_alpha(::Cones.Cone) = Float64[]

@@ -520,6 +520,168 @@ class HypoGeoMean(Cone):
         return d3
 
 
+class EpiRelEntropy(Cone):
+    """epirelentropy.jl:8-410: (u, v, w) with v, w in R^d_++, u >= sum_i w_i log(w_i / v_i); barrier
+    -log(u - sum w_i log(w_i / v_i)) - sum log v_i - sum log w_i, nu = dim = 1 + 2d."""
+    ctype = M.CONE_EPIRELENTROPY
+
+    _CENTRAL = np.array([      # epirelentropy.jl:398-409
+        [0.827838399, 1.290927714, 0.805102005], [0.708612491, 1.256859155, 0.818070438],
+        [0.622618845, 1.231401008, 0.829317079], [0.558111266, 1.211710888, 0.838978357],
+        [0.508038611, 1.196018952, 0.847300431], [0.468039614, 1.183194753, 0.854521307],
+        [0.435316653, 1.172492397, 0.860840992], [0.408009282, 1.163403374, 0.866420017],
+        [0.38483862, 1.155570329, 0.871385499], [0.364899122, 1.148735192, 0.875838068]])
+
+    def __init__(self, dim, use_dual=False):
+        assert dim >= 3 and dim % 2 == 1
+        self.use_dual_barrier = use_dual
+        self.d = (dim - 1) // 2
+        super().__init__(dim)
+
+    @property
+    def nu(self):
+        return float(self.dim)
+
+    @classmethod
+    def central_ray(cls, d):
+        # epirelentropy.jl:377-396
+        if d <= 10:
+            return cls._CENTRAL[d - 1]
+        rt = np.sqrt(d)
+        if d <= 20:
+            return np.array([1.2023 / rt - 0.015, 0.432 / rt + 1.0125, -0.3057 / rt + 0.972])
+        return np.array([1.1513 / rt - 0.0069, 0.4873 / rt + 1.0008, -0.4247 / rt + 0.9961])
+
+    def set_initial_point(self, arr):
+        u, v, w = self.central_ray(self.d)
+        arr[0] = u
+        arr[1:1 + self.d] = v
+        arr[1 + self.d:] = w
+        return arr
+
+    def _uvw(self, vec):
+        return vec[0], vec[1:1 + self.d], vec[1 + self.d:]
+
+    def update_feas(self):
+        # epirelentropy.jl:91-108
+        u, v, w = self._uvw(self.point)
+        if (v > EPS).all() and (w > EPS).all():
+            self.lwv = np.log(w / v)
+            self.z = float(u - w @ self.lwv)
+            return self.z > EPS
+        return False
+
+    def is_dual_feas(self):
+        # epirelentropy.jl:110-121
+        u, v, w = self._uvw(self.dual_point)
+        if (v > EPS).all() and u > EPS:
+            return bool((u * (1 + np.log(v / u)) + w > EPS).all())
+        return False
+
+    def update_grad(self):
+        # epirelentropy.jl:123-140
+        u, v, w = self._uvw(self.point)
+        z = self.z
+        self.sigma = w / v / z
+        self.tau = (self.lwv + 1) / -z
+        self._grad[0] = -1.0 / z
+        self._grad[1:1 + self.d] = -self.sigma - 1.0 / v
+        self._grad[1 + self.d:] = -self.tau - 1.0 / w
+
+    def update_hess(self):
+        # epirelentropy.jl:142-186
+        self.grad()
+        d, z, sigma, tau = self.d, self.z, self.sigma, self.tau
+        u, v, w = self._uvw(self.point)
+        H = np.zeros((self.dim, self.dim))
+        vi, wi = np.arange(1, 1 + d), np.arange(1 + d, self.dim)
+        H[0, 0] = z ** -2
+        H[0, vi] = H[vi, 0] = sigma / z
+        H[0, wi] = H[wi, 0] = tau / z
+        H[np.ix_(vi, vi)] = np.outer(sigma, sigma)
+        H[np.ix_(wi, wi)] = np.outer(tau, tau)
+        H[np.ix_(vi, wi)] = np.outer(sigma, tau)
+        H[vi, vi] = sigma ** 2 + (sigma + 1.0 / v) / v
+        H[wi, wi] = tau ** 2 + (1.0 / z + 1.0 / w) / w
+        H[vi, wi] -= 1.0 / z / v
+        H[np.ix_(wi, vi)] = H[np.ix_(vi, wi)].T
+        return H
+
+    def hess_prod(self, arr):
+        # epirelentropy.jl:260-293
+        self.grad()
+        a, vec = _as2d(arr)
+        d, z, sigma, tau = self.d, self.z, self.sigma, self.tau
+        u, v, w = self._uvw(self.point)
+        p, av, aw = a[0], a[1:1 + d], a[1 + d:]
+        up = sigma @ av + tau @ aw + p / z
+        prod = np.empty_like(a)
+        prod[1:1 + d] = sigma[:, None] * up[None, :] + (sigma[:, None] * av + av / v[:, None] - aw / z) / v[:, None]
+        prod[1 + d:] = tau[:, None] * up[None, :] + (aw / z + aw / w[:, None]) / w[:, None] - av / v[:, None] / z
+        prod[0] = up / z
+        return _ret(prod, vec)
+
+    def _inv_hess_aux(self):
+        # epirelentropy.jl:188-222
+        u, v, w = self._uvw(self.point)
+        z, lwv = self.z, self.lwv
+        zw = z + w
+        z2w = zw + w
+        wz2w = w / z2w
+        vz2w = v / z2w
+        uvv = w * (w * lwv - z)
+        uww = w * (z + lwv * zw) * wz2w
+        HiuHu = float(np.sum(wz2w * uvv - uww * (lwv + 1)))
+        return dict(Hiuu=z * z - HiuHu, Hiuv=vz2w * uvv, Hiuw=uww, Hivw=w * v * wz2w, Hiww=w * zw * wz2w,
+                    Hivv=v * zw * vz2w)
+
+    def update_inv_hess(self):
+        # epirelentropy.jl:224-258 (sparse arrow + diagonal bands, formed dense here)
+        self.grad()
+        d, x = self.d, self._inv_hess_aux()
+        vi, wi = np.arange(1, 1 + d), np.arange(1 + d, self.dim)
+        Hi = np.zeros((self.dim, self.dim))
+        Hi[0, 0] = x["Hiuu"]
+        Hi[0, vi] = Hi[vi, 0] = x["Hiuv"]
+        Hi[0, wi] = Hi[wi, 0] = x["Hiuw"]
+        Hi[vi, vi] = x["Hivv"]
+        Hi[wi, wi] = x["Hiww"]
+        Hi[vi, wi] = Hi[wi, vi] = x["Hivw"]
+        return Hi
+
+    def inv_hess_prod(self, arr):
+        # epirelentropy.jl:295-321
+        self.grad()
+        a, vec = _as2d(arr)
+        d, x = self.d, self._inv_hess_aux()
+        p, av, aw = a[0], a[1:1 + d], a[1 + d:]
+        prod = np.empty_like(a)
+        prod[0] = x["Hiuu"] * p + x["Hiuv"] @ av + x["Hiuw"] @ aw
+        prod[1:1 + d] = x["Hiuv"][:, None] * p[None, :] + x["Hivv"][:, None] * av + x["Hivw"][:, None] * aw
+        prod[1 + d:] = x["Hiuw"][:, None] * p[None, :] + x["Hivw"][:, None] * av + x["Hiww"][:, None] * aw
+        return _ret(prod, vec)
+
+    def dder3(self, direction):
+        # epirelentropy.jl:323-364
+        self.grad()
+        d, z, tau = self.d, self.z, self.tau
+        u, v, w = self._uvw(self.point)
+        p, dv, dw = direction[0], direction[1:1 + d], direction[1 + d:]
+        i2z = 1.0 / (2 * z)
+        wdw = dw / w
+        vdv = dv / v
+        const0 = (p + w @ vdv) / z + tau @ dw
+        const1 = const0 ** 2 + float(np.sum(w * vdv ** 2 + dw * (wdw - 2 * vdv))) / (2 * z)
+        d3 = np.empty(self.dim)
+        d3[0] = const1 / z
+        t = const1 + (const0 + vdv) * vdv - i2z * wdw * dw
+        t = t * w + (z * vdv - dw) * vdv + (-const0 + i2z * dw) * dw
+        d3[1:1 + d] = t / v / z
+        d3[1 + d:] = (const1 * tau + ((const0 - w * vdv / z) / z + (1.0 / w + i2z) * wdw) * wdw
+                      + (-const0 + dw / z - vdv / 2) / z * vdv)
+        return d3
+
+
 class GeneralizedPower(Cone):
     """generalizedpower.jl:8-236: (u in R^m_++, w in R^n), prod u_i^(alpha_i) >= |w|_2; barrier
     -log(prod u_i^(2 alpha_i) - |w|^2) - sum (1 - alpha_i) log u_i, nu = m + 1.  No closed-form inverse Hessian:

@@ -510,6 +510,59 @@ for _k, (_hk, _hp) in enumerate(SEP_SPECTRAL_FUNS):
     SPECTRAL_VEC.append(_named(lambda hk=_hk, hp=_hp: _spectral_vector3(hk, hp), f"epipersepspectral_vector3_h{_hk}"))
     SPECTRAL_VEC.append(_named(lambda hk=_hk, hp=_hp: _spectral_vector4(hk, hp), f"epipersepspectral_vector4_h{_hk}"))
 
+def _epirelentropy1(d):  # :2099-2119: min u : (u, 1, w) in K => sum w log w
+    w = np.random.default_rng(1).random(d) + 1
+    dim = 1 + 2 * d
+    G = np.zeros((dim, 1))
+    G[0, 0] = -1
+    h = np.concatenate(([0.0], np.ones(d), w))
+    return _m([1], None, None, G, h, [M.EpiRelEntropy(dim)]), \
+        dict(status="Optimal", primal_obj=float(np.sum(w * np.log(w))))
+
+
+def _epirelentropy2(d):  # :2121-2141
+    dim = 1 + 2 * d
+    G = np.zeros((dim, d))
+    G[1 + d + np.arange(d), np.arange(d)] = -1
+    h = np.zeros(dim)
+    h[1:1 + d] = 1
+    return _m(-np.ones(d), None, None, G, h, [M.EpiRelEntropy(dim)]), \
+        dict(status="Optimal", primal_obj=-d, x=np.ones(d))
+
+
+def _epirelentropy3(d):  # :2143-2163
+    dim = 1 + 2 * d
+    G = np.zeros((dim, d))
+    G[1 + np.arange(d), np.arange(d)] = -1
+    h = np.zeros(dim)
+    h[1 + d:] = 1
+    return _m(-np.ones(d), np.ones((1, d)), [dim], G, h, [M.EpiRelEntropy(dim)]), \
+        dict(status="Optimal", primal_obj=-dim, x=np.full(d, dim / d))
+
+
+def epirelentropy4():  # :2165-2181
+    G = np.zeros((5, 1))
+    G[0, 0] = -1
+    entr = 2 * np.log(2.0) + 3 * np.log(3 / 5.0)
+    return _m([1], None, None, G, [0, 1, 5, 2, 3], [M.EpiRelEntropy(5)]), \
+        dict(status="Optimal", primal_obj=entr, s=[entr, 1, 5, 2, 3],
+             z=[1, 2, 3 / 5.0, np.log(0.5) - 1, np.log(5 / 3.0) - 1])
+
+
+def epirelentropy5():  # :2183-2198
+    G = np.vstack((np.zeros((4, 2)), -np.ones((3, 2)), [[-1.0, 0.0]]))
+    h = np.zeros(8)
+    h[1:4] = 1
+    return _m([0, -1], None, None, G, h, [M.EpiRelEntropy(7), M.Nonnegative(1)]), \
+        dict(status="Optimal", primal_obj=-1, s=[0, 1, 1, 1, 1, 1, 1, 0],
+             z=np.array([1, 1, 1, 1, -1, -1, -1, 3]) / 3.0)
+
+
+RELENT = [_named(lambda d=_d: _epirelentropy1(d), f"epirelentropy1_d{_d}") for _d in (1, 2, 3)] + \
+    [_named(lambda d=_d: _epirelentropy2(d), f"epirelentropy2_d{_d}") for _d in (1, 2, 4)] + \
+    [_named(lambda d=_d: _epirelentropy3(d), f"epirelentropy3_d{_d}") for _d in (2, 4)] + \
+    [epirelentropy4, epirelentropy5]
+
 GPOW = []
 for _f in (_generalizedpower1, _generalizedpower2, _generalizedpower3, _generalizedpower4):
     for _ud in (False, True):
@@ -519,7 +572,7 @@ HPM = [_named(lambda f=_f, ud=_ud: f(ud), _f.__name__[1:] + ("_dual" if _ud else
        for _f in (_hypopowermean1, _hypopowermean2) for _ud in (False, True)] + \
     [hypopowermean4, hypopowermean5, hypopowermean6]
 
-NEW_CONES = GPOW + HPM + [hypogeomean1, hypogeomean1_dual, hypogeomean2, hypogeomean2_dual, hypogeomean4, hypogeomean5,
+NEW_CONES = GPOW + HPM + RELENT + [hypogeomean1, hypogeomean1_dual, hypogeomean2, hypogeomean2_dual, hypogeomean4, hypogeomean5,
              hypogeomean6, epinorminf1, epinorminf2, epinorminf3, epinorminf3_dual, epinorminf4, dualinfeas1,
              primalinfeas3, dualinfeas2, dualinfeas3, epipersquare1, epipersquare2, epipersquare3,
              epipersquare4, hypoperlog1, hypoperlog2, hypoperlog3, hypoperlog4, hypoperlog5, hypoperlog6,

@@ -25,10 +25,12 @@ def _cone(kind, dim, dual, hk, hp):
         return M.EpiNormInf(dim, use_dual=dual)
     if kind == "hypogeomean":
         return M.HypoGeoMean(dim, use_dual=dual)
+    if kind == "epirelentropy":
+        return M.EpiRelEntropy(1 + 2 * max(dim // 2, 1), use_dual=dual)
     return M.EpiPerSepSpectralVec(max(dim, 3), hk, hp, use_dual=dual)
 
 
-KINDS = ["epipersquare", "hypoperlog", "epinorminf", "hypogeomean", "sepspec_vec"]
+KINDS = ["epipersquare", "hypoperlog", "epinorminf", "hypogeomean", "sepspec_vec", "epirelentropy"]
 
 
 @settings(max_examples=25, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.too_slow])

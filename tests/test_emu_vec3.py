@@ -26,6 +26,8 @@ SETS = {
                          M.EpiPerSepSpectralVec(9, M.SSF_INV), M.EpiPerSepSpectralVec(40, M.SSF_POWER12, 2.0, use_dual=True)],
     "hypogeomean": [M.HypoGeoMean(d) for d in (2, 3, 6, 33, 34, 70)],
     "hypogeomean_dual": [M.HypoGeoMean(4, use_dual=True), M.HypoGeoMean(9), M.HypoGeoMean(40, use_dual=True)],
+    "epirelentropy": [M.EpiRelEntropy(1 + 2 * d) for d in (1, 2, 4, 16, 33, 40)],
+    "epirelentropy_dual": [M.EpiRelEntropy(5, use_dual=True), M.EpiRelEntropy(9), M.EpiRelEntropy(71, use_dual=True)],
     "hypoperlog_dual": [M.HypoPerLog(5, use_dual=True), M.HypoPerLog(9), M.HypoPerLog(40, use_dual=True)],
 }
 

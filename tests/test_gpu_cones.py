@@ -48,6 +48,8 @@ CONE_SETS = {
                     M.EpiPerSepSpectralVec(7, M.SSF_NEGENTROPY, use_dual=True)],
     "hypogeomean": [M.HypoGeoMean(2), M.HypoGeoMean(6), M.HypoGeoMean(34), M.HypoGeoMean(70),
                     M.HypoGeoMean(9, use_dual=True)],
+    "epirelentropy": [M.EpiRelEntropy(3), M.EpiRelEntropy(9), M.EpiRelEntropy(35), M.EpiRelEntropy(81),
+                      M.EpiRelEntropy(7, use_dual=True)],
     "gpow": [M.GeneralizedPower([0.5, 0.5], 1), M.GeneralizedPower([0.2, 0.3, 0.5], 2),
              M.GeneralizedPower(np.full(20, 0.05), 30), M.GeneralizedPower([0.7, 0.3], 1, use_dual=True),
              M.GeneralizedPower(np.full(4, 0.25), 60)],
@@ -59,7 +61,8 @@ CONE_SETS = {
                M.HypoPerLog(5), M.HypoPerLog(4, use_dual=True), M.EpiNormInf(5), M.EpiNormInf(4, use_dual=True),
                M.EpiPerSepSpectralVec(6, M.SSF_NEGENTROPY), M.HypoGeoMean(5), M.HypoGeoMean(4, use_dual=True),
                M.GeneralizedPower([0.3, 0.7], 2), M.GeneralizedPower([0.5, 0.5], 1, use_dual=True),
-               M.HypoPowerMean([0.25, 0.35, 0.4]), M.HypoPowerMean([0.5, 0.5], use_dual=True)],
+               M.HypoPowerMean([0.25, 0.35, 0.4]), M.HypoPowerMean([0.5, 0.5], use_dual=True),
+               M.EpiRelEntropy(7), M.EpiRelEntropy(5, use_dual=True)],
 }
 
 

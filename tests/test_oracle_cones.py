@@ -183,6 +183,13 @@ def test_hypopowermean(dw, init_only):
     run_oracles(HypoPowerMean(a / a.sum()), init_tol=1e-1 if init_only else 1e-2, init_only=init_only)
 
 
+@pytest.mark.parametrize("dw,init_only", [(1, False), (2, False), (4, False), (15, True), (40, True), (100, True)])
+def test_epirelentropy(dw, init_only):
+    # reference: test/cone.jl:707-715
+    from oracle.cones_vec3 import EpiRelEntropy
+    run_oracles(EpiRelEntropy(1 + 2 * dw), init_tol=1e-1 if init_only else 1e-5, init_only=init_only)
+
+
 SSF = [(0, 0.0), (1, 0.0), (2, 0.0), (3, 1.5), (3, 2.0), (3, 1.1)]   # Inv, NegLog, NegEntropy, Power12(p)
 
 
