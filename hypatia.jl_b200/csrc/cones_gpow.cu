@@ -1,4 +1,4 @@
-// GeneralizedPower and HypoPowerMean on the device, and the generic inverse-Hessian fallback of the Cone API (kernels:
+// GeneralizedPower, HypoPowerMean and EpiNormSpectral (real; src/Cones/epinormspectral.jl:107-294) on the device, and the generic inverse-Hessian fallback of the Cone API (kernels:
 // cones_gpow_kernels.cuh).
 //
 // reference: src/Cones/generalizedpower.jl:77-236, src/Cones/hypopowermean.jl:74-203; generic oracles src/Cones/Cones.jl:113-118 (inv_hess_prod! =
@@ -21,7 +21,37 @@ T* upload_vec(const std::vector<T>& v) {
 
 }  // namespace
 
+// EpiNormSpectral: d_hkind = d1 (rows of W), d_vecs / d_voff = per-cone workspace (tau, Zitau, Zi, Cholesky factor of Z,
+// scratch: 3 d1 d2 + 2 d1^2 doubles)
+static void ens_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
+    g.h_voff.assign(g.count, 0);
+    int64_t tot = 0;
+    for (int i = 0; i < g.count; i++) {
+        const int k = g.h_kidx[i];
+        const int d = g.h_dim[i], d1 = ctx->h_cone_hkind[k];
+        if (d1 < 1 || d < 2 || (d - 1) % d1 != 0 || d1 > (d - 1) / d1)
+            throw HypError{"EpiNormSpectral: hyp_set_cone_params must give the number of rows d1 with dim = 1 + d1 * d2, d1 <= d2"};
+        if (d > 128) throw HypError{"EpiNormSpectral: dim above 128 is not supported (batched Cholesky limit)"};
+        g.h_hkind.push_back(d1);
+        g.h_side[i] = d;
+        g.h_voff[i] = tot;
+        tot += 3 * (int64_t)(d - 1) + 2 * (int64_t)d1 * d1;
+    }
+    g.max_side = g.max_dim;
+    cudaFree(g.d_side);
+    g.d_side = upload_vec(g.h_side);
+    g.d_hkind = upload_vec(g.h_hkind);
+    g.d_voff = upload_vec(g.h_voff);
+    CUDA_TRY(cudaMalloc(&g.d_vecs, (size_t)std::max<int64_t>(tot, 1) * sizeof(double)));
+    CUDA_TRY(cudaMemset(g.d_vecs, 0, (size_t)std::max<int64_t>(tot, 1) * sizeof(double)));
+    hyp_mat_alloc_group(ctx, g);
+}
+
 void hyp_gpow_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
+    if (g.type == HYP_CONE_EPINORMSPECTRAL) {
+        ens_alloc_group(ctx, g);
+        return;
+    }
     std::vector<double> alpha;
     g.h_voff.assign(g.count, 0);
     for (int i = 0; i < g.count; i++) {
@@ -58,7 +88,11 @@ void hyp_gpow_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
 }
 
 void hyp_gpow_update_state(hyp_ctx* ctx, ConeGroup& g) {
-    if (g.type == HYP_CONE_HYPOPOWERMEAN)
+    if (g.type == HYP_CONE_EPINORMSPECTRAL)
+        hypdev::ens_state_kernel<<<ceil_div(g.count, 8), 256, 0, ctx->stream>>>(
+            g.count, g.d_off, g.d_dim, g.d_hkind, g.d_voff, g.d_vecs, g.d_kidx, g.d_moff, ctx->d_point, ctx->d_dual,
+            ctx->d_grad, g.d_scal, g.d_W, ctx->d_feas, ctx->d_dual_feas);
+    else if (g.type == HYP_CONE_HYPOPOWERMEAN)
         hypdev::hpm_state_kernel<<<ceil_div(g.count, 8), 256, 0, ctx->stream>>>(
             g.count, g.d_off, g.d_dim, g.d_voff, g.d_vecs, g.d_kidx, g.d_moff, ctx->d_point, ctx->d_dual, ctx->d_grad,
             g.d_scal, g.d_W, ctx->d_feas, ctx->d_dual_feas);
@@ -87,7 +121,11 @@ void hyp_gpow_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr, 
     else if (mode == HYP_PROD_BLOCK_INV) { hess_dual = 1; inv_dual = 0; }
     else throw HypError{"hyp_gpow_prod: bad mode"};
     if (hess_dual > -2) {
-        if (g.type == HYP_CONE_HYPOPOWERMEAN)
+        if (g.type == HYP_CONE_EPINORMSPECTRAL)
+            hypdev::ens_prod_kernel<<<grid, 256, 0, ctx->stream>>>(g.count, hess_dual, g.d_off, g.d_dim, g.d_hkind,
+                                                                  g.d_voff, g.d_vecs, g.d_dual, g.d_scal, ctx->d_point,
+                                                                  arr, ld_arr, prod, ld_prod, ncols, row_shift);
+        else if (g.type == HYP_CONE_HYPOPOWERMEAN)
             hypdev::hpm_prod_kernel<<<grid, 256, 0, ctx->stream>>>(g.count, hess_dual, g.d_off, g.d_dim, g.d_voff,
                                                                   g.d_vecs, g.d_dual, g.d_scal, ctx->d_point, arr,
                                                                   ld_arr, prod, ld_prod, ncols, row_shift);
@@ -108,7 +146,10 @@ void hyp_gpow_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr, 
 }
 
 void hyp_gpow_dder3(hyp_ctx* ctx, ConeGroup& g, double* out, const double* dir) {
-    if (g.type == HYP_CONE_HYPOPOWERMEAN)
+    if (g.type == HYP_CONE_EPINORMSPECTRAL)
+        hypdev::ens_dder3_kernel<<<ceil_div(g.count, 4), 128, 0, ctx->stream>>>(
+            g.count, g.d_off, g.d_dim, g.d_hkind, g.d_voff, g.d_vecs, g.d_scal, ctx->d_point, dir, out);
+    else if (g.type == HYP_CONE_HYPOPOWERMEAN)
         hypdev::hpm_dder3_kernel<<<ceil_div(g.count, 8), 256, 0, ctx->stream>>>(
             g.count, g.d_off, g.d_dim, g.d_voff, g.d_vecs, g.d_scal, ctx->d_point, dir, out);
     else

@@ -330,4 +330,326 @@ gen_invhess_prod_kernel(int ncones, int want_dual, const int64_t* __restrict__ o
     }
 }
 
+// ---- EpiNormSpectral (real), epinormspectral.jl:107-294 ----
+// point = (u, vec(W)) with W d1 x d2 column-major, d1 <= d2, dim = 1 + d1 d2 <= 128 (so d1 <= 11).  Per-cone
+// workspace at vecs + voff[c]: tau = Z^-1 W (d1 d2), Zitau = Z^-1 tau (d1 d2), Zi = Z^-1 (d1^2), Uz = upper Cholesky
+// factor of Z = u^2 I - W W' (d1^2), scratch (d1 d2).  scal: 0 Huu, 1 trZi2.  Every product with the d2 x d2 matrices
+// of the reference (W' tau + I, W_dir' tau) is re-associated through d1 x d1 intermediates.
+
+// x <- Z^-1 x for one column (Z = U'U, U upper, column-major with leading dimension d1); run by ONE thread
+__device__ __forceinline__ void ens_zsolve_col(const double* U, int d1, double* x) {
+    for (int i = 0; i < d1; i++) {
+        double s = x[i];
+        for (int k = 0; k < i; k++) s -= U[k + i * d1] * x[k];
+        x[i] = s / U[i + i * d1];
+    }
+    for (int i = d1 - 1; i >= 0; i--) {
+        double s = x[i];
+        for (int k = i + 1; k < d1; k++) s -= U[i + k * d1] * x[k];
+        x[i] = s / U[i + i * d1];
+    }
+}
+// warp-wide helpers (lane-strided); callers separate dependent steps with __syncwarp()
+__device__ __forceinline__ void ens_zsolve(const double* U, double* X, int d1, int d2, int lane) {
+    for (int k = lane; k < d2; k += 32) ens_zsolve_col(U, d1, X + k * d1);
+}
+// S (d1 x d1) = [S +] X Y'
+__device__ __forceinline__ void ens_mm_nt(double* S, const double* X, const double* Y, int d1, int d2, int lane,
+                                          bool acc) {
+    for (int idx = lane; idx < d1 * d1; idx += 32) {
+        const int a = idx % d1, b = idx / d1;
+        double s = acc ? S[idx] : 0.0;
+        for (int k = 0; k < d2; k++) s += X[a + k * d1] * Y[b + k * d1];
+        S[idx] = s;
+    }
+}
+// O (d1 x d2) = beta O + S Y
+__device__ __forceinline__ void ens_mm_sy(double* O, const double* S, const double* Y, int d1, int d2, int lane,
+                                          double beta) {
+    for (int idx = lane; idx < d1 * d2; idx += 32) {
+        const int r = idx % d1, k = idx / d1;
+        double s = 0.0;
+        for (int m = 0; m < d1; m++) s += S[r + m * d1] * Y[m + k * d1];
+        O[idx] = beta == 0.0 ? s : beta * O[idx] + s;
+    }
+}
+
+static __global__ void __launch_bounds__(256)
+ens_state_kernel(int ncones, const int64_t* __restrict__ off, const int* __restrict__ dim,
+                 const int* __restrict__ d1s, const int64_t* __restrict__ voff, double* __restrict__ vecs,
+                 const int* __restrict__ kidx, const int64_t* __restrict__ moff,
+                 const double* __restrict__ point, const double* __restrict__ dual, double* __restrict__ grad,
+                 double* __restrict__ scal, double* __restrict__ H, uint8_t* feas, uint8_t* dual_feas) {
+    const int lane = threadIdx.x & 31;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= ncones) return;
+    const int64_t o = off[c];
+    const int d = dim[c], d1 = d1s[c], d2 = (d - 1) / d1, n12 = d1 * d2, lde = (d + 1) & ~1;
+    double* tau = vecs + voff[c];
+    double* Zitau = tau + n12;
+    double* Zi = Zitau + n12;
+    double* Uz = Zi + d1 * d1;
+    double* scr = Uz + d1 * d1;
+    const double u = point[o];
+    const double* W = point + o + 1;
+    // update_feas (:107-124): Z = u^2 I - W W', Cholesky
+    for (int idx = lane; idx < d1 * d1; idx += 32) {
+        const int a = idx % d1, b = idx / d1;
+        double s = a == b ? u * u : 0.0;
+        for (int k = 0; k < d2; k++) s -= W[a + k * d1] * W[b + k * d1];
+        Uz[idx] = s;
+    }
+    __syncwarp();
+    int ok = u > HYP_EPS ? 1 : 0;
+    if (lane == 0) {
+        for (int j = 0; j < d1; j++) {
+            double s = Uz[j + j * d1];
+            for (int k = 0; k < j; k++) s -= Uz[k + j * d1] * Uz[k + j * d1];
+            if (!(s > 0.0)) {
+                ok = 0;
+                s = 1.0;
+            }
+            const double r = sqrt(s);
+            Uz[j + j * d1] = r;
+            for (int i = j + 1; i < d1; i++) {
+                double t = Uz[j + i * d1];
+                for (int k = 0; k < j; k++) t -= Uz[k + j * d1] * Uz[k + i * d1];
+                Uz[j + i * d1] = t / r;
+            }
+        }
+    }
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    __syncwarp();
+    // update_grad (:135-151): tau = Z^-1 W, Zi = Z^-1; update_hess_aux (:153-172): Zitau, trZi2, Huu
+    for (int b = lane; b < d1; b += 32) {
+        double* x = Zi + b * d1;
+        for (int i = 0; i < d1; i++) x[i] = i == b ? 1.0 : 0.0;
+        ens_zsolve_col(Uz, d1, x);
+    }
+    for (int i = lane; i < n12; i += 32) tau[i] = W[i];
+    __syncwarp();
+    ens_zsolve(Uz, tau, d1, d2, lane);
+    __syncwarp();
+    for (int idx = lane; idx < d1 * d1; idx += 32) {     // copytri!(Zi, 'U')
+        const int a = idx % d1, b = idx / d1;
+        if (a > b) Zi[idx] = Zi[b + a * d1];
+    }
+    for (int i = lane; i < n12; i += 32) Zitau[i] = tau[i];
+    __syncwarp();
+    ens_zsolve(Uz, Zitau, d1, d2, lane);
+    double tr = 0.0, tr2 = 0.0;
+    for (int idx = lane; idx < d1 * d1; idx += 32) {
+        const double z = Zi[idx];
+        if (idx % d1 == idx / d1) tr += z;
+        tr2 += z * z;
+    }
+    tr = warp_sum(tr);
+    tr2 = warp_sum(tr2);
+    __syncwarp();
+    const double g0 = -2.0 * u * tr + (d1 - 1) / u;
+    const double Huu = 4.0 * u * u * tr2 + (g0 - 2.0 * (d1 - 1) / u) / u;
+    for (int i = lane; i < n12; i += 32) grad[o + 1 + i] = 2.0 * tau[i];
+    // is_dual_feas (:126-133): u - sum of the singular values of the dual W; one-sided Jacobi on its d1 rows
+    const double du = dual[o];
+    for (int i = lane; i < n12; i += 32) scr[i] = dual[o + 1 + i];
+    __syncwarp();
+    for (int sweep = 0; sweep < 40; sweep++) {
+        int rotated = 0;
+        for (int p = 0; p < d1 - 1; p++)
+            for (int q = p + 1; q < d1; q++) {
+                double al = 0.0, be = 0.0, ga = 0.0;
+                for (int k = lane; k < d2; k += 32) {
+                    const double x = scr[p + k * d1], y = scr[q + k * d1];
+                    al += x * x;
+                    be += y * y;
+                    ga += x * y;
+                }
+                al = warp_sum(al);
+                be = warp_sum(be);
+                ga = warp_sum(ga);
+                if (ga != 0.0 && fabs(ga) > HYP_EPS * sqrt(al * be)) {
+                    rotated = 1;
+                    const double zeta = (be - al) / (2.0 * ga);
+                    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+                    for (int k = lane; k < d2; k += 32) {
+                        const double x = scr[p + k * d1], y = scr[q + k * d1];
+                        scr[p + k * d1] = cs * x - sn * y;
+                        scr[q + k * d1] = sn * x + cs * y;
+                    }
+                    __syncwarp();
+                }
+            }
+        if (!rotated) break;
+    }
+    double nuc = 0.0;
+    for (int p = 0; p < d1; p++) {
+        double al = 0.0;
+        for (int k = lane; k < d2; k += 32) al += scr[p + k * d1] * scr[p + k * d1];
+        nuc += sqrt(warp_sum(al));
+    }
+    const bool dok = du > HYP_EPS && (du - nuc) > HYP_EPS;
+    if (lane == 0) {
+        grad[o] = g0;
+        scal[8 * c] = Huu;
+        scal[8 * c + 1] = tr2;
+        if (!ok) feas[kidx[c]] = 0;
+        if (!dok) dual_feas[kidx[c]] = 0;
+    }
+    // explicit Hessian, both triangles (:174-214): H[(j,i),(l,k)] = 2 (Zi[l,j] (W'tau + I)[i,k] + tau[l,i] tau[j,k])
+    double* Hc = H + moff[c];
+    for (int idx = lane; idx < d * d; idx += 32) {
+        const int r = idx % d, cc = idx / d;
+        double v;
+        if (r == 0 && cc == 0) {
+            v = Huu;
+        } else if (r == 0 || cc == 0) {
+            v = -4.0 * u * Zitau[r + cc - 1];
+        } else {
+            const int j = (r - 1) % d1, i = (r - 1) / d1, l = (cc - 1) % d1, k = (cc - 1) / d1;
+            double wt = i == k ? 1.0 : 0.0;
+            for (int m = 0; m < d1; m++) wt += W[m + i * d1] * tau[m + k * d1];
+            v = 2.0 * (Zi[l + j * d1] * wt + tau[l + i * d1] * tau[j + k * d1]);
+        }
+        Hc[r + (int64_t)cc * lde] = v;
+    }
+}
+
+// hess_prod!, epinormspectral.jl:216-246
+static __global__ void __launch_bounds__(256)
+ens_prod_kernel(int ncones, int want_dual, const int64_t* __restrict__ off, const int* __restrict__ dim,
+                const int* __restrict__ d1s, const int64_t* __restrict__ voff, const double* __restrict__ vecs,
+                const int* __restrict__ dualf, const double* __restrict__ scal,
+                const double* __restrict__ point, const double* arr, int64_t ld_arr, double* prod,
+                int64_t ld_prod, int64_t ncols, int64_t row_shift) {
+    __shared__ double sh[8][256];
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= ncones) return;
+    if (want_dual >= 0 && (dualf[c] != 0) != (want_dual != 0)) return;
+    double* T = sh[threadIdx.x >> 5];
+    double* X = T + 128;
+    const int64_t o = off[c];
+    const int d = dim[c], d1 = d1s[c], d2 = (d - 1) / d1, n12 = d1 * d2;
+    const double* tau = vecs + voff[c];
+    const double* Zitau = tau + n12;
+    const double* Uz = Zitau + n12 + d1 * d1;
+    const double u = point[o], Huu = scal[8 * c];
+    const double* W = point + o + 1;
+    for (int64_t j = blockIdx.y; j < ncols; j += gridDim.y) {
+        const double* a = arr + j * ld_arr + (o - row_shift);
+        double* pr = prod + j * ld_prod + (o - row_shift);
+        const double p = a[0];
+        const double* R = a + 1;
+        double s0 = 0.0;
+        for (int i = lane; i < n12; i += 32) s0 += Zitau[i] * R[i];
+        const double p0 = Huu * p - 4.0 * u * warp_sum(s0);
+        for (int idx = lane; idx < d1 * d1; idx += 32) {
+            const int r = idx % d1, b = idx / d1;
+            double s = r == b ? -2.0 * u * p : 0.0;
+            for (int k = 0; k < d2; k++) s += R[r + k * d1] * W[b + k * d1] + R[b + k * d1] * W[r + k * d1];
+            T[idx] = s;
+        }
+        __syncwarp();
+        for (int idx = lane; idx < n12; idx += 32) {
+            const int r = idx % d1, k = idx / d1;
+            double s = 0.0;
+            for (int m = 0; m < d1; m++) s += T[r + m * d1] * tau[m + k * d1];
+            X[idx] = 2.0 * s + 2.0 * R[idx];
+        }
+        __syncwarp();
+        ens_zsolve(Uz, X, d1, d2, lane);
+        __syncwarp();
+        for (int idx = lane; idx < n12; idx += 32) pr[1 + idx] = X[idx];
+        if (lane == 0) pr[0] = p0;
+        __syncwarp();
+    }
+}
+
+// dder3, epinormspectral.jl:248-294; one warp per cone, 4 warps per CTA
+static __global__ void __launch_bounds__(128)
+ens_dder3_kernel(int ncones, const int64_t* __restrict__ off, const int* __restrict__ dim,
+                 const int* __restrict__ d1s, const int64_t* __restrict__ voff, const double* __restrict__ vecs,
+                 const double* __restrict__ scal, const double* __restrict__ point,
+                 const double* __restrict__ dir, double* __restrict__ out) {
+    __shared__ double sh[4][9 * 128];
+    const int lane = threadIdx.x & 31;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= ncones) return;
+    double* M0 = sh[threadIdx.x >> 5];
+    double *M1 = M0 + 128, *M2 = M0 + 256, *M3 = M0 + 384, *M4 = M0 + 512, *M5 = M0 + 640;
+    double *S0 = M0 + 768, *S1 = M0 + 896, *S2 = M0 + 1024;
+    const int64_t o = off[c];
+    const int d = dim[c], d1 = d1s[c], d2 = (d - 1) / d1, n12 = d1 * d2;
+    const double* tau = vecs + voff[c];
+    const double* Zitau = tau + n12;
+    const double* Zi = Zitau + n12;
+    const double* Uz = Zi + d1 * d1;
+    const double u = point[o], ud = dir[o], trZi2 = scal[8 * c + 1];
+    const double* W = point + o + 1;
+    const double* A = dir + o + 1;
+    for (int i = lane; i < n12; i += 32) M0[i] = A[i];
+    __syncwarp();
+    ens_zsolve(Uz, M0, d1, d2, lane);                  // D = Z^-1 A
+    __syncwarp();
+    ens_mm_nt(S0, M0, W, d1, d2, lane, false);         // F = D W'
+    ens_mm_nt(S2, M0, tau, d1, d2, lane, false);       // D tau'
+    ens_mm_nt(S1, tau, A, d1, d2, lane, false);        // tau A'
+    __syncwarp();
+    for (int i = lane; i < n12; i += 32) M1[i] = M0[i];
+    __syncwarp();
+    ens_mm_sy(M1, S0, tau, d1, d2, lane, 1.0);         // E = D (W'tau + I)
+    ens_mm_sy(M2, S2, A, d1, d2, lane, 0.0);           // C = D (A'tau)'
+    ens_mm_sy(M3, S1, tau, d1, d2, lane, 0.0);         // P = tau (A'tau)
+    __syncwarp();
+    ens_mm_nt(S2, M3, A, d1, d2, lane, false);         // P A' + C W' + E A'
+    __syncwarp();
+    ens_mm_nt(S2, M2, W, d1, d2, lane, true);
+    __syncwarp();
+    ens_mm_nt(S2, M1, A, d1, d2, lane, true);
+    __syncwarp();
+    for (int i = lane; i < n12; i += 32) M4[i] = M2[i];
+    __syncwarp();
+    ens_mm_sy(M4, S2, tau, d1, d2, lane, 1.0);         // D2 = (...) tau + (tau A') E + C
+    __syncwarp();
+    ens_mm_sy(M4, S1, M1, d1, d2, lane, 1.0);
+    for (int i = lane; i < n12; i += 32) M3[i] = M1[i];
+    __syncwarp();
+    ens_zsolve(Uz, M3, d1, d2, lane);                  // Z^-1 E
+    ens_mm_nt(S2, Zitau, A, d1, d2, lane, false);      // Zitau A'
+    __syncwarp();
+    ens_mm_sy(M3, S2, tau, d1, d2, lane, 1.0);         // E2 = Z^-1 E + Zitau (A'tau)
+    __syncwarp();
+    for (int idx = lane; idx < d1 * d1; idx += 32) S2[idx] = S0[idx] + S1[idx];    // F2 = F + tau A'
+    __syncwarp();
+    ens_mm_sy(M3, S2, Zitau, d1, d2, lane, 1.0);
+    const double const1 = 4.0 * u * ud * u;
+    for (int i = lane; i < n12; i += 32) M5[i] = const1 * Zitau[i] - ud * tau[i];
+    __syncwarp();
+    ens_zsolve(Uz, M5, d1, d2, lane);                  // C2
+    __syncwarp();
+    double dot = 0.0;
+    for (int i = lane; i < n12; i += 32) {
+        const double e4 = -2.0 * u * M3[i] + M5[i];     // E4 = E3 + C2
+        out[o + 1 + i] = -2.0 * ud * e4 - 2.0 * M4[i];
+        dot += A[i] * (e4 + 3.0 * M5[i]);
+    }
+    dot = warp_sum(dot);
+    // trZi3 = |U^-T Zi|_F^2
+    double t3 = 0.0;
+    for (int b = lane; b < d1; b += 32) {
+        double* y = S0 + b * d1;
+        for (int i = 0; i < d1; i++) {
+            double s = Zi[i + b * d1];
+            for (int k = 0; k < i; k++) s -= Uz[k + i * d1] * y[k];
+            y[i] = s / Uz[i + i * d1];
+            t3 += y[i] * y[i];
+        }
+    }
+    t3 = warp_sum(t3);
+    if (lane == 0)
+        out[o] = -dot - u * ud * (6.0 * trZi2 - 8.0 * u * t3 * u) * ud - (d1 - 1) * (ud / u) * (ud / u) / u;
+}
+
+
 }  // namespace hypdev

@@ -918,6 +918,7 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
                                 : t == HYP_CONE_HYPOROOTDETTRI ? 1.0 + side
                                 : t == HYP_CONE_EPIPERSEPSPECTRAL_MAT ? 2.0 + side
                                 : t == HYP_CONE_EPIPERSQUARE ? 2.0
+                                : t == HYP_CONE_EPINORMSPECTRAL ? (double)ctx->h_cone_hkind[k] + 1.0   // epinormspectral.jl:95
                                 : t == HYP_CONE_GENERALIZEDPOWER
                                     ? ((int)ctx->h_cone_aoff.size() == K + 1
                                            ? (double)(ctx->h_cone_aoff[k + 1] - ctx->h_cone_aoff[k]) + 1.0
@@ -928,6 +929,8 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
             if ((t == HYP_CONE_EPIPERSQUARE || t == HYP_CONE_HYPOPERLOG || t == HYP_CONE_EPIPERSEPSPECTRAL_MAT ||
                  t == HYP_CONE_EPIPERSEPSPECTRAL_VEC) && d < 3)
                 throw HypError{"hyp_load_model: this cone type needs dimension >= 3"};
+            if (t == HYP_CONE_EPINORMSPECTRAL && (!have_params || ctx->h_cone_hkind[k] < 1))
+                throw HypError{"hyp_load_model: EpiNormSpectral cones need hyp_set_cone_params (number of rows d1) first"};
             if (t == HYP_CONE_EPIRELENTROPY && (d < 3 || d % 2 == 0))
                 throw HypError{"hyp_load_model: EpiRelEntropy needs an odd dimension >= 3"};   // epirelentropy.jl:51-52
             if (t == HYP_CONE_EPIPERSEPSPECTRAL_MAT || t == HYP_CONE_EPIPERSEPSPECTRAL_VEC) {

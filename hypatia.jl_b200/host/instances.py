@@ -106,6 +106,8 @@ def cone_initial_point(spec):
         arr[2:] = w
     elif spec.ctype == M.CONE_EPINORMINF:
         arr[0] = np.sqrt(spec.dim)      # epinorminf.jl:88-95
+    elif spec.ctype == M.CONE_EPINORMSPECTRAL:
+        arr[0] = np.sqrt(spec.hkind + 1.0)      # epinormspectral.jl:97-105
     elif spec.ctype == M.CONE_EPIRELENTROPY:
         d = (spec.dim - 1) // 2           # epirelentropy.jl:84-89, :377-409
         u, v, w = _central_ray_epirelentropy(d)
@@ -169,6 +171,8 @@ def _central_ray_epirelentropy(d):
 
 def _cone_dual_initial(spec, prim):
     """-grad at the central point, closed form per cone (dual of the central point)."""
+    if spec.ctype == M.CONE_EPINORMSPECTRAL:
+        return prim.copy()      # -grad at (sqrt(d1 + 1), 0) = ((d1 + 1) / u, 0): the central point is self-dual
     if spec.ctype == M.CONE_EPIRELENTROPY:
         # -grad, epirelentropy.jl:123-140
         d = (spec.dim - 1) // 2
@@ -278,7 +282,7 @@ def _perturb(rng, spec, vec, noise):
     if spec.ctype == M.CONE_GENERALIZEDPOWER:
         vec += 0.5 * noise / np.sqrt(vec.size) * (2 * rng.random(vec.size) - 1)
         return vec
-    if spec.ctype in (M.CONE_HYPOGEOMEAN, M.CONE_HYPOPOWERMEAN, M.CONE_EPIRELENTROPY):
+    if spec.ctype in (M.CONE_HYPOGEOMEAN, M.CONE_HYPOPOWERMEAN, M.CONE_EPIRELENTROPY, M.CONE_EPINORMSPECTRAL):
         vec[0] += 0.5 * noise * (2 * rng.random() - 1)
         vec[1:] += noise / np.sqrt(vec.size) * (2 * rng.random(vec.size - 1) - 1)
         return vec

@@ -26,6 +26,7 @@ CONE_HYPOGEOMEAN = 10
 CONE_GENERALIZEDPOWER = 11
 CONE_HYPOPOWERMEAN = 12
 CONE_EPIRELENTROPY = 13
+CONE_EPINORMSPECTRAL = 14
 
 # separable spectral functions of EpiPerSepSpectral (sepspectralfun.jl:17-116), HYP_SSF_*
 SSF_INV, SSF_NEGLOG, SSF_NEGENTROPY, SSF_POWER12 = 0, 1, 2, 3
@@ -45,6 +46,7 @@ CONE_NAMES = {
     CONE_GENERALIZEDPOWER: "GeneralizedPower",
     CONE_HYPOPOWERMEAN: "HypoPowerMean",
     CONE_EPIRELENTROPY: "EpiRelEntropy",
+    CONE_EPINORMSPECTRAL: "EpiNormSpectral",
 }
 
 
@@ -98,6 +100,9 @@ class ConeSpec:
             assert dim >= 3
         elif ctype == CONE_HYPOPERLOG:
             assert dim >= 3
+        elif ctype == CONE_EPINORMSPECTRAL:
+            # hkind = d1 (rows), d2 = (dim - 1) / d1 columns, d1 <= d2 (epinormspectral.jl:55-66)
+            assert dim >= 2 and hkind >= 1 and (dim - 1) % hkind == 0 and hkind <= (dim - 1) // hkind
         elif ctype == CONE_EPIRELENTROPY:
             assert dim >= 3 and dim % 2 == 1      # epirelentropy.jl:51-52
         elif ctype in (CONE_EPINORMINF, CONE_HYPOGEOMEAN):
@@ -141,6 +146,8 @@ class ConeSpec:
             return 2.0
         if self.ctype == CONE_GENERALIZEDPOWER:
             return float(len(self.alpha) + 1)
+        if self.ctype == CONE_EPINORMSPECTRAL:
+            return float(self.hkind + 1)      # epinormspectral.jl:95
         if self.ctype in (CONE_HYPOPERLOG, CONE_EPINORMINF, CONE_EPIPERSEPSPECTRAL_VEC, CONE_HYPOGEOMEAN,
                           CONE_HYPOPOWERMEAN, CONE_EPIRELENTROPY):
             return float(self.dim)
@@ -196,6 +203,13 @@ def GeneralizedPower(alpha, n, use_dual=False):
     """GeneralizedPower{Float64}(alpha, n): (u in R^m_+, w in R^n), prod u_i^alpha_i >= |w|; MOI's PowerCone(a) is
     GeneralizedPower([a, 1 - a], 1) (MathOptInterface/cones.jl:33-37)."""
     return ConeSpec(CONE_GENERALIZEDPOWER, len(alpha) + n, use_dual, alpha=alpha)
+
+
+def EpiNormSpectral(d1, d2, use_dual=False):
+    """EpiNormSpectral{Float64, Float64}(d1, d2): (u, vec(W)), W of d1 <= d2 rows x columns, u >= sigma_max(W);
+    use_dual = True gives the nuclear-norm epigraph (MOI NormSpectralCone / NormNuclearCone)."""
+    assert 1 <= d1 <= d2
+    return ConeSpec(CONE_EPINORMSPECTRAL, 1 + d1 * d2, use_dual, hkind=d1)
 
 
 def EpiRelEntropy(dim, use_dual=False):

@@ -51,6 +51,8 @@ typedef struct hyp_ctx hyp_ctx;
 #define HYP_CONE_GENERALIZEDPOWER 11 /* generalizedpower.jl (powers via hyp_set_cone_alpha; dim <= 128) */
 #define HYP_CONE_HYPOPOWERMEAN 12   /* hypopowermean.jl (dim - 1 powers via hyp_set_cone_alpha; dim <= 128) */
 #define HYP_CONE_EPIRELENTROPY 13   /* epirelentropy.jl (u, v[d], w[d]); dim = 1 + 2 d */
+#define HYP_CONE_EPINORMSPECTRAL 14 /* epinormspectral.jl (real): (u, vec(W)), W d1 x d2 column-major, d1 <= d2; d1 is given
+                                       as the integer parameter of hyp_set_cone_params; use_dual = 1: nuclear norm; dim <= 128 */
 
 /* separable spectral functions of EpiPerSepSpectral (epipersepspectral/sepspectralfun.jl:17-116) */
 #define HYP_SSF_INV 0        /* InvSSF        x -> 1/x      */

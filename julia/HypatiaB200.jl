@@ -44,6 +44,7 @@ cone_code(::Cones.HypoGeoMean) = Cint(10)
 cone_code(::Cones.GeneralizedPower) = Cint(11)
 cone_code(::Cones.HypoPowerMean) = Cint(12)
 cone_code(::Cones.EpiRelEntropy) = Cint(13)
+cone_code(::Cones.EpiNormSpectral{Float64, Float64}) = Cint(14)
 cone_alpha(c::Cones.GeneralizedPower) = Vector{Float64}(c.α)
 cone_alpha(c::Cones.HypoPowerMean) = Vector{Float64}(c.α)
 cone_alpha(::Cones.Cone) = Float64[]
@@ -55,6 +56,7 @@ ssf_code(::Cones.NegLogSSF) = (Cint(1), 0.0)
 ssf_code(::Cones.NegEntropySSF) = (Cint(2), 0.0)
 ssf_code(h::Cones.Power12SSF) = (Cint(3), Float64(h.p))
 cone_ssf(c::Cones.EpiPerSepSpectral) = ssf_code(c.h)
+cone_ssf(c::Cones.EpiNormSpectral) = (Cint(c.d1), 0.0)    # integer parameter = number of rows of W
 cone_ssf(::Cones.Cone) = (Cint(0), 0.0)
 
 function check(ctx::Ctx, rc::Cint, what::String)

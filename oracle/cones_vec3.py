@@ -6,6 +6,7 @@ src/Cones/hypoperlog.jl:54-287 (hypograph of the perspective of sum-log, (u, v, 
 u <= v sum log(w_i / v), barrier -log(v sum log(w_i/v) - u) - log v - sum log w_i, nu = dim).
 """
 import numpy as np
+import scipy.linalg as sla
 
 from hypatia_b200.host import models as M
 from .cones import Cone, EPS, _as2d, _ret, get_central_ray_hypoperlog
@@ -679,6 +680,123 @@ class EpiRelEntropy(Cone):
         d3[1:1 + d] = t / v / z
         d3[1 + d:] = (const1 * tau + ((const0 - w * vdv / z) / z + (1.0 / w + i2z) * wdw) * wdw
                       + (-const0 + dw / z - vdv / 2) / z * vdv)
+        return d3
+
+
+class EpiNormSpectral(Cone):
+    """epinormspectral.jl:10-294 (real case): (u, W) with W a d1 x d2 matrix stacked column-wise, d1 <= d2,
+    u >= sigma_max(W); barrier -logdet(u I - W W' / u) - log u, nu = d1 + 1; the dual cone is the nuclear-norm
+    epigraph.  No closed-form inverse Hessian: inv_hess_prod!, inv_hess and the sqrt oracles are the generic ones of
+    Cones.jl:113-118, 189-259 (explicit Hessian + posdef_fact_copy!)."""
+    ctype = M.CONE_EPINORMSPECTRAL
+
+    def __init__(self, d1, d2, use_dual=False):
+        assert 1 <= d1 <= d2
+        self.d1, self.d2 = d1, d2
+        self.use_dual_barrier = use_dual
+        super().__init__(1 + d1 * d2)
+
+    @property
+    def nu(self):
+        return float(self.d1 + 1)
+
+    def set_initial_point(self, arr):
+        arr[:] = 0.0
+        arr[0] = np.sqrt(self.d1 + 1.0)
+        return arr
+
+    def _mat(self, vec):
+        return vec.reshape(self.d1, self.d2, order="F")
+
+    def update_feas(self):
+        # epinormspectral.jl:107-124
+        u = self.point[0]
+        if u > EPS:
+            self.W = self._mat(self.point[1:]).copy()
+            Z = u * u * np.eye(self.d1) - self.W @ self.W.T
+            try:
+                self.fact_Z = sla.cho_factor(Z, lower=False, check_finite=False)
+            except np.linalg.LinAlgError:
+                return False
+            return True
+        return False
+
+    def is_dual_feas(self):
+        # epinormspectral.jl:126-133
+        u = self.dual_point[0]
+        if u > EPS:
+            return bool(u - np.sum(np.linalg.svd(self._mat(self.dual_point[1:]), compute_uv=False)) > EPS)
+        return False
+
+    def _zsolve(self, X):
+        return sla.cho_solve(self.fact_Z, X, check_finite=False)
+
+    def update_grad(self):
+        # epinormspectral.jl:135-151
+        u = self.point[0]
+        self.tau = self._zsolve(self.W)
+        self.Zi = self._zsolve(np.eye(self.d1))
+        self.Zi = (self.Zi + self.Zi.T) / 2
+        self._grad[0] = -2 * u * np.trace(self.Zi) + (self.d1 - 1) / u
+        self._grad[1:] = 2 * self.tau.ravel(order="F")
+        # update_hess_aux, epinormspectral.jl:153-172
+        self.Zitau = self._zsolve(self.tau)
+        self.HuW = -4 * u * self.Zitau
+        self.trZi2 = float(np.sum(self.Zi ** 2))
+        self.Huu = 4 * u * u * self.trZi2 + (self._grad[0] - 2 * (self.d1 - 1) / u) / u
+        self.WtauI = np.eye(self.d2) + self.W.T @ self.tau
+
+    def update_hess(self):
+        # epinormspectral.jl:174-214: H[(j,i),(l,k)] = 2 (Zi[l,j] WtauI[i,k] + tau[l,i] tau[j,k]), row index j + i d1
+        self.grad()
+        d1, d2 = self.d1, self.d2
+        H = np.empty((self.dim, self.dim))
+        T1 = np.einsum("lj,ik->jilk", self.Zi, self.WtauI)
+        T2 = np.einsum("li,jk->jilk", self.tau, self.tau)
+        HW = 2 * (T1 + T2)                                  # [j, i, l, k]
+        H[1:, 1:] = HW.transpose(1, 0, 3, 2).reshape(d1 * d2, d1 * d2)   # (i, j) -> i * d1 + j
+        H[0, 1:] = H[1:, 0] = self.HuW.ravel(order="F")
+        H[0, 0] = self.Huu
+        return H
+
+    def hess_prod(self, arr):
+        # epinormspectral.jl:216-246
+        self.grad()
+        a, vec = _as2d(arr)
+        u = self.point[0]
+        prod = np.empty_like(a)
+        for j in range(a.shape[1]):
+            p, R = a[0, j], self._mat(a[1:, j])
+            prod[0, j] = self.Huu * p + float(np.sum(self.HuW * R))
+            T = R @ self.W.T
+            T = T + T.T - 2 * u * p * np.eye(self.d1)
+            prod[1:, j] = self._zsolve(2 * (T @ self.tau) + 2 * R).ravel(order="F")
+        return _ret(prod, vec)
+
+    def dder3(self, direction):
+        # epinormspectral.jl:248-294
+        self.grad()
+        u, W, tau, Zitau, WtauI, Zi = self.point[0], self.W, self.tau, self.Zitau, self.WtauI, self.Zi
+        ud, Wd = direction[0], self._mat(direction[1:])
+        B = Wd.T @ tau
+        D = self._zsolve(Wd)
+        E = D @ WtauI
+        C = D @ B.T
+        F = D @ W.T
+        G = B @ B + Wd.T @ E
+        D2 = tau @ G + C @ WtauI + E @ B
+        E2 = self._zsolve(E) + Zitau @ B
+        F2 = F + tau @ Wd.T
+        E3 = -2 * u * (E2 + F2 @ Zitau)
+        C2 = self._zsolve(4 * u * u * ud * Zitau - ud * tau)
+        E4 = E3 + C2
+        d3 = np.empty(self.dim)
+        d3[1:] = (-2 * ud * E4 - 2 * D2).ravel(order="F")
+        U = self.fact_Z[0]
+        trZi3 = float(np.sum(sla.solve_triangular(U, Zi, trans="T", lower=False, check_finite=False) ** 2))
+        E5 = E4 + 3 * C2
+        d3[0] = -float(np.sum(Wd * E5)) - u * ud * (6 * self.trZi2 - 8 * u * trZi3 * u) * ud \
+            - (self.d1 - 1) * (ud / u) ** 2 / u
         return d3
 
 

@@ -297,12 +297,18 @@ class EmuGpowGroup:
     def __init__(self, specs):
         self.K = len(specs)
         self.hpm = specs[0].ctype == 12          # HypoPowerMean, else GeneralizedPower
+        self.ens = specs[0].ctype == 14          # EpiNormSpectral: d1 per cone, workspace instead of powers
+        if self.ens:
+            self.d1 = np.array([s.hkind for s in specs], dtype=np.int32)
+            sizes = [3 * (s.dim - 1) + 2 * s.hkind ** 2 for s in specs]
+            self.voff = np.concatenate(([0], np.cumsum(sizes)))[:-1].astype(np.int64)
+            self.vecs = np.zeros(int(sum(sizes)))
         self.dims = np.array([s.dim for s in specs], dtype=np.int32)
         self.off = np.concatenate(([0], np.cumsum(self.dims)))[:-1].astype(np.int64)
         self.q = int(self.dims.sum())
         self.mu = np.array([len(s.alpha) for s in specs], dtype=np.int32)
         self.aoff = np.concatenate(([0], np.cumsum(self.mu)))[:-1].astype(np.int64)
-        self.alpha = np.concatenate([np.asarray(s.alpha, dtype=np.float64) for s in specs])
+        self.alpha = np.concatenate([np.asarray(s.alpha, dtype=np.float64) for s in specs] + [np.zeros(0)])
         self.kidx = np.arange(self.K, dtype=np.int32)
         self.dualf = np.array([1 if s.use_dual else 0 for s in specs], dtype=np.int32)
         self.lay = MatLayout(self.dims)
@@ -315,7 +321,11 @@ class EmuGpowGroup:
         self.dual_feas = np.ones(self.K, dtype=np.uint8)
         self.grad = np.zeros(self.q)
         self.H = np.zeros(self.lay.total)
-        if self.hpm:
+        if self.ens:
+            lib().emu_ens_state(self.K, p(self.off), p(self.dims), p(self.d1), p(self.voff), p(self.vecs), p(self.kidx),
+                                p(self.lay.moff), p(self.point), p(self.dual), p(self.grad), p(self.scal), p(self.H),
+                                p(self.feas), p(self.dual_feas))
+        elif self.hpm:
             lib().emu_hpm_state(self.K, p(self.off), p(self.dims), p(self.aoff), p(self.alpha), p(self.kidx),
                                 p(self.lay.moff), p(self.point), p(self.dual), p(self.grad), p(self.scal), p(self.H),
                                 p(self.feas), p(self.dual_feas))
@@ -337,7 +347,11 @@ class EmuGpowGroup:
         out = a if in_place else np.zeros_like(a, order="F")
         hess_dual, inv_dual = {0: (-1, -2), 1: (-2, -1), 4: (0, 1), 5: (1, 0)}[int(mode)]
         L = lib()
-        if hess_dual > -2 and self.hpm:
+        if hess_dual > -2 and self.ens:
+            L.emu_ens_prod(self.K, hess_dual, p(self.off), p(self.dims), p(self.d1), p(self.voff), p(self.vecs),
+                           p(self.dualf), p(self.scal), p(self.point), p(a), i64(self.q), p(out), i64(self.q),
+                           i64(a.shape[1]), i64(0))
+        elif hess_dual > -2 and self.hpm:
             L.emu_hpm_prod(self.K, hess_dual, p(self.off), p(self.dims), p(self.aoff), p(self.alpha), p(self.dualf),
                            p(self.scal), p(self.point), p(a), i64(self.q), p(out), i64(self.q), i64(a.shape[1]), i64(0))
         elif hess_dual > -2:
@@ -352,7 +366,10 @@ class EmuGpowGroup:
     def dder3(self, direction):
         d = np.ascontiguousarray(direction, dtype=np.float64)
         out = np.zeros(self.q)
-        if self.hpm:
+        if self.ens:
+            lib().emu_ens_dder3(self.K, p(self.off), p(self.dims), p(self.d1), p(self.voff), p(self.vecs), p(self.scal),
+                                p(self.point), p(d), p(out))
+        elif self.hpm:
             lib().emu_hpm_dder3(self.K, p(self.off), p(self.dims), p(self.aoff), p(self.alpha), p(self.scal),
                                 p(self.point), p(d), p(out))
         else:

@@ -558,6 +558,66 @@ def epirelentropy5():  # :2183-2198
              z=np.array([1, 1, 1, 1, -1, -1, -1, 3]) / 3.0)
 
 
+def _svals(vec, d1, d2):
+    return np.linalg.svd(vec.reshape(d1, d2, order="F"), compute_uv=False)
+
+
+def _epinormspectral1(use_dual):  # :1038-1073 (real case)
+    rng = np.random.default_rng(1)
+    d1, d2 = 3, 4
+    dim = d1 * d2
+    c = np.concatenate(([1.0], np.zeros(dim)))
+    A = np.hstack((np.zeros((dim, 1)), np.eye(dim)))
+    b = rng.random(dim)
+    h = np.concatenate(([0.0], rng.random(dim)))
+
+    def check(s, z, approx):
+        ps, ds = _svals(s[1:], d1, d2), _svals(z[1:], d1, d2)
+        if use_dual:
+            assert approx(ps.sum(), s[0]) and approx(ds[0], z[0])
+        else:
+            assert approx(ps[0], s[0]) and approx(ds.sum(), z[0])
+    return _m(c, A, b, -np.eye(dim + 1), h, [M.EpiNormSpectral(d1, d2, use_dual=use_dual)]), \
+        dict(status="Optimal", check=check)
+
+
+def _epinormspectral2(use_dual):  # :1075-1103 (real case)
+    d1, d2 = 3, 4
+    dim = d1 * d2
+    mat = np.random.default_rng(1).random((d1, d2))
+    G = np.vstack((np.zeros((1, dim)), -np.eye(dim)))
+    h = np.concatenate(([1.0], np.zeros(dim)))
+    sv = np.linalg.svd(mat, compute_uv=False)
+    return _m(-mat.ravel(order="F"), None, None, G, h, [M.EpiNormSpectral(d1, d2, use_dual=use_dual)]), \
+        dict(status="Optimal", primal_obj=-sv[0] if use_dual else -sv.sum())
+
+
+def _epinormspectral3(d1, d2, use_dual):  # :1105-1125 (real case)
+    dim = d1 * d2
+    G = np.vstack((np.zeros((1, dim)), -np.eye(dim)))
+    return _m(-np.ones(dim), None, None, G, np.zeros(dim + 1), [M.EpiNormSpectral(d1, d2, use_dual=use_dual)]), \
+        dict(status="Optimal", primal_obj=0, x=np.zeros(dim))
+
+
+def _epinormspectral4(use_dual):  # :1127-1155
+    G = np.zeros((7, 1))
+    G[0, 0] = -1
+    h = np.array([0, 1, 1, 1, -1, 0, 1.0])
+    rt2, rt3 = np.sqrt(2.0), np.sqrt(3.0)
+    if use_dual:
+        exp = dict(status="Optimal", primal_obj=rt2 + rt3, s=[rt2 + rt3, 1, 1, 1, -1, 0, 1],
+                   z=[1, -1 / rt2, -1 / rt3, -1 / rt2, 1 / rt3, 0, -1 / rt3])
+    else:
+        exp = dict(status="Optimal", primal_obj=rt3, s=[rt3, 1, 1, 1, -1, 0, 1],
+                   z=[1, 0, -1 / rt3, 0, 1 / rt3, 0, -1 / rt3])
+    return _m([1], None, None, G, h, [M.EpiNormSpectral(2, 3, use_dual=use_dual)]), exp
+
+
+NORMSPEC = [_named(lambda f=_f, ud=_ud: f(ud), _f.__name__[1:] + ("_dual" if _ud else ""))
+            for _f in (_epinormspectral1, _epinormspectral2, _epinormspectral4) for _ud in (False, True)] + \
+    [_named(lambda a=_a, b=_b, ud=_ud: _epinormspectral3(a, b, ud), f"epinormspectral3_{_a}x{_b}" + ("_dual" if _ud else ""))
+     for (_a, _b) in ((1, 1), (1, 3), (2, 2), (3, 4)) for _ud in (False, True)]
+
 RELENT = [_named(lambda d=_d: _epirelentropy1(d), f"epirelentropy1_d{_d}") for _d in (1, 2, 3)] + \
     [_named(lambda d=_d: _epirelentropy2(d), f"epirelentropy2_d{_d}") for _d in (1, 2, 4)] + \
     [_named(lambda d=_d: _epirelentropy3(d), f"epirelentropy3_d{_d}") for _d in (2, 4)] + \
@@ -572,7 +632,7 @@ HPM = [_named(lambda f=_f, ud=_ud: f(ud), _f.__name__[1:] + ("_dual" if _ud else
        for _f in (_hypopowermean1, _hypopowermean2) for _ud in (False, True)] + \
     [hypopowermean4, hypopowermean5, hypopowermean6]
 
-NEW_CONES = GPOW + HPM + RELENT + [hypogeomean1, hypogeomean1_dual, hypogeomean2, hypogeomean2_dual, hypogeomean4, hypogeomean5,
+NEW_CONES = GPOW + HPM + RELENT + NORMSPEC + [hypogeomean1, hypogeomean1_dual, hypogeomean2, hypogeomean2_dual, hypogeomean4, hypogeomean5,
              hypogeomean6, epinorminf1, epinorminf2, epinorminf3, epinorminf3_dual, epinorminf4, dualinfeas1,
              primalinfeas3, dualinfeas2, dualinfeas3, epipersquare1, epipersquare2, epipersquare3,
              epipersquare4, hypoperlog1, hypoperlog2, hypoperlog3, hypoperlog4, hypoperlog5, hypoperlog6,
@@ -621,3 +681,5 @@ def check_solution(solver, model, expected, tol=TOL):
         assert _approx(x[i], v, tol)
     for i, v in expected.get("z_idx", {}).items():
         assert _approx(z[i], v, tol)
+    if "check" in expected:       # instance-specific assertions on (s, z), e.g. singular values
+        expected["check"](s, z, lambda a, b: _approx(a, b, tol))

@@ -1,4 +1,4 @@
-"""CPU-tier checks of the device code of GeneralizedPower, HypoPowerMean and of the generic inverse-Hessian product
+"""CPU-tier checks of the device code of GeneralizedPower, HypoPowerMean, EpiNormSpectral and of the generic inverse-Hessian product
 (csrc/cones_gpow_kernels.cuh, compiled for the host by tests/emu/) against the CPU oracle."""
 import numpy as np
 import pytest
@@ -31,15 +31,21 @@ def _sets():
         "hpm": [M.HypoPowerMean(_bal(rng, d)) for d in (1, 2, 5, 33, 70)],
         "hpm_dual": [M.HypoPowerMean(_bal(rng, 3), use_dual=True), M.HypoPowerMean(_bal(rng, 6)),
                      M.HypoPowerMean(_bal(rng, 40), use_dual=True)],
+        "normspec": [M.EpiNormSpectral(a, b) for a, b in ((1, 1), (1, 2), (2, 2), (2, 4), (3, 4), (5, 9), (1, 127), (11, 11))],
+        "normspec_dual": [M.EpiNormSpectral(2, 3, use_dual=True), M.EpiNormSpectral(3, 5),
+                          M.EpiNormSpectral(4, 20, use_dual=True)],
         "gpow_dual": [M.GeneralizedPower(_alpha(rng, 2), 1, use_dual=True), M.GeneralizedPower(_alpha(rng, 3), 3),
                       M.GeneralizedPower(_alpha(rng, 5), 33, use_dual=True)],
     }
 
 
-@pytest.mark.parametrize("name", ["gpow", "gpow_dual", "hpm", "hpm_dual"])
+NAMES = ["gpow", "gpow_dual", "hpm", "hpm_dual", "normspec", "normspec_dual"]
+
+
+@pytest.mark.parametrize("name", NAMES)
 def test_gpow_kernels_match_oracle(name):
     cones = _sets()[name]
-    I = inst.synthetic(name, 3, 0, cones, seed=600 + ["gpow", "gpow_dual", "hpm", "hpm_dual"].index(name))
+    I = inst.synthetic(name, 3, 0, cones, seed=600 + NAMES.index(name))
     ora = OracleConeBlock(I.model)
     prim, dual = I.point.primal_dual(ora.dual_mask)
     scal = 1 / np.sqrt(I.mu)
@@ -79,3 +85,35 @@ def test_gpow_kernels_flag_infeasible_points():
     dev.load_point(prim, dual)
     assert (dev.feas.astype(bool) == ora.is_feas()).all() and not dev.feas[:2].any() and dev.feas[2]
     assert (dev.dual_feas.astype(bool) == ora.is_dual_feas()).all() and not dev.dual_feas[2]
+
+
+def test_normspec_kernels_flag_infeasible_points():
+    """u must exceed the largest singular value (primal) / the nuclear norm (dual): the device Cholesky of
+    u^2 I - W W' and the one-sided Jacobi singular values against the oracle (LAPACK) at the boundary."""
+    cones = [M.EpiNormSpectral(2, 3), M.EpiNormSpectral(3, 4), M.EpiNormSpectral(2, 2), M.EpiNormSpectral(1, 4)]
+    I = inst.synthetic("nsinf", 2, 0, cones, seed=13)
+    prim, dual = (x.copy() for x in I.point.primal_dual(None))
+    rng = np.random.default_rng(2)
+    W = rng.standard_normal((2, 3))
+    sv = np.linalg.svd(W, compute_uv=False)
+    prim[0] = sv[0] * (1 - 1e-9)                    # cone 0: u just below sigma_max
+    prim[1:7] = W.ravel(order="F")
+    o1 = 7
+    Wd = rng.standard_normal((3, 4))
+    dual[o1] = np.linalg.svd(Wd, compute_uv=False).sum() * (1 - 1e-9)      # cone 1: dual u just below the nuclear norm
+    dual[o1 + 1:o1 + 13] = Wd.ravel(order="F")
+    o2 = o1 + 13
+    W2 = rng.standard_normal((2, 2))
+    prim[o2] = np.linalg.svd(W2, compute_uv=False)[0] * (1 + 1e-6)         # cone 2: just inside
+    prim[o2 + 1:o2 + 5] = W2.ravel(order="F")
+    dual[o2] = np.linalg.svd(W2, compute_uv=False).sum() * (1 + 1e-9)
+    dual[o2 + 1:o2 + 5] = W2.ravel(order="F")
+    ora = OracleConeBlock(I.model)
+    ora.load_point(prim, dual, 1.0)
+    dev = eu.EmuGpowGroup(cones)
+    dev.load_point(prim, dual)
+    assert (ora.is_feas() == np.array([False, True, True, True])).all()
+    assert (ora.is_dual_feas() == np.array([True, False, True, True])).all()
+    # the explicit Hessian of cone 2 (1e-6 from the boundary) may fail its Cholesky on either side: compare the cone's own flag
+    assert (dev.feas.astype(bool)[[0, 1, 3]] == ora.is_feas()[[0, 1, 3]]).all()
+    assert (dev.dual_feas.astype(bool) == ora.is_dual_feas()).all()

@@ -50,6 +50,9 @@ CONE_SETS = {
                     M.HypoGeoMean(9, use_dual=True)],
     "epirelentropy": [M.EpiRelEntropy(3), M.EpiRelEntropy(9), M.EpiRelEntropy(35), M.EpiRelEntropy(81),
                       M.EpiRelEntropy(7, use_dual=True)],
+    "normspec": [M.EpiNormSpectral(1, 1), M.EpiNormSpectral(2, 2), M.EpiNormSpectral(3, 4), M.EpiNormSpectral(5, 9),
+                 M.EpiNormSpectral(1, 127), M.EpiNormSpectral(11, 11), M.EpiNormSpectral(2, 3, use_dual=True),
+                 M.EpiNormSpectral(4, 20, use_dual=True)],
     "gpow": [M.GeneralizedPower([0.5, 0.5], 1), M.GeneralizedPower([0.2, 0.3, 0.5], 2),
              M.GeneralizedPower(np.full(20, 0.05), 30), M.GeneralizedPower([0.7, 0.3], 1, use_dual=True),
              M.GeneralizedPower(np.full(4, 0.25), 60)],
@@ -62,7 +65,8 @@ CONE_SETS = {
                M.EpiPerSepSpectralVec(6, M.SSF_NEGENTROPY), M.HypoGeoMean(5), M.HypoGeoMean(4, use_dual=True),
                M.GeneralizedPower([0.3, 0.7], 2), M.GeneralizedPower([0.5, 0.5], 1, use_dual=True),
                M.HypoPowerMean([0.25, 0.35, 0.4]), M.HypoPowerMean([0.5, 0.5], use_dual=True),
-               M.EpiRelEntropy(7), M.EpiRelEntropy(5, use_dual=True)],
+               M.EpiRelEntropy(7), M.EpiRelEntropy(5, use_dual=True), M.EpiNormSpectral(2, 3),
+               M.EpiNormSpectral(2, 2, use_dual=True)],
 }
 
 

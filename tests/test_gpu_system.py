@@ -145,7 +145,7 @@ def test_spectral_and_perspective_cones(p):
              M.HypoGeoMean(4, use_dual=True), M.GeneralizedPower([0.25, 0.75], 1),
              M.GeneralizedPower([0.2, 0.3, 0.5], 3, use_dual=True), M.HypoPowerMean([0.3, 0.7]),
              M.HypoPowerMean([0.2, 0.2, 0.6], use_dual=True), M.EpiRelEntropy(9),
-             M.EpiRelEntropy(5, use_dual=True)]
+             M.EpiRelEntropy(5, use_dual=True), M.EpiNormSpectral(2, 4), M.EpiNormSpectral(3, 3, use_dual=True)]
     I = inst.synthetic("specmix", 20 + p, p, cones, seed=21)
     Ap = None
     if p:

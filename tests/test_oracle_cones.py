@@ -190,6 +190,50 @@ def test_epirelentropy(dw, init_only):
     run_oracles(EpiRelEntropy(1 + 2 * dw), init_tol=1e-1 if init_only else 1e-5, init_only=init_only)
 
 
+@pytest.mark.parametrize("dr,ds", [(1, 1), (1, 2), (2, 2), (2, 4), (3, 4)])
+def test_epinormspectral(dr, ds):
+    # reference: test/cone.jl:499-503
+    from oracle.cones_vec3 import EpiNormSpectral
+    run_oracles(EpiNormSpectral(dr, ds))
+
+
+def test_epinormspectral_barrier():
+    """test_barrier of test/cone.jl:505-513 with central differences: grad, hess_prod and dder3 against derivatives of
+    -logdet(u^2 I - W W') + (d1 - 1) log u."""
+    from oracle.cones_vec3 import EpiNormSpectral
+    dr, ds = 2, 3
+    cone = EpiNormSpectral(dr, ds)
+
+    def barrier(s):
+        W = s[1:].reshape(dr, ds, order="F")
+        return -np.linalg.slogdet(s[0] ** 2 * np.eye(dr) - W @ W.T)[1] + (dr - 1) * np.log(s[0])
+
+    rng = np.random.default_rng(1)
+    point = np.zeros(cone.dim)
+    cone.set_initial_point(point)
+    perturb_scale(rng, point, 0.1, 1.0)
+
+    def grad_at(s):
+        cone.reset_data()
+        cone.load_point(s)
+        assert cone.is_feas()
+        return cone.grad().copy()
+
+    g = grad_at(point)
+    eps = 1e-6
+    fd_grad = np.array([(barrier(point + eps * e) - barrier(point - eps * e)) / (2 * eps) for e in np.eye(cone.dim)])
+    assert close(g, fd_grad, 1e-7)
+    direction = rng.standard_normal(cone.dim)
+    fd_hess_dir = (grad_at(point + eps * direction) - grad_at(point - eps * direction)) / (2 * eps)
+    grad_at(point)
+    assert close(cone.hess_prod(direction), fd_hess_dir, 1e-7)
+    assert close(cone.hess() @ direction, fd_hess_dir, 1e-7)
+    e2 = 1e-4
+    fd_third = (grad_at(point + e2 * direction) - 2 * g + grad_at(point - e2 * direction)) / e2 ** 2
+    grad_at(point)
+    assert close(-2 * cone.dder3(direction), fd_third, 1e-5)
+
+
 SSF = [(0, 0.0), (1, 0.0), (2, 0.0), (3, 1.5), (3, 2.0), (3, 1.1)]   # Inv, NegLog, NegEntropy, Power12(p)
 
 
