@@ -1540,7 +1540,16 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
             continue;
         }
         if (use_cluster == 2) {
-            // (P, J): tile rows 2P, 2P+1 of tile column J, for 2P <= J, column by column
+            // (P, J): tile rows 2P, 2P+1 of tile column J, for 2P <= J.  Two orders of the list (the clusters take
+            // consecutive entries, so the order decides which operand panel stays in L2):
+            //   column by column (default): the 128-column B panel of tile column J (15 MB per 16 k rows) is L2-resident,
+            //     the 256-row A panels (30 MB each) stream from DRAM once per (P, J);
+            //   row by row (HYP_OZAKI_ORDER=row): the A panel of row pair P is resident and the B panels, half the size,
+            //     stream - about half the DRAM bytes for the same L2 footprint.
+            static const bool row_order = [] {
+                const char* e = getenv("HYP_OZAKI_ORDER");
+                return e && e[0] == 'r';
+            }();
             static std::vector<std::pair<int, std::pair<int2*, int>>> pcache;
             int2* d_pairs = nullptr;
             int n_pairs = 0;
@@ -1551,8 +1560,13 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
                 }
             if (!d_pairs) {
                 std::vector<int2> pl;
-                for (int tj = 0; tj < nt; tj++)
-                    for (int pp = 0; 2 * pp <= tj; pp++) pl.push_back(make_int2(pp, tj));
+                if (row_order) {
+                    for (int pp = 0; 2 * pp < nt; pp++)
+                        for (int tj = 2 * pp; tj < nt; tj++) pl.push_back(make_int2(pp, tj));
+                } else {
+                    for (int tj = 0; tj < nt; tj++)
+                        for (int pp = 0; 2 * pp <= tj; pp++) pl.push_back(make_int2(pp, tj));
+                }
                 n_pairs = (int)pl.size();
                 CUDA_TRY(cudaMalloc(&d_pairs, pl.size() * sizeof(int2)));
                 CUDA_TRY(cudaMemcpyAsync(d_pairs, pl.data(), pl.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
