@@ -47,9 +47,53 @@ static void ens_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
     hyp_mat_alloc_group(ctx, g);
 }
 
+// WSOSInterpNonnegative: d_vecs / d_voff = per-cone region [nP][L_1 .. L_nP][P_1 .. P_nP] (as passed to
+// hyp_set_cone_alpha) followed by the workspace of wsos_state_kernel / wsos_dder3_kernel
+static void wsos_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
+    if ((int)ctx->h_cone_aoff.size() != ctx->K + 1)
+        throw HypError{"WSOSInterpNonnegative cones need hyp_set_cone_alpha (packed Ps) before hyp_load_model"};
+    g.h_voff.assign(g.count, 0);
+    std::vector<double> buf;
+    for (int i = 0; i < g.count; i++) {
+        const int k = g.h_kidx[i];
+        const int64_t a0 = ctx->h_cone_aoff[k], a1 = ctx->h_cone_aoff[k + 1];
+        const int U = g.h_dim[i];
+        if (U > 128) throw HypError{"WSOSInterpNonnegative: dimension above 128 is not supported (batched Cholesky limit)"};
+        if (a1 - a0 < 2) throw HypError{"WSOSInterpNonnegative: missing Ps data"};
+        const int nP = (int)ctx->h_cone_alpha[a0];
+        if (nP < 1 || a1 - a0 < 1 + nP) throw HypError{"WSOSInterpNonnegative: bad number of Ps matrices"};
+        int64_t sumL = 0, wsz = 0, Lmax = 0;
+        for (int j = 0; j < nP; j++) {
+            const int64_t L = (int64_t)ctx->h_cone_alpha[a0 + 1 + j];
+            if (L < 1 || L > U) throw HypError{"WSOSInterpNonnegative: need 1 <= L_k <= U"};
+            sumL += L;
+            wsz += L * U + L * L;
+            Lmax = std::max(Lmax, L);
+        }
+        if (a1 - a0 != 1 + nP + (int64_t)U * sumL) throw HypError{"WSOSInterpNonnegative: Ps data has the wrong length"};
+        g.h_voff[i] = (int64_t)buf.size();
+        buf.insert(buf.end(), ctx->h_cone_alpha.begin() + a0, ctx->h_cone_alpha.begin() + a1);
+        buf.resize(buf.size() + (size_t)(wsz + Lmax * Lmax), 0.0);
+        g.h_hkind.push_back(nP);
+        g.h_side[i] = U;
+    }
+    g.max_side = g.max_dim;
+    cudaFree(g.d_side);
+    g.d_side = upload_vec(g.h_side);
+    g.d_hkind = upload_vec(g.h_hkind);
+    g.d_voff = upload_vec(g.h_voff);
+    CUDA_TRY(cudaMalloc(&g.d_vecs, std::max<size_t>(buf.size(), 1) * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(g.d_vecs, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice));
+    hyp_mat_alloc_group(ctx, g);
+}
+
 void hyp_gpow_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
     if (g.type == HYP_CONE_EPINORMSPECTRAL) {
         ens_alloc_group(ctx, g);
+        return;
+    }
+    if (g.type == HYP_CONE_WSOSINTERPNONNEGATIVE) {
+        wsos_alloc_group(ctx, g);
         return;
     }
     std::vector<double> alpha;
@@ -88,7 +132,10 @@ void hyp_gpow_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
 }
 
 void hyp_gpow_update_state(hyp_ctx* ctx, ConeGroup& g) {
-    if (g.type == HYP_CONE_EPINORMSPECTRAL)
+    if (g.type == HYP_CONE_WSOSINTERPNONNEGATIVE)
+        hypdev::wsos_state_kernel<<<g.count, 256, 0, ctx->stream>>>(g.count, g.d_off, g.d_dim, g.d_voff, g.d_vecs, g.d_kidx,
+                                                                   g.d_moff, ctx->d_point, ctx->d_grad, g.d_W, ctx->d_feas);
+    else if (g.type == HYP_CONE_EPINORMSPECTRAL)
         hypdev::ens_state_kernel<<<ceil_div(g.count, 8), 256, 0, ctx->stream>>>(
             g.count, g.d_off, g.d_dim, g.d_hkind, g.d_voff, g.d_vecs, g.d_kidx, g.d_moff, ctx->d_point, ctx->d_dual,
             ctx->d_grad, g.d_scal, g.d_W, ctx->d_feas, ctx->d_dual_feas);
@@ -121,7 +168,11 @@ void hyp_gpow_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr, 
     else if (mode == HYP_PROD_BLOCK_INV) { hess_dual = 1; inv_dual = 0; }
     else throw HypError{"hyp_gpow_prod: bad mode"};
     if (hess_dual > -2) {
-        if (g.type == HYP_CONE_EPINORMSPECTRAL)
+        if (g.type == HYP_CONE_WSOSINTERPNONNEGATIVE)
+            hypdev::gen_hess_prod_kernel<<<grid, 256, 0, ctx->stream>>>(g.count, hess_dual, g.d_off, g.d_dim, g.d_moff,
+                                                                       g.d_dual, g.d_W, arr, ld_arr, prod, ld_prod, ncols,
+                                                                       row_shift);
+        else if (g.type == HYP_CONE_EPINORMSPECTRAL)
             hypdev::ens_prod_kernel<<<grid, 256, 0, ctx->stream>>>(g.count, hess_dual, g.d_off, g.d_dim, g.d_hkind,
                                                                   g.d_voff, g.d_vecs, g.d_dual, g.d_scal, ctx->d_point,
                                                                   arr, ld_arr, prod, ld_prod, ncols, row_shift);
@@ -146,7 +197,9 @@ void hyp_gpow_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr, 
 }
 
 void hyp_gpow_dder3(hyp_ctx* ctx, ConeGroup& g, double* out, const double* dir) {
-    if (g.type == HYP_CONE_EPINORMSPECTRAL)
+    if (g.type == HYP_CONE_WSOSINTERPNONNEGATIVE)
+        hypdev::wsos_dder3_kernel<<<g.count, 256, 0, ctx->stream>>>(g.count, g.d_off, g.d_dim, g.d_voff, g.d_vecs, dir, out);
+    else if (g.type == HYP_CONE_EPINORMSPECTRAL)
         hypdev::ens_dder3_kernel<<<ceil_div(g.count, 4), 128, 0, ctx->stream>>>(
             g.count, g.d_off, g.d_dim, g.d_hkind, g.d_voff, g.d_vecs, g.d_scal, ctx->d_point, dir, out);
     else if (g.type == HYP_CONE_HYPOPOWERMEAN)

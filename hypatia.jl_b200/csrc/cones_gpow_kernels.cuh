@@ -652,4 +652,165 @@ ens_dder3_kernel(int ncones, const int64_t* __restrict__ off, const int* __restr
 }
 
 
+// ---- WSOSInterpNonnegative (real, U <= 128), wsosinterpnonnegative.jl:91-200 ----
+// Region of cone c at vecs + voff[c]: [nP][L_1 .. L_nP][P_1 .. P_nP] (the data of hyp_set_cone_alpha: P_k is U x L_k,
+// column-major), then per k the workspace F_k = L_k^-1 P_k' (L_k x U, "LFLP" of the reference) and the lower Cholesky
+// factor of Lambda_k = P_k' Diagonal(point) P_k (L_k x L_k), then one L_max x L_max scratch for dder3.
+// One CTA of 256 threads per cone; thread j < U owns entry j of the gradient / dder3.
+
+static __global__ void __launch_bounds__(256)
+wsos_state_kernel(int ncones, const int64_t* __restrict__ off, const int* __restrict__ dim,
+                  const int64_t* __restrict__ voff, double* __restrict__ vecs, const int* __restrict__ kidx,
+                  const int64_t* __restrict__ moff, const double* __restrict__ point, double* __restrict__ grad,
+                  double* __restrict__ H, uint8_t* feas) {
+    __shared__ int s_ok;
+    const int c = blockIdx.x, tid = threadIdx.x;
+    if (c >= ncones) return;
+    const int64_t o = off[c];
+    const int U = dim[c], lde = (U + 1) & ~1;
+    double* reg = vecs + voff[c];
+    const int nP = (int)reg[0];
+    int sumL = 0;
+    for (int k = 0; k < nP; k++) sumL += (int)reg[1 + k];
+    const double* P = reg + 1 + nP;
+    double* ws = reg + 1 + nP + (int64_t)U * sumL;
+    double* Hc = H + moff[c];
+    if (tid == 0) s_ok = 1;
+    double gacc = 0.0;
+    for (int k = 0; k < nP; k++) {
+        const int L = (int)reg[1 + k];
+        double* F = ws;
+        double* Lc = F + (int64_t)L * U;
+        ws = Lc + L * L;
+        // update_feas (:91-121): Lambda = P' Diagonal(point) P and its Cholesky (lower, in place, right-looking)
+        for (int idx = tid; idx < L * L; idx += 256) {
+            const int a = idx % L, b = idx / L;
+            double s = 0.0;
+            for (int i = 0; i < U; i++) s += P[i + (int64_t)a * U] * point[o + i] * P[i + (int64_t)b * U];
+            Lc[idx] = s;
+        }
+        __syncthreads();
+        for (int j = 0; j < L; j++) {
+            if (tid == 0) {
+                double dg = Lc[j + j * L];
+                if (!(dg > 0.0)) {
+                    s_ok = 0;
+                    dg = 1.0;
+                }
+                Lc[j + j * L] = sqrt(dg);
+            }
+            __syncthreads();
+            const double dj = Lc[j + j * L];
+            for (int i = j + 1 + tid; i < L; i += 256) Lc[i + j * L] /= dj;
+            __syncthreads();
+            const int r = L - j - 1;
+            for (int idx = tid; idx < r * r; idx += 256) {
+                const int ii = j + 1 + idx % r, kk = j + 1 + idx / r;
+                if (kk <= ii) Lc[ii + kk * L] -= Lc[ii + j * L] * Lc[kk + j * L];
+            }
+            __syncthreads();
+        }
+        // update_grad (:123-138): F = L^-1 P', grad_j -= |F[:, j]|^2
+        for (int jj = tid; jj < U; jj += 256) {
+            double* f = F + (int64_t)jj * L;
+            double acc = 0.0;
+            for (int a = 0; a < L; a++) {
+                double s = P[jj + (int64_t)a * U];
+                for (int b = 0; b < a; b++) s -= Lc[a + b * L] * f[b];
+                f[a] = s / Lc[a + a * L];
+                acc += f[a] * f[a];
+            }
+            gacc -= acc;
+        }
+        __syncthreads();
+        // update_hess (:140-156): H += (F'F).^2, both triangles
+        for (int idx = tid; idx < U * U; idx += 256) {
+            const int i = idx % U, j = idx / U;
+            double s = 0.0;
+            for (int a = 0; a < L; a++) s += F[a + (int64_t)i * L] * F[a + (int64_t)j * L];
+            const double v = s * s;
+            Hc[i + (int64_t)j * lde] = k == 0 ? v : Hc[i + (int64_t)j * lde] + v;
+        }
+        __syncthreads();
+        P += (int64_t)U * L;
+    }
+    if (tid < U) grad[o + tid] = gacc;
+    if (tid == 0 && !s_ok) feas[kidx[c]] = 0;
+}
+
+// dder3 (:180-200): per k, S = F Diagonal(dir) F', out_j += |S F[:, j]|^2
+static __global__ void __launch_bounds__(256)
+wsos_dder3_kernel(int ncones, const int64_t* __restrict__ off, const int* __restrict__ dim,
+                  const int64_t* __restrict__ voff, double* __restrict__ vecs, const double* __restrict__ dir,
+                  double* __restrict__ out) {
+    const int c = blockIdx.x, tid = threadIdx.x;
+    if (c >= ncones) return;
+    const int64_t o = off[c];
+    const int U = dim[c];
+    double* reg = vecs + voff[c];
+    const int nP = (int)reg[0];
+    int64_t sumL = 0, wsz = 0;
+    for (int k = 0; k < nP; k++) {
+        const int L = (int)reg[1 + k];
+        sumL += L;
+        wsz += (int64_t)L * U + (int64_t)L * L;
+    }
+    double* ws = reg + 1 + nP + (int64_t)U * sumL;
+    double* S = ws + wsz;
+    double acc = 0.0;
+    for (int k = 0; k < nP; k++) {
+        const int L = (int)reg[1 + k];
+        const double* F = ws;
+        ws += (int64_t)L * U + (int64_t)L * L;
+        for (int idx = tid; idx < L * L; idx += 256) {
+            const int a = idx % L, b = idx / L;
+            double s = 0.0;
+            for (int j = 0; j < U; j++) s += F[a + (int64_t)j * L] * dir[o + j] * F[b + (int64_t)j * L];
+            S[idx] = s;
+        }
+        __syncthreads();
+        for (int jj = tid; jj < U; jj += 256) {
+            const double* f = F + (int64_t)jj * L;
+            for (int a = 0; a < L; a++) {
+                double t = 0.0;
+                for (int b = 0; b < L; b++) t += S[a + b * L] * f[b];
+                acc += t * t;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid < U) out[o + tid] = acc;
+}
+
+// generic hess_prod! of the Cone API (Cones.jl:101-105): prod = H arr with the explicit Hessian; one warp per
+// (cone, column), dim <= 128, in-place safe
+static __global__ void __launch_bounds__(256)
+gen_hess_prod_kernel(int ncones, int want_dual, const int64_t* __restrict__ off, const int* __restrict__ dim,
+                     const int64_t* __restrict__ moff, const int* __restrict__ dualf, const double* __restrict__ H,
+                     const double* arr, int64_t ld_arr, double* prod, int64_t ld_prod, int64_t ncols,
+                     int64_t row_shift) {
+    __shared__ double xs[8][128];
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= ncones) return;
+    if (want_dual >= 0 && (dualf[c] != 0) != (want_dual != 0)) return;
+    double* x = xs[threadIdx.x >> 5];
+    const int64_t o = off[c];
+    const int d = dim[c], lde = (d + 1) & ~1;
+    const double* Hc = H + moff[c];
+    for (int64_t j = blockIdx.y; j < ncols; j += gridDim.y) {
+        const double* a = arr + j * ld_arr + (o - row_shift);
+        double* pr = prod + j * ld_prod + (o - row_shift);
+        for (int i = lane; i < d; i += 32) x[i] = a[i];
+        __syncwarp();
+        for (int i = lane; i < d; i += 32) {
+            double s = 0.0;
+            for (int jj = 0; jj < d; jj++) s += Hc[i + (int64_t)jj * lde] * x[jj];
+            pr[i] = s;
+        }
+        __syncwarp();
+    }
+}
+
+
 }  // namespace hypdev

@@ -866,6 +866,17 @@ int hyp_sync(hyp_ctx* ctx) {
     });
 }
 
+// nu of a WSOSInterpNonnegative cone = sum of the L_k in its packed data (hyp_set_cone_alpha)
+static double wsos_nu(hyp_ctx* ctx, int k) {
+    if ((int)ctx->h_cone_aoff.size() != ctx->K + 1) return 0.0;
+    const int64_t a0 = ctx->h_cone_aoff[k], a1 = ctx->h_cone_aoff[k + 1];
+    if (a1 - a0 < 2) return 0.0;
+    const int nP = (int)ctx->h_cone_alpha[a0];
+    double nu = 0.0;
+    for (int j = 0; j < nP && a0 + 1 + j < a1; j++) nu += ctx->h_cone_alpha[a0 + 1 + j];
+    return nu;
+}
+
 int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* G_local, int64_t ldG,
                    const double* A, int64_t ldA, const double* c, const double* b, const double* h, int K,
                    const int* cone_type, const int64_t* cone_dim, const int* cone_dual, int cone_lo,
@@ -919,6 +930,7 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
                                 : t == HYP_CONE_EPIPERSEPSPECTRAL_MAT ? 2.0 + side
                                 : t == HYP_CONE_EPIPERSQUARE ? 2.0
                                 : t == HYP_CONE_EPINORMSPECTRAL ? (double)ctx->h_cone_hkind[k] + 1.0   // epinormspectral.jl:95
+                                : t == HYP_CONE_WSOSINTERPNONNEGATIVE ? wsos_nu(ctx, k)               // wsosinterpnonnegative.jl:62
                                 : t == HYP_CONE_GENERALIZEDPOWER
                                     ? ((int)ctx->h_cone_aoff.size() == K + 1
                                            ? (double)(ctx->h_cone_aoff[k + 1] - ctx->h_cone_aoff[k]) + 1.0

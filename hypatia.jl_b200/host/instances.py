@@ -106,6 +106,8 @@ def cone_initial_point(spec):
         arr[2:] = w
     elif spec.ctype == M.CONE_EPINORMINF:
         arr[0] = np.sqrt(spec.dim)      # epinorminf.jl:88-95
+    elif spec.ctype == M.CONE_WSOSINTERPNONNEGATIVE:
+        arr[:] = 1.0                            # wsosinterpnonnegative.jl:89
     elif spec.ctype == M.CONE_EPINORMSPECTRAL:
         arr[0] = np.sqrt(spec.hkind + 1.0)      # epinormspectral.jl:97-105
     elif spec.ctype == M.CONE_EPIRELENTROPY:
@@ -171,6 +173,13 @@ def _central_ray_epirelentropy(d):
 
 def _cone_dual_initial(spec, prim):
     """-grad at the central point, closed form per cone (dual of the central point)."""
+    if spec.ctype == M.CONE_WSOSINTERPNONNEGATIVE:
+        # -grad_j = sum_k (P_k (P_k' D P_k)^-1 P_k')_jj, wsosinterpnonnegative.jl:123-138
+        out = np.zeros_like(prim)
+        for P in M.wsos_unpack(spec):
+            Lam = P.T @ (prim[:, None] * P)
+            out += np.einsum("ij,ji->i", P, np.linalg.solve(Lam, P.T))
+        return out
     if spec.ctype == M.CONE_EPINORMSPECTRAL:
         return prim.copy()      # -grad at (sqrt(d1 + 1), 0) = ((d1 + 1) / u, 0): the central point is self-dual
     if spec.ctype == M.CONE_EPIRELENTROPY:
@@ -279,7 +288,7 @@ def _perturb(rng, spec, vec, noise):
     if spec.ctype == M.CONE_EPIPERSEPSPECTRAL_VEC:
         vec += noise / (2.0 * (vec.size - 2)) * (2 * rng.random(vec.size) - 1)   # the initial point is not central
         return vec
-    if spec.ctype == M.CONE_GENERALIZEDPOWER:
+    if spec.ctype in (M.CONE_GENERALIZEDPOWER, M.CONE_WSOSINTERPNONNEGATIVE):
         vec += 0.5 * noise / np.sqrt(vec.size) * (2 * rng.random(vec.size) - 1)
         return vec
     if spec.ctype in (M.CONE_HYPOGEOMEAN, M.CONE_HYPOPOWERMEAN, M.CONE_EPIRELENTROPY, M.CONE_EPINORMSPECTRAL):

@@ -27,6 +27,7 @@ CONE_GENERALIZEDPOWER = 11
 CONE_HYPOPOWERMEAN = 12
 CONE_EPIRELENTROPY = 13
 CONE_EPINORMSPECTRAL = 14
+CONE_WSOSINTERPNONNEGATIVE = 15
 
 # separable spectral functions of EpiPerSepSpectral (sepspectralfun.jl:17-116), HYP_SSF_*
 SSF_INV, SSF_NEGLOG, SSF_NEGENTROPY, SSF_POWER12 = 0, 1, 2, 3
@@ -47,6 +48,7 @@ CONE_NAMES = {
     CONE_HYPOPOWERMEAN: "HypoPowerMean",
     CONE_EPIRELENTROPY: "EpiRelEntropy",
     CONE_EPINORMSPECTRAL: "EpiNormSpectral",
+    CONE_WSOSINTERPNONNEGATIVE: "WSOSInterpNonnegative",
 }
 
 
@@ -100,6 +102,12 @@ class ConeSpec:
             assert dim >= 3
         elif ctype == CONE_HYPOPERLOG:
             assert dim >= 3
+        elif ctype == CONE_WSOSINTERPNONNEGATIVE:
+            # alpha = packed data [nP, L_1 .. L_nP, vec(P_1) .. vec(P_nP)] with P_k of dim x L_k, column-major
+            nP = int(self.alpha[0])
+            Ls = [int(x) for x in self.alpha[1:1 + nP]]
+            assert dim >= 1 and nP >= 1 and all(1 <= L <= dim for L in Ls)
+            assert len(self.alpha) == 1 + nP + dim * sum(Ls)
         elif ctype == CONE_EPINORMSPECTRAL:
             # hkind = d1 (rows), d2 = (dim - 1) / d1 columns, d1 <= d2 (epinormspectral.jl:55-66)
             assert dim >= 2 and hkind >= 1 and (dim - 1) % hkind == 0 and hkind <= (dim - 1) // hkind
@@ -148,6 +156,8 @@ class ConeSpec:
             return float(len(self.alpha) + 1)
         if self.ctype == CONE_EPINORMSPECTRAL:
             return float(self.hkind + 1)      # epinormspectral.jl:95
+        if self.ctype == CONE_WSOSINTERPNONNEGATIVE:
+            return float(sum(self.alpha[1:1 + int(self.alpha[0])]))    # wsosinterpnonnegative.jl:62
         if self.ctype in (CONE_HYPOPERLOG, CONE_EPINORMINF, CONE_EPIPERSEPSPECTRAL_VEC, CONE_HYPOGEOMEAN,
                           CONE_HYPOPOWERMEAN, CONE_EPIRELENTROPY):
             return float(self.dim)
@@ -203,6 +213,28 @@ def GeneralizedPower(alpha, n, use_dual=False):
     """GeneralizedPower{Float64}(alpha, n): (u in R^m_+, w in R^n), prod u_i^alpha_i >= |w|; MOI's PowerCone(a) is
     GeneralizedPower([a, 1 - a], 1) (MathOptInterface/cones.jl:33-37)."""
     return ConeSpec(CONE_GENERALIZEDPOWER, len(alpha) + n, use_dual, alpha=alpha)
+
+
+def WSOSInterpNonnegative(U, Ps, use_dual=False):
+    """WSOSInterpNonnegative{Float64, Float64}(U, Ps, use_dual): Ps[k] is U x L_k.  As in the reference
+    (wsosinterpnonnegative.jl:59) the barrier is the dual cone's, so the spec's use_dual (= use_dual_barrier) is
+    `not use_dual`.  The matrices travel in the per-cone double array of hyp_set_cone_alpha."""
+    Ps = [np.asarray(P, dtype=np.float64) for P in Ps]
+    assert all(P.ndim == 2 and P.shape[0] == U for P in Ps)
+    packed = np.concatenate([[float(len(Ps))], [float(P.shape[1]) for P in Ps]] + [P.ravel(order="F") for P in Ps])
+    return ConeSpec(CONE_WSOSINTERPNONNEGATIVE, U, not use_dual, alpha=packed)
+
+
+def wsos_unpack(spec):
+    """The Ps matrices of a WSOSInterpNonnegative spec."""
+    nP = int(spec.alpha[0])
+    Ls = [int(x) for x in spec.alpha[1:1 + nP]]
+    data = np.asarray(spec.alpha[1 + nP:], dtype=np.float64)
+    out, o = [], 0
+    for L in Ls:
+        out.append(data[o:o + spec.dim * L].reshape(spec.dim, L, order="F"))
+        o += spec.dim * L
+    return out
 
 
 def EpiNormSpectral(d1, d2, use_dual=False):

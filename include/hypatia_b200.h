@@ -51,6 +51,9 @@ typedef struct hyp_ctx hyp_ctx;
 #define HYP_CONE_GENERALIZEDPOWER 11 /* generalizedpower.jl (powers via hyp_set_cone_alpha; dim <= 128) */
 #define HYP_CONE_HYPOPOWERMEAN 12   /* hypopowermean.jl (dim - 1 powers via hyp_set_cone_alpha; dim <= 128) */
 #define HYP_CONE_EPIRELENTROPY 13   /* epirelentropy.jl (u, v[d], w[d]); dim = 1 + 2 d */
+#define HYP_CONE_WSOSINTERPNONNEGATIVE 15 /* wsosinterpnonnegative.jl (real): dim = U <= 128; the interpolation matrices travel
+                                       in the per-cone array of hyp_set_cone_alpha as [nP, L_1 .. L_nP, vec(P_1) .. vec(P_nP)]
+                                       (P_k is U x L_k, column-major); use_dual_barrier = 1 is the reference's default */
 #define HYP_CONE_EPINORMSPECTRAL 14 /* epinormspectral.jl (real): (u, vec(W)), W d1 x d2 column-major, d1 <= d2; d1 is given
                                        as the integer parameter of hyp_set_cone_params; use_dual = 1: nuclear norm; dim <= 128 */
 

@@ -45,6 +45,10 @@ cone_code(::Cones.GeneralizedPower) = Cint(11)
 cone_code(::Cones.HypoPowerMean) = Cint(12)
 cone_code(::Cones.EpiRelEntropy) = Cint(13)
 cone_code(::Cones.EpiNormSpectral{Float64, Float64}) = Cint(14)
+cone_code(::Cones.WSOSInterpNonnegative{Float64, Float64}) = Cint(15)
+# packed interpolation data [nP, L_1 .. L_nP, vec(P_1) .. vec(P_nP)]
+cone_alpha(c::Cones.WSOSInterpNonnegative{Float64, Float64}) =
+    vcat(Float64(length(c.Ps)), Float64[size(P, 2) for P in c.Ps], (vec(P) for P in c.Ps)...)
 cone_alpha(c::Cones.GeneralizedPower) = Vector{Float64}(c.α)
 cone_alpha(c::Cones.HypoPowerMean) = Vector{Float64}(c.α)
 cone_alpha(::Cones.Cone) = Float64[]

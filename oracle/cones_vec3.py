@@ -800,6 +800,65 @@ class EpiNormSpectral(Cone):
         return d3
 
 
+class WSOSInterpNonnegative(Cone):
+    """wsosinterpnonnegative.jl:15-200 (real case): interpolant-basis weighted sum-of-squares cone of dimension U,
+    parametrised by matrices Ps[k] (U x L_k); the barrier is that of the DUAL cone
+    {s : Ps[k]' Diagonal(s) Ps[k] psd for all k}, -sum_k logdet(Ps[k]' Diagonal(s) Ps[k]), so use_dual_barrier =
+    !use_dual (wsosinterpnonnegative.jl:59); nu = sum L_k.  hess_prod! is the generic explicit-Hessian product
+    (Cones.jl:101-105), inv_hess_prod! the generic factorisation fallback (Cones.jl:113-118), is_dual_feas the generic
+    `true` (Cones.jl:64)."""
+    ctype = M.CONE_WSOSINTERPNONNEGATIVE
+
+    def __init__(self, U, Ps, use_dual=False):
+        self.Ps = [np.asarray(P, dtype=np.float64) for P in Ps]
+        assert all(P.shape[0] == U for P in self.Ps)
+        self.use_dual_barrier = not use_dual
+        super().__init__(U)
+
+    @property
+    def nu(self):
+        return float(sum(P.shape[1] for P in self.Ps))
+
+    def set_initial_point(self, arr):
+        arr[:] = 1.0
+        return arr
+
+    def update_feas(self):
+        # wsosinterpnonnegative.jl:91-121: Lambda_k = P_k' Diagonal(point) P_k, Cholesky (lower)
+        self.LF = []
+        for P in self.Ps:
+            Lam = P.T @ (self.point[:, None] * P)
+            try:
+                self.LF.append(np.linalg.cholesky(Lam))
+            except np.linalg.LinAlgError:
+                return False
+        return True
+
+    def update_grad(self):
+        # wsosinterpnonnegative.jl:123-138: LFLP_k = L_k^-1 P_k'; grad_j = -sum_k |LFLP_k[:, j]|^2
+        self.LFLP = [sla.solve_triangular(L, P.T, lower=True, check_finite=False) for L, P in zip(self.LF, self.Ps)]
+        self._grad[:] = -sum(np.sum(F * F, axis=0) for F in self.LFLP)
+
+    def update_hess(self):
+        # wsosinterpnonnegative.jl:140-156
+        self.grad()
+        return sum((F.T @ F) ** 2 for F in self.LFLP)
+
+    def hess_prod(self, arr):
+        a, vec = _as2d(arr)
+        return _ret(np.asarray(self.hess()) @ a, vec)
+
+    def dder3(self, direction):
+        # wsosinterpnonnegative.jl:180-200
+        self.grad()
+        d3 = np.zeros(self.dim)
+        for F in self.LFLP:
+            S = (F * direction[None, :]) @ F.T
+            T = S @ F
+            d3 += np.sum(T * T, axis=0)
+        return d3
+
+
 class GeneralizedPower(Cone):
     """generalizedpower.jl:8-236: (u in R^m_++, w in R^n), prod u_i^(alpha_i) >= |w|_2; barrier
     -log(prod u_i^(2 alpha_i) - |w|^2) - sum (1 - alpha_i) log u_i, nu = m + 1.  No closed-form inverse Hessian:

@@ -243,6 +243,29 @@ int emu_gpow_dder3(int ncones, const int64_t* off, const int* dim, const int* mu
 
 extern "C" {
 
+int emu_wsos_state(int ncones, const int64_t* off, const int* dim, const int64_t* voff, double* vecs, const int* kidx,
+                   const int64_t* moff, const double* point, double* grad, double* H, uint8_t* feas) {
+    emu::launch(dim3(ncones), dim3(256), 0,
+                [&] { hypdev::wsos_state_kernel(ncones, off, dim, voff, vecs, kidx, moff, point, grad, H, feas); });
+    return 0;
+}
+
+int emu_wsos_dder3(int ncones, const int64_t* off, const int* dim, const int64_t* voff, double* vecs, const double* dir,
+                   double* out) {
+    emu::launch(dim3(ncones), dim3(256), 0, [&] { hypdev::wsos_dder3_kernel(ncones, off, dim, voff, vecs, dir, out); });
+    return 0;
+}
+
+int emu_gen_hess_prod(int ncones, int want_dual, const int64_t* off, const int* dim, const int64_t* moff,
+                      const int* dualf, const double* H, const double* arr, int64_t ld_arr, double* prod,
+                      int64_t ld_prod, int64_t ncols, int64_t row_shift) {
+    emu::launch(dim3((ncones + 1) / 2, 2), dim3(64), 0, [&] {
+        hypdev::gen_hess_prod_kernel(ncones, want_dual, off, dim, moff, dualf, H, arr, ld_arr, prod, ld_prod, ncols,
+                                     row_shift);
+    });
+    return 0;
+}
+
 int emu_ens_state(int ncones, const int64_t* off, const int* dim, const int* d1s, const int64_t* voff, double* vecs,
                   const int* kidx, const int64_t* moff, const double* point, const double* dual, double* grad,
                   double* scal, double* H, uint8_t* feas, uint8_t* dual_feas) {

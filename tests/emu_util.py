@@ -298,6 +298,16 @@ class EmuGpowGroup:
         self.K = len(specs)
         self.hpm = specs[0].ctype == 12          # HypoPowerMean, else GeneralizedPower
         self.ens = specs[0].ctype == 14          # EpiNormSpectral: d1 per cone, workspace instead of powers
+        self.wsos = specs[0].ctype == 15         # WSOSInterpNonnegative: packed Ps + workspace
+        if self.wsos:
+            regions = []
+            for s in specs:
+                nP = int(s.alpha[0])
+                Ls = [int(x) for x in s.alpha[1:1 + nP]]
+                wsz = sum(L * s.dim + L * L for L in Ls) + max(Ls) ** 2
+                regions.append(np.concatenate((np.asarray(s.alpha, dtype=np.float64), np.zeros(wsz))))
+            self.voff = np.concatenate(([0], np.cumsum([r.size for r in regions])))[:-1].astype(np.int64)
+            self.vecs = np.concatenate(regions)
         if self.ens:
             self.d1 = np.array([s.hkind for s in specs], dtype=np.int32)
             sizes = [3 * (s.dim - 1) + 2 * s.hkind ** 2 for s in specs]
@@ -308,7 +318,7 @@ class EmuGpowGroup:
         self.q = int(self.dims.sum())
         self.mu = np.array([len(s.alpha) for s in specs], dtype=np.int32)
         self.aoff = np.concatenate(([0], np.cumsum(self.mu)))[:-1].astype(np.int64)
-        self.alpha = np.concatenate([np.asarray(s.alpha, dtype=np.float64) for s in specs] + [np.zeros(0)])
+        self.alpha = np.concatenate([np.asarray(s.alpha, dtype=np.float64) for s in specs] + [np.zeros(1)])
         self.kidx = np.arange(self.K, dtype=np.int32)
         self.dualf = np.array([1 if s.use_dual else 0 for s in specs], dtype=np.int32)
         self.lay = MatLayout(self.dims)
@@ -321,7 +331,10 @@ class EmuGpowGroup:
         self.dual_feas = np.ones(self.K, dtype=np.uint8)
         self.grad = np.zeros(self.q)
         self.H = np.zeros(self.lay.total)
-        if self.ens:
+        if self.wsos:
+            lib().emu_wsos_state(self.K, p(self.off), p(self.dims), p(self.voff), p(self.vecs), p(self.kidx),
+                                 p(self.lay.moff), p(self.point), p(self.grad), p(self.H), p(self.feas))
+        elif self.ens:
             lib().emu_ens_state(self.K, p(self.off), p(self.dims), p(self.d1), p(self.voff), p(self.vecs), p(self.kidx),
                                 p(self.lay.moff), p(self.point), p(self.dual), p(self.grad), p(self.scal), p(self.H),
                                 p(self.feas), p(self.dual_feas))
@@ -347,7 +360,10 @@ class EmuGpowGroup:
         out = a if in_place else np.zeros_like(a, order="F")
         hess_dual, inv_dual = {0: (-1, -2), 1: (-2, -1), 4: (0, 1), 5: (1, 0)}[int(mode)]
         L = lib()
-        if hess_dual > -2 and self.ens:
+        if hess_dual > -2 and self.wsos:
+            L.emu_gen_hess_prod(self.K, hess_dual, p(self.off), p(self.dims), p(self.lay.moff), p(self.dualf), p(self.H),
+                                p(a), i64(self.q), p(out), i64(self.q), i64(a.shape[1]), i64(0))
+        elif hess_dual > -2 and self.ens:
             L.emu_ens_prod(self.K, hess_dual, p(self.off), p(self.dims), p(self.d1), p(self.voff), p(self.vecs),
                            p(self.dualf), p(self.scal), p(self.point), p(a), i64(self.q), p(out), i64(self.q),
                            i64(a.shape[1]), i64(0))
@@ -366,7 +382,9 @@ class EmuGpowGroup:
     def dder3(self, direction):
         d = np.ascontiguousarray(direction, dtype=np.float64)
         out = np.zeros(self.q)
-        if self.ens:
+        if self.wsos:
+            lib().emu_wsos_dder3(self.K, p(self.off), p(self.dims), p(self.voff), p(self.vecs), p(d), p(out))
+        elif self.ens:
             lib().emu_ens_dder3(self.K, p(self.off), p(self.dims), p(self.d1), p(self.voff), p(self.vecs), p(self.scal),
                                 p(self.point), p(d), p(out))
         elif self.hpm:

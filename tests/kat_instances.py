@@ -618,6 +618,32 @@ NORMSPEC = [_named(lambda f=_f, ud=_ud: f(ud), _f.__name__[1:] + ("_dual" if _ud
     [_named(lambda a=_a, b=_b, ud=_ud: _epinormspectral3(a, b, ud), f"epinormspectral3_{_a}x{_b}" + ("_dual" if _ud else ""))
      for (_a, _b) in ((1, 1), (1, 3), (2, 2), (3, 4)) for _ud in (False, True)]
 
+def _wsos_box(lo, hi, fn):
+    from wsos_util import interpolate_box
+    U, pts, Ps = interpolate_box(lo, hi, 2)
+    return U, Ps, np.array([fn(*p) for p in pts])
+
+
+def wsosinterpnonnegative1():  # :2286-2304: min of x^4 + x^2 y^2 + 4 y^2 + 4 over [0, 1]^2
+    U, Ps, vals = _wsos_box([0, 0], [1, 1], lambda x, y: x ** 4 + x ** 2 * y ** 2 + 4 * y ** 2 + 4)
+    return _m([-1], None, None, np.ones((U, 1)), vals, [M.WSOSInterpNonnegative(U, Ps)]), \
+        dict(status="Optimal", primal_obj=-4, x=[4.0])
+
+
+def wsosinterpnonnegative2():  # :2306-2324: min of (x - 2)^2 + (x y - 3)^2 over [0, 3]^2
+    U, Ps, vals = _wsos_box([0, 0], [3, 3], lambda x, y: (x - 2) ** 2 + (x * y - 3) ** 2)
+    return _m([-1], None, None, np.ones((U, 1)), vals, [M.WSOSInterpNonnegative(U, Ps)]), \
+        dict(status="Optimal", primal_obj=0, x=[0.0])
+
+
+def wsosinterpnonnegative3():  # :2326-2343: the dual formulation with use_dual = true
+    U, Ps, vals = _wsos_box([0, 0], [3, 3], lambda x, y: (x - 2) ** 2 + (x * y - 3) ** 2)
+    return _m(vals, np.ones((1, U)), [1], -np.eye(U), np.zeros(U), [M.WSOSInterpNonnegative(U, Ps, use_dual=True)]), \
+        dict(status="Optimal", primal_obj=0)
+
+
+WSOS = [wsosinterpnonnegative1, wsosinterpnonnegative2, wsosinterpnonnegative3]
+
 RELENT = [_named(lambda d=_d: _epirelentropy1(d), f"epirelentropy1_d{_d}") for _d in (1, 2, 3)] + \
     [_named(lambda d=_d: _epirelentropy2(d), f"epirelentropy2_d{_d}") for _d in (1, 2, 4)] + \
     [_named(lambda d=_d: _epirelentropy3(d), f"epirelentropy3_d{_d}") for _d in (2, 4)] + \
@@ -632,7 +658,7 @@ HPM = [_named(lambda f=_f, ud=_ud: f(ud), _f.__name__[1:] + ("_dual" if _ud else
        for _f in (_hypopowermean1, _hypopowermean2) for _ud in (False, True)] + \
     [hypopowermean4, hypopowermean5, hypopowermean6]
 
-NEW_CONES = GPOW + HPM + RELENT + NORMSPEC + [hypogeomean1, hypogeomean1_dual, hypogeomean2, hypogeomean2_dual, hypogeomean4, hypogeomean5,
+NEW_CONES = GPOW + HPM + RELENT + NORMSPEC + WSOS + [hypogeomean1, hypogeomean1_dual, hypogeomean2, hypogeomean2_dual, hypogeomean4, hypogeomean5,
              hypogeomean6, epinorminf1, epinorminf2, epinorminf3, epinorminf3_dual, epinorminf4, dualinfeas1,
              primalinfeas3, dualinfeas2, dualinfeas3, epipersquare1, epipersquare2, epipersquare3,
              epipersquare4, hypoperlog1, hypoperlog2, hypoperlog3, hypoperlog4, hypoperlog5, hypoperlog6,

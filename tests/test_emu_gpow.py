@@ -24,9 +24,17 @@ def _bal(rng, d):
     return a / a.sum()
 
 
+def _wsos(n, halfdeg, use_dual=False):
+    from wsos_util import interpolate_box
+    U, _, Ps = interpolate_box(-np.ones(n), np.ones(n), halfdeg)
+    return M.WSOSInterpNonnegative(U, Ps, use_dual=use_dual)
+
+
 def _sets():
     rng = np.random.default_rng(7)
     return {
+        "wsos": [_wsos(1, 1), _wsos(1, 3), _wsos(2, 2), _wsos(3, 1), _wsos(2, 4), _wsos(1, 2, use_dual=True),
+                 _wsos(3, 2)],
         "gpow": [M.GeneralizedPower(_alpha(rng, m), n) for m, n in ((2, 1), (3, 2), (4, 1), (2, 4), (20, 30), (40, 5))],
         "hpm": [M.HypoPowerMean(_bal(rng, d)) for d in (1, 2, 5, 33, 70)],
         "hpm_dual": [M.HypoPowerMean(_bal(rng, 3), use_dual=True), M.HypoPowerMean(_bal(rng, 6)),
@@ -39,7 +47,7 @@ def _sets():
     }
 
 
-NAMES = ["gpow", "gpow_dual", "hpm", "hpm_dual", "normspec", "normspec_dual"]
+NAMES = ["gpow", "gpow_dual", "hpm", "hpm_dual", "normspec", "normspec_dual", "wsos"]
 
 
 @pytest.mark.parametrize("name", NAMES)

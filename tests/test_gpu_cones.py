@@ -18,6 +18,12 @@ def _blocks(model):
     return DeviceConeBlock(model), OracleConeBlock(model)
 
 
+def _wsos(n, halfdeg, use_dual=False):
+    from wsos_util import interpolate_box
+    U, _, Ps = interpolate_box(-np.ones(n), np.ones(n), halfdeg)
+    return M.WSOSInterpNonnegative(U, Ps, use_dual=use_dual)
+
+
 CONE_SETS = {
     "nonneg": [M.Nonnegative(1), M.Nonnegative(6), M.Nonnegative(700)],
     "soc": [M.EpiNormEucl(2), M.EpiNormEucl(3), M.EpiNormEucl(25), M.EpiNormEucl(33), M.EpiNormEucl(70)],
@@ -53,6 +59,8 @@ CONE_SETS = {
     "normspec": [M.EpiNormSpectral(1, 1), M.EpiNormSpectral(2, 2), M.EpiNormSpectral(3, 4), M.EpiNormSpectral(5, 9),
                  M.EpiNormSpectral(1, 127), M.EpiNormSpectral(11, 11), M.EpiNormSpectral(2, 3, use_dual=True),
                  M.EpiNormSpectral(4, 20, use_dual=True)],
+    "wsos": [_wsos(1, 1), _wsos(1, 3), _wsos(2, 2), _wsos(3, 1), _wsos(2, 4), _wsos(1, 2, use_dual=True), _wsos(3, 2),
+             _wsos(2, 6)],
     "gpow": [M.GeneralizedPower([0.5, 0.5], 1), M.GeneralizedPower([0.2, 0.3, 0.5], 2),
              M.GeneralizedPower(np.full(20, 0.05), 30), M.GeneralizedPower([0.7, 0.3], 1, use_dual=True),
              M.GeneralizedPower(np.full(4, 0.25), 60)],
@@ -66,7 +74,7 @@ CONE_SETS = {
                M.GeneralizedPower([0.3, 0.7], 2), M.GeneralizedPower([0.5, 0.5], 1, use_dual=True),
                M.HypoPowerMean([0.25, 0.35, 0.4]), M.HypoPowerMean([0.5, 0.5], use_dual=True),
                M.EpiRelEntropy(7), M.EpiRelEntropy(5, use_dual=True), M.EpiNormSpectral(2, 3),
-               M.EpiNormSpectral(2, 2, use_dual=True)],
+               M.EpiNormSpectral(2, 2, use_dual=True), _wsos(2, 2), _wsos(1, 2, use_dual=True)],
 }
 
 

@@ -40,7 +40,7 @@ def test_kat_device_default(build):
 
 # the reference's instances for the cones added in the widening step (EpiPerSquare, HypoPerLog,
 # EpiPerSepSpectral{MatrixCSqr} with every separable spectral function, primal and dual barrier)
-NEW_CONE_KATS = kat.GPOW + kat.HPM + kat.RELENT + kat.NORMSPEC + [kat.hypogeomean1, kat.hypogeomean2_dual, kat.hypogeomean4, kat.hypogeomean6, kat.epinorminf1, kat.epinorminf2, kat.epinorminf4, kat.dualinfeas1, kat.primalinfeas3, kat.dualinfeas2, kat.epipersquare1, kat.epipersquare2, kat.epipersquare4,
+NEW_CONE_KATS = kat.GPOW + kat.HPM + kat.RELENT + kat.NORMSPEC + kat.WSOS + [kat.hypogeomean1, kat.hypogeomean2_dual, kat.hypogeomean4, kat.hypogeomean6, kat.epinorminf1, kat.epinorminf2, kat.epinorminf4, kat.dualinfeas1, kat.primalinfeas3, kat.dualinfeas2, kat.epipersquare1, kat.epipersquare2, kat.epipersquare4,
                  kat.hypoperlog1, kat.hypoperlog4, kat.hypoperlog5, kat.hypoperlog7] + \
     [f for f in kat.SPECTRAL if "_d3_" in f.__name__ or "_d2_" in f.__name__] + \
     [f for f in kat.SPECTRAL_VEC if "_d3_" in f.__name__ or "_d4_" in f.__name__ or "vector3" in f.__name__

@@ -13,6 +13,12 @@ from hypatia_b200.host import models as M
 from hypatia_b200.host.point import Point, SubPoint
 
 pytestmark = pytest.mark.gpu
+
+
+def _wsos(n, halfdeg, use_dual=False):
+    from wsos_util import interpolate_box
+    U, _, Ps = interpolate_box(-np.ones(n), np.ones(n), halfdeg)
+    return M.WSOSInterpNonnegative(U, Ps, use_dual=use_dual)
 DIR_TOL = 1e-8
 
 
@@ -145,7 +151,8 @@ def test_spectral_and_perspective_cones(p):
              M.HypoGeoMean(4, use_dual=True), M.GeneralizedPower([0.25, 0.75], 1),
              M.GeneralizedPower([0.2, 0.3, 0.5], 3, use_dual=True), M.HypoPowerMean([0.3, 0.7]),
              M.HypoPowerMean([0.2, 0.2, 0.6], use_dual=True), M.EpiRelEntropy(9),
-             M.EpiRelEntropy(5, use_dual=True), M.EpiNormSpectral(2, 4), M.EpiNormSpectral(3, 3, use_dual=True)]
+             M.EpiRelEntropy(5, use_dual=True), M.EpiNormSpectral(2, 4), M.EpiNormSpectral(3, 3, use_dual=True),
+             _wsos(2, 2), _wsos(1, 3, use_dual=True)]
     I = inst.synthetic("specmix", 20 + p, p, cones, seed=21)
     Ap = None
     if p:

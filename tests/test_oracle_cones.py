@@ -234,6 +234,51 @@ def test_epinormspectral_barrier():
     assert close(-2 * cone.dder3(direction), fd_third, 1e-5)
 
 
+@pytest.mark.parametrize("n,halfdeg", [(1, 1), (1, 3), (2, 2), (3, 1)])
+def test_wsosinterpnonnegative(n, halfdeg):
+    # reference: test/cone.jl WSOSInterpNonnegative block (interpolations of free / box domains, init_tol = Inf)
+    from oracle.cones_vec3 import WSOSInterpNonnegative
+    from wsos_util import interpolate_box
+    U, _, Ps = interpolate_box(-np.ones(n), np.ones(n), halfdeg)
+    run_oracles(WSOSInterpNonnegative(U, Ps), init_tol=np.inf)
+    run_oracles(WSOSInterpNonnegative(U, Ps, use_dual=True), init_tol=np.inf)
+
+
+def test_wsosinterpnonnegative_barrier():
+    """grad, hess_prod and dder3 against central differences of -sum_k logdet(P_k' Diagonal(s) P_k)
+    (test/cone.jl WSOSInterpNonnegative test_barrier)."""
+    from oracle.cones_vec3 import WSOSInterpNonnegative
+    from wsos_util import interpolate_box
+    U, _, Ps = interpolate_box([-1.0, 0.0], [1.0, 2.0], 2)
+    cone = WSOSInterpNonnegative(U, Ps)
+
+    def barrier(s):
+        return -sum(np.linalg.slogdet(P.T @ (s[:, None] * P))[1] for P in Ps)
+
+    rng = np.random.default_rng(1)
+    point = np.ones(U)
+    perturb_scale(rng, point, 0.1, 1.0)
+
+    def grad_at(s):
+        cone.reset_data()
+        cone.load_point(s)
+        assert cone.is_feas()
+        return cone.grad().copy()
+
+    g = grad_at(point)
+    eps = 1e-6
+    fd_grad = np.array([(barrier(point + eps * e) - barrier(point - eps * e)) / (2 * eps) for e in np.eye(U)])
+    assert close(g, fd_grad, 1e-7)
+    direction = rng.standard_normal(U)
+    fd_hess_dir = (grad_at(point + eps * direction) - grad_at(point - eps * direction)) / (2 * eps)
+    grad_at(point)
+    assert close(cone.hess_prod(direction), fd_hess_dir, 1e-6)
+    e2 = 1e-4
+    fd_third = (grad_at(point + e2 * direction) - 2 * g + grad_at(point - e2 * direction)) / e2 ** 2
+    grad_at(point)
+    assert close(-2 * cone.dder3(direction), fd_third, 1e-5)
+
+
 SSF = [(0, 0.0), (1, 0.0), (2, 0.0), (3, 1.5), (3, 2.0), (3, 1.1)]   # Inv, NegLog, NegEntropy, Power12(p)
 
 
