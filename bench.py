@@ -68,10 +68,9 @@ WORKLOADS = {
 
 # DRAM traffic of the Schur SYRK launch from the committed `ncu --set full` capture (per launch)
 NCU_TRAFFIC = {"C3": 31.497622e9 + 0.411380e9,                       # FP64 DMMA kernel, one launch
-               # tcgen05 CTA-pair kernel, radix-256 digits: the four launches of one SYRK in
-               # profiles/r01_ozaki_pair_radix256_ncu.txt (K cut 3 x 16384 + 848 in that capture; the
-               # current build cuts 3 equal chunks - the traffic is proportional to the rows)
-               "C3:i8": (61.103e9 + 0.814e9) + (66.283e9 + 0.814e9) + (65.187e9 + 0.815e9) + (1.370e9 + 0.571e9)}
+               # tcgen05 CTA-pair kernel, radix-256 digits, row-major tile order: the three launches (K chunks) of
+               # one SYRK in profiles/r01_ozaki_pair_row_order_ncu.txt
+               "C3:i8": (42.40e9 + 0.809e9) + (44.78e9 + 0.808e9) + (44.62e9 + 0.808e9)}
 
 
 class PanelModel:
@@ -473,7 +472,7 @@ def run_ours(args):
                     "int8_frac": (int8_tops / int8_peak) if int8_tops and int8_peak else None,
                     "traffic": NCU_TRAFFIC.get(args.workload + ":i8") if world == 1 else None,
                     "traffic_unit": "bytes per SYRK (dram__bytes_read.sum + dram__bytes_write.sum over its launches, "
-                                    "profiles/r01_ozaki_pair_radix256_ncu.txt)",
+                                    "profiles/r01_ozaki_pair_row_order_ncu.txt)",
                     "algorithmic_flops_per_launch": syrk_flops, "avg_launch_ms": syrk_ms,
                     "step_share": syrk_ms / (ms / args.steps) if syrk_ms == syrk_ms else None,
                     "phase_ms": phases}

@@ -1542,13 +1542,14 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
         if (use_cluster == 2) {
             // (P, J): tile rows 2P, 2P+1 of tile column J, for 2P <= J.  Two orders of the list (the clusters take
             // consecutive entries, so the order decides which operand panel stays in L2):
-            //   column by column (default): the 128-column B panel of tile column J (15 MB per 16 k rows) is L2-resident,
-            //     the 256-row A panels (30 MB each) stream from DRAM once per (P, J);
-            //   row by row (HYP_OZAKI_ORDER=row): the A panel of row pair P is resident and the B panels, half the size,
-            //     stream - about half the DRAM bytes for the same L2 footprint.
+            //   row by row (default): the 256-row A panel of row pair P (30 MB per 16 k rows) is L2-resident and the
+            //     128-column B panels (15 MB each) stream from DRAM once per (P, J);
+            //   column by column (HYP_OZAKI_ORDER=col, the first version): the B panel is resident and the A panels, twice
+            //     the size, stream.  Measured on C3 (same box): 134 vs 197 GB of DRAM traffic per SYRK, L2 hit rate
+            //     72 vs 65 %, 84.8 vs 86.6 ms (profiles/r01_ozaki_pair_row_order_ncu.txt).
             static const bool row_order = [] {
                 const char* e = getenv("HYP_OZAKI_ORDER");
-                return e && e[0] == 'r';
+                return !(e && e[0] == 'c');
             }();
             static std::vector<std::pair<int, std::pair<int2*, int>>> pcache;
             int2* d_pairs = nullptr;
