@@ -12,6 +12,9 @@ RT2 = np.sqrt(2.0)
 RT3 = np.sqrt(3.0)
 
 
+TOL_EPS4 = np.finfo(np.float64).eps ** 0.25      # test_tol of the reference (nativeinstances.jl:29)
+
+
 def _m(c, A, b, G, h, cones, obj_offset=0.0):
     c = np.asarray(c, float)
     A = np.zeros((0, c.size)) if A is None else np.asarray(A, float)
@@ -644,6 +647,203 @@ def wsosinterpnonnegative3():  # :2326-2343: the dual formulation with use_dual 
 
 WSOS = [wsosinterpnonnegative1, wsosinterpnonnegative2, wsosinterpnonnegative3]
 
+# ---- further instances of the reference for the cones of the path: seeded-random data with closed-form optima or
+# certificate-only checks (the optimum does not depend on the RNG stream, so NumPy's generator stands in for Julia's) ----
+def _randint(rng, lo, hi, *shape):
+    return rng.integers(lo, hi + 1, size=shape).astype(float)
+
+
+def consistent1():  # :110-130: dependent equality rows and dependent columns that preprocessing must remove
+    rng = np.random.default_rng(1)
+    n, p, q = 30, 15, 30
+    c = np.zeros(n)
+    A = _randint(rng, -9, 9, p, n)
+    G = 10.0 * np.eye(q, n)
+    r1, r2 = rng.random(2)
+    A[10:15] = r1 * A[0:5] - r2 * A[5:10]
+    b = A.sum(axis=1)
+    r1, r2 = rng.random(2)
+    A[:, 10:15] = r1 * A[:, 0:5] - r2 * A[:, 5:10]
+    G[:, 10:15] = r1 * G[:, 0:5] - r2 * G[:, 5:10]
+    c[10:15] = r1 * c[0:5] - r2 * c[5:10]
+    return _m(c, A, b, G, np.zeros(q), [M.Nonnegative(q)]), dict(status="Optimal", tol_scale=10)
+
+
+def inconsistent1():  # :132-149
+    rng = np.random.default_rng(1)
+    n, p, q = 30, 15, 30
+    c = _randint(rng, 0, 9, n)
+    A = _randint(rng, -9, 9, p, n)
+    b = rng.random(p)
+    r1, r2 = rng.random(2)
+    A[10:15] = r1 * A[0:5] - r2 * A[5:10]
+    b[10:15] = 2 * (r1 * b[0:5] - r2 * b[5:10])
+    return _m(c, A, b, -np.eye(q, n), np.zeros(q), [M.Nonnegative(q)]), dict(status="PrimalInconsistent")
+
+
+def inconsistent2():  # :151-168
+    rng = np.random.default_rng(1)
+    n, p, q = 30, 15, 30
+    c = _randint(rng, 0, 9, n)
+    A = _randint(rng, -9, 9, p, n)
+    G = -np.eye(q, n)
+    b = rng.random(p)
+    r1, r2 = rng.random(2)
+    A[:, 10:15] = r1 * A[:, 0:5] - r2 * A[:, 5:10]
+    G[:, 10:15] = r1 * G[:, 0:5] - r2 * G[:, 5:10]
+    c[10:15] = 2 * (r1 * c[0:5] - r2 * c[5:10])
+    return _m(c, A, b, G, np.zeros(q), [M.Nonnegative(q)]), dict(status="DualInconsistent")
+
+
+def nonnegative1():  # :249-263
+    rng = np.random.default_rng(1)
+    n, p, q = 6, 3, 6
+    c = _randint(rng, 0, 9, n)
+    A = _randint(rng, -9, 9, p, n)
+    return _m(c, A, A.sum(axis=1), -np.eye(q, n), np.zeros(q), [M.Nonnegative(q)], obj_offset=1.0), dict(status="Optimal")
+
+
+def nonnegative2():  # :265-278
+    rng = np.random.default_rng(1)
+    n, p, q = 5, 2, 10
+    c = _randint(rng, 0, 9, n)
+    A = _randint(rng, 1, 9, p, n)
+    G = rng.random((q, n)) - 2.0 * np.eye(q, n)
+    return _m(c, A, A.sum(axis=1), G, G.sum(axis=1), [M.Nonnegative(q)]), dict(status="Optimal", tol_scale=2)
+
+
+def nonnegative3():  # :280-293
+    rng = np.random.default_rng(1)
+    n, p, q = 15, 6, 15
+    c = _randint(rng, 0, 9, n)
+    A = _randint(rng, -9, 9, p, n)
+    return _m(c, A, A.sum(axis=1), -np.eye(q), np.zeros(q), [M.Nonnegative(q)]), dict(status="Optimal", tol_scale=2)
+
+
+def _randsym(rng, s):
+    X = rng.random((s, s))
+    return np.triu(X) + np.triu(X, 1).T        # Hermitian(rand(s, s), :U)
+
+
+def possemideftri3():  # :342-360: min x : x I - M psd  =>  lambda_max(M)
+    Mx = _randsym(np.random.default_rng(1), 2)
+    emax = float(np.linalg.eigvalsh(Mx)[-1])
+    return _m([1], None, None, [[-1.0], [0.0], [-1.0]], -_svec(Mx), [M.PosSemidefTri(3)]), \
+        dict(status="Optimal", primal_obj=emax, x=[emax])
+
+
+def possemideftri4():  # :362-380: max <M, X> : tr X = 1, X psd  =>  lambda_max(M)
+    s = 3
+    Mx = _randsym(np.random.default_rng(1), s)
+    dim = M.svec_length(s)
+    return _m(-_svec(Mx), _svec(np.eye(s))[None, :], [1], -np.eye(dim), np.zeros(dim), [M.PosSemidefTri(dim)]), \
+        dict(status="Optimal", primal_obj=-float(np.linalg.eigvalsh(Mx)[-1]))
+
+
+def _smat(v):
+    from oracle import arrayutil as au
+    return au.svec_to_smat(np.asarray(v, float))
+
+
+def hyporootdettri1():  # :1569-1598 (real case)
+    side = 3
+    H = np.random.default_rng(1).random((side, side))
+    dim = 1 + M.svec_length(side)
+    G = np.zeros((dim, 1))
+    G[0, 0] = -1
+    h = np.concatenate(([0.0], _svec(H @ H.T)))
+
+    def check(s, z, approx):
+        assert approx(np.linalg.det(_smat(s[1:])) ** (1 / side), s[0])
+        assert approx(np.linalg.det(_smat(z[1:] * side)) ** (1 / side), -z[0])
+    return _m([-1], None, None, G, h, [M.HypoRootdetTri(dim)]), dict(status="Optimal", check=check)
+
+
+def hyporootdettri2():  # :1600-1629 (real case, dual barrier)
+    side = 4
+    H = np.random.default_rng(1).random((side, side))
+    dim = 1 + M.svec_length(side)
+    G = np.zeros((dim, 1))
+    G[0, 0] = -1
+    h = np.concatenate(([0.0], _svec(H @ H.T)))
+
+    def check(s, z, approx):
+        assert approx(np.linalg.det(_smat(s[1:] * side)) ** (1 / side), -s[0])
+        assert approx(np.linalg.det(_smat(z[1:])) ** (1 / side), z[0])
+    return _m([1], None, None, G, h, [M.HypoRootdetTri(dim, use_dual=True)]), dict(status="Optimal", check=check)
+
+
+def hyporootdettri3():  # :1631-1655: W not full rank => optimum 0 (tol eps^0.15)
+    side = 3
+    H = 0.2 * np.random.default_rng(1).random((side, side - 1))
+    dim = 1 + M.svec_length(side)
+    G = np.zeros((dim, 1))
+    G[0, 0] = -1
+    h = np.concatenate(([0.0], _svec(H @ H.T)))
+    return _m([-1], None, None, G, h, [M.HypoRootdetTri(dim)]), \
+        dict(status="Optimal", primal_obj=0, x=[0.0], tol_scale=np.finfo(float).eps ** 0.15 / TOL_EPS4)
+
+
+def hypoperlogdettri1():  # :1797-1827 (real case)
+    side = 4
+    H = np.random.default_rng(1).random((side, side))
+    dim = 2 + M.svec_length(side)
+    G = np.zeros((dim, 2))
+    G[0, 0] = G[1, 1] = -1
+    h = np.concatenate(([0.0, 0.0], _svec(H @ H.T + np.eye(side))))
+
+    def check(s, z, approx):
+        assert approx(s[1] * np.linalg.slogdet(_smat(s[2:] / s[1]))[1], s[0])
+        assert approx(z[0] * (np.linalg.slogdet(_smat(-z[2:] / z[0]))[1] + side), z[1])
+    return _m([-1, 0], [[0.0, 1.0]], [1], G, h, [M.HypoPerLogdetTri(dim)]), \
+        dict(status="Optimal", x_idx={1: 1.0}, check=check)
+
+
+def hypoperlogdettri2():  # :1829-1859 (real case, dual barrier)
+    side = 2
+    H = np.random.default_rng(1).random((side, side))
+    dim = 2 + M.svec_length(side)
+    G = np.zeros((dim, 2))
+    G[0, 0] = G[1, 1] = -1
+    h = np.concatenate(([0.0, 0.0], _svec(H @ H.T)))
+
+    def check(s, z, approx):
+        assert approx(s[0] * (np.linalg.slogdet(_smat(-s[2:] / s[0]))[1] + side), s[1])
+        assert approx(z[1] * np.linalg.slogdet(_smat(z[2:] / z[1]))[1], z[0])
+    return _m([0, 1], [[1.0, 0.0]], [-1], G, h, [M.HypoPerLogdetTri(dim, use_dual=True)]), \
+        dict(status="Optimal", x_idx={0: -1.0}, check=check)
+
+
+def hypoperlogdettri3():  # :1861-1884 (real case): perspective variable forced to 0
+    side = 3
+    H = np.random.default_rng(1).random((side, side))
+    dim = 2 + M.svec_length(side)
+    G = np.zeros((dim, 2))
+    G[0, 0] = G[1, 1] = -1
+    h = np.concatenate(([0.0, 0.0], _svec(H @ H.T)))
+    return _m([-1, 0], [[0.0, 1.0]], [0], G, h, [M.HypoPerLogdetTri(dim)]), dict(status="Optimal", x=[0.0, 0.0])
+
+
+def _hypogeomean3(use_dual):  # :1498-1515
+    l = 4
+    G = np.vstack((np.zeros((1, l)), -np.eye(l)))
+    return _m(np.ones(l), None, None, G, np.zeros(l + 1), [M.HypoGeoMean(l + 1, use_dual=use_dual)]), \
+        dict(status="Optimal", primal_obj=0, x=np.zeros(l))
+
+
+def _hypopowermean3(use_dual):  # :1387-1405
+    l = 4
+    G = np.vstack((np.zeros((1, l)), -np.eye(l)))
+    return _m(np.ones(l), None, None, G, np.zeros(l + 1), [M.HypoPowerMean(np.full(l, 1 / l), use_dual=use_dual)]), \
+        dict(status="Optimal", primal_obj=0, x=np.zeros(l))
+
+
+EXTRA = [consistent1, inconsistent1, inconsistent2, nonnegative1, nonnegative2, nonnegative3, possemideftri3,
+         possemideftri4, hyporootdettri1, hyporootdettri2, hyporootdettri3, hypoperlogdettri1, hypoperlogdettri2,
+         hypoperlogdettri3] + \
+    [_named(lambda f=_f, ud=_ud: f(ud), _f.__name__[1:] + ("_dual" if _ud else ""))
+     for _f in (_hypogeomean3, _hypopowermean3) for _ud in (False, True)]
+
 RELENT = [_named(lambda d=_d: _epirelentropy1(d), f"epirelentropy1_d{_d}") for _d in (1, 2, 3)] + \
     [_named(lambda d=_d: _epirelentropy2(d), f"epirelentropy2_d{_d}") for _d in (1, 2, 4)] + \
     [_named(lambda d=_d: _epirelentropy3(d), f"epirelentropy3_d{_d}") for _d in (2, 4)] + \
@@ -668,7 +868,7 @@ ALL = [dimension1, nonnegative4, possemideftri1, possemideftri2, possemideftri8,
        epinormeucl1, epinormeucl2, epinormeucl3, hyporootdettri4, hypoperlogdettri4,
        primalinfeas1, primalinfeas2, dualinfeas_lp]
 
-TOL = np.finfo(np.float64).eps ** 0.25
+TOL = TOL_EPS4
 
 
 def _approx(a, b, tol):

@@ -21,7 +21,7 @@ def solve(model, syssolver, **kw):
     return s
 
 
-@pytest.mark.parametrize("build", kat.ALL + kat.NEW_CONES + kat.SPECTRAL + kat.SPECTRAL_VEC, ids=lambda f: f.__name__)
+@pytest.mark.parametrize("build", kat.ALL + kat.EXTRA + kat.NEW_CONES + kat.SPECTRAL + kat.SPECTRAL_VEC, ids=lambda f: f.__name__)
 def test_kat_qrchol_default(build):
     model, expected = build()
     s = solve(model, osys.QRCholDenseSystemSolver())
