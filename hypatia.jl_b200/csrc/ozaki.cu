@@ -1547,9 +1547,13 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
             //   column by column (HYP_OZAKI_ORDER=col, the first version): the B panel is resident and the A panels, twice
             //     the size, stream.  Measured on C3 (same box): 134 vs 197 GB of DRAM traffic per SYRK, L2 hit rate
             //     72 vs 65 %, 84.8 vs 86.6 ms (profiles/r01_ozaki_pair_row_order_ncu.txt).
-            static const bool row_order = [] {
+            //   HYP_OZAKI_ORDER=row2 (experimental, not measured yet): two row pairs resident (60 MB), their tiles of one
+            //     tile column adjacent in the list, so that one B panel stream can serve both.
+            static const int row_order = [] {
                 const char* e = getenv("HYP_OZAKI_ORDER");
-                return !(e && e[0] == 'c');
+                if (e && e[0] == 'c') return 0;
+                if (e && !strcmp(e, "row2")) return 2;
+                return 1;
             }();
             static std::vector<std::pair<int, std::pair<int2*, int>>> pcache;
             int2* d_pairs = nullptr;
@@ -1561,7 +1565,13 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
                 }
             if (!d_pairs) {
                 std::vector<int2> pl;
-                if (row_order) {
+                if (row_order == 2) {
+                    for (int pp = 0; 2 * pp < nt; pp += 2)
+                        for (int tj = 2 * pp; tj < nt; tj++) {
+                            pl.push_back(make_int2(pp, tj));
+                            if (2 * (pp + 1) <= tj) pl.push_back(make_int2(pp + 1, tj));
+                        }
+                } else if (row_order == 1) {
                     for (int pp = 0; 2 * pp < nt; pp++)
                         for (int tj = 2 * pp; tj < nt; tj++) pl.push_back(make_int2(pp, tj));
                 } else {

@@ -67,3 +67,30 @@ def test_product_package_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "from oracle" not in text and "import oracle" not in text, f
+
+
+def test_cone_codes_agree_between_header_host_mirror_and_julia_shim():
+    """HYP_CONE_* / HYP_SSF_* of include/hypatia_b200.h, CONE_* / SSF_* of the Python host mirror and the cone_code
+    methods of the Julia shim must name the same integers (the codes cross the ABI as plain ints)."""
+    import re
+    from pathlib import Path
+    from hypatia_b200.host import models as M
+    root = Path(__file__).resolve().parents[1]
+    header = (root / "include" / "hypatia_b200.h").read_text()
+    cones = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define HYP_CONE_(\w+)\s+(\d+)", header)}
+    ssf = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define HYP_SSF_(\w+)\s+(\d+)", header)}
+    assert len(cones) == len(M.CONE_NAMES) and sorted(cones.values()) == list(range(len(cones)))
+    for name, code in cones.items():
+        assert getattr(M, "CONE_" + name) == code, name
+    for name, code in ssf.items():
+        assert getattr(M, "SSF_" + name) == code, name
+    # Julia shim: cone_code(::Cones.<Type>...) = Cint(<code>)
+    julia = (root / "julia" / "HypatiaB200.jl").read_text()
+    shim = {m.group(1).lower(): int(m.group(2))
+            for m in re.finditer(r"cone_code\(::Cones\.(\w+)[^)]*\)\s*=\s*Cint\((\d+)\)", julia)}
+    by_code = {v: k.lower().replace("_", "") for k, v in cones.items()}
+    for jname, code in shim.items():
+        assert by_code[code].startswith(jname[:8]), (jname, code, by_code[code])
+    # the library's group table is sized for every code
+    common = (root / "hypatia.jl_b200" / "csrc" / "common.cuh").read_text()
+    assert int(re.search(r"#define HYP_NUM_CONE_TYPES\s+(\d+)", common).group(1)) == len(cones)
