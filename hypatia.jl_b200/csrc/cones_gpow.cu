@@ -87,7 +87,43 @@ static void wsos_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
     hyp_mat_alloc_group(ctx, g);
 }
 
+// LinMatrixIneq: d_vecs / d_voff = per-cone region [side][A_1 .. A_dim] (as passed to hyp_set_cone_alpha) followed by
+// the workspace of lmi_state_kernel / lmi_dder3_kernel (Cholesky factor, B_i, two scratch matrices)
+static void lmi_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
+    if ((int)ctx->h_cone_aoff.size() != ctx->K + 1)
+        throw HypError{"LinMatrixIneq cones need hyp_set_cone_alpha (packed As) before hyp_load_model"};
+    g.h_voff.assign(g.count, 0);
+    std::vector<double> buf;
+    for (int i = 0; i < g.count; i++) {
+        const int k = g.h_kidx[i];
+        const int64_t a0 = ctx->h_cone_aoff[k], a1 = ctx->h_cone_aoff[k + 1];
+        const int d = g.h_dim[i];
+        if (d > 128) throw HypError{"LinMatrixIneq: dimension above 128 is not supported (batched Cholesky limit)"};
+        if (d < 2 || a1 - a0 < 2) throw HypError{"LinMatrixIneq: need at least two matrices"};
+        const int64_t sd = (int64_t)ctx->h_cone_alpha[a0];
+        if (sd < 1 || sd > 256 || sd * (sd + 1) / 2 < d || a1 - a0 != 1 + (int64_t)d * sd * sd)
+            throw HypError{"LinMatrixIneq: As data has the wrong length (need svec_length(side) >= dim, side <= 256)"};
+        g.h_voff[i] = (int64_t)buf.size();
+        buf.insert(buf.end(), ctx->h_cone_alpha.begin() + a0, ctx->h_cone_alpha.begin() + a1);
+        buf.resize(buf.size() + (size_t)((d + 3) * sd * sd), 0.0);
+        g.h_hkind.push_back((int)sd);
+        g.h_side[i] = d;
+    }
+    g.max_side = g.max_dim;
+    cudaFree(g.d_side);
+    g.d_side = upload_vec(g.h_side);
+    g.d_hkind = upload_vec(g.h_hkind);
+    g.d_voff = upload_vec(g.h_voff);
+    CUDA_TRY(cudaMalloc(&g.d_vecs, std::max<size_t>(buf.size(), 1) * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(g.d_vecs, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice));
+    hyp_mat_alloc_group(ctx, g);
+}
+
 void hyp_gpow_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
+    if (g.type == HYP_CONE_LINMATRIXINEQ) {
+        lmi_alloc_group(ctx, g);
+        return;
+    }
     if (g.type == HYP_CONE_EPINORMSPECTRAL) {
         ens_alloc_group(ctx, g);
         return;
@@ -132,7 +168,10 @@ void hyp_gpow_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
 }
 
 void hyp_gpow_update_state(hyp_ctx* ctx, ConeGroup& g) {
-    if (g.type == HYP_CONE_WSOSINTERPNONNEGATIVE)
+    if (g.type == HYP_CONE_LINMATRIXINEQ)
+        hypdev::lmi_state_kernel<<<g.count, 256, 0, ctx->stream>>>(g.count, g.d_off, g.d_dim, g.d_voff, g.d_vecs, g.d_kidx,
+                                                                  g.d_moff, ctx->d_point, ctx->d_grad, g.d_W, ctx->d_feas);
+    else if (g.type == HYP_CONE_WSOSINTERPNONNEGATIVE)
         hypdev::wsos_state_kernel<<<g.count, 256, 0, ctx->stream>>>(g.count, g.d_off, g.d_dim, g.d_voff, g.d_vecs, g.d_kidx,
                                                                    g.d_moff, ctx->d_point, ctx->d_grad, g.d_W, ctx->d_feas);
     else if (g.type == HYP_CONE_EPINORMSPECTRAL)
@@ -168,7 +207,7 @@ void hyp_gpow_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr, 
     else if (mode == HYP_PROD_BLOCK_INV) { hess_dual = 1; inv_dual = 0; }
     else throw HypError{"hyp_gpow_prod: bad mode"};
     if (hess_dual > -2) {
-        if (g.type == HYP_CONE_WSOSINTERPNONNEGATIVE)
+        if (g.type == HYP_CONE_WSOSINTERPNONNEGATIVE || g.type == HYP_CONE_LINMATRIXINEQ)
             hypdev::gen_hess_prod_kernel<<<grid, 256, 0, ctx->stream>>>(g.count, hess_dual, g.d_off, g.d_dim, g.d_moff,
                                                                        g.d_dual, g.d_W, arr, ld_arr, prod, ld_prod, ncols,
                                                                        row_shift);
@@ -197,7 +236,9 @@ void hyp_gpow_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr, 
 }
 
 void hyp_gpow_dder3(hyp_ctx* ctx, ConeGroup& g, double* out, const double* dir) {
-    if (g.type == HYP_CONE_WSOSINTERPNONNEGATIVE)
+    if (g.type == HYP_CONE_LINMATRIXINEQ)
+        hypdev::lmi_dder3_kernel<<<g.count, 256, 0, ctx->stream>>>(g.count, g.d_off, g.d_dim, g.d_voff, g.d_vecs, dir, out);
+    else if (g.type == HYP_CONE_WSOSINTERPNONNEGATIVE)
         hypdev::wsos_dder3_kernel<<<g.count, 256, 0, ctx->stream>>>(g.count, g.d_off, g.d_dim, g.d_voff, g.d_vecs, dir, out);
     else if (g.type == HYP_CONE_EPINORMSPECTRAL)
         hypdev::ens_dder3_kernel<<<ceil_div(g.count, 4), 128, 0, ctx->stream>>>(

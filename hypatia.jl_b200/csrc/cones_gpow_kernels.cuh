@@ -813,4 +813,130 @@ gen_hess_prod_kernel(int ncones, int want_dual, const int64_t* __restrict__ off,
 }
 
 
+// ---- LinMatrixIneq (real dense A_i, dim <= 128), linmatrixineq.jl:87-159 ----
+// Region of cone c at vecs + voff[c]: [side][A_1 .. A_dim] (the data of hyp_set_cone_alpha, side x side column-major
+// each), then the workspace: the lower Cholesky factor of S = sum_i w_i A_i (side^2), B_i = L^-1 A_i L^-T for every i
+// (dim side^2, "sumAinvAs" of the reference) and two side^2 scratch matrices for dder3.
+// One CTA of 256 threads per cone.
+
+static __global__ void __launch_bounds__(256)
+lmi_state_kernel(int ncones, const int64_t* __restrict__ off, const int* __restrict__ dim,
+                 const int64_t* __restrict__ voff, double* __restrict__ vecs, const int* __restrict__ kidx,
+                 const int64_t* __restrict__ moff, const double* __restrict__ point, double* __restrict__ grad,
+                 double* __restrict__ H, uint8_t* feas) {
+    __shared__ int s_ok;
+    const int c = blockIdx.x, tid = threadIdx.x;
+    if (c >= ncones) return;
+    const int64_t o = off[c];
+    const int d = dim[c], lde = (d + 1) & ~1;
+    double* reg = vecs + voff[c];
+    const int sd = (int)reg[0], s2 = sd * sd;
+    const double* A = reg + 1;
+    double* Lc = reg + 1 + (int64_t)d * s2;
+    double* B = Lc + s2;
+    double* Hc = H + moff[c];
+    if (tid == 0) s_ok = 1;
+    // update_feas (:87-96): S = sum_i w_i A_i and its Cholesky (lower, in place, right-looking)
+    for (int idx = tid; idx < s2; idx += 256) {
+        double s = 0.0;
+        for (int i = 0; i < d; i++) s += point[o + i] * A[(int64_t)i * s2 + idx];
+        Lc[idx] = s;
+    }
+    __syncthreads();
+    for (int j = 0; j < sd; j++) {
+        if (tid == 0) {
+            double dg = Lc[j + j * sd];
+            if (!(dg > 0.0)) {
+                s_ok = 0;
+                dg = 1.0;
+            }
+            Lc[j + j * sd] = sqrt(dg);
+        }
+        __syncthreads();
+        const double dj = Lc[j + j * sd];
+        for (int i = j + 1 + tid; i < sd; i += 256) Lc[i + j * sd] /= dj;
+        __syncthreads();
+        const int r = sd - j - 1;
+        for (int idx = tid; idx < r * r; idx += 256) {
+            const int ii = j + 1 + idx % r, kk = j + 1 + idx / r;
+            if (kk <= ii) Lc[ii + kk * sd] -= Lc[ii + j * sd] * Lc[kk + j * sd];
+        }
+        __syncthreads();
+    }
+    // update_grad (:98-109): B_i = L^-1 A_i L^-T.  Pass 1: every column of A_i through L^-1 (in place in B_i);
+    // pass 2: every row of the result through L^-1 (row a of X L^-T is L^-1 applied to row a of X; rows are disjoint).
+    for (int idx = tid; idx < d * sd; idx += 256) {
+        const int i = idx / sd, col = idx % sd;
+        const double* a = A + (int64_t)i * s2 + (int64_t)col * sd;
+        double* x = B + (int64_t)i * s2 + (int64_t)col * sd;
+        for (int r = 0; r < sd; r++) {
+            double s = a[r];
+            for (int b = 0; b < r; b++) s -= Lc[r + b * sd] * x[b];
+            x[r] = s / Lc[r + r * sd];
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < d * sd; idx += 256) {
+        const int i = idx / sd, row = idx % sd;
+        double* x = B + (int64_t)i * s2 + row;          // stride sd along the row
+        for (int r = 0; r < sd; r++) {
+            double s = x[(int64_t)r * sd];
+            for (int b = 0; b < r; b++) s -= Lc[r + b * sd] * x[(int64_t)b * sd];
+            x[(int64_t)r * sd] = s / Lc[r + r * sd];
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < d; i += 256) {
+        double tr = 0.0;
+        for (int r = 0; r < sd; r++) tr += B[(int64_t)i * s2 + r + r * sd];
+        grad[o + i] = -tr;
+    }
+    // update_hess (:111-123): H_ij = <B_i, B_j>, both triangles
+    for (int idx = tid; idx < d * d; idx += 256) {
+        const int i = idx % d, j = idx / d;
+        const double* bi = B + (int64_t)i * s2;
+        const double* bj = B + (int64_t)j * s2;
+        double s = 0.0;
+        for (int e = 0; e < s2; e++) s += bi[e] * bj[e];
+        Hc[i + (int64_t)j * lde] = s;
+    }
+    if (tid == 0 && !s_ok) feas[kidx[c]] = 0;
+}
+
+// dder3 (:147-159): D = sum_i dir_i B_i, Z = D D', out_i = <Z, B_i>
+static __global__ void __launch_bounds__(256)
+lmi_dder3_kernel(int ncones, const int64_t* __restrict__ off, const int* __restrict__ dim,
+                 const int64_t* __restrict__ voff, double* __restrict__ vecs, const double* __restrict__ dir,
+                 double* __restrict__ out) {
+    const int c = blockIdx.x, tid = threadIdx.x;
+    if (c >= ncones) return;
+    const int64_t o = off[c];
+    const int d = dim[c];
+    double* reg = vecs + voff[c];
+    const int sd = (int)reg[0], s2 = sd * sd;
+    const double* B = reg + 1 + (int64_t)d * s2 + s2;
+    double* D = reg + 1 + (int64_t)d * s2 + s2 + (int64_t)d * s2;
+    double* Z = D + s2;
+    for (int idx = tid; idx < s2; idx += 256) {
+        double s = 0.0;
+        for (int i = 0; i < d; i++) s += dir[o + i] * B[(int64_t)i * s2 + idx];
+        D[idx] = s;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < s2; idx += 256) {
+        const int a = idx % sd, b = idx / sd;
+        double s = 0.0;
+        for (int k = 0; k < sd; k++) s += D[a + k * sd] * D[b + k * sd];
+        Z[idx] = s;
+    }
+    __syncthreads();
+    for (int i = tid; i < d; i += 256) {
+        const double* bi = B + (int64_t)i * s2;
+        double s = 0.0;
+        for (int e = 0; e < s2; e++) s += Z[e] * bi[e];
+        out[o + i] = s;
+    }
+}
+
+
 }  // namespace hypdev

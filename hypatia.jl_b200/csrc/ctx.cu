@@ -877,6 +877,13 @@ static double wsos_nu(hyp_ctx* ctx, int k) {
     return nu;
 }
 
+// nu of a LinMatrixIneq cone = the side of its matrices (first entry of its packed data)
+static double lmi_nu(hyp_ctx* ctx, int k) {
+    if ((int)ctx->h_cone_aoff.size() != ctx->K + 1) return 0.0;
+    const int64_t a0 = ctx->h_cone_aoff[k], a1 = ctx->h_cone_aoff[k + 1];
+    return a1 - a0 >= 1 ? ctx->h_cone_alpha[a0] : 0.0;
+}
+
 int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* G_local, int64_t ldG,
                    const double* A, int64_t ldA, const double* c, const double* b, const double* h, int K,
                    const int* cone_type, const int64_t* cone_dim, const int* cone_dual, int cone_lo,
@@ -931,6 +938,7 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
                                 : t == HYP_CONE_EPIPERSQUARE ? 2.0
                                 : t == HYP_CONE_EPINORMSPECTRAL ? (double)ctx->h_cone_hkind[k] + 1.0   // epinormspectral.jl:95
                                 : t == HYP_CONE_WSOSINTERPNONNEGATIVE ? wsos_nu(ctx, k)               // wsosinterpnonnegative.jl:62
+                                : t == HYP_CONE_LINMATRIXINEQ ? lmi_nu(ctx, k)                        // linmatrixineq.jl:72
                                 : t == HYP_CONE_GENERALIZEDPOWER
                                     ? ((int)ctx->h_cone_aoff.size() == K + 1
                                            ? (double)(ctx->h_cone_aoff[k + 1] - ctx->h_cone_aoff[k]) + 1.0

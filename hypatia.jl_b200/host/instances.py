@@ -106,6 +106,8 @@ def cone_initial_point(spec):
         arr[2:] = w
     elif spec.ctype == M.CONE_EPINORMINF:
         arr[0] = np.sqrt(spec.dim)      # epinorminf.jl:88-95
+    elif spec.ctype == M.CONE_LINMATRIXINEQ:
+        arr[0] = 1.0                            # linmatrixineq.jl:74-82
     elif spec.ctype == M.CONE_WSOSINTERPNONNEGATIVE:
         arr[:] = 1.0                            # wsosinterpnonnegative.jl:89
     elif spec.ctype == M.CONE_EPINORMSPECTRAL:
@@ -173,6 +175,11 @@ def _central_ray_epirelentropy(d):
 
 def _cone_dual_initial(spec, prim):
     """-grad at the central point, closed form per cone (dual of the central point)."""
+    if spec.ctype == M.CONE_LINMATRIXINEQ:
+        # -grad_i = tr(S^-1 A_i) with S = sum_j w_j A_j, linmatrixineq.jl:98-109
+        As = M.lmi_unpack(spec)
+        Si = np.linalg.inv(sum(w * A for w, A in zip(prim, As)))
+        return np.array([np.sum(Si * A) for A in As])
     if spec.ctype == M.CONE_WSOSINTERPNONNEGATIVE:
         # -grad_j = sum_k (P_k (P_k' D P_k)^-1 P_k')_jj, wsosinterpnonnegative.jl:123-138
         out = np.zeros_like(prim)
@@ -287,6 +294,9 @@ def _perturb(rng, spec, vec, noise):
         return vec
     if spec.ctype == M.CONE_EPIPERSEPSPECTRAL_VEC:
         vec += noise / (2.0 * (vec.size - 2)) * (2 * rng.random(vec.size) - 1)   # the initial point is not central
+        return vec
+    if spec.ctype == M.CONE_LINMATRIXINEQ:
+        vec += 0.1 * noise / np.sqrt(vec.size) * (2 * rng.random(vec.size) - 1)    # test/cone.jl:426 uses noise 1e-2
         return vec
     if spec.ctype in (M.CONE_GENERALIZEDPOWER, M.CONE_WSOSINTERPNONNEGATIVE):
         vec += 0.5 * noise / np.sqrt(vec.size) * (2 * rng.random(vec.size) - 1)

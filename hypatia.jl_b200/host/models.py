@@ -28,6 +28,7 @@ CONE_HYPOPOWERMEAN = 12
 CONE_EPIRELENTROPY = 13
 CONE_EPINORMSPECTRAL = 14
 CONE_WSOSINTERPNONNEGATIVE = 15
+CONE_LINMATRIXINEQ = 16
 
 # separable spectral functions of EpiPerSepSpectral (sepspectralfun.jl:17-116), HYP_SSF_*
 SSF_INV, SSF_NEGLOG, SSF_NEGENTROPY, SSF_POWER12 = 0, 1, 2, 3
@@ -49,6 +50,7 @@ CONE_NAMES = {
     CONE_EPIRELENTROPY: "EpiRelEntropy",
     CONE_EPINORMSPECTRAL: "EpiNormSpectral",
     CONE_WSOSINTERPNONNEGATIVE: "WSOSInterpNonnegative",
+    CONE_LINMATRIXINEQ: "LinMatrixIneq",
 }
 
 
@@ -102,6 +104,11 @@ class ConeSpec:
             assert dim >= 3
         elif ctype == CONE_HYPOPERLOG:
             assert dim >= 3
+        elif ctype == CONE_LINMATRIXINEQ:
+            # alpha = packed data [side, vec(A_1) .. vec(A_dim)], A_i symmetric side x side (linmatrixineq.jl:38-66)
+            side = int(self.alpha[0])
+            assert dim > 1 and side >= 1 and side * (side + 1) // 2 >= dim
+            assert len(self.alpha) == 1 + dim * side * side
         elif ctype == CONE_WSOSINTERPNONNEGATIVE:
             # alpha = packed data [nP, L_1 .. L_nP, vec(P_1) .. vec(P_nP)] with P_k of dim x L_k, column-major
             nP = int(self.alpha[0])
@@ -156,6 +163,8 @@ class ConeSpec:
             return float(len(self.alpha) + 1)
         if self.ctype == CONE_EPINORMSPECTRAL:
             return float(self.hkind + 1)      # epinormspectral.jl:95
+        if self.ctype == CONE_LINMATRIXINEQ:
+            return float(int(self.alpha[0]))      # linmatrixineq.jl:72
         if self.ctype == CONE_WSOSINTERPNONNEGATIVE:
             return float(sum(self.alpha[1:1 + int(self.alpha[0])]))    # wsosinterpnonnegative.jl:62
         if self.ctype in (CONE_HYPOPERLOG, CONE_EPINORMINF, CONE_EPIPERSEPSPECTRAL_VEC, CONE_HYPOGEOMEAN,
@@ -223,6 +232,23 @@ def WSOSInterpNonnegative(U, Ps, use_dual=False):
     assert all(P.ndim == 2 and P.shape[0] == U for P in Ps)
     packed = np.concatenate([[float(len(Ps))], [float(P.shape[1]) for P in Ps]] + [P.ravel(order="F") for P in Ps])
     return ConeSpec(CONE_WSOSINTERPNONNEGATIVE, U, not use_dual, alpha=packed)
+
+
+def LinMatrixIneq(As, use_dual=False):
+    """LinMatrixIneq{Float64}(As): {w : sum_i w_i A_i psd}, dense real symmetric A_i, A_1 positive definite; the matrices
+    travel in the per-cone double array of hyp_set_cone_alpha as [side, vec(A_1) .. vec(A_dim)]."""
+    As = [np.asarray(A, dtype=np.float64) for A in As]
+    side = As[0].shape[0]
+    assert all(A.shape == (side, side) for A in As)
+    packed = np.concatenate([[float(side)]] + [A.ravel(order="F") for A in As])
+    return ConeSpec(CONE_LINMATRIXINEQ, len(As), use_dual, alpha=packed)
+
+
+def lmi_unpack(spec):
+    """The As matrices of a LinMatrixIneq spec."""
+    side = int(spec.alpha[0])
+    data = np.asarray(spec.alpha[1:], dtype=np.float64)
+    return [data[i * side * side:(i + 1) * side * side].reshape(side, side, order="F") for i in range(spec.dim)]
 
 
 def wsos_unpack(spec):

@@ -46,6 +46,10 @@ cone_code(::Cones.HypoPowerMean) = Cint(12)
 cone_code(::Cones.EpiRelEntropy) = Cint(13)
 cone_code(::Cones.EpiNormSpectral{Float64, Float64}) = Cint(14)
 cone_code(::Cones.WSOSInterpNonnegative{Float64, Float64}) = Cint(15)
+cone_code(::Cones.LinMatrixIneq{Float64}) = Cint(16)
+# packed matrices [side, vec(A_1) .. vec(A_dim)] (dense real symmetric A_i; UniformScaling entries are materialised)
+cone_alpha(c::Cones.LinMatrixIneq{Float64}) =
+    vcat(Float64(c.side), (vec(Matrix{Float64}(A isa UniformScaling ? A(c.side) : A)) for A in c.As)...)
 # packed interpolation data [nP, L_1 .. L_nP, vec(P_1) .. vec(P_nP)]
 cone_alpha(c::Cones.WSOSInterpNonnegative{Float64, Float64}) =
     vcat(Float64(length(c.Ps)), Float64[size(P, 2) for P in c.Ps], (vec(P) for P in c.Ps)...)

@@ -859,6 +859,65 @@ class WSOSInterpNonnegative(Cone):
         return d3
 
 
+class LinMatrixIneq(Cone):
+    """linmatrixineq.jl:8-159 (real dense matrices): {w : sum_i w_i A_i psd} for symmetric A_i (side x side, A_1 positive
+    definite), barrier -logdet(sum_i w_i A_i), nu = side.  hess_prod! / inv_hess_prod! are the generic explicit-Hessian
+    oracles of Cones.jl:101-118; is_dual_feas the generic `true`."""
+    ctype = M.CONE_LINMATRIXINEQ
+
+    def __init__(self, As, use_dual=False):
+        self.As = [np.asarray(A, dtype=np.float64) for A in As]
+        self.side = self.As[0].shape[0]
+        assert len(self.As) > 1 and all(A.shape == (self.side, self.side) and np.allclose(A, A.T) for A in self.As)
+        assert self.side * (self.side + 1) // 2 >= len(self.As)
+        self.use_dual_barrier = use_dual
+        super().__init__(len(self.As))
+
+    @property
+    def nu(self):
+        return float(self.side)
+
+    def set_initial_point(self, arr):
+        arr[:] = 0.0
+        arr[0] = 1.0
+        return arr
+
+    def update_feas(self):
+        # linmatrixineq.jl:87-96
+        S = sum(w * A for w, A in zip(self.point, self.As))
+        try:
+            self.L = np.linalg.cholesky(S)
+        except np.linalg.LinAlgError:
+            return False
+        return True
+
+    def update_grad(self):
+        # linmatrixineq.jl:98-109: B_i = L^-1 A_i L^-T, grad_i = -tr(B_i)
+        L = self.L
+        self.B = []
+        for A in self.As:
+            X = sla.solve_triangular(L, A, lower=True, check_finite=False)
+            self.B.append(sla.solve_triangular(L, X.T, lower=True, check_finite=False).T)
+        self._grad[:] = [-np.trace(B) for B in self.B]
+
+    def update_hess(self):
+        # linmatrixineq.jl:111-123
+        self.grad()
+        Bm = np.stack([B.ravel() for B in self.B])
+        return Bm @ Bm.T
+
+    def hess_prod(self, arr):
+        a, vec = _as2d(arr)
+        return _ret(np.asarray(self.hess()) @ a, vec)
+
+    def dder3(self, direction):
+        # linmatrixineq.jl:147-159
+        self.grad()
+        D = sum(d * B for d, B in zip(direction, self.B))
+        Z = D @ D.T
+        return np.array([np.sum(Z * B) for B in self.B])
+
+
 class GeneralizedPower(Cone):
     """generalizedpower.jl:8-236: (u in R^m_++, w in R^n), prod u_i^(alpha_i) >= |w|_2; barrier
     -log(prod u_i^(2 alpha_i) - |w|^2) - sum (1 - alpha_i) log u_i, nu = m + 1.  No closed-form inverse Hessian:

@@ -298,6 +298,14 @@ class EmuGpowGroup:
         self.K = len(specs)
         self.hpm = specs[0].ctype == 12          # HypoPowerMean, else GeneralizedPower
         self.ens = specs[0].ctype == 14          # EpiNormSpectral: d1 per cone, workspace instead of powers
+        self.lmi = specs[0].ctype == 16          # LinMatrixIneq: packed As + workspace
+        if self.lmi:
+            regions = []
+            for s in specs:
+                sd = int(s.alpha[0])
+                regions.append(np.concatenate((np.asarray(s.alpha, dtype=np.float64), np.zeros((s.dim + 3) * sd * sd))))
+            self.voff = np.concatenate(([0], np.cumsum([r.size for r in regions])))[:-1].astype(np.int64)
+            self.vecs = np.concatenate(regions)
         self.wsos = specs[0].ctype == 15         # WSOSInterpNonnegative: packed Ps + workspace
         if self.wsos:
             regions = []
@@ -331,7 +339,10 @@ class EmuGpowGroup:
         self.dual_feas = np.ones(self.K, dtype=np.uint8)
         self.grad = np.zeros(self.q)
         self.H = np.zeros(self.lay.total)
-        if self.wsos:
+        if self.lmi:
+            lib().emu_lmi_state(self.K, p(self.off), p(self.dims), p(self.voff), p(self.vecs), p(self.kidx),
+                                p(self.lay.moff), p(self.point), p(self.grad), p(self.H), p(self.feas))
+        elif self.wsos:
             lib().emu_wsos_state(self.K, p(self.off), p(self.dims), p(self.voff), p(self.vecs), p(self.kidx),
                                  p(self.lay.moff), p(self.point), p(self.grad), p(self.H), p(self.feas))
         elif self.ens:
@@ -360,7 +371,7 @@ class EmuGpowGroup:
         out = a if in_place else np.zeros_like(a, order="F")
         hess_dual, inv_dual = {0: (-1, -2), 1: (-2, -1), 4: (0, 1), 5: (1, 0)}[int(mode)]
         L = lib()
-        if hess_dual > -2 and self.wsos:
+        if hess_dual > -2 and (self.wsos or self.lmi):
             L.emu_gen_hess_prod(self.K, hess_dual, p(self.off), p(self.dims), p(self.lay.moff), p(self.dualf), p(self.H),
                                 p(a), i64(self.q), p(out), i64(self.q), i64(a.shape[1]), i64(0))
         elif hess_dual > -2 and self.ens:
@@ -382,7 +393,9 @@ class EmuGpowGroup:
     def dder3(self, direction):
         d = np.ascontiguousarray(direction, dtype=np.float64)
         out = np.zeros(self.q)
-        if self.wsos:
+        if self.lmi:
+            lib().emu_lmi_dder3(self.K, p(self.off), p(self.dims), p(self.voff), p(self.vecs), p(d), p(out))
+        elif self.wsos:
             lib().emu_wsos_dder3(self.K, p(self.off), p(self.dims), p(self.voff), p(self.vecs), p(d), p(out))
         elif self.ens:
             lib().emu_ens_dder3(self.K, p(self.off), p(self.dims), p(self.d1), p(self.voff), p(self.vecs), p(self.scal),

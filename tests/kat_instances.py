@@ -844,6 +844,44 @@ EXTRA = [consistent1, inconsistent1, inconsistent2, nonnegative1, nonnegative2, 
     [_named(lambda f=_f, ud=_ud: f(ud), _f.__name__[1:] + ("_dual" if _ud else ""))
      for _f in (_hypogeomean3, _hypopowermean3) for _ud in (False, True)]
 
+def _linmatrixineq1(side):  # :696-719 (real case): min w_1 : w_1 A_1 - 2 v v' psd  =>  2 / lambda_max(A_1)
+    H = np.random.default_rng(side).random((side, side))
+    A1 = H @ H.T + 2 * np.eye(side)
+    vals, vecs = np.linalg.eigh(A1)
+    v = vecs[:, -1]
+    G = np.zeros((2, 1))
+    G[0, 0] = -1
+    return _m([1], None, None, G, [0, 2], [M.LinMatrixIneq([A1, -np.outer(v, v)])]), \
+        dict(status="Optimal", primal_obj=2 / vals[-1], s=[2 / vals[-1], 2])
+
+
+def _linmatrixineq2(dim):  # :721-745 (real case)
+    rng = np.random.default_rng(1)
+    As = []
+    for _ in range(dim):
+        H = rng.random((3, 3))
+        As.append(H @ H.T)
+    As[0] = As[0] + np.eye(3)
+    G = np.vstack((np.zeros((1, dim - 1)), -np.eye(dim - 1)))
+    h = np.zeros(dim)
+    h[0] = 1
+
+    def check(s, z, approx):
+        assert float(np.sum(s[1:])) < 0       # x = s[1:] and c = 1: the reference asserts primal_obj < 0
+    return _m(np.ones(dim - 1), None, None, G, h, [M.LinMatrixIneq(As)]), dict(status="Optimal", check=check)
+
+
+def linmatrixineq3():  # :747-788 (dense case): min w_1 : w_1 I - diag(1, -1) psd => 1
+    G = np.zeros((2, 1))
+    G[0, 0] = -1
+    return _m([1], None, None, G, [0, -1], [M.LinMatrixIneq([np.eye(2), np.diag([1.0, -1.0])])]), \
+        dict(status="Optimal", primal_obj=1, s=[1, -1])
+
+
+LMI = [_named(lambda s=_s: _linmatrixineq1(s), f"linmatrixineq1_side{_s}") for _s in (2, 4)] + \
+    [_named(lambda d=_d: _linmatrixineq2(d), f"linmatrixineq2_dim{_d}") for _d in (2, 3)] + [linmatrixineq3]
+EXTRA = EXTRA + LMI
+
 RELENT = [_named(lambda d=_d: _epirelentropy1(d), f"epirelentropy1_d{_d}") for _d in (1, 2, 3)] + \
     [_named(lambda d=_d: _epirelentropy2(d), f"epirelentropy2_d{_d}") for _d in (1, 2, 4)] + \
     [_named(lambda d=_d: _epirelentropy3(d), f"epirelentropy3_d{_d}") for _d in (2, 4)] + \

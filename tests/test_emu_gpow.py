@@ -30,9 +30,19 @@ def _wsos(n, halfdeg, use_dual=False):
     return M.WSOSInterpNonnegative(U, Ps, use_dual=use_dual)
 
 
+def _lmi(rng, side, dim, use_dual=False):
+    As = []
+    for i in range(dim):
+        X = rng.random((side, side))
+        As.append(X @ X.T + np.eye(side) if i == 0 else (X + X.T) / 2 - 0.5)
+    return M.LinMatrixIneq(As, use_dual=use_dual)
+
+
 def _sets():
     rng = np.random.default_rng(7)
     return {
+        "lmi": [_lmi(rng, 2, 2), _lmi(rng, 3, 2), _lmi(rng, 4, 3), _lmi(rng, 3, 6), _lmi(rng, 12, 40),
+                _lmi(rng, 5, 4, use_dual=True), _lmi(rng, 33, 20)],
         "wsos": [_wsos(1, 1), _wsos(1, 3), _wsos(2, 2), _wsos(3, 1), _wsos(2, 4), _wsos(1, 2, use_dual=True),
                  _wsos(3, 2)],
         "gpow": [M.GeneralizedPower(_alpha(rng, m), n) for m, n in ((2, 1), (3, 2), (4, 1), (2, 4), (20, 30), (40, 5))],
@@ -47,7 +57,7 @@ def _sets():
     }
 
 
-NAMES = ["gpow", "gpow_dual", "hpm", "hpm_dual", "normspec", "normspec_dual", "wsos"]
+NAMES = ["gpow", "gpow_dual", "hpm", "hpm_dual", "normspec", "normspec_dual", "wsos", "lmi"]
 
 
 @pytest.mark.parametrize("name", NAMES)

@@ -1,0 +1,83 @@
+"""-m gpu tests of code that has NOT yet run on a B200: the GPU budget of the round was spent before it was written.
+The kernels involved (LinMatrixIneq: lmi_state_kernel / lmi_dder3_kernel + the generic explicit-Hessian products) pass
+the CPU emulation tier (tests/test_emu_gpow.py) like every other cone kernel did before its first GPU run; the
+reference instances listed in kat.EXTRA use only device code that is already GPU-verified, but were first added in the
+CPU (oracle) tier.  The file name sorts last on purpose: a failure here cannot mask a verified test under `pytest -x`."""
+import numpy as np
+import pytest
+
+import kat_instances as kat
+from gpu_util import iterate_solver, rel
+from hypatia_b200.host import instances as inst
+from hypatia_b200.host import models as M
+from hypatia_b200.host.point import Point
+
+pytestmark = pytest.mark.gpu
+
+
+def _lmi(rng, side, dim, use_dual=False):
+    As = []
+    for i in range(dim):
+        X = rng.random((side, side))
+        As.append(X @ X.T + np.eye(side) if i == 0 else (X + X.T) / 2 - 0.5)
+    return M.LinMatrixIneq(As, use_dual=use_dual)
+
+
+def test_linmatrixineq_oracles_match_cpu_oracle():
+    from hypatia_b200.cones import DeviceConeBlock
+    from oracle.cones import OracleConeBlock
+    rng = np.random.default_rng(7)
+    cones = [_lmi(rng, 2, 2), _lmi(rng, 3, 2), _lmi(rng, 4, 3), _lmi(rng, 3, 6), _lmi(rng, 12, 40),
+             _lmi(rng, 5, 4, use_dual=True), _lmi(rng, 33, 20), M.Nonnegative(3)]
+    I = inst.synthetic("lmi", 4, 0, cones, seed=77)
+    dev, ora = DeviceConeBlock(I.model), OracleConeBlock(I.model)
+    prim, dual = I.point.primal_dual(ora.dual_mask)
+    scal = 1 / np.sqrt(I.mu)
+    dev.load_point(prim, dual, scal)
+    ora.load_point(prim, dual, scal)
+    assert dev.is_feas().all() and ora.is_feas().all()
+    g = dev.grad()
+    assert rel(g, ora.grad()) <= 1e-11
+    arr = np.random.default_rng(1).standard_normal((I.model.q, 3))
+    assert rel(dev.hess_prod(arr), ora.hess_prod(arr)) <= 1e-10
+    assert rel(dev.inv_hess_prod(arr), ora.inv_hess_prod(arr)) <= 1e-9
+    assert rel(dev.block_hess_prod(arr[:, 0]), ora.block_hess_prod(arr[:, 0])) <= 1e-9
+    assert rel(dev.dder3(arr[:, 1]), ora.dder3(arr[:, 1])) <= 1e-10
+    pt = scal * prim
+    assert rel(dev.hess_prod(pt), -g) <= 1e-10                      # test/cone.jl:50,78
+    assert abs(float(pt @ g) + I.model.nu) <= 1e-9 * I.model.nu     # test/cone.jl:71
+    dev.free()
+
+
+def test_linmatrixineq_in_the_system_solve():
+    from hypatia_b200.syssolver import QRCholDenseSystemSolver as DevQRChol
+    from oracle.syssolvers import QRCholDenseSystemSolver as OraQRChol
+    rng = np.random.default_rng(8)
+    cones = [_lmi(rng, 4, 5), M.EpiNormEucl(5), _lmi(rng, 3, 3, use_dual=True), M.Nonnegative(4)]
+    I = inst.synthetic("lmimix", 9, 0, cones, seed=31)
+    dev, ora = iterate_solver(I, DevQRChol()), iterate_solver(I, OraQRChol())
+    try:
+        assert rel(dev.syssolver.lhs_full(), ora.syssolver.lhs_full()) <= 1e-11
+        rhs = Point(I.model)
+        rhs.vec[:] = np.random.default_rng(3).standard_normal(rhs.vec.size)
+        sd, so = Point(I.model), Point(I.model)
+        dev.syssolver.solve_system(dev, sd, rhs)
+        ora.syssolver.solve_system(ora, so, rhs)
+        assert rel(sd.vec, so.vec) <= 1e-8
+    finally:
+        dev.syssolver.free_memory()
+
+
+def _solve_dev(model):
+    from hypatia_b200.cones import DeviceConeBlock
+    from hypatia_b200.host.solver import Solver
+    from hypatia_b200.syssolver import QRCholDenseSystemSolver as DevQRChol
+    s = Solver(model, DevQRChol(), DeviceConeBlock, default_tol_relax=10)    # test/runnativetests.jl:13-18
+    s.solve()
+    return s
+
+
+@pytest.mark.parametrize("build", kat.EXTRA, ids=lambda f: f.__name__)
+def test_kat_device_extra(build):
+    model, expected = build()
+    kat.check_solution(_solve_dev(model), model, expected)

@@ -279,6 +279,56 @@ def test_wsosinterpnonnegative_barrier():
     assert close(-2 * cone.dder3(direction), fd_third, 1e-5)
 
 
+def rand_lmi(rng, side, dim):
+    """rand_herms of test/cone.jl (real case): symmetric matrices with a positive definite first one."""
+    As = []
+    for i in range(dim):
+        X = rng.random((side, side))
+        As.append(X @ X.T + np.eye(side) if i == 0 else (X + X.T) / 2 - 0.5)
+    return As
+
+
+@pytest.mark.parametrize("side,dim", [(2, 2), (3, 2), (4, 3), (3, 6)])
+def test_linmatrixineq(side, dim):
+    # reference: test/cone.jl:423-429 (noise 1e-2, init_tol = Inf)
+    from oracle.cones_vec3 import LinMatrixIneq
+    run_oracles(LinMatrixIneq(rand_lmi(np.random.default_rng(1), side, dim)), init_tol=np.inf, noise=1e-2)
+
+
+def test_linmatrixineq_barrier():
+    """test/cone.jl:431-436 with central differences: -logdet(sum_i s_i A_i)."""
+    from oracle.cones_vec3 import LinMatrixIneq
+    As = rand_lmi(np.random.default_rng(1), 3, 3)
+    cone = LinMatrixIneq(As)
+
+    def barrier(s):
+        return -np.linalg.slogdet(sum(w * A for w, A in zip(s, As)))[1]
+
+    rng = np.random.default_rng(2)
+    point = np.zeros(3)
+    cone.set_initial_point(point)
+    perturb_scale(rng, point, 0.01, 1.0)
+
+    def grad_at(s):
+        cone.reset_data()
+        cone.load_point(s)
+        assert cone.is_feas()
+        return cone.grad().copy()
+
+    g = grad_at(point)
+    eps = 1e-6
+    fd_grad = np.array([(barrier(point + eps * e) - barrier(point - eps * e)) / (2 * eps) for e in np.eye(3)])
+    assert close(g, fd_grad, 1e-7)
+    direction = 0.1 * rng.standard_normal(3)
+    fd_hess_dir = (grad_at(point + eps * direction) - grad_at(point - eps * direction)) / (2 * eps)
+    grad_at(point)
+    assert close(cone.hess_prod(direction), fd_hess_dir, 1e-6)
+    e2 = 1e-4
+    fd_third = (grad_at(point + e2 * direction) - 2 * g + grad_at(point - e2 * direction)) / e2 ** 2
+    grad_at(point)
+    assert close(-2 * cone.dder3(direction), fd_third, 1e-5)
+
+
 SSF = [(0, 0.0), (1, 0.0), (2, 0.0), (3, 1.5), (3, 2.0), (3, 1.1)]   # Inv, NegLog, NegEntropy, Power12(p)
 
 
