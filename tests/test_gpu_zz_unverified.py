@@ -1,8 +1,7 @@
-"""-m gpu tests of code that has NOT yet run on a B200: the GPU budget of the round was spent before it was written.
-The kernels involved (LinMatrixIneq: lmi_state_kernel / lmi_dder3_kernel + the generic explicit-Hessian products) pass
-the CPU emulation tier (tests/test_emu_gpow.py) like every other cone kernel did before its first GPU run; the
-reference instances listed in kat.EXTRA use only device code that is already GPU-verified, but were first added in the
-CPU (oracle) tier.  The file name sorts last on purpose: a failure here cannot mask a verified test under `pytest -x`."""
+"""-m gpu tests written when the GPU budget of the round was (almost) spent.  The two LinMatrixIneq tests passed on a B200
+with the last seconds of it (profiles/r01_pytest_gpu_lmi.log); test_kat_device_extra - full device solves of the
+reference instances added late in the CPU (oracle) tier, all on device code that is already GPU-verified - has NOT run on
+a GPU yet.  The file name sorts last on purpose: a failure here cannot mask a verified test under `pytest -x`."""
 import numpy as np
 import pytest
 
