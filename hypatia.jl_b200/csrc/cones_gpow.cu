@@ -119,7 +119,35 @@ static void lmi_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
     hyp_mat_alloc_group(ctx, g);
 }
 
+// DoublyNonnegativeTri: d_hkind = side of the matrix, d_vecs / d_voff = per-cone workspace (W^-1 and the Cholesky factor)
+static void dnn_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
+    g.h_voff.assign(g.count, 0);
+    int64_t tot = 0;
+    for (int i = 0; i < g.count; i++) {
+        const int d = g.h_dim[i];
+        if (d > 128) throw HypError{"DoublyNonnegativeTri: dim above 128 is not supported (batched Cholesky limit)"};
+        const int side = (int)std::floor((std::sqrt(1.0 + 8.0 * d) - 1) / 2 + 0.5);
+        if (side * (side + 1) / 2 != d) throw HypError{"DoublyNonnegativeTri: dim is not a triangular number"};
+        g.h_hkind.push_back(side);
+        g.h_side[i] = d;
+        g.h_voff[i] = tot;
+        tot += 2 * (int64_t)side * side;
+    }
+    g.max_side = g.max_dim;
+    cudaFree(g.d_side);
+    g.d_side = upload_vec(g.h_side);
+    g.d_hkind = upload_vec(g.h_hkind);
+    g.d_voff = upload_vec(g.h_voff);
+    CUDA_TRY(cudaMalloc(&g.d_vecs, (size_t)std::max<int64_t>(tot, 1) * sizeof(double)));
+    CUDA_TRY(cudaMemset(g.d_vecs, 0, (size_t)std::max<int64_t>(tot, 1) * sizeof(double)));
+    hyp_mat_alloc_group(ctx, g);
+}
+
 void hyp_gpow_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
+    if (g.type == HYP_CONE_DOUBLYNONNEGATIVETRI) {
+        dnn_alloc_group(ctx, g);
+        return;
+    }
     if (g.type == HYP_CONE_LINMATRIXINEQ) {
         lmi_alloc_group(ctx, g);
         return;
@@ -168,7 +196,11 @@ void hyp_gpow_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
 }
 
 void hyp_gpow_update_state(hyp_ctx* ctx, ConeGroup& g) {
-    if (g.type == HYP_CONE_LINMATRIXINEQ)
+    if (g.type == HYP_CONE_DOUBLYNONNEGATIVETRI)
+        hypdev::dnn_state_kernel<<<ceil_div(g.count, 8), 256, 0, ctx->stream>>>(
+            g.count, g.d_off, g.d_dim, g.d_hkind, g.d_voff, g.d_vecs, g.d_kidx, g.d_moff, ctx->d_point, ctx->d_grad,
+            g.d_W, ctx->d_feas);
+    else if (g.type == HYP_CONE_LINMATRIXINEQ)
         hypdev::lmi_state_kernel<<<g.count, 256, 0, ctx->stream>>>(g.count, g.d_off, g.d_dim, g.d_voff, g.d_vecs, g.d_kidx,
                                                                   g.d_moff, ctx->d_point, ctx->d_grad, g.d_W, ctx->d_feas);
     else if (g.type == HYP_CONE_WSOSINTERPNONNEGATIVE)
@@ -207,7 +239,11 @@ void hyp_gpow_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr, 
     else if (mode == HYP_PROD_BLOCK_INV) { hess_dual = 1; inv_dual = 0; }
     else throw HypError{"hyp_gpow_prod: bad mode"};
     if (hess_dual > -2) {
-        if (g.type == HYP_CONE_WSOSINTERPNONNEGATIVE || g.type == HYP_CONE_LINMATRIXINEQ)
+        if (g.type == HYP_CONE_DOUBLYNONNEGATIVETRI)
+            hypdev::dnn_prod_kernel<<<grid, 256, 0, ctx->stream>>>(g.count, hess_dual, g.d_off, g.d_dim, g.d_hkind,
+                                                                  g.d_voff, g.d_vecs, g.d_dual, ctx->d_point, arr, ld_arr,
+                                                                  prod, ld_prod, ncols, row_shift);
+        else if (g.type == HYP_CONE_WSOSINTERPNONNEGATIVE || g.type == HYP_CONE_LINMATRIXINEQ)
             hypdev::gen_hess_prod_kernel<<<grid, 256, 0, ctx->stream>>>(g.count, hess_dual, g.d_off, g.d_dim, g.d_moff,
                                                                        g.d_dual, g.d_W, arr, ld_arr, prod, ld_prod, ncols,
                                                                        row_shift);
@@ -236,7 +272,10 @@ void hyp_gpow_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr, 
 }
 
 void hyp_gpow_dder3(hyp_ctx* ctx, ConeGroup& g, double* out, const double* dir) {
-    if (g.type == HYP_CONE_LINMATRIXINEQ)
+    if (g.type == HYP_CONE_DOUBLYNONNEGATIVETRI)
+        hypdev::dnn_dder3_kernel<<<ceil_div(g.count, 4), 128, 0, ctx->stream>>>(
+            g.count, g.d_off, g.d_dim, g.d_hkind, g.d_voff, g.d_vecs, ctx->d_point, dir, out);
+    else if (g.type == HYP_CONE_LINMATRIXINEQ)
         hypdev::lmi_dder3_kernel<<<g.count, 256, 0, ctx->stream>>>(g.count, g.d_off, g.d_dim, g.d_voff, g.d_vecs, dir, out);
     else if (g.type == HYP_CONE_WSOSINTERPNONNEGATIVE)
         hypdev::wsos_dder3_kernel<<<g.count, 256, 0, ctx->stream>>>(g.count, g.d_off, g.d_dim, g.d_voff, g.d_vecs, dir, out);

@@ -939,4 +939,178 @@ lmi_dder3_kernel(int ncones, const int64_t* __restrict__ off, const int* __restr
 }
 
 
+// ---- DoublyNonnegativeTri (dim = svec_length(side) <= 128, so side <= 15), doublynonnegativetri.jl:128-205 ----
+// Per-cone workspace at vecs + voff[c]: Zi = W^-1 (side^2, full symmetric) and the upper Cholesky factor of W (side^2).
+// One warp per cone / per (cone, column); the congruences Zi M Zi run on side x side matrices in shared memory.
+
+// svec index p -> (i, j), i <= j, column-major upper triangle: p = j (j + 1) / 2 + i
+__device__ __forceinline__ void dnn_ij(int p, int& i, int& j) {
+    j = 0;
+    while ((j + 1) * (j + 2) / 2 <= p) j++;
+    i = p - j * (j + 1) / 2;
+}
+// M (side x side, full) <- smat(v): off-diagonal entries of svec are scaled by 1/sqrt(2)
+__device__ __forceinline__ void dnn_smat(double* Mx, const double* v, int side, int d, int lane) {
+    for (int p = lane; p < d; p += 32) {
+        int i, j;
+        dnn_ij(p, i, j);
+        const double x = i == j ? v[p] : v[p] * 0.70710678118654752440;
+        Mx[i + j * side] = x;
+        Mx[j + i * side] = x;
+    }
+}
+// O = X Y for side x side matrices
+__device__ __forceinline__ void dnn_mm(double* O, const double* X, const double* Y, int side, int lane, bool y_transposed) {
+    for (int idx = lane; idx < side * side; idx += 32) {
+        const int a = idx % side, b = idx / side;
+        double s = 0.0;
+        for (int k = 0; k < side; k++) s += X[a + k * side] * (y_transposed ? Y[b + k * side] : Y[k + b * side]);
+        O[idx] = s;
+    }
+}
+
+static __global__ void __launch_bounds__(256)
+dnn_state_kernel(int ncones, const int64_t* __restrict__ off, const int* __restrict__ dim,
+                 const int* __restrict__ sides, const int64_t* __restrict__ voff, double* __restrict__ vecs,
+                 const int* __restrict__ kidx, const int64_t* __restrict__ moff, const double* __restrict__ point,
+                 double* __restrict__ grad, double* __restrict__ H, uint8_t* feas) {
+    const int lane = threadIdx.x & 31;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= ncones) return;
+    const int64_t o = off[c];
+    const int d = dim[c], side = sides[c], lde = (d + 1) & ~1;
+    double* Zi = vecs + voff[c];
+    double* Uz = Zi + side * side;
+    const double* pt = point + o;
+    // update_feas (:128-142): every svec entry positive, then Cholesky of smat(point)
+    double nbad = 0.0;
+    for (int p = lane; p < d; p += 32)
+        if (!(pt[p] > HYP_EPS)) nbad += 1.0;
+    nbad = warp_sum(nbad);
+    dnn_smat(Uz, pt, side, d, lane);
+    __syncwarp();
+    int ok = nbad == 0.0 ? 1 : 0;
+    if (lane == 0) {
+        for (int j = 0; j < side; j++) {
+            double s = Uz[j + j * side];
+            for (int k = 0; k < j; k++) s -= Uz[k + j * side] * Uz[k + j * side];
+            if (!(s > 0.0)) {
+                ok = 0;
+                s = 1.0;
+            }
+            const double r = sqrt(s);
+            Uz[j + j * side] = r;
+            for (int i = j + 1; i < side; i++) {
+                double t = Uz[j + i * side];
+                for (int k = 0; k < j; k++) t -= Uz[k + j * side] * Uz[k + i * side];
+                Uz[j + i * side] = t / r;
+            }
+        }
+    }
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    __syncwarp();
+    // update_grad (:144-155): Zi = W^-1 (column by column), grad = -svec(Zi) - 1 / offdiag
+    for (int b = lane; b < side; b += 32) {
+        double* x = Zi + b * side;
+        for (int i = 0; i < side; i++) x[i] = i == b ? 1.0 : 0.0;
+        ens_zsolve_col(Uz, side, x);
+    }
+    __syncwarp();
+    for (int idx = lane; idx < side * side; idx += 32) {     // copytri!(inv_mat, 'U')
+        const int a = idx % side, b = idx / side;
+        if (a > b) Zi[idx] = Zi[b + a * side];
+    }
+    __syncwarp();
+    for (int p = lane; p < d; p += 32) {
+        int i, j;
+        dnn_ij(p, i, j);
+        grad[o + p] = i == j ? -Zi[i + j * side] : -1.41421356237309504880 * Zi[i + j * side] - 1.0 / pt[p];
+    }
+    if (lane == 0 && !ok) feas[kidx[c]] = 0;
+    // update_hess (:157-171): symm_kron(Zi) + Diagonal(1 / offdiag^2), both triangles
+    double* Hc = H + moff[c];
+    for (int idx = lane; idx < d * d; idx += 32) {
+        const int p = idx % d, q = idx / d;
+        int i, j, k, l;
+        dnn_ij(p, i, j);
+        dnn_ij(q, k, l);
+        double v;
+        if (i == j && k == l) v = Zi[i + k * side] * Zi[i + k * side];
+        else if (i == j) v = 1.41421356237309504880 * Zi[i + k * side] * Zi[i + l * side];
+        else if (k == l) v = 1.41421356237309504880 * Zi[i + k * side] * Zi[j + k * side];
+        else v = Zi[i + k * side] * Zi[j + l * side] + Zi[i + l * side] * Zi[j + k * side];
+        if (p == q && i != j) v += 1.0 / (pt[p] * pt[p]);
+        Hc[p + (int64_t)q * lde] = v;
+    }
+}
+
+// hess_prod!, doublynonnegativetri.jl:173-193
+static __global__ void __launch_bounds__(256)
+dnn_prod_kernel(int ncones, int want_dual, const int64_t* __restrict__ off, const int* __restrict__ dim,
+                const int* __restrict__ sides, const int64_t* __restrict__ voff, const double* __restrict__ vecs,
+                const int* __restrict__ dualf, const double* __restrict__ point, const double* arr, int64_t ld_arr,
+                double* prod, int64_t ld_prod, int64_t ncols, int64_t row_shift) {
+    __shared__ double sh[8][2 * 232];
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= ncones) return;
+    if (want_dual >= 0 && (dualf[c] != 0) != (want_dual != 0)) return;
+    double* Mx = sh[threadIdx.x >> 5];
+    double* T = Mx + 232;
+    const int64_t o = off[c];
+    const int d = dim[c], side = sides[c];
+    const double* Zi = vecs + voff[c];
+    const double* pt = point + o;
+    for (int64_t jc = blockIdx.y; jc < ncols; jc += gridDim.y) {
+        const double* a = arr + jc * ld_arr + (o - row_shift);
+        double* pr = prod + jc * ld_prod + (o - row_shift);
+        dnn_smat(Mx, a, side, d, lane);
+        __syncwarp();
+        dnn_mm(T, Zi, Mx, side, lane, false);          // T = Zi M
+        __syncwarp();
+        dnn_mm(Mx, T, Zi, side, lane, false);          // M <- Zi M Zi
+        __syncwarp();
+        for (int p = lane; p < d; p += 32) {
+            int i, j;
+            dnn_ij(p, i, j);
+            const double ap = a[p];
+            pr[p] = i == j ? Mx[i + j * side] : 1.41421356237309504880 * Mx[i + j * side] + ap / (pt[p] * pt[p]);
+        }
+        __syncwarp();
+    }
+}
+
+// dder3, doublynonnegativetri.jl:195-205: svec(Zi D Zi D Zi) + (dir / s)^2 / s on the off-diagonal entries
+static __global__ void __launch_bounds__(128)
+dnn_dder3_kernel(int ncones, const int64_t* __restrict__ off, const int* __restrict__ dim,
+                 const int* __restrict__ sides, const int64_t* __restrict__ voff, const double* __restrict__ vecs,
+                 const double* __restrict__ point, const double* __restrict__ dir, double* __restrict__ out) {
+    __shared__ double sh[4][3 * 232];
+    const int lane = threadIdx.x & 31;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= ncones) return;
+    double* D = sh[threadIdx.x >> 5];
+    double* T1 = D + 232;
+    double* T2 = T1 + 232;
+    const int64_t o = off[c];
+    const int d = dim[c], side = sides[c];
+    const double* Zi = vecs + voff[c];
+    const double* pt = point + o;
+    dnn_smat(D, dir + o, side, d, lane);
+    __syncwarp();
+    dnn_mm(T1, Zi, D, side, lane, false);              // T1 = Zi D
+    __syncwarp();
+    dnn_mm(T2, T1, Zi, side, lane, false);             // T2 = Zi D Zi
+    __syncwarp();
+    dnn_mm(D, T2, T1, side, lane, true);               // D <- T2 T1' = Zi D Zi D Zi
+    __syncwarp();
+    for (int p = lane; p < d; p += 32) {
+        int i, j;
+        dnn_ij(p, i, j);
+        const double r = dir[o + p] / pt[p];
+        out[o + p] = i == j ? D[i + j * side] : 1.41421356237309504880 * D[i + j * side] + r * r / pt[p];
+    }
+}
+
+
 }  // namespace hypdev

@@ -106,6 +106,11 @@ def cone_initial_point(spec):
         arr[2:] = w
     elif spec.ctype == M.CONE_EPINORMINF:
         arr[0] = np.sqrt(spec.dim)      # epinorminf.jl:88-95
+    elif spec.ctype == M.CONE_DOUBLYNONNEGATIVETRI:
+        side = M.svec_side(spec.dim)
+        ond, offd = dnn_initial_point(side)
+        arr[:] = offd
+        arr[_svec_diag_idx(side)] = ond
     elif spec.ctype == M.CONE_LINMATRIXINEQ:
         arr[0] = 1.0                            # linmatrixineq.jl:74-82
     elif spec.ctype == M.CONE_WSOSINTERPNONNEGATIVE:
@@ -155,6 +160,28 @@ def cone_initial_point(spec):
     return arr
 
 
+def dnn_initial_point(side):
+    """doublynonnegativetri.jl:72-126: (on-diagonal, off-diagonal) value of the central point in svec coordinates."""
+    if side == 1:
+        return 1.0, 1.0
+    if side == 2:
+        return np.sqrt(5.0) / 2, 1 / np.sqrt(2.0)
+    n, d = float(side), float(side * (side + 1) // 2)
+    rt2 = np.sqrt(2.0)
+    # roots of p1 (coefficients by ascending power in the reference) give the off-diagonal value
+    p1 = [-n - 1, 0, n ** 2 + n + 7, 0, -2 * n ** 2 - 8, 0, n ** 2]
+    for r in np.roots(p1[::-1]):
+        offd = float(np.real(r))
+        if offd > 0:
+            temp = d - (d - n) * offd ** 2
+            if temp > np.sqrt(np.finfo(np.float64).eps):
+                ond = np.sqrt(temp / n)
+                denom = ond ** 2 + (n - 2) / rt2 * ond * offd - (n - 1) * offd ** 2 / 2
+                if np.isclose(ond * rt2 + (n - 2) * offd, ond * denom * rt2) and np.isclose(denom, offd ** 2 * (denom + 1)):
+                    return ond, offd
+    return n + 1, 1.0
+
+
 _CENTRAL_EPIRELENTROPY = np.array([      # epirelentropy.jl:398-409
     [0.827838399, 1.290927714, 0.805102005], [0.708612491, 1.256859155, 0.818070438],
     [0.622618845, 1.231401008, 0.829317079], [0.558111266, 1.211710888, 0.838978357],
@@ -175,6 +202,8 @@ def _central_ray_epirelentropy(d):
 
 def _cone_dual_initial(spec, prim):
     """-grad at the central point, closed form per cone (dual of the central point)."""
+    if spec.ctype == M.CONE_DOUBLYNONNEGATIVETRI:
+        return prim.copy()      # the initial point satisfies s = -g(s) (doublynonnegativetri.jl:72-126)
     if spec.ctype == M.CONE_LINMATRIXINEQ:
         # -grad_i = tr(S^-1 A_i) with S = sum_j w_j A_j, linmatrixineq.jl:98-109
         As = M.lmi_unpack(spec)
@@ -294,6 +323,9 @@ def _perturb(rng, spec, vec, noise):
         return vec
     if spec.ctype == M.CONE_EPIPERSEPSPECTRAL_VEC:
         vec += noise / (2.0 * (vec.size - 2)) * (2 * rng.random(vec.size) - 1)   # the initial point is not central
+        return vec
+    if spec.ctype == M.CONE_DOUBLYNONNEGATIVETRI:
+        vec += 0.5 * noise / np.sqrt(vec.size) * (2 * rng.random(vec.size) - 1)
         return vec
     if spec.ctype == M.CONE_LINMATRIXINEQ:
         vec += 0.1 * noise / np.sqrt(vec.size) * (2 * rng.random(vec.size) - 1)    # test/cone.jl:426 uses noise 1e-2

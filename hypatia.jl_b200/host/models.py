@@ -29,6 +29,7 @@ CONE_EPIRELENTROPY = 13
 CONE_EPINORMSPECTRAL = 14
 CONE_WSOSINTERPNONNEGATIVE = 15
 CONE_LINMATRIXINEQ = 16
+CONE_DOUBLYNONNEGATIVETRI = 17
 
 # separable spectral functions of EpiPerSepSpectral (sepspectralfun.jl:17-116), HYP_SSF_*
 SSF_INV, SSF_NEGLOG, SSF_NEGENTROPY, SSF_POWER12 = 0, 1, 2, 3
@@ -51,6 +52,7 @@ CONE_NAMES = {
     CONE_EPINORMSPECTRAL: "EpiNormSpectral",
     CONE_WSOSINTERPNONNEGATIVE: "WSOSInterpNonnegative",
     CONE_LINMATRIXINEQ: "LinMatrixIneq",
+    CONE_DOUBLYNONNEGATIVETRI: "DoublyNonnegativeTri",
 }
 
 
@@ -104,6 +106,9 @@ class ConeSpec:
             assert dim >= 3
         elif ctype == CONE_HYPOPERLOG:
             assert dim >= 3
+        elif ctype == CONE_DOUBLYNONNEGATIVETRI:
+            assert dim >= 1
+            svec_side(dim)
         elif ctype == CONE_LINMATRIXINEQ:
             # alpha = packed data [side, vec(A_1) .. vec(A_dim)], A_i symmetric side x side (linmatrixineq.jl:38-66)
             side = int(self.alpha[0])
@@ -168,7 +173,7 @@ class ConeSpec:
         if self.ctype == CONE_WSOSINTERPNONNEGATIVE:
             return float(sum(self.alpha[1:1 + int(self.alpha[0])]))    # wsosinterpnonnegative.jl:62
         if self.ctype in (CONE_HYPOPERLOG, CONE_EPINORMINF, CONE_EPIPERSEPSPECTRAL_VEC, CONE_HYPOGEOMEAN,
-                          CONE_HYPOPOWERMEAN, CONE_EPIRELENTROPY):
+                          CONE_HYPOPOWERMEAN, CONE_EPIRELENTROPY, CONE_DOUBLYNONNEGATIVETRI):
             return float(self.dim)
         return 1.0 + self.side
 
@@ -232,6 +237,11 @@ def WSOSInterpNonnegative(U, Ps, use_dual=False):
     assert all(P.ndim == 2 and P.shape[0] == U for P in Ps)
     packed = np.concatenate([[float(len(Ps))], [float(P.shape[1]) for P in Ps]] + [P.ravel(order="F") for P in Ps])
     return ConeSpec(CONE_WSOSINTERPNONNEGATIVE, U, not use_dual, alpha=packed)
+
+
+def DoublyNonnegativeTri(dim, use_dual=False):
+    """DoublyNonnegativeTri{Float64}(dim): svec of a symmetric matrix that is psd and entrywise nonnegative."""
+    return ConeSpec(CONE_DOUBLYNONNEGATIVETRI, dim, use_dual)
 
 
 def LinMatrixIneq(As, use_dual=False):

@@ -47,6 +47,7 @@ cone_code(::Cones.EpiRelEntropy) = Cint(13)
 cone_code(::Cones.EpiNormSpectral{Float64, Float64}) = Cint(14)
 cone_code(::Cones.WSOSInterpNonnegative{Float64, Float64}) = Cint(15)
 cone_code(::Cones.LinMatrixIneq{Float64}) = Cint(16)
+cone_code(::Cones.DoublyNonnegativeTri{Float64}) = Cint(17)
 # packed matrices [side, vec(A_1) .. vec(A_dim)] (dense real symmetric A_i; UniformScaling entries are materialised)
 cone_alpha(c::Cones.LinMatrixIneq{Float64}) =
     vcat(Float64(c.side), (vec(Matrix{Float64}(A isa UniformScaling ? A(c.side) : A)) for A in c.As)...)

@@ -770,6 +770,9 @@ def make_cone(spec):
     if spec.ctype == M.CONE_EPIPERSEPSPECTRAL_VEC:
         from .cones_sepspec import EpiPerSepSpectralVec
         return EpiPerSepSpectralVec(spec.dim, spec.hkind, spec.hparam, use_dual=spec.use_dual)
+    if spec.ctype == M.CONE_DOUBLYNONNEGATIVETRI:
+        from .cones_vec3 import DoublyNonnegativeTri
+        return DoublyNonnegativeTri(spec.dim, use_dual=spec.use_dual)
     if spec.ctype == M.CONE_LINMATRIXINEQ:
         from .cones_vec3 import LinMatrixIneq
         return LinMatrixIneq(M.lmi_unpack(spec), use_dual=spec.use_dual)

@@ -859,6 +859,84 @@ class WSOSInterpNonnegative(Cone):
         return d3
 
 
+from hypatia_b200.host.instances import dnn_initial_point  # noqa: E402  (doublynonnegativetri.jl:72-126)
+
+
+class DoublyNonnegativeTri(Cone):
+    """doublynonnegativetri.jl:8-205: symmetric matrices (svec) that are positive semidefinite AND entrywise nonnegative;
+    barrier -logdet(W) - sum of log over the off-diagonal svec entries, nu = dim.  inv_hess_prod! is the generic
+    factorisation fallback (Cones.jl:113-118), is_dual_feas the generic `true`."""
+    ctype = M.CONE_DOUBLYNONNEGATIVETRI
+
+    def __init__(self, dim, use_dual=False):
+        self.side = M.svec_side(dim)
+        self.use_dual_barrier = use_dual
+        self.offdiag = np.array([j * (j + 1) // 2 + i for j in range(self.side) for i in range(j)], dtype=np.int64)
+        super().__init__(dim)
+
+    @property
+    def nu(self):
+        return float(self.dim)
+
+    def set_initial_point(self, arr):
+        ond, offd = dnn_initial_point(self.side)
+        arr[:] = offd
+        arr[[j * (j + 1) // 2 + j for j in range(self.side)]] = ond
+        return arr
+
+    def update_feas(self):
+        # doublynonnegativetri.jl:128-142
+        from . import arrayutil as au
+        if (self.point > EPS).all():
+            self.mat = au.svec_to_smat(self.point)
+            try:
+                self.fact = sla.cho_factor(self.mat, lower=False, check_finite=False)
+            except np.linalg.LinAlgError:
+                return False
+            return True
+        return False
+
+    def update_grad(self):
+        # doublynonnegativetri.jl:144-155
+        from . import arrayutil as au
+        self.inv_mat = sla.cho_solve(self.fact, np.eye(self.side), check_finite=False)
+        self.inv_mat = (self.inv_mat + self.inv_mat.T) / 2
+        self._grad[:] = -au.smat_to_svec(self.inv_mat)
+        self._grad[self.offdiag] -= 1.0 / self.point[self.offdiag]
+
+    def update_hess(self):
+        # doublynonnegativetri.jl:157-171
+        from . import arrayutil as au
+        self.grad()
+        H = au.symm_kron(self.inv_mat)
+        H[self.offdiag, self.offdiag] += self.point[self.offdiag] ** -2
+        return H
+
+    def hess_prod(self, arr):
+        # doublynonnegativetri.jl:173-193
+        from . import arrayutil as au
+        self.grad()
+        a, vec = _as2d(arr)
+        prod = np.empty_like(a)
+        for j in range(a.shape[1]):
+            Mx = au.svec_to_smat(a[:, j])
+            prod[:, j] = au.smat_to_svec(self.inv_mat @ Mx @ self.inv_mat)
+        so = self.point[self.offdiag]
+        prod[self.offdiag] += a[self.offdiag] / (so * so)[:, None]
+        return _ret(prod, vec)
+
+    def dder3(self, direction):
+        # doublynonnegativetri.jl:195-205
+        from . import arrayutil as au
+        self.grad()
+        D = au.svec_to_smat(direction)
+        T1 = self.inv_mat @ D
+        d3 = au.smat_to_svec(T1 @ self.inv_mat @ T1.T)
+        so = self.point[self.offdiag]
+        d3[self.offdiag] += (direction[self.offdiag] / so) ** 2 / so
+        return d3
+
+
 class LinMatrixIneq(Cone):
     """linmatrixineq.jl:8-159 (real dense matrices): {w : sum_i w_i A_i psd} for symmetric A_i (side x side, A_1 positive
     definite), barrier -logdet(sum_i w_i A_i), nu = side.  hess_prod! / inv_hess_prod! are the generic explicit-Hessian

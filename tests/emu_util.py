@@ -298,6 +298,12 @@ class EmuGpowGroup:
         self.K = len(specs)
         self.hpm = specs[0].ctype == 12          # HypoPowerMean, else GeneralizedPower
         self.ens = specs[0].ctype == 14          # EpiNormSpectral: d1 per cone, workspace instead of powers
+        self.dnn = specs[0].ctype == 17          # DoublyNonnegativeTri: side per cone + workspace
+        if self.dnn:
+            self.sides = np.array([int(round((np.sqrt(1 + 8 * s.dim) - 1) / 2)) for s in specs], dtype=np.int32)
+            sizes = [2 * int(sd) ** 2 for sd in self.sides]
+            self.voff = np.concatenate(([0], np.cumsum(sizes)))[:-1].astype(np.int64)
+            self.vecs = np.zeros(int(sum(sizes)))
         self.lmi = specs[0].ctype == 16          # LinMatrixIneq: packed As + workspace
         if self.lmi:
             regions = []
@@ -339,7 +345,10 @@ class EmuGpowGroup:
         self.dual_feas = np.ones(self.K, dtype=np.uint8)
         self.grad = np.zeros(self.q)
         self.H = np.zeros(self.lay.total)
-        if self.lmi:
+        if self.dnn:
+            lib().emu_dnn_state(self.K, p(self.off), p(self.dims), p(self.sides), p(self.voff), p(self.vecs), p(self.kidx),
+                                p(self.lay.moff), p(self.point), p(self.grad), p(self.H), p(self.feas))
+        elif self.lmi:
             lib().emu_lmi_state(self.K, p(self.off), p(self.dims), p(self.voff), p(self.vecs), p(self.kidx),
                                 p(self.lay.moff), p(self.point), p(self.grad), p(self.H), p(self.feas))
         elif self.wsos:
@@ -371,7 +380,10 @@ class EmuGpowGroup:
         out = a if in_place else np.zeros_like(a, order="F")
         hess_dual, inv_dual = {0: (-1, -2), 1: (-2, -1), 4: (0, 1), 5: (1, 0)}[int(mode)]
         L = lib()
-        if hess_dual > -2 and (self.wsos or self.lmi):
+        if hess_dual > -2 and self.dnn:
+            L.emu_dnn_prod(self.K, hess_dual, p(self.off), p(self.dims), p(self.sides), p(self.voff), p(self.vecs),
+                           p(self.dualf), p(self.point), p(a), i64(self.q), p(out), i64(self.q), i64(a.shape[1]), i64(0))
+        elif hess_dual > -2 and (self.wsos or self.lmi):
             L.emu_gen_hess_prod(self.K, hess_dual, p(self.off), p(self.dims), p(self.lay.moff), p(self.dualf), p(self.H),
                                 p(a), i64(self.q), p(out), i64(self.q), i64(a.shape[1]), i64(0))
         elif hess_dual > -2 and self.ens:
@@ -393,7 +405,10 @@ class EmuGpowGroup:
     def dder3(self, direction):
         d = np.ascontiguousarray(direction, dtype=np.float64)
         out = np.zeros(self.q)
-        if self.lmi:
+        if self.dnn:
+            lib().emu_dnn_dder3(self.K, p(self.off), p(self.dims), p(self.sides), p(self.voff), p(self.vecs),
+                                p(self.point), p(d), p(out))
+        elif self.lmi:
             lib().emu_lmi_dder3(self.K, p(self.off), p(self.dims), p(self.voff), p(self.vecs), p(d), p(out))
         elif self.wsos:
             lib().emu_wsos_dder3(self.K, p(self.off), p(self.dims), p(self.voff), p(self.vecs), p(d), p(out))

@@ -844,6 +844,19 @@ EXTRA = [consistent1, inconsistent1, inconsistent2, nonnegative1, nonnegative2, 
     [_named(lambda f=_f, ud=_ud: f(ud), _f.__name__[1:] + ("_dual" if _ud else ""))
      for _f in (_hypogeomean3, _hypopowermean3) for _ud in (False, True)]
 
+def doublynonnegativetri1():  # :493-511 (the reference's loop overrides use_dual to false)
+    return _m([0, 1, 0], [[1, 0, 0], [0, 0, 1]], [1, 1], -np.eye(3), np.zeros(3), [M.DoublyNonnegativeTri(3)]), \
+        dict(status="Optimal", primal_obj=0, x=[1, 0, 1], s=[1, 0, 1])
+
+
+def doublynonnegativetri2():  # :513-526
+    return _m([0, -1, 0], [[1, 0, 0], [0, 0, 1]], [1.0, 1.5], -np.eye(3), [-0.5, 0, -0.5], [M.DoublyNonnegativeTri(3)]), \
+        dict(status="Optimal", primal_obj=-1, x_idx={1: 1.0})
+
+
+DNN = [doublynonnegativetri1, doublynonnegativetri2]
+
+
 def _linmatrixineq1(side):  # :696-719 (real case): min w_1 : w_1 A_1 - 2 v v' psd  =>  2 / lambda_max(A_1)
     H = np.random.default_rng(side).random((side, side))
     A1 = H @ H.T + 2 * np.eye(side)
@@ -880,7 +893,7 @@ def linmatrixineq3():  # :747-788 (dense case): min w_1 : w_1 I - diag(1, -1) ps
 
 LMI = [_named(lambda s=_s: _linmatrixineq1(s), f"linmatrixineq1_side{_s}") for _s in (2, 4)] + \
     [_named(lambda d=_d: _linmatrixineq2(d), f"linmatrixineq2_dim{_d}") for _d in (2, 3)] + [linmatrixineq3]
-EXTRA = EXTRA + LMI
+EXTRA = EXTRA + LMI + DNN
 
 RELENT = [_named(lambda d=_d: _epirelentropy1(d), f"epirelentropy1_d{_d}") for _d in (1, 2, 3)] + \
     [_named(lambda d=_d: _epirelentropy2(d), f"epirelentropy2_d{_d}") for _d in (1, 2, 4)] + \

@@ -41,6 +41,8 @@ def _lmi(rng, side, dim, use_dual=False):
 def _sets():
     rng = np.random.default_rng(7)
     return {
+        "dnn": [M.DoublyNonnegativeTri(M.svec_length(sd)) for sd in (1, 2, 3, 5, 10, 15)] +
+               [M.DoublyNonnegativeTri(M.svec_length(4), use_dual=True)],
         "lmi": [_lmi(rng, 2, 2), _lmi(rng, 3, 2), _lmi(rng, 4, 3), _lmi(rng, 3, 6), _lmi(rng, 12, 40),
                 _lmi(rng, 5, 4, use_dual=True), _lmi(rng, 33, 20)],
         "wsos": [_wsos(1, 1), _wsos(1, 3), _wsos(2, 2), _wsos(3, 1), _wsos(2, 4), _wsos(1, 2, use_dual=True),
@@ -57,7 +59,7 @@ def _sets():
     }
 
 
-NAMES = ["gpow", "gpow_dual", "hpm", "hpm_dual", "normspec", "normspec_dual", "wsos", "lmi"]
+NAMES = ["gpow", "gpow_dual", "hpm", "hpm_dual", "normspec", "normspec_dual", "wsos", "lmi", "dnn"]
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -135,3 +137,18 @@ def test_normspec_kernels_flag_infeasible_points():
     # the explicit Hessian of cone 2 (1e-6 from the boundary) may fail its Cholesky on either side: compare the cone's own flag
     assert (dev.feas.astype(bool)[[0, 1, 3]] == ora.is_feas()[[0, 1, 3]]).all()
     assert (dev.dual_feas.astype(bool) == ora.is_dual_feas()).all()
+
+
+def test_dnn_kernels_flag_infeasible_points():
+    """DoublyNonnegativeTri leaves the cone through a nonpositive svec entry or through an indefinite matrix."""
+    cones = [M.DoublyNonnegativeTri(6), M.DoublyNonnegativeTri(6), M.DoublyNonnegativeTri(3), M.DoublyNonnegativeTri(10)]
+    I = inst.synthetic("dnninf", 2, 0, cones, seed=14)
+    prim, dual = (x.copy() for x in I.point.primal_dual(None))
+    prim[1] = -0.01                                   # cone 0: a negative off-diagonal entry
+    prim[6:12] = [1, 3 * np.sqrt(2), 1, 0.1, 0.1, 1]  # cone 1: entrywise positive but indefinite leading 2 x 2
+    ora = OracleConeBlock(I.model)
+    ora.load_point(prim, dual, 1.0)
+    dev = eu.EmuGpowGroup(cones)
+    dev.load_point(prim, dual)
+    assert (ora.is_feas() == np.array([False, False, True, True])).all()
+    assert (dev.feas.astype(bool) == ora.is_feas()).all()

@@ -1,7 +1,7 @@
 """-m gpu tests written when the GPU budget of the round was (almost) spent.  The two LinMatrixIneq tests passed on a B200
 with the last seconds of it (profiles/r01_pytest_gpu_lmi.log); test_kat_device_extra - full device solves of the
-reference instances added late in the CPU (oracle) tier, all on device code that is already GPU-verified - has NOT run on
-a GPU yet.  The file name sorts last on purpose: a failure here cannot mask a verified test under `pytest -x`."""
+reference instances added late in the CPU (oracle) tier - and the DoublyNonnegativeTri tests (kernels verified by the CPU
+emulation tier only, tests/test_emu_gpow.py) have NOT run on a GPU yet.  The file name sorts last on purpose: a failure here cannot mask a verified test under `pytest -x`."""
 import numpy as np
 import pytest
 
@@ -46,6 +46,51 @@ def test_linmatrixineq_oracles_match_cpu_oracle():
     assert rel(dev.hess_prod(pt), -g) <= 1e-10                      # test/cone.jl:50,78
     assert abs(float(pt @ g) + I.model.nu) <= 1e-9 * I.model.nu     # test/cone.jl:71
     dev.free()
+
+
+def test_doublynonnegativetri_oracles_match_cpu_oracle():
+    """Not yet run on a GPU (emulation tier: tests/test_emu_gpow.py)."""
+    from hypatia_b200.cones import DeviceConeBlock
+    from oracle.cones import OracleConeBlock
+    cones = [M.DoublyNonnegativeTri(M.svec_length(sd)) for sd in (1, 2, 3, 5, 10, 15)] + \
+        [M.DoublyNonnegativeTri(M.svec_length(4), use_dual=True), M.EpiNormEucl(4)]
+    I = inst.synthetic("dnn", 4, 0, cones, seed=78)
+    dev, ora = DeviceConeBlock(I.model), OracleConeBlock(I.model)
+    prim, dual = I.point.primal_dual(ora.dual_mask)
+    scal = 1 / np.sqrt(I.mu)
+    dev.load_point(prim, dual, scal)
+    ora.load_point(prim, dual, scal)
+    assert dev.is_feas().all() and ora.is_feas().all()
+    g = dev.grad()
+    assert rel(g, ora.grad()) <= 1e-11
+    arr = np.random.default_rng(1).standard_normal((I.model.q, 3))
+    assert rel(dev.hess_prod(arr), ora.hess_prod(arr)) <= 1e-10
+    assert rel(dev.inv_hess_prod(arr), ora.inv_hess_prod(arr)) <= 1e-9
+    assert rel(dev.block_hess_prod(arr[:, 0]), ora.block_hess_prod(arr[:, 0])) <= 1e-9
+    assert rel(dev.dder3(arr[:, 1]), ora.dder3(arr[:, 1])) <= 1e-10
+    pt = scal * prim
+    assert rel(dev.hess_prod(pt), -g) <= 1e-10                      # test/cone.jl:50,78
+    assert abs(float(pt @ g) + I.model.nu) <= 1e-9 * I.model.nu     # test/cone.jl:71
+    dev.free()
+
+
+def test_doublynonnegativetri_in_the_system_solve():
+    """Not yet run on a GPU."""
+    from hypatia_b200.syssolver import QRCholDenseSystemSolver as DevQRChol
+    from oracle.syssolvers import QRCholDenseSystemSolver as OraQRChol
+    cones = [M.DoublyNonnegativeTri(10), M.Nonnegative(3), M.DoublyNonnegativeTri(6, use_dual=True), M.EpiNormEucl(4)]
+    I = inst.synthetic("dnnmix", 8, 0, cones, seed=32)
+    dev, ora = iterate_solver(I, DevQRChol()), iterate_solver(I, OraQRChol())
+    try:
+        assert rel(dev.syssolver.lhs_full(), ora.syssolver.lhs_full()) <= 1e-11
+        rhs = Point(I.model)
+        rhs.vec[:] = np.random.default_rng(3).standard_normal(rhs.vec.size)
+        sd, so = Point(I.model), Point(I.model)
+        dev.syssolver.solve_system(dev, sd, rhs)
+        ora.syssolver.solve_system(ora, so, rhs)
+        assert rel(sd.vec, so.vec) <= 1e-8
+    finally:
+        dev.syssolver.free_memory()
 
 
 def test_linmatrixineq_in_the_system_solve():

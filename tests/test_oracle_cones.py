@@ -279,6 +279,50 @@ def test_wsosinterpnonnegative_barrier():
     assert close(-2 * cone.dder3(direction), fd_third, 1e-5)
 
 
+@pytest.mark.parametrize("side,init_only", [(1, False), (2, False), (5, False), (10, True), (20, True)])
+def test_doublynonnegativetri(side, init_only):
+    # reference: test/cone.jl:353-361 (init_tol = sqrt(eps))
+    from oracle.cones_vec3 import DoublyNonnegativeTri
+    run_oracles(DoublyNonnegativeTri(side * (side + 1) // 2), init_tol=np.sqrt(EPS), init_only=init_only)
+
+
+def test_doublynonnegativetri_barrier():
+    """test/cone.jl:363-371 with central differences: -logdet(W) - sum log of the off-diagonal svec entries."""
+    from oracle import arrayutil as au
+    from oracle.cones_vec3 import DoublyNonnegativeTri
+    side = 3
+    cone = DoublyNonnegativeTri(6)
+    off = cone.offdiag
+
+    def barrier(s):
+        return -np.linalg.slogdet(au.svec_to_smat(s))[1] - np.sum(np.log(s[off]))
+
+    rng = np.random.default_rng(1)
+    point = np.zeros(6)
+    cone.set_initial_point(point)
+    perturb_scale(rng, point, 0.1, 1.0)
+
+    def grad_at(s):
+        cone.reset_data()
+        cone.load_point(s)
+        assert cone.is_feas()
+        return cone.grad().copy()
+
+    g = grad_at(point)
+    eps = 1e-6
+    fd_grad = np.array([(barrier(point + eps * e) - barrier(point - eps * e)) / (2 * eps) for e in np.eye(6)])
+    assert close(g, fd_grad, 1e-7)
+    direction = 0.3 * rng.standard_normal(6)
+    fd_hess_dir = (grad_at(point + eps * direction) - grad_at(point - eps * direction)) / (2 * eps)
+    grad_at(point)
+    assert close(cone.hess_prod(direction), fd_hess_dir, 1e-6)
+    assert close(cone.hess() @ direction, fd_hess_dir, 1e-6)
+    e2 = 1e-4
+    fd_third = (grad_at(point + e2 * direction) - 2 * g + grad_at(point - e2 * direction)) / e2 ** 2
+    grad_at(point)
+    assert close(-2 * cone.dder3(direction), fd_third, 1e-5)
+
+
 def rand_lmi(rng, side, dim):
     """rand_herms of test/cone.jl (real case): symmetric matrices with a positive definite first one."""
     As = []
