@@ -48,6 +48,41 @@ def test_linmatrixineq_oracles_match_cpu_oracle():
     dev.free()
 
 
+def test_linmatrixineq_in_the_system_solve():
+    from hypatia_b200.syssolver import QRCholDenseSystemSolver as DevQRChol
+    from oracle.syssolvers import QRCholDenseSystemSolver as OraQRChol
+    rng = np.random.default_rng(8)
+    cones = [_lmi(rng, 4, 5), M.EpiNormEucl(5), _lmi(rng, 3, 3, use_dual=True), M.Nonnegative(4)]
+    I = inst.synthetic("lmimix", 9, 0, cones, seed=31)
+    dev, ora = iterate_solver(I, DevQRChol()), iterate_solver(I, OraQRChol())
+    try:
+        assert rel(dev.syssolver.lhs_full(), ora.syssolver.lhs_full()) <= 1e-11
+        rhs = Point(I.model)
+        rhs.vec[:] = np.random.default_rng(3).standard_normal(rhs.vec.size)
+        sd, so = Point(I.model), Point(I.model)
+        dev.syssolver.solve_system(dev, sd, rhs)
+        ora.syssolver.solve_system(ora, so, rhs)
+        assert rel(sd.vec, so.vec) <= 1e-8
+    finally:
+        dev.syssolver.free_memory()
+
+
+def _solve_dev(model):
+    from hypatia_b200.cones import DeviceConeBlock
+    from hypatia_b200.host.solver import Solver
+    from hypatia_b200.syssolver import QRCholDenseSystemSolver as DevQRChol
+    s = Solver(model, DevQRChol(), DeviceConeBlock, default_tol_relax=10)    # test/runnativetests.jl:13-18
+    s.solve()
+    return s
+
+
+@pytest.mark.parametrize("build", kat.EXTRA, ids=lambda f: f.__name__)
+def test_kat_device_extra(build):
+    model, expected = build()
+    kat.check_solution(_solve_dev(model), model, expected)
+
+
+# the DoublyNonnegativeTri kernels have not run on a GPU at all: keep them after everything else
 def test_doublynonnegativetri_oracles_match_cpu_oracle():
     """Not yet run on a GPU (emulation tier: tests/test_emu_gpow.py)."""
     from hypatia_b200.cones import DeviceConeBlock
@@ -91,37 +126,3 @@ def test_doublynonnegativetri_in_the_system_solve():
         assert rel(sd.vec, so.vec) <= 1e-8
     finally:
         dev.syssolver.free_memory()
-
-
-def test_linmatrixineq_in_the_system_solve():
-    from hypatia_b200.syssolver import QRCholDenseSystemSolver as DevQRChol
-    from oracle.syssolvers import QRCholDenseSystemSolver as OraQRChol
-    rng = np.random.default_rng(8)
-    cones = [_lmi(rng, 4, 5), M.EpiNormEucl(5), _lmi(rng, 3, 3, use_dual=True), M.Nonnegative(4)]
-    I = inst.synthetic("lmimix", 9, 0, cones, seed=31)
-    dev, ora = iterate_solver(I, DevQRChol()), iterate_solver(I, OraQRChol())
-    try:
-        assert rel(dev.syssolver.lhs_full(), ora.syssolver.lhs_full()) <= 1e-11
-        rhs = Point(I.model)
-        rhs.vec[:] = np.random.default_rng(3).standard_normal(rhs.vec.size)
-        sd, so = Point(I.model), Point(I.model)
-        dev.syssolver.solve_system(dev, sd, rhs)
-        ora.syssolver.solve_system(ora, so, rhs)
-        assert rel(sd.vec, so.vec) <= 1e-8
-    finally:
-        dev.syssolver.free_memory()
-
-
-def _solve_dev(model):
-    from hypatia_b200.cones import DeviceConeBlock
-    from hypatia_b200.host.solver import Solver
-    from hypatia_b200.syssolver import QRCholDenseSystemSolver as DevQRChol
-    s = Solver(model, DevQRChol(), DeviceConeBlock, default_tol_relax=10)    # test/runnativetests.jl:13-18
-    s.solve()
-    return s
-
-
-@pytest.mark.parametrize("build", kat.EXTRA, ids=lambda f: f.__name__)
-def test_kat_device_extra(build):
-    model, expected = build()
-    kat.check_solution(_solve_dev(model), model, expected)
