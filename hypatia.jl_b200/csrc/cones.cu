@@ -10,321 +10,13 @@
 #include "common.cuh"
 #include "cones_mat.cuh"
 #include "cones_vec3_kernels.cuh"
+#include "cones_vec_kernels.cuh"
+
+static_assert(VK_HESS == HYP_PROD_HESS && VK_INV_HESS == HYP_PROD_INV_HESS && VK_SQRT_HESS == HYP_PROD_SQRT_HESS &&
+                  VK_INV_SQRT_HESS == HYP_PROD_INV_SQRT_HESS && VK_NONNEGATIVE == HYP_CONE_NONNEGATIVE,
+              "cones_vec_kernels.cuh constants must match the ABI");
 
 namespace {
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// ------------------------------------------------------------------ Nonnegative
-// nonnegative.jl:44-60: is_feas = all(point > eps), is_dual_feas likewise, grad = -1 / point
-__global__ void nn_state_kernel(int64_t nrows, const int* __restrict__ rows,
-                                const int* __restrict__ rowcone, const double* __restrict__ point,
-                                const double* __restrict__ dual, double* __restrict__ grad,
-                                uint8_t* feas, uint8_t* dual_feas) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nrows;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        int r = rows[i];
-        double s = point[r], z = dual[r];
-        grad[r] = -1.0 / s;
-        if (!(s > HYP_EPS)) feas[rowcone[i]] = 0;
-        if (!(z > HYP_EPS)) dual_feas[rowcone[i]] = 0;
-    }
-}
-
-// nonnegative.jl:82-120: hess arr/s/s, inv_hess arr*s*s, sqrt arr/s, inv_sqrt arr*s
-template <int MODE>
-__global__ void nn_prod_kernel(int64_t nrows, const int* __restrict__ rows,
-                               const double* __restrict__ point, const double* arr, int64_t ld_arr,
-                               double* prod, int64_t ld_prod, int64_t ncols, int64_t row_shift) {
-    for (int64_t j = blockIdx.y; j < ncols; j += gridDim.y) {
-        const double* a = arr + j * ld_arr - row_shift;
-        double* pr = prod + j * ld_prod - row_shift;
-        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nrows;
-             i += (int64_t)gridDim.x * blockDim.x) {
-            int r = rows[i];
-            double s = point[r], v = a[r];
-            double out;
-            if (MODE == HYP_PROD_HESS) out = v / s / s;
-            else if (MODE == HYP_PROD_INV_HESS) out = v * s * s;
-            else if (MODE == HYP_PROD_SQRT_HESS) out = v / s;
-            else out = v * s;
-            pr[r] = out;
-        }
-    }
-}
-
-// nonnegative.jl:122-125
-__global__ void nn_dder3_kernel(int64_t nrows, const int* __restrict__ rows,
-                                const double* __restrict__ point, const double* __restrict__ dir,
-                                double* __restrict__ out) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nrows;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        int r = rows[i];
-        double s = point[r], t = dir[r] / s;
-        out[r] = t * t / s;
-    }
-}
-
-// ------------------------------------------------------------------ EpiNormEucl
-// one warp per cone.  scal[8*c+0] = dist.  epinormeucl.jl:54-90
-__global__ void soc_state_kernel(int ncones, const int64_t* __restrict__ off,
-                                 const int* __restrict__ dim, const int* __restrict__ kidx,
-                                 const double* __restrict__ point, const double* __restrict__ dual,
-                                 double* __restrict__ grad, double* __restrict__ scal, uint8_t* feas,
-                                 uint8_t* dual_feas) {
-    const int lane = threadIdx.x & 31;
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (c >= ncones) return;
-    const int64_t o = off[c];
-    const int d = dim[c];
-    double sw = 0.0, sdw = 0.0;
-    for (int i = 1 + lane; i < d; i += 32) {
-        double w = point[o + i], dw = dual[o + i];
-        sw += w * w;
-        sdw += dw * dw;
-    }
-    sw = warp_sum(sw);
-    sdw = warp_sum(sdw);
-    const double u = point[o], du = dual[o];
-    double dist = 0.0;
-    bool ok = false;
-    if (u > HYP_EPS) {
-        dist = (u * u - sw) / 2;
-        ok = dist > HYP_EPS;
-    }
-    bool dok = (du > HYP_EPS) && ((du * du - sdw) > 2 * HYP_EPS);
-    for (int i = lane; i < d; i += 32) {
-        double v = point[o + i] / dist;
-        grad[o + i] = (i == 0) ? -v : v;
-    }
-    if (lane == 0) {
-        scal[8 * c] = dist;
-        feas[kidx[c]] = ok ? 1 : 0;
-        dual_feas[kidx[c]] = dok ? 1 : 0;
-    }
-}
-
-// one warp per (cone, column).  epinormeucl.jl:121-206
-template <int MODE>
-__global__ void __launch_bounds__(256)
-soc_prod_kernel(int ncones, const int64_t* __restrict__ off, const int* __restrict__ dim,
-                const double* __restrict__ scal, const double* __restrict__ point, const double* arr,
-                int64_t ld_arr, double* prod, int64_t ld_prod, int64_t ncols, int64_t row_shift) {
-    const int lane = threadIdx.x & 31;
-    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (c >= ncones) return;
-    const int64_t o = off[c];
-    const int d = dim[c];
-    const double dist = scal[8 * c];
-    const double u = point[o];
-    const double rt2 = 1.4142135623730951;
-    for (int64_t j = blockIdx.y; j < ncols; j += gridDim.y) {
-        const double* a = arr + j * ld_arr + (o - row_shift);
-        double* pr = prod + j * ld_prod + (o - row_shift);
-        // pass 1: dot(w, wj); the first chunk of the column stays in a register
-        double dotw = 0.0;
-        const double a_first = (lane < d) ? a[lane] : 0.0;
-        if (lane >= 1 && lane < d) dotw = point[o + lane] * a_first;
-        for (int i = lane + 32; i < d; i += 32) dotw += point[o + i] * a[i];
-        dotw = warp_sum(dotw);
-        const double uj = __shfl_sync(0xffffffffu, a_first, 0);
-        double c0, cw, cj;   // prod[0] = c0 ; prod[i] = cw * w[i] + cj * arr[i]
-        if (MODE == HYP_PROD_HESS) {
-            double ga = (dotw - u * uj) / dist;
-            c0 = (-ga * u - uj) / dist;
-            cw = ga / dist;
-            cj = 1.0 / dist;
-        } else if (MODE == HYP_PROD_INV_HESS) {
-            double pa = u * uj + dotw;
-            c0 = pa * u - dist * uj;
-            cw = pa;
-            cj = dist;
-        } else if (MODE == HYP_PROD_SQRT_HESS) {
-            double distrt2 = dist * rt2, rtdist = sqrt(dist), urtdist = u + rtdist * rt2;
-            c0 = (u * uj - dotw) / distrt2;
-            cw = (dotw / urtdist - uj) / distrt2;
-            cj = 1.0 / rtdist;
-        } else {
-            double rtdist = sqrt(dist), urtdist = u + rtdist * rt2;
-            c0 = (u * uj + dotw) / rt2;
-            cw = (dotw / urtdist + uj) / rt2;
-            cj = rtdist;
-        }
-        if (lane < d) pr[lane] = (lane == 0) ? c0 : (cw * point[o + lane] + cj * a_first);
-        for (int i = lane + 32; i < d; i += 32) pr[i] = cw * point[o + i] + cj * a[i];
-    }
-}
-
-// Many-column variant used by the Schur pre-pass (K8): a CTA stages the rows of a chunk of
-// consecutive cones of ONE column in shared memory with fully coalesced loads (a column of the
-// panel is contiguous over all cones), one thread per cone then applies the rank-one update
-// from shared memory (cone dims are mostly odd, e.g. 25: conflict-free strides), and the result
-// goes back with coalesced stores.  chunk table: crow0[b], crows[b] = first row / number of rows
-// of chunk b, ccone0[b], ccount[b] = first cone (index in the group) / number of cones.
-template <int MODE>
-__global__ void __launch_bounds__(256)
-soc_prod_chunk_kernel(const int64_t* __restrict__ crow0, const int* __restrict__ crows,
-                      const int* __restrict__ ccone0, const int* __restrict__ ccount,
-                      const int64_t* __restrict__ off, const int* __restrict__ dim,
-                      const double* __restrict__ scal, const double* __restrict__ point, const double* arr,
-                      int64_t ld_arr, double* prod, int64_t ld_prod, int64_t ncols, int64_t row_shift) {
-    extern __shared__ double srow[];
-    const int b = blockIdx.x;
-    const int64_t r0 = crow0[b];
-    const int nr = crows[b], c0 = ccone0[b], nc = ccount[b];
-    const double rt2 = 1.4142135623730951;
-    for (int64_t j = blockIdx.y; j < ncols; j += gridDim.y) {
-        const double* a = arr + j * ld_arr + (r0 - row_shift);
-        double* pr = prod + j * ld_prod + (r0 - row_shift);
-        for (int i = threadIdx.x; i < nr; i += blockDim.x) srow[i] = a[i];
-        __syncthreads();
-        for (int t = threadIdx.x; t < nc; t += blockDim.x) {
-            const int c = c0 + t;
-            const int64_t o = off[c];
-            const int d = dim[c];
-            double* v = srow + (o - r0);
-            const double* w = point + o;
-            const double dist = scal[8 * c], u = w[0], uj = v[0];
-            double dotw = 0.0;
-            for (int i = 1; i < d; i++) dotw += w[i] * v[i];
-            double k0, kw, kj;
-            if (MODE == HYP_PROD_HESS) {
-                double ga = (dotw - u * uj) / dist;
-                k0 = (-ga * u - uj) / dist; kw = ga / dist; kj = 1.0 / dist;
-            } else if (MODE == HYP_PROD_INV_HESS) {
-                double pa = u * uj + dotw;
-                k0 = pa * u - dist * uj; kw = pa; kj = dist;
-            } else if (MODE == HYP_PROD_SQRT_HESS) {
-                double distrt2 = dist * rt2, rtdist = sqrt(dist), urtdist = u + rtdist * rt2;
-                k0 = (u * uj - dotw) / distrt2; kw = (dotw / urtdist - uj) / distrt2; kj = 1.0 / rtdist;
-            } else {
-                double rtdist = sqrt(dist), urtdist = u + rtdist * rt2;
-                k0 = (u * uj + dotw) / rt2; kw = (dotw / urtdist + uj) / rt2; kj = rtdist;
-            }
-            v[0] = k0;
-            for (int i = 1; i < d; i++) v[i] = kw * w[i] + kj * v[i];
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < nr; i += blockDim.x) pr[i] = srow[i];
-        __syncthreads();
-    }
-}
-
-// epinormeucl.jl:208-228
-__global__ void soc_dder3_kernel(int ncones, const int64_t* __restrict__ off,
-                                 const int* __restrict__ dim, const double* __restrict__ scal,
-                                 const double* __restrict__ point, const double* __restrict__ dir,
-                                 double* __restrict__ out) {
-    const int lane = threadIdx.x & 31;
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (c >= ncones) return;
-    const int64_t o = off[c];
-    const int d = dim[c];
-    const double dist = scal[8 * c];
-    const double u = point[o], ud = dir[o];
-    double sww = 0.0, swd = 0.0, sdd = 0.0;
-    for (int i = 1 + lane; i < d; i += 32) {
-        double w = point[o + i], wd = dir[o + i];
-        sww += w * w;
-        swd += w * wd;
-        sdd += wd * wd;
-    }
-    sww = warp_sum(sww);
-    swd = warp_sum(swd);
-    sdd = warp_sum(sdd);
-    const double jdotpd = u * ud - swd;
-    const double ga = (swd - u * ud) / dist;
-    const double h0 = (-ga * u - ud) / dist;                 // (H dir)[0]
-    // (H dir)[i] = (ga * w_i + wd_i) / dist
-    const double dHd = ud * h0 + (ga * swd + sdd) / dist;    // dir' H dir
-    const double pHd = u * h0 + (ga * sww + swd) / dist;     // point' H dir
-    const double dotdHd = -dHd, dotpHd = pHd;
-    const double inv2d = 1.0 / (2 * dist);
-    for (int i = lane; i < d; i += 32) {
-        double r;
-        if (i == 0) {
-            r = h0 * jdotpd - dotdHd * u - dotpHd * ud;
-        } else {
-            double w = point[o + i], wd = dir[o + i];
-            r = (ga * w + wd) / dist * jdotpd + dotdHd * w + dotpHd * wd;
-        }
-        out[o + i] = r * inv2d;
-    }
-}
-
-// ------------------------------------------------------------------ per-cone reductions
-// One CTA per local cone.  check_numerics (Cones.jl:273-290) + get_proxsqr (Cones.jl:294-310;
-// nonnegative.jl:137-145 for the orthant).  v1 = irtmu*dual + grad, v2 = Hinv v1, v3 = Hinv grad.
-__global__ void __launch_bounds__(128)
-cone_prox_kernel(int cone_lo, const int* __restrict__ ctype, const int64_t* __restrict__ coff,
-                 const int64_t* __restrict__ cdim, const double* __restrict__ cnu,
-                 const double* __restrict__ point, const double* __restrict__ dual,
-                 const double* __restrict__ grad, const double* __restrict__ v1,
-                 const double* __restrict__ v2, const double* __restrict__ v3, double irtmu,
-                 int use_max, double* __restrict__ proxsqr, uint8_t* __restrict__ num_ok) {
-    __shared__ double sm[4][4];
-    const int k = cone_lo + blockIdx.x;
-    const int64_t o = coff[k], d = cdim[k];
-    const int type = ctype[k];
-    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;   // v2.v1, grad.point, v3.grad, nonneg aggregate
-    for (int64_t i = threadIdx.x; i < d; i += blockDim.x) {
-        double g = grad[o + i];
-        a0 += v2[o + i] * v1[o + i];
-        a1 += g * point[o + i];
-        a2 += v3[o + i] * g;
-        if (type == HYP_CONE_NONNEGATIVE) {
-            double t = point[o + i] * dual[o + i] * irtmu - 1.0;
-            t = t * t;
-            a3 = use_max ? fmax(a3, t) : a3 + t;
-        }
-    }
-    a0 = warp_sum(a0);
-    a1 = warp_sum(a1);
-    a2 = warp_sum(a2);
-    if (use_max) {
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) a3 = fmax(a3, __shfl_xor_sync(0xffffffffu, a3, s));
-    } else {
-        a3 = warp_sum(a3);
-    }
-    const int w = threadIdx.x >> 5;
-    if ((threadIdx.x & 31) == 0) {
-        sm[w][0] = a0;
-        sm[w][1] = a1;
-        sm[w][2] = a2;
-        sm[w][3] = a3;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double d0 = 0, d1 = 0, d2 = 0, d3 = 0;
-        for (int i = 0; i < 4; i++) {
-            d0 += sm[i][0];
-            d1 += sm[i][1];
-            d2 += sm[i][2];
-            d3 = use_max ? fmax(d3, sm[i][3]) : d3 + sm[i][3];
-        }
-        const double nu = cnu[k];
-        const double gtol = 1.220703125e-4;              // eps^(1/4)
-        const double Htol = 10 * 0.011048543456039806;   // 10 * sqrt(gtol)
-        bool ok = true;
-        if (fabs(1 + d1 / nu) > gtol * (double)d) ok = false;
-        if (ok && fabs(1 - d2 / nu) > Htol * (double)d) ok = false;
-        if (!(d1 == d1) || !(d2 == d2)) ok = false;
-        num_ok[k] = ok ? 1 : 0;
-        double prox;
-        if (type == HYP_CONE_NONNEGATIVE) {
-            prox = d3;
-        } else {
-            const double negtol = 1.4901161193847656e-08;   // sqrt(eps)
-            prox = (d0 < -negtol * (double)d) ? INFINITY : fabs(d0);
-        }
-        proxsqr[k] = prox;
-    }
-}
 
 inline int grid_for(hyp_ctx* ctx, int64_t len, int threads, int mult = 8) {
     int64_t blocks = (len + threads - 1) / threads;
@@ -349,15 +41,15 @@ void launch_vec_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr
     int gy = (int)std::min<int64_t>(ncols, 65535);
     if (g.type == HYP_CONE_NONNEGATIVE) {
         int gx = grid_for(ctx, g.rows, 256, ncols > 1 ? 1 : 8);
-        nn_prod_kernel<MODE><<<dim3(gx, gy), 256, 0, ctx->stream>>>(
+        hypdev::nn_prod_kernel<MODE><<<dim3(gx, gy), 256, 0, ctx->stream>>>(
             g.rows, g.d_rows, ctx->d_point, arr, ld_arr, prod, ld_prod, ncols, row_shift);
     } else if (ncols >= 16 && g.n_chunks > 0 && g.chunks_cover_all) {
-        soc_prod_chunk_kernel<MODE><<<dim3(g.n_chunks, gy), 256, g.chunk_smem, ctx->stream>>>(
+        hypdev::soc_prod_chunk_kernel<MODE><<<dim3(g.n_chunks, gy), 256, g.chunk_smem, ctx->stream>>>(
             g.d_crow0, g.d_crows, g.d_ccone0, g.d_ccount, g.d_off, g.d_dim, g.d_scal, ctx->d_point, arr,
             ld_arr, prod, ld_prod, ncols, row_shift);
     } else {
         int gx = ceil_div(g.count, 8);
-        soc_prod_kernel<MODE><<<dim3(gx, gy), 256, 0, ctx->stream>>>(
+        hypdev::soc_prod_kernel<MODE><<<dim3(gx, gy), 256, 0, ctx->stream>>>(
             g.count, g.d_off, g.d_dim, g.d_scal, ctx->d_point, arr, ld_arr, prod, ld_prod, ncols,
             row_shift);
     }
@@ -511,12 +203,12 @@ void hyp_cones_update_state(hyp_ctx* ctx) {
     CUDA_TRY(cudaMemsetAsync(ctx->d_dual_feas, 1, ctx->K, ctx->stream));
     for (auto& g : ctx->groups) {
         if (g.type == HYP_CONE_NONNEGATIVE) {
-            nn_state_kernel<<<grid_for(ctx, g.rows, 256), 256, 0, ctx->stream>>>(
+            hypdev::nn_state_kernel<<<grid_for(ctx, g.rows, 256), 256, 0, ctx->stream>>>(
                 g.rows, g.d_rows, g.d_rowcone, ctx->d_point, ctx->d_dual, ctx->d_grad, ctx->d_feas,
                 ctx->d_dual_feas);
             ctx->launches++;
         } else if (g.type == HYP_CONE_EPINORMEUCL) {
-            soc_state_kernel<<<ceil_div(g.count, 8), 256, 0, ctx->stream>>>(
+            hypdev::soc_state_kernel<<<ceil_div(g.count, 8), 256, 0, ctx->stream>>>(
                 g.count, g.d_off, g.d_dim, g.d_kidx, ctx->d_point, ctx->d_dual, ctx->d_grad, g.d_scal,
                 ctx->d_feas, ctx->d_dual_feas);
             ctx->launches++;
@@ -614,11 +306,11 @@ void hyp_cones_dder3_dev(hyp_ctx* ctx, double* out, const double* dir) {
     TimeScope ts(ctx, T_CONE_PROD);
     for (auto& g : ctx->groups) {
         if (g.type == HYP_CONE_NONNEGATIVE) {
-            nn_dder3_kernel<<<grid_for(ctx, g.rows, 256), 256, 0, ctx->stream>>>(
+            hypdev::nn_dder3_kernel<<<grid_for(ctx, g.rows, 256), 256, 0, ctx->stream>>>(
                 g.rows, g.d_rows, ctx->d_point, dir, out);
             ctx->launches++;
         } else if (g.type == HYP_CONE_EPINORMEUCL) {
-            soc_dder3_kernel<<<ceil_div(g.count, 8), 256, 0, ctx->stream>>>(
+            hypdev::soc_dder3_kernel<<<ceil_div(g.count, 8), 256, 0, ctx->stream>>>(
                 g.count, g.d_off, g.d_dim, g.d_scal, ctx->d_point, dir, out);
             ctx->launches++;
         } else if (cone_is_genfact(g.type)) {
@@ -648,7 +340,7 @@ void hyp_cones_prox_dev(hyp_ctx* ctx, double irtmu, int use_max) {
         hyp_lincomb3(ctx, ctx->q, ctx->d_vq1, irtmu, ctx->d_dual, 1.0, ctx->d_grad, 0.0, nullptr);
         hyp_cones_prod(ctx, ctx->d_vq2, ctx->d_vq1, 1, ctx->q, ctx->q, HYP_PROD_INV_HESS, 0);
         hyp_cones_prod(ctx, ctx->d_vq3, ctx->d_grad, 1, ctx->q, ctx->q, HYP_PROD_INV_HESS, 0);
-        cone_prox_kernel<<<nloc, 128, 0, ctx->stream>>>(
+        hypdev::cone_prox_kernel<<<nloc, 128, 0, ctx->stream>>>(
             ctx->cone_lo, ctx->d_cone_type, ctx->d_cone_off, ctx->d_cone_dim, ctx->d_cone_nu,
             ctx->d_point, ctx->d_dual, ctx->d_grad, ctx->d_vq1, ctx->d_vq2, ctx->d_vq3, irtmu, use_max,
             ctx->d_proxsqr, ctx->d_num_ok);

@@ -358,3 +358,86 @@ int emu_hpm_dder3(int ncones, const int64_t* off, const int* dim, const int64_t*
 }
 
 }  // extern "C"
+
+// ---- Nonnegative / EpiNormEucl and the proximity reductions (csrc/cones_vec_kernels.cuh) ----
+#include "../../hypatia.jl_b200/csrc/cones_vec_kernels.cuh"
+
+extern "C" {
+
+int emu_nn_state(int64_t nrows, const int* rows, const int* rowcone, const double* point, const double* dual,
+                 double* grad, uint8_t* feas, uint8_t* dual_feas) {
+    emu::launch(dim3(2), dim3(64), 0,
+                [&] { hypdev::nn_state_kernel(nrows, rows, rowcone, point, dual, grad, feas, dual_feas); });
+    return 0;
+}
+
+int emu_nn_prod(int mode, int64_t nrows, const int* rows, const double* point, const double* arr, int64_t ld_arr,
+                double* prod, int64_t ld_prod, int64_t ncols, int64_t row_shift) {
+    emu::launch(dim3(2, 2), dim3(64), 0, [&] {
+        if (mode == 0) hypdev::nn_prod_kernel<0>(nrows, rows, point, arr, ld_arr, prod, ld_prod, ncols, row_shift);
+        else if (mode == 1) hypdev::nn_prod_kernel<1>(nrows, rows, point, arr, ld_arr, prod, ld_prod, ncols, row_shift);
+        else if (mode == 2) hypdev::nn_prod_kernel<2>(nrows, rows, point, arr, ld_arr, prod, ld_prod, ncols, row_shift);
+        else hypdev::nn_prod_kernel<3>(nrows, rows, point, arr, ld_arr, prod, ld_prod, ncols, row_shift);
+    });
+    return 0;
+}
+
+int emu_nn_dder3(int64_t nrows, const int* rows, const double* point, const double* dir, double* out) {
+    emu::launch(dim3(2), dim3(64), 0, [&] { hypdev::nn_dder3_kernel(nrows, rows, point, dir, out); });
+    return 0;
+}
+
+int emu_soc_state(int ncones, const int64_t* off, const int* dim, const int* kidx, const double* point,
+                  const double* dual, double* grad, double* scal, uint8_t* feas, uint8_t* dual_feas) {
+    emu::launch(dim3((ncones + 1) / 2), dim3(64), 0, [&] {
+        hypdev::soc_state_kernel(ncones, off, dim, kidx, point, dual, grad, scal, feas, dual_feas);
+    });
+    return 0;
+}
+
+int emu_soc_prod(int mode, int ncones, const int64_t* off, const int* dim, const double* scal, const double* point,
+                 const double* arr, int64_t ld_arr, double* prod, int64_t ld_prod, int64_t ncols, int64_t row_shift) {
+    emu::launch(dim3((ncones + 1) / 2, 2), dim3(64), 0, [&] {
+        if (mode == 0) hypdev::soc_prod_kernel<0>(ncones, off, dim, scal, point, arr, ld_arr, prod, ld_prod, ncols, row_shift);
+        else if (mode == 1) hypdev::soc_prod_kernel<1>(ncones, off, dim, scal, point, arr, ld_arr, prod, ld_prod, ncols, row_shift);
+        else if (mode == 2) hypdev::soc_prod_kernel<2>(ncones, off, dim, scal, point, arr, ld_arr, prod, ld_prod, ncols, row_shift);
+        else hypdev::soc_prod_kernel<3>(ncones, off, dim, scal, point, arr, ld_arr, prod, ld_prod, ncols, row_shift);
+    });
+    return 0;
+}
+
+int emu_soc_prod_chunk(int mode, int nchunks, int smem_bytes, const int64_t* crow0, const int* crows, const int* ccone0,
+                       const int* ccount, const int64_t* off, const int* dim, const double* scal, const double* point,
+                       const double* arr, int64_t ld_arr, double* prod, int64_t ld_prod, int64_t ncols,
+                       int64_t row_shift) {
+    emu::launch(dim3(nchunks, 2), dim3(64), smem_bytes, [&] {
+        if (mode == 0)
+            hypdev::soc_prod_chunk_kernel<0>(crow0, crows, ccone0, ccount, off, dim, scal, point, arr, ld_arr, prod, ld_prod, ncols, row_shift);
+        else if (mode == 1)
+            hypdev::soc_prod_chunk_kernel<1>(crow0, crows, ccone0, ccount, off, dim, scal, point, arr, ld_arr, prod, ld_prod, ncols, row_shift);
+        else if (mode == 2)
+            hypdev::soc_prod_chunk_kernel<2>(crow0, crows, ccone0, ccount, off, dim, scal, point, arr, ld_arr, prod, ld_prod, ncols, row_shift);
+        else
+            hypdev::soc_prod_chunk_kernel<3>(crow0, crows, ccone0, ccount, off, dim, scal, point, arr, ld_arr, prod, ld_prod, ncols, row_shift);
+    });
+    return 0;
+}
+
+int emu_soc_dder3(int ncones, const int64_t* off, const int* dim, const double* scal, const double* point,
+                  const double* dir, double* out) {
+    emu::launch(dim3((ncones + 1) / 2), dim3(64), 0,
+                [&] { hypdev::soc_dder3_kernel(ncones, off, dim, scal, point, dir, out); });
+    return 0;
+}
+
+int emu_cone_prox(int ncones, const int* ctype, const int64_t* coff, const int64_t* cdim, const double* cnu,
+                  const double* point, const double* dual, const double* grad, const double* v1, const double* v2,
+                  const double* v3, double irtmu, int use_max, double* proxsqr, uint8_t* num_ok) {
+    emu::launch(dim3(ncones), dim3(128), 0, [&] {
+        hypdev::cone_prox_kernel(0, ctype, coff, cdim, cnu, point, dual, grad, v1, v2, v3, irtmu, use_max, proxsqr,
+                                 num_ok);
+    });
+    return 0;
+}
+
+}  // extern "C"
