@@ -19,6 +19,7 @@
 // (C_int32 = A' B, both operands K-major, SWIZZLE_128B, accumulator in TMEM), (3) a reference
 // recombination used by the tests.
 #include "common.cuh"
+#include "ozaki_slice_kernels.cuh"
 
 namespace {
 
@@ -233,108 +234,8 @@ void make_map_i8(CUtensorMap* map, const int8_t* base, int64_t K, int64_t cols, 
     if (r != CUDA_SUCCESS) throw HypError{"cuTensorMapEncodeTiled (int8) failed"};
 }
 
-// ---- slicing: column exponents and the S signed 7-bit digit matrices ----------------------------
-__global__ void colmax_kernel(int64_t K, int64_t ncols, const double* __restrict__ A, int64_t lda,
-                              int* __restrict__ expo, double* __restrict__ dscale, int radix256) {
-    // expo[j] = smallest e with max_k |A[k, j]| < 2^e  (0 for an all-zero column); radix-256 digits need
-    // max |A| <= (127/128) 2^e so that the leading digit stays below 128 after a carry
-    __shared__ double sm[8];
-    const int64_t j = blockIdx.x;
-    if (j >= ncols) return;
-    const double* col = A + j * lda;
-    double mx = 0.0;
-    for (int64_t k = threadIdx.x; k < K; k += blockDim.x) mx = fmax(mx, fabs(col[k]));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mx;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < (int)(blockDim.x >> 5); w++) mx = fmax(mx, sm[w]);
-        int e = 0;
-        if (mx > 0.0) {
-            const double f = frexp(mx, &e);          // mx = f * 2^e, f in [0.5, 1)  =>  mx < 2^e
-            if (radix256 && f > 127.0 / 128.0) e++;
-        }
-        expo[j] = e;
-        if (dscale) dscale[j] = ldexp(1.0, e);
-    }
-}
-
-// D[s][k + j * ldd] = s-th signed digit of A[k, j] * 2^-expo[j].  A thread cuts 8 consecutive rows
-// and stores one packed 8-byte word per slice (ldd is a multiple of 16, so the words are aligned).
-__global__ void slice_kernel(int64_t K, int64_t ncols, const double* __restrict__ A, int64_t lda,
-                             const int* __restrict__ expo, int nslices, int8_t* __restrict__ D, int64_t ldd,
-                             int64_t slice_stride) {
-    const int64_t K8 = (K + 7) / 8;
-    for (int64_t j = blockIdx.y; j < ncols; j += gridDim.y) {
-        const double sc = ldexp(1.0, 6 - expo[j]);
-        const double* col = A + j * lda;
-        for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < K8;
-             g += (int64_t)gridDim.x * blockDim.x) {
-            double r[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int64_t k = g * 8 + u;
-                r[u] = (k < K) ? col[k] * sc : 0.0;          // |r| < 64
-            }
-            for (int s = 0; s < nslices; s++) {
-                uint64_t w = 0;
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const double d = rint(r[u]);
-                    w |= (uint64_t)(uint8_t)(int8_t)(int)d << (8 * u);
-                    r[u] = (r[u] - d) * 128.0;               // exact: |r - d| <= 0.5
-                }
-                *reinterpret_cast<uint64_t*>(D + s * slice_stride + g * 8 + j * ldd) = w;
-            }
-        }
-    }
-}
-
-// Radix-256 variant: balanced signed digits d_s in [-128, 127], a = 2^e sum_s 2^-(7 + 8 s) d_s.  rint can produce
-// +128 (remainder >= 0.498): a backward carry pass turns it into -128 and adds one to the next higher digit; the
-// leading digit cannot overflow because |a| 2^(7 - e) <= 127.  Seven such digits carry the same 56 bits as eight
-// radix-128 digits, so the product needs 28 digit pairs (s + t <= 6) instead of 36 at the same truncation error.
-__global__ void slice256_kernel(int64_t K, int64_t ncols, const double* __restrict__ A, int64_t lda,
-                                const int* __restrict__ expo, int nslices, int8_t* __restrict__ D, int64_t ldd,
-                                int64_t slice_stride) {
-    const int64_t K8 = (K + 7) / 8;
-    for (int64_t j = blockIdx.y; j < ncols; j += gridDim.y) {
-        const double sc = ldexp(1.0, 7 - expo[j]);
-        const double* col = A + j * lda;
-        for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < K8;
-             g += (int64_t)gridDim.x * blockDim.x) {
-            uint64_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int64_t k = g * 8 + u;
-                double r = (k < K) ? col[k] * sc : 0.0;          // |r| <= 127
-                int dg[8];
-#pragma unroll
-                for (int s = 0; s < 8; s++) {
-                    if (s < nslices) {
-                        const double d = rint(r);
-                        dg[s] = (int)d;
-                        r = (r - d) * 256.0;                     // exact: |r - d| <= 0.5
-                    } else {
-                        dg[s] = 0;
-                    }
-                }
-#pragma unroll
-                for (int s = 7; s >= 1; s--)
-                    if (dg[s] >= 128) {
-                        dg[s] -= 256;
-                        dg[s - 1] += 1;
-                    }
-#pragma unroll
-                for (int s = 0; s < 8; s++) w[s] |= (uint64_t)(uint8_t)(int8_t)dg[s] << (8 * u);
-            }
-            for (int s = 0; s < nslices; s++)
-                *reinterpret_cast<uint64_t*>(D + s * slice_stride + g * 8 + j * ldd) = w[s];
-        }
-    }
-}
-
+// ---- slicing: column exponents and the signed digit matrices: ozaki_slice_kernels.cuh (hypdev::colmax_kernel,
+// slice_kernel, slice256_kernel), shared with the CPU-tier emulation ----
 }  // namespace
 namespace {
 // =====================================================================================================
@@ -1316,12 +1217,12 @@ extern "C" int hyp_test_ozaki_slices(hyp_ctx* ctx, const double* A, int64_t lda,
         CUDA_TRY(cudaMalloc(&dD, (size_t)nslices * ldd * ncols));
         CUDA_TRY(cudaMalloc(&dE, (size_t)ncols * 4));
         CUDA_TRY(cudaMemcpy2DAsync(dA, K * 8, A, lda * 8, K * 8, ncols, cudaMemcpyDefault, ctx->stream));
-        colmax_kernel<<<(unsigned)ncols, 256, 0, ctx->stream>>>(K, ncols, dA, K, dE, nullptr, r256 ? 1 : 0);
+        hypdev::colmax_kernel<<<(unsigned)ncols, 256, 0, ctx->stream>>>(K, ncols, dA, K, dE, nullptr, r256 ? 1 : 0);
         dim3 grid(std::max(1, std::min(ceil_div(K, 2048), 64)), (unsigned)std::min<int64_t>(ncols, 65535));
         if (r256)
-            slice256_kernel<<<grid, 256, 0, ctx->stream>>>(K, ncols, dA, K, dE, nslices, dD, ldd, ldd * ncols);
+            hypdev::slice256_kernel<<<grid, 256, 0, ctx->stream>>>(K, ncols, dA, K, dE, nslices, dD, ldd, ldd * ncols);
         else
-            slice_kernel<<<grid, 256, 0, ctx->stream>>>(K, ncols, dA, K, dE, nslices, dD, ldd, ldd * ncols);
+            hypdev::slice_kernel<<<grid, 256, 0, ctx->stream>>>(K, ncols, dA, K, dE, nslices, dD, ldd, ldd * ncols);
         ctx->launches += 2;
         CUDA_TRY(cudaGetLastError());
         for (int s = 0; s < nslices; s++)
@@ -1359,12 +1260,12 @@ void hyp_ozaki_slice(hyp_ctx* ctx, const double* A, int64_t lda, int64_t K, int6
                      int64_t ldd, int64_t slice_stride, int* expo, double* dscale) {
     if (K <= 0 || ncols <= 0) return;
     const bool r256 = ozaki_radix() == 256;
-    colmax_kernel<<<(unsigned)ncols, 256, 0, ctx->stream>>>(K, ncols, A, lda, expo, dscale, r256 ? 1 : 0);
+    hypdev::colmax_kernel<<<(unsigned)ncols, 256, 0, ctx->stream>>>(K, ncols, A, lda, expo, dscale, r256 ? 1 : 0);
     dim3 grid(std::max(1, std::min(ceil_div(K, 2048), 32)), (unsigned)std::min<int64_t>(ncols, 65535));
     if (r256)
-        slice256_kernel<<<grid, 256, 0, ctx->stream>>>(K, ncols, A, lda, expo, 7, digits, ldd, slice_stride);
+        hypdev::slice256_kernel<<<grid, 256, 0, ctx->stream>>>(K, ncols, A, lda, expo, 7, digits, ldd, slice_stride);
     else
-        slice_kernel<<<grid, 256, 0, ctx->stream>>>(K, ncols, A, lda, expo, OZ_S, digits, ldd, slice_stride);
+        hypdev::slice_kernel<<<grid, 256, 0, ctx->stream>>>(K, ncols, A, lda, expo, OZ_S, digits, ldd, slice_stride);
     ctx->launches += 2;
     CUDA_TRY(cudaGetLastError());
 }

@@ -1,0 +1,112 @@
+// Digit slicing of the FP64-accurate tcgen05 SYRK (ozaki.cu): per-column power-of-two scale and the signed 8-bit digit
+// matrices.  Pure FP64 / integer arithmetic - every step is exact - so the kernels are compiled for the host as well
+// (tests/emu/) and the exactness of the decomposition and of its recombination is checked in the CPU test tier
+// (tests/test_emu_ozaki.py).
+#pragma once
+#include "devdefs.cuh"
+
+namespace hypdev {
+
+// ---- slicing: column exponents and the S signed 7-bit digit matrices ----------------------------
+static __global__ void colmax_kernel(int64_t K, int64_t ncols, const double* __restrict__ A, int64_t lda,
+                              int* __restrict__ expo, double* __restrict__ dscale, int radix256) {
+    // expo[j] = smallest e with max_k |A[k, j]| < 2^e  (0 for an all-zero column); radix-256 digits need
+    // max |A| <= (127/128) 2^e so that the leading digit stays below 128 after a carry
+    __shared__ double sm[8];
+    const int64_t j = blockIdx.x;
+    if (j >= ncols) return;
+    const double* col = A + j * lda;
+    double mx = 0.0;
+    for (int64_t k = threadIdx.x; k < K; k += blockDim.x) mx = fmax(mx, fabs(col[k]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) mx = fmax(mx, sm[w]);
+        int e = 0;
+        if (mx > 0.0) {
+            const double f = frexp(mx, &e);          // mx = f * 2^e, f in [0.5, 1)  =>  mx < 2^e
+            if (radix256 && f > 127.0 / 128.0) e++;
+        }
+        expo[j] = e;
+        if (dscale) dscale[j] = ldexp(1.0, e);
+    }
+}
+
+// D[s][k + j * ldd] = s-th signed digit of A[k, j] * 2^-expo[j].  A thread cuts 8 consecutive rows
+// and stores one packed 8-byte word per slice (ldd is a multiple of 16, so the words are aligned).
+static __global__ void slice_kernel(int64_t K, int64_t ncols, const double* __restrict__ A, int64_t lda,
+                             const int* __restrict__ expo, int nslices, int8_t* __restrict__ D, int64_t ldd,
+                             int64_t slice_stride) {
+    const int64_t K8 = (K + 7) / 8;
+    for (int64_t j = blockIdx.y; j < ncols; j += gridDim.y) {
+        const double sc = ldexp(1.0, 6 - expo[j]);
+        const double* col = A + j * lda;
+        for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < K8;
+             g += (int64_t)gridDim.x * blockDim.x) {
+            double r[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int64_t k = g * 8 + u;
+                r[u] = (k < K) ? col[k] * sc : 0.0;          // |r| < 64
+            }
+            for (int s = 0; s < nslices; s++) {
+                uint64_t w = 0;
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const double d = rint(r[u]);
+                    w |= (uint64_t)(uint8_t)(int8_t)(int)d << (8 * u);
+                    r[u] = (r[u] - d) * 128.0;               // exact: |r - d| <= 0.5
+                }
+                *reinterpret_cast<uint64_t*>(D + s * slice_stride + g * 8 + j * ldd) = w;
+            }
+        }
+    }
+}
+
+// Radix-256 variant: balanced signed digits d_s in [-128, 127], a = 2^e sum_s 2^-(7 + 8 s) d_s.  rint can produce
+// +128 (remainder >= 0.498): a backward carry pass turns it into -128 and adds one to the next higher digit; the
+// leading digit cannot overflow because |a| 2^(7 - e) <= 127.  Seven such digits carry the same 56 bits as eight
+// radix-128 digits, so the product needs 28 digit pairs (s + t <= 6) instead of 36 at the same truncation error.
+static __global__ void slice256_kernel(int64_t K, int64_t ncols, const double* __restrict__ A, int64_t lda,
+                                const int* __restrict__ expo, int nslices, int8_t* __restrict__ D, int64_t ldd,
+                                int64_t slice_stride) {
+    const int64_t K8 = (K + 7) / 8;
+    for (int64_t j = blockIdx.y; j < ncols; j += gridDim.y) {
+        const double sc = ldexp(1.0, 7 - expo[j]);
+        const double* col = A + j * lda;
+        for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < K8;
+             g += (int64_t)gridDim.x * blockDim.x) {
+            uint64_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int64_t k = g * 8 + u;
+                double r = (k < K) ? col[k] * sc : 0.0;          // |r| <= 127
+                int dg[8];
+#pragma unroll
+                for (int s = 0; s < 8; s++) {
+                    if (s < nslices) {
+                        const double d = rint(r);
+                        dg[s] = (int)d;
+                        r = (r - d) * 256.0;                     // exact: |r - d| <= 0.5
+                    } else {
+                        dg[s] = 0;
+                    }
+                }
+#pragma unroll
+                for (int s = 7; s >= 1; s--)
+                    if (dg[s] >= 128) {
+                        dg[s] -= 256;
+                        dg[s - 1] += 1;
+                    }
+#pragma unroll
+                for (int s = 0; s < 8; s++) w[s] |= (uint64_t)(uint8_t)(int8_t)dg[s] << (8 * u);
+            }
+            for (int s = 0; s < nslices; s++)
+                *reinterpret_cast<uint64_t*>(D + s * slice_stride + g * 8 + j * ldd) = w[s];
+        }
+    }
+}
+
+}  // namespace hypdev

@@ -441,3 +441,22 @@ int emu_cone_prox(int ncones, const int* ctype, const int64_t* coff, const int64
 }
 
 }  // extern "C"
+
+// ---- digit slicing of the FP64-accurate SYRK (csrc/ozaki_slice_kernels.cuh) ----
+#include "../../hypatia.jl_b200/csrc/ozaki_slice_kernels.cuh"
+
+extern "C" {
+
+// expo / dscale and the digit slices D[s][k + j * ldd] of the K x ncols matrix A; radix = 128 or 256
+int emu_ozaki_slice(int radix, int64_t K, int64_t ncols, const double* A, int64_t lda, int nslices, int* expo,
+                    double* dscale, int8_t* D, int64_t ldd, int64_t slice_stride) {
+    emu::launch(dim3((unsigned)ncols), dim3(64), 0,
+                [&] { hypdev::colmax_kernel(K, ncols, A, lda, expo, dscale, radix == 256 ? 1 : 0); });
+    emu::launch(dim3(2, 2), dim3(64), 0, [&] {
+        if (radix == 256) hypdev::slice256_kernel(K, ncols, A, lda, expo, nslices, D, ldd, slice_stride);
+        else hypdev::slice_kernel(K, ncols, A, lda, expo, nslices, D, ldd, slice_stride);
+    });
+    return 0;
+}
+
+}  // extern "C"
