@@ -460,3 +460,38 @@ int emu_ozaki_slice(int radix, int64_t K, int64_t ncols, const double* A, int64_
 }
 
 }  // extern "C"
+
+// ---- the single-product GEMV kernels (csrc/gemv_kernels.cuh), launched as hyp_gemv_t / hyp_gemv_n do (gemv.cu) ----
+extern "C" {
+
+// y = alpha * M' x + beta * y; kind 0: CTA per column (vectorised loads), 1: CTA per column (scalar), 2: warp per column
+int emu_gemv_t(int kind, int64_t rows, int64_t ncols, const double* M, int64_t ld, const double* x, double alpha,
+               double beta, double* y) {
+    if (kind == 2) {
+        emu::launch(dim3(2), dim3(256), 0, [&] { hypdev::gemv_t_warp_kernel(rows, ncols, M, ld, x, alpha, beta, y); });
+    } else {
+        emu::launch(dim3(3), dim3(256), 0, [&] {
+            if (kind == 0) hypdev::gemv_t_cta_kernel<true>(rows, ncols, M, ld, x, alpha, beta, y);
+            else hypdev::gemv_t_cta_kernel<false>(rows, ncols, M, ld, x, alpha, beta, y);
+        });
+    }
+    return 0;
+}
+
+// y = alpha * M x + beta * y through the column-chunked partial sums
+int emu_gemv_n(int vec, int64_t rows, int64_t ncols, const double* M, int64_t ld, const double* x, int nchunks,
+               double alpha, double beta, double* y) {
+    const int rb = (int)((rows + 255) / 256);
+    const int64_t cpc = (ncols + nchunks - 1) / nchunks;
+    nchunks = (int)((ncols + cpc - 1) / cpc);
+    std::vector<double> part((size_t)nchunks * rows + 2);
+    emu::launch(dim3(rb, nchunks), dim3(128), 0, [&] {
+        if (vec) hypdev::gemv_n_kernel<true>(rows, ncols, M, ld, x, cpc, part.data());
+        else hypdev::gemv_n_kernel<false>(rows, ncols, M, ld, x, cpc, part.data());
+    });
+    emu::launch(dim3(2), dim3(256), 0,
+                [&] { hypdev::gemv_n_reduce_kernel(rows, nchunks, part.data(), alpha, beta, y); });
+    return 0;
+}
+
+}  // extern "C"
