@@ -17,11 +17,11 @@
 //   acquire flags, so a solve is one launch instead of 2 * m / 128.  Bound: HBM (reads the
 //   triangle once: 4 m^2 bytes) - in practice latency of the block dependency chain.
 #include "common.cuh"
+#include "chol_kernels.cuh"
+
+using namespace hypdev;   // NB, LDU, PT, panel_kernel, chol_batched_kernel
 
 namespace {
-
-constexpr int NB = 128;
-constexpr int LDU = NB + 1;   // padded leading dimension of the shared-memory block
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
     int v;
@@ -30,338 +30,6 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
 }
 __device__ __forceinline__ void st_release(int* p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-// Factor (FACTOR) and invert one upper-triangular diagonal block of at most 128 x 128, by one CTA
-// of 256 threads, entirely in shared memory (sA: 128 x 128, ld LDU; the upper triangle holds
-// A -> U, the strictly lower triangle receives X' where X = U^-1, diagX the diagonal of X).
-// Blocked right-looking algorithm with 32 x 32 sub-blocks:
-//   (a) warp 0 factors and inverts the diagonal sub-block in REGISTERS (lane = column, pivots
-//       broadcast with shuffles: no shared-memory round trips or block barriers on the pivot chain),
-//   (b) all warps form the block row U_bc = X_bb' A_bc and (c) apply the rank-32 trailing update,
-//       both as 4 x 4 register-tiled products;
-//   (d) afterwards the off-diagonal block columns of X follow from
-//       X[0:c, c] = -X[0:c, 0:c] U[0:c, c] X[c, c].
-// Ab: the block in global memory (upper part is read; U is written back, optionally with zeros
-// below the diagonal); Db receives X (dn x dn entries, leading dim ldd; rows / columns past nb are
-// identity padding).  Returns the 1-based index of the first non-positive pivot or 0.
-constexpr int SB = 32;
-constexpr int PT = 256;          // threads of a panel CTA
-constexpr int LDX = SB + 1;
-constexpr int LDT = 3 * SB + 1;  // sT holds up to 96 x 32
-
-template <bool FACTOR>
-__device__ __forceinline__ void base_block(double* sA, double* diagX, double* sX, int o, int lane,
-                                           int* s_bad) {
-    // Lane c holds column c of the 32 x 32 block (col) and column c of W (wcol), where W starts as
-    // the identity and receives the same row operations as the factorisation, so that it ends as
-    // U^-T = X': the inverse comes out of the pivot loop instead of a second substitution sweep.
-    const unsigned FULL = 0xffffffffu;
-    double col[SB], wcol[SB];
-#pragma unroll
-    for (int r = 0; r < SB; r++) {
-        col[r] = sA[(o + r) + (o + lane) * LDU];
-        wcol[r] = (r == lane) ? 1.0 : 0.0;
-    }
-#pragma unroll
-    for (int j = 0; j < SB; j++) {
-        const double d = __shfl_sync(FULL, col[j], j);
-        double rinv = 0.0;
-        if (FACTOR) {
-            if (d > 0.0) {
-                rinv = rsqrt(d);
-                // one Newton step on the reciprocal square root: keeps sd * sd = d to the last bits
-                rinv = rinv + 0.5 * rinv * (1.0 - d * rinv * rinv);
-            } else if (lane == 0 && *s_bad == 0) {
-                *s_bad = o + j + 1;
-            }
-        } else {
-            rinv = (d != 0.0) ? 1.0 / d : 0.0;
-        }
-        double u;
-        if (FACTOR) {
-            u = (lane > j) ? col[j] * rinv : 0.0;
-            if (lane == j) col[j] = d * rinv;
-            else if (lane > j) col[j] = u;
-        } else {
-            u = (lane > j) ? col[j] : 0.0;     // U is given: row j of U, not rescaled
-        }
-        const double wj = wcol[j] * rinv;      // row j of W (nonzero for lanes <= j)
-        wcol[j] = wj;
-        if (lane == j) diagX[o + j] = rinv;
-#pragma unroll
-        for (int r = j + 1; r < SB; r++) {
-            const double ur = __shfl_sync(FULL, u, r);     // U[j, r]
-            if (FACTOR) col[r] = fma(-ur, u, col[r]);
-            wcol[r] = fma(-ur, wj, wcol[r]);
-        }
-    }
-    if (FACTOR) {
-#pragma unroll
-        for (int r = 0; r < SB; r++)
-            if (r <= lane) sA[(o + r) + (o + lane) * LDU] = col[r];
-    }
-    // lane k holds row k of X: X[k, i] = W[i, k] = wcol[i] (i >= k).  X' goes below the diagonal
-    // of the block, and a dense copy of X' (sX[i + k * LDX] = X[k, i]) serves the block row.
-#pragma unroll
-    for (int i = 0; i < SB; i++) {
-        if (i > lane) sA[(o + i) + (o + lane) * LDU] = wcol[i];
-        sX[i + lane * LDX] = (i >= lane) ? wcol[i] : 0.0;
-    }
-    __syncwarp();
-}
-
-template <bool FACTOR>
-__device__ __forceinline__ int panel_body(double* __restrict__ Ab, int64_t lda, int nb,
-                                          double* __restrict__ Db, int ldd, int dn, bool zero_lower,
-                                          double* sA, double* diagX, double* sX, double* sT, int* s_bad) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) *s_bad = 0;
-    // 64 elements per thread, 16 global loads in flight at a time
-    for (int base = 0; base < NB * NB; base += PT * 16) {
-        double v[16];
-#pragma unroll
-        for (int u = 0; u < 16; u++) {
-            int idx = base + u * PT + tid;
-            int r = idx & (NB - 1), c = idx >> 7;
-            double x = 0.0;
-            if (r < nb && c < nb) {
-                if (r <= c) x = Ab[r + (int64_t)c * lda];
-            } else if (r == c) {
-                x = 1.0;
-            }
-            v[u] = x;
-        }
-#pragma unroll
-        for (int u = 0; u < 16; u++) {
-            int idx = base + u * PT + tid;
-            sA[(idx & (NB - 1)) + (idx >> 7) * LDU] = v[u];
-        }
-    }
-    __syncthreads();
-
-    for (int b = 0; b < NB / SB; b++) {
-        const int o = b * SB;
-        if (warp == 0) base_block<FACTOR>(sA, diagX, sX, o, lane, s_bad);
-        __syncthreads();
-        if (FACTOR && b < NB / SB - 1) {
-            const int t0 = o + SB;
-            const int ncol = NB - t0;
-            // (b) block row U[o + i, c] = sum_k X[k, i] A[o + k, c]: 4 x 4 tiles, 8 row tiles
-            {
-                const int ti = tid & 7, tj = tid >> 3;          // tj: 0..31 column tiles
-                const bool act = tj * 4 < ncol;
-                double acc[4][4];
-#pragma unroll
-                for (int a = 0; a < 4; a++)
-#pragma unroll
-                    for (int q = 0; q < 4; q++) acc[a][q] = 0.0;
-                if (act) {
-                    const double* xp = sX + ti * 4;
-                    const double* ap = sA + o + (t0 + tj * 4) * LDU;
-#pragma unroll 4
-                    for (int k = 0; k < SB; k++) {
-                        double xa[4], av[4];
-#pragma unroll
-                        for (int a = 0; a < 4; a++) xa[a] = xp[a + k * LDX];
-#pragma unroll
-                        for (int q = 0; q < 4; q++) av[q] = ap[k + q * LDU];
-#pragma unroll
-                        for (int a = 0; a < 4; a++)
-#pragma unroll
-                            for (int q = 0; q < 4; q++) acc[a][q] = fma(xa[a], av[q], acc[a][q]);
-                    }
-                }
-                __syncthreads();
-                if (act) {
-#pragma unroll
-                    for (int a = 0; a < 4; a++)
-#pragma unroll
-                        for (int q = 0; q < 4; q++) sA[(o + ti * 4 + a) + (t0 + tj * 4 + q) * LDU] = acc[a][q];
-                }
-                __syncthreads();
-            }
-            // (c) trailing update A[r, c] -= sum_k U[o + k, r] U[o + k, c] on 4 x 4 tiles with r-tile <= c-tile
-            {
-                const int nt4 = ncol / 4;
-                const int ntiles = nt4 * (nt4 + 1) / 2;
-                for (int t = tid; t < ntiles; t += PT) {
-                    // tile (tr, tc) with tr <= tc from the linear index t = tc (tc + 1) / 2 + tr
-                    int tc = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-                    while ((tc + 1) * (tc + 2) / 2 <= t) tc++;
-                    while (tc * (tc + 1) / 2 > t) tc--;
-                    const int tr = t - tc * (tc + 1) / 2;
-                    const double* ur = sA + o + (t0 + tr * 4) * LDU;
-                    const double* uc = sA + o + (t0 + tc * 4) * LDU;
-                    double acc[4][4];
-#pragma unroll
-                    for (int a = 0; a < 4; a++)
-#pragma unroll
-                        for (int q = 0; q < 4; q++) acc[a][q] = 0.0;
-#pragma unroll 4
-                    for (int k = 0; k < SB; k++) {
-                        double rv[4], cv[4];
-#pragma unroll
-                        for (int a = 0; a < 4; a++) rv[a] = ur[k + a * LDU];
-#pragma unroll
-                        for (int q = 0; q < 4; q++) cv[q] = uc[k + q * LDU];
-#pragma unroll
-                        for (int a = 0; a < 4; a++)
-#pragma unroll
-                            for (int q = 0; q < 4; q++) acc[a][q] = fma(rv[a], cv[q], acc[a][q]);
-                    }
-#pragma unroll
-                    for (int a = 0; a < 4; a++)
-#pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            const int r = t0 + tr * 4 + a, c = t0 + tc * 4 + q;
-                            if (r <= c) sA[r + c * LDU] -= acc[a][q];
-                        }
-                }
-                __syncthreads();
-            }
-        }
-    }
-
-    // (d) off-diagonal block columns of X.  For cb = 1..3 with h = 32 cb:
-    //   T = X[0:h, 0:h] U[0:h, h:h+32]   (X upper triangular: X[i, k] for k > i sits at sA[k + i LDU])
-    //   X[0:h, h:h+32] = -T X[cb, cb]
-    for (int cb = 1; cb < NB / SB; cb++) {
-        const int h = cb * SB;
-        // dense copy of X[cb, cb] (upper triangular): sX[k + j * LDX] = X[h + k, h + j]
-        for (int idx = tid; idx < SB * SB; idx += PT) {
-            int k = idx & 31, j = idx >> 5;
-            double v = 0.0;
-            if (k < j) v = sA[(h + j) + (h + k) * LDU];
-            else if (k == j) v = diagX[h + j];
-            sX[k + j * LDX] = v;
-        }
-        // T tiles: rows i0..i0+3 (i0 = 4 ti), cols 4 tj..; h/4 x 8 tiles
-        const int ntile = (h / 4) * 8;
-        for (int t = tid; t < ntile; t += PT) {
-            const int ti = t % (h / 4), tj = t / (h / 4);
-            const int i0 = ti * 4;
-            double acc[4][4];
-#pragma unroll
-            for (int a = 0; a < 4; a++)
-#pragma unroll
-                for (int q = 0; q < 4; q++) acc[a][q] = 0.0;
-            const double* up = sA + (h + tj * 4) * LDU;     // up[k + q * LDU] = U[k, h + 4 tj + q]
-            // diagonal 4 x 4 piece: k in i0 .. i0 + 3 with the triangular structure
-#pragma unroll
-            for (int kk = 0; kk < 4; kk++) {
-                const int k = i0 + kk;
-#pragma unroll
-                for (int a = 0; a < 4; a++) {
-                    double xv = 0.0;
-                    if (kk > a) xv = sA[k + (i0 + a) * LDU];
-                    else if (kk == a) xv = diagX[k];
-#pragma unroll
-                    for (int q = 0; q < 4; q++) acc[a][q] = fma(xv, up[k + q * LDU], acc[a][q]);
-                }
-            }
-            for (int k = i0 + 4; k < h; k++) {
-                double xv[4], uv[4];
-#pragma unroll
-                for (int a = 0; a < 4; a++) xv[a] = sA[k + (i0 + a) * LDU];
-#pragma unroll
-                for (int q = 0; q < 4; q++) uv[q] = up[k + q * LDU];
-#pragma unroll
-                for (int a = 0; a < 4; a++)
-#pragma unroll
-                    for (int q = 0; q < 4; q++) acc[a][q] = fma(xv[a], uv[q], acc[a][q]);
-            }
-#pragma unroll
-            for (int a = 0; a < 4; a++)
-#pragma unroll
-                for (int q = 0; q < 4; q++) sT[(i0 + a) + (tj * 4 + q) * LDT] = acc[a][q];
-        }
-        __syncthreads();
-        // X[i, h + j] = -sum_{k <= j} T[i, k] X[cb, cb][k, j]; stored at sA[(h + j) + i * LDU]
-        for (int t = tid; t < ntile; t += PT) {
-            const int ti = t % (h / 4), tj = t / (h / 4);
-            const int i0 = ti * 4, j0 = tj * 4;
-            double acc[4][4];
-#pragma unroll
-            for (int a = 0; a < 4; a++)
-#pragma unroll
-                for (int q = 0; q < 4; q++) acc[a][q] = 0.0;
-            for (int k = 0; k < j0 + 4; k++) {
-                double tv[4], xv[4];
-#pragma unroll
-                for (int a = 0; a < 4; a++) tv[a] = sT[(i0 + a) + k * LDT];
-#pragma unroll
-                for (int q = 0; q < 4; q++) xv[q] = sX[k + (j0 + q) * LDX];
-#pragma unroll
-                for (int a = 0; a < 4; a++)
-#pragma unroll
-                    for (int q = 0; q < 4; q++) acc[a][q] = fma(tv[a], xv[q], acc[a][q]);
-            }
-#pragma unroll
-            for (int a = 0; a < 4; a++)
-#pragma unroll
-                for (int q = 0; q < 4; q++) sA[(h + j0 + q) + (i0 + a) * LDU] = -acc[a][q];
-        }
-        __syncthreads();
-    }
-
-    if (FACTOR) {
-        for (int idx = tid; idx < NB * NB; idx += PT) {
-            int r = idx & (NB - 1), c = idx >> 7;
-            if (r < nb && c < nb) {
-                if (r <= c) Ab[r + (int64_t)c * lda] = sA[r + c * LDU];
-                else if (zero_lower) Ab[r + (int64_t)c * lda] = 0.0;
-            }
-        }
-    }
-    for (int idx = tid; idx < dn * dn; idx += PT) {
-        int r = idx % dn, c = idx / dn;
-        double x = 0.0;
-        if (r < c) x = sA[c + r * LDU];
-        else if (r == c) x = diagX[r];
-        Db[r + (int64_t)c * ldd] = x;
-    }
-    return *s_bad;
-}
-
-//   FACTOR:  grid = 1; diagonal block blk0 of the m x m matrix A; a bad pivot sets *info.
-//   !FACTOR: grid = number of diagonal blocks of the m x m triangular matrix A; inverts only.
-template <bool FACTOR>
-__global__ void __launch_bounds__(PT, 1)
-panel_kernel(double* __restrict__ A, int64_t lda, int64_t m, int64_t blk0, double* __restrict__ dinv,
-             int* __restrict__ info) {
-    extern __shared__ double sU[];            // NB x NB col-major, ld = LDU
-    __shared__ double diagX[NB];
-    __shared__ double sX[SB * LDX];
-    __shared__ double sT[SB * LDT];
-    __shared__ int s_bad;
-    const int64_t blk = FACTOR ? blk0 : (int64_t)blockIdx.x;
-    const int64_t k0 = blk * NB;
-    const int nb = (int)min((int64_t)NB, m - k0);
-    int bad = panel_body<FACTOR>(A + k0 + k0 * lda, lda, nb, dinv + blk * (int64_t)NB * NB, NB, NB, false,
-                                 sU, diagX, sX, sT, &s_bad);
-    if (FACTOR && bad && threadIdx.x == 0) atomicCAS(info, 0, (int)(k0 + bad));
-}
-
-// Batched variant for the matrix cones: CTA c factors the side x side matrix at U + moff[c]
-// (leading dim = side rounded up to even) in place and writes its inverse to Ui + moff[c].
-// A failed factorisation clears flag[kidx[c]].  Cones with side > 128 are skipped (blocked path).
-__global__ void __launch_bounds__(PT, 1)
-chol_batched_kernel(int ncones, const int* __restrict__ sides, const int64_t* __restrict__ moff,
-                    const int* __restrict__ kidx, double* __restrict__ U, double* __restrict__ Ui,
-                    uint8_t* __restrict__ flag) {
-    extern __shared__ double sU[];
-    __shared__ double diagX[NB];
-    __shared__ double sX[SB * LDX];
-    __shared__ double sT[SB * LDT];
-    __shared__ int s_bad;
-    const int c = blockIdx.x;
-    if (c >= ncones) return;
-    const int side = sides[c];
-    if (side > NB) return;
-    const int lde = (side + 1) & ~1;
-    int bad = panel_body<true>(U + moff[c], lde, side, Ui + moff[c], lde, side, true, sU, diagX, sX, sT, &s_bad);
-    if (bad && threadIdx.x == 0) flag[kidx[c]] = 0;
 }
 
 // ---- triangular solve with the blocked factor -------------------------------------------

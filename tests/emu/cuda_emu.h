@@ -76,6 +76,15 @@ static inline double __shfl_sync(unsigned, double v, int lane) {
     return emu_shfl(v, (int)((threadIdx.x & ~31u) + (unsigned)lane));
 }
 
+static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
+
+// blocks run one after the other and the callers below are single-threaded at the call site (threadIdx.x == 0)
+static inline int atomicCAS(int* addr, int compare, int val) {
+    int old = __atomic_load_n(addr, __ATOMIC_SEQ_CST);
+    __atomic_compare_exchange_n(addr, &compare, val, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+    return old;
+}
+
 namespace emu {
 // run `body` for every thread of every block of the grid (1-D blocks, up to 2-D grids)
 void launch(dim3 grid, dim3 block, size_t dyn_smem, const std::function<void()>& body);

@@ -495,3 +495,32 @@ int emu_gemv_n(int vec, int64_t rows, int64_t ncols, const double* M, int64_t ld
 }
 
 }  // extern "C"
+
+// ---- factor-and-invert kernel of the blocked Cholesky and its batched variant (csrc/chol_kernels.cuh) ----
+#include "../../hypatia.jl_b200/csrc/chol_kernels.cuh"
+
+extern "C" {
+
+// diagonal block blk0 of the m x m matrix A (upper triangle): A -> U in place, dinv block <- U^-1; info as dpotrf
+int emu_panel_factor(double* A, int64_t lda, int64_t m, int64_t blk0, double* dinv, int* info) {
+    emu::launch(dim3(1), dim3(hypdev::PT), (size_t)hypdev::NB * hypdev::LDU * 8,
+                [&] { hypdev::panel_kernel<true>(A, lda, m, blk0, dinv, info); });
+    return 0;
+}
+
+// inverts every diagonal block of the upper triangular m x m matrix A (hyp_trtri_diag)
+int emu_panel_invert(double* A, int64_t lda, int64_t m, double* dinv) {
+    const int nblk = (int)((m + hypdev::NB - 1) / hypdev::NB);
+    emu::launch(dim3(nblk), dim3(hypdev::PT), (size_t)hypdev::NB * hypdev::LDU * 8,
+                [&] { hypdev::panel_kernel<false>(A, lda, m, 0, dinv, nullptr); });
+    return 0;
+}
+
+int emu_chol_batched(int ncones, const int* sides, const int64_t* moff, const int* kidx, double* U, double* Ui,
+                     uint8_t* flag) {
+    emu::launch(dim3(ncones), dim3(hypdev::PT), (size_t)hypdev::NB * hypdev::LDU * 8,
+                [&] { hypdev::chol_batched_kernel(ncones, sides, moff, kidx, U, Ui, flag); });
+    return 0;
+}
+
+}  // extern "C"

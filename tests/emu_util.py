@@ -292,7 +292,7 @@ class EmuMatGroup:
 
 class EmuGpowGroup:
     """Mirrors hyp_gpow_update_state / hyp_gpow_prod / hyp_gpow_dder3 (csrc/cones_gpow.cu) for a list of
-    GeneralizedPower cones; the batched Cholesky + inverse of the explicit Hessians (chol.cu) is NumPy here."""
+    GeneralizedPower cones, including the batched Cholesky + inverse of the explicit Hessians (chol_kernels.cuh)."""
 
     def __init__(self, specs):
         self.K = len(specs)
@@ -366,14 +366,11 @@ class EmuGpowGroup:
             lib().emu_gpow_state(self.K, p(self.off), p(self.dims), p(self.mu), p(self.aoff), p(self.alpha),
                                  p(self.kidx), p(self.lay.moff), p(self.point), p(self.dual), p(self.grad),
                                  p(self.scal), p(self.H), p(self.feas), p(self.dual_feas))
+        # hess_fact: the batched factor-and-invert kernel of chol.cu on a copy of the explicit Hessians
+        self.U = self.H.copy()
         self.Ui = np.zeros(self.lay.total)
-        for c in range(self.K):
-            Hc = self.lay.get(self.H, c)
-            try:
-                U = np.linalg.cholesky(Hc).T
-                self.lay.get(self.Ui, c)[:] = np.linalg.inv(U)
-            except np.linalg.LinAlgError:
-                self.feas[c] = 0
+        lib().emu_chol_batched(self.K, p(self.lay.sides), p(self.lay.moff), p(self.kidx), p(self.U), p(self.Ui),
+                               p(self.feas))
 
     def prod(self, arr, mode, in_place=False):
         a = np.asfortranarray(np.asarray(arr, dtype=np.float64).reshape(self.q, -1, order="F")).copy(order="F")
