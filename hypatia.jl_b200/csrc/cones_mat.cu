@@ -19,7 +19,13 @@
 #include <cstdlib>
 #include "cones_mat_kernels.cuh"
 
+static_assert(MK_POSSEMIDEFTRI == HYP_CONE_POSSEMIDEFTRI && MK_HYPOPERLOGDETTRI == HYP_CONE_HYPOPERLOGDETTRI &&
+                  MK_HYPOROOTDETTRI == HYP_CONE_HYPOROOTDETTRI,
+              "cones_mat_kernels.cuh type codes must match the ABI");
+
 using hypdev::block_sum;
+using hypdev::mat_dualfeas_kernel;
+using hypdev::mat_post_kernel;
 using hypdev::pack_cols_kernel;
 using hypdev::svec_rc;
 using hypdev::unpack_cols_kernel;
@@ -29,121 +35,6 @@ using hypdev::warp_sum;
 namespace {
 
 constexpr double RT2 = 1.4142135623730951;
-
-// scal layout (8 doubles per cone): 0 logdet W, 1 phi, 2 zeta, 3 u, 4 v, 5 pzd (rootdet) / sigma (logdet)
-// One CTA per cone: U', U^-T, W^-1 (side <= 128; larger cones get W^-1 from a GEMM beforehand),
-// log det, the cone's scalars, feasibility, gradient and svec(W^-1).
-__global__ void __launch_bounds__(256)
-mat_post_kernel(int type, int ncones, const int64_t* __restrict__ off, const int* __restrict__ sides,
-                const int64_t* __restrict__ moff, const int* __restrict__ kidx,
-                const double* __restrict__ point, const double* __restrict__ U,
-                const double* __restrict__ Ui, double* __restrict__ Ut, double* __restrict__ Uit,
-                double* __restrict__ Wi, double* __restrict__ scal, double* __restrict__ grad,
-                double* __restrict__ wivec, uint8_t* __restrict__ feas) {
-    __shared__ double sm[8];
-    const int c = blockIdx.x;
-    if (c >= ncones) return;
-    const int d = sides[c], lde = (d + 1) & ~1;
-    const int64_t mo = moff[c], o = off[c];
-    const double* Uc = U + mo;
-    const double* Uic = Ui + mo;
-    double* Wic = Wi + mo;
-    const int lead = type == HYP_CONE_POSSEMIDEFTRI ? 0 : type == HYP_CONE_HYPOPERLOGDETTRI ? 2 : 1;
-    for (int idx = threadIdx.x; idx < d * d; idx += blockDim.x) {
-        int a = idx % d, b = idx / d;
-        Ut[mo + a + (int64_t)b * lde] = Uc[b + (int64_t)a * lde];
-        Uit[mo + a + (int64_t)b * lde] = Uic[b + (int64_t)a * lde];
-        if (d <= 128 && a <= b) {
-            // W^-1 = U^-1 U^-T : entry (a, b) = sum_{k >= b} Ui[a, k] Ui[b, k]
-            double s = 0.0;
-            for (int k = b; k < d; k++) s += Uic[a + (int64_t)k * lde] * Uic[b + (int64_t)k * lde];
-            Wic[a + (int64_t)b * lde] = s;
-            Wic[b + (int64_t)a * lde] = s;
-        }
-    }
-    double ld = 0.0;
-    for (int k = threadIdx.x; k < d; k += blockDim.x) ld += log(Uc[k + (int64_t)k * lde]);
-    ld = 2.0 * block_sum(ld, sm);
-    __syncthreads();
-    double gscale = -1.0;   // grad matrix part = gscale * svec(W^-1)
-    bool ok = true;
-    double* sc = scal + 8 * c;
-    if (type == HYP_CONE_HYPOPERLOGDETTRI) {
-        // hypoperlogdettri.jl:96-151
-        const double u = point[o], v = point[o + 1];
-        double phi = 0, zeta = 0;
-        if (v > HYP_EPS) {
-            phi = ld - d * log(v);
-            zeta = v * phi - u;
-            ok = zeta > HYP_EPS;
-        } else {
-            ok = false;
-        }
-        gscale = -1.0 - v / zeta;
-        if (threadIdx.x == 0) {
-            sc[0] = ld; sc[1] = phi; sc[2] = zeta; sc[3] = u; sc[4] = v; sc[5] = phi - d;
-            grad[o] = 1.0 / zeta;
-            grad[o + 1] = -1.0 / v - (phi - d) / zeta;
-            wivec[o] = 0.0;
-            wivec[o + 1] = 0.0;
-        }
-    } else if (type == HYP_CONE_HYPOROOTDETTRI) {
-        // hyporootdettri.jl:100-145
-        const double u = point[o];
-        const double phi = exp(ld / d), zeta = phi - u;
-        ok = zeta > HYP_EPS;
-        const double pzd = phi / zeta / d;
-        gscale = -pzd - 1.0;
-        if (threadIdx.x == 0) {
-            sc[0] = ld; sc[1] = phi; sc[2] = zeta; sc[3] = u; sc[4] = 0.0; sc[5] = pzd;
-            grad[o] = 1.0 / zeta;
-            wivec[o] = 0.0;
-        }
-    } else if (threadIdx.x == 0) {
-        sc[0] = ld;
-    }
-    if (!ok && threadIdx.x == 0) feas[kidx[c]] = 0;
-    const int64_t len = (int64_t)d * (d + 1) / 2;
-    for (int64_t idx = threadIdx.x; idx < len; idx += blockDim.x) {
-        int a, b;
-        svec_rc(idx, a, b);
-        double x = Wic[a + (int64_t)b * lde];
-        if (a != b) x *= RT2;
-        wivec[o + lead + idx] = x;
-        grad[o + lead + idx] = gscale * x;
-    }
-}
-
-// dual feasibility beyond "Cholesky of smat(dual) succeeded" (hypoperlogdettri.jl:119-132,
-// hyporootdettri.jl:117-129); U2 holds the factor of the dual matrix
-__global__ void __launch_bounds__(128)
-mat_dualfeas_kernel(int type, int ncones, const int64_t* __restrict__ off, const int* __restrict__ sides,
-                    const int64_t* __restrict__ moff, const int* __restrict__ kidx,
-                    const double* __restrict__ dual, const double* __restrict__ U2,
-                    uint8_t* __restrict__ dual_feas) {
-    __shared__ double sm[4];
-    const int c = blockIdx.x;
-    if (c >= ncones) return;
-    const int d = sides[c], lde = (d + 1) & ~1;
-    const double* Uc = U2 + moff[c];
-    double ld = 0.0;
-    for (int k = threadIdx.x; k < d; k += blockDim.x) ld += log(Uc[k + (int64_t)k * lde]);
-    ld = 2.0 * block_sum(ld, sm);
-    if (threadIdx.x == 0) {
-        const int64_t o = off[c];
-        const double u = dual[o];
-        bool ok = false;
-        if (u < -HYP_EPS) {
-            if (type == HYP_CONE_HYPOPERLOGDETTRI) {
-                const double v = dual[o + 1];
-                ok = (v - u * (ld + d * (1.0 - log(-u)))) > HYP_EPS;
-            } else {
-                ok = (ld - d * log(-u / d)) > HYP_EPS;
-            }
-        }
-        if (!ok) dual_feas[kidx[c]] = 0;
-    }
-}
 
 __global__ void info_to_flag_kernel(const int* __restrict__ info, uint8_t* __restrict__ flag, int k) {
     if (threadIdx.x == 0 && blockIdx.x == 0 && info[0] != 0) flag[k] = 0;

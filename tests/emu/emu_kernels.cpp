@@ -524,3 +524,33 @@ int emu_chol_batched(int ncones, const int* sides, const int64_t* moff, const in
 }
 
 }  // extern "C"
+
+// ---- the whole state update of a group of PosSemidefTri / HypoPerLogdetTri / HypoRootdetTri cones with sides <= 128,
+// as hyp_mat_update_state (cones_mat.cu) launches it: unpack -> batched Cholesky + inverse -> mat_post, then the dual
+// point: unpack -> batched Cholesky -> mat_dualfeas ----
+extern "C" {
+
+int emu_mat_state(int type, int ncones, const int64_t* off, const int* sides, const int64_t* moff, const int* kidx,
+                  const double* point, const double* dual, double* W, double* U, double* Ui, double* Ut, double* Uit,
+                  double* Wi, double* U2, double* Ui2, double* scal, double* grad, double* wivec, uint8_t* feas,
+                  uint8_t* dual_feas) {
+    const int lead = type == 2 ? 0 : type == 3 ? 2 : 1;
+    const size_t csm = (size_t)hypdev::NB * hypdev::LDU * 8;
+    emu::launch(dim3(ncones, 2), dim3(64), 0,
+                [&] { hypdev::unpack_state_kernel(ncones, off, sides, moff, lead, point, W, U); });
+    emu::launch(dim3(ncones), dim3(hypdev::PT), csm,
+                [&] { hypdev::chol_batched_kernel(ncones, sides, moff, kidx, U, Ui, feas); });
+    emu::launch(dim3(ncones), dim3(256), 0, [&] {
+        hypdev::mat_post_kernel(type, ncones, off, sides, moff, kidx, point, U, Ui, Ut, Uit, Wi, scal, grad, wivec, feas);
+    });
+    emu::launch(dim3(ncones, 2), dim3(64), 0,
+                [&] { hypdev::unpack_state_kernel(ncones, off, sides, moff, lead, dual, U2, nullptr); });
+    emu::launch(dim3(ncones), dim3(hypdev::PT), csm,
+                [&] { hypdev::chol_batched_kernel(ncones, sides, moff, kidx, U2, Ui2, dual_feas); });
+    if (type != 2)
+        emu::launch(dim3(ncones), dim3(128), 0,
+                    [&] { hypdev::mat_dualfeas_kernel(type, ncones, off, sides, moff, kidx, dual, U2, dual_feas); });
+    return 0;
+}
+
+}  // extern "C"

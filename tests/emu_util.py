@@ -271,6 +271,24 @@ class EmuMatGroup:
             elif self.type == 4:
                 self.scal[8 * c + 1], self.scal[8 * c + 2], self.scal[8 * c + 5] = ck.phi, ck.zeta, ck.pzd
 
+    def device_state(self, point, dual):
+        """Replaces the NumPy-built state by the device pipeline of hyp_mat_update_state (sides <= 128): unpack ->
+        batched Cholesky + inverse -> mat_post_kernel, and the dual-feasibility pass.  Returns (grad, feas, dual_feas)."""
+        lay = self.lay
+        self.point = np.ascontiguousarray(point, dtype=np.float64)
+        dual = np.ascontiguousarray(dual, dtype=np.float64)
+        self.W, self.Wi, self.Ui, self.Ut, self.Uit = (np.zeros(lay.total) for _ in range(5))
+        U, U2, Ui2 = (np.zeros(lay.total) for _ in range(3))
+        self.scal = np.zeros(8 * self.K)
+        self.wivec = np.zeros(self.q)
+        grad = np.zeros(self.q)
+        kidx = np.arange(self.K, dtype=np.int32)
+        feas, dfeas = np.ones(self.K, dtype=np.uint8), np.ones(self.K, dtype=np.uint8)
+        lib().emu_mat_state(self.type, self.K, p(self.off), p(lay.sides), p(lay.moff), p(kidx), p(self.point), p(dual),
+                            p(self.W), p(U), p(self.Ui), p(self.Ut), p(self.Uit), p(self.Wi), p(U2), p(Ui2), p(self.scal),
+                            p(grad), p(self.wivec), p(feas), p(dfeas))
+        return grad, feas, dfeas
+
     def dder3(self, direction, threads=64):
         d = np.ascontiguousarray(direction, dtype=np.float64)
         out = np.zeros(self.q)
