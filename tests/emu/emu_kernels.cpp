@@ -554,3 +554,39 @@ int emu_mat_state(int type, int ncones, const int64_t* off, const int* sides, co
 }
 
 }  // extern "C"
+
+// ---- rook-pivoted LDL' factorisation and solve (csrc/ldlt_kernels.cuh); the launch loop mirrors hyp_ldlt_factor /
+// hyp_ldlt_solve of ldlt.cu (one five-kernel sequence per column, device-side cursor in st) ----
+#include "../../hypatia.jl_b200/csrc/ldlt_kernels.cuh"
+
+extern "C" {
+
+// A: upper triangle on entry -> L, D in place; ipiv: 3 m ints; returns info (0 or the first exactly singular column)
+int emu_ldlt_factor(double* A, int64_t lda, int64_t m, int* ipiv) {
+    std::vector<int> st(hypdev::ST_NUM + 1, 0);
+    std::vector<double> work((size_t)4 * m + 4, 0.0);
+    int info = 0;
+    emu::launch(dim3(1), dim3(32), 0, [&] { hypdev::init_state_kernel(st.data()); });
+    emu::launch(dim3(1, (unsigned)m), dim3(64), 0, [&] { hypdev::symmetrize_kernel(A, lda, m); });
+    for (int64_t seq = 0; seq < m; seq++) {
+        emu::launch(dim3(1), dim3(1024), 0, [&] { hypdev::pivot_kernel(A, lda, m, st.data(), ipiv); });
+        emu::launch(dim3(2), dim3(64), 0, [&] { hypdev::swap_kernel(A, lda, m, st.data(), 0); });
+        emu::launch(dim3(2), dim3(64), 0, [&] { hypdev::swap_kernel(A, lda, m, st.data(), 1); });
+        emu::launch(dim3(2), dim3(64), 0, [&] { hypdev::colprep_kernel(A, lda, m, st.data(), work.data()); });
+        emu::launch(dim3(2, 3), dim3(256), 0, [&] { hypdev::update_kernel(A, lda, m, st.data(), work.data()); });
+    }
+    emu::launch(dim3(1), dim3(32), 0, [&] { hypdev::finish_info_kernel(st.data(), &info); });
+    return info;
+}
+
+int emu_ldlt_solve(const double* A, int64_t lda, int64_t m, const int* ipiv, double* x) {
+    emu::launch(dim3(1), dim3(1024), 0, [&] { hypdev::ldlt_solve_kernel(A, lda, m, ipiv, x); });
+    return 0;
+}
+
+int emu_increase_diag(double* A, int64_t lda, int64_t m) {
+    emu::launch(dim3(2), dim3(64), 0, [&] { hypdev::increase_diag_kernel(A, lda, m); });
+    return 0;
+}
+
+}  // extern "C"
