@@ -343,4 +343,175 @@ chol_batched_kernel(int ncones, const int* __restrict__ sides, const int64_t* __
     if (bad && threadIdx.x == 0) flag[kidx[c]] = 0;
 }
 
+#ifdef HYP_EMU
+// host emulation (tests/emu/): blocks run one after the other, so the first CTA takes every ticket in dependency order
+// and the flag protocol degenerates to plain loads / stores; the arithmetic of the solve is what gets checked
+__device__ __forceinline__ int ld_acquire(const int* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+__device__ __forceinline__ void st_release(int* p, int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+#else
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+#endif
+
+// ---- triangular solve with the blocked factor -------------------------------------------
+// flags[0] = ticket counter (zeroed by the host before the launch), flags[1 + k] = epoch when
+// block k of the solution is final.  CTA for block k: the inverted diagonal block goes to shared
+// memory up front, and every off-diagonal tile is loaded into registers BEFORE the CTA waits for
+// the solution block it multiplies, so the dependency chain only sees: flag -> 1 KB vector load ->
+// 64 FMAs per thread -> reduction -> 128 x 128 matvec from shared memory -> publish.
+constexpr int TRSV_SMEM = NB * NB * 8;
+
+template <bool TRANS>
+__global__ void __launch_bounds__(256, 1)
+trsv_kernel(const double* __restrict__ F, int64_t ldf, int64_t m, const double* __restrict__ dinv,
+            double* x, int* flags, int nblk, int epoch) {
+    HYP_DYN_SMEM(double, sD);                // Dinv_k, 128 x 128 col-major
+    __shared__ double sv[2][NB];
+    __shared__ double sacc[2][NB];
+    __shared__ int s_ticket;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    while (true) {
+        if (tid == 0) s_ticket = atomicAdd(&flags[0], 1);
+        __syncthreads();
+        const int t = s_ticket;
+        __syncthreads();
+        if (t >= nblk) return;
+        const int k = TRANS ? t : nblk - 1 - t;
+        const int64_t c0 = (int64_t)k * NB;
+        {
+            const double* Dk = dinv + (int64_t)k * NB * NB;
+#pragma unroll 8
+            for (int idx = tid; idx < NB * NB; idx += 256) sD[idx] = Dk[idx];
+        }
+
+        if (TRANS) {
+            // y_k = Dinv_k' (b_k - sum_{j<k} U[j-block, k-block]' y_j); warp w owns 16 columns,
+            // lane l rows l, l+32, l+64, l+96 of every tile
+            double pacc[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) pacc[i] = 0.0;
+            const int64_t cw = c0 + warp * 16;
+            for (int j = 0; j < k; j++) {
+                double tl[16][4];
+                const double* Ut = F + (int64_t)j * NB + cw * ldf;
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const bool ok = cw + i < m;
+                    const double* col = Ut + (int64_t)i * ldf;
+#pragma unroll
+                    for (int h = 0; h < 4; h++) tl[i][h] = ok ? col[lane + 32 * h] : 0.0;
+                }
+                if (tid == 0) {
+                    while (ld_acquire(&flags[1 + j]) != epoch) {
+                    }
+                }
+                __syncthreads();
+                double* svj = sv[j & 1];
+                if (tid < NB) svj[tid] = __ldcg(x + (int64_t)j * NB + tid);
+                __syncthreads();
+                const double v0 = svj[lane], v1 = svj[lane + 32], v2 = svj[lane + 64], v3 = svj[lane + 96];
+#pragma unroll
+                for (int i = 0; i < 16; i++)
+                    pacc[i] += tl[i][0] * v0 + tl[i][1] * v1 + tl[i][2] * v2 + tl[i][3] * v3;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                double a = pacc[i];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                pacc[i] = a;
+            }
+            __syncthreads();
+            double* vb = sv[0];
+            if (lane == 0) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    int64_t c = cw + i;
+                    vb[warp * 16 + i] = (c < m) ? (x[c] - pacc[i]) : 0.0;
+                }
+            }
+            __syncthreads();
+            // y[c] = sum_{r <= c} Dinv[r, c] v[r]
+            const double v0 = vb[lane], v1 = vb[lane + 32], v2 = vb[lane + 64], v3 = vb[lane + 96];
+            double res[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const double* col = sD + (warp * 16 + i) * NB;
+                double a = col[lane] * v0 + col[lane + 32] * v1 + col[lane + 64] * v2 + col[lane + 96] * v3;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                res[i] = a;
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    int64_t c = cw + i;
+                    if (c < m) x[c] = res[i];
+                }
+            }
+        } else {
+            // x_k = Dinv_k (y_k - sum_{j>k} U[k-block, j-block] x_j); thread owns a row, the two
+            // halves of the CTA split the 128 columns of a tile
+            const int r = tid & (NB - 1), half = tid >> 7;
+            const int64_t grow = c0 + r;
+            double acc = 0.0;
+            for (int j = nblk - 1; j > k; j--) {
+                double tl[64];
+                const int64_t cb = (int64_t)j * NB + half * 64;
+                const double* Ut = F + grow + cb * ldf;
+#pragma unroll
+                for (int c = 0; c < 64; c++) tl[c] = (grow < m && cb + c < m) ? Ut[(int64_t)c * ldf] : 0.0;
+                if (tid == 0) {
+                    while (ld_acquire(&flags[1 + j]) != epoch) {
+                    }
+                }
+                __syncthreads();
+                double* svj = sv[j & 1];
+                if (tid < NB) {
+                    int64_t c = (int64_t)j * NB + tid;
+                    svj[tid] = (c < m) ? __ldcg(x + c) : 0.0;
+                }
+                __syncthreads();
+                const double* svh = svj + half * 64;
+                double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                for (int c = 0; c < 64; c += 2) {
+                    a0 += tl[c] * svh[c];
+                    a1 += tl[c + 1] * svh[c + 1];
+                }
+                acc += a0 + a1;
+            }
+            sacc[half][r] = acc;
+            __syncthreads();
+            double* vb = sv[0];
+            if (tid < NB) vb[tid] = (c0 + tid < m) ? (x[c0 + tid] - sacc[0][tid] - sacc[1][tid]) : 0.0;
+            __syncthreads();
+            // x[r] = sum_{c >= r} Dinv[r, c] v[c]
+            double a0 = 0.0, a1 = 0.0;
+            {
+                const double* row = sD + r + (half * 64) * NB;
+                const double* svh = vb + half * 64;
+#pragma unroll 16
+                for (int c = 0; c < 64; c += 2) {
+                    a0 += row[c * NB] * svh[c];
+                    a1 += row[(c + 1) * NB] * svh[c + 1];
+                }
+            }
+            __syncthreads();
+            sacc[half][r] = a0 + a1;
+            __syncthreads();
+            if (tid < NB && c0 + tid < m) x[c0 + tid] = sacc[0][tid] + sacc[1][tid];
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) st_release(&flags[1 + k], epoch);
+    }
+}
+
 }  // namespace hypdev

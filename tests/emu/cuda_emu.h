@@ -77,6 +77,9 @@ static inline double __shfl_sync(unsigned, double v, int lane) {
 }
 
 static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
+static inline int atomicAdd(int* addr, int val) { return __atomic_fetch_add(addr, val, __ATOMIC_SEQ_CST); }
+static inline double __ldcg(const double* p) { return *p; }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
 // blocks run one after the other and the callers below are single-threaded at the call site (threadIdx.x == 0)
 static inline int atomicCAS(int* addr, int compare, int val) {

@@ -590,3 +590,20 @@ int emu_increase_diag(double* A, int64_t lda, int64_t m) {
 }
 
 }  // extern "C"
+
+// ---- triangular solves with the blocked factor (trsv_kernel of csrc/chol_kernels.cuh, launched as hyp_trsv_upper) ----
+extern "C" {
+
+// x <- U^-T x (trans = 1) or U^-1 x (trans = 0) with the inverted diagonal blocks `dinv` of the upper factor F
+int emu_trsv_upper(const double* F, int64_t ldf, int64_t m, const double* dinv, double* x, int trans) {
+    const int nblk = (int)((m + hypdev::NB - 1) / hypdev::NB);
+    std::vector<int> flags((size_t)nblk + 2, 0);
+    const int epoch = 7;
+    emu::launch(dim3(nblk < 3 ? nblk : 3), dim3(256), (size_t)hypdev::NB * hypdev::NB * 8, [&] {
+        if (trans) hypdev::trsv_kernel<true>(F, ldf, m, dinv, x, flags.data(), nblk, epoch);
+        else hypdev::trsv_kernel<false>(F, ldf, m, dinv, x, flags.data(), nblk, epoch);
+    });
+    return 0;
+}
+
+}  // extern "C"

@@ -92,3 +92,24 @@ def test_batched_cholesky_of_cone_groups():
         got = lay.get(U, c)
         assert rel(np.triu(got), R) <= 1e-13 and not np.tril(got, -1).any()      # zero_lower
         assert rel(lay.get(Ui, c), np.linalg.inv(R)) <= 1e-11
+
+
+@pytest.mark.parametrize("m", [1, 100, 128, 129, 300, 390])
+def test_blocked_triangular_solves_give_potrs(m):
+    """dpotrs = two sweeps of trsv_kernel over 128-blocks with the inverted diagonal blocks of the factor
+    (ldiv!(x, fact, rhs), qrchol.jl:68).  In the emulation the first CTA takes every ticket, so this checks the
+    arithmetic of the sweeps, not the inter-CTA flag protocol (that is covered by the -m gpu tier)."""
+    rng = np.random.default_rng(m)
+    S = _spd(rng, m, cond=1e2)
+    U = np.asfortranarray(np.linalg.cholesky(S).T)
+    nblk = (m + NB - 1) // NB
+    dinv = np.zeros(nblk * NB * NB)
+    lib().emu_panel_invert(p(U), i64(m), i64(m), p(dinv))
+    b = rng.standard_normal(m)
+    y = b.copy()
+    lib().emu_trsv_upper(p(U), i64(m), i64(m), p(dinv), p(y), 1)          # y = U^-T b
+    assert rel(y, np.linalg.solve(U.T, b)) <= 1e-11
+    x = y.copy()
+    lib().emu_trsv_upper(p(U), i64(m), i64(m), p(dinv), p(x), 0)          # x = U^-1 y
+    assert rel(x, np.linalg.solve(S, b)) <= 1e-10
+    assert rel(S @ x, b) <= 1e-11
