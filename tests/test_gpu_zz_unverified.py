@@ -13,6 +13,10 @@ from hypatia_b200.host.point import Point
 
 pytestmark = pytest.mark.gpu
 
+# Never run on a GPU so far: reported as XPASS / XFAIL instead of pass / fail until a round with GPU budget has seen them
+# pass (then the marker goes away).  The two LinMatrixIneq tests below HAVE passed on a B200 and carry no marker.
+not_yet_on_gpu = pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent; CPU-tier verified only")
+
 
 def _lmi(rng, side, dim, use_dual=False):
     As = []
@@ -76,6 +80,7 @@ def _solve_dev(model):
     return s
 
 
+@not_yet_on_gpu
 @pytest.mark.parametrize("build", kat.EXTRA, ids=lambda f: f.__name__)
 def test_kat_device_extra(build):
     model, expected = build()
@@ -83,6 +88,7 @@ def test_kat_device_extra(build):
 
 
 # the DoublyNonnegativeTri kernels have not run on a GPU at all: keep them after everything else
+@not_yet_on_gpu
 def test_doublynonnegativetri_oracles_match_cpu_oracle():
     """Not yet run on a GPU (emulation tier: tests/test_emu_gpow.py)."""
     from hypatia_b200.cones import DeviceConeBlock
@@ -109,6 +115,7 @@ def test_doublynonnegativetri_oracles_match_cpu_oracle():
     dev.free()
 
 
+@not_yet_on_gpu
 def test_doublynonnegativetri_in_the_system_solve():
     """Not yet run on a GPU."""
     from hypatia_b200.syssolver import QRCholDenseSystemSolver as DevQRChol
