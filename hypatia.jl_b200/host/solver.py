@@ -420,13 +420,14 @@ class Solver:
                 if time.perf_counter() - start >= self.time_limit:
                     self.status = "TimeLimit"
                     break
-                if improv < self.tol_slow:
-                    if prev_is_slow and prev2_is_slow:
-                        self.status = "SlowProgress"
-                        break
-                    prev2_is_slow, prev_is_slow = prev_is_slow, True
-                else:
-                    prev2_is_slow, prev_is_slow = prev_is_slow, False
+                if stepper.expect_improvement():              # Solvers.jl:362-377
+                    if improv < self.tol_slow:
+                        if prev_is_slow and prev2_is_slow:
+                            self.status = "SlowProgress"
+                            break
+                        prev2_is_slow, prev_is_slow = prev_is_slow, True
+                    else:
+                        prev2_is_slow, prev_is_slow = prev_is_slow, False
 
                 self.res_norm_cutoff = 1e-4 * max(self.x_norm_res, self.y_norm_res,
                                                   self.z_norm_res, self.tau_feas)

@@ -347,3 +347,142 @@ class CombinedStepper:
         if self.cent_only:
             return "cent" if self.unadj_only else "ce-a"
         return "comb" if self.unadj_only else "co-a"
+
+    def expect_improvement(self):
+        return True                     # combined.jl:122
+
+
+# --------------------------------------------------------------------------------------
+# predict-or-center stepper (steppers/predorcent.jl)
+# --------------------------------------------------------------------------------------
+class PredOrCentStepper:
+    """reference: predorcent.jl:5-203.  One direction pair per iteration - a prediction when the last accepted point
+    was close to the central path (or after max_cent_steps centerings), a centering otherwise - so an iteration costs
+    update_lhs + 1 or 2 solve_system calls instead of the combined stepper's 4."""
+
+    def __init__(self, use_adjustment: bool = True, use_curve_search=None, max_cent_steps: int = 4,
+                 pred_prox_bound: float = 0.0332, **searcher_options):
+        if use_curve_search is None:
+            use_curve_search = use_adjustment
+        assert use_adjustment or not use_curve_search     # curve search needs the adjustment direction
+        self.use_adjustment = use_adjustment
+        self.use_curve_search = use_curve_search
+        self.max_cent_steps = max_cent_steps
+        self.pred_prox_bound = pred_prox_bound
+        self.searcher_options = searcher_options
+
+    def load(self, solver):
+        """reference: predorcent.jl:46-70"""
+        model = solver.model
+        if self.use_adjustment and not solver.cones.use_dder3().any():
+            self.use_adjustment = self.use_curve_search = False
+        self.prev_alpha = 1.0
+        self.cent_count = 0
+        self.rhs = Point(model)
+        self.dir = Point(model)
+        self.temp = Point(model)
+        self.dir_noadj = Point(model)
+        self.dir_adj = Point(model)
+        self.dir_temp = np.zeros_like(self.rhs.vec)
+        self.searcher = StepSearcher(model, **self.searcher_options)
+        self.unadj_only = False
+        self.unadj_alpha = 0.0
+        self.is_pred = True
+        return self
+
+    def start_sched(self):
+        return 1                          # search.jl:72
+
+    def step(self, solver) -> bool:
+        """reference: predorcent.jl:72-163"""
+        point, rhs, d = solver.point, self.rhs, self.dir
+        t0 = time.perf_counter()
+        solver.syssolver.update_lhs(solver)
+        solver.time_upsys += time.perf_counter() - t0
+
+        is_pred = self.cent_count >= self.max_cent_steps or self.searcher.prox < self.pred_prox_bound
+        self.cent_count = 0 if is_pred else self.cent_count + 1
+        self.is_pred = is_pred
+
+        t0 = time.perf_counter()
+        (update_rhs_pred if is_pred else update_rhs_cent)(solver, rhs)
+        t1 = time.perf_counter()
+        get_directions(self, solver)
+        t2 = time.perf_counter()
+        solver.time_uprhs += t1 - t0
+        solver.time_getdir += t2 - t1
+        self.dir_noadj.vec[:] = d.vec
+        try_noadj = True
+        alpha = 0.0
+
+        if self.use_adjustment:
+            t0 = time.perf_counter()
+            (update_rhs_predadj if is_pred else update_rhs_centadj)(solver, rhs, d)
+            t1 = time.perf_counter()
+            get_directions(self, solver)
+            t2 = time.perf_counter()
+            solver.time_uprhs += t1 - t0
+            solver.time_getdir += t2 - t1
+            self.dir_adj.vec[:] = d.vec
+
+            t0 = time.perf_counter()
+            if self.use_curve_search:
+                self.unadj_only = False                  # one curve search with the adjustment
+                alpha = search_alpha(solver, self)
+                solver.time_search += time.perf_counter() - t0
+                if alpha != 0.0:
+                    self.update_stepper_points(alpha, point, False)
+                    self.prev_alpha = alpha
+                    return True
+            else:
+                try_noadj = False                        # two line searches: unadjusted alpha, then the corrected one
+                self.unadj_only = True
+                alpha = search_alpha(solver, self)
+                self.unadj_alpha = alpha
+                unadj_sched = self.searcher.prev_sched
+                if alpha != 0.0:
+                    self.unadj_only = False
+                    alpha = search_alpha(solver, self)
+                    if alpha == 0.0:
+                        self.unadj_only = True           # fall back to the unadjusted direction at the alpha found
+                        alpha = search_alpha(solver, self, sched=unadj_sched)
+                        assert self.searcher.prev_sched == unadj_sched
+                    solver.time_search += time.perf_counter() - t0
+                    self.update_stepper_points(alpha, point, False)
+                    self.prev_alpha = alpha
+                    return True
+                solver.time_search += time.perf_counter() - t0
+
+        if try_noadj:
+            t0 = time.perf_counter()
+            self.unadj_only = True
+            alpha = search_alpha(solver, self)
+            solver.time_search += time.perf_counter() - t0
+
+        if alpha == 0.0:
+            solver.status = "NumericalFailure"
+            self.prev_alpha = alpha
+            return False
+        self.update_stepper_points(alpha, point, False)
+        self.prev_alpha = alpha
+        return True
+
+    def expect_improvement(self):
+        return self.cent_count == 0       # predorcent.jl:165
+
+    def update_stepper_points(self, alpha, point, ztsk_only: bool):
+        """reference: predorcent.jl:167-191"""
+        if ztsk_only:
+            cand = self.temp.ztsk
+            cand[:] = point.ztsk
+            sel = lambda P: P.ztsk
+        else:
+            cand = point.vec
+            sel = lambda P: P.vec
+        cand += alpha * sel(self.dir_noadj)
+        if not self.unadj_only:
+            adj_factor = alpha ** 2 if self.use_curve_search else alpha * self.unadj_alpha
+            cand += adj_factor * sel(self.dir_adj)
+
+    def step_label(self):
+        return "pred" if self.cent_count == 0 else "cent"

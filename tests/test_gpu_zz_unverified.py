@@ -133,3 +133,21 @@ def test_doublynonnegativetri_in_the_system_solve():
         assert rel(sd.vec, so.vec) <= 1e-8
     finally:
         dev.syssolver.free_memory()
+
+
+# the predict-or-center stepper (host control flow added late; it drives the same, GPU-verified, C-ABI calls in a new order)
+@not_yet_on_gpu
+@pytest.mark.parametrize("adj,curv", [(False, False), (True, False), (True, True)])
+@pytest.mark.parametrize("build", [kat.primalinfeas3, kat.dualinfeas3, kat.epinorminf4, kat.hyporootdettri4],
+                         ids=lambda f: f.__name__)
+def test_predorcent_stepper_device(build, adj, curv):
+    """test/runnativetests.jl:120-132 with the device plug-ins."""
+    from hypatia_b200.cones import DeviceConeBlock
+    from hypatia_b200.host.solver import Solver
+    from hypatia_b200.host.stepper import PredOrCentStepper
+    from hypatia_b200.syssolver import QRCholDenseSystemSolver as DevQRChol
+    model, expected = build()
+    s = Solver(model, DevQRChol(), DeviceConeBlock, default_tol_relax=10,
+               stepper=PredOrCentStepper(use_adjustment=adj, use_curve_search=curv))
+    s.solve()
+    kat.check_solution(s, model, expected)

@@ -113,3 +113,45 @@ def test_directions_qrchol_vs_naive_mixed_cones(p):
     res = Point(I.model)
     a.syssolver.apply_lhs(a, sa, res)
     assert np.linalg.norm(res.vec - rhs.vec) <= 1e-9 * np.linalg.norm(rhs.vec)
+
+
+# ---- stepper tests of the reference (test/runnativetests.jl:120-158) on inst_minimal (test/nativesets.jl:21-26) ----
+INST_MINIMAL = [kat.primalinfeas3, kat.dualinfeas3, kat.epinorminf4, kat.hyporootdettri4]
+
+
+@pytest.mark.parametrize("adj,curv", [(False, False), (True, False), (True, True)])
+@pytest.mark.parametrize("build", INST_MINIMAL, ids=lambda f: f.__name__)
+def test_predorcent_stepper(build, adj, curv):
+    from hypatia_b200.host.stepper import PredOrCentStepper
+    model, expected = build()
+    s = solve(model, osys.QRCholDenseSystemSolver(), stepper=PredOrCentStepper(use_adjustment=adj, use_curve_search=curv))
+    kat.check_solution(s, model, expected)
+
+
+@pytest.mark.parametrize("build", INST_MINIMAL, ids=lambda f: f.__name__)
+def test_predorcent_stepper_other_options(build):
+    from hypatia_b200.host.stepper import PredOrCentStepper
+    model, expected = build()
+    stepper = PredOrCentStepper(use_adjustment=False, use_curve_search=False, max_cent_steps=8, pred_prox_bound=0.0332,
+                                min_prox=0.0, prox_bound=0.2844, use_max_prox=False,
+                                alpha_sched=[0.9999 * 0.7 ** i for i in range(23)])
+    kat.check_solution(solve(model, osys.QRCholDenseSystemSolver(), stepper=stepper), model, expected)
+
+
+@pytest.mark.parametrize("shift", [0, 2])
+@pytest.mark.parametrize("build", INST_MINIMAL, ids=lambda f: f.__name__)
+def test_combined_stepper_shift_sched(build, shift):
+    from hypatia_b200.host.stepper import CombinedStepper
+    model, expected = build()
+    kat.check_solution(solve(model, osys.QRCholDenseSystemSolver(), stepper=CombinedStepper(shift_sched=shift)), model, expected)
+
+
+def test_predorcent_needs_fewer_system_solves_per_iteration():
+    """One direction pair per iteration instead of the combined stepper's four directions (predorcent.jl:72-110)."""
+    from hypatia_b200.host.stepper import CombinedStepper, PredOrCentStepper
+    model, expected = kat.epinormeucl1()
+    a = solve(model, osys.QRCholDenseSystemSolver(), stepper=CombinedStepper(), max_ref_steps=0)
+    model, expected = kat.epinormeucl1()
+    b = solve(model, osys.QRCholDenseSystemSolver(), stepper=PredOrCentStepper(), max_ref_steps=0)
+    kat.check_solution(b, model, expected)
+    assert a.n_solve_system == 4 * a.num_iters and b.n_solve_system == 2 * b.num_iters
