@@ -13,9 +13,11 @@
 // 36 pair products with s + t <= 7, K <= 65472 rows per launch.  Both carry 56 bits below the column
 // maximum; the chip runs this kernel at its power cap, so the 22 % fewer MMAs of radix 256 are what
 // makes it faster (measured 101 -> 91 ms on C3), not memory traffic (the quad kernel below cuts the
-// L2 -> SM bytes by a third and is not faster).
+// L2 -> SM bytes by a third and is not faster).  The order of the tile list decides which operand panel stays in
+// L2: row-major (default) keeps the 256-row A panel resident and streams the B panels (134 GB of DRAM traffic per C3
+// SYRK instead of 197 GB, 84.8 instead of 86.6 ms).
 //
-// This file: (1) column scaling + slicing kernels, (2) a TMA + tcgen05 int8 TN GEMM
+// This file: (1) the slicing kernels are in ozaki_slice_kernels.cuh, (2) a TMA + tcgen05 int8 TN GEMM
 // (C_int32 = A' B, both operands K-major, SWIZZLE_128B, accumulator in TMEM), (3) a reference
 // recombination used by the tests.
 #include "common.cuh"
@@ -1270,8 +1272,9 @@ void hyp_ozaki_slice(hyp_ctx* ctx, const double* A, int64_t lda, int64_t K, int6
     CUDA_TRY(cudaGetLastError());
 }
 
-// digit slices entering the product (CTA-pair kernel): 8 (default) or 7 (HYP_OZAKI_SLICES=7: 28 instead of
-// 36 pair products; truncation error <= 2^-48 |a_i|_max |a_j|_max K instead of 2^-55)
+// radix-128 scheme only (HYP_OZAKI_RADIX=128): digit slices entering the product of the CTA-pair kernel, 8 or 7
+// (HYP_OZAKI_SLICES=7: 28 instead of 36 pair products; truncation error <= 2^-48 |a_i|_max |a_j|_max K instead of
+// 2^-55).  The default radix-256 scheme always uses its 7 digits.
 static int ozaki_slices() {
     static int n = 0;
     if (!n) {
