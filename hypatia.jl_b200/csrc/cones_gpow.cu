@@ -143,7 +143,39 @@ static void dnn_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
     hyp_mat_alloc_group(ctx, g);
 }
 
+// MatrixEpiPerSquare: d_hkind = d1, d_vecs / d_voff = per-cone state (Zi, Cholesky factor of Z, smat(U), ZiUZi, ZiW,
+// ZiUZiW) followed by the scratch of mep_dder3_kernel
+static void mep_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
+    g.h_voff.assign(g.count, 0);
+    int64_t tot = 0;
+    for (int i = 0; i < g.count; i++) {
+        const int k = g.h_kidx[i];
+        const int d = g.h_dim[i], d1 = ctx->h_cone_hkind[k];
+        const int rest = d - d1 * (d1 + 1) / 2 - 1;
+        if (d1 < 1 || rest < d1 * d1 || rest % d1 != 0)
+            throw HypError{"MatrixEpiPerSquare: hyp_set_cone_params must give d1 with dim = svec_length(d1) + 1 + d1 * d2, d1 <= d2"};
+        if (d > 128) throw HypError{"MatrixEpiPerSquare: dim above 128 is not supported (batched Cholesky limit)"};
+        const int64_t d2 = rest / d1, n11 = (int64_t)d1 * d1, n12 = d1 * d2, n22 = d2 * d2;
+        g.h_hkind.push_back(d1);
+        g.h_side[i] = d;
+        g.h_voff[i] = tot;
+        tot += (4 + 17) * n11 + (2 + 11) * n12 + 3 * n22;
+    }
+    g.max_side = g.max_dim;
+    cudaFree(g.d_side);
+    g.d_side = upload_vec(g.h_side);
+    g.d_hkind = upload_vec(g.h_hkind);
+    g.d_voff = upload_vec(g.h_voff);
+    CUDA_TRY(cudaMalloc(&g.d_vecs, (size_t)std::max<int64_t>(tot, 1) * sizeof(double)));
+    CUDA_TRY(cudaMemset(g.d_vecs, 0, (size_t)std::max<int64_t>(tot, 1) * sizeof(double)));
+    hyp_mat_alloc_group(ctx, g);
+}
+
 void hyp_gpow_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
+    if (g.type == HYP_CONE_MATRIXEPIPERSQUARE) {
+        mep_alloc_group(ctx, g);
+        return;
+    }
     if (g.type == HYP_CONE_DOUBLYNONNEGATIVETRI) {
         dnn_alloc_group(ctx, g);
         return;
@@ -196,7 +228,11 @@ void hyp_gpow_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
 }
 
 void hyp_gpow_update_state(hyp_ctx* ctx, ConeGroup& g) {
-    if (g.type == HYP_CONE_DOUBLYNONNEGATIVETRI)
+    if (g.type == HYP_CONE_MATRIXEPIPERSQUARE)
+        hypdev::mep_state_kernel<<<ceil_div(g.count, 4), 128, 0, ctx->stream>>>(
+            g.count, g.d_off, g.d_dim, g.d_hkind, g.d_voff, g.d_vecs, g.d_kidx, g.d_moff, ctx->d_point, ctx->d_dual,
+            ctx->d_grad, g.d_scal, g.d_W, ctx->d_feas, ctx->d_dual_feas);
+    else if (g.type == HYP_CONE_DOUBLYNONNEGATIVETRI)
         hypdev::dnn_state_kernel<<<ceil_div(g.count, 8), 256, 0, ctx->stream>>>(
             g.count, g.d_off, g.d_dim, g.d_hkind, g.d_voff, g.d_vecs, g.d_kidx, g.d_moff, ctx->d_point, ctx->d_grad,
             g.d_W, ctx->d_feas);
@@ -239,7 +275,11 @@ void hyp_gpow_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr, 
     else if (mode == HYP_PROD_BLOCK_INV) { hess_dual = 1; inv_dual = 0; }
     else throw HypError{"hyp_gpow_prod: bad mode"};
     if (hess_dual > -2) {
-        if (g.type == HYP_CONE_DOUBLYNONNEGATIVETRI)
+        if (g.type == HYP_CONE_MATRIXEPIPERSQUARE)
+            hypdev::mep_prod_kernel<<<grid, 256, 0, ctx->stream>>>(g.count, hess_dual, g.d_off, g.d_dim, g.d_hkind,
+                                                                  g.d_voff, g.d_vecs, g.d_dual, g.d_scal, ctx->d_point,
+                                                                  arr, ld_arr, prod, ld_prod, ncols, row_shift);
+        else if (g.type == HYP_CONE_DOUBLYNONNEGATIVETRI)
             hypdev::dnn_prod_kernel<<<grid, 256, 0, ctx->stream>>>(g.count, hess_dual, g.d_off, g.d_dim, g.d_hkind,
                                                                   g.d_voff, g.d_vecs, g.d_dual, ctx->d_point, arr, ld_arr,
                                                                   prod, ld_prod, ncols, row_shift);
@@ -272,7 +312,10 @@ void hyp_gpow_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr, 
 }
 
 void hyp_gpow_dder3(hyp_ctx* ctx, ConeGroup& g, double* out, const double* dir) {
-    if (g.type == HYP_CONE_DOUBLYNONNEGATIVETRI)
+    if (g.type == HYP_CONE_MATRIXEPIPERSQUARE)
+        hypdev::mep_dder3_kernel<<<ceil_div(g.count, 4), 128, 0, ctx->stream>>>(
+            g.count, g.d_off, g.d_dim, g.d_hkind, g.d_voff, g.d_vecs, g.d_scal, ctx->d_point, dir, out);
+    else if (g.type == HYP_CONE_DOUBLYNONNEGATIVETRI)
         hypdev::dnn_dder3_kernel<<<ceil_div(g.count, 4), 128, 0, ctx->stream>>>(
             g.count, g.d_off, g.d_dim, g.d_hkind, g.d_voff, g.d_vecs, ctx->d_point, dir, out);
     else if (g.type == HYP_CONE_LINMATRIXINEQ)

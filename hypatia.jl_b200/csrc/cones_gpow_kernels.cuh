@@ -1113,4 +1113,378 @@ dnn_dder3_kernel(int ncones, const int64_t* __restrict__ off, const int* __restr
 }
 
 
+// ---- MatrixEpiPerSquare (real), matrixepipersquare.jl:118-397 ----
+// point = (svec(U) [per = d1 (d1 + 1) / 2], v, vec(W) [d1 x d2 column-major]), d1 <= d2, dim <= 128 (so d1 <= 8).
+// Per-cone state at vecs + voff[c]: Zi = Z^-1 (d1^2), Uz = upper Cholesky factor of Z = 2 v U - W W' (d1^2),
+// Um = smat(U) (d1^2), ZiUZi (d1^2), ZiW (d1 d2), ZiUZiW (d1 d2), then the dder3 scratch (17 d1^2 + 11 d1 d2 + 3 d2^2).
+// scal: 0 Hvv, 1 v.  One warp per cone / per (cone, column); every product below is a tiny dense GEMM done lane-strided.
+
+// O (r x c) = beta O + alpha op(X) op(Y), op(X) r x k, op(Y) k x c, all column-major and dense; O must not alias X, Y
+__device__ __forceinline__ void mep_mm(double* O, const double* X, const double* Y, int r, int k, int c, bool tx,
+                                       bool ty, double alpha, double beta, int lane) {
+    for (int idx = lane; idx < r * c; idx += 32) {
+        const int i = idx % r, j = idx / r;
+        double s = 0.0;
+        for (int t = 0; t < k; t++) s += (tx ? X[t + i * k] : X[i + t * r]) * (ty ? Y[j + t * c] : Y[t + j * k]);
+        O[idx] = (beta == 0.0 ? 0.0 : beta * O[idx]) + alpha * s;
+    }
+    __syncwarp();
+}
+// O = a X + b Y (elementwise, n entries; O may alias X or Y)
+__device__ __forceinline__ void mep_axpby(double* O, double a, const double* X, double b, const double* Y, int n,
+                                          int lane) {
+    for (int i = lane; i < n; i += 32) O[i] = a * X[i] + (Y ? b * Y[i] : 0.0);
+    __syncwarp();
+}
+// O = X + X' (d x d); O must not alias X
+__device__ __forceinline__ void mep_symsum(double* O, const double* X, int d, int lane) {
+    for (int idx = lane; idx < d * d; idx += 32) O[idx] = X[idx] + X[(idx / d) + (idx % d) * d];
+    __syncwarp();
+}
+__device__ __forceinline__ double mep_dot(const double* X, const double* Y, int n, int lane) {
+    double s = 0.0;
+    for (int i = lane; i < n; i += 32) s += X[i] * Y[i];
+    return warp_sum(s);
+}
+// X <- Z^-1 X for the d1 x cols matrix X (lane per column)
+__device__ __forceinline__ void mep_zsolve(const double* Uz, double* X, int d1, int cols, int lane) {
+    for (int k = lane; k < cols; k += 32) ens_zsolve_col(Uz, d1, X + k * d1);
+    __syncwarp();
+}
+
+// hess_prod! for one column (matrixepipersquare.jl:281-325).  a: input column, pr: output column (may alias a),
+// sc: 5 * 128 doubles of scratch private to the warp.
+__device__ __forceinline__ void mep_hess_col(const double* a, double* pr, int d1, int d2, const double* st,
+                                             const double* W, double v, double Hvv, double* sc, int lane) {
+    const int per = d1 * (d1 + 1) / 2, n11 = d1 * d1, n12 = d1 * d2;
+    const double* Zi = st;
+    const double* Uz = st + n11;
+    const double* Um = st + 2 * n11;
+    const double* ZiUZi = st + 3 * n11;
+    const double* ZiW = st + 4 * n11;
+    double* tU = sc;
+    double* U3 = sc + 128;
+    double* T = sc + 256;
+    double* U2 = sc + 384;
+    double* ZiWd = sc + 512;
+    const double va = a[per], v2 = 2.0 * v;
+    dnn_smat(tU, a, d1, per, lane);
+    for (int i = lane; i < n12; i += 32) ZiWd[i] = a[per + 1 + i];
+    __syncwarp();
+    mep_zsolve(Uz, ZiWd, d1, d2, lane);
+    mep_mm(U3, ZiWd, ZiW, d1, d2, d1, false, true, 1.0, 0.0, lane);          // U3 = ZiWd ZiW'
+    mep_mm(T, Zi, tU, d1, d1, d1, false, false, 1.0, 0.0, lane);
+    mep_mm(U2, T, Zi, d1, d1, d1, false, false, 1.0, 0.0, lane);             // Zi tU Zi
+    mep_symsum(T, U3, d1, lane);
+    mep_axpby(U2, -v2, U2, 1.0, T, n11, lane);                               // U2 = U3 + U3' - 2 v Zi tU Zi
+    const double dT2 = 2.0 * v2 * mep_dot(ZiUZi, tU, n11, lane) - 2.0 * mep_dot(Zi, tU, n11, lane);
+    const double dUU3 = mep_dot(Um, U3, n11, lane);
+    mep_axpby(T, 1.0, U2, -2.0 * va, ZiUZi, n11, lane);                      // T1 = U2 - 2 va ZiUZi
+    mep_mm(U3, T, W, d1, d1, d2, false, false, 2.0, 0.0, lane);              // (U3 reused, d1 x d2) 2 T1 W
+    for (int i = lane; i < n12; i += 32) pr[per + 1 + i] = U3[i] + 2.0 * ZiWd[i];
+    // prod_U = svec(va (2 v2 ZiUZi - 2 Zi) - v2 U2)
+    for (int p = lane; p < per; p += 32) {
+        int i, j;
+        dnn_ij(p, i, j);
+        const int e = i + j * d1;
+        const double x = va * (2.0 * v2 * ZiUZi[e] - 2.0 * Zi[e]) - v2 * U2[e];
+        pr[p] = i == j ? x : 1.41421356237309504880 * x;
+    }
+    if (lane == 0) pr[per] = dT2 - 4.0 * dUU3 + Hvv * va;
+    __syncwarp();
+}
+
+static __global__ void __launch_bounds__(128)
+mep_state_kernel(int ncones, const int64_t* __restrict__ off, const int* __restrict__ dim,
+                 const int* __restrict__ d1s, const int64_t* __restrict__ voff, double* __restrict__ vecs,
+                 const int* __restrict__ kidx, const int64_t* __restrict__ moff, const double* __restrict__ point,
+                 const double* __restrict__ dual, double* __restrict__ grad, double* __restrict__ scal,
+                 double* __restrict__ H, uint8_t* feas, uint8_t* dual_feas) {
+    __shared__ double sh[4][6 * 128];
+    const int lane = threadIdx.x & 31;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= ncones) return;
+    double* sc = sh[threadIdx.x >> 5];
+    const int64_t o = off[c];
+    const int d = dim[c], d1 = d1s[c], per = d1 * (d1 + 1) / 2, d2 = (d - per - 1) / d1;
+    const int n11 = d1 * d1, n12 = d1 * d2, lde = (d + 1) & ~1;
+    double* st = vecs + voff[c];
+    double* Zi = st;
+    double* Uz = st + n11;
+    double* Um = st + 2 * n11;
+    double* ZiUZi = st + 3 * n11;
+    double* ZiW = st + 4 * n11;
+    double* ZiUZiW = ZiW + n12;
+    const double v = point[o + per];
+    const double* W = point + o + per + 1;
+    // update_feas (:118-135): Z = 2 v U - W W' and its Cholesky
+    dnn_smat(Um, point + o, d1, per, lane);
+    __syncwarp();
+    mep_mm(Uz, W, W, d1, d2, d1, false, true, -1.0, 0.0, lane);
+    for (int i = lane; i < n11; i += 32) Uz[i] += 2.0 * v * Um[i];
+    __syncwarp();
+    int ok = v > HYP_EPS ? 1 : 0;
+    if (lane == 0) {
+        for (int j = 0; j < d1; j++) {
+            double s = Uz[j + j * d1];
+            for (int k = 0; k < j; k++) s -= Uz[k + j * d1] * Uz[k + j * d1];
+            if (!(s > 0.0)) {
+                ok = 0;
+                s = 1.0;
+            }
+            const double r = sqrt(s);
+            Uz[j + j * d1] = r;
+            for (int i = j + 1; i < d1; i++) {
+                double t = Uz[j + i * d1];
+                for (int k = 0; k < j; k++) t -= Uz[k + j * d1] * Uz[k + i * d1];
+                Uz[j + i * d1] = t / r;
+            }
+        }
+    }
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    __syncwarp();
+    // update_grad (:152-170) and update_hess_aux (:172-185)
+    for (int i = lane; i < n11; i += 32) Zi[i] = (i % d1 == i / d1) ? 1.0 : 0.0;
+    for (int i = lane; i < n12; i += 32) ZiW[i] = W[i];
+    __syncwarp();
+    mep_zsolve(Uz, Zi, d1, d1, lane);
+    mep_zsolve(Uz, ZiW, d1, d2, lane);
+    for (int idx = lane; idx < n11; idx += 32) {          // symmetric part, as inv_fact! + Hermitian(:U) reads it
+        const int a = idx % d1, b = idx / d1;
+        if (a > b) Zi[idx] = Zi[b + a * d1];
+    }
+    __syncwarp();
+    mep_mm(sc, Zi, Um, d1, d1, d1, false, false, 1.0, 0.0, lane);
+    mep_mm(ZiUZi, sc, Zi, d1, d1, d1, false, false, 1.0, 0.0, lane);
+    mep_symsum(sc, ZiUZi, d1, lane);
+    mep_axpby(ZiUZi, 0.5, sc, 0.0, nullptr, n11, lane);
+    mep_mm(ZiUZiW, ZiUZi, W, d1, d1, d2, false, false, 1.0, 0.0, lane);
+    const double trZiU = mep_dot(Zi, Um, n11, lane);
+    const double Hvv = 4.0 * mep_dot(ZiUZi, Um, n11, lane) - (d1 - 1) / v / v;
+    for (int p = lane; p < per; p += 32) {
+        int i, j;
+        dnn_ij(p, i, j);
+        const double x = -2.0 * v * Zi[i + j * d1];
+        grad[o + p] = i == j ? x : 1.41421356237309504880 * x;
+    }
+    for (int i = lane; i < n12; i += 32) grad[o + per + 1 + i] = 2.0 * ZiW[i];
+    // is_dual_feas (:137-150): dual U positive definite and 2 v - |R^-T W|_F^2 > eps with U = R'R
+    const double dv = dual[o + per];
+    double* R = sc;                 // d1^2
+    double* LW = sc + 128;          // d1 d2
+    dnn_smat(R, dual + o, d1, per, lane);
+    for (int i = lane; i < n12; i += 32) LW[i] = dual[o + per + 1 + i];
+    __syncwarp();
+    int dok = dv > HYP_EPS ? 1 : 0;
+    if (lane == 0) {
+        for (int j = 0; j < d1; j++) {
+            double s = R[j + j * d1];
+            for (int k = 0; k < j; k++) s -= R[k + j * d1] * R[k + j * d1];
+            if (!(s > 0.0)) {
+                dok = 0;
+                s = 1.0;
+            }
+            const double r = sqrt(s);
+            R[j + j * d1] = r;
+            for (int i = j + 1; i < d1; i++) {
+                double t = R[j + i * d1];
+                for (int k = 0; k < j; k++) t -= R[k + j * d1] * R[k + i * d1];
+                R[j + i * d1] = t / r;
+            }
+        }
+    }
+    dok = __shfl_sync(0xffffffffu, dok, 0);
+    __syncwarp();
+    double tr = 0.0;
+    for (int k = lane; k < d2; k += 32) {
+        double* x = LW + k * d1;
+        for (int i = 0; i < d1; i++) {                      // forward substitution with R'
+            double s = x[i];
+            for (int b = 0; b < i; b++) s -= R[b + i * d1] * x[b];
+            x[i] = s / R[i + i * d1];
+            tr += x[i] * x[i];
+        }
+    }
+    tr = warp_sum(tr);
+    if (!(2.0 * dv - tr > HYP_EPS)) dok = 0;
+    if (lane == 0) {
+        grad[o + per] = -2.0 * trZiU + (d1 - 1) / v;
+        scal[8 * c] = Hvv;
+        scal[8 * c + 1] = v;
+        if (!ok) feas[kidx[c]] = 0;
+        if (!dok) dual_feas[kidx[c]] = 0;
+    }
+    __syncwarp();
+    // explicit Hessian: hess_prod! applied to the unit vectors (equal to update_hess, :187-279), then symmetrised
+    double* Hc = H + moff[c];
+    double* unit = sc + 5 * 128;
+    for (int j = 0; j < d; j++) {
+        for (int i = lane; i < d; i += 32) unit[i] = i == j ? 1.0 : 0.0;
+        __syncwarp();
+        mep_hess_col(unit, Hc + (int64_t)j * lde, d1, d2, st, W, v, Hvv, sc, lane);
+    }
+    for (int idx = lane; idx < d * d; idx += 32) {
+        const int i = idx % d, j = idx / d;
+        if (i < j) {
+            const double x = 0.5 * (Hc[i + (int64_t)j * lde] + Hc[j + (int64_t)i * lde]);
+            Hc[i + (int64_t)j * lde] = x;
+            Hc[j + (int64_t)i * lde] = x;
+        }
+    }
+}
+
+static __global__ void __launch_bounds__(256)
+mep_prod_kernel(int ncones, int want_dual, const int64_t* __restrict__ off, const int* __restrict__ dim,
+                const int* __restrict__ d1s, const int64_t* __restrict__ voff, const double* __restrict__ vecs,
+                const int* __restrict__ dualf, const double* __restrict__ scal, const double* __restrict__ point,
+                const double* arr, int64_t ld_arr, double* prod, int64_t ld_prod, int64_t ncols, int64_t row_shift) {
+    __shared__ double sh[8][5 * 128];
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= ncones) return;
+    if (want_dual >= 0 && (dualf[c] != 0) != (want_dual != 0)) return;
+    double* sc = sh[threadIdx.x >> 5];
+    const int64_t o = off[c];
+    const int d = dim[c], d1 = d1s[c], per = d1 * (d1 + 1) / 2, d2 = (d - per - 1) / d1;
+    const double* st = vecs + voff[c];
+    const double* W = point + o + per + 1;
+    for (int64_t j = blockIdx.y; j < ncols; j += gridDim.y)
+        mep_hess_col(arr + j * ld_arr + (o - row_shift), prod + j * ld_prod + (o - row_shift), d1, d2, st, W,
+                     scal[8 * c + 1], scal[8 * c], sc, lane);
+}
+
+// dder3 (matrixepipersquare.jl:327-397), transcribed product by product; one warp per cone, scratch in global memory
+static __global__ void __launch_bounds__(128)
+mep_dder3_kernel(int ncones, const int64_t* __restrict__ off, const int* __restrict__ dim,
+                 const int* __restrict__ d1s, const int64_t* __restrict__ voff, double* __restrict__ vecs,
+                 const double* __restrict__ scal, const double* __restrict__ point, const double* __restrict__ dir,
+                 double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= ncones) return;
+    const int64_t o = off[c];
+    const int d = dim[c], d1 = d1s[c], per = d1 * (d1 + 1) / 2, d2 = (d - per - 1) / d1;
+    const int n11 = d1 * d1, n12 = d1 * d2, n22 = d2 * d2;
+    double* st = vecs + voff[c];
+    const double* Zi = st;
+    const double* Uz = st + n11;
+    const double* U = st + 2 * n11;
+    const double* ZiUZi = st + 3 * n11;
+    const double* ZiW = st + 4 * n11;
+    const double* ZiUZiW = ZiW + n12;
+    double* ws = st + 4 * n11 + 2 * n12;
+    double* S[17];
+    double* Mx[11];
+    for (int i = 0; i < 17; i++) S[i] = ws + i * n11;
+    for (int i = 0; i < 11; i++) Mx[i] = ws + 17 * n11 + i * n12;
+    double* B0 = ws + 17 * n11 + 11 * n12;
+    double* B1 = B0 + n22;
+    double* B2 = B1 + n22;
+    const double v = point[o + per], vd = dir[o + per], v2 = 2.0 * v, vd2 = 2.0 * vd;
+    const double* W = point + o + per + 1;
+    const double* Wd = dir + o + per + 1;
+    double *Ud = S[0], *ZiU = S[1], *ZiUd = S[2], *Z3 = S[3] /* ZiUZiUZi */, *Z2v = S[4] /* ZiUZi2v */,
+           *WdWZi = S[5], *ZiWdWZi = S[6], *ZiWdWZi2 = S[7], *ZiUZiWdWZi = S[8], *ZiWdWZiUZi2 = S[9], *ZiUdZi = S[10],
+           *ZiUZiUdZi2 = S[11], *ZiUdZiWdWZi = S[12], *vZ = S[13] /* vZiUZiUdZi2 */, *Ut = S[14], *T0 = S[15],
+           *T1 = S[16];
+    double *ZiWd = Mx[0], *UdZiW = Mx[1], *ZiUdZiW = Mx[2], *ZiUZiUdZiW = Mx[3], *ZiWdWtZiWI = Mx[4],
+           *vdZW = Mx[5] /* vdZiUZiUZiW */, *WdWtZiWI = Mx[6], *ZWWI = Mx[7] /* ZiUZiWdWZiWI */, *Wt = Mx[8], *N0 = Mx[9],
+           *N1 = Mx[10];
+    double *WdZiW = B0, *WtZiWI = B1, *Bt = B2;
+
+    dnn_smat(Ud, dir + o, d1, per, lane);
+    for (int i = lane; i < n11; i += 32) {
+        ZiU[i] = U[i];
+        ZiUd[i] = 0.0;
+    }
+    for (int i = lane; i < n12; i += 32) ZiWd[i] = Wd[i];
+    __syncwarp();
+    for (int i = lane; i < n11; i += 32) ZiUd[i] = Ud[i];
+    __syncwarp();
+    mep_zsolve(Uz, ZiU, d1, d1, lane);                                             // ZiU = Z \ U
+    mep_zsolve(Uz, ZiWd, d1, d2, lane);                                            // ZiWd = Z \ Wd
+    mep_zsolve(Uz, ZiUd, d1, d1, lane);                                            // ZiUd = Z \ Ud
+    mep_mm(T0, ZiUZi, ZiU, d1, d1, d1, false, true, 1.0, 0.0, lane);               // ZiUZi ZiU'
+    mep_symsum(Z3, T0, d1, lane);
+    mep_axpby(Z3, 0.5, Z3, 0.0, nullptr, n11, lane);                               // ZiUZiUZi (symmetric part)
+    mep_axpby(Z2v, 1.0, ZiUZi, -v2, Z3, n11, lane);                                // ZiUZi2v
+    mep_mm(WdWZi, Wd, ZiW, d1, d2, d1, false, true, 1.0, 0.0, lane);               // Wd ZiW'
+    mep_mm(WdZiW, Wd, ZiW, d2, d1, d2, true, false, 1.0, 0.0, lane);               // Wd' ZiW
+    mep_mm(UdZiW, Ud, ZiW, d1, d1, d2, false, false, 1.0, 0.0, lane);              // Ud ZiW
+    for (int i = lane; i < n11; i += 32) ZiWdWZi[i] = WdWZi[i];
+    for (int i = lane; i < n12; i += 32) ZiUdZiW[i] = UdZiW[i];
+    __syncwarp();
+    mep_zsolve(Uz, ZiWdWZi, d1, d1, lane);                                         // Z \ WdWZi
+    mep_zsolve(Uz, ZiUdZiW, d1, d2, lane);                                         // Z \ UdZiW
+    mep_symsum(ZiWdWZi2, ZiWdWZi, d1, lane);
+    mep_mm(ZiUZiWdWZi, ZiU, ZiWdWZi, d1, d1, d1, false, false, 1.0, 0.0, lane);    // ZiU ZiWdWZi
+    mep_mm(ZiUZiUdZiW, ZiU, ZiUdZiW, d1, d1, d2, false, false, 1.0, 0.0, lane);
+    mep_mm(ZiUZiUdZiW, ZiUd, ZiUZiW, d1, d1, d2, false, false, 1.0, 1.0, lane);    // + ZiUd ZiUZiW
+    mep_mm(T0, ZiWdWZi, ZiU, d1, d1, d1, false, true, 1.0, 0.0, lane);             // ZiWdWZiUZi = ZiWdWZi ZiU'
+    mep_symsum(ZiWdWZiUZi2, T0, d1, lane);
+    for (int idx = lane; idx < n11; idx += 32)                                     // + ZiUZiWdWZi'
+        ZiWdWZiUZi2[idx] += ZiUZiWdWZi[(idx / d1) + (idx % d1) * d1];
+    __syncwarp();
+    mep_mm(T0, ZiUd, Zi, d1, d1, d1, false, false, 1.0, 0.0, lane);                // ZiUd / Z
+    mep_symsum(ZiUdZi, T0, d1, lane);
+    mep_axpby(ZiUdZi, 0.5, ZiUdZi, 0.0, nullptr, n11, lane);
+    mep_mm(T0, ZiU, ZiUdZi, d1, d1, d1, false, false, 1.0, 0.0, lane);             // ZiUZiUdZi
+    mep_symsum(ZiUZiUdZi2, T0, d1, lane);
+    mep_mm(T0, ZiUd, ZiWdWZi, d1, d1, d1, false, false, 1.0, 0.0, lane);
+    mep_mm(T0, ZiWdWZi, ZiUd, d1, d1, d1, false, true, 1.0, 1.0, lane);            // ZiUd ZiWdWZi + ZiWdWZi ZiUd'
+    mep_axpby(ZiUdZiWdWZi, 1.0, T0, 0.0, nullptr, n11, lane);
+    mep_mm(WtZiWI, W, ZiW, d2, d1, d2, true, false, 1.0, 0.0, lane);               // W' ZiW + I
+    for (int i = lane; i < d2; i += 32) WtZiWI[i + i * d2] += 1.0;
+    __syncwarp();
+    mep_mm(ZiWdWtZiWI, ZiWd, WtZiWI, d1, d2, d2, false, false, 1.0, 0.0, lane);
+    mep_mm(vdZW, Z3, W, d1, d1, d2, false, false, vd2, 0.0, lane);                 // vd2 ZiUZiUZi W
+    mep_mm(WdWtZiWI, Wd, WtZiWI, d1, d2, d2, false, false, 1.0, 0.0, lane);
+    mep_mm(ZWWI, ZiUZi, WdWtZiWI, d1, d1, d2, false, false, 1.0, 0.0, lane);
+    mep_mm(ZWWI, ZiWdWZiUZi2, W, d1, d1, d2, false, false, 1.0, 1.0, lane);        // ZiUZiWdWZiWI
+    mep_axpby(vZ, v, ZiUZiUdZi2, -1.0, ZiUdZi, n11, lane);                         // vZiUZiUdZi2
+
+    // Utemp (:372-376)
+    mep_mm(Ut, ZiWdWZi, WdWZi, d1, d1, d1, false, false, 1.0, 0.0, lane);
+    mep_mm(Ut, WdWZi, ZiWdWZi2, d1, d1, d1, true, false, 1.0, 1.0, lane);
+    mep_mm(Ut, ZiWdWtZiWI, ZiWd, d1, d2, d1, false, true, 1.0, 1.0, lane);
+    mep_mm(T0, ZiUd, ZiUdZi, d1, d1, d1, false, false, 1.0, 0.0, lane);
+    for (int idx = lane; idx < n11; idx += 32) {
+        const int tr = (idx / d1) + (idx % d1) * d1;
+        const double inner = v2 * T0[idx] - ZiUdZiWdWZi[idx] - ZiUdZiWdWZi[tr];
+        const double a1 = -vd2 * Z2v[idx] + ZiWdWZi2[idx] - v2 * (ZiUZiWdWZi[idx] + ZiWdWZiUZi2[idx] - 2.0 * vZ[idx]);
+        T1[idx] = vd2 * a1 + v2 * (Ut[idx] + v2 * inner);
+    }
+    __syncwarp();
+    for (int p = lane; p < per; p += 32) {
+        int i, j;
+        dnn_ij(p, i, j);
+        const double x = 0.5 * (T1[i + j * d1] + T1[j + i * d1]);
+        out[o + p] = i == j ? x : 1.41421356237309504880 * x;
+    }
+    // v_Wd_dot and the v entry (:379-383)
+    for (int i = lane; i < n12; i += 32) N0[i] = -4.0 * (v * ZiUZiUdZiW[i] + vdZW[i]) + ZWWI[i] + 2.0 * ZiUdZiW[i];
+    __syncwarp();
+    const double dv1 = mep_dot(Z2v, Ud, n11, lane), dv2 = mep_dot(Z3, U, n11, lane), dv3 = mep_dot(vZ, Ud, n11, lane),
+                 dv4 = mep_dot(N0, Wd, n12, lane);
+    if (lane == 0)
+        out[o + per] = vd * (-8.0 * dv1 + vd * (8.0 * dv2 - (d1 - 1) / v / v / v)) + 4.0 * v * dv3 + 2.0 * dv4;
+    // Wtemp (:385-390)
+    for (int i = lane; i < n12; i += 32)
+        Wt[i] = 4.0 * vd * (ZiUdZiW[i] - v2 * ZiUZiUdZiW[i] + ZWWI[i] - vdZW[i]);
+    __syncwarp();
+    mep_mm(N0, ZiUdZiW, WdZiW, d1, d2, d2, false, false, 1.0, 0.0, lane);
+    mep_mm(N0, ZiWdWZi, UdZiW, d1, d1, d2, false, false, 1.0, 1.0, lane);
+    mep_mm(N0, WdWZi, ZiUdZiW, d1, d1, d2, true, false, 1.0, 1.0, lane);
+    mep_mm(N0, ZiUdZi, WdWtZiWI, d1, d1, d2, false, false, 1.0, 1.0, lane);
+    mep_mm(N0, ZiUd, ZiUdZiW, d1, d1, d2, false, false, -v2, 1.0, lane);
+    mep_mm(Bt, WdZiW, WdZiW, d2, d2, d2, false, false, 1.0, 0.0, lane);
+    mep_mm(N1, ZiW, Bt, d1, d2, d2, false, false, 1.0, 0.0, lane);                 // ZiW WdZiW WdZiW
+    mep_mm(N1, WdWZi, ZiWdWtZiWI, d1, d1, d2, true, false, 1.0, 1.0, lane);
+    mep_mm(N1, ZiWdWtZiWI, WdZiW, d1, d2, d2, false, false, 1.0, 1.0, lane);
+    mep_mm(Bt, WdZiW, WtZiWI, d2, d2, d2, true, false, 1.0, 0.0, lane);            // WdZiW' WtZiWI
+    mep_mm(N1, ZiWd, Bt, d1, d2, d2, false, false, 1.0, 1.0, lane);
+    for (int i = lane; i < n12; i += 32) out[o + per + 1 + i] = Wt[i] + 4.0 * v * N0[i] - 2.0 * N1[i];
+}
+
+
 }  // namespace hypdev

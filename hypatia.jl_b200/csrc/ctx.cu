@@ -936,7 +936,8 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
                                 : t == HYP_CONE_HYPOROOTDETTRI ? 1.0 + side
                                 : t == HYP_CONE_EPIPERSEPSPECTRAL_MAT ? 2.0 + side
                                 : t == HYP_CONE_EPIPERSQUARE ? 2.0
-                                : t == HYP_CONE_EPINORMSPECTRAL ? (double)ctx->h_cone_hkind[k] + 1.0   // epinormspectral.jl:95
+                                : (t == HYP_CONE_EPINORMSPECTRAL || t == HYP_CONE_MATRIXEPIPERSQUARE)
+                                    ? (double)ctx->h_cone_hkind[k] + 1.0   // epinormspectral.jl:95, matrixepipersquare.jl:101
                                 : t == HYP_CONE_WSOSINTERPNONNEGATIVE ? wsos_nu(ctx, k)               // wsosinterpnonnegative.jl:62
                                 : t == HYP_CONE_LINMATRIXINEQ ? lmi_nu(ctx, k)                        // linmatrixineq.jl:72
                                 : t == HYP_CONE_GENERALIZEDPOWER
@@ -949,8 +950,9 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
             if ((t == HYP_CONE_EPIPERSQUARE || t == HYP_CONE_HYPOPERLOG || t == HYP_CONE_EPIPERSEPSPECTRAL_MAT ||
                  t == HYP_CONE_EPIPERSEPSPECTRAL_VEC) && d < 3)
                 throw HypError{"hyp_load_model: this cone type needs dimension >= 3"};
-            if (t == HYP_CONE_EPINORMSPECTRAL && (!have_params || ctx->h_cone_hkind[k] < 1))
-                throw HypError{"hyp_load_model: EpiNormSpectral cones need hyp_set_cone_params (number of rows d1) first"};
+            if ((t == HYP_CONE_EPINORMSPECTRAL || t == HYP_CONE_MATRIXEPIPERSQUARE) &&
+                (!have_params || ctx->h_cone_hkind[k] < 1))
+                throw HypError{"hyp_load_model: EpiNormSpectral / MatrixEpiPerSquare cones need hyp_set_cone_params (number of rows d1) first"};
             if (t == HYP_CONE_EPIRELENTROPY && (d < 3 || d % 2 == 0))
                 throw HypError{"hyp_load_model: EpiRelEntropy needs an odd dimension >= 3"};   // epirelentropy.jl:51-52
             if (t == HYP_CONE_EPIPERSEPSPECTRAL_MAT || t == HYP_CONE_EPIPERSEPSPECTRAL_VEC) {

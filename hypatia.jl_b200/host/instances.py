@@ -106,6 +106,10 @@ def cone_initial_point(spec):
         arr[2:] = w
     elif spec.ctype == M.CONE_EPINORMINF:
         arr[0] = np.sqrt(spec.dim)      # epinorminf.jl:88-95
+    elif spec.ctype == M.CONE_MATRIXEPIPERSQUARE:
+        d1 = spec.hkind                         # matrixepipersquare.jl:103-116: U = I, v = 1, W = 0
+        arr[_svec_diag_idx(d1)] = 1.0
+        arr[d1 * (d1 + 1) // 2] = 1.0
     elif spec.ctype == M.CONE_DOUBLYNONNEGATIVETRI:
         side = M.svec_side(spec.dim)
         ond, offd = dnn_initial_point(side)
@@ -202,6 +206,9 @@ def _central_ray_epirelentropy(d):
 
 def _cone_dual_initial(spec, prim):
     """-grad at the central point, closed form per cone (dual of the central point)."""
+    if spec.ctype == M.CONE_MATRIXEPIPERSQUARE:
+        # -grad at (I, 1, 0): Z = 2 I, Zi = I / 2 => -g_U = svec(I), -g_v = 2 tr(Zi U) - (d1 - 1) = 1, -g_W = 0
+        return prim.copy()
     if spec.ctype == M.CONE_DOUBLYNONNEGATIVETRI:
         return prim.copy()      # the initial point satisfies s = -g(s) (doublynonnegativetri.jl:72-126)
     if spec.ctype == M.CONE_LINMATRIXINEQ:
@@ -323,6 +330,9 @@ def _perturb(rng, spec, vec, noise):
         return vec
     if spec.ctype == M.CONE_EPIPERSEPSPECTRAL_VEC:
         vec += noise / (2.0 * (vec.size - 2)) * (2 * rng.random(vec.size) - 1)   # the initial point is not central
+        return vec
+    if spec.ctype == M.CONE_MATRIXEPIPERSQUARE:
+        vec += 0.5 * noise / np.sqrt(vec.size) * (2 * rng.random(vec.size) - 1)
         return vec
     if spec.ctype == M.CONE_DOUBLYNONNEGATIVETRI:
         vec += 0.5 * noise / np.sqrt(vec.size) * (2 * rng.random(vec.size) - 1)

@@ -30,6 +30,7 @@ CONE_EPINORMSPECTRAL = 14
 CONE_WSOSINTERPNONNEGATIVE = 15
 CONE_LINMATRIXINEQ = 16
 CONE_DOUBLYNONNEGATIVETRI = 17
+CONE_MATRIXEPIPERSQUARE = 18
 
 # separable spectral functions of EpiPerSepSpectral (sepspectralfun.jl:17-116), HYP_SSF_*
 SSF_INV, SSF_NEGLOG, SSF_NEGENTROPY, SSF_POWER12 = 0, 1, 2, 3
@@ -53,6 +54,7 @@ CONE_NAMES = {
     CONE_WSOSINTERPNONNEGATIVE: "WSOSInterpNonnegative",
     CONE_LINMATRIXINEQ: "LinMatrixIneq",
     CONE_DOUBLYNONNEGATIVETRI: "DoublyNonnegativeTri",
+    CONE_MATRIXEPIPERSQUARE: "MatrixEpiPerSquare",
 }
 
 
@@ -106,6 +108,11 @@ class ConeSpec:
             assert dim >= 3
         elif ctype == CONE_HYPOPERLOG:
             assert dim >= 3
+        elif ctype == CONE_MATRIXEPIPERSQUARE:
+            # hkind = d1: dim = svec_length(d1) + 1 + d1 * d2 with d1 <= d2 (matrixepipersquare.jl:56-74)
+            d1 = hkind
+            rest = dim - d1 * (d1 + 1) // 2 - 1
+            assert d1 >= 1 and rest >= d1 * d1 and rest % d1 == 0
         elif ctype == CONE_DOUBLYNONNEGATIVETRI:
             assert dim >= 1
             svec_side(dim)
@@ -166,8 +173,8 @@ class ConeSpec:
             return 2.0
         if self.ctype == CONE_GENERALIZEDPOWER:
             return float(len(self.alpha) + 1)
-        if self.ctype == CONE_EPINORMSPECTRAL:
-            return float(self.hkind + 1)      # epinormspectral.jl:95
+        if self.ctype in (CONE_EPINORMSPECTRAL, CONE_MATRIXEPIPERSQUARE):
+            return float(self.hkind + 1)      # epinormspectral.jl:95, matrixepipersquare.jl:101
         if self.ctype == CONE_LINMATRIXINEQ:
             return float(int(self.alpha[0]))      # linmatrixineq.jl:72
         if self.ctype == CONE_WSOSINTERPNONNEGATIVE:
@@ -237,6 +244,13 @@ def WSOSInterpNonnegative(U, Ps, use_dual=False):
     assert all(P.ndim == 2 and P.shape[0] == U for P in Ps)
     packed = np.concatenate([[float(len(Ps))], [float(P.shape[1]) for P in Ps]] + [P.ravel(order="F") for P in Ps])
     return ConeSpec(CONE_WSOSINTERPNONNEGATIVE, U, not use_dual, alpha=packed)
+
+
+def MatrixEpiPerSquare(d1, d2, use_dual=False):
+    """MatrixEpiPerSquare{Float64, Float64}(d1, d2): (svec(U), v, vec(W)), U symmetric d1 x d1, W d1 x d2, d1 <= d2,
+    2 v U - W W' psd."""
+    assert 1 <= d1 <= d2
+    return ConeSpec(CONE_MATRIXEPIPERSQUARE, d1 * (d1 + 1) // 2 + 1 + d1 * d2, use_dual, hkind=d1)
 
 
 def DoublyNonnegativeTri(dim, use_dual=False):

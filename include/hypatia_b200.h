@@ -57,6 +57,8 @@ typedef struct hyp_ctx hyp_ctx;
 #define HYP_CONE_LINMATRIXINEQ 16   /* linmatrixineq.jl (real dense A_i): dim = number of matrices <= 128; the matrices travel in the
                                        per-cone array of hyp_set_cone_alpha as [side, vec(A_1) .. vec(A_dim)] */
 #define HYP_CONE_DOUBLYNONNEGATIVETRI 17 /* doublynonnegativetri.jl: svec of a psd AND entrywise nonnegative matrix; dim <= 128 */
+#define HYP_CONE_MATRIXEPIPERSQUARE 18 /* matrixepipersquare.jl (real): (svec(U), v, vec(W)), U d1 x d1, W d1 x d2, d1 <= d2;
+                                       d1 is given as the integer parameter of hyp_set_cone_params; dim <= 128 */
 #define HYP_CONE_EPINORMSPECTRAL 14 /* epinormspectral.jl (real): (u, vec(W)), W d1 x d2 column-major, d1 <= d2; d1 is given
                                        as the integer parameter of hyp_set_cone_params; use_dual = 1: nuclear norm; dim <= 128 */
 

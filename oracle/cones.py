@@ -770,6 +770,10 @@ def make_cone(spec):
     if spec.ctype == M.CONE_EPIPERSEPSPECTRAL_VEC:
         from .cones_sepspec import EpiPerSepSpectralVec
         return EpiPerSepSpectralVec(spec.dim, spec.hkind, spec.hparam, use_dual=spec.use_dual)
+    if spec.ctype == M.CONE_MATRIXEPIPERSQUARE:
+        from .cones_vec3 import MatrixEpiPerSquare
+        d1 = spec.hkind
+        return MatrixEpiPerSquare(d1, (spec.dim - d1 * (d1 + 1) // 2 - 1) // d1, use_dual=spec.use_dual)
     if spec.ctype == M.CONE_DOUBLYNONNEGATIVETRI:
         from .cones_vec3 import DoublyNonnegativeTri
         return DoublyNonnegativeTri(spec.dim, use_dual=spec.use_dual)

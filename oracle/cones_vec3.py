@@ -937,6 +937,155 @@ class DoublyNonnegativeTri(Cone):
         return d3
 
 
+class MatrixEpiPerSquare(Cone):
+    """matrixepipersquare.jl:10-397 (real case): (svec(U), v, vec(W)) with U symmetric d1 x d1, W d1 x d2 (d1 <= d2),
+    2 v U - W W' psd; barrier -logdet(2 v U - W W') + (d1 - 1) log v, nu = d1 + 1.  inv_hess_prod! is the generic
+    factorisation fallback (Cones.jl:113-118); the explicit Hessian is assembled column by column from hess_prod!
+    (equal to update_hess, matrixepipersquare.jl:187-279, which the identity tests check through hess * inv_hess)."""
+    ctype = M.CONE_MATRIXEPIPERSQUARE
+
+    def __init__(self, d1, d2, use_dual=False):
+        assert 1 <= d1 <= d2
+        self.d1, self.d2 = d1, d2
+        self.v_idx = d1 * (d1 + 1) // 2
+        self.use_dual_barrier = use_dual
+        super().__init__(self.v_idx + 1 + d1 * d2)
+
+    @property
+    def nu(self):
+        return float(self.d1 + 1)
+
+    def set_initial_point(self, arr):
+        # matrixepipersquare.jl:103-116: U = I, v = 1, W = 0
+        arr[:] = 0.0
+        arr[[j * (j + 1) // 2 + j for j in range(self.d1)]] = 1.0
+        arr[self.v_idx] = 1.0
+        return arr
+
+    def _split(self, vec):
+        from . import arrayutil as au
+        return (au.svec_to_smat(vec[:self.v_idx]), vec[self.v_idx],
+                vec[self.v_idx + 1:].reshape(self.d1, self.d2, order="F"))
+
+    def update_feas(self):
+        # matrixepipersquare.jl:118-135
+        U, v, W = self._split(self.point)
+        if v > EPS:
+            self.U, self.v, self.W = U, float(v), W.copy()
+            try:
+                self.fact_Z = sla.cho_factor(2 * v * U - W @ W.T, lower=False, check_finite=False)
+            except np.linalg.LinAlgError:
+                return False
+            return True
+        return False
+
+    def is_dual_feas(self):
+        # matrixepipersquare.jl:137-150
+        U, v, W = self._split(self.dual_point)
+        if v > EPS:
+            try:
+                R = np.linalg.cholesky(U).T
+            except np.linalg.LinAlgError:
+                return False
+            LW = sla.solve_triangular(R, W, trans="T", lower=False, check_finite=False)
+            return bool(2 * v - float(np.sum(LW * LW)) > EPS)
+        return False
+
+    def _zs(self, X):
+        return sla.cho_solve(self.fact_Z, X, check_finite=False)
+
+    def update_grad(self):
+        # matrixepipersquare.jl:152-170, update_hess_aux :172-185
+        from . import arrayutil as au
+        U, v, W, d1 = self.U, self.v, self.W, self.d1
+        Zi = self._zs(np.eye(d1))
+        self.Zi = (Zi + Zi.T) / 2
+        self.ZiW = self._zs(W)
+        self._grad[:self.v_idx] = -2 * v * au.smat_to_svec(self.Zi)
+        self._grad[self.v_idx] = -2 * float(np.sum(self.Zi * U)) + (d1 - 1) / v
+        self._grad[self.v_idx + 1:] = 2 * self.ZiW.ravel(order="F")
+        ZiUZi = self._zs(self._zs(U).T).T
+        self.ZiUZi = (ZiUZi + ZiUZi.T) / 2
+        self.Hvv = 4 * float(np.sum(self.ZiUZi * U)) - (d1 - 1) / v / v
+        self.ZiUZiW = self.ZiUZi @ W
+        self.WtZiW = W.T @ self.ZiW
+
+    def hess_prod(self, arr):
+        # matrixepipersquare.jl:281-325
+        from . import arrayutil as au
+        self.grad()
+        a, vec = _as2d(arr)
+        U, v, W = self.U, self.v, self.W
+        v2 = 2 * v
+        prod = np.empty_like(a)
+        for i in range(a.shape[1]):
+            tU, va, tW = self._split(a[:, i])
+            ZiWd = self._zs(tW)
+            U3 = ZiWd @ self.ZiW.T
+            ZtUZ = self._zs(self._zs(tU).T).T
+            U2 = U3 + U3.T - v2 * ZtUZ
+            T1 = U2 - 2 * va * self.ZiUZi
+            prod[self.v_idx + 1:, i] = (2 * (T1 @ W) + 2 * ZiWd).ravel(order="F")
+            T2 = 2 * v2 * self.ZiUZi - 2 * self.Zi
+            prod[self.v_idx, i] = float(np.sum(T2 * tU)) - 4 * float(np.sum(U * U3)) + self.Hvv * va
+            prod[:self.v_idx, i] = au.smat_to_svec(va * T2 - v2 * U2)
+        return _ret(prod, vec)
+
+    def update_hess(self):
+        H = self.hess_prod(np.eye(self.dim))
+        return (H + H.T) / 2
+
+    def dder3(self, direction):
+        # matrixepipersquare.jl:327-397
+        from . import arrayutil as au
+        self.grad()
+        d1, U, v, W = self.d1, self.U, self.v, self.W
+        Ud, vd, Wd = self._split(direction)
+        v2, vd2 = 2 * v, 2 * vd
+        ZiW, ZiUZi = self.ZiW, self.ZiUZi
+        ZiU = self._zs(U)
+        ZiWd = self._zs(Wd)
+        ZiUd = self._zs(Ud)
+        ZiUZiUZi = ZiUZi @ ZiU.T
+        ZiUZiUZi = (ZiUZiUZi + ZiUZiUZi.T) / 2
+        ZiUZi2v = ZiUZi - v2 * ZiUZiUZi
+        WdWZi = Wd @ ZiW.T
+        WdZiW = Wd.T @ ZiW
+        UdZiW = Ud @ ZiW
+        ZiWdWZi = self._zs(WdWZi)
+        ZiWdWZi2 = ZiWdWZi + ZiWdWZi.T
+        ZiUdZiW = self._zs(UdZiW)
+        ZiUZiWdWZi = ZiU @ ZiWdWZi
+        ZiUZiUdZiW = ZiU @ ZiUdZiW + ZiUd @ self.ZiUZiW
+        ZiWdWZiUZi = ZiWdWZi @ ZiU.T
+        ZiWdWZiUZi2 = ZiWdWZiUZi + ZiWdWZiUZi.T + ZiUZiWdWZi.T
+        ZiUdZi = self._zs(ZiUd.T).T
+        ZiUdZi = (ZiUdZi + ZiUdZi.T) / 2
+        ZiUZiUdZi = ZiU @ ZiUdZi
+        ZiUZiUdZi2 = ZiUZiUdZi + ZiUZiUdZi.T
+        ZiUdZiWdWZi = ZiUd @ ZiWdWZi + ZiWdWZi @ ZiUd.T
+        WtZiWI = self.WtZiW + np.eye(self.d2)
+        ZiWdWtZiWI = ZiWd @ WtZiWI
+        vdZiUZiUZiW = vd2 * ZiUZiUZi @ W
+        WdWtZiWI = Wd @ WtZiWI
+        ZiUZiWdWZiWI = ZiUZi @ WdWtZiWI + ZiWdWZiUZi2 @ W
+        vZiUZiUdZi2 = v * ZiUZiUdZi2 - ZiUdZi
+        Utemp = vd2 * (-vd2 * ZiUZi2v + ZiWdWZi2 - v2 * (ZiUZiWdWZi + ZiWdWZiUZi2 - 2 * vZiUZiUdZi2)) + \
+            v2 * (ZiWdWZi @ WdWZi + WdWZi.T @ ZiWdWZi2 + ZiWdWtZiWI @ ZiWd.T +
+                  v2 * (v2 * ZiUd @ ZiUdZi - ZiUdZiWdWZi - ZiUdZiWdWZi.T))
+        d3 = np.empty(self.dim)
+        d3[:self.v_idx] = au.smat_to_svec((Utemp + Utemp.T) / 2)
+        v_Wd_dot = -4 * (v * ZiUZiUdZiW + vdZiUZiUZiW) + ZiUZiWdWZiWI + 2 * ZiUdZiW
+        d3[self.v_idx] = vd * (-8 * float(np.sum(ZiUZi2v * Ud)) + vd * (8 * float(np.sum(ZiUZiUZi * U)) -
+                                                                        (d1 - 1) / v / v / v)) + \
+            4 * v * float(np.sum(vZiUZiUdZi2 * Ud)) + 2 * float(np.sum(v_Wd_dot * Wd))
+        Wtemp = 4 * vd * (ZiUdZiW - v2 * ZiUZiUdZiW + ZiUZiWdWZiWI - vdZiUZiUZiW) + \
+            4 * v * (ZiUdZiW @ WdZiW + ZiWdWZi @ UdZiW + WdWZi.T @ ZiUdZiW + ZiUdZi @ WdWtZiWI - v2 * ZiUd @ ZiUdZiW) + \
+            -2 * (ZiW @ WdZiW @ WdZiW + WdWZi.T @ ZiWdWtZiWI + ZiWdWtZiWI @ WdZiW + ZiWd @ WdZiW.T @ WtZiWI)
+        d3[self.v_idx + 1:] = Wtemp.ravel(order="F")
+        return d3
+
+
 class LinMatrixIneq(Cone):
     """linmatrixineq.jl:8-159 (real dense matrices): {w : sum_i w_i A_i psd} for symmetric A_i (side x side, A_1 positive
     definite), barrier -logdet(sum_i w_i A_i), nu = side.  hess_prod! / inv_hess_prod! are the generic explicit-Hessian

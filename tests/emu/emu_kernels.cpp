@@ -243,6 +243,33 @@ int emu_gpow_dder3(int ncones, const int64_t* off, const int* dim, const int* mu
 
 extern "C" {
 
+int emu_mep_state(int ncones, const int64_t* off, const int* dim, const int* d1s, const int64_t* voff, double* vecs,
+                  const int* kidx, const int64_t* moff, const double* point, const double* dual, double* grad,
+                  double* scal, double* H, uint8_t* feas, uint8_t* dual_feas) {
+    emu::launch(dim3((ncones + 1) / 2), dim3(64), 0, [&] {
+        hypdev::mep_state_kernel(ncones, off, dim, d1s, voff, vecs, kidx, moff, point, dual, grad, scal, H, feas,
+                                 dual_feas);
+    });
+    return 0;
+}
+
+int emu_mep_prod(int ncones, int want_dual, const int64_t* off, const int* dim, const int* d1s, const int64_t* voff,
+                 const double* vecs, const int* dualf, const double* scal, const double* point, const double* arr,
+                 int64_t ld_arr, double* prod, int64_t ld_prod, int64_t ncols, int64_t row_shift) {
+    emu::launch(dim3((ncones + 1) / 2, 2), dim3(64), 0, [&] {
+        hypdev::mep_prod_kernel(ncones, want_dual, off, dim, d1s, voff, vecs, dualf, scal, point, arr, ld_arr, prod,
+                                ld_prod, ncols, row_shift);
+    });
+    return 0;
+}
+
+int emu_mep_dder3(int ncones, const int64_t* off, const int* dim, const int* d1s, const int64_t* voff, double* vecs,
+                  const double* scal, const double* point, const double* dir, double* out) {
+    emu::launch(dim3((ncones + 1) / 2), dim3(64), 0,
+                [&] { hypdev::mep_dder3_kernel(ncones, off, dim, d1s, voff, vecs, scal, point, dir, out); });
+    return 0;
+}
+
 int emu_dnn_state(int ncones, const int64_t* off, const int* dim, const int* sides, const int64_t* voff, double* vecs,
                   const int* kidx, const int64_t* moff, const double* point, double* grad, double* H, uint8_t* feas) {
     emu::launch(dim3((ncones + 1) / 2), dim3(64), 0, [&] {

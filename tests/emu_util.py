@@ -316,6 +316,16 @@ class EmuGpowGroup:
         self.K = len(specs)
         self.hpm = specs[0].ctype == 12          # HypoPowerMean, else GeneralizedPower
         self.ens = specs[0].ctype == 14          # EpiNormSpectral: d1 per cone, workspace instead of powers
+        self.mep = specs[0].ctype == 18          # MatrixEpiPerSquare: d1 per cone, state + dder3 scratch
+        if self.mep:
+            self.d1 = np.array([s.hkind for s in specs], dtype=np.int32)
+            sizes = []
+            for s in specs:
+                d1 = s.hkind
+                d2 = (s.dim - d1 * (d1 + 1) // 2 - 1) // d1
+                sizes.append(21 * d1 * d1 + 13 * d1 * d2 + 3 * d2 * d2)
+            self.voff = np.concatenate(([0], np.cumsum(sizes)))[:-1].astype(np.int64)
+            self.vecs = np.zeros(int(sum(sizes)))
         self.dnn = specs[0].ctype == 17          # DoublyNonnegativeTri: side per cone + workspace
         if self.dnn:
             self.sides = np.array([int(round((np.sqrt(1 + 8 * s.dim) - 1) / 2)) for s in specs], dtype=np.int32)
@@ -363,7 +373,11 @@ class EmuGpowGroup:
         self.dual_feas = np.ones(self.K, dtype=np.uint8)
         self.grad = np.zeros(self.q)
         self.H = np.zeros(self.lay.total)
-        if self.dnn:
+        if self.mep:
+            lib().emu_mep_state(self.K, p(self.off), p(self.dims), p(self.d1), p(self.voff), p(self.vecs), p(self.kidx),
+                                p(self.lay.moff), p(self.point), p(self.dual), p(self.grad), p(self.scal), p(self.H),
+                                p(self.feas), p(self.dual_feas))
+        elif self.dnn:
             lib().emu_dnn_state(self.K, p(self.off), p(self.dims), p(self.sides), p(self.voff), p(self.vecs), p(self.kidx),
                                 p(self.lay.moff), p(self.point), p(self.grad), p(self.H), p(self.feas))
         elif self.lmi:
@@ -395,7 +409,11 @@ class EmuGpowGroup:
         out = a if in_place else np.zeros_like(a, order="F")
         hess_dual, inv_dual = {0: (-1, -2), 1: (-2, -1), 4: (0, 1), 5: (1, 0)}[int(mode)]
         L = lib()
-        if hess_dual > -2 and self.dnn:
+        if hess_dual > -2 and self.mep:
+            L.emu_mep_prod(self.K, hess_dual, p(self.off), p(self.dims), p(self.d1), p(self.voff), p(self.vecs),
+                           p(self.dualf), p(self.scal), p(self.point), p(a), i64(self.q), p(out), i64(self.q),
+                           i64(a.shape[1]), i64(0))
+        elif hess_dual > -2 and self.dnn:
             L.emu_dnn_prod(self.K, hess_dual, p(self.off), p(self.dims), p(self.sides), p(self.voff), p(self.vecs),
                            p(self.dualf), p(self.point), p(a), i64(self.q), p(out), i64(self.q), i64(a.shape[1]), i64(0))
         elif hess_dual > -2 and (self.wsos or self.lmi):
@@ -420,7 +438,10 @@ class EmuGpowGroup:
     def dder3(self, direction):
         d = np.ascontiguousarray(direction, dtype=np.float64)
         out = np.zeros(self.q)
-        if self.dnn:
+        if self.mep:
+            lib().emu_mep_dder3(self.K, p(self.off), p(self.dims), p(self.d1), p(self.voff), p(self.vecs), p(self.scal),
+                                p(self.point), p(d), p(out))
+        elif self.dnn:
             lib().emu_dnn_dder3(self.K, p(self.off), p(self.dims), p(self.sides), p(self.voff), p(self.vecs),
                                 p(self.point), p(d), p(out))
         elif self.lmi:

@@ -844,6 +844,64 @@ EXTRA = [consistent1, inconsistent1, inconsistent2, nonnegative1, nonnegative2, 
     [_named(lambda f=_f, ud=_ud: f(ud), _f.__name__[1:] + ("_dual" if _ud else ""))
      for _f in (_hypogeomean3, _hypopowermean3) for _ud in (False, True)]
 
+def _matrixepipersquare1(d1, d2, use_dual):  # :1157-1195 (real case): U = I, minimise v
+    W = np.random.default_rng(d1 * 10 + d2).random((d1, d2))
+    per = d1 * (d1 + 1) // 2
+    dim = per + 1 + d1 * d2
+    G = np.zeros((dim, 1))
+    G[per, 0] = -1
+    h = np.zeros(dim)
+    h[:per] = _svec(np.eye(d1))
+    h[per + 1:] = W.ravel(order="F")
+    WWt = W @ W.T
+    epi = np.trace(WWt) / 2 if use_dual else np.linalg.eigvalsh(WWt)[-1] / 2
+    return _m([1], None, None, G, h, [M.MatrixEpiPerSquare(d1, d2, use_dual=use_dual)]), \
+        dict(status="Optimal", primal_obj=epi, s_idx={per: epi}, z_idx={per: 1.0})
+
+
+def _matrixepipersquare2(use_dual):  # :1197-1231 (real case; tol 100 x)
+    rng = np.random.default_rng(1)
+    d1, d2 = 2, 3
+    per = d1 * (d1 + 1) // 2
+    dim = per + 1 + d1 * d2
+    G = np.zeros((dim, 1))
+    G[per, 0] = -1
+    Uh = rng.random((d1, d1))
+    U = Uh @ Uh.T
+    W = rng.random((d1, d2))
+    h = np.zeros(dim)
+    h[:per] = _svec(U)
+    h[per + 1:] = W.ravel(order="F")
+
+    def check(s, z, approx):
+        if use_dual:
+            assert approx(2 * s[per], np.trace(W.T @ np.linalg.solve(U, W)))
+        else:
+            assert approx(np.linalg.eigvalsh(2 * s[per] * U - W @ W.T)[0], 0.0)
+    return _m([1], None, None, G, h, [M.MatrixEpiPerSquare(d1, d2, use_dual=use_dual)]), \
+        dict(status="Optimal", tol_scale=100, check=check)
+
+
+def _matrixepipersquare3(use_dual):  # :1233-1259 (real case; tol 5 x, 2 x for the norm)
+    rng = np.random.default_rng(1)
+    d1, d2 = 3, 4
+    per = d1 * (d1 + 1) // 2
+    wd = d1 * d2
+    dim = per + 1 + wd
+    G = np.vstack((np.zeros((per + 1, wd)), -10.0 * np.eye(wd)))
+    Uh = rng.random((d1, d1))
+    h = np.zeros(dim)
+    h[:per] = _svec(Uh @ Uh.T)
+    return _m(np.ones(wd), None, None, G, h, [M.MatrixEpiPerSquare(d1, d2, use_dual=use_dual)]), \
+        dict(status="Optimal", x=np.zeros(wd), tol_scale=10)
+
+
+MEPS = [_named(lambda a=_a, b=_b, ud=_ud: _matrixepipersquare1(a, b, ud), f"matrixepipersquare1_{_a}x{_b}" + ("_dual" if _ud else ""))
+        for (_a, _b) in ((1, 1), (1, 3), (2, 2), (2, 3)) for _ud in (False, True)] + \
+    [_named(lambda f=_f, ud=_ud: f(ud), _f.__name__[1:] + ("_dual" if _ud else ""))
+     for _f in (_matrixepipersquare2, _matrixepipersquare3) for _ud in (False, True)]
+
+
 def doublynonnegativetri1():  # :493-511 (the reference's loop overrides use_dual to false)
     return _m([0, 1, 0], [[1, 0, 0], [0, 0, 1]], [1, 1], -np.eye(3), np.zeros(3), [M.DoublyNonnegativeTri(3)]), \
         dict(status="Optimal", primal_obj=0, x=[1, 0, 1], s=[1, 0, 1])
@@ -893,7 +951,7 @@ def linmatrixineq3():  # :747-788 (dense case): min w_1 : w_1 I - diag(1, -1) ps
 
 LMI = [_named(lambda s=_s: _linmatrixineq1(s), f"linmatrixineq1_side{_s}") for _s in (2, 4)] + \
     [_named(lambda d=_d: _linmatrixineq2(d), f"linmatrixineq2_dim{_d}") for _d in (2, 3)] + [linmatrixineq3]
-EXTRA = EXTRA + LMI + DNN
+EXTRA = EXTRA + LMI + DNN + MEPS
 
 RELENT = [_named(lambda d=_d: _epirelentropy1(d), f"epirelentropy1_d{_d}") for _d in (1, 2, 3)] + \
     [_named(lambda d=_d: _epirelentropy2(d), f"epirelentropy2_d{_d}") for _d in (1, 2, 4)] + \
@@ -958,5 +1016,7 @@ def check_solution(solver, model, expected, tol=TOL):
         assert _approx(x[i], v, tol)
     for i, v in expected.get("z_idx", {}).items():
         assert _approx(z[i], v, tol)
+    for i, v in expected.get("s_idx", {}).items():
+        assert _approx(s[i], v, tol)
     if "check" in expected:       # instance-specific assertions on (s, z), e.g. singular values
         expected["check"](s, z, lambda a, b: _approx(a, b, tol))

@@ -43,6 +43,8 @@ def _sets():
     return {
         "dnn": [M.DoublyNonnegativeTri(M.svec_length(sd)) for sd in (1, 2, 3, 5, 10, 15)] +
                [M.DoublyNonnegativeTri(M.svec_length(4), use_dual=True)],
+        "meps": [M.MatrixEpiPerSquare(a, b) for a, b in ((1, 1), (1, 2), (2, 2), (2, 4), (3, 4), (1, 100), (8, 11), (5, 9))] +
+                [M.MatrixEpiPerSquare(2, 3, use_dual=True)],
         "lmi": [_lmi(rng, 2, 2), _lmi(rng, 3, 2), _lmi(rng, 4, 3), _lmi(rng, 3, 6), _lmi(rng, 12, 40),
                 _lmi(rng, 5, 4, use_dual=True), _lmi(rng, 33, 20)],
         "wsos": [_wsos(1, 1), _wsos(1, 3), _wsos(2, 2), _wsos(3, 1), _wsos(2, 4), _wsos(1, 2, use_dual=True),
@@ -59,7 +61,7 @@ def _sets():
     }
 
 
-NAMES = ["gpow", "gpow_dual", "hpm", "hpm_dual", "normspec", "normspec_dual", "wsos", "lmi", "dnn"]
+NAMES = ["gpow", "gpow_dual", "hpm", "hpm_dual", "normspec", "normspec_dual", "wsos", "lmi", "dnn", "meps"]
 
 
 @pytest.mark.parametrize("name", NAMES)

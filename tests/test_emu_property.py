@@ -98,6 +98,10 @@ def _genfact_cone(kind, a, b, dual, rng):
         d1 = 1 + a % 5
         d2 = d1 + b % 7
         return M.EpiNormSpectral(d1, d2, use_dual=dual)
+    if kind == "meps":
+        d1 = 1 + a % 4
+        d2 = d1 + b % 6
+        return M.MatrixEpiPerSquare(d1, d2, use_dual=dual)
     if kind == "dnn":
         return M.DoublyNonnegativeTri(M.svec_length(1 + a % 9), use_dual=dual)
     if kind == "lmi":
@@ -114,7 +118,7 @@ def _genfact_cone(kind, a, b, dual, rng):
     return M.WSOSInterpNonnegative(U, Ps, use_dual=dual)
 
 
-GENFACT_KINDS = ["gpow", "hpm", "normspec", "dnn", "lmi", "wsos"]
+GENFACT_KINDS = ["gpow", "hpm", "normspec", "dnn", "lmi", "wsos", "meps"]
 
 
 @settings(max_examples=30, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.too_slow])

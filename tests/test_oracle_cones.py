@@ -323,6 +323,50 @@ def test_doublynonnegativetri_barrier():
     assert close(-2 * cone.dder3(direction), fd_third, 1e-5)
 
 
+@pytest.mark.parametrize("dr,ds", [(1, 1), (1, 2), (2, 2), (2, 4), (3, 4)])
+def test_matrixepipersquare(dr, ds):
+    # reference: test/cone.jl:519-523
+    from oracle.cones_vec3 import MatrixEpiPerSquare
+    run_oracles(MatrixEpiPerSquare(dr, ds))
+
+
+def test_matrixepipersquare_barrier():
+    """test/cone.jl:525-535 with central differences: -logdet(2 v U - W W') + (d1 - 1) log v."""
+    from oracle import arrayutil as au
+    from oracle.cones_vec3 import MatrixEpiPerSquare
+    dr, ds = 2, 2
+    cone = MatrixEpiPerSquare(dr, ds)
+    du = dr * (dr + 1) // 2
+
+    def barrier(s):
+        U, v, W = au.svec_to_smat(s[:du]), s[du], s[du + 1:].reshape(dr, ds, order="F")
+        return -np.linalg.slogdet(2 * v * U - W @ W.T)[1] + (dr - 1) * np.log(v)
+
+    rng = np.random.default_rng(1)
+    point = np.zeros(cone.dim)
+    cone.set_initial_point(point)
+    perturb_scale(rng, point, 0.1, 1.0)
+
+    def grad_at(s):
+        cone.reset_data()
+        cone.load_point(s)
+        assert cone.is_feas()
+        return cone.grad().copy()
+
+    g = grad_at(point)
+    eps = 1e-6
+    fd_grad = np.array([(barrier(point + eps * e) - barrier(point - eps * e)) / (2 * eps) for e in np.eye(cone.dim)])
+    assert close(g, fd_grad, 1e-7)
+    direction = 0.3 * rng.standard_normal(cone.dim)
+    fd_hess_dir = (grad_at(point + eps * direction) - grad_at(point - eps * direction)) / (2 * eps)
+    grad_at(point)
+    assert close(cone.hess_prod(direction), fd_hess_dir, 1e-6)
+    e2 = 1e-4
+    fd_third = (grad_at(point + e2 * direction) - 2 * g + grad_at(point - e2 * direction)) / e2 ** 2
+    grad_at(point)
+    assert close(-2 * cone.dder3(direction), fd_third, 1e-5)
+
+
 def rand_lmi(rng, side, dim):
     """rand_herms of test/cone.jl (real case): symmetric matrices with a positive definite first one."""
     As = []
