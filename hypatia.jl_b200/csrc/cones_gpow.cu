@@ -171,7 +171,54 @@ static void mep_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
     hyp_mat_alloc_group(ctx, g);
 }
 
+// WSOSInterpPosSemidefTri: d_hkind = R, d_vecs / d_voff = per-cone region [nP][L_1 .. L_nP][P_1 .. P_nP] (as passed to
+// hyp_set_cone_alpha) followed by the workspace of wpsd_state_kernel / wpsd_dder3_kernel
+static void wpsd_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
+    if ((int)ctx->h_cone_aoff.size() != ctx->K + 1)
+        throw HypError{"WSOSInterpPosSemidefTri cones need hyp_set_cone_alpha (packed Ps) before hyp_load_model"};
+    g.h_voff.assign(g.count, 0);
+    std::vector<double> buf;
+    for (int i = 0; i < g.count; i++) {
+        const int k = g.h_kidx[i];
+        const int64_t a0 = ctx->h_cone_aoff[k], a1 = ctx->h_cone_aoff[k + 1];
+        const int d = g.h_dim[i], R = ctx->h_cone_hkind[k];
+        if (d > 128) throw HypError{"WSOSInterpPosSemidefTri: dimension above 128 is not supported (batched Cholesky limit)"};
+        if (R < 1 || d % (R * (R + 1) / 2) != 0)
+            throw HypError{"WSOSInterpPosSemidefTri: hyp_set_cone_params must give R with dim = U * svec_length(R)"};
+        const int64_t U = d / (R * (R + 1) / 2);
+        if (a1 - a0 < 2) throw HypError{"WSOSInterpPosSemidefTri: missing Ps data"};
+        const int nP = (int)ctx->h_cone_alpha[a0];
+        if (nP < 1 || a1 - a0 < 1 + nP) throw HypError{"WSOSInterpPosSemidefTri: bad number of Ps matrices"};
+        int64_t sumL = 0, wsz = 0, Lmax = 0;
+        for (int j = 0; j < nP; j++) {
+            const int64_t L = (int64_t)ctx->h_cone_alpha[a0 + 1 + j];
+            if (L < 1 || L > U) throw HypError{"WSOSInterpPosSemidefTri: need 1 <= L_k <= U"};
+            sumL += L;
+            wsz += R * L * R * U + R * L * R * L;
+            Lmax = std::max(Lmax, L);
+        }
+        if (a1 - a0 != 1 + nP + U * sumL) throw HypError{"WSOSInterpPosSemidefTri: Ps data has the wrong length"};
+        g.h_voff[i] = (int64_t)buf.size();
+        buf.insert(buf.end(), ctx->h_cone_alpha.begin() + a0, ctx->h_cone_alpha.begin() + a1);
+        buf.resize(buf.size() + (size_t)(wsz + R * U * R * U + R * Lmax * R * Lmax + R * Lmax * R * U), 0.0);
+        g.h_hkind.push_back(R);
+        g.h_side[i] = d;
+    }
+    g.max_side = g.max_dim;
+    cudaFree(g.d_side);
+    g.d_side = upload_vec(g.h_side);
+    g.d_hkind = upload_vec(g.h_hkind);
+    g.d_voff = upload_vec(g.h_voff);
+    CUDA_TRY(cudaMalloc(&g.d_vecs, std::max<size_t>(buf.size(), 1) * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(g.d_vecs, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice));
+    hyp_mat_alloc_group(ctx, g);
+}
+
 void hyp_gpow_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
+    if (g.type == HYP_CONE_WSOSINTERPPOSSEMIDEFTRI) {
+        wpsd_alloc_group(ctx, g);
+        return;
+    }
     if (g.type == HYP_CONE_MATRIXEPIPERSQUARE) {
         mep_alloc_group(ctx, g);
         return;
@@ -228,7 +275,11 @@ void hyp_gpow_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
 }
 
 void hyp_gpow_update_state(hyp_ctx* ctx, ConeGroup& g) {
-    if (g.type == HYP_CONE_MATRIXEPIPERSQUARE)
+    if (g.type == HYP_CONE_WSOSINTERPPOSSEMIDEFTRI)
+        hypdev::wpsd_state_kernel<<<g.count, 256, 0, ctx->stream>>>(g.count, g.d_off, g.d_dim, g.d_hkind, g.d_voff, g.d_vecs,
+                                                                   g.d_kidx, g.d_moff, ctx->d_point, ctx->d_grad, g.d_W,
+                                                                   ctx->d_feas);
+    else if (g.type == HYP_CONE_MATRIXEPIPERSQUARE)
         hypdev::mep_state_kernel<<<ceil_div(g.count, 4), 128, 0, ctx->stream>>>(
             g.count, g.d_off, g.d_dim, g.d_hkind, g.d_voff, g.d_vecs, g.d_kidx, g.d_moff, ctx->d_point, ctx->d_dual,
             ctx->d_grad, g.d_scal, g.d_W, ctx->d_feas, ctx->d_dual_feas);
@@ -283,7 +334,8 @@ void hyp_gpow_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr, 
             hypdev::dnn_prod_kernel<<<grid, 256, 0, ctx->stream>>>(g.count, hess_dual, g.d_off, g.d_dim, g.d_hkind,
                                                                   g.d_voff, g.d_vecs, g.d_dual, ctx->d_point, arr, ld_arr,
                                                                   prod, ld_prod, ncols, row_shift);
-        else if (g.type == HYP_CONE_WSOSINTERPNONNEGATIVE || g.type == HYP_CONE_LINMATRIXINEQ)
+        else if (g.type == HYP_CONE_WSOSINTERPNONNEGATIVE || g.type == HYP_CONE_LINMATRIXINEQ ||
+                 g.type == HYP_CONE_WSOSINTERPPOSSEMIDEFTRI)
             hypdev::gen_hess_prod_kernel<<<grid, 256, 0, ctx->stream>>>(g.count, hess_dual, g.d_off, g.d_dim, g.d_moff,
                                                                        g.d_dual, g.d_W, arr, ld_arr, prod, ld_prod, ncols,
                                                                        row_shift);
@@ -312,7 +364,10 @@ void hyp_gpow_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr, 
 }
 
 void hyp_gpow_dder3(hyp_ctx* ctx, ConeGroup& g, double* out, const double* dir) {
-    if (g.type == HYP_CONE_MATRIXEPIPERSQUARE)
+    if (g.type == HYP_CONE_WSOSINTERPPOSSEMIDEFTRI)
+        hypdev::wpsd_dder3_kernel<<<g.count, 256, 0, ctx->stream>>>(g.count, g.d_off, g.d_dim, g.d_hkind, g.d_voff, g.d_vecs,
+                                                                   dir, out);
+    else if (g.type == HYP_CONE_MATRIXEPIPERSQUARE)
         hypdev::mep_dder3_kernel<<<ceil_div(g.count, 4), 128, 0, ctx->stream>>>(
             g.count, g.d_off, g.d_dim, g.d_hkind, g.d_voff, g.d_vecs, g.d_scal, ctx->d_point, dir, out);
     else if (g.type == HYP_CONE_DOUBLYNONNEGATIVETRI)

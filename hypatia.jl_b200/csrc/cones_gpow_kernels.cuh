@@ -1487,4 +1487,189 @@ mep_dder3_kernel(int ncones, const int64_t* __restrict__ off, const int* __restr
 }
 
 
+// ---- WSOSInterpPosSemidefTri (R x R matrix polynomials, dim = U svec_length(R) <= 128), wsosinterppossemideftri.jl:108-321 ----
+// Region of cone c at vecs + voff[c]: [nP][L_1 .. L_nP][P_1 .. P_nP] (hyp_set_cone_alpha; P_k is U x L_k), then per k
+// F_k = Lc_k^-1 (I_R kron P_k)' (R L_k x R U) and the lower Cholesky factor Lc_k of Lambda_k = (I kron P_k)' D(point)
+// (I kron P_k) (R L_k x R L_k), then G = F'F (R U x R U) and the dder3 scratch S (R L_max)^2, T (R L_max x R U).
+// D(s) has the diagonal blocks Diagonal(smat(s)_pq) (off-diagonal svec blocks scaled by 1 / sqrt 2).  Dense restatement
+// of the reference's block-triangular algebra; one CTA of 256 threads per cone; thread i < dim owns entry i.
+
+// entry (pL + a, qL + b) of (I kron P)' D(vec) (I kron P)
+__device__ __forceinline__ double wpsd_lambda(const double* P, const double* vec, int U, int L, int row, int col) {
+    const int p = row / L, a = row % L, q = col / L, b = col % L;
+    const int hi = p > q ? p : q, lo = p > q ? q : p;
+    const double* v = vec + (int64_t)(hi * (hi + 1) / 2 + lo) * U;
+    double s = 0.0;
+    for (int u = 0; u < U; u++) s += P[u + (int64_t)a * U] * v[u] * P[u + (int64_t)b * U];
+    return p == q ? s : s * 0.70710678118654752440;
+}
+
+static __global__ void __launch_bounds__(256)
+wpsd_state_kernel(int ncones, const int64_t* __restrict__ off, const int* __restrict__ dim,
+                  const int* __restrict__ Rs, const int64_t* __restrict__ voff, double* __restrict__ vecs,
+                  const int* __restrict__ kidx, const int64_t* __restrict__ moff, const double* __restrict__ point,
+                  double* __restrict__ grad, double* __restrict__ H, uint8_t* feas) {
+    __shared__ int s_ok;
+    const int c = blockIdx.x, tid = threadIdx.x;
+    if (c >= ncones) return;
+    const int64_t o = off[c];
+    const int d = dim[c], R = Rs[c], nb = R * (R + 1) / 2, U = d / nb, RU = R * U, lde = (d + 1) & ~1;
+    double* reg = vecs + voff[c];
+    const int nP = (int)reg[0];
+    int64_t sumL = 0, wsz = 0;
+    for (int k = 0; k < nP; k++) {
+        const int64_t L = (int64_t)reg[1 + k];
+        sumL += L;
+        wsz += R * L * RU + R * L * R * L;
+    }
+    const double* P = reg + 1 + nP;
+    double* ws = reg + 1 + nP + (int64_t)U * sumL;
+    double* G = ws + wsz;
+    double* Hc = H + moff[c];
+    const double* pt = point + o;
+    if (tid == 0) s_ok = 1;
+    double gacc = 0.0;
+    int gp = 0, gq = 0;                      // block (gp, gq), gq <= gp, and point index gu of entry tid
+    if (tid < d) dnn_ij(tid / U, gq, gp);
+    const int gu = tid % U;
+    for (int k = 0; k < nP; k++) {
+        const int L = (int)reg[1 + k], RL = R * L;
+        double* F = ws;
+        double* Lc = F + (int64_t)RL * RU;
+        ws = Lc + RL * RL;
+        for (int idx = tid; idx < RL * RL; idx += 256) Lc[idx] = wpsd_lambda(P, pt, U, L, idx % RL, idx / RL);
+        __syncthreads();
+        for (int j = 0; j < RL; j++) {                     // Cholesky (lower, in place, right-looking)
+            if (tid == 0) {
+                double dg = Lc[j + j * RL];
+                if (!(dg > 0.0)) {
+                    s_ok = 0;
+                    dg = 1.0;
+                }
+                Lc[j + j * RL] = sqrt(dg);
+            }
+            __syncthreads();
+            const double dj = Lc[j + j * RL];
+            for (int i = j + 1 + tid; i < RL; i += 256) Lc[i + j * RL] /= dj;
+            __syncthreads();
+            const int r = RL - j - 1;
+            for (int idx = tid; idx < r * r; idx += 256) {
+                const int ii = j + 1 + idx % r, kk = j + 1 + idx / r;
+                if (kk <= ii) Lc[ii + kk * RL] -= Lc[ii + j * RL] * Lc[kk + j * RL];
+            }
+            __syncthreads();
+        }
+        // F = Lc^-1 (I kron P)': column (p, u) has P[u, :] in block p
+        for (int jj = tid; jj < RU; jj += 256) {
+            const int p = jj / U, u = jj % U;
+            double* f = F + (int64_t)jj * RL;
+            for (int a = 0; a < RL; a++) {
+                double s = (a / L == p) ? P[u + (int64_t)(a % L) * U] : 0.0;
+                for (int b = 0; b < a; b++) s -= Lc[a + b * RL] * f[b];
+                f[a] = s / Lc[a + a * RL];
+            }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < RU * RU; idx += 256) {   // G = F'F ("PLambdaiP")
+            const int i = idx % RU, j = idx / RU;
+            double s = 0.0;
+            for (int a = 0; a < RL; a++) s += F[a + (int64_t)i * RL] * F[a + (int64_t)j * RL];
+            G[idx] = s;
+        }
+        __syncthreads();
+        // gradient (:144-188) and Hessian (:190-239)
+        if (tid < d)
+            gacc -= G[(gq * U + gu) + (int64_t)(gp * U + gu) * RU] * (gp == gq ? 1.0 : 1.41421356237309504880);
+        for (int idx = tid; idx < d * d; idx += 256) {
+            const int e1 = idx % d, e2 = idx / d;
+            int p1, q1, p2, q2;
+            dnn_ij(e1 / U, q1, p1);
+            dnn_ij(e2 / U, q2, p2);
+            const int u1 = e1 % U, u2 = e2 % U;
+#define WPSD_B(x, y) G[((x) * U + u1) + (int64_t)((y) * U + u2) * RU]
+            double v = WPSD_B(p1, p2) * WPSD_B(q1, q2) * (((p1 == q1) != (p2 == q2)) ? 1.41421356237309504880 : 1.0);
+            if (p1 != q1 && p2 != q2) v += WPSD_B(p1, q2) * WPSD_B(q1, p2);
+#undef WPSD_B
+            Hc[e1 + (int64_t)e2 * lde] = k == 0 ? v : Hc[e1 + (int64_t)e2 * lde] + v;
+        }
+        __syncthreads();
+        P += (int64_t)U * L;
+    }
+    if (tid < d) grad[o + tid] = gacc;
+    if (tid == 0 && !s_ok) feas[kidx[c]] = 0;
+}
+
+// dder3 = partial_prod! with use_symm_prod (:284-321): per k, S = Lc^-1 (I kron P)' D(dir) (I kron P) Lc^-T, T = S F,
+// out[(p, q), u] += <T[:, (p, u)], T[:, (q, u)]> (sqrt 2 off the diagonal blocks)
+static __global__ void __launch_bounds__(256)
+wpsd_dder3_kernel(int ncones, const int64_t* __restrict__ off, const int* __restrict__ dim,
+                  const int* __restrict__ Rs, const int64_t* __restrict__ voff, double* __restrict__ vecs,
+                  const double* __restrict__ dir, double* __restrict__ out) {
+    const int c = blockIdx.x, tid = threadIdx.x;
+    if (c >= ncones) return;
+    const int64_t o = off[c];
+    const int d = dim[c], R = Rs[c], nb = R * (R + 1) / 2, U = d / nb, RU = R * U;
+    double* reg = vecs + voff[c];
+    const int nP = (int)reg[0];
+    int64_t sumL = 0, wsz = 0, Lmax = 0;
+    for (int k = 0; k < nP; k++) {
+        const int64_t L = (int64_t)reg[1 + k];
+        sumL += L;
+        wsz += R * L * RU + R * L * R * L;
+        Lmax = L > Lmax ? L : Lmax;
+    }
+    const double* P = reg + 1 + nP;
+    double* ws = reg + 1 + nP + (int64_t)U * sumL;
+    double* S = ws + wsz + (int64_t)RU * RU;
+    double* T = S + (R * Lmax) * (R * Lmax);
+    double acc = 0.0;
+    int gp = 0, gq = 0;
+    if (tid < d) dnn_ij(tid / U, gq, gp);
+    const int gu = tid % U;
+    for (int k = 0; k < nP; k++) {
+        const int L = (int)reg[1 + k], RL = R * L;
+        const double* F = ws;
+        const double* Lc = F + (int64_t)RL * RU;
+        ws += (int64_t)RL * RU + RL * RL;
+        for (int idx = tid; idx < RL * RL; idx += 256) S[idx] = wpsd_lambda(P, dir + o, U, L, idx % RL, idx / RL);
+        __syncthreads();
+        for (int col = tid; col < RL; col += 256) {        // S <- Lc^-1 S (columns)
+            double* x = S + (int64_t)col * RL;
+            for (int r = 0; r < RL; r++) {
+                double s = x[r];
+                for (int b = 0; b < r; b++) s -= Lc[r + b * RL] * x[b];
+                x[r] = s / Lc[r + r * RL];
+            }
+        }
+        __syncthreads();
+        for (int row = tid; row < RL; row += 256) {        // S <- S Lc^-T (rows)
+            double* x = S + row;
+            for (int r = 0; r < RL; r++) {
+                double s = x[(int64_t)r * RL];
+                for (int b = 0; b < r; b++) s -= Lc[r + b * RL] * x[(int64_t)b * RL];
+                x[(int64_t)r * RL] = s / Lc[r + r * RL];
+            }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < RL * RU; idx += 256) {   // T = S F
+            const int a = idx % RL, j = idx / RL;
+            double s = 0.0;
+            for (int b = 0; b < RL; b++) s += S[a + (int64_t)b * RL] * F[b + (int64_t)j * RL];
+            T[idx] = s;
+        }
+        __syncthreads();
+        if (tid < d) {
+            const double* t1 = T + (int64_t)(gp * U + gu) * RL;
+            const double* t2 = T + (int64_t)(gq * U + gu) * RL;
+            double s = 0.0;
+            for (int a = 0; a < RL; a++) s += t1[a] * t2[a];
+            acc += s * (gp == gq ? 1.0 : 1.41421356237309504880);
+        }
+        __syncthreads();
+        P += (int64_t)U * L;
+    }
+    if (tid < d) out[o + tid] = acc;
+}
+
+
 }  // namespace hypdev

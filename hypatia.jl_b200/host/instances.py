@@ -106,6 +106,12 @@ def cone_initial_point(spec):
         arr[2:] = w
     elif spec.ctype == M.CONE_EPINORMINF:
         arr[0] = np.sqrt(spec.dim)      # epinorminf.jl:88-95
+    elif spec.ctype == M.CONE_WSOSINTERPPOSSEMIDEFTRI:
+        Rr = spec.hkind                         # wsosinterppossemideftri.jl:98-106: ones on the diagonal blocks
+        Uu = spec.dim // (Rr * (Rr + 1) // 2)
+        for p in range(Rr):
+            b = p * (p + 1) // 2 + p
+            arr[b * Uu:(b + 1) * Uu] = 1.0
     elif spec.ctype == M.CONE_MATRIXEPIPERSQUARE:
         d1 = spec.hkind                         # matrixepipersquare.jl:103-116: U = I, v = 1, W = 0
         arr[_svec_diag_idx(d1)] = 1.0
@@ -206,6 +212,19 @@ def _central_ray_epirelentropy(d):
 
 def _cone_dual_initial(spec, prim):
     """-grad at the central point, closed form per cone (dual of the central point)."""
+    if spec.ctype == M.CONE_WSOSINTERPPOSSEMIDEFTRI:
+        # -grad at the initial point: D = I, so every diagonal block gets diag(P_k (P_k' P_k)^-1 P_k') summed over k and
+        # the off-diagonal blocks vanish (wsosinterppossemideftri.jl:144-188)
+        Rr = spec.hkind
+        Uu = spec.dim // (Rr * (Rr + 1) // 2)
+        dg = np.zeros(Uu)
+        for P in M.wsos_unpack(spec):
+            dg += np.einsum("ij,ji->i", P, np.linalg.solve(P.T @ P, P.T))
+        out = np.zeros_like(prim)
+        for p in range(Rr):
+            b = p * (p + 1) // 2 + p
+            out[b * Uu:(b + 1) * Uu] = dg
+        return out
     if spec.ctype == M.CONE_MATRIXEPIPERSQUARE:
         # -grad at (I, 1, 0): Z = 2 I, Zi = I / 2 => -g_U = svec(I), -g_v = 2 tr(Zi U) - (d1 - 1) = 1, -g_W = 0
         return prim.copy()
@@ -340,7 +359,7 @@ def _perturb(rng, spec, vec, noise):
     if spec.ctype == M.CONE_LINMATRIXINEQ:
         vec += 0.1 * noise / np.sqrt(vec.size) * (2 * rng.random(vec.size) - 1)    # test/cone.jl:426 uses noise 1e-2
         return vec
-    if spec.ctype in (M.CONE_GENERALIZEDPOWER, M.CONE_WSOSINTERPNONNEGATIVE):
+    if spec.ctype in (M.CONE_GENERALIZEDPOWER, M.CONE_WSOSINTERPNONNEGATIVE, M.CONE_WSOSINTERPPOSSEMIDEFTRI):
         vec += 0.5 * noise / np.sqrt(vec.size) * (2 * rng.random(vec.size) - 1)
         return vec
     if spec.ctype in (M.CONE_HYPOGEOMEAN, M.CONE_HYPOPOWERMEAN, M.CONE_EPIRELENTROPY, M.CONE_EPINORMSPECTRAL):

@@ -31,6 +31,7 @@ CONE_WSOSINTERPNONNEGATIVE = 15
 CONE_LINMATRIXINEQ = 16
 CONE_DOUBLYNONNEGATIVETRI = 17
 CONE_MATRIXEPIPERSQUARE = 18
+CONE_WSOSINTERPPOSSEMIDEFTRI = 19
 
 # separable spectral functions of EpiPerSepSpectral (sepspectralfun.jl:17-116), HYP_SSF_*
 SSF_INV, SSF_NEGLOG, SSF_NEGENTROPY, SSF_POWER12 = 0, 1, 2, 3
@@ -55,6 +56,7 @@ CONE_NAMES = {
     CONE_LINMATRIXINEQ: "LinMatrixIneq",
     CONE_DOUBLYNONNEGATIVETRI: "DoublyNonnegativeTri",
     CONE_MATRIXEPIPERSQUARE: "MatrixEpiPerSquare",
+    CONE_WSOSINTERPPOSSEMIDEFTRI: "WSOSInterpPosSemidefTri",
 }
 
 
@@ -108,6 +110,14 @@ class ConeSpec:
             assert dim >= 3
         elif ctype == CONE_HYPOPERLOG:
             assert dim >= 3
+        elif ctype == CONE_WSOSINTERPPOSSEMIDEFTRI:
+            # hkind = R; alpha = packed data [nP, L_1 .. L_nP, vec(P_1) .. vec(P_nP)], P_k of U x L_k, dim = U svec_length(R)
+            Rr = hkind
+            assert Rr >= 1 and dim % (Rr * (Rr + 1) // 2) == 0
+            Uu = dim // (Rr * (Rr + 1) // 2)
+            nP = int(self.alpha[0])
+            Ls = [int(x) for x in self.alpha[1:1 + nP]]
+            assert nP >= 1 and all(1 <= L <= Uu for L in Ls) and len(self.alpha) == 1 + nP + Uu * sum(Ls)
         elif ctype == CONE_MATRIXEPIPERSQUARE:
             # hkind = d1: dim = svec_length(d1) + 1 + d1 * d2 with d1 <= d2 (matrixepipersquare.jl:56-74)
             d1 = hkind
@@ -177,6 +187,8 @@ class ConeSpec:
             return float(self.hkind + 1)      # epinormspectral.jl:95, matrixepipersquare.jl:101
         if self.ctype == CONE_LINMATRIXINEQ:
             return float(int(self.alpha[0]))      # linmatrixineq.jl:72
+        if self.ctype == CONE_WSOSINTERPPOSSEMIDEFTRI:
+            return float(self.hkind * sum(self.alpha[1:1 + int(self.alpha[0])]))    # wsosinterppossemideftri.jl:66
         if self.ctype == CONE_WSOSINTERPNONNEGATIVE:
             return float(sum(self.alpha[1:1 + int(self.alpha[0])]))    # wsosinterpnonnegative.jl:62
         if self.ctype in (CONE_HYPOPERLOG, CONE_EPINORMINF, CONE_EPIPERSEPSPECTRAL_VEC, CONE_HYPOGEOMEAN,
@@ -275,15 +287,28 @@ def lmi_unpack(spec):
     return [data[i * side * side:(i + 1) * side * side].reshape(side, side, order="F") for i in range(spec.dim)]
 
 
+def WSOSInterpPosSemidefTri(R, U, Ps, use_dual=False):
+    """WSOSInterpPosSemidefTri{Float64}(R, U, Ps, use_dual): R x R matrix polynomials in svec block order, dim =
+    U svec_length(R); dual barrier by default like WSOSInterpNonnegative.  R travels as the integer parameter of
+    hyp_set_cone_params, the Ps in hyp_set_cone_alpha."""
+    Ps = [np.asarray(P, dtype=np.float64) for P in Ps]
+    assert all(P.ndim == 2 and P.shape[0] == U for P in Ps)
+    packed = np.concatenate([[float(len(Ps))], [float(P.shape[1]) for P in Ps]] + [P.ravel(order="F") for P in Ps])
+    return ConeSpec(CONE_WSOSINTERPPOSSEMIDEFTRI, U * R * (R + 1) // 2, not use_dual, hkind=R, alpha=packed)
+
+
 def wsos_unpack(spec):
-    """The Ps matrices of a WSOSInterpNonnegative spec."""
+    """The Ps matrices of a WSOSInterpNonnegative / WSOSInterpPosSemidefTri spec."""
+    U = spec.dim
+    if spec.ctype == CONE_WSOSINTERPPOSSEMIDEFTRI:
+        U = spec.dim // (spec.hkind * (spec.hkind + 1) // 2)
     nP = int(spec.alpha[0])
     Ls = [int(x) for x in spec.alpha[1:1 + nP]]
     data = np.asarray(spec.alpha[1 + nP:], dtype=np.float64)
     out, o = [], 0
     for L in Ls:
-        out.append(data[o:o + spec.dim * L].reshape(spec.dim, L, order="F"))
-        o += spec.dim * L
+        out.append(data[o:o + U * L].reshape(U, L, order="F"))
+        o += U * L
     return out
 
 

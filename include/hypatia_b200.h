@@ -59,6 +59,8 @@ typedef struct hyp_ctx hyp_ctx;
 #define HYP_CONE_DOUBLYNONNEGATIVETRI 17 /* doublynonnegativetri.jl: svec of a psd AND entrywise nonnegative matrix; dim <= 128 */
 #define HYP_CONE_MATRIXEPIPERSQUARE 18 /* matrixepipersquare.jl (real): (svec(U), v, vec(W)), U d1 x d1, W d1 x d2, d1 <= d2;
                                        d1 is given as the integer parameter of hyp_set_cone_params; dim <= 128 */
+#define HYP_CONE_WSOSINTERPPOSSEMIDEFTRI 19 /* wsosinterppossemideftri.jl: R x R matrix polynomials, dim = U svec_length(R) <= 128;
+                                       R is the integer parameter of hyp_set_cone_params, the Ps travel like code 15 */
 #define HYP_CONE_EPINORMSPECTRAL 14 /* epinormspectral.jl (real): (u, vec(W)), W d1 x d2 column-major, d1 <= d2; d1 is given
                                        as the integer parameter of hyp_set_cone_params; use_dual = 1: nuclear norm; dim <= 128 */
 

@@ -49,6 +49,9 @@ cone_code(::Cones.WSOSInterpNonnegative{Float64, Float64}) = Cint(15)
 cone_code(::Cones.LinMatrixIneq{Float64}) = Cint(16)
 cone_code(::Cones.DoublyNonnegativeTri{Float64}) = Cint(17)
 cone_code(::Cones.MatrixEpiPerSquare{Float64, Float64}) = Cint(18)
+cone_code(::Cones.WSOSInterpPosSemidefTri{Float64}) = Cint(19)
+cone_alpha(c::Cones.WSOSInterpPosSemidefTri{Float64}) =
+    vcat(Float64(length(c.Ps)), Float64[size(P, 2) for P in c.Ps], (vec(P) for P in c.Ps)...)
 # packed matrices [side, vec(A_1) .. vec(A_dim)] (dense real symmetric A_i; UniformScaling entries are materialised)
 cone_alpha(c::Cones.LinMatrixIneq{Float64}) =
     vcat(Float64(c.side), (vec(Matrix{Float64}(A isa UniformScaling ? A(c.side) : A)) for A in c.As)...)
@@ -68,6 +71,7 @@ ssf_code(h::Cones.Power12SSF) = (Cint(3), Float64(h.p))
 cone_ssf(c::Cones.EpiPerSepSpectral) = ssf_code(c.h)
 cone_ssf(c::Cones.EpiNormSpectral) = (Cint(c.d1), 0.0)    # integer parameter = number of rows of W
 cone_ssf(c::Cones.MatrixEpiPerSquare) = (Cint(c.d1), 0.0)
+cone_ssf(c::Cones.WSOSInterpPosSemidefTri) = (Cint(c.R), 0.0)
 cone_ssf(::Cones.Cone) = (Cint(0), 0.0)
 
 function check(ctx::Ctx, rc::Cint, what::String)

@@ -770,6 +770,10 @@ def make_cone(spec):
     if spec.ctype == M.CONE_EPIPERSEPSPECTRAL_VEC:
         from .cones_sepspec import EpiPerSepSpectralVec
         return EpiPerSepSpectralVec(spec.dim, spec.hkind, spec.hparam, use_dual=spec.use_dual)
+    if spec.ctype == M.CONE_WSOSINTERPPOSSEMIDEFTRI:
+        from .cones_vec3 import WSOSInterpPosSemidefTri
+        Rr = spec.hkind
+        return WSOSInterpPosSemidefTri(Rr, spec.dim // (Rr * (Rr + 1) // 2), M.wsos_unpack(spec), use_dual=not spec.use_dual)
     if spec.ctype == M.CONE_MATRIXEPIPERSQUARE:
         from .cones_vec3 import MatrixEpiPerSquare
         d1 = spec.hkind

@@ -937,6 +937,106 @@ class DoublyNonnegativeTri(Cone):
         return d3
 
 
+class WSOSInterpPosSemidefTri(Cone):
+    """wsosinterppossemideftri.jl:14-321: interpolant-basis weighted sum-of-squares cone of R x R matrix polynomials
+    (svec order of the blocks, U coefficients each); the barrier is the dual cone's,
+    -sum_k logdet((I_R kron P_k)' D(s) (I_R kron P_k)) with D(s) the R U x R U matrix of diagonal blocks
+    Diagonal(smat(s)_pq), so use_dual_barrier = !use_dual; nu = R sum L_k.  hess_prod! / inv_hess_prod! are the generic
+    explicit-Hessian oracles (Cones.jl:101-118).  Dense restatement: the reference exploits the block-triangular
+    structure of the factors, the mathematics is the same."""
+    ctype = M.CONE_WSOSINTERPPOSSEMIDEFTRI
+
+    def __init__(self, R, U, Ps, use_dual=False):
+        self.R, self.U = R, U
+        self.Ps = [np.asarray(P, dtype=np.float64) for P in Ps]
+        assert all(P.shape[0] == U for P in self.Ps)
+        self.use_dual_barrier = not use_dual
+        self.blocks = [(p, q) for p in range(R) for q in range(p + 1)]        # svec order: (p, q), q <= p
+        super().__init__(U * R * (R + 1) // 2)
+
+    @property
+    def nu(self):
+        return float(self.R * sum(P.shape[1] for P in self.Ps))
+
+    def set_initial_point(self, arr):
+        arr[:] = 0.0
+        for b, (p, q) in enumerate(self.blocks):
+            if p == q:
+                arr[b * self.U:(b + 1) * self.U] = 1.0
+        return arr
+
+    def _D(self, s):
+        R, U = self.R, self.U
+        D = np.zeros((R * U, R * U))
+        idx = np.arange(U)
+        for b, (p, q) in enumerate(self.blocks):
+            v = s[b * U:(b + 1) * U] * (1.0 if p == q else 1 / np.sqrt(2.0))
+            D[p * U + idx, q * U + idx] = v
+            D[q * U + idx, p * U + idx] = v
+        return D
+
+    def update_feas(self):
+        # wsosinterppossemideftri.jl:108-142
+        D = self._D(self.point)
+        self.Pb = [np.kron(np.eye(self.R), P) for P in self.Ps]
+        self.LF = []
+        for Pb in self.Pb:
+            try:
+                self.LF.append(np.linalg.cholesky(Pb.T @ D @ Pb))
+            except np.linalg.LinAlgError:
+                return False
+        return True
+
+    def _blockdiag(self, G, G2=None):
+        # block_diag_prod! (:259-282): diagonal of every (p, q) block of G (= mat1' mat2), sqrt(2) off the diagonal blocks
+        U = self.U
+        idx = np.arange(U)
+        out = np.empty(self.dim)
+        for b, (p, q) in enumerate(self.blocks):
+            out[b * U:(b + 1) * U] = G[q * U + idx, p * U + idx] * (1.0 if p == q else np.sqrt(2.0))
+        return out
+
+    def update_grad(self):
+        # wsosinterppossemideftri.jl:144-188
+        self.F = [sla.solve_triangular(L, Pb.T, lower=True, check_finite=False) for L, Pb in zip(self.LF, self.Pb)]
+        self.G = [F.T @ F for F in self.F]
+        self._grad[:] = -sum(self._blockdiag(G) for G in self.G)
+
+    def update_hess(self):
+        # wsosinterppossemideftri.jl:190-239
+        self.grad()
+        U = self.U
+        H = np.zeros((self.dim, self.dim))
+        rt2 = np.sqrt(2.0)
+        for G in self.G:
+            B = lambda p, q: G[p * U:(p + 1) * U, q * U:(q + 1) * U]
+            for b, (p, q) in enumerate(self.blocks):
+                for b2, (p2, q2) in enumerate(self.blocks):
+                    scal = rt2 if (p == q) != (p2 == q2) else 1.0
+                    blk = B(p, p2) * B(q, q2) * scal
+                    if p != q and p2 != q2:
+                        blk = blk + B(p, q2) * B(q, p2)
+                    H[b * U:(b + 1) * U, b2 * U:(b2 + 1) * U] += blk
+        return (H + H.T) / 2
+
+    def hess_prod(self, arr):
+        a, vec = _as2d(arr)
+        return _ret(np.asarray(self.hess()) @ a, vec)
+
+    def dder3(self, direction):
+        # partial_prod! with use_symm_prod = true (:284-321)
+        self.grad()
+        Dd = self._D(direction)
+        out = np.zeros(self.dim)
+        for L, Pb, F in zip(self.LF, self.Pb, self.F):
+            S = Pb.T @ Dd @ Pb
+            S = sla.solve_triangular(L, S, lower=True, check_finite=False)
+            S = sla.solve_triangular(L, S.T, lower=True, check_finite=False).T
+            T = ((S + S.T) / 2) @ F
+            out += self._blockdiag(T.T @ T)
+        return out
+
+
 class MatrixEpiPerSquare(Cone):
     """matrixepipersquare.jl:10-397 (real case): (svec(U), v, vec(W)) with U symmetric d1 x d1, W d1 x d2 (d1 <= d2),
     2 v U - W W' psd; barrier -logdet(2 v U - W W') + (d1 - 1) log v, nu = d1 + 1.  inv_hess_prod! is the generic

@@ -316,6 +316,20 @@ class EmuGpowGroup:
         self.K = len(specs)
         self.hpm = specs[0].ctype == 12          # HypoPowerMean, else GeneralizedPower
         self.ens = specs[0].ctype == 14          # EpiNormSpectral: d1 per cone, workspace instead of powers
+        self.wpsd = specs[0].ctype == 19         # WSOSInterpPosSemidefTri: R per cone, packed Ps + workspace
+        if self.wpsd:
+            self.Rs = np.array([s.hkind for s in specs], dtype=np.int32)
+            regions = []
+            for s in specs:
+                Rr = s.hkind
+                U = s.dim // (Rr * (Rr + 1) // 2)
+                nP = int(s.alpha[0])
+                Ls = [int(x) for x in s.alpha[1:1 + nP]]
+                wsz = sum(Rr * L * Rr * U + (Rr * L) ** 2 for L in Ls) + (Rr * U) ** 2 + (Rr * max(Ls)) ** 2 + \
+                    Rr * max(Ls) * Rr * U
+                regions.append(np.concatenate((np.asarray(s.alpha, dtype=np.float64), np.zeros(wsz))))
+            self.voff = np.concatenate(([0], np.cumsum([r.size for r in regions])))[:-1].astype(np.int64)
+            self.vecs = np.concatenate(regions)
         self.mep = specs[0].ctype == 18          # MatrixEpiPerSquare: d1 per cone, state + dder3 scratch
         if self.mep:
             self.d1 = np.array([s.hkind for s in specs], dtype=np.int32)
@@ -373,7 +387,10 @@ class EmuGpowGroup:
         self.dual_feas = np.ones(self.K, dtype=np.uint8)
         self.grad = np.zeros(self.q)
         self.H = np.zeros(self.lay.total)
-        if self.mep:
+        if self.wpsd:
+            lib().emu_wpsd_state(self.K, p(self.off), p(self.dims), p(self.Rs), p(self.voff), p(self.vecs), p(self.kidx),
+                                 p(self.lay.moff), p(self.point), p(self.grad), p(self.H), p(self.feas))
+        elif self.mep:
             lib().emu_mep_state(self.K, p(self.off), p(self.dims), p(self.d1), p(self.voff), p(self.vecs), p(self.kidx),
                                 p(self.lay.moff), p(self.point), p(self.dual), p(self.grad), p(self.scal), p(self.H),
                                 p(self.feas), p(self.dual_feas))
@@ -416,7 +433,7 @@ class EmuGpowGroup:
         elif hess_dual > -2 and self.dnn:
             L.emu_dnn_prod(self.K, hess_dual, p(self.off), p(self.dims), p(self.sides), p(self.voff), p(self.vecs),
                            p(self.dualf), p(self.point), p(a), i64(self.q), p(out), i64(self.q), i64(a.shape[1]), i64(0))
-        elif hess_dual > -2 and (self.wsos or self.lmi):
+        elif hess_dual > -2 and (self.wsos or self.lmi or self.wpsd):
             L.emu_gen_hess_prod(self.K, hess_dual, p(self.off), p(self.dims), p(self.lay.moff), p(self.dualf), p(self.H),
                                 p(a), i64(self.q), p(out), i64(self.q), i64(a.shape[1]), i64(0))
         elif hess_dual > -2 and self.ens:
@@ -438,7 +455,9 @@ class EmuGpowGroup:
     def dder3(self, direction):
         d = np.ascontiguousarray(direction, dtype=np.float64)
         out = np.zeros(self.q)
-        if self.mep:
+        if self.wpsd:
+            lib().emu_wpsd_dder3(self.K, p(self.off), p(self.dims), p(self.Rs), p(self.voff), p(self.vecs), p(d), p(out))
+        elif self.mep:
             lib().emu_mep_dder3(self.K, p(self.off), p(self.dims), p(self.d1), p(self.voff), p(self.vecs), p(self.scal),
                                 p(self.point), p(d), p(out))
         elif self.dnn:

@@ -645,6 +645,25 @@ def wsosinterpnonnegative3():  # :2326-2343: the dual formulation with use_dual 
         dict(status="Optimal", primal_obj=0)
 
 
+def wsosinterppossemideftri1():  # :2385-2405: convexity parameter of (x + 1)^2 (x - 1)^2 on [-1, 1]: H = 12 x^2 - 4
+    from wsos_util import interpolate_box
+    U, pts, Ps = interpolate_box([-1.0], [1.0], 1)
+    h = 12 * pts[:, 0] ** 2 - 4
+    return _m([-1], None, None, np.ones((U, 1)), h, [M.WSOSInterpPosSemidefTri(1, U, Ps)]), \
+        dict(status="Optimal", primal_obj=4, x=[-4.0])
+
+
+def wsosinterppossemideftri2():  # :2407-2428: convexity parameter of x1^4 - 3 x2^2: H = [12 x1^2, 0; 0, -6]
+    from wsos_util import interpolate_free
+    U, pts, Ps = interpolate_free(2, 1)
+    G = np.vstack((np.ones((U, 1)), np.zeros((U, 1)), np.ones((U, 1))))
+    h = np.concatenate((12 * pts[:, 0] ** 2, np.zeros(U), -6 * np.ones(U)))     # blocks (1,1), (2,1), (2,2)
+    return _m([-1], None, None, G, h, [M.WSOSInterpPosSemidefTri(2, U, Ps)]), \
+        dict(status="Optimal", primal_obj=6, x=[-6.0])
+
+
+WSOSPSD = [wsosinterppossemideftri1, wsosinterppossemideftri2]
+
 WSOS = [wsosinterpnonnegative1, wsosinterpnonnegative2, wsosinterpnonnegative3]
 
 # ---- further instances of the reference for the cones of the path: seeded-random data with closed-form optima or
@@ -951,7 +970,7 @@ def linmatrixineq3():  # :747-788 (dense case): min w_1 : w_1 I - diag(1, -1) ps
 
 LMI = [_named(lambda s=_s: _linmatrixineq1(s), f"linmatrixineq1_side{_s}") for _s in (2, 4)] + \
     [_named(lambda d=_d: _linmatrixineq2(d), f"linmatrixineq2_dim{_d}") for _d in (2, 3)] + [linmatrixineq3]
-EXTRA = EXTRA + LMI + DNN + MEPS
+EXTRA = EXTRA + LMI + DNN + MEPS + WSOSPSD
 
 RELENT = [_named(lambda d=_d: _epirelentropy1(d), f"epirelentropy1_d{_d}") for _d in (1, 2, 3)] + \
     [_named(lambda d=_d: _epirelentropy2(d), f"epirelentropy2_d{_d}") for _d in (1, 2, 4)] + \

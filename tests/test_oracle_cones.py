@@ -367,6 +367,53 @@ def test_matrixepipersquare_barrier():
     assert close(-2 * cone.dder3(direction), fd_third, 1e-5)
 
 
+@pytest.mark.parametrize("R,n,halfdeg", [(1, 1, 1), (2, 1, 2), (3, 1, 1), (2, 2, 1), (3, 2, 1)])
+def test_wsosinterppossemideftri(R, n, halfdeg):
+    # reference: test/cone.jl WSOSInterpPosSemidefTri block (init_tol = Inf)
+    from oracle.cones_vec3 import WSOSInterpPosSemidefTri
+    from wsos_util import interpolate_box
+    U, _, Ps = interpolate_box(-np.ones(n), np.ones(n), halfdeg)
+    run_oracles(WSOSInterpPosSemidefTri(R, U, Ps), init_tol=np.inf)
+    run_oracles(WSOSInterpPosSemidefTri(R, U, Ps, use_dual=True), init_tol=np.inf)
+
+
+def test_wsosinterppossemideftri_barrier():
+    """grad, hess_prod and dder3 against central differences of -sum_k logdet((I kron P_k)' D(s) (I kron P_k))."""
+    from oracle.cones_vec3 import WSOSInterpPosSemidefTri
+    from wsos_util import interpolate_box
+    R = 2
+    U, _, Ps = interpolate_box([-1.0], [1.0], 2)
+    cone = WSOSInterpPosSemidefTri(R, U, Ps)
+
+    def barrier(s):
+        D = cone._D(s)
+        return -sum(np.linalg.slogdet(np.kron(np.eye(R), P).T @ D @ np.kron(np.eye(R), P))[1] for P in Ps)
+
+    rng = np.random.default_rng(1)
+    point = np.zeros(cone.dim)
+    cone.set_initial_point(point)
+    perturb_scale(rng, point, 0.1, 1.0)
+
+    def grad_at(s):
+        cone.reset_data()
+        cone.load_point(s)
+        assert cone.is_feas()
+        return cone.grad().copy()
+
+    g = grad_at(point)
+    eps = 1e-6
+    fd_grad = np.array([(barrier(point + eps * e) - barrier(point - eps * e)) / (2 * eps) for e in np.eye(cone.dim)])
+    assert close(g, fd_grad, 1e-7)
+    direction = 0.3 * rng.standard_normal(cone.dim)
+    fd_hess_dir = (grad_at(point + eps * direction) - grad_at(point - eps * direction)) / (2 * eps)
+    grad_at(point)
+    assert close(cone.hess_prod(direction), fd_hess_dir, 1e-6)
+    e2 = 1e-4
+    fd_third = (grad_at(point + e2 * direction) - 2 * g + grad_at(point - e2 * direction)) / e2 ** 2
+    grad_at(point)
+    assert close(-2 * cone.dder3(direction), fd_third, 1e-5)
+
+
 def rand_lmi(rng, side, dim):
     """rand_herms of test/cone.jl (real case): symmetric matrices with a positive definite first one."""
     As = []

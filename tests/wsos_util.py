@@ -33,3 +33,9 @@ def interpolate_box(lo, hi, halfdeg):
         g = (pts[:, i] - lo[i]) * (hi[i] - pts[:, i])
         Ps.append(np.sqrt(np.maximum(g, 0.0))[:, None] * P0[:, :L1])
     return pts.shape[0], pts, Ps
+
+
+def interpolate_free(n, halfdeg):
+    """FreeDomain: no weights, Ps = [P0] (the points are those of the box [-1, 1]^n)."""
+    U, pts, Ps = interpolate_box(-np.ones(n), np.ones(n), halfdeg)
+    return U, pts, Ps[:1]
