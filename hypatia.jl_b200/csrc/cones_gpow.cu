@@ -182,10 +182,12 @@ static void wpsd_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
         const int k = g.h_kidx[i];
         const int64_t a0 = ctx->h_cone_aoff[k], a1 = ctx->h_cone_aoff[k + 1];
         const int d = g.h_dim[i], R = ctx->h_cone_hkind[k];
-        if (d > 128) throw HypError{"WSOSInterpPosSemidefTri: dimension above 128 is not supported (batched Cholesky limit)"};
-        if (R < 1 || d % (R * (R + 1) / 2) != 0)
-            throw HypError{"WSOSInterpPosSemidefTri: hyp_set_cone_params must give R with dim = U * svec_length(R)"};
-        const int64_t U = d / (R * (R + 1) / 2);
+        const bool eucl = g.type == HYP_CONE_WSOSINTERPEPINORMEUCL;     // dim = U R (R >= 2) instead of U svec_length(R)
+        if (d > 128) throw HypError{"WSOSInterpPosSemidefTri / EpiNormEucl: dimension above 128 is not supported (batched Cholesky limit)"};
+        const int nblk = eucl ? R : R * (R + 1) / 2;
+        if (R < (eucl ? 2 : 1) || d % nblk != 0)
+            throw HypError{"WSOSInterpPosSemidefTri / EpiNormEucl: hyp_set_cone_params must give R with dim = U * svec_length(R) / U * R"};
+        const int64_t U = d / nblk;
         if (a1 - a0 < 2) throw HypError{"WSOSInterpPosSemidefTri: missing Ps data"};
         const int nP = (int)ctx->h_cone_alpha[a0];
         if (nP < 1 || a1 - a0 < 1 + nP) throw HypError{"WSOSInterpPosSemidefTri: bad number of Ps matrices"};
@@ -200,7 +202,9 @@ static void wpsd_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
         if (a1 - a0 != 1 + nP + U * sumL) throw HypError{"WSOSInterpPosSemidefTri: Ps data has the wrong length"};
         g.h_voff[i] = (int64_t)buf.size();
         buf.insert(buf.end(), ctx->h_cone_alpha.begin() + a0, ctx->h_cone_alpha.begin() + a1);
-        buf.resize(buf.size() + (size_t)(wsz + R * U * R * U + R * Lmax * R * Lmax + R * Lmax * R * U), 0.0);
+        buf.resize(buf.size() + (size_t)(wsz + R * U * R * U + R * Lmax * R * Lmax + R * Lmax * R * U +
+                                         (eucl ? U * U + Lmax * Lmax + Lmax * U : 0)),
+                   0.0);
         g.h_hkind.push_back(R);
         g.h_side[i] = d;
     }
@@ -215,7 +219,7 @@ static void wpsd_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
 }
 
 void hyp_gpow_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
-    if (g.type == HYP_CONE_WSOSINTERPPOSSEMIDEFTRI) {
+    if (g.type == HYP_CONE_WSOSINTERPPOSSEMIDEFTRI || g.type == HYP_CONE_WSOSINTERPEPINORMEUCL) {
         wpsd_alloc_group(ctx, g);
         return;
     }
@@ -275,7 +279,11 @@ void hyp_gpow_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
 }
 
 void hyp_gpow_update_state(hyp_ctx* ctx, ConeGroup& g) {
-    if (g.type == HYP_CONE_WSOSINTERPPOSSEMIDEFTRI)
+    if (g.type == HYP_CONE_WSOSINTERPEPINORMEUCL)
+        hypdev::weuc_state_kernel<<<g.count, 256, 0, ctx->stream>>>(g.count, g.d_off, g.d_dim, g.d_hkind, g.d_voff, g.d_vecs,
+                                                                   g.d_kidx, g.d_moff, ctx->d_point, ctx->d_grad, g.d_W,
+                                                                   ctx->d_feas);
+    else if (g.type == HYP_CONE_WSOSINTERPPOSSEMIDEFTRI)
         hypdev::wpsd_state_kernel<<<g.count, 256, 0, ctx->stream>>>(g.count, g.d_off, g.d_dim, g.d_hkind, g.d_voff, g.d_vecs,
                                                                    g.d_kidx, g.d_moff, ctx->d_point, ctx->d_grad, g.d_W,
                                                                    ctx->d_feas);
@@ -335,7 +343,7 @@ void hyp_gpow_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr, 
                                                                   g.d_voff, g.d_vecs, g.d_dual, ctx->d_point, arr, ld_arr,
                                                                   prod, ld_prod, ncols, row_shift);
         else if (g.type == HYP_CONE_WSOSINTERPNONNEGATIVE || g.type == HYP_CONE_LINMATRIXINEQ ||
-                 g.type == HYP_CONE_WSOSINTERPPOSSEMIDEFTRI)
+                 g.type == HYP_CONE_WSOSINTERPPOSSEMIDEFTRI || g.type == HYP_CONE_WSOSINTERPEPINORMEUCL)
             hypdev::gen_hess_prod_kernel<<<grid, 256, 0, ctx->stream>>>(g.count, hess_dual, g.d_off, g.d_dim, g.d_moff,
                                                                        g.d_dual, g.d_W, arr, ld_arr, prod, ld_prod, ncols,
                                                                        row_shift);
@@ -364,7 +372,10 @@ void hyp_gpow_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr, 
 }
 
 void hyp_gpow_dder3(hyp_ctx* ctx, ConeGroup& g, double* out, const double* dir) {
-    if (g.type == HYP_CONE_WSOSINTERPPOSSEMIDEFTRI)
+    if (g.type == HYP_CONE_WSOSINTERPEPINORMEUCL)
+        hypdev::weuc_dder3_kernel<<<g.count, 256, 0, ctx->stream>>>(g.count, g.d_off, g.d_dim, g.d_hkind, g.d_voff, g.d_vecs,
+                                                                   dir, out);
+    else if (g.type == HYP_CONE_WSOSINTERPPOSSEMIDEFTRI)
         hypdev::wpsd_dder3_kernel<<<g.count, 256, 0, ctx->stream>>>(g.count, g.d_off, g.d_dim, g.d_hkind, g.d_voff, g.d_vecs,
                                                                    dir, out);
     else if (g.type == HYP_CONE_MATRIXEPIPERSQUARE)

@@ -1672,4 +1672,239 @@ wpsd_dder3_kernel(int ncones, const int64_t* __restrict__ off, const int* __rest
 }
 
 
+// ---- WSOSInterpEpiNormEucl (R polynomials of U coefficients, dim = R U <= 128), wsosinterpepinormeucl.jl:119-382 ----
+// Dense restatement: with A(s) the R L x R L block-arrow matrix (L11 = P' Diagonal(s_1) P on every diagonal block,
+// L1r = P' Diagonal(s_r) P on the first block row / column) the reference's barrier -logdet L11 - logdet(Schur) equals
+// -logdet A + (R - 2) logdet L11, two logdets of matrices that are linear in s.  The Cholesky factor of L11 is the leading
+// L x L block of the factor of A, and L11^-1-type quantities are the leading rows of F = Lc^-1 (I kron P)'.
+// Region of cone c: [nP][L_k ..][P_k ..] (hyp_set_cone_alpha), then per k F_k (R L x R U) and Lc_k (R L x R L), then
+// G (R U)^2, G11 U^2 and the dder3 scratch S (R L_max)^2, T (R L_max x R U), S11 L_max^2, T11 (L_max x U).
+// One CTA of 256 threads per cone; thread i < dim owns entry i = r U + u.
+
+// entry (pL + a, qL + b) of the arrow matrix A(vec)
+__device__ __forceinline__ double weuc_arrow(const double* P, const double* vec, int U, int L, int row, int col) {
+    const int p = row / L, a = row % L, q = col / L, b = col % L;
+    int blk;
+    if (p == q) blk = 0;
+    else if (p == 0 || q == 0) blk = p > q ? p : q;
+    else return 0.0;
+    const double* v = vec + (int64_t)blk * U;
+    double s = 0.0;
+    for (int u = 0; u < U; u++) s += P[u + (int64_t)a * U] * v[u] * P[u + (int64_t)b * U];
+    return s;
+}
+
+static __global__ void __launch_bounds__(256)
+weuc_state_kernel(int ncones, const int64_t* __restrict__ off, const int* __restrict__ dim,
+                  const int* __restrict__ Rs, const int64_t* __restrict__ voff, double* __restrict__ vecs,
+                  const int* __restrict__ kidx, const int64_t* __restrict__ moff, const double* __restrict__ point,
+                  double* __restrict__ grad, double* __restrict__ H, uint8_t* feas) {
+    __shared__ int s_ok;
+    const int c = blockIdx.x, tid = threadIdx.x;
+    if (c >= ncones) return;
+    const int64_t o = off[c];
+    const int d = dim[c], R = Rs[c], U = d / R, RU = d, lde = (d + 1) & ~1;
+    double* reg = vecs + voff[c];
+    const int nP = (int)reg[0];
+    int64_t sumL = 0, wsz = 0;
+    for (int k = 0; k < nP; k++) {
+        const int64_t L = (int64_t)reg[1 + k];
+        sumL += L;
+        wsz += R * L * RU + R * L * R * L;
+    }
+    const double* P = reg + 1 + nP;
+    double* ws = reg + 1 + nP + (int64_t)U * sumL;
+    double* G = ws + wsz;
+    double* G11 = G + (int64_t)RU * RU;
+    double* Hc = H + moff[c];
+    const double* pt = point + o;
+    if (tid == 0) s_ok = 1;
+    double gacc = 0.0;
+    const int gr = tid / U, gu = tid % U;
+    for (int k = 0; k < nP; k++) {
+        const int L = (int)reg[1 + k], RL = R * L;
+        double* F = ws;
+        double* Lc = F + (int64_t)RL * RU;
+        ws = Lc + RL * RL;
+        for (int idx = tid; idx < RL * RL; idx += 256) Lc[idx] = weuc_arrow(P, pt, U, L, idx % RL, idx / RL);
+        __syncthreads();
+        for (int j = 0; j < RL; j++) {                     // Cholesky (lower, in place, right-looking)
+            if (tid == 0) {
+                double dg = Lc[j + j * RL];
+                if (!(dg > 0.0)) {
+                    s_ok = 0;
+                    dg = 1.0;
+                }
+                Lc[j + j * RL] = sqrt(dg);
+            }
+            __syncthreads();
+            const double dj = Lc[j + j * RL];
+            for (int i = j + 1 + tid; i < RL; i += 256) Lc[i + j * RL] /= dj;
+            __syncthreads();
+            const int r = RL - j - 1;
+            for (int idx = tid; idx < r * r; idx += 256) {
+                const int ii = j + 1 + idx % r, kk = j + 1 + idx / r;
+                if (kk <= ii) Lc[ii + kk * RL] -= Lc[ii + j * RL] * Lc[kk + j * RL];
+            }
+            __syncthreads();
+        }
+        for (int jj = tid; jj < RU; jj += 256) {           // F = Lc^-1 (I kron P)'
+            const int p = jj / U, u = jj % U;
+            double* f = F + (int64_t)jj * RL;
+            for (int a = 0; a < RL; a++) {
+                double s = (a / L == p) ? P[u + (int64_t)(a % L) * U] : 0.0;
+                for (int b = 0; b < a; b++) s -= Lc[a + b * RL] * f[b];
+                f[a] = s / Lc[a + a * RL];
+            }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < RU * RU; idx += 256) {   // G = F'F; G11 from the leading L rows of the first block
+            const int i = idx % RU, j = idx / RU;
+            double s = 0.0;
+            for (int a = 0; a < RL; a++) s += F[a + (int64_t)i * RL] * F[a + (int64_t)j * RL];
+            G[idx] = s;
+            if (i < U && j < U) {
+                double s1 = 0.0;
+                for (int a = 0; a < L; a++) s1 += F[a + (int64_t)i * RL] * F[a + (int64_t)j * RL];
+                G11[i + (int64_t)j * U] = s1;
+            }
+        }
+        __syncthreads();
+#define WEUC_G(x, u1_, y, u2_) G[((x) * U + (u1_)) + (int64_t)((y) * U + (u2_)) * RU]
+        if (tid < d) {                                      // gradient (:169-211)
+            if (gr == 0) {
+                double s = -(double)(R - 2) * G11[gu + (int64_t)gu * U];
+                for (int rr = 0; rr < R; rr++) s += WEUC_G(rr, gu, rr, gu);
+                gacc -= s;
+            } else {
+                gacc -= 2.0 * WEUC_G(0, gu, gr, gu);
+            }
+        }
+        for (int idx = tid; idx < d * d; idx += 256) {      // Hessian (:213-290)
+            const int e1 = idx % d, e2 = idx / d;
+            const int r1 = e1 / U, u1 = e1 % U, r2 = e2 / U, u2 = e2 % U;
+            double v;
+            if (r1 == 0 && r2 == 0) {
+                const double g11 = G11[u1 + (int64_t)u2 * U];
+                v = -(double)(R - 2) * g11 * g11;
+                for (int a = 0; a < R; a++)
+                    for (int b = 0; b < R; b++) {
+                        const double g = WEUC_G(a, u1, b, u2);
+                        v += g * g;
+                    }
+            } else if (r1 == 0) {
+                v = 0.0;
+                for (int a = 0; a < R; a++) v += WEUC_G(a, u1, 0, u2) * WEUC_G(a, u1, r2, u2);
+                v *= 2.0;
+            } else if (r2 == 0) {
+                v = 0.0;
+                for (int a = 0; a < R; a++) v += WEUC_G(a, u2, 0, u1) * WEUC_G(a, u2, r1, u1);
+                v *= 2.0;
+            } else {
+                v = 2.0 * (WEUC_G(0, u1, 0, u2) * WEUC_G(r1, u1, r2, u2) + WEUC_G(0, u1, r2, u2) * WEUC_G(r1, u1, 0, u2));
+            }
+            Hc[e1 + (int64_t)e2 * lde] = k == 0 ? v : Hc[e1 + (int64_t)e2 * lde] + v;
+        }
+#undef WEUC_G
+        __syncthreads();
+        P += (int64_t)U * L;
+    }
+    if (tid < d) grad[o + tid] = gacc;
+    if (tid == 0 && !s_ok) feas[kidx[c]] = 0;
+}
+
+// dder3 (:292-382): Q = F' S^2 F with S = Lc^-1 A(dir) Lc^-T, Q11 likewise with the leading blocks and dir_1
+static __global__ void __launch_bounds__(256)
+weuc_dder3_kernel(int ncones, const int64_t* __restrict__ off, const int* __restrict__ dim,
+                  const int* __restrict__ Rs, const int64_t* __restrict__ voff, double* __restrict__ vecs,
+                  const double* __restrict__ dir, double* __restrict__ out) {
+    const int c = blockIdx.x, tid = threadIdx.x;
+    if (c >= ncones) return;
+    const int64_t o = off[c];
+    const int d = dim[c], R = Rs[c], U = d / R, RU = d;
+    double* reg = vecs + voff[c];
+    const int nP = (int)reg[0];
+    int64_t sumL = 0, wsz = 0, Lmax = 0;
+    for (int k = 0; k < nP; k++) {
+        const int64_t L = (int64_t)reg[1 + k];
+        sumL += L;
+        wsz += R * L * RU + R * L * R * L;
+        Lmax = L > Lmax ? L : Lmax;
+    }
+    const double* P = reg + 1 + nP;
+    double* ws = reg + 1 + nP + (int64_t)U * sumL;
+    double* S = ws + wsz + (int64_t)RU * RU + (int64_t)U * U;
+    double* T = S + (R * Lmax) * (R * Lmax);
+    double* S11 = T + (R * Lmax) * RU;
+    double* T11 = S11 + Lmax * Lmax;
+    double acc = 0.0;
+    const int gr = tid / U, gu = tid % U;
+    for (int k = 0; k < nP; k++) {
+        const int L = (int)reg[1 + k], RL = R * L;
+        const double* F = ws;
+        const double* Lc = F + (int64_t)RL * RU;
+        ws += (int64_t)RL * RU + RL * RL;
+        for (int idx = tid; idx < RL * RL; idx += 256) S[idx] = weuc_arrow(P, dir + o, U, L, idx % RL, idx / RL);
+        for (int idx = tid; idx < L * L; idx += 256) S11[idx] = weuc_arrow(P, dir + o, U, L, idx % L, idx / L);
+        __syncthreads();
+        for (int col = tid; col < RL + L; col += 256) {    // Lc^-1 S and L11^-1 S11 (columns)
+            const bool big = col < RL;
+            const int n = big ? RL : L;
+            double* x = big ? S + (int64_t)col * RL : S11 + (int64_t)(col - RL) * L;
+            for (int r = 0; r < n; r++) {
+                double s = x[r];
+                for (int b = 0; b < r; b++) s -= Lc[r + b * RL] * x[b];
+                x[r] = s / Lc[r + r * RL];
+            }
+        }
+        __syncthreads();
+        for (int row = tid; row < RL + L; row += 256) {    // ... Lc^-T and L11^-T (rows)
+            const bool big = row < RL;
+            const int n = big ? RL : L;
+            double* x = big ? S + row : S11 + (row - RL);
+            for (int r = 0; r < n; r++) {
+                double s = x[(int64_t)r * n];
+                for (int b = 0; b < r; b++) s -= Lc[r + b * RL] * x[(int64_t)b * n];
+                x[(int64_t)r * n] = s / Lc[r + r * RL];
+            }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < RL * RU; idx += 256) {   // T = S F
+            const int a = idx % RL, j = idx / RL;
+            double s = 0.0;
+            for (int b = 0; b < RL; b++) s += S[a + (int64_t)b * RL] * F[b + (int64_t)j * RL];
+            T[idx] = s;
+        }
+        for (int idx = tid; idx < L * U; idx += 256) {     // T11 = S11 F11, F11 = leading L rows of the columns (0, u) of F
+            const int a = idx % L, j = idx / L;
+            double s = 0.0;
+            for (int b = 0; b < L; b++) s += S11[a + (int64_t)b * L] * F[b + (int64_t)j * RL];
+            T11[idx] = s;
+        }
+        __syncthreads();
+        if (tid < d) {
+            if (gr == 0) {
+                double s = 0.0;
+                for (int rr = 0; rr < R; rr++) {
+                    const double* t = T + (int64_t)(rr * U + gu) * RL;
+                    for (int a = 0; a < RL; a++) s += t[a] * t[a];
+                }
+                double s1 = 0.0;
+                for (int a = 0; a < L; a++) s1 += T11[a + (int64_t)gu * L] * T11[a + (int64_t)gu * L];
+                acc += s - (double)(R - 2) * s1;
+            } else {
+                const double* t1 = T + (int64_t)gu * RL;
+                const double* t2 = T + (int64_t)(gr * U + gu) * RL;
+                double s = 0.0;
+                for (int a = 0; a < RL; a++) s += t1[a] * t2[a];
+                acc += 2.0 * s;
+            }
+        }
+        __syncthreads();
+        P += (int64_t)U * L;
+    }
+    if (tid < d) out[o + tid] = acc;
+}
+
+
 }  // namespace hypdev

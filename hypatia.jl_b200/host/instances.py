@@ -106,6 +106,8 @@ def cone_initial_point(spec):
         arr[2:] = w
     elif spec.ctype == M.CONE_EPINORMINF:
         arr[0] = np.sqrt(spec.dim)      # epinorminf.jl:88-95
+    elif spec.ctype == M.CONE_WSOSINTERPEPINORMEUCL:
+        arr[:spec.dim // spec.hkind] = 1.0       # wsosinterpepinormeucl.jl:113-117
     elif spec.ctype == M.CONE_WSOSINTERPPOSSEMIDEFTRI:
         Rr = spec.hkind                         # wsosinterppossemideftri.jl:98-106: ones on the diagonal blocks
         Uu = spec.dim // (Rr * (Rr + 1) // 2)
@@ -212,6 +214,13 @@ def _central_ray_epirelentropy(d):
 
 def _cone_dual_initial(spec, prim):
     """-grad at the central point, closed form per cone (dual of the central point)."""
+    if spec.ctype == M.CONE_WSOSINTERPEPINORMEUCL:
+        # -grad at (1, 0, .., 0): the arrow matrix is block diagonal, so -g_1 = (R - (R - 2)) diag(P (P'P)^-1 P') summed over k
+        Uu = spec.dim // spec.hkind
+        out = np.zeros_like(prim)
+        for P in M.wsos_unpack(spec):
+            out[:Uu] += 2 * np.einsum("ij,ji->i", P, np.linalg.solve(P.T @ P, P.T))
+        return out
     if spec.ctype == M.CONE_WSOSINTERPPOSSEMIDEFTRI:
         # -grad at the initial point: D = I, so every diagonal block gets diag(P_k (P_k' P_k)^-1 P_k') summed over k and
         # the off-diagonal blocks vanish (wsosinterppossemideftri.jl:144-188)
@@ -359,7 +368,8 @@ def _perturb(rng, spec, vec, noise):
     if spec.ctype == M.CONE_LINMATRIXINEQ:
         vec += 0.1 * noise / np.sqrt(vec.size) * (2 * rng.random(vec.size) - 1)    # test/cone.jl:426 uses noise 1e-2
         return vec
-    if spec.ctype in (M.CONE_GENERALIZEDPOWER, M.CONE_WSOSINTERPNONNEGATIVE, M.CONE_WSOSINTERPPOSSEMIDEFTRI):
+    if spec.ctype in (M.CONE_GENERALIZEDPOWER, M.CONE_WSOSINTERPNONNEGATIVE, M.CONE_WSOSINTERPPOSSEMIDEFTRI,
+                      M.CONE_WSOSINTERPEPINORMEUCL):
         vec += 0.5 * noise / np.sqrt(vec.size) * (2 * rng.random(vec.size) - 1)
         return vec
     if spec.ctype in (M.CONE_HYPOGEOMEAN, M.CONE_HYPOPOWERMEAN, M.CONE_EPIRELENTROPY, M.CONE_EPINORMSPECTRAL):

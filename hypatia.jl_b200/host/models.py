@@ -32,6 +32,7 @@ CONE_LINMATRIXINEQ = 16
 CONE_DOUBLYNONNEGATIVETRI = 17
 CONE_MATRIXEPIPERSQUARE = 18
 CONE_WSOSINTERPPOSSEMIDEFTRI = 19
+CONE_WSOSINTERPEPINORMEUCL = 20
 
 # separable spectral functions of EpiPerSepSpectral (sepspectralfun.jl:17-116), HYP_SSF_*
 SSF_INV, SSF_NEGLOG, SSF_NEGENTROPY, SSF_POWER12 = 0, 1, 2, 3
@@ -57,6 +58,7 @@ CONE_NAMES = {
     CONE_DOUBLYNONNEGATIVETRI: "DoublyNonnegativeTri",
     CONE_MATRIXEPIPERSQUARE: "MatrixEpiPerSquare",
     CONE_WSOSINTERPPOSSEMIDEFTRI: "WSOSInterpPosSemidefTri",
+    CONE_WSOSINTERPEPINORMEUCL: "WSOSInterpEpiNormEucl",
 }
 
 
@@ -110,6 +112,14 @@ class ConeSpec:
             assert dim >= 3
         elif ctype == CONE_HYPOPERLOG:
             assert dim >= 3
+        elif ctype == CONE_WSOSINTERPEPINORMEUCL:
+            # hkind = R >= 2; alpha = packed Ps; dim = U R
+            Rr = hkind
+            assert Rr >= 2 and dim % Rr == 0
+            Uu = dim // Rr
+            nP = int(self.alpha[0])
+            Ls = [int(x) for x in self.alpha[1:1 + nP]]
+            assert nP >= 1 and all(1 <= L <= Uu for L in Ls) and len(self.alpha) == 1 + nP + Uu * sum(Ls)
         elif ctype == CONE_WSOSINTERPPOSSEMIDEFTRI:
             # hkind = R; alpha = packed data [nP, L_1 .. L_nP, vec(P_1) .. vec(P_nP)], P_k of U x L_k, dim = U svec_length(R)
             Rr = hkind
@@ -187,6 +197,8 @@ class ConeSpec:
             return float(self.hkind + 1)      # epinormspectral.jl:95, matrixepipersquare.jl:101
         if self.ctype == CONE_LINMATRIXINEQ:
             return float(int(self.alpha[0]))      # linmatrixineq.jl:72
+        if self.ctype == CONE_WSOSINTERPEPINORMEUCL:
+            return float(2 * sum(self.alpha[1:1 + int(self.alpha[0])]))    # wsosinterpepinormeucl.jl:68
         if self.ctype == CONE_WSOSINTERPPOSSEMIDEFTRI:
             return float(self.hkind * sum(self.alpha[1:1 + int(self.alpha[0])]))    # wsosinterppossemideftri.jl:66
         if self.ctype == CONE_WSOSINTERPNONNEGATIVE:
@@ -297,11 +309,22 @@ def WSOSInterpPosSemidefTri(R, U, Ps, use_dual=False):
     return ConeSpec(CONE_WSOSINTERPPOSSEMIDEFTRI, U * R * (R + 1) // 2, not use_dual, hkind=R, alpha=packed)
 
 
+def WSOSInterpEpiNormEucl(R, U, Ps, use_dual=False):
+    """WSOSInterpEpiNormEucl{Float64}(R, U, Ps, use_dual): R polynomials of U coefficients, the first one an epigraph of the
+    Euclidean norm of the others; dual barrier by default.  R in hyp_set_cone_params, the Ps in hyp_set_cone_alpha."""
+    Ps = [np.asarray(P, dtype=np.float64) for P in Ps]
+    assert R >= 2 and all(P.ndim == 2 and P.shape[0] == U for P in Ps)
+    packed = np.concatenate([[float(len(Ps))], [float(P.shape[1]) for P in Ps]] + [P.ravel(order="F") for P in Ps])
+    return ConeSpec(CONE_WSOSINTERPEPINORMEUCL, U * R, not use_dual, hkind=R, alpha=packed)
+
+
 def wsos_unpack(spec):
     """The Ps matrices of a WSOSInterpNonnegative / WSOSInterpPosSemidefTri spec."""
     U = spec.dim
     if spec.ctype == CONE_WSOSINTERPPOSSEMIDEFTRI:
         U = spec.dim // (spec.hkind * (spec.hkind + 1) // 2)
+    if spec.ctype == CONE_WSOSINTERPEPINORMEUCL:
+        U = spec.dim // spec.hkind
     nP = int(spec.alpha[0])
     Ls = [int(x) for x in spec.alpha[1:1 + nP]]
     data = np.asarray(spec.alpha[1 + nP:], dtype=np.float64)

@@ -50,6 +50,10 @@ cone_code(::Cones.LinMatrixIneq{Float64}) = Cint(16)
 cone_code(::Cones.DoublyNonnegativeTri{Float64}) = Cint(17)
 cone_code(::Cones.MatrixEpiPerSquare{Float64, Float64}) = Cint(18)
 cone_code(::Cones.WSOSInterpPosSemidefTri{Float64}) = Cint(19)
+cone_code(::Cones.WSOSInterpEpiNormEucl{Float64}) = Cint(20)
+cone_alpha(c::Cones.WSOSInterpEpiNormEucl{Float64}) =
+    vcat(Float64(length(c.Ps)), Float64[size(P, 2) for P in c.Ps], (vec(P) for P in c.Ps)...)
+cone_ssf(c::Cones.WSOSInterpEpiNormEucl) = (Cint(c.R), 0.0)
 cone_alpha(c::Cones.WSOSInterpPosSemidefTri{Float64}) =
     vcat(Float64(length(c.Ps)), Float64[size(P, 2) for P in c.Ps], (vec(P) for P in c.Ps)...)
 # packed matrices [side, vec(A_1) .. vec(A_dim)] (dense real symmetric A_i; UniformScaling entries are materialised)

@@ -1037,6 +1037,111 @@ class WSOSInterpPosSemidefTri(Cone):
         return out
 
 
+class WSOSInterpEpiNormEucl(Cone):
+    """wsosinterpepinormeucl.jl:14-382: (f_1, .., f_R) polynomials (U interpolant coefficients each) with
+    f_1 >= |(f_2 .. f_R)|_2 in the WSOS sense; the barrier is the dual cone's,
+    -sum_k [logdet(L11_k) + logdet(L11_k - sum_r L1r_k L11_k^-1 L1r_k)] with L1r_k = P_k' Diagonal(s_r) P_k, nu = 2 sum L_k,
+    use_dual_barrier = !use_dual.  Dense restatement: with A_k(s) the R L x R L block-arrow matrix (L11 on the diagonal
+    blocks, L1r on the first block row / column), the barrier is -logdet A_k + (R - 2) logdet L11_k, so gradient, Hessian
+    and dder3 are the logdet derivatives of two matrices that are LINEAR in s (the reference exploits the arrow structure,
+    the mathematics is the same).  hess_prod! / inv_hess_prod! are the generic explicit-Hessian oracles."""
+    ctype = M.CONE_WSOSINTERPEPINORMEUCL
+
+    def __init__(self, R, U, Ps, use_dual=False):
+        assert R >= 2
+        self.R, self.U = R, U
+        self.Ps = [np.asarray(P, dtype=np.float64) for P in Ps]
+        assert all(P.shape[0] == U for P in self.Ps)
+        self.use_dual_barrier = not use_dual
+        super().__init__(U * R)
+
+    @property
+    def nu(self):
+        return float(2 * sum(P.shape[1] for P in self.Ps))
+
+    def set_initial_point(self, arr):
+        arr[:] = 0.0
+        arr[:self.U] = 1.0
+        return arr
+
+    def _D(self, s):
+        R, U = self.R, self.U
+        D = np.zeros((R * U, R * U))
+        idx = np.arange(U)
+        for r in range(R):
+            D[r * U + idx, r * U + idx] = s[:U]
+        for j in range(1, R):
+            D[idx, j * U + idx] = s[j * U:(j + 1) * U]
+            D[j * U + idx, idx] = s[j * U:(j + 1) * U]
+        return D
+
+    def update_feas(self):
+        # wsosinterpepinormeucl.jl:119-167: L11 and the Schur complement positive definite <=> the arrow matrix is
+        D = self._D(self.point)
+        self.Pb = [np.kron(np.eye(self.R), P) for P in self.Ps]
+        self.LA, self.L11 = [], []
+        for P, Pb in zip(self.Ps, self.Pb):
+            try:
+                self.L11.append(np.linalg.cholesky(P.T @ (self.point[:self.U, None] * P)))
+                self.LA.append(np.linalg.cholesky(Pb.T @ D @ Pb))
+            except np.linalg.LinAlgError:
+                return False
+        return True
+
+    def _collect(self, G, G11):
+        """Derivative of logdet A (through G = (I kron P) X (I kron P)') minus (R - 2) times that of logdet L11."""
+        R, U = self.R, self.U
+        idx = np.arange(U)
+        out = np.empty(self.dim)
+        out[:U] = sum(G[r * U + idx, r * U + idx] for r in range(R)) - (R - 2) * G11[idx, idx]
+        for j in range(1, R):
+            out[j * U:(j + 1) * U] = 2 * G[idx, j * U + idx]
+        return out
+
+    def update_grad(self):
+        # wsosinterpepinormeucl.jl:169-211
+        tri = lambda L, B: sla.solve_triangular(L, B, lower=True, check_finite=False)
+        self.F = [tri(L, Pb.T) for L, Pb in zip(self.LA, self.Pb)]
+        self.F11 = [tri(L, P.T) for L, P in zip(self.L11, self.Ps)]
+        self.G = [F.T @ F for F in self.F]
+        self.G11 = [F.T @ F for F in self.F11]
+        self._grad[:] = -sum(self._collect(G, G11) for G, G11 in zip(self.G, self.G11))
+
+    def update_hess(self):
+        # wsosinterpepinormeucl.jl:213-290: H_ij = tr(A^-1 E_i A^-1 E_j) - (R - 2) tr(L11^-1 E_i L11^-1 E_j)
+        self.grad()
+        R, U = self.R, self.U
+        H = np.zeros((self.dim, self.dim))
+        for G, G11 in zip(self.G, self.G11):
+            B = lambda x, y: G[x * U:(x + 1) * U, y * U:(y + 1) * U]
+            H[:U, :U] += sum(B(r, r2) ** 2 for r in range(R) for r2 in range(R)) - (R - 2) * G11 ** 2
+            for j in range(1, R):
+                blk = 2 * sum(B(r, 0) * B(r, j) for r in range(R))
+                H[:U, j * U:(j + 1) * U] += blk
+                H[j * U:(j + 1) * U, :U] += blk.T
+                for j2 in range(1, R):
+                    H[j * U:(j + 1) * U, j2 * U:(j2 + 1) * U] += 2 * (B(0, 0) * B(j, j2) + B(0, j2) * B(j, 0))
+        return (H + H.T) / 2
+
+    def hess_prod(self, arr):
+        a, vec = _as2d(arr)
+        return _ret(np.asarray(self.hess()) @ a, vec)
+
+    def dder3(self, direction):
+        # wsosinterpepinormeucl.jl:292-382
+        self.grad()
+        tri = lambda L, B: sla.solve_triangular(L, B, lower=True, check_finite=False)
+        Dd = self._D(direction)
+        out = np.zeros(self.dim)
+        for P, Pb, L, L11, F, F11 in zip(self.Ps, self.Pb, self.LA, self.L11, self.F, self.F11):
+            S = tri(L, tri(L, Pb.T @ Dd @ Pb).T).T
+            T = S @ F
+            S11 = tri(L11, tri(L11, P.T @ (direction[:self.U, None] * P)).T).T
+            T11 = S11 @ F11
+            out += self._collect(T.T @ T, T11.T @ T11)
+        return out
+
+
 class MatrixEpiPerSquare(Cone):
     """matrixepipersquare.jl:10-397 (real case): (svec(U), v, vec(W)) with U symmetric d1 x d1, W d1 x d2 (d1 <= d2),
     2 v U - W W' psd; barrier -logdet(2 v U - W W') + (d1 - 1) log v, nu = d1 + 1.  inv_hess_prod! is the generic

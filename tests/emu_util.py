@@ -316,17 +316,18 @@ class EmuGpowGroup:
         self.K = len(specs)
         self.hpm = specs[0].ctype == 12          # HypoPowerMean, else GeneralizedPower
         self.ens = specs[0].ctype == 14          # EpiNormSpectral: d1 per cone, workspace instead of powers
+        self.weuc = specs[0].ctype == 20         # WSOSInterpEpiNormEucl: like 19 with dim = U R and two more scratch blocks
         self.wpsd = specs[0].ctype == 19         # WSOSInterpPosSemidefTri: R per cone, packed Ps + workspace
-        if self.wpsd:
+        if self.wpsd or self.weuc:
             self.Rs = np.array([s.hkind for s in specs], dtype=np.int32)
             regions = []
             for s in specs:
                 Rr = s.hkind
-                U = s.dim // (Rr * (Rr + 1) // 2)
+                U = s.dim // (Rr if self.weuc else Rr * (Rr + 1) // 2)
                 nP = int(s.alpha[0])
                 Ls = [int(x) for x in s.alpha[1:1 + nP]]
                 wsz = sum(Rr * L * Rr * U + (Rr * L) ** 2 for L in Ls) + (Rr * U) ** 2 + (Rr * max(Ls)) ** 2 + \
-                    Rr * max(Ls) * Rr * U
+                    Rr * max(Ls) * Rr * U + (U * U + max(Ls) ** 2 + max(Ls) * U if self.weuc else 0)
                 regions.append(np.concatenate((np.asarray(s.alpha, dtype=np.float64), np.zeros(wsz))))
             self.voff = np.concatenate(([0], np.cumsum([r.size for r in regions])))[:-1].astype(np.int64)
             self.vecs = np.concatenate(regions)
@@ -387,7 +388,10 @@ class EmuGpowGroup:
         self.dual_feas = np.ones(self.K, dtype=np.uint8)
         self.grad = np.zeros(self.q)
         self.H = np.zeros(self.lay.total)
-        if self.wpsd:
+        if self.weuc:
+            lib().emu_weuc_state(self.K, p(self.off), p(self.dims), p(self.Rs), p(self.voff), p(self.vecs), p(self.kidx),
+                                 p(self.lay.moff), p(self.point), p(self.grad), p(self.H), p(self.feas))
+        elif self.wpsd:
             lib().emu_wpsd_state(self.K, p(self.off), p(self.dims), p(self.Rs), p(self.voff), p(self.vecs), p(self.kidx),
                                  p(self.lay.moff), p(self.point), p(self.grad), p(self.H), p(self.feas))
         elif self.mep:
@@ -433,7 +437,7 @@ class EmuGpowGroup:
         elif hess_dual > -2 and self.dnn:
             L.emu_dnn_prod(self.K, hess_dual, p(self.off), p(self.dims), p(self.sides), p(self.voff), p(self.vecs),
                            p(self.dualf), p(self.point), p(a), i64(self.q), p(out), i64(self.q), i64(a.shape[1]), i64(0))
-        elif hess_dual > -2 and (self.wsos or self.lmi or self.wpsd):
+        elif hess_dual > -2 and (self.wsos or self.lmi or self.wpsd or self.weuc):
             L.emu_gen_hess_prod(self.K, hess_dual, p(self.off), p(self.dims), p(self.lay.moff), p(self.dualf), p(self.H),
                                 p(a), i64(self.q), p(out), i64(self.q), i64(a.shape[1]), i64(0))
         elif hess_dual > -2 and self.ens:
@@ -455,7 +459,9 @@ class EmuGpowGroup:
     def dder3(self, direction):
         d = np.ascontiguousarray(direction, dtype=np.float64)
         out = np.zeros(self.q)
-        if self.wpsd:
+        if self.weuc:
+            lib().emu_weuc_dder3(self.K, p(self.off), p(self.dims), p(self.Rs), p(self.voff), p(self.vecs), p(d), p(out))
+        elif self.wpsd:
             lib().emu_wpsd_dder3(self.K, p(self.off), p(self.dims), p(self.Rs), p(self.voff), p(self.vecs), p(d), p(out))
         elif self.mep:
             lib().emu_mep_dder3(self.K, p(self.off), p(self.dims), p(self.d1), p(self.voff), p(self.vecs), p(self.scal),

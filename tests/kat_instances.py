@@ -662,6 +662,26 @@ def wsosinterppossemideftri2():  # :2407-2428: convexity parameter of x1^4 - 3 x
         dict(status="Optimal", primal_obj=6, x=[-6.0])
 
 
+def wsosinterpepinormeucl1():  # :2522-2542: min constant t : t^2 >= x^4 on [-1, 1]  =>  t = 1
+    from wsos_util import interpolate_box
+    U, pts, Ps = interpolate_box([-1.0], [1.0], 1)
+    G = np.vstack((-np.eye(U), np.zeros((U, U))))
+    h = np.concatenate((np.zeros(U), pts[:, 0] ** 2))
+    return _m(np.ones(U), [[1, -1, 0], [1, 0, -1]], [0, 0], G, h, [M.WSOSInterpEpiNormEucl(2, U, Ps)]), \
+        dict(status="Optimal", primal_obj=U, x=np.ones(U))
+
+
+def wsosinterpepinormeucl2():  # :2544-2565: t^2 >= x^4 + (x - 1)^2 on [-1, 1]  =>  t = sqrt 5
+    from wsos_util import interpolate_box
+    U, pts, Ps = interpolate_box([-1.0], [1.0], 1)
+    G = np.vstack((-np.eye(U), np.zeros((U, U)), np.zeros((U, U))))
+    h = np.concatenate((np.zeros(U), pts[:, 0] ** 2, pts[:, 0] - 1))
+    return _m(np.ones(U), [[1, -1, 0], [1, 0, -1]], [0, 0], G, h, [M.WSOSInterpEpiNormEucl(3, U, Ps)]), \
+        dict(status="Optimal", primal_obj=np.sqrt(5.0) * U, x=np.full(U, np.sqrt(5.0)))
+
+
+WSOSEUCL = [wsosinterpepinormeucl1, wsosinterpepinormeucl2]
+
 WSOSPSD = [wsosinterppossemideftri1, wsosinterppossemideftri2]
 
 WSOS = [wsosinterpnonnegative1, wsosinterpnonnegative2, wsosinterpnonnegative3]
@@ -970,7 +990,7 @@ def linmatrixineq3():  # :747-788 (dense case): min w_1 : w_1 I - diag(1, -1) ps
 
 LMI = [_named(lambda s=_s: _linmatrixineq1(s), f"linmatrixineq1_side{_s}") for _s in (2, 4)] + \
     [_named(lambda d=_d: _linmatrixineq2(d), f"linmatrixineq2_dim{_d}") for _d in (2, 3)] + [linmatrixineq3]
-EXTRA = EXTRA + LMI + DNN + MEPS + WSOSPSD
+EXTRA = EXTRA + LMI + DNN + MEPS + WSOSPSD + WSOSEUCL
 
 RELENT = [_named(lambda d=_d: _epirelentropy1(d), f"epirelentropy1_d{_d}") for _d in (1, 2, 3)] + \
     [_named(lambda d=_d: _epirelentropy2(d), f"epirelentropy2_d{_d}") for _d in (1, 2, 4)] + \
