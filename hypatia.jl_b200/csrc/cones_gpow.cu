@@ -182,7 +182,8 @@ static void wpsd_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
         const int k = g.h_kidx[i];
         const int64_t a0 = ctx->h_cone_aoff[k], a1 = ctx->h_cone_aoff[k + 1];
         const int d = g.h_dim[i], R = ctx->h_cone_hkind[k];
-        const bool eucl = g.type == HYP_CONE_WSOSINTERPEPINORMEUCL;     // dim = U R (R >= 2) instead of U svec_length(R)
+        const bool one = g.type == HYP_CONE_WSOSINTERPEPINORMONE;       // R - 1 pair (2 L x 2 L) factorisations per P_k
+        const bool eucl = g.type == HYP_CONE_WSOSINTERPEPINORMEUCL || one;   // dim = U R (R >= 2) instead of U svec_length(R)
         if (d > 128) throw HypError{"WSOSInterpPosSemidefTri / EpiNormEucl: dimension above 128 is not supported (batched Cholesky limit)"};
         const int nblk = eucl ? R : R * (R + 1) / 2;
         if (R < (eucl ? 2 : 1) || d % nblk != 0)
@@ -196,13 +197,14 @@ static void wpsd_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
             const int64_t L = (int64_t)ctx->h_cone_alpha[a0 + 1 + j];
             if (L < 1 || L > U) throw HypError{"WSOSInterpPosSemidefTri: need 1 <= L_k <= U"};
             sumL += L;
-            wsz += R * L * R * U + R * L * R * L;
+            wsz += one ? (R - 1) * (4 * L * U + 4 * L * L) : R * L * R * U + R * L * R * L;
             Lmax = std::max(Lmax, L);
         }
         if (a1 - a0 != 1 + nP + U * sumL) throw HypError{"WSOSInterpPosSemidefTri: Ps data has the wrong length"};
         g.h_voff[i] = (int64_t)buf.size();
         buf.insert(buf.end(), ctx->h_cone_alpha.begin() + a0, ctx->h_cone_alpha.begin() + a1);
-        buf.resize(buf.size() + (size_t)(wsz + R * U * R * U + R * Lmax * R * Lmax + R * Lmax * R * U +
+        const int64_t Rb = one ? 2 : R;      // block count of the factorised matrices
+        buf.resize(buf.size() + (size_t)(wsz + Rb * U * Rb * U + Rb * Lmax * Rb * Lmax + Rb * Lmax * Rb * U +
                                          (eucl ? U * U + Lmax * Lmax + Lmax * U : 0)),
                    0.0);
         g.h_hkind.push_back(R);
@@ -219,7 +221,8 @@ static void wpsd_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
 }
 
 void hyp_gpow_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
-    if (g.type == HYP_CONE_WSOSINTERPPOSSEMIDEFTRI || g.type == HYP_CONE_WSOSINTERPEPINORMEUCL) {
+    if (g.type == HYP_CONE_WSOSINTERPPOSSEMIDEFTRI || g.type == HYP_CONE_WSOSINTERPEPINORMEUCL ||
+        g.type == HYP_CONE_WSOSINTERPEPINORMONE) {
         wpsd_alloc_group(ctx, g);
         return;
     }
@@ -279,7 +282,11 @@ void hyp_gpow_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
 }
 
 void hyp_gpow_update_state(hyp_ctx* ctx, ConeGroup& g) {
-    if (g.type == HYP_CONE_WSOSINTERPEPINORMEUCL)
+    if (g.type == HYP_CONE_WSOSINTERPEPINORMONE)
+        hypdev::wone_state_kernel<<<g.count, 256, 0, ctx->stream>>>(g.count, g.d_off, g.d_dim, g.d_hkind, g.d_voff, g.d_vecs,
+                                                                   g.d_kidx, g.d_moff, ctx->d_point, ctx->d_grad, g.d_W,
+                                                                   ctx->d_feas);
+    else if (g.type == HYP_CONE_WSOSINTERPEPINORMEUCL)
         hypdev::weuc_state_kernel<<<g.count, 256, 0, ctx->stream>>>(g.count, g.d_off, g.d_dim, g.d_hkind, g.d_voff, g.d_vecs,
                                                                    g.d_kidx, g.d_moff, ctx->d_point, ctx->d_grad, g.d_W,
                                                                    ctx->d_feas);
@@ -343,7 +350,8 @@ void hyp_gpow_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr, 
                                                                   g.d_voff, g.d_vecs, g.d_dual, ctx->d_point, arr, ld_arr,
                                                                   prod, ld_prod, ncols, row_shift);
         else if (g.type == HYP_CONE_WSOSINTERPNONNEGATIVE || g.type == HYP_CONE_LINMATRIXINEQ ||
-                 g.type == HYP_CONE_WSOSINTERPPOSSEMIDEFTRI || g.type == HYP_CONE_WSOSINTERPEPINORMEUCL)
+                 g.type == HYP_CONE_WSOSINTERPPOSSEMIDEFTRI || g.type == HYP_CONE_WSOSINTERPEPINORMEUCL ||
+                 g.type == HYP_CONE_WSOSINTERPEPINORMONE)
             hypdev::gen_hess_prod_kernel<<<grid, 256, 0, ctx->stream>>>(g.count, hess_dual, g.d_off, g.d_dim, g.d_moff,
                                                                        g.d_dual, g.d_W, arr, ld_arr, prod, ld_prod, ncols,
                                                                        row_shift);
@@ -372,7 +380,10 @@ void hyp_gpow_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr, 
 }
 
 void hyp_gpow_dder3(hyp_ctx* ctx, ConeGroup& g, double* out, const double* dir) {
-    if (g.type == HYP_CONE_WSOSINTERPEPINORMEUCL)
+    if (g.type == HYP_CONE_WSOSINTERPEPINORMONE)
+        hypdev::wone_dder3_kernel<<<g.count, 256, 0, ctx->stream>>>(g.count, g.d_off, g.d_dim, g.d_hkind, g.d_voff, g.d_vecs,
+                                                                   dir, out);
+    else if (g.type == HYP_CONE_WSOSINTERPEPINORMEUCL)
         hypdev::weuc_dder3_kernel<<<g.count, 256, 0, ctx->stream>>>(g.count, g.d_off, g.d_dim, g.d_hkind, g.d_voff, g.d_vecs,
                                                                    dir, out);
     else if (g.type == HYP_CONE_WSOSINTERPPOSSEMIDEFTRI)

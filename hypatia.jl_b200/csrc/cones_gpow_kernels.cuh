@@ -1907,4 +1907,244 @@ weuc_dder3_kernel(int ncones, const int64_t* __restrict__ off, const int* __rest
 }
 
 
+// ---- WSOSInterpEpiNormOne (R polynomials of U coefficients, dim = R U <= 128), wsosinterpepinormone.jl:147-493 ----
+// Dense restatement: the reference's barrier -logdet L11 - sum_{r >= 2} logdet(L11 - L1r L11^-1 L1r) equals
+// sum_{r >= 2} -logdet A2(s_1, s_r) + (R - 2) logdet L11 with A2 the 2 L x 2 L arrow matrix [L11 L1r; L1r L11] of the
+// R = 2 Euclidean-norm cone above: every oracle is a sum over the R - 1 pairs plus the L11 correction.
+// Region of cone c: [nP][L_k ..][P_k ..], then per (k, r) F (2 L x 2 U) and Lc (2 L x 2 L), then G (2 U)^2, G11 U^2 and
+// the dder3 scratch S (2 L_max)^2, T (2 L_max x 2 U), S11 L_max^2, T11 (L_max x U).  One CTA of 256 threads per cone.
+
+// entry (pL + a, qL + b), p, q in {0, 1}, of the pair arrow matrix built from the coefficient vectors v0 (diagonal) and v1
+__device__ __forceinline__ double wone_arrow(const double* P, const double* v0, const double* v1, int U, int L, int row,
+                                             int col) {
+    const int p = row / L, a = row % L, q = col / L, b = col % L;
+    const double* v = p == q ? v0 : v1;
+    double s = 0.0;
+    for (int u = 0; u < U; u++) s += P[u + (int64_t)a * U] * v[u] * P[u + (int64_t)b * U];
+    return s;
+}
+
+static __global__ void __launch_bounds__(256)
+wone_state_kernel(int ncones, const int64_t* __restrict__ off, const int* __restrict__ dim,
+                  const int* __restrict__ Rs, const int64_t* __restrict__ voff, double* __restrict__ vecs,
+                  const int* __restrict__ kidx, const int64_t* __restrict__ moff, const double* __restrict__ point,
+                  double* __restrict__ grad, double* __restrict__ H, uint8_t* feas) {
+    __shared__ int s_ok;
+    const int c = blockIdx.x, tid = threadIdx.x;
+    if (c >= ncones) return;
+    const int64_t o = off[c];
+    const int d = dim[c], R = Rs[c], U = d / R, U2 = 2 * U, lde = (d + 1) & ~1;
+    double* reg = vecs + voff[c];
+    const int nP = (int)reg[0];
+    int64_t sumL = 0, wsz = 0;
+    for (int k = 0; k < nP; k++) {
+        const int64_t L = (int64_t)reg[1 + k];
+        sumL += L;
+        wsz += (R - 1) * (2 * L * U2 + 4 * L * L);
+    }
+    const double* P = reg + 1 + nP;
+    double* ws = reg + 1 + nP + (int64_t)U * sumL;
+    double* G = ws + wsz;
+    double* G11 = G + (int64_t)U2 * U2;
+    double* Hc = H + moff[c];
+    const double* pt = point + o;
+    if (tid == 0) s_ok = 1;
+    for (int idx = tid; idx < d * d; idx += 256) Hc[(idx % d) + (int64_t)(idx / d) * lde] = 0.0;
+    __syncthreads();
+    double gacc = 0.0;
+    const int gr = tid / U, gu = tid % U;
+    for (int k = 0; k < nP; k++) {
+        const int L = (int)reg[1 + k], L2 = 2 * L;
+        for (int r = 1; r < R; r++) {
+            double* F = ws;
+            double* Lc = F + (int64_t)L2 * U2;
+            ws = Lc + L2 * L2;
+            for (int idx = tid; idx < L2 * L2; idx += 256)
+                Lc[idx] = wone_arrow(P, pt, pt + (int64_t)r * U, U, L, idx % L2, idx / L2);
+            __syncthreads();
+            for (int j = 0; j < L2; j++) {                 // Cholesky (lower, in place, right-looking)
+                if (tid == 0) {
+                    double dg = Lc[j + j * L2];
+                    if (!(dg > 0.0)) {
+                        s_ok = 0;
+                        dg = 1.0;
+                    }
+                    Lc[j + j * L2] = sqrt(dg);
+                }
+                __syncthreads();
+                const double dj = Lc[j + j * L2];
+                for (int i = j + 1 + tid; i < L2; i += 256) Lc[i + j * L2] /= dj;
+                __syncthreads();
+                const int rr = L2 - j - 1;
+                for (int idx = tid; idx < rr * rr; idx += 256) {
+                    const int ii = j + 1 + idx % rr, kk = j + 1 + idx / rr;
+                    if (kk <= ii) Lc[ii + kk * L2] -= Lc[ii + j * L2] * Lc[kk + j * L2];
+                }
+                __syncthreads();
+            }
+            for (int jj = tid; jj < U2; jj += 256) {       // F = Lc^-1 (I_2 kron P)'
+                const int p = jj / U, u = jj % U;
+                double* f = F + (int64_t)jj * L2;
+                for (int a = 0; a < L2; a++) {
+                    double s = (a / L == p) ? P[u + (int64_t)(a % L) * U] : 0.0;
+                    for (int b = 0; b < a; b++) s -= Lc[a + b * L2] * f[b];
+                    f[a] = s / Lc[a + a * L2];
+                }
+            }
+            __syncthreads();
+            for (int idx = tid; idx < U2 * U2; idx += 256) {
+                const int i = idx % U2, j = idx / U2;
+                double s = 0.0;
+                for (int a = 0; a < L2; a++) s += F[a + (int64_t)i * L2] * F[a + (int64_t)j * L2];
+                G[idx] = s;
+                if (r == 1 && i < U && j < U) {
+                    double s1 = 0.0;
+                    for (int a = 0; a < L; a++) s1 += F[a + (int64_t)i * L2] * F[a + (int64_t)j * L2];
+                    G11[i + (int64_t)j * U] = s1;
+                }
+            }
+            __syncthreads();
+#define WONE_G(x, u1_, y, u2_) G[((x) * U + (u1_)) + (int64_t)((y) * U + (u2_)) * U2]
+            if (tid < d) {
+                if (gr == 0) gacc -= WONE_G(0, gu, 0, gu) + WONE_G(1, gu, 1, gu);
+                else if (gr == r) gacc -= 2.0 * WONE_G(0, gu, 1, gu);
+            }
+            for (int idx = tid; idx < d * d; idx += 256) {
+                const int e1 = idx % d, e2 = idx / d;
+                const int r1 = e1 / U, u1 = e1 % U, r2 = e2 / U, u2 = e2 % U;
+                double v;
+                if (r1 == 0 && r2 == 0) {
+                    v = 0.0;
+                    for (int a = 0; a < 2; a++)
+                        for (int b = 0; b < 2; b++) {
+                            const double g = WONE_G(a, u1, b, u2);
+                            v += g * g;
+                        }
+                } else if (r1 == 0 && r2 == r) {
+                    v = 2.0 * (WONE_G(0, u1, 0, u2) * WONE_G(0, u1, 1, u2) + WONE_G(1, u1, 0, u2) * WONE_G(1, u1, 1, u2));
+                } else if (r1 == r && r2 == 0) {
+                    v = 2.0 * (WONE_G(0, u2, 0, u1) * WONE_G(0, u2, 1, u1) + WONE_G(1, u2, 0, u1) * WONE_G(1, u2, 1, u1));
+                } else if (r1 == r && r2 == r) {
+                    v = 2.0 * (WONE_G(0, u1, 0, u2) * WONE_G(1, u1, 1, u2) + WONE_G(0, u1, 1, u2) * WONE_G(1, u1, 0, u2));
+                } else {
+                    continue;
+                }
+                Hc[e1 + (int64_t)e2 * lde] += v;
+            }
+#undef WONE_G
+            __syncthreads();
+        }
+        // the (R - 2) logdet L11 correction
+        if (tid < d && gr == 0) gacc += (double)(R - 2) * G11[gu + (int64_t)gu * U];
+        for (int idx = tid; idx < U * U; idx += 256) {
+            const double g11 = G11[idx];
+            Hc[(idx % U) + (int64_t)(idx / U) * lde] -= (double)(R - 2) * g11 * g11;
+        }
+        __syncthreads();
+        P += (int64_t)U * L;
+    }
+    if (tid < d) grad[o + tid] = gacc;
+    if (tid == 0 && !s_ok) feas[kidx[c]] = 0;
+}
+
+static __global__ void __launch_bounds__(256)
+wone_dder3_kernel(int ncones, const int64_t* __restrict__ off, const int* __restrict__ dim,
+                  const int* __restrict__ Rs, const int64_t* __restrict__ voff, double* __restrict__ vecs,
+                  const double* __restrict__ dir, double* __restrict__ out) {
+    const int c = blockIdx.x, tid = threadIdx.x;
+    if (c >= ncones) return;
+    const int64_t o = off[c];
+    const int d = dim[c], R = Rs[c], U = d / R, U2 = 2 * U;
+    double* reg = vecs + voff[c];
+    const int nP = (int)reg[0];
+    int64_t sumL = 0, wsz = 0, Lmax = 0;
+    for (int k = 0; k < nP; k++) {
+        const int64_t L = (int64_t)reg[1 + k];
+        sumL += L;
+        wsz += (R - 1) * (2 * L * U2 + 4 * L * L);
+        Lmax = L > Lmax ? L : Lmax;
+    }
+    const double* P = reg + 1 + nP;
+    double* ws = reg + 1 + nP + (int64_t)U * sumL;
+    double* S = ws + wsz + (int64_t)U2 * U2 + (int64_t)U * U;
+    double* T = S + 4 * Lmax * Lmax;
+    double* S11 = T + 2 * Lmax * U2;
+    double* T11 = S11 + Lmax * Lmax;
+    const double* dr = dir + o;
+    double acc = 0.0;
+    const int gr = tid / U, gu = tid % U;
+    for (int k = 0; k < nP; k++) {
+        const int L = (int)reg[1 + k], L2 = 2 * L;
+        for (int r = 1; r < R; r++) {
+            const double* F = ws;
+            const double* Lc = F + (int64_t)L2 * U2;
+            ws += (int64_t)L2 * U2 + L2 * L2;
+            for (int idx = tid; idx < L2 * L2; idx += 256)
+                S[idx] = wone_arrow(P, dr, dr + (int64_t)r * U, U, L, idx % L2, idx / L2);
+            if (r == 1)
+                for (int idx = tid; idx < L * L; idx += 256) S11[idx] = wone_arrow(P, dr, dr, U, L, idx % L, idx / L);
+            __syncthreads();
+            const int ncol = L2 + (r == 1 ? L : 0);
+            for (int col = tid; col < ncol; col += 256) {  // Lc^-1 S (and L11^-1 S11: leading block of Lc), columns
+                const bool big = col < L2;
+                const int n = big ? L2 : L;
+                double* x = big ? S + (int64_t)col * L2 : S11 + (int64_t)(col - L2) * L;
+                for (int a = 0; a < n; a++) {
+                    double s = x[a];
+                    for (int b = 0; b < a; b++) s -= Lc[a + b * L2] * x[b];
+                    x[a] = s / Lc[a + a * L2];
+                }
+            }
+            __syncthreads();
+            for (int row = tid; row < ncol; row += 256) {  // ... Lc^-T, rows
+                const bool big = row < L2;
+                const int n = big ? L2 : L;
+                double* x = big ? S + row : S11 + (row - L2);
+                for (int a = 0; a < n; a++) {
+                    double s = x[(int64_t)a * n];
+                    for (int b = 0; b < a; b++) s -= Lc[a + b * L2] * x[(int64_t)b * n];
+                    x[(int64_t)a * n] = s / Lc[a + a * L2];
+                }
+            }
+            __syncthreads();
+            for (int idx = tid; idx < L2 * U2; idx += 256) {
+                const int a = idx % L2, j = idx / L2;
+                double s = 0.0;
+                for (int b = 0; b < L2; b++) s += S[a + (int64_t)b * L2] * F[b + (int64_t)j * L2];
+                T[idx] = s;
+            }
+            if (r == 1)
+                for (int idx = tid; idx < L * U; idx += 256) {
+                    const int a = idx % L, j = idx / L;
+                    double s = 0.0;
+                    for (int b = 0; b < L; b++) s += S11[a + (int64_t)b * L] * F[b + (int64_t)j * L2];
+                    T11[idx] = s;
+                }
+            __syncthreads();
+            if (tid < d) {
+                const double* t0 = T + (int64_t)gu * L2;
+                const double* t1 = T + (int64_t)(U + gu) * L2;
+                if (gr == 0) {
+                    double s = 0.0;
+                    for (int a = 0; a < L2; a++) s += t0[a] * t0[a] + t1[a] * t1[a];
+                    acc += s;
+                    if (r == 1) {
+                        double s1 = 0.0;
+                        for (int a = 0; a < L; a++) s1 += T11[a + (int64_t)gu * L] * T11[a + (int64_t)gu * L];
+                        acc -= (double)(R - 2) * s1;
+                    }
+                } else if (gr == r) {
+                    double s = 0.0;
+                    for (int a = 0; a < L2; a++) s += t0[a] * t1[a];
+                    acc += 2.0 * s;
+                }
+            }
+            __syncthreads();
+        }
+        P += (int64_t)U * L;
+    }
+    if (tid < d) out[o + tid] = acc;
+}
+
+
 }  // namespace hypdev

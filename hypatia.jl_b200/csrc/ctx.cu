@@ -940,7 +940,7 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
                                     ? (double)ctx->h_cone_hkind[k] + 1.0   // epinormspectral.jl:95, matrixepipersquare.jl:101
                                 : t == HYP_CONE_WSOSINTERPNONNEGATIVE ? wsos_nu(ctx, k)               // wsosinterpnonnegative.jl:62
                                 : t == HYP_CONE_WSOSINTERPEPINORMEUCL ? 2.0 * wsos_nu(ctx, k)         // wsosinterpepinormeucl.jl:68
-                                : t == HYP_CONE_WSOSINTERPPOSSEMIDEFTRI                               // wsosinterppossemideftri.jl:66
+                                : (t == HYP_CONE_WSOSINTERPPOSSEMIDEFTRI || t == HYP_CONE_WSOSINTERPEPINORMONE)   // wsosinterppossemideftri.jl:66, wsosinterpepinormone.jl:88
                                     ? (double)ctx->h_cone_hkind[k] * wsos_nu(ctx, k)
                                 : t == HYP_CONE_LINMATRIXINEQ ? lmi_nu(ctx, k)                        // linmatrixineq.jl:72
                                 : t == HYP_CONE_GENERALIZEDPOWER

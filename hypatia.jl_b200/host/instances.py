@@ -106,7 +106,7 @@ def cone_initial_point(spec):
         arr[2:] = w
     elif spec.ctype == M.CONE_EPINORMINF:
         arr[0] = np.sqrt(spec.dim)      # epinorminf.jl:88-95
-    elif spec.ctype == M.CONE_WSOSINTERPEPINORMEUCL:
+    elif spec.ctype in (M.CONE_WSOSINTERPEPINORMEUCL, M.CONE_WSOSINTERPEPINORMONE):
         arr[:spec.dim // spec.hkind] = 1.0       # wsosinterpepinormeucl.jl:113-117
     elif spec.ctype == M.CONE_WSOSINTERPPOSSEMIDEFTRI:
         Rr = spec.hkind                         # wsosinterppossemideftri.jl:98-106: ones on the diagonal blocks
@@ -214,12 +214,14 @@ def _central_ray_epirelentropy(d):
 
 def _cone_dual_initial(spec, prim):
     """-grad at the central point, closed form per cone (dual of the central point)."""
-    if spec.ctype == M.CONE_WSOSINTERPEPINORMEUCL:
-        # -grad at (1, 0, .., 0): the arrow matrix is block diagonal, so -g_1 = (R - (R - 2)) diag(P (P'P)^-1 P') summed over k
+    if spec.ctype in (M.CONE_WSOSINTERPEPINORMEUCL, M.CONE_WSOSINTERPEPINORMONE):
+        # -grad at (1, 0, .., 0): the arrow matrices are block diagonal, so -g_1 = c diag(P (P'P)^-1 P') summed over k with
+        # c = R - (R - 2) = 2 (Euclidean norm) or 2 (R - 1) - (R - 2) = R (l1 norm)
         Uu = spec.dim // spec.hkind
+        cf = 2.0 if spec.ctype == M.CONE_WSOSINTERPEPINORMEUCL else float(spec.hkind)
         out = np.zeros_like(prim)
         for P in M.wsos_unpack(spec):
-            out[:Uu] += 2 * np.einsum("ij,ji->i", P, np.linalg.solve(P.T @ P, P.T))
+            out[:Uu] += cf * np.einsum("ij,ji->i", P, np.linalg.solve(P.T @ P, P.T))
         return out
     if spec.ctype == M.CONE_WSOSINTERPPOSSEMIDEFTRI:
         # -grad at the initial point: D = I, so every diagonal block gets diag(P_k (P_k' P_k)^-1 P_k') summed over k and
@@ -369,7 +371,7 @@ def _perturb(rng, spec, vec, noise):
         vec += 0.1 * noise / np.sqrt(vec.size) * (2 * rng.random(vec.size) - 1)    # test/cone.jl:426 uses noise 1e-2
         return vec
     if spec.ctype in (M.CONE_GENERALIZEDPOWER, M.CONE_WSOSINTERPNONNEGATIVE, M.CONE_WSOSINTERPPOSSEMIDEFTRI,
-                      M.CONE_WSOSINTERPEPINORMEUCL):
+                      M.CONE_WSOSINTERPEPINORMEUCL, M.CONE_WSOSINTERPEPINORMONE):
         vec += 0.5 * noise / np.sqrt(vec.size) * (2 * rng.random(vec.size) - 1)
         return vec
     if spec.ctype in (M.CONE_HYPOGEOMEAN, M.CONE_HYPOPOWERMEAN, M.CONE_EPIRELENTROPY, M.CONE_EPINORMSPECTRAL):

@@ -33,6 +33,7 @@ CONE_DOUBLYNONNEGATIVETRI = 17
 CONE_MATRIXEPIPERSQUARE = 18
 CONE_WSOSINTERPPOSSEMIDEFTRI = 19
 CONE_WSOSINTERPEPINORMEUCL = 20
+CONE_WSOSINTERPEPINORMONE = 21
 
 # separable spectral functions of EpiPerSepSpectral (sepspectralfun.jl:17-116), HYP_SSF_*
 SSF_INV, SSF_NEGLOG, SSF_NEGENTROPY, SSF_POWER12 = 0, 1, 2, 3
@@ -59,6 +60,7 @@ CONE_NAMES = {
     CONE_MATRIXEPIPERSQUARE: "MatrixEpiPerSquare",
     CONE_WSOSINTERPPOSSEMIDEFTRI: "WSOSInterpPosSemidefTri",
     CONE_WSOSINTERPEPINORMEUCL: "WSOSInterpEpiNormEucl",
+    CONE_WSOSINTERPEPINORMONE: "WSOSInterpEpiNormOne",
 }
 
 
@@ -112,7 +114,7 @@ class ConeSpec:
             assert dim >= 3
         elif ctype == CONE_HYPOPERLOG:
             assert dim >= 3
-        elif ctype == CONE_WSOSINTERPEPINORMEUCL:
+        elif ctype in (CONE_WSOSINTERPEPINORMEUCL, CONE_WSOSINTERPEPINORMONE):
             # hkind = R >= 2; alpha = packed Ps; dim = U R
             Rr = hkind
             assert Rr >= 2 and dim % Rr == 0
@@ -199,7 +201,7 @@ class ConeSpec:
             return float(int(self.alpha[0]))      # linmatrixineq.jl:72
         if self.ctype == CONE_WSOSINTERPEPINORMEUCL:
             return float(2 * sum(self.alpha[1:1 + int(self.alpha[0])]))    # wsosinterpepinormeucl.jl:68
-        if self.ctype == CONE_WSOSINTERPPOSSEMIDEFTRI:
+        if self.ctype in (CONE_WSOSINTERPPOSSEMIDEFTRI, CONE_WSOSINTERPEPINORMONE):   # R sum L (wsosinterpepinormone.jl:88)
             return float(self.hkind * sum(self.alpha[1:1 + int(self.alpha[0])]))    # wsosinterppossemideftri.jl:66
         if self.ctype == CONE_WSOSINTERPNONNEGATIVE:
             return float(sum(self.alpha[1:1 + int(self.alpha[0])]))    # wsosinterpnonnegative.jl:62
@@ -318,12 +320,19 @@ def WSOSInterpEpiNormEucl(R, U, Ps, use_dual=False):
     return ConeSpec(CONE_WSOSINTERPEPINORMEUCL, U * R, not use_dual, hkind=R, alpha=packed)
 
 
+def WSOSInterpEpiNormOne(R, U, Ps, use_dual=False):
+    """WSOSInterpEpiNormOne{Float64}(R, U, Ps, use_dual): like WSOSInterpEpiNormEucl with the l1 norm of the other
+    polynomials."""
+    spec = WSOSInterpEpiNormEucl(R, U, Ps, use_dual)
+    return ConeSpec(CONE_WSOSINTERPEPINORMONE, spec.dim, spec.use_dual, hkind=R, alpha=spec.alpha)
+
+
 def wsos_unpack(spec):
     """The Ps matrices of a WSOSInterpNonnegative / WSOSInterpPosSemidefTri spec."""
     U = spec.dim
     if spec.ctype == CONE_WSOSINTERPPOSSEMIDEFTRI:
         U = spec.dim // (spec.hkind * (spec.hkind + 1) // 2)
-    if spec.ctype == CONE_WSOSINTERPEPINORMEUCL:
+    if spec.ctype in (CONE_WSOSINTERPEPINORMEUCL, CONE_WSOSINTERPEPINORMONE):
         U = spec.dim // spec.hkind
     nP = int(spec.alpha[0])
     Ls = [int(x) for x in spec.alpha[1:1 + nP]]

@@ -62,6 +62,7 @@ typedef struct hyp_ctx hyp_ctx;
 #define HYP_CONE_WSOSINTERPPOSSEMIDEFTRI 19 /* wsosinterppossemideftri.jl: R x R matrix polynomials, dim = U svec_length(R) <= 128;
                                        R is the integer parameter of hyp_set_cone_params, the Ps travel like code 15 */
 #define HYP_CONE_WSOSINTERPEPINORMEUCL 20 /* wsosinterpepinormeucl.jl: R >= 2 polynomials, dim = U R <= 128; R and the Ps as for 19 */
+#define HYP_CONE_WSOSINTERPEPINORMONE 21 /* wsosinterpepinormone.jl: R >= 2 polynomials, dim = U R <= 128; R and the Ps as for 19 */
 #define HYP_CONE_EPINORMSPECTRAL 14 /* epinormspectral.jl (real): (u, vec(W)), W d1 x d2 column-major, d1 <= d2; d1 is given
                                        as the integer parameter of hyp_set_cone_params; use_dual = 1: nuclear norm; dim <= 128 */
 

@@ -51,6 +51,10 @@ cone_code(::Cones.DoublyNonnegativeTri{Float64}) = Cint(17)
 cone_code(::Cones.MatrixEpiPerSquare{Float64, Float64}) = Cint(18)
 cone_code(::Cones.WSOSInterpPosSemidefTri{Float64}) = Cint(19)
 cone_code(::Cones.WSOSInterpEpiNormEucl{Float64}) = Cint(20)
+cone_code(::Cones.WSOSInterpEpiNormOne{Float64}) = Cint(21)
+cone_alpha(c::Cones.WSOSInterpEpiNormOne{Float64}) =
+    vcat(Float64(length(c.Ps)), Float64[size(P, 2) for P in c.Ps], (vec(P) for P in c.Ps)...)
+cone_ssf(c::Cones.WSOSInterpEpiNormOne) = (Cint(c.R), 0.0)
 cone_alpha(c::Cones.WSOSInterpEpiNormEucl{Float64}) =
     vcat(Float64(length(c.Ps)), Float64[size(P, 2) for P in c.Ps], (vec(P) for P in c.Ps)...)
 cone_ssf(c::Cones.WSOSInterpEpiNormEucl) = (Cint(c.R), 0.0)

@@ -770,6 +770,9 @@ def make_cone(spec):
     if spec.ctype == M.CONE_EPIPERSEPSPECTRAL_VEC:
         from .cones_sepspec import EpiPerSepSpectralVec
         return EpiPerSepSpectralVec(spec.dim, spec.hkind, spec.hparam, use_dual=spec.use_dual)
+    if spec.ctype == M.CONE_WSOSINTERPEPINORMONE:
+        from .cones_vec3 import WSOSInterpEpiNormOne
+        return WSOSInterpEpiNormOne(spec.hkind, spec.dim // spec.hkind, M.wsos_unpack(spec), use_dual=not spec.use_dual)
     if spec.ctype == M.CONE_WSOSINTERPEPINORMEUCL:
         from .cones_vec3 import WSOSInterpEpiNormEucl
         return WSOSInterpEpiNormEucl(spec.hkind, spec.dim // spec.hkind, M.wsos_unpack(spec), use_dual=not spec.use_dual)

@@ -1142,6 +1142,94 @@ class WSOSInterpEpiNormEucl(Cone):
         return out
 
 
+class WSOSInterpEpiNormOne(Cone):
+    """wsosinterpepinormone.jl:14-493: (f_1, .., f_R) polynomials with f_1 >= sum_r |f_r| in the WSOS sense; dual barrier
+    -sum_k [logdet L11_k + sum_{r >= 2} logdet(L11_k - L1r_k L11_k^-1 L1r_k)], nu = R sum L_k, use_dual_barrier = !use_dual.
+    Dense restatement: the barrier is sum_{r >= 2} -logdet A2(s_1, s_r) + (R - 2) logdet L11 with A2 the 2 x 2 block-arrow
+    matrix of the R = 2 Euclidean-norm cone above, so every oracle is a sum of those of R - 1 pair cones plus the L11
+    correction.  The reference has closed forms for hess_prod! / inv_hess_prod! that exploit the arrow-shaped Hessian; here
+    the generic explicit-Hessian oracles (Cones.jl:101-118) are used - the same linear maps."""
+    ctype = M.CONE_WSOSINTERPEPINORMONE
+
+    def __init__(self, R, U, Ps, use_dual=False):
+        assert R >= 2
+        self.R, self.U = R, U
+        self.Ps = [np.asarray(P, dtype=np.float64) for P in Ps]
+        self.use_dual_barrier = not use_dual
+        self.pairs = [WSOSInterpEpiNormEucl(2, U, self.Ps) for _ in range(R - 1)]
+        for pc in self.pairs:
+            pc.setup_data()
+        super().__init__(U * R)
+
+    @property
+    def nu(self):
+        return float(self.R * sum(P.shape[1] for P in self.Ps))
+
+    def set_initial_point(self, arr):
+        arr[:] = 0.0
+        arr[:self.U] = 1.0
+        return arr
+
+    def _pair_vec(self, vec, r):
+        return np.concatenate((vec[:self.U], vec[r * self.U:(r + 1) * self.U]))
+
+    def update_feas(self):
+        # wsosinterpepinormone.jl:147-204
+        for r, pc in enumerate(self.pairs, start=1):
+            pc.reset_data()
+            pc.load_point(self._pair_vec(self.point, r))
+            if not pc.is_feas():
+                return False
+        return True
+
+    def update_grad(self):
+        # wsosinterpepinormone.jl:206-245
+        U, R = self.U, self.R
+        g = np.zeros(self.dim)
+        for r, pc in enumerate(self.pairs, start=1):
+            gp = pc.grad()
+            g[:U] += gp[:U]
+            g[r * U:(r + 1) * U] = gp[U:]
+        self.G11 = self.pairs[0].G11
+        g[:U] += (R - 2) * sum(np.diag(G11) for G11 in self.G11)
+        self._grad[:] = g
+
+    def update_hess(self):
+        self.grad()
+        U, R = self.U, self.R
+        H = np.zeros((self.dim, self.dim))
+        for r, pc in enumerate(self.pairs, start=1):
+            Hp = np.asarray(pc.hess())
+            sl = slice(r * U, (r + 1) * U)
+            H[:U, :U] += Hp[:U, :U]
+            H[:U, sl] = Hp[:U, U:]
+            H[sl, :U] = Hp[U:, :U]
+            H[sl, sl] = Hp[U:, U:]
+        H[:U, :U] -= (R - 2) * sum(G11 ** 2 for G11 in self.G11)
+        return H
+
+    def hess_prod(self, arr):
+        a, vec = _as2d(arr)
+        return _ret(np.asarray(self.hess()) @ a, vec)
+
+    def dder3(self, direction):
+        # wsosinterpepinormone.jl:406-493
+        self.grad()
+        U, R = self.U, self.R
+        tri = lambda L, B: sla.solve_triangular(L, B, lower=True, check_finite=False)
+        out = np.zeros(self.dim)
+        for r, pc in enumerate(self.pairs, start=1):
+            dp = pc.dder3(self._pair_vec(direction, r))
+            out[:U] += dp[:U]
+            out[r * U:(r + 1) * U] = dp[U:]
+        pc = self.pairs[0]
+        for P, L11, F11 in zip(self.Ps, pc.L11, pc.F11):
+            S11 = tri(L11, tri(L11, P.T @ (direction[:U, None] * P)).T).T
+            T11 = S11 @ F11
+            out[:U] -= (R - 2) * np.sum(T11 * T11, axis=0)
+        return out
+
+
 class MatrixEpiPerSquare(Cone):
     """matrixepipersquare.jl:10-397 (real case): (svec(U), v, vec(W)) with U symmetric d1 x d1, W d1 x d2 (d1 <= d2),
     2 v U - W W' psd; barrier -logdet(2 v U - W W') + (d1 - 1) log v, nu = d1 + 1.  inv_hess_prod! is the generic

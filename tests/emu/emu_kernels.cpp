@@ -243,6 +243,20 @@ int emu_gpow_dder3(int ncones, const int64_t* off, const int* dim, const int* mu
 
 extern "C" {
 
+int emu_wone_state(int ncones, const int64_t* off, const int* dim, const int* Rs, const int64_t* voff, double* vecs,
+                   const int* kidx, const int64_t* moff, const double* point, double* grad, double* H, uint8_t* feas) {
+    emu::launch(dim3(ncones), dim3(256), 0,
+                [&] { hypdev::wone_state_kernel(ncones, off, dim, Rs, voff, vecs, kidx, moff, point, grad, H, feas); });
+    return 0;
+}
+
+int emu_wone_dder3(int ncones, const int64_t* off, const int* dim, const int* Rs, const int64_t* voff, double* vecs,
+                   const double* dir, double* out) {
+    emu::launch(dim3(ncones), dim3(256), 0,
+                [&] { hypdev::wone_dder3_kernel(ncones, off, dim, Rs, voff, vecs, dir, out); });
+    return 0;
+}
+
 int emu_weuc_state(int ncones, const int64_t* off, const int* dim, const int* Rs, const int64_t* voff, double* vecs,
                    const int* kidx, const int64_t* moff, const double* point, double* grad, double* H, uint8_t* feas) {
     emu::launch(dim3(ncones), dim3(256), 0,

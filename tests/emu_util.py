@@ -316,18 +316,23 @@ class EmuGpowGroup:
         self.K = len(specs)
         self.hpm = specs[0].ctype == 12          # HypoPowerMean, else GeneralizedPower
         self.ens = specs[0].ctype == 14          # EpiNormSpectral: d1 per cone, workspace instead of powers
+        self.wone = specs[0].ctype == 21         # WSOSInterpEpiNormOne: R - 1 pair factorisations per P_k
         self.weuc = specs[0].ctype == 20         # WSOSInterpEpiNormEucl: like 19 with dim = U R and two more scratch blocks
         self.wpsd = specs[0].ctype == 19         # WSOSInterpPosSemidefTri: R per cone, packed Ps + workspace
-        if self.wpsd or self.weuc:
+        if self.wpsd or self.weuc or self.wone:
             self.Rs = np.array([s.hkind for s in specs], dtype=np.int32)
             regions = []
             for s in specs:
                 Rr = s.hkind
-                U = s.dim // (Rr if self.weuc else Rr * (Rr + 1) // 2)
+                U = s.dim // (Rr if (self.weuc or self.wone) else Rr * (Rr + 1) // 2)
                 nP = int(s.alpha[0])
                 Ls = [int(x) for x in s.alpha[1:1 + nP]]
-                wsz = sum(Rr * L * Rr * U + (Rr * L) ** 2 for L in Ls) + (Rr * U) ** 2 + (Rr * max(Ls)) ** 2 + \
-                    Rr * max(Ls) * Rr * U + (U * U + max(Ls) ** 2 + max(Ls) * U if self.weuc else 0)
+                if self.wone:
+                    wsz = sum((Rr - 1) * (4 * L * U + 4 * L * L) for L in Ls) + 5 * U * U + 5 * max(Ls) ** 2 + \
+                        5 * max(Ls) * U
+                else:
+                    wsz = sum(Rr * L * Rr * U + (Rr * L) ** 2 for L in Ls) + (Rr * U) ** 2 + (Rr * max(Ls)) ** 2 + \
+                        Rr * max(Ls) * Rr * U + (U * U + max(Ls) ** 2 + max(Ls) * U if self.weuc else 0)
                 regions.append(np.concatenate((np.asarray(s.alpha, dtype=np.float64), np.zeros(wsz))))
             self.voff = np.concatenate(([0], np.cumsum([r.size for r in regions])))[:-1].astype(np.int64)
             self.vecs = np.concatenate(regions)
@@ -388,7 +393,10 @@ class EmuGpowGroup:
         self.dual_feas = np.ones(self.K, dtype=np.uint8)
         self.grad = np.zeros(self.q)
         self.H = np.zeros(self.lay.total)
-        if self.weuc:
+        if self.wone:
+            lib().emu_wone_state(self.K, p(self.off), p(self.dims), p(self.Rs), p(self.voff), p(self.vecs), p(self.kidx),
+                                 p(self.lay.moff), p(self.point), p(self.grad), p(self.H), p(self.feas))
+        elif self.weuc:
             lib().emu_weuc_state(self.K, p(self.off), p(self.dims), p(self.Rs), p(self.voff), p(self.vecs), p(self.kidx),
                                  p(self.lay.moff), p(self.point), p(self.grad), p(self.H), p(self.feas))
         elif self.wpsd:
@@ -437,7 +445,7 @@ class EmuGpowGroup:
         elif hess_dual > -2 and self.dnn:
             L.emu_dnn_prod(self.K, hess_dual, p(self.off), p(self.dims), p(self.sides), p(self.voff), p(self.vecs),
                            p(self.dualf), p(self.point), p(a), i64(self.q), p(out), i64(self.q), i64(a.shape[1]), i64(0))
-        elif hess_dual > -2 and (self.wsos or self.lmi or self.wpsd or self.weuc):
+        elif hess_dual > -2 and (self.wsos or self.lmi or self.wpsd or self.weuc or self.wone):
             L.emu_gen_hess_prod(self.K, hess_dual, p(self.off), p(self.dims), p(self.lay.moff), p(self.dualf), p(self.H),
                                 p(a), i64(self.q), p(out), i64(self.q), i64(a.shape[1]), i64(0))
         elif hess_dual > -2 and self.ens:
@@ -459,7 +467,9 @@ class EmuGpowGroup:
     def dder3(self, direction):
         d = np.ascontiguousarray(direction, dtype=np.float64)
         out = np.zeros(self.q)
-        if self.weuc:
+        if self.wone:
+            lib().emu_wone_dder3(self.K, p(self.off), p(self.dims), p(self.Rs), p(self.voff), p(self.vecs), p(d), p(out))
+        elif self.weuc:
             lib().emu_weuc_dder3(self.K, p(self.off), p(self.dims), p(self.Rs), p(self.voff), p(self.vecs), p(d), p(out))
         elif self.wpsd:
             lib().emu_wpsd_dder3(self.K, p(self.off), p(self.dims), p(self.Rs), p(self.voff), p(self.vecs), p(d), p(out))

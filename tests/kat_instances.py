@@ -680,6 +680,17 @@ def wsosinterpepinormeucl2():  # :2544-2565: t^2 >= x^4 + (x - 1)^2 on [-1, 1]  
         dict(status="Optimal", primal_obj=np.sqrt(5.0) * U, x=np.full(U, np.sqrt(5.0)))
 
 
+def wsosinterpepinormone1():  # :2452-2472: min constant t : t >= |x^2| on [-1, 1]  =>  t = 1
+    from wsos_util import interpolate_box
+    U, pts, Ps = interpolate_box([-1.0], [1.0], 1)
+    G = np.vstack((-np.eye(U), np.zeros((U, U))))
+    h = np.concatenate((np.zeros(U), pts[:, 0] ** 2))
+    return _m(np.ones(U), [[1, -1, 0], [1, 0, -1]], [0, 0], G, h, [M.WSOSInterpEpiNormOne(2, U, Ps)]), \
+        dict(status="Optimal", primal_obj=U, x=np.ones(U))
+
+
+WSOSONE = [wsosinterpepinormone1]
+
 WSOSEUCL = [wsosinterpepinormeucl1, wsosinterpepinormeucl2]
 
 WSOSPSD = [wsosinterppossemideftri1, wsosinterppossemideftri2]
@@ -990,7 +1001,7 @@ def linmatrixineq3():  # :747-788 (dense case): min w_1 : w_1 I - diag(1, -1) ps
 
 LMI = [_named(lambda s=_s: _linmatrixineq1(s), f"linmatrixineq1_side{_s}") for _s in (2, 4)] + \
     [_named(lambda d=_d: _linmatrixineq2(d), f"linmatrixineq2_dim{_d}") for _d in (2, 3)] + [linmatrixineq3]
-EXTRA = EXTRA + LMI + DNN + MEPS + WSOSPSD + WSOSEUCL
+EXTRA = EXTRA + LMI + DNN + MEPS + WSOSPSD + WSOSEUCL + WSOSONE
 
 RELENT = [_named(lambda d=_d: _epirelentropy1(d), f"epirelentropy1_d{_d}") for _d in (1, 2, 3)] + \
     [_named(lambda d=_d: _epirelentropy2(d), f"epirelentropy2_d{_d}") for _d in (1, 2, 4)] + \

@@ -42,6 +42,12 @@ def _weuc(R, n, halfdeg, use_dual=False):
     return M.WSOSInterpEpiNormEucl(R, U, Ps, use_dual=use_dual)
 
 
+def _wone(R, n, halfdeg, use_dual=False):
+    from wsos_util import interpolate_box
+    U, _, Ps = interpolate_box(-np.ones(n), np.ones(n), halfdeg)
+    return M.WSOSInterpEpiNormOne(R, U, Ps, use_dual=use_dual)
+
+
 def _lmi(rng, side, dim, use_dual=False):
     As = []
     for i in range(dim):
@@ -61,6 +67,8 @@ def _sets():
                     _wpsd(2, 1, 3, use_dual=True), _wpsd(4, 1, 2)],
         "wsoseucl": [_weuc(2, 1, 1), _weuc(2, 1, 2), _weuc(3, 1, 2), _weuc(3, 2, 1), _weuc(4, 2, 1), _weuc(2, 2, 2),
                      _weuc(3, 1, 3, use_dual=True), _weuc(8, 2, 2)],
+        "wsosone": [_wone(2, 1, 1), _wone(2, 1, 2), _wone(3, 1, 2), _wone(3, 2, 1), _wone(4, 2, 1), _wone(2, 2, 2),
+                    _wone(3, 1, 3, use_dual=True), _wone(8, 2, 2)],
         "lmi": [_lmi(rng, 2, 2), _lmi(rng, 3, 2), _lmi(rng, 4, 3), _lmi(rng, 3, 6), _lmi(rng, 12, 40),
                 _lmi(rng, 5, 4, use_dual=True), _lmi(rng, 33, 20)],
         "wsos": [_wsos(1, 1), _wsos(1, 3), _wsos(2, 2), _wsos(3, 1), _wsos(2, 4), _wsos(1, 2, use_dual=True),
@@ -77,7 +85,7 @@ def _sets():
     }
 
 
-NAMES = ["gpow", "gpow_dual", "hpm", "hpm_dual", "normspec", "normspec_dual", "wsos", "lmi", "dnn", "meps", "wsospsd", "wsoseucl"]
+NAMES = ["gpow", "gpow_dual", "hpm", "hpm_dual", "normspec", "normspec_dual", "wsos", "lmi", "dnn", "meps", "wsospsd", "wsoseucl", "wsosone"]
 
 
 @pytest.mark.parametrize("name", NAMES)

@@ -98,6 +98,12 @@ def _genfact_cone(kind, a, b, dual, rng):
         d1 = 1 + a % 5
         d2 = d1 + b % 7
         return M.EpiNormSpectral(d1, d2, use_dual=dual)
+    if kind == "wsosone":
+        from wsos_util import interpolate_box
+        Rr = 2 + a % 4
+        n, halfdeg = ((1, 1 + b % 3), (2, 1))[b % 2]
+        U, _, Ps = interpolate_box(-np.ones(n), np.ones(n), halfdeg)
+        return M.WSOSInterpEpiNormOne(Rr, U, Ps, use_dual=dual)
     if kind == "wsoseucl":
         from wsos_util import interpolate_box
         Rr = 2 + a % 4
@@ -130,7 +136,7 @@ def _genfact_cone(kind, a, b, dual, rng):
     return M.WSOSInterpNonnegative(U, Ps, use_dual=dual)
 
 
-GENFACT_KINDS = ["gpow", "hpm", "normspec", "dnn", "lmi", "wsos", "meps", "wsospsd", "wsoseucl"]
+GENFACT_KINDS = ["gpow", "hpm", "normspec", "dnn", "lmi", "wsos", "meps", "wsospsd", "wsoseucl", "wsosone"]
 
 
 @settings(max_examples=30, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.too_slow])

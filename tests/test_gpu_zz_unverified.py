@@ -240,3 +240,34 @@ def test_wsosinterpepinormeucl_oracles_match_cpu_oracle():
     assert rel(dev.hess_prod(pt), -g) <= 1e-10                      # test/cone.jl:50,78
     assert abs(float(pt @ g) + I.model.nu) <= 1e-9 * I.model.nu     # test/cone.jl:71
     dev.free()
+
+
+# WSOSInterpEpiNormOne: emulation tier only so far (tests/test_emu_gpow.py)
+@not_yet_on_gpu
+def test_wsosinterpepinormone_oracles_match_cpu_oracle():
+    from hypatia_b200.cones import DeviceConeBlock
+    from oracle.cones import OracleConeBlock
+    from wsos_util import interpolate_box
+
+    def wone(R, n, halfdeg, use_dual=False):
+        U, _, Ps = interpolate_box(-np.ones(n), np.ones(n), halfdeg)
+        return M.WSOSInterpEpiNormOne(R, U, Ps, use_dual=use_dual)
+    cones = [wone(2, 1, 1), wone(2, 1, 2), wone(3, 1, 2), wone(3, 2, 1), wone(4, 2, 1), wone(2, 2, 2),
+             wone(3, 1, 3, use_dual=True), wone(8, 2, 2), M.Nonnegative(2)]
+    I = inst.synthetic("wsosone", 4, 0, cones, seed=82)
+    dev, ora = DeviceConeBlock(I.model), OracleConeBlock(I.model)
+    prim, dual = I.point.primal_dual(ora.dual_mask)
+    scal = 1 / np.sqrt(I.mu)
+    dev.load_point(prim, dual, scal)
+    ora.load_point(prim, dual, scal)
+    assert dev.is_feas().all() and ora.is_feas().all()
+    g = dev.grad()
+    assert rel(g, ora.grad()) <= 1e-11
+    arr = np.random.default_rng(1).standard_normal((I.model.q, 3))
+    assert rel(dev.hess_prod(arr), ora.hess_prod(arr)) <= 1e-10
+    assert rel(dev.inv_hess_prod(arr), ora.inv_hess_prod(arr)) <= 1e-8
+    assert rel(dev.dder3(arr[:, 1]), ora.dder3(arr[:, 1])) <= 1e-10
+    pt = scal * prim
+    assert rel(dev.hess_prod(pt), -g) <= 1e-10                      # test/cone.jl:50,78
+    assert abs(float(pt @ g) + I.model.nu) <= 1e-9 * I.model.nu     # test/cone.jl:71
+    dev.free()

@@ -469,6 +469,60 @@ def test_wsosinterpepinormeucl_barrier():
     assert close(-2 * cone.dder3(direction), fd_third, 1e-5)
 
 
+@pytest.mark.parametrize("R,n,halfdeg", [(2, 1, 1), (2, 1, 2), (3, 1, 2), (3, 2, 1), (4, 2, 1)])
+def test_wsosinterpepinormone(R, n, halfdeg):
+    # reference: test/cone.jl WSOSInterpEpiNormOne block (init_tol = Inf)
+    from oracle.cones_vec3 import WSOSInterpEpiNormOne
+    from wsos_util import interpolate_box
+    U, _, Ps = interpolate_box(-np.ones(n), np.ones(n), halfdeg)
+    run_oracles(WSOSInterpEpiNormOne(R, U, Ps), init_tol=np.inf)
+    run_oracles(WSOSInterpEpiNormOne(R, U, Ps, use_dual=True), init_tol=np.inf)
+
+
+def test_wsosinterpepinormone_barrier():
+    """grad, hess_prod and dder3 of the pairwise (arrow-matrix) restatement against central differences of the REFERENCE's
+    barrier -sum_k [logdet L11 + sum_r logdet(L11 - L1r L11^-1 L1r)] (wsosinterpepinormone.jl:147-204)."""
+    from oracle.cones_vec3 import WSOSInterpEpiNormOne
+    from wsos_util import interpolate_box
+    R = 4
+    U, _, Ps = interpolate_box([-1.0], [1.0], 2)
+    cone = WSOSInterpEpiNormOne(R, U, Ps)
+
+    def barrier(s):
+        tot = 0.0
+        for P in Ps:
+            L11 = P.T @ (s[:U, None] * P)
+            tot -= np.linalg.slogdet(L11)[1]
+            for r in range(1, R):
+                L1r = P.T @ (s[r * U:(r + 1) * U, None] * P)
+                tot -= np.linalg.slogdet(L11 - L1r @ np.linalg.solve(L11, L1r))[1]
+        return tot
+
+    rng = np.random.default_rng(1)
+    point = np.zeros(cone.dim)
+    cone.set_initial_point(point)
+    perturb_scale(rng, point, 0.1, 1.0)
+
+    def grad_at(s):
+        cone.reset_data()
+        cone.load_point(s)
+        assert cone.is_feas()
+        return cone.grad().copy()
+
+    g = grad_at(point)
+    eps = 1e-6
+    fd_grad = np.array([(barrier(point + eps * e) - barrier(point - eps * e)) / (2 * eps) for e in np.eye(cone.dim)])
+    assert close(g, fd_grad, 1e-7)
+    direction = 0.3 * rng.standard_normal(cone.dim)
+    fd_hess_dir = (grad_at(point + eps * direction) - grad_at(point - eps * direction)) / (2 * eps)
+    grad_at(point)
+    assert close(cone.hess_prod(direction), fd_hess_dir, 1e-6)
+    e2 = 1e-4
+    fd_third = (grad_at(point + e2 * direction) - 2 * g + grad_at(point - e2 * direction)) / e2 ** 2
+    grad_at(point)
+    assert close(-2 * cone.dder3(direction), fd_third, 1e-5)
+
+
 def rand_lmi(rng, side, dim):
     """rand_herms of test/cone.jl (real case): symmetric matrices with a positive definite first one."""
     As = []
