@@ -220,7 +220,50 @@ static void wpsd_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
     hyp_mat_alloc_group(ctx, g);
 }
 
+// PosSemidefTriSparse: d_vecs / d_voff = per-cone region [side][rows][cols] (as passed to hyp_set_cone_alpha) followed by
+// the workspace of sps_state_kernel / sps_dder3_kernel (5 side^2 doubles)
+static void sps_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
+    if ((int)ctx->h_cone_aoff.size() != ctx->K + 1)
+        throw HypError{"PosSemidefTriSparse cones need hyp_set_cone_alpha (side and the sparsity pattern) before hyp_load_model"};
+    g.h_voff.assign(g.count, 0);
+    std::vector<double> buf;
+    for (int i = 0; i < g.count; i++) {
+        const int k = g.h_kidx[i];
+        const int64_t a0 = ctx->h_cone_aoff[k], a1 = ctx->h_cone_aoff[k + 1];
+        const int d = g.h_dim[i];
+        if (d > 128) throw HypError{"PosSemidefTriSparse: more than 128 nonzeros are not supported (batched Cholesky limit)"};
+        if (a1 - a0 != 1 + 2 * (int64_t)d) throw HypError{"PosSemidefTriSparse: pattern data has the wrong length"};
+        const int64_t sd = (int64_t)ctx->h_cone_alpha[a0];
+        if (sd < 1 || sd > d) throw HypError{"PosSemidefTriSparse: bad side"};
+        std::vector<int> seen((size_t)sd, 0);
+        for (int e = 0; e < d; e++) {
+            const int64_t r = (int64_t)ctx->h_cone_alpha[a0 + 1 + e], c = (int64_t)ctx->h_cone_alpha[a0 + 1 + d + e];
+            if (c < 0 || c > r || r >= sd) throw HypError{"PosSemidefTriSparse: need 0 <= col <= row < side"};
+            if (r == c) seen[(size_t)r]++;
+        }
+        for (int64_t r = 0; r < sd; r++)
+            if (seen[(size_t)r] != 1) throw HypError{"PosSemidefTriSparse: every diagonal entry must appear exactly once"};
+        g.h_voff[i] = (int64_t)buf.size();
+        buf.insert(buf.end(), ctx->h_cone_alpha.begin() + a0, ctx->h_cone_alpha.begin() + a1);
+        buf.resize(buf.size() + (size_t)(5 * sd * sd), 0.0);
+        g.h_hkind.push_back((int)sd);
+        g.h_side[i] = d;
+    }
+    g.max_side = g.max_dim;
+    cudaFree(g.d_side);
+    g.d_side = upload_vec(g.h_side);
+    g.d_hkind = upload_vec(g.h_hkind);
+    g.d_voff = upload_vec(g.h_voff);
+    CUDA_TRY(cudaMalloc(&g.d_vecs, std::max<size_t>(buf.size(), 1) * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(g.d_vecs, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice));
+    hyp_mat_alloc_group(ctx, g);
+}
+
 void hyp_gpow_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
+    if (g.type == HYP_CONE_POSSEMIDEFTRISPARSE) {
+        sps_alloc_group(ctx, g);
+        return;
+    }
     if (g.type == HYP_CONE_WSOSINTERPPOSSEMIDEFTRI || g.type == HYP_CONE_WSOSINTERPEPINORMEUCL ||
         g.type == HYP_CONE_WSOSINTERPEPINORMONE) {
         wpsd_alloc_group(ctx, g);
@@ -282,7 +325,10 @@ void hyp_gpow_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
 }
 
 void hyp_gpow_update_state(hyp_ctx* ctx, ConeGroup& g) {
-    if (g.type == HYP_CONE_WSOSINTERPEPINORMONE)
+    if (g.type == HYP_CONE_POSSEMIDEFTRISPARSE)
+        hypdev::sps_state_kernel<<<g.count, 256, 0, ctx->stream>>>(g.count, g.d_off, g.d_dim, g.d_voff, g.d_vecs, g.d_kidx,
+                                                                  g.d_moff, ctx->d_point, ctx->d_grad, g.d_W, ctx->d_feas);
+    else if (g.type == HYP_CONE_WSOSINTERPEPINORMONE)
         hypdev::wone_state_kernel<<<g.count, 256, 0, ctx->stream>>>(g.count, g.d_off, g.d_dim, g.d_hkind, g.d_voff, g.d_vecs,
                                                                    g.d_kidx, g.d_moff, ctx->d_point, ctx->d_grad, g.d_W,
                                                                    ctx->d_feas);
@@ -351,7 +397,7 @@ void hyp_gpow_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr, 
                                                                   prod, ld_prod, ncols, row_shift);
         else if (g.type == HYP_CONE_WSOSINTERPNONNEGATIVE || g.type == HYP_CONE_LINMATRIXINEQ ||
                  g.type == HYP_CONE_WSOSINTERPPOSSEMIDEFTRI || g.type == HYP_CONE_WSOSINTERPEPINORMEUCL ||
-                 g.type == HYP_CONE_WSOSINTERPEPINORMONE)
+                 g.type == HYP_CONE_WSOSINTERPEPINORMONE || g.type == HYP_CONE_POSSEMIDEFTRISPARSE)
             hypdev::gen_hess_prod_kernel<<<grid, 256, 0, ctx->stream>>>(g.count, hess_dual, g.d_off, g.d_dim, g.d_moff,
                                                                        g.d_dual, g.d_W, arr, ld_arr, prod, ld_prod, ncols,
                                                                        row_shift);
@@ -380,7 +426,9 @@ void hyp_gpow_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr, 
 }
 
 void hyp_gpow_dder3(hyp_ctx* ctx, ConeGroup& g, double* out, const double* dir) {
-    if (g.type == HYP_CONE_WSOSINTERPEPINORMONE)
+    if (g.type == HYP_CONE_POSSEMIDEFTRISPARSE)
+        hypdev::sps_dder3_kernel<<<g.count, 256, 0, ctx->stream>>>(g.count, g.d_off, g.d_dim, g.d_voff, g.d_vecs, dir, out);
+    else if (g.type == HYP_CONE_WSOSINTERPEPINORMONE)
         hypdev::wone_dder3_kernel<<<g.count, 256, 0, ctx->stream>>>(g.count, g.d_off, g.d_dim, g.d_hkind, g.d_voff, g.d_vecs,
                                                                    dir, out);
     else if (g.type == HYP_CONE_WSOSINTERPEPINORMEUCL)

@@ -2147,4 +2147,136 @@ wone_dder3_kernel(int ncones, const int64_t* __restrict__ off, const int* __rest
 }
 
 
+// ---- PosSemidefTriSparse (real, dense implementation as the reference's PSDSparseDense; dim = nnz <= 128),
+// possemideftrisparse/denseimpl.jl:30-167 ----
+// Region of cone c at vecs + voff[c]: [side][row_1 .. row_dim][col_1 .. col_dim] (hyp_set_cone_alpha; 0-based, col <= row,
+// every diagonal entry present), then the workspace: lower Cholesky factor of the dense matrix (side^2), its inverse
+// Li (side^2) and three side^2 scratch matrices for dder3.  One CTA of 256 threads per cone.
+
+static __global__ void __launch_bounds__(256)
+sps_state_kernel(int ncones, const int64_t* __restrict__ off, const int* __restrict__ dim,
+                 const int64_t* __restrict__ voff, double* __restrict__ vecs, const int* __restrict__ kidx,
+                 const int64_t* __restrict__ moff, const double* __restrict__ point, double* __restrict__ grad,
+                 double* __restrict__ H, uint8_t* feas) {
+    __shared__ int s_ok;
+    const int c = blockIdx.x, tid = threadIdx.x;
+    if (c >= ncones) return;
+    const int64_t o = off[c];
+    const int d = dim[c], lde = (d + 1) & ~1;
+    double* reg = vecs + voff[c];
+    const int sd = (int)reg[0], s2 = sd * sd;
+    const double* rows = reg + 1;
+    const double* cols = reg + 1 + d;
+    double* Lc = reg + 1 + 2 * d;
+    double* Li = Lc + s2;
+    double* Hc = H + moff[c];
+    if (tid == 0) s_ok = 1;
+    for (int idx = tid; idx < s2; idx += 256) Lc[idx] = 0.0;
+    __syncthreads();
+    for (int e = tid; e < d; e += 256) {                  // svec_to_smat_sparse! (:207-222), both triangles
+        const int i = (int)rows[e], j = (int)cols[e];
+        const double x = i == j ? point[o + e] : point[o + e] * 0.70710678118654752440;
+        Lc[i + j * sd] = x;
+        Lc[j + i * sd] = x;
+    }
+    __syncthreads();
+    for (int j = 0; j < sd; j++) {                        // Cholesky (lower, in place, right-looking)
+        if (tid == 0) {
+            double dg = Lc[j + j * sd];
+            if (!(dg > 0.0)) {
+                s_ok = 0;
+                dg = 1.0;
+            }
+            Lc[j + j * sd] = sqrt(dg);
+        }
+        __syncthreads();
+        const double dj = Lc[j + j * sd];
+        for (int i = j + 1 + tid; i < sd; i += 256) Lc[i + j * sd] /= dj;
+        __syncthreads();
+        const int r = sd - j - 1;
+        for (int idx = tid; idx < r * r; idx += 256) {
+            const int ii = j + 1 + idx % r, kk = j + 1 + idx / r;
+            if (kk <= ii) Lc[ii + kk * sd] -= Lc[ii + j * sd] * Lc[kk + j * sd];
+        }
+        __syncthreads();
+    }
+    for (int b = tid; b < sd; b += 256) {                 // Li = (L L')^-1, column by column
+        double* x = Li + (int64_t)b * sd;
+        for (int r = 0; r < sd; r++) {
+            double s = r == b ? 1.0 : 0.0;
+            for (int k = 0; k < r; k++) s -= Lc[r + k * sd] * x[k];
+            x[r] = s / Lc[r + r * sd];
+        }
+        for (int r = sd - 1; r >= 0; r--) {
+            double s = x[r];
+            for (int k = r + 1; k < sd; k++) s -= Lc[k + r * sd] * x[k];
+            x[r] = s / Lc[r + r * sd];
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < d; e += 256) {                  // update_grad (:43-55)
+        const int i = (int)rows[e], j = (int)cols[e];
+        grad[o + e] = -Li[i + j * sd] * (i == j ? 1.0 : 1.41421356237309504880);
+    }
+    for (int idx = tid; idx < d * d; idx += 256) {        // update_hess (:57-83), both triangles
+        const int e1 = idx % d, e2 = idx / d;
+        const int i1 = (int)rows[e1], j1 = (int)cols[e1], i2 = (int)rows[e2], j2 = (int)cols[e2];
+        double v;
+        if (i1 == j1 && i2 == j2) v = Li[i1 + i2 * sd] * Li[i1 + i2 * sd];
+        else if ((i1 == j1) != (i2 == j2)) v = 1.41421356237309504880 * Li[i1 + i2 * sd] * Li[j1 + j2 * sd];
+        else v = Li[i1 + i2 * sd] * Li[j1 + j2 * sd] + Li[i1 + j2 * sd] * Li[j1 + i2 * sd];
+        Hc[e1 + (int64_t)e2 * lde] = v;
+    }
+    if (tid == 0 && !s_ok) feas[kidx[c]] = 0;
+}
+
+// dder3 (:153-167): entries of Li D Li D Li on the pattern, D = smat(dir)
+static __global__ void __launch_bounds__(256)
+sps_dder3_kernel(int ncones, const int64_t* __restrict__ off, const int* __restrict__ dim,
+                 const int64_t* __restrict__ voff, double* __restrict__ vecs, const double* __restrict__ dir,
+                 double* __restrict__ out) {
+    const int c = blockIdx.x, tid = threadIdx.x;
+    if (c >= ncones) return;
+    const int64_t o = off[c];
+    const int d = dim[c];
+    double* reg = vecs + voff[c];
+    const int sd = (int)reg[0], s2 = sd * sd;
+    const double* rows = reg + 1;
+    const double* cols = reg + 1 + d;
+    const double* Li = reg + 1 + 2 * d + s2;
+    double* D = reg + 1 + 2 * d + 2 * s2;
+    double* W1 = D + s2;
+    double* W2 = W1 + s2;
+    for (int idx = tid; idx < s2; idx += 256) D[idx] = 0.0;
+    __syncthreads();
+    for (int e = tid; e < d; e += 256) {
+        const int i = (int)rows[e], j = (int)cols[e];
+        const double x = i == j ? dir[o + e] : dir[o + e] * 0.70710678118654752440;
+        D[i + j * sd] = x;
+        D[j + i * sd] = x;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < s2; idx += 256) {           // W1 = Li D
+        const int a = idx % sd, b = idx / sd;
+        double s = 0.0;
+        for (int k = 0; k < sd; k++) s += Li[a + k * sd] * D[k + b * sd];
+        W1[idx] = s;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < s2; idx += 256) {           // W2 = W1 Li
+        const int a = idx % sd, b = idx / sd;
+        double s = 0.0;
+        for (int k = 0; k < sd; k++) s += W1[a + k * sd] * Li[k + b * sd];
+        W2[idx] = s;
+    }
+    __syncthreads();
+    for (int e = tid; e < d; e += 256) {                  // (W2 W1')[i, j] = (Li D Li D Li)[i, j]
+        const int i = (int)rows[e], j = (int)cols[e];
+        double s = 0.0;
+        for (int k = 0; k < sd; k++) s += W2[i + k * sd] * W1[j + k * sd];
+        out[o + e] = s * (i == j ? 1.0 : 1.41421356237309504880);
+    }
+}
+
+
 }  // namespace hypdev

@@ -942,7 +942,8 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
                                 : t == HYP_CONE_WSOSINTERPEPINORMEUCL ? 2.0 * wsos_nu(ctx, k)         // wsosinterpepinormeucl.jl:68
                                 : (t == HYP_CONE_WSOSINTERPPOSSEMIDEFTRI || t == HYP_CONE_WSOSINTERPEPINORMONE)   // wsosinterppossemideftri.jl:66, wsosinterpepinormone.jl:88
                                     ? (double)ctx->h_cone_hkind[k] * wsos_nu(ctx, k)
-                                : t == HYP_CONE_LINMATRIXINEQ ? lmi_nu(ctx, k)                        // linmatrixineq.jl:72
+                                : (t == HYP_CONE_LINMATRIXINEQ || t == HYP_CONE_POSSEMIDEFTRISPARSE)
+                                    ? lmi_nu(ctx, k)   // linmatrixineq.jl:72, possemideftrisparse.jl:101: first entry of the packed data = side
                                 : t == HYP_CONE_GENERALIZEDPOWER
                                     ? ((int)ctx->h_cone_aoff.size() == K + 1
                                            ? (double)(ctx->h_cone_aoff[k + 1] - ctx->h_cone_aoff[k]) + 1.0

@@ -114,6 +114,9 @@ def cone_initial_point(spec):
         for p in range(Rr):
             b = p * (p + 1) // 2 + p
             arr[b * Uu:(b + 1) * Uu] = 1.0
+    elif spec.ctype == M.CONE_POSSEMIDEFTRISPARSE:
+        a = np.asarray(spec.alpha)              # possemideftrisparse.jl:103-116: the identity
+        arr[:] = (a[1:1 + spec.dim] == a[1 + spec.dim:]).astype(float)
     elif spec.ctype == M.CONE_MATRIXEPIPERSQUARE:
         d1 = spec.hkind                         # matrixepipersquare.jl:103-116: U = I, v = 1, W = 0
         arr[_svec_diag_idx(d1)] = 1.0
@@ -236,6 +239,8 @@ def _cone_dual_initial(spec, prim):
             b = p * (p + 1) // 2 + p
             out[b * Uu:(b + 1) * Uu] = dg
         return out
+    if spec.ctype == M.CONE_POSSEMIDEFTRISPARSE:
+        return prim.copy()      # -grad at the identity is the identity
     if spec.ctype == M.CONE_MATRIXEPIPERSQUARE:
         # -grad at (I, 1, 0): Z = 2 I, Zi = I / 2 => -g_U = svec(I), -g_v = 2 tr(Zi U) - (d1 - 1) = 1, -g_W = 0
         return prim.copy()
@@ -360,6 +365,9 @@ def _perturb(rng, spec, vec, noise):
         return vec
     if spec.ctype == M.CONE_EPIPERSEPSPECTRAL_VEC:
         vec += noise / (2.0 * (vec.size - 2)) * (2 * rng.random(vec.size) - 1)   # the initial point is not central
+        return vec
+    if spec.ctype == M.CONE_POSSEMIDEFTRISPARSE:
+        vec += 0.5 * noise / np.sqrt(vec.size) * (2 * rng.random(vec.size) - 1)
         return vec
     if spec.ctype == M.CONE_MATRIXEPIPERSQUARE:
         vec += 0.5 * noise / np.sqrt(vec.size) * (2 * rng.random(vec.size) - 1)

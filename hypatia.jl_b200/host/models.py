@@ -34,6 +34,7 @@ CONE_MATRIXEPIPERSQUARE = 18
 CONE_WSOSINTERPPOSSEMIDEFTRI = 19
 CONE_WSOSINTERPEPINORMEUCL = 20
 CONE_WSOSINTERPEPINORMONE = 21
+CONE_POSSEMIDEFTRISPARSE = 22
 
 # separable spectral functions of EpiPerSepSpectral (sepspectralfun.jl:17-116), HYP_SSF_*
 SSF_INV, SSF_NEGLOG, SSF_NEGENTROPY, SSF_POWER12 = 0, 1, 2, 3
@@ -61,6 +62,7 @@ CONE_NAMES = {
     CONE_WSOSINTERPPOSSEMIDEFTRI: "WSOSInterpPosSemidefTri",
     CONE_WSOSINTERPEPINORMEUCL: "WSOSInterpEpiNormEucl",
     CONE_WSOSINTERPEPINORMONE: "WSOSInterpEpiNormOne",
+    CONE_POSSEMIDEFTRISPARSE: "PosSemidefTriSparse",
 }
 
 
@@ -135,6 +137,14 @@ class ConeSpec:
             d1 = hkind
             rest = dim - d1 * (d1 + 1) // 2 - 1
             assert d1 >= 1 and rest >= d1 * d1 and rest % d1 == 0
+        elif ctype == CONE_POSSEMIDEFTRISPARSE:
+            # alpha = packed pattern [side, row_1 .. row_dim, col_1 .. col_dim] (0-based, col <= row, every diagonal present)
+            side = int(self.alpha[0])
+            assert len(self.alpha) == 1 + 2 * dim and 1 <= side <= dim
+            rows = [int(x) for x in self.alpha[1:1 + dim]]
+            cols = [int(x) for x in self.alpha[1 + dim:]]
+            assert all(0 <= c <= r < side for r, c in zip(rows, cols))
+            assert sorted(r for r, c in zip(rows, cols) if r == c) == list(range(side))
         elif ctype == CONE_DOUBLYNONNEGATIVETRI:
             assert dim >= 1
             svec_side(dim)
@@ -197,8 +207,8 @@ class ConeSpec:
             return float(len(self.alpha) + 1)
         if self.ctype in (CONE_EPINORMSPECTRAL, CONE_MATRIXEPIPERSQUARE):
             return float(self.hkind + 1)      # epinormspectral.jl:95, matrixepipersquare.jl:101
-        if self.ctype == CONE_LINMATRIXINEQ:
-            return float(int(self.alpha[0]))      # linmatrixineq.jl:72
+        if self.ctype in (CONE_LINMATRIXINEQ, CONE_POSSEMIDEFTRISPARSE):
+            return float(int(self.alpha[0]))      # linmatrixineq.jl:72, possemideftrisparse.jl:101 (= side)
         if self.ctype == CONE_WSOSINTERPEPINORMEUCL:
             return float(2 * sum(self.alpha[1:1 + int(self.alpha[0])]))    # wsosinterpepinormeucl.jl:68
         if self.ctype in (CONE_WSOSINTERPPOSSEMIDEFTRI, CONE_WSOSINTERPEPINORMONE):   # R sum L (wsosinterpepinormone.jl:88)
@@ -277,6 +287,14 @@ def MatrixEpiPerSquare(d1, d2, use_dual=False):
     2 v U - W W' psd."""
     assert 1 <= d1 <= d2
     return ConeSpec(CONE_MATRIXEPIPERSQUARE, d1 * (d1 + 1) // 2 + 1 + d1 * d2, use_dual, hkind=d1)
+
+
+def PosSemidefTriSparse(side, row_idxs, col_idxs, use_dual=False):
+    """PosSemidefTriSparse{PSDSparseDense, Float64, Float64}(side, row_idxs, col_idxs): 0-based lower-triangle pattern with
+    every diagonal entry; the pattern travels in the per-cone double array of hyp_set_cone_alpha."""
+    rows, cols = np.asarray(row_idxs, dtype=np.float64), np.asarray(col_idxs, dtype=np.float64)
+    assert rows.size == cols.size
+    return ConeSpec(CONE_POSSEMIDEFTRISPARSE, rows.size, use_dual, alpha=np.concatenate(([float(side)], rows, cols)))
 
 
 def DoublyNonnegativeTri(dim, use_dual=False):

@@ -63,6 +63,9 @@ typedef struct hyp_ctx hyp_ctx;
                                        R is the integer parameter of hyp_set_cone_params, the Ps travel like code 15 */
 #define HYP_CONE_WSOSINTERPEPINORMEUCL 20 /* wsosinterpepinormeucl.jl: R >= 2 polynomials, dim = U R <= 128; R and the Ps as for 19 */
 #define HYP_CONE_WSOSINTERPEPINORMONE 21 /* wsosinterpepinormone.jl: R >= 2 polynomials, dim = U R <= 128; R and the Ps as for 19 */
+#define HYP_CONE_POSSEMIDEFTRISPARSE 22 /* possemideftrisparse/ (real; dense implementation like the reference's PSDSparseDense):
+                                       dim = number of pattern entries <= 128; hyp_set_cone_alpha carries
+                                       [side, row_1 .. row_dim, col_1 .. col_dim] (0-based, col <= row, every diagonal once) */
 #define HYP_CONE_EPINORMSPECTRAL 14 /* epinormspectral.jl (real): (u, vec(W)), W d1 x d2 column-major, d1 <= d2; d1 is given
                                        as the integer parameter of hyp_set_cone_params; use_dual = 1: nuclear norm; dim <= 128 */
 

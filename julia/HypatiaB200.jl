@@ -52,6 +52,9 @@ cone_code(::Cones.MatrixEpiPerSquare{Float64, Float64}) = Cint(18)
 cone_code(::Cones.WSOSInterpPosSemidefTri{Float64}) = Cint(19)
 cone_code(::Cones.WSOSInterpEpiNormEucl{Float64}) = Cint(20)
 cone_code(::Cones.WSOSInterpEpiNormOne{Float64}) = Cint(21)
+cone_code(::Cones.PosSemidefTriSparse{<:Cones.PSDSparseImpl, Float64, Float64}) = Cint(22)
+cone_alpha(c::Cones.PosSemidefTriSparse{<:Cones.PSDSparseImpl, Float64, Float64}) =
+    vcat(Float64(c.side), Float64.(c.row_idxs .- 1), Float64.(c.col_idxs .- 1))      # 0-based pattern
 cone_alpha(c::Cones.WSOSInterpEpiNormOne{Float64}) =
     vcat(Float64(length(c.Ps)), Float64[size(P, 2) for P in c.Ps], (vec(P) for P in c.Ps)...)
 cone_ssf(c::Cones.WSOSInterpEpiNormOne) = (Cint(c.R), 0.0)

@@ -780,6 +780,11 @@ def make_cone(spec):
         from .cones_vec3 import WSOSInterpPosSemidefTri
         Rr = spec.hkind
         return WSOSInterpPosSemidefTri(Rr, spec.dim // (Rr * (Rr + 1) // 2), M.wsos_unpack(spec), use_dual=not spec.use_dual)
+    if spec.ctype == M.CONE_POSSEMIDEFTRISPARSE:
+        from .cones_vec3 import PosSemidefTriSparse
+        a = np.asarray(spec.alpha)
+        return PosSemidefTriSparse(int(a[0]), a[1:1 + spec.dim].astype(int), a[1 + spec.dim:].astype(int),
+                                   use_dual=spec.use_dual)
     if spec.ctype == M.CONE_MATRIXEPIPERSQUARE:
         from .cones_vec3 import MatrixEpiPerSquare
         d1 = spec.hkind

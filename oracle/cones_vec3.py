@@ -1230,6 +1230,75 @@ class WSOSInterpEpiNormOne(Cone):
         return out
 
 
+class PosSemidefTriSparse(Cone):
+    """possemideftrisparse/{possemideftrisparse,denseimpl}.jl (real case, the reference's dense implementation
+    PSDSparseDense): the entries (row_idxs, col_idxs) of the lower triangle of a symmetric side x side matrix (every
+    diagonal entry present, off-diagonals scaled by sqrt 2) such that the matrix with zeros elsewhere is psd; barrier
+    -logdet, nu = side.  use_dual = true gives the cone of psd-completable partial matrices.  hess_prod! /
+    inv_hess_prod! are the generic explicit-Hessian oracles."""
+    ctype = M.CONE_POSSEMIDEFTRISPARSE
+
+    def __init__(self, side, row_idxs, col_idxs, use_dual=False):
+        self.side = side
+        self.rows = np.asarray(row_idxs, dtype=np.int64)      # 0-based, col <= row
+        self.cols = np.asarray(col_idxs, dtype=np.int64)
+        assert (self.cols <= self.rows).all() and (self.rows < side).all()
+        assert sorted(self.rows[self.rows == self.cols]) == list(range(side))
+        self.use_dual_barrier = use_dual
+        self.scal = np.where(self.rows == self.cols, 1.0, np.sqrt(2.0))
+        super().__init__(self.rows.size)
+
+    @property
+    def nu(self):
+        return float(self.side)
+
+    def set_initial_point(self, arr):
+        arr[:] = (self.rows == self.cols).astype(float)
+        return arr
+
+    def _smat(self, vec):
+        Mx = np.zeros((self.side, self.side))
+        Mx[self.rows, self.cols] = vec / self.scal
+        Mx[self.cols, self.rows] = vec / self.scal
+        return Mx
+
+    def update_feas(self):
+        # denseimpl.jl:30-41
+        try:
+            self.fact = sla.cho_factor(self._smat(self.point), lower=True, check_finite=False)
+        except np.linalg.LinAlgError:
+            return False
+        return True
+
+    def update_grad(self):
+        # denseimpl.jl:43-55
+        Li = sla.cho_solve(self.fact, np.eye(self.side), check_finite=False)
+        self.Li = (Li + Li.T) / 2
+        self._grad[:] = -self.Li[self.rows, self.cols] * self.scal
+
+    def update_hess(self):
+        # denseimpl.jl:57-83
+        self.grad()
+        Li, i, j = self.Li, self.rows, self.cols
+        H = Li[np.ix_(i, i)] * Li[np.ix_(j, j)] + Li[np.ix_(i, j)] * Li[np.ix_(j, i)]
+        dg = (i == j)
+        H[np.ix_(dg, dg)] = Li[np.ix_(i[dg], i[dg])] ** 2
+        mixed = np.logical_xor.outer(dg, dg)
+        Hm = np.sqrt(2.0) * Li[np.ix_(i, i)] * Li[np.ix_(j, j)]
+        H[mixed] = Hm[mixed]
+        return H
+
+    def hess_prod(self, arr):
+        a, vec = _as2d(arr)
+        return _ret(np.asarray(self.hess()) @ a, vec)
+
+    def dder3(self, direction):
+        # denseimpl.jl:153-167
+        self.grad()
+        T = self.Li @ self._smat(direction) @ self.Li @ self._smat(direction) @ self.Li
+        return T[self.rows, self.cols] * self.scal
+
+
 class MatrixEpiPerSquare(Cone):
     """matrixepipersquare.jl:10-397 (real case): (svec(U), v, vec(W)) with U symmetric d1 x d1, W d1 x d2 (d1 <= d2),
     2 v U - W W' psd; barrier -logdet(2 v U - W W') + (d1 - 1) log v, nu = d1 + 1.  inv_hess_prod! is the generic

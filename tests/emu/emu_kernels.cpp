@@ -243,6 +243,19 @@ int emu_gpow_dder3(int ncones, const int64_t* off, const int* dim, const int* mu
 
 extern "C" {
 
+int emu_sps_state(int ncones, const int64_t* off, const int* dim, const int64_t* voff, double* vecs, const int* kidx,
+                  const int64_t* moff, const double* point, double* grad, double* H, uint8_t* feas) {
+    emu::launch(dim3(ncones), dim3(256), 0,
+                [&] { hypdev::sps_state_kernel(ncones, off, dim, voff, vecs, kidx, moff, point, grad, H, feas); });
+    return 0;
+}
+
+int emu_sps_dder3(int ncones, const int64_t* off, const int* dim, const int64_t* voff, double* vecs, const double* dir,
+                  double* out) {
+    emu::launch(dim3(ncones), dim3(256), 0, [&] { hypdev::sps_dder3_kernel(ncones, off, dim, voff, vecs, dir, out); });
+    return 0;
+}
+
 int emu_wone_state(int ncones, const int64_t* off, const int* dim, const int* Rs, const int64_t* voff, double* vecs,
                    const int* kidx, const int64_t* moff, const double* point, double* grad, double* H, uint8_t* feas) {
     emu::launch(dim3(ncones), dim3(256), 0,

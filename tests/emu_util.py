@@ -316,6 +316,12 @@ class EmuGpowGroup:
         self.K = len(specs)
         self.hpm = specs[0].ctype == 12          # HypoPowerMean, else GeneralizedPower
         self.ens = specs[0].ctype == 14          # EpiNormSpectral: d1 per cone, workspace instead of powers
+        self.sps = specs[0].ctype == 22          # PosSemidefTriSparse: packed pattern + workspace
+        if self.sps:
+            regions = [np.concatenate((np.asarray(s.alpha, dtype=np.float64), np.zeros(5 * int(s.alpha[0]) ** 2)))
+                       for s in specs]
+            self.voff = np.concatenate(([0], np.cumsum([r.size for r in regions])))[:-1].astype(np.int64)
+            self.vecs = np.concatenate(regions)
         self.wone = specs[0].ctype == 21         # WSOSInterpEpiNormOne: R - 1 pair factorisations per P_k
         self.weuc = specs[0].ctype == 20         # WSOSInterpEpiNormEucl: like 19 with dim = U R and two more scratch blocks
         self.wpsd = specs[0].ctype == 19         # WSOSInterpPosSemidefTri: R per cone, packed Ps + workspace
@@ -393,7 +399,10 @@ class EmuGpowGroup:
         self.dual_feas = np.ones(self.K, dtype=np.uint8)
         self.grad = np.zeros(self.q)
         self.H = np.zeros(self.lay.total)
-        if self.wone:
+        if self.sps:
+            lib().emu_sps_state(self.K, p(self.off), p(self.dims), p(self.voff), p(self.vecs), p(self.kidx),
+                                p(self.lay.moff), p(self.point), p(self.grad), p(self.H), p(self.feas))
+        elif self.wone:
             lib().emu_wone_state(self.K, p(self.off), p(self.dims), p(self.Rs), p(self.voff), p(self.vecs), p(self.kidx),
                                  p(self.lay.moff), p(self.point), p(self.grad), p(self.H), p(self.feas))
         elif self.weuc:
@@ -445,7 +454,7 @@ class EmuGpowGroup:
         elif hess_dual > -2 and self.dnn:
             L.emu_dnn_prod(self.K, hess_dual, p(self.off), p(self.dims), p(self.sides), p(self.voff), p(self.vecs),
                            p(self.dualf), p(self.point), p(a), i64(self.q), p(out), i64(self.q), i64(a.shape[1]), i64(0))
-        elif hess_dual > -2 and (self.wsos or self.lmi or self.wpsd or self.weuc or self.wone):
+        elif hess_dual > -2 and (self.wsos or self.lmi or self.wpsd or self.weuc or self.wone or self.sps):
             L.emu_gen_hess_prod(self.K, hess_dual, p(self.off), p(self.dims), p(self.lay.moff), p(self.dualf), p(self.H),
                                 p(a), i64(self.q), p(out), i64(self.q), i64(a.shape[1]), i64(0))
         elif hess_dual > -2 and self.ens:
@@ -467,7 +476,9 @@ class EmuGpowGroup:
     def dder3(self, direction):
         d = np.ascontiguousarray(direction, dtype=np.float64)
         out = np.zeros(self.q)
-        if self.wone:
+        if self.sps:
+            lib().emu_sps_dder3(self.K, p(self.off), p(self.dims), p(self.voff), p(self.vecs), p(d), p(out))
+        elif self.wone:
             lib().emu_wone_dder3(self.K, p(self.off), p(self.dims), p(self.Rs), p(self.voff), p(self.vecs), p(d), p(out))
         elif self.weuc:
             lib().emu_weuc_dder3(self.K, p(self.off), p(self.dims), p(self.Rs), p(self.voff), p(self.vecs), p(d), p(out))

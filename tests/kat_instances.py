@@ -952,6 +952,26 @@ MEPS = [_named(lambda a=_a, b=_b, ud=_ud: _matrixepipersquare1(a, b, ud), f"matr
      for _f in (_matrixepipersquare2, _matrixepipersquare3) for _ud in (False, True)]
 
 
+def possemideftrisparse1():  # :543-563
+    return _m([0, -1, 0], [[1, 0, 0], [0, 0, 1]], [0.5, 1], -np.eye(3), np.zeros(3),
+              [M.PosSemidefTriSparse(2, [0, 1, 1], [0, 0, 1])]), dict(status="Optimal", primal_obj=-1, x_idx={1: 1.0})
+
+
+def possemideftrisparse4():  # :631-661
+    rt2, rt3 = np.sqrt(2.0), np.sqrt(3.0)
+    G = np.zeros((10, 1))
+    G[[0, 1, 2, 5, 9], 0] = -1
+    h = np.zeros(10)
+    h[[3, 4, 6, 7, 8]] = rt2 * np.array([1, 1, 1, -1, 1.0])
+    rows = np.array([1, 2, 3, 4, 4, 4, 5, 5, 5, 5]) - 1
+    cols = np.array([1, 2, 3, 1, 2, 4, 1, 2, 3, 5]) - 1
+    return _m([1], None, None, G, h, [M.PosSemidefTriSparse(5, rows, cols)]), \
+        dict(status="Optimal", primal_obj=rt3, s=[rt3, rt3, rt3, rt2, rt2, rt3, rt2, -rt2, rt2, rt3])
+
+
+PSDSPARSE = [possemideftrisparse1, possemideftrisparse4]
+
+
 def doublynonnegativetri1():  # :493-511 (the reference's loop overrides use_dual to false)
     return _m([0, 1, 0], [[1, 0, 0], [0, 0, 1]], [1, 1], -np.eye(3), np.zeros(3), [M.DoublyNonnegativeTri(3)]), \
         dict(status="Optimal", primal_obj=0, x=[1, 0, 1], s=[1, 0, 1])
@@ -1001,7 +1021,7 @@ def linmatrixineq3():  # :747-788 (dense case): min w_1 : w_1 I - diag(1, -1) ps
 
 LMI = [_named(lambda s=_s: _linmatrixineq1(s), f"linmatrixineq1_side{_s}") for _s in (2, 4)] + \
     [_named(lambda d=_d: _linmatrixineq2(d), f"linmatrixineq2_dim{_d}") for _d in (2, 3)] + [linmatrixineq3]
-EXTRA = EXTRA + LMI + DNN + MEPS + WSOSPSD + WSOSEUCL + WSOSONE
+EXTRA = EXTRA + LMI + DNN + MEPS + WSOSPSD + WSOSEUCL + WSOSONE + PSDSPARSE
 
 RELENT = [_named(lambda d=_d: _epirelentropy1(d), f"epirelentropy1_d{_d}") for _d in (1, 2, 3)] + \
     [_named(lambda d=_d: _epirelentropy2(d), f"epirelentropy2_d{_d}") for _d in (1, 2, 4)] + \

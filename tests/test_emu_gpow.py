@@ -48,6 +48,15 @@ def _wone(R, n, halfdeg, use_dual=False):
     return M.WSOSInterpEpiNormOne(R, U, Ps, use_dual=use_dual)
 
 
+def _sps(rng, side, use_dual=False):
+    mask = np.tril(rng.random((side, side)) < 1 / np.sqrt(side)) | np.eye(side, dtype=bool)
+    rows, cols = np.nonzero(mask)
+    if rows.size > 128:            # keep within the batched path: drop off-diagonal entries
+        keep = np.concatenate((np.nonzero(rows == cols)[0], np.nonzero(rows != cols)[0][:128 - side]))
+        rows, cols = rows[np.sort(keep)], cols[np.sort(keep)]
+    return M.PosSemidefTriSparse(side, rows, cols, use_dual=use_dual)
+
+
 def _lmi(rng, side, dim, use_dual=False):
     As = []
     for i in range(dim):
@@ -69,6 +78,7 @@ def _sets():
                      _weuc(3, 1, 3, use_dual=True), _weuc(8, 2, 2)],
         "wsosone": [_wone(2, 1, 1), _wone(2, 1, 2), _wone(3, 1, 2), _wone(3, 2, 1), _wone(4, 2, 1), _wone(2, 2, 2),
                     _wone(3, 1, 3, use_dual=True), _wone(8, 2, 2)],
+        "psdsparse": [_sps(rng, sd) for sd in (1, 2, 5, 10, 25, 40)] + [_sps(rng, 6, use_dual=True)],
         "lmi": [_lmi(rng, 2, 2), _lmi(rng, 3, 2), _lmi(rng, 4, 3), _lmi(rng, 3, 6), _lmi(rng, 12, 40),
                 _lmi(rng, 5, 4, use_dual=True), _lmi(rng, 33, 20)],
         "wsos": [_wsos(1, 1), _wsos(1, 3), _wsos(2, 2), _wsos(3, 1), _wsos(2, 4), _wsos(1, 2, use_dual=True),
@@ -85,7 +95,7 @@ def _sets():
     }
 
 
-NAMES = ["gpow", "gpow_dual", "hpm", "hpm_dual", "normspec", "normspec_dual", "wsos", "lmi", "dnn", "meps", "wsospsd", "wsoseucl", "wsosone"]
+NAMES = ["gpow", "gpow_dual", "hpm", "hpm_dual", "normspec", "normspec_dual", "wsos", "lmi", "dnn", "meps", "wsospsd", "wsoseucl", "wsosone", "psdsparse"]
 
 
 @pytest.mark.parametrize("name", NAMES)

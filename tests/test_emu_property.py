@@ -98,6 +98,11 @@ def _genfact_cone(kind, a, b, dual, rng):
         d1 = 1 + a % 5
         d2 = d1 + b % 7
         return M.EpiNormSpectral(d1, d2, use_dual=dual)
+    if kind == "psdsparse":
+        side = 1 + a % 20
+        mask = np.tril(rng.random((side, side)) < 1 / np.sqrt(side)) | np.eye(side, dtype=bool)
+        rows, cols = np.nonzero(mask)
+        return M.PosSemidefTriSparse(side, rows, cols, use_dual=dual)
     if kind == "wsosone":
         from wsos_util import interpolate_box
         Rr = 2 + a % 4
@@ -136,7 +141,7 @@ def _genfact_cone(kind, a, b, dual, rng):
     return M.WSOSInterpNonnegative(U, Ps, use_dual=dual)
 
 
-GENFACT_KINDS = ["gpow", "hpm", "normspec", "dnn", "lmi", "wsos", "meps", "wsospsd", "wsoseucl", "wsosone"]
+GENFACT_KINDS = ["gpow", "hpm", "normspec", "dnn", "lmi", "wsos", "meps", "wsospsd", "wsoseucl", "wsosone", "psdsparse"]
 
 
 @settings(max_examples=30, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.too_slow])

@@ -523,6 +523,21 @@ def test_wsosinterpepinormone_barrier():
     assert close(-2 * cone.dder3(direction), fd_third, 1e-5)
 
 
+def rand_sppsd_pattern(rng, side):
+    """rand_sppsd_pattern of test/cone.jl: a random sparse lower-triangular pattern that contains the diagonal."""
+    mask = np.tril(rng.random((side, side)) < 1 / np.sqrt(side)) | np.eye(side, dtype=bool)
+    rows, cols = np.nonzero(mask)
+    return rows, cols
+
+
+@pytest.mark.parametrize("side", [1, 2, 10, 25, 40])
+def test_possemideftrisparse(side):
+    # reference: test/cone.jl:377-381
+    from oracle.cones_vec3 import PosSemidefTriSparse
+    rows, cols = rand_sppsd_pattern(np.random.default_rng(side), side)
+    run_oracles(PosSemidefTriSparse(side, rows, cols))
+
+
 def rand_lmi(rng, side, dim):
     """rand_herms of test/cone.jl (real case): symmetric matrices with a positive definite first one."""
     As = []
