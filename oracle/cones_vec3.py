@@ -1715,3 +1715,183 @@ class HypoPowerMean(Cone):
         d3[0] = -c1 / zeta
         d3[1:] = (alpha * (c7 + rwi * (c8 + zip_ * rwi)) + rwi ** 2) / w
         return d3
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# EpiTrRelEntropyTri: oracle restatement only (no device kernels yet)
+# ---------------------------------------------------------------------------------------------------------------------
+def _log_divdiff(nodes):
+    """Divided difference log[x_0, .., x_k] with confluent nodes handled by the derivative limit: sort the nodes; a run of
+    equal nodes gives log^(k)(x) / k!, otherwise the usual recursion (the Δ2 / Δ3 / Δ4 matrices of
+    epitrrelentropytri.jl:385-573 are these numbers for k = 1, 2, 3)."""
+    xs = sorted(float(x) for x in nodes)
+
+    def dd(i, j):
+        k = j - i
+        if k == 0:
+            return np.log(xs[i])
+        if abs(xs[j] - xs[i]) <= 1e-9 * max(abs(xs[i]), abs(xs[j])):
+            x = 0.5 * (xs[i] + xs[j])
+            # log^(k)(x) / k! = (-1)^(k-1) / (k x^k)
+            return (-1.0) ** (k - 1) / (k * x ** k)
+        return (dd(i + 1, j) - dd(i, j - 1)) / (xs[j] - xs[i])
+    return dd(0, len(xs) - 1)
+
+
+class _LogFrechet:
+    """Frechet derivatives of the matrix logarithm at X = Q diag(lam) Q' (Daleckii-Krein)."""
+
+    def __init__(self, X):
+        self.lam, self.Q = np.linalg.eigh(X)
+        d = self.lam.size
+        lam = self.lam
+        self.D1 = np.array([[_log_divdiff((lam[i], lam[j])) for j in range(d)] for i in range(d)])
+        self.D2 = np.array([[[_log_divdiff((lam[i], lam[j], lam[k])) for k in range(d)] for j in range(d)]
+                            for i in range(d)])
+        self._D3 = None
+        self.log = (self.Q * np.log(lam)) @ self.Q.T
+
+    @property
+    def D3(self):
+        if self._D3 is None:
+            lam, d = self.lam, self.lam.size
+            self._D3 = np.array([[[[_log_divdiff((lam[i], lam[j], lam[k], lam[l])) for l in range(d)] for k in range(d)]
+                                  for j in range(d)] for i in range(d)])
+        return self._D3
+
+    def _in(self, H):
+        return self.Q.T @ H @ self.Q
+
+    def _out(self, Ht):
+        return self.Q @ Ht @ self.Q.T
+
+    def d1(self, H):
+        return self._out(self.D1 * self._in(H))
+
+    def d2(self, H, K):
+        """D^2 log(X)[H, K] (symmetric bilinear)."""
+        Ht, Kt = self._in(H), self._in(K)
+        out = np.einsum("ikj,ik,kj->ij", self.D2, Ht, Kt) + np.einsum("ikj,ik,kj->ij", self.D2, Kt, Ht)
+        return self._out(out)
+
+    def d3(self, A, B, C):
+        """D^3 log(X)[A, B, C] (symmetric trilinear): sum over the six orderings of D3[i,k,l,j] a_ik b_kl c_lj."""
+        import itertools
+        mats = [self._in(A), self._in(B), self._in(C)]
+        out = np.zeros_like(mats[0])
+        for p in itertools.permutations(range(3)):
+            out += np.einsum("iklj,ik,kl,lj->ij", self.D3, mats[p[0]], mats[p[1]], mats[p[2]])
+        return self._out(out)
+
+
+class EpiTrRelEntropyTri(Cone):
+    """epitrrelentropytri.jl:8-573: (u, svec(V), svec(W)) with V, W positive definite d x d and
+    u >= tr(W log W - W log V); barrier -log(u - tr(W log W - W log V)) - logdet V - logdet W, nu = 2 d + 1.
+    Restated through the Frechet derivatives of the matrix logarithm (Daleckii-Krein with confluent divided differences):
+    with z = u - phi, phi = tr(W log W) - tr(W log V),
+        phi_W = log W + I - log V,         phi_V = -Dlog(V)[W],
+        phi_WW[H] = Dlog(W)[H],            phi_WV[K] = -Dlog(V)[K],     phi_VV[K] = -D2log(V)[W, K],
+    and the third derivatives D2log(W)[.,.], D2log(V)[.,.], D3log(V)[W,.,.]; the barrier derivatives follow from
+    F = -log z - logdet V - logdet W.  inv_hess_prod! is the generic factorisation fallback.  Oracle only: the device
+    kernels of this cone (two batched Jacobi decompositions + a post kernel, like EpiPerSepSpectral) are not built yet."""
+
+    def __init__(self, dim, use_dual=False):
+        assert dim > 2 and dim % 2 == 1
+        self.vw = (dim - 1) // 2
+        self.d = M.svec_side(self.vw)
+        self.use_dual_barrier = use_dual
+        super().__init__(dim)
+
+    @property
+    def nu(self):
+        return float(2 * self.d + 1)
+
+    def set_initial_point(self, arr):
+        # epitrrelentropytri.jl:121-135: diagonal V, W from the vector cone's central ray
+        arr[:] = 0.0
+        u, v, w = EpiRelEntropy.central_ray(self.d)
+        arr[0] = u
+        dg = np.array([j * (j + 1) // 2 + j for j in range(self.d)])
+        arr[1 + dg] = v
+        arr[1 + self.vw + dg] = w
+        return arr
+
+    def _split(self, vec):
+        from . import arrayutil as au
+        return vec[0], au.svec_to_smat(vec[1:1 + self.vw]), au.svec_to_smat(vec[1 + self.vw:])
+
+    def _join(self, u, Vm, Wm):
+        from . import arrayutil as au
+        return np.concatenate(([u], au.smat_to_svec((Vm + Vm.T) / 2), au.smat_to_svec((Wm + Wm.T) / 2)))
+
+    def update_feas(self):
+        # epitrrelentropytri.jl:137-166
+        u, V, W = self._split(self.point)
+        for X in (V, W):
+            try:
+                np.linalg.cholesky(X)
+            except np.linalg.LinAlgError:
+                return False
+        self.V, self.W = V, W
+        self.LV, self.LW = _LogFrechet(V), _LogFrechet(W)
+        if self.LV.lam.min() <= 0 or self.LW.lam.min() <= 0:
+            return False
+        self.z = float(u - np.sum(W * (self.LW.log - self.LV.log)))
+        return self.z > 0
+
+    def _dz(self):
+        """Gradient of z = u - phi as (1, dz/dV, dz/dW) (matrices)."""
+        d = self.d
+        return 1.0, self.LV.d1(self.W), -(self.LW.log + np.eye(d) - self.LV.log)
+
+    def update_grad(self):
+        # epitrrelentropytri.jl:168-208
+        self.Vi, self.Wi = np.linalg.inv(self.V), np.linalg.inv(self.W)
+        zu, zV, zW = self._dz()
+        self._grad[:] = self._join(-zu / self.z, -zV / self.z - self.Vi, -zW / self.z - self.Wi)
+
+    def _d2z(self, dV, dW):
+        """Hessian of z applied to the direction (0, dV, dW): returns (matrix for V, matrix for W)."""
+        hV = self.LV.d2(self.W, dV) + self.LV.d1(dW)
+        hW = self.LV.d1(dV) - self.LW.d1(dW)
+        return hV, hW
+
+    def hess_prod(self, arr):
+        # epitrrelentropytri.jl:210-267 (update_hess; hess_prod! is the generic explicit product there)
+        self.grad()
+        a, vec = _as2d(arr)
+        z = self.z
+        zu, zV, zW = self._dz()
+        prod = np.empty_like(a)
+        for j in range(a.shape[1]):
+            du, dV, dW = self._split(a[:, j])
+            dz = zu * du + float(np.sum(zV * dV)) + float(np.sum(zW * dW))
+            hV, hW = self._d2z(dV, dW)
+            prod[:, j] = self._join(dz * zu / z ** 2,
+                                    dz * zV / z ** 2 - hV / z + self.Vi @ dV @ self.Vi,
+                                    dz * zW / z ** 2 - hW / z + self.Wi @ dW @ self.Wi)
+        return _ret(prod, vec)
+
+    def update_hess(self):
+        H = self.hess_prod(np.eye(self.dim))
+        return (H + H.T) / 2
+
+    def dder3(self, direction):
+        # epitrrelentropytri.jl:269-383: -1/2 of the third directional derivative of the barrier
+        self.grad()
+        z = self.z
+        zu, zV, zW = self._dz()
+        du, dV, dW = self._split(direction)
+        dz = zu * du + float(np.sum(zV * dV)) + float(np.sum(zW * dW))
+        hV, hW = self._d2z(dV, dW)
+        dHd = float(np.sum(hV * dV)) + float(np.sum(hW * dW))
+        # third derivative of z along (dV, dW) twice
+        tV = self.LV.d3(self.W, dV, dV) + 2 * self.LV.d2(dW, dV)
+        tW = self.LV.d2(dV, dV) - self.LW.d2(dW, dW)
+        c1 = -2 * dz ** 2 / z ** 3
+        c2 = 2 * dz / z ** 2
+        c3 = dHd / z ** 2
+        t3u = c1 * zu + c3 * zu
+        t3V = c1 * zV + c2 * hV + c3 * zV - tV / z - 2 * self.Vi @ dV @ self.Vi @ dV @ self.Vi
+        t3W = c1 * zW + c2 * hW + c3 * zW - tW / z - 2 * self.Wi @ dW @ self.Wi @ dW @ self.Wi
+        return -0.5 * self._join(t3u, t3V, t3W)

@@ -538,6 +538,55 @@ def test_possemideftrisparse(side):
     run_oracles(PosSemidefTriSparse(side, rows, cols))
 
 
+@pytest.mark.parametrize("dW,init_only", [(1, False), (2, False), (4, False), (6, True), (10, True)])
+def test_epitrrelentropytri(dW, init_only):
+    # reference: test/cone.jl:731-739 (init_tol 1e-4 / 1e-1).  Oracle restatement only: no device kernels for this cone yet
+    from oracle.cones_vec3 import EpiTrRelEntropyTri
+    run_oracles(EpiTrRelEntropyTri(1 + 2 * (dW * (dW + 1) // 2)), init_tol=1e-1 if init_only else 1e-4,
+                init_only=init_only)
+
+
+def test_epitrrelentropytri_barrier():
+    """grad, hess_prod and dder3 against central differences of
+    -log(u - tr(W log W - W log V)) - logdet V - logdet W (test/cone.jl:741-752)."""
+    from oracle import arrayutil as au
+    from oracle.cones_vec3 import EpiTrRelEntropyTri
+    cone = EpiTrRelEntropyTri(1 + 2 * 6)
+
+    def mlog(X):
+        lam, Q = np.linalg.eigh(X)
+        return (Q * np.log(lam)) @ Q.T, lam
+
+    def barrier(s):
+        V, W = au.svec_to_smat(s[1:7]), au.svec_to_smat(s[7:13])
+        (lV, lamV), (lW, lamW) = mlog(V), mlog(W)
+        return -np.log(s[0] - np.sum(W * (lW - lV))) - np.sum(np.log(lamV)) - np.sum(np.log(lamW))
+
+    rng = np.random.default_rng(1)
+    point = np.zeros(cone.dim)
+    cone.set_initial_point(point)
+    perturb_scale(rng, point, 0.1, 1.0)
+
+    def grad_at(s):
+        cone.reset_data()
+        cone.load_point(s)
+        assert cone.is_feas()
+        return cone.grad().copy()
+
+    g = grad_at(point)
+    eps = 1e-6
+    fd_grad = np.array([(barrier(point + eps * e) - barrier(point - eps * e)) / (2 * eps) for e in np.eye(cone.dim)])
+    assert close(g, fd_grad, 1e-7)
+    direction = 0.3 * rng.standard_normal(cone.dim)
+    fd_hess_dir = (grad_at(point + eps * direction) - grad_at(point - eps * direction)) / (2 * eps)
+    grad_at(point)
+    assert close(cone.hess_prod(direction), fd_hess_dir, 1e-6)
+    e2 = 1e-4
+    fd_third = (grad_at(point + e2 * direction) - 2 * g + grad_at(point - e2 * direction)) / e2 ** 2
+    grad_at(point)
+    assert close(-2 * cone.dder3(direction), fd_third, 1e-5)
+
+
 def rand_lmi(rng, side, dim):
     """rand_herms of test/cone.jl (real case): symmetric matrices with a positive definite first one."""
     As = []
