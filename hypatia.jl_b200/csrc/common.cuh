@@ -19,7 +19,7 @@
 
 #include "../../include/hypatia_b200.h"
 
-#define HYP_NUM_CONE_TYPES 23
+#define HYP_NUM_CONE_TYPES 24
 // internal product mode: inv_hess for primal-barrier cones, hess for dual-barrier cones
 #define HYP_PROD_BLOCK_INV 5
 #define HYP_EPS 2.220446049250313e-16
@@ -63,7 +63,7 @@ static inline bool cone_allows_dual(int t) {
            t == HYP_CONE_WSOSINTERPNONNEGATIVE || t == HYP_CONE_LINMATRIXINEQ || t == HYP_CONE_DOUBLYNONNEGATIVETRI ||
            t == HYP_CONE_MATRIXEPIPERSQUARE || t == HYP_CONE_WSOSINTERPPOSSEMIDEFTRI ||
            t == HYP_CONE_WSOSINTERPEPINORMEUCL || t == HYP_CONE_WSOSINTERPEPINORMONE ||
-           t == HYP_CONE_POSSEMIDEFTRISPARSE;
+           t == HYP_CONE_POSSEMIDEFTRISPARSE || t == HYP_CONE_EPITRRELENTROPYTRI;
 }
 // cones whose inverse-Hessian oracles are the generic Hessian-factorisation fallback (cones_gpow.cu)
 static inline bool cone_is_genfact(int t) {
@@ -71,7 +71,7 @@ static inline bool cone_is_genfact(int t) {
            t == HYP_CONE_WSOSINTERPNONNEGATIVE || t == HYP_CONE_LINMATRIXINEQ || t == HYP_CONE_DOUBLYNONNEGATIVETRI ||
            t == HYP_CONE_MATRIXEPIPERSQUARE || t == HYP_CONE_WSOSINTERPPOSSEMIDEFTRI ||
            t == HYP_CONE_WSOSINTERPEPINORMEUCL || t == HYP_CONE_WSOSINTERPEPINORMONE ||
-           t == HYP_CONE_POSSEMIDEFTRISPARSE;
+           t == HYP_CONE_POSSEMIDEFTRISPARSE || t == HYP_CONE_EPITRRELENTROPYTRI;
 }
 // vector cones served by cones_vec3_kernels.cuh
 static inline bool cone_is_vec3(int t) {

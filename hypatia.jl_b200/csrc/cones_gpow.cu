@@ -259,7 +259,40 @@ static void sps_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
     hyp_mat_alloc_group(ctx, g);
 }
 
+// EpiTrRelEntropyTri: d_vecs / d_voff = per-cone state (eigen-decompositions, matrix logs, inverses, divided differences
+// of log up to third order) followed by the scratch of etr_dder3_kernel
+static void etr_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
+    g.h_voff.assign(g.count, 0);
+    int64_t tot = 0;
+    for (int i = 0; i < g.count; i++) {
+        const int dm = g.h_dim[i];
+        if (dm > 128) throw HypError{"EpiTrRelEntropyTri: dim above 128 is not supported (batched Cholesky limit)"};
+        const int vw = (dm - 1) / 2;
+        int64_t d = 1;
+        while (d * (d + 1) / 2 < vw) d++;
+        if (dm < 3 || dm % 2 == 0 || d * (d + 1) / 2 != vw)
+            throw HypError{"EpiTrRelEntropyTri: need dim = 1 + 2 * svec_length(d)"};
+        const int64_t n = d * d;
+        g.h_hkind.push_back((int)d);
+        g.h_side[i] = dm;
+        g.h_voff[i] = tot;
+        tot += 23 * n + 2 * d + 2 * d * n + n * n;
+    }
+    g.max_side = g.max_dim;
+    cudaFree(g.d_side);
+    g.d_side = upload_vec(g.h_side);
+    g.d_hkind = upload_vec(g.h_hkind);
+    g.d_voff = upload_vec(g.h_voff);
+    CUDA_TRY(cudaMalloc(&g.d_vecs, (size_t)std::max<int64_t>(tot, 1) * sizeof(double)));
+    CUDA_TRY(cudaMemset(g.d_vecs, 0, (size_t)std::max<int64_t>(tot, 1) * sizeof(double)));
+    hyp_mat_alloc_group(ctx, g);
+}
+
 void hyp_gpow_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
+    if (g.type == HYP_CONE_EPITRRELENTROPYTRI) {
+        etr_alloc_group(ctx, g);
+        return;
+    }
     if (g.type == HYP_CONE_POSSEMIDEFTRISPARSE) {
         sps_alloc_group(ctx, g);
         return;
@@ -325,7 +358,11 @@ void hyp_gpow_alloc_group(hyp_ctx* ctx, ConeGroup& g) {
 }
 
 void hyp_gpow_update_state(hyp_ctx* ctx, ConeGroup& g) {
-    if (g.type == HYP_CONE_POSSEMIDEFTRISPARSE)
+    if (g.type == HYP_CONE_EPITRRELENTROPYTRI)
+        hypdev::etr_state_kernel<<<ceil_div(g.count, 4), 128, 0, ctx->stream>>>(
+            g.count, g.d_off, g.d_dim, g.d_voff, g.d_vecs, g.d_kidx, g.d_moff, ctx->d_point, ctx->d_grad, g.d_scal, g.d_W,
+            ctx->d_feas);
+    else if (g.type == HYP_CONE_POSSEMIDEFTRISPARSE)
         hypdev::sps_state_kernel<<<g.count, 256, 0, ctx->stream>>>(g.count, g.d_off, g.d_dim, g.d_voff, g.d_vecs, g.d_kidx,
                                                                   g.d_moff, ctx->d_point, ctx->d_grad, g.d_W, ctx->d_feas);
     else if (g.type == HYP_CONE_WSOSINTERPEPINORMONE)
@@ -387,7 +424,12 @@ void hyp_gpow_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr, 
     else if (mode == HYP_PROD_BLOCK_INV) { hess_dual = 1; inv_dual = 0; }
     else throw HypError{"hyp_gpow_prod: bad mode"};
     if (hess_dual > -2) {
-        if (g.type == HYP_CONE_MATRIXEPIPERSQUARE)
+        if (g.type == HYP_CONE_EPITRRELENTROPYTRI) {
+            dim3 grid4(ceil_div(g.count, 4), (unsigned)std::min<int64_t>(ncols, 65535));
+            hypdev::etr_prod_kernel<<<grid4, 128, 0, ctx->stream>>>(g.count, hess_dual, g.d_off, g.d_dim, g.d_voff, g.d_vecs,
+                                                                   g.d_dual, g.d_scal, arr, ld_arr, prod, ld_prod, ncols,
+                                                                   row_shift);
+        } else if (g.type == HYP_CONE_MATRIXEPIPERSQUARE)
             hypdev::mep_prod_kernel<<<grid, 256, 0, ctx->stream>>>(g.count, hess_dual, g.d_off, g.d_dim, g.d_hkind,
                                                                   g.d_voff, g.d_vecs, g.d_dual, g.d_scal, ctx->d_point,
                                                                   arr, ld_arr, prod, ld_prod, ncols, row_shift);
@@ -426,7 +468,10 @@ void hyp_gpow_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr, 
 }
 
 void hyp_gpow_dder3(hyp_ctx* ctx, ConeGroup& g, double* out, const double* dir) {
-    if (g.type == HYP_CONE_POSSEMIDEFTRISPARSE)
+    if (g.type == HYP_CONE_EPITRRELENTROPYTRI)
+        hypdev::etr_dder3_kernel<<<ceil_div(g.count, 4), 128, 0, ctx->stream>>>(
+            g.count, g.d_off, g.d_dim, g.d_voff, g.d_vecs, g.d_scal, dir, out);
+    else if (g.type == HYP_CONE_POSSEMIDEFTRISPARSE)
         hypdev::sps_dder3_kernel<<<g.count, 256, 0, ctx->stream>>>(g.count, g.d_off, g.d_dim, g.d_voff, g.d_vecs, dir, out);
     else if (g.type == HYP_CONE_WSOSINTERPEPINORMONE)
         hypdev::wone_dder3_kernel<<<g.count, 256, 0, ctx->stream>>>(g.count, g.d_off, g.d_dim, g.d_hkind, g.d_voff, g.d_vecs,

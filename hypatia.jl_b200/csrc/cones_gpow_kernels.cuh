@@ -2279,4 +2279,410 @@ sps_dder3_kernel(int ncones, const int64_t* __restrict__ off, const int* __restr
 }
 
 
+// ---- EpiTrRelEntropyTri (dim = 1 + 2 svec_length(d) <= 128, so d <= 10), epitrrelentropytri.jl:137-573 ----
+// point = (u, svec(V), svec(W)); z = u - tr(W log W - W log V).  Restated through the Frechet derivatives of the matrix
+// logarithm at V = Qv diag(lv) Qv' and W = Qw diag(lw) Qw' (Daleckii-Krein; D1 / D2 / D3 = first / second / third divided
+// differences of log with confluent nodes, the "Delta" arrays of the reference).  Per-cone state at vecs + voff[c]:
+// Qv, Qw, logV, logW, Vi, Wi, D1v, D1w, zV, zW (10 d^2), lv, lw (2 d), D2v, D2w (2 d^3), D3v (d^4), then 12 d^2 of scratch
+// for dder3.  scal: 0 z.  One warp per cone / per (cone, column); eigen-decompositions by cyclic Jacobi inside the warp.
+
+// log[x_0 .. x_k], k <= 3, with confluent nodes: sort, then the divided-difference table where a run of (nearly) equal
+// nodes takes the derivative limit log^(m)(x) / m! = (-1)^(m-1) / (m x^m)
+__device__ __forceinline__ double etr_logdd(double x0, double x1, double x2, double x3, int k) {
+    double xs[4] = {x0, x1, x2, x3};
+    for (int i = 1; i <= k; i++)
+        for (int j = i; j > 0 && xs[j] < xs[j - 1]; j--) {
+            const double t = xs[j];
+            xs[j] = xs[j - 1];
+            xs[j - 1] = t;
+        }
+    double tb[4];
+    for (int i = 0; i <= k; i++) tb[i] = log(xs[i]);
+    for (int m = 1; m <= k; m++)
+        for (int i = 0; i + m <= k; i++) {
+            const double a = xs[i], b = xs[i + m];
+            if (fabs(b - a) <= 1e-9 * fmax(fabs(a), fabs(b))) {
+                const double x = 0.5 * (a + b);
+                double pw = x;
+                for (int e = 1; e < m; e++) pw *= x;
+                tb[i] = ((m & 1) ? 1.0 : -1.0) / (m * pw);
+            } else {
+                tb[i] = (tb[i + 1] - tb[i]) / (b - a);
+            }
+        }
+    return tb[0];
+}
+
+// eigen-decomposition of the symmetric d x d matrix A (destroyed) by cyclic Jacobi, one warp: Q (columns), lam
+__device__ __forceinline__ void etr_jacobi(double* A, double* Q, double* lam, int d, int lane) {
+    for (int i = lane; i < d * d; i += 32) Q[i] = (i % d == i / d) ? 1.0 : 0.0;
+    __syncwarp();
+    for (int sweep = 0; sweep < 40; sweep++) {
+        double offn = 0.0, dn = 0.0;
+        for (int i = lane; i < d * d; i += 32) {
+            const double x = A[i] * A[i];
+            if (i % d == i / d) dn += x;
+            else offn += x;
+        }
+        offn = warp_sum(offn);
+        dn = warp_sum(dn);
+        if (offn <= 1e-30 * dn || offn == 0.0) break;
+        for (int p = 0; p < d - 1; p++)
+            for (int q = p + 1; q < d; q++) {
+                const double apq = A[p + q * d];
+                if (apq == 0.0) continue;
+                const double app = A[p + p * d], aqq = A[q + q * d];
+                const double th = (aqq - app) / (2.0 * apq);
+                const double t = copysign(1.0, th) / (fabs(th) + sqrt(1.0 + th * th));
+                const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+                __syncwarp();
+                for (int k = lane; k < d; k += 32) {         // columns p, q of A and Q
+                    const double akp = A[k + p * d], akq = A[k + q * d];
+                    A[k + p * d] = cs * akp - sn * akq;
+                    A[k + q * d] = sn * akp + cs * akq;
+                    const double qkp = Q[k + p * d], qkq = Q[k + q * d];
+                    Q[k + p * d] = cs * qkp - sn * qkq;
+                    Q[k + q * d] = sn * qkp + cs * qkq;
+                }
+                __syncwarp();
+                for (int k = lane; k < d; k += 32) {         // rows p, q of A
+                    const double apk = A[p + k * d], aqk = A[q + k * d];
+                    A[p + k * d] = cs * apk - sn * aqk;
+                    A[q + k * d] = sn * apk + cs * aqk;
+                }
+                __syncwarp();
+            }
+    }
+    for (int i = lane; i < d; i += 32) lam[i] = A[i + i * d];
+    __syncwarp();
+}
+
+// O = Q diag(f) Q'
+__device__ __forceinline__ void etr_spectral(double* O, const double* Q, const double* f, int d, int lane) {
+    for (int idx = lane; idx < d * d; idx += 32) {
+        const int i = idx % d, j = idx / d;
+        double s = 0.0;
+        for (int k = 0; k < d; k++) s += Q[i + k * d] * f[k] * Q[j + k * d];
+        O[idx] = s;
+    }
+    __syncwarp();
+}
+// O = Q' H Q (t1: scratch)
+__device__ __forceinline__ void etr_in(double* O, const double* Q, const double* H, double* t1, int d, int lane) {
+    mep_mm(t1, Q, H, d, d, d, true, false, 1.0, 0.0, lane);
+    mep_mm(O, t1, Q, d, d, d, false, false, 1.0, 0.0, lane);
+}
+// O = Q T Q'
+__device__ __forceinline__ void etr_out(double* O, const double* Q, const double* T, double* t1, int d, int lane) {
+    mep_mm(t1, Q, T, d, d, d, false, false, 1.0, 0.0, lane);
+    mep_mm(O, t1, Q, d, d, d, false, true, 1.0, 0.0, lane);
+}
+// O = Dlog(X)[H]; t1, t2 scratch
+__device__ __forceinline__ void etr_d1(double* O, const double* Q, const double* D1, const double* H, double* t1,
+                                       double* t2, int d, int lane) {
+    etr_in(t2, Q, H, t1, d, lane);
+    for (int i = lane; i < d * d; i += 32) t2[i] *= D1[i];
+    __syncwarp();
+    etr_out(O, Q, t2, t1, d, lane);
+}
+// O = D2log(X)[H, K] from the rotated Ht = Q'HQ, Kt = Q'KQ; t1, t2 scratch
+__device__ __forceinline__ void etr_d2t(double* O, const double* Q, const double* D2, const double* Ht, const double* Kt,
+                                        double* t1, double* t2, int d, int lane) {
+    for (int idx = lane; idx < d * d; idx += 32) {
+        const int i = idx % d, j = idx / d;
+        double s = 0.0;
+        for (int k = 0; k < d; k++)
+            s += D2[i + d * (k + d * j)] * (Ht[i + k * d] * Kt[k + j * d] + Kt[i + k * d] * Ht[k + j * d]);
+        t2[idx] = s;
+    }
+    __syncwarp();
+    etr_out(O, Q, t2, t1, d, lane);
+}
+
+// hess_prod for one column (epitrrelentropytri.jl:210-267).  sc: 8 * 104 doubles of scratch private to the warp.
+__device__ __forceinline__ void etr_hess_col(const double* a, double* pr, int d, const double* st, double z, double* sc,
+                                             int lane) {
+    const int n = d * d, vw = d * (d + 1) / 2;
+    const double* Qv = st;
+    const double* Qw = st + n;
+    const double* Vi = st + 4 * n;
+    const double* Wi = st + 5 * n;
+    const double* D1v = st + 6 * n;
+    const double* D1w = st + 7 * n;
+    const double* zV = st + 8 * n;
+    const double* zW = st + 9 * n;
+    const double* D2v = st + 10 * n + 2 * d;
+    const double* Wt = st + 10 * n + 2 * d + 2 * d * n + n * n;      // Qv' W Qv, stored by the state kernel
+    double* dV = sc;
+    double* dW = sc + 104;
+    double* hV = sc + 2 * 104;
+    double* hW = sc + 3 * 104;
+    double* t1 = sc + 4 * 104;
+    double* t2 = sc + 5 * 104;
+    double* t3 = sc + 6 * 104;
+    double* t4 = sc + 7 * 104;
+    const double du = a[0];
+    dnn_smat(dV, a + 1, d, vw, lane);
+    dnn_smat(dW, a + 1 + vw, d, vw, lane);
+    __syncwarp();
+    const double dz = du + mep_dot(zV, dV, n, lane) + mep_dot(zW, dW, n, lane);
+    // hV = D2log(V)[W, dV] + Dlog(V)[dW];  hW = Dlog(V)[dV] - Dlog(W)[dW]
+    etr_in(t3, Qv, dV, t1, d, lane);
+    etr_d2t(hV, Qv, D2v, Wt, t3, t1, t2, d, lane);
+    etr_d1(t4, Qv, D1v, dW, t1, t2, d, lane);
+    mep_axpby(hV, 1.0, hV, 1.0, t4, n, lane);
+    etr_d1(hW, Qv, D1v, dV, t1, t2, d, lane);
+    etr_d1(t4, Qw, D1w, dW, t1, t2, d, lane);
+    mep_axpby(hW, 1.0, hW, -1.0, t4, n, lane);
+    // + Vi dV Vi, + Wi dW Wi
+    mep_mm(t1, Vi, dV, d, d, d, false, false, 1.0, 0.0, lane);
+    mep_mm(t3, t1, Vi, d, d, d, false, false, 1.0, 0.0, lane);
+    mep_mm(t1, Wi, dW, d, d, d, false, false, 1.0, 0.0, lane);
+    mep_mm(t4, t1, Wi, d, d, d, false, false, 1.0, 0.0, lane);
+    const double c = dz / (z * z), zi = 1.0 / z;
+    for (int p = lane; p < vw; p += 32) {
+        int i, j;
+        dnn_ij(p, i, j);
+        const int e = i + j * d, et = j + i * d;
+        const double sV = c * zV[e] - zi * 0.5 * (hV[e] + hV[et]) + 0.5 * (t3[e] + t3[et]);
+        const double sW = c * zW[e] - zi * 0.5 * (hW[e] + hW[et]) + 0.5 * (t4[e] + t4[et]);
+        const double f = i == j ? 1.0 : 1.41421356237309504880;
+        pr[1 + p] = f * sV;
+        pr[1 + vw + p] = f * sW;
+    }
+    if (lane == 0) pr[0] = c;
+    __syncwarp();
+}
+
+static __global__ void __launch_bounds__(128)
+etr_state_kernel(int ncones, const int64_t* __restrict__ off, const int* __restrict__ dim,
+                 const int64_t* __restrict__ voff, double* __restrict__ vecs, const int* __restrict__ kidx,
+                 const int64_t* __restrict__ moff, const double* __restrict__ point, double* __restrict__ grad,
+                 double* __restrict__ scal, double* __restrict__ H, uint8_t* feas) {
+    __shared__ double sh[4][8 * 104 + 128];
+    const int lane = threadIdx.x & 31;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= ncones) return;
+    double* sc = sh[threadIdx.x >> 5];
+    const int64_t o = off[c];
+    const int dm = dim[c], vw = (dm - 1) / 2, lde = (dm + 1) & ~1;
+    int d = 1;
+    while (d * (d + 1) / 2 < vw) d++;
+    const int n = d * d;
+    double* st = vecs + voff[c];
+    double* Qv = st;
+    double* Qw = st + n;
+    double* logV = st + 2 * n;
+    double* logW = st + 3 * n;
+    double* Vi = st + 4 * n;
+    double* Wi = st + 5 * n;
+    double* D1v = st + 6 * n;
+    double* D1w = st + 7 * n;
+    double* zV = st + 8 * n;
+    double* zW = st + 9 * n;
+    double* lv = st + 10 * n;
+    double* lw = lv + d;
+    double* D2v = lw + d;
+    double* D2w = D2v + d * n;
+    double* D3v = D2w + d * n;
+    double* Wt = D3v + n * n;
+    double* Vm = sc;                 // smat(V), smat(W): kept (Jacobi works on copies)
+    double* Wm = sc + 104;
+    double* t1 = sc + 2 * 104;
+    double* t2 = sc + 3 * 104;
+    double* f = sc + 4 * 104;
+    const double u = point[o];
+    dnn_smat(Vm, point + o + 1, d, vw, lane);
+    dnn_smat(Wm, point + o + 1 + vw, d, vw, lane);
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+        t1[i] = Vm[i];
+        t2[i] = Wm[i];
+    }
+    __syncwarp();
+    etr_jacobi(t1, Qv, lv, d, lane);
+    etr_jacobi(t2, Qw, lw, d, lane);
+    // update_feas (:137-166): both matrices positive definite and z > 0
+    double lmin = 1e300;
+    for (int i = 0; i < d; i++) lmin = fmin(lmin, fmin(lv[i], lw[i]));
+    const bool pd = lmin > 0.0;
+    for (int i = lane; i < d; i += 32) f[i] = pd ? log(lv[i]) : 0.0;
+    __syncwarp();
+    etr_spectral(logV, Qv, f, d, lane);
+    for (int i = lane; i < d; i += 32) f[i] = pd ? log(lw[i]) : 0.0;
+    __syncwarp();
+    etr_spectral(logW, Qw, f, d, lane);
+    for (int i = lane; i < d; i += 32) f[i] = pd ? 1.0 / lv[i] : 1.0;
+    __syncwarp();
+    etr_spectral(Vi, Qv, f, d, lane);
+    for (int i = lane; i < d; i += 32) f[i] = pd ? 1.0 / lw[i] : 1.0;
+    __syncwarp();
+    etr_spectral(Wi, Qw, f, d, lane);
+    double tr = 0.0;
+    for (int i = lane; i < n; i += 32) tr += Wm[i] * (logW[i] - logV[i]);
+    const double z = u - warp_sum(tr);
+    const bool ok = pd && z > 0.0;
+    // divided differences of log at the eigenvalues (1.0 in place of a nonpositive eigenvalue keeps the arithmetic finite)
+    for (int idx = lane; idx < n; idx += 32) {
+        const int i = idx % d, j = idx / d;
+        D1v[idx] = pd ? etr_logdd(lv[i], lv[j], 0, 0, 1) : 1.0;
+        D1w[idx] = pd ? etr_logdd(lw[i], lw[j], 0, 0, 1) : 1.0;
+    }
+    for (int idx = lane; idx < d * n; idx += 32) {
+        const int i = idx % d, k = (idx / d) % d, j = idx / n;
+        D2v[idx] = pd ? etr_logdd(lv[i], lv[k], lv[j], 0, 2) : 0.0;
+        D2w[idx] = pd ? etr_logdd(lw[i], lw[k], lw[j], 0, 2) : 0.0;
+    }
+    for (int idx = lane; idx < n * n; idx += 32) {
+        const int i = idx % d, k = (idx / d) % d, l = (idx / n) % d, j = idx / (d * n);
+        D3v[idx] = pd ? etr_logdd(lv[i], lv[k], lv[l], lv[j], 3) : 0.0;
+    }
+    __syncwarp();
+    // dz/dV = Dlog(V)[W], dz/dW = -(log W + I - log V); Wt = Qv' W Qv is kept for the second derivatives
+    etr_in(Wt, Qv, Wm, t1, d, lane);
+    for (int i = lane; i < n; i += 32) t2[i] = Wt[i] * D1v[i];
+    __syncwarp();
+    etr_out(zV, Qv, t2, t1, d, lane);
+    for (int i = lane; i < n; i += 32) zW[i] = -(logW[i] + ((i % d == i / d) ? 1.0 : 0.0) - logV[i]);
+    __syncwarp();
+    // update_grad (:168-208)
+    const double zi = 1.0 / z;
+    for (int p = lane; p < vw; p += 32) {
+        int i, j;
+        dnn_ij(p, i, j);
+        const int e = i + j * d;
+        const double fs = i == j ? 1.0 : 1.41421356237309504880;
+        grad[o + 1 + p] = fs * (-zi * zV[e] - Vi[e]);
+        grad[o + 1 + vw + p] = fs * (-zi * zW[e] - Wi[e]);
+    }
+    if (lane == 0) {
+        grad[o] = -zi;
+        scal[8 * c] = z;
+        if (!ok) feas[kidx[c]] = 0;
+    }
+    __syncwarp();
+    // explicit Hessian: hess_prod applied to the unit vectors, then symmetrised
+    double* Hc = H + moff[c];
+    double* unit = sc + 8 * 104;
+    for (int j = 0; j < dm; j++) {
+        for (int i = lane; i < dm; i += 32) unit[i] = i == j ? 1.0 : 0.0;
+        __syncwarp();
+        etr_hess_col(unit, Hc + (int64_t)j * lde, d, st, z, sc, lane);
+    }
+    for (int idx = lane; idx < dm * dm; idx += 32) {
+        const int i = idx % dm, j = idx / dm;
+        if (i < j) {
+            const double x = 0.5 * (Hc[i + (int64_t)j * lde] + Hc[j + (int64_t)i * lde]);
+            Hc[i + (int64_t)j * lde] = x;
+            Hc[j + (int64_t)i * lde] = x;
+        }
+    }
+}
+
+static __global__ void __launch_bounds__(128)
+etr_prod_kernel(int ncones, int want_dual, const int64_t* __restrict__ off, const int* __restrict__ dim,
+                const int64_t* __restrict__ voff, const double* __restrict__ vecs, const int* __restrict__ dualf,
+                const double* __restrict__ scal, const double* arr, int64_t ld_arr, double* prod, int64_t ld_prod,
+                int64_t ncols, int64_t row_shift) {
+    __shared__ double sh[4][8 * 104];
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= ncones) return;
+    if (want_dual >= 0 && (dualf[c] != 0) != (want_dual != 0)) return;
+    const int64_t o = off[c];
+    const int vw = (dim[c] - 1) / 2;
+    int d = 1;
+    while (d * (d + 1) / 2 < vw) d++;
+    for (int64_t j = blockIdx.y; j < ncols; j += gridDim.y)
+        etr_hess_col(arr + j * ld_arr + (o - row_shift), prod + j * ld_prod + (o - row_shift), d, vecs + voff[c],
+                     scal[8 * c], sh[threadIdx.x >> 5], lane);
+}
+
+// dder3 (:269-383): -1/2 of the third directional derivative of the barrier; scratch in global memory
+static __global__ void __launch_bounds__(128)
+etr_dder3_kernel(int ncones, const int64_t* __restrict__ off, const int* __restrict__ dim,
+                 const int64_t* __restrict__ voff, double* __restrict__ vecs, const double* __restrict__ scal,
+                 const double* __restrict__ dir, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= ncones) return;
+    const int64_t o = off[c];
+    const int vw = (dim[c] - 1) / 2;
+    int d = 1;
+    while (d * (d + 1) / 2 < vw) d++;
+    const int n = d * d;
+    double* st = vecs + voff[c];
+    const double* Qv = st;
+    const double* Qw = st + n;
+    const double* Vi = st + 4 * n;
+    const double* Wi = st + 5 * n;
+    const double* D1v = st + 6 * n;
+    const double* D1w = st + 7 * n;
+    const double* zV = st + 8 * n;
+    const double* zW = st + 9 * n;
+    const double* D2v = st + 10 * n + 2 * d;
+    const double* D2w = D2v + d * n;
+    const double* D3v = D2w + d * n;
+    const double* Wt = D3v + n * n;
+    double* ws = st + 10 * n + 2 * d + 2 * d * n + n * n + n;
+    double *dV = ws, *dW = ws + n, *hV = ws + 2 * n, *hW = ws + 3 * n, *t1 = ws + 4 * n, *t2 = ws + 5 * n, *dVt = ws + 6 * n,
+           *dWt = ws + 7 * n, *tV = ws + 8 * n, *tW = ws + 9 * n, *t3 = ws + 10 * n, *dWw = ws + 11 * n;
+    const double z = scal[8 * c], du = dir[o];
+    dnn_smat(dV, dir + o + 1, d, vw, lane);
+    dnn_smat(dW, dir + o + 1 + vw, d, vw, lane);
+    __syncwarp();
+    const double dz = du + mep_dot(zV, dV, n, lane) + mep_dot(zW, dW, n, lane);
+    etr_in(dVt, Qv, dV, t1, d, lane);          // Qv' dV Qv
+    etr_in(dWt, Qv, dW, t1, d, lane);          // Qv' dW Qv
+    etr_in(dWw, Qw, dW, t1, d, lane);          // Qw' dW Qw
+    // second derivative of z along the direction: hV = D2log(V)[W, dV] + Dlog(V)[dW], hW = Dlog(V)[dV] - Dlog(W)[dW]
+    etr_d2t(hV, Qv, D2v, Wt, dVt, t1, t2, d, lane);
+    etr_d1(t3, Qv, D1v, dW, t1, t2, d, lane);
+    mep_axpby(hV, 1.0, hV, 1.0, t3, n, lane);
+    etr_d1(hW, Qv, D1v, dV, t1, t2, d, lane);
+    etr_d1(t3, Qw, D1w, dW, t1, t2, d, lane);
+    mep_axpby(hW, 1.0, hW, -1.0, t3, n, lane);
+    const double dHd = mep_dot(hV, dV, n, lane) + mep_dot(hW, dW, n, lane);
+    // third derivative of z: tV = D3log(V)[W, dV, dV] + 2 D2log(V)[dW, dV], tW = D2log(V)[dV, dV] - D2log(W)[dW, dW]
+    for (int idx = lane; idx < n; idx += 32) {
+        const int i = idx % d, j = idx / d;
+        double s = 0.0;
+        for (int k = 0; k < d; k++)
+            for (int l = 0; l < d; l++) {
+                const double w = D3v[i + d * (k + d * (l + d * j))];
+                // the six orderings of (W, dV, dV): two of each distinct arrangement
+                s += 2.0 * w * (Wt[i + k * d] * dVt[k + l * d] * dVt[l + j * d] + dVt[i + k * d] * Wt[k + l * d] * dVt[l + j * d] +
+                                dVt[i + k * d] * dVt[k + l * d] * Wt[l + j * d]);
+            }
+        t2[idx] = s;
+    }
+    __syncwarp();
+    etr_out(tV, Qv, t2, t1, d, lane);
+    etr_d2t(t3, Qv, D2v, dWt, dVt, t1, t2, d, lane);
+    mep_axpby(tV, 1.0, tV, 2.0, t3, n, lane);
+    etr_d2t(tW, Qv, D2v, dVt, dVt, t1, t2, d, lane);
+    etr_d2t(t3, Qw, D2w, dWw, dWw, t1, t2, d, lane);
+    mep_axpby(tW, 1.0, tW, -1.0, t3, n, lane);
+    // -2 Vi dV Vi dV Vi and -2 Wi dW Wi dW Wi
+    mep_mm(t1, Vi, dV, d, d, d, false, false, 1.0, 0.0, lane);
+    mep_mm(t2, t1, Vi, d, d, d, false, false, 1.0, 0.0, lane);
+    mep_mm(dVt, t2, t1, d, d, d, false, true, 1.0, 0.0, lane);      // (Vi dV Vi)(Vi dV)' = Vi dV Vi dV Vi
+    mep_mm(t1, Wi, dW, d, d, d, false, false, 1.0, 0.0, lane);
+    mep_mm(t2, t1, Wi, d, d, d, false, false, 1.0, 0.0, lane);
+    mep_mm(dWt, t2, t1, d, d, d, false, true, 1.0, 0.0, lane);
+    const double c1 = -2.0 * dz * dz / (z * z * z), c2 = 2.0 * dz / (z * z), c3 = dHd / (z * z), zi = 1.0 / z;
+    for (int p = lane; p < vw; p += 32) {
+        int i, j;
+        dnn_ij(p, i, j);
+        const int e = i + j * d, et = j + i * d;
+        const double xV = (c1 + c3) * zV[e] + c2 * 0.5 * (hV[e] + hV[et]) - zi * 0.5 * (tV[e] + tV[et]) - (dVt[e] + dVt[et]);
+        const double xW = (c1 + c3) * zW[e] + c2 * 0.5 * (hW[e] + hW[et]) - zi * 0.5 * (tW[e] + tW[et]) - (dWt[e] + dWt[et]);
+        const double fs = i == j ? 1.0 : 1.41421356237309504880;
+        out[o + 1 + p] = -0.5 * fs * xV;
+        out[o + 1 + vw + p] = -0.5 * fs * xW;
+    }
+    if (lane == 0) out[o] = -0.5 * (c1 + c3);
+}
+
+
 }  // namespace hypdev

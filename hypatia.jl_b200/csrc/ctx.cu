@@ -938,6 +938,8 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
                                 : t == HYP_CONE_EPIPERSQUARE ? 2.0
                                 : (t == HYP_CONE_EPINORMSPECTRAL || t == HYP_CONE_MATRIXEPIPERSQUARE)
                                     ? (double)ctx->h_cone_hkind[k] + 1.0   // epinormspectral.jl:95, matrixepipersquare.jl:101
+                                : t == HYP_CONE_EPITRRELENTROPYTRI                                    // epitrrelentropytri.jl:119: 2 d + 1
+                                    ? 2.0 * std::floor((std::sqrt(1.0 + 4.0 * (d - 1)) - 1) / 2 + 0.5) + 1.0
                                 : t == HYP_CONE_WSOSINTERPNONNEGATIVE ? wsos_nu(ctx, k)               // wsosinterpnonnegative.jl:62
                                 : t == HYP_CONE_WSOSINTERPEPINORMEUCL ? 2.0 * wsos_nu(ctx, k)         // wsosinterpepinormeucl.jl:68
                                 : (t == HYP_CONE_WSOSINTERPPOSSEMIDEFTRI || t == HYP_CONE_WSOSINTERPEPINORMONE)   // wsosinterppossemideftri.jl:66, wsosinterpepinormone.jl:88

@@ -114,6 +114,13 @@ def cone_initial_point(spec):
         for p in range(Rr):
             b = p * (p + 1) // 2 + p
             arr[b * Uu:(b + 1) * Uu] = 1.0
+    elif spec.ctype == M.CONE_EPITRRELENTROPYTRI:
+        vw = (spec.dim - 1) // 2                # epitrrelentropytri.jl:121-135: diagonal V, W from the vector cone's ray
+        d = M.svec_side(vw)
+        u, v, w = _central_ray_epirelentropy(d)
+        arr[0] = u
+        arr[1 + _svec_diag_idx(d)] = v
+        arr[1 + vw + _svec_diag_idx(d)] = w
     elif spec.ctype == M.CONE_POSSEMIDEFTRISPARSE:
         a = np.asarray(spec.alpha)              # possemideftrisparse.jl:103-116: the identity
         arr[:] = (a[1:1 + spec.dim] == a[1 + spec.dim:]).astype(float)
@@ -238,6 +245,17 @@ def _cone_dual_initial(spec, prim):
         for p in range(Rr):
             b = p * (p + 1) // 2 + p
             out[b * Uu:(b + 1) * Uu] = dg
+        return out
+    if spec.ctype == M.CONE_EPITRRELENTROPYTRI:
+        # -grad at diagonal (u, v I, w I): as the vector cone (epirelentropy.jl:123-140) on the diagonals
+        vw = (spec.dim - 1) // 2
+        d = M.svec_side(vw)
+        u, v, w = prim[0], prim[1], prim[1 + vw]
+        z = u - d * w * np.log(w / v)
+        out = np.zeros_like(prim)
+        out[0] = 1.0 / z
+        out[1 + _svec_diag_idx(d)] = w / v / z + 1.0 / v
+        out[1 + vw + _svec_diag_idx(d)] = -(np.log(w / v) + 1) / z + 1.0 / w
         return out
     if spec.ctype == M.CONE_POSSEMIDEFTRISPARSE:
         return prim.copy()      # -grad at the identity is the identity
@@ -365,6 +383,9 @@ def _perturb(rng, spec, vec, noise):
         return vec
     if spec.ctype == M.CONE_EPIPERSEPSPECTRAL_VEC:
         vec += noise / (2.0 * (vec.size - 2)) * (2 * rng.random(vec.size) - 1)   # the initial point is not central
+        return vec
+    if spec.ctype == M.CONE_EPITRRELENTROPYTRI:
+        vec += 0.5 * noise / np.sqrt(vec.size) * (2 * rng.random(vec.size) - 1)
         return vec
     if spec.ctype == M.CONE_POSSEMIDEFTRISPARSE:
         vec += 0.5 * noise / np.sqrt(vec.size) * (2 * rng.random(vec.size) - 1)

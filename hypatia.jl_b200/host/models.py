@@ -35,6 +35,7 @@ CONE_WSOSINTERPPOSSEMIDEFTRI = 19
 CONE_WSOSINTERPEPINORMEUCL = 20
 CONE_WSOSINTERPEPINORMONE = 21
 CONE_POSSEMIDEFTRISPARSE = 22
+CONE_EPITRRELENTROPYTRI = 23
 
 # separable spectral functions of EpiPerSepSpectral (sepspectralfun.jl:17-116), HYP_SSF_*
 SSF_INV, SSF_NEGLOG, SSF_NEGENTROPY, SSF_POWER12 = 0, 1, 2, 3
@@ -63,6 +64,7 @@ CONE_NAMES = {
     CONE_WSOSINTERPEPINORMEUCL: "WSOSInterpEpiNormEucl",
     CONE_WSOSINTERPEPINORMONE: "WSOSInterpEpiNormOne",
     CONE_POSSEMIDEFTRISPARSE: "PosSemidefTriSparse",
+    CONE_EPITRRELENTROPYTRI: "EpiTrRelEntropyTri",
 }
 
 
@@ -137,6 +139,9 @@ class ConeSpec:
             d1 = hkind
             rest = dim - d1 * (d1 + 1) // 2 - 1
             assert d1 >= 1 and rest >= d1 * d1 and rest % d1 == 0
+        elif ctype == CONE_EPITRRELENTROPYTRI:
+            assert dim > 2 and dim % 2 == 1       # epitrrelentropytri.jl:70-71
+            svec_side((dim - 1) // 2)
         elif ctype == CONE_POSSEMIDEFTRISPARSE:
             # alpha = packed pattern [side, row_1 .. row_dim, col_1 .. col_dim] (0-based, col <= row, every diagonal present)
             side = int(self.alpha[0])
@@ -205,6 +210,8 @@ class ConeSpec:
             return 2.0
         if self.ctype == CONE_GENERALIZEDPOWER:
             return float(len(self.alpha) + 1)
+        if self.ctype == CONE_EPITRRELENTROPYTRI:
+            return float(2 * svec_side((self.dim - 1) // 2) + 1)      # epitrrelentropytri.jl:119
         if self.ctype in (CONE_EPINORMSPECTRAL, CONE_MATRIXEPIPERSQUARE):
             return float(self.hkind + 1)      # epinormspectral.jl:95, matrixepipersquare.jl:101
         if self.ctype in (CONE_LINMATRIXINEQ, CONE_POSSEMIDEFTRISPARSE):
@@ -295,6 +302,11 @@ def PosSemidefTriSparse(side, row_idxs, col_idxs, use_dual=False):
     rows, cols = np.asarray(row_idxs, dtype=np.float64), np.asarray(col_idxs, dtype=np.float64)
     assert rows.size == cols.size
     return ConeSpec(CONE_POSSEMIDEFTRISPARSE, rows.size, use_dual, alpha=np.concatenate(([float(side)], rows, cols)))
+
+
+def EpiTrRelEntropyTri(dim, use_dual=False):
+    """EpiTrRelEntropyTri{Float64}(dim): (u, svec(V), svec(W)), u >= tr(W log W - W log V), dim = 1 + 2 svec_length(d)."""
+    return ConeSpec(CONE_EPITRRELENTROPYTRI, dim, use_dual)
 
 
 def DoublyNonnegativeTri(dim, use_dual=False):

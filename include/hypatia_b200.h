@@ -66,6 +66,7 @@ typedef struct hyp_ctx hyp_ctx;
 #define HYP_CONE_POSSEMIDEFTRISPARSE 22 /* possemideftrisparse/ (real; dense implementation like the reference's PSDSparseDense):
                                        dim = number of pattern entries <= 128; hyp_set_cone_alpha carries
                                        [side, row_1 .. row_dim, col_1 .. col_dim] (0-based, col <= row, every diagonal once) */
+#define HYP_CONE_EPITRRELENTROPYTRI 23 /* epitrrelentropytri.jl: (u, svec(V), svec(W)), dim = 1 + 2 svec_length(d) <= 128 */
 #define HYP_CONE_EPINORMSPECTRAL 14 /* epinormspectral.jl (real): (u, vec(W)), W d1 x d2 column-major, d1 <= d2; d1 is given
                                        as the integer parameter of hyp_set_cone_params; use_dual = 1: nuclear norm; dim <= 128 */
 

@@ -51,6 +51,7 @@ cone_code(::Cones.DoublyNonnegativeTri{Float64}) = Cint(17)
 cone_code(::Cones.MatrixEpiPerSquare{Float64, Float64}) = Cint(18)
 cone_code(::Cones.WSOSInterpPosSemidefTri{Float64}) = Cint(19)
 cone_code(::Cones.WSOSInterpEpiNormEucl{Float64}) = Cint(20)
+cone_code(::Cones.EpiTrRelEntropyTri{Float64}) = Cint(23)
 cone_code(::Cones.WSOSInterpEpiNormOne{Float64}) = Cint(21)
 cone_code(::Cones.PosSemidefTriSparse{<:Cones.PSDSparseImpl, Float64, Float64}) = Cint(22)
 cone_alpha(c::Cones.PosSemidefTriSparse{<:Cones.PSDSparseImpl, Float64, Float64}) =

@@ -780,6 +780,9 @@ def make_cone(spec):
         from .cones_vec3 import WSOSInterpPosSemidefTri
         Rr = spec.hkind
         return WSOSInterpPosSemidefTri(Rr, spec.dim // (Rr * (Rr + 1) // 2), M.wsos_unpack(spec), use_dual=not spec.use_dual)
+    if spec.ctype == M.CONE_EPITRRELENTROPYTRI:
+        from .cones_vec3 import EpiTrRelEntropyTri
+        return EpiTrRelEntropyTri(spec.dim, use_dual=spec.use_dual)
     if spec.ctype == M.CONE_POSSEMIDEFTRISPARSE:
         from .cones_vec3 import PosSemidefTriSparse
         a = np.asarray(spec.alpha)

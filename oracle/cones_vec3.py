@@ -1787,6 +1787,7 @@ class _LogFrechet:
 class EpiTrRelEntropyTri(Cone):
     """epitrrelentropytri.jl:8-573: (u, svec(V), svec(W)) with V, W positive definite d x d and
     u >= tr(W log W - W log V); barrier -log(u - tr(W log W - W log V)) - logdet V - logdet W, nu = 2 d + 1.
+    (ctype = M.CONE_EPITRRELENTROPYTRI.)
     Restated through the Frechet derivatives of the matrix logarithm (Daleckii-Krein with confluent divided differences):
     with z = u - phi, phi = tr(W log W) - tr(W log V),
         phi_W = log W + I - log V,         phi_V = -Dlog(V)[W],

@@ -243,6 +243,31 @@ int emu_gpow_dder3(int ncones, const int64_t* off, const int* dim, const int* mu
 
 extern "C" {
 
+int emu_etr_state(int ncones, const int64_t* off, const int* dim, const int64_t* voff, double* vecs, const int* kidx,
+                  const int64_t* moff, const double* point, double* grad, double* scal, double* H, uint8_t* feas) {
+    emu::launch(dim3((ncones + 1) / 2), dim3(64), 0, [&] {
+        hypdev::etr_state_kernel(ncones, off, dim, voff, vecs, kidx, moff, point, grad, scal, H, feas);
+    });
+    return 0;
+}
+
+int emu_etr_prod(int ncones, int want_dual, const int64_t* off, const int* dim, const int64_t* voff, const double* vecs,
+                 const int* dualf, const double* scal, const double* arr, int64_t ld_arr, double* prod, int64_t ld_prod,
+                 int64_t ncols, int64_t row_shift) {
+    emu::launch(dim3((ncones + 1) / 2, 2), dim3(64), 0, [&] {
+        hypdev::etr_prod_kernel(ncones, want_dual, off, dim, voff, vecs, dualf, scal, arr, ld_arr, prod, ld_prod, ncols,
+                                row_shift);
+    });
+    return 0;
+}
+
+int emu_etr_dder3(int ncones, const int64_t* off, const int* dim, const int64_t* voff, double* vecs, const double* scal,
+                  const double* dir, double* out) {
+    emu::launch(dim3((ncones + 1) / 2), dim3(64), 0,
+                [&] { hypdev::etr_dder3_kernel(ncones, off, dim, voff, vecs, scal, dir, out); });
+    return 0;
+}
+
 int emu_sps_state(int ncones, const int64_t* off, const int* dim, const int64_t* voff, double* vecs, const int* kidx,
                   const int64_t* moff, const double* point, double* grad, double* H, uint8_t* feas) {
     emu::launch(dim3(ncones), dim3(256), 0,

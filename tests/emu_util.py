@@ -316,6 +316,15 @@ class EmuGpowGroup:
         self.K = len(specs)
         self.hpm = specs[0].ctype == 12          # HypoPowerMean, else GeneralizedPower
         self.ens = specs[0].ctype == 14          # EpiNormSpectral: d1 per cone, workspace instead of powers
+        self.etr = specs[0].ctype == 23          # EpiTrRelEntropyTri: state + dder3 scratch
+        if self.etr:
+            sizes = []
+            for s in specs:
+                d = int(round((np.sqrt(1 + 4 * (s.dim - 1)) - 1) / 2))
+                n = d * d
+                sizes.append(23 * n + 2 * d + 2 * d * n + n * n)
+            self.voff = np.concatenate(([0], np.cumsum(sizes)))[:-1].astype(np.int64)
+            self.vecs = np.zeros(int(sum(sizes)))
         self.sps = specs[0].ctype == 22          # PosSemidefTriSparse: packed pattern + workspace
         if self.sps:
             regions = [np.concatenate((np.asarray(s.alpha, dtype=np.float64), np.zeros(5 * int(s.alpha[0]) ** 2)))
@@ -399,7 +408,10 @@ class EmuGpowGroup:
         self.dual_feas = np.ones(self.K, dtype=np.uint8)
         self.grad = np.zeros(self.q)
         self.H = np.zeros(self.lay.total)
-        if self.sps:
+        if self.etr:
+            lib().emu_etr_state(self.K, p(self.off), p(self.dims), p(self.voff), p(self.vecs), p(self.kidx),
+                                p(self.lay.moff), p(self.point), p(self.grad), p(self.scal), p(self.H), p(self.feas))
+        elif self.sps:
             lib().emu_sps_state(self.K, p(self.off), p(self.dims), p(self.voff), p(self.vecs), p(self.kidx),
                                 p(self.lay.moff), p(self.point), p(self.grad), p(self.H), p(self.feas))
         elif self.wone:
@@ -447,7 +459,10 @@ class EmuGpowGroup:
         out = a if in_place else np.zeros_like(a, order="F")
         hess_dual, inv_dual = {0: (-1, -2), 1: (-2, -1), 4: (0, 1), 5: (1, 0)}[int(mode)]
         L = lib()
-        if hess_dual > -2 and self.mep:
+        if hess_dual > -2 and self.etr:
+            L.emu_etr_prod(self.K, hess_dual, p(self.off), p(self.dims), p(self.voff), p(self.vecs), p(self.dualf),
+                           p(self.scal), p(a), i64(self.q), p(out), i64(self.q), i64(a.shape[1]), i64(0))
+        elif hess_dual > -2 and self.mep:
             L.emu_mep_prod(self.K, hess_dual, p(self.off), p(self.dims), p(self.d1), p(self.voff), p(self.vecs),
                            p(self.dualf), p(self.scal), p(self.point), p(a), i64(self.q), p(out), i64(self.q),
                            i64(a.shape[1]), i64(0))
@@ -476,7 +491,9 @@ class EmuGpowGroup:
     def dder3(self, direction):
         d = np.ascontiguousarray(direction, dtype=np.float64)
         out = np.zeros(self.q)
-        if self.sps:
+        if self.etr:
+            lib().emu_etr_dder3(self.K, p(self.off), p(self.dims), p(self.voff), p(self.vecs), p(self.scal), p(d), p(out))
+        elif self.sps:
             lib().emu_sps_dder3(self.K, p(self.off), p(self.dims), p(self.voff), p(self.vecs), p(d), p(out))
         elif self.wone:
             lib().emu_wone_dder3(self.K, p(self.off), p(self.dims), p(self.Rs), p(self.voff), p(self.vecs), p(d), p(out))

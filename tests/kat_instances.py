@@ -952,6 +952,50 @@ MEPS = [_named(lambda a=_a, b=_b, ud=_ud: _matrixepipersquare1(a, b, ud), f"matr
      for _f in (_matrixepipersquare2, _matrixepipersquare3) for _ud in (False, True)]
 
 
+def _mlog(X):
+    lam, Q = np.linalg.eigh(X)
+    return (Q * np.log(lam)) @ Q.T
+
+
+def epitrrelentropytri1():  # :2200-2223: min u : (u, V, W) in K  =>  tr(W (log W - log V))
+    rng = np.random.default_rng(1)
+    side = 4
+    sv = M.svec_length(side)
+    dim = 2 * sv + 1
+    W = rng.random((side, side))
+    W = W @ W.T
+    V = rng.random((side, side))
+    V = V @ V.T
+    G = np.zeros((dim, 1))
+    G[0, 0] = -1
+    h = np.concatenate(([0.0], _svec(V), _svec(W)))
+    return _m([1], None, None, G, h, [M.EpiTrRelEntropyTri(dim)]), \
+        dict(status="Optimal", primal_obj=float(np.sum(W * (_mlog(W) - _mlog(V)))))
+
+
+def epitrrelentropytri3():  # :2247-2265
+    side = 3
+    sv = M.svec_length(side)
+    dim = 2 * sv + 1
+    c = np.concatenate((np.zeros(sv + 1), np.ones(sv)))
+    A = np.concatenate(([1.0], np.zeros(2 * sv)))[None, :]
+    return _m(c, A, [0], -np.eye(dim), np.zeros(dim), [M.EpiTrRelEntropyTri(dim)]), \
+        dict(status="Optimal", primal_obj=0, s_idx={0: 0.0})
+
+
+def epitrrelentropytri4():  # :2267-2284
+    side = 3
+    sv = M.svec_length(side)
+    dim = 2 * sv + 1
+    c = np.concatenate(([0.0], np.ones(sv), np.zeros(sv)))
+    A = np.concatenate(([1.0], np.zeros(2 * sv)))[None, :]
+    return _m(c, A, [0], -np.eye(dim), np.zeros(dim), [M.EpiTrRelEntropyTri(dim)]), \
+        dict(status="Optimal", primal_obj=0, s=np.zeros(dim))
+
+
+TRRELENT = [epitrrelentropytri1, epitrrelentropytri3, epitrrelentropytri4]
+
+
 def possemideftrisparse1():  # :543-563
     return _m([0, -1, 0], [[1, 0, 0], [0, 0, 1]], [0.5, 1], -np.eye(3), np.zeros(3),
               [M.PosSemidefTriSparse(2, [0, 1, 1], [0, 0, 1])]), dict(status="Optimal", primal_obj=-1, x_idx={1: 1.0})
@@ -1021,7 +1065,7 @@ def linmatrixineq3():  # :747-788 (dense case): min w_1 : w_1 I - diag(1, -1) ps
 
 LMI = [_named(lambda s=_s: _linmatrixineq1(s), f"linmatrixineq1_side{_s}") for _s in (2, 4)] + \
     [_named(lambda d=_d: _linmatrixineq2(d), f"linmatrixineq2_dim{_d}") for _d in (2, 3)] + [linmatrixineq3]
-EXTRA = EXTRA + LMI + DNN + MEPS + WSOSPSD + WSOSEUCL + WSOSONE + PSDSPARSE
+EXTRA = EXTRA + LMI + DNN + MEPS + WSOSPSD + WSOSEUCL + WSOSONE + PSDSPARSE + TRRELENT
 
 RELENT = [_named(lambda d=_d: _epirelentropy1(d), f"epirelentropy1_d{_d}") for _d in (1, 2, 3)] + \
     [_named(lambda d=_d: _epirelentropy2(d), f"epirelentropy2_d{_d}") for _d in (1, 2, 4)] + \

@@ -79,6 +79,8 @@ def _sets():
         "wsosone": [_wone(2, 1, 1), _wone(2, 1, 2), _wone(3, 1, 2), _wone(3, 2, 1), _wone(4, 2, 1), _wone(2, 2, 2),
                     _wone(3, 1, 3, use_dual=True), _wone(8, 2, 2)],
         "psdsparse": [_sps(rng, sd) for sd in (1, 2, 5, 10, 25, 40)] + [_sps(rng, 6, use_dual=True)],
+        "epitrrelent": [M.EpiTrRelEntropyTri(1 + 2 * M.svec_length(d)) for d in (1, 2, 3, 4, 6, 10)] +
+                       [M.EpiTrRelEntropyTri(1 + 2 * M.svec_length(3), use_dual=True)],
         "lmi": [_lmi(rng, 2, 2), _lmi(rng, 3, 2), _lmi(rng, 4, 3), _lmi(rng, 3, 6), _lmi(rng, 12, 40),
                 _lmi(rng, 5, 4, use_dual=True), _lmi(rng, 33, 20)],
         "wsos": [_wsos(1, 1), _wsos(1, 3), _wsos(2, 2), _wsos(3, 1), _wsos(2, 4), _wsos(1, 2, use_dual=True),
@@ -95,7 +97,7 @@ def _sets():
     }
 
 
-NAMES = ["gpow", "gpow_dual", "hpm", "hpm_dual", "normspec", "normspec_dual", "wsos", "lmi", "dnn", "meps", "wsospsd", "wsoseucl", "wsosone", "psdsparse"]
+NAMES = ["gpow", "gpow_dual", "hpm", "hpm_dual", "normspec", "normspec_dual", "wsos", "lmi", "dnn", "meps", "wsospsd", "wsoseucl", "wsosone", "psdsparse", "epitrrelent"]
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -119,7 +121,8 @@ def test_gpow_kernels_match_oracle(name):
     assert rel(dev.prod(arr, 1), ora.inv_hess_prod(arr)) <= 1e-10
     assert rel(dev.prod(arr, 1, in_place=True), ora.inv_hess_prod(arr)) <= 1e-10
     assert rel(dev.prod(arr, 4), ora.block_hess_prod(arr)) <= 1e-10
-    assert rel(dev.dder3(arr[:, 1]), ora.dder3(arr[:, 1])) <= 1e-12
+    # EpiTrRelEntropyTri: third divided differences of log over Jacobi (device) vs LAPACK (oracle) eigenvalues
+    assert rel(dev.dder3(arr[:, 1]), ora.dder3(arr[:, 1])) <= (1e-10 if name == "epitrrelent" else 1e-12)
     pt = scal * prim
     assert rel(dev.prod(pt, 0), -dev.grad) <= 1e-12
     assert rel(dev.prod(dev.grad, 1), -pt) <= 1e-10

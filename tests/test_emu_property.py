@@ -98,6 +98,8 @@ def _genfact_cone(kind, a, b, dual, rng):
         d1 = 1 + a % 5
         d2 = d1 + b % 7
         return M.EpiNormSpectral(d1, d2, use_dual=dual)
+    if kind == "epitrrelent":
+        return M.EpiTrRelEntropyTri(1 + 2 * M.svec_length(1 + a % 6), use_dual=dual)
     if kind == "psdsparse":
         side = 1 + a % 20
         mask = np.tril(rng.random((side, side)) < 1 / np.sqrt(side)) | np.eye(side, dtype=bool)
@@ -141,7 +143,7 @@ def _genfact_cone(kind, a, b, dual, rng):
     return M.WSOSInterpNonnegative(U, Ps, use_dual=dual)
 
 
-GENFACT_KINDS = ["gpow", "hpm", "normspec", "dnn", "lmi", "wsos", "meps", "wsospsd", "wsoseucl", "wsosone", "psdsparse"]
+GENFACT_KINDS = ["gpow", "hpm", "normspec", "dnn", "lmi", "wsos", "meps", "wsospsd", "wsoseucl", "wsosone", "psdsparse", "epitrrelent"]
 
 
 @settings(max_examples=30, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.too_slow])

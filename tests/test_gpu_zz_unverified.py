@@ -305,3 +305,29 @@ def test_possemideftrisparse_oracles_match_cpu_oracle():
     assert rel(dev.hess_prod(pt), -g) <= 1e-10                      # test/cone.jl:50,78
     assert abs(float(pt @ g) + I.model.nu) <= 1e-9 * I.model.nu     # test/cone.jl:71
     dev.free()
+
+
+# EpiTrRelEntropyTri: emulation tier only so far (tests/test_emu_gpow.py)
+@not_yet_on_gpu
+def test_epitrrelentropytri_oracles_match_cpu_oracle():
+    from hypatia_b200.cones import DeviceConeBlock
+    from oracle.cones import OracleConeBlock
+    cones = [M.EpiTrRelEntropyTri(1 + 2 * M.svec_length(d)) for d in (1, 2, 3, 4, 6, 10)] + \
+        [M.EpiTrRelEntropyTri(1 + 2 * M.svec_length(3), use_dual=True), M.Nonnegative(2)]
+    I = inst.synthetic("epitrrelent", 4, 0, cones, seed=84)
+    dev, ora = DeviceConeBlock(I.model), OracleConeBlock(I.model)
+    prim, dual = I.point.primal_dual(ora.dual_mask)
+    scal = 1 / np.sqrt(I.mu)
+    dev.load_point(prim, dual, scal)
+    ora.load_point(prim, dual, scal)
+    assert dev.is_feas().all() and ora.is_feas().all()
+    g = dev.grad()
+    assert rel(g, ora.grad()) <= 1e-11
+    arr = np.random.default_rng(1).standard_normal((I.model.q, 3))
+    assert rel(dev.hess_prod(arr), ora.hess_prod(arr)) <= 1e-10
+    assert rel(dev.inv_hess_prod(arr), ora.inv_hess_prod(arr)) <= 1e-8
+    assert rel(dev.dder3(arr[:, 1]), ora.dder3(arr[:, 1])) <= 1e-9
+    pt = scal * prim
+    assert rel(dev.hess_prod(pt), -g) <= 1e-10                      # test/cone.jl:50,78
+    assert abs(float(pt @ g) + I.model.nu) <= 1e-9 * I.model.nu     # test/cone.jl:71
+    dev.free()
