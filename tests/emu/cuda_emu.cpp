@@ -1,5 +1,8 @@
 #include "cuda_emu.h"
 
+#include <cstdlib>
+#include <new>
+
 thread_local dim3 threadIdx;
 thread_local dim3 blockIdx;
 dim3 blockDim;
@@ -12,8 +15,11 @@ void launch(dim3 grid, dim3 block, size_t dyn_smem, const std::function<void()>&
     gridDim = grid;
     blockDim = block;
     const int nt = (int)block.x;
-    std::vector<char> smem(dyn_smem + 64);
-    g_dyn_smem = (void*)(((uintptr_t)smem.data() + 63) & ~(uintptr_t)63);
+    // exact-size heap block: under -fsanitize=address (HYP_EMU_ASAN=1) an overrun of the dynamic
+    // shared-memory request is reported the way compute-sanitizer would report it on the device
+    void* smem = nullptr;
+    if (posix_memalign(&smem, 64, dyn_smem ? dyn_smem : 1) != 0) throw std::bad_alloc();
+    g_dyn_smem = smem;
     for (unsigned by = 0; by < grid.y; by++)
         for (unsigned bx = 0; bx < grid.x; bx++) {
             BlockState st;
@@ -38,5 +44,6 @@ void launch(dim3 grid, dim3 block, size_t dyn_smem, const std::function<void()>&
         }
     g_block = nullptr;
     g_dyn_smem = nullptr;
+    free(smem);
 }
 }  // namespace emu

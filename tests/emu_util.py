@@ -12,7 +12,10 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 EMU = os.path.join(HERE, "emu")
 BUILD = os.path.join(EMU, "_build")
-LIB = os.path.join(BUILD, "libemu.so")
+# HYP_EMU_ASAN=1 builds the emulation with AddressSanitizer + UBSan (run the tests with
+# LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0; see tools/emu_asan.sh)
+ASAN = os.environ.get("HYP_EMU_ASAN", "0") == "1"
+LIB = os.path.join(BUILD, "libemu_asan.so" if ASAN else "libemu.so")
 CSRC = os.path.join(os.path.dirname(HERE), "hypatia.jl_b200", "csrc")
 _lib = None
 
@@ -26,7 +29,8 @@ def lib():
     deps = srcs + [os.path.join(EMU, "cuda_emu.h")] + \
         [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith("_kernels.cuh") or f == "devdefs.cuh"]
     if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
-        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", LIB] + srcs
+        opt = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer"] if ASAN else ["-O2"]
+        cmd = ["g++"] + opt + ["-std=c++17", "-fPIC", "-shared", "-pthread", "-o", LIB] + srcs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("emulation build failed:\n" + r.stderr)
