@@ -279,6 +279,9 @@ v3_prod_kernel(int type, int mode_in, int ncones, const int64_t* __restrict__ of
         const double* a = arr + j * ld_arr + (o - row_shift);
         double* pr = prod + j * ld_prod + (o - row_shift);
         const double p = a[0], q = a[1];
+        // in-place use (prod == arr): every lane holds its copy of the two leading entries before any
+        // lane stores to them (found by the ThreadSanitizer run of the emulation, tools/emu_tsan.sh)
+        __syncwarp();
         if (type == V3_EPIRELENTROPY) {
             const int n = (d - 1) / 2;
             const double z = scal[8 * c];

@@ -12,6 +12,15 @@
 #define HYP_DYN_SMEM(type, name) extern __shared__ type name[]
 #endif
 
+// Several threads of a block raising the same shared flag between two barriers (all store the same
+// value; it is read after the next __syncthreads).  A plain store on the device; the emulation
+// spells it as a relaxed atomic so that ThreadSanitizer (tools/emu_tsan.sh) does not report it.
+#ifdef HYP_EMU
+#define HYP_RAISE_FLAG(flag) __atomic_store_n(&(flag), 1, __ATOMIC_RELAXED)
+#else
+#define HYP_RAISE_FLAG(flag) (flag) = 1
+#endif
+
 #ifndef HYP_EPS
 #define HYP_EPS 2.220446049250313e-16
 #endif

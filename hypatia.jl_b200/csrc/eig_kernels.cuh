@@ -104,7 +104,7 @@ syevj_batched_kernel(int nmat, const int* __restrict__ sides, const int64_t* __r
                             cs = 1.0 / sqrt(t * t + 1.0);
                             sn = t * cs;
                             pp = p;
-                            s_rot = 1;
+                            HYP_RAISE_FLAG(s_rot);
                         }
                     }
                     rc[tid] = cs;

@@ -15,7 +15,10 @@ BUILD = os.path.join(EMU, "_build")
 # HYP_EMU_ASAN=1 builds the emulation with AddressSanitizer + UBSan (run the tests with
 # LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0; see tools/emu_asan.sh)
 ASAN = os.environ.get("HYP_EMU_ASAN", "0") == "1"
-LIB = os.path.join(BUILD, "libemu_asan.so" if ASAN else "libemu.so")
+# HYP_EMU_TSAN=1: ThreadSanitizer build - one pthread per CUDA thread, so a missing __syncthreads / __syncwarp
+# between a shared-memory write and another thread's read is a reported data race (tools/emu_tsan.sh)
+TSAN = os.environ.get("HYP_EMU_TSAN", "0") == "1"
+LIB = os.path.join(BUILD, "libemu_asan.so" if ASAN else "libemu_tsan.so" if TSAN else "libemu.so")
 CSRC = os.path.join(os.path.dirname(HERE), "hypatia.jl_b200", "csrc")
 _lib = None
 
@@ -29,7 +32,8 @@ def lib():
     deps = srcs + [os.path.join(EMU, "cuda_emu.h")] + \
         [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith("_kernels.cuh") or f == "devdefs.cuh"]
     if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
-        opt = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer"] if ASAN else ["-O2"]
+        opt = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer"] if ASAN else \
+            ["-O1", "-g", "-fsanitize=thread", "-fno-omit-frame-pointer"] if TSAN else ["-O2"]
         cmd = ["g++"] + opt + ["-std=c++17", "-fPIC", "-shared", "-pthread", "-o", LIB] + srcs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
