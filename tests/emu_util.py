@@ -104,7 +104,7 @@ class EmuSpecGroup:
         self.dual = np.ascontiguousarray(dual, dtype=np.float64)
         self.feas = np.ones(K, dtype=np.uint8)
         self.dual_feas = np.ones(K, dtype=np.uint8)
-        self.grad = np.zeros(self.q)
+        self.grad = np.full(self.q, np.nan)
         W = np.zeros(lay.total)
         Wc = np.zeros(lay.total)
         L.emu_unpack_state(K, p(self.off), p(lay.sides), p(lay.moff), 2, p(self.point), p(W), p(Wc), 2)
@@ -147,7 +147,7 @@ class EmuSpecGroup:
         L = lib()
         a = np.asfortranarray(np.asarray(arr, dtype=np.float64).reshape(self.q, -1, order="F"))
         ncols = a.shape[1]
-        out = np.zeros_like(a, order="F")
+        out = np.full_like(a, np.nan, order="F")
         for c in range(self.K):
             d, lde = int(self.lay.sides[c]), int(self.lay.lde[c])
             ln = d * (d + 1) // 2
@@ -170,7 +170,7 @@ class EmuSpecGroup:
     def small_prod(self, arr, mode, in_place=False):
         """The fused few-column kernel (spec_small_prod_kernel): one launch for all cones and columns."""
         a = np.asfortranarray(np.asarray(arr, dtype=np.float64).reshape(self.q, -1, order="F")).copy(order="F")
-        out = a if in_place else np.zeros_like(a, order="F")
+        out = a if in_place else np.full_like(a, np.nan, order="F")
         lay = self.lay
         dualf = np.array([1 if s.use_dual else 0 for s in self.specs], dtype=np.int32)
         lib().emu_spec_small_prod(int(mode), self.K, int(lay.sides.max()), p(self.off), p(lay.sides), p(lay.moff),
@@ -182,7 +182,7 @@ class EmuSpecGroup:
     def dder3(self, direction):
         L = lib()
         dirv = np.ascontiguousarray(direction, dtype=np.float64)
-        out = np.zeros(self.q)
+        out = np.full(self.q, np.nan)
         for c in range(self.K):
             d, lde = int(self.lay.sides[c]), int(self.lay.lde[c])
             ln = d * (d + 1) // 2
@@ -222,14 +222,14 @@ class EmuVec3Group:
         self.dual = np.ascontiguousarray(dual, dtype=np.float64)
         self.feas = np.ones(self.K, dtype=np.uint8)
         self.dual_feas = np.ones(self.K, dtype=np.uint8)
-        self.grad = np.zeros(self.q)
+        self.grad = np.full(self.q, np.nan)
         lib().emu_v3_state(self.type, self.K, p(self.off), p(self.dims), p(self.kidx), p(self.hkind), p(self.hparam),
                            p(self.point), p(self.dual),
                            p(self.grad), p(self.scal), p(self.feas), p(self.dual_feas))
 
     def prod(self, arr, mode, in_place=False):
         a = np.asfortranarray(np.asarray(arr, dtype=np.float64).reshape(self.q, -1, order="F")).copy(order="F")
-        out = a if in_place else np.zeros_like(a, order="F")
+        out = a if in_place else np.full_like(a, np.nan, order="F")
         lib().emu_v3_prod(self.type, int(mode), self.K, p(self.off), p(self.dims), p(self.dualf), p(self.hkind),
                           p(self.hparam), p(self.scal),
                           p(self.point), p(a), i64(self.q), p(out), i64(self.q), i64(a.shape[1]), i64(0), 2)
@@ -237,7 +237,7 @@ class EmuVec3Group:
 
     def dder3(self, direction):
         d = np.ascontiguousarray(direction, dtype=np.float64)
-        out = np.zeros(self.q)
+        out = np.full(self.q, np.nan)
         lib().emu_v3_dder3(self.type, self.K, p(self.off), p(self.dims), p(self.hkind), p(self.hparam), p(self.scal),
                            p(self.point), p(d), p(out))
         return out
@@ -299,7 +299,7 @@ class EmuMatGroup:
 
     def dder3(self, direction, threads=64):
         d = np.ascontiguousarray(direction, dtype=np.float64)
-        out = np.zeros(self.q)
+        out = np.full(self.q, np.nan)
         lay = self.lay
         lib().emu_mat_small_dder3(self.type, self.K, int(lay.sides.max()), p(self.off), p(lay.sides), p(lay.moff),
                                   p(self.Ui), p(self.Uit), p(self.scal), p(d), p(out), threads)
@@ -307,7 +307,7 @@ class EmuMatGroup:
 
     def prod(self, arr, mode, threads=64, in_place=False):
         a = np.asfortranarray(np.asarray(arr, dtype=np.float64).reshape(self.q, -1, order="F")).copy(order="F")
-        out = a if in_place else np.zeros_like(a, order="F")
+        out = a if in_place else np.full_like(a, np.nan, order="F")
         lay = self.lay
         lib().emu_mat_small_prod(self.type, int(mode), self.K, int(lay.sides.max()), p(self.off), p(lay.sides),
                                  p(lay.moff), p(self.dualf), p(self.W), p(self.Wi), p(self.Ui), p(self.Ut),
@@ -414,8 +414,11 @@ class EmuGpowGroup:
         self.dual = np.ascontiguousarray(dual, dtype=np.float64)
         self.feas = np.ones(self.K, dtype=np.uint8)
         self.dual_feas = np.ones(self.K, dtype=np.uint8)
-        self.grad = np.zeros(self.q)
-        self.H = np.zeros(self.lay.total)
+        # outputs start out poisoned: on the device they hold the previous iterate's values (or whatever
+        # cudaMalloc returned), so a kernel that accumulates into them or skips an entry must fail here
+        self.grad = np.full(self.q, np.nan)
+        self.H = np.full(self.lay.total, np.nan)
+        self.scal[:] = np.nan
         if self.etr:
             lib().emu_etr_state(self.K, p(self.off), p(self.dims), p(self.voff), p(self.vecs), p(self.kidx),
                                 p(self.lay.moff), p(self.point), p(self.grad), p(self.scal), p(self.H), p(self.feas))
@@ -458,13 +461,13 @@ class EmuGpowGroup:
                                  p(self.scal), p(self.H), p(self.feas), p(self.dual_feas))
         # hess_fact: the batched factor-and-invert kernel of chol.cu on a copy of the explicit Hessians
         self.U = self.H.copy()
-        self.Ui = np.zeros(self.lay.total)
+        self.Ui = np.full(self.lay.total, np.nan)
         lib().emu_chol_batched(self.K, p(self.lay.sides), p(self.lay.moff), p(self.kidx), p(self.U), p(self.Ui),
                                p(self.feas))
 
     def prod(self, arr, mode, in_place=False):
         a = np.asfortranarray(np.asarray(arr, dtype=np.float64).reshape(self.q, -1, order="F")).copy(order="F")
-        out = a if in_place else np.zeros_like(a, order="F")
+        out = a if in_place else np.full_like(a, np.nan, order="F")
         hess_dual, inv_dual = {0: (-1, -2), 1: (-2, -1), 4: (0, 1), 5: (1, 0)}[int(mode)]
         L = lib()
         if hess_dual > -2 and self.etr:
@@ -498,7 +501,7 @@ class EmuGpowGroup:
 
     def dder3(self, direction):
         d = np.ascontiguousarray(direction, dtype=np.float64)
-        out = np.zeros(self.q)
+        out = np.full(self.q, np.nan)
         if self.etr:
             lib().emu_etr_dder3(self.K, p(self.off), p(self.dims), p(self.voff), p(self.vecs), p(self.scal), p(d), p(out))
         elif self.sps:
