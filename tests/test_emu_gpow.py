@@ -129,6 +129,33 @@ def test_gpow_kernels_match_oracle(name):
     assert rel(-dev.dder3(pt), dev.grad) <= 1e-11
 
 
+@pytest.mark.parametrize("name", [n for n in NAMES if not n.endswith("_dual")])
+def test_gpow_group_reused_across_iterates(name):
+    """The per-cone scratch of a device group (g.d_vecs, the explicit Hessian, its factor) persists from one
+    interior-point iterate to the next, and an infeasible trial point of the line search comes in between: a group
+    that has seen another point and an infeasible point must give bit-identical results to a fresh one."""
+    cones = _sets()[name]
+    I = inst.synthetic(name, 3, 0, cones, seed=600 + NAMES.index(name))
+    ora = OracleConeBlock(I.model)
+    prim, dual = I.point.primal_dual(ora.dual_mask)
+    rng = np.random.default_rng(11)
+    first = prim * (1.0 + 0.02 * rng.standard_normal(prim.shape))     # a nearby interior point
+    dev = eu.EmuGpowGroup(cones)
+    dev.load_point(first, dual)
+    assert dev.feas.all()
+    dev.load_point(-prim, dual)                                          # every cone rejects it
+    assert not dev.feas.any()
+    dev.load_point(prim, dual)
+    fresh = eu.EmuGpowGroup(cones)
+    fresh.load_point(prim, dual)
+    assert dev.feas.all() and fresh.feas.all()
+    assert np.array_equal(dev.grad, fresh.grad)
+    arr = rng.standard_normal((I.model.q, 2))
+    for mode in (0, 1):
+        assert np.array_equal(dev.prod(arr, mode), fresh.prod(arr, mode))
+    assert np.array_equal(dev.dder3(arr[:, 0]), fresh.dder3(arr[:, 0]))
+
+
 def test_gpow_kernels_flag_infeasible_points():
     rng = np.random.default_rng(8)
     cones = [M.GeneralizedPower(_alpha(rng, 2), 2), M.GeneralizedPower(_alpha(rng, 3), 1),
