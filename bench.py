@@ -16,24 +16,38 @@ cent / centadj / pred / predadj right-hand sides of the first iterate, built onc
   value : steps/s with every input resident in HBM (device pointers through the C ABI)
   e2e   : the same calls with HOST (pinned) buffers: the H2D copies of the point and the four
           right-hand sides and the D2H copies of the directions / residuals are inside the timing
-  roofline : the Schur SYRK kernel (TMA + DMMA), algorithmic flops q*m*(m+1) per launch
-  cpu_baseline : the CPU oracle restatement (OpenBLAS dsyrk/dpotrf/dgemv, all host cores), rank 0
+  roofline : the Schur SYRK kernel (tcgen05 int8 digit slicing); frac = executed int8 TOP/s over
+             2 x bf16_tflops_sustained of MEASURED_PEAKS.json; the FP64-equivalent rate is a side field
+  cpu_baseline : the CPU oracle restatement (OpenBLAS dsyrk/dpotrf/dgemv, all host cores), rank 0, N = 1
+  parity : at EVERY N, rank 0 solves the same four right-hand sides with the CPU oracle
+           (dir_vs_oracle) and applies the ORACLE's 6x6 operator to the device directions (kkt_residual)
+  full_step : wall time of one complete CombinedStepper.step (refinement rounds + line-search sweeps)
+  batched_solves : the same unit with the independent right-hand sides solved by hyp_solve_system_multi
+  other_workloads : C2 / C4 / C5a at full size (value, phase_ms, parity), --other to select
 
 Launch: `python bench.py --gpus 1 --steps K --warmup W`, or under torchrun for N > 1 (one rank per
-GPU, cones / G row panels sharded over ranks, one NCCL allreduce of the Schur matrix per step;
+GPU, cones / G row panels sharded over ranks, one NCCL reduction of the Schur matrix per step;
 "scaling": "strong" - the instance is fixed).  `--impl reference` times the CPU oracle instead.
 """
 from __future__ import annotations
 
-import argparse
-import json
 import os
-import subprocess
 import sys
-import threading
-import time
 
-import numpy as np
+# torch.distributed.run exports OMP_NUM_THREADS=1 when nproc > 1; rank 0 runs the CPU oracle (parity at every
+# N, and the whole `--impl reference` arm), which must see all host cores: undo it BEFORE NumPy / OpenBLAS load
+if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        if os.environ.get(_v) == "1":
+            del os.environ[_v]
+
+import argparse  # noqa: E402
+import json  # noqa: E402
+import subprocess  # noqa: E402
+import threading  # noqa: E402
+import time  # noqa: E402
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -52,6 +66,8 @@ WORKLOADS = {
                 desc="n=1000 p=0, 200 x EpiNormEucl(25), q=5000 (smoke-size)"),
     "C4": dict(n=20000, cones=lambda M: [M.PosSemidefTri(5050) for _ in range(50)],
                desc="n=20000 p=0, 50 x PosSemidefTri(side 100), q=252500"),
+    "C4s": dict(n=600, cones=lambda M: [M.PosSemidefTri(M.svec_length(16)) for _ in range(6)],
+                desc="n=600 p=0, 6 x PosSemidefTri(side 16), q=816 (smoke-size)"),
     # natvsext-faithful shape of BASELINE config 5 (SURVEY.md 8(d) "C5a"): the largest `nat` log-det
     # D-optimal-design instance (examples/doptimaldesign/JuMP_benchmark.jl:2-5, native.jl:18-86) after
     # the QR reduction: one HypoPerLogdetTri of side 1000 (dim 500502 > m, so the hess_prod! + GEMM
@@ -59,18 +75,26 @@ WORKLOADS = {
     "C5a": dict(n=2000, cones=lambda M: [M.Nonnegative(2000), M.Nonnegative(2000),
                                          M.HypoPerLogdetTri(2 + M.svec_length(1000))],
                 desc="n=2000 p=0, Nonnegative(2000) x 2 + HypoPerLogdetTri(side 1000), q=504502"),
+    "C5as": dict(n=120, cones=lambda M: [M.Nonnegative(100), M.Nonnegative(100),
+                                          M.HypoPerLogdetTri(2 + M.svec_length(40))],
+                 desc="n=120 p=0, Nonnegative(100) x 2 + HypoPerLogdetTri(side 40), q=1022 (smoke-size)"),
+    # many-cone mix of BASELINE config 5 (SURVEY.md 8(d) "C5b"): 40 x HypoPerLogdetTri(side 100) +
+    # 10000 x EpiNormEucl(25) + Nonnegative(47920), n = 20000, q = 500000
+    "C5b": dict(n=20000, cones=lambda M: [M.HypoPerLogdetTri(2 + M.svec_length(100)) for _ in range(40)] +
+                [M.EpiNormEucl(25) for _ in range(10000)] + [M.Nonnegative(47920)],
+                desc="n=20000 p=0, 40 x HypoPerLogdetTri(side 100) + 10000 x EpiNormEucl(25) + Nonnegative(47920), q=500000"),
     # widening rows (not BASELINE configs): spectral cones through the batched Jacobi eigensolver
     "S1": dict(n=2000, cones=lambda M: [M.EpiPerSepSpectralMat(2 + M.svec_length(100), M.SSF_NEGENTROPY)
                                         for _ in range(24)],
                desc="n=2000 p=0, 24 x EpiPerSepSpectral{MatrixCSqr}(NegEntropy, side 100), q=121248"),
 }
 
-
-# DRAM traffic of the Schur SYRK launch from the committed `ncu --set full` capture (per launch)
-NCU_TRAFFIC = {"C3": 31.497622e9 + 0.411380e9,                       # FP64 DMMA kernel, one launch
-               # tcgen05 CTA-pair kernel, radix-256 digits, row-major tile order: the three launches (K chunks) of
-               # one SYRK in profiles/r01_ozaki_pair_row_order_ncu.txt
-               "C3:i8": (42.40e9 + 0.809e9) + (44.78e9 + 0.808e9) + (44.62e9 + 0.808e9)}
+# DRAM traffic of the Schur SYRK (dram__bytes_read.sum + dram__bytes_write.sum over the launches of ONE SYRK) from the
+# committed `ncu --set full` capture of the same kernel build - a CONSTANT taken from that profile, not measured by
+# the run that prints it (ncu cannot run inside a timed bench); the source file is named next to it
+NCU_TRAFFIC = {"C3:i8": ((42.40e9 + 0.809e9) + (44.78e9 + 0.808e9) + (44.62e9 + 0.808e9),
+                         "constant from profiles/r01_ozaki_pair_row_order_ncu.txt (three K-chunk launches of one SYRK)"),
+               "C3": (31.497622e9 + 0.411380e9, "constant from profiles/r01_syrk_schur_ncu_full.txt (one launch)")}
 
 
 class PanelModel:
@@ -105,8 +129,45 @@ def gen_panel(n, row_lo, row_hi, seed, block=2048):
     return G
 
 
-def build_instance(workload, rank, nranks, dist=None, device=None):
+def gen_panel_device(torch, device, n, row_lo, row_hi, seed, block=4096):
+    """The same idea on the device for the multi-GB workloads (C4: 40 GB): rows [row_lo, row_hi) of a
+    block-seeded N(0,1) matrix, returned as the (n, rows) row-major tensor = the column-major panel."""
+    rows = row_hi - row_lo
+    GT = torch.empty((n, rows), dtype=torch.float64, device=device)
+    gen = torch.Generator(device=device)
+    b0, b1 = row_lo // block, (row_hi + block - 1) // block
+    for b in range(b0, b1):
+        gen.manual_seed(seed * 1000003 + b)
+        blk = torch.randn((n, block), dtype=torch.float64, device=device, generator=gen)
+        lo, hi = max(row_lo, b * block), min(row_hi, (b + 1) * block)
+        GT[:, lo - row_lo:hi - row_lo] = blk[:, lo - b * block:hi - b * block]
+        del blk
+    return GT
+
+
+def _planted_point(cones, model, seed):
+    """Planted interior primal-dual pair: cone central points perturbed like
+    test/cone.jl:236-248.  Returns s0, z0 and the svec off-diagonal rows of G that carry sqrt(2)."""
     from hypatia_b200.host import instances as inst
+    rng = np.random.Generator(np.random.PCG64(seed + 7))
+    q = model.q
+    s0, z0 = np.empty(q), np.empty(q)
+    rt2_rows = []
+    for ck, sl in zip(cones, model.cone_idxs):
+        prim = inst.cone_initial_point(ck)
+        dual = inst._cone_dual_initial(ck, prim)
+        s0[sl] = inst._perturb(rng, ck, prim, 0.1)
+        z0[sl] = inst._perturb(rng, ck, dual, 0.1)
+        if ck.side:
+            rt2_rows.append(sl.start + inst.mat_offset(ck) + np.nonzero(inst._svec_offdiag_mask(ck.side))[0])
+    rt2_rows = np.concatenate(rt2_rows) if rt2_rows else np.zeros(0, dtype=np.int64)
+    return s0, z0, rt2_rows, rng
+
+
+def build_instance(workload, rank, nranks, dist=None, device=None, on_device=False, replicate_rows=False):
+    """This rank's share of the synthetic instance.  on_device: G is generated on the GPU (torch) and stays
+    there (`G_dev`, the (n, rows) tensor); otherwise NumPy on the host (`G_local`).  replicate_rows: every rank
+    holds ALL rows (single-giant-cone workloads that shard by COLUMNS of G_k)."""
     from hypatia_b200.host import models as M
     from hypatia_b200.syssolver import partition_cones
     w = WORKLOADS[workload]
@@ -115,30 +176,34 @@ def build_instance(workload, rank, nranks, dist=None, device=None):
     seed = 1000 + sorted(WORKLOADS).index(workload)
     model = PanelModel(n, cones, None, None)
     q = model.q
-    ranges = partition_cones(model, nranks) if nranks > 1 else [(0, len(cones))]
-    lo, hi = ranges[rank]
     K = len(cones)
+    if replicate_rows or nranks == 1:
+        lo, hi = 0, K
+    else:
+        lo, hi = partition_cones(model, nranks)[rank]
     row_lo = int(model.cone_offsets[lo]) if lo < K else q
     row_hi = int(model.cone_offsets[hi]) if hi < K else q
-    G_local = gen_panel(n, row_lo, row_hi, seed)
-    # planted interior primal-dual pair: cone central points perturbed like
-    # test/cone.jl:236-248
-    rng = np.random.Generator(np.random.PCG64(seed + 7))
-    s0, z0 = np.empty(q), np.empty(q)
-    for ck, sl in zip(cones, model.cone_idxs):
-        prim = inst.cone_initial_point(ck)
-        dual = inst._cone_dual_initial(ck, prim)
-        s0[sl] = inst._perturb(rng, ck, prim, 0.1)
-        z0[sl] = inst._perturb(rng, ck, dual, 0.1)
-        if ck.side:
-            rows = sl.start + inst.mat_offset(ck) + np.nonzero(inst._svec_offdiag_mask(ck.side))[0]
-            rows = rows[(rows >= row_lo) & (rows < row_hi)] - row_lo
-            G_local[rows] *= np.sqrt(2.0)
+    s0, z0, rt2_rows, rng = _planted_point(cones, model, seed)
     x0 = rng.standard_normal(n)
+    rows = rt2_rows[(rt2_rows >= row_lo) & (rt2_rows < row_hi)] - row_lo
     h = np.zeros(q)
-    h[row_lo:row_hi] = G_local @ x0 + s0[row_lo:row_hi]
-    c = -(G_local.T @ z0[row_lo:row_hi])
-    if nranks > 1:
+    G_local = G_dev = None
+    if on_device:
+        import torch
+        G_dev = gen_panel_device(torch, device, n, row_lo, row_hi, seed)
+        if rows.size:
+            G_dev[:, torch.from_numpy(rows).to(device)] *= float(np.sqrt(2.0))
+        tx = torch.from_numpy(x0).to(device)
+        tz = torch.from_numpy(z0[row_lo:row_hi].copy()).to(device)
+        h[row_lo:row_hi] = torch.mv(G_dev.t(), tx).cpu().numpy() + s0[row_lo:row_hi]
+        c = -torch.mv(G_dev, tz).cpu().numpy()
+    else:
+        G_local = gen_panel(n, row_lo, row_hi, seed)
+        if rows.size:
+            G_local[rows] *= np.sqrt(2.0)
+        h[row_lo:row_hi] = G_local @ x0 + s0[row_lo:row_hi]
+        c = -(G_local.T @ z0[row_lo:row_hi])
+    if nranks > 1 and not replicate_rows:
         import torch
         th = torch.from_numpy(h).to(device)
         tc = torch.from_numpy(c).to(device)
@@ -147,7 +212,7 @@ def build_instance(workload, rank, nranks, dist=None, device=None):
         h, c = th.cpu().numpy(), tc.cpu().numpy()
     model.c, model.h = c, h
     mu = (float(z0 @ s0) + 1.0) / (model.nu + 1)
-    return dict(model=model, G_local=G_local, s0=s0, z0=z0, x0=x0, mu=mu, cone_range=(lo, hi),
+    return dict(model=model, G_local=G_local, G_dev=G_dev, s0=s0, z0=z0, x0=x0, mu=mu, cone_range=(lo, hi),
                 rows=(row_lo, row_hi), desc=w["desc"])
 
 
@@ -217,7 +282,7 @@ def measured_peaks():
 
 def dgemm_peak_tflops(torch, device):
     """FP64 tensor (DMMA) peak measured live with cuBLAS DGEMM 8192^3 (MEASURED_PEAKS.json has
-    only HBM and bf16 entries; the Schur SYRK runs on the FP64 tensor pipe)."""
+    only HBM and bf16 entries); the roofline of the FP64 DMMA kernels (Cholesky trailing updates)."""
     n = 8192
     a = torch.randn(n, n, dtype=torch.float64, device=device)
     b = torch.randn(n, n, dtype=torch.float64, device=device)
@@ -235,22 +300,33 @@ def dgemm_peak_tflops(torch, device):
     return best
 
 
+def use_all_cores():
+    """BLAS threads = all host cores, whatever the launcher exported (torchrun: OMP_NUM_THREADS=1)."""
+    try:
+        import threadpoolctl
+        n = os.cpu_count() or 1
+        threadpoolctl.threadpool_limits(limits=n)
+        return max([p.get("num_threads", 1) for p in threadpoolctl.threadpool_info()] or [1])
+    except Exception:
+        return None
+
+
 # --------------------------------------------------------------------------------------------
-def cpu_unit(workload, steps, warmup, budget_s=25.0, rhs_list=None):
-    """CPU oracle restatement of the same unit on the host cores.  Returns (seconds per unit,
-    sample description, cores, threadpool info, directions of the last unit).  The SYRK is timed on a
-    bounded row sample when a full unit would exceed the budget (its cost is linear in the rows; the
-    factorisation then uses the Schur matrix of one full, untimed assembly), everything else runs in
-    full.  `rhs_list` replaces the oracle's own four right-hand sides (bench.py's parity check hands in
-    the ones the device solved)."""
-    import threadpoolctl
+def cpu_unit(workload, steps, warmup, budget_s=25.0, rhs_list=None, check_sols=None):
+    """CPU oracle restatement of the same unit on the host cores.  Returns a dict: seconds per unit, sample
+    description, cores, BLAS threads, directions of the last unit, and - when `check_sols` (device directions)
+    is given - the residual of each one under the ORACLE's 6x6 operator, ||K_oracle d - r|| / ||r||.
+    The SYRK is timed on a bounded row sample only when `steps + warmup` full units would exceed `budget_s`
+    (its cost is linear in the rows; the factorisation then uses the Schur matrix of one full, untimed
+    assembly), everything else always runs in full.  `rhs_list` replaces the oracle's own four right-hand
+    sides (the parity check hands in the ones the device solved)."""
     from scipy.linalg import blas as _blas
     from hypatia_b200.host import models as M
-    from hypatia_b200.host.point import Point
-    from oracle import syssolvers as osys
     from oracle.cones import OracleConeBlock
     from oracle.bench_unit import iterate_shell
+    from oracle.layout import OraclePoint
     cores = os.cpu_count() or 1
+    blas_threads = use_all_cores()
     I = build_instance(workload, 0, 1)
     pm = I["model"]
     model = M.Model(pm.c, None, pm.b, I["G_local"], pm.h, pm.cones)
@@ -278,49 +354,78 @@ def cpu_unit(workload, steps, warmup, budget_s=25.0, rhs_list=None):
     sample = (f"{steps} full unit(s) of {workload}" if frac >= 1.0 else
               f"{steps} unit(s) of {workload}; dsyrk timed on the first {frac:.3f} of the rows and "
               f"scaled by 1/{frac:.3f}, Cholesky and all solves in full")
-    return float(np.median(times)), sample, cores, threadpoolctl.threadpool_info(), shell.sols
+    kkt = None
+    if check_sols is not None:
+        d, r = (OraclePoint(n, model.p, q) for _ in range(2))
+        kkt = []
+        for v, rv in zip(check_sols, rhs_list):
+            d.vec[:] = v
+            shell.syssolver.apply_lhs(shell, d, r)
+            kkt.append(float(np.linalg.norm(r.vec - rv) / max(np.linalg.norm(rv), 1e-300)))
+    return dict(sec=float(np.median(times)), sample=sample, cores=cores, blas_threads=blas_threads,
+                sols=shell.sols, kkt_oracle=kkt)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    sec, sample, cores, _, _ = cpu_unit(args.workload, max(1, args.steps), min(args.warmup, 1))
-    v = 1.0 / sec
+    # full units (no dsyrk sampling) as long as the whole run stays within ~12 minutes of host time
+    r = cpu_unit(args.workload, max(1, args.steps), min(args.warmup, 1), budget_s=720.0)
+    v = 1.0 / r["sec"]
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["sec"] * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": {"workload": f"{args.workload}: {WORKLOADS[args.workload]['desc']}"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": r["cores"], "blas_threads": r["blas_threads"],
+                             "kind": "port", "sample": r["sample"]},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
 # --------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-    rank = int(os.environ.get("RANK", 0))
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    local_rank = int(os.environ.get("LOCAL_RANK", 0))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device - libhypatia_b200 has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # keep stdout to the single JSON line: NCCL prints its version banner there at VERSION/INFO
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=device)
+class DeviceShell:
+    """What the host RHS builders / stepper (hypatia.jl_b200/host/stepper.py) read from `solver`, positioned at
+    the planted first iterate, with the device plug-ins behind it."""
+
+    def __init__(self, I, ctx, cones):
+        from hypatia_b200.host.point import Point
+        from hypatia_b200.syssolver import QRCholDenseSystemSolver
+        model = I["model"]
+        self.model, self.mu, self.cones = model, I["mu"], cones
+        pt = self.point = Point(model)
+        pt.x[:] = I["x0"]
+        pt.z[:] = I["z0"]
+        pt.s[:] = I["s0"]
+        pt.tau = pt.kap = 1.0
+        self.x_residual = np.zeros(model.n)
+        self.y_residual = np.zeros(0)
+        self.z_residual = np.zeros(model.q)
+        self.tau_residual = float(model.c @ pt.x) + float(model.h @ pt.z) + pt.kap
+        sysv = self.syssolver = QRCholDenseSystemSolver()
+        sysv.ctx, sysv.cones = ctx, cones
+        self.max_ref_steps = 5                        # Solvers.jl:264
+        self.res_norm_cutoff = 1e-4 * abs(self.tau_residual)      # Solvers.jl:381-382 at this iterate
+        self.time_upsys = self.time_uprhs = self.time_getdir = self.time_search = 0.0
+        self.n_solve_system = self.n_apply_lhs = 0
+        self.worst_dir_res = 0.0
+        self.status = "SolveCalled"
+
+
+def measure_workload(args, workload, torch, dist, device, rank, world, local_rank, full):
+    """Times one workload on this process group.  full: the headline treatment (e2e pass with host buffers,
+    clocks, CPU oracle parity, full step, batched solves); otherwise value + phases + an independent KKT
+    residual only (other_workloads)."""
     from hypatia_b200 import capi
     from hypatia_b200.cones import DeviceConeBlock
     from hypatia_b200.host.point import Point
     from hypatia_b200.host import stepper as st
 
-    I = build_instance(args.workload, rank, world, dist, device)
+    big = workload in ("C4", "C5a", "C5b") or (not full)
+    M_types = WORKLOADS[workload]["cones"](__import__("hypatia_b200.host.models", fromlist=["x"]))
+    giant = world > 1 and max(ck.dim for ck in M_types) > 0.5 * sum(ck.dim for ck in M_types)
+    I = build_instance(workload, rank, world, dist, device, on_device=big, replicate_rows=giant)
     model = I["model"]
     n, q = model.n, model.q
     ctx = capi.Context(local_rank)
@@ -329,29 +434,25 @@ def run_ours(args):
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(rank, world, uid[0])
     lo, hi = I["cone_range"]
-    ctx.load_model(model, G_local=I["G_local"], cone_lo=lo, cone_hi=hi)
+    if giant:
+        ctx.set_column_sharding(True)
+    ctx.load_model(model, G_local=I["G_dev"] if big else I["G_local"], cone_lo=lo, cone_hi=hi)
     # models with a cone that has no closed-form square root assemble S with the two-operand FP64 DMMA
     # product (qrchol.jl:240-246 branch); the one-operand tcgen05 SYRK needs every cone in sqrt form
+    syrk = args.syrk
     if any(ck.ctype not in (0, 1, 2, 6) for ck in model.cones):
-        args.syrk = "dmma"
-    ctx.set_syrk_mode(1 if args.syrk == "i8" else 0)
-    I["G_local"] = None
+        syrk = "dmma"
+    ctx.set_syrk_mode(1 if syrk == "i8" else 0)
+    # the library keeps its own copy of the panel: drop ours before update_lhs allocates its work buffers
+    # (C4: G 40 GB + H^{1/2}G 40 GB + digit slices 40 GB + Schur / factor 6.4 GB of the 180 GB)
+    I["G_local"] = I["G_dev"] = None
+    if big:
+        torch.cuda.empty_cache()
     cones = DeviceConeBlock(model, ctx=ctx)
 
     # ---- the four right-hand sides of the first iterate (built once, untimed) ----
-    class Shell:
-        pass
-    sh = Shell()
-    sh.model, sh.mu, sh.cones = model, I["mu"], cones
-    pt = sh.point = Point(model)
-    pt.x[:] = I["x0"]
-    pt.z[:] = I["z0"]
-    pt.s[:] = I["s0"]
-    pt.tau = pt.kap = 1.0
-    sh.x_residual = np.zeros(n)
-    sh.y_residual = np.zeros(0)
-    sh.z_residual = np.zeros(q)
-    sh.tau_residual = float(model.c @ pt.x) + float(model.h @ pt.z) + pt.kap
+    sh = DeviceShell(I, ctx, cones)
+    pt = sh.point
     irtmu = 1.0 / np.sqrt(sh.mu)
     cones.load_point(pt.s, pt.z, irtmu)
     ctx.set_mu_tau(sh.mu, pt.tau)
@@ -389,11 +490,25 @@ def run_ours(args):
             ctx.solve_system(out["sol"][i], inp["rhs"][i])
             ctx.apply_lhs(out["res"][i], out["sol"][i])
 
+    # batched variant: the data flow of combined.jl:67-79 allows {cent, pred} and {centadj, predadj} to share
+    # one multi-column sweep each; a stepper-side change, hence reported separately
+    dev_in["rhs2"] = [torch.stack([dev_in["rhs"][0], dev_in["rhs"][2]]).contiguous(),
+                      torch.stack([dev_in["rhs"][1], dev_in["rhs"][3]]).contiguous()]
+    dev_out["sol2"] = [torch.empty((2, dim6), dtype=torch.float64, device=device) for _ in range(2)]
+    dev_out["res2"] = [torch.empty((2, dim6), dtype=torch.float64, device=device) for _ in range(2)]
+
+    def step_batched(inp, out):
+        ctx.cones_load_point(inp["s"], inp["z"], irtmu)
+        ctx.update_lhs()
+        for i in range(2):
+            ctx.solve_system_multi(out["sol2"][i], inp["rhs2"][i], 2)
+            ctx.apply_lhs_multi(out["res2"][i], out["sol2"][i], 2)
+
     ext = torch.cuda.ExternalStream(ctx.stream(), device=device)
 
-    def timed(inp, out, steps, warmup, sample_clocks):
+    def timed(fn, inp, out, steps, warmup, sample_clocks):
         for _ in range(warmup):
-            step(inp, out)
+            fn(inp, out)
         ctx.sync()
         torch.cuda.synchronize()
         if dist is not None:
@@ -406,7 +521,7 @@ def run_ours(args):
         with torch.cuda.stream(ext):
             e0.record()
         for _ in range(steps):
-            step(inp, out)
+            fn(inp, out)
         with torch.cuda.stream(ext):
             e1.record()
         ctx.sync()
@@ -421,12 +536,34 @@ def run_ours(args):
             ms = float(t.item())
         return ms, ctx.launch_count() - l0, clocks
 
-    ms, launches, clocks = timed(dev_in, dev_out, args.steps, args.warmup, True)
-    value = args.steps / (ms * 1e-3)
-    ms_e2e, _, _ = timed(host_in, host_out, args.steps, 1, False)
-    e2e_value = args.steps / (ms_e2e * 1e-3)
-    h2d = 8 * (2 * q + 4 * dim6 + 4 * dim6)       # point + 4 rhs + 4 dirs (apply_lhs input)
-    d2h = 8 * (4 * dim6 + 4 * dim6) + 4           # 4 dirs + 4 residuals + Cholesky info word
+    steps, warmup = (args.steps, args.warmup) if full else (args.other_steps, 1)
+    ms, launches, clocks = timed(step, dev_in, dev_out, steps, warmup, full)
+    out = {"workload": f"{workload}: {I['desc']}", "value": steps / (ms * 1e-3), "ms_per_step": ms / steps,
+           "steps": steps, "gpu_launches": launches, "syrk": syrk, "clocks": clocks,
+           "sharding": ("columns of the giant cone (all-gather)" if giant else "cones / row panels") if world > 1 else "none"}
+    if full:
+        ms_e2e, _, _ = timed(step, host_in, host_out, args.steps, 1, False)
+        out["e2e"] = {"value": args.steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                      "h2d_bytes_per_step": 8 * (2 * q + 4 * dim6 + 4 * dim6),     # point + 4 rhs + 4 dirs (apply_lhs input)
+                      "d2h_bytes_per_step": 8 * (4 * dim6 + 4 * dim6) + 4}        # 4 dirs + 4 residuals + Cholesky info word
+        dev_sols = [t.numpy().copy() for t in host_out["sol"]]
+        dev_res = [t.numpy().copy() for t in host_out["res"]]
+    else:
+        dev_sols = [t.cpu().numpy() for t in dev_out["sol"]]
+        dev_res = [t.cpu().numpy() for t in dev_out["res"]]
+    if ctx.has_multi():
+        try:
+            ms_b, launches_b, _ = timed(step_batched, dev_in, dev_out, steps, 1, False)
+            solb = [dev_out["sol2"][0][0], dev_out["sol2"][1][0], dev_out["sol2"][0][1], dev_out["sol2"][1][1]]
+            dmax = max(float(torch.linalg.norm(solb[i] - dev_out["sol"][i]) /
+                             torch.linalg.norm(dev_out["sol"][i])) for i in range(4))
+            out["batched_solves"] = {"value": steps / (ms_b * 1e-3), "unit": UNIT, "ms_per_step": ms_b / steps,
+                                     "gpu_launches": launches_b, "max_rel_diff_vs_single_column": dmax,
+                                     "what": "same unit with {cent, pred} and {centadj, predadj} solved by "
+                                             "hyp_solve_system_multi / hyp_apply_lhs_multi (2 columns per sweep); a stepper-side "
+                                             "change of the call sequence, so NOT the headline"}
+        except Exception as e:
+            out["batched_solves"] = {"error": f"{type(e).__name__}: {e}"}
 
     # per-phase device times (library CUDA-event timers; separate untimed pass)
     ctx.timing_enable(True)
@@ -435,61 +572,192 @@ def run_ours(args):
     for _ in range(nprof):
         step(dev_in, dev_out)
     ctx.sync()
-    phases = {k: v[0] / nprof for k, v in ctx.timing().items() if v[1]}
+    out["phase_ms"] = {k: v[0] / nprof for k, v in ctx.timing().items() if v[1]}
     ctx.timing_enable(False)
-    m = n
-    qloc = I["rows"][1] - I["rows"][0]
-    syrk_ms = phases.get("schur_syrk", float("nan"))
-    syrk_flops = float(qloc) * m * (m + 1)
-    achieved = syrk_flops / (syrk_ms * 1e-3) / 1e12 if syrk_ms == syrk_ms and syrk_ms > 0 else None
+    out["rows"] = I["rows"]
+    out["dims"] = (n, q)
 
+    relerr = lambda a, b: float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+    parity = {"tol": 1e-8, "kkt_residual_device_operator": [relerr(dev_res[i], rhs_list[i]) for i in range(4)]}
+    out["parity"] = parity
+    out["_dev_sols"], out["_rhs_list"] = dev_sols, rhs_list
+
+    if full:
+        # one complete CombinedStepper.step at this iterate: update_lhs, four get_directions WITH iterative refinement
+        # (up to 5 rounds each, common.jl:15-76), the line search with its cone-oracle sweeps (search.jl:46-138)
+        try:
+            out["full_step"] = full_step(sh, I, ctx, cones, irtmu, torch)
+        except Exception as e:
+            out["full_step"] = {"error": f"{type(e).__name__}: {e}"}
+    ctx.close()
+    if big:
+        torch.cuda.empty_cache()
+    if not full:
+        # independent KKT operator: the two G products by torch (cuBLAS dgemv on the regenerated panel), the cone
+        # Hessian products by the CPU oracle's cones - nothing of libhypatia_b200 in it
+        try:
+            I2 = build_instance(workload, rank, world, dist, device, on_device=True, replicate_rows=giant)
+            parity["kkt_residual_independent"] = independent_kkt(torch, dist, device, I2, sh, dev_sols, rhs_list, giant)
+            parity["kkt_operator"] = "torch dgemv on the generated G panel + CPU-oracle cone Hessians (no libhypatia_b200 code)"
+            del I2
+            torch.cuda.empty_cache()
+        except Exception as e:
+            parity["kkt_residual_independent"] = f"failed: {type(e).__name__}: {e}"
+    return out
+
+
+def independent_kkt(torch, dist, device, I, sh, dev_sols, rhs_list, giant):
+    """||K d - r|| / ||r|| of the device directions with an operator that shares no code with the library."""
+    from oracle.cones import OracleConeBlock
+    from oracle.layout import OraclePoint
+    model = I["model"]
+    n, q = model.n, model.q
+    row_lo, row_hi = I["rows"]
+    GT = I["G_dev"]                                # (n, rows) on the device
+    ora = OracleConeBlock(model)
+    pt = sh.point
+    ora.load_point(pt.s, pt.z, 1.0 / np.sqrt(sh.mu))
+    world = dist.get_world_size() if dist is not None else 1
+    out = []
+    d, r = OraclePoint(n, 0, q), OraclePoint(n, 0, q)
+    for v, rv in zip(dev_sols, rhs_list):
+        d.vec[:] = v
+        tz = torch.from_numpy(d.z[row_lo:row_hi].copy()).to(device)
+        tx = torch.from_numpy(d.x.copy()).to(device)
+        gtz = torch.mv(GT, tz)
+        gx = torch.zeros(q, dtype=torch.float64, device=device)
+        gx[row_lo:row_hi] = torch.mv(GT.t(), tx)
+        if world > 1 and not giant:
+            dist.all_reduce(gtz)
+            dist.all_reduce(gx)
+        gtz, gx = gtz.cpu().numpy(), gx.cpu().numpy()
+        r.x[:] = gtz + model.c * d.tau                                   # common.jl:91-94
+        r.z[:] = model.h * d.tau - d.s - gx                              # common.jl:100-103
+        r.tau = -float(model.c @ d.x) - float(model.h @ d.z) - d.kap
+        r.s[:] = ora.hess_prod(d.s) + d.z                                # common.jl:109-115 (primal-barrier cones)
+        r.kap = sh.mu / pt.tau * d.tau / pt.tau + d.kap
+        out.append(float(np.linalg.norm(r.vec - rv) / max(np.linalg.norm(rv), 1e-300)))
+    return out
+
+
+def full_step(sh, I, ctx, cones, irtmu, torch):
+    from hypatia_b200.host import stepper as st
+    stp = st.CombinedStepper().load(sh)
+    pt = sh.point
+    p0 = pt.vec.copy()
+    times, info = [], None
+    for it in range(3):
+        pt.vec[:] = p0
+        sh.n_solve_system = sh.n_apply_lhs = 0
+        sh.worst_dir_res = 0.0
+        stp.searcher.n_oracle_sweeps = 0
+        ctx.sync()
+        t0 = time.perf_counter()
+        cones.load_point(pt.s, pt.z, irtmu)
+        ok = stp.step(sh)
+        ctx.sync()
+        times.append(time.perf_counter() - t0)
+        info = {"ok": bool(ok), "alpha": float(stp.prev_alpha), "n_solve_system": sh.n_solve_system,
+                "n_apply_lhs": sh.n_apply_lhs, "n_oracle_sweeps": stp.searcher.n_oracle_sweeps,
+                "worst_dir_res": float(sh.worst_dir_res)}
+    pt.vec[:] = p0
+    info.update({"ms": float(np.median(times[1:])) * 1e3, "value": 1.0 / float(np.median(times[1:])), "unit": UNIT,
+                 "timing": "host wall clock around CombinedStepper.step (host control flow, device plug-ins), median of 2 after 1 warm-up",
+                 "what": "load_point + update_lhs + 4 x get_directions incl. iterative refinement (max_ref_steps 5, cutoff "
+                         "1e-4 x residual norm) + search_alpha with its cone-oracle sweeps + point update"})
+    return info
+
+
+def run_ours(args):
+    import torch
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - libhypatia_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # keep stdout to the single JSON line: NCCL prints its version banner there at VERSION/INFO
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=device)
+
+    main = measure_workload(args, args.workload, torch, dist, device, rank, world, local_rank, True)
+    others = {}
+    for w in [x for x in args.other.split(",") if x and x != "none"]:
+        try:
+            r = measure_workload(args, w, torch, dist, device, rank, world, local_rank, False)
+            r.pop("_dev_sols", None), r.pop("_rhs_list", None), r.pop("clocks", None)
+            others[w] = r
+        except Exception as e:
+            others[w] = {"error": f"{type(e).__name__}: {e}"}
     if rank != 0:
         if dist is not None:
             dist.barrier()
             dist.destroy_process_group()
         return
+
+    ms_step = main["ms_per_step"]
+    phases = main["phase_ms"]
+    n, q = main["dims"]
+    m = n
+    qloc = main["rows"][1] - main["rows"][0]
+    syrk_ms = phases.get("schur_syrk", float("nan"))
+    syrk_flops = float(qloc) * m * (m + 1)
+    fp64_eq = syrk_flops / (syrk_ms * 1e-3) / 1e12 if syrk_ms == syrk_ms and syrk_ms > 0 else None
     peaks = measured_peaks()
     fp64_peak = dgemm_peak_tflops(torch, device)
-    if args.syrk == "i8":
+    if main["syrk"] == "i8":
         # exact int8 digit-pair products per FP64 product: 28 (seven balanced radix-256 digits, s + t <= 6; default)
         # or 36 (eight radix-128 digits, s + t <= 7: HYP_OZAKI_RADIX=128 or the single-CTA / cluster kernels)
         r128 = os.environ.get("HYP_OZAKI_RADIX") == "128" or os.environ.get("HYP_OZAKI_CLUSTER", "2")[:1] in ("0", "1")
         npairs = 28 if (not r128 or os.environ.get("HYP_OZAKI_SLICES") == "7") else 36
         nt = (m + 127) // 128
         int8_ops = 2.0 * npairs * float(qloc) * 128 * 128 * (nt * (nt + 1) // 2)
-        int8_tops = int8_ops / (syrk_ms * 1e-3) / 1e12 if achieved else None
-        int8_peak = 2.0 * peaks["bf16_tflops"] if peaks.get("bf16_tflops") else None
+        int8_tops = int8_ops / (syrk_ms * 1e-3) / 1e12 if fp64_eq else None
+        # the kernel is timed inside a long step: the sustained bf16 figure is the denominator (x 2 for int8)
+        bf16 = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops")
+        int8_peak = 2.0 * bf16 if bf16 else None
+        traffic = NCU_TRAFFIC.get(args.workload + ":i8") if world == 1 else None
         roofline = {"bound": "tensor",
                     "kernel": "ozaki_syrk_pair_kernel (Schur SYRK: FP64-accurate digit slicing, %d exact int8 digit-pair "
                               "products, tcgen05 kind::i8 cta_group::2 M=256, TMEM accumulators, 3-D TMA) + slicing kernels" % npairs,
-                    "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s (algorithmic FP64)",
-                    "frac": (achieved / fp64_peak) if achieved else None,
-                    "peak_source": "cuBLAS DGEMM 8192^3 measured live in this run = the FP64 tensor (DMMA) roofline; "
-                                   "frac > 1 because the contraction runs as exact int8 products on tcgen05",
-                    "int8_top_s_executed": int8_tops,
-                    "int8_peak_top_s": int8_peak,
-                    "int8_peak_source": "2 x bf16_tflops of MEASURED_PEAKS.json (int8 dense = 2 x bf16 on B200)",
-                    "int8_frac": (int8_tops / int8_peak) if int8_tops and int8_peak else None,
-                    "traffic": NCU_TRAFFIC.get(args.workload + ":i8") if world == 1 else None,
-                    "traffic_unit": "bytes per SYRK (dram__bytes_read.sum + dram__bytes_write.sum over its launches, "
-                                    "profiles/r01_ozaki_pair_row_order_ncu.txt)",
-                    "algorithmic_flops_per_launch": syrk_flops, "avg_launch_ms": syrk_ms,
-                    "step_share": syrk_ms / (ms / args.steps) if syrk_ms == syrk_ms else None,
+                    "achieved": int8_tops, "peak": int8_peak, "unit": "TOP/s (int8 MACs x 2 executed on tcgen05 kind::i8)",
+                    "frac": (int8_tops / int8_peak) if int8_tops and int8_peak else None,
+                    "peak_source": "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (assumes int8 dense = 2 x bf16 on B200; "
+                                   "no int8 peak is measured by the driver)",
+                    "fp64_equivalent_tflops": fp64_eq, "fp64_dgemm_peak_tflops": fp64_peak,
+                    "fp64_equivalent_over_dgemm": (fp64_eq / fp64_peak) if fp64_eq else None,
+                    "fp64_note": "algorithmic FP64 flops q*m*(m+1) per SYRK over its time, next to cuBLAS DGEMM 8192^3 measured "
+                                 "live in this run (the FP64 DMMA roofline the digit-sliced kernel replaces)",
+                    "traffic": traffic[0] if traffic else None,
+                    "traffic_source": traffic[1] if traffic else None,
+                    "algorithmic_flops_per_launch": syrk_flops, "executed_int8_ops_per_launch": int8_ops,
+                    "avg_launch_ms": syrk_ms,
+                    "step_share": syrk_ms / ms_step if syrk_ms == syrk_ms else None,
                     "phase_ms": phases}
     else:
+        traffic = NCU_TRAFFIC.get(args.workload) if world == 1 else None
         roofline = {"bound": "tensor", "kernel": "atb_upper_kernel (Schur SYRK, TMA + FP64 DMMA)",
-                    "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                    "frac": (achieved / fp64_peak) if achieved else None,
+                    "achieved": fp64_eq, "peak": fp64_peak, "unit": "TFLOP/s",
+                    "frac": (fp64_eq / fp64_peak) if fp64_eq else None,
                     "peak_source": "cuBLAS DGEMM 8192^3 measured live in this run (FP64 tensor pipe; "
                                    "MEASURED_PEAKS.json has no FP64 entry)",
-                    "peak_bf16_measured": peaks.get("bf16_tflops"),
-                    "frac_of_bf16_peak": (achieved / peaks["bf16_tflops"]) if achieved and peaks.get("bf16_tflops") else None,
-                    "traffic": NCU_TRAFFIC.get(args.workload) if world == 1 else None,
-                    "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, "
-                                    "profiles/r01_syrk_schur_ncu_full.txt)",
+                    "traffic": traffic[0] if traffic else None,
+                    "traffic_source": traffic[1] if traffic else None,
                     "algorithmic_flops_per_launch": syrk_flops, "avg_launch_ms": syrk_ms,
-                    "step_share": syrk_ms / (ms / args.steps) if syrk_ms == syrk_ms else None,
+                    "step_share": syrk_ms / ms_step if syrk_ms == syrk_ms else None,
                     "phase_ms": phases}
+    potrf_ms = phases.get("potrf")
+    if potrf_ms:
+        roofline["potrf"] = {"kernel": "hyp_potrf_upper (blocked Cholesky: panel kernel + FP64 DMMA / digit-sliced trailing updates)",
+                             "algorithmic_flops": m ** 3 / 3.0, "ms": potrf_ms,
+                             "fp64_tflops": m ** 3 / 3.0 / (potrf_ms * 1e-3) / 1e12,
+                             "frac_of_dgemm": m ** 3 / 3.0 / (potrf_ms * 1e-3) / 1e12 / fp64_peak}
     g_bytes = 8.0 * qloc * n
     gemv_ms = phases.get("gemv")
     if gemv_ms:
@@ -502,35 +770,40 @@ def run_ours(args):
                                  "peak_gbs": peaks.get("hbm_gbs"),
                                  "note": "%d passes per step (reference count 22; the s-lift reuses G*x; apply_lhs "
                                          "reads G once for G'z and G x when the panel is not sharded)" % npass}
-    # parity at the benchmarked size (SURVEY.md 8(d) "parity reported with every timing"): the directions
-    # and residuals that came back over the C ABI in the end-to-end pass.  kkt_residual is the size-independent
-    # property ||K d - r|| / ||r|| with the device operator; dir_vs_oracle compares each direction with the CPU
-    # oracle's solve of the SAME right-hand side (filled in by the cpu_baseline leg below, N = 1 only).
-    relerr = lambda a, b: float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
-    dev_sols = [t.numpy().copy() for t in host_out["sol"]]
-    parity = {"tol": 1e-8,
-              "kkt_residual": [relerr(host_out["res"][i].numpy(), rhs_list[i]) for i in range(4)],
-              "dir_vs_oracle": None}
+    trsv_ms = phases.get("trsv")
+    if trsv_ms:
+        roofline["trsv"] = {"algorithmic_bytes_per_step": 5 * 8.0 * m * m, "achieved_gbs": 5 * 8.0 * m * m / (trsv_ms * 1e-3) / 1e9,
+                            "peak_gbs": peaks.get("hbm_gbs"), "note": "5 potrs per step, two triangular sweeps each (4 m^2 B per sweep)"}
+
+    # parity at the benchmarked size, at EVERY N: rank 0 runs the CPU oracle on the full instance
+    parity = main["parity"]
+    parity["dir_vs_oracle"] = parity["kkt_residual"] = None
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if not args.no_cpu_baseline:
         try:
-            sec, sample, cores, _, ora_sols = cpu_unit(args.workload, 1, 0, rhs_list=rhs_list)
-            cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
-            parity["dir_vs_oracle"] = [relerr(dev_sols[i], ora_sols[i]) for i in range(4)]
+            r = cpu_unit(args.workload, 1, 0, rhs_list=main["_rhs_list"], check_sols=main["_dev_sols"])
+            relerr = lambda a, b: float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+            parity["dir_vs_oracle"] = [relerr(main["_dev_sols"][i], r["sols"][i]) for i in range(4)]
+            parity["kkt_residual"] = r["kkt_oracle"]
+            parity["kkt_operator"] = "oracle apply_lhs (NumPy, CPU) applied to the directions returned over the C ABI"
+            if world == 1:
+                cpu = {"value": 1.0 / r["sec"], "unit": UNIT, "cores": r["cores"], "blas_threads": r["blas_threads"],
+                       "kind": "port", "sample": r["sample"]}
         except Exception as e:      # the baseline is reported, never required
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                    "sample": f"failed: {type(e).__name__}: {e}"}
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+    line = {"metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {I['desc']}",
+            "config": {"workload": main["workload"],
                        "unit_of_work": "load_point + update_lhs + 4 x (solve_system + apply_lhs)",
                        "parallelism": f"cone/row-panel sharding over {world} rank(s)",
-                       "schur_syrk": "tcgen05 int8 digit slicing (FP64-accurate)" if args.syrk == "i8" else "FP64 DMMA",
+                       "schur_syrk": "tcgen05 int8 digit slicing (FP64-accurate)" if main["syrk"] == "i8" else "FP64 DMMA",
                        "l2": "inputs larger than L2 (G panel %.1f GB, Schur %.2f GB)" % (g_bytes / 1e9, 8e-9 * m * m)},
-            "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                                      "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "parity": parity}
+            "clocks": main["clocks"], "e2e": main["e2e"],
+            "gpu_launches": main["gpu_launches"], "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+            "full_step": main.get("full_step"), "batched_solves": main.get("batched_solves"),
+            "other_workloads": others}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -544,6 +817,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
+    ap.add_argument("--other", default=os.environ.get("HYP_BENCH_OTHER", "C2,C4,C5a"),
+                    help="comma-separated extra workloads reported under other_workloads ('none' to skip)")
+    ap.add_argument("--other-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--syrk", default=os.environ.get("HYP_SCHUR_SYRK", "i8"), choices=["dmma", "i8"],
                     help="Schur SYRK kernel: FP64 DMMA or FP64-accurate digit slicing on the int8 tcgen05 pipe")

@@ -50,6 +50,8 @@ _SIGS = {
     "hyp_solve_subsystem3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "hyp_solve_system": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "hyp_apply_lhs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hyp_solve_system_multi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64]),
+    "hyp_apply_lhs_multi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64]),
     "hyp_calc_residuals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hyp_get_schur": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "hyp_launch_count": (C.c_int64, [C.c_void_p]),
@@ -270,6 +272,24 @@ class Context:
 
     def apply_lhs(self, res, direction):
         self.check(self.lib.hyp_apply_lhs(self.h, ptr(res), ptr(direction)), "hyp_apply_lhs")
+
+    def _ld(self, a, ncols):
+        dim6 = self.n + self.p + 2 * self.q + 2
+        if hasattr(a, "stride") and not isinstance(a, np.ndarray):
+            return int(a.stride(0)) if ncols > 1 else dim6
+        return int(a.strides[0] // 8) if ncols > 1 else dim6
+
+    def has_multi(self):
+        return True
+
+    def solve_system_multi(self, sol, rhs, ncols):
+        """sol / rhs: (ncols, n+p+2q+2) row-major arrays or tensors - one Point per row."""
+        self.check(self.lib.hyp_solve_system_multi(self.h, ptr(sol), ptr(rhs), int(ncols), self._ld(rhs, ncols)),
+                   "hyp_solve_system_multi")
+
+    def apply_lhs_multi(self, res, direction, ncols):
+        self.check(self.lib.hyp_apply_lhs_multi(self.h, ptr(res), ptr(direction), int(ncols), self._ld(direction, ncols)),
+                   "hyp_apply_lhs_multi")
 
     def calc_residuals(self, point_vec):
         """(x_residual, y_residual, z_residual, stats[10]) of calc_convergence_params (Solvers.jl:425-483)."""

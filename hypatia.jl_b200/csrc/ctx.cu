@@ -559,6 +559,20 @@ void calc_residuals_dev(hyp_ctx* ctx, const double* pt, double* xres, double* yr
     CUDA_TRY(cudaGetLastError());
 }
 
+// ---- multi-column solves: see the batched kernels below; until a model / rank layout is supported the C entry
+// points fall back to one column at a time (same results, no amortisation) ----
+bool hyp_multi_supported(hyp_ctx* ctx, int ncols) {
+    (void)ctx;
+    (void)ncols;
+    return false;
+}
+void solve_system_multi_dev(hyp_ctx* ctx, double* sol, const double* rhs, int ncols, int64_t ld) {
+    for (int j = 0; j < ncols; j++) solve_system_dev(ctx, sol + j * ld, rhs + j * ld);
+}
+void apply_lhs_multi_dev(hyp_ctx* ctx, double* res, const double* dir, int ncols, int64_t ld) {
+    for (int j = 0; j < ncols; j++) apply_lhs_dev(ctx, res + j * ld, dir + j * ld);
+}
+
 // Schur assembly + factorisation (update_lhs_fact, qrchol.jl:201-257)
 int update_lhs_fact(hyp_ctx* ctx) {
     const int64_t nmp = ctx->nmp, p = ctx->p;
@@ -1343,6 +1357,52 @@ int hyp_apply_lhs(hyp_ctx* ctx, double* res, const double* dir) {
     });
 }
 
+// Multi-column variants (the data flow of combined.jl:67-79 lets {cent, pred} and {centadj, predadj}
+// share one sweep each).  Column j of `sol` / `rhs` / `res` / `dir` is the full Point at offset j * ld (ld >= n+p+2q+2).
+int hyp_solve_system_multi(hyp_ctx* ctx, double* sol, const double* rhs, int ncols, int64_t ld) {
+    return guarded(ctx, [&] {
+        need_model(ctx);
+        if (!ctx->lhs_ready) throw HypError{"hyp_solve_system_multi: call hyp_update_lhs first"};
+        const int64_t dim6 = ctx->n + ctx->p + 2 * ctx->q + 2;
+        if (ncols < 0 || (ncols > 0 && ld < dim6)) throw HypError{"hyp_solve_system_multi: bad ncols / ld"};
+        if (ncols == 0) return 0;
+        const bool dev = is_device_ptr(sol) && is_device_ptr(rhs) && sol != rhs;
+        if (dev && ncols > 1 && hyp_multi_supported(ctx, ncols)) {
+            solve_system_multi_dev(ctx, sol, rhs, ncols, ld);
+            return 0;
+        }
+        for (int j = 0; j < ncols; j++) {
+            const double* drhs = stage_in(ctx, rhs + j * ld, dim6, ctx->d_rhs);
+            double* dsol = is_device_ptr(sol) ? sol + j * ld : ctx->d_sol;
+            if (dsol == drhs) dsol = ctx->d_sol;
+            solve_system_dev(ctx, dsol, drhs);
+            stage_out(ctx, sol + j * ld, dim6, dsol);
+        }
+        return 0;
+    });
+}
+int hyp_apply_lhs_multi(hyp_ctx* ctx, double* res, const double* dir, int ncols, int64_t ld) {
+    return guarded(ctx, [&] {
+        need_model(ctx);
+        if (!ctx->cones_loaded) throw HypError{"hyp_apply_lhs_multi: no cone point loaded"};
+        const int64_t dim6 = ctx->n + ctx->p + 2 * ctx->q + 2;
+        if (ncols < 0 || (ncols > 0 && ld < dim6)) throw HypError{"hyp_apply_lhs_multi: bad ncols / ld"};
+        if (ncols == 0) return 0;
+        const bool dev = is_device_ptr(res) && is_device_ptr(dir) && res != dir;
+        if (dev && ncols > 1 && hyp_multi_supported(ctx, ncols)) {
+            apply_lhs_multi_dev(ctx, res, dir, ncols, ld);
+            return 0;
+        }
+        for (int j = 0; j < ncols; j++) {
+            const double* ddir = stage_in(ctx, dir + j * ld, dim6, ctx->d_rhs);
+            double* dres = is_device_ptr(res) ? res + j * ld : ctx->d_sol;
+            if (dres == ddir) dres = ctx->d_sol;
+            apply_lhs_dev(ctx, dres, ddir);
+            stage_out(ctx, res + j * ld, dim6, dres);
+        }
+        return 0;
+    });
+}
 int hyp_calc_residuals(hyp_ctx* ctx, const double* point, double* x_residual, double* y_residual,
                        double* z_residual, double* stats) {
     return guarded(ctx, [&] {

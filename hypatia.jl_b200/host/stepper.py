@@ -207,7 +207,9 @@ def check_cone_points(solver, stepper) -> bool:
         return False
     proxsqr = cones.get_proxsqr(irtmu, searcher.use_max_prox)
     if searcher.use_max_prox:
-        agg = max(taukap_proxsqr, float(proxsqr.max())) if proxsqr.size else taukap_proxsqr
+        # Julia's max propagates NaN (search.jl:112-135: a NaN proximity must reject the candidate);
+        # Python's builtin max(x, nan) returns x, so aggregate with np.maximum instead
+        agg = float(np.maximum(taukap_proxsqr, proxsqr.max())) if proxsqr.size else taukap_proxsqr
     else:
         agg = taukap_proxsqr + float(proxsqr.sum())
     if not (agg < proxsqr_bound):

@@ -168,6 +168,12 @@ int hyp_solve_subsystem3(hyp_ctx* ctx, double* sol, const double* rhs);
 int hyp_solve_system(hyp_ctx* ctx, double* sol, const double* rhs);
 /* apply_lhs(stepper, solver) restricted to its data flow: res = LHS6x6 * dir, common.jl:79-121 */
 int hyp_apply_lhs(hyp_ctx* ctx, double* res, const double* dir);
+/* Multi-column forms of the two calls above: column j is the full Point at offset j * ld (ld >= n+p+2q+2).
+ * The stepper's data flow (src/Solvers/steppers/combined.jl:67-79) allows {cent, pred} and then
+ * {centadj, predadj} to be solved together, so that the triangular sweeps and the passes over G are shared
+ * (SURVEY.md 8(d)); results are identical to ncols calls of hyp_solve_system / hyp_apply_lhs. */
+int hyp_solve_system_multi(hyp_ctx* ctx, double* sol, const double* rhs, int ncols, int64_t ld);
+int hyp_apply_lhs_multi(hyp_ctx* ctx, double* res, const double* dir, int ncols, int64_t ld);
 
 /* residual step on the other side of the path: the vectors and norms of
  * calc_convergence_params(solver), Solvers.jl:425-483, for the full Point `point`, with the two passes

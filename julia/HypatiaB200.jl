@@ -4,7 +4,11 @@ Hypatia.jl's two plug-in slots for the per-iteration hot path:
 
   * Solvers.SystemSolver{Float64}   ->  B200QRCholSystemSolver      (load / update_lhs / solve_system /
                                                                       solve_subsystem3 / free_memory)
-  * the per-cone oracle loops of the stepper and the line search  ->  batched hyp_cones_* calls
+  * the per-cone oracle loops of the stepper and the line search  ->  batched hyp_cones_* calls: the five
+    reference functions that contain those loops (apply_lhs, update_rhs_cent, update_rhs_centadj,
+    update_rhs_predadj, check_cone_points) get Float64 methods here that take the batched path when the
+    solver carries a B200QRCholSystemSolver and `invoke` the stock generic method otherwise - no edit of
+    the Hypatia.jl sources is needed (INTEGRATION.md lists each override next to the lines it replaces)
 
 Everything else (Solver, steppers, preprocessing, MOI) stays stock Hypatia.jl; usage:
 
@@ -103,8 +107,18 @@ mutable struct B200QRCholSystemSolver <: QRCholSystemSolver{Float64}
     sol_sub::Point{Float64}
     rhs_const::Point{Float64}
     sol_const::Point{Float64}
+    # batched cone-oracle state (plug-in slot 2): the scaled primal point the device cones are loaded at
+    # (= cone.point of every cone, Cones.jl:157-161) and q-vector scratch
+    cone_point::Vector{Float64}
+    vq1::Vector{Float64}
+    vq2::Vector{Float64}
+    vq3::Vector{Float64}
     B200QRCholSystemSolver(; device::Int = 0) = (s = new(); s.ctx = C_NULL; s.device = device; s)
 end
+
+# check_cone_points(model, stepper) (search.jl:74) is not handed the solver: the context is found by model
+const CTX_OF_MODEL = IdDict{Any, B200QRCholSystemSolver}()
+b200(solver::Solver{Float64}) = solver.syssolver isa B200QRCholSystemSolver ? solver.syssolver : nothing
 
 # load(syssolver, solver): qrchol.jl:138-179.  G is uploaded once; Ap_Q / Ap_R only when p > 0.
 function Solvers.load(syssolver::B200QRCholSystemSolver, solver::Solver{Float64})
@@ -118,8 +132,10 @@ function Solvers.load(syssolver::B200QRCholSystemSolver, solver::Solver{Float64}
     ctype = Cint[cone_code(c) for c in model.cones]
     cdim = Int64[Cones.dimension(c) for c in model.cones]
     cdual = Cint[Cones.use_dual_barrier(c) for c in model.cones]
-    ApQ = iszero(p) ? C_NULL : pointer(Matrix{Float64}(solver.Ap_Q * I(n)))
-    ApR = iszero(p) ? C_NULL : pointer(Matrix{Float64}(solver.Ap_R))
+    # Ap_Q is a QR "Q" object (or UniformScaling when p = 0), Ap_R an UpperTriangular (Solvers.jl:104-105):
+    # materialise both as dense column-major matrices bound to locals, so that the ccall below roots them
+    Qm = iszero(p) ? zeros(Float64, 0, 0) : Matrix{Float64}(solver.Ap_Q * Matrix{Float64}(I, n, n))
+    Rm = iszero(p) ? zeros(Float64, 0, 0) : Matrix{Float64}(solver.Ap_R)
     ssf = [cone_ssf(c) for c in model.cones]
     (hkind, hparam) = (Cint[first(t) for t in ssf], Float64[last(t) for t in ssf])
     check(syssolver.ctx, ccall((:hyp_set_cone_params, LIB), Cint, (Ctx, Cint, Ptr{Cint}, Ptr{Float64}),
@@ -128,7 +144,9 @@ function Solvers.load(syssolver::B200QRCholSystemSolver, solver::Solver{Float64}
     aoff = Int64[0; cumsum(length.(alphas))]
     check(syssolver.ctx, ccall((:hyp_set_cone_alpha, LIB), Cint, (Ctx, Cint, Ptr{Int64}, Ptr{Float64}),
         syssolver.ctx, K, aoff, vcat(alphas..., Float64[0])), "hyp_set_cone_alpha")
-    GC.@preserve G A ctype cdim cdual begin
+    GC.@preserve G A ctype cdim cdual Qm Rm begin
+        ApQ = iszero(p) ? Ptr{Float64}(C_NULL) : pointer(Qm)
+        ApR = iszero(p) ? Ptr{Float64}(C_NULL) : pointer(Rm)
         rc = ccall((:hyp_load_model, LIB), Cint,
             (Ctx, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Float64},
              Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Cint}, Ptr{Int64}, Ptr{Cint}, Cint, Cint,
@@ -138,6 +156,9 @@ function Solvers.load(syssolver::B200QRCholSystemSolver, solver::Solver{Float64}
         check(syssolver.ctx, rc, "hyp_load_model")
     end
     Solvers.setup_point_sub(syssolver, model)
+    syssolver.cone_point = zeros(q)
+    (syssolver.vq1, syssolver.vq2, syssolver.vq3) = (zeros(q), zeros(q), zeros(q))
+    CTX_OF_MODEL[model] = syssolver
     return syssolver
 end
 
@@ -150,6 +171,7 @@ function Solvers.update_lhs(syssolver::B200QRCholSystemSolver, solver::Solver{Fl
     (primal, dual) = primal_dual_vectors(solver.model, point)
     check(ctx, ccall((:hyp_cones_load_point, LIB), Cint, (Ctx, Ptr{Float64}, Ptr{Float64}, Float64),
         ctx, primal, dual, irtmu), "hyp_cones_load_point")
+    @. syssolver.cone_point = irtmu * primal
     check(ctx, ccall((:hyp_set_mu_tau, LIB), Cint, (Ctx, Float64, Float64), ctx, solver.mu,
         point.tau[]), "hyp_set_mu_tau")
     kind = Ref{Cint}(0)
@@ -179,23 +201,29 @@ function Solvers.solve_subsystem3(syssolver::B200QRCholSystemSolver, solver::Sol
     return sol
 end
 
-# apply_lhs(stepper, solver): common.jl:79-121.  The reference's function is not dispatched on the
-# system solver, so the shim adds a method for solvers that carry the B200 system solver.
-function Solvers.apply_lhs(stepper::Solvers.Stepper{Float64},
-    solver::Solver{Float64, <:Any, B200QRCholSystemSolver})
-    ctx = solver.syssolver.ctx
+# apply_lhs(stepper, solver): common.jl:79-121.  The reference's function is generic in T and not dispatched
+# on the system solver (Solver{T} has ONE type parameter, Solvers.jl:62), so the shim adds the more specific
+# Float64 method and falls through to the stock method for every other system solver.  It fills
+# stepper.temp from stepper.dir exactly like common.jl:84-85.
+const GENERIC_APPLY_LHS = Tuple{Solvers.Stepper{T}, Solver{T}} where {T <: Real}
+function Solvers.apply_lhs(stepper::Solvers.Stepper{Float64}, solver::Solver{Float64})
+    sys = b200(solver)
+    isnothing(sys) && return invoke(Solvers.apply_lhs, GENERIC_APPLY_LHS, stepper, solver)
+    ctx = sys.ctx
     check(ctx, ccall((:hyp_set_mu_tau, LIB), Cint, (Ctx, Float64, Float64), ctx, solver.mu,
         solver.point.tau[]), "hyp_set_mu_tau")
     check(ctx, ccall((:hyp_apply_lhs, LIB), Cint, (Ctx, Ptr{Float64}, Ptr{Float64}),
-        ctx, stepper.res.vec, stepper.dir.vec), "hyp_apply_lhs")
-    return stepper.res
+        ctx, stepper.temp.vec, stepper.dir.vec), "hyp_apply_lhs")
+    return stepper.temp
 end
 
 # calc_convergence_params(solver): Solvers.jl:425-483.  Optional: the residual vectors and norms with the
 # two passes over G done on the device (hyp_calc_residuals); the remaining scalar bookkeeping of the
 # reference's function (x_feas .. improv, primal_obj, dual_obj, gap) is unchanged host code.
-function device_residuals!(solver::Solver{Float64, <:Any, B200QRCholSystemSolver})
-    ctx = solver.syssolver.ctx
+function device_residuals!(solver::Solver{Float64})
+    sys = b200(solver)
+    isnothing(sys) && error("device_residuals! needs a B200QRCholSystemSolver")
+    ctx = sys.ctx
     stats = zeros(10)
     check(ctx, ccall((:hyp_calc_residuals, LIB), Cint,
         (Ctx, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
@@ -215,6 +243,9 @@ end
 function Solvers.free_memory(syssolver::B200QRCholSystemSolver)
     syssolver.ctx == C_NULL || ccall((:hyp_destroy, LIB), Cvoid, (Ctx,), syssolver.ctx)
     syssolver.ctx = C_NULL
+    for (m, s) in collect(CTX_OF_MODEL)
+        s === syssolver && delete!(CTX_OF_MODEL, m)
+    end
     return
 end
 
@@ -268,6 +299,131 @@ function cones_proxsqr(ctx::Ctx, K::Int, irtmu::Float64, use_max_prox::Bool)
     check(ctx, ccall((:hyp_cones_proxsqr, LIB), Cint, (Ctx, Float64, Cint, Ptr{Float64}, Ptr{UInt8}),
         ctx, irtmu, use_max_prox, prox, ok), "hyp_cones_proxsqr")
     return (prox, all(!iszero, ok))
+end
+
+
+# ---------------------------------------------------------------------------------------------
+# The four caller loops of plug-in slot 2, batched.  Each method has the reference's name and a Float64
+# signature (more specific than the stock `where {T <: Real}` method), runs the batched device oracles when the
+# solver carries the B200 system solver, and otherwise `invoke`s the stock method - Hypatia.jl is not edited.
+# ---------------------------------------------------------------------------------------------
+const GENERIC_RHS2 = Tuple{Solver{T}, Point{T}} where {T <: Real}
+const GENERIC_RHS3 = Tuple{Solver{T}, Point{T}, Point{T}} where {T <: Real}
+const GENERIC_CHECK = Tuple{Models.Model{T}, Solvers.Stepper{T}} where {T <: Real}
+
+seg_dot(model::Models.Model{Float64}, a::Vector{Float64}, b::Vector{Float64}) =
+    Float64[dot(view(a, idxs), view(b, idxs)) for idxs in model.cone_idxs]
+
+# update_rhs_cent: steppers/common.jl:62-82 (rhs.s_k = -dual_k - sqrt(mu) grad_k)
+function Solvers.update_rhs_cent(solver::Solver{Float64}, rhs::Point{Float64})
+    sys = b200(solver)
+    isnothing(sys) && return invoke(Solvers.update_rhs_cent, GENERIC_RHS2, solver, rhs)
+    rhs.x .= 0
+    rhs.y .= 0
+    rhs.z .= 0
+    rhs.tau[] = 0
+    rtmu = sqrt(solver.mu)
+    grad = cones_grad!(sys.vq1, sys.ctx)
+    (_, dual) = primal_dual_vectors(solver.model, solver.point)
+    @. rhs.s = -dual - rtmu * grad
+    rhs.kap[] = -solver.point.kap[] + solver.mu / solver.point.tau[]
+    return rhs
+end
+
+# shared body of update_rhs_predadj (steppers/common.jl:26-59) and update_rhs_centadj (:85-118)
+function adj_rhs!(sys::B200QRCholSystemSolver, solver::Solver{Float64}, rhs::Point{Float64},
+    dir::Point{Float64}, pred::Bool)
+    model = solver.model
+    rhs.vec .= 0
+    rteps = sqrt(eps(Float64))
+    irtrtmu = inv(sqrt(sqrt(solver.mu)))
+    (prim_dir, _) = primal_dual_vectors(model, dir)
+    prim_scal = sys.vq1
+    @. prim_scal = irtrtmu * prim_dir
+    # hess_prod_slow!(H_prim_dir_k, prim_dir_k) for pred (:39), of the scaled direction for cent (:98)
+    H_prim = cones_hess_prod!(sys.vq2, pred ? prim_dir : prim_scal, sys.ctx, 0)
+    dder3 = cones_dder3!(sys.vq3, prim_scal, sys.ctx)
+    dot1 = seg_dot(model, dder3, sys.cone_point)
+    dot2 = seg_dot(model, prim_scal, H_prim)
+    pred && (dot2 .*= irtrtmu)
+    for (k, cone_k) in enumerate(model.cones)
+        Cones.use_dder3(cone_k) || continue
+        dder3_viol = abs(dot1[k] - dot2[k]) / (rteps + abs(dot2[k]))
+        if dder3_viol < 1e-4
+            idxs = model.cone_idxs[k]
+            if pred
+                @views @. rhs.s[idxs] = H_prim[idxs] + dder3[idxs]
+            else
+                @views rhs.s[idxs] .= dder3[idxs]
+            end
+        end
+    end
+    taubar = solver.point.tau[]
+    tau_dir_tau = dir.tau[] / taubar
+    rhs.kap[] = tau_dir_tau * solver.mu / taubar * (pred ? 1 + tau_dir_tau : tau_dir_tau)
+    return rhs
+end
+
+function Solvers.update_rhs_predadj(solver::Solver{Float64}, rhs::Point{Float64}, dir::Point{Float64})
+    sys = b200(solver)
+    isnothing(sys) && return invoke(Solvers.update_rhs_predadj, GENERIC_RHS3, solver, rhs, dir)
+    return adj_rhs!(sys, solver, rhs, dir, true)
+end
+
+function Solvers.update_rhs_centadj(solver::Solver{Float64}, rhs::Point{Float64}, dir::Point{Float64})
+    sys = b200(solver)
+    isnothing(sys) && return invoke(Solvers.update_rhs_centadj, GENERIC_RHS3, solver, rhs, dir)
+    return adj_rhs!(sys, solver, rhs, dir, false)
+end
+
+# check_cone_points: search.jl:74-138.  The cheap scalar tests are the reference's; the per-cone oracle sweep
+# (:112-135) is ONE batched sweep - all cones are evaluated instead of leaving at the first failing cone, the
+# Boolean outcome is identical.  Julia's `max` propagates NaN, so a NaN proximity rejects the candidate.
+function Solvers.check_cone_points(model::Models.Model{Float64}, stepper::Solvers.Stepper{Float64})
+    sys = get(CTX_OF_MODEL, model, nothing)
+    isnothing(sys) && return invoke(Solvers.check_cone_points, GENERIC_CHECK, model, stepper)
+    searcher = stepper.searcher
+    cand = stepper.temp
+    szk = searcher.szk
+    cones = model.cones
+    min_prox = searcher.min_prox
+    use_max_prox = searcher.use_max_prox
+    proxsqr_bound = abs2(searcher.prox_bound)
+    taukap = cand.tau[] * cand.kap[]
+    (min(cand.tau[], cand.kap[], taukap) < eps(Float64)) && return false
+    for k in eachindex(cones)
+        szk[k] = dot(cand.primal_views[k], cand.dual_views[k])
+        (szk[k] < eps(Float64)) && return false
+    end
+    mu = (sum(szk) + taukap) / searcher.nup1
+    (mu < eps(Float64)) && return false
+    taukap_rel = taukap / mu
+    (taukap_rel < min_prox) && return false
+    taukap_proxsqr = abs2(taukap_rel - 1)
+    (taukap_proxsqr > proxsqr_bound) && return false
+    for k in eachindex(cones)
+        nu_k = Cones.get_nu(cones[k])
+        sz_rel_k = szk[k] / (mu * nu_k)
+        if (sz_rel_k < min_prox) || (nu_k * abs2(sz_rel_k - 1) > proxsqr_bound)
+            return false
+        end
+    end
+    irtmu = inv(sqrt(mu))
+    (primal, dual) = primal_dual_vectors(model, cand)
+    cones_load_point(sys.ctx, primal, dual, irtmu)
+    @. sys.cone_point = irtmu * primal
+    (feas, dual_feas) = cones_feas(sys.ctx, length(cones))
+    (feas && dual_feas) || return false
+    (proxsqr, numerics_ok) = cones_proxsqr(sys.ctx, length(cones), irtmu, use_max_prox)
+    numerics_ok || return false
+    agg_proxsqr = taukap_proxsqr
+    aggfun = (use_max_prox ? max : +)
+    for proxsqr_k in proxsqr
+        agg_proxsqr = aggfun(agg_proxsqr, proxsqr_k)
+    end
+    (agg_proxsqr < proxsqr_bound) || return false
+    searcher.prox = sqrt(agg_proxsqr)
+    return true
 end
 
 end # module

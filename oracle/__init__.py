@@ -8,7 +8,9 @@ LAPACK routines Julia's stdlib calls) of the reference algorithms on the hot pat
   oracle/cones.py       <- src/Cones/{Cones,nonnegative,epinormeucl,possemideftri,
                                       hypoperlogdettri,hyporootdettri}.jl
   oracle/syssolvers.py  <- src/Solvers/systemsolvers/{common,qrchol,symindef,naive}.jl
-  oracle/generators.py  <- examples/linearopt/native.jl + the synthetic configs of SURVEY.md 8(d)
+  oracle/layout.py      <- src/Solvers/point.jl, common.jl:184-208 (the oracle's own Point / SubPoint / cone loops)
+  (instance generators live with the host driver: hypatia.jl_b200/host/instances.py <- examples/linearopt/native.jl
+   + the synthetic configs of SURVEY.md 8(d); they only build inputs, both sides read the same Model)
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs
 may import it, and only as the checker / the reported CPU baseline.  Nothing under

@@ -11,7 +11,7 @@ import numpy as np
 from scipy.linalg import blas as _blas
 
 from hypatia_b200.host import stepper as st
-from hypatia_b200.host.point import Point
+from .layout import OraclePoint
 from . import linalg as la
 from . import syssolvers as osys
 
@@ -55,7 +55,7 @@ def iterate_shell(model, s0, z0, x0, mu, cone_cls, syrk_row_fraction=1.0):
     sh = Shell()
     sh.model, sh.mu = model, mu
     sh.Ap_Q, sh.Ap_R = None, np.zeros((0, 0))
-    pt = sh.point = Point(model)
+    pt = sh.point = OraclePoint(model.n, model.p, model.q)
     pt.x[:] = x0
     pt.z[:] = z0
     pt.s[:] = s0
@@ -71,7 +71,7 @@ def iterate_shell(model, s0, z0, x0, mu, cone_cls, syrk_row_fraction=1.0):
     sh.cones.load_point(pt.s, pt.z, irtmu)
     sys_.update_lhs(sh)              # full (also fills the Schur cache of the sampled variant)
     sys_.frac = syrk_row_fraction
-    rhs, d = Point(model), Point(model)
+    rhs, d = (OraclePoint(model.n, model.p, model.q) for _ in range(2))
     rhs_list = []
     st.update_rhs_cent(sh, rhs)
     rhs_list.append(rhs.vec.copy())
@@ -85,7 +85,7 @@ def iterate_shell(model, s0, z0, x0, mu, cone_cls, syrk_row_fraction=1.0):
     rhs_list.append(rhs.vec.copy())
     sh.rhs_list = rhs_list
 
-    sol, res, r = Point(model), Point(model), Point(model)
+    sol, res, r = (OraclePoint(model.n, model.p, model.q) for _ in range(3))
 
     def unit(rhs_vecs):
         """Runs one unit; returns the extrapolated extra seconds of a sampled dsyrk."""

@@ -2,7 +2,7 @@
 
 Per-cone classes follow the reference's lazily-updated state machine (feas -> grad -> hess /
 inv_hess / hess_fact) and method names; `OracleConeBlock` adapts a list of them to the batched
-host.coneblock.ConeBlock interface by looping over cones, as the reference's callers do.
+batched ConeBlock interface (oracle/layout.py) by looping over cones, as the reference's callers do.
 
 reference: src/Cones/Cones.jl:27-310 (generic API, use_sqrt_hess_oracles, update_hess_fact,
 check_numerics, get_proxsqr), nonnegative.jl:42-145, epinormeucl.jl:44-228,
@@ -13,7 +13,7 @@ import numpy as np
 import scipy.linalg as sla
 
 from hypatia_b200.host import models as M
-from hypatia_b200.host.coneblock import ConeBlock
+from .layout import OracleConeBlockBase as ConeBlock
 from . import arrayutil as au
 from . import linalg as la
 

@@ -13,7 +13,7 @@ import numpy as np
 import scipy.linalg as sla
 from scipy.linalg import blas as _blas
 
-from hypatia_b200.host.point import SubPoint
+from .layout import OracleSubPoint as SubPoint
 from . import linalg as la
 
 

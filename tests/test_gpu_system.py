@@ -80,6 +80,82 @@ def test_baseline_configs_at_full_size(name):
     _check_system(inst.config(name, 1.0))
 
 
+def _device_workload(name):
+    """bench.py's device-generated instance of a multi-GB BASELINE config + a loaded context at its first iterate."""
+    import torch
+    import bench
+    from hypatia_b200 import capi
+    from hypatia_b200.cones import DeviceConeBlock
+    dev = torch.device("cuda", 0)
+    I = bench.build_instance(name, 0, 1, None, dev, on_device=True)
+    model = I["model"]
+    ctx = capi.Context(0)
+    ctx.load_model(model, G_local=I["G_dev"])
+    return torch, bench, dev, I, model, ctx, DeviceConeBlock(model, ctx=ctx)
+
+
+@pytest.mark.parametrize("name,ncheck", [("C4", 192), ("C5a", 96)])
+def test_baseline_configs_4_and_5_at_full_size(name, ncheck):
+    """BASELINE.json configs[3] (C4: n = 20000, 50 x PosSemidefTri(side 100), q = 252500 - a 40 GB G) and the
+    natvsext-shaped configs[4] (C5a: n = 2000, Nonnegative x 2 + ONE HypoPerLogdetTri of side 1000, q = 504502) at
+    their FULL sizes on one GPU.  G is generated on the device (bench.py's block-seeded generator).  Checked:
+      * a `ncheck` x `ncheck` sub-block of the Schur matrix (columns from both ends of the range) against the CPU
+        oracle's G_J' H G_J built from the same columns (qrchol.jl:219-246) at 1e-12;
+      * the directions of two right-hand sides through an INDEPENDENT 6x6 operator (torch dgemv on the panel +
+        the CPU oracle's cone Hessians, no library code): ||K d - r|| / ||r|| <= 1e-8;
+      * fact_kind = 0 (Cholesky succeeds, as for the oracle on the reduced-size versions of these configs)."""
+    from oracle.cones import OracleConeBlock
+    from hypatia_b200.host.point import Point
+    torch, bench, dev, I, model, ctx, cones = _device_workload(name)
+    try:
+        n, q = model.n, model.q
+        J = np.concatenate([np.arange(ncheck // 2), np.arange(n - ncheck // 2, n)])
+        GJ = I["G_dev"][torch.from_numpy(J).to(dev)].t().contiguous().cpu().numpy()      # q x ncheck
+        I["G_dev"] = None
+        torch.cuda.empty_cache()
+        pt_s, pt_z, mu = I["s0"], I["z0"], I["mu"]
+        irtmu = 1.0 / np.sqrt(mu)
+        cones.load_point(pt_s, pt_z, irtmu)
+        ctx.set_mu_tau(mu, 1.0)
+        if any(ck.ctype not in (0, 1, 2, 6) for ck in model.cones):
+            ctx.set_syrk_mode(0)
+        rc, kind = ctx.update_lhs()
+        assert rc == 0 and kind == 0
+        ora = OracleConeBlock(model)
+        ora.load_point(pt_s, pt_z, irtmu)
+        S_ora = GJ.T @ ora.hess_prod(GJ)
+        S = ctx.get_schur()
+        S = np.triu(S) + np.triu(S, 1).T
+        S_dev = S[np.ix_(J, J)]
+        del S
+        assert rel(S_dev, S_ora) <= 1e-12, f"Schur sub-block parity {rel(S_dev, S_ora):.2e}"
+        rng = np.random.default_rng(17)
+        rhs_list, sols = [], []
+        for _ in range(2):
+            rhs, sol = Point(model), Point(model)
+            rhs.vec[:] = rng.standard_normal(rhs.vec.size)
+            ctx.solve_system(sol.vec, rhs.vec)
+            assert np.isfinite(sol.vec).all()
+            rhs_list.append(rhs.vec.copy())
+            sols.append(sol.vec.copy())
+    finally:
+        ctx.close()
+        torch.cuda.empty_cache()
+
+    class Sh:
+        pass
+    sh = Sh()
+    sh.mu = mu
+    sh.point = Point(model)
+    sh.point.s[:], sh.point.z[:] = pt_s, pt_z
+    sh.point.tau = sh.point.kap = 1.0
+    I2 = bench.build_instance(name, 0, 1, None, dev, on_device=True)
+    res = bench.independent_kkt(torch, None, dev, I2, sh, sols, rhs_list, False)
+    del I2
+    torch.cuda.empty_cache()
+    assert max(res) <= DIR_TOL, f"independent KKT residuals {res}"
+
+
 @pytest.mark.parametrize("syrk", ["i8", "dmma"])
 def test_schur_matrix_accuracy_vs_extended_precision(syrk, monkeypatch):
     """The assembled Schur matrix against a long-double reference of G'HG: both kernels must be at
@@ -115,14 +191,55 @@ def test_matrix_cone_configs():
 
 def test_cholesky_failure_takes_the_bunch_kaufman_fallback():
     """q < n: the Schur complement G'HG is singular, Cholesky fails and the device takes the
-    posdef_fact_copy! chain (dense.jl:194-215) like the oracle does.  Directions of a singular
-    system are not comparable; what must agree is the outcome of the chain."""
+    posdef_fact_copy! chain (dense.jl:194-215).  Directions of a numerically singular system are
+    rounding noise on both sides; what must agree with the oracle is the outcome of the chain, and
+    the solves must come back finite."""
     from hypatia_b200.syssolver import QRCholDenseSystemSolver as DevQRChol
+    from oracle.syssolvers import QRCholDenseSystemSolver as OraQRChol
     cones = [M.PosSemidefTri(M.svec_length(10)) for _ in range(2)]
     I = inst.synthetic("rankdef", 200, 0, cones, seed=5)
     dev = iterate_solver(I, DevQRChol())
-    assert dev.syssolver.fact_kind in (1, 2)
-    dev.syssolver.free_memory()
+    ora = iterate_solver(I, OraQRChol())
+    try:
+        assert ora.syssolver.fact_kind in (1, 2)
+        assert dev.syssolver.fact_kind == ora.syssolver.fact_kind
+        rhs, sd = Point(I.model), Point(I.model)
+        rhs.vec[:] = np.random.default_rng(3).standard_normal(rhs.vec.size)
+        dev.syssolver.solve_system(dev, sd, rhs)
+        assert np.isfinite(sd.vec).all()
+    finally:
+        dev.syssolver.free_memory()
+
+
+def test_shifted_bunch_kaufman_end_of_the_chain_matches_oracle():
+    """Two all-zero columns of G give the Schur complement two exactly-zero rows / columns: Cholesky
+    fails, dsytrf_rook reports an exactly singular D (info > 0), and the chain ends in increase_diag!
+    (dense.jl:106-113: A_jj <- (1 + 1e-5) max(A_jj, 1000 eps)) + Bunch-Kaufman = fact_kind 2.  The shifted
+    system is nonsingular and decoupled in those two unknowns, so the directions ARE comparable: same
+    fact_kind and direction parity at the north-star tolerance."""
+    from hypatia_b200.syssolver import QRCholDenseSystemSolver as DevQRChol
+    from oracle.syssolvers import QRCholDenseSystemSolver as OraQRChol
+    cones = [M.EpiNormEucl(5) for _ in range(30)] + [M.Nonnegative(40)]
+    I = inst.synthetic("zerocols", 60, 0, cones, seed=9)
+    m = I.model
+    zero = [7, 41]
+    m.G[:, zero] = 0.0
+    m.h[:] = m.G @ I.point.x + I.point.s
+    m.c[:] = -(m.G.T @ I.point.z)
+    dev = iterate_solver(I, DevQRChol())
+    ora = iterate_solver(I, OraQRChol())
+    try:
+        assert ora.syssolver.fact_kind == 2
+        assert dev.syssolver.fact_kind == 2
+        rng = np.random.default_rng(4)
+        for _ in range(2):
+            rhs, sd, so = Point(m), Point(m), Point(m)
+            rhs.vec[:] = rng.standard_normal(rhs.vec.size)
+            dev.syssolver.solve_system(dev, sd, rhs)
+            ora.syssolver.solve_system(ora, so, rhs)
+            assert rel(sd.vec, so.vec) <= DIR_TOL, f"direction parity {rel(sd.vec, so.vec):.2e}"
+    finally:
+        dev.syssolver.free_memory()
 
 
 @pytest.mark.parametrize("p", [0, 3, 40])

@@ -1,7 +1,7 @@
-"""-m gpu tests written when the GPU budget of the round was (almost) spent.  The two LinMatrixIneq tests passed on a B200
-with the last seconds of it (profiles/r01_pytest_gpu_lmi.log); test_kat_device_extra - full device solves of the
-reference instances added late in the CPU (oracle) tier - and the DoublyNonnegativeTri tests (kernels verified by the CPU
-emulation tier only, tests/test_emu_gpow.py) have NOT run on a GPU yet.  The file name sorts last on purpose: a failure here cannot mask a verified test under `pytest -x`."""
+"""-m gpu tests of the cone types added at the end of round 1 (LinMatrixIneq, DoublyNonnegativeTri, MatrixEpiPerSquare,
+PosSemidefTriSparse, EpiTrRelEntropyTri, the three matrix / norm WSOS cones), the late reference instances (kat.EXTRA) and
+PredOrCentStepper with the device plug-ins.  All of them passed on a B200 in the round-1 driver run (GPUTEST_r01: 67 XPASS)
+and are ordinary tests since round 2: a regression here fails the suite.  The file name still sorts last."""
 import numpy as np
 import pytest
 
@@ -13,9 +13,6 @@ from hypatia_b200.host.point import Point
 
 pytestmark = pytest.mark.gpu
 
-# Never run on a GPU so far: reported as XPASS / XFAIL instead of pass / fail until a round with GPU budget has seen them
-# pass (then the marker goes away).  The two LinMatrixIneq tests below HAVE passed on a B200 and carry no marker.
-not_yet_on_gpu = pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent; CPU-tier verified only")
 
 
 def _lmi(rng, side, dim, use_dual=False):
@@ -80,7 +77,6 @@ def _solve_dev(model):
     return s
 
 
-@not_yet_on_gpu
 @pytest.mark.parametrize("build", kat.EXTRA, ids=lambda f: f.__name__)
 def test_kat_device_extra(build):
     model, expected = build()
@@ -88,7 +84,6 @@ def test_kat_device_extra(build):
 
 
 # the DoublyNonnegativeTri kernels have not run on a GPU at all: keep them after everything else
-@not_yet_on_gpu
 def test_doublynonnegativetri_oracles_match_cpu_oracle():
     """Not yet run on a GPU (emulation tier: tests/test_emu_gpow.py)."""
     from hypatia_b200.cones import DeviceConeBlock
@@ -115,7 +110,6 @@ def test_doublynonnegativetri_oracles_match_cpu_oracle():
     dev.free()
 
 
-@not_yet_on_gpu
 def test_doublynonnegativetri_in_the_system_solve():
     """Not yet run on a GPU."""
     from hypatia_b200.syssolver import QRCholDenseSystemSolver as DevQRChol
@@ -136,7 +130,6 @@ def test_doublynonnegativetri_in_the_system_solve():
 
 
 # the predict-or-center stepper (host control flow added late; it drives the same, GPU-verified, C-ABI calls in a new order)
-@not_yet_on_gpu
 @pytest.mark.parametrize("adj,curv", [(False, False), (True, False), (True, True)])
 @pytest.mark.parametrize("build", [kat.primalinfeas3, kat.dualinfeas3, kat.epinorminf4, kat.hyporootdettri4],
                          ids=lambda f: f.__name__)
@@ -154,7 +147,6 @@ def test_predorcent_stepper_device(build, adj, curv):
 
 
 # the MatrixEpiPerSquare kernels have not run on a GPU either (emulation tier: tests/test_emu_gpow.py)
-@not_yet_on_gpu
 def test_matrixepipersquare_oracles_match_cpu_oracle():
     from hypatia_b200.cones import DeviceConeBlock
     from oracle.cones import OracleConeBlock
@@ -181,7 +173,6 @@ def test_matrixepipersquare_oracles_match_cpu_oracle():
 
 
 # WSOSInterpPosSemidefTri: emulation tier only so far (tests/test_emu_gpow.py)
-@not_yet_on_gpu
 def test_wsosinterppossemideftri_oracles_match_cpu_oracle():
     from hypatia_b200.cones import DeviceConeBlock
     from oracle.cones import OracleConeBlock
@@ -212,7 +203,6 @@ def test_wsosinterppossemideftri_oracles_match_cpu_oracle():
 
 
 # WSOSInterpEpiNormEucl: emulation tier only so far (tests/test_emu_gpow.py)
-@not_yet_on_gpu
 def test_wsosinterpepinormeucl_oracles_match_cpu_oracle():
     from hypatia_b200.cones import DeviceConeBlock
     from oracle.cones import OracleConeBlock
@@ -243,7 +233,6 @@ def test_wsosinterpepinormeucl_oracles_match_cpu_oracle():
 
 
 # WSOSInterpEpiNormOne: emulation tier only so far (tests/test_emu_gpow.py)
-@not_yet_on_gpu
 def test_wsosinterpepinormone_oracles_match_cpu_oracle():
     from hypatia_b200.cones import DeviceConeBlock
     from oracle.cones import OracleConeBlock
@@ -274,7 +263,6 @@ def test_wsosinterpepinormone_oracles_match_cpu_oracle():
 
 
 # PosSemidefTriSparse: emulation tier only so far (tests/test_emu_gpow.py)
-@not_yet_on_gpu
 def test_possemideftrisparse_oracles_match_cpu_oracle():
     from hypatia_b200.cones import DeviceConeBlock
     from oracle.cones import OracleConeBlock
@@ -308,7 +296,6 @@ def test_possemideftrisparse_oracles_match_cpu_oracle():
 
 
 # EpiTrRelEntropyTri: emulation tier only so far (tests/test_emu_gpow.py)
-@not_yet_on_gpu
 def test_epitrrelentropytri_oracles_match_cpu_oracle():
     from hypatia_b200.cones import DeviceConeBlock
     from oracle.cones import OracleConeBlock

@@ -1,0 +1,128 @@
+"""Static checks of julia/HypatiaB200.jl against the reference's Julia sources (CPU tier).
+
+Julia is not in the image, so the shim cannot be executed; what CAN be checked is that every struct field and
+every Solvers / Cones function the shim touches exists in the reference with that name - the class of error the
+round-1 review found (a three-parameter `Solver`, `stepper.res`).  The reference tree only exists in the build
+container: the tests skip on the GPU box."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference/src"
+SHIM = os.path.join(ROOT, "julia", "HypatiaB200.jl")
+
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
+
+
+def _read(rel):
+    with open(os.path.join(REF, rel)) as f:
+        return f.read()
+
+
+def _struct_fields(src, name):
+    m = re.search(r"mutable struct %s\b.*?\n(.*?)\n(?:    function |end)" % re.escape(name), src, re.S)
+    assert m, f"struct {name} not found"
+    fields = set()
+    for line in m.group(1).splitlines():
+        line = line.split("#")[0].strip()
+        mm = re.match(r"([A-Za-z_][A-Za-z_0-9]*)\s*(::|$)", line)
+        if mm:
+            fields.add(mm.group(1))
+    return fields
+
+
+def _shim():
+    with open(SHIM) as f:
+        src = f.read()
+    # drop the block comment header and line comments
+    src = re.sub(r"#=.*?=#", "", src, flags=re.S)
+    return "\n".join(l.split("#")[0] for l in src.splitlines())
+
+
+def _used(src, var):
+    return set(re.findall(r"\b%s\.([A-Za-z_][A-Za-z_0-9]*)" % re.escape(var), src))
+
+
+def test_solver_has_one_type_parameter_and_the_shim_respects_it():
+    assert re.search(r"mutable struct Solver\{T <: Real\}", _read("Solvers/Solvers.jl"))
+    shim = _shim()
+    assert not re.search(r"Solver\{Float64\s*,", shim), "Solver has a single type parameter (Solvers.jl:62)"
+
+
+def test_fields_the_shim_touches_exist_in_the_reference():
+    shim = _shim()
+    solver_fields = _struct_fields(_read("Solvers/Solvers.jl"), "Solver")
+    assert _used(shim, "solver") <= solver_fields, _used(shim, "solver") - solver_fields
+    stepper_fields = _struct_fields(_read("Solvers/steppers/combined.jl"), "CombinedStepper") & \
+        _struct_fields(_read("Solvers/steppers/predorcent.jl"), "PredOrCentStepper")
+    assert _used(shim, "stepper") <= stepper_fields, _used(shim, "stepper") - stepper_fields
+    searcher_fields = _struct_fields(_read("Solvers/search.jl"), "StepSearcher")
+    assert _used(shim, "searcher") <= searcher_fields, _used(shim, "searcher") - searcher_fields
+    point_fields = _struct_fields(_read("Solvers/point.jl"), "Point")
+    for var in ("point", "rhs", "dir", "cand", "sol"):
+        assert _used(shim, var) <= point_fields, (var, _used(shim, var) - point_fields)
+    model_fields = _struct_fields(_read("Models/Models.jl"), "Model")
+    assert _used(shim, "model") <= model_fields, _used(shim, "model") - model_fields
+
+
+def test_overridden_functions_exist_with_those_names_and_arities():
+    shim = _shim()
+    common = _read("Solvers/systemsolvers/common.jl")
+    stp = _read("Solvers/steppers/common.jl")
+    search = _read("Solvers/search.jl")
+    solvers = _read("Solvers/Solvers.jl")
+    qrchol = _read("Solvers/systemsolvers/qrchol.jl")
+    want = {"apply_lhs": (common, 2), "update_rhs_cent": (stp, 2), "update_rhs_centadj": (stp, 3),
+            "update_rhs_predadj": (stp, 3), "check_cone_points": (search, 2), "load": (qrchol, 2),
+            "update_lhs": (qrchol, 2), "solve_subsystem3": (qrchol, 4), "solve_system": (common, 4),
+            "free_memory": (solvers, 1), "setup_point_sub": (common, 2)}
+    for name, (src, arity) in want.items():
+        assert re.search(r"\bSolvers\.%s\b" % name, shim), f"shim does not touch Solvers.{name}"
+        m = re.search(r"^function %s\(\s*(.*?)\)\s*(?:where|\n)" % name, src, re.S | re.M) or \
+            re.search(r"^%s\(\s*(.*?)\)\s*=" % name, src, re.S | re.M)
+        assert m, f"{name} not found in the reference"
+        flat, depth = "", 0                    # split on top-level commas only (Union{A{T}, B{T}} is one argument)
+        for ch in m.group(1).split(";")[0]:
+            depth += ch == "{"
+            depth -= ch == "}"
+            flat += "\0" if (ch == "," and depth == 0) else ch
+        args = [a for a in flat.split("\0") if a.strip()]
+        assert len(args) == arity, (name, args)
+    # apply_lhs writes stepper.temp from stepper.dir (common.jl:84-85)
+    assert re.search(r"dir = stepper\.dir\s*\n\s*res = stepper\.temp", common)
+    body = shim[shim.index("function Solvers.apply_lhs"):]
+    body = body[:body.index("\nend")]
+    assert "stepper.temp.vec" in body and "stepper.dir.vec" in body and "stepper.res" not in shim
+
+
+def test_cone_api_names_used_by_the_shim_exist():
+    shim = _shim()
+    cones = _read("Cones/Cones.jl")
+    for name in set(re.findall(r"\bCones\.([a-z_0-9!]+)\(", shim)):
+        assert re.search(r"^(?:function )?%s\(" % re.escape(name), cones, re.M) or \
+            re.search(r"^%s\(" % re.escape(name), cones, re.M), f"Cones.{name} not in Cones.jl"
+
+
+def test_temporaries_passed_by_pointer_are_gc_preserved():
+    with open(SHIM) as f:
+        src = f.read()
+    # every `pointer(X)` handed to a ccall must sit inside a GC.@preserve that names X
+    for m in re.finditer(r"pointer\((\w+)(?:\.vec)?\)", src):
+        var = m.group(1)
+        before = src[:m.start()]
+        k = before.rfind("GC.@preserve")
+        assert k >= 0, var
+        line = before[k:before.index("\n", k)] if "\n" in before[k:] else before[k:]
+        assert re.search(r"\b%s\b" % var, line), f"pointer({var}) outside GC.@preserve"
+    assert "pointer(Matrix" not in src
+
+
+def test_c_symbols_called_by_the_shim_are_declared_in_the_header():
+    with open(os.path.join(ROOT, "include", "hypatia_b200.h")) as f:
+        hdr = f.read()
+    with open(SHIM) as f:
+        src = f.read()
+    for sym in set(re.findall(r"\(:(hyp_\w+), LIB\)", src)):
+        assert re.search(r"\b%s\(" % sym, hdr), sym
