@@ -423,8 +423,10 @@ def measure_workload(args, workload, torch, dist, device, rank, world, local_ran
     from hypatia_b200.host import stepper as st
 
     big = workload in ("C4", "C5a", "C5b") or (not full)
-    M_types = WORKLOADS[workload]["cones"](__import__("hypatia_b200.host.models", fromlist=["x"]))
-    giant = world > 1 and max(ck.dim for ck in M_types) > 0.5 * sum(ck.dim for ck in M_types)
+    from hypatia_b200.host import models as M_
+    from hypatia_b200.syssolver import giant_cone
+    # one cone carrying most of the assembly work cannot be split by whole-cone sharding: shard by columns instead
+    giant = world > 1 and giant_cone(PanelModel(WORKLOADS[workload]["n"], WORKLOADS[workload]["cones"](M_), None, None))
     I = build_instance(workload, rank, world, dist, device, on_device=big, replicate_rows=giant)
     model = I["model"]
     n, q = model.n, model.q

@@ -45,6 +45,7 @@ _SIGS = {
     "hyp_cones_hess_blocks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "hyp_set_syssolver": (C.c_int, [C.c_void_p, C.c_int]),
     "hyp_set_syrk_mode": (C.c_int, [C.c_void_p, C.c_int]),
+    "hyp_set_column_sharding": (C.c_int, [C.c_void_p, C.c_int]),
     "hyp_set_mu_tau": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "hyp_update_lhs": (C.c_int, [C.c_void_p, c_ip]),
     "hyp_solve_subsystem3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -252,6 +253,10 @@ class Context:
     # ---- system solver ----
     def set_syssolver(self, kind: int):
         self.check(self.lib.hyp_set_syssolver(self.h, int(kind)), "hyp_set_syssolver")
+
+    def set_column_sharding(self, on: bool = True):
+        """Single-giant-cone models: every rank loads ALL rows, the Schur assembly is split by columns."""
+        self.check(self.lib.hyp_set_column_sharding(self.h, 1 if on else 0), "hyp_set_column_sharding")
 
     def set_syrk_mode(self, mode: int):
         self.check(self.lib.hyp_set_syrk_mode(self.h, int(mode)), "hyp_set_syrk_mode")

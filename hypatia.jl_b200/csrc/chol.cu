@@ -18,6 +18,8 @@
 //   triangle once: 4 m^2 bytes) - in practice latency of the block dependency chain.
 #include "common.cuh"
 #include "chol_kernels.cuh"
+#include <cstring>
+#include <cstdlib>
 
 using namespace hypdev;   // NB, LDU, PT, panel_kernel, chol_batched_kernel
 
@@ -41,6 +43,13 @@ void set_panel_attr() {
 
 void hyp_potrf_upper(hyp_ctx* ctx, double* A, int64_t lda, int64_t m, double* d_dinv, int* d_info) {
     if (m <= 0) return;
+    // default: the task-graph kernel (chol_dag.cu), one launch for the whole factorisation;
+    // HYP_POTRF=stream keeps the two-stream version below (also the fallback for unaligned input)
+    {
+        const char* pv = getenv("HYP_POTRF");
+        const bool want_stream = pv && !strcmp(pv, "stream");
+        if (!want_stream && hyp_potrf_upper_dag(ctx, A, lda, m, d_dinv, d_info)) return;
+    }
     TimeScope ts(ctx, T_POTRF);
     set_panel_attr();
     cudaStream_t bulk = ctx->stream, chain = ctx->stream2;
@@ -55,6 +64,9 @@ void hyp_potrf_upper(hyp_ctx* ctx, double* A, int64_t lda, int64_t m, double* d_
     //                 the bulk stream finishes the update (its persistent grids leave 8 SMs free).
     const int64_t OB = 512;
     const bool lookahead = m > 2 * OB;
+    // profiling aid (tools/potrf_probe.py): 1 = only the latency chain, 2 = only the bulk GEMMs (results are garbage)
+    const char* pm = getenv("HYP_POTRF_MODE");
+    const int probe = pm ? atoi(pm) : 0;
     auto on = [&](cudaStream_t s, int cap) {
         ctx->launch_stream = s;
         ctx->grid_cap = cap;
@@ -72,10 +84,12 @@ void hyp_potrf_upper(hyp_ctx* ctx, double* A, int64_t lda, int64_t m, double* d_
         for (int64_t k0 = K0; k0 < Kend; k0 += NB) {
             const int64_t nb = std::min<int64_t>(NB, m - k0);
             const int64_t k = k0 / NB;
-            panel_kernel<true><<<1, PT, NB * LDU * 8, chain>>>(A, lda, m, k, d_dinv, d_info);
-            ctx->launches++;
+            if (probe != 2) {
+                panel_kernel<true><<<1, PT, NB * LDU * 8, chain>>>(A, lda, m, k, d_dinv, d_info);
+                ctx->launches++;
+            }
             const int64_t rin = Kend - (k0 + nb);       // columns / rows of this outer block right of / below the panel
-            if (rin > 0) {
+            if (rin > 0 && probe != 2) {
                 double* A12 = A + k0 + (k0 + nb) * lda;
                 double* A22 = A + (k0 + nb) + (k0 + nb) * lda;
                 const double* Dk = d_dinv + k * NB * NB;
@@ -85,6 +99,7 @@ void hyp_potrf_upper(hyp_ctx* ctx, double* A, int64_t lda, int64_t m, double* d_
         }
         CUDA_TRY(cudaEventRecord(ctx->ev_chain[nblk_outer & 1], chain));
         if (rest2 <= 0) break;
+        if (probe == 1) continue;
         // ---- bulk: block row right of the outer block, panel by panel ----
         CUDA_TRY(cudaStreamWaitEvent(bulk, ctx->ev_chain[nblk_outer & 1], 0));
         on(bulk, cap);

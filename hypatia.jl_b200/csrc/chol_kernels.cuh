@@ -90,7 +90,20 @@ __device__ __forceinline__ void base_block(double* sA, double* diagX, double* sX
     __syncwarp();
 }
 
-template <bool FACTOR>
+// BARID = 0: the CTA is exactly the PT threads of the panel (block barrier).  BARID > 0: the PT panel threads are a
+// subset of a larger CTA (the task-graph Cholesky of chol_dag.cu keeps a TMA producer warp beside them) and
+// synchronise on named barrier BARID.  LDCG: read the block through L2 (another CTA of the same launch wrote it).
+template <int BARID>
+__device__ __forceinline__ void panel_sync() {
+#ifdef HYP_EMU
+    __syncthreads();
+#else
+    if (BARID == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"n"(BARID), "n"(PT) : "memory");
+#endif
+}
+
+template <bool FACTOR, int BARID = 0, bool LDCG = false>
 __device__ __forceinline__ int panel_body(double* __restrict__ Ab, int64_t lda, int nb,
                                           double* __restrict__ Db, int ldd, int dn, bool zero_lower,
                                           double* sA, double* diagX, double* sX, double* sT, int* s_bad) {
@@ -105,7 +118,13 @@ __device__ __forceinline__ int panel_body(double* __restrict__ Ab, int64_t lda, 
             int r = idx & (NB - 1), c = idx >> 7;
             double x = 0.0;
             if (r < nb && c < nb) {
-                if (r <= c) x = Ab[r + (int64_t)c * lda];
+                if (r <= c) {
+#ifdef HYP_EMU
+                    x = Ab[r + (int64_t)c * lda];
+#else
+                    x = LDCG ? __ldcg(Ab + r + (int64_t)c * lda) : Ab[r + (int64_t)c * lda];
+#endif
+                }
             } else if (r == c) {
                 x = 1.0;
             }
@@ -117,12 +136,12 @@ __device__ __forceinline__ int panel_body(double* __restrict__ Ab, int64_t lda, 
             sA[(idx & (NB - 1)) + (idx >> 7) * LDU] = v[u];
         }
     }
-    __syncthreads();
+    panel_sync<BARID>();
 
     for (int b = 0; b < NB / SB; b++) {
         const int o = b * SB;
         if (warp == 0) base_block<FACTOR>(sA, diagX, sX, o, lane, s_bad);
-        __syncthreads();
+        panel_sync<BARID>();
         if (FACTOR && b < NB / SB - 1) {
             const int t0 = o + SB;
             const int ncol = NB - t0;
@@ -151,14 +170,14 @@ __device__ __forceinline__ int panel_body(double* __restrict__ Ab, int64_t lda, 
                             for (int q = 0; q < 4; q++) acc[a][q] = fma(xa[a], av[q], acc[a][q]);
                     }
                 }
-                __syncthreads();
+                panel_sync<BARID>();
                 if (act) {
 #pragma unroll
                     for (int a = 0; a < 4; a++)
 #pragma unroll
                         for (int q = 0; q < 4; q++) sA[(o + ti * 4 + a) + (t0 + tj * 4 + q) * LDU] = acc[a][q];
                 }
-                __syncthreads();
+                panel_sync<BARID>();
             }
             // (c) trailing update A[r, c] -= sum_k U[o + k, r] U[o + k, c] on 4 x 4 tiles with r-tile <= c-tile
             {
@@ -197,7 +216,7 @@ __device__ __forceinline__ int panel_body(double* __restrict__ Ab, int64_t lda, 
                             if (r <= c) sA[r + c * LDU] -= acc[a][q];
                         }
                 }
-                __syncthreads();
+                panel_sync<BARID>();
             }
         }
     }
@@ -255,7 +274,7 @@ __device__ __forceinline__ int panel_body(double* __restrict__ Ab, int64_t lda, 
 #pragma unroll
                 for (int q = 0; q < 4; q++) sT[(i0 + a) + (tj * 4 + q) * LDT] = acc[a][q];
         }
-        __syncthreads();
+        panel_sync<BARID>();
         // X[i, h + j] = -sum_{k <= j} T[i, k] X[cb, cb][k, j]; stored at sA[(h + j) + i * LDU]
         for (int t = tid; t < ntile; t += PT) {
             const int ti = t % (h / 4), tj = t / (h / 4);
@@ -281,7 +300,7 @@ __device__ __forceinline__ int panel_body(double* __restrict__ Ab, int64_t lda, 
 #pragma unroll
                 for (int q = 0; q < 4; q++) sA[(h + j0 + q) + (i0 + a) * LDU] = -acc[a][q];
         }
-        __syncthreads();
+        panel_sync<BARID>();
     }
 
     if (FACTOR) {

@@ -163,6 +163,11 @@ struct hyp_ctx {
     int64_t nmp = 0;                   // n - p
     int K = 0;                         // global number of cones
     int cone_lo = 0, cone_hi = 0;      // locally owned cones [lo, hi)
+    // Column sharding (single giant cone): every rank holds ALL rows of G and all cone state; only the
+    // Schur assembly is split - rank r builds the column panel S[:, J_r] = GQ2' (H GQ2)[:, J_r] and the panels are
+    // all-gathered.  Everything else (solves, oracles) runs replicated without communication.
+    bool col_shard = false;
+    int64_t col_shard_width = 0;       // columns of S per rank (0 when not column-sharded)
     int64_t row_lo = 0, row_hi = 0;    // locally owned rows
     int64_t qloc = 0;                  // row_hi - row_lo
     int64_t ldg = 0;                   // leading dim of G / HG panels (even)
@@ -230,6 +235,9 @@ struct hyp_ctx {
     double* d_blk_arr = nullptr;       // q x maxdim identity pattern / products (2 buffers)
     int64_t blk_maxdim = 0;
     int* d_flags = nullptr;            // TRSV ticket + block-ready flags
+    int* d_dag_ver = nullptr;          // task-graph Cholesky (chol_dag.cu): tile version counters + tickets
+    int64_t dag_ver_len = 0;
+    unsigned long long* d_dag_dbg = nullptr;   // HYP_POTRF_DEBUG: per-CTA wait / busy times
     int trsv_epoch = 0;
 
     // ---- vectors (device) ----
@@ -291,6 +299,10 @@ void hyp_zero_outside(hyp_ctx* ctx, double* v);   // zero rows outside [row_lo,r
 
 // ---- nccl_shim.cu ----
 void hyp_allreduce_sum(hyp_ctx* ctx, double* buf, int64_t count);
+// in-place all-gather: rank r's `count` doubles sit at buf + r * count
+void hyp_allgather_inplace(hyp_ctx* ctx, double* buf, int64_t count);
+// rows of G (and cones) are split over ranks: partial results need the exchange steps
+static inline bool hyp_row_sharded(const hyp_ctx* ctx) { return ctx->nranks > 1 && !ctx->col_shard; }
 void hyp_allreduce_min_u8(hyp_ctx* ctx, uint8_t* buf, int64_t count);
 // make the local rows of a global q-vector visible on every rank
 void hyp_replicate_q(hyp_ctx* ctx, double* v);
@@ -359,6 +371,7 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
 // in-place blocked upper Cholesky; d_dinv receives the inverted 128 x 128 diagonal blocks
 // (ceil(m/128) blocks of 128*128 doubles); d_info[0] = 0 or 1-based index of the first bad pivot
 void hyp_potrf_upper(hyp_ctx* ctx, double* A, int64_t lda, int64_t m, double* d_dinv, int* d_info);
+bool hyp_potrf_upper_dag(hyp_ctx* ctx, double* A, int64_t lda, int64_t m, double* d_dinv, int* d_info);
 // batched Cholesky + triangular inverse of the (side <= 128) matrices of a cone group
 void hyp_chol_batched(hyp_ctx* ctx, int ncones, const int* d_sides, const int64_t* d_moff,
                       const int* d_kidx, double* U, double* Ui, uint8_t* d_flag);

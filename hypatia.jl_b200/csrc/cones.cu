@@ -226,7 +226,7 @@ void hyp_cones_update_state(hyp_ctx* ctx) {
         }
     }
     CUDA_TRY(cudaGetLastError());
-    if (ctx->nranks > 1) {
+    if (hyp_row_sharded(ctx)) {
         hyp_allreduce_min_u8(ctx, ctx->d_feas, ctx->K);
         hyp_allreduce_min_u8(ctx, ctx->d_dual_feas, ctx->K);
         hyp_replicate_q(ctx, ctx->d_grad);
@@ -347,7 +347,7 @@ void hyp_cones_prox_dev(hyp_ctx* ctx, double irtmu, int use_max) {
         ctx->launches++;
     }
     CUDA_TRY(cudaGetLastError());
-    if (ctx->nranks > 1) {
+    if (hyp_row_sharded(ctx)) {
         hyp_allreduce_sum(ctx, ctx->d_proxsqr, ctx->K);
         hyp_allreduce_min_u8(ctx, ctx->d_num_ok, ctx->K);
     }

@@ -271,7 +271,7 @@ inline int vgrid(hyp_ctx* ctx, int64_t len) {
 void G_t(hyp_ctx* ctx, const double* Gp, const double* vq, double alpha, double beta, double* yn,
          int64_t ncols = -1) {
     if (ncols < 0) ncols = ctx->n;
-    if (ctx->nranks == 1) {
+    if (!hyp_row_sharded(ctx)) {
         hyp_gemv_t(ctx, ctx->qloc, ncols, Gp, ctx->ldg, vq + ctx->row_lo, alpha, beta, yn);
     } else {
         hyp_gemv_t(ctx, ctx->qloc, ncols, Gp, ctx->ldg, vq + ctx->row_lo, alpha, 0.0, ctx->d_t2);
@@ -343,7 +343,7 @@ void solve_subsystem3_dev(hyp_ctx* ctx, double* sol, const double* rhs) {
         TimeScope ts(ctx, T_CONE_PROD);
         hyp_cones_prod(ctx, ctx->d_HGx, ctx->d_Gx, 1, q, q, HYP_PROD_BLOCK, 0);
     }
-    if (ctx->nranks > 1) {
+    if (hyp_row_sharded(ctx)) {
         hyp_replicate_q(ctx, ctx->d_Gx);
         hyp_replicate_q(ctx, ctx->d_HGx);
     }
@@ -388,7 +388,7 @@ void solve_system_dev(hyp_ctx* ctx, double* sol, const double* rhs) {
             v = ctx->d_vq1;
         }
         hyp_cones_prod(ctx, ctx->d_vq2, v, 1, q, q, HYP_PROD_BLOCK, 0);
-        if (ctx->nranks > 1) hyp_replicate_q(ctx, ctx->d_vq2);
+        if (hyp_row_sharded(ctx)) hyp_replicate_q(ctx, ctx->d_vq2);
         rhs3_post_kernel<<<vgrid(ctx, q), 256, 0, ctx->stream>>>(q, ctx->d_row_dual, ctx->d_vq2, rs,
                                                               sub_rhs + n + p);
         ctx->launches++;
@@ -425,7 +425,7 @@ void apply_lhs_dev(hyp_ctx* ctx, double* res, const double* dir) {
                                                              dir + tau_idx, c);
     ctx->launches++;
     // one pass over G for G'z (here) and G x (res.z below) when the panel is not sharded
-    const bool fuse_g = ctx->nranks == 1 && q > 0 && n > 0;
+    const bool fuse_g = !hyp_row_sharded(ctx) && q > 0 && n > 0;
     if (fuse_g)
         hyp_gemv_nt(ctx, ctx->qloc, n, ctx->d_Graw, ctx->ldg, dx, dz, 1.0, 0.0, ctx->d_vq1, 1.0, 1.0, res);
     else
@@ -441,7 +441,7 @@ void apply_lhs_dev(hyp_ctx* ctx, double* res, const double* dir) {
     if (q > 0) {
         // res.z = h tau - s - G x
         if (!fuse_g) G_n(ctx, ctx->d_Graw, dx, ctx->d_vq1);
-        if (ctx->nranks > 1) hyp_replicate_q(ctx, ctx->d_vq1);
+        if (hyp_row_sharded(ctx)) hyp_replicate_q(ctx, ctx->d_vq1);
         axpbypcz_dev_kernel<<<vgrid(ctx, q), 256, 0, ctx->stream>>>(q, res + n + p, -1.0, ds, -1.0, ctx->d_vq1,
                                                                  1.0, dir + tau_idx, h);
         ctx->launches++;
@@ -457,7 +457,7 @@ void apply_lhs_dev(hyp_ctx* ctx, double* res, const double* dir) {
             dual = ctx->d_vq3;
         }
         hyp_cones_prod(ctx, ctx->d_vq4, prim, 1, q, q, HYP_PROD_HESS, 0);
-        if (ctx->nranks > 1) hyp_replicate_q(ctx, ctx->d_vq4);
+        if (hyp_row_sharded(ctx)) hyp_replicate_q(ctx, ctx->d_vq4);
         hyp_lincomb3(ctx, q, res + tau_idx + 1, 1.0, ctx->d_vq4, 1.0, dual, 0.0, nullptr);
     }
     // res.tau = -c'x - b'y - h'z - kap ; res.kap = mu/tau^2 * tau_dir + kap_dir
@@ -512,7 +512,7 @@ void calc_residuals_dev(hyp_ctx* ctx, const double* pt, double* xres, double* yr
     CUDA_TRY(cudaMemsetAsync(st, 0, 10 * sizeof(double), ctx->stream));
     {
         TimeScope ts(ctx, T_GEMV);
-        const bool fuse_g = ctx->nranks == 1 && q > 0 && n > 0;
+        const bool fuse_g = !hyp_row_sharded(ctx) && q > 0 && n > 0;
         if (fuse_g) hyp_gemv_nt(ctx, ctx->qloc, n, ctx->d_Graw, ctx->ldg, px, pz, 1.0, 0.0, ctx->d_vq1, 1.0, 0.0, ctx->d_t);
         if (n > 0) {
             if (fuse_g) {
@@ -525,7 +525,7 @@ void calc_residuals_dev(hyp_ctx* ctx, const double* pt, double* xres, double* yr
             if (fuse_g) {
             } else if (n > 0) G_n(ctx, ctx->d_Graw, px, ctx->d_vq1);
             else hyp_fill(ctx, q, ctx->d_vq1, 0.0);
-            if (ctx->nranks > 1) hyp_replicate_q(ctx, ctx->d_vq1);
+            if (hyp_row_sharded(ctx)) hyp_replicate_q(ctx, ctx->d_vq1);
         }
     }
     TimeScope tv(ctx, T_VEC);
@@ -576,6 +576,27 @@ void apply_lhs_multi_dev(hyp_ctx* ctx, double* res, const double* dir, int ncols
 // Schur assembly + factorisation (update_lhs_fact, qrchol.jl:201-257)
 int update_lhs_fact(hyp_ctx* ctx) {
     const int64_t nmp = ctx->nmp, p = ctx->p;
+    if (ctx->col_shard && ctx->nranks > 1) {
+        // single giant cone: hess_prod! is independent per column of G_k (hypoperlogdettri.jl:196-237,
+        // possemideftri.jl:126-142), so rank r takes the columns J_r = [c_lo, c_hi) of GQ2, forms (H GQ2)[:, J_r] for
+        // every cone (the hess_prod! + mul! branch qrchol.jl:240-246 applied to all cones) and the upper part of the
+        // column panel S[0:c_hi, J_r] = GQ2[:, 0:c_hi]' (H GQ2)[:, J_r]; the panels are contiguous column ranges of the
+        // column-major S, so one in-place ncclAllGather completes S on every rank - no reduction.
+        const int64_t cw = ctx->col_shard_width;
+        const int64_t c_lo = std::min<int64_t>(nmp, (int64_t)ctx->rank * cw), c_hi = std::min<int64_t>(nmp, c_lo + cw);
+        const double* GQ2 = ctx->d_GQ + p * ctx->ldg;
+        if (c_hi > c_lo) {
+            {
+                TimeScope ts(ctx, T_SQRT_PREPASS);
+                hyp_cones_prod(ctx, ctx->d_HG + c_lo * ctx->ldg, GQ2 + c_lo * ctx->ldg, c_hi - c_lo, ctx->ldg, ctx->ldg,
+                               HYP_PROD_BLOCK, 0);
+            }
+            TimeScope ts(ctx, T_SYRK);
+            hyp_gemm_tn(ctx, GQ2, ctx->ldg, ctx->d_HG + c_lo * ctx->ldg, ctx->ldg, ctx->qloc, c_hi, c_hi - c_lo,
+                        ctx->d_S + c_lo * ctx->lds, ctx->lds, 1.0, 0.0);
+        }
+        hyp_allgather_inplace(ctx, ctx->d_S, cw * ctx->lds);
+    } else {
     hyp_cones_schur_prepass(ctx);
     {
         TimeScope ts(ctx, T_SYRK);
@@ -603,6 +624,7 @@ int update_lhs_fact(hyp_ctx* ctx) {
             CUDA_TRY(cudaMemsetAsync(ctx->d_S, 0, (size_t)ctx->lds * nmp * 8, ctx->stream));
     }
     if (ctx->nranks > 1) hyp_allreduce_sum(ctx, ctx->d_S, ctx->lds * nmp);
+    }
     (void)p;
     // posdef_fact_copy! (dense.jl:194-215): Cholesky -> Bunch-Kaufman -> shifted Bunch-Kaufman
     int info = 0;
@@ -866,6 +888,8 @@ void hyp_destroy(hyp_ctx* ctx) {
         if (ctx->ev_chain[i]) cudaEventDestroy(ctx->ev_chain[i]);
         if (ctx->ev_bulk[i]) cudaEventDestroy(ctx->ev_bulk[i]);
     }
+    if (ctx->d_dag_ver) cudaFree(ctx->d_dag_ver);
+    if (ctx->d_dag_dbg) cudaFree(ctx->d_dag_dbg);
     cudaStreamDestroy(ctx->stream2);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -1097,7 +1121,9 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
 
         // Schur matrix, factor, inverted diagonal blocks
         ctx->lds = round_up(std::max<int64_t>(nmp, 2), 2);
-        dalloc(&ctx->d_S, ctx->lds * std::max<int64_t>(nmp, 1));
+        // column sharding: equal panels of col_shard_width columns per rank (ncclAllGather needs equal counts)
+        ctx->col_shard_width = (ctx->col_shard && ctx->nranks > 1) ? round_up(ceil_div(std::max<int64_t>(nmp, 1), ctx->nranks), 2) : 0;
+        dalloc(&ctx->d_S, ctx->lds * std::max<int64_t>(std::max<int64_t>(nmp, ctx->col_shard_width * ctx->nranks), 1));
         dalloc(&ctx->d_F, ctx->lds * std::max<int64_t>(nmp, 1));
         dalloc(&ctx->d_Dinv, (int64_t)ceil_div(std::max<int64_t>(nmp, 1), 128) * 128 * 128);
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -1127,6 +1153,13 @@ int hyp_set_cone_alpha(hyp_ctx* ctx, int K, const int64_t* alpha_off, const doub
     });
 }
 
+int hyp_set_column_sharding(hyp_ctx* ctx, int on) {
+    return guarded(ctx, [&] {
+        if (ctx->model_loaded) throw HypError{"hyp_set_column_sharding: call before hyp_load_model"};
+        ctx->col_shard = on != 0;
+        return 0;
+    });
+}
 int hyp_set_syrk_mode(hyp_ctx* ctx, int mode) {
     return guarded(ctx, [&] {
         if (mode != 0 && mode != 1) throw HypError{"hyp_set_syrk_mode: 0 = FP64 DMMA, 1 = sliced int8 tcgen05"};
@@ -1271,7 +1304,7 @@ int hyp_cones_dder3(hyp_ctx* ctx, double* out, const double* dir) {
         ensure_stage(ctx, q + 2);
         const double* dd = stage_in(ctx, dir, q, ctx->d_stage);
         hyp_cones_dder3_dev(ctx, ctx->d_vq4, dd);
-        if (ctx->nranks > 1) hyp_replicate_q(ctx, ctx->d_vq4);
+        if (hyp_row_sharded(ctx)) hyp_replicate_q(ctx, ctx->d_vq4);
         stage_out(ctx, out, q, ctx->d_vq4);
         return 0;
     });
@@ -1307,7 +1340,7 @@ int hyp_update_lhs(hyp_ctx* ctx, int* fact_kind) {
         if (q > 0 && ctx->solver_kind == 0) {
             TimeScope ts(ctx, T_CONE_PROD);
             hyp_cones_prod(ctx, ctx->d_const_rhs + n + p, ctx->d_cbh + n + p, 1, q, q, HYP_PROD_BLOCK, 0);
-            if (ctx->nranks > 1) hyp_replicate_q(ctx, ctx->d_const_rhs + n + p);
+            if (hyp_row_sharded(ctx)) hyp_replicate_q(ctx, ctx->d_const_rhs + n + p);
         }
         solve_subsystem3_dev(ctx, ctx->d_const_sol, ctx->d_const_rhs);
         hyp_copy(ctx, q, ctx->d_Gx_const, ctx->d_Gx);

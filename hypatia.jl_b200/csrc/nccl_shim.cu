@@ -17,6 +17,7 @@ typedef struct { char internal[128]; } nccl_uid;
 typedef int (*fn_get_uid)(nccl_uid*);
 typedef int (*fn_init_rank)(void**, int, nccl_uid, int);
 typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_allgather)(const void*, void*, size_t, int, void*, cudaStream_t);
 typedef int (*fn_destroy)(void*);
 typedef const char* (*fn_errstr)(int);
 
@@ -25,6 +26,7 @@ struct NcclApi {
     fn_get_uid get_uid = nullptr;
     fn_init_rank init_rank = nullptr;
     fn_allreduce allreduce = nullptr;
+    fn_allgather allgather = nullptr;
     fn_destroy destroy = nullptr;
     fn_errstr errstr = nullptr;
 } g_nccl;
@@ -44,6 +46,7 @@ void load_nccl() {
     g_nccl.get_uid = (fn_get_uid)dlsym(g_nccl.handle, "ncclGetUniqueId");
     g_nccl.init_rank = (fn_init_rank)dlsym(g_nccl.handle, "ncclCommInitRank");
     g_nccl.allreduce = (fn_allreduce)dlsym(g_nccl.handle, "ncclAllReduce");
+    g_nccl.allgather = (fn_allgather)dlsym(g_nccl.handle, "ncclAllGather");
     g_nccl.destroy = (fn_destroy)dlsym(g_nccl.handle, "ncclCommDestroy");
     g_nccl.errstr = (fn_errstr)dlsym(g_nccl.handle, "ncclGetErrorString");
     if (!g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.allreduce || !g_nccl.destroy)
@@ -74,8 +77,17 @@ void hyp_allreduce_min_u8(hyp_ctx* ctx, uint8_t* buf, int64_t count) {
                "ncclAllReduce(min)");
 }
 
+void hyp_allgather_inplace(hyp_ctx* ctx, double* buf, int64_t count) {
+    if (ctx->nranks <= 1 || count <= 0) return;
+    if (!g_nccl.allgather) throw HypError{"NCCL library lacks ncclAllGather"};
+    TimeScope ts(ctx, T_ALLREDUCE);
+    nccl_check(g_nccl.allgather(buf + (int64_t)ctx->rank * count, buf, (size_t)count, NCCL_FLOAT64, ctx->nccl_comm,
+                                ctx->stream),
+               "ncclAllGather");
+}
+
 void hyp_replicate_q(hyp_ctx* ctx, double* v) {
-    if (ctx->nranks <= 1) return;
+    if (!hyp_row_sharded(ctx)) return;
     hyp_zero_outside(ctx, v);
     hyp_allreduce_sum(ctx, v, ctx->q);
 }

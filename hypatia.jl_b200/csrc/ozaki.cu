@@ -735,7 +735,10 @@ ozaki_syrk_pair_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid_c
                        const __grid_constant__ CUtensorMap mapB4, const __grid_constant__ CUtensorMap mapB8,
                        const int2* __restrict__ pairs, int n_pairs, int k0, int nkb,
                        const double* __restrict__ dscale, int64_t ncols, double* __restrict__ C, int64_t ldc,
-                       double alpha, double beta, int nsl, int wbits) {
+                       double alpha, double beta, int nsl, int wbits_probe) {
+    // bits 8.. of the last argument: profiling probes (HYP_OZAKI_PROBE; results are garbage, timing only):
+    //   1 = no TMA loads (the MMA issuer runs on stale shared memory), 2 = no MMAs (loads + epilogue only)
+    const int wbits = wbits_probe & 0xff, probe = wbits_probe >> 8;
     // nsl = number of digit slices that enter the product (7 or 8): pairs with s + t <= nsl - 1;
     // wbits = bits per digit (7: radix 128, 8: radix 256): digit s has weight 2^-(wbits - 1 + wbits s)
     extern __shared__ uint8_t smem_raw[];
@@ -791,6 +794,14 @@ ozaki_syrk_pair_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid_c
                         mbar_wait(bar_empty + stage * 8, phase ^ 1u);
                         const uint32_t full_leader = mapa_u32(bar_full + stage * 8, 0);
                         // pass 1 loads only the nsl slices that enter the product (host passes nsl-slice boxes)
+                        if (probe == 1) {
+                            if (leader) mbar_arrive(bar_full + stage * 8);
+                            if (++stage == OZP_STAGES) {
+                                stage = 0;
+                                phase ^= 1u;
+                            }
+                            continue;
+                        }
                         if (leader)
                             mbar_expect_tx(bar_full + stage * 8,
                                            pass == 0 ? 2u * OZP_STAGE : 2u * (uint32_t)nsl * (OZ_TILE + OZ_TILE / 2));
@@ -827,7 +838,7 @@ ozaki_syrk_pair_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid_c
                     for (int it = 0; it < nst; it++) {
                         mbar_wait(bar_full + stage * 8, phase);
                         asm volatile("tcgen05.fence::after_thread_sync;");
-                        for (int h = 0; h < nhalf; h++) {
+                        for (int h = 0; h < (probe == 2 ? 0 : nhalf); h++) {
                             const uint32_t sa = stg + stage * OZP_STAGE + h * (OZP_STAGE / 2);
                             const uint32_t sb = sa + ns * OZ_TILE;
                             for (int s = 0; s <= smax; s++) {
@@ -1506,7 +1517,8 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
             cfg.numAttrs = 1;
             CUDA_TRY(cudaLaunchKernelEx(&cfg, ozaki_syrk_pair_kernel, mapD4, mapA8, mapB4, mapB8, (const int2*)d_pairs,
                                         n_pairs, (int)k0, (int)ceil_div(klen, OZ_KB), dscale, ncols, C, ldc, alpha,
-                                        k0 == 0 ? beta : 1.0, nsl_eff, wbits));
+                                        k0 == 0 ? beta : 1.0, nsl_eff,
+                                        wbits | ((getenv("HYP_OZAKI_PROBE") ? atoi(getenv("HYP_OZAKI_PROBE")) : 0) << 8)));
             ctx->launches++;
             continue;
         }
@@ -1574,7 +1586,10 @@ extern "C" int hyp_test_ozaki_syrk(hyp_ctx* ctx, const double* A, int64_t lda, i
         CUDA_TRY(cudaMemsetAsync(dC, 0, (size_t)ncols * ncols * 8, ctx->stream));
         CUDA_TRY(cudaMemcpy2DAsync(dA, K * 8, A, lda * 8, K * 8, ncols, cudaMemcpyDefault, ctx->stream));
         hyp_ozaki_slice(ctx, dA, K, K, ncols, dD, ldd, ldd * ncols, dE, dSc);
-        hyp_ozaki_syrk(ctx, dD, ldd, ldd * ncols, dE, dSc, K, ncols, dC, ncols, 1.0, 0.0);
+        {
+            TimeScope ts(ctx, T_SYRK);      // tools/syrk_probe.py reads this timer
+            hyp_ozaki_syrk(ctx, dD, ldd, ldd * ncols, dE, dSc, K, ncols, dC, ncols, 1.0, 0.0);
+        }
         CUDA_TRY(cudaMemcpy2DAsync(C, ldc * 8, dC, ncols * 8, ncols * 8, ncols, cudaMemcpyDefault, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         cudaFree(dA);

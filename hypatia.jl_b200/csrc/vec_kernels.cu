@@ -96,7 +96,7 @@ void hyp_axpy_dev(hyp_ctx* ctx, int64_t len, double* out, double a, const double
 }
 
 void hyp_zero_outside(hyp_ctx* ctx, double* v) {
-    if (ctx->nranks == 1 || ctx->q == 0) return;
+    if (!hyp_row_sharded(ctx) || ctx->q == 0) return;
     zero_outside_kernel<<<grid_for(ctx, ctx->q, 256), 256, 0, ctx->stream>>>(v, ctx->q, ctx->row_lo,
                                                                              ctx->row_hi);
     ctx->launches++;

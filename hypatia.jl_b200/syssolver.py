@@ -47,6 +47,23 @@ def partition_cones(model, nranks):
     return [(bounds[r], bounds[r + 1]) for r in range(nranks)]
 
 
+def giant_cone(model, frac: float = 0.5) -> bool:
+    """True when one cone carries more than `frac` of the Schur-assembly work: whole-cone (row-panel) sharding cannot
+    split it, so the assembly is sharded by COLUMNS of G_k instead (hess_prod! is independent per
+    column, hypoperlogdettri.jl:196-237)."""
+    m = model.n - model.p
+    w = [cone_work(c, m) for c in model.cones]
+    return bool(w) and max(w) > frac * sum(w)
+
+
+def column_ranges(nmp: int, nranks: int):
+    """Column panel [lo, hi) of the Schur matrix each rank assembles under column sharding (equal widths, rounded up
+    to an even number of columns: ncclAllGather needs equal counts) - mirrors hyp_load_model."""
+    cw = -(-max(nmp, 1) // nranks)
+    cw += cw & 1
+    return [(min(nmp, r * cw), min(nmp, (r + 1) * cw)) for r in range(nranks)]
+
+
 class QRCholDenseSystemSolver:
     NEEDS_QR = True
     FAIL_MESSAGE = "positive definite linear system factorization failed"    # qrchol.jl:252-254
@@ -54,8 +71,11 @@ class QRCholDenseSystemSolver:
     def _after_load(self):
         pass
 
-    def __init__(self, device: int | None = None, dist_group=None, device_residuals: bool = False):
+    def __init__(self, device: int | None = None, dist_group=None, device_residuals: bool = False,
+                 column_sharding: bool | None = None):
         self.device = device
+        # None: decide per model (giant_cone); True / False: force
+        self.column_sharding = column_sharding
         self.dist_group = dist_group
         # True: the driver's calc_convergence_params takes its residuals from hyp_calc_residuals (two
         # passes over G on the device) instead of the host products the reference does (Solvers.jl:425-483)
@@ -73,7 +93,11 @@ class QRCholDenseSystemSolver:
             self.ctx = capi.Context(self.device if self.device is not None else 0)
             if self.nranks > 1:
                 self._join_comm()
-        lo, hi = partition_cones(model, self.nranks)[self.rank] if self.nranks > 1 \
+        self.col_shard = self.nranks > 1 and (giant_cone(model) if self.column_sharding is None
+                                              else bool(self.column_sharding))
+        if self.col_shard:
+            self.ctx.set_column_sharding(True)      # every rank keeps all rows; only the assembly is split
+        lo, hi = partition_cones(model, self.nranks)[self.rank] if (self.nranks > 1 and not self.col_shard) \
             else (0, len(model.cones))
         self.cone_range = (lo, hi)
         Q = getattr(solver, "Ap_Q", None)

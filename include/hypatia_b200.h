@@ -153,6 +153,13 @@ int hyp_set_syssolver(hyp_ctx* ctx, int kind);
 /* how the Schur SYRK runs: 0 = FP64 DMMA (mma.sync), 1 = FP64-accurate digit slicing on the int8
  * tcgen05 pipe (csrc/ozaki.cu).  Default 1 (0 when the environment has HYP_SCHUR_SYRK=dmma).  Models
  * that mix square-root and non-square-root cones (two-operand product) always use mode 0. */
+/* Column sharding for models dominated by ONE cone (BASELINE config 5's natvsext shape: one
+ * HypoPerLogdetTri of side 1000).  Call after hyp_comm_init and BEFORE hyp_load_model, then load the model with ALL
+ * rows on every rank (cone_lo = 0, cone_hi = K, G_local = G).  hess_prod! is independent per column of G_k
+ * (src/Cones/hypoperlogdettri.jl:196-237), so rank r assembles the column panel S[:, J_r] = GQ2' (H GQ2)[:, J_r]
+ * (the branch src/Solvers/systemsolvers/qrchol.jl:240-246) and one ncclAllGather completes S; solves and oracles
+ * run replicated with no further exchange. */
+int hyp_set_column_sharding(hyp_ctx* ctx, int on);
 int hyp_set_syrk_mode(hyp_ctx* ctx, int mode);
 /* mu and tau of the current iterate (solver.mu, solver.point.tau[]) used by
  * solve_subsystem4 / solve_system / apply_lhs (common.jl:117,171-175,147) */

@@ -26,10 +26,20 @@ def build_instance():
     return inst.synthetic("dist", 260, 0, cones, seed=2024)
 
 
+def build_giant_instance():
+    """One dominant log-det cone + small ones: whole-cone sharding cannot split it."""
+    from hypatia_b200.host import instances as inst
+    from hypatia_b200.host import models as M
+    cones = [M.Nonnegative(30), M.HypoPerLogdetTri(2 + M.svec_length(36)), M.EpiNormEucl(9), M.Nonnegative(12)]
+    return inst.synthetic("giant", 150, 0, cones, seed=2025)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--impl", default="oracle")
     args = ap.parse_args()
+    if args.impl.endswith("_cols"):
+        return main_cols(args.impl)
     import torch
     import torch.distributed as dist
     from gpu_util import iterate_solver, rel
@@ -98,6 +108,65 @@ def main():
         dev.syssolver.free_memory()
         if rank == 0:
             print(f"DIST_OK device world={world} dir_err={err:.2e} lhs_err={err_r:.2e} schur_err={err_S:.2e}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def main_cols(impl):
+    """Column sharding of the Schur assembly: rank r builds S[:, J_r] = G' (H G)[:, J_r], the panels are all-gathered."""
+    import torch
+    import torch.distributed as dist
+    from gpu_util import iterate_solver, rel
+    from hypatia_b200.host.point import Point
+    from hypatia_b200.syssolver import column_ranges, giant_cone
+    from oracle.syssolvers import QRCholDenseSystemSolver as OraQRChol
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    I = build_giant_instance()
+    model = I.model
+    assert giant_cone(model)
+    ora = iterate_solver(I, OraQRChol())
+    S_ref = np.triu(ora.syssolver.lhs_full())
+    rhs, so = Point(model), Point(model)
+    rhs.vec[:] = np.random.default_rng(5).standard_normal(rhs.vec.size)
+    ora.syssolver.solve_system(ora, so, rhs)
+    if impl == "oracle_cols":
+        dist.init_process_group("gloo")
+        rg = column_ranges(model.n, world)
+        assert rg[0][0] == 0 and rg[-1][1] == model.n and all(a[1] == b[0] for a, b in zip(rg, rg[1:]))
+        lo, hi = rg[rank]
+        cw = rg[0][1] - rg[0][0]
+        panel = np.zeros((cw, model.n))                         # row c of `panel` = column lo + c of S
+        HGJ = ora.cones.hess_prod(model.G[:, lo:hi])            # hess_prod! on my columns of G, all cones
+        panel[:hi - lo] = (model.G.T @ HGJ).T
+        out = [torch.zeros(cw, model.n, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(out, torch.from_numpy(panel))
+        S = torch.cat(out)[:model.n].numpy().T
+        err_S = rel(np.triu(S), S_ref)
+        assert err_S <= 1e-12, err_S
+        if rank == 0:
+            print(f"DIST_OK oracle_cols world={world} schur_err={err_S:.2e}")
+    else:
+        local_rank = int(os.environ.get("LOCAL_RANK", rank))
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        from hypatia_b200.syssolver import QRCholDenseSystemSolver as DevQRChol
+        dev = iterate_solver(I, DevQRChol(device=local_rank))
+        assert dev.syssolver.nranks == world and dev.syssolver.col_shard
+        sd = Point(model)
+        dev.syssolver.solve_system(dev, sd, rhs)
+        err = rel(sd.vec, so.vec)
+        rd, ro = Point(model), Point(model)
+        dev.syssolver.apply_lhs(dev, so, rd)
+        ora.syssolver.apply_lhs(ora, so, ro)
+        err_r = rel(rd.vec, ro.vec)
+        err_S = rel(np.triu(dev.syssolver.lhs_full()), S_ref)
+        assert err <= 1e-8 and err_r <= 1e-10 and err_S <= 1e-12, (err, err_r, err_S)
+        assert np.allclose(dev.cones.get_proxsqr(0.9, True), ora.cones.get_proxsqr(0.9, True), rtol=1e-8, atol=1e-12)
+        dev.syssolver.free_memory()
+        if rank == 0:
+            print(f"DIST_OK device_cols world={world} dir_err={err:.2e} lhs_err={err_r:.2e} schur_err={err_S:.2e}")
     dist.barrier()
     dist.destroy_process_group()
 

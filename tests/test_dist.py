@@ -24,6 +24,11 @@ def test_sharded_schur_sum_gloo_world2():
     _run("oracle", 29531)
 
 
+def test_column_sharded_schur_allgather_gloo_world2():
+    """single-giant-cone path: column panels of S all-gathered, checked against the unsharded oracle"""
+    _run("oracle_cols", 29533)
+
+
 def test_partition_cones_balances_and_covers():
     import numpy as np
     from hypatia_b200.host import instances as inst
@@ -43,3 +48,11 @@ def test_sharded_device_path_nccl_world2():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     _run("device", 29532)
+
+
+@pytest.mark.gpu
+def test_column_sharded_device_path_nccl_world2():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run("device_cols", 29534)
