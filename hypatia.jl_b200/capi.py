@@ -66,6 +66,7 @@ _SIGS = {
     "hyp_test_gemm_tn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
                                    C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_double, C.c_double]),
     "hyp_test_potrf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, c_ip]),
+    "hyp_test_panel_clocks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "hyp_test_potrs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "hyp_test_gemv": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
                                 C.c_void_p, C.c_double, C.c_double, C.c_void_p]),
@@ -73,6 +74,7 @@ _SIGS = {
                                       C.c_int64, C.c_int64, C.c_void_p, C.c_int64]),
     "hyp_test_ozaki_slices": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int,
                                         C.c_void_p, C.c_void_p]),
+    "hyp_test_mma_rate": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "hyp_test_ozaki_syrk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
                                       C.c_int64]),
     "hyp_test_ldlt_solve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, c_ip]),

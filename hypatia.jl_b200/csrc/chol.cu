@@ -172,3 +172,32 @@ void hyp_chol_batched(hyp_ctx* ctx, int ncones, const int* d_sides, const int64_
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
 }
+
+// phase timestamps of the last panel_kernel<true> launch (tools/panel_probe.py): cycles relative to the start
+extern "C" int hyp_test_panel_clocks(hyp_ctx* ctx, double* A, int64_t lda, int64_t m, double* cycles16) {
+    if (!ctx || m > NB) return -1;
+    try {
+        set_panel_attr();
+        double *dA = nullptr, *dD = nullptr;
+        int* dI = nullptr;
+        CUDA_TRY(cudaMalloc(&dA, (size_t)lda * m * 8));
+        CUDA_TRY(cudaMalloc(&dD, (size_t)NB * NB * 8));
+        CUDA_TRY(cudaMalloc(&dI, 8));
+        long long clk[16];
+        for (int rep = 0; rep < 3; rep++) {
+            CUDA_TRY(cudaMemcpyAsync(dA, A, (size_t)lda * m * 8, cudaMemcpyDefault, ctx->stream));
+            CUDA_TRY(cudaMemsetAsync(dI, 0, 8, ctx->stream));
+            panel_kernel<true><<<1, PT, NB * LDU * 8, ctx->stream>>>(dA, lda, m, 0, dD, dI);
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        }
+        CUDA_TRY(cudaMemcpyFromSymbol(clk, g_panel_clk, sizeof(clk)));
+        for (int i = 0; i < 16; i++) cycles16[i] = (double)(clk[i] - clk[0]);
+        cudaFree(dA);
+        cudaFree(dD);
+        cudaFree(dI);
+        return 0;
+    } catch (HypError& e) {
+        ctx->last_error = e.msg;
+        return -1;
+    }
+}

@@ -305,8 +305,8 @@ potrf_dag_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             int* s_bad = reinterpret_cast<int*>(ring_ptr + PANEL_SA + PANEL_DIAGX + PANEL_SX + PANEL_ST);
             const int64_t r0 = (int64_t)ti * NB;
             const int nb = (int)((int64_t)NB < m - r0 ? (int64_t)NB : m - r0);
-            const int bad = panel_body<true, 1, true>(A + r0 + r0 * lda, lda, nb, dinv + (int64_t)ti * NB * NB, NB, NB,
-                                                      false, sA, diagX, sX, sT, s_bad);
+            const int bad = panel_body_fast<1, true>(A + r0 + r0 * lda, lda, nb, dinv + (int64_t)ti * NB * NB, NB, NB,
+                                                    false, sA, diagX, sX, sT, s_bad);
             if (bad && threadIdx.x == 0) atomicCAS(info, 0, (int)(r0 + bad));
             cnext = t_fin(ti, ti, nt);
         } else {

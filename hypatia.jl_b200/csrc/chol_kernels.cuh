@@ -26,6 +26,16 @@ constexpr int LDU = NB + 1;   // padded leading dimension of the shared-memory b
 // identity padding).  Returns the 1-based index of the first non-positive pivot or 0.
 constexpr int SB = 32;
 constexpr int PT = 256;          // threads of a panel CTA
+
+// phase timestamps of the LAST panel_body call of a launch (clock64 of thread 0; read back by hyp_test_panel_clocks):
+// [0] start, [1] tile loaded, then per 32-column sub-block b: [2 + 3 b] diagonal sub-block factored + inverted,
+// [3 + 3 b] block row, [4 + 3 b] trailing update; [14] inverse assembled, [15] results stored
+#ifndef HYP_EMU
+static __device__ long long g_panel_clk[16];
+#define HYP_PANEL_CLK(i) do { if (threadIdx.x == 0) g_panel_clk[i] = clock64(); } while (0)
+#else
+#define HYP_PANEL_CLK(i) do { } while (0)
+#endif
 constexpr int LDX = SB + 1;
 constexpr int LDT = 3 * SB + 1;  // sT holds up to 96 x 32
 
@@ -109,6 +119,7 @@ __device__ __forceinline__ int panel_body(double* __restrict__ Ab, int64_t lda, 
                                           double* sA, double* diagX, double* sX, double* sT, int* s_bad) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) *s_bad = 0;
+    HYP_PANEL_CLK(0);
     // 64 elements per thread, 16 global loads in flight at a time
     for (int base = 0; base < NB * NB; base += PT * 16) {
         double v[16];
@@ -137,11 +148,13 @@ __device__ __forceinline__ int panel_body(double* __restrict__ Ab, int64_t lda, 
         }
     }
     panel_sync<BARID>();
+    HYP_PANEL_CLK(1);
 
     for (int b = 0; b < NB / SB; b++) {
         const int o = b * SB;
         if (warp == 0) base_block<FACTOR>(sA, diagX, sX, o, lane, s_bad);
         panel_sync<BARID>();
+        HYP_PANEL_CLK(2 + 3 * b);
         if (FACTOR && b < NB / SB - 1) {
             const int t0 = o + SB;
             const int ncol = NB - t0;
@@ -178,6 +191,7 @@ __device__ __forceinline__ int panel_body(double* __restrict__ Ab, int64_t lda, 
                         for (int q = 0; q < 4; q++) sA[(o + ti * 4 + a) + (t0 + tj * 4 + q) * LDU] = acc[a][q];
                 }
                 panel_sync<BARID>();
+                HYP_PANEL_CLK(3 + 3 * b);
             }
             // (c) trailing update A[r, c] -= sum_k U[o + k, r] U[o + k, c] on 4 x 4 tiles with r-tile <= c-tile
             {
@@ -217,6 +231,7 @@ __device__ __forceinline__ int panel_body(double* __restrict__ Ab, int64_t lda, 
                         }
                 }
                 panel_sync<BARID>();
+                HYP_PANEL_CLK(4 + 3 * b);
             }
         }
     }
@@ -303,6 +318,7 @@ __device__ __forceinline__ int panel_body(double* __restrict__ Ab, int64_t lda, 
         panel_sync<BARID>();
     }
 
+    HYP_PANEL_CLK(14);
     if (FACTOR) {
         for (int idx = tid; idx < NB * NB; idx += PT) {
             int r = idx & (NB - 1), c = idx >> 7;
@@ -319,6 +335,315 @@ __device__ __forceinline__ int panel_body(double* __restrict__ Ab, int64_t lda, 
         else if (r == c) x = diagX[r];
         Db[r + (int64_t)c * ldd] = x;
     }
+    HYP_PANEL_CLK(15);
+    return *s_bad;
+}
+
+// ---- software-pipelined factor-and-invert (the latency-critical PANEL of the blocked Cholesky) -------------------------
+// Same arithmetic as panel_body<true> (same base_block, same 4 x 4 register-tiled products, same results up to the
+// order of independent updates), re-scheduled so that ONLY the chain of 128 dependent pivots (warp 0: 4 diagonal
+// sub-blocks of 32) and the short hand-offs between them are on the critical path.  Measured phase costs of the
+// bulk-synchronous version (clock64, tools/panel_probe.py, 147.5 k cycles): load 9.3 k, 4 x diag 13.2 k, block rows
+// 11.1 k, trailing updates 23.2 k, inverse assembly 42.3 k, stores 8.5 k.  Here, between two block barriers:
+//   A_b: warp 0 factors + inverts diagonal sub-block b in registers  ||  warps 1-7: the work nobody waits for yet -
+//        loading the rest of the tile (b = 0), the trailing update of row b - 1 except the next diagonal sub-block,
+//        T_b = X[0:h, 0:h] U[0:h, b] (the expensive half of the inverse's block column b), and, for b = 3, the global
+//        stores of everything that is already final;
+//   B_b: all warps: X[0:h, b] = -T_b X_bb, block row U[b, b+1:], barrier, update of the next diagonal sub-block.
+// sT must hold 96 x 32 (ld LDT), sX 32 x 32 (ld LDX).
+template <int BARID, bool LDCG>
+__device__ __forceinline__ double panel_ld(const double* p) {
+#ifdef HYP_EMU
+    return *p;
+#else
+    return LDCG ? __ldcg(p) : *p;
+#endif
+}
+
+template <int BARID = 0, bool LDCG = false>
+__device__ __forceinline__ int panel_body_fast(double* __restrict__ Ab, int64_t lda, int nb, double* __restrict__ Db,
+                                               int ldd, int dn, bool zero_lower, double* sA, double* diagX, double* sX,
+                                               double* sT, int* s_bad) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = PT - 32;                       // worker threads beside warp 0
+    if (tid == 0) *s_bad = 0;
+    HYP_PANEL_CLK(0);
+    // ---- I0: the first diagonal sub-block (upper part), one load per thread x 4 ----
+    for (int idx = tid; idx < SB * SB; idx += PT) {
+        const int r = idx & (SB - 1), c = idx >> 5;
+        double x = 0.0;
+        if (r < nb && c < nb) {
+            if (r <= c) x = panel_ld<BARID, LDCG>(Ab + r + (int64_t)c * lda);
+        } else if (r == c) {
+            x = 1.0;
+        }
+        sA[r + c * LDU] = x;
+    }
+    panel_sync<BARID>();
+    HYP_PANEL_CLK(1);
+
+    for (int b = 0; b < NB / SB; b++) {
+        const int o = b * SB;           // this diagonal sub-block
+        const int h = o;                // rows above it
+        // ================= A_b =================
+        if (warp == 0) {
+            base_block<true>(sA, diagX, sX, o, lane, s_bad);
+        } else {
+            const int wt = tid - 32;
+            if (b == 0) {
+                // rest of the tile: everything but the (0, 0) sub-block; 16 loads in flight per thread
+                for (int base = 0; base < NB * NB; base += NW * 16) {
+                    double v[16];
+#pragma unroll
+                    for (int u = 0; u < 16; u++) {
+                        const int idx = base + u * NW + wt;
+                        const int r = idx & (NB - 1), c = idx >> 7;
+                        double x = 0.0;
+                        if (idx < NB * NB && !(r < SB && c < SB)) {
+                            if (r < nb && c < nb) {
+                                if (r <= c) x = panel_ld<BARID, LDCG>(Ab + r + (int64_t)c * lda);
+                            } else if (r == c) {
+                                x = 1.0;
+                            }
+                        }
+                        v[u] = x;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 16; u++) {
+                        const int idx = base + u * NW + wt;
+                        const int r = idx & (NB - 1), c = idx >> 7;
+                        if (idx < NB * NB && !(r < SB && c < SB)) sA[r + c * LDU] = v[u];
+                    }
+                }
+            } else {
+                // (1) trailing update of row b - 1 on everything right / below the sub-block (b, b), which the
+                //     previous B interval already updated:  A[r, c] -= sum_k U[op + k, r] U[op + k, c]
+                const int op = o - SB;
+                const int t0 = o;
+                const int ncol = NB - t0;
+                const int nt4 = ncol / 4;
+                const int ntiles = nt4 * (nt4 + 1) / 2;
+                for (int t = wt; t < ntiles; t += NW) {
+                    int tc = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+                    while ((tc + 1) * (tc + 2) / 2 <= t) tc++;
+                    while (tc * (tc + 1) / 2 > t) tc--;
+                    const int tr = t - tc * (tc + 1) / 2;
+                    if (tc < SB / 4) continue;                   // inside (b, b): done already
+                    const double* ur = sA + op + (t0 + tr * 4) * LDU;
+                    const double* uc = sA + op + (t0 + tc * 4) * LDU;
+                    double acc[4][4];
+#pragma unroll
+                    for (int a = 0; a < 4; a++)
+#pragma unroll
+                        for (int q = 0; q < 4; q++) acc[a][q] = 0.0;
+#pragma unroll 4
+                    for (int k = 0; k < SB; k++) {
+                        double rv[4], cv[4];
+#pragma unroll
+                        for (int a = 0; a < 4; a++) rv[a] = ur[k + a * LDU];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) cv[q] = uc[k + q * LDU];
+#pragma unroll
+                        for (int a = 0; a < 4; a++)
+#pragma unroll
+                            for (int q = 0; q < 4; q++) acc[a][q] = fma(rv[a], cv[q], acc[a][q]);
+                    }
+#pragma unroll
+                    for (int a = 0; a < 4; a++)
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const int r = t0 + tr * 4 + a, c = t0 + tc * 4 + q;
+                            if (r <= c) sA[r + c * LDU] -= acc[a][q];
+                        }
+                }
+                // (2) T_b = X[0:h, 0:h] U[0:h, o:o+32]   (X[i, k] for k > i sits at sA[k + i LDU], diagonal in diagX)
+                const int ntile = (h / 4) * 8;
+                for (int t = wt; t < ntile; t += NW) {
+                    const int ti = t % (h / 4), tj = t / (h / 4);
+                    const int i0 = ti * 4;
+                    double acc[4][4];
+#pragma unroll
+                    for (int a = 0; a < 4; a++)
+#pragma unroll
+                        for (int q = 0; q < 4; q++) acc[a][q] = 0.0;
+                    const double* up = sA + (o + tj * 4) * LDU;     // up[k + q * LDU] = U[k, o + 4 tj + q]
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++) {
+                        const int k = i0 + kk;
+#pragma unroll
+                        for (int a = 0; a < 4; a++) {
+                            double xv = 0.0;
+                            if (kk > a) xv = sA[k + (i0 + a) * LDU];
+                            else if (kk == a) xv = diagX[k];
+#pragma unroll
+                            for (int q = 0; q < 4; q++) acc[a][q] = fma(xv, up[k + q * LDU], acc[a][q]);
+                        }
+                    }
+                    for (int k = i0 + 4; k < h; k++) {
+                        double xv[4], uv[4];
+#pragma unroll
+                        for (int a = 0; a < 4; a++) xv[a] = sA[k + (i0 + a) * LDU];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) uv[q] = up[k + q * LDU];
+#pragma unroll
+                        for (int a = 0; a < 4; a++)
+#pragma unroll
+                            for (int q = 0; q < 4; q++) acc[a][q] = fma(xv[a], uv[q], acc[a][q]);
+                    }
+#pragma unroll
+                    for (int a = 0; a < 4; a++)
+#pragma unroll
+                        for (int q = 0; q < 4; q++) sT[(i0 + a) + (tj * 4 + q) * LDT] = acc[a][q];
+                }
+                if (b == NB / SB - 1) {
+                    // (3) everything above / left of the last sub-block is final: store it while warp 0 finishes the chain
+                    for (int idx = wt; idx < NB * NB; idx += NW) {
+                        const int r = idx & (NB - 1), c = idx >> 7;
+                        if (r < o && r < nb && c < nb) {             // U rows 0 .. o-1
+                            if (r <= c) Ab[r + (int64_t)c * lda] = sA[r + c * LDU];
+                            else if (zero_lower) Ab[r + (int64_t)c * lda] = 0.0;
+                        } else if (zero_lower && r >= o && c < o && r < nb && c < nb) {
+                            Ab[r + (int64_t)c * lda] = 0.0;            // below the diagonal, left of the last sub-block
+                        }
+                    }
+                    for (int idx = wt; idx < dn * o; idx += NW) {     // X columns 0 .. o-1
+                        const int r = idx % dn, c = idx / dn;
+                        double x = 0.0;
+                        if (r < c) x = sA[c + r * LDU];
+                        else if (r == c) x = diagX[r];
+                        if (c < dn) Db[r + (int64_t)c * ldd] = x;
+                    }
+                }
+            }
+        }
+        panel_sync<BARID>();
+        HYP_PANEL_CLK(2 + 3 * b);
+        // ================= B_b =================
+        // X[0:h, o + j] = -sum_{k <= j} T[i, k] X_bb[k, j]   (X_bb[k, j] = sX[j + k LDX]); stored at sA[(o + j) + i LDU]
+        if (b > 0) {
+            const int ntile = (h / 4) * 8;
+            for (int t = tid; t < ntile; t += PT) {
+                const int ti = t % (h / 4), tj = t / (h / 4);
+                const int i0 = ti * 4, j0 = tj * 4;
+                double acc[4][4];
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int q = 0; q < 4; q++) acc[a][q] = 0.0;
+                for (int k = 0; k < j0 + 4; k++) {
+                    double tv[4], xv[4];
+#pragma unroll
+                    for (int a = 0; a < 4; a++) tv[a] = sT[(i0 + a) + k * LDT];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) xv[q] = sX[(j0 + q) + k * LDX];
+#pragma unroll
+                    for (int a = 0; a < 4; a++)
+#pragma unroll
+                        for (int q = 0; q < 4; q++) acc[a][q] = fma(tv[a], xv[q], acc[a][q]);
+                }
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int q = 0; q < 4; q++) sA[(o + j0 + q) + (i0 + a) * LDU] = -acc[a][q];
+            }
+        }
+        if (b < NB / SB - 1) {
+            const int t0 = o + SB;
+            const int ncol = NB - t0;
+            // block row U[o + i, c] = sum_k X_bb[k, i] A[o + k, c]: 4 x 4 tiles, 8 row tiles
+            {
+                const int ti = tid & 7, tj = tid >> 3;
+                const bool act = tj * 4 < ncol;
+                double acc[4][4];
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int q = 0; q < 4; q++) acc[a][q] = 0.0;
+                if (act) {
+                    const double* xp = sX + ti * 4;
+                    const double* ap = sA + o + (t0 + tj * 4) * LDU;
+#pragma unroll 4
+                    for (int k = 0; k < SB; k++) {
+                        double xa[4], av[4];
+#pragma unroll
+                        for (int a = 0; a < 4; a++) xa[a] = xp[a + k * LDX];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) av[q] = ap[k + q * LDU];
+#pragma unroll
+                        for (int a = 0; a < 4; a++)
+#pragma unroll
+                            for (int q = 0; q < 4; q++) acc[a][q] = fma(xa[a], av[q], acc[a][q]);
+                    }
+                }
+                panel_sync<BARID>();
+                if (act) {
+#pragma unroll
+                    for (int a = 0; a < 4; a++)
+#pragma unroll
+                        for (int q = 0; q < 4; q++) sA[(o + ti * 4 + a) + (t0 + tj * 4 + q) * LDU] = acc[a][q];
+                }
+                panel_sync<BARID>();
+            }
+            HYP_PANEL_CLK(3 + 3 * b);
+            // the next diagonal sub-block: A[r, c] -= sum_k U[o + k, r] U[o + k, c], r, c in [t0, t0 + 32): 36 upper tiles
+            if (tid < 36) {
+                int tc = (int)((sqrtf(8.0f * (float)tid + 1.0f) - 1.0f) * 0.5f);
+                while ((tc + 1) * (tc + 2) / 2 <= tid) tc++;
+                while (tc * (tc + 1) / 2 > tid) tc--;
+                const int tr = tid - tc * (tc + 1) / 2;
+                const double* ur = sA + o + (t0 + tr * 4) * LDU;
+                const double* uc = sA + o + (t0 + tc * 4) * LDU;
+                double acc[4][4];
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int q = 0; q < 4; q++) acc[a][q] = 0.0;
+#pragma unroll 4
+                for (int k = 0; k < SB; k++) {
+                    double rv[4], cv[4];
+#pragma unroll
+                    for (int a = 0; a < 4; a++) rv[a] = ur[k + a * LDU];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) cv[q] = uc[k + q * LDU];
+#pragma unroll
+                    for (int a = 0; a < 4; a++)
+#pragma unroll
+                        for (int q = 0; q < 4; q++) acc[a][q] = fma(rv[a], cv[q], acc[a][q]);
+                }
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int r = t0 + tr * 4 + a, c = t0 + tc * 4 + q;
+                        if (r <= c) sA[r + c * LDU] -= acc[a][q];
+                    }
+            }
+            panel_sync<BARID>();
+            HYP_PANEL_CLK(4 + 3 * b);
+        } else {
+            panel_sync<BARID>();
+        }
+    }
+    HYP_PANEL_CLK(14);
+    // ---- what is left: U rows 96 .. 127 and the last block column of X ----
+    {
+        const int o = NB - SB;
+        for (int idx = tid; idx < SB * NB; idx += PT) {
+            const int r = o + (idx & (SB - 1)), c = idx >> 5;
+            if (r < nb && c < nb) {
+                if (r <= c) Ab[r + (int64_t)c * lda] = sA[r + c * LDU];
+                else if (zero_lower && c >= o) Ab[r + (int64_t)c * lda] = 0.0;
+            }
+        }
+        for (int idx = tid; idx < dn * SB; idx += PT) {
+            const int r = idx % dn, c = o + idx / dn;
+            double x = 0.0;
+            if (r < c) x = sA[c + r * LDU];
+            else if (r == c) x = diagX[r];
+            if (c < dn) Db[r + (int64_t)c * ldd] = x;
+        }
+    }
+    HYP_PANEL_CLK(15);
     return *s_bad;
 }
 
@@ -336,8 +661,13 @@ panel_kernel(double* __restrict__ A, int64_t lda, int64_t m, int64_t blk0, doubl
     const int64_t blk = FACTOR ? blk0 : (int64_t)blockIdx.x;
     const int64_t k0 = blk * NB;
     const int nb = (int)((int64_t)NB < m - k0 ? (int64_t)NB : m - k0);
-    int bad = panel_body<FACTOR>(A + k0 + k0 * lda, lda, nb, dinv + blk * (int64_t)NB * NB, NB, NB, false,
-                                 sU, diagX, sX, sT, &s_bad);
+    int bad;
+    if (FACTOR)
+        bad = panel_body_fast<0, false>(A + k0 + k0 * lda, lda, nb, dinv + blk * (int64_t)NB * NB, NB, NB, false, sU, diagX,
+                                        sX, sT, &s_bad);
+    else
+        bad = panel_body<false>(A + k0 + k0 * lda, lda, nb, dinv + blk * (int64_t)NB * NB, NB, NB, false, sU, diagX, sX,
+                                sT, &s_bad);
     if (FACTOR && bad && threadIdx.x == 0) atomicCAS(info, 0, (int)(k0 + bad));
 }
 
@@ -358,7 +688,7 @@ chol_batched_kernel(int ncones, const int* __restrict__ sides, const int64_t* __
     const int side = sides[c];
     if (side > NB) return;
     const int lde = (side + 1) & ~1;
-    int bad = panel_body<true>(U + moff[c], lde, side, Ui + moff[c], lde, side, true, sU, diagX, sX, sT, &s_bad);
+    int bad = panel_body_fast<0, false>(U + moff[c], lde, side, Ui + moff[c], lde, side, true, sU, diagX, sX, sT, &s_bad);
     if (bad && threadIdx.x == 0) flag[kidx[c]] = 0;
 }
 

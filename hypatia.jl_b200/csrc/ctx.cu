@@ -573,6 +573,46 @@ void apply_lhs_multi_dev(hyp_ctx* ctx, double* res, const double* dir, int ncols
     for (int j = 0; j < ncols; j++) apply_lhs_dev(ctx, res + j * ld, dir + j * ld);
 }
 
+// ---- packed upper triangle for the Schur reduction ------------------------------------------
+// Only the upper triangle of the partial Schur matrices is meaningful (outer_prod! = syrk 'U', dense.jl:80-86), so the
+// allreduce moves the upper-triangular 128-column blocks only: block column b (columns [128 b, 128 b + 128)) keeps its
+// rows [0, 128 (b + 1)), stored contiguously one block column after the other - 0.41 GB instead of the 0.8 GB square at
+// m = 10000.  pack: S -> buf, unpack: buf -> S.
+__global__ void tri_pack_kernel(int64_t m, const double* __restrict__ S, int64_t lds, double* __restrict__ buf, int unpack) {
+    const int64_t b = blockIdx.y;                                   // block column
+    const int64_t c0 = b * 128, nc = min((int64_t)128, m - c0);
+    const int64_t nr = min(m, c0 + 128);                            // rows kept
+    const int64_t off = 128 * 128 * (b * (b + 1) / 2);              // doubles in front of this block column
+    const int64_t total = nr * nc;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = idx % nr, c = idx / nr;
+        double* sp = const_cast<double*>(S) + r + (c0 + c) * lds;
+        if (unpack) *sp = buf[off + idx];
+        else buf[off + idx] = *sp;
+    }
+}
+
+int64_t tri_packed_len(int64_t m) {
+    const int64_t nb = (m + 127) / 128;
+    return 128 * 128 * (nb * (nb + 1) / 2);
+}
+
+void allreduce_upper(hyp_ctx* ctx, double* S, int64_t lds, int64_t m, double* buf) {
+    if (m <= 0) return;
+    const int64_t nb = (m + 127) / 128;
+    dim3 grid(std::max(1, std::min(64, ctx->sm_count)), (unsigned)nb);
+    {
+        TimeScope ts(ctx, T_VEC);
+        tri_pack_kernel<<<grid, 256, 0, ctx->stream>>>(m, S, lds, buf, 0);
+        ctx->launches++;
+    }
+    hyp_allreduce_sum(ctx, buf, tri_packed_len(m));
+    TimeScope ts(ctx, T_VEC);
+    tri_pack_kernel<<<grid, 256, 0, ctx->stream>>>(m, S, lds, buf, 1);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+}
+
 // Schur assembly + factorisation (update_lhs_fact, qrchol.jl:201-257)
 int update_lhs_fact(hyp_ctx* ctx) {
     const int64_t nmp = ctx->nmp, p = ctx->p;
@@ -623,7 +663,14 @@ int update_lhs_fact(hyp_ctx* ctx) {
         else
             CUDA_TRY(cudaMemsetAsync(ctx->d_S, 0, (size_t)ctx->lds * nmp * 8, ctx->stream));
     }
-    if (ctx->nranks > 1) hyp_allreduce_sum(ctx, ctx->d_S, ctx->lds * nmp);
+    if (ctx->nranks > 1) {
+        // the factor buffer is idle until the copy below: it holds the packed upper triangle during the reduction
+        // (the ragged last block column is padded to 128 x 128-row blocks, still within lds * nmp doubles for m >= 256)
+        static int packed = -1;
+        if (packed < 0) packed = getenv("HYP_ALLREDUCE_FULL") ? 0 : 1;
+        if (packed && tri_packed_len(nmp) <= ctx->lds * nmp) allreduce_upper(ctx, ctx->d_S, ctx->lds, nmp, ctx->d_F);
+        else hyp_allreduce_sum(ctx, ctx->d_S, ctx->lds * nmp);
+    }
     }
     (void)p;
     // posdef_fact_copy! (dense.jl:194-215): Cholesky -> Bunch-Kaufman -> shifted Bunch-Kaufman

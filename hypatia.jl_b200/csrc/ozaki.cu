@@ -1604,3 +1604,142 @@ extern "C" int hyp_test_ozaki_syrk(hyp_ctx* ctx, const double* A, int64_t lda, i
         return -1;
     }
 }
+
+// ---- tcgen05.mma kind::i8 issue-rate probe (tools/mma_probe.py) -----------------------------------------------------
+// How fast can one SM (or an SM pair) retire int8 MMAs whose operands sit in shared memory, as a function of the
+// shared-memory layout (SWIZZLE_32B / 64B / 128B K-major), of N (128 / 256) and of cta_group?  No TMA, no epilogue: the
+// MMA issuer loops over a few operand tiles in (zeroed) shared memory.  The Schur SYRK's digit products use 32-byte K
+// rows (K = 32 int8 per instruction) in SWIZZLE_32B tiles; `profiles/r02_syrk_probe_mma_vs_tma.json` shows its MMA
+// stream alone already needs 88 % of the kernel time, so this is the number that bounds it.
+__device__ __forceinline__ uint64_t make_desc_kmajor(uint32_t smem_addr, int swz) {
+    // swz: 0 = SWIZZLE_32B (8-row group pitch 256 B), 1 = 64B (512 B), 2 = 128B (1024 B)
+    const uint32_t sbo = 256u << swz;
+    const uint64_t layout = swz == 0 ? 6 : (swz == 1 ? 4 : 2);
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(sbo >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= layout << 61;
+    return d;
+}
+__device__ __forceinline__ void umma_i8_n(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, int cg2) {
+    if (cg2) umma_i8_2sm(tmem_d, adesc, bdesc, idesc, 1u);
+    else umma_i8(tmem_d, adesc, bdesc, idesc, 1u);
+}
+
+__global__ void __launch_bounds__(128, 1)
+mma_rate_kernel(int swz, int N, int cg2, int nmma, long long* __restrict__ cycles) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(8) uint64_t s_bar;
+    const uint32_t base = smem_u32(smem_raw);
+    const uint32_t stg = (base + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t crank = 0;
+    if (cg2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    // zero the operand area: 192 KB
+    for (int i = threadIdx.x; i < 192 * 1024 / 16; i += blockDim.x)
+        reinterpret_cast<uint4*>(smem_raw + (stg - base))[i] = make_uint4(0, 0, 0, 0);
+    const uint32_t bar = smem_u32(&s_bar);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        if (cg2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
+    }
+    // generic-proxy writes (the zero fill) must be visible to the tensor core's async-proxy reads
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (cg2) cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem0 = s_tmem;
+    if (warp == 1 && lane == 0 && crank == 0) {
+        const uint32_t idesc = make_idesc_i8(cg2 ? 256 : 128, N);
+        const int row_bytes = 32 << swz;                       // bytes of K per shared-memory row
+        const int ksub = row_bytes / 32;                       // MMAs (K = 32) per row
+        const uint32_t a_tile = 128u * row_bytes;              // A: 128 rows per CTA
+        const uint32_t b_rows = cg2 ? N / 2 : N;               // B rows held by each CTA
+        const uint32_t b_tile = b_rows * row_bytes;
+        const int na = 4, nbt = 4;                             // operand tiles cycled through (like digit slices)
+        const uint32_t a0 = stg, b0 = stg + na * a_tile;       // <= 4 * 16 KB + 4 * 32 KB = 192 KB
+        const int nacc = 512 / N;
+        const long long t0 = clock64();
+        for (int i = 0; i < nmma; i++) {
+            const int ks = i % ksub;
+            const int sa = (i / ksub) % na, sb = (i / (ksub * na)) % nbt;
+            const uint64_t ad = make_desc_kmajor(a0 + sa * a_tile + ks * 32, swz);
+            const uint64_t bd = make_desc_kmajor(b0 + sb * b_tile + ks * 32, swz);
+            umma_i8_n(tmem0 + (uint32_t)((i % nacc) * N), ad, bd, idesc, cg2);
+        }
+        if (cg2) umma_commit_2sm(bar, 3);
+        else umma_commit(bar);
+        mbar_wait(bar, 0);
+        const long long t1 = clock64();
+        if (blockIdx.x == 0) cycles[0] = t1 - t0;
+    } else if (cg2 && crank == 1 && warp == 1 && lane == 0) {
+        mbar_wait(bar, 0);            // the multicast commit also arrives here
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (cg2) cluster_sync_all();
+    if (warp == 2) {
+        if (cg2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem0), "r"(512));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem0), "r"(512));
+    }
+}
+
+// out[0] = SM cycles per MMA seen by CTA 0, out[1] = wall-clock ms of the launch (all SMs busy: `ctas` CTAs)
+extern "C" int hyp_test_mma_rate(hyp_ctx* ctx, int swz, int N, int cg2, int nmma, int ctas, double* out) {
+    if (!ctx) return -1;
+    try {
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        const int smem = 193 * 1024 + 1024;
+        CUDA_TRY(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        long long* d_cyc = nullptr;
+        CUDA_TRY(cudaMalloc(&d_cyc, 8));
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        float ms = 0;
+        for (int rep = 0; rep < 2; rep++) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(cg2 ? (ctas & ~1) : ctas);
+            cfg.blockDim = dim3(128);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = ctx->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = cg2 ? 2 : 1;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            CUDA_TRY(cudaEventRecord(e0, ctx->stream));
+            CUDA_TRY(cudaLaunchKernelEx(&cfg, mma_rate_kernel, swz, N, cg2, nmma, d_cyc));
+            CUDA_TRY(cudaEventRecord(e1, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            cudaEventElapsedTime(&ms, e0, e1);
+        }
+        long long cyc = 0;
+        CUDA_TRY(cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost));
+        out[0] = (double)cyc / nmma;
+        out[1] = ms;
+        cudaFree(d_cyc);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        return 0;
+    } catch (HypError& e) {
+        ctx->last_error = e.msg;
+        cudaGetLastError();
+        return -1;
+    }
+}

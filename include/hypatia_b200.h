@@ -213,6 +213,8 @@ int hyp_test_gemm_tn(hyp_ctx* ctx, const double* P, int64_t ldp, const double* R
                      double alpha, double beta);
 /* in-place upper Cholesky A = U'U; *info = 0 or index (1-based) of the failing pivot block */
 int hyp_test_potrf(hyp_ctx* ctx, double* A, int64_t lda, int64_t m, int* info);
+/* profiling aid: clock64 phase timestamps of the one-CTA factor-and-invert kernel on an m x m block (m <= 128) */
+int hyp_test_panel_clocks(hyp_ctx* ctx, double* A, int64_t lda, int64_t m, double* cycles16);
 /* x = (U'U)^-1 x with the factor of the last hyp_test_potrf */
 int hyp_test_potrs(hyp_ctx* ctx, const double* F, int64_t ldf, int64_t m, double* x);
 /* y = alpha * op(M) x + beta * y */
@@ -231,6 +233,9 @@ int hyp_test_i8_gemm_tn(hyp_ctx* ctx, const int8_t* A, int64_t lda, const int8_t
 int hyp_test_ozaki_slices(hyp_ctx* ctx, const double* A, int64_t lda, int64_t K, int64_t ncols,
                           int nslices, int8_t* digits, int* expo);
 /* C(upper 128-tiles) = A' A through slicing + tcgen05 (FP64-accurate) */
+/* profiling aid: issue rate of tcgen05.mma kind::i8 from shared memory (swz 0/1/2 = SWIZZLE_32B/64B/128B K-major,
+ * N = 128 / 256, cg2 = cta_group::2): out[0] = SM cycles per MMA, out[1] = ms of the launch on `ctas` CTAs */
+int hyp_test_mma_rate(hyp_ctx* ctx, int swz, int N, int cg2, int nmma, int ctas, double* out);
 int hyp_test_ozaki_syrk(hyp_ctx* ctx, const double* A, int64_t lda, int64_t K, int64_t ncols, double* C,
                         int64_t ldc);
 
