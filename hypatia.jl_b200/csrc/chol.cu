@@ -36,6 +36,8 @@ void set_panel_attr() {
                                   NB * LDU * 8));
     CUDA_TRY(cudaFuncSetAttribute(trsv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(trsv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(trsv_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(trsv_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
     g_panel_attr_set = true;
 }
 
@@ -159,6 +161,24 @@ void hyp_trsv_upper(hyp_ctx* ctx, const double* F, int64_t ldf, int64_t m, const
         trsv_kernel<true><<<grid, 256, TRSV_SMEM, ctx->stream>>>(F, ldf, m, d_dinv, x, ctx->d_flags, nblk, epoch);
     else
         trsv_kernel<false><<<grid, 256, TRSV_SMEM, ctx->stream>>>(F, ldf, m, d_dinv, x, ctx->d_flags, nblk, epoch);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+}
+
+// two right-hand sides x and x + xstride per sweep: every tile of the factor is read once for both
+void hyp_trsv_upper2(hyp_ctx* ctx, const double* F, int64_t ldf, int64_t m, const double* d_dinv, double* x,
+                     int64_t xstride, bool trans) {
+    if (m <= 0) return;
+    TimeScope ts(ctx, T_TRSV);
+    int nblk = ceil_div(m, NB);
+    CUDA_TRY(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
+    int epoch = ++ctx->trsv_epoch;
+    set_panel_attr();
+    int grid = std::min(nblk, ctx->sm_count);
+    if (trans)
+        trsv_kernel<true, 2><<<grid, 256, TRSV_SMEM, ctx->stream>>>(F, ldf, m, d_dinv, x, ctx->d_flags, nblk, epoch, xstride);
+    else
+        trsv_kernel<false, 2><<<grid, 256, TRSV_SMEM, ctx->stream>>>(F, ldf, m, d_dinv, x, ctx->d_flags, nblk, epoch, xstride);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
 }

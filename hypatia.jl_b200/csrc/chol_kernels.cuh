@@ -360,6 +360,12 @@ __device__ __forceinline__ double panel_ld(const double* p) {
 #endif
 }
 
+// Register tiles are 4 x 4 with INTERLEAVED indices: tile t of a 32-wide block owns the indices t, t + 8, t + 16, t + 24
+// of that block.  Threads of a warp then read consecutive columns of the (odd-pitch) shared-memory block - conflict-free -
+// where contiguous 4 x 4 tiles put them 4 columns = 8 banks apart (2- to 4-way conflicts; measured: the 4 x 4 products
+// of the bulk-synchronous version ran at ~ 200 cycles per k-step instead of ~ 64).
+__device__ __forceinline__ int il_idx(int t8, int a) { return t8 + 8 * a; }
+
 template <int BARID = 0, bool LDCG = false>
 __device__ __forceinline__ int panel_body_fast(double* __restrict__ Ab, int64_t lda, int nb, double* __restrict__ Db,
                                                int ldd, int dn, bool zero_lower, double* sA, double* diagX, double* sX,
@@ -368,7 +374,7 @@ __device__ __forceinline__ int panel_body_fast(double* __restrict__ Ab, int64_t 
     constexpr int NW = PT - 32;                       // worker threads beside warp 0
     if (tid == 0) *s_bad = 0;
     HYP_PANEL_CLK(0);
-    // ---- I0: the first diagonal sub-block (upper part), one load per thread x 4 ----
+    // ---- I0: the first diagonal sub-block ----
     for (int idx = tid; idx < SB * SB; idx += PT) {
         const int r = idx & (SB - 1), c = idx >> 5;
         double x = 0.0;
@@ -382,6 +388,9 @@ __device__ __forceinline__ int panel_body_fast(double* __restrict__ Ab, int64_t 
     panel_sync<BARID>();
     HYP_PANEL_CLK(1);
 
+    // one copy of the loop body: unrolled over b the kernel grows to 240 KB of code and every phase runs on a cold
+    // instruction cache (measured: the 192-tile X column of b = 3 took 34 k cycles, 10 x its arithmetic)
+#pragma unroll 1
     for (int b = 0; b < NB / SB; b++) {
         const int o = b * SB;           // this diagonal sub-block
         const int h = o;                // rows above it
@@ -418,31 +427,31 @@ __device__ __forceinline__ int panel_body_fast(double* __restrict__ Ab, int64_t 
             } else {
                 // (1) trailing update of row b - 1 on everything right / below the sub-block (b, b), which the
                 //     previous B interval already updated:  A[r, c] -= sum_k U[op + k, r] U[op + k, c]
+                //     32 x 32 blocks (br <= bc) of the trailing region, 8 x 8 interleaved tiles each
                 const int op = o - SB;
-                const int t0 = o;
-                const int ncol = NB - t0;
-                const int nt4 = ncol / 4;
-                const int ntiles = nt4 * (nt4 + 1) / 2;
-                for (int t = wt; t < ntiles; t += NW) {
-                    int tc = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-                    while ((tc + 1) * (tc + 2) / 2 <= t) tc++;
-                    while (tc * (tc + 1) / 2 > t) tc--;
-                    const int tr = t - tc * (tc + 1) / 2;
-                    if (tc < SB / 4) continue;                   // inside (b, b): done already
-                    const double* ur = sA + op + (t0 + tr * 4) * LDU;
-                    const double* uc = sA + op + (t0 + tc * 4) * LDU;
+                const int nblk = (NB - o) / SB;
+                const int npair = nblk * (nblk + 1) / 2;
+                for (int t = wt; t < npair * 64; t += NW) {
+                    const int pr = t >> 6;
+                    if (pr == 0) continue;                               // block (0, 0) = sub-block (b, b): done
+                    // pairs in the order (0,0) (0,1) (1,1) (0,2) (1,2) (2,2)
+                    const int bc = pr >= 3 ? 2 : (pr >= 1 ? 1 : 0);
+                    const int br = pr - bc * (bc + 1) / 2;
+                    const int tr8 = t & 7, tc8 = (t >> 3) & 7;
+                    const double* ur = sA + op + (o + 32 * br + tr8) * LDU;
+                    const double* uc = sA + op + (o + 32 * bc + tc8) * LDU;
                     double acc[4][4];
 #pragma unroll
                     for (int a = 0; a < 4; a++)
 #pragma unroll
                         for (int q = 0; q < 4; q++) acc[a][q] = 0.0;
-#pragma unroll 4
+#pragma unroll 2
                     for (int k = 0; k < SB; k++) {
                         double rv[4], cv[4];
 #pragma unroll
-                        for (int a = 0; a < 4; a++) rv[a] = ur[k + a * LDU];
+                        for (int a = 0; a < 4; a++) rv[a] = ur[k + 8 * a * LDU];
 #pragma unroll
-                        for (int q = 0; q < 4; q++) cv[q] = uc[k + q * LDU];
+                        for (int q = 0; q < 4; q++) cv[q] = uc[k + 8 * q * LDU];
 #pragma unroll
                         for (int a = 0; a < 4; a++)
 #pragma unroll
@@ -452,39 +461,31 @@ __device__ __forceinline__ int panel_body_fast(double* __restrict__ Ab, int64_t 
                     for (int a = 0; a < 4; a++)
 #pragma unroll
                         for (int q = 0; q < 4; q++) {
-                            const int r = t0 + tr * 4 + a, c = t0 + tc * 4 + q;
+                            const int r = o + 32 * br + il_idx(tr8, a), c = o + 32 * bc + il_idx(tc8, q);
                             if (r <= c) sA[r + c * LDU] -= acc[a][q];
                         }
                 }
                 // (2) T_b = X[0:h, 0:h] U[0:h, o:o+32]   (X[i, k] for k > i sits at sA[k + i LDU], diagonal in diagX)
-                const int ntile = (h / 4) * 8;
-                for (int t = wt; t < ntile; t += NW) {
-                    const int ti = t % (h / 4), tj = t / (h / 4);
-                    const int i0 = ti * 4;
+                for (int t = wt; t < b * 64; t += NW) {
+                    const int ib = t >> 6, tr8 = t & 7, tc8 = (t >> 3) & 7;
+                    const int ibase = 32 * ib + tr8;
                     double acc[4][4];
 #pragma unroll
                     for (int a = 0; a < 4; a++)
 #pragma unroll
                         for (int q = 0; q < 4; q++) acc[a][q] = 0.0;
-                    const double* up = sA + (o + tj * 4) * LDU;     // up[k + q * LDU] = U[k, o + 4 tj + q]
-#pragma unroll
-                    for (int kk = 0; kk < 4; kk++) {
-                        const int k = i0 + kk;
-#pragma unroll
-                        for (int a = 0; a < 4; a++) {
-                            double xv = 0.0;
-                            if (kk > a) xv = sA[k + (i0 + a) * LDU];
-                            else if (kk == a) xv = diagX[k];
-#pragma unroll
-                            for (int q = 0; q < 4; q++) acc[a][q] = fma(xv, up[k + q * LDU], acc[a][q]);
-                        }
-                    }
-                    for (int k = i0 + 4; k < h; k++) {
+                    const double* up = sA + (o + tc8) * LDU;         // up[k + 8 q LDU] = U[k, o + tc8 + 8 q]
+                    const double* xp = sA + ibase * LDU;             // xp[k + 8 a LDU] = X[ibase + 8 a, k] for k > row
+                    for (int k = ibase; k < h; k++) {
                         double xv[4], uv[4];
 #pragma unroll
-                        for (int a = 0; a < 4; a++) xv[a] = sA[k + (i0 + a) * LDU];
+                        for (int a = 0; a < 4; a++) {
+                            const int row = ibase + 8 * a;
+                            const double off = xp[k + 8 * a * LDU];
+                            xv[a] = k > row ? off : (k == row ? diagX[k] : 0.0);
+                        }
 #pragma unroll
-                        for (int q = 0; q < 4; q++) uv[q] = up[k + q * LDU];
+                        for (int q = 0; q < 4; q++) uv[q] = up[k + 8 * q * LDU];
 #pragma unroll
                         for (int a = 0; a < 4; a++)
 #pragma unroll
@@ -493,82 +494,86 @@ __device__ __forceinline__ int panel_body_fast(double* __restrict__ Ab, int64_t 
 #pragma unroll
                     for (int a = 0; a < 4; a++)
 #pragma unroll
-                        for (int q = 0; q < 4; q++) sT[(i0 + a) + (tj * 4 + q) * LDT] = acc[a][q];
+                        for (int q = 0; q < 4; q++) sT[(ibase + 8 * a) + (tc8 + 8 * q) * LDT] = acc[a][q];
                 }
                 if (b == NB / SB - 1) {
                     // (3) everything above / left of the last sub-block is final: store it while warp 0 finishes the chain
-                    for (int idx = wt; idx < NB * NB; idx += NW) {
-                        const int r = idx & (NB - 1), c = idx >> 7;
-                        if (r < o && r < nb && c < nb) {             // U rows 0 .. o-1
+                    const int ww = warp - 1;                             // 0 .. 6
+                    const int rmax = o < nb ? o : nb;
+                    for (int c = ww; c < nb; c += PT / 32 - 1) {
+                        for (int r = lane; r < rmax; r += 32) {          // U rows 0 .. o-1 (and zeros below the diagonal)
                             if (r <= c) Ab[r + (int64_t)c * lda] = sA[r + c * LDU];
                             else if (zero_lower) Ab[r + (int64_t)c * lda] = 0.0;
-                        } else if (zero_lower && r >= o && c < o && r < nb && c < nb) {
-                            Ab[r + (int64_t)c * lda] = 0.0;            // below the diagonal, left of the last sub-block
                         }
+                        if (zero_lower && c < o)
+                            for (int r = o + lane; r < nb; r += 32) Ab[r + (int64_t)c * lda] = 0.0;
                     }
-                    for (int idx = wt; idx < dn * o; idx += NW) {     // X columns 0 .. o-1
-                        const int r = idx % dn, c = idx / dn;
-                        double x = 0.0;
-                        if (r < c) x = sA[c + r * LDU];
-                        else if (r == c) x = diagX[r];
-                        if (c < dn) Db[r + (int64_t)c * ldd] = x;
-                    }
+                    const int cmax = o < dn ? o : dn;
+                    for (int c = ww; c < cmax; c += PT / 32 - 1)         // X columns 0 .. o-1
+                        for (int r = lane; r < dn; r += 32) {
+                            double x = 0.0;
+                            if (r < c) x = sA[c + r * LDU];
+                            else if (r == c) x = diagX[r];
+                            Db[r + (int64_t)c * ldd] = x;
+                        }
                 }
             }
         }
         panel_sync<BARID>();
         HYP_PANEL_CLK(2 + 3 * b);
         // ================= B_b =================
-        // X[0:h, o + j] = -sum_{k <= j} T[i, k] X_bb[k, j]   (X_bb[k, j] = sX[j + k LDX]); stored at sA[(o + j) + i LDU]
-        if (b > 0) {
-            const int ntile = (h / 4) * 8;
-            for (int t = tid; t < ntile; t += PT) {
-                const int ti = t % (h / 4), tj = t / (h / 4);
-                const int i0 = ti * 4, j0 = tj * 4;
-                double acc[4][4];
+        // X[0:h, o + j] = -sum_{k <= j} T[i, k] X_bb[k, j]   (X_bb[k, j] = sX[j + k LDX], zero for k > j);
+        // stored at sA[(o + j) + i LDU]
+        for (int t = tid; t < b * 64; t += PT) {
+            const int ib = t >> 6, tr8 = t & 7, tc8 = (t >> 3) & 7;
+            const int ibase = 32 * ib + tr8;
+            double acc[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) acc[a][q] = 0.0;
+            const int kend = tc8 + 24;                                   // largest column of this tile
+#pragma unroll 2
+            for (int k = 0; k <= kend; k++) {
+                double tv[4], xv[4];
+#pragma unroll
+                for (int a = 0; a < 4; a++) tv[a] = sT[(ibase + 8 * a) + k * LDT];
+#pragma unroll
+                for (int q = 0; q < 4; q++) xv[q] = sX[(tc8 + 8 * q) + k * LDX];
 #pragma unroll
                 for (int a = 0; a < 4; a++)
 #pragma unroll
-                    for (int q = 0; q < 4; q++) acc[a][q] = 0.0;
-                for (int k = 0; k < j0 + 4; k++) {
-                    double tv[4], xv[4];
-#pragma unroll
-                    for (int a = 0; a < 4; a++) tv[a] = sT[(i0 + a) + k * LDT];
-#pragma unroll
-                    for (int q = 0; q < 4; q++) xv[q] = sX[(j0 + q) + k * LDX];
-#pragma unroll
-                    for (int a = 0; a < 4; a++)
-#pragma unroll
-                        for (int q = 0; q < 4; q++) acc[a][q] = fma(tv[a], xv[q], acc[a][q]);
-                }
-#pragma unroll
-                for (int a = 0; a < 4; a++)
-#pragma unroll
-                    for (int q = 0; q < 4; q++) sA[(o + j0 + q) + (i0 + a) * LDU] = -acc[a][q];
+                    for (int q = 0; q < 4; q++) acc[a][q] = fma(tv[a], xv[q], acc[a][q]);
             }
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) sA[(o + tc8 + 8 * q) + (ibase + 8 * a) * LDU] = -acc[a][q];
         }
+        if (b == NB / SB - 1) HYP_PANEL_CLK(12);       // thread 0's own share of the last X column
         if (b < NB / SB - 1) {
             const int t0 = o + SB;
             const int ncol = NB - t0;
-            // block row U[o + i, c] = sum_k X_bb[k, i] A[o + k, c]: 4 x 4 tiles, 8 row tiles
+            // block row U[o + i, c] = sum_k X_bb[k, i] A[o + k, c]: 8 row tiles x ncol / 4 column tiles
             {
-                const int ti = tid & 7, tj = tid >> 3;
+                const int tr8 = tid & 7, tj = tid >> 3;
                 const bool act = tj * 4 < ncol;
+                const int cbase = t0 + 32 * (tj >> 3) + (tj & 7);
                 double acc[4][4];
 #pragma unroll
                 for (int a = 0; a < 4; a++)
 #pragma unroll
                     for (int q = 0; q < 4; q++) acc[a][q] = 0.0;
                 if (act) {
-                    const double* xp = sX + ti * 4;
-                    const double* ap = sA + o + (t0 + tj * 4) * LDU;
-#pragma unroll 4
+                    const double* xp = sX + tr8;
+                    const double* ap = sA + o + cbase * LDU;
+#pragma unroll 2
                     for (int k = 0; k < SB; k++) {
                         double xa[4], av[4];
 #pragma unroll
-                        for (int a = 0; a < 4; a++) xa[a] = xp[a + k * LDX];
+                        for (int a = 0; a < 4; a++) xa[a] = xp[8 * a + k * LDX];
 #pragma unroll
-                        for (int q = 0; q < 4; q++) av[q] = ap[k + q * LDU];
+                        for (int q = 0; q < 4; q++) av[q] = ap[k + 8 * q * LDU];
 #pragma unroll
                         for (int a = 0; a < 4; a++)
 #pragma unroll
@@ -580,43 +585,31 @@ __device__ __forceinline__ int panel_body_fast(double* __restrict__ Ab, int64_t 
 #pragma unroll
                     for (int a = 0; a < 4; a++)
 #pragma unroll
-                        for (int q = 0; q < 4; q++) sA[(o + ti * 4 + a) + (t0 + tj * 4 + q) * LDU] = acc[a][q];
+                        for (int q = 0; q < 4; q++) sA[(o + tr8 + 8 * a) + (cbase + 8 * q) * LDU] = acc[a][q];
                 }
                 panel_sync<BARID>();
             }
             HYP_PANEL_CLK(3 + 3 * b);
-            // the next diagonal sub-block: A[r, c] -= sum_k U[o + k, r] U[o + k, c], r, c in [t0, t0 + 32): 36 upper tiles
-            if (tid < 36) {
-                int tc = (int)((sqrtf(8.0f * (float)tid + 1.0f) - 1.0f) * 0.5f);
-                while ((tc + 1) * (tc + 2) / 2 <= tid) tc++;
-                while (tc * (tc + 1) / 2 > tid) tc--;
-                const int tr = tid - tc * (tc + 1) / 2;
-                const double* ur = sA + o + (t0 + tr * 4) * LDU;
-                const double* uc = sA + o + (t0 + tc * 4) * LDU;
-                double acc[4][4];
-#pragma unroll
-                for (int a = 0; a < 4; a++)
-#pragma unroll
-                    for (int q = 0; q < 4; q++) acc[a][q] = 0.0;
-#pragma unroll 4
+            // the next diagonal sub-block: A[r, c] -= sum_k U[o + k, r] U[o + k, c], r, c in [t0, t0 + 32): all 256
+            // threads, 2 x 2 interleaved tiles (rows tr, tr + 16; columns tc, tc + 16)
+            {
+                const int tr = tid & 15, tc = tid >> 4;
+                const double* ur = sA + o + (t0 + tr) * LDU;
+                const double* uc = sA + o + (t0 + tc) * LDU;
+                double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+#pragma unroll 8
                 for (int k = 0; k < SB; k++) {
-                    double rv[4], cv[4];
-#pragma unroll
-                    for (int a = 0; a < 4; a++) rv[a] = ur[k + a * LDU];
-#pragma unroll
-                    for (int q = 0; q < 4; q++) cv[q] = uc[k + q * LDU];
-#pragma unroll
-                    for (int a = 0; a < 4; a++)
-#pragma unroll
-                        for (int q = 0; q < 4; q++) acc[a][q] = fma(rv[a], cv[q], acc[a][q]);
+                    const double r0 = ur[k], r1 = ur[k + 16 * LDU], c0 = uc[k], c1 = uc[k + 16 * LDU];
+                    a00 = fma(r0, c0, a00);
+                    a01 = fma(r0, c1, a01);
+                    a10 = fma(r1, c0, a10);
+                    a11 = fma(r1, c1, a11);
                 }
-#pragma unroll
-                for (int a = 0; a < 4; a++)
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const int r = t0 + tr * 4 + a, c = t0 + tc * 4 + q;
-                        if (r <= c) sA[r + c * LDU] -= acc[a][q];
-                    }
+                const int r_0 = t0 + tr, r_1 = r_0 + 16, c_0 = t0 + tc, c_1 = c_0 + 16;
+                if (r_0 <= c_0) sA[r_0 + c_0 * LDU] -= a00;
+                if (r_0 <= c_1) sA[r_0 + c_1 * LDU] -= a01;
+                if (r_1 <= c_0) sA[r_1 + c_0 * LDU] -= a10;
+                if (r_1 <= c_1) sA[r_1 + c_1 * LDU] -= a11;
             }
             panel_sync<BARID>();
             HYP_PANEL_CLK(4 + 3 * b);
@@ -628,20 +621,18 @@ __device__ __forceinline__ int panel_body_fast(double* __restrict__ Ab, int64_t 
     // ---- what is left: U rows 96 .. 127 and the last block column of X ----
     {
         const int o = NB - SB;
-        for (int idx = tid; idx < SB * NB; idx += PT) {
-            const int r = o + (idx & (SB - 1)), c = idx >> 5;
-            if (r < nb && c < nb) {
+        for (int c = warp; c < nb; c += PT / 32)
+            for (int r = o + lane; r < nb; r += 32) {
                 if (r <= c) Ab[r + (int64_t)c * lda] = sA[r + c * LDU];
                 else if (zero_lower && c >= o) Ab[r + (int64_t)c * lda] = 0.0;
             }
-        }
-        for (int idx = tid; idx < dn * SB; idx += PT) {
-            const int r = idx % dn, c = o + idx / dn;
-            double x = 0.0;
-            if (r < c) x = sA[c + r * LDU];
-            else if (r == c) x = diagX[r];
-            if (c < dn) Db[r + (int64_t)c * ldd] = x;
-        }
+        for (int c = o + warp; c < dn; c += PT / 32)
+            for (int r = lane; r < dn; r += 32) {
+                double x = 0.0;
+                if (r < c) x = sA[c + r * LDU];
+                else if (r == c) x = diagX[r];
+                Db[r + (int64_t)c * ldd] = x;
+            }
     }
     HYP_PANEL_CLK(15);
     return *s_bad;
@@ -716,13 +707,15 @@ __device__ __forceinline__ void st_release(int* p, int v) {
 // 64 FMAs per thread -> reduction -> 128 x 128 matvec from shared memory -> publish.
 constexpr int TRSV_SMEM = NB * NB * 8;
 
-template <bool TRANS>
+// NRHS right-hand sides share every tile of the factor (hyp_solve_system_multi): x_v = x + v * xstride.  Per right-hand
+// side the arithmetic and its order are those of the single-vector solve.
+template <bool TRANS, int NRHS = 1>
 __global__ void __launch_bounds__(256, 1)
 trsv_kernel(const double* __restrict__ F, int64_t ldf, int64_t m, const double* __restrict__ dinv,
-            double* x, int* flags, int nblk, int epoch) {
+            double* x, int* flags, int nblk, int epoch, int64_t xstride = 0) {
     HYP_DYN_SMEM(double, sD);                // Dinv_k, 128 x 128 col-major
-    __shared__ double sv[2][NB];
-    __shared__ double sacc[2][NB];
+    __shared__ double sv[NRHS][2][NB];
+    __shared__ double sacc[NRHS][2][NB];
     __shared__ int s_ticket;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     while (true) {
@@ -742,9 +735,11 @@ trsv_kernel(const double* __restrict__ F, int64_t ldf, int64_t m, const double* 
         if (TRANS) {
             // y_k = Dinv_k' (b_k - sum_{j<k} U[j-block, k-block]' y_j); warp w owns 16 columns,
             // lane l rows l, l+32, l+64, l+96 of every tile
-            double pacc[16];
+            double pacc[NRHS][16];
 #pragma unroll
-            for (int i = 0; i < 16; i++) pacc[i] = 0.0;
+            for (int v = 0; v < NRHS; v++)
+#pragma unroll
+                for (int i = 0; i < 16; i++) pacc[v][i] = 0.0;
             const int64_t cw = c0 + warp * 16;
             for (int j = 0; j < k; j++) {
                 double tl[16][4];
@@ -761,47 +756,60 @@ trsv_kernel(const double* __restrict__ F, int64_t ldf, int64_t m, const double* 
                     }
                 }
                 __syncthreads();
-                double* svj = sv[j & 1];
-                if (tid < NB) svj[tid] = __ldcg(x + (int64_t)j * NB + tid);
+                if (tid < NB) {
+#pragma unroll
+                    for (int v = 0; v < NRHS; v++) sv[v][j & 1][tid] = __ldcg(x + v * xstride + (int64_t)j * NB + tid);
+                }
                 __syncthreads();
-                const double v0 = svj[lane], v1 = svj[lane + 32], v2 = svj[lane + 64], v3 = svj[lane + 96];
 #pragma unroll
-                for (int i = 0; i < 16; i++)
-                    pacc[i] += tl[i][0] * v0 + tl[i][1] * v1 + tl[i][2] * v2 + tl[i][3] * v3;
+                for (int v = 0; v < NRHS; v++) {
+                    const double* svj = sv[v][j & 1];
+                    const double v0 = svj[lane], v1 = svj[lane + 32], v2 = svj[lane + 64], v3 = svj[lane + 96];
+#pragma unroll
+                    for (int i = 0; i < 16; i++)
+                        pacc[v][i] += tl[i][0] * v0 + tl[i][1] * v1 + tl[i][2] * v2 + tl[i][3] * v3;
+                }
             }
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
-                double a = pacc[i];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-                pacc[i] = a;
-            }
-            __syncthreads();
-            double* vb = sv[0];
-            if (lane == 0) {
+            for (int v = 0; v < NRHS; v++)
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
-                    int64_t c = cw + i;
-                    vb[warp * 16 + i] = (c < m) ? (x[c] - pacc[i]) : 0.0;
+                    double a = pacc[v][i];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                    pacc[v][i] = a;
                 }
+            __syncthreads();
+            if (lane == 0) {
+#pragma unroll
+                for (int v = 0; v < NRHS; v++)
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        int64_t c = cw + i;
+                        sv[v][0][warp * 16 + i] = (c < m) ? (x[v * xstride + c] - pacc[v][i]) : 0.0;
+                    }
             }
             __syncthreads();
             // y[c] = sum_{r <= c} Dinv[r, c] v[r]
-            const double v0 = vb[lane], v1 = vb[lane + 32], v2 = vb[lane + 64], v3 = vb[lane + 96];
-            double res[16];
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const double* col = sD + (warp * 16 + i) * NB;
-                double a = col[lane] * v0 + col[lane + 32] * v1 + col[lane + 64] * v2 + col[lane + 96] * v3;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-                res[i] = a;
-            }
-            if (lane == 0) {
+            for (int v = 0; v < NRHS; v++) {
+                const double* vb = sv[v][0];
+                const double v0 = vb[lane], v1 = vb[lane + 32], v2 = vb[lane + 64], v3 = vb[lane + 96];
+                double res[16];
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
-                    int64_t c = cw + i;
-                    if (c < m) x[c] = res[i];
+                    const double* col = sD + (warp * 16 + i) * NB;
+                    double a = col[lane] * v0 + col[lane + 32] * v1 + col[lane + 64] * v2 + col[lane + 96] * v3;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                    res[i] = a;
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        int64_t c = cw + i;
+                        if (c < m) x[v * xstride + c] = res[i];
+                    }
                 }
             }
         } else {
@@ -809,7 +817,9 @@ trsv_kernel(const double* __restrict__ F, int64_t ldf, int64_t m, const double* 
             // halves of the CTA split the 128 columns of a tile
             const int r = tid & (NB - 1), half = tid >> 7;
             const int64_t grow = c0 + r;
-            double acc = 0.0;
+            double acc[NRHS];
+#pragma unroll
+            for (int v = 0; v < NRHS; v++) acc[v] = 0.0;
             for (int j = nblk - 1; j > k; j--) {
                 double tl[64];
                 const int64_t cb = (int64_t)j * NB + half * 64;
@@ -821,41 +831,55 @@ trsv_kernel(const double* __restrict__ F, int64_t ldf, int64_t m, const double* 
                     }
                 }
                 __syncthreads();
-                double* svj = sv[j & 1];
                 if (tid < NB) {
                     int64_t c = (int64_t)j * NB + tid;
-                    svj[tid] = (c < m) ? __ldcg(x + c) : 0.0;
+#pragma unroll
+                    for (int v = 0; v < NRHS; v++) sv[v][j & 1][tid] = (c < m) ? __ldcg(x + v * xstride + c) : 0.0;
                 }
                 __syncthreads();
-                const double* svh = svj + half * 64;
-                double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-                for (int c = 0; c < 64; c += 2) {
-                    a0 += tl[c] * svh[c];
-                    a1 += tl[c + 1] * svh[c + 1];
+                for (int v = 0; v < NRHS; v++) {
+                    const double* svh = sv[v][j & 1] + half * 64;
+                    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 64; c += 2) {
+                        a0 += tl[c] * svh[c];
+                        a1 += tl[c + 1] * svh[c + 1];
+                    }
+                    acc[v] += a0 + a1;
                 }
-                acc += a0 + a1;
             }
-            sacc[half][r] = acc;
+#pragma unroll
+            for (int v = 0; v < NRHS; v++) sacc[v][half][r] = acc[v];
             __syncthreads();
-            double* vb = sv[0];
-            if (tid < NB) vb[tid] = (c0 + tid < m) ? (x[c0 + tid] - sacc[0][tid] - sacc[1][tid]) : 0.0;
+            if (tid < NB) {
+#pragma unroll
+                for (int v = 0; v < NRHS; v++)
+                    sv[v][0][tid] = (c0 + tid < m) ? (x[v * xstride + c0 + tid] - sacc[v][0][tid] - sacc[v][1][tid]) : 0.0;
+            }
             __syncthreads();
             // x[r] = sum_{c >= r} Dinv[r, c] v[c]
-            double a0 = 0.0, a1 = 0.0;
-            {
+            double o0[NRHS];
+#pragma unroll
+            for (int v = 0; v < NRHS; v++) {
+                double a0 = 0.0, a1 = 0.0;
                 const double* row = sD + r + (half * 64) * NB;
-                const double* svh = vb + half * 64;
+                const double* svh = sv[v][0] + half * 64;
 #pragma unroll 16
                 for (int c = 0; c < 64; c += 2) {
                     a0 += row[c * NB] * svh[c];
                     a1 += row[(c + 1) * NB] * svh[c + 1];
                 }
+                o0[v] = a0 + a1;
             }
             __syncthreads();
-            sacc[half][r] = a0 + a1;
+#pragma unroll
+            for (int v = 0; v < NRHS; v++) sacc[v][half][r] = o0[v];
             __syncthreads();
-            if (tid < NB && c0 + tid < m) x[c0 + tid] = sacc[0][tid] + sacc[1][tid];
+            if (tid < NB && c0 + tid < m) {
+#pragma unroll
+                for (int v = 0; v < NRHS; v++) x[v * xstride + c0 + tid] = sacc[v][0][tid] + sacc[v][1][tid];
+            }
         }
         __threadfence();
         __syncthreads();

@@ -235,6 +235,12 @@ struct hyp_ctx {
     double* d_blk_arr = nullptr;       // q x maxdim identity pattern / products (2 buffers)
     int64_t blk_maxdim = 0;
     int* d_flags = nullptr;            // TRSV ticket + block-ready flags
+    // two-column solves (hyp_solve_system_multi): partial buffers of the two-vector GEMV kernels and a second set of
+    // the work vectors of solve_system_dev / apply_lhs_dev
+    double *d_partial3 = nullptr, *d_partial4 = nullptr;
+    int64_t partial3_doubles = 0, partial4_doubles = 0;
+    double* d_multi = nullptr;
+    int64_t multi_doubles = 0;
     int* d_dag_ver = nullptr;          // task-graph Cholesky (chol_dag.cu): tile version counters + tickets
     int64_t dag_ver_len = 0;
     unsigned long long* d_dag_dbg = nullptr;   // HYP_POTRF_DEBUG: per-CTA wait / busy times
@@ -319,6 +325,16 @@ void hyp_gemv_t(hyp_ctx* ctx, int64_t rows, int64_t ncols, const double* M, int6
 void hyp_gemv_n(hyp_ctx* ctx, int64_t rows, int64_t ncols, const double* M, int64_t ld,
                 const double* x, double alpha, double beta, double* y);
 // both products in one pass over M: w = alphaN * M x + betaN * w, y = alphaT * M' z + betaT * y
+bool hyp_gemv2_ok(hyp_ctx* ctx, int64_t rows, int64_t ncols, const double* M, int64_t ld, const double* a, const double* b);
+void hyp_gemv_t2(hyp_ctx* ctx, int64_t rows, int64_t ncols, const double* M, int64_t ld, const double* x0,
+                 const double* x1, double alpha, double beta, double* y0, double* y1);
+void hyp_gemv_n2(hyp_ctx* ctx, int64_t rows, int64_t ncols, const double* M, int64_t ld, const double* x0,
+                 const double* x1, double alpha, double beta, double* y0, double* y1);
+void hyp_gemv_nt2(hyp_ctx* ctx, int64_t rows, int64_t ncols, const double* M, int64_t ld, const double* xa,
+                  const double* xb, const double* za, const double* zb, double alphaN, double betaN, double* wa,
+                  double* wb, double alphaT, double betaT, double* ya, double* yb);
+void hyp_trsv_upper2(hyp_ctx* ctx, const double* F, int64_t ldf, int64_t m, const double* d_dinv, double* x,
+                     int64_t xstride, bool trans);
 void hyp_gemv_nt(hyp_ctx* ctx, int64_t rows, int64_t ncols, const double* M, int64_t ld, const double* x,
                  const double* z, double alphaN, double betaN, double* w, double alphaT, double betaT, double* y);
 

@@ -158,6 +158,11 @@ void free_model(hyp_ctx* ctx) {
     dfree(ctx->d_partial);
     dfree(ctx->d_scalars);
     dfree(ctx->d_partial2);
+    dfree(ctx->d_partial3);
+    dfree(ctx->d_partial4);
+    ctx->partial3_doubles = ctx->partial4_doubles = 0;
+    dfree(ctx->d_multi);
+    ctx->multi_doubles = 0;
     ctx->partial2_doubles = 0;
     dfree(ctx->d_stage);
     ctx->stage_doubles = 0;
@@ -559,18 +564,179 @@ void calc_residuals_dev(hyp_ctx* ctx, const double* pt, double* xres, double* yr
     CUDA_TRY(cudaGetLastError());
 }
 
-// ---- multi-column solves: see the batched kernels below; until a model / rank layout is supported the C entry
-// points fall back to one column at a time (same results, no amortisation) ----
+// ---- two-column solves (hyp_solve_system_multi / hyp_apply_lhs_multi) -----------------------------------------------
+// The pair {cent, pred} and the pair {centadj, predadj} of one iteration are independent (combined.jl:67-79): solved
+// together, every pass over G and every triangular sweep serves two right-hand sides.  Supported for the reduced model
+// the default preprocessing produces (p = 0), the Cholesky factor, one rank (or column sharding); anything else
+// falls back to one column at a time in the C entry points.  Column v of every product below is bit-identical to the
+// single-column call (same kernels' thread mappings and reduction orders).
 bool hyp_multi_supported(hyp_ctx* ctx, int ncols) {
-    (void)ctx;
-    (void)ncols;
-    return false;
+    return ncols >= 2 && ctx->p == 0 && ctx->solver_kind == 0 && ctx->fact_kind == 0 && !ctx->d_Q && !hyp_row_sharded(ctx) &&
+           ctx->q > 0 && ctx->n > 0 && !getenv("HYP_NO_MULTI");
 }
+
+struct Multi2 {
+    double *sub_rhs[2], *sub_sol[2], *t[2], *Gx[2], *HGx[2], *vq1[2], *vq2[2], *vq3[2], *vq4[2];
+};
+
+Multi2 multi_buffers(hyp_ctx* ctx) {
+    const int64_t n = ctx->n, q = ctx->q, dim3 = n + ctx->p + q;
+    const int64_t e = [](int64_t v) { return (v + 1) & ~(int64_t)1; }(1);   // keep every buffer 16-byte aligned
+    (void)e;
+    auto ev = [](int64_t v) { return (v + 1) & ~(int64_t)1; };
+    const int64_t per = 2 * ev(dim3) + ev(n) + 6 * ev(q);
+    if (ctx->multi_doubles < 2 * per) {
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        dfree(ctx->d_multi);
+        dalloc(&ctx->d_multi, 2 * per);
+        ctx->multi_doubles = 2 * per;
+    }
+    Multi2 b;
+    double* w = ctx->d_multi;
+    // the q-vector pairs are laid out as two consecutive columns (ld = ev(q)) so that hyp_cones_prod can take both at once
+    for (int v = 0; v < 2; v++) b.sub_rhs[v] = w + v * ev(dim3);
+    w += 2 * ev(dim3);
+    for (int v = 0; v < 2; v++) b.sub_sol[v] = w + v * ev(dim3);
+    w += 2 * ev(dim3);
+    for (int v = 0; v < 2; v++) b.t[v] = w + v * ev(n);
+    w += 2 * ev(n);
+    double** qs[6] = {b.Gx, b.HGx, b.vq1, b.vq2, b.vq3, b.vq4};
+    for (auto arr : qs) {
+        for (int v = 0; v < 2; v++) arr[v] = w + v * ev(q);
+        w += 2 * ev(q);
+    }
+    return b;
+}
+
+void solve_system_pair_dev(hyp_ctx* ctx, double* sol, const double* rhs, int64_t ld) {
+    const int64_t n = ctx->n, q = ctx->q;
+    const int64_t dim3 = n + q, tau_idx = dim3, kap_idx = dim3 + q + 1;
+    const int64_t ldq = (q + 1) & ~(int64_t)1;
+    Multi2 b = multi_buffers(ctx);
+    const double* rz[2] = {rhs + n, rhs + ld + n};
+    const double* rs[2] = {rhs + tau_idx + 1, rhs + ld + tau_idx + 1};
+    for (int v = 0; v < 2; v++) hyp_copy(ctx, n, b.sub_rhs[v], rhs + v * ld);
+    {
+        // setup_rhs3 (qrchol.jl:16-37) for both columns
+        TimeScope ts(ctx, T_CONE_PROD);
+        const double* arr = rz[0];
+        int64_t ld_arr = ld;
+        if (ctx->any_dual) {
+            for (int v = 0; v < 2; v++) {
+                rhs3_pre_kernel<<<vgrid(ctx, q), 256, 0, ctx->stream>>>(q, ctx->d_row_dual, rz[v], rs[v], b.vq1[v]);
+                ctx->launches++;
+            }
+            arr = b.vq1[0];
+            ld_arr = ldq;
+        }
+        hyp_cones_prod(ctx, b.vq2[0], arr, 2, ldq, ld_arr, HYP_PROD_BLOCK, 0);
+        for (int v = 0; v < 2; v++) {
+            rhs3_post_kernel<<<vgrid(ctx, q), 256, 0, ctx->stream>>>(q, ctx->d_row_dual, b.vq2[v], rs[v], b.sub_rhs[v] + n);
+            ctx->launches++;
+        }
+    }
+    // solve_subsystem3 (qrchol.jl:39-85 with p = 0, Ap_Q = I): t = x + G'z ; x = S^-1 t ; z = H G x - z
+    for (int v = 0; v < 2; v++) {
+        hyp_copy(ctx, dim3, b.sub_sol[v], b.sub_rhs[v]);
+        hyp_copy(ctx, n, b.t[v], b.sub_sol[v]);
+    }
+    if (hyp_gemv2_ok(ctx, ctx->qloc, n, ctx->d_Graw, ctx->ldg, b.sub_sol[0] + n, b.sub_sol[1] + n))
+        hyp_gemv_t2(ctx, ctx->qloc, n, ctx->d_Graw, ctx->ldg, b.sub_sol[0] + n, b.sub_sol[1] + n, 1.0, 1.0, b.t[0], b.t[1]);
+    else
+        for (int v = 0; v < 2; v++) hyp_gemv_t(ctx, ctx->qloc, n, ctx->d_Graw, ctx->ldg, b.sub_sol[v] + n, 1.0, 1.0, b.t[v]);
+    hyp_trsv_upper2(ctx, ctx->d_F, ctx->lds, ctx->nmp, ctx->d_Dinv, b.t[0], b.t[1] - b.t[0], true);
+    hyp_trsv_upper2(ctx, ctx->d_F, ctx->lds, ctx->nmp, ctx->d_Dinv, b.t[0], b.t[1] - b.t[0], false);
+    for (int v = 0; v < 2; v++) hyp_copy(ctx, n, b.sub_sol[v], b.t[v]);
+    if (hyp_gemv2_ok(ctx, ctx->qloc, n, ctx->d_Graw, ctx->ldg, b.sub_sol[0], b.sub_sol[1]))
+        hyp_gemv_n2(ctx, ctx->qloc, n, ctx->d_Graw, ctx->ldg, b.sub_sol[0], b.sub_sol[1], 1.0, 0.0, b.Gx[0], b.Gx[1]);
+    else
+        for (int v = 0; v < 2; v++) hyp_gemv_n(ctx, ctx->qloc, n, ctx->d_Graw, ctx->ldg, b.sub_sol[v], 1.0, 0.0, b.Gx[v]);
+    {
+        TimeScope ts(ctx, T_CONE_PROD);
+        hyp_cones_prod(ctx, b.HGx[0], b.Gx[0], 2, ldq, ldq, HYP_PROD_BLOCK, 0);
+    }
+    for (int v = 0; v < 2; v++) hyp_axpby(ctx, q, 1.0, b.HGx[v], -1.0, b.sub_sol[v] + n);
+    // tau lift, s lift, kap (common.jl:129-182) column by column: O(q) work
+    const double mu_tt = ctx->mu / ctx->tau_bar / ctx->tau_bar;
+    for (int v = 0; v < 2; v++) {
+        double* so = sol + v * ld;
+        const double* rh = rhs + v * ld;
+        hyp_dot(ctx, dim3, ctx->d_cbh, b.sub_sol[v], ctx->d_scalars + 0, false);
+        tau_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_scalars, rh, so, tau_idx, kap_idx, mu_tt);
+        ctx->launches++;
+        hyp_axpy_dev(ctx, dim3, so, 1.0, b.sub_sol[v], ctx->d_scalars + 2, 1.0, ctx->d_const_sol);
+        s_lift_kernel<<<vgrid(ctx, q), 256, 0, ctx->stream>>>(q, ctx->d_scalars, b.Gx[v], ctx->d_Gx_const, ctx->d_cbh + n, rz[v],
+                                                           so + tau_idx + 1);
+        ctx->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+}
+
+void apply_lhs_pair_dev(hyp_ctx* ctx, double* res, const double* dir, int64_t ld) {
+    const int64_t n = ctx->n, q = ctx->q;
+    const int64_t dim3 = n + q, tau_idx = dim3, kap_idx = dim3 + q + 1;
+    const int64_t ldq = (q + 1) & ~(int64_t)1;
+    Multi2 b = multi_buffers(ctx);
+    const double* c = ctx->d_cbh;
+    const double* h = ctx->d_cbh + n;
+    const double *dx[2], *dz[2], *ds[2];
+    double* r[2];
+    for (int v = 0; v < 2; v++) {
+        dx[v] = dir + v * ld;
+        dz[v] = dx[v] + n;
+        ds[v] = dx[v] + tau_idx + 1;
+        r[v] = res + v * ld;
+        // res.x = c tau (+ G'z below)
+        axpbypcz_dev_kernel<<<vgrid(ctx, n), 256, 0, ctx->stream>>>(n, r[v], 0.0, nullptr, 0.0, nullptr, 1.0, dx[v] + tau_idx, c);
+        ctx->launches++;
+    }
+    if (hyp_gemv2_ok(ctx, ctx->qloc, n, ctx->d_Graw, ctx->ldg, dx[0], dx[1]) && ((uintptr_t)dz[0] % 16 == 0) &&
+        ((uintptr_t)dz[1] % 16 == 0))
+        hyp_gemv_nt2(ctx, ctx->qloc, n, ctx->d_Graw, ctx->ldg, dx[0], dx[1], dz[0], dz[1], 1.0, 0.0, b.vq1[0], b.vq1[1], 1.0, 1.0,
+                     r[0], r[1]);
+    else
+        for (int v = 0; v < 2; v++)
+            hyp_gemv_nt(ctx, ctx->qloc, n, ctx->d_Graw, ctx->ldg, dx[v], dz[v], 1.0, 0.0, b.vq1[v], 1.0, 1.0, r[v]);
+    for (int v = 0; v < 2; v++) {
+        // res.z = h tau - s - G x
+        axpbypcz_dev_kernel<<<vgrid(ctx, q), 256, 0, ctx->stream>>>(q, r[v] + n, -1.0, ds[v], -1.0, b.vq1[v], 1.0, dx[v] + tau_idx, h);
+        ctx->launches++;
+    }
+    {
+        // res.s = H prim + dual
+        TimeScope ts(ctx, T_CONE_PROD);
+        const double* prim = ds[0];
+        int64_t ld_prim = ld;
+        if (ctx->any_dual) {
+            for (int v = 0; v < 2; v++) {
+                primal_dual_kernel<<<vgrid(ctx, q), 256, 0, ctx->stream>>>(q, ctx->d_row_dual, dz[v], ds[v], b.vq2[v], b.vq3[v]);
+                ctx->launches++;
+            }
+            prim = b.vq2[0];
+            ld_prim = ldq;
+        }
+        hyp_cones_prod(ctx, b.vq4[0], prim, 2, ldq, ld_prim, HYP_PROD_HESS, 0);
+        for (int v = 0; v < 2; v++)
+            hyp_lincomb3(ctx, q, r[v] + tau_idx + 1, 1.0, b.vq4[v], 1.0, ctx->any_dual ? b.vq3[v] : dz[v], 0.0, nullptr);
+    }
+    const double mu_tt = ctx->mu / ctx->tau_bar / ctx->tau_bar;
+    for (int v = 0; v < 2; v++) {
+        hyp_dot(ctx, dim3, ctx->d_cbh, dx[v], ctx->d_scalars + 3, false);
+        lhs_tail_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_scalars, dx[v], r[v], tau_idx, kap_idx, mu_tt);
+        ctx->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+}
+
 void solve_system_multi_dev(hyp_ctx* ctx, double* sol, const double* rhs, int ncols, int64_t ld) {
-    for (int j = 0; j < ncols; j++) solve_system_dev(ctx, sol + j * ld, rhs + j * ld);
+    int j = 0;
+    for (; j + 1 < ncols; j += 2) solve_system_pair_dev(ctx, sol + j * ld, rhs + j * ld, ld);
+    for (; j < ncols; j++) solve_system_dev(ctx, sol + j * ld, rhs + j * ld);
 }
 void apply_lhs_multi_dev(hyp_ctx* ctx, double* res, const double* dir, int ncols, int64_t ld) {
-    for (int j = 0; j < ncols; j++) apply_lhs_dev(ctx, res + j * ld, dir + j * ld);
+    int j = 0;
+    for (; j + 1 < ncols; j += 2) apply_lhs_pair_dev(ctx, res + j * ld, dir + j * ld, ld);
+    for (; j < ncols; j++) apply_lhs_dev(ctx, res + j * ld, dir + j * ld);
 }
 
 // ---- packed upper triangle for the Schur reduction ------------------------------------------

@@ -236,4 +236,212 @@ static __global__ void gemv_n_reduce_kernel(int64_t rows, int nchunks, const dou
     }
 }
 
+
+// ---- two right-hand sides per pass over G (hyp_solve_system_multi / hyp_apply_lhs_multi) -------------------------------
+// The stepper's data flow (steppers/combined.jl:67-79) allows {cent, pred} and {centadj, predadj} to be solved
+// together; every entry of G then serves two products.  Same thread mappings and reduction orders as the
+// single-vector kernels above, so column v of a two-column call is bit-identical to a single-column call.
+
+// y_v[j] = alpha * dot(M[:, j], x_v) + beta * y_v[j], v = 0, 1;  one CTA per column of M.
+static __global__ void __launch_bounds__(256)
+gemv_t2_cta_kernel(int64_t rows, int64_t ncols, const double* __restrict__ M, int64_t ld, const double* __restrict__ x0,
+                   const double* __restrict__ x1, double alpha, double beta, double* __restrict__ y0,
+                   double* __restrict__ y1) {
+    __shared__ double sm[2][8];
+    for (int64_t j = blockIdx.x; j < ncols; j += gridDim.x) {
+        const double* col = M + j * ld;
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+        const double2* c2 = reinterpret_cast<const double2*>(col);
+        const double2* p0 = reinterpret_cast<const double2*>(x0);
+        const double2* p1 = reinterpret_cast<const double2*>(x1);
+        const int64_t n2 = rows >> 1;
+        int64_t i = threadIdx.x;
+        for (; i + 3 * 256 < n2; i += 4 * 256) {
+            const double2 m0 = __ldg(c2 + i), m1 = __ldg(c2 + i + 256), m2 = __ldg(c2 + i + 512), m3 = __ldg(c2 + i + 768);
+            const double2 v0 = p0[i], v1 = p0[i + 256], v2 = p0[i + 512], v3 = p0[i + 768];
+            const double2 w0 = p1[i], w1 = p1[i + 256], w2 = p1[i + 512], w3 = p1[i + 768];
+            a0 += m0.x * v0.x + m0.y * v0.y;
+            a1 += m1.x * v1.x + m1.y * v1.y;
+            a2 += m2.x * v2.x + m2.y * v2.y;
+            a3 += m3.x * v3.x + m3.y * v3.y;
+            b0 += m0.x * w0.x + m0.y * w0.y;
+            b1 += m1.x * w1.x + m1.y * w1.y;
+            b2 += m2.x * w2.x + m2.y * w2.y;
+            b3 += m3.x * w3.x + m3.y * w3.y;
+        }
+        for (; i < n2; i += 256) {
+            const double2 m0 = __ldg(c2 + i);
+            const double2 v0 = p0[i], w0 = p1[i];
+            a0 += m0.x * v0.x + m0.y * v0.y;
+            b0 += m0.x * w0.x + m0.y * w0.y;
+        }
+        if ((rows & 1) && threadIdx.x == 0) {
+            a1 += col[rows - 1] * x0[rows - 1];
+            b1 += col[rows - 1] * x1[rows - 1];
+        }
+        const double sa = warp_sum((a0 + a1) + (a2 + a3)), sb = warp_sum((b0 + b1) + (b2 + b3));
+        if ((threadIdx.x & 31) == 0) {
+            sm[0][threadIdx.x >> 5] = sa;
+            sm[1][threadIdx.x >> 5] = sb;
+        }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            double t = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) t += sm[threadIdx.x][w];
+            double* y = threadIdx.x ? y1 : y0;
+            y[j] = alpha * t + (beta == 0.0 ? 0.0 : beta * y[j]);
+        }
+        __syncthreads();
+    }
+}
+
+// partial_v[chunk][r] = sum_{j in chunk} M[r, j] x_v[j], v = 0, 1 (partial_1 = partial_0 + pstride)
+static __global__ void __launch_bounds__(128)
+gemv_n2_kernel(int64_t rows, int64_t ncols, const double* __restrict__ M, int64_t ld, const double* __restrict__ x0,
+               const double* __restrict__ x1, int64_t cols_per_chunk, double* __restrict__ partial, int64_t pstride) {
+    const int64_t r = (blockIdx.x * 128 + threadIdx.x) * 2;
+    const int64_t j0 = blockIdx.y * cols_per_chunk;
+    const int64_t j1 = j0 + cols_per_chunk < ncols ? j0 + cols_per_chunk : ncols;
+    if (r >= rows) return;
+    const bool ok1 = r + 1 < rows;
+    double ax = 0, ay = 0, bx = 0, by = 0, cx = 0, cy = 0, dx = 0, dy = 0;
+    const double* base = M + r;
+    int64_t j = j0;
+    if (ok1) {
+        for (; j + 7 < j1; j += 8) {
+            double2 m[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) m[u] = __ldg(reinterpret_cast<const double2*>(base + (j + u) * ld));
+#pragma unroll
+            for (int u = 0; u < 8; u += 2) {
+                const double p0 = x0[j + u], p1 = x0[j + u + 1], q0 = x1[j + u], q1 = x1[j + u + 1];
+                ax += m[u].x * p0;
+                ay += m[u].y * p0;
+                bx += m[u + 1].x * p1;
+                by += m[u + 1].y * p1;
+                cx += m[u].x * q0;
+                cy += m[u].y * q0;
+                dx += m[u + 1].x * q1;
+                dy += m[u + 1].y * q1;
+            }
+        }
+    }
+    for (; j < j1; j++) {
+        const double m0 = base[j * ld], m1 = ok1 ? base[j * ld + 1] : 0.0;
+        const double p0 = x0[j], q0 = x1[j];
+        ax += m0 * p0;
+        ay += m1 * p0;
+        cx += m0 * q0;
+        cy += m1 * q0;
+    }
+    double* out = partial + blockIdx.y * rows + r;
+    out[0] = ax + bx;
+    out[pstride] = cx + dx;
+    if (ok1) {
+        out[1] = ay + by;
+        out[pstride + 1] = cy + dy;
+    }
+}
+
+// two (x, z) pairs per pass:  w_v = M x_v  and  y_v = M' z_v  (see gemv_nt_kernel); partial buffers of pair 1 follow
+// those of pair 0 at pstrideN / pstrideT
+static __global__ void __launch_bounds__(128)
+gemv_nt2_kernel(int64_t rows, int64_t ncols, const double* __restrict__ M, int64_t ld, const double* __restrict__ xa,
+                const double* __restrict__ xb, const double* __restrict__ za, const double* __restrict__ zb,
+                int64_t cols_per_chunk, double* __restrict__ partialN, int64_t pstrideN, double* __restrict__ partialT,
+                int64_t pstrideT) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r = ((int64_t)blockIdx.x * 128 + threadIdx.x) * 2;
+    const int64_t j0 = (int64_t)blockIdx.y * cols_per_chunk;
+    const int64_t j1 = j0 + cols_per_chunk < ncols ? j0 + cols_per_chunk : ncols;
+    const bool ok0 = r < rows, ok1 = r + 1 < rows;
+    const double za0 = ok0 ? za[r] : 0.0, za1 = ok1 ? za[r + 1] : 0.0;
+    const double zb0 = ok0 ? zb[r] : 0.0, zb1 = ok1 ? zb[r + 1] : 0.0;
+    const double* base = M + r;
+    double* pTa = partialT + ((int64_t)blockIdx.x * 4 + warp) * ncols;
+    double* pTb = pTa + pstrideT;
+    double axa = 0.0, aya = 0.0, axb = 0.0, ayb = 0.0;
+    const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+    int64_t j = j0;
+    for (; j + 7 < j1; j += 8) {
+        double ta[8], tb[8];
+        double2 mm[8];
+        if (ok1) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) mm[u] = __ldg(reinterpret_cast<const double2*>(base + (j + u) * ld));
+        } else {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                mm[u].x = ok0 ? base[(j + u) * ld] : 0.0;
+                mm[u].y = 0.0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const double xja = xa[j + u], xjb = xb[j + u];
+            axa += mm[u].x * xja;
+            aya += mm[u].y * xja;
+            axb += mm[u].x * xjb;
+            ayb += mm[u].y * xjb;
+            ta[u] = mm[u].x * za0 + mm[u].y * za1;
+            tb[u] = mm[u].x * zb0 + mm[u].y * zb1;
+        }
+#pragma unroll
+        for (int v = 0; v < 2; v++) {
+            double* t = v ? tb : ta;
+            double u4[4], u2[2], u1;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const double send = b4 ? t[i] : t[i + 4];
+                const double keep = b4 ? t[i + 4] : t[i];
+                u4[i] = keep + shfl_xor_d(send, 16);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const double send = b3 ? u4[i] : u4[i + 2];
+                const double keep = b3 ? u4[i + 2] : u4[i];
+                u2[i] = keep + shfl_xor_d(send, 8);
+            }
+            {
+                const double send = b2 ? u2[0] : u2[1];
+                const double keep = b2 ? u2[1] : u2[0];
+                u1 = keep + shfl_xor_d(send, 4);
+            }
+            u1 += shfl_xor_d(u1, 2);
+            u1 += shfl_xor_d(u1, 1);
+            if ((lane & 3) == 0) (v ? pTb : pTa)[j + (lane >> 2)] = u1;
+        }
+    }
+    for (; j < j1; j++) {
+        double m0 = 0.0, m1 = 0.0;
+        if (ok0) m0 = base[j * ld];
+        if (ok1) m1 = base[j * ld + 1];
+        const double xja = xa[j], xjb = xb[j];
+        axa += m0 * xja;
+        aya += m1 * xja;
+        axb += m0 * xjb;
+        ayb += m1 * xjb;
+        double t0 = m0 * za0 + m1 * za1, t1 = m0 * zb0 + m1 * zb1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            t0 += shfl_xor_d(t0, o);
+            t1 += shfl_xor_d(t1, o);
+        }
+        if (lane == 0) {
+            pTa[j] = t0;
+            pTb[j] = t1;
+        }
+    }
+    double* outN = partialN + (int64_t)blockIdx.y * rows + r;
+    if (ok0) {
+        outN[0] = axa;
+        outN[pstrideN] = axb;
+    }
+    if (ok1) {
+        outN[1] = aya;
+        outN[pstrideN + 1] = ayb;
+    }
+}
+
 }  // namespace hypdev

@@ -264,6 +264,18 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // K-major SWIZZLE_32B descriptor: rows of 32 B, 8-row groups 256 B apart
 __device__ __forceinline__ uint64_t make_desc_sw32(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -730,6 +742,54 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
+// ---- MMA issue loop of the CTA-pair kernel for seven radix-256 digits (28 pair products) --------------------------
+// The first version ran the generic (s, t) loops in ONE thread: 35 SASS instructions per tcgen05.mma (descriptor
+// construction, R2UR moves into the uniform registers UTCIMMA reads), i.e. 143 cycles per MMA against the 64-cycle
+// floor of a 256 x 128 x 32 int8 MMA - the issuing thread, not the tensor pipe or the operand traffic, bounded the kernel
+// (profiles/r02_syrk_probe_mma_vs_tma.json: the MMA stream alone needed 88 % of the kernel time).  Here the WHOLE warp
+// runs the loop, so every value is warp-uniform and stays in uniform registers; the digit pairs of a pass are unrolled
+// at compile time, each descriptor is the stage's base descriptor plus a constant, and one elected lane issues.
+template <int PASS>
+__device__ __forceinline__ void issue_pass_r256(uint64_t dbase, uint32_t tmem0, uint32_t idesc, int nst, uint32_t bar_full,
+                                                uint32_t bar_empty, uint32_t bar_tfull, int& stage, uint32_t& phase,
+                                                bool issuer) {
+    constexpr int NSL = 7;
+    constexpr int D0 = PASS * 4;
+    constexpr int NS = PASS == 0 ? 4 : OZ_S;          // A slice slots in front of the B half slices
+    constexpr int NHALF = PASS == 0 ? 2 : 1;
+    constexpr int SMAX = PASS == 0 ? 3 : NSL - 1;
+    for (int it = 0; it < nst; it++) {
+        mbar_wait(bar_full + stage * 8, phase);
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        const uint64_t sd = dbase + (uint64_t)((uint32_t)(stage * OZP_STAGE) >> 4);
+        const uint32_t first = it > 0 ? 1u : 0u;
+#pragma unroll
+        for (int h = 0; h < NHALF; h++) {
+#pragma unroll
+            for (int sl = 0; sl <= SMAX; sl++) {
+                constexpr int dummy = 0;
+                (void)dummy;
+                const int tlo = D0 - sl > 0 ? D0 - sl : 0;
+                const int thi = (D0 + 3 - sl) < (NSL - 1 - sl) ? (D0 + 3 - sl) : (NSL - 1 - sl);
+#pragma unroll
+                for (int tt = 0; tt < NSL; tt++) {
+                    if (tt < tlo || tt > thi) continue;
+                    const uint32_t offA = (uint32_t)(h * (OZP_STAGE / 2) + sl * OZ_TILE) >> 4;
+                    const uint32_t offB = (uint32_t)(h * (OZP_STAGE / 2) + NS * OZ_TILE + tt * (OZ_TILE / 2)) >> 4;
+                    const uint32_t accum = (h > 0 || sl > 0) ? 1u : first;
+                    if (issuer) umma_i8_2sm(tmem0 + (uint32_t)((sl + tt - D0) * TN), sd + offA, sd + offB, idesc, accum);
+                }
+            }
+        }
+        if (issuer) umma_commit_2sm(bar_empty + stage * 8, 3);       // frees the stage in both CTAs
+        if (++stage == OZP_STAGES) {
+            stage = 0;
+            phase ^= 1u;
+        }
+    }
+    if (issuer) umma_commit_2sm(bar_tfull, 3);                        // accumulators ready in both CTAs
+}
+
 __global__ void __launch_bounds__(I8_THREADS, 1)
 ozaki_syrk_pair_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid_constant__ CUtensorMap mapA8,
                        const __grid_constant__ CUtensorMap mapB4, const __grid_constant__ CUtensorMap mapB8,
@@ -738,7 +798,7 @@ ozaki_syrk_pair_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid_c
                        double alpha, double beta, int nsl, int wbits_probe) {
     // bits 8.. of the last argument: profiling probes (HYP_OZAKI_PROBE; results are garbage, timing only):
     //   1 = no TMA loads (the MMA issuer runs on stale shared memory), 2 = no MMAs (loads + epilogue only)
-    const int wbits = wbits_probe & 0xff, probe = wbits_probe >> 8;
+    const int wbits = wbits_probe & 0xff, probe = (wbits_probe >> 8) & 3;
     // nsl = number of digit slices that enter the product (7 or 8): pairs with s + t <= nsl - 1;
     // wbits = bits per digit (7: radix 128, 8: radix 256): digit s has weight 2^-(wbits - 1 + wbits s)
     extern __shared__ uint8_t smem_raw[];
@@ -822,6 +882,25 @@ ozaki_syrk_pair_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid_c
         }
     } else if (warp == 1) {
         // ===== MMA issuer (leader CTA only) =====
+        static_assert(true, "");
+        if (leader && nsl == 7 && probe != 2 && !(wbits_probe & 0x4000)) {
+            // radix-256 digits: warp-uniform issue loop, one elected lane issues (issue_pass_r256)
+            const uint32_t idesc = make_idesc_i8(2 * TM, TN);
+            const uint64_t dbase = make_desc_sw32(stg);
+            const bool issuer = elect_one_sync();
+            int stage = 0;
+            uint32_t phase = 0, item = 0;
+            for (int pi = (int)cid; pi < n_pairs; pi += (int)ncl) {
+                for (int pass = 0; pass < 2; pass++, item++) {
+                    if (item > 0) mbar_wait(bar_tempty, (item - 1) & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    if (pass == 0)
+                        issue_pass_r256<0>(dbase, tmem0, idesc, (nkb + 1) / 2, bar_full, bar_empty, bar_tfull, stage, phase, issuer);
+                    else
+                        issue_pass_r256<1>(dbase, tmem0, idesc, nkb, bar_full, bar_empty, bar_tfull, stage, phase, issuer);
+                }
+            }
+        } else
         if (leader && lane == 0) {
             const uint32_t idesc = make_idesc_i8(2 * TM, TN);
             int stage = 0;
@@ -1518,7 +1597,8 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
             CUDA_TRY(cudaLaunchKernelEx(&cfg, ozaki_syrk_pair_kernel, mapD4, mapA8, mapB4, mapB8, (const int2*)d_pairs,
                                         n_pairs, (int)k0, (int)ceil_div(klen, OZ_KB), dscale, ncols, C, ldc, alpha,
                                         k0 == 0 ? beta : 1.0, nsl_eff,
-                                        wbits | ((getenv("HYP_OZAKI_PROBE") ? atoi(getenv("HYP_OZAKI_PROBE")) : 0) << 8)));
+                                        wbits | ((getenv("HYP_OZAKI_PROBE") ? atoi(getenv("HYP_OZAKI_PROBE")) : 0) << 8) |
+                                            (getenv("HYP_OZAKI_OLD_ISSUE") ? 0x4000 : 0)));
             ctx->launches++;
             continue;
         }
@@ -1662,7 +1742,11 @@ mma_rate_kernel(int swz, int N, int cg2, int nmma, long long* __restrict__ cycle
     if (cg2) cluster_sync_all();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem0 = s_tmem;
-    if (warp == 1 && lane == 0 && crank == 0) {
+    const int style = swz >> 4;
+    swz &= 15;
+    if (warp == 1 && crank == 0 && (style == 1 || lane == 0)) {
+        // style 0: one thread runs the whole issue loop (operands live in ordinary registers: R2UR per MMA);
+        // style 1: the warp runs it uniformly and an elected lane issues (operands can stay in uniform registers)
         const uint32_t idesc = make_idesc_i8(cg2 ? 256 : 128, N);
         const int row_bytes = 32 << swz;                       // bytes of K per shared-memory row
         const int ksub = row_bytes / 32;                       // MMAs (K = 32) per row
@@ -1672,19 +1756,30 @@ mma_rate_kernel(int swz, int N, int cg2, int nmma, long long* __restrict__ cycle
         const int na = 4, nbt = 4;                             // operand tiles cycled through (like digit slices)
         const uint32_t a0 = stg, b0 = stg + na * a_tile;       // <= 4 * 16 KB + 4 * 32 KB = 192 KB
         const int nacc = 512 / N;
-        const long long t0 = clock64();
-        for (int i = 0; i < nmma; i++) {
-            const int ks = i % ksub;
-            const int sa = (i / ksub) % na, sb = (i / (ksub * na)) % nbt;
-            const uint64_t ad = make_desc_kmajor(a0 + sa * a_tile + ks * 32, swz);
-            const uint64_t bd = make_desc_kmajor(b0 + sb * b_tile + ks * 32, swz);
-            umma_i8_n(tmem0 + (uint32_t)((i % nacc) * N), ad, bd, idesc, cg2);
+        uint64_t ad[16], bd[16];
+        uint32_t td[16];
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            const int ks = u % ksub;
+            const int sa = (u / ksub) % na, sb = (u / 4) % nbt;
+            ad[u] = make_desc_kmajor(a0 + sa * a_tile + ks * 32, swz);
+            bd[u] = make_desc_kmajor(b0 + sb * b_tile + ks * 32, swz);
+            td[u] = tmem0 + (uint32_t)((u % nacc) * N);
         }
-        if (cg2) umma_commit_2sm(bar, 3);
-        else umma_commit(bar);
+        const bool issuer = style == 0 ? true : elect_one_sync();
+        const long long t0 = clock64();
+        for (int i = 0; i < nmma; i += 16) {
+#pragma unroll
+            for (int u = 0; u < 16; u++)
+                if (issuer) umma_i8_n(td[u], ad[u], bd[u], idesc, cg2);
+        }
+        if (issuer) {
+            if (cg2) umma_commit_2sm(bar, 3);
+            else umma_commit(bar);
+        }
         mbar_wait(bar, 0);
         const long long t1 = clock64();
-        if (blockIdx.x == 0) cycles[0] = t1 - t0;
+        if (blockIdx.x == 0 && issuer) cycles[0] = t1 - t0;
     } else if (cg2 && crank == 1 && warp == 1 && lane == 0) {
         mbar_wait(bar, 0);            // the multicast commit also arrives here
     }

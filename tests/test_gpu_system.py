@@ -383,3 +383,43 @@ def test_calc_residuals_matches_host_formulas(p):
         assert np.allclose(st, ref, rtol=1e-11, atol=1e-11)
     finally:
         dev.syssolver.free_memory()
+
+
+@pytest.mark.parametrize("name,scale,ncols", [("C3", 0.1, 2), ("C3", 0.1, 3), ("C3", 0.02, 2), ("C2", 1.0, 2)])
+def test_multi_column_solves_match_single_column_calls(name, scale, ncols):
+    """hyp_solve_system_multi / hyp_apply_lhs_multi (the {cent, pred} and {centadj, predadj} pairs of
+    steppers/combined.jl:67-79 solved together: shared passes over G, shared triangular sweeps) against ncols calls of
+    hyp_solve_system / hyp_apply_lhs, on device and on host buffers, and against the oracle."""
+    import torch
+    I = inst.config(name, scale)
+    dev, ora = _pair(I)
+    try:
+        ctx = dev.syssolver.ctx
+        dim6 = I.model.n + I.model.p + 2 * I.model.q + 2
+        rng = np.random.default_rng(21)
+        R = rng.standard_normal((ncols, dim6))
+        single = np.empty_like(R)
+        res_single = np.empty_like(R)
+        for j in range(ncols):
+            ctx.solve_system(single[j], R[j])
+            ctx.apply_lhs(res_single[j], single[j])
+        # host buffers
+        multi = np.empty_like(R)
+        ctx.solve_system_multi(multi, R, ncols)
+        assert rel(multi, single) <= 1e-13
+        # device buffers (the path that shares the passes)
+        dR = torch.from_numpy(R).cuda()
+        dS = torch.empty_like(dR)
+        dA = torch.empty_like(dR)
+        ctx.solve_system_multi(dS, dR, ncols)
+        ctx.apply_lhs_multi(dA, dS, ncols)
+        ctx.sync()
+        assert rel(dS.cpu().numpy(), single) <= 1e-13
+        assert rel(dA.cpu().numpy(), res_single) <= 1e-12
+        for j in range(ncols):
+            rhs, so = Point(I.model), Point(I.model)
+            rhs.vec[:] = R[j]
+            ora.syssolver.solve_system(ora, so, rhs)
+            assert rel(dS[j].cpu().numpy(), so.vec) <= DIR_TOL
+    finally:
+        dev.syssolver.free_memory()

@@ -11,6 +11,7 @@ A = np.asfortranarray(B.T @ B + 0.5 * np.eye(128))
 clk = np.zeros(16)
 ctx.check(ctx.lib.hyp_test_panel_clocks(ctx.h, capi.ptr(A), 128, 128, capi.ptr(clk)), "panel clocks")
 names = ["start", "loaded"] + [f"b{b}:{p}" for b in range(4) for p in ("diag", "row", "trail")] + ["inverse", "stored"]
+names[12] = "b3:xcol_thread0"
 prev = 0.0
 out = {}
 for n, c in zip(names, clk):
