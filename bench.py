@@ -53,6 +53,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+DEFAULT_OTHER = "C2,C4,C5a"
 METRIC = "IPM iterations/sec (KKT assemble+factor+solve)"
 UNIT = "iter/s"
 
@@ -689,19 +690,53 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=device)
 
     main = measure_workload(args, args.workload, torch, dist, device, rank, world, local_rank, True)
+    # the headline line is complete (roofline, CPU oracle parity) BEFORE the extra workloads start
+    line = build_line(args, torch, device, world, main) if rank == 0 else None
     others = {}
-    for w in [x for x in args.other.split(",") if x and x != "none"]:
+    names = [x for x in args.other.split(",") if x and x != "none"]
+    # BASELINE config 5's many-cone mix needs 240 GB of panels (G, H G, the mixed left operand): from 4 GPUs on
+    if world >= 4 and names and "C5b" not in names and args.other == DEFAULT_OTHER:
+        names.append("C5b")
+
+    # The extra workloads must never cost the headline line: if one of them hangs (a rank lost in a collective inside
+    # a C call - a Python signal handler would never run), a watchdog THREAD makes every rank leave after
+    # `--other-timeout` seconds and rank 0 print what it has.
+    lock = threading.Lock()
+    state = {"printed": False}
+
+    def emit():
+        with lock:
+            if rank == 0 and not state["printed"]:
+                state["printed"] = True
+                line["other_workloads"] = others
+                print(json.dumps(line), flush=True)
+
+    def on_timeout():
+        others["_watchdog"] = f"other_workloads abandoned after {args.other_timeout} s"
+        emit()
+        os._exit(0)
+
+    dog = None
+    if names:
+        dog = threading.Timer(float(args.other_timeout), on_timeout)
+        dog.daemon = True
+        dog.start()
+    for w in names:
         try:
             r = measure_workload(args, w, torch, dist, device, rank, world, local_rank, False)
             r.pop("_dev_sols", None), r.pop("_rhs_list", None), r.pop("clocks", None)
             others[w] = r
         except Exception as e:
             others[w] = {"error": f"{type(e).__name__}: {e}"}
-    if rank != 0:
-        if dist is not None:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
+    if dog is not None:
+        dog.cancel()
+    emit()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def build_line(args, torch, device, world, main):
 
     ms_step = main["ms_per_step"]
     phases = main["phase_ms"]
@@ -805,11 +840,8 @@ def run_ours(args):
             "clocks": main["clocks"], "e2e": main["e2e"],
             "gpu_launches": main["gpu_launches"], "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
             "full_step": main.get("full_step"), "batched_solves": main.get("batched_solves"),
-            "other_workloads": others}
-    print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+            "other_workloads": {}}
+    return line
 
 
 def main():
@@ -819,9 +851,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
-    ap.add_argument("--other", default=os.environ.get("HYP_BENCH_OTHER", "C2,C4,C5a"),
+    ap.add_argument("--other", default=os.environ.get("HYP_BENCH_OTHER", DEFAULT_OTHER),
                     help="comma-separated extra workloads reported under other_workloads ('none' to skip)")
     ap.add_argument("--other-steps", type=int, default=2)
+    ap.add_argument("--other-timeout", type=float, default=900.0,
+                    help="seconds after which the extra workloads are abandoned and the line is printed without them")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--syrk", default=os.environ.get("HYP_SCHUR_SYRK", "i8"), choices=["dmma", "i8"],
                     help="Schur SYRK kernel: FP64 DMMA or FP64-accurate digit slicing on the int8 tcgen05 pipe")

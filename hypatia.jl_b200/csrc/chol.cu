@@ -204,6 +204,11 @@ extern "C" int hyp_test_panel_clocks(hyp_ctx* ctx, double* A, int64_t lda, int64
         CUDA_TRY(cudaMalloc(&dD, (size_t)NB * NB * 8));
         CUDA_TRY(cudaMalloc(&dI, 8));
         long long clk[16];
+        {
+            const char* pf = getenv("HYP_PANEL_FLAGS");
+            int flags = pf ? atoi(pf) : 0;
+            CUDA_TRY(cudaMemcpyToSymbol(g_panel_flags, &flags, sizeof(int)));
+        }
         for (int rep = 0; rep < 3; rep++) {
             CUDA_TRY(cudaMemcpyAsync(dA, A, (size_t)lda * m * 8, cudaMemcpyDefault, ctx->stream));
             CUDA_TRY(cudaMemsetAsync(dI, 0, 8, ctx->stream));

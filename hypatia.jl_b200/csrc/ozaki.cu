@@ -752,7 +752,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 template <int PASS>
 __device__ __forceinline__ void issue_pass_r256(uint64_t dbase, uint32_t tmem0, uint32_t idesc, int nst, uint32_t bar_full,
                                                 uint32_t bar_empty, uint32_t bar_tfull, int& stage, uint32_t& phase,
-                                                bool issuer) {
+                                                bool issuer, uint16_t empty_mask = 3, uint16_t tfull_mask = 3) {
     constexpr int NSL = 7;
     constexpr int D0 = PASS * 4;
     constexpr int NS = PASS == 0 ? 4 : OZ_S;          // A slice slots in front of the B half slices
@@ -781,13 +781,13 @@ __device__ __forceinline__ void issue_pass_r256(uint64_t dbase, uint32_t tmem0, 
                 }
             }
         }
-        if (issuer) umma_commit_2sm(bar_empty + stage * 8, 3);       // frees the stage in both CTAs
+        if (issuer) umma_commit_2sm(bar_empty + stage * 8, empty_mask);       // frees the stage in the CTAs that filled it
         if (++stage == OZP_STAGES) {
             stage = 0;
             phase ^= 1u;
         }
     }
-    if (issuer) umma_commit_2sm(bar_tfull, 3);                        // accumulators ready in both CTAs
+    if (issuer) umma_commit_2sm(bar_tfull, tfull_mask);                        // accumulators ready in both CTAs of the pair
 }
 
 __global__ void __launch_bounds__(I8_THREADS, 1)
@@ -1022,7 +1022,8 @@ ozaki_syrk_quad_kernel(const __grid_constant__ CUtensorMap mapA2, const __grid_c
                        const __grid_constant__ CUtensorMap mapB4, const __grid_constant__ CUtensorMap mapB8,
                        const int2* __restrict__ quads, int n_quads, int k0, int nkb,
                        const double* __restrict__ dscale, int64_t ncols, double* __restrict__ C, int64_t ldc,
-                       double alpha, double beta, int nsl, int wbits) {
+                       double alpha, double beta, int nsl, int wbits_flags) {
+    const int wbits = wbits_flags & 0xff;
     // nsl = number of digit slices that enter the product (7 or 8): pairs with s + t <= nsl - 1;
     // wbits = bits per digit (7: radix 128, 8: radix 256): digit s has weight 2^-(wbits - 1 + wbits s)
     extern __shared__ uint8_t smem_raw[];
@@ -1122,6 +1123,24 @@ ozaki_syrk_quad_kernel(const __grid_constant__ CUtensorMap mapA2, const __grid_c
                         }
                     }
                 }
+            }
+        }
+    } else if (warp == 1 && nsl == 7 && !(wbits_flags & 0x4000)) {
+        // ===== MMA issuer (leader CTA of each pair), radix-256 digits: warp-uniform loop, elected lane issues =====
+        const uint32_t idesc = make_idesc_i8(2 * TM, TN);
+        const uint64_t dbase = make_desc_sw32(stg);
+        const bool issuer = elect_one_sync();
+        int stage = 0;
+        uint32_t phase = 0, item = 0;
+        for (int qi = (int)cid; qi < n_quads; qi += (int)ncl) {
+            for (int pass = 0; pass < 2; pass++, item++) {
+                if (item > 0) mbar_wait(bar_tempty, (item - 1) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                if (pass == 0)
+                    issue_pass_r256<0>(dbase, tmem0, idesc, (nkb + 1) / 2, bar_full, bar_empty, bar_tfull, stage, phase, issuer, 0xF,
+                                       mask_pair);
+                else
+                    issue_pass_r256<1>(dbase, tmem0, idesc, nkb, bar_full, bar_empty, bar_tfull, stage, phase, issuer, 0xF, mask_pair);
             }
         }
     } else if (warp == 1) {
@@ -1529,7 +1548,7 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
             cfg.numAttrs = 1;
             CUDA_TRY(cudaLaunchKernelEx(&cfg, ozaki_syrk_quad_kernel, mapD2, mapD4, mapB4, mapB8, (const int2*)d_quads,
                                         n_quads, (int)k0, (int)ceil_div(klen, OZ_KB), dscale, ncols, C, ldc, alpha,
-                                        k0 == 0 ? beta : 1.0, nsl_eff, wbits));
+                                        k0 == 0 ? beta : 1.0, nsl_eff, wbits | (getenv("HYP_OZAKI_OLD_ISSUE") ? 0x4000 : 0)));
             ctx->launches++;
             continue;
         }
