@@ -123,6 +123,7 @@ struct ConeGroup {
     // chunk table of the many-column EpiNormEucl kernel (cones.cu)
     int n_chunks = 0, chunk_smem = 0;
     bool chunks_cover_all = false;
+    int chunk_align8 = -1;        // fused pre-pass: every chunk starts at a multiple of 8 local rows (-1 = not checked yet)
     int64_t* d_crow0 = nullptr;
     int *d_crows = nullptr, *d_ccone0 = nullptr, *d_ccount = nullptr;
 };
@@ -239,6 +240,7 @@ struct hyp_ctx {
     // the work vectors of solve_system_dev / apply_lhs_dev
     double *d_partial3 = nullptr, *d_partial4 = nullptr;
     int64_t partial3_doubles = 0, partial4_doubles = 0;
+    unsigned long long* d_colbits = nullptr;   // column maxima (bit patterns) of the fused pre-pass
     double* d_multi = nullptr;
     int64_t multi_doubles = 0;
     int* d_dag_ver = nullptr;          // task-graph Cholesky (chol_dag.cu): tile version counters + tickets
@@ -378,6 +380,9 @@ void hyp_gemm_simple(hyp_ctx* ctx, bool transA, bool transB, int64_t M, int64_t 
                      int64_t ldc);
 
 // ---- ozaki.cu ----
+int hyp_ozaki_radix();
+// fused Schur pre-pass + digit slicing for second-order-cone models (cones.cu); false = not applicable
+bool hyp_cones_prepass_sliced(hyp_ctx* ctx, int8_t* digits, int64_t ldd, int64_t slice_stride, int* expo, double* dscale);
 void hyp_ozaki_slice(hyp_ctx* ctx, const double* A, int64_t lda, int64_t K, int64_t ncols, int8_t* digits,
                      int64_t ldd, int64_t slice_stride, int* expo, double* dscale);
 void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t slice_stride, const int* expo,

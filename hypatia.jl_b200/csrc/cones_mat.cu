@@ -241,16 +241,19 @@ void hyp_mat_update_state(hyp_ctx* ctx, ConeGroup& g) {
             ctx->launches++;
         }
     } else {
-        // large cones: factor the dual matrices one by one in a private scratch copy
-        double* scratch = nullptr;
-        CUDA_TRY(cudaMalloc(&scratch, (size_t)(g.mat_total + 16) * sizeof(double)));
+        // large cones: factor the dual matrices one by one in a scratch copy that lives behind the Dinv blocks of the
+        // blocked Cholesky in the context's matrix workspace (no cudaMalloc / cudaFree - and no implicit device
+        // synchronisation - inside the per-iteration state update)
+        int64_t dinv_len = 0;
+        for (int i = 0; i < g.count; i++)
+            dinv_len = std::max<int64_t>(dinv_len, (int64_t)ceil_div(g.h_side[i], 128) * 128 * 128 + 16);
+        ensure_matwork(ctx, dinv_len + g.mat_total + 16);
+        double* scratch = ctx->d_matwork + dinv_len;
         unpack_state_kernel<<<ugrid, 256, 0, ctx->stream>>>(g.count, g.d_off, g.d_side, g.d_moff, lead,
                                                             ctx->d_dual, scratch, nullptr);
         ctx->launches++;
         for (int i = 0; i < g.count; i++) {
             int d = g.h_side[i], lde = (d + 1) & ~1;
-            int nblk = ceil_div(d, 128);
-            ensure_matwork(ctx, (int64_t)nblk * 128 * 128 + 16);
             hyp_potrf_upper(ctx, scratch + g.h_moff[i], lde, d, ctx->d_matwork, ctx->d_info + 12);
             info_to_flag_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_info + 12, ctx->d_dual_feas, g.h_kidx[i]);
             ctx->launches++;
@@ -260,8 +263,6 @@ void hyp_mat_update_state(hyp_ctx* ctx, ConeGroup& g) {
                                                                  g.d_kidx, ctx->d_dual, scratch, ctx->d_dual_feas);
             ctx->launches++;
         }
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        cudaFree(scratch);
     }
     CUDA_TRY(cudaGetLastError());
 }

@@ -5,6 +5,7 @@
 // product.  Launched from cones.cu; compiled for the host by tests/emu/ (CPU-tier tests: tests/test_emu_vec.py).
 #pragma once
 #include "devdefs.cuh"
+#include "ozaki_slice_kernels.cuh"
 
 // product modes (= HYP_PROD_* of the ABI; cones.cu static_asserts the equality) and the orthant's type code
 #define VK_HESS 0
@@ -161,13 +162,19 @@ soc_prod_kernel(int ncones, const int64_t* __restrict__ off, const int* __restri
 // from shared memory (cone dims are mostly odd, e.g. 25: conflict-free strides), and the result
 // goes back with coalesced stores.  chunk table: crow0[b], crows[b] = first row / number of rows
 // of chunk b, ccone0[b], ccount[b] = first cone (index in the group) / number of cones.
-template <int MODE>
+// OUT selects what happens to the product (the fused Schur pre-pass of the digit-sliced SYRK, ozaki.cu, never
+// materialises H^{1/2} G): 0 = store it; 1 = only the column maxima of |.| (atomicMax of the bit patterns into
+// colbits[j]); 2 = cut it into radix-256 digit slices with the column exponents expo[j] and store the digits
+// (chunks start at multiples of 8 rows, checked by the host, so the packed 8-byte words are aligned).
+template <int MODE, int OUT = 0>
 __global__ void __launch_bounds__(256)
 soc_prod_chunk_kernel(const int64_t* __restrict__ crow0, const int* __restrict__ crows,
                       const int* __restrict__ ccone0, const int* __restrict__ ccount,
                       const int64_t* __restrict__ off, const int* __restrict__ dim,
                       const double* __restrict__ scal, const double* __restrict__ point, const double* arr,
-                      int64_t ld_arr, double* prod, int64_t ld_prod, int64_t ncols, int64_t row_shift) {
+                      int64_t ld_arr, double* prod, int64_t ld_prod, int64_t ncols, int64_t row_shift,
+                      unsigned long long* __restrict__ colbits = nullptr, const int* __restrict__ expo = nullptr,
+                      int8_t* __restrict__ digits = nullptr, int64_t ldd = 0, int64_t slice_stride = 0, int nslices = 0) {
     HYP_DYN_SMEM(double, srow);
     const int b = blockIdx.x;
     const int64_t r0 = crow0[b];
@@ -205,7 +212,35 @@ soc_prod_chunk_kernel(const int64_t* __restrict__ crow0, const int* __restrict__
             for (int i = 1; i < d; i++) v[i] = kw * w[i] + kj * v[i];
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < nr; i += blockDim.x) pr[i] = srow[i];
+        if (OUT == 0) {
+            for (int i = threadIdx.x; i < nr; i += blockDim.x) pr[i] = srow[i];
+        } else if (OUT == 1) {
+            __shared__ double smx[8];
+            double mx = 0.0;
+            for (int i = threadIdx.x; i < nr; i += blockDim.x) mx = fmax(mx, fabs(srow[i]));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            if ((threadIdx.x & 31) == 0) smx[threadIdx.x >> 5] = mx;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int w = 1; w < (int)(blockDim.x >> 5); w++) mx = fmax(mx, smx[w]);
+                unsigned long long b;
+                memcpy(&b, &mx, sizeof(double));
+                if (b) atomicMax(colbits + j, b);
+            }
+        } else {
+            const double sc = ldexp(1.0, 7 - expo[j]);
+            int8_t* dcol = digits + j * ldd + (r0 - row_shift);
+            for (int g8 = threadIdx.x; g8 * 8 < nr; g8 += blockDim.x) {
+                double rr[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) rr[u] = (g8 * 8 + u < nr) ? srow[g8 * 8 + u] * sc : 0.0;
+                uint64_t w[8];
+                slice256_pack8(rr, nslices, w);
+                for (int sl = 0; sl < nslices; sl++)
+                    *reinterpret_cast<uint64_t*>(dcol + sl * slice_stride + g8 * 8) = w[sl];
+            }
+        }
         __syncthreads();
     }
 }

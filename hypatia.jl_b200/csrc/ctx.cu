@@ -163,6 +163,7 @@ void free_model(hyp_ctx* ctx) {
     ctx->partial3_doubles = ctx->partial4_doubles = 0;
     dfree(ctx->d_multi);
     ctx->multi_doubles = 0;
+    dfree(ctx->d_colbits);
     ctx->partial2_doubles = 0;
     dfree(ctx->d_stage);
     ctx->stage_doubles = 0;
@@ -803,7 +804,19 @@ int update_lhs_fact(hyp_ctx* ctx) {
         }
         hyp_allgather_inplace(ctx, ctx->d_S, cw * ctx->lds);
     } else {
-    hyp_cones_schur_prepass(ctx);
+    // digit-sliced SYRK on second-order-cone models: pre-pass and slicing fused, H^{1/2} G is never written
+    bool sliced = false;
+    const bool want_i8 = ctx->qloc > 0 && ctx->syrk_mode == 1 && !ctx->d_PG;
+    if (want_i8) {
+        if (!ctx->d_digits) {
+            ctx->ldd = round_up(std::max<int64_t>(ctx->qloc, 16), 16);
+            dalloc(&ctx->d_digits, 8 * ctx->ldd * nmp);
+            dalloc(&ctx->d_expo, nmp);
+            dalloc(&ctx->d_dscale, nmp);
+        }
+        sliced = hyp_cones_prepass_sliced(ctx, ctx->d_digits, ctx->ldd, ctx->ldd * nmp, ctx->d_expo, ctx->d_dscale);
+    }
+    if (!sliced) hyp_cones_schur_prepass(ctx);
     {
         TimeScope ts(ctx, T_SYRK);
         const double* P = ctx->d_HG;
@@ -820,8 +833,9 @@ int update_lhs_fact(hyp_ctx* ctx) {
                 dalloc(&ctx->d_expo, nmp);
                 dalloc(&ctx->d_dscale, nmp);
             }
-            hyp_ozaki_slice(ctx, ctx->d_HG, ctx->ldg, ctx->qloc, nmp, ctx->d_digits, ctx->ldd, ctx->ldd * nmp,
-                            ctx->d_expo, ctx->d_dscale);
+            if (!sliced)
+                hyp_ozaki_slice(ctx, ctx->d_HG, ctx->ldg, ctx->qloc, nmp, ctx->d_digits, ctx->ldd, ctx->ldd * nmp,
+                                ctx->d_expo, ctx->d_dscale);
             hyp_ozaki_syrk(ctx, ctx->d_digits, ctx->ldd, ctx->ldd * nmp, ctx->d_expo, ctx->d_dscale, ctx->qloc, nmp, ctx->d_S,
                            ctx->lds, 1.0, 0.0);
         } else if (ctx->qloc > 0)

@@ -1253,6 +1253,270 @@ ozaki_syrk_quad_kernel(const __grid_constant__ CUtensorMap mapA2, const __grid_c
     }
 }
 
+// ---- CTA-pair kernel with 64-byte k rows (SWIZZLE_64B): the production kernel for radix-256 digits ---------------
+// The pair kernel above moves its operands in 32-byte rows (one MMA K step per row, SWIZZLE_32B): every TMA request is
+// one 32-byte sector of a different column.  Its loads alone (HYP_OZAKI_PROBE=2: no MMAs) need 70 ms on C3 = 28 B per
+// clock per SM, i.e. about one request per clock per SM, while its MMA stream alone (HYP_OZAKI_PROBE=1) needs 40 ms
+// (74 cycles per 256 x 128 x 32 MMA): the request rate of the TMA unit, not the L2 slices (6300 B/clk chip-wide =
+// 42 B/clk/SM) and not the tensor pipe, bounds it.  Here a stage holds TWO MMA K steps in 64-byte rows, so every
+// request carries two sectors of one line: half the requests per byte.  Shared memory: pass 0 (digit sums 0..3, slices
+// 0..3 of both operands) 4 stages x 48 KB, pass 1 (digit sums 4..6, all 7 slices) 2 stages x 84 KB, both rings in the
+// same 192 KB; the producer starts the ring of the next pass when the accumulator-full barrier of the previous one
+// has fired (all MMAs that read the other ring have retired).  Everything else (cta_group::2, M = 256, four int32
+// accumulators in the 512 TMEM columns, warp-uniform unrolled issue loop, epilogue) is the pair kernel.
+constexpr int P64_KB = 64;                                  // k bytes per shared-memory row = 2 MMA K steps
+constexpr int P64_TA = TM * P64_KB;                         // 8 KB: one digit slice of my 128-row A tile
+constexpr int P64_TB = (TN / 2) * P64_KB;                   // 4 KB: one digit slice of my 64-row half of the B tile
+constexpr int P64_NSL = 7;
+constexpr int P64_STAGE0 = 4 * (P64_TA + P64_TB);           // 48 KB
+constexpr int P64_STAGE1 = P64_NSL * (P64_TA + P64_TB);     // 84 KB
+constexpr int P64_STAGES0 = 4, P64_STAGES1 = 2;
+constexpr int P64_RING = P64_STAGES0 * P64_STAGE0 > P64_STAGES1 * P64_STAGE1 ? P64_STAGES0 * P64_STAGE0
+                                                                             : P64_STAGES1 * P64_STAGE1;
+constexpr int P64_SMEM = P64_RING + 1024 + 256;
+
+// K-major SWIZZLE_64B descriptor: rows of 64 B, 8-row groups 512 B apart
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
+
+template <int PASS>
+__device__ __forceinline__ void issue_pass64(uint64_t dbase, uint32_t tmem0, uint32_t idesc, int nst, uint32_t bar_full,
+                                             uint32_t bar_empty, uint32_t bar_tfull, int& stage, uint32_t& phase,
+                                             bool issuer, bool no_mma) {
+    constexpr int NSL = P64_NSL;
+    constexpr int D0 = PASS * 4;
+    constexpr int NS = PASS == 0 ? 4 : NSL;             // A slices in front of the B half slices
+    constexpr int SMAX = NS - 1;
+    constexpr int STAGE = PASS == 0 ? P64_STAGE0 : P64_STAGE1;
+    constexpr int NSTAGES = PASS == 0 ? P64_STAGES0 : P64_STAGES1;
+    for (int it = 0; it < nst; it++) {
+        mbar_wait(bar_full + stage * 8, phase);
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        const uint64_t sd = dbase + (uint64_t)((uint32_t)(stage * STAGE) >> 4);
+        const uint32_t first = it > 0 ? 1u : 0u;
+        if (!no_mma) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {                // the two 32-byte K steps inside the 64-byte rows
+#pragma unroll
+                for (int sl = 0; sl <= SMAX; sl++) {
+                    const int tlo = D0 - sl > 0 ? D0 - sl : 0;
+                    const int thi = (D0 + 3 - sl) < (NSL - 1 - sl) ? (D0 + 3 - sl) : (NSL - 1 - sl);
+#pragma unroll
+                    for (int tt = 0; tt < NSL; tt++) {
+                        if (tt < tlo || tt > thi) continue;
+                        const uint32_t offA = (uint32_t)(sl * P64_TA + h * 32) >> 4;
+                        const uint32_t offB = (uint32_t)(NS * P64_TA + tt * P64_TB + h * 32) >> 4;
+                        const uint32_t accum = (h > 0 || sl > 0) ? 1u : first;
+                        if (issuer) umma_i8_2sm(tmem0 + (uint32_t)((sl + tt - D0) * TN), sd + offA, sd + offB, idesc, accum);
+                    }
+                }
+            }
+        }
+        if (issuer) umma_commit_2sm(bar_empty + stage * 8, 3);              // frees the stage in both CTAs
+        if (++stage == NSTAGES) {
+            stage = 0;
+            phase ^= 1u;
+        }
+    }
+    if (issuer) umma_commit_2sm(bar_tfull, 3);                               // accumulators ready in both CTAs
+}
+
+__global__ void __launch_bounds__(I8_THREADS, 1)
+ozaki_syrk_pair64_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid_constant__ CUtensorMap mapA7,
+                         const __grid_constant__ CUtensorMap mapB4, const __grid_constant__ CUtensorMap mapB7,
+                         const int2* __restrict__ pairs, int n_pairs, int k0, int nst,
+                         const double* __restrict__ dscale, int64_t ncols, double* __restrict__ C, int64_t ldc,
+                         double alpha, double beta, int probe) {
+    // probe (HYP_OZAKI_PROBE; results are garbage, timing only): 1 = no TMA loads, 2 = no MMAs (loads + epilogue only)
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint32_t s_tmem;
+    const uint32_t base = smem_u32(smem_raw);
+    const uint32_t stg = (base + 1023u) & ~1023u;
+    const uint32_t bar_full0 = stg + P64_RING;
+    const uint32_t bar_empty0 = bar_full0 + P64_STAGES0 * 8;
+    const uint32_t bar_full1 = bar_empty0 + P64_STAGES0 * 8;
+    const uint32_t bar_empty1 = bar_full1 + P64_STAGES1 * 8;
+    const uint32_t bar_tfull = bar_empty1 + P64_STAGES1 * 8;
+    const uint32_t bar_tempty = bar_tfull + 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t crank, cid, ncl;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(cid));
+    asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(ncl));
+    const bool leader = crank == 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < P64_STAGES0; s++) {
+            mbar_init(bar_full0 + s * 8, 1);     // leader: its own expect_tx arrival (+ the bytes of both CTAs)
+            mbar_init(bar_empty0 + s * 8, 1);    // one multicast commit from the leader
+        }
+        for (int s = 0; s < P64_STAGES1; s++) {
+            mbar_init(bar_full1 + s * 8, 1);
+            mbar_init(bar_empty1 + s * 8, 1);
+        }
+        mbar_init(bar_tfull, 1);
+        mbar_init(bar_tempty, 8);                // 4 epilogue warps of each CTA (used in the leader only)
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                     "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem0 = s_tmem;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): my A tile and my half of the B tile =====
+        if (lane == 0) {
+            int stage[2] = {0, 0};
+            uint32_t phase[2] = {0, 0};
+            uint32_t item = 0;
+            for (int pi = (int)cid; pi < n_pairs; pi += (int)ncl) {
+                const int2 pr = pairs[pi];
+                const int tI = 2 * pr.x + (int)crank, tJ = pr.y;
+                for (int pass = 0; pass < 2; pass++, item++) {
+                    // the two rings share their shared memory: the previous item's MMAs must all have retired
+                    if (item > 0) mbar_wait(bar_tfull, (item - 1) & 1u);
+                    const int ns = pass == 0 ? 4 : P64_NSL;
+                    const int nstages = pass == 0 ? P64_STAGES0 : P64_STAGES1;
+                    const uint32_t sbytes = pass == 0 ? P64_STAGE0 : P64_STAGE1;
+                    const uint32_t bfull = pass == 0 ? bar_full0 : bar_full1;
+                    const uint32_t bempty = pass == 0 ? bar_empty0 : bar_empty1;
+                    const CUtensorMap* ma = pass == 0 ? &mapA4 : &mapA7;
+                    const CUtensorMap* mb = pass == 0 ? &mapB4 : &mapB7;
+                    int st = stage[pass];
+                    uint32_t ph = phase[pass];
+                    for (int it = 0; it < nst; it++) {
+                        mbar_wait(bempty + st * 8, ph ^ 1u);
+                        if (probe == 1) {
+                            if (leader) mbar_arrive(bfull + st * 8);
+                        } else {
+                            const uint32_t full_leader = mapa_u32(bfull + st * 8, 0);
+                            if (leader) mbar_expect_tx(bfull + st * 8, 2u * sbytes);
+                            const uint32_t dst = stg + st * sbytes;
+                            const int kc = k0 + it * P64_KB;
+                            tma_load_3d_2sm(dst, ma, kc, tI * TM, 0, full_leader);
+                            tma_load_3d_2sm(dst + ns * P64_TA, mb, kc, tJ * TN + (int)crank * (TN / 2), 0, full_leader);
+                        }
+                        if (++st == nstages) {
+                            st = 0;
+                            ph ^= 1u;
+                        }
+                    }
+                    stage[pass] = st;
+                    phase[pass] = ph;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA only): warp-uniform issue loop, one elected lane issues =====
+        if (leader) {
+            const uint32_t idesc = make_idesc_i8(2 * TM, TN);
+            const uint64_t dbase = make_desc_sw64(stg);
+            const bool issuer = elect_one_sync();
+            int stage0 = 0, stage1 = 0;
+            uint32_t phase0 = 0, phase1 = 0, item = 0;
+            for (int pi = (int)cid; pi < n_pairs; pi += (int)ncl) {
+                for (int pass = 0; pass < 2; pass++, item++) {
+                    if (item > 0) mbar_wait(bar_tempty, (item - 1) & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    if (pass == 0)
+                        issue_pass64<0>(dbase, tmem0, idesc, nst, bar_full0, bar_empty0, bar_tfull, stage0, phase0, issuer, probe == 2);
+                    else
+                        issue_pass64<1>(dbase, tmem0, idesc, nst, bar_full1, bar_empty1, bar_tfull, stage1, phase1, issuer, probe == 2);
+                }
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs, own TMEM half) =====
+        const int lg = warp & 3;
+        const uint32_t tempty_leader = mapa_u32(bar_tempty, 0);
+        uint32_t item = 0;
+        for (int pi = (int)cid; pi < n_pairs; pi += (int)ncl) {
+            const int2 pr = pairs[pi];
+            const int tI = 2 * pr.x + (int)crank, tJ = pr.y;
+            const int64_t row = (int64_t)tI * TM + lg * 32 + lane;
+            const bool store = tI <= tJ;
+            const double rs = (row < ncols) ? alpha * dscale[row] : 0.0;
+            for (int pass = 0; pass < 2; pass++, item++) {
+                mbar_wait(bar_tfull, item & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                const int d0 = pass * 4;
+                // digit sum d has weight 2^-(14 + 8 d); the fourth accumulator of pass 1 (d = 7) was never written
+                const double g0 = ldexp(1.0, -(14 + 8 * d0)), g1 = ldexp(1.0, -(14 + 8 * (d0 + 1))),
+                             g2 = ldexp(1.0, -(14 + 8 * (d0 + 2))), g3 = pass == 0 ? ldexp(1.0, -(14 + 8 * 3)) : 0.0;
+#pragma unroll 1
+                for (int c0 = 0; c0 < TN; c0 += 16) {
+                    uint32_t v[4][16];
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        const uint32_t taddr = tmem0 + ((uint32_t)(lg * 32) << 16) + (uint32_t)(g * TN + c0);
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                            : "=r"(v[g][0]), "=r"(v[g][1]), "=r"(v[g][2]), "=r"(v[g][3]), "=r"(v[g][4]),
+                              "=r"(v[g][5]), "=r"(v[g][6]), "=r"(v[g][7]), "=r"(v[g][8]), "=r"(v[g][9]),
+                              "=r"(v[g][10]), "=r"(v[g][11]), "=r"(v[g][12]), "=r"(v[g][13]), "=r"(v[g][14]),
+                              "=r"(v[g][15])
+                            : "r"(taddr));
+                    }
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (store && row < ncols) {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            const int64_t col = (int64_t)tJ * TN + c0 + j;
+                            if (col < ncols) {
+                                double x = (double)(int32_t)v[3][j] * g3;
+                                x += (double)(int32_t)v[2][j] * g2;
+                                x += (double)(int32_t)v[1][j] * g1;
+                                x += (double)(int32_t)v[0][j] * g0;
+                                x *= rs * dscale[col];
+                                double* cp = C + row + col * ldc;
+                                if (pass == 0) *cp = (beta == 0.0) ? x : (x + beta * *cp);
+                                else *cp += x;
+                            }
+                        }
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(tempty_leader);
+            }
+        }
+    }
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem0), "r"(512));
+    }
+}
+
+// digit-slice tensor map with 64-byte k rows (SWIZZLE_64B) for the kernel above
+void make_map_digits64(CUtensorMap* map, const int8_t* base, int64_t K, int64_t cols, int64_t ldd,
+                       int64_t slice_stride, int nslices, int box_slices, int box_rows) {
+    if (((uintptr_t)base & 15) || (ldd & 15) || (slice_stride & 15))
+        throw HypError{"digit slices must be 16-byte aligned with ld % 16 == 0"};
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)cols, (cuuint64_t)nslices};
+    cuuint64_t strides[2] = {(cuuint64_t)ldd, (cuuint64_t)slice_stride};
+    cuuint32_t box[3] = {P64_KB, (cuuint32_t)box_rows, (cuuint32_t)box_slices};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw HypError{"cuTensorMapEncodeTiled (digit slices, 64-byte rows) failed"};
+}
+
 void make_map_digits(CUtensorMap* map, const int8_t* base, int64_t K, int64_t cols, int64_t ldd,
                      int64_t slice_stride, int nslices, int box_slices, int box_rows = TM) {
     if (((uintptr_t)base & 15) || (ldd & 15) || (slice_stride & 15))
@@ -1367,6 +1631,8 @@ static int ozaki_radix() {
     return r;
 }
 
+int hyp_ozaki_radix() { return ozaki_radix(); }
+
 void hyp_ozaki_slice(hyp_ctx* ctx, const double* A, int64_t lda, int64_t K, int64_t ncols, int8_t* digits,
                      int64_t ldd, int64_t slice_stride, int* expo, double* dscale) {
     if (K <= 0 || ncols <= 0) return;
@@ -1435,8 +1701,29 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
         const char* e = getenv("HYP_OZAKI_CLUSTER");
         // 0: one CTA per tile; 1: 2 x 2 clusters with TMA multicast; 2 (default): CTA pairs, cta_group::2;
         // 3: quads = two CTA pairs sharing their A tiles by multicast
-        use_cluster = e ? (e[0] - '0') : 2;
-        if (use_cluster < 0 || use_cluster > 3) use_cluster = 2;
+        // 4 (default with radix-256 digits): CTA pairs with 64-byte k rows
+        use_cluster = e ? (e[0] - '0') : (ozaki_radix() == 256 ? 4 : 2);
+        if (use_cluster < 0 || use_cluster > 4) use_cluster = 2;
+        if (use_cluster == 4 && ozaki_radix() != 256) use_cluster = 2;
+        if (use_cluster == 4) {
+            CUDA_TRY(cudaFuncSetAttribute(ozaki_syrk_pair64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P64_SMEM));
+            cudaLaunchConfig_t q = {};
+            q.gridDim = dim3(2 * 128);
+            q.blockDim = dim3(I8_THREADS);
+            q.dynamicSmemBytes = P64_SMEM;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            q.attrs = at;
+            q.numAttrs = 1;
+            if (cudaOccupancyMaxActiveClusters(&max_clusters, ozaki_syrk_pair64_kernel, &q) != cudaSuccess ||
+                max_clusters < 1) {
+                cudaGetLastError();
+                use_cluster = 2;
+            }
+        }
         if (use_cluster == 3) {
             CUDA_TRY(cudaFuncSetAttribute(ozaki_syrk_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZP_SMEM));
             cudaLaunchConfig_t q = {};
@@ -1552,7 +1839,7 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
             ctx->launches++;
             continue;
         }
-        if (use_cluster == 2) {
+        if (use_cluster == 2 || use_cluster == 4) {
             // (P, J): tile rows 2P, 2P+1 of tile column J, for 2P <= J.  Two orders of the list (the clusters take
             // consecutive entries, so the order decides which operand panel stays in L2):
             //   row by row (default): the 256-row A panel of row pair P (30 MB per 16 k rows) is L2-resident and the
@@ -1596,6 +1883,31 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
                 CUDA_TRY(cudaMemcpyAsync(d_pairs, pl.data(), pl.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
                 CUDA_TRY(cudaStreamSynchronize(ctx->stream));
                 pcache.push_back({nt, {d_pairs, n_pairs}});
+            }
+            if (use_cluster == 4) {
+                CUtensorMap mA4, mA7, mB4, mB7;
+                make_map_digits64(&mA4, digits, K, ncols, ldd, slice_stride, OZ_S, 4, TM);
+                make_map_digits64(&mA7, digits, K, ncols, ldd, slice_stride, OZ_S, P64_NSL, TM);
+                make_map_digits64(&mB4, digits, K, ncols, ldd, slice_stride, OZ_S, 4, TN / 2);
+                make_map_digits64(&mB7, digits, K, ncols, ldd, slice_stride, OZ_S, P64_NSL, TN / 2);
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(2 * std::min(n_pairs, max_clusters));
+                cfg.blockDim = dim3(I8_THREADS);
+                cfg.dynamicSmemBytes = P64_SMEM;
+                cfg.stream = ctx->stream;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = 2;
+                at[0].val.clusterDim.y = 1;
+                at[0].val.clusterDim.z = 1;
+                cfg.attrs = at;
+                cfg.numAttrs = 1;
+                const int probe = getenv("HYP_OZAKI_PROBE") ? atoi(getenv("HYP_OZAKI_PROBE")) : 0;   // tools/syrk_probe.py
+                CUDA_TRY(cudaLaunchKernelEx(&cfg, ozaki_syrk_pair64_kernel, mA4, mA7, mB4, mB7, (const int2*)d_pairs, n_pairs,
+                                            (int)k0, (int)ceil_div(klen, P64_KB), dscale, ncols, C, ldc, alpha,
+                                            k0 == 0 ? beta : 1.0, probe));
+                ctx->launches++;
+                continue;
             }
             CUtensorMap mapB4, mapB8, mapA8;
             make_map_digits(&mapB4, digits, K, ncols, ldd, slice_stride, OZ_S, 4, TN / 2);

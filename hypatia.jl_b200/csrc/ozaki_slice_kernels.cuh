@@ -65,6 +65,55 @@ static __global__ void slice_kernel(int64_t K, int64_t ncols, const double* __re
     }
 }
 
+
+// Eight consecutive rows r[0..7] (already multiplied by 2^(7 - e)) -> one packed 8-byte word per radix-256 digit slice
+// (the arithmetic of slice256_kernel below, shared with the fused Schur pre-pass of cones_vec_kernels.cuh).
+__device__ __forceinline__ void slice256_pack8(const double (&rr)[8], int nslices, uint64_t (&w)[8]) {
+#pragma unroll
+    for (int s = 0; s < 8; s++) w[s] = 0;
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        double r = rr[u];                                    // |r| <= 127
+        int dg[8];
+#pragma unroll
+        for (int s = 0; s < 8; s++) {
+            if (s < nslices) {
+                const double d = rint(r);
+                dg[s] = (int)d;
+                r = (r - d) * 256.0;                         // exact: |r - d| <= 0.5
+            } else {
+                dg[s] = 0;
+            }
+        }
+#pragma unroll
+        for (int s = 7; s >= 1; s--)
+            if (dg[s] >= 128) {
+                dg[s] -= 256;
+                dg[s - 1] += 1;
+            }
+#pragma unroll
+        for (int s = 0; s < 8; s++) w[s] |= (uint64_t)(uint8_t)(int8_t)dg[s] << (8 * u);
+    }
+}
+
+// expo / dscale of every column from the bit patterns of the column maxima (non-negative doubles order like their
+// bit patterns, so the maxima are collected with atomicMax on 64-bit words); same rule as colmax_kernel
+static __global__ void expo_from_bits_kernel(int64_t ncols, const unsigned long long* __restrict__ bits,
+                                             int* __restrict__ expo, double* __restrict__ dscale, int radix256) {
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < ncols; j += (int64_t)gridDim.x * blockDim.x) {
+        double mx;
+        const unsigned long long b = bits[j];
+        memcpy(&mx, &b, sizeof(double));
+        int e = 0;
+        if (mx > 0.0) {
+            const double f = frexp(mx, &e);
+            if (radix256 && f > 127.0 / 128.0) e++;
+        }
+        expo[j] = e;
+        if (dscale) dscale[j] = ldexp(1.0, e);
+    }
+}
+
 // Radix-256 variant: balanced signed digits d_s in [-128, 127], a = 2^e sum_s 2^-(7 + 8 s) d_s.  rint can produce
 // +128 (remainder >= 0.498): a backward carry pass turns it into -128 and adds one to the next higher digit; the
 // leading digit cannot overflow because |a| 2^(7 - e) <= 127.  Seven such digits carry the same 56 bits as eight
@@ -78,31 +127,14 @@ static __global__ void slice256_kernel(int64_t K, int64_t ncols, const double* _
         const double* col = A + j * lda;
         for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < K8;
              g += (int64_t)gridDim.x * blockDim.x) {
-            uint64_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            double rr[8];
 #pragma unroll
             for (int u = 0; u < 8; u++) {
                 const int64_t k = g * 8 + u;
-                double r = (k < K) ? col[k] * sc : 0.0;          // |r| <= 127
-                int dg[8];
-#pragma unroll
-                for (int s = 0; s < 8; s++) {
-                    if (s < nslices) {
-                        const double d = rint(r);
-                        dg[s] = (int)d;
-                        r = (r - d) * 256.0;                     // exact: |r - d| <= 0.5
-                    } else {
-                        dg[s] = 0;
-                    }
-                }
-#pragma unroll
-                for (int s = 7; s >= 1; s--)
-                    if (dg[s] >= 128) {
-                        dg[s] -= 256;
-                        dg[s - 1] += 1;
-                    }
-#pragma unroll
-                for (int s = 0; s < 8; s++) w[s] |= (uint64_t)(uint8_t)(int8_t)dg[s] << (8 * u);
+                rr[u] = (k < K) ? col[k] * sc : 0.0;            // |r| <= 127
             }
+            uint64_t w[8];
+            slice256_pack8(rr, nslices, w);
             for (int s = 0; s < nslices; s++)
                 *reinterpret_cast<uint64_t*>(D + s * slice_stride + g * 8 + j * ldd) = w[s];
         }

@@ -78,6 +78,12 @@ static inline double __shfl_sync(unsigned, double v, int lane) {
 
 static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 static inline int atomicAdd(int* addr, int val) { return __atomic_fetch_add(addr, val, __ATOMIC_SEQ_CST); }
+static inline unsigned long long atomicMax(unsigned long long* addr, unsigned long long val) {
+    unsigned long long old = __atomic_load_n(addr, __ATOMIC_SEQ_CST);
+    while (old < val && !__atomic_compare_exchange_n(addr, &old, val, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {
+    }
+    return old;
+}
 static inline double __ldcg(const double* p) { return *p; }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
