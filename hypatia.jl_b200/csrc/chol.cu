@@ -43,13 +43,117 @@ void set_panel_attr() {
 
 }  // namespace
 
+// ---- blocked Cholesky whose depth-512 trailing updates run on the 5th-generation tensor cores --------------------------
+// The FP64 DMMA pipe bounds the task-graph kernel (chol_dag.cu): 333 GFLOP at 35 TFLOP/s are 9.5 ms for m = 10000 before
+// any dependency stall (measured 16.9 ms).  81 % of those flops are the depth-512 updates of the trailing matrix
+// A22 -= U12' U12, a SYRK - exactly what the digit-sliced tcgen05 kernel of the Schur assembly (ozaki.cu) computes at
+// 2.5 x the DMMA rate: the finished block row U12 (512 x rest) is cut into seven int8 digit slices (one pass, 75 MB) and
+// ozaki_syrk_pair64_kernel subtracts the 28 exact digit-pair products from the trailing tiles (alpha = -1, beta = 1).
+// What stays on CUDA cores / DMMA is the latency chain: the 128-wide panels of the 512 x 512 diagonal block and the
+// triangular solves of the block row (products with the inverted diagonal blocks).
+// Two streams.  chain: diag(b) -> block row over the NEXT block's columns -> DMMA update of the next diagonal block ->
+// diag(b + 1) ...; bulk: block row over the far columns -> slicing -> SYRK part a (tile rows of the next two blocks, the
+// chain waits for it before its near block row) -> SYRK part b (the rest).  The bulk grids leave 8 SMs to the chain.
+static bool potrf_upper_i8(hyp_ctx* ctx, double* A, int64_t lda, int64_t m, double* d_dinv, int* d_info) {
+    const int64_t OB = 512;
+    if (m <= 2 * OB || !hyp_ozaki_pair64_ready(ctx)) return false;
+    TimeScope ts(ctx, T_POTRF);
+    set_panel_attr();
+    cudaStream_t bulk = ctx->stream, chain = ctx->stream2;
+    // digit slices of one block row: 7 x 512 x m bytes, and the column scales
+    if (ctx->chol_digits_cols < m) {
+        CUDA_TRY(cudaStreamSynchronize(bulk));
+        if (ctx->d_chol_digits) cudaFree(ctx->d_chol_digits);
+        if (ctx->d_chol_dscale) cudaFree(ctx->d_chol_dscale);
+        ctx->d_chol_digits = nullptr;
+        ctx->d_chol_dscale = nullptr;
+        CUDA_TRY(cudaMalloc((void**)&ctx->d_chol_digits, (size_t)7 * OB * m));
+        CUDA_TRY(cudaMalloc((void**)&ctx->d_chol_dscale, (size_t)m * sizeof(double)));
+        ctx->chol_digits_cols = m;
+    }
+    const int64_t ldd = OB, sstride = OB * ctx->chol_digits_cols;
+    CUDA_TRY(cudaMemsetAsync(d_info, 0, sizeof(int), bulk));
+    auto on = [&](cudaStream_t s, int cap) {
+        ctx->launch_stream = s;
+        ctx->grid_cap = cap;
+    };
+    const int cap = std::max(2, (ctx->sm_count - 8) & ~1);
+    // profiling aid (tools/potrf_probe.py; results are garbage): 1 = no digit-sliced updates, 2 = chain stream only,
+    // 3 = bulk stream only (no panels / in-block products)
+    const char* pm = getenv("HYP_POTRF_MODE");
+    const int probe = pm ? atoi(pm) : 0;
+    // block row of outer block [K0, Kend) over the columns [c0, c0 + nc): U = U11^-T A, panel by panel
+    auto block_row = [&](int64_t K0, int64_t Kend, int64_t c0, int64_t nc) {
+        for (int64_t k0 = K0; k0 < Kend; k0 += NB) {
+            const int64_t nb = std::min<int64_t>(NB, m - k0);
+            double* Ar = A + k0 + c0 * lda;                       // rows of the panel
+            hyp_gemm_tn(ctx, d_dinv + (k0 / NB) * NB * NB, NB, Ar, lda, nb, nb, nc, Ar, lda, 1.0, 0.0);
+            const int64_t rin = Kend - (k0 + nb);
+            if (rin > 0)                                          // rows below the panel inside the outer block
+                hyp_gemm_tn(ctx, A + k0 + (k0 + nb) * lda, lda, Ar, lda, nb, rin, nc, A + (k0 + nb) + c0 * lda, lda, -1.0, 1.0);
+        }
+    };
+    CUDA_TRY(cudaEventRecord(ctx->ev_bulk[0], bulk));
+    CUDA_TRY(cudaStreamWaitEvent(chain, ctx->ev_bulk[0], 0));
+    int b = 0;
+    for (int64_t K0 = 0; K0 < m; K0 += OB, b++) {
+        const int64_t Kend = std::min(K0 + OB, m);
+        const int64_t rest = m - Kend, kd = Kend - K0;
+        // ---- chain: the diagonal block ----
+        on(chain, 0);
+        for (int64_t k0 = K0; k0 < Kend && probe != 3; k0 += NB) {
+            const int64_t nb = std::min<int64_t>(NB, m - k0);
+            panel_kernel<true><<<1, PT, NB * LDU * 8, chain>>>(A, lda, m, k0 / NB, d_dinv, d_info);
+            ctx->launches++;
+            const int64_t rin = Kend - (k0 + nb);
+            if (rin > 0) {
+                double* A12 = A + k0 + (k0 + nb) * lda;
+                hyp_gemm_tn(ctx, d_dinv + (k0 / NB) * NB * NB, NB, A12, lda, nb, nb, rin, A12, lda, 1.0, 0.0);
+                hyp_atb_upper(ctx, A12, lda, A12, lda, nb, rin, A + (k0 + nb) + (k0 + nb) * lda, lda, -1.0, 1.0);
+            }
+        }
+        CUDA_TRY(cudaEventRecord(ctx->ev_chain[b & 1], chain));
+        if (rest <= 0) break;
+        const int64_t near = std::min(OB, rest);
+        double* P = A + K0 + Kend * lda;                           // the block row right of the block (kd x rest)
+        double* T = A + Kend + Kend * lda;                         // the trailing matrix
+        // ---- chain: block row over the next block's columns (they carry block b - 1's update from SYRK part a) ----
+        if (b >= 1) CUDA_TRY(cudaStreamWaitEvent(chain, ctx->ev_bulk[(b - 1) & 1], 0));
+        if (probe != 3) block_row(K0, Kend, Kend, near);
+        CUDA_TRY(cudaEventRecord(ctx->ev_near[b & 1], chain));
+        if (probe != 3) hyp_atb_upper(ctx, P, lda, P, lda, kd, near, T, lda, -1.0, 1.0);
+        // ---- bulk: far block row, slicing, digit-sliced trailing update ----
+        on(bulk, cap);
+        CUDA_TRY(cudaStreamWaitEvent(bulk, ctx->ev_chain[b & 1], 0));
+        if (rest > near && probe != 2) {
+            block_row(K0, Kend, Kend + near, rest - near);
+            CUDA_TRY(cudaStreamWaitEvent(bulk, ctx->ev_near[b & 1], 0));
+            hyp_ozaki_slice_short(ctx, P, lda, kd, rest, ctx->d_chol_digits, ldd, sstride, ctx->d_chol_dscale);
+            if (probe != 1)
+                hyp_ozaki_syrk_rows(ctx, ctx->d_chol_digits, ldd, sstride, ctx->d_chol_dscale, kd, rest, T, lda, -1.0, 1.0, 0, 4,
+                                    (int)(near / NB));
+        }
+        CUDA_TRY(cudaEventRecord(ctx->ev_bulk[b & 1], bulk));
+        if (rest > near && probe != 2 && probe != 1)
+            hyp_ozaki_syrk_rows(ctx, ctx->d_chol_digits, ldd, sstride, ctx->d_chol_dscale, kd, rest, T, lda, -1.0, 1.0, 4, -1, 0);
+    }
+    // the caller's stream continues after the last diagonal block
+    CUDA_TRY(cudaStreamWaitEvent(bulk, ctx->ev_chain[b & 1], 0));
+    on(nullptr, 0);
+    CUDA_TRY(cudaGetLastError());
+    return true;
+}
+
 void hyp_potrf_upper(hyp_ctx* ctx, double* A, int64_t lda, int64_t m, double* d_dinv, int* d_info) {
     if (m <= 0) return;
-    // default: the task-graph kernel (chol_dag.cu), one launch for the whole factorisation;
-    // HYP_POTRF=stream keeps the two-stream version below (also the fallback for unaligned input)
+    // default for large matrices: tcgen05 trailing updates (potrf_upper_i8 above); otherwise, and with HYP_POTRF=dag, the
+    // task-graph kernel (chol_dag.cu), one launch for the whole factorisation; HYP_POTRF=stream keeps the two-stream
+    // FP64-DMMA version below (also the fallback for unaligned input)
     {
         const char* pv = getenv("HYP_POTRF");
         const bool want_stream = pv && !strcmp(pv, "stream");
+        const bool want_dag = pv && !strcmp(pv, "dag");
+        if (!want_stream && !want_dag && potrf_upper_i8(ctx, A, lda, m, d_dinv, d_info)) return;
         if (!want_stream && hyp_potrf_upper_dag(ctx, A, lda, m, d_dinv, d_info)) return;
     }
     TimeScope ts(ctx, T_POTRF);

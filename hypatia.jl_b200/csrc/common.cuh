@@ -156,7 +156,10 @@ struct hyp_ctx {
     cudaStream_t stream2 = nullptr;    // side stream of the Cholesky look-ahead chain
     cudaStream_t launch_stream = nullptr;   // stream the GEMM / panel launch helpers use (stream or stream2)
     int grid_cap = 0;                  // > 0: persistent GEMM grids leave SMs free for the side stream
-    cudaEvent_t ev_chain[2] = {nullptr, nullptr}, ev_bulk[2] = {nullptr, nullptr};
+    cudaEvent_t ev_chain[2] = {nullptr, nullptr}, ev_bulk[2] = {nullptr, nullptr}, ev_near[2] = {nullptr, nullptr};
+    int8_t* d_chol_digits = nullptr;   // digit slices of one 512-row block row of the Cholesky (chol.cu, potrf_upper_i8)
+    double* d_chol_dscale = nullptr;
+    int64_t chol_digits_cols = 0;
     std::string last_error;
 
     // ---- model ----
@@ -383,6 +386,12 @@ void hyp_gemm_simple(hyp_ctx* ctx, bool transA, bool transB, int64_t M, int64_t 
 int hyp_ozaki_radix();
 // fused Schur pre-pass + digit slicing for second-order-cone models (cones.cu); false = not applicable
 bool hyp_cones_prepass_sliced(hyp_ctx* ctx, int8_t* digits, int64_t ldd, int64_t slice_stride, int* expo, double* dscale);
+bool hyp_ozaki_pair64_ready(hyp_ctx* ctx);
+void hyp_ozaki_slice_short(hyp_ctx* ctx, const double* A, int64_t lda, int64_t K, int64_t ncols, int8_t* digits, int64_t ldd,
+                           int64_t slice_stride, double* dscale);
+void hyp_ozaki_syrk_rows(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t slice_stride, const double* dscale,
+                         int64_t K, int64_t ncols, double* C, int64_t ldc, double alpha, double beta, int p_lo, int p_hi,
+                         int skip_diag);
 void hyp_ozaki_slice(hyp_ctx* ctx, const double* A, int64_t lda, int64_t K, int64_t ncols, int8_t* digits,
                      int64_t ldd, int64_t slice_stride, int* expo, double* dscale);
 void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t slice_stride, const int* expo,

@@ -1097,6 +1097,7 @@ hyp_ctx* hyp_create(int device) {
     for (int i = 0; i < 2; i++) {
         cudaEventCreateWithFlags(&ctx->ev_chain[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_bulk[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_near[i], cudaEventDisableTiming);
     }
     return ctx;
 }
@@ -1114,7 +1115,10 @@ void hyp_destroy(hyp_ctx* ctx) {
     for (int i = 0; i < 2; i++) {
         if (ctx->ev_chain[i]) cudaEventDestroy(ctx->ev_chain[i]);
         if (ctx->ev_bulk[i]) cudaEventDestroy(ctx->ev_bulk[i]);
+        if (ctx->ev_near[i]) cudaEventDestroy(ctx->ev_near[i]);
     }
+    if (ctx->d_chol_digits) cudaFree(ctx->d_chol_digits);
+    if (ctx->d_chol_dscale) cudaFree(ctx->d_chol_dscale);
     if (ctx->d_dag_ver) cudaFree(ctx->d_dag_ver);
     if (ctx->d_dag_dbg) cudaFree(ctx->d_dag_dbg);
     cudaStreamDestroy(ctx->stream2);

@@ -1268,12 +1268,18 @@ constexpr int P64_KB = 64;                                  // k bytes per share
 constexpr int P64_TA = TM * P64_KB;                         // 8 KB: one digit slice of my 128-row A tile
 constexpr int P64_TB = (TN / 2) * P64_KB;                   // 4 KB: one digit slice of my 64-row half of the B tile
 constexpr int P64_NSL = 7;
-constexpr int P64_STAGE0 = 4 * (P64_TA + P64_TB);           // 48 KB
-constexpr int P64_STAGE1 = P64_NSL * (P64_TA + P64_TB);     // 84 KB
-constexpr int P64_STAGES0 = 4, P64_STAGES1 = 2;
-constexpr int P64_RING = P64_STAGES0 * P64_STAGE0 > P64_STAGES1 * P64_STAGE1 ? P64_STAGES0 * P64_STAGE0
-                                                                             : P64_STAGES1 * P64_STAGE1;
+// L1 = number of digit sums collected by pass 0 (template parameter of the kernel): pass 0 needs the slices 0 .. L1 - 1 of
+// both operands, pass 1 (digit sums L1 .. 6, at most four accumulators: L1 >= 3) all seven.  L1 = 3 (default) moves
+// 3 + 7 = 10 slices per k step and output tile, L1 = 4 (the first version, HYP_OZAKI_SPLIT=4) 4 + 7 = 11.
+constexpr int P64_UNIT = P64_TA + P64_TB;                   // 12 KB: one slice of my A tile and of my B half tile
+constexpr int P64_STAGE1 = P64_NSL * P64_UNIT;              // 84 KB
+constexpr int P64_STAGES1 = 2;
+constexpr int P64_RING = 192 * 1024;
+constexpr int P64_MAXST0 = 5;                               // barrier slots reserved for the pass-0 ring
 constexpr int P64_SMEM = P64_RING + 1024 + 256;
+__host__ __device__ constexpr int p64_stage0(int L1) { return L1 * P64_UNIT; }              // 36 / 48 KB
+__host__ __device__ constexpr int p64_stages0(int L1) { return P64_RING / (L1 * P64_UNIT) > P64_MAXST0 ? P64_MAXST0 : P64_RING / (L1 * P64_UNIT); }
+static_assert(P64_STAGES1 * P64_STAGE1 <= P64_RING, "pass-1 ring");
 
 // K-major SWIZZLE_64B descriptor: rows of 64 B, 8-row groups 512 B apart
 __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr) {
@@ -1286,16 +1292,18 @@ __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr) {
     return d;
 }
 
-template <int PASS>
+template <int PASS, int L1>
 __device__ __forceinline__ void issue_pass64(uint64_t dbase, uint32_t tmem0, uint32_t idesc, int nst, uint32_t bar_full,
                                              uint32_t bar_empty, uint32_t bar_tfull, int& stage, uint32_t& phase,
                                              bool issuer, bool no_mma) {
     constexpr int NSL = P64_NSL;
-    constexpr int D0 = PASS * 4;
-    constexpr int NS = PASS == 0 ? 4 : NSL;             // A slices in front of the B half slices
+    constexpr int D0 = PASS * L1;                       // first digit sum of the pass
+    constexpr int NACC = PASS == 0 ? L1 : NSL - L1;     // accumulators (digit sums) of the pass
+    constexpr int NS = PASS == 0 ? L1 : NSL;            // A slices in front of the B half slices
     constexpr int SMAX = NS - 1;
-    constexpr int STAGE = PASS == 0 ? P64_STAGE0 : P64_STAGE1;
-    constexpr int NSTAGES = PASS == 0 ? P64_STAGES0 : P64_STAGES1;
+    constexpr int STAGE = PASS == 0 ? p64_stage0(L1) : P64_STAGE1;
+    constexpr int NSTAGES = PASS == 0 ? p64_stages0(L1) : P64_STAGES1;
+    static_assert(NACC <= 4, "four 128-column accumulators fill the tensor memory");
     for (int it = 0; it < nst; it++) {
         mbar_wait(bar_full + stage * 8, phase);
         asm volatile("tcgen05.fence::after_thread_sync;");
@@ -1307,7 +1315,7 @@ __device__ __forceinline__ void issue_pass64(uint64_t dbase, uint32_t tmem0, uin
 #pragma unroll
                 for (int sl = 0; sl <= SMAX; sl++) {
                     const int tlo = D0 - sl > 0 ? D0 - sl : 0;
-                    const int thi = (D0 + 3 - sl) < (NSL - 1 - sl) ? (D0 + 3 - sl) : (NSL - 1 - sl);
+                    const int thi = (D0 + NACC - 1 - sl) < (NSL - 1 - sl) ? (D0 + NACC - 1 - sl) : (NSL - 1 - sl);
 #pragma unroll
                     for (int tt = 0; tt < NSL; tt++) {
                         if (tt < tlo || tt > thi) continue;
@@ -1328,6 +1336,7 @@ __device__ __forceinline__ void issue_pass64(uint64_t dbase, uint32_t tmem0, uin
     if (issuer) umma_commit_2sm(bar_tfull, 3);                               // accumulators ready in both CTAs
 }
 
+template <int L1>
 __global__ void __launch_bounds__(I8_THREADS, 1)
 ozaki_syrk_pair64_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid_constant__ CUtensorMap mapA7,
                          const __grid_constant__ CUtensorMap mapB4, const __grid_constant__ CUtensorMap mapB7,
@@ -1339,9 +1348,10 @@ ozaki_syrk_pair64_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid
     __shared__ uint32_t s_tmem;
     const uint32_t base = smem_u32(smem_raw);
     const uint32_t stg = (base + 1023u) & ~1023u;
+    constexpr int P64_STAGES0 = p64_stages0(L1), P64_STAGE0 = p64_stage0(L1);
     const uint32_t bar_full0 = stg + P64_RING;
-    const uint32_t bar_empty0 = bar_full0 + P64_STAGES0 * 8;
-    const uint32_t bar_full1 = bar_empty0 + P64_STAGES0 * 8;
+    const uint32_t bar_empty0 = bar_full0 + P64_MAXST0 * 8;
+    const uint32_t bar_full1 = bar_empty0 + P64_MAXST0 * 8;
     const uint32_t bar_empty1 = bar_full1 + P64_STAGES1 * 8;
     const uint32_t bar_tfull = bar_empty1 + P64_STAGES1 * 8;
     const uint32_t bar_tempty = bar_tfull + 8;
@@ -1388,7 +1398,7 @@ ozaki_syrk_pair64_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid
                 for (int pass = 0; pass < 2; pass++, item++) {
                     // the two rings share their shared memory: the previous item's MMAs must all have retired
                     if (item > 0) mbar_wait(bar_tfull, (item - 1) & 1u);
-                    const int ns = pass == 0 ? 4 : P64_NSL;
+                    const int ns = pass == 0 ? L1 : P64_NSL;
                     const int nstages = pass == 0 ? P64_STAGES0 : P64_STAGES1;
                     const uint32_t sbytes = pass == 0 ? P64_STAGE0 : P64_STAGE1;
                     const uint32_t bfull = pass == 0 ? bar_full0 : bar_full1;
@@ -1432,9 +1442,9 @@ ozaki_syrk_pair64_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid
                     if (item > 0) mbar_wait(bar_tempty, (item - 1) & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     if (pass == 0)
-                        issue_pass64<0>(dbase, tmem0, idesc, nst, bar_full0, bar_empty0, bar_tfull, stage0, phase0, issuer, probe == 2);
+                        issue_pass64<0, L1>(dbase, tmem0, idesc, nst, bar_full0, bar_empty0, bar_tfull, stage0, phase0, issuer, probe == 2);
                     else
-                        issue_pass64<1>(dbase, tmem0, idesc, nst, bar_full1, bar_empty1, bar_tfull, stage1, phase1, issuer, probe == 2);
+                        issue_pass64<1, L1>(dbase, tmem0, idesc, nst, bar_full1, bar_empty1, bar_tfull, stage1, phase1, issuer, probe == 2);
                 }
             }
         }
@@ -1450,12 +1460,21 @@ ozaki_syrk_pair64_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid
             const bool store = tI <= tJ;
             const double rs = (row < ncols) ? alpha * dscale[row] : 0.0;
             for (int pass = 0; pass < 2; pass++, item++) {
+                if (pass == 0 && beta != 0.0 && store && row < ncols) {
+                    // C += ...: pull my rows of the tile into L2 while the MMAs of this pass run (the tile comes from DRAM)
+#pragma unroll 8
+                    for (int j = lane & 1; j < TN; j += 2) {              // 16 lanes share a 128-byte line: two lanes per line suffice
+                        const int64_t col = (int64_t)tJ * TN + j;
+                        if (col < ncols && (lane & 15) < 2)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(C + row + col * ldc));
+                    }
+                }
                 mbar_wait(bar_tfull, item & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;");
-                const int d0 = pass * 4;
-                // digit sum d has weight 2^-(14 + 8 d); the fourth accumulator of pass 1 (d = 7) was never written
+                const int d0 = pass * L1, nacc = pass == 0 ? L1 : P64_NSL - L1;
+                // digit sum d has weight 2^-(14 + 8 d); accumulators the pass never wrote get weight 0
                 const double g0 = ldexp(1.0, -(14 + 8 * d0)), g1 = ldexp(1.0, -(14 + 8 * (d0 + 1))),
-                             g2 = ldexp(1.0, -(14 + 8 * (d0 + 2))), g3 = pass == 0 ? ldexp(1.0, -(14 + 8 * 3)) : 0.0;
+                             g2 = ldexp(1.0, -(14 + 8 * (d0 + 2))), g3 = nacc > 3 ? ldexp(1.0, -(14 + 8 * (d0 + 3))) : 0.0;
 #pragma unroll 1
                 for (int c0 = 0; c0 < TN; c0 += 16) {
                     uint32_t v[4][16];
@@ -1471,6 +1490,18 @@ ozaki_syrk_pair64_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid
                               "=r"(v[g][15])
                             : "r"(taddr));
                     }
+                    // the old values of C (second pass, or beta != 0): all 16 loads in flight BEFORE the TMEM wait and the
+                    // stores - written as 16 load / store pairs they serialise on 16 L2 (or DRAM) round trips per chunk
+                    double cold[16];
+                    const bool rmw = pass == 1 || beta != 0.0;
+                    const double bt = pass == 1 ? 1.0 : beta;
+                    if (store && row < ncols && rmw) {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            const int64_t col = (int64_t)tJ * TN + c0 + j;
+                            cold[j] = (col < ncols) ? __ldcg(C + row + col * ldc) : 0.0;
+                        }
+                    }
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     if (store && row < ncols) {
 #pragma unroll
@@ -1482,9 +1513,283 @@ ozaki_syrk_pair64_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid
                                 x += (double)(int32_t)v[1][j] * g1;
                                 x += (double)(int32_t)v[0][j] * g0;
                                 x *= rs * dscale[col];
-                                double* cp = C + row + col * ldc;
-                                if (pass == 0) *cp = (beta == 0.0) ? x : (x + beta * *cp);
-                                else *cp += x;
+                                C[row + col * ldc] = rmw ? (x + bt * cold[j]) : x;
+                            }
+                        }
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(tempty_leader);
+            }
+        }
+    }
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem0), "r"(512));
+    }
+}
+
+// ---- quad variant of the 64-byte-row kernel: two CTA pairs of a 4-CTA cluster share their A tiles ---------------------
+// Quad (P, Jq): tile rows 2P, 2P + 1 and tile columns 2Jq, 2Jq + 1.  Pair p (cluster ranks 2p, 2p + 1) owns column
+// 2Jq + p and runs the pair kernel above; the A tile of row 2P + r is needed by CTA r of BOTH pairs, so each of the two
+// loads half of its slices (one TMA per slice) and multicasts them to the other: a third fewer bytes leave the L2 slices
+// per MMA, and the L2 -> SM path is what bounds the pair kernel once its requests are 64 bytes wide (loads alone 48 ms,
+// MMAs alone 39 ms on C3).  Barriers: a multicast signals the full barrier of each destination CTA itself, so the second
+// CTA of a pair forwards "my A tile has landed" to its leader; a stage is refilled only after BOTH pair leaders have
+// retired the MMAs that read it (commits multicast to all four CTAs); the ring of the next pass is started when both
+// leaders have committed the end of the previous pass (drain barrier).
+template <int PASS, int L1>
+__device__ __forceinline__ void issue_pass64q(uint64_t dbase, uint32_t tmem0, uint32_t idesc, int nst, uint32_t bar_full,
+                                              uint32_t bar_empty, uint32_t bar_tfull, uint32_t bar_drain, int& stage,
+                                              uint32_t& phase, bool issuer, uint16_t mask_pair) {
+    constexpr int NSL = P64_NSL;
+    constexpr int D0 = PASS * L1;
+    constexpr int NACC = PASS == 0 ? L1 : NSL - L1;
+    constexpr int NS = PASS == 0 ? L1 : NSL;
+    constexpr int STAGE = PASS == 0 ? p64_stage0(L1) : P64_STAGE1;
+    constexpr int NSTAGES = PASS == 0 ? p64_stages0(L1) : P64_STAGES1;
+    for (int it = 0; it < nst; it++) {
+        mbar_wait(bar_full + stage * 8, phase);
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        const uint64_t sd = dbase + (uint64_t)((uint32_t)(stage * STAGE) >> 4);
+        const uint32_t first = it > 0 ? 1u : 0u;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+#pragma unroll
+            for (int sl = 0; sl < NS; sl++) {
+                const int tlo = D0 - sl > 0 ? D0 - sl : 0;
+                const int thi = (D0 + NACC - 1 - sl) < (NSL - 1 - sl) ? (D0 + NACC - 1 - sl) : (NSL - 1 - sl);
+#pragma unroll
+                for (int tt = 0; tt < NSL; tt++) {
+                    if (tt < tlo || tt > thi) continue;
+                    const uint32_t offA = (uint32_t)(sl * P64_TA + h * 32) >> 4;
+                    const uint32_t offB = (uint32_t)(NS * P64_TA + tt * P64_TB + h * 32) >> 4;
+                    const uint32_t accum = (h > 0 || sl > 0) ? 1u : first;
+                    if (issuer) umma_i8_2sm(tmem0 + (uint32_t)((sl + tt - D0) * TN), sd + offA, sd + offB, idesc, accum);
+                }
+            }
+        }
+        if (issuer) umma_commit_2sm(bar_empty + stage * 8, 0xF);     // one of the two releases of this stage, in all four CTAs
+        if (++stage == NSTAGES) {
+            stage = 0;
+            phase ^= 1u;
+        }
+    }
+    if (issuer) {
+        umma_commit_2sm(bar_tfull, mask_pair);                       // accumulators ready in both CTAs of my pair
+        umma_commit_2sm(bar_drain, 0xF);                             // my pair no longer reads the ring of this pass
+    }
+}
+
+template <int L1>
+__global__ void __launch_bounds__(I8_THREADS, 1)
+ozaki_syrk_quad64_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB0,
+                         const __grid_constant__ CUtensorMap mapB1, const int2* __restrict__ quads, int n_quads, int k0,
+                         int nst, const double* __restrict__ dscale, int64_t ncols, double* __restrict__ C, int64_t ldc,
+                         double alpha, double beta) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint32_t s_tmem;
+    constexpr int P64_STAGES0 = p64_stages0(L1), P64_STAGE0 = p64_stage0(L1);
+    const uint32_t base = smem_u32(smem_raw);
+    const uint32_t stg = (base + 1023u) & ~1023u;
+    const uint32_t bar_full0 = stg + P64_RING;
+    const uint32_t bar_empty0 = bar_full0 + P64_MAXST0 * 8;
+    const uint32_t bar_full1 = bar_empty0 + P64_MAXST0 * 8;
+    const uint32_t bar_empty1 = bar_full1 + P64_STAGES1 * 8;
+    const uint32_t bar_tfull = bar_empty1 + P64_STAGES1 * 8;
+    const uint32_t bar_tempty = bar_tfull + 8;
+    const uint32_t bar_drain = bar_tempty + 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t crank, cid, ncl;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(cid));
+    asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(ncl));
+    const uint32_t pr = crank >> 1, r = crank & 1u;        // pair inside the quad, CTA inside the pair
+    const bool leader = r == 0;
+    const uint32_t leader_rank = crank & ~1u;
+    const uint16_t mask_a = (uint16_t)((1u << r) | (1u << (2 + r)));      // the CTAs that hold tile row 2P + r
+    const uint16_t mask_pair = (uint16_t)(3u << (2 * pr));                // my CTA pair
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < P64_STAGES0; s++) {
+            // leader: its own expect_tx arrival + the peer's forwarded "my A tile has landed";
+            // peer: its own expect_tx arrival (A bytes only; its B half signals the leader directly)
+            mbar_init(bar_full0 + s * 8, leader ? 2 : 1);
+            mbar_init(bar_empty0 + s * 8, 2);    // one multicast commit from each of the two pair leaders
+        }
+        for (int s = 0; s < P64_STAGES1; s++) {
+            mbar_init(bar_full1 + s * 8, leader ? 2 : 1);
+            mbar_init(bar_empty1 + s * 8, 2);
+        }
+        mbar_init(bar_tfull, 1);
+        mbar_init(bar_tempty, 8);                // 4 epilogue warps of each CTA of the pair (used in the leader only)
+        mbar_init(bar_drain, 2);                 // both pair leaders
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                     "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem0 = s_tmem;
+
+    if (warp == 0) {
+        // ===== TMA producer (all four CTAs): my share of the slices of my A tile (multicast) and my half of the B tile =====
+        if (lane == 0) {
+            int stage[2] = {0, 0};
+            uint32_t phase[2] = {0, 0};
+            uint32_t item = 0;
+            for (int qi = (int)cid; qi < n_quads; qi += (int)ncl) {
+                const int2 qd = quads[qi];
+                const int tI = 2 * qd.x + (int)r, tJ = 2 * qd.y + (int)pr;
+                for (int pass = 0; pass < 2; pass++, item++) {
+                    // the two rings share their shared memory: BOTH pairs must have retired the previous item's MMAs
+                    if (item > 0) mbar_wait(bar_drain, (item - 1) & 1u);
+                    const int ns = pass == 0 ? L1 : P64_NSL;
+                    const int s_lo = pr == 0 ? 0 : (ns + 1) / 2, s_hi = pr == 0 ? (ns + 1) / 2 : ns;   // my share of the A slices
+                    const int nstages = pass == 0 ? P64_STAGES0 : P64_STAGES1;
+                    const uint32_t sbytes = pass == 0 ? P64_STAGE0 : P64_STAGE1;
+                    const uint32_t bfull = pass == 0 ? bar_full0 : bar_full1;
+                    const uint32_t bempty = pass == 0 ? bar_empty0 : bar_empty1;
+                    const CUtensorMap* mb = pass == 0 ? &mapB0 : &mapB1;
+                    const uint32_t bytes_a = (uint32_t)ns * P64_TA, bytes_bh = (uint32_t)ns * P64_TB;
+                    int st = stage[pass];
+                    uint32_t ph = phase[pass];
+                    for (int it = 0; it < nst; it++) {
+                        mbar_wait(bempty + st * 8, ph ^ 1u);
+                        const uint32_t full = bfull + st * 8;
+                        const uint32_t full_leader = mapa_u32(full, leader_rank);
+                        mbar_expect_tx(full, leader ? bytes_a + 2u * bytes_bh : bytes_a);
+                        const uint32_t dst = stg + st * sbytes;
+                        const int kc = k0 + it * P64_KB;
+                        for (int sl = s_lo; sl < s_hi; sl++)
+                            tma_load_3d_mc(dst + sl * P64_TA, &mapA1, kc, tI * TM, sl, full, mask_a);
+                        tma_load_3d_2sm(dst + ns * P64_TA, mb, kc, tJ * TN + (int)r * (TN / 2), 0, full_leader);
+                        if (++st == nstages) {
+                            st = 0;
+                            ph ^= 1u;
+                        }
+                    }
+                    stage[pass] = st;
+                    phase[pass] = ph;
+                }
+            }
+        }
+    } else if (warp == 1 && !leader) {
+        // ===== forwarder (second CTA of a pair): tells the pair leader when my A tile of a stage has landed =====
+        if (lane == 0) {
+            int stage[2] = {0, 0};
+            uint32_t phase[2] = {0, 0};
+            for (int qi = (int)cid; qi < n_quads; qi += (int)ncl) {
+                for (int pass = 0; pass < 2; pass++) {
+                    const int nstages = pass == 0 ? P64_STAGES0 : P64_STAGES1;
+                    const uint32_t bfull = pass == 0 ? bar_full0 : bar_full1;
+                    int st = stage[pass];
+                    uint32_t ph = phase[pass];
+                    for (int it = 0; it < nst; it++) {
+                        mbar_wait(bfull + st * 8, ph);
+                        mbar_arrive_cluster(mapa_u32(bfull + st * 8, leader_rank));
+                        if (++st == nstages) {
+                            st = 0;
+                            ph ^= 1u;
+                        }
+                    }
+                    stage[pass] = st;
+                    phase[pass] = ph;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA of each pair): warp-uniform loop, one elected lane issues =====
+        const uint32_t idesc = make_idesc_i8(2 * TM, TN);
+        const uint64_t dbase = make_desc_sw64(stg);
+        const bool issuer = elect_one_sync();
+        int stage0 = 0, stage1 = 0;
+        uint32_t phase0 = 0, phase1 = 0, item = 0;
+        for (int qi = (int)cid; qi < n_quads; qi += (int)ncl) {
+            for (int pass = 0; pass < 2; pass++, item++) {
+                if (item > 0) mbar_wait(bar_tempty, (item - 1) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                if (pass == 0)
+                    issue_pass64q<0, L1>(dbase, tmem0, idesc, nst, bar_full0, bar_empty0, bar_tfull, bar_drain, stage0, phase0, issuer,
+                                         mask_pair);
+                else
+                    issue_pass64q<1, L1>(dbase, tmem0, idesc, nst, bar_full1, bar_empty1, bar_tfull, bar_drain, stage1, phase1, issuer,
+                                         mask_pair);
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs, own TMEM half) =====
+        const int lg = warp & 3;
+        const uint32_t tempty_leader = mapa_u32(bar_tempty, leader_rank);
+        uint32_t item = 0;
+        for (int qi = (int)cid; qi < n_quads; qi += (int)ncl) {
+            const int2 qd = quads[qi];
+            const int tI = 2 * qd.x + (int)r, tJ = 2 * qd.y + (int)pr;
+            const int64_t row = (int64_t)tI * TM + lg * 32 + lane;
+            const bool store = tI <= tJ;
+            const double rs = (row < ncols) ? alpha * dscale[row] : 0.0;
+            for (int pass = 0; pass < 2; pass++, item++) {
+                if (pass == 0 && beta != 0.0 && store && row < ncols) {
+                    // C += ...: pull my rows of the tile into L2 while the MMAs of this pass run (the tile comes from DRAM)
+#pragma unroll 8
+                    for (int j = lane & 1; j < TN; j += 2) {              // 16 lanes share a 128-byte line: two lanes per line suffice
+                        const int64_t col = (int64_t)tJ * TN + j;
+                        if (col < ncols && (lane & 15) < 2)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(C + row + col * ldc));
+                    }
+                }
+                mbar_wait(bar_tfull, item & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                const int d0 = pass * L1, nacc = pass == 0 ? L1 : P64_NSL - L1;
+                // digit sum d has weight 2^-(14 + 8 d); accumulators the pass never wrote get weight 0
+                const double g0 = ldexp(1.0, -(14 + 8 * d0)), g1 = ldexp(1.0, -(14 + 8 * (d0 + 1))),
+                             g2 = ldexp(1.0, -(14 + 8 * (d0 + 2))), g3 = nacc > 3 ? ldexp(1.0, -(14 + 8 * (d0 + 3))) : 0.0;
+#pragma unroll 1
+                for (int c0 = 0; c0 < TN; c0 += 16) {
+                    uint32_t v[4][16];
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        const uint32_t taddr = tmem0 + ((uint32_t)(lg * 32) << 16) + (uint32_t)(g * TN + c0);
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                            : "=r"(v[g][0]), "=r"(v[g][1]), "=r"(v[g][2]), "=r"(v[g][3]), "=r"(v[g][4]),
+                              "=r"(v[g][5]), "=r"(v[g][6]), "=r"(v[g][7]), "=r"(v[g][8]), "=r"(v[g][9]),
+                              "=r"(v[g][10]), "=r"(v[g][11]), "=r"(v[g][12]), "=r"(v[g][13]), "=r"(v[g][14]),
+                              "=r"(v[g][15])
+                            : "r"(taddr));
+                    }
+                    // the old values of C (second pass, or beta != 0): all 16 loads in flight BEFORE the TMEM wait and the
+                    // stores - written as 16 load / store pairs they serialise on 16 L2 (or DRAM) round trips per chunk
+                    double cold[16];
+                    const bool rmw = pass == 1 || beta != 0.0;
+                    const double bt = pass == 1 ? 1.0 : beta;
+                    if (store && row < ncols && rmw) {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            const int64_t col = (int64_t)tJ * TN + c0 + j;
+                            cold[j] = (col < ncols) ? __ldcg(C + row + col * ldc) : 0.0;
+                        }
+                    }
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (store && row < ncols) {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            const int64_t col = (int64_t)tJ * TN + c0 + j;
+                            if (col < ncols) {
+                                double x = (double)(int32_t)v[3][j] * g3;
+                                x += (double)(int32_t)v[2][j] * g2;
+                                x += (double)(int32_t)v[1][j] * g1;
+                                x += (double)(int32_t)v[0][j] * g0;
+                                x *= rs * dscale[col];
+                                C[row + col * ldc] = rmw ? (x + bt * cold[j]) : x;
                             }
                         }
                     }
@@ -1515,6 +1820,38 @@ void make_map_digits64(CUtensorMap* map, const int8_t* base, int64_t K, int64_t 
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw HypError{"cuTensorMapEncodeTiled (digit slices, 64-byte rows) failed"};
+}
+
+// pass split of the 64-byte-row kernel: digit sums 0 .. L1 - 1 in pass 0 (3 by default, HYP_OZAKI_SPLIT=4: 4)
+int p64_split() {
+    static int l1 = 0;
+    if (!l1) {
+        const char* e = getenv("HYP_OZAKI_SPLIT");
+        l1 = (e && e[0] == '4') ? 4 : 3;
+        CUDA_TRY(cudaFuncSetAttribute(ozaki_syrk_pair64_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, P64_SMEM));
+        CUDA_TRY(cudaFuncSetAttribute(ozaki_syrk_pair64_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, P64_SMEM));
+    }
+    return l1;
+}
+
+// one launch of the 64-byte-row CTA-pair kernel over a pair list (cfg carries grid, stream and the cluster attribute)
+void launch_pair64(hyp_ctx* ctx, cudaLaunchConfig_t* cfg, const int8_t* digits, int64_t K, int64_t ncols, int64_t ldd,
+                   int64_t slice_stride, int nslices_alloc, const int2* d_pairs, int n_pairs, int k0, int64_t klen,
+                   const double* dscale, double* C, int64_t ldc, double alpha, double beta, int probe) {
+    const int l1 = p64_split();
+    CUtensorMap mA0, mA1, mB0, mB1;
+    make_map_digits64(&mA0, digits, K, ncols, ldd, slice_stride, nslices_alloc, l1, TM);
+    make_map_digits64(&mA1, digits, K, ncols, ldd, slice_stride, nslices_alloc, P64_NSL, TM);
+    make_map_digits64(&mB0, digits, K, ncols, ldd, slice_stride, nslices_alloc, l1, TN / 2);
+    make_map_digits64(&mB1, digits, K, ncols, ldd, slice_stride, nslices_alloc, P64_NSL, TN / 2);
+    const int nst = (int)ceil_div(klen, P64_KB);
+    if (l1 == 3)
+        CUDA_TRY(cudaLaunchKernelEx(cfg, ozaki_syrk_pair64_kernel<3>, mA0, mA1, mB0, mB1, d_pairs, n_pairs, k0, nst, dscale, ncols,
+                                    C, ldc, alpha, beta, probe));
+    else
+        CUDA_TRY(cudaLaunchKernelEx(cfg, ozaki_syrk_pair64_kernel<4>, mA0, mA1, mB0, mB1, d_pairs, n_pairs, k0, nst, dscale, ncols,
+                                    C, ldc, alpha, beta, probe));
+    ctx->launches++;
 }
 
 void make_map_digits(CUtensorMap* map, const int8_t* base, int64_t K, int64_t cols, int64_t ldd,
@@ -1703,10 +2040,30 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
         // 3: quads = two CTA pairs sharing their A tiles by multicast
         // 4 (default with radix-256 digits): CTA pairs with 64-byte k rows
         use_cluster = e ? (e[0] - '0') : (ozaki_radix() == 256 ? 4 : 2);
-        if (use_cluster < 0 || use_cluster > 4) use_cluster = 2;
-        if (use_cluster == 4 && ozaki_radix() != 256) use_cluster = 2;
+        // 5: quads of the 64-byte-row kernel (two CTA pairs share their A tiles by multicast)
+        if (use_cluster < 0 || use_cluster > 5) use_cluster = 2;
+        if (use_cluster >= 4 && ozaki_radix() != 256) use_cluster = 2;
+        if (use_cluster == 5) {
+            p64_split();
+            CUDA_TRY(cudaFuncSetAttribute(ozaki_syrk_quad64_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, P64_SMEM));
+            cudaLaunchConfig_t q = {};
+            q.gridDim = dim3(4 * 64);
+            q.blockDim = dim3(I8_THREADS);
+            q.dynamicSmemBytes = P64_SMEM;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 4;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            q.attrs = at;
+            q.numAttrs = 1;
+            if (cudaOccupancyMaxActiveClusters(&max_clusters, ozaki_syrk_quad64_kernel<3>, &q) != cudaSuccess || max_clusters < 1) {
+                cudaGetLastError();
+                use_cluster = 4;
+            }
+        }
         if (use_cluster == 4) {
-            CUDA_TRY(cudaFuncSetAttribute(ozaki_syrk_pair64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P64_SMEM));
+            p64_split();
             cudaLaunchConfig_t q = {};
             q.gridDim = dim3(2 * 128);
             q.blockDim = dim3(I8_THREADS);
@@ -1718,7 +2075,7 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
             at[0].val.clusterDim.z = 1;
             q.attrs = at;
             q.numAttrs = 1;
-            if (cudaOccupancyMaxActiveClusters(&max_clusters, ozaki_syrk_pair64_kernel, &q) != cudaSuccess ||
+            if (cudaOccupancyMaxActiveClusters(&max_clusters, ozaki_syrk_pair64_kernel<3>, &q) != cudaSuccess ||
                 max_clusters < 1) {
                 cudaGetLastError();
                 use_cluster = 2;
@@ -1798,6 +2155,48 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
     const int grid = std::min(n_tiles, ctx->sm_count);
     for (int64_t k0 = 0; k0 < K; k0 += CHUNK) {
         const int64_t klen = std::min(CHUNK, K - k0);
+        if (use_cluster == 5) {
+            // (P, Jq): tile rows 2P, 2P+1 x tile columns 2Jq, 2Jq+1 for P <= Jq, row pair by row pair (the A panel of
+            // the row pair stays in L2 while the B panels stream, as in the pair kernel's default order)
+            static std::vector<std::pair<int, std::pair<int2*, int>>> q64cache;
+            int2* d_quads = nullptr;
+            int n_quads = 0;
+            for (auto& e : q64cache)
+                if (e.first == nt) {
+                    d_quads = e.second.first;
+                    n_quads = e.second.second;
+                }
+            if (!d_quads) {
+                std::vector<int2> ql;
+                for (int pp = 0; 2 * pp < nt; pp++)
+                    for (int jq = pp; 2 * jq < nt; jq++) ql.push_back(make_int2(pp, jq));
+                n_quads = (int)ql.size();
+                CUDA_TRY(cudaMalloc(&d_quads, ql.size() * sizeof(int2)));
+                CUDA_TRY(cudaMemcpyAsync(d_quads, ql.data(), ql.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+                CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+                q64cache.push_back({nt, {d_quads, n_quads}});
+            }
+            CUtensorMap mA1, mB0, mB1;
+            make_map_digits64(&mA1, digits, K, ncols, ldd, slice_stride, OZ_S, 1, TM);
+            make_map_digits64(&mB0, digits, K, ncols, ldd, slice_stride, OZ_S, 3, TN / 2);
+            make_map_digits64(&mB1, digits, K, ncols, ldd, slice_stride, OZ_S, P64_NSL, TN / 2);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(4 * std::min(n_quads, max_clusters));
+            cfg.blockDim = dim3(I8_THREADS);
+            cfg.dynamicSmemBytes = P64_SMEM;
+            cfg.stream = ctx->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 4;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            CUDA_TRY(cudaLaunchKernelEx(&cfg, ozaki_syrk_quad64_kernel<3>, mA1, mB0, mB1, (const int2*)d_quads, n_quads, (int)k0,
+                                        (int)ceil_div(klen, P64_KB), dscale, ncols, C, ldc, alpha, k0 == 0 ? beta : 1.0));
+            ctx->launches++;
+            continue;
+        }
         if (use_cluster == 3) {
             // (P, Jq): tile rows 2P, 2P+1 x tile columns 2Jq, 2Jq+1, for 2P <= 2Jq+1, column pair by column pair
             static std::vector<std::pair<int, std::pair<int2*, int>>> qcache;
@@ -1885,11 +2284,6 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
                 pcache.push_back({nt, {d_pairs, n_pairs}});
             }
             if (use_cluster == 4) {
-                CUtensorMap mA4, mA7, mB4, mB7;
-                make_map_digits64(&mA4, digits, K, ncols, ldd, slice_stride, OZ_S, 4, TM);
-                make_map_digits64(&mA7, digits, K, ncols, ldd, slice_stride, OZ_S, P64_NSL, TM);
-                make_map_digits64(&mB4, digits, K, ncols, ldd, slice_stride, OZ_S, 4, TN / 2);
-                make_map_digits64(&mB7, digits, K, ncols, ldd, slice_stride, OZ_S, P64_NSL, TN / 2);
                 cudaLaunchConfig_t cfg = {};
                 cfg.gridDim = dim3(2 * std::min(n_pairs, max_clusters));
                 cfg.blockDim = dim3(I8_THREADS);
@@ -1903,10 +2297,8 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
                 cfg.attrs = at;
                 cfg.numAttrs = 1;
                 const int probe = getenv("HYP_OZAKI_PROBE") ? atoi(getenv("HYP_OZAKI_PROBE")) : 0;   // tools/syrk_probe.py
-                CUDA_TRY(cudaLaunchKernelEx(&cfg, ozaki_syrk_pair64_kernel, mA4, mA7, mB4, mB7, (const int2*)d_pairs, n_pairs,
-                                            (int)k0, (int)ceil_div(klen, P64_KB), dscale, ncols, C, ldc, alpha,
-                                            k0 == 0 ? beta : 1.0, probe));
-                ctx->launches++;
+                launch_pair64(ctx, &cfg, digits, K, ncols, ldd, slice_stride, OZ_S, d_pairs, n_pairs, (int)k0, klen, dscale, C, ldc,
+                              alpha, k0 == 0 ? beta : 1.0, probe);
                 continue;
             }
             CUtensorMap mapB4, mapB8, mapA8;
@@ -1974,6 +2366,123 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
                                                                      k0 == 0 ? beta : 1.0, getenv("HYP_OZAKI_NO_TMA") ? 1 : 0);
         ctx->launches++;
     }
+    CUDA_TRY(cudaGetLastError());
+}
+
+// ---- pieces of the blocked Cholesky (chol.cu): its depth-512 trailing updates run on the digit-sliced kernel ----------
+// true when the CTA-pair kernel with 64-byte rows can be launched on this device (radix-256 digits, default kernel choice)
+bool hyp_ozaki_pair64_ready(hyp_ctx* ctx) {
+    static int ready = -1;
+    if (ready < 0) {
+        ready = 0;
+        const char* c = getenv("HYP_OZAKI_CLUSTER");
+        if (ozaki_radix() == 256 && (!c || c[0] == '4')) {
+            cudaLaunchConfig_t q = {};
+            q.gridDim = dim3(2 * 128);
+            q.blockDim = dim3(I8_THREADS);
+            q.dynamicSmemBytes = P64_SMEM;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            q.attrs = at;
+            q.numAttrs = 1;
+            int mc = 0;
+            p64_split();
+            if (cudaOccupancyMaxActiveClusters(&mc, ozaki_syrk_pair64_kernel<3>, &q) == cudaSuccess && mc >= 1)
+                ready = mc;
+            else
+                cudaGetLastError();
+        }
+    }
+    (void)ctx;
+    return ready > 0;
+}
+
+// digit slices + scales of a block row of at most 512 rows, one kernel, on the launch stream
+void hyp_ozaki_slice_short(hyp_ctx* ctx, const double* A, int64_t lda, int64_t K, int64_t ncols, int8_t* digits, int64_t ldd,
+                           int64_t slice_stride, double* dscale) {
+    if (K <= 0 || ncols <= 0) return;
+    if (K > 512 || (ldd & 15) || ldd < K) throw HypError{"hyp_ozaki_slice_short: at most 512 rows, ldd % 16 == 0"};
+    cudaStream_t s = ctx->launch_stream ? ctx->launch_stream : ctx->stream;
+    const int grid = (int)std::min<int64_t>(ceil_div(ncols, 8), 4 * ctx->sm_count);
+    hypdev::slice256_short_kernel<<<grid, 256, 0, s>>>((int)K, ncols, A, lda, dscale, P64_NSL, digits, ldd, slice_stride);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+}
+
+// C(upper tiles of the tile rows 2 p_lo .. 2 p_hi - 1) = alpha A' A + beta C from the digit slices of A (K <= 18688 rows),
+// on the launch stream, with at most grid_cap CTAs (chol.cu leaves SMs to its look-ahead chain).  skip_diag > 0: the
+// leading skip_diag x skip_diag TILE block is left alone (the chain already updated the next diagonal block itself).
+void hyp_ozaki_syrk_rows(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t slice_stride, const double* dscale,
+                         int64_t K, int64_t ncols, double* C, int64_t ldc, double alpha, double beta, int p_lo, int p_hi,
+                         int skip_diag) {
+    if (K <= 0 || ncols <= 0) return;
+    if (K > 18688 || (K & 63)) throw HypError{"hyp_ozaki_syrk_rows: K must be a multiple of 64, at most 18688"};
+    if (!hyp_ozaki_pair64_ready(ctx)) throw HypError{"hyp_ozaki_syrk_rows: CTA-pair kernel not available"};
+    const int nt = ceil_div(ncols, TM);
+    const int np = (nt + 1) / 2;
+    p_hi = std::min(p_hi < 0 ? np : p_hi, np);
+    if (p_lo >= p_hi) return;
+    struct Entry {
+        int device, nt, p_lo, p_hi, skip;
+        int2* d_pairs;
+        int n_pairs;
+    };
+    static std::vector<Entry> cache;
+    int2* d_pairs = nullptr;
+    int n_pairs = 0;
+    for (auto& e : cache)
+        if (e.device == ctx->device && e.nt == nt && e.p_lo == p_lo && e.p_hi == p_hi && e.skip == skip_diag) {
+            d_pairs = e.d_pairs;
+            n_pairs = e.n_pairs;
+        }
+    cudaStream_t s = ctx->launch_stream ? ctx->launch_stream : ctx->stream;
+    if (!d_pairs) {
+        std::vector<int2> pl;
+        for (int pp = p_lo; pp < p_hi; pp++)
+            for (int tj = 2 * pp; tj < nt; tj++) {
+                if (2 * pp + 1 < skip_diag && tj < skip_diag) continue;      // both tile rows of the pair inside the block
+                pl.push_back(make_int2(pp, tj));
+            }
+        n_pairs = (int)pl.size();
+        CUDA_TRY(cudaMalloc(&d_pairs, std::max<size_t>(pl.size(), 1) * sizeof(int2)));
+        if (n_pairs) CUDA_TRY(cudaMemcpyAsync(d_pairs, pl.data(), pl.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        cache.push_back({ctx->device, nt, p_lo, p_hi, skip_diag, d_pairs, n_pairs});
+    }
+    if (!n_pairs) return;
+    static int max_clusters = 0;
+    if (!max_clusters) {
+        cudaLaunchConfig_t q = {};
+        q.gridDim = dim3(2 * 128);
+        q.blockDim = dim3(I8_THREADS);
+        q.dynamicSmemBytes = P64_SMEM;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        q.attrs = at;
+        q.numAttrs = 1;
+        CUDA_TRY(cudaOccupancyMaxActiveClusters(&max_clusters, ozaki_syrk_pair64_kernel<3>, &q));
+    }
+    int ncl = std::min(n_pairs, max_clusters);
+    if (ctx->grid_cap > 0) ncl = std::min(ncl, std::max(1, ctx->grid_cap / 2));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * ncl);
+    cfg.blockDim = dim3(I8_THREADS);
+    cfg.dynamicSmemBytes = P64_SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    launch_pair64(ctx, &cfg, digits, K, ncols, ldd, slice_stride, P64_NSL, d_pairs, n_pairs, 0, K, dscale, C, ldc, alpha, beta, 0);
     CUDA_TRY(cudaGetLastError());
 }
 

@@ -114,6 +114,50 @@ static __global__ void expo_from_bits_kernel(int64_t ncols, const unsigned long 
     }
 }
 
+// Column maximum, exponent and the radix-256 digit slices of a SHORT block row (K <= 512 rows: the depth-512 panel of the
+// blocked Cholesky, chol.cu) in one pass: one warp per column keeps its (up to) 16 values per lane in registers.
+// Lane l holds rows 8 l .. 8 l + 7 and 256 + 8 l .. 256 + 8 l + 7, so the loads are 2 KB contiguous per warp and each
+// slice gets one 8-byte word per lane (256 B contiguous per warp).  Rows K .. ldd - 1 of the digit columns are zeroed.
+static __global__ void __launch_bounds__(256)
+slice256_short_kernel(int K, int64_t ncols, const double* __restrict__ A, int64_t lda, double* __restrict__ dscale,
+                      int nslices, int8_t* __restrict__ D, int64_t ldd, int64_t slice_stride) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int64_t j = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); j < ncols; j += (int64_t)gridDim.x * wpb) {
+        const double* col = A + j * lda;
+        double v[2][8];
+        double mx = 0.0;
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int k = h * 256 + lane * 8 + u;
+                v[h][u] = (k < K) ? col[k] : 0.0;
+                mx = fmax(mx, fabs(v[h][u]));
+            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        int e = 0;
+        if (mx > 0.0) {
+            const double f = frexp(mx, &e);
+            if (f > 127.0 / 128.0) e++;
+        }
+        if (lane == 0) dscale[j] = ldexp(1.0, e);
+        const double sc = ldexp(1.0, 7 - e);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int k0 = h * 256 + lane * 8;
+            if (k0 >= ldd) continue;
+            double rr[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) rr[u] = v[h][u] * sc;
+            uint64_t w[8];
+            slice256_pack8(rr, nslices, w);
+            for (int s = 0; s < nslices; s++) *reinterpret_cast<uint64_t*>(D + s * slice_stride + j * ldd + k0) = w[s];
+        }
+    }
+}
+
 // Radix-256 variant: balanced signed digits d_s in [-128, 127], a = 2^e sum_s 2^-(7 + 8 s) d_s.  rint can produce
 // +128 (remainder >= 0.498): a backward carry pass turns it into -128 and adds one to the next higher digit; the
 // leading digit cannot overflow because |a| 2^(7 - e) <= 127.  Seven such digits carry the same 56 bits as eight

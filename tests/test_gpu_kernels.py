@@ -52,7 +52,7 @@ def test_gemm_tn(cx, klen, mrows, ncols):
     assert rel(Cm, 2.0 * (P.T @ R) - C0) <= 50 * klen * EPS
 
 
-@pytest.mark.parametrize("m", [1, 5, 128, 129, 300, 1000, 2500])
+@pytest.mark.parametrize("m", [1, 5, 128, 129, 300, 1000, 1025, 1537, 2500, 3210])
 def test_potrf_potrs(cx, m):
     rng = np.random.default_rng(m)
     B = rng.standard_normal((m + 20, m))
@@ -81,6 +81,30 @@ def test_potrf_not_posdef(cx):
     info = C.c_int(0)
     cx.check(cx.lib.hyp_test_potrf(cx.h, _p(A), m, m, C.byref(info)), "potrf")
     assert info.value > 0
+
+
+def test_potrf_large_not_posdef_and_dag_agreement(cx, monkeypatch):
+    """m > 1024 takes the blocked Cholesky with tcgen05 (digit-sliced) trailing updates (chol.cu, potrf_upper_i8): a
+    matrix that loses definiteness deep inside the trailing part is reported, and on a definite one the factor agrees
+    with the task-graph FP64-DMMA kernel (HYP_POTRF=dag) to rounding."""
+    m = 2200
+    rng = np.random.default_rng(5)
+    B = rng.standard_normal((m + 30, m))
+    A = np.asfortranarray(B.T @ B + 0.5 * np.eye(m))
+    F1 = A.copy(order="F")
+    info = C.c_int(-1)
+    cx.check(cx.lib.hyp_test_potrf(cx.h, _p(F1), m, m, C.byref(info)), "potrf")
+    assert info.value == 0
+    monkeypatch.setenv("HYP_POTRF", "dag")
+    F2 = A.copy(order="F")
+    cx.check(cx.lib.hyp_test_potrf(cx.h, _p(F2), m, m, C.byref(info)), "potrf")
+    monkeypatch.delenv("HYP_POTRF")
+    assert info.value == 0
+    assert rel(np.triu(F1), np.triu(F2)) <= 1e-11
+    Abad = A.copy(order="F")
+    Abad[1800, 1800] = -1.0
+    cx.check(cx.lib.hyp_test_potrf(cx.h, _p(Abad), m, m, C.byref(info)), "potrf")
+    assert info.value == 1801
 
 
 @pytest.mark.parametrize("rows,cols", [(1, 1), (25, 7), (5000, 33), (4097, 300), (300, 4097), (20000, 64)])

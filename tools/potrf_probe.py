@@ -23,7 +23,10 @@ def main():
         A = X.t() @ X + 0.5 * torch.eye(m, dtype=torch.float64, device=dev)
         del X
         res = {}
-        modes = ("0",) if os.environ.get("HYP_POTRF") != "stream" else ("0", "1", "2")
+        impl = os.environ.get("HYP_POTRF", "i8")
+        modes = {"stream": ("0", "1", "2"), "i8": ("0", "1", "2", "3")}.get(impl, ("0",))
+        names = {"0": "full_ms", "1": "chain_only_ms", "2": "bulk_only_ms"} if impl == "stream" else \
+            {"0": "full_ms", "1": "no_sliced_updates_ms", "2": "chain_stream_only_ms", "3": "bulk_stream_only_ms"}
         for mode in modes:
             os.environ["HYP_POTRF_MODE"] = mode
             ts = []
@@ -44,13 +47,13 @@ def main():
                     res["info"] = info.value
                     del Lw
                 del F
-            res[{"0": "full_ms", "1": "chain_only_ms", "2": "bulk_only_ms"}[mode]] = float(np.median(ts[1:]))
+            res[names[mode]] = float(np.median(ts[1:]))
         res["tflops"] = m ** 3 / 3 / (res["full_ms"] * 1e-3) / 1e12
         out[m] = res
         del A
         torch.cuda.empty_cache()
     os.environ.pop("HYP_POTRF_MODE", None)
-    print(json.dumps({"potrf_probe": out, "impl": os.environ.get("HYP_POTRF", "dag")}))
+    print(json.dumps({"potrf_probe": out, "impl": os.environ.get("HYP_POTRF", "i8")}))
 
 
 if __name__ == "__main__":
