@@ -90,11 +90,22 @@ WORKLOADS = {
                desc="n=2000 p=0, 24 x EpiPerSepSpectral{MatrixCSqr}(NegEntropy, side 100), q=121248"),
 }
 
+def syrk_kernel_name():
+    """Name of the digit-sliced SYRK kernel the library launches under the current environment (ozaki.cu, hyp_ozaki_syrk)."""
+    c = os.environ.get("HYP_OZAKI_CLUSTER", "")[:1]
+    r128 = os.environ.get("HYP_OZAKI_RADIX") == "128"
+    if c in ("0", "1") or r128:
+        return {"0": "ozaki_syrk_kernel", "1": "ozaki_syrk_cluster_kernel"}.get(c, "ozaki_syrk_pair_kernel")
+    return {"2": "ozaki_syrk_pair_kernel", "3": "ozaki_syrk_quad_kernel", "5": "ozaki_syrk_quad64_kernel"}.get(
+        c, "ozaki_syrk_pair64_kernel (64-byte k rows, SWIZZLE_64B)")
+
+
 # DRAM traffic of the Schur SYRK (dram__bytes_read.sum + dram__bytes_write.sum over the launches of ONE SYRK) from the
 # committed `ncu --set full` capture of the same kernel build - a CONSTANT taken from that profile, not measured by
 # the run that prints it (ncu cannot run inside a timed bench); the source file is named next to it
 NCU_TRAFFIC = {"C3:i8": ((42.40e9 + 0.809e9) + (44.78e9 + 0.808e9) + (44.62e9 + 0.808e9),
-                         "constant from profiles/r01_ozaki_pair_row_order_ncu.txt (three K-chunk launches of one SYRK)"),
+                         "constant from profiles/r01_ozaki_pair_row_order_ncu.txt (three K-chunk launches of one SYRK; the "
+                         "32-byte-row pair kernel - same tile order and digit slices as the 64-byte-row default)"),
                "C3": (31.497622e9 + 0.411380e9, "constant from profiles/r01_syrk_schur_ncu_full.txt (one launch)")}
 
 
@@ -761,8 +772,8 @@ def build_line(args, torch, device, world, main):
         int8_peak = 2.0 * bf16 if bf16 else None
         traffic = NCU_TRAFFIC.get(args.workload + ":i8") if world == 1 else None
         roofline = {"bound": "tensor",
-                    "kernel": "ozaki_syrk_pair_kernel (Schur SYRK: FP64-accurate digit slicing, %d exact int8 digit-pair "
-                              "products, tcgen05 kind::i8 cta_group::2 M=256, TMEM accumulators, 3-D TMA) + slicing kernels" % npairs,
+                    "kernel": "%s (Schur SYRK: FP64-accurate digit slicing, %d exact int8 digit-pair products, tcgen05 kind::i8 "
+                              "cta_group::2 M=256, TMEM accumulators, 3-D TMA) + slicing kernels" % (syrk_kernel_name(), npairs),
                     "achieved": int8_tops, "peak": int8_peak, "unit": "TOP/s (int8 MACs x 2 executed on tcgen05 kind::i8)",
                     "frac": (int8_tops / int8_peak) if int8_tops and int8_peak else None,
                     "peak_source": "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (assumes int8 dense = 2 x bf16 on B200; "
@@ -791,7 +802,8 @@ def build_line(args, torch, device, world, main):
                     "phase_ms": phases}
     potrf_ms = phases.get("potrf")
     if potrf_ms:
-        roofline["potrf"] = {"kernel": "hyp_potrf_upper (blocked Cholesky: panel kernel + FP64 DMMA / digit-sliced trailing updates)",
+        roofline["potrf"] = {"kernel": "hyp_potrf_upper (blocked Cholesky: panel kernel + FP64 DMMA block rows + tcgen05 digit-sliced depth-512 "
+                                       "trailing updates; HYP_POTRF=dag: task-graph FP64-DMMA kernel)",
                              "algorithmic_flops": m ** 3 / 3.0, "ms": potrf_ms,
                              "fp64_tflops": m ** 3 / 3.0 / (potrf_ms * 1e-3) / 1e12,
                              "frac_of_dgemm": m ** 3 / 3.0 / (potrf_ms * 1e-3) / 1e12 / fp64_peak}
