@@ -18,6 +18,7 @@
 //   triangle once: 4 m^2 bytes) - in practice latency of the block dependency chain.
 #include "common.cuh"
 #include "chol_kernels.cuh"
+#include "trsv_tasks.h"
 #include <cstring>
 #include <cstdlib>
 
@@ -38,7 +39,52 @@ void set_panel_attr() {
     CUDA_TRY(cudaFuncSetAttribute(trsv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(trsv_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(trsv_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(trsv_seg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(trsv_seg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(trsv_seg_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(trsv_seg_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
     g_panel_attr_set = true;
+}
+
+// ticket lists of the segmented triangular solve, per (device, nblk, sweep direction), and its partial-sum scratch
+struct TrsvLists {
+    int device, nblk, trans, ntasks, maxseg;
+    TrsvTask* d_tasks;
+};
+std::vector<TrsvLists> g_trsv_lists;
+int trsv_seg_len() {
+    static int seg = 0;
+    if (!seg) {
+        const char* e = getenv("HYP_TRSV_SEG");           // 0 (default) = one ticket per block column; n > 0: segments of n tiles
+        seg = e ? atoi(e) : 0;
+        if (seg < 0) seg = 8;
+        if (seg == 0) seg = -1;
+    }
+    return seg;
+}
+const TrsvLists& trsv_lists(hyp_ctx* ctx, int nblk, bool trans) {
+    for (auto& e : g_trsv_lists)
+        if (e.device == ctx->device && e.nblk == nblk && e.trans == (trans ? 1 : 0)) return e;
+    int maxseg = 1;
+    std::vector<TrsvTask> t = trsv_build_tasks(nblk, trans, trsv_seg_len(), &maxseg);
+    TrsvLists e{ctx->device, nblk, trans ? 1 : 0, (int)t.size(), maxseg, nullptr};
+    CUDA_TRY(cudaMalloc((void**)&e.d_tasks, t.size() * sizeof(TrsvTask)));
+    CUDA_TRY(cudaMemcpyAsync(e.d_tasks, t.data(), t.size() * sizeof(TrsvTask), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    g_trsv_lists.push_back(e);
+    return g_trsv_lists.back();
+}
+// partial sums: nblk x maxseg x (up to 2 right-hand sides) x 128 doubles, per context
+double* trsv_part(hyp_ctx* ctx, int nblk, int maxseg) {
+    const int64_t need = (int64_t)nblk * maxseg * 2 * NB;
+    if (ctx->trsv_part_len < need) {
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_trsv_part) cudaFree(ctx->d_trsv_part);
+        ctx->d_trsv_part = nullptr;
+        CUDA_TRY(cudaMalloc((void**)&ctx->d_trsv_part, (size_t)need * sizeof(double)));
+        ctx->trsv_part_len = need;
+    }
+    return ctx->d_trsv_part;
 }
 
 }  // namespace
@@ -55,35 +101,59 @@ void set_panel_attr() {
 // diag(b + 1) ...; bulk: block row over the far columns -> slicing -> SYRK part a (tile rows of the next two blocks, the
 // chain waits for it before its near block row) -> SYRK part b (the rest).  The bulk grids leave 8 SMs to the chain.
 static bool potrf_upper_i8(hyp_ctx* ctx, double* A, int64_t lda, int64_t m, double* d_dinv, int* d_info) {
-    const int64_t OB = 512;
-    if (m <= 2 * OB || !hyp_ozaki_pair64_ready(ctx)) return false;
+    // outer block = depth of the trailing updates: 512 (default) or 1024 (HYP_POTRF_OB=1024: half as many passes over the
+    // trailing tiles, each twice as deep, against a longer diagonal-block chain)
+    static const int ob_env = getenv("HYP_POTRF_OB") ? atoi(getenv("HYP_POTRF_OB")) : 0;
+    const int64_t OB = (ob_env == 512 || ob_env == 1024) ? ob_env : (m >= 8192 ? 1024 : 512);   // measured: r02_potrf_i8_ob{512,1024}.json
+    if (m <= 1024 || !hyp_ozaki_pair64_ready(ctx)) return false;
     TimeScope ts(ctx, T_POTRF);
     set_panel_attr();
     cudaStream_t bulk = ctx->stream, chain = ctx->stream2;
-    // digit slices of one block row: 7 x 512 x m bytes, and the column scales
+    // digit slices of one block row: 7 x OB x m bytes, and the column scales
     if (ctx->chol_digits_cols < m) {
         CUDA_TRY(cudaStreamSynchronize(bulk));
         if (ctx->d_chol_digits) cudaFree(ctx->d_chol_digits);
         if (ctx->d_chol_dscale) cudaFree(ctx->d_chol_dscale);
         ctx->d_chol_digits = nullptr;
         ctx->d_chol_dscale = nullptr;
-        CUDA_TRY(cudaMalloc((void**)&ctx->d_chol_digits, (size_t)7 * OB * m));
+        CUDA_TRY(cudaMalloc((void**)&ctx->d_chol_digits, (size_t)7 * 1024 * m));       // sized for the deeper outer block
         CUDA_TRY(cudaMalloc((void**)&ctx->d_chol_dscale, (size_t)m * sizeof(double)));
         ctx->chol_digits_cols = m;
     }
     const int64_t ldd = OB, sstride = OB * ctx->chol_digits_cols;
     CUDA_TRY(cudaMemsetAsync(d_info, 0, sizeof(int), bulk));
+    struct LaunchStateGuard {                      // the launch helpers go back to the context's stream on every exit path
+        hyp_ctx* c;
+        ~LaunchStateGuard() {
+            c->launch_stream = nullptr;
+            c->grid_cap = 0;
+            c->small_tiles = false;
+        }
+    } guard{ctx};
+    // the chain stream's products are small (128 x <= 512 outputs): latency tile shape unless HYP_POTRF_TILES=big
+    static const bool narrow_chain = !(getenv("HYP_POTRF_TILES") && !strcmp(getenv("HYP_POTRF_TILES"), "big"));
     auto on = [&](cudaStream_t s, int cap) {
         ctx->launch_stream = s;
         ctx->grid_cap = cap;
+        ctx->small_tiles = narrow_chain && s == chain;
     };
     const int cap = std::max(2, (ctx->sm_count - 8) & ~1);
+    const int pa_rows = (int)(2 * OB / 256);       // SYRK part a: the 256-row tile pairs of the next two outer blocks
     // profiling aid (tools/potrf_probe.py; results are garbage): 1 = no digit-sliced updates, 2 = chain stream only,
     // 3 = bulk stream only (no panels / in-block products)
     const char* pm = getenv("HYP_POTRF_MODE");
     const int probe = pm ? atoi(pm) : 0;
-    // block row of outer block [K0, Kend) over the columns [c0, c0 + nc): U = U11^-T A, panel by panel
+    // block row of outer block [K0, Kend) over the columns [c0, c0 + nc): U = U11^-T A, panel by panel.  2 * OB / 128 - 1
+    // dependent launches of depth 128: the latency tile shape (128 x 32) unless the panel is wide enough to fill the
+    // chip several times over with 128 x 128 tiles
     auto block_row = [&](int64_t K0, int64_t Kend, int64_t c0, int64_t nc) {
+        const bool saved = ctx->small_tiles;
+        if (narrow_chain && nc <= (int64_t)4 * 128 * ctx->sm_count) ctx->small_tiles = true;
+        struct Restore {
+            hyp_ctx* c;
+            bool v;
+            ~Restore() { c->small_tiles = v; }
+        } restore{ctx, saved};
         for (int64_t k0 = K0; k0 < Kend; k0 += NB) {
             const int64_t nb = std::min<int64_t>(NB, m - k0);
             double* Ar = A + k0 + c0 * lda;                       // rows of the panel
@@ -130,16 +200,17 @@ static bool potrf_upper_i8(hyp_ctx* ctx, double* A, int64_t lda, int64_t m, doub
             CUDA_TRY(cudaStreamWaitEvent(bulk, ctx->ev_near[b & 1], 0));
             hyp_ozaki_slice_short(ctx, P, lda, kd, rest, ctx->d_chol_digits, ldd, sstride, ctx->d_chol_dscale);
             if (probe != 1)
-                hyp_ozaki_syrk_rows(ctx, ctx->d_chol_digits, ldd, sstride, ctx->d_chol_dscale, kd, rest, T, lda, -1.0, 1.0, 0, 4,
+                hyp_ozaki_syrk_rows(ctx, ctx->d_chol_digits, ldd, sstride, ctx->d_chol_dscale, kd, rest, T, lda, -1.0, 1.0, 0, pa_rows,
                                     (int)(near / NB));
         }
         CUDA_TRY(cudaEventRecord(ctx->ev_bulk[b & 1], bulk));
         if (rest > near && probe != 2 && probe != 1)
-            hyp_ozaki_syrk_rows(ctx, ctx->d_chol_digits, ldd, sstride, ctx->d_chol_dscale, kd, rest, T, lda, -1.0, 1.0, 4, -1, 0);
+            hyp_ozaki_syrk_rows(ctx, ctx->d_chol_digits, ldd, sstride, ctx->d_chol_dscale, kd, rest, T, lda, -1.0, 1.0, pa_rows, -1, 0);
     }
     // the caller's stream continues after the last diagonal block
     CUDA_TRY(cudaStreamWaitEvent(bulk, ctx->ev_chain[b & 1], 0));
     on(nullptr, 0);
+    ctx->small_tiles = false;
     CUDA_TRY(cudaGetLastError());
     return true;
 }
@@ -257,9 +328,25 @@ void hyp_trsv_upper(hyp_ctx* ctx, const double* F, int64_t ldf, int64_t m, const
     if (m <= 0) return;
     TimeScope ts(ctx, T_TRSV);
     int nblk = ceil_div(m, NB);
-    CUDA_TRY(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
     int epoch = ++ctx->trsv_epoch;
     set_panel_attr();
+    if (trsv_seg_len() > 0) {
+        // flags: ticket, nblk block flags, nblk segment counters (see hyp_load_model / hyp_test_potrs for the size)
+        const TrsvLists& L = trsv_lists(ctx, nblk, trans);
+        double* part = trsv_part(ctx, nblk, L.maxseg);
+        CUDA_TRY(cudaMemsetAsync(ctx->d_flags, 0, (size_t)(1 + 2 * nblk) * sizeof(int), ctx->stream));
+        const int grid = std::min(L.ntasks, ctx->sm_count);
+        if (trans)
+            trsv_seg_kernel<true><<<grid, 256, TRSV_SMEM, ctx->stream>>>(F, ldf, m, d_dinv, x, ctx->d_flags, L.d_tasks, L.ntasks, nblk,
+                                                                         epoch, part, L.maxseg);
+        else
+            trsv_seg_kernel<false><<<grid, 256, TRSV_SMEM, ctx->stream>>>(F, ldf, m, d_dinv, x, ctx->d_flags, L.d_tasks, L.ntasks, nblk,
+                                                                          epoch, part, L.maxseg);
+        ctx->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return;
+    }
+    CUDA_TRY(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
     int grid = std::min(nblk, ctx->sm_count);
     if (trans)
         trsv_kernel<true><<<grid, 256, TRSV_SMEM, ctx->stream>>>(F, ldf, m, d_dinv, x, ctx->d_flags, nblk, epoch);
@@ -275,9 +362,24 @@ void hyp_trsv_upper2(hyp_ctx* ctx, const double* F, int64_t ldf, int64_t m, cons
     if (m <= 0) return;
     TimeScope ts(ctx, T_TRSV);
     int nblk = ceil_div(m, NB);
-    CUDA_TRY(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
     int epoch = ++ctx->trsv_epoch;
     set_panel_attr();
+    if (trsv_seg_len() > 0) {
+        const TrsvLists& L = trsv_lists(ctx, nblk, trans);
+        double* part = trsv_part(ctx, nblk, L.maxseg);
+        CUDA_TRY(cudaMemsetAsync(ctx->d_flags, 0, (size_t)(1 + 2 * nblk) * sizeof(int), ctx->stream));
+        const int grid = std::min(L.ntasks, ctx->sm_count);
+        if (trans)
+            trsv_seg_kernel<true, 2><<<grid, 256, TRSV_SMEM, ctx->stream>>>(F, ldf, m, d_dinv, x, ctx->d_flags, L.d_tasks, L.ntasks,
+                                                                            nblk, epoch, part, L.maxseg, xstride);
+        else
+            trsv_seg_kernel<false, 2><<<grid, 256, TRSV_SMEM, ctx->stream>>>(F, ldf, m, d_dinv, x, ctx->d_flags, L.d_tasks, L.ntasks,
+                                                                             nblk, epoch, part, L.maxseg, xstride);
+        ctx->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return;
+    }
+    CUDA_TRY(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
     int grid = std::min(nblk, ctx->sm_count);
     if (trans)
         trsv_kernel<true, 2><<<grid, 256, TRSV_SMEM, ctx->stream>>>(F, ldf, m, d_dinv, x, ctx->d_flags, nblk, epoch, xstride);

@@ -772,6 +772,22 @@ constexpr int TRSV_SMEM = NB * NB * 8;
 
 // NRHS right-hand sides share every tile of the factor (hyp_solve_system_multi): x_v = x + v * xstride.  Per right-hand
 // side the arithmetic and its order are those of the single-vector solve.
+// pull the 128 x 128 tile at `tile` (leading dimension ldf) into L2: 1024 lines of 128 B, four per thread of a 256-thread CTA.
+// The sweeps read every tile exactly once, from DRAM; issued one tile ahead this turns the DRAM latency of the register
+// loads into an L2 hit.
+__device__ __forceinline__ void trsv_prefetch_tile(const double* tile, int64_t ldf, int64_t rows_left, int64_t cols_left) {
+#ifndef HYP_EMU
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int L = (int)threadIdx.x + 256 * q;
+        const int c = L >> 3, r = (L & 7) * 16;
+        if (c < cols_left && r < rows_left) asm volatile("prefetch.global.L2 [%0];" ::"l"(tile + r + (int64_t)c * ldf));
+    }
+#else
+    (void)tile; (void)ldf; (void)rows_left; (void)cols_left;
+#endif
+}
+
 template <bool TRANS, int NRHS = 1>
 __global__ void __launch_bounds__(256, 1)
 trsv_kernel(const double* __restrict__ F, int64_t ldf, int64_t m, const double* __restrict__ dinv,
@@ -807,6 +823,7 @@ trsv_kernel(const double* __restrict__ F, int64_t ldf, int64_t m, const double* 
             for (int j = 0; j < k; j++) {
                 double tl[16][4];
                 const double* Ut = F + (int64_t)j * NB + cw * ldf;
+                if (j + 1 < k) trsv_prefetch_tile(F + (int64_t)(j + 1) * NB + c0 * ldf, ldf, NB, m - c0);
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
                     const bool ok = cw + i < m;
@@ -886,6 +903,7 @@ trsv_kernel(const double* __restrict__ F, int64_t ldf, int64_t m, const double* 
             for (int j = nblk - 1; j > k; j--) {
                 double tl[64];
                 const int64_t cb = (int64_t)j * NB + half * 64;
+                if (j - 1 > k) trsv_prefetch_tile(F + c0 + (int64_t)(j - 1) * NB * ldf, ldf, m - c0, NB);
                 const double* Ut = F + grow + cb * ldf;
 #pragma unroll
                 for (int c = 0; c < 64; c++) tl[c] = (grow < m && cb + c < m) ? Ut[(int64_t)c * ldf] : 0.0;
@@ -919,6 +937,268 @@ trsv_kernel(const double* __restrict__ F, int64_t ldf, int64_t m, const double* 
 #pragma unroll
                 for (int v = 0; v < NRHS; v++)
                     sv[v][0][tid] = (c0 + tid < m) ? (x[v * xstride + c0 + tid] - sacc[v][0][tid] - sacc[v][1][tid]) : 0.0;
+            }
+            __syncthreads();
+            // x[r] = sum_{c >= r} Dinv[r, c] v[c]
+            double o0[NRHS];
+#pragma unroll
+            for (int v = 0; v < NRHS; v++) {
+                double a0 = 0.0, a1 = 0.0;
+                const double* row = sD + r + (half * 64) * NB;
+                const double* svh = sv[v][0] + half * 64;
+#pragma unroll 16
+                for (int c = 0; c < 64; c += 2) {
+                    a0 += row[c * NB] * svh[c];
+                    a1 += row[(c + 1) * NB] * svh[c + 1];
+                }
+                o0[v] = a0 + a1;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int v = 0; v < NRHS; v++) sacc[v][half][r] = o0[v];
+            __syncthreads();
+            if (tid < NB && c0 + tid < m) {
+#pragma unroll
+                for (int v = 0; v < NRHS; v++) x[v * xstride + c0 + tid] = sacc[v][0][tid] + sacc[v][1][tid];
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) st_release(&flags[1 + k], epoch);
+    }
+}
+
+struct TrsvTask {
+    int k, j0, nj, w;     // block column, first tile (TRANS: ascending from j0, else descending), tiles, nseg << 16 | seg << 1 | final
+};
+
+// Segmented variant (default): a block column is cut into segments of at most SEG tiles; every segment is a ticket.
+// Non-final segments write their partial sums to global scratch and bump a counter, the block's FINAL segment (the one
+// that ends at the block just solved) adds them in segment order, applies the inverted diagonal block and publishes.
+// With one ticket per block column the late columns were bound by their own serial loop (78 tiles x ~4.7 us per sweep at
+// m = 10000), not by the dependency chain (~2 us per block); here only <= SEG tiles of a column sit in front of the chain.
+// Ticket order = the order in which a ticket's last input becomes available (host: trsv_tasks), a topological order of the
+// dependency graph, so the earliest unfinished ticket is always held by a resident CTA: no deadlock.
+template <bool TRANS, int NRHS = 1>
+__global__ void __launch_bounds__(256, 1)
+trsv_seg_kernel(const double* __restrict__ F, int64_t ldf, int64_t m, const double* __restrict__ dinv,
+                double* x, int* flags, const TrsvTask* __restrict__ tasks, int ntasks, int nblk, int epoch,
+                double* __restrict__ part, int maxseg, int64_t xstride = 0) {
+    int* cnt = flags + 1 + nblk;             // finished non-final segments per block column (zeroed per solve)
+    HYP_DYN_SMEM(double, sD);                // Dinv_k, 128 x 128 col-major
+    __shared__ double sv[NRHS][2][NB];
+    __shared__ double sacc[NRHS][2][NB];
+    __shared__ int s_ticket;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    while (true) {
+        if (tid == 0) s_ticket = atomicAdd(&flags[0], 1);
+        __syncthreads();
+        const int t = s_ticket;
+        __syncthreads();
+        if (t >= ntasks) return;
+        const TrsvTask task = tasks[t];
+        const int k = task.k, j0 = task.j0, nj = task.nj;
+        const bool final = task.w & 1;
+        const int seg = (task.w >> 1) & 0x7fff, nseg = task.w >> 16;
+        const int64_t c0 = (int64_t)k * NB;
+        if (final) {
+            const double* Dk = dinv + (int64_t)k * NB * NB;
+#pragma unroll 8
+            for (int idx = tid; idx < NB * NB; idx += 256) sD[idx] = Dk[idx];
+        }
+
+        if (TRANS) {
+            // y_k = Dinv_k' (b_k - sum_{j<k} U[j-block, k-block]' y_j); warp w owns 16 columns,
+            // lane l rows l, l+32, l+64, l+96 of every tile
+            double pacc[NRHS][16];
+#pragma unroll
+            for (int v = 0; v < NRHS; v++)
+#pragma unroll
+                for (int i = 0; i < 16; i++) pacc[v][i] = 0.0;
+            const int64_t cw = c0 + warp * 16;
+            double psum[NRHS][16];            // lane 0: partial sums of the earlier segments (final ticket only)
+#pragma unroll
+            for (int v = 0; v < NRHS; v++)
+#pragma unroll
+                for (int i = 0; i < 16; i++) psum[v][i] = 0.0;
+            for (int jj = 0; jj < nj; jj++) {
+                const int j = j0 + jj;
+                double tl[16][4];
+                const double* Ut = F + (int64_t)j * NB + cw * ldf;
+                if (jj + 1 < nj) trsv_prefetch_tile(F + (int64_t)(j + 1) * NB + c0 * ldf, ldf, NB, m - c0);
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const bool ok = cw + i < m;
+                    const double* col = Ut + (int64_t)i * ldf;
+#pragma unroll
+                    for (int h = 0; h < 4; h++) tl[i][h] = ok ? col[lane + 32 * h] : 0.0;
+                }
+                if (final && jj == nj - 1 && nseg > 1) {
+                    // the earlier segments of this column finished several chain steps ago: their sums are fetched here,
+                    // behind the tile loads and in front of the wait for the last block - not on the chain
+                    if (tid == 0) {
+                        while (ld_acquire(&cnt[k]) < nseg - 1) {
+                        }
+                    }
+                    __syncthreads();
+                    if (lane == 0) {
+                        for (int sg = 0; sg < nseg - 1; sg++)
+#pragma unroll
+                            for (int v = 0; v < NRHS; v++)
+#pragma unroll
+                                for (int i = 0; i < 16; i++)
+                                    psum[v][i] += __ldcg(part + (((int64_t)k * maxseg + sg) * NRHS + v) * NB + warp * 16 + i);
+                    }
+                }
+                if (tid == 0) {
+                    while (ld_acquire(&flags[1 + j]) != epoch) {
+                    }
+                }
+                __syncthreads();
+                if (tid < NB) {
+#pragma unroll
+                    for (int v = 0; v < NRHS; v++) sv[v][j & 1][tid] = __ldcg(x + v * xstride + (int64_t)j * NB + tid);
+                }
+                __syncthreads();
+#pragma unroll
+                for (int v = 0; v < NRHS; v++) {
+                    const double* svj = sv[v][j & 1];
+                    const double v0 = svj[lane], v1 = svj[lane + 32], v2 = svj[lane + 64], v3 = svj[lane + 96];
+#pragma unroll
+                    for (int i = 0; i < 16; i++)
+                        pacc[v][i] += tl[i][0] * v0 + tl[i][1] * v1 + tl[i][2] * v2 + tl[i][3] * v3;
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < NRHS; v++)
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    double a = pacc[v][i];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                    pacc[v][i] = a;
+                }
+            __syncthreads();
+            if (!final) {
+                // partial sums of this segment -> global scratch; the block's final segment adds them up in segment order
+                if (lane == 0) {
+#pragma unroll
+                    for (int v = 0; v < NRHS; v++)
+#pragma unroll
+                        for (int i = 0; i < 16; i++)
+                            part[(((int64_t)k * maxseg + seg) * NRHS + v) * NB + warp * 16 + i] = pacc[v][i];
+                }
+                __threadfence();
+                __syncthreads();
+                if (tid == 0) atomicAdd(&cnt[k], 1);
+                continue;
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int v = 0; v < NRHS; v++)
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        int64_t c = cw + i;
+                        sv[v][0][warp * 16 + i] = (c < m) ? (x[v * xstride + c] - (pacc[v][i] + psum[v][i])) : 0.0;
+                    }
+            }
+            __syncthreads();
+            // y[c] = sum_{r <= c} Dinv[r, c] v[r]
+#pragma unroll
+            for (int v = 0; v < NRHS; v++) {
+                const double* vb = sv[v][0];
+                const double v0 = vb[lane], v1 = vb[lane + 32], v2 = vb[lane + 64], v3 = vb[lane + 96];
+                double res[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const double* col = sD + (warp * 16 + i) * NB;
+                    double a = col[lane] * v0 + col[lane + 32] * v1 + col[lane + 64] * v2 + col[lane + 96] * v3;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                    res[i] = a;
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        int64_t c = cw + i;
+                        if (c < m) x[v * xstride + c] = res[i];
+                    }
+                }
+            }
+        } else {
+            // x_k = Dinv_k (y_k - sum_{j>k} U[k-block, j-block] x_j); thread owns a row, the two
+            // halves of the CTA split the 128 columns of a tile
+            const int r = tid & (NB - 1), half = tid >> 7;
+            const int64_t grow = c0 + r;
+            double acc[NRHS];
+#pragma unroll
+            for (int v = 0; v < NRHS; v++) acc[v] = 0.0;
+            double psum[NRHS];                // threads 0 .. 127: partial sums of the earlier segments (final ticket only)
+#pragma unroll
+            for (int v = 0; v < NRHS; v++) psum[v] = 0.0;
+            for (int jj = 0; jj < nj; jj++) {
+                const int j = j0 - jj;
+                double tl[64];
+                const int64_t cb = (int64_t)j * NB + half * 64;
+                if (jj + 1 < nj) trsv_prefetch_tile(F + c0 + (int64_t)(j - 1) * NB * ldf, ldf, m - c0, NB);
+                const double* Ut = F + grow + cb * ldf;
+#pragma unroll
+                for (int c = 0; c < 64; c++) tl[c] = (grow < m && cb + c < m) ? Ut[(int64_t)c * ldf] : 0.0;
+                if (final && jj == nj - 1 && nseg > 1) {
+                    if (tid == 0) {
+                        while (ld_acquire(&cnt[k]) < nseg - 1) {
+                        }
+                    }
+                    __syncthreads();
+                    if (tid < NB) {
+                        for (int sg = 0; sg < nseg - 1; sg++)
+#pragma unroll
+                            for (int v = 0; v < NRHS; v++) psum[v] += __ldcg(part + (((int64_t)k * maxseg + sg) * NRHS + v) * NB + tid);
+                    }
+                }
+                if (tid == 0) {
+                    while (ld_acquire(&flags[1 + j]) != epoch) {
+                    }
+                }
+                __syncthreads();
+                if (tid < NB) {
+                    int64_t c = (int64_t)j * NB + tid;
+#pragma unroll
+                    for (int v = 0; v < NRHS; v++) sv[v][j & 1][tid] = (c < m) ? __ldcg(x + v * xstride + c) : 0.0;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int v = 0; v < NRHS; v++) {
+                    const double* svh = sv[v][j & 1] + half * 64;
+                    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 64; c += 2) {
+                        a0 += tl[c] * svh[c];
+                        a1 += tl[c + 1] * svh[c + 1];
+                    }
+                    acc[v] += a0 + a1;
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < NRHS; v++) sacc[v][half][r] = acc[v];
+            __syncthreads();
+            if (!final) {
+                if (tid < NB) {
+#pragma unroll
+                    for (int v = 0; v < NRHS; v++)
+                        part[(((int64_t)k * maxseg + seg) * NRHS + v) * NB + tid] = sacc[v][0][tid] + sacc[v][1][tid];
+                }
+                __threadfence();
+                __syncthreads();
+                if (tid == 0) atomicAdd(&cnt[k], 1);
+                continue;
+            }
+            if (tid < NB) {
+#pragma unroll
+                for (int v = 0; v < NRHS; v++) {
+                    const double a = sacc[v][0][tid] + sacc[v][1][tid] + psum[v];
+                    sv[v][0][tid] = (c0 + tid < m) ? (x[v * xstride + c0 + tid] - a) : 0.0;
+                }
             }
             __syncthreads();
             // x[r] = sum_{c >= r} Dinv[r, c] v[c]

@@ -156,6 +156,7 @@ struct hyp_ctx {
     cudaStream_t stream2 = nullptr;    // side stream of the Cholesky look-ahead chain
     cudaStream_t launch_stream = nullptr;   // stream the GEMM / panel launch helpers use (stream or stream2)
     int grid_cap = 0;                  // > 0: persistent GEMM grids leave SMs free for the side stream
+    bool small_tiles = false;          // GEMM launch helpers use the 128 x 32 latency tile shape (Cholesky chain stream)
     cudaEvent_t ev_chain[2] = {nullptr, nullptr}, ev_bulk[2] = {nullptr, nullptr}, ev_near[2] = {nullptr, nullptr};
     int8_t* d_chol_digits = nullptr;   // digit slices of one 512-row block row of the Cholesky (chol.cu, potrf_upper_i8)
     double* d_chol_dscale = nullptr;
@@ -238,7 +239,9 @@ struct hyp_ctx {
     int* d_row_cone = nullptr;         // q: global cone index of every row
     double* d_blk_arr = nullptr;       // q x maxdim identity pattern / products (2 buffers)
     int64_t blk_maxdim = 0;
-    int* d_flags = nullptr;            // TRSV ticket + block-ready flags
+    int* d_flags = nullptr;            // TRSV ticket + block-ready flags + segment counters (1 + 2 nblk ints)
+    double* d_trsv_part = nullptr;     // partial sums of the segmented triangular solve
+    int64_t trsv_part_len = 0;
     // two-column solves (hyp_solve_system_multi): partial buffers of the two-vector GEMV kernels and a second set of
     // the work vectors of solve_system_dev / apply_lhs_dev
     double *d_partial3 = nullptr, *d_partial4 = nullptr;
@@ -385,15 +388,16 @@ void hyp_gemm_simple(hyp_ctx* ctx, bool transA, bool transB, int64_t M, int64_t 
 // ---- ozaki.cu ----
 int hyp_ozaki_radix();
 // fused Schur pre-pass + digit slicing for second-order-cone models (cones.cu); false = not applicable
-bool hyp_cones_prepass_sliced(hyp_ctx* ctx, int8_t* digits, int64_t ldd, int64_t slice_stride, int* expo, double* dscale);
+int hyp_cones_prepass_sliced(hyp_ctx* ctx, int8_t* digits, int64_t ldd, int64_t slice_stride, int* expo, double* dscale);
 bool hyp_ozaki_pair64_ready(hyp_ctx* ctx);
 void hyp_ozaki_slice_short(hyp_ctx* ctx, const double* A, int64_t lda, int64_t K, int64_t ncols, int8_t* digits, int64_t ldd,
                            int64_t slice_stride, double* dscale);
 void hyp_ozaki_syrk_rows(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t slice_stride, const double* dscale,
                          int64_t K, int64_t ncols, double* C, int64_t ldc, double alpha, double beta, int p_lo, int p_hi,
                          int skip_diag);
+// have_expo: expo / dscale are already filled (the pre-pass collected the column maxima): only the digit slicing runs
 void hyp_ozaki_slice(hyp_ctx* ctx, const double* A, int64_t lda, int64_t K, int64_t ncols, int8_t* digits,
-                     int64_t ldd, int64_t slice_stride, int* expo, double* dscale);
+                     int64_t ldd, int64_t slice_stride, int* expo, double* dscale, bool have_expo = false);
 void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t slice_stride, const int* expo,
                     const double* dscale, int64_t K, int64_t ncols, double* C, int64_t ldc, double alpha, double beta);
 

@@ -306,15 +306,37 @@ void hyp_cones_schur_prepass(hyp_ctx* ctx) {
 // the rows of H^{1/2} G are never written - pass 1 recomputes them chunk by chunk in shared memory and keeps the
 // column maxima, pass 2 recomputes them and stores the radix-256 digit slices directly (qrchol.jl:219-234 + the
 // slicing of ozaki.cu in two reads of G and one write of the digits: 11.5 GB instead of 19.5 GB on C3).
-bool hyp_cones_prepass_sliced(hyp_ctx* ctx, int8_t* digits, int64_t ldd, int64_t slice_stride, int* expo, double* dscale) {
-    // opt-in (HYP_FUSED_PREPASS=1): measured on C3 (profiles/r02_bench_c3_pair64_{fused,nofuse}.json) the two recomputing
-    // passes cost 7.6 ms against 3.0 ms (pre-pass) + 3.4 ms (colmax + slice256) of the three-kernel sequence - the
-    // second-order-cone product kernel is bound by its shared-memory sweeps, not by HBM, so computing it twice loses
-    static int enabled = -1;
-    if (enabled < 0) enabled = getenv("HYP_FUSED_PREPASS") ? 1 : 0;
-    if (!enabled || hyp_ozaki_radix() != 256 || ctx->groups.size() != 1 || ctx->nmp < 16) return false;
+int hyp_cones_prepass_sliced(hyp_ctx* ctx, int8_t* digits, int64_t ldd, int64_t slice_stride, int* expo, double* dscale) {
+    // returns 0 = not applicable (caller runs the plain pre-pass and the slicer), 1 = digit slices written (H^{1/2} G never
+    // stored; opt-in), 2 = H^{1/2} G stored and the column exponents / scales ready (default: the slicer skips its
+    // column-maximum pass over the 4 GB product)
+    // full fusion is opt-in (HYP_FUSED_PREPASS=1): measured on C3 (profiles/r02_bench_c3_pair64_{fused,nofuse}.json) the two
+    // recomputing passes cost 7.6 ms against 3.0 ms (pre-pass) + 3.4 ms (colmax + slice256) of the three-kernel sequence -
+    // the second-order-cone product kernel is bound by its shared-memory sweeps, not by HBM, so computing it twice loses
+    static int fused = -1, with_max = -1;
+    if (fused < 0) {
+        fused = getenv("HYP_FUSED_PREPASS") ? 1 : 0;
+        with_max = getenv("HYP_NO_PREPASS_COLMAX") ? 0 : 1;
+    }
+    if ((!fused && !with_max) || hyp_ozaki_radix() != 256 || ctx->groups.size() != 1 || ctx->nmp < 16) return 0;
     ConeGroup& g = ctx->groups[0];
-    if (g.type != HYP_CONE_EPINORMEUCL || g.n_chunks <= 0 || !g.chunks_cover_all || g.rows != ctx->qloc) return false;
+    if (g.type != HYP_CONE_EPINORMEUCL || g.n_chunks <= 0 || !g.chunks_cover_all || g.rows != ctx->qloc) return 0;
+    const double* GQ2 = ctx->d_GQ + ctx->p * ctx->ldg;
+    const int64_t ncols = ctx->nmp;
+    const int gy = (int)std::min<int64_t>(ncols, 65535);
+    if (!ctx->d_colbits) CUDA_TRY(cudaMalloc((void**)&ctx->d_colbits, (size_t)std::max<int64_t>(ncols, 1) * 8));
+    if (!fused) {
+        TimeScope ts(ctx, T_SQRT_PREPASS);
+        CUDA_TRY(cudaMemsetAsync(ctx->d_colbits, 0, (size_t)ncols * 8, ctx->stream));
+        hypdev::soc_prod_chunk_kernel<HYP_PROD_SQRT_HESS, 3><<<dim3(g.n_chunks, gy), 256, g.chunk_smem, ctx->stream>>>(
+            g.d_crow0, g.d_crows, g.d_ccone0, g.d_ccount, g.d_off, g.d_dim, g.d_scal, ctx->d_point, GQ2, ctx->ldg, ctx->d_HG,
+            ctx->ldg, ncols, ctx->row_lo, ctx->d_colbits);
+        hypdev::expo_from_bits_kernel<<<std::max(1, std::min(ceil_div(ncols, 256), ctx->sm_count)), 256, 0, ctx->stream>>>(
+            ncols, ctx->d_colbits, expo, dscale, 1);
+        ctx->launches += 2;
+        CUDA_TRY(cudaGetLastError());
+        return 2;
+    }
     // chunk starts (local row numbers) must be multiples of 8: the digit words are 8 rows wide
     if (g.chunk_align8 < 0) {
         g.chunk_align8 = 1;
@@ -332,13 +354,9 @@ bool hyp_cones_prepass_sliced(hyp_ctx* ctx, int8_t* digits, int64_t ldd, int64_t
             expect = r0 + rows_c;
         }
     }
-    if (!g.chunk_align8) return false;
+    if (!g.chunk_align8) return 0;
     TimeScope ts(ctx, T_SQRT_PREPASS);
-    const double* GQ2 = ctx->d_GQ + ctx->p * ctx->ldg;
-    const int64_t ncols = ctx->nmp;
-    if (!ctx->d_colbits) CUDA_TRY(cudaMalloc((void**)&ctx->d_colbits, (size_t)std::max<int64_t>(ncols, 1) * 8));
     CUDA_TRY(cudaMemsetAsync(ctx->d_colbits, 0, (size_t)ncols * 8, ctx->stream));
-    const int gy = (int)std::min<int64_t>(ncols, 65535);
     hypdev::soc_prod_chunk_kernel<HYP_PROD_SQRT_HESS, 1><<<dim3(g.n_chunks, gy), 256, g.chunk_smem, ctx->stream>>>(
         g.d_crow0, g.d_crows, g.d_ccone0, g.d_ccount, g.d_off, g.d_dim, g.d_scal, ctx->d_point, GQ2, ctx->ldg, nullptr, 0,
         ncols, ctx->row_lo, ctx->d_colbits);
@@ -349,7 +367,7 @@ bool hyp_cones_prepass_sliced(hyp_ctx* ctx, int8_t* digits, int64_t ldd, int64_t
         ncols, ctx->row_lo, nullptr, expo, digits, ldd, slice_stride, 7);
     ctx->launches += 3;
     CUDA_TRY(cudaGetLastError());
-    return true;
+    return 1;
 }
 
 void hyp_cones_dder3_dev(hyp_ctx* ctx, double* out, const double* dir) {

@@ -163,8 +163,9 @@ soc_prod_kernel(int ncones, const int64_t* __restrict__ off, const int* __restri
 // goes back with coalesced stores.  chunk table: crow0[b], crows[b] = first row / number of rows
 // of chunk b, ccone0[b], ccount[b] = first cone (index in the group) / number of cones.
 // OUT selects what happens to the product (the fused Schur pre-pass of the digit-sliced SYRK, ozaki.cu, never
-// materialises H^{1/2} G): 0 = store it; 1 = only the column maxima of |.| (atomicMax of the bit patterns into
-// colbits[j]); 2 = cut it into radix-256 digit slices with the column exponents expo[j] and store the digits
+// materialises H^{1/2} G): 0 = store it; 3 = store it AND collect the column maxima (saves the slicer's first pass over
+// the stored product); 1 = only the column maxima of |.| (atomicMax of the bit patterns into colbits[j]); 2 = cut it
+// into radix-256 digit slices with the column exponents expo[j] and store the digits
 // (chunks start at multiples of 8 rows, checked by the host, so the packed 8-byte words are aligned).
 template <int MODE, int OUT = 0>
 __global__ void __launch_bounds__(256)
@@ -212,9 +213,10 @@ soc_prod_chunk_kernel(const int64_t* __restrict__ crow0, const int* __restrict__
             for (int i = 1; i < d; i++) v[i] = kw * w[i] + kj * v[i];
         }
         __syncthreads();
-        if (OUT == 0) {
+        if (OUT == 0 || OUT == 3) {
             for (int i = threadIdx.x; i < nr; i += blockDim.x) pr[i] = srow[i];
-        } else if (OUT == 1) {
+        }
+        if (OUT == 1 || OUT == 3) {
             __shared__ double smx[8];
             double mx = 0.0;
             for (int i = threadIdx.x; i < nr; i += blockDim.x) mx = fmax(mx, fabs(srow[i]));
@@ -228,7 +230,7 @@ soc_prod_chunk_kernel(const int64_t* __restrict__ crow0, const int* __restrict__
                 memcpy(&b, &mx, sizeof(double));
                 if (b) atomicMax(colbits + j, b);
             }
-        } else {
+        } else if (OUT == 2) {
             const double sc = ldexp(1.0, 7 - expo[j]);
             int8_t* dcol = digits + j * ldd + (r0 - row_shift);
             for (int g8 = threadIdx.x; g8 * 8 < nr; g8 += blockDim.x) {

@@ -805,7 +805,7 @@ int update_lhs_fact(hyp_ctx* ctx) {
         hyp_allgather_inplace(ctx, ctx->d_S, cw * ctx->lds);
     } else {
     // digit-sliced SYRK on second-order-cone models: pre-pass and slicing fused, H^{1/2} G is never written
-    bool sliced = false;
+    int sliced = 0;       // 1: the digit slices are written, 2: H^{1/2} G is stored and the column exponents are ready
     const bool want_i8 = ctx->qloc > 0 && ctx->syrk_mode == 1 && !ctx->d_PG;
     if (want_i8) {
         if (!ctx->d_digits) {
@@ -817,6 +817,8 @@ int update_lhs_fact(hyp_ctx* ctx) {
         sliced = hyp_cones_prepass_sliced(ctx, ctx->d_digits, ctx->ldd, ctx->ldd * nmp, ctx->d_expo, ctx->d_dscale);
     }
     if (!sliced) hyp_cones_schur_prepass(ctx);
+    const bool have_expo = sliced == 2;
+    if (sliced == 2) sliced = 0;
     {
         TimeScope ts(ctx, T_SYRK);
         const double* P = ctx->d_HG;
@@ -835,7 +837,7 @@ int update_lhs_fact(hyp_ctx* ctx) {
             }
             if (!sliced)
                 hyp_ozaki_slice(ctx, ctx->d_HG, ctx->ldg, ctx->qloc, nmp, ctx->d_digits, ctx->ldd, ctx->ldd * nmp,
-                                ctx->d_expo, ctx->d_dscale);
+                                ctx->d_expo, ctx->d_dscale, have_expo);
             hyp_ozaki_syrk(ctx, ctx->d_digits, ctx->ldd, ctx->ldd * nmp, ctx->d_expo, ctx->d_dscale, ctx->qloc, nmp, ctx->d_S,
                            ctx->lds, 1.0, 0.0);
         } else if (ctx->qloc > 0)
@@ -1119,6 +1121,7 @@ void hyp_destroy(hyp_ctx* ctx) {
     }
     if (ctx->d_chol_digits) cudaFree(ctx->d_chol_digits);
     if (ctx->d_chol_dscale) cudaFree(ctx->d_chol_dscale);
+    if (ctx->d_trsv_part) cudaFree(ctx->d_trsv_part);
     if (ctx->d_dag_ver) cudaFree(ctx->d_dag_ver);
     if (ctx->d_dag_dbg) cudaFree(ctx->d_dag_dbg);
     cudaStreamDestroy(ctx->stream2);
@@ -1347,7 +1350,7 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
         ctx->partial_doubles = std::max<int64_t>(4096, 32 * std::max<int64_t>(std::max(ctx->qloc, n), p));
         dalloc(&ctx->d_partial, ctx->partial_doubles);
         dalloc(&ctx->d_info, 16);
-        dalloc(&ctx->d_flags, ceil_div(std::max<int64_t>(std::max(nmp, p), 1), 128) + 8);
+        dalloc(&ctx->d_flags, 2 * ceil_div(std::max<int64_t>(std::max(nmp, p), 1), 128) + 8);
         ctx->trsv_epoch = 0;
 
         // Schur matrix, factor, inverted diagonal blocks
@@ -1821,7 +1824,7 @@ int hyp_test_potrs(hyp_ctx* ctx, const double* F, int64_t ldf, int64_t m, double
         double* dx = tmp.in(x, m, m, 1, &lx);
         int* saved = ctx->d_flags;
         int* flags = nullptr;
-        dalloc(&flags, ceil_div(m, 128) + 8);
+        dalloc(&flags, 2 * ceil_div(m, 128) + 8);
         tmp.ptrs.push_back(flags);
         ctx->d_flags = flags;
         hyp_trsv_upper(ctx, dF, lf, m, g_tf.dinv, dx, true);

@@ -1469,6 +1469,17 @@ ozaki_syrk_pair64_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid
                             asm volatile("prefetch.global.L2 [%0];" ::"l"(C + row + col * ldc));
                     }
                 }
+                // the old values of C (second pass, or beta != 0) are loaded one 16-column chunk AHEAD of their use: the
+                // first chunk before the accumulators are even ready, chunk c + 1 while chunk c is converted and stored
+                // (written as 16 load / store pairs they serialise on 16 L2 or DRAM round trips per chunk)
+                const bool rmw = (pass == 1 || beta != 0.0) && store && row < ncols;
+                const double bt = pass == 1 ? 1.0 : beta;
+                double cold[16], cnext[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const int64_t col = (int64_t)tJ * TN + j;
+                    cold[j] = (rmw && col < ncols) ? __ldcg(C + row + col * ldc) : 0.0;
+                }
                 mbar_wait(bar_tfull, item & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const int d0 = pass * L1, nacc = pass == 0 ? L1 : P64_NSL - L1;
@@ -1490,16 +1501,11 @@ ozaki_syrk_pair64_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid
                               "=r"(v[g][15])
                             : "r"(taddr));
                     }
-                    // the old values of C (second pass, or beta != 0): all 16 loads in flight BEFORE the TMEM wait and the
-                    // stores - written as 16 load / store pairs they serialise on 16 L2 (or DRAM) round trips per chunk
-                    double cold[16];
-                    const bool rmw = pass == 1 || beta != 0.0;
-                    const double bt = pass == 1 ? 1.0 : beta;
-                    if (store && row < ncols && rmw) {
+                    if (c0 + 16 < TN) {
 #pragma unroll
                         for (int j = 0; j < 16; j++) {
-                            const int64_t col = (int64_t)tJ * TN + c0 + j;
-                            cold[j] = (col < ncols) ? __ldcg(C + row + col * ldc) : 0.0;
+                            const int64_t col = (int64_t)tJ * TN + c0 + 16 + j;
+                            cnext[j] = (rmw && col < ncols) ? __ldcg(C + row + col * ldc) : 0.0;
                         }
                     }
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -1517,6 +1523,8 @@ ozaki_syrk_pair64_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid
                             }
                         }
                     }
+#pragma unroll
+                    for (int j = 0; j < 16; j++) cold[j] = cnext[j];
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;");
                 __syncwarp();
@@ -1971,10 +1979,11 @@ static int ozaki_radix() {
 int hyp_ozaki_radix() { return ozaki_radix(); }
 
 void hyp_ozaki_slice(hyp_ctx* ctx, const double* A, int64_t lda, int64_t K, int64_t ncols, int8_t* digits,
-                     int64_t ldd, int64_t slice_stride, int* expo, double* dscale) {
+                     int64_t ldd, int64_t slice_stride, int* expo, double* dscale, bool have_expo) {
     if (K <= 0 || ncols <= 0) return;
     const bool r256 = ozaki_radix() == 256;
-    hypdev::colmax_kernel<<<(unsigned)ncols, 256, 0, ctx->stream>>>(K, ncols, A, lda, expo, dscale, r256 ? 1 : 0);
+    if (!have_expo)
+        hypdev::colmax_kernel<<<(unsigned)ncols, 256, 0, ctx->stream>>>(K, ncols, A, lda, expo, dscale, r256 ? 1 : 0);
     dim3 grid(std::max(1, std::min(ceil_div(K, 2048), 32)), (unsigned)std::min<int64_t>(ncols, 65535));
     if (r256)
         hypdev::slice256_kernel<<<grid, 256, 0, ctx->stream>>>(K, ncols, A, lda, expo, 7, digits, ldd, slice_stride);
@@ -2400,14 +2409,17 @@ bool hyp_ozaki_pair64_ready(hyp_ctx* ctx) {
     return ready > 0;
 }
 
-// digit slices + scales of a block row of at most 512 rows, one kernel, on the launch stream
+// digit slices + scales of a block row of at most 1024 rows, one kernel, on the launch stream
 void hyp_ozaki_slice_short(hyp_ctx* ctx, const double* A, int64_t lda, int64_t K, int64_t ncols, int8_t* digits, int64_t ldd,
                            int64_t slice_stride, double* dscale) {
     if (K <= 0 || ncols <= 0) return;
-    if (K > 512 || (ldd & 15) || ldd < K) throw HypError{"hyp_ozaki_slice_short: at most 512 rows, ldd % 16 == 0"};
+    if (K > 1024 || (ldd & 15) || ldd < K) throw HypError{"hyp_ozaki_slice_short: at most 1024 rows, ldd % 16 == 0"};
     cudaStream_t s = ctx->launch_stream ? ctx->launch_stream : ctx->stream;
     const int grid = (int)std::min<int64_t>(ceil_div(ncols, 8), 4 * ctx->sm_count);
-    hypdev::slice256_short_kernel<<<grid, 256, 0, s>>>((int)K, ncols, A, lda, dscale, P64_NSL, digits, ldd, slice_stride);
+    if (K <= 512)
+        hypdev::slice256_short_kernel<2><<<grid, 256, 0, s>>>((int)K, ncols, A, lda, dscale, P64_NSL, digits, ldd, slice_stride);
+    else
+        hypdev::slice256_short_kernel<4><<<grid, 256, 0, s>>>((int)K, ncols, A, lda, dscale, P64_NSL, digits, ldd, slice_stride);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
 }

@@ -114,10 +114,11 @@ static __global__ void expo_from_bits_kernel(int64_t ncols, const unsigned long 
     }
 }
 
-// Column maximum, exponent and the radix-256 digit slices of a SHORT block row (K <= 512 rows: the depth-512 panel of the
-// blocked Cholesky, chol.cu) in one pass: one warp per column keeps its (up to) 16 values per lane in registers.
-// Lane l holds rows 8 l .. 8 l + 7 and 256 + 8 l .. 256 + 8 l + 7, so the loads are 2 KB contiguous per warp and each
-// slice gets one 8-byte word per lane (256 B contiguous per warp).  Rows K .. ldd - 1 of the digit columns are zeroed.
+// Column maximum, exponent and the radix-256 digit slices of a SHORT block row (K <= 256 NH rows, NH = 2 or 4: the depth-512
+// / depth-1024 panel of the blocked Cholesky, chol.cu) in one pass: one warp per column keeps its (up to) 8 NH values per
+// lane in registers.  Lane l holds rows 256 h + 8 l .. + 7 for h < NH, so the loads are 2 KB contiguous per warp and each
+// slice gets one 8-byte word per lane and h (256 B contiguous per warp).  Rows K .. ldd - 1 of the digit columns are zeroed.
+template <int NH>
 static __global__ void __launch_bounds__(256)
 slice256_short_kernel(int K, int64_t ncols, const double* __restrict__ A, int64_t lda, double* __restrict__ dscale,
                       int nslices, int8_t* __restrict__ D, int64_t ldd, int64_t slice_stride) {
@@ -125,10 +126,10 @@ slice256_short_kernel(int K, int64_t ncols, const double* __restrict__ A, int64_
     const int wpb = blockDim.x >> 5;
     for (int64_t j = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); j < ncols; j += (int64_t)gridDim.x * wpb) {
         const double* col = A + j * lda;
-        double v[2][8];
+        double v[NH][8];
         double mx = 0.0;
 #pragma unroll
-        for (int h = 0; h < 2; h++)
+        for (int h = 0; h < NH; h++)
 #pragma unroll
             for (int u = 0; u < 8; u++) {
                 const int k = h * 256 + lane * 8 + u;
@@ -145,7 +146,7 @@ slice256_short_kernel(int K, int64_t ncols, const double* __restrict__ A, int64_
         if (lane == 0) dscale[j] = ldexp(1.0, e);
         const double sc = ldexp(1.0, 7 - e);
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
+        for (int h = 0; h < NH; h++) {
             const int k0 = h * 256 + lane * 8;
             if (k0 >= ldd) continue;
             double rr[8];

@@ -77,11 +77,22 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
+// Template: the 8 consumer warps form a WM x WN grid, each warp owns MI x NJ blocks of 8 x 8: tile = (64 WM MI / 8 ...)
+//   <2, 4, 8, 4>: 128 x 128 tiles (throughput shape: the Schur SYRK, the bulk GEMMs);
+//   <4, 2, 4, 2>: 128 x 32 tiles  (latency shape for the small products on the Cholesky's critical chain: a quarter of
+//                 the work per CTA, four times the CTAs; the 128-row P tile keeps in-place TRSM products safe - every
+//                 CTA reads all 128 rows of its column block before it writes them).
+template <int WM, int WN, int MI, int NJ>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 atb_upper_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapR,
                  const int4* __restrict__ tiles, int n_tiles, int nkb, int same_operand,
                  int64_t mrows, int64_t ncols, double* __restrict__ Cbase, int64_t ldc,
                  int64_t c_group_stride, double alpha, double beta) {
+    static_assert(WM * WN == NUM_CONSUMER_WARPS, "8 consumer warps");
+    constexpr int TSM = WM * MI * 8, TSN = WN * NJ * 8;          // tile rows / cols of C
+    constexpr int P_BYTES = TSM * BK * 8, R_BYTES = TSN * BK * 8;
+    constexpr int STAGE_BYTES = P_BYTES + R_BYTES;
+    static_assert(TSM == BM && (TSN == BN || TSN == 32), "tile shapes the host knows");
     extern __shared__ uint8_t smem_raw[];
     uint32_t base = smem_u32(smem_raw);
     uint32_t tiles_smem = (base + 1023u) & ~1023u;
@@ -107,14 +118,14 @@ atb_upper_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
                 int4 tile = tiles[t];
-                bool single = same_operand && (tile.x == tile.y);
+                bool single = TSM == TSN && same_operand && (tile.x == tile.y);
                 for (int kb = 0; kb < nkb; kb++) {
                     mbar_wait(bar_empty + stage * 8, phase ^ 1u);
                     uint32_t full = bar_full + stage * 8;
-                    mbar_expect_tx(full, single ? TILE_BYTES : STAGE_BYTES);
+                    mbar_expect_tx(full, single ? P_BYTES : STAGE_BYTES);
                     uint32_t dst = tiles_smem + stage * STAGE_BYTES;
-                    tma_load_2d(dst, &mapP, kb * BK, tile.x * BM, full);
-                    if (!single) tma_load_2d(dst + TILE_BYTES, &mapR, tile.z + kb * BK, tile.y * BN, full);
+                    tma_load_2d(dst, &mapP, kb * BK, tile.x * TSM, full);
+                    if (!single) tma_load_2d(dst + P_BYTES, &mapR, tile.z + kb * BK, tile.y * TSN, full);
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1u;
@@ -126,44 +137,44 @@ atb_upper_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant
     }
 
     // ===== DMMA consumers =====
-    const int warp_m = warp >> 2;      // 0..1  -> 64 rows of the tile
-    const int warp_n = warp & 3;       // 0..3  -> 32 cols of the tile
+    const int warp_m = warp / WN;      // MI * 8 rows of the tile
+    const int warp_n = warp % WN;      // NJ * 8 cols of the tile
     const int g = lane >> 2;           // 0..7
     const int t4 = lane & 3;
     uint32_t koff[4];
 #pragma unroll
     for (int s = 0; s < 4; s++) koff[s] = (uint32_t)((((2 * s + (t4 >> 1)) ^ g) << 4) + ((t4 & 1) << 3));
-    const uint32_t offA = (uint32_t)((warp_m * 64 + g) * 128);
-    const uint32_t offB = (uint32_t)((warp_n * 32 + g) * 128);
+    const uint32_t offA = (uint32_t)((warp_m * MI * 8 + g) * 128);
+    const uint32_t offB = (uint32_t)((warp_n * NJ * 8 + g) * 128);
 
     int stage = 0;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         int4 tile = tiles[t];
-        bool single = same_operand && (tile.x == tile.y);
+        bool single = TSM == TSN && same_operand && (tile.x == tile.y);
         double* __restrict__ C = Cbase + (int64_t)tile.w * c_group_stride;
-        double acc[8][4][2];
+        double acc[MI][NJ][2];
 #pragma unroll
-        for (int i = 0; i < 8; i++)
+        for (int i = 0; i < MI; i++)
 #pragma unroll
-            for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+            for (int j = 0; j < NJ; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
         for (int kb = 0; kb < nkb; kb++) {
             mbar_wait(bar_full + stage * 8, phase);
             uint32_t sA = tiles_smem + stage * STAGE_BYTES;
-            uint32_t sB = single ? sA : sA + TILE_BYTES;
+            uint32_t sB = single ? sA : sA + P_BYTES;
             uint32_t pa = sA + offA, pb = sB + offB;
 #pragma unroll
             for (int s = 0; s < 4; s++) {
-                double a[8], b[4];
+                double a[MI], b[NJ];
 #pragma unroll
-                for (int i = 0; i < 8; i++) a[i] = lds64(pa + i * 1024 + koff[s]);
+                for (int i = 0; i < MI; i++) a[i] = lds64(pa + i * 1024 + koff[s]);
 #pragma unroll
-                for (int j = 0; j < 4; j++) b[j] = lds64(pb + j * 1024 + koff[s]);
+                for (int j = 0; j < NJ; j++) b[j] = lds64(pb + j * 1024 + koff[s]);
 #pragma unroll
-                for (int i = 0; i < 8; i++)
+                for (int i = 0; i < MI; i++)
 #pragma unroll
-                    for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                    for (int j = 0; j < NJ; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + stage * 8);
@@ -174,17 +185,17 @@ atb_upper_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant
         }
 
         // epilogue: C[row, col] = alpha * acc + beta * C  (upper tiles; masked at the edges)
-        const int64_t row0 = (int64_t)tile.x * BM + warp_m * 64 + g;
-        const int64_t col0 = (int64_t)tile.y * BN + warp_n * 32 + 2 * t4;
+        const int64_t row0 = (int64_t)tile.x * TSM + warp_m * MI * 8 + g;
+        const int64_t col0 = (int64_t)tile.y * TSN + warp_n * NJ * 8 + 2 * t4;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < NJ; j++) {
 #pragma unroll
             for (int e = 0; e < 2; e++) {
                 int64_t col = col0 + 8 * j + e;
                 if (col >= ncols) continue;
                 double* cp = C + col * ldc;
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
+                for (int i = 0; i < MI; i++) {
                     int64_t row = row0 + 8 * i;
                     if (row < mrows) {
                         double v = alpha * acc[i][j][e];
@@ -215,12 +226,12 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-void make_map(CUtensorMap* map, const double* base, int64_t klen, int64_t ncols, int64_t ld) {
+void make_map(CUtensorMap* map, const double* base, int64_t klen, int64_t ncols, int64_t ld, int box_rows = BM) {
     if (((uintptr_t)base & 15) || (ld & 1))
         throw HypError{"atb: operand must be 16-byte aligned with an even leading dimension"};
     cuuint64_t dims[2] = {(cuuint64_t)klen, (cuuint64_t)ncols};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
-    cuuint32_t box[2] = {BK, BM};
+    cuuint32_t box[2] = {BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = get_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, dims, strides,
                                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -259,6 +270,15 @@ std::vector<int4> build_full_tiles(int mt, int nt, int ngroups, int kstride) {
     return tiles;
 }
 
+// narrow (128 x 32) tiles of the latency shape: upper = every tile with an element on or above the diagonal
+std::vector<int4> build_narrow_tiles(int kind, int mt, int nt32) {
+    std::vector<int4> tiles;
+    for (int tj = 0; tj < nt32; tj++)
+        for (int ti = 0; ti < mt; ti++)
+            if (kind != 0 || ti <= tj / 4) tiles.push_back(make_int4(ti, tj, 0, 0));
+    return tiles;
+}
+
 struct TileCacheEntry {
     int device, kind, mt, nt, ngroups, kstride;
     int4* d_tiles;
@@ -276,7 +296,8 @@ void get_tiles(hyp_ctx* ctx, int kind, int mt, int nt, int ngroups, int kstride,
             *n_tiles = e.n_tiles;
             return;
         }
-    std::vector<int4> tiles = kind == 0 ? build_upper_tiles(nt) : build_full_tiles(mt, nt, ngroups, kstride);
+    std::vector<int4> tiles = kind >= 2 ? build_narrow_tiles(kind - 2, mt, nt)
+                              : (kind == 0 ? build_upper_tiles(nt) : build_full_tiles(mt, nt, ngroups, kstride));
     TileCacheEntry e{ctx->device, kind, mt, nt, ngroups, kstride, nullptr, (int)tiles.size()};
     CUDA_TRY(cudaMalloc(&e.d_tiles, tiles.size() * sizeof(int4)));
     CUDA_TRY(cudaMemcpyAsync(e.d_tiles, tiles.data(), tiles.size() * sizeof(int4),
@@ -294,25 +315,32 @@ void launch_atb(hyp_ctx* ctx, int kind, const double* P, int64_t ldp, const doub
     if (ngroups > 1 && (r_kstride & 1)) throw HypError{"grouped GEMM: the k stride must be even (TMA coordinates are 16-byte aligned)"};
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(atb_upper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(atb_upper_kernel<2, 4, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(atb_upper_kernel<4, 2, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
+    // latency shape (128 x 32 tiles) for the small products of the Cholesky's chain stream (chol.cu sets small_tiles)
+    const bool narrow = ctx->small_tiles && ngroups == 1;
     int4* d_tiles = nullptr;
     int n_tiles = 0;
-    get_tiles(ctx, kind, ceil_div(mrows, BM), ceil_div(ncols, BN), ngroups, (int)r_kstride, &d_tiles,
-              &n_tiles);
+    if (narrow) get_tiles(ctx, kind + 2, ceil_div(mrows, BM), ceil_div(ncols, 32), 1, 0, &d_tiles, &n_tiles);
+    else get_tiles(ctx, kind, ceil_div(mrows, BM), ceil_div(ncols, BN), ngroups, (int)r_kstride, &d_tiles, &n_tiles);
     CUtensorMap mapP, mapR;
     make_map(&mapP, P, klen, mrows, ldp);
     // grouped products read R at k offsets g * r_kstride; rows past a group's klen meet the
     // zero-filled out-of-range rows of P, so they contribute nothing
-    make_map(&mapR, R, ngroups > 1 ? r_kstride * (ngroups - 1) + klen : klen, ncols, ldr);
+    make_map(&mapR, R, ngroups > 1 ? r_kstride * (ngroups - 1) + klen : klen, ncols, ldr, narrow ? 32 : BN);
     int nkb = ceil_div(klen, BK);
     int grid = std::min(n_tiles, ctx->sm_count);
     if (ctx->grid_cap > 0) grid = std::min(grid, ctx->grid_cap);
     int same = (kind == 0 && P == R && ldp == ldr) ? 1 : 0;
-    atb_upper_kernel<<<grid, NUM_THREADS, SMEM_BYTES, ctx->launch_stream ? ctx->launch_stream : ctx->stream>>>(
-        mapP, mapR, d_tiles, n_tiles, nkb, same, mrows, ncols, C, ldc, c_group_stride, alpha, beta);
+    cudaStream_t st = ctx->launch_stream ? ctx->launch_stream : ctx->stream;
+    if (narrow)
+        atb_upper_kernel<4, 2, 4, 2><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mapP, mapR, d_tiles, n_tiles, nkb, same, mrows, ncols, C,
+                                                                            ldc, c_group_stride, alpha, beta);
+    else
+        atb_upper_kernel<2, 4, 8, 4><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mapP, mapR, d_tiles, n_tiles, nkb, same, mrows, ncols, C,
+                                                                            ldc, c_group_stride, alpha, beta);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
 }

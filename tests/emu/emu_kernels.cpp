@@ -605,6 +605,7 @@ int emu_gemv_n(int vec, int64_t rows, int64_t ncols, const double* M, int64_t ld
 
 // ---- factor-and-invert kernel of the blocked Cholesky and its batched variant (csrc/chol_kernels.cuh) ----
 #include "../../hypatia.jl_b200/csrc/chol_kernels.cuh"
+#include "../../hypatia.jl_b200/csrc/trsv_tasks.h"
 
 extern "C" {
 
@@ -709,6 +710,25 @@ int emu_trsv_upper(const double* F, int64_t ldf, int64_t m, const double* dinv, 
     emu::launch(dim3(nblk < 3 ? nblk : 3), dim3(256), (size_t)hypdev::NB * hypdev::NB * 8, [&] {
         if (trans) hypdev::trsv_kernel<true>(F, ldf, m, dinv, x, flags.data(), nblk, epoch);
         else hypdev::trsv_kernel<false>(F, ldf, m, dinv, x, flags.data(), nblk, epoch);
+    });
+    return 0;
+}
+
+// the segmented variant (trsv_seg_kernel, the default of hyp_trsv_upper) with block columns cut into runs of `seg` tiles
+int emu_trsv_upper_seg(const double* F, int64_t ldf, int64_t m, const double* dinv, double* x, int trans, int seg) {
+    const int nblk = (int)((m + hypdev::NB - 1) / hypdev::NB);
+    int maxseg = 1;
+    std::vector<hypdev::TrsvTask> tasks = hypdev::trsv_build_tasks(nblk, trans != 0, seg, &maxseg);
+    std::vector<int> flags((size_t)2 * nblk + 2, 0);
+    std::vector<double> part((size_t)nblk * maxseg * 2 * hypdev::NB, std::nan(""));
+    const int epoch = 5;
+    emu::launch(dim3(3), dim3(256), (size_t)hypdev::NB * hypdev::NB * 8, [&] {
+        if (trans)
+            hypdev::trsv_seg_kernel<true>(F, ldf, m, dinv, x, flags.data(), tasks.data(), (int)tasks.size(), nblk, epoch,
+                                          part.data(), maxseg);
+        else
+            hypdev::trsv_seg_kernel<false>(F, ldf, m, dinv, x, flags.data(), tasks.data(), (int)tasks.size(), nblk, epoch,
+                                           part.data(), maxseg);
     });
     return 0;
 }

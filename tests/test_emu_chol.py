@@ -113,3 +113,25 @@ def test_blocked_triangular_solves_give_potrs(m):
     lib().emu_trsv_upper(p(U), i64(m), i64(m), p(dinv), p(x), 0)          # x = U^-1 y
     assert rel(x, np.linalg.solve(S, b)) <= 1e-10
     assert rel(S @ x, b) <= 1e-11
+
+
+@pytest.mark.parametrize("m,seg", [(1, 8), (129, 1), (390, 1), (390, 2), (700, 2), (700, 8), (641, 3)])
+def test_segmented_triangular_solves_give_potrs(m, seg):
+    """The default sweeps (trsv_seg_kernel): block columns cut into runs of `seg` tiles, partial sums through global
+    scratch (NaN-filled here), the final run of a column adds them up.  Ticket order = trsv_build_tasks (the same
+    builder the library uses); the first emulated CTA takes every ticket in that order, so a ticket whose inputs came
+    later in the list would spin forever - the test also checks the order is topological."""
+    rng = np.random.default_rng(m + seg)
+    S = _spd(rng, m, cond=1e2)
+    U = np.asfortranarray(np.linalg.cholesky(S).T)
+    nblk = (m + NB - 1) // NB
+    dinv = np.zeros(nblk * NB * NB)
+    lib().emu_panel_invert(p(U), i64(m), i64(m), p(dinv))
+    b = rng.standard_normal(m)
+    y = b.copy()
+    lib().emu_trsv_upper_seg(p(U), i64(m), i64(m), p(dinv), p(y), 1, seg)
+    assert rel(y, np.linalg.solve(U.T, b)) <= 1e-11
+    x = y.copy()
+    lib().emu_trsv_upper_seg(p(U), i64(m), i64(m), p(dinv), p(x), 0, seg)
+    assert rel(x, np.linalg.solve(S, b)) <= 1e-10
+    assert rel(S @ x, b) <= 1e-11
