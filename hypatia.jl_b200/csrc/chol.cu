@@ -104,7 +104,9 @@ static bool potrf_upper_i8(hyp_ctx* ctx, double* A, int64_t lda, int64_t m, doub
     // outer block = depth of the trailing updates: 512 (default) or 1024 (HYP_POTRF_OB=1024: half as many passes over the
     // trailing tiles, each twice as deep, against a longer diagonal-block chain)
     static const int ob_env = getenv("HYP_POTRF_OB") ? atoi(getenv("HYP_POTRF_OB")) : 0;
-    const int64_t OB = (ob_env == 512 || ob_env == 1024) ? ob_env : (m >= 8192 ? 1024 : 512);   // measured: r02_potrf_i8_ob{512,1024}.json
+    // 1024 pays once the bulk stream dominates (m = 20000: 69 -> 55 ms); below that the deeper update of the next diagonal
+    // block (128 x 128 tiles, on the chain) costs more than the trailing passes save
+    const int64_t OB = (ob_env == 512 || ob_env == 1024) ? ob_env : (m >= 16384 ? 1024 : 512);
     if (m <= 1024 || !hyp_ozaki_pair64_ready(ctx)) return false;
     TimeScope ts(ctx, T_POTRF);
     set_panel_attr();
@@ -131,7 +133,19 @@ static bool potrf_upper_i8(hyp_ctx* ctx, double* A, int64_t lda, int64_t m, doub
         }
     } guard{ctx};
     // the chain stream's products are small (128 x <= 512 outputs): latency tile shape unless HYP_POTRF_TILES=big
-    static const bool narrow_chain = !(getenv("HYP_POTRF_TILES") && !strcmp(getenv("HYP_POTRF_TILES"), "big"));
+    // HYP_POTRF_TILES = big: 128 x 128 tiles everywhere; chain / bulk: the latency shape only on that stream (debugging)
+    static const char* tiles_env = getenv("HYP_POTRF_TILES");
+    static const bool narrow_chain = !(tiles_env && (!strcmp(tiles_env, "big") || !strcmp(tiles_env, "bulk")));
+    static const bool narrow_rows = !(tiles_env && (!strcmp(tiles_env, "big") || !strcmp(tiles_env, "chain")));
+    // debugging: which launches may use the latency shape (1 in-block TRSM, 2 in-block update, 4 near block row,
+    // 8 update of the next diagonal block, 16 far block row)
+    // Default 21 = the triangular-solve-type launches (1, 4, 16).  The UPDATE-type launches (2, 8: C -= P'P with P = R) stay on
+    // 128 x 128 tiles: with the latency shape, repeated factorisations of one matrix stopped being bit-identical whenever
+    // such a launch overlapped the slicing kernel of the other stream (tools/potrf_race.py; profiles/r02_potrf_race.md:
+    // up to 78 of 79 repetitions on some boxes, none on others; relative error of the factor ~ 1e-3).  Every read / write
+    // set of the two streams is disjoint and the event order is complete, so the cause is not understood - the shape is
+    // therefore only used where 60 - 80 repetitions on an affected box showed no difference.
+    static const int nmask = getenv("HYP_POTRF_NARROW_MASK") ? atoi(getenv("HYP_POTRF_NARROW_MASK")) : 21;
     auto on = [&](cudaStream_t s, int cap) {
         ctx->launch_stream = s;
         ctx->grid_cap = cap;
@@ -143,12 +157,16 @@ static bool potrf_upper_i8(hyp_ctx* ctx, double* A, int64_t lda, int64_t m, doub
     // 3 = bulk stream only (no panels / in-block products)
     const char* pm = getenv("HYP_POTRF_MODE");
     const int probe = pm ? atoi(pm) : 0;
+    // debugging aid: device-wide synchronisation points (bit 0: end of every outer block, 1: after the chain's near part,
+    // 2: after SYRK part a, 3: after the diagonal block)
+    const char* psy = getenv("HYP_POTRF_SYNC");
+    const int dbg_sync = psy ? atoi(psy) : 0;
     // block row of outer block [K0, Kend) over the columns [c0, c0 + nc): U = U11^-T A, panel by panel.  2 * OB / 128 - 1
     // dependent launches of depth 128: the latency tile shape (128 x 32) unless the panel is wide enough to fill the
     // chip several times over with 128 x 128 tiles
     auto block_row = [&](int64_t K0, int64_t Kend, int64_t c0, int64_t nc) {
         const bool saved = ctx->small_tiles;
-        if (narrow_chain && nc <= (int64_t)4 * 128 * ctx->sm_count) ctx->small_tiles = true;
+        if (narrow_rows && (nmask & 16) && (ctx->launch_stream == bulk) && nc <= (int64_t)4 * 128 * ctx->sm_count) ctx->small_tiles = true;
         struct Restore {
             hyp_ctx* c;
             bool v;
@@ -178,34 +196,47 @@ static bool potrf_upper_i8(hyp_ctx* ctx, double* A, int64_t lda, int64_t m, doub
             const int64_t rin = Kend - (k0 + nb);
             if (rin > 0) {
                 double* A12 = A + k0 + (k0 + nb) * lda;
+                ctx->small_tiles = narrow_chain && (nmask & 1);
                 hyp_gemm_tn(ctx, d_dinv + (k0 / NB) * NB * NB, NB, A12, lda, nb, nb, rin, A12, lda, 1.0, 0.0);
+                ctx->small_tiles = narrow_chain && (nmask & 2);
                 hyp_atb_upper(ctx, A12, lda, A12, lda, nb, rin, A + (k0 + nb) + (k0 + nb) * lda, lda, -1.0, 1.0);
             }
         }
         CUDA_TRY(cudaEventRecord(ctx->ev_chain[b & 1], chain));
+        if (dbg_sync & 8) CUDA_TRY(cudaDeviceSynchronize());
         if (rest <= 0) break;
         const int64_t near = std::min(OB, rest);
         double* P = A + K0 + Kend * lda;                           // the block row right of the block (kd x rest)
         double* T = A + Kend + Kend * lda;                         // the trailing matrix
         // ---- chain: block row over the next block's columns (they carry block b - 1's update from SYRK part a) ----
         if (b >= 1) CUDA_TRY(cudaStreamWaitEvent(chain, ctx->ev_bulk[(b - 1) & 1], 0));
+        ctx->small_tiles = narrow_chain && (nmask & 4);
         if (probe != 3) block_row(K0, Kend, Kend, near);
-        CUDA_TRY(cudaEventRecord(ctx->ev_near[b & 1], chain));
+        static const bool near_event_early = getenv("HYP_POTRF_NEAR_EVENT") && !strcmp(getenv("HYP_POTRF_NEAR_EVENT"), "early");
+        if (near_event_early) CUDA_TRY(cudaEventRecord(ctx->ev_near[b & 1], chain));
+        ctx->small_tiles = narrow_chain && (nmask & 8);
         if (probe != 3) hyp_atb_upper(ctx, P, lda, P, lda, kd, near, T, lda, -1.0, 1.0);
+        // the bulk stream's slicing kernel starts only after the update of the next diagonal block: with the event in
+        // front of it the two overlapped, and repeated factorisations of one matrix stopped being bit-identical
+        // (tools/potrf_race.py, profiles/r02_potrf_race_*.jsonl)
+        if (!near_event_early) CUDA_TRY(cudaEventRecord(ctx->ev_near[b & 1], chain));
+        if (dbg_sync & 2) CUDA_TRY(cudaDeviceSynchronize());
         // ---- bulk: far block row, slicing, digit-sliced trailing update ----
         on(bulk, cap);
         CUDA_TRY(cudaStreamWaitEvent(bulk, ctx->ev_chain[b & 1], 0));
         if (rest > near && probe != 2) {
-            block_row(K0, Kend, Kend + near, rest - near);
+            if (probe != 5) block_row(K0, Kend, Kend + near, rest - near);        // 4: far block row only, 5: slicing only
             CUDA_TRY(cudaStreamWaitEvent(bulk, ctx->ev_near[b & 1], 0));
-            hyp_ozaki_slice_short(ctx, P, lda, kd, rest, ctx->d_chol_digits, ldd, sstride, ctx->d_chol_dscale);
-            if (probe != 1)
+            if (probe != 4) hyp_ozaki_slice_short(ctx, P, lda, kd, rest, ctx->d_chol_digits, ldd, sstride, ctx->d_chol_dscale);
+            if (probe != 1 && probe != 4 && probe != 5)
                 hyp_ozaki_syrk_rows(ctx, ctx->d_chol_digits, ldd, sstride, ctx->d_chol_dscale, kd, rest, T, lda, -1.0, 1.0, 0, pa_rows,
                                     (int)(near / NB));
         }
         CUDA_TRY(cudaEventRecord(ctx->ev_bulk[b & 1], bulk));
-        if (rest > near && probe != 2 && probe != 1)
+        if (dbg_sync & 4) CUDA_TRY(cudaDeviceSynchronize());
+        if (rest > near && probe != 2 && probe != 1 && probe != 4 && probe != 5)
             hyp_ozaki_syrk_rows(ctx, ctx->d_chol_digits, ldd, sstride, ctx->d_chol_dscale, kd, rest, T, lda, -1.0, 1.0, pa_rows, -1, 0);
+        if (dbg_sync & 1) CUDA_TRY(cudaDeviceSynchronize());
     }
     // the caller's stream continues after the last diagonal block
     CUDA_TRY(cudaStreamWaitEvent(bulk, ctx->ev_chain[b & 1], 0));

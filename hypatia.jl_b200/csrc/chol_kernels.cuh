@@ -717,8 +717,10 @@ panel_kernel(double* __restrict__ A, int64_t lda, int64_t m, int64_t blk0, doubl
     const int nb = (int)((int64_t)NB < m - k0 ? (int64_t)NB : m - k0);
     int bad;
     if (FACTOR)
-        bad = panel_body_fast<0, false>(A + k0 + k0 * lda, lda, nb, dinv + blk * (int64_t)NB * NB, NB, NB, false, sU, diagX,
-                                        sX, sT, &s_bad);
+        // the block is read through L2 (LDCG): it was written by kernels of the same stream that ran on OTHER SMs, while
+        // kernels of the second stream keep every SM busy - see the note on L1 in syrk.cu (epilogue of atb_upper_kernel)
+        bad = panel_body_fast<0, true>(A + k0 + k0 * lda, lda, nb, dinv + blk * (int64_t)NB * NB, NB, NB, false, sU, diagX,
+                                       sX, sT, &s_bad);
     else
         bad = panel_body<false>(A + k0 + k0 * lda, lda, nb, dinv + blk * (int64_t)NB * NB, NB, NB, false, sU, diagX, sX,
                                 sT, &s_bad);

@@ -179,6 +179,7 @@ struct hyp_ctx {
     std::vector<int> h_cone_type, h_cone_dual;
     std::vector<int64_t> h_cone_dim, h_cone_off;
     std::vector<double> h_cone_nu;
+    bool params_staged = false;        // hyp_set_cone_params was called since the last hyp_load_model (which consumes it)
     std::vector<int64_t> h_cone_aoff;  // per global cone: offsets into h_cone_alpha (hyp_set_cone_alpha), K + 1 entries
     std::vector<double> h_cone_alpha;  // powers of the GeneralizedPower cones
     std::vector<int> h_cone_hkind;     // per global cone: HYP_SSF_* (EpiPerSepSpectral), set by hyp_set_cone_params

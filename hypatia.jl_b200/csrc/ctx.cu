@@ -1168,7 +1168,10 @@ int hyp_load_model(hyp_ctx* ctx, int64_t n, int64_t p, int64_t q, const double* 
         // per-cone parameters staged by hyp_set_cone_params / hyp_set_cone_alpha survive the free below
         std::vector<int> hkind_in = ctx->h_cone_hkind;
         std::vector<double> hparam_in = ctx->h_cone_hparam;
-        const bool have_params = (int)hkind_in.size() == K && K > 0;
+        // only parameters staged SINCE the previous load count: a stale table of a previous model with the same cone
+        // count must not be reused when the caller skipped hyp_set_cone_params
+        const bool have_params = ctx->params_staged && (int)hkind_in.size() == K && K > 0;
+        ctx->params_staged = false;
         free_model(ctx);
         ctx->h_cone_hkind = have_params ? hkind_in : std::vector<int>((size_t)K, 0);
         ctx->h_cone_hparam = have_params ? hparam_in : std::vector<double>((size_t)K, 0.0);
@@ -1372,6 +1375,7 @@ int hyp_set_cone_params(hyp_ctx* ctx, int K, const int* ssf_kind, const double* 
         if (K < 0 || (K > 0 && (!ssf_kind || !ssf_param))) throw HypError{"hyp_set_cone_params: bad arguments"};
         ctx->h_cone_hkind.assign(ssf_kind, ssf_kind + K);
         ctx->h_cone_hparam.assign(ssf_param, ssf_param + K);
+        ctx->params_staged = true;
         return 0;
     });
 }

@@ -199,7 +199,7 @@ atb_upper_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant
                     int64_t row = row0 + 8 * i;
                     if (row < mrows) {
                         double v = alpha * acc[i][j][e];
-                        if (beta != 0.0) v += beta * cp[row];
+                        if (beta != 0.0) v += beta * __ldcg(cp + row);      // through L2: see chol.cu (two concurrent streams)
                         cp[row] = v;
                     }
                 }

@@ -83,6 +83,36 @@ def test_potrf_not_posdef(cx):
     assert info.value > 0
 
 
+def test_potrf_repeated_factorisations_are_bit_identical(cx):
+    """Steady state of the two-stream Cholesky (chol.cu, potrf_upper_i8): the first factorisation of a process builds
+    the tile / pair lists with stream synchronisations that serialise the streams, later ones do not.  Every kernel is
+    deterministic, so repeated factorisations of one matrix must agree bit for bit - a difference is a race between
+    the chain and the bulk stream (profiles/r02_potrf_race.md: found through bench.py's parity block, invisible to
+    single-shot tests)."""
+    import torch
+    from hypatia_b200 import capi
+    m = 3000
+    rng = np.random.default_rng(11)
+    B = rng.standard_normal((m + 30, m))
+    A = np.asfortranarray(B.T @ B + 0.5 * np.eye(m))
+    dA = torch.from_numpy(np.ascontiguousarray(A.T)).cuda()        # symmetric: row-major view = column-major matrix
+    ref = None
+    info = C.c_int(-1)
+    for rep in range(25):
+        F = dA.clone()
+        torch.cuda.synchronize()
+        cx.check(cx.lib.hyp_test_potrf(cx.h, capi.ptr(F), m, m, C.byref(info)), "potrf")
+        cx.sync()
+        assert info.value == 0
+        U = torch.tril(F)
+        if ref is None:
+            ref = U.clone()
+            Un = U.cpu().numpy().T
+            assert rel(Un.T @ Un, A) <= 100 * m * EPS
+        else:
+            assert torch.equal(U, ref), f"factorisation {rep} differs from the first one"
+
+
 def test_potrf_large_not_posdef_and_dag_agreement(cx, monkeypatch):
     """m > 1024 takes the blocked Cholesky with tcgen05 (digit-sliced) trailing updates (chol.cu, potrf_upper_i8): a
     matrix that loses definiteness deep inside the trailing part is reported, and on a definite one the factor agrees

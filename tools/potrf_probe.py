@@ -39,11 +39,12 @@ def main():
                 ctx.sync()
                 ts.append(ctx.timing()["potrf"][0])
                 ctx.timing_enable(False)
-                if mode == "0" and rep == 0:
+                if mode == "0" and rep in (0, 3):
+                    # rep 0 = first call (tile / pair lists are built, with their stream synchronisations), rep 3 = steady state
                     # the library is column-major: its upper factor U is the LOWER triangle of the row-major view
                     Lw = torch.tril(F)
                     r = torch.linalg.norm(Lw @ Lw.t() - A) / torch.linalg.norm(A)
-                    res["residual"] = float(r)
+                    res["residual" if rep == 0 else "residual_steady_state"] = float(r)
                     res["info"] = info.value
                     del Lw
                 del F
