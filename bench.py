@@ -103,9 +103,9 @@ def syrk_kernel_name():
 # DRAM traffic of the Schur SYRK (dram__bytes_read.sum + dram__bytes_write.sum over the launches of ONE SYRK) from the
 # committed `ncu --set full` capture of the same kernel build - a CONSTANT taken from that profile, not measured by
 # the run that prints it (ncu cannot run inside a timed bench); the source file is named next to it
-NCU_TRAFFIC = {"C3:i8": ((42.40e9 + 0.809e9) + (44.78e9 + 0.808e9) + (44.62e9 + 0.808e9),
-                         "constant from profiles/r01_ozaki_pair_row_order_ncu.txt (three K-chunk launches of one SYRK; the "
-                         "32-byte-row pair kernel - same tile order and digit slices as the 64-byte-row default)"),
+NCU_TRAFFIC = {"C3:i8": ((38.800736e9 + 0.807690e9) + (39.362148e9 + 0.810906e9) + (39.040170e9 + 0.809051e9),
+                         "constant from profiles/r02_ozaki_pair64_ncu_full.txt (three K-chunk launches of one SYRK, "
+                         "ozaki_syrk_pair64_kernel; only quoted when that kernel runs)"),
                "C3": (31.497622e9 + 0.411380e9, "constant from profiles/r01_syrk_schur_ncu_full.txt (one launch)")}
 
 
@@ -770,7 +770,7 @@ def build_line(args, torch, device, world, main):
         # the kernel is timed inside a long step: the sustained bf16 figure is the denominator (x 2 for int8)
         bf16 = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops")
         int8_peak = 2.0 * bf16 if bf16 else None
-        traffic = NCU_TRAFFIC.get(args.workload + ":i8") if world == 1 else None
+        traffic = NCU_TRAFFIC.get(args.workload + ":i8") if (world == 1 and "pair64" in syrk_kernel_name()) else None
         roofline = {"bound": "tensor",
                     "kernel": "%s (Schur SYRK: FP64-accurate digit slicing, %d exact int8 digit-pair products, tcgen05 kind::i8 "
                               "cta_group::2 M=256, TMEM accumulators, 3-D TMA) + slicing kernels" % (syrk_kernel_name(), npairs),
