@@ -248,6 +248,9 @@ struct hyp_ctx {
     double *d_partial3 = nullptr, *d_partial4 = nullptr;
     int64_t partial3_doubles = 0, partial4_doubles = 0;
     unsigned long long* d_colbits = nullptr;   // column maxima (bit patterns) of the fused pre-pass
+    int8_t* d_digitsP = nullptr;               // digit slices / scales of the P operand of the two-operand Schur product (mixed models)
+    int* d_expoP = nullptr;
+    double* d_dscaleP = nullptr;
     double* d_multi = nullptr;
     int64_t multi_doubles = 0;
     int* d_dag_ver = nullptr;          // task-graph Cholesky (chol_dag.cu): tile version counters + tickets
@@ -400,7 +403,8 @@ void hyp_ozaki_syrk_rows(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_
 void hyp_ozaki_slice(hyp_ctx* ctx, const double* A, int64_t lda, int64_t K, int64_t ncols, int8_t* digits,
                      int64_t ldd, int64_t slice_stride, int* expo, double* dscale, bool have_expo = false);
 void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t slice_stride, const int* expo,
-                    const double* dscale, int64_t K, int64_t ncols, double* C, int64_t ldc, double alpha, double beta);
+                    const double* dscale, int64_t K, int64_t ncols, double* C, int64_t ldc, double alpha, double beta,
+                    const int8_t* digitsB = nullptr, const double* dscaleB = nullptr);   // B side of C = P' R (nullptr: SYRK)
 
 // ---- chol.cu ----
 // in-place blocked upper Cholesky; d_dinv receives the inverted 128 x 128 diagonal blocks

@@ -164,6 +164,9 @@ void free_model(hyp_ctx* ctx) {
     dfree(ctx->d_multi);
     ctx->multi_doubles = 0;
     dfree(ctx->d_colbits);
+    dfree(ctx->d_digitsP);
+    dfree(ctx->d_expoP);
+    dfree(ctx->d_dscaleP);
     ctx->partial2_doubles = 0;
     dfree(ctx->d_stage);
     ctx->stage_doubles = 0;
@@ -840,6 +843,27 @@ int update_lhs_fact(hyp_ctx* ctx) {
                                 ctx->d_expo, ctx->d_dscale, have_expo);
             hyp_ozaki_syrk(ctx, ctx->d_digits, ctx->ldd, ctx->ldd * nmp, ctx->d_expo, ctx->d_dscale, ctx->qloc, nmp, ctx->d_S,
                            ctx->lds, 1.0, 0.0);
+        } else if (ctx->qloc > 0 && ctx->syrk_mode == 1 && ctx->d_PG && nmp >= 16 && hyp_ozaki_pair64_ready(ctx) &&
+                   !getenv("HYP_K2_DMMA")) {
+            // mixed / log-det models (the hess_prod! + mul! branch, qrchol.jl:240-246): S = P' (HG) with two DIFFERENT
+            // operands, also on the int8 tensor pipe - both are cut into digit slices (their own column scales) and the
+            // CTA-pair kernel takes the A-side tiles from P and the B-side tiles from HG
+            if (!ctx->d_digits) {
+                ctx->ldd = round_up(std::max<int64_t>(ctx->qloc, 16), 16);
+                dalloc(&ctx->d_digits, 8 * ctx->ldd * nmp);
+                dalloc(&ctx->d_expo, nmp);
+                dalloc(&ctx->d_dscale, nmp);
+            }
+            if (!ctx->d_digitsP) {
+                dalloc(&ctx->d_digitsP, 8 * ctx->ldd * nmp);
+                dalloc(&ctx->d_expoP, nmp);
+                dalloc(&ctx->d_dscaleP, nmp);
+            }
+            hyp_ozaki_slice(ctx, P, ctx->ldg, ctx->qloc, nmp, ctx->d_digitsP, ctx->ldd, ctx->ldd * nmp, ctx->d_expoP, ctx->d_dscaleP);
+            hyp_ozaki_slice(ctx, ctx->d_HG, ctx->ldg, ctx->qloc, nmp, ctx->d_digits, ctx->ldd, ctx->ldd * nmp, ctx->d_expo,
+                            ctx->d_dscale);
+            hyp_ozaki_syrk(ctx, ctx->d_digitsP, ctx->ldd, ctx->ldd * nmp, ctx->d_expoP, ctx->d_dscaleP, ctx->qloc, nmp, ctx->d_S,
+                           ctx->lds, 1.0, 0.0, ctx->d_digits, ctx->d_dscale);
         } else if (ctx->qloc > 0)
             hyp_atb_upper(ctx, P, ctx->ldg, ctx->d_HG, ctx->ldg, ctx->qloc, nmp, ctx->d_S, ctx->lds, 1.0, 0.0);
         else

@@ -1341,8 +1341,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
 ozaki_syrk_pair64_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid_constant__ CUtensorMap mapA7,
                          const __grid_constant__ CUtensorMap mapB4, const __grid_constant__ CUtensorMap mapB7,
                          const int2* __restrict__ pairs, int n_pairs, int k0, int nst,
-                         const double* __restrict__ dscale, int64_t ncols, double* __restrict__ C, int64_t ldc,
-                         double alpha, double beta, int probe) {
+                         const double* __restrict__ dscale, const double* __restrict__ dscale_col, int64_t ncols,
+                         double* __restrict__ C, int64_t ldc, double alpha, double beta, int probe) {
+    // dscale: column scales of the A-side operand (rows of C), dscale_col: of the B-side operand (columns of C); the
+    // same array for the SYRK, two arrays for the two-operand product C = P' R (mixed / log-det models, qrchol.jl:245)
     // probe (HYP_OZAKI_PROBE; results are garbage, timing only): 1 = no TMA loads, 2 = no MMAs (loads + epilogue only)
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint32_t s_tmem;
@@ -1518,7 +1520,7 @@ ozaki_syrk_pair64_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid
                                 x += (double)(int32_t)v[2][j] * g2;
                                 x += (double)(int32_t)v[1][j] * g1;
                                 x += (double)(int32_t)v[0][j] * g0;
-                                x *= rs * dscale[col];
+                                x *= rs * dscale_col[col];
                                 C[row + col * ldc] = rmw ? (x + bt * cold[j]) : x;
                             }
                         }
@@ -1843,22 +1845,26 @@ int p64_split() {
 }
 
 // one launch of the 64-byte-row CTA-pair kernel over a pair list (cfg carries grid, stream and the cluster attribute)
+// digitsB / dscaleB (same layout as digits): the B-side operand of the two-operand product; nullptr = SYRK
 void launch_pair64(hyp_ctx* ctx, cudaLaunchConfig_t* cfg, const int8_t* digits, int64_t K, int64_t ncols, int64_t ldd,
                    int64_t slice_stride, int nslices_alloc, const int2* d_pairs, int n_pairs, int k0, int64_t klen,
-                   const double* dscale, double* C, int64_t ldc, double alpha, double beta, int probe) {
+                   const double* dscale, double* C, int64_t ldc, double alpha, double beta, int probe,
+                   const int8_t* digitsB = nullptr, const double* dscaleB = nullptr) {
     const int l1 = p64_split();
+    if (!digitsB) digitsB = digits;
+    if (!dscaleB) dscaleB = dscale;
     CUtensorMap mA0, mA1, mB0, mB1;
     make_map_digits64(&mA0, digits, K, ncols, ldd, slice_stride, nslices_alloc, l1, TM);
     make_map_digits64(&mA1, digits, K, ncols, ldd, slice_stride, nslices_alloc, P64_NSL, TM);
-    make_map_digits64(&mB0, digits, K, ncols, ldd, slice_stride, nslices_alloc, l1, TN / 2);
-    make_map_digits64(&mB1, digits, K, ncols, ldd, slice_stride, nslices_alloc, P64_NSL, TN / 2);
+    make_map_digits64(&mB0, digitsB, K, ncols, ldd, slice_stride, nslices_alloc, l1, TN / 2);
+    make_map_digits64(&mB1, digitsB, K, ncols, ldd, slice_stride, nslices_alloc, P64_NSL, TN / 2);
     const int nst = (int)ceil_div(klen, P64_KB);
     if (l1 == 3)
-        CUDA_TRY(cudaLaunchKernelEx(cfg, ozaki_syrk_pair64_kernel<3>, mA0, mA1, mB0, mB1, d_pairs, n_pairs, k0, nst, dscale, ncols,
-                                    C, ldc, alpha, beta, probe));
+        CUDA_TRY(cudaLaunchKernelEx(cfg, ozaki_syrk_pair64_kernel<3>, mA0, mA1, mB0, mB1, d_pairs, n_pairs, k0, nst, dscale, dscaleB,
+                                    ncols, C, ldc, alpha, beta, probe));
     else
-        CUDA_TRY(cudaLaunchKernelEx(cfg, ozaki_syrk_pair64_kernel<4>, mA0, mA1, mB0, mB1, d_pairs, n_pairs, k0, nst, dscale, ncols,
-                                    C, ldc, alpha, beta, probe));
+        CUDA_TRY(cudaLaunchKernelEx(cfg, ozaki_syrk_pair64_kernel<4>, mA0, mA1, mB0, mB1, d_pairs, n_pairs, k0, nst, dscale, dscaleB,
+                                    ncols, C, ldc, alpha, beta, probe));
     ctx->launches++;
 }
 
@@ -2008,8 +2014,10 @@ static int ozaki_slices() {
 // C(upper 128-tiles) = alpha * A' A + beta * C from the digit slices of A
 void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t slice_stride, const int* expo,
                     const double* dscale, int64_t K, int64_t ncols, double* C, int64_t ldc, double alpha,
-                    double beta) {
+                    double beta, const int8_t* digitsB, const double* dscaleB) {
     if (K <= 0 || ncols <= 0) return;
+    if (digitsB && !hyp_ozaki_pair64_ready(ctx))
+        throw HypError{"two-operand digit-sliced product needs the 64-byte-row CTA-pair kernel"};
     static bool attr = false;
     if (!attr) {
         CUDA_TRY(cudaFuncSetAttribute(ozaki_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
@@ -2307,7 +2315,7 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
                 cfg.numAttrs = 1;
                 const int probe = getenv("HYP_OZAKI_PROBE") ? atoi(getenv("HYP_OZAKI_PROBE")) : 0;   // tools/syrk_probe.py
                 launch_pair64(ctx, &cfg, digits, K, ncols, ldd, slice_stride, OZ_S, d_pairs, n_pairs, (int)k0, klen, dscale, C, ldc,
-                              alpha, k0 == 0 ? beta : 1.0, probe);
+                              alpha, k0 == 0 ? beta : 1.0, probe, digitsB, dscaleB);
                 continue;
             }
             CUtensorMap mapB4, mapB8, mapA8;
