@@ -451,11 +451,9 @@ def measure_workload(args, workload, torch, dist, device, rank, world, local_ran
     if giant:
         ctx.set_column_sharding(True)
     ctx.load_model(model, G_local=I["G_dev"] if big else I["G_local"], cone_lo=lo, cone_hi=hi)
-    # models with a cone that has no closed-form square root assemble S with the two-operand FP64 DMMA
-    # product (qrchol.jl:240-246 branch); the one-operand tcgen05 SYRK needs every cone in sqrt form
+    # models with a cone that has no closed-form square root assemble S with the TWO-operand product P'(HG)
+    # (qrchol.jl:240-246 branch); since round 2 the library runs that one on the int8 tensor pipe as well
     syrk = args.syrk
-    if any(ck.ctype not in (0, 1, 2, 6) for ck in model.cones):
-        syrk = "dmma"
     ctx.set_syrk_mode(1 if syrk == "i8" else 0)
     # the library keeps its own copy of the panel: drop ours before update_lhs allocates its work buffers
     # (C4: G 40 GB + H^{1/2}G 40 GB + digit slices 40 GB + Schur / factor 6.4 GB of the 180 GB)

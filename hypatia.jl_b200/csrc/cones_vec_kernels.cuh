@@ -181,65 +181,12 @@ soc_prod_chunk_kernel(const int64_t* __restrict__ crow0, const int* __restrict__
     const int64_t r0 = crow0[b];
     const int nr = crows[b], c0 = ccone0[b], nc = ccount[b];
     const double rt2 = 1.4142135623730951;
-    // Everything that does not depend on the column is computed once per cone: the point w (in registers for cones of
-    // dimension <= 32, the case of the benchmarked models) and the scalars of the rank-one formula - the square root and
-    // the three divisions used to be redone for each of the (up to) 10 000 columns.  A thread owns the cones
-    // t = threadIdx.x, threadIdx.x + blockDim.x, ...; the register copy covers its first cone (chunks hold <= 256 cones).
-    constexpr int WREG = 32;
-    const int t0 = threadIdx.x;
-    const bool mine = t0 < nc;
-    const int cm = c0 + t0;
-    const int64_t om = mine ? off[cm] : 0;
-    const int dm = mine ? dim[cm] : 0;
-    const bool inreg = mine && dm <= WREG;
-    double wr[WREG];
-#pragma unroll
-    for (int i = 0; i < WREG; i++) wr[i] = (inreg && i < dm) ? point[om + i] : 0.0;
-    double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;          // mode-dependent scalars of my first cone
-    if (mine) {
-        const double dist = scal[8 * cm], u = wr[0];
-        if (MODE == VK_HESS) {
-            q0 = 1.0 / dist;
-        } else if (MODE == VK_INV_HESS) {
-            q0 = dist;
-        } else {
-            const double rtdist = sqrt(dist);
-            q0 = 1.0 / (dist * rt2);                          // 1 / (dist sqrt 2)
-            q1 = 1.0 / (u + rtdist * rt2);                    // 1 / (u + sqrt(2 dist))
-            q2 = 1.0 / rtdist;
-            q3 = rtdist;
-        }
-    }
     for (int64_t j = blockIdx.y; j < ncols; j += gridDim.y) {
         const double* a = arr + j * ld_arr + (r0 - row_shift);
         double* pr = prod + j * ld_prod + (r0 - row_shift);
         for (int i = threadIdx.x; i < nr; i += blockDim.x) srow[i] = a[i];
         __syncthreads();
-        if (inreg) {
-            double* v = srow + (om - r0);
-            const double u = wr[0], uj = v[0];
-            double dotw = 0.0;
-#pragma unroll
-            for (int i = 1; i < WREG; i++)
-                if (i < dm) dotw += wr[i] * v[i];
-            double k0, kw, kj;
-            if (MODE == VK_HESS) {
-                const double ga = (dotw - u * uj) * q0;
-                k0 = (-ga * u - uj) * q0; kw = ga * q0; kj = q0;
-            } else if (MODE == VK_INV_HESS) {
-                const double pa = u * uj + dotw;
-                k0 = pa * u - q0 * uj; kw = pa; kj = q0;
-            } else if (MODE == VK_SQRT_HESS) {
-                k0 = (u * uj - dotw) * q0; kw = (dotw * q1 - uj) * q0; kj = q2;
-            } else {
-                k0 = (u * uj + dotw) / rt2; kw = (dotw * q1 + uj) / rt2; kj = q3;
-            }
-            v[0] = k0;
-#pragma unroll
-            for (int i = 1; i < WREG; i++)
-                if (i < dm) v[i] = kw * wr[i] + kj * v[i];
-        }
-        for (int t = threadIdx.x + (inreg ? blockDim.x : 0); t < nc; t += blockDim.x) {
+        for (int t = threadIdx.x; t < nc; t += blockDim.x) {
             const int c = c0 + t;
             const int64_t o = off[c];
             const int d = dim[c];
