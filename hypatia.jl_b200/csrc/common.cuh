@@ -248,6 +248,9 @@ struct hyp_ctx {
     double *d_partial3 = nullptr, *d_partial4 = nullptr;
     int64_t partial3_doubles = 0, partial4_doubles = 0;
     unsigned long long* d_colbits = nullptr;   // column maxima (bit patterns) of the fused pre-pass
+    int8_t *d_gemm_digA = nullptr, *d_gemm_digB = nullptr;   // digit workspaces of hyp_ozaki_gemm_tn (matrix-cone congruences)
+    double* d_gemm_scal = nullptr;
+    int64_t gemm_digA_bytes = 0, gemm_digB_bytes = 0, gemm_scal_bytes = 0;
     int8_t* d_digitsP = nullptr;               // digit slices / scales of the P operand of the two-operand Schur product (mixed models)
     int* d_expoP = nullptr;
     double* d_dscaleP = nullptr;
@@ -394,6 +397,9 @@ int hyp_ozaki_radix();
 // fused Schur pre-pass + digit slicing for second-order-cone models (cones.cu); false = not applicable
 int hyp_cones_prepass_sliced(hyp_ctx* ctx, int8_t* digits, int64_t ldd, int64_t slice_stride, int* expo, double* dscale);
 bool hyp_ozaki_pair64_ready(hyp_ctx* ctx);
+bool hyp_ozaki_gemm_tn(hyp_ctx* ctx, const double* P, int64_t ldp, const double* R, int64_t ldr, int64_t klen, int64_t mrows,
+                       int64_t ncols, double* C, int64_t ldc, double alpha, double beta, int ngroups = 1,
+                       int64_t r_kstride = 0, int64_t c_group_stride = 0);
 void hyp_ozaki_slice_short(hyp_ctx* ctx, const double* A, int64_t lda, int64_t K, int64_t ncols, int8_t* digits, int64_t ldd,
                            int64_t slice_stride, double* dscale);
 void hyp_ozaki_syrk_rows(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t slice_stride, const double* dscale,

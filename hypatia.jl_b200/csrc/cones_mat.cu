@@ -166,11 +166,17 @@ void big_chol_inverse(hyp_ctx* ctx, double* U, double* Ui, int d, int lde, uint8
 // Y_j = X' M_j X for cc matrices stored side by side in Mall (in place); C1 is (d*cc) x d scratch
 void congruence(hyp_ctx* ctx, const double* X, int d, int lde, double* Mall, int64_t cc, double* C1,
                 int64_t ldc1) {
+    // Large cones (side >= 512, e.g. the side-1000 log-det cone of the natvsext-shaped config 5): both products on the
+    // int8 tensor pipe by digit slicing (ozaki.cu, hyp_ozaki_gemm_tn) - 2.5 x the FP64 DMMA rate at this depth; below
+    // that the contraction is too short for the two-pass tcgen05 kernel and the DMMA products stay.
+    static const int i8_min = getenv("HYP_CONG_I8_MIN") ? atoi(getenv("HYP_CONG_I8_MIN")) : 512;
+    const bool i8 = d >= i8_min && ctx->syrk_mode == 1;
     // T = [M_1 ... M_cc]' X : row block j (lde rows, the last one padding when d is odd) = M_j X
-    hyp_gemm_tn(ctx, Mall, lde, X, lde, d, (int64_t)lde * cc, d, C1, ldc1, 1.0, 0.0);
+    if (!(i8 && hyp_ozaki_gemm_tn(ctx, Mall, lde, X, lde, d, (int64_t)lde * cc, d, C1, ldc1, 1.0, 0.0)))
+        hyp_gemm_tn(ctx, Mall, lde, X, lde, d, (int64_t)lde * cc, d, C1, ldc1, 1.0, 0.0);
     // Y_j = X' T_j
-    hyp_gemm_tn_grouped(ctx, X, lde, C1, ldc1, d, d, d, (int)cc, lde, Mall, lde, (int64_t)lde * lde, 1.0,
-                        0.0);
+    if (!(i8 && hyp_ozaki_gemm_tn(ctx, X, lde, C1, ldc1, d, d, d, Mall, lde, 1.0, 0.0, (int)cc, lde, (int64_t)lde * lde)))
+        hyp_gemm_tn_grouped(ctx, X, lde, C1, ldc1, d, d, d, (int)cc, lde, Mall, lde, (int64_t)lde * lde, 1.0, 0.0);
 }
 
 }  // namespace

@@ -1146,6 +1146,9 @@ void hyp_destroy(hyp_ctx* ctx) {
     if (ctx->d_chol_digits) cudaFree(ctx->d_chol_digits);
     if (ctx->d_chol_dscale) cudaFree(ctx->d_chol_dscale);
     if (ctx->d_trsv_part) cudaFree(ctx->d_trsv_part);
+    if (ctx->d_gemm_digA) cudaFree(ctx->d_gemm_digA);
+    if (ctx->d_gemm_digB) cudaFree(ctx->d_gemm_digB);
+    if (ctx->d_gemm_scal) cudaFree(ctx->d_gemm_scal);
     if (ctx->d_dag_ver) cudaFree(ctx->d_dag_ver);
     if (ctx->d_dag_dbg) cudaFree(ctx->d_dag_dbg);
     cudaStreamDestroy(ctx->stream2);

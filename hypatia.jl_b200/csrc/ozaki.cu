@@ -1340,9 +1340,15 @@ template <int L1>
 __global__ void __launch_bounds__(I8_THREADS, 1)
 ozaki_syrk_pair64_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid_constant__ CUtensorMap mapA7,
                          const __grid_constant__ CUtensorMap mapB4, const __grid_constant__ CUtensorMap mapB7,
-                         const int2* __restrict__ pairs, int n_pairs, int k0, int nst,
-                         const double* __restrict__ dscale, const double* __restrict__ dscale_col, int64_t ncols,
-                         double* __restrict__ C, int64_t ldc, double alpha, double beta, int probe) {
+                         const int4* __restrict__ pairs, int n_pairs, int k0, int nst,
+                         const double* __restrict__ dscale, const double* __restrict__ dscale_col, int64_t mrows,
+                         int64_t ncols, double* __restrict__ C, int64_t ldc, int64_t c_group_stride, double alpha,
+                         double beta, int probe_full) {
+    // pairs[i] = {P, J, k offset of the B-side operand, output group}: tile rows 2P, 2P + 1 of tile column J; the last two
+    // are 0 except for grouped products (C_g = A' B[g * kstride .. , :], the congruences of the matrix cones).
+    // probe_full bit 8: store every tile (general product C = A' B) instead of the upper ones (SYRK / P'(HG)).
+    const int probe = probe_full & 0xff;
+    const bool full = (probe_full & 0x100) != 0;
     // dscale: column scales of the A-side operand (rows of C), dscale_col: of the B-side operand (columns of C); the
     // same array for the SYRK, two arrays for the two-operand product C = P' R (mixed / log-det models, qrchol.jl:245)
     // probe (HYP_OZAKI_PROBE; results are garbage, timing only): 1 = no TMA loads, 2 = no MMAs (loads + epilogue only)
@@ -1395,8 +1401,8 @@ ozaki_syrk_pair64_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid
             uint32_t phase[2] = {0, 0};
             uint32_t item = 0;
             for (int pi = (int)cid; pi < n_pairs; pi += (int)ncl) {
-                const int2 pr = pairs[pi];
-                const int tI = 2 * pr.x + (int)crank, tJ = pr.y;
+                const int4 pr = pairs[pi];
+                const int tI = 2 * pr.x + (int)crank, tJ = pr.y, kboff = pr.z;
                 for (int pass = 0; pass < 2; pass++, item++) {
                     // the two rings share their shared memory: the previous item's MMAs must all have retired
                     if (item > 0) mbar_wait(bar_tfull, (item - 1) & 1u);
@@ -1419,7 +1425,7 @@ ozaki_syrk_pair64_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid
                             const uint32_t dst = stg + st * sbytes;
                             const int kc = k0 + it * P64_KB;
                             tma_load_3d_2sm(dst, ma, kc, tI * TM, 0, full_leader);
-                            tma_load_3d_2sm(dst + ns * P64_TA, mb, kc, tJ * TN + (int)crank * (TN / 2), 0, full_leader);
+                            tma_load_3d_2sm(dst + ns * P64_TA, mb, kc + kboff, tJ * TN + (int)crank * (TN / 2), 0, full_leader);
                         }
                         if (++st == nstages) {
                             st = 0;
@@ -1455,14 +1461,17 @@ ozaki_syrk_pair64_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid
         const int lg = warp & 3;
         const uint32_t tempty_leader = mapa_u32(bar_tempty, 0);
         uint32_t item = 0;
+        double* const C0 = C;
+        const int64_t ncols_rows = mrows;
         for (int pi = (int)cid; pi < n_pairs; pi += (int)ncl) {
-            const int2 pr = pairs[pi];
+            const int4 pr = pairs[pi];
             const int tI = 2 * pr.x + (int)crank, tJ = pr.y;
+            double* C = C0 + (int64_t)pr.w * c_group_stride;
             const int64_t row = (int64_t)tI * TM + lg * 32 + lane;
-            const bool store = tI <= tJ;
-            const double rs = (row < ncols) ? alpha * dscale[row] : 0.0;
+            const bool store = full || tI <= tJ;
+            const double rs = (row < ncols_rows) ? alpha * dscale[row] : 0.0;
             for (int pass = 0; pass < 2; pass++, item++) {
-                if (pass == 0 && beta != 0.0 && store && row < ncols) {
+                if (pass == 0 && beta != 0.0 && store && row < ncols_rows) {
                     // C += ...: pull my rows of the tile into L2 while the MMAs of this pass run (the tile comes from DRAM)
 #pragma unroll 8
                     for (int j = lane & 1; j < TN; j += 2) {              // 16 lanes share a 128-byte line: two lanes per line suffice
@@ -1474,7 +1483,7 @@ ozaki_syrk_pair64_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid
                 // the old values of C (second pass, or beta != 0) are loaded one 16-column chunk AHEAD of their use: the
                 // first chunk before the accumulators are even ready, chunk c + 1 while chunk c is converted and stored
                 // (written as 16 load / store pairs they serialise on 16 L2 or DRAM round trips per chunk)
-                const bool rmw = (pass == 1 || beta != 0.0) && store && row < ncols;
+                const bool rmw = (pass == 1 || beta != 0.0) && store && row < ncols_rows;
                 const double bt = pass == 1 ? 1.0 : beta;
                 double cold[16], cnext[16];
 #pragma unroll
@@ -1511,7 +1520,7 @@ ozaki_syrk_pair64_kernel(const __grid_constant__ CUtensorMap mapA4, const __grid
                         }
                     }
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (store && row < ncols) {
+                    if (store && row < ncols_rows) {
 #pragma unroll
                         for (int j = 0; j < 16; j++) {
                             const int64_t col = (int64_t)tJ * TN + c0 + j;
@@ -1845,27 +1854,41 @@ int p64_split() {
 }
 
 // one launch of the 64-byte-row CTA-pair kernel over a pair list (cfg carries grid, stream and the cluster attribute)
+// One launch of the 64-byte-row CTA-pair kernel.  A side: digits / dscale of the K x mrows operand (tile rows of C);
+// B side (digitsB .. ; nullptr = the A side: SYRK): digits / dscaleB of the Kb x ncols operand (tile columns of C).
+struct P64Operand {
+    const int8_t* digits;
+    int64_t K, cols, ldd, slice_stride;
+    int nslices_alloc;
+    const double* dscale;
+};
+void launch_pair64_ex(hyp_ctx* ctx, cudaLaunchConfig_t* cfg, const P64Operand& A, const P64Operand& B, const int4* d_pairs,
+                      int n_pairs, int k0, int64_t klen, double* C, int64_t ldc, int64_t c_group_stride, double alpha,
+                      double beta, int probe, bool full) {
+    const int l1 = p64_split();
+    CUtensorMap mA0, mA1, mB0, mB1;
+    make_map_digits64(&mA0, A.digits, A.K, A.cols, A.ldd, A.slice_stride, A.nslices_alloc, l1, TM);
+    make_map_digits64(&mA1, A.digits, A.K, A.cols, A.ldd, A.slice_stride, A.nslices_alloc, P64_NSL, TM);
+    make_map_digits64(&mB0, B.digits, B.K, B.cols, B.ldd, B.slice_stride, B.nslices_alloc, l1, TN / 2);
+    make_map_digits64(&mB1, B.digits, B.K, B.cols, B.ldd, B.slice_stride, B.nslices_alloc, P64_NSL, TN / 2);
+    const int nst = (int)ceil_div(klen, P64_KB);
+    const int pf = (probe & 0xff) | (full ? 0x100 : 0);
+    if (l1 == 3)
+        CUDA_TRY(cudaLaunchKernelEx(cfg, ozaki_syrk_pair64_kernel<3>, mA0, mA1, mB0, mB1, d_pairs, n_pairs, k0, nst, A.dscale,
+                                    B.dscale, A.cols, B.cols, C, ldc, c_group_stride, alpha, beta, pf));
+    else
+        CUDA_TRY(cudaLaunchKernelEx(cfg, ozaki_syrk_pair64_kernel<4>, mA0, mA1, mB0, mB1, d_pairs, n_pairs, k0, nst, A.dscale,
+                                    B.dscale, A.cols, B.cols, C, ldc, c_group_stride, alpha, beta, pf));
+    ctx->launches++;
+}
 // digitsB / dscaleB (same layout as digits): the B-side operand of the two-operand product; nullptr = SYRK
 void launch_pair64(hyp_ctx* ctx, cudaLaunchConfig_t* cfg, const int8_t* digits, int64_t K, int64_t ncols, int64_t ldd,
-                   int64_t slice_stride, int nslices_alloc, const int2* d_pairs, int n_pairs, int k0, int64_t klen,
+                   int64_t slice_stride, int nslices_alloc, const int4* d_pairs, int n_pairs, int k0, int64_t klen,
                    const double* dscale, double* C, int64_t ldc, double alpha, double beta, int probe,
                    const int8_t* digitsB = nullptr, const double* dscaleB = nullptr) {
-    const int l1 = p64_split();
-    if (!digitsB) digitsB = digits;
-    if (!dscaleB) dscaleB = dscale;
-    CUtensorMap mA0, mA1, mB0, mB1;
-    make_map_digits64(&mA0, digits, K, ncols, ldd, slice_stride, nslices_alloc, l1, TM);
-    make_map_digits64(&mA1, digits, K, ncols, ldd, slice_stride, nslices_alloc, P64_NSL, TM);
-    make_map_digits64(&mB0, digitsB, K, ncols, ldd, slice_stride, nslices_alloc, l1, TN / 2);
-    make_map_digits64(&mB1, digitsB, K, ncols, ldd, slice_stride, nslices_alloc, P64_NSL, TN / 2);
-    const int nst = (int)ceil_div(klen, P64_KB);
-    if (l1 == 3)
-        CUDA_TRY(cudaLaunchKernelEx(cfg, ozaki_syrk_pair64_kernel<3>, mA0, mA1, mB0, mB1, d_pairs, n_pairs, k0, nst, dscale, dscaleB,
-                                    ncols, C, ldc, alpha, beta, probe));
-    else
-        CUDA_TRY(cudaLaunchKernelEx(cfg, ozaki_syrk_pair64_kernel<4>, mA0, mA1, mB0, mB1, d_pairs, n_pairs, k0, nst, dscale, dscaleB,
-                                    ncols, C, ldc, alpha, beta, probe));
-    ctx->launches++;
+    P64Operand A{digits, K, ncols, ldd, slice_stride, nslices_alloc, dscale};
+    P64Operand B{digitsB ? digitsB : digits, K, ncols, ldd, slice_stride, nslices_alloc, dscaleB ? dscaleB : dscale};
+    launch_pair64_ex(ctx, cfg, A, B, d_pairs, n_pairs, k0, klen, C, ldc, 0, alpha, beta, probe, false);
 }
 
 void make_map_digits(CUtensorMap* map, const int8_t* base, int64_t K, int64_t cols, int64_t ldd,
@@ -2314,7 +2337,23 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
                 cfg.attrs = at;
                 cfg.numAttrs = 1;
                 const int probe = getenv("HYP_OZAKI_PROBE") ? atoi(getenv("HYP_OZAKI_PROBE")) : 0;   // tools/syrk_probe.py
-                launch_pair64(ctx, &cfg, digits, K, ncols, ldd, slice_stride, OZ_S, d_pairs, n_pairs, (int)k0, klen, dscale, C, ldc,
+                // the 64-byte-row kernel takes {P, J, k offset of B, group} entries
+                static std::vector<std::pair<int, int4*>> p4cache;
+                int4* d_pairs4 = nullptr;
+                for (auto& e : p4cache)
+                    if (e.first == nt) d_pairs4 = e.second;
+                if (!d_pairs4) {
+                    std::vector<int2> h2((size_t)n_pairs);
+                    CUDA_TRY(cudaMemcpyAsync(h2.data(), d_pairs, h2.size() * sizeof(int2), cudaMemcpyDeviceToHost, ctx->stream));
+                    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+                    std::vector<int4> h4((size_t)n_pairs);
+                    for (int i = 0; i < n_pairs; i++) h4[i] = make_int4(h2[i].x, h2[i].y, 0, 0);
+                    CUDA_TRY(cudaMalloc(&d_pairs4, std::max<size_t>(h4.size(), 1) * sizeof(int4)));
+                    CUDA_TRY(cudaMemcpyAsync(d_pairs4, h4.data(), h4.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+                    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+                    p4cache.push_back({nt, d_pairs4});
+                }
+                launch_pair64(ctx, &cfg, digits, K, ncols, ldd, slice_stride, OZ_S, d_pairs4, n_pairs, (int)k0, klen, dscale, C, ldc,
                               alpha, k0 == 0 ? beta : 1.0, probe, digitsB, dscaleB);
                 continue;
             }
@@ -2447,11 +2486,11 @@ void hyp_ozaki_syrk_rows(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_
     if (p_lo >= p_hi) return;
     struct Entry {
         int device, nt, p_lo, p_hi, skip;
-        int2* d_pairs;
+        int4* d_pairs;
         int n_pairs;
     };
     static std::vector<Entry> cache;
-    int2* d_pairs = nullptr;
+    int4* d_pairs = nullptr;
     int n_pairs = 0;
     for (auto& e : cache)
         if (e.device == ctx->device && e.nt == nt && e.p_lo == p_lo && e.p_hi == p_hi && e.skip == skip_diag) {
@@ -2460,15 +2499,15 @@ void hyp_ozaki_syrk_rows(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_
         }
     cudaStream_t s = ctx->launch_stream ? ctx->launch_stream : ctx->stream;
     if (!d_pairs) {
-        std::vector<int2> pl;
+        std::vector<int4> pl;
         for (int pp = p_lo; pp < p_hi; pp++)
             for (int tj = 2 * pp; tj < nt; tj++) {
                 if (2 * pp + 1 < skip_diag && tj < skip_diag) continue;      // both tile rows of the pair inside the block
-                pl.push_back(make_int2(pp, tj));
+                pl.push_back(make_int4(pp, tj, 0, 0));
             }
         n_pairs = (int)pl.size();
-        CUDA_TRY(cudaMalloc(&d_pairs, std::max<size_t>(pl.size(), 1) * sizeof(int2)));
-        if (n_pairs) CUDA_TRY(cudaMemcpyAsync(d_pairs, pl.data(), pl.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMalloc(&d_pairs, std::max<size_t>(pl.size(), 1) * sizeof(int4)));
+        if (n_pairs) CUDA_TRY(cudaMemcpyAsync(d_pairs, pl.data(), pl.size() * sizeof(int4), cudaMemcpyHostToDevice, s));
         CUDA_TRY(cudaStreamSynchronize(s));
         cache.push_back({ctx->device, nt, p_lo, p_hi, skip_diag, d_pairs, n_pairs});
     }
@@ -2504,6 +2543,102 @@ void hyp_ozaki_syrk_rows(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_
     cfg.numAttrs = 1;
     launch_pair64(ctx, &cfg, digits, K, ncols, ldd, slice_stride, P64_NSL, d_pairs, n_pairs, 0, K, dscale, C, ldc, alpha, beta, 0);
     CUDA_TRY(cudaGetLastError());
+}
+
+// General product C_g = alpha * P' R_g + beta * C_g on the int8 tensor pipe (the congruences of large matrix cones,
+// cones_mat.cu): P is klen x mrows, R holds ngroups blocks of klen rows at row offsets g * r_kstride (ncols columns each),
+// C_g = C + g * c_group_stride.  Both operands are cut into digit slices (column scales over ALL rows of a column, i.e.
+// over all groups of R) in workspaces of the context; every 128 x 128 tile of every C_g is stored.  Returns false when
+// the digit-sliced kernel does not apply (caller falls back to the FP64 DMMA product).
+bool hyp_ozaki_gemm_tn(hyp_ctx* ctx, const double* P, int64_t ldp, const double* R, int64_t ldr, int64_t klen, int64_t mrows,
+                       int64_t ncols, double* C, int64_t ldc, double alpha, double beta, int ngroups, int64_t r_kstride,
+                       int64_t c_group_stride) {
+    if (klen <= 0 || mrows <= 0 || ncols <= 0 || ngroups <= 0) return true;
+    if (klen > 18688 || !hyp_ozaki_pair64_ready(ctx) || getenv("HYP_CONG_DMMA")) return false;
+    // digit rows of group g start at g * ks64 (a multiple of 64): TMA coordinates must be 16-byte aligned, the row pitch of
+    // the FP64 operand (an even number) need not be
+    const int64_t Kb = ngroups > 1 ? r_kstride * (ngroups - 1) + klen : klen;           // rows of R (FP64 layout)
+    const int64_t ks64 = round_up(r_kstride, 64);
+    const int64_t Kd = ngroups > 1 ? ks64 * (ngroups - 1) + klen : klen;                // rows of the digit columns of R
+    const int64_t lddA = round_up(std::max<int64_t>(klen, 16), 16), lddB = round_up(std::max<int64_t>(Kd, 16), 16);
+    const int64_t sA = lddA * mrows, sB = lddB * ncols;
+    auto grow = [&](void** p, int64_t* have, int64_t need) {
+        if (*have >= need) return;
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+        CUDA_TRY(cudaMalloc(p, (size_t)need));
+        *have = need;
+    };
+    grow((void**)&ctx->d_gemm_digA, &ctx->gemm_digA_bytes, P64_NSL * sA);
+    grow((void**)&ctx->d_gemm_digB, &ctx->gemm_digB_bytes, P64_NSL * sB);
+    grow((void**)&ctx->d_gemm_scal, &ctx->gemm_scal_bytes, (mrows + ncols) * 16);
+    double* scaleA = ctx->d_gemm_scal;
+    double* scaleB = scaleA + mrows;
+    int* expoA = reinterpret_cast<int*>(scaleB + ncols);
+    int* expoB = expoA + mrows;
+    hyp_ozaki_slice(ctx, P, ldp, klen, mrows, ctx->d_gemm_digA, lddA, sA, expoA, scaleA);
+    if (ngroups == 1) {
+        hyp_ozaki_slice(ctx, R, ldr, Kb, ncols, ctx->d_gemm_digB, lddB, sB, expoB, scaleB);
+    } else {
+        // one scale per column over all groups, then the groups' rows to their padded digit offsets
+        hypdev::colmax_kernel<<<(unsigned)ncols, 256, 0, ctx->stream>>>(Kb, ncols, R, ldr, expoB, scaleB, 1);
+        dim3 grid(std::max(1, std::min(ceil_div(klen, 2048), 32)), (unsigned)std::min<int64_t>(ncols, 65535), (unsigned)ngroups);
+        hypdev::slice256_kernel<<<grid, 256, 0, ctx->stream>>>(klen, ncols, R, ldr, expoB, P64_NSL, ctx->d_gemm_digB, lddB, sB,
+                                                               r_kstride, ks64);
+        ctx->launches += 2;
+        CUDA_TRY(cudaGetLastError());
+    }
+    // pair list: every tile-row pair x tile column of every group
+    const int mt = ceil_div(mrows, TM), nt = ceil_div(ncols, TN), np = (mt + 1) / 2;
+    struct Entry {
+        int device, mt, nt, ng;
+        int64_t ks;
+        int4* d_pairs;
+        int n_pairs;
+    };
+    static std::vector<Entry> cache;
+    int4* d_pairs = nullptr;
+    int n_pairs = 0;
+    for (auto& e : cache)
+        if (e.device == ctx->device && e.mt == mt && e.nt == nt && e.ng == ngroups && e.ks == r_kstride) {
+            d_pairs = e.d_pairs;
+            n_pairs = e.n_pairs;
+        }
+    if (!d_pairs) {
+        std::vector<int4> pl;
+        pl.reserve((size_t)ngroups * np * nt);
+        for (int g = 0; g < ngroups; g++)
+            for (int pp = 0; pp < np; pp++)
+                for (int tj = 0; tj < nt; tj++) pl.push_back(make_int4(pp, tj, (int)(g * ks64), g));
+        n_pairs = (int)pl.size();
+        CUDA_TRY(cudaMalloc(&d_pairs, pl.size() * sizeof(int4)));
+        CUDA_TRY(cudaMemcpyAsync(d_pairs, pl.data(), pl.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        cache.push_back({ctx->device, mt, nt, ngroups, r_kstride, d_pairs, n_pairs});
+    }
+    static int max_clusters = 0;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(I8_THREADS);
+    cfg.dynamicSmemBytes = P64_SMEM;
+    cfg.stream = ctx->stream;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if (!max_clusters) {
+        cfg.gridDim = dim3(2 * 128);
+        CUDA_TRY(cudaOccupancyMaxActiveClusters(&max_clusters, ozaki_syrk_pair64_kernel<3>, &cfg));
+    }
+    cfg.gridDim = dim3(2 * std::min(n_pairs, max_clusters));
+    P64Operand A{ctx->d_gemm_digA, klen, mrows, lddA, sA, P64_NSL, scaleA};
+    P64Operand B{ctx->d_gemm_digB, Kd, ncols, lddB, sB, P64_NSL, scaleB};
+    launch_pair64_ex(ctx, &cfg, A, B, d_pairs, n_pairs, 0, klen, C, ldc, c_group_stride, alpha, beta, 0, true);
+    CUDA_TRY(cudaGetLastError());
+    return true;
 }
 
 // C = A' A (upper 128-tiles) for a host/device FP64 matrix A, through slicing + tcgen05 (unit test)

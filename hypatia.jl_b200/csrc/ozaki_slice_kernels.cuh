@@ -165,7 +165,12 @@ slice256_short_kernel(int K, int64_t ncols, const double* __restrict__ A, int64_
 // radix-128 digits, so the product needs 28 digit pairs (s + t <= 6) instead of 36 at the same truncation error.
 static __global__ void slice256_kernel(int64_t K, int64_t ncols, const double* __restrict__ A, int64_t lda,
                                 const int* __restrict__ expo, int nslices, int8_t* __restrict__ D, int64_t ldd,
-                                int64_t slice_stride) {
+                                int64_t slice_stride, int64_t a_gstride = 0, int64_t d_gstride = 0) {
+    // gridDim.z > 1: row groups (the grouped products of the matrix-cone congruences): group z reads its K rows at row
+    // offset z * a_gstride of every column and writes its digit rows at offset z * d_gstride (a multiple of 64, so that
+    // the TMA coordinates of the groups stay 16-byte aligned whatever the row pitch of the FP64 operand is)
+    A += (int64_t)blockIdx.z * a_gstride;
+    D += (int64_t)blockIdx.z * d_gstride;
     const int64_t K8 = (K + 7) / 8;
     for (int64_t j = blockIdx.y; j < ncols; j += gridDim.y) {
         const double sc = ldexp(1.0, 7 - expo[j]);
