@@ -822,6 +822,14 @@ trsv_kernel(const double* __restrict__ F, int64_t ldf, int64_t m, const double* 
 #pragma unroll
                 for (int i = 0; i < 16; i++) pacc[v][i] = 0.0;
             const int64_t cw = c0 + warp * 16;
+            // my own block of the right-hand side does not depend on the chain: fetched now, used after the last tile
+            double xown[NRHS][16];
+            if (lane == 0) {
+#pragma unroll
+                for (int v = 0; v < NRHS; v++)
+#pragma unroll
+                    for (int i = 0; i < 16; i++) xown[v][i] = (cw + i < m) ? x[v * xstride + cw + i] : 0.0;
+            }
             for (int j = 0; j < k; j++) {
                 double tl[16][4];
                 const double* Ut = F + (int64_t)j * NB + cw * ldf;
@@ -868,7 +876,7 @@ trsv_kernel(const double* __restrict__ F, int64_t ldf, int64_t m, const double* 
 #pragma unroll
                     for (int i = 0; i < 16; i++) {
                         int64_t c = cw + i;
-                        sv[v][0][warp * 16 + i] = (c < m) ? (x[v * xstride + c] - pacc[v][i]) : 0.0;
+                        sv[v][0][warp * 16 + i] = (c < m) ? (xown[v][i] - pacc[v][i]) : 0.0;
                     }
             }
             __syncthreads();
@@ -902,6 +910,9 @@ trsv_kernel(const double* __restrict__ F, int64_t ldf, int64_t m, const double* 
             double acc[NRHS];
 #pragma unroll
             for (int v = 0; v < NRHS; v++) acc[v] = 0.0;
+            double xown[NRHS];               // my own entry of the right-hand side (threads 0 .. 127), fetched off the chain
+#pragma unroll
+            for (int v = 0; v < NRHS; v++) xown[v] = (tid < NB && c0 + tid < m) ? x[v * xstride + c0 + tid] : 0.0;
             for (int j = nblk - 1; j > k; j--) {
                 double tl[64];
                 const int64_t cb = (int64_t)j * NB + half * 64;
@@ -938,7 +949,7 @@ trsv_kernel(const double* __restrict__ F, int64_t ldf, int64_t m, const double* 
             if (tid < NB) {
 #pragma unroll
                 for (int v = 0; v < NRHS; v++)
-                    sv[v][0][tid] = (c0 + tid < m) ? (x[v * xstride + c0 + tid] - sacc[v][0][tid] - sacc[v][1][tid]) : 0.0;
+                    sv[v][0][tid] = (c0 + tid < m) ? (xown[v] - sacc[v][0][tid] - sacc[v][1][tid]) : 0.0;
             }
             __syncthreads();
             // x[r] = sum_{c >= r} Dinv[r, c] v[c]
@@ -964,7 +975,8 @@ trsv_kernel(const double* __restrict__ F, int64_t ldf, int64_t m, const double* 
                 for (int v = 0; v < NRHS; v++) x[v * xstride + c0 + tid] = sacc[v][0][tid] + sacc[v][1][tid];
             }
         }
-        __threadfence();
+        // only the threads that stored entries of x need the fence in front of the barrier; thread 0 then publishes
+        if (TRANS ? (lane == 0) : (tid < NB)) __threadfence();
         __syncthreads();
         if (tid == 0) st_release(&flags[1 + k], epoch);
     }
