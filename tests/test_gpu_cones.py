@@ -36,6 +36,10 @@ CONE_SETS = {
     # reference oracles hypoperlogdettri.jl:196-368; and two of config 4's side-100 PSD cones
     "logdet_side1000": [M.HypoPerLogdetTri(2 + M.svec_length(1000))],
     "psd_side100": [M.PosSemidefTri(M.svec_length(100)), M.PosSemidefTri(M.svec_length(100))],
+    # sides above 512: the congruences run on the int8 tensor pipe (hyp_ozaki_gemm_tn; sides not multiples of 16 or 64:
+    # padded digit rows, zero-filled TMA edges, grouped right-hand operand)
+    "big_sides_i8": [M.PosSemidefTri(M.svec_length(520)), M.HypoPerLogdetTri(2 + M.svec_length(531)),
+                     M.HypoRootdetTri(1 + M.svec_length(513))],
     "rootdet": [M.HypoRootdetTri(2), M.HypoRootdetTri(4), M.HypoRootdetTri(11),
                 M.HypoRootdetTri(1 + M.svec_length(33)), M.HypoRootdetTri(7, use_dual=True)],
     "sepspec": [M.EpiPerSepSpectralMat(2 + M.svec_length(1), M.SSF_NEGLOG),
@@ -103,7 +107,7 @@ def test_cone_oracles_match_cpu_oracle(name):
     # side-130 spectral cone: its eigenvalues cluster near 1 (spacing ~1e-3), and the second divided
     # differences of dder3 (matrixcsqr.jl:449-502) divide by those gaps, amplifying the O(side * eps)
     # difference between the Jacobi and LAPACK eigen-decompositions (measured 2e-10 .. 1.3e-9)
-    tol = 1e-9 if name == "logdet_side1000" else 1e-10
+    tol = 1e-9 if name in ("logdet_side1000", "big_sides_i8") else 1e-10
     d3tol = 1e-8 if name == "sepspec_big" else tol
     assert rel(dev.hess_prod(arr), ora.hess_prod(arr)) <= tol
     assert rel(dev.inv_hess_prod(arr), ora.inv_hess_prod(arr)) <= tol
