@@ -43,6 +43,22 @@ _SIGS = {
     "hyp_cones_dder3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "hyp_cones_proxsqr": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]),
     "hyp_cones_hess_blocks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "hyp_cone_create": (C.c_void_p, [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int64]),
+    "hyp_cone_destroy": (None, [C.c_void_p]),
+    "hyp_cone_last_error": (C.c_char_p, [C.c_void_p]),
+    "hyp_cone_dimension": (C.c_int64, [C.c_void_p]),
+    "hyp_cone_nu": (C.c_double, [C.c_void_p]),
+    "hyp_cone_use_dual_barrier": (C.c_int, [C.c_void_p]),
+    "hyp_cone_load_point": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double]),
+    "hyp_cone_load_dual_point": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hyp_cone_reset_data": (C.c_int, [C.c_void_p]),
+    "hyp_cone_is_feas": (C.c_int, [C.c_void_p, c_ip, c_ip]),
+    "hyp_cone_grad": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hyp_cone_hess": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "hyp_cone_hess_prod": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int]),
+    "hyp_cone_use_sqrt_hess_oracles": (C.c_int, [C.c_void_p]),
+    "hyp_cone_dder3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hyp_cone_proxsqr": (C.c_int, [C.c_void_p, C.c_double, C.c_int, c_dp, c_ip]),
     "hyp_set_syssolver": (C.c_int, [C.c_void_p, C.c_int]),
     "hyp_set_syrk_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "hyp_set_column_sharding": (C.c_int, [C.c_void_p, C.c_int]),

@@ -145,6 +145,46 @@ int hyp_cones_proxsqr(hyp_ctx* ctx, double irtmu, int use_max, double* proxsqr,
  * the other (block k starts at sum_{j<k} dim_j^2). */
 int hyp_cones_hess_blocks(hyp_ctx* ctx, double* blocks, int inverse);
 
+/* ---- cone oracles, ONE cone per handle (plugin slot 2, SURVEY.md 8(b) "per-cone single-block variants") -------
+ * What a `B200Cone <: Cones.Cone{Float64}` object of the Julia shim forwards its methods to: the per-cone oracle API of
+ * src/Cones/Cones.jl:34-310 with the reference's lazy evaluation (the loads only copy, the first query evaluates).
+ * Each handle owns a private one-cone context and runs the same kernels as the batched calls above (a batch of one);
+ * the batched calls remain the hot path of a solve. */
+typedef struct hyp_cone hyp_cone;
+/* constructor + setup_data!(cone) (Cones.jl:139-152).  iparam / dparam: the integer / real parameter of
+ * hyp_set_cone_params for this cone type (HYP_SSF_* code and power of EpiPerSepSpectral, d1 of EpiNormSpectral /
+ * MatrixEpiPerSquare, R of the WSOS matrix / norm cones; 0 otherwise); alpha[0 .. nalpha): the per-cone array of
+ * hyp_set_cone_alpha (NULL / 0 for cone types without one).  NULL on failure (message on stderr). */
+hyp_cone* hyp_cone_create(int device, int cone_type, int64_t dim, int use_dual_barrier, int iparam, double dparam,
+                          const double* alpha, int64_t nalpha);
+void hyp_cone_destroy(hyp_cone* cone);
+const char* hyp_cone_last_error(hyp_cone* cone);
+int64_t hyp_cone_dimension(hyp_cone* cone);      /* dimension(cone), Cones.jl:34 */
+double hyp_cone_nu(hyp_cone* cone);              /* get_nu(cone), Cones.jl:41 */
+int hyp_cone_use_dual_barrier(hyp_cone* cone);   /* use_dual_barrier(cone), Cones.jl:138 */
+/* load_point(cone, point, scal): cone.point = scal * point (Cones.jl:157-161; scal = 1 for the two-argument form
+ * :163-166) followed by reset_data(cone); load_dual_point(cone, point) (:168-171); reset_data(cone) (:185-186) */
+int hyp_cone_load_point(hyp_cone* cone, const double* point, double scal);
+int hyp_cone_load_dual_point(hyp_cone* cone, const double* dual_point);
+int hyp_cone_reset_data(hyp_cone* cone);
+/* is_feas(cone) / is_dual_feas(cone) (Cones.jl:56-69); either output pointer may be NULL */
+int hyp_cone_is_feas(hyp_cone* cone, int* is_feas, int* is_dual_feas);
+/* grad(cone) (Cones.jl:71-77): dim values */
+int hyp_cone_grad(hyp_cone* cone, double* grad);
+/* hess(cone) (inverse = 0, Cones.jl:79-84) / inv_hess(cone) (inverse = 1, :86-93): dim x dim, column-major */
+int hyp_cone_hess(hyp_cone* cone, double* H, int inverse);
+/* hess_prod! / inv_hess_prod! / sqrt_hess_prod! / inv_sqrt_hess_prod! (mode = HYP_PROD_*; Cones.jl:101-118,198-218
+ * and the per-cone files) on a dim x ncols array */
+int hyp_cone_hess_prod(hyp_cone* cone, double* prod, const double* arr, int64_t ncols, int64_t ld_prod,
+                       int64_t ld_arr, int mode);
+/* use_sqrt_hess_oracles(arr_dim, cone) of the cone types with closed-form square-root oracles (1 / 0) */
+int hyp_cone_use_sqrt_hess_oracles(hyp_cone* cone);
+/* dder3(cone, dir) (Cones.jl:134 and the per-cone files) */
+int hyp_cone_dder3(hyp_cone* cone, double* out, const double* dir);
+/* get_proxsqr(cone, irtmu, use_max_prox) (Cones.jl:294-310) and check_numerics(cone) (:273-290) from one sweep;
+ * either output pointer may be NULL */
+int hyp_cone_proxsqr(hyp_cone* cone, double irtmu, int use_max_prox, double* proxsqr, int* numerics_ok);
+
 /* ---- system solver (plugin slot 1) ------------------------------------------------------ */
 /* which reference system solver the context restates: 0 = QRCholDenseSystemSolver (default,
  * qrchol.jl:104-257), 1 = SymIndefDenseSystemSolver (symindef.jl:203-271: dense (n+p+q)^2

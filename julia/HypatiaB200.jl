@@ -426,4 +426,178 @@ function Solvers.check_cone_points(model::Models.Model{Float64}, stepper::Solver
     return true
 end
 
+# ---------------------------------------------------------------------------------------------
+# plug-in slot 2, per-cone form: B200Cone <: Cones.Cone{Float64}.  One device cone behind the reference's per-cone
+# oracle API (Cones.jl:34-310), bound to the single-block entry points hyp_cone_* (SURVEY.md 8(b)).  It carries every
+# field the generic code of Cones.jl touches and the reference's lazy evaluation (the loads write cone.point /
+# cone.dual_point on the host, reset_data clears the flags, the first query uploads and evaluates), so stock code that
+# handles ONE cone - tests, initialize_cone_point (Solvers.jl:530-548), user callbacks, the stock system solvers -
+# runs unchanged on it:  model.cones .= HypatiaB200.B200Cone.(model.cones).
+# With the B200 system solver the batched hyp_cones_* path above serves all K cones per launch and remains the hot path.
+# ---------------------------------------------------------------------------------------------
+const ConeHandle = Ptr{Cvoid}
+
+mutable struct B200Cone <: Cones.Cone{Float64}
+    inner::Cones.Cone{Float64}            # the stock cone this object stands in for (type, parameters, initial point)
+    device::Int
+    handle::ConeHandle
+    use_dual_barrier::Bool
+    dim::Int
+    nu::Float64
+    # fields of the generic Cone code (Cones.jl:34-310)
+    point::Vector{Float64}
+    dual_point::Vector{Float64}
+    grad::Vector{Float64}
+    dder3::Vector{Float64}
+    vec1::Vector{Float64}
+    vec2::Vector{Float64}
+    feas_updated::Bool
+    grad_updated::Bool
+    hess_updated::Bool
+    inv_hess_updated::Bool
+    hess_fact_updated::Bool
+    is_feas::Bool
+    use_hess_prod_slow::Bool
+    use_hess_prod_slow_updated::Bool
+    hess::Symmetric{Float64, Matrix{Float64}}
+    inv_hess::Symmetric{Float64, Matrix{Float64}}
+    hess_fact_mat::Symmetric{Float64, Matrix{Float64}}
+    hess_fact::Factorization{Float64}
+
+    function B200Cone(inner::Cones.Cone{Float64}; device::Int = 0)
+        cone = new()
+        cone.inner = inner
+        cone.device = device
+        cone.handle = C_NULL
+        cone.use_dual_barrier = Cones.use_dual_barrier(inner)
+        cone.dim = Cones.dimension(inner)
+        cone.nu = Cones.get_nu(inner)
+        cone.use_hess_prod_slow = cone.use_hess_prod_slow_updated = false
+        return cone
+    end
+end
+
+cone_check(cone::B200Cone, rc::Cint, what::String) = (rc < 0 &&
+    error("$what: " * unsafe_string(ccall((:hyp_cone_last_error, LIB), Cstring, (ConeHandle,), cone.handle))); rc)
+
+# setup_data!(cone) (Cones.jl:139-152) allocates the generic fields and calls this hook: create the device cone
+function Cones.setup_extra_data!(cone::B200Cone)
+    free_cone!(cone)
+    (iparam, dparam) = cone_ssf(cone.inner)
+    alpha = cone_alpha(cone.inner)
+    cone.handle = ccall((:hyp_cone_create, LIB), ConeHandle,
+        (Cint, Cint, Int64, Cint, Cint, Float64, Ptr{Float64}, Int64),
+        cone.device, cone_code(cone.inner), cone.dim, cone.use_dual_barrier, iparam, dparam, alpha, length(alpha))
+    cone.handle == C_NULL && error("hyp_cone_create failed for $(typeof(cone.inner)) (no CPU fallback)")
+    finalizer(free_cone!, cone)
+    return cone
+end
+
+function free_cone!(cone::B200Cone)
+    cone.handle == C_NULL || ccall((:hyp_cone_destroy, LIB), Cvoid, (ConeHandle,), cone.handle)
+    cone.handle = C_NULL
+    return
+end
+
+Cones.set_initial_point!(arr::AbstractVector, cone::B200Cone) = Cones.set_initial_point!(arr, cone.inner)
+
+# update_feas(cone): the per-cone files read cone.point here for the first time after load_point / reset_data
+# (e.g. epinormeucl.jl:54-68); the device cone receives cone.point and cone.dual_point at the same moment
+function Cones.update_feas(cone::B200Cone)
+    @assert !cone.feas_updated
+    cone_check(cone, ccall((:hyp_cone_load_point, LIB), Cint, (ConeHandle, Ptr{Float64}, Float64),
+        cone.handle, cone.point, 1.0), "hyp_cone_load_point")
+    cone_check(cone, ccall((:hyp_cone_load_dual_point, LIB), Cint, (ConeHandle, Ptr{Float64}),
+        cone.handle, cone.dual_point), "hyp_cone_load_dual_point")
+    feas = Ref{Cint}(0)
+    cone_check(cone, ccall((:hyp_cone_is_feas, LIB), Cint, (ConeHandle, Ptr{Cint}, Ptr{Cint}),
+        cone.handle, feas, C_NULL), "hyp_cone_is_feas")
+    cone.is_feas = !iszero(feas[])
+    cone.feas_updated = true
+    return cone.is_feas
+end
+
+# is_dual_feas(cone) is not cached by the reference (Cones.jl:69 and the per-cone overrides read cone.dual_point)
+function Cones.is_dual_feas(cone::B200Cone)
+    cone.feas_updated || Cones.update_feas(cone)
+    dual_feas = Ref{Cint}(0)
+    cone_check(cone, ccall((:hyp_cone_is_feas, LIB), Cint, (ConeHandle, Ptr{Cint}, Ptr{Cint}),
+        cone.handle, C_NULL, dual_feas), "hyp_cone_is_feas")
+    return !iszero(dual_feas[])
+end
+
+function Cones.update_grad(cone::B200Cone)
+    @assert Cones.is_feas(cone)
+    cone_check(cone, ccall((:hyp_cone_grad, LIB), Cint, (ConeHandle, Ptr{Float64}), cone.handle, cone.grad),
+        "hyp_cone_grad")
+    cone.grad_updated = true
+    return cone.grad
+end
+
+function Cones.update_hess(cone::B200Cone)
+    Cones.grad(cone)
+    isdefined(cone, :hess) || Cones.alloc_hess!(cone)
+    cone_check(cone, ccall((:hyp_cone_hess, LIB), Cint, (ConeHandle, Ptr{Float64}, Cint),
+        cone.handle, cone.hess.data, 0), "hyp_cone_hess")
+    cone.hess_updated = true
+    return cone.hess
+end
+
+function Cones.update_inv_hess(cone::B200Cone)
+    Cones.grad(cone)
+    isdefined(cone, :inv_hess) || Cones.alloc_inv_hess!(cone)
+    cone_check(cone, ccall((:hyp_cone_hess, LIB), Cint, (ConeHandle, Ptr{Float64}, Cint),
+        cone.handle, cone.inv_hess.data, 1), "hyp_cone_hess")
+    cone.inv_hess_updated = true
+    return cone.inv_hess
+end
+
+# prod / arr may be views of columns of a larger matrix (qrchol.jl:219-246): unit stride down a column is required
+# (as for the reference's BLAS calls), the column stride travels as the leading dimension
+function cone_prod!(prod::AbstractVecOrMat{Float64}, arr::AbstractVecOrMat{Float64}, cone::B200Cone, mode::Int)
+    Cones.grad(cone)
+    @assert size(prod) == size(arr) && size(arr, 1) == cone.dim
+    @assert stride(arr, 1) == 1 && stride(prod, 1) == 1
+    ncols = size(arr, 2)
+    ld_arr = (ncols > 1 ? stride(arr, 2) : cone.dim)
+    ld_prod = (ncols > 1 ? stride(prod, 2) : cone.dim)
+    GC.@preserve prod arr cone_check(cone, ccall((:hyp_cone_hess_prod, LIB), Cint,
+        (ConeHandle, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Int64, Cint),
+        cone.handle, pointer(prod), pointer(arr), ncols, ld_prod, ld_arr, mode), "hyp_cone_hess_prod")
+    return prod
+end
+
+Cones.hess_prod!(prod::AbstractVecOrMat{Float64}, arr::AbstractVecOrMat{Float64}, cone::B200Cone) =
+    cone_prod!(prod, arr, cone, 0)
+Cones.inv_hess_prod!(prod::AbstractVecOrMat{Float64}, arr::AbstractVecOrMat{Float64}, cone::B200Cone) =
+    cone_prod!(prod, arr, cone, 1)
+Cones.sqrt_hess_prod!(prod::AbstractVecOrMat{Float64}, arr::AbstractVecOrMat{Float64}, cone::B200Cone) =
+    cone_prod!(prod, arr, cone, 2)
+Cones.inv_sqrt_hess_prod!(prod::AbstractVecOrMat{Float64}, arr::AbstractVecOrMat{Float64}, cone::B200Cone) =
+    cone_prod!(prod, arr, cone, 3)
+
+# closed-form square-root oracles only (nonnegative.jl:38, epinormeucl.jl:40, possemideftri.jl:54, epipersquare.jl:48);
+# the generic Cholesky-of-the-Hessian route of Cones.jl:189-196 is not offered, callers take the hess_prod! branch
+Cones.use_sqrt_hess_oracles(arr_dim::Int, cone::B200Cone) =
+    !iszero(ccall((:hyp_cone_use_sqrt_hess_oracles, LIB), Cint, (ConeHandle,), cone.handle))
+
+function Cones.dder3(cone::B200Cone, dir::AbstractVector{Float64})
+    Cones.grad(cone)
+    dirv = Vector{Float64}(dir)
+    cone_check(cone, ccall((:hyp_cone_dder3, LIB), Cint, (ConeHandle, Ptr{Float64}, Ptr{Float64}),
+        cone.handle, cone.dder3, dirv), "hyp_cone_dder3")
+    return cone.dder3
+end
+
+function cone_prox(cone::B200Cone, irtmu::Float64, use_max_prox::Bool)
+    Cones.grad(cone)
+    (proxsqr, ok) = (Ref{Float64}(0.0), Ref{Cint}(0))
+    cone_check(cone, ccall((:hyp_cone_proxsqr, LIB), Cint, (ConeHandle, Float64, Cint, Ptr{Float64}, Ptr{Cint}),
+        cone.handle, irtmu, use_max_prox, proxsqr, ok), "hyp_cone_proxsqr")
+    return (proxsqr[], !iszero(ok[]))
+end
+
+Cones.check_numerics(cone::B200Cone) = last(cone_prox(cone, 1.0, true))
+Cones.get_proxsqr(cone::B200Cone, irtmu::Float64, use_max_prox::Bool) = first(cone_prox(cone, irtmu, use_max_prox))
+
 end # module

@@ -7,6 +7,12 @@ thread_local dim3 threadIdx;
 thread_local dim3 blockIdx;
 dim3 blockDim;
 dim3 gridDim;
+// every __shared__ variable of the kernel headers lives in the ELF section "emu_shared" (cuda_emu.h); the linker
+// brackets it with these two symbols
+extern "C" {
+extern char __start_emu_shared[];
+extern char __stop_emu_shared[];
+}
 namespace emu {
 BlockState* g_block = nullptr;
 void* g_dyn_smem = nullptr;
@@ -30,6 +36,12 @@ void launch(dim3 grid, dim3 block, size_t dyn_smem, const std::function<void()>&
             for (int w = 0; w < nw; w++) pthread_barrier_init(&st.warp_bar[w], nullptr, std::min(32, nt - 32 * w));
             st.shf.assign(nt, 0.0);
             g_block = &st;
+            // Shared memory is undefined at the start of a block on the device; the statics that stand in for it would
+            // otherwise keep the previous block's (plausible) values.  All-ones bytes = NaN for doubles, -1 for ints: a
+            // kernel that reads a shared entry it did not write in THIS block now fails its test, as the NaN-poisoned
+            // output buffers of the wrappers do for global memory.
+            memset(__start_emu_shared, 0xFF, (size_t)(__stop_emu_shared - __start_emu_shared));
+            if (dyn_smem) memset(smem, 0xFF, dyn_smem);
             std::vector<std::thread> th;
             th.reserve(nt);
             for (int t = 0; t < nt; t++)

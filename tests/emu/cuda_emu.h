@@ -4,7 +4,9 @@
 // One pthread per CUDA thread of a block, blocks run one after the other; __syncthreads is a
 // pthread barrier over the block, warp shuffles exchange through a per-block buffer guarded by
 // per-warp barriers; __shared__ variables become function-level statics (blocks are sequential, so
-// a static is "per block").  Only what the kernel headers use is provided.
+// a static is "per block") collected in one ELF section, which emu::launch fills with NaN bytes before
+// every block - shared memory does not survive a block on the device either.  Only what the kernel
+// headers use is provided.
 #pragma once
 #include <pthread.h>
 #include <cmath>
@@ -46,7 +48,7 @@ extern dim3 gridDim;
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
-#define __shared__ static
+#define __shared__ static __attribute__((section("emu_shared")))
 #define HYP_DYN_SMEM(type, name) type* name = (type*)emu::g_dyn_smem
 #define INFINITY_EMU INFINITY
 

@@ -100,9 +100,30 @@ def test_overridden_functions_exist_with_those_names_and_arities():
 def test_cone_api_names_used_by_the_shim_exist():
     shim = _shim()
     cones = _read("Cones/Cones.jl")
+    # update_feas / update_grad / update_hess / update_inv_hess are the per-cone hooks: defined in the cone files
+    percone = _read("Cones/epinormeucl.jl") + _read("Cones/hypoperlogdettri.jl")
     for name in set(re.findall(r"\bCones\.([a-z_0-9!]+)\(", shim)):
-        assert re.search(r"^(?:function )?%s\(" % re.escape(name), cones, re.M) or \
-            re.search(r"^%s\(" % re.escape(name), cones, re.M), f"Cones.{name} not in Cones.jl"
+        pat = r"^(?:function )?%s\(" % re.escape(name)
+        assert re.search(pat, cones, re.M) or re.search(pat, percone, re.M), f"Cones.{name} not in src/Cones"
+
+
+def test_b200cone_declares_every_field_the_generic_cone_code_touches():
+    """Cones.jl's generic methods read and write `cone.<field>` on any Cone subtype (Cones.jl:34-310): the shim's
+    B200Cone must carry all of them, be a Cone{Float64}, and create / free its device handle in the reference's
+    setup hook."""
+    with open(SHIM) as f:
+        src = f.read()
+    m = re.search(r"mutable struct B200Cone <: Cones\.Cone\{Float64\}\n(.*?)\n    function B200Cone", src, re.S)
+    assert m, "B200Cone <: Cones.Cone{Float64} not found"
+    declared = set(re.findall(r"^\s+([a-z_0-9]+)::", m.group(1), re.M))
+    touched = set(re.findall(r"\bcone\.([a-z_][a-z_0-9]*)", _read("Cones/Cones.jl")))
+    assert touched <= declared, touched - declared
+    assert "Cones.setup_extra_data!(cone::B200Cone)" in src and ":hyp_cone_create" in src and ":hyp_cone_destroy" in src
+    # every oracle of the per-cone API has a B200Cone method
+    for fn in ("update_feas", "is_dual_feas", "update_grad", "update_hess", "update_inv_hess", "hess_prod!",
+               "inv_hess_prod!", "sqrt_hess_prod!", "inv_sqrt_hess_prod!", "use_sqrt_hess_oracles", "dder3",
+               "check_numerics", "get_proxsqr", "set_initial_point!"):
+        assert re.search(r"Cones\.%s\([^)]*::B200Cone" % re.escape(fn), src), fn
 
 
 def test_temporaries_passed_by_pointer_are_gc_preserved():
