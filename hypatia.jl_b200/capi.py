@@ -83,6 +83,7 @@ _SIGS = {
                                    C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_double, C.c_double]),
     "hyp_test_potrf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, c_ip]),
     "hyp_test_panel_clocks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
+    "hyp_test_set_trsv_pkt": (C.c_int, [C.c_int]),
     "hyp_test_potrs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "hyp_test_gemv": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
                                 C.c_void_p, C.c_double, C.c_double, C.c_void_p]),

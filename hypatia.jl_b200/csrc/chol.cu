@@ -39,6 +39,10 @@ void set_panel_attr() {
     CUDA_TRY(cudaFuncSetAttribute(trsv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(trsv_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(trsv_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(trsv_pkt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(trsv_pkt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(trsv_pkt_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(trsv_pkt_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(trsv_seg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(trsv_seg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(trsv_seg_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
@@ -75,6 +79,34 @@ const TrsvLists& trsv_lists(hyp_ctx* ctx, int nblk, bool trans) {
     return g_trsv_lists.back();
 }
 // partial sums: nblk x maxseg x (up to 2 right-hand sides) x 128 doubles, per context
+// packet variant: opt-in (HYP_TRSV_PKT=1 or hyp_test_set_trsv_pkt).  Measured on C3 / C2 (profiles/r02_bench_trsv_packets_ab.md):
+// 3.69 vs 3.67 ms and 1.21 vs 1.28 ms per step - the sweeps are bound by the 128 KB tile every CTA pulls into ONE SM per
+// dependency step (~42 B/clk per SM from L2), not by the flag / fence protocol the packets remove.
+int g_trsv_pkt = -1;
+bool trsv_use_pkt() {
+    if (g_trsv_pkt < 0) {
+        const char* e = getenv("HYP_TRSV_PKT");
+        g_trsv_pkt = (e && atoi(e) == 1) ? 1 : 0;
+    }
+    return g_trsv_pkt == 1;
+}
+
+// packet buffer of trsv_pkt_kernel: 2 words per entry, nblk blocks of 128 entries, nrhs right-hand sides; zeroed when
+// (re)allocated - epochs of the context start at 1 and only grow, so a zero word never looks published
+unsigned long long* trsv_pkt(hyp_ctx* ctx, int nblk, int nrhs) {
+    const int64_t need = (int64_t)nrhs * nblk * NB * 2;
+    if (ctx->trsv_pkt_words < need) {
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_trsv_pkt) cudaFree(ctx->d_trsv_pkt);
+        ctx->d_trsv_pkt = nullptr;
+        ctx->trsv_pkt_words = 0;
+        CUDA_TRY(cudaMalloc((void**)&ctx->d_trsv_pkt, (size_t)need * 8));
+        CUDA_TRY(cudaMemset(ctx->d_trsv_pkt, 0, (size_t)need * 8));
+        ctx->trsv_pkt_words = need;
+    }
+    return ctx->d_trsv_pkt;
+}
+
 double* trsv_part(hyp_ctx* ctx, int nblk, int maxseg) {
     const int64_t need = (int64_t)nblk * maxseg * 2 * NB;
     if (ctx->trsv_part_len < need) {
@@ -377,9 +409,14 @@ void hyp_trsv_upper(hyp_ctx* ctx, const double* F, int64_t ldf, int64_t m, const
         CUDA_TRY(cudaGetLastError());
         return;
     }
+    unsigned long long* pkt = trsv_use_pkt() ? trsv_pkt(ctx, nblk, 1) : nullptr;
     CUDA_TRY(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
     int grid = std::min(nblk, ctx->sm_count);
-    if (trans)
+    if (pkt && trans)
+        trsv_pkt_kernel<true><<<grid, 256, TRSV_SMEM, ctx->stream>>>(F, ldf, m, d_dinv, x, ctx->d_flags, pkt, nblk, epoch);
+    else if (pkt)
+        trsv_pkt_kernel<false><<<grid, 256, TRSV_SMEM, ctx->stream>>>(F, ldf, m, d_dinv, x, ctx->d_flags, pkt, nblk, epoch);
+    else if (trans)
         trsv_kernel<true><<<grid, 256, TRSV_SMEM, ctx->stream>>>(F, ldf, m, d_dinv, x, ctx->d_flags, nblk, epoch);
     else
         trsv_kernel<false><<<grid, 256, TRSV_SMEM, ctx->stream>>>(F, ldf, m, d_dinv, x, ctx->d_flags, nblk, epoch);
@@ -410,9 +447,14 @@ void hyp_trsv_upper2(hyp_ctx* ctx, const double* F, int64_t ldf, int64_t m, cons
         CUDA_TRY(cudaGetLastError());
         return;
     }
+    unsigned long long* pkt = trsv_use_pkt() ? trsv_pkt(ctx, nblk, 2) : nullptr;
     CUDA_TRY(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
     int grid = std::min(nblk, ctx->sm_count);
-    if (trans)
+    if (pkt && trans)
+        trsv_pkt_kernel<true, 2><<<grid, 256, TRSV_SMEM, ctx->stream>>>(F, ldf, m, d_dinv, x, ctx->d_flags, pkt, nblk, epoch, xstride);
+    else if (pkt)
+        trsv_pkt_kernel<false, 2><<<grid, 256, TRSV_SMEM, ctx->stream>>>(F, ldf, m, d_dinv, x, ctx->d_flags, pkt, nblk, epoch, xstride);
+    else if (trans)
         trsv_kernel<true, 2><<<grid, 256, TRSV_SMEM, ctx->stream>>>(F, ldf, m, d_dinv, x, ctx->d_flags, nblk, epoch, xstride);
     else
         trsv_kernel<false, 2><<<grid, 256, TRSV_SMEM, ctx->stream>>>(F, ldf, m, d_dinv, x, ctx->d_flags, nblk, epoch, xstride);
@@ -463,3 +505,5 @@ extern "C" int hyp_test_panel_clocks(hyp_ctx* ctx, double* A, int64_t lda, int64
         return -1;
     }
 }
+
+void hyp_trsv_set_pkt(int on) { g_trsv_pkt = on ? 1 : 0; }

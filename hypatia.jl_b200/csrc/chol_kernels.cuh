@@ -982,6 +982,237 @@ trsv_kernel(const double* __restrict__ F, int64_t ldf, int64_t m, const double* 
     }
 }
 
+// ---- packet variant of the triangular solve (default) ----------------------------------------------------------
+// The dependency step of trsv_kernel is: producer stores x_k, __threadfence, st.release of the block flag; consumer
+// polls the flag (one L2 round trip per poll), barrier, THEN loads the 128 values (a second round trip).  Here every
+// value travels as two 8-byte words {32 bits of the double, epoch} (the LL idea of NCCL: an aligned 8-byte access is
+// single-copy atomic, so a word whose epoch matches carries valid data - no fence, no separate flag), and the consumer
+// threads poll the very words they need: one round trip per dependency step, and the producer's fence + flag store
+// leave the chain.  pkt: 2 words per entry, entry (v, k, r) at ((v * nblk + k) * 128 + r) * 2; zeroed at allocation,
+// epochs start at 1 and grow with every sweep of the context.  Arithmetic and its order are those of trsv_kernel.
+#ifdef HYP_EMU
+__device__ __forceinline__ void trsv_pkt_post(unsigned long long* p, double val, int epoch) {
+    unsigned long long b;
+    memcpy(&b, &val, 8);
+    const unsigned long long e = (unsigned long long)(unsigned)epoch << 32;
+    __atomic_store_n(p, (b & 0xffffffffull) | e, __ATOMIC_RELEASE);
+    __atomic_store_n(p + 1, (b >> 32) | e, __ATOMIC_RELEASE);
+}
+__device__ __forceinline__ double trsv_pkt_wait(const unsigned long long* p, int epoch) {
+    unsigned long long w0, w1;
+    do {
+        w0 = __atomic_load_n(p, __ATOMIC_ACQUIRE);
+        w1 = __atomic_load_n(p + 1, __ATOMIC_ACQUIRE);
+    } while ((unsigned)(w0 >> 32) != (unsigned)epoch || (unsigned)(w1 >> 32) != (unsigned)epoch);
+    const unsigned long long b = (w0 & 0xffffffffull) | (w1 << 32);
+    double val;
+    memcpy(&val, &b, 8);
+    return val;
+}
+#else
+__device__ __forceinline__ void trsv_pkt_post(unsigned long long* p, double val, int epoch) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(val);
+    const unsigned long long e = (unsigned long long)(unsigned)epoch << 32;
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"((b & 0xffffffffull) | e), "l"((b >> 32) | e)
+                 : "memory");
+}
+__device__ __forceinline__ double trsv_pkt_wait(const unsigned long long* p, int epoch) {
+    unsigned long long w0, w1;
+    do {
+        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+    } while ((unsigned)(w0 >> 32) != (unsigned)epoch || (unsigned)(w1 >> 32) != (unsigned)epoch);
+    return __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+}
+#endif
+
+template <bool TRANS, int NRHS = 1>
+__global__ void __launch_bounds__(256, 1)
+trsv_pkt_kernel(const double* __restrict__ F, int64_t ldf, int64_t m, const double* __restrict__ dinv,
+                double* x, int* flags, unsigned long long* pkt, int nblk, int epoch, int64_t xstride = 0) {
+    HYP_DYN_SMEM(double, sD);                // Dinv_k, 128 x 128 col-major
+    __shared__ double sv[NRHS][2][NB];
+    __shared__ double sacc[NRHS][2][NB];
+    __shared__ int s_ticket;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    while (true) {
+        if (tid == 0) s_ticket = atomicAdd(&flags[0], 1);
+        __syncthreads();
+        const int t = s_ticket;
+        __syncthreads();
+        if (t >= nblk) return;
+        const int k = TRANS ? t : nblk - 1 - t;
+        const int64_t c0 = (int64_t)k * NB;
+        {
+            const double* Dk = dinv + (int64_t)k * NB * NB;
+#pragma unroll 8
+            for (int idx = tid; idx < NB * NB; idx += 256) sD[idx] = Dk[idx];
+        }
+
+        if (TRANS) {
+            // y_k = Dinv_k' (b_k - sum_{j<k} U[j-block, k-block]' y_j); warp w owns 16 columns,
+            // lane l rows l, l+32, l+64, l+96 of every tile
+            double pacc[NRHS][16];
+#pragma unroll
+            for (int v = 0; v < NRHS; v++)
+#pragma unroll
+                for (int i = 0; i < 16; i++) pacc[v][i] = 0.0;
+            const int64_t cw = c0 + warp * 16;
+            // my own block of the right-hand side does not depend on the chain: fetched now, used after the last tile
+            double xown[NRHS][16];
+            if (lane == 0) {
+#pragma unroll
+                for (int v = 0; v < NRHS; v++)
+#pragma unroll
+                    for (int i = 0; i < 16; i++) xown[v][i] = (cw + i < m) ? x[v * xstride + cw + i] : 0.0;
+            }
+            for (int j = 0; j < k; j++) {
+                double tl[16][4];
+                const double* Ut = F + (int64_t)j * NB + cw * ldf;
+                if (j + 1 < k) trsv_prefetch_tile(F + (int64_t)(j + 1) * NB + c0 * ldf, ldf, NB, m - c0);
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const bool ok = cw + i < m;
+                    const double* col = Ut + (int64_t)i * ldf;
+#pragma unroll
+                    for (int h = 0; h < 4; h++) tl[i][h] = ok ? col[lane + 32 * h] : 0.0;
+                }
+                // one L2 round trip: every thread polls the packet of the entry it stages (no flag, no second load)
+                if (tid < NB * NRHS) {
+                    const int v = tid >> 7, r = tid & (NB - 1);
+                    sv[v][j & 1][r] = trsv_pkt_wait(pkt + (((int64_t)v * nblk + j) * NB + r) * 2, epoch);
+                }
+                __syncthreads();
+#pragma unroll
+                for (int v = 0; v < NRHS; v++) {
+                    const double* svj = sv[v][j & 1];
+                    const double v0 = svj[lane], v1 = svj[lane + 32], v2 = svj[lane + 64], v3 = svj[lane + 96];
+#pragma unroll
+                    for (int i = 0; i < 16; i++)
+                        pacc[v][i] += tl[i][0] * v0 + tl[i][1] * v1 + tl[i][2] * v2 + tl[i][3] * v3;
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < NRHS; v++)
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    double a = pacc[v][i];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                    pacc[v][i] = a;
+                }
+            __syncthreads();
+            if (lane == 0) {
+#pragma unroll
+                for (int v = 0; v < NRHS; v++)
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        int64_t c = cw + i;
+                        sv[v][0][warp * 16 + i] = (c < m) ? (xown[v][i] - pacc[v][i]) : 0.0;
+                    }
+            }
+            __syncthreads();
+            // y[c] = sum_{r <= c} Dinv[r, c] v[r]
+#pragma unroll
+            for (int v = 0; v < NRHS; v++) {
+                const double* vb = sv[v][0];
+                const double v0 = vb[lane], v1 = vb[lane + 32], v2 = vb[lane + 64], v3 = vb[lane + 96];
+                double res[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const double* col = sD + (warp * 16 + i) * NB;
+                    double a = col[lane] * v0 + col[lane + 32] * v1 + col[lane + 64] * v2 + col[lane + 96] * v3;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                    res[i] = a;
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        int64_t c = cw + i;
+                        if (c < m) x[v * xstride + c] = res[i];
+                        // entries past m of the last block are published as zeros (their factor entries are read as zeros)
+                        trsv_pkt_post(pkt + (((int64_t)v * nblk + k) * NB + warp * 16 + i) * 2, (c < m) ? res[i] : 0.0, epoch);
+                    }
+                }
+            }
+        } else {
+            // x_k = Dinv_k (y_k - sum_{j>k} U[k-block, j-block] x_j); thread owns a row, the two
+            // halves of the CTA split the 128 columns of a tile
+            const int r = tid & (NB - 1), half = tid >> 7;
+            const int64_t grow = c0 + r;
+            double acc[NRHS];
+#pragma unroll
+            for (int v = 0; v < NRHS; v++) acc[v] = 0.0;
+            double xown[NRHS];               // my own entry of the right-hand side (threads 0 .. 127), fetched off the chain
+#pragma unroll
+            for (int v = 0; v < NRHS; v++) xown[v] = (tid < NB && c0 + tid < m) ? x[v * xstride + c0 + tid] : 0.0;
+            for (int j = nblk - 1; j > k; j--) {
+                double tl[64];
+                const int64_t cb = (int64_t)j * NB + half * 64;
+                if (j - 1 > k) trsv_prefetch_tile(F + c0 + (int64_t)(j - 1) * NB * ldf, ldf, m - c0, NB);
+                const double* Ut = F + grow + cb * ldf;
+#pragma unroll
+                for (int c = 0; c < 64; c++) tl[c] = (grow < m && cb + c < m) ? Ut[(int64_t)c * ldf] : 0.0;
+                // one L2 round trip: every thread polls the packet of the entry it stages (no flag, no second load)
+                if (tid < NB * NRHS) {
+                    const int v = tid >> 7, r = tid & (NB - 1);
+                    sv[v][j & 1][r] = trsv_pkt_wait(pkt + (((int64_t)v * nblk + j) * NB + r) * 2, epoch);
+                }
+                __syncthreads();
+#pragma unroll
+                for (int v = 0; v < NRHS; v++) {
+                    const double* svh = sv[v][j & 1] + half * 64;
+                    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 64; c += 2) {
+                        a0 += tl[c] * svh[c];
+                        a1 += tl[c + 1] * svh[c + 1];
+                    }
+                    acc[v] += a0 + a1;
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < NRHS; v++) sacc[v][half][r] = acc[v];
+            __syncthreads();
+            if (tid < NB) {
+#pragma unroll
+                for (int v = 0; v < NRHS; v++)
+                    sv[v][0][tid] = (c0 + tid < m) ? (xown[v] - sacc[v][0][tid] - sacc[v][1][tid]) : 0.0;
+            }
+            __syncthreads();
+            // x[r] = sum_{c >= r} Dinv[r, c] v[c]
+            double o0[NRHS];
+#pragma unroll
+            for (int v = 0; v < NRHS; v++) {
+                double a0 = 0.0, a1 = 0.0;
+                const double* row = sD + r + (half * 64) * NB;
+                const double* svh = sv[v][0] + half * 64;
+#pragma unroll 16
+                for (int c = 0; c < 64; c += 2) {
+                    a0 += row[c * NB] * svh[c];
+                    a1 += row[(c + 1) * NB] * svh[c + 1];
+                }
+                o0[v] = a0 + a1;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int v = 0; v < NRHS; v++) sacc[v][half][r] = o0[v];
+            __syncthreads();
+            if (tid < NB) {
+#pragma unroll
+                for (int v = 0; v < NRHS; v++) {
+                    const double xv = (c0 + tid < m) ? sacc[v][0][tid] + sacc[v][1][tid] : 0.0;
+                    if (c0 + tid < m) x[v * xstride + c0 + tid] = xv;
+                    trsv_pkt_post(pkt + (((int64_t)v * nblk + k) * NB + tid) * 2, xv, epoch);
+                }
+            }
+        }
+        // nothing to fence or to flag: a packet carries its own epoch.  The barrier only protects the shared buffers
+        // (sD, sv, sacc) against the next ticket of this CTA.
+        __syncthreads();
+    }
+}
+
 struct TrsvTask {
     int k, j0, nj, w;     // block column, first tile (TRANS: ascending from j0, else descending), tiles, nseg << 16 | seg << 1 | final
 };

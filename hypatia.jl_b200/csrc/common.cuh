@@ -242,6 +242,8 @@ struct hyp_ctx {
     int64_t blk_maxdim = 0;
     int* d_flags = nullptr;            // TRSV ticket + block-ready flags + segment counters (1 + 2 nblk ints)
     double* d_trsv_part = nullptr;     // partial sums of the segmented triangular solve
+    unsigned long long* d_trsv_pkt = nullptr;   // {value half, epoch} packets of the triangular solves (trsv_pkt_kernel)
+    int64_t trsv_pkt_words = 0;
     int64_t trsv_part_len = 0;
     // two-column solves (hyp_solve_system_multi): partial buffers of the two-vector GEMV kernels and a second set of
     // the work vectors of solve_system_dev / apply_lhs_dev
@@ -350,6 +352,8 @@ void hyp_gemv_nt2(hyp_ctx* ctx, int64_t rows, int64_t ncols, const double* M, in
                   double* wb, double alphaT, double betaT, double* ya, double* yb);
 void hyp_trsv_upper2(hyp_ctx* ctx, const double* F, int64_t ldf, int64_t m, const double* d_dinv, double* x,
                      int64_t xstride, bool trans);
+// 1: the triangular solves publish {value half, epoch} packets (trsv_pkt_kernel) instead of flags; 0 (default): flags
+void hyp_trsv_set_pkt(int on);
 void hyp_gemv_nt(hyp_ctx* ctx, int64_t rows, int64_t ncols, const double* M, int64_t ld, const double* x,
                  const double* z, double alphaN, double betaN, double* w, double alphaT, double betaT, double* y);
 

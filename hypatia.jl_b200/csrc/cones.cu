@@ -35,6 +35,11 @@ T* upload(const std::vector<T>& v) {
     return d;
 }
 
+// columns are dealt round-robin to gridDim.y CTAs per chunk: about four columns per CTA amortise the staging of the points
+inline int soc_chunk_gy(int64_t ncols) {
+    return (int)std::min<int64_t>(std::min<int64_t>(ncols, 65535), std::max<int64_t>(64, ncols / 4));
+}
+
 template <int MODE>
 void launch_vec_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr, int64_t ncols,
                      int64_t ld_prod, int64_t ld_arr, int64_t row_shift) {
@@ -44,7 +49,7 @@ void launch_vec_prod(hyp_ctx* ctx, ConeGroup& g, double* prod, const double* arr
         hypdev::nn_prod_kernel<MODE><<<dim3(gx, gy), 256, 0, ctx->stream>>>(
             g.rows, g.d_rows, ctx->d_point, arr, ld_arr, prod, ld_prod, ncols, row_shift);
     } else if (ncols >= 16 && g.n_chunks > 0 && g.chunks_cover_all) {
-        hypdev::soc_prod_chunk_kernel<MODE><<<dim3(g.n_chunks, gy), 256, g.chunk_smem, ctx->stream>>>(
+        hypdev::soc_prod_chunk_kernel<MODE><<<dim3(g.n_chunks, soc_chunk_gy(ncols)), 256, g.chunk_smem, ctx->stream>>>(
             g.d_crow0, g.d_crows, g.d_ccone0, g.d_ccount, g.d_off, g.d_dim, g.d_scal, ctx->d_point, arr,
             ld_arr, prod, ld_prod, ncols, row_shift);
     } else {
@@ -120,7 +125,7 @@ void hyp_cones_build_groups(hyp_ctx* ctx) {
         }
         if (type == HYP_CONE_EPINORMEUCL) {
             // chunks of consecutive cones with at most CHUNK_ROWS rows (shared-memory staging)
-            const int CHUNK_ROWS = 3200, CHUNK_CONES = 256;
+            const int CHUNK_ROWS = hypdev::SOC_CHUNK_ROWS, CHUNK_CONES = 256;
             std::vector<int64_t> crow0;
             std::vector<int> crows, ccone0, ccount;
             g.chunks_cover_all = true;
@@ -142,7 +147,7 @@ void hyp_cones_build_groups(hyp_ctx* ctx) {
             }
             if (g.chunks_cover_all) {
                 g.n_chunks = (int)crow0.size();
-                g.chunk_smem = CHUNK_ROWS * (int)sizeof(double);
+                g.chunk_smem = 2 * CHUNK_ROWS * (int)sizeof(double);   // the staged column and the staged points
                 g.d_crow0 = upload(crow0);
                 g.d_crows = upload(crows);
                 g.d_ccone0 = upload(ccone0);
@@ -323,7 +328,7 @@ int hyp_cones_prepass_sliced(hyp_ctx* ctx, int8_t* digits, int64_t ldd, int64_t 
     if (g.type != HYP_CONE_EPINORMEUCL || g.n_chunks <= 0 || !g.chunks_cover_all || g.rows != ctx->qloc) return 0;
     const double* GQ2 = ctx->d_GQ + ctx->p * ctx->ldg;
     const int64_t ncols = ctx->nmp;
-    const int gy = (int)std::min<int64_t>(ncols, 65535);
+    const int gy = soc_chunk_gy(ncols);
     if (!ctx->d_colbits) CUDA_TRY(cudaMalloc((void**)&ctx->d_colbits, (size_t)std::max<int64_t>(ncols, 1) * 8));
     if (!fused) {
         TimeScope ts(ctx, T_SQRT_PREPASS);
@@ -345,7 +350,7 @@ int hyp_cones_prepass_sliced(hyp_ctx* ctx, int8_t* digits, int64_t ldd, int64_t 
             // re-walk the chunk construction of hyp_cones_build_groups
             int64_t r0 = g.h_off[i];
             int rows_c = 0, n_c = 0;
-            while (i < g.h_off.size() && n_c < 256 && rows_c + g.h_dim[i] <= 3200 && g.h_off[i] == r0 + rows_c) {
+            while (i < g.h_off.size() && n_c < 256 && rows_c + g.h_dim[i] <= hypdev::SOC_CHUNK_ROWS && g.h_off[i] == r0 + rows_c) {
                 rows_c += g.h_dim[i];
                 n_c++;
                 i++;

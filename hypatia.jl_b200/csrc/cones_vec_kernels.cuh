@@ -167,6 +167,10 @@ soc_prod_kernel(int ncones, const int64_t* __restrict__ off, const int* __restri
 // the stored product); 1 = only the column maxima of |.| (atomicMax of the bit patterns into colbits[j]); 2 = cut it
 // into radix-256 digit slices with the column exponents expo[j] and store the digits
 // (chunks start at multiples of 8 rows, checked by the host, so the packed 8-byte words are aligned).
+// rows per chunk: two staged arrays (the column of the panel and the cones' points) of this many doubles fit the 48 KB
+// of dynamic shared memory that need no opt-in; dynamic shared memory of a launch = 2 * SOC_CHUNK_ROWS doubles
+constexpr int SOC_CHUNK_ROWS = 3000;
+
 template <int MODE, int OUT = 0>
 __global__ void __launch_bounds__(256)
 soc_prod_chunk_kernel(const int64_t* __restrict__ crow0, const int* __restrict__ crows,
@@ -181,36 +185,107 @@ soc_prod_chunk_kernel(const int64_t* __restrict__ crow0, const int* __restrict__
     const int64_t r0 = crow0[b];
     const int nr = crows[b], c0 = ccone0[b], nc = ccount[b];
     const double rt2 = 1.4142135623730951;
+    // The points w of the chunk's cones, staged once per CTA (a chunk is a run of consecutive rows, so this is one coalesced
+    // copy).  Read from global memory by one thread per cone they cost 32 sectors per load instruction (lanes 25 doubles
+    // apart), twice per entry and column - about half of the load / store pipe time of a column; the host gives every
+    // CTA several columns (gridDim.y < ncols) so the copy is amortised.
+    double* sw = srow + SOC_CHUNK_ROWS;
+    for (int i = threadIdx.x; i < nr; i += blockDim.x) sw[i] = point[r0 + i];
+    // Thread t owns cone c0 + t for every column this CTA handles (a chunk holds at most blockDim.x cones: host), so
+    // whatever does not depend on the column is computed here, once: the square root and the reciprocals of the rank-one
+    // formulas (epinormeucl.jl:117-205).  The columns then cost multiplications only - the kernel was bound by its
+    // instruction count (ncu, profiles/r02_soc_prepass_ncu.md: issue slots 46 % busy at 50 % occupancy, FP64 divisions
+    // and the square root being ~30-instruction sequences each).  Products by a reciprocal differ from the quotient by
+    // at most an ulp; the one- and two-column kernels above keep the divisions.
+    const bool has = (int)threadIdx.x < nc;
+    int vo = 0, d = 0;
+    double u = 0.0, q0 = 0.0, q1 = 0.0, q2 = 0.0;
+    if (has) {
+        const int c = c0 + (int)threadIdx.x;
+        const int64_t o = off[c];
+        d = dim[c];
+        vo = (int)(o - r0);
+        const double dist = scal[8 * c];
+        u = point[o];
+        if (MODE == VK_HESS) {
+            q0 = 1.0 / dist;
+        } else if (MODE == VK_INV_HESS) {
+            q0 = dist;
+        } else {
+            const double rtdist = sqrt(dist);
+            q1 = 1.0 / (u + rtdist * rt2);
+            if (MODE == VK_SQRT_HESS) {
+                q0 = 1.0 / (dist * rt2);
+                q2 = 1.0 / rtdist;
+            } else {
+                q0 = 1.0 / rt2;
+                q2 = rtdist;
+            }
+        }
+    }
     for (int64_t j = blockIdx.y; j < ncols; j += gridDim.y) {
         const double* a = arr + j * ld_arr + (r0 - row_shift);
         double* pr = prod + j * ld_prod + (r0 - row_shift);
-        for (int i = threadIdx.x; i < nr; i += blockDim.x) srow[i] = a[i];
+        // eight loads in flight per thread before the first shared-memory store: with one load per loop trip the pass ran at
+        // 2.7 TB/s, bound by memory-level parallelism (64 warps x 256 B per SM against ~1 us of DRAM latency), not by HBM
+        for (int i0 = threadIdx.x; i0 < nr; i0 += 8 * blockDim.x) {
+            double t8[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int i = i0 + u * (int)blockDim.x;
+                t8[u] = (i < nr) ? a[i] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int i = i0 + u * (int)blockDim.x;
+                if (i < nr) srow[i] = t8[u];
+            }
+        }
         __syncthreads();
-        for (int t = threadIdx.x; t < nc; t += blockDim.x) {
-            const int c = c0 + t;
-            const int64_t o = off[c];
-            const int d = dim[c];
-            double* v = srow + (o - r0);
-            const double* w = point + o;
-            const double dist = scal[8 * c], u = w[0], uj = v[0];
-            double dotw = 0.0;
-            for (int i = 1; i < d; i++) dotw += w[i] * v[i];
+        double mx = 0.0;   // OUT 1 / 3: largest |entry| this thread produced for column j
+        if (has) {
+            double* v = srow + vo;
+            const double* w = sw + vo;
+            const double uj = v[0];
+            double s0 = 0.0, s1 = 0.0;
+            int i = 1;
+            for (; i + 8 <= d; i += 8) {
+#pragma unroll
+                for (int e = 0; e < 8; e += 2) {
+                    s0 += w[i + e] * v[i + e];
+                    s1 += w[i + e + 1] * v[i + e + 1];
+                }
+            }
+            for (; i < d; i++) s0 += w[i] * v[i];
+            const double dotw = s0 + s1;
             double k0, kw, kj;
             if (MODE == VK_HESS) {
-                double ga = (dotw - u * uj) / dist;
-                k0 = (-ga * u - uj) / dist; kw = ga / dist; kj = 1.0 / dist;
+                const double ga = (dotw - u * uj) * q0;
+                k0 = (-ga * u - uj) * q0; kw = ga * q0; kj = q0;
             } else if (MODE == VK_INV_HESS) {
-                double pa = u * uj + dotw;
-                k0 = pa * u - dist * uj; kw = pa; kj = dist;
+                const double pa = u * uj + dotw;
+                k0 = pa * u - q0 * uj; kw = pa; kj = q0;
             } else if (MODE == VK_SQRT_HESS) {
-                double distrt2 = dist * rt2, rtdist = sqrt(dist), urtdist = u + rtdist * rt2;
-                k0 = (u * uj - dotw) / distrt2; kw = (dotw / urtdist - uj) / distrt2; kj = 1.0 / rtdist;
+                k0 = (u * uj - dotw) * q0; kw = (dotw * q1 - uj) * q0; kj = q2;
             } else {
-                double rtdist = sqrt(dist), urtdist = u + rtdist * rt2;
-                k0 = (u * uj + dotw) / rt2; kw = (dotw / urtdist + uj) / rt2; kj = rtdist;
+                k0 = (u * uj + dotw) * q0; kw = (dotw * q1 + uj) * q0; kj = q2;
             }
             v[0] = k0;
-            for (int i = 1; i < d; i++) v[i] = kw * w[i] + kj * v[i];
+            mx = fabs(k0);
+            i = 1;
+            for (; i + 8 <= d; i += 8) {
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    const double r = kw * w[i + e] + kj * v[i + e];
+                    v[i + e] = r;
+                    mx = fmax(mx, fabs(r));
+                }
+            }
+            for (; i < d; i++) {
+                const double r = kw * w[i] + kj * v[i];
+                v[i] = r;
+                mx = fmax(mx, fabs(r));
+            }
         }
         __syncthreads();
         if (OUT == 0 || OUT == 3) {
@@ -218,8 +293,6 @@ soc_prod_chunk_kernel(const int64_t* __restrict__ crow0, const int* __restrict__
         }
         if (OUT == 1 || OUT == 3) {
             __shared__ double smx[8];
-            double mx = 0.0;
-            for (int i = threadIdx.x; i < nr; i += blockDim.x) mx = fmax(mx, fabs(srow[i]));
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             if ((threadIdx.x & 31) == 0) smx[threadIdx.x >> 5] = mx;

@@ -1146,6 +1146,7 @@ void hyp_destroy(hyp_ctx* ctx) {
     if (ctx->d_chol_digits) cudaFree(ctx->d_chol_digits);
     if (ctx->d_chol_dscale) cudaFree(ctx->d_chol_dscale);
     if (ctx->d_trsv_part) cudaFree(ctx->d_trsv_part);
+    if (ctx->d_trsv_pkt) cudaFree(ctx->d_trsv_pkt);
     if (ctx->d_gemm_digA) cudaFree(ctx->d_gemm_digA);
     if (ctx->d_gemm_digB) cudaFree(ctx->d_gemm_digB);
     if (ctx->d_gemm_scal) cudaFree(ctx->d_gemm_scal);
@@ -1844,6 +1845,11 @@ int hyp_test_potrf(hyp_ctx* ctx, double* A, int64_t lda, int64_t m, int* info) {
         tmp.out(A, lda, dA, la, m, m);
         return 0;
     });
+}
+
+int hyp_test_set_trsv_pkt(int on) {
+    hyp_trsv_set_pkt(on);
+    return 0;
 }
 
 int hyp_test_potrs(hyp_ctx* ctx, const double* F, int64_t ldf, int64_t m, double* x) {

@@ -66,34 +66,51 @@ static __global__ void slice_kernel(int64_t K, int64_t ncols, const double* __re
 }
 
 
-// Eight consecutive rows r[0..7] (already multiplied by 2^(7 - e)) -> one packed 8-byte word per radix-256 digit slice
-// (the arithmetic of slice256_kernel below, shared with the fused Schur pre-pass of cones_vec_kernels.cuh).
+// Eight consecutive rows r[0..7] (already multiplied by 2^(7 - e), |r| <= 127) -> one packed 8-byte word per radix-256
+// digit slice (the arithmetic of slice256_kernel below, shared with the fused Schur pre-pass of cones_vec_kernels.cuh).
+//
+// Byte-parallel formulation.  The balanced digits d_0 .. d_{S-1} in [-128, 127] of r are those of the integer
+// X = rint(r 256^(S-1)) = sum_s d_s 256^(S-1-s)  (the top-down scheme d_s = rint(r_s), r_{s+1} = 256 (r_s - d_s) with its
+// backward carry pass rounds the same tail to nearest-even - every partial sum it subtracts is a multiple of 256 - and a
+// balanced representation is unique).  Adding the bias B = sum_s 128 * 256^s makes every digit an ordinary unsigned
+// byte: X + B = sum_s (d_s + 128) 256^(S-1-s), and d_s + 128 -> d_s as a two's-complement byte is an XOR with 0x80.  So
+// ONE conversion, one 64-bit add and one XOR per value replace 7 x (rint, subtract, scale, convert) + the carry pass -
+// the top-down version kept the FP64 conversion pipe busy for longer than the 7.5 GB of the pass take to move - and
+// the 8 x 8 byte transpose into per-slice words is 32 byte permutes.  tests/test_emu_ozaki.py holds golden digits
+// of the top-down version (ties at every level, carry chains, range ends): bit-identical.
 __device__ __forceinline__ void slice256_pack8(const double (&rr)[8], int nslices, uint64_t (&w)[8]) {
-#pragma unroll
-    for (int s = 0; s < 8; s++) w[s] = 0;
+    const int S = nslices < 1 ? 1 : (nslices > 8 ? 8 : nslices);
+    const uint64_t bias = 0x8080808080808080ull >> (8 * (8 - S));
+    // 256^(S-1) as a double, built from its exponent field (exact; r * up <= 127 * 2^56 < 2^63)
+    const double up = __longlong_as_double((long long)(1023 + 8 * (S - 1)) << 52);
+    uint32_t lo[8], hi[8];
 #pragma unroll
     for (int u = 0; u < 8; u++) {
-        double r = rr[u];                                    // |r| <= 127
-        int dg[8];
+        // digit s of row u in byte 7 - s whatever S is (static register indices below); bytes of unused slices are zero
+        const uint64_t y = (((uint64_t)__double2ll_rn(rr[u] * up) + bias) ^ bias) << (8 * (8 - S));
+        lo[u] = (uint32_t)y;
+        hi[u] = (uint32_t)(y >> 32);
+    }
+    // 8 x 8 byte transpose: t[b] = byte b of rows 0 .. 7
+    uint64_t t[8];
 #pragma unroll
-        for (int s = 0; s < 8; s++) {
-            if (s < nslices) {
-                const double d = rint(r);
-                dg[s] = (int)d;
-                r = (r - d) * 256.0;                         // exact: |r - d| <= 0.5
-            } else {
-                dg[s] = 0;
-            }
+    for (int h = 0; h < 2; h++) {
+        uint32_t A[4], B[4];                       // row pair p: A = [r0.b0 r1.b0 r0.b1 r1.b1], B = [r0.b2 r1.b2 r0.b3 r1.b3]
+#pragma unroll
+        for (int pr = 0; pr < 4; pr++) {
+            const uint32_t x0 = h ? hi[2 * pr] : lo[2 * pr], x1 = h ? hi[2 * pr + 1] : lo[2 * pr + 1];
+            A[pr] = __byte_perm(x0, x1, 0x5140);
+            B[pr] = __byte_perm(x0, x1, 0x7362);
         }
 #pragma unroll
-        for (int s = 7; s >= 1; s--)
-            if (dg[s] >= 128) {
-                dg[s] -= 256;
-                dg[s - 1] += 1;
-            }
-#pragma unroll
-        for (int s = 0; s < 8; s++) w[s] |= (uint64_t)(uint8_t)(int8_t)dg[s] << (8 * u);
+        for (int c = 0; c < 4; c++) {
+            const uint32_t* F = (c < 2) ? A : B;
+            const uint32_t sel = (c & 1) ? 0x7632 : 0x5410;
+            t[4 * h + c] = (uint64_t)__byte_perm(F[0], F[1], sel) | ((uint64_t)__byte_perm(F[2], F[3], sel) << 32);
+        }
     }
+#pragma unroll
+    for (int s = 0; s < 8; s++) w[s] = t[7 - s];
 }
 
 // expo / dscale of every column from the bit patterns of the column maxima (non-negative doubles order like their
@@ -178,10 +195,21 @@ static __global__ void slice256_kernel(int64_t K, int64_t ncols, const double* _
         for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < K8;
              g += (int64_t)gridDim.x * blockDim.x) {
             double rr[8];
+            if (g * 8 + 8 <= K && ((reinterpret_cast<uintptr_t>(col) & 15) == 0)) {
+                // 16-byte loads: half the load instructions, and every lane uses half of each 32-byte sector it touches
+                const double2* c2 = reinterpret_cast<const double2*>(col + g * 8);
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int64_t k = g * 8 + u;
-                rr[u] = (k < K) ? col[k] * sc : 0.0;            // |r| <= 127
+                for (int u = 0; u < 4; u++) {
+                    const double2 v = c2[u];
+                    rr[2 * u] = v.x * sc;
+                    rr[2 * u + 1] = v.y * sc;
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int64_t k = g * 8 + u;
+                    rr[u] = (k < K) ? col[k] * sc : 0.0;        // |r| <= 127
+                }
             }
             uint64_t w[8];
             slice256_pack8(rr, nslices, w);

@@ -255,6 +255,9 @@ int hyp_test_gemm_tn(hyp_ctx* ctx, const double* P, int64_t ldp, const double* R
 int hyp_test_potrf(hyp_ctx* ctx, double* A, int64_t lda, int64_t m, int* info);
 /* profiling aid: clock64 phase timestamps of the one-CTA factor-and-invert kernel on an m x m block (m <= 128) */
 int hyp_test_panel_clocks(hyp_ctx* ctx, double* A, int64_t lda, int64_t m, double* cycles16);
+/* protocol of the triangular solves (process-wide): 0 = block flags (default), 1 = {value half, epoch} packets polled by
+ * the consumer threads themselves (csrc/chol_kernels.cuh trsv_pkt_kernel; also HYP_TRSV_PKT=1).  Same arithmetic, same bits. */
+int hyp_test_set_trsv_pkt(int on);
 /* x = (U'U)^-1 x with the factor of the last hyp_test_potrf */
 int hyp_test_potrs(hyp_ctx* ctx, const double* F, int64_t ldf, int64_t m, double* x);
 /* y = alpha * op(M) x + beta * y */

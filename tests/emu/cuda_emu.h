@@ -87,6 +87,19 @@ static inline unsigned long long atomicMax(unsigned long long* addr, unsigned lo
     return old;
 }
 static inline double __ldcg(const double* p) { return *p; }
+// conversions / byte permute of the digit slicing (ozaki_slice_kernels.cuh)
+static inline long long __double2ll_rn(double x) { return llrint(x); }   // default rounding mode: to nearest even
+static inline double __longlong_as_double(long long v) {
+    double d;
+    memcpy(&d, &v, sizeof d);
+    return d;
+}
+static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
+    const uint64_t v = (uint64_t)x | ((uint64_t)y << 32);
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) r |= (uint32_t)((v >> (8 * ((s >> (4 * i)) & 7))) & 0xff) << (8 * i);
+    return r;
+}
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
 // blocks run one after the other and the callers below are single-threaded at the call site (threadIdx.x == 0)

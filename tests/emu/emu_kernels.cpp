@@ -714,6 +714,24 @@ int emu_trsv_upper(const double* F, int64_t ldf, int64_t m, const double* dinv, 
     return 0;
 }
 
+// the packet variant (trsv_pkt_kernel, the default of hyp_trsv_upper / hyp_trsv_upper2): nrhs = 1 or 2 right-hand sides at
+// stride xstride; the packet buffer is zeroed once and reused by both sweeps with growing epochs, as in the library
+int emu_trsv_upper_pkt(const double* F, int64_t ldf, int64_t m, const double* dinv, double* x, int64_t xstride, int nrhs,
+                       int trans, unsigned long long* pkt, int epoch) {
+    const int nblk = (int)((m + hypdev::NB - 1) / hypdev::NB);
+    std::vector<int> flags((size_t)nblk + 2, 0);
+    emu::launch(dim3(nblk < 3 ? nblk : 3), dim3(256), (size_t)hypdev::NB * hypdev::NB * 8, [&] {
+        if (nrhs == 2) {
+            if (trans) hypdev::trsv_pkt_kernel<true, 2>(F, ldf, m, dinv, x, flags.data(), pkt, nblk, epoch, xstride);
+            else hypdev::trsv_pkt_kernel<false, 2>(F, ldf, m, dinv, x, flags.data(), pkt, nblk, epoch, xstride);
+        } else {
+            if (trans) hypdev::trsv_pkt_kernel<true>(F, ldf, m, dinv, x, flags.data(), pkt, nblk, epoch);
+            else hypdev::trsv_pkt_kernel<false>(F, ldf, m, dinv, x, flags.data(), pkt, nblk, epoch);
+        }
+    });
+    return 0;
+}
+
 // the segmented variant (trsv_seg_kernel, the default of hyp_trsv_upper) with block columns cut into runs of `seg` tiles
 int emu_trsv_upper_seg(const double* F, int64_t ldf, int64_t m, const double* dinv, double* x, int trans, int seg) {
     const int nblk = (int)((m + hypdev::NB - 1) / hypdev::NB);

@@ -115,6 +115,36 @@ def test_blocked_triangular_solves_give_potrs(m):
     assert rel(S @ x, b) <= 1e-11
 
 
+@pytest.mark.parametrize("m", [1, 100, 128, 129, 300, 390])
+@pytest.mark.parametrize("nrhs", [1, 2])
+def test_packet_triangular_solves_equal_the_flag_protocol_bit_for_bit(m, nrhs):
+    """trsv_pkt_kernel (default): the solution blocks travel as {32 bits of the double, epoch} words that the consumer
+    threads poll themselves.  Same arithmetic in the same order as trsv_kernel => identical bits; the packet buffer is
+    reused by both sweeps (epochs 1, 2), as in the library; entries past m of the last block are published as zeros."""
+    import ctypes as C
+    rng = np.random.default_rng(7 * m + nrhs)
+    S = _spd(rng, m, cond=1e2)
+    U = np.asfortranarray(np.linalg.cholesky(S).T)
+    nblk = (m + NB - 1) // NB
+    dinv = np.zeros(nblk * NB * NB)
+    lib().emu_panel_invert(p(U), i64(m), i64(m), p(dinv))
+    stride = m + 3
+    b = rng.standard_normal((nrhs, stride))
+    ref = b.copy()
+    for v in range(nrhs):
+        col = np.ascontiguousarray(ref[v, :m])
+        lib().emu_trsv_upper(p(U), i64(m), i64(m), p(dinv), p(col), 1)
+        lib().emu_trsv_upper(p(U), i64(m), i64(m), p(dinv), p(col), 0)
+        ref[v, :m] = col
+    x = np.ascontiguousarray(b.copy())
+    pkt = np.zeros(nrhs * nblk * NB * 2, dtype=np.uint64)
+    lib().emu_trsv_upper_pkt(p(U), i64(m), i64(m), p(dinv), p(x), i64(stride), nrhs, 1, p(pkt), 1)
+    lib().emu_trsv_upper_pkt(p(U), i64(m), i64(m), p(dinv), p(x), i64(stride), nrhs, 0, p(pkt), 2)
+    assert np.array_equal(x, ref)                     # the padding entries past m are untouched as well
+    assert rel(S @ x[0, :m], b[0, :m]) <= 1e-11
+    assert ((pkt >> np.uint64(32)) == 2).all()        # every entry of every block was published in the second sweep
+
+
 @pytest.mark.parametrize("m,seg", [(1, 8), (129, 1), (390, 1), (390, 2), (700, 2), (700, 8), (641, 3)])
 def test_segmented_triangular_solves_give_potrs(m, seg):
     """The default sweeps (trsv_seg_kernel): block columns cut into runs of `seg` tiles, partial sums through global

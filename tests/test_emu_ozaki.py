@@ -86,3 +86,15 @@ def test_recombined_digit_products_give_the_gram_matrix(radix, nslices, w, w0):
             if absum[i, j] > 0 and i != 1 and j != 1:
                 col_ratio = float(2.0 ** (int(expo[i]) + int(expo[j])) * K / absum[i, j])
                 assert float(err) <= 2.0 ** -50 * col_ratio * absum[i, j]
+
+
+@pytest.mark.parametrize("nslices", [1, 3, 5, 7, 8])
+def test_radix256_digits_match_the_golden_digits_of_the_top_down_formulation(nslices):
+    """tests/golden/slice256_digits.npz was written by the `rint`-per-digit formulation (make_slice256_golden.py); the
+    byte-parallel formulation of slice256_pack8 must give the same digits and exponents bit for bit - including the
+    rounding ties at every digit level, the +128 -> -128 carry chains and the range ends the fixture contains."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "slice256_digits.npz"))
+    D, expo, _, _ = slice_emu(g["A"], 256, nslices)
+    assert np.array_equal(expo, g[f"expo{nslices}"])
+    assert np.array_equal(D, g[f"D{nslices}"])

@@ -102,7 +102,7 @@ def test_epinormeucl_kernels_match_oracle():
     crows = np.array([int(T.dims[a:a + n].sum()) for a, n in zip(ccone0, ccount)], dtype=np.int32)
     for mode, ref in refs:
         out = np.zeros_like(arr, order="F")
-        lib().emu_soc_prod_chunk(mode, 3, int(crows.max()) * 8, p(crow0), p(crows), p(ccone0), p(ccount), p(T.off),
+        lib().emu_soc_prod_chunk(mode, 3, 2 * 3000 * 8, p(crow0), p(crows), p(ccone0), p(ccount), p(T.off),
                                  p(T.dims), p(scal), p(pt), p(arr), i64(T.q), p(out), i64(T.q), i64(3), i64(0))
         assert rel(out, ref(arr)) <= 1e-13
     out = np.zeros(T.q)

@@ -73,6 +73,34 @@ def test_potrf_potrs(cx, m):
     assert rel(A @ x, b) <= 1e-10 * np.linalg.cond(A)
 
 
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("m", [129, 1025, 3210, 10000])
+def test_packet_triangular_solves_equal_the_flag_protocol_bit_for_bit(cx, m):
+    """trsv_pkt_kernel (opt-in): the solution blocks travel between CTAs as {32 bits of the double, epoch} words that the
+    consumer threads poll themselves - the inter-CTA protocol the CPU emulation cannot exercise.  Same arithmetic in the
+    same order as the flag protocol, so the solves must agree bit for bit; repeated so that epochs and the packet buffer
+    are reused."""
+    rng = np.random.default_rng(m)
+    B = rng.standard_normal((m + 20, m))
+    A = np.asfortranarray(B.T @ B + 0.5 * np.eye(m))
+    F = A.copy(order="F")
+    info = C.c_int(-1)
+    cx.check(cx.lib.hyp_test_potrf(cx.h, _p(F), m, m, C.byref(info)), "potrf")
+    assert info.value == 0
+    b = rng.standard_normal(m)
+    x_flag = b.copy()
+    cx.check(cx.lib.hyp_test_potrs(cx.h, _p(F), m, m, _p(x_flag)), "potrs")
+    try:
+        cx.lib.hyp_test_set_trsv_pkt(1)
+        for _ in range(3):
+            x_pkt = b.copy()
+            cx.check(cx.lib.hyp_test_potrs(cx.h, _p(F), m, m, _p(x_pkt)), "potrs")
+            assert np.array_equal(x_pkt, x_flag)
+    finally:
+        cx.lib.hyp_test_set_trsv_pkt(0)
+    assert rel(A @ x_flag, b) <= 1e-10 * np.linalg.cond(A)
+
+
 def test_potrf_not_posdef(cx):
     m = 300
     rng = np.random.default_rng(3)
