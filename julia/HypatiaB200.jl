@@ -10,6 +10,10 @@ Hypatia.jl's two plug-in slots for the per-iteration hot path:
     solver carries a B200QRCholSystemSolver and `invoke` the stock generic method otherwise - no edit of
     the Hypatia.jl sources is needed (INTEGRATION.md lists each override next to the lines it replaces)
 
+  * Cones.Cone{Float64}             ->  B200Cone                    (one device cone behind the per-cone oracle API of
+    Cones.jl:34-310, bound to the single-block entry points hyp_cone_*: the drop-in for code that handles ONE cone -
+    cone tests, initialize_cone_point, user callbacks, the stock system solvers; end of this file)
+
 Everything else (Solver, steppers, preprocessing, MOI) stays stock Hypatia.jl; usage:
 
     using Hypatia, HypatiaB200
