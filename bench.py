@@ -103,9 +103,12 @@ def syrk_kernel_name():
 # DRAM traffic of the Schur SYRK (dram__bytes_read.sum + dram__bytes_write.sum over the launches of ONE SYRK) from the
 # committed `ncu --set full` capture of the same kernel build - a CONSTANT taken from that profile, not measured by
 # the run that prints it (ncu cannot run inside a timed bench); the source file is named next to it
-NCU_TRAFFIC = {"C3:i8": ((38.800736e9 + 0.807690e9) + (39.362148e9 + 0.810906e9) + (39.040170e9 + 0.809051e9),
-                         "constant from profiles/r02_ozaki_pair64_ncu_full.txt (three K-chunk launches of one SYRK, "
-                         "ozaki_syrk_pair64_kernel; only quoted when that kernel runs)"),
+NCU_TRAFFIC = {"C3:i8": ((17.548279e9 + 0.805614e9) + (18.609838e9 + 0.805811e9) + (18.045313e9 + 0.805962e9),
+                         "constant from profiles/r02_ozaki_pair64_tile_order_ncu.md (ncu metrics pass over the three K-chunk "
+                         "launches of one SYRK, ozaki_syrk_pair64_kernel with the default tile order of six resident row pairs; "
+                         "only quoted when that kernel and that order run)"),
+               "C3:i8:row1": ((38.071887e9 + 0.806117e9) + (38.576262e9 + 0.806978e9) + (38.530823e9 + 0.806765e9),
+                              "constant from profiles/r02_ozaki_pair64_tile_order_ncu.md (HYP_OZAKI_ORDER=row: one resident row pair)"),
                "C3": (31.497622e9 + 0.411380e9, "constant from profiles/r01_syrk_schur_ncu_full.txt (one launch)")}
 
 
@@ -768,7 +771,9 @@ def build_line(args, torch, device, world, main):
         # the kernel is timed inside a long step: the sustained bf16 figure is the denominator (x 2 for int8)
         bf16 = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops")
         int8_peak = 2.0 * bf16 if bf16 else None
-        traffic = NCU_TRAFFIC.get(args.workload + ":i8") if (world == 1 and "pair64" in syrk_kernel_name()) else None
+        order = os.environ.get("HYP_OZAKI_ORDER", "row6")
+        tkey = {"row6": ":i8", "row": ":i8:row1", "row1": ":i8:row1"}.get(order)
+        traffic = NCU_TRAFFIC.get(args.workload + tkey) if (world == 1 and tkey and "pair64" in syrk_kernel_name()) else None
         roofline = {"bound": "tensor",
                     "kernel": "%s (Schur SYRK: FP64-accurate digit slicing, %d exact int8 digit-pair products, tcgen05 kind::i8 "
                               "cta_group::2 M=256, TMEM accumulators, 3-D TMA) + slicing kernels" % (syrk_kernel_name(), npairs),

@@ -2279,20 +2279,26 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
             continue;
         }
         if (use_cluster == 2 || use_cluster == 4) {
-            // (P, J): tile rows 2P, 2P+1 of tile column J, for 2P <= J.  Two orders of the list (the clusters take
-            // consecutive entries, so the order decides which operand panel stays in L2):
-            //   row by row (default): the 256-row A panel of row pair P (30 MB per 16 k rows) is L2-resident and the
-            //     128-column B panels (15 MB each) stream from DRAM once per (P, J);
+            // (P, J): tile rows 2P, 2P+1 of tile column J, for 2P <= J.  Orders of the list (the clusters take
+            // consecutive entries, so the order decides which operand panels stay in L2):
+            //   row by row (HYP_OZAKI_ORDER=row, the default until the end of round 2): the 256-row A panel of row pair P
+            //     (30 MB per 16 k rows) is L2-resident and the 128-column B panels (15 MB each) stream from DRAM once per (P, J);
             //   column by column (HYP_OZAKI_ORDER=col, the first version): the B panel is resident and the A panels, twice
             //     the size, stream.  Measured on C3 (same box): 134 vs 197 GB of DRAM traffic per SYRK, L2 hit rate
             //     72 vs 65 %, 84.8 vs 86.6 ms (profiles/r01_ozaki_pair_row_order_ncu.txt).
             //   HYP_OZAKI_ORDER=row2 (experimental, not measured yet): two row pairs resident (60 MB), their tiles of one
             //     tile column adjacent in the list, so that one B panel stream can serve both.
+            //   HYP_OZAKI_ORDER=row<N> (N = 2 .. 16; N = 6 is the default): N row pairs resident, their tiles of one tile
+            //     column adjacent in the list.  The clusters stride through the list (entry cid, cid + ncl, ...), so the 74
+            //     clusters of a round then cover an N x 74/N block of tiles: every B panel serves N clusters and every A
+            //     panel 74/N instead of one B panel stream per cluster.  ncu on C3 (profiles/r02_ozaki_pair64_tile_order_ncu.md):
+            //     DRAM traffic per SYRK 117.6 -> 56.6 GB, L2 hit rate 68 -> 80 %, 53.8 -> 50.9 ms for the three launches
+            //     (timed alone); bit-identical results (the order does not touch the arithmetic of a tile).
             static const int row_order = [] {
                 const char* e = getenv("HYP_OZAKI_ORDER");
                 if (e && e[0] == 'c') return 0;
-                if (e && !strcmp(e, "row2")) return 2;
-                return 1;
+                if (e && !strncmp(e, "row", 3)) return e[3] ? std::max(1, std::min(16, atoi(e + 3))) : 1;
+                return 6;
             }();
             static std::vector<std::pair<int, std::pair<int2*, int>>> pcache;
             int2* d_pairs = nullptr;
@@ -2304,12 +2310,11 @@ void hyp_ozaki_syrk(hyp_ctx* ctx, const int8_t* digits, int64_t ldd, int64_t sli
                 }
             if (!d_pairs) {
                 std::vector<int2> pl;
-                if (row_order == 2) {
-                    for (int pp = 0; 2 * pp < nt; pp += 2)
-                        for (int tj = 2 * pp; tj < nt; tj++) {
-                            pl.push_back(make_int2(pp, tj));
-                            if (2 * (pp + 1) <= tj) pl.push_back(make_int2(pp + 1, tj));
-                        }
+                if (row_order >= 2) {
+                    for (int pp = 0; 2 * pp < nt; pp += row_order)
+                        for (int tj = 2 * pp; tj < nt; tj++)
+                            for (int r = 0; r < row_order; r++)
+                                if (2 * (pp + r) <= tj && 2 * (pp + r) < nt) pl.push_back(make_int2(pp + r, tj));
                 } else if (row_order == 1) {
                     for (int pp = 0; 2 * pp < nt; pp++)
                         for (int tj = 2 * pp; tj < nt; tj++) pl.push_back(make_int2(pp, tj));
