@@ -190,9 +190,6 @@ int hyp_cone_proxsqr(hyp_cone* cone, double irtmu, int use_max_prox, double* pro
  * qrchol.jl:104-257), 1 = SymIndefDenseSystemSolver (symindef.jl:203-271: dense (n+p+q)^2
  * symmetric-indefinite LHS, rook Bunch-Kaufman).  Call after hyp_load_model. */
 int hyp_set_syssolver(hyp_ctx* ctx, int kind);
-/* how the Schur SYRK runs: 0 = FP64 DMMA (mma.sync), 1 = FP64-accurate digit slicing on the int8
- * tcgen05 pipe (csrc/ozaki.cu).  Default 1 (0 when the environment has HYP_SCHUR_SYRK=dmma).  Models
- * that mix square-root and non-square-root cones (two-operand product) always use mode 0. */
 /* Column sharding for models dominated by ONE cone (BASELINE config 5's natvsext shape: one
  * HypoPerLogdetTri of side 1000).  Call after hyp_comm_init and BEFORE hyp_load_model, then load the model with ALL
  * rows on every rank (cone_lo = 0, cone_hi = K, G_local = G).  hess_prod! is independent per column of G_k
@@ -200,6 +197,10 @@ int hyp_set_syssolver(hyp_ctx* ctx, int kind);
  * (the branch src/Solvers/systemsolvers/qrchol.jl:240-246) and one ncclAllGather completes S; solves and oracles
  * run replicated with no further exchange. */
 int hyp_set_column_sharding(hyp_ctx* ctx, int on);
+/* how the Schur SYRK runs: 0 = FP64 DMMA (mma.sync), 1 = FP64-accurate digit slicing on the int8
+ * tcgen05 pipe (csrc/ozaki.cu).  Default 1 (0 when the environment has HYP_SCHUR_SYRK=dmma).  Models that
+ * mix square-root and non-square-root cones take the two-operand product S = P'(HG), digit-sliced on tcgen05
+ * as well since round 2 (HYP_K2_DMMA=1 restores FP64 DMMA for it). */
 int hyp_set_syrk_mode(hyp_ctx* ctx, int mode);
 /* mu and tau of the current iterate (solver.mu, solver.point.tau[]) used by
  * solve_subsystem4 / solve_system / apply_lhs (common.jl:117,171-175,147) */
