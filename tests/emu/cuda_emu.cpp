@@ -9,10 +9,12 @@ dim3 blockDim;
 dim3 gridDim;
 // every __shared__ variable of the kernel headers lives in the ELF section "emu_shared" (cuda_emu.h); the linker
 // brackets it with these two symbols
+#ifndef HYP_EMU_PLAIN_SHARED
 extern "C" {
 extern char __start_emu_shared[];
 extern char __stop_emu_shared[];
 }
+#endif
 namespace emu {
 BlockState* g_block = nullptr;
 void* g_dyn_smem = nullptr;
@@ -40,7 +42,9 @@ void launch(dim3 grid, dim3 block, size_t dyn_smem, const std::function<void()>&
             // otherwise keep the previous block's (plausible) values.  All-ones bytes = NaN for doubles, -1 for ints: a
             // kernel that reads a shared entry it did not write in THIS block now fails its test, as the NaN-poisoned
             // output buffers of the wrappers do for global memory.
+#ifndef HYP_EMU_PLAIN_SHARED
             memset(__start_emu_shared, 0xFF, (size_t)(__stop_emu_shared - __start_emu_shared));
+#endif
             if (dyn_smem) memset(smem, 0xFF, dyn_smem);
             std::vector<std::thread> th;
             th.reserve(nt);

@@ -48,7 +48,13 @@ extern dim3 gridDim;
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
+#ifdef HYP_EMU_PLAIN_SHARED
+// AddressSanitizer build (tools/emu_asan.sh): plain statics, so that every __shared__ array keeps its red zones
+// (globals in a named section are not instrumented); the per-block NaN fill then covers dynamic shared memory only
+#define __shared__ static
+#else
 #define __shared__ static __attribute__((section("emu_shared")))
+#endif
 #define HYP_DYN_SMEM(type, name) type* name = (type*)emu::g_dyn_smem
 #define INFINITY_EMU INFINITY
 

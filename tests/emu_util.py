@@ -32,7 +32,7 @@ def lib():
     deps = srcs + [os.path.join(EMU, "cuda_emu.h")] + \
         [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith("_kernels.cuh") or f == "devdefs.cuh"]
     if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
-        opt = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer"] if ASAN else \
+        opt = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-DHYP_EMU_PLAIN_SHARED"] if ASAN else \
             ["-O1", "-g", "-fsanitize=thread", "-fno-omit-frame-pointer"] if TSAN else ["-O2"]
         cmd = ["g++"] + opt + ["-std=c++17", "-fPIC", "-shared", "-pthread", "-o", LIB] + srcs
         r = subprocess.run(cmd, capture_output=True, text=True)
