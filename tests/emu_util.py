@@ -34,10 +34,14 @@ def lib():
     if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
         opt = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-DHYP_EMU_PLAIN_SHARED"] if ASAN else \
             ["-O1", "-g", "-fsanitize=thread", "-fno-omit-frame-pointer"] if TSAN else ["-O2"]
-        cmd = ["g++"] + opt + ["-std=c++17", "-fPIC", "-shared", "-pthread", "-o", LIB] + srcs
+        # built under a private name and renamed into place: with pytest-xdist several workers may get here at once,
+        # and none of them may dlopen a half-written file
+        tmp = f"{LIB}.{os.getpid()}.tmp"
+        cmd = ["g++"] + opt + ["-std=c++17", "-fPIC", "-shared", "-pthread", "-o", tmp] + srcs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("emulation build failed:\n" + r.stderr)
+        os.replace(tmp, LIB)
     _lib = C.CDLL(LIB)
     return _lib
 

@@ -134,8 +134,9 @@ def test_gpow_group_reused_across_iterates(name):
     """The per-cone scratch of a device group (g.d_vecs, the explicit Hessian, its factor) persists from one
     interior-point iterate to the next, and an infeasible trial point of the line search comes in between: a group
     that has seen another point and an infeasible point must give bit-identical results to a fresh one."""
-    cones = _sets()[name]
-    I = inst.synthetic(name, 3, 0, cones, seed=600 + NAMES.index(name))
+    full = _sets()[name]
+    cones = full[:2] + full[-1:] if len(full) > 3 else full     # state reuse does not depend on the sizes: three cones keep
+    I = inst.synthetic(name, 3, 0, cones, seed=600 + NAMES.index(name))   # the CPU tier short (one pthread per CUDA thread)
     ora = OracleConeBlock(I.model)
     prim, dual = I.point.primal_dual(ora.dual_mask)
     rng = np.random.default_rng(11)

@@ -105,6 +105,23 @@ def test_epinormeucl_kernels_match_oracle():
         lib().emu_soc_prod_chunk(mode, 3, 2 * 3000 * 8, p(crow0), p(crows), p(ccone0), p(ccount), p(T.off),
                                  p(T.dims), p(scal), p(pt), p(arr), i64(T.q), p(out), i64(T.q), i64(3), i64(0))
         assert rel(out, ref(arr)) <= 1e-13
+    # the same kernel on a rank's LOCAL row panel (row sharding): the group holds the local cones only, offsets
+    # and the point stay global, the panel starts at row_shift = first local row
+    lo = int(T.off[3])
+    off_g = np.ascontiguousarray(T.off[3:])
+    dims_g = np.ascontiguousarray(T.dims[3:])
+    scal_g = np.ascontiguousarray(scal[8 * 3:])
+    crow0_g = np.array([T.off[3], T.off[5]], dtype=np.int64)
+    ccone0_g = np.array([0, 2], dtype=np.int32)
+    ccount_g = np.array([2, 2], dtype=np.int32)
+    crows_g = np.array([int(T.dims[3:5].sum()), int(T.dims[5:7].sum())], dtype=np.int32)
+    arr_loc = np.asfortranarray(arr[lo:])
+    for mode, ref in refs:
+        out = np.full_like(arr_loc, np.nan, order="F")
+        lib().emu_soc_prod_chunk(mode, 2, 2 * 3000 * 8, p(crow0_g), p(crows_g), p(ccone0_g), p(ccount_g), p(off_g),
+                                 p(dims_g), p(scal_g), p(pt), p(arr_loc), i64(T.q - lo), p(out), i64(T.q - lo), i64(3),
+                                 i64(lo))
+        assert rel(out, ref(arr)[lo:]) <= 1e-13
     out = np.zeros(T.q)
     d = np.ascontiguousarray(arr[:, 1])
     lib().emu_soc_dder3(T.K, p(T.off), p(T.dims), p(scal), p(pt), p(d), p(out))
