@@ -167,3 +167,28 @@ def test_prox_and_numerics_reductions_match_oracle(use_max):
                         eu.C.c_double(irtmu), int(use_max), p(prox), p(ok))
     assert np.allclose(prox, ora.get_proxsqr(irtmu, use_max), rtol=1e-10, atol=1e-14)
     assert (ok.astype(bool) == ora.check_numerics()).all()
+
+
+def test_soc_chunk_kernel_several_columns_per_cta_at_c3_shape():
+    """The Schur pre-pass layout of BASELINE config 3 in small: chunks of 50 x EpiNormEucl(25) (and a ragged last chunk),
+    five columns dealt to gridDim.y = 2 CTAs per chunk, so every CTA reuses its staged points and per-cone constants for
+    two or three columns (the emulation wrapper launches 64 threads per CTA: at most 64 cones per chunk)."""
+    cones = [M.EpiNormEucl(25) for _ in range(110)] + [M.EpiNormEucl(7), M.EpiNormEucl(31)]
+    I, ora, pt, dual = _setup(cones, 5)
+    T = Table(cones)
+    grad, scal, feas, dfeas = _soc_state(T, pt, dual)
+    assert feas.all()
+    starts = [0, 50, 100]
+    counts = [50, 50, 12]
+    crow0 = np.array([T.off[a] for a in starts], dtype=np.int64)
+    ccone0 = np.array(starts, dtype=np.int32)
+    ccount = np.array(counts, dtype=np.int32)
+    crows = np.array([int(T.dims[a:a + n].sum()) for a, n in zip(starts, counts)], dtype=np.int32)
+    assert crows.max() <= 3000
+    arr = _cols(np.random.default_rng(8).standard_normal((T.q, 5)), T.q)
+    refs = ((0, ora.hess_prod), (1, ora.inv_hess_prod), (2, ora.sqrt_hess_prod), (3, ora.inv_sqrt_hess_prod))
+    for mode, ref in refs:
+        out = np.full_like(arr, np.nan, order="F")
+        lib().emu_soc_prod_chunk(mode, 3, 2 * 3000 * 8, p(crow0), p(crows), p(ccone0), p(ccount), p(T.off), p(T.dims),
+                                 p(scal), p(pt), p(arr), i64(T.q), p(out), i64(T.q), i64(5), i64(0))
+        assert rel(out, ref(arr)) <= 1e-13
